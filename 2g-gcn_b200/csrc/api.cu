@@ -1,0 +1,332 @@
+// C ABI (include/tggcn_b200.h): workspace layout and the launch sequence of one TGGCN forward
+// (vhoi/models.py:584-933).  No allocation, no device synchronisation, no state between calls.
+#include <stdarg.h>
+
+#include "common.cuh"
+#include "gemm.h"
+#include "bigru.h"
+#include "frame.h"
+
+namespace tg {
+
+static thread_local char g_err[1024] = "";
+
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+int num_sms() {
+    static int cached = 0;
+    if (cached == 0) {
+        int dev = 0, n = 0;
+        if (cudaGetDevice(&dev) == cudaSuccess &&
+            cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0)
+            cached = n;
+        else
+            return 148;
+    }
+    return cached;
+}
+
+struct Layout {
+    size_t off[TGGCN_BUF_COUNT];
+    size_t bytes[TGGCN_BUF_COUNT];
+    size_t total;
+};
+
+static int nkh_of(const tggcn_dims& d) { return d.hh ? 2 : 1; }
+
+static void make_layout(const tggcn_dims& d, Layout& L) {
+    const size_t N = (size_t)d.B * d.T, H = d.H, O = d.O, D = d.D, V = d.V;
+    const size_t f = sizeof(float);
+    const size_t nkh = nkh_of(d);
+    size_t sz[TGGCN_BUF_COUNT];
+    sz[TGGCN_BUF_GCN_OUT] = N * 128 * V * f;
+    sz[TGGCN_BUF_GEO_HID] = N * 2048 * f;
+    sz[TGGCN_BUF_S_H] = N * H * 2 * D * f;
+    sz[TGGCN_BUF_S_O] = N * O * 2 * D * f;
+    sz[TGGCN_BUF_S_G] = N * 2 * D * f;
+    sz[TGGCN_BUF_GI_H] = N * H * 6 * D * f;
+    sz[TGGCN_BUF_GI_O] = N * O * 6 * D * f;
+    sz[TGGCN_BUF_GI_G] = N * 6 * D * f;
+    sz[TGGCN_BUF_HFR_H] = N * H * 2 * D * f;
+    sz[TGGCN_BUF_HFR_O] = N * O * 2 * D * f;
+    sz[TGGCN_BUF_HFR_G] = N * 2 * D * f;
+    sz[TGGCN_BUF_MSG_HH] = N * H * D * f;
+    sz[TGGCN_BUF_MSG_HO] = N * H * D * f;
+    sz[TGGCN_BUF_MSG_OH] = N * O * D * f;
+    sz[TGGCN_BUF_MSG_OO] = N * O * D * f;
+    sz[TGGCN_BUF_MSG_GO] = N * D * f;
+    sz[TGGCN_BUF_XX_H] = N * H * (1 + nkh) * D * f;
+    sz[TGGCN_BUF_XX_O] = N * O * 4 * D * f;
+    sz[TGGCN_BUF_GS_H] = N * H * 6 * D * f;
+    sz[TGGCN_BUF_GS_O] = N * O * 6 * D * f;
+    sz[TGGCN_BUF_HX_H] = N * H * 2 * D * f;
+    sz[TGGCN_BUF_HX_O] = N * O * 2 * D * f;
+    sz[TGGCN_BUF_REIDX] = N * (H + O) * sizeof(int);
+    sz[TGGCN_BUF_SEG_SCRATCH] = (2 * (size_t)d.B * H * nkh * D + 2 * (size_t)d.B * O * 2 * D + 8 * V) * f;
+    sz[TGGCN_BUF_SYNC] = 64;
+    size_t off = 0;
+    for (int i = 0; i < TGGCN_BUF_COUNT; ++i) {
+        L.off[i] = off;
+        L.bytes[i] = sz[i];
+        off += align_up(sz[i], 256);
+    }
+    L.total = off;
+}
+
+static int check_dims(const tggcn_dims& d) {
+    TG_REQUIRE(d.B >= 1 && d.T >= 1 && d.H >= 1 && d.O >= 1, "dims: B,T,H,O must be positive");
+    TG_REQUIRE(d.D >= 16 && d.D % 16 == 0, "dims: hidden_size=%d must be a positive multiple of 16", d.D);
+    TG_REQUIRE(d.V >= 1 && d.V <= 32, "dims: gcn_node=%d unsupported", d.V);
+    TG_REQUIRE(d.Fh == 2048 + 4 * d.V, "dims: human feature size %d != 2048 + 4*gcn_node", d.Fh);
+    TG_REQUIRE(d.C_sub >= 1 && d.C_sub <= 32 && d.C_aff >= 0 && d.C_aff <= 32, "dims: class counts out of range");
+    TG_REQUIRE((size_t)d.B * d.T * (size_t)(d.H > d.O ? d.H : d.O) * 6 * d.D < (1ull << 31),
+               "dims: problem too large for 32-bit tile indexing");
+    return 0;
+}
+
+}  // namespace tg
+
+using namespace tg;
+
+extern "C" {
+
+int tggcn_abi_version(void) { return TGGCN_ABI_VERSION; }
+const char* tggcn_last_error(void) { return g_err; }
+
+size_t tggcn_workspace_bytes(const tggcn_dims* dims) {
+    if (dims == nullptr || check_dims(*dims)) return 0;
+    Layout L;
+    make_layout(*dims, L);
+    return L.total;
+}
+
+int tggcn_workspace_view(const tggcn_dims* dims, int buf_id, size_t* offset, size_t* bytes) {
+    TG_REQUIRE(dims != nullptr && buf_id >= 0 && buf_id < TGGCN_BUF_COUNT, "workspace_view: bad arguments");
+    if (int rc = check_dims(*dims)) return rc;
+    Layout L;
+    make_layout(*dims, L);
+    if (offset) *offset = L.off[buf_id];
+    if (bytes) *bytes = L.bytes[buf_id];
+    return 0;
+}
+
+int tggcn_sync_status(const tggcn_dims* dims, const void* workspace, void* stream) {
+    TG_REQUIRE(dims && workspace, "sync_status: null argument");
+    if (int rc = check_dims(*dims)) return rc;
+    Layout L;
+    make_layout(*dims, L);
+    unsigned int flags[4] = {0, 0, 0, 0};
+    TG_CUDA_OK(cudaMemcpyAsync(flags, (const char*)workspace + L.off[TGGCN_BUF_SYNC], sizeof(flags), cudaMemcpyDeviceToHost,
+                               (cudaStream_t)stream));
+    TG_CUDA_OK(cudaStreamSynchronize((cudaStream_t)stream));
+    if (flags[1] || flags[3]) {
+        set_error("persistent kernel grid barrier timed out (bigru=%u, segment=%u)", flags[1], flags[3]);
+        return 1;
+    }
+    return 0;
+}
+
+int tggcn_geo_gcn_fwd(const float* x_human, const void* const* weights, float* out, float* bn_running_mean,
+                      float* bn_running_var, int64_t* bn_num_batches, void* workspace, int B, int T, int H, int V,
+                      int Fh, int bn_train, void* stream) {
+    TG_REQUIRE(x_human && weights && out, "geo_gcn_fwd: null pointer");
+    return launch_geo_gcn(x_human, weights, out, bn_running_mean, bn_running_var, bn_num_batches, (float*)workspace, B,
+                          T, H, V, Fh, bn_train, (cudaStream_t)stream);
+}
+
+int tggcn_linear_fwd(const float* A, int lda, const float* W, int ldw, const float* bias, float* C, int ldc, int M,
+                     int N, int K, int relu, int gemm_path, void* stream) {
+    TG_REQUIRE(A && W && C, "linear_fwd: null pointer");
+    GemmGroup g;
+    g.count = 0;
+    gemm_add(g, A, lda, W, ldw, bias, C, ldc, M, N, K, relu);
+    return launch_gemm(g, gemm_path, (cudaStream_t)stream);
+}
+
+int tggcn_forward(const tggcn_dims* dims, const void* const* weights, int n_weights, const tggcn_io* io,
+                  void* workspace, size_t workspace_bytes, void* stream_) {
+    TG_REQUIRE(dims && weights && io && workspace, "forward: null argument");
+    TG_REQUIRE(n_weights == TGGCN_W_COUNT, "forward: expected %d weight pointers, got %d", (int)TGGCN_W_COUNT, n_weights);
+    const tggcn_dims& d = *dims;
+    if (int rc = check_dims(d)) return rc;
+    Layout L;
+    make_layout(d, L);
+    TG_REQUIRE(workspace_bytes >= L.total, "forward: workspace too small (%zu < %zu)", workspace_bytes, L.total);
+    TG_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 255) == 0, "forward: workspace must be 256-byte aligned");
+    cudaStream_t stream = (cudaStream_t)stream_;
+    const int B = d.B, T = d.T, H = d.H, O = d.O, D = d.D, V = d.V, N = B * T;
+    const int nkh = nkh_of(d);
+    auto W = [&](int id) { return (const float*)weights[id]; };
+    auto buf = [&](int id) { return (float*)((char*)workspace + L.off[id]); };
+
+    // required pointers
+    TG_REQUIRE(io->x_human && io->x_objects && io->objects_mask, "forward: missing inputs");
+    TG_REQUIRE(io->y_hs && io->y_hss && io->y_os && io->y_oss, "forward: missing gate outputs");
+    for (int i = 0; i < 4; ++i) TG_REQUIRE(io->out_h[i], "forward: missing human head output %d", i);
+    if (d.C_aff > 0)
+        for (int i = 0; i < 4; ++i) TG_REQUIRE(io->out_o[i], "forward: missing object head output %d", i);
+    TG_REQUIRE((d.human_seg_given != 0) == (io->human_seg != nullptr), "forward: human_seg_given flag disagrees with pointer");
+    TG_REQUIRE((d.object_seg_given != 0) == (io->object_seg != nullptr), "forward: object_seg_given flag disagrees with pointer");
+    TG_REQUIRE((d.human_seg_given && d.object_seg_given) || io->noise, "forward: Gumbel noise tensor required");
+    static const int required[] = {
+        TGGCN_W_GCN_W, TGGCN_W_GCN_BN_W, TGGCN_W_GCN_BN_B, TGGCN_W_GCN_BN_MEAN, TGGCN_W_GCN_BN_VAR, TGGCN_W_GCN_C1_W,
+        TGGCN_W_GCN_C1_B, TGGCN_W_GCN_C3_W, TGGCN_W_GCN_C3_B, TGGCN_W_GCN_S1_W, TGGCN_W_GCN_S1_B, TGGCN_W_GCN_S2_W,
+        TGGCN_W_GCN_S2_B, TGGCN_W_GEO_MLP0_W, TGGCN_W_GEO_MLP0_B, TGGCN_W_GEO_MLP2_W, TGGCN_W_GEO_MLP2_B,
+        TGGCN_W_HUM_EMB_W, TGGCN_W_HUM_EMB_B, TGGCN_W_OBJ_EMB_W, TGGCN_W_OBJ_EMB_B, TGGCN_W_GEO_BD_W, TGGCN_W_HUM_BD_W,
+        TGGCN_W_OBJ_BD_W, TGGCN_W_MSG_HO_W, TGGCN_W_MSG_OH_W, TGGCN_W_MSG_OO_W, TGGCN_W_MSG_GO_W, TGGCN_W_SMSG_HO_W,
+        TGGCN_W_SMSG_OH_W, TGGCN_W_SMSG_OO_W, TGGCN_W_UPD_H_W, TGGCN_W_UPD_O_W, TGGCN_W_HSEG_F_WIH, TGGCN_W_OSEG_F_WIH,
+        TGGCN_W_HEAD_H_FREC_W, TGGCN_W_HEAD_H_FPRED_W, TGGCN_W_HEAD_H_REC_W, TGGCN_W_HEAD_H_PRED_W};
+    for (size_t i = 0; i < sizeof(required) / sizeof(required[0]); ++i)
+        TG_REQUIRE(weights[required[i]] != nullptr, "forward: weight #%d is null", required[i]);
+    if (d.hh) TG_REQUIRE(W(TGGCN_W_MSG_HH_W) && W(TGGCN_W_SMSG_HH_W), "forward: humans->human weights missing");
+    if (d.C_aff > 0) TG_REQUIRE(W(TGGCN_W_HEAD_O_REC_W) && W(TGGCN_W_HEAD_O_FREC_W), "forward: object head weights missing");
+
+    float* scratch = buf(TGGCN_BUF_SEG_SCRATCH);
+    float* mg_h = scratch;
+    float* mg_o = mg_h + 2 * (size_t)B * H * nkh * D;
+    float* bn_stats = mg_o + 2 * (size_t)B * O * 2 * D;
+    unsigned int* sync = (unsigned int*)buf(TGGCN_BUF_SYNC);
+
+    // 1. geometry GCN (stored (B,128,V,T); the scrambled view is a reinterpretation as (B*T, 128V))
+    if (int rc = launch_geo_gcn(io->x_human, weights, buf(TGGCN_BUF_GCN_OUT), io->bn_running_mean, io->bn_running_var,
+                                io->bn_num_batches, bn_stats, B, T, H, V, d.Fh, d.bn_train, stream))
+        return rc;
+
+    GemmGroup g;
+    // 2. ROI embeddings and the first geometry MLP layer (models.py:646)
+    g.count = 0;
+    gemm_add(g, io->x_human, d.Fh, W(TGGCN_W_HUM_EMB_W), 2048, W(TGGCN_W_HUM_EMB_B), buf(TGGCN_BUF_S_H), 2 * D, N * H, D, 2048, 1);
+    gemm_add(g, io->x_objects, 2048, W(TGGCN_W_OBJ_EMB_W), 2048, W(TGGCN_W_OBJ_EMB_B), buf(TGGCN_BUF_S_O), 2 * D, N * O, D, 2048, 1);
+    gemm_add(g, buf(TGGCN_BUF_GCN_OUT), 128 * V, W(TGGCN_W_GEO_MLP0_W), 128 * V, W(TGGCN_W_GEO_MLP0_B), buf(TGGCN_BUF_GEO_HID), 2048, N, 2048, 128 * V, 1);
+    if (int rc = launch_gemm(g, d.gemm_path, stream)) return rc;
+    // 3. second geometry MLP layer
+    g.count = 0;
+    gemm_add(g, buf(TGGCN_BUF_GEO_HID), 2048, W(TGGCN_W_GEO_MLP2_W), 2048, W(TGGCN_W_GEO_MLP2_B), buf(TGGCN_BUF_S_G), 2 * D, N, D, 2048, 1);
+    if (int rc = launch_gemm(g, d.gemm_path, stream)) return rc;
+    // 4. BiGRU input pre-activations for both directions (hoisted W_ih x + b_ih)
+    g.count = 0;
+    gemm_add(g, buf(TGGCN_BUF_S_H), 2 * D, W(TGGCN_W_HUM_RNN_WIH_F), D, W(TGGCN_W_HUM_RNN_BIH_F), buf(TGGCN_BUF_GI_H), 6 * D, N * H, 3 * D, D, 0);
+    gemm_add(g, buf(TGGCN_BUF_S_H), 2 * D, W(TGGCN_W_HUM_RNN_WIH_B), D, W(TGGCN_W_HUM_RNN_BIH_B), buf(TGGCN_BUF_GI_H) + 3 * D, 6 * D, N * H, 3 * D, D, 0);
+    gemm_add(g, buf(TGGCN_BUF_S_O), 2 * D, W(TGGCN_W_OBJ_RNN_WIH_F), D, W(TGGCN_W_OBJ_RNN_BIH_F), buf(TGGCN_BUF_GI_O), 6 * D, N * O, 3 * D, D, 0);
+    gemm_add(g, buf(TGGCN_BUF_S_O), 2 * D, W(TGGCN_W_OBJ_RNN_WIH_B), D, W(TGGCN_W_OBJ_RNN_BIH_B), buf(TGGCN_BUF_GI_O) + 3 * D, 6 * D, N * O, 3 * D, D, 0);
+    gemm_add(g, buf(TGGCN_BUF_S_G), 2 * D, W(TGGCN_W_GEO_RNN_WIH_F), D, W(TGGCN_W_GEO_RNN_BIH_F), buf(TGGCN_BUF_GI_G), 6 * D, N, 3 * D, D, 0);
+    gemm_add(g, buf(TGGCN_BUF_S_G), 2 * D, W(TGGCN_W_GEO_RNN_WIH_B), D, W(TGGCN_W_GEO_RNN_BIH_B), buf(TGGCN_BUF_GI_G) + 3 * D, 6 * D, N, 3 * D, D, 0);
+    if (int rc = launch_gemm(g, d.gemm_path, stream)) return rc;
+    // 5. frame-level BiGRU recurrences (models.py:649-651)
+    {
+        BiGruParams P;
+        memset(&P, 0, sizeof(P));
+        P.ngroups = 3; P.B = B; P.T = T; P.D = D;
+        const int gi_id[3] = {TGGCN_BUF_GI_H, TGGCN_BUF_GI_O, TGGCN_BUF_GI_G};
+        const int hfr_id[3] = {TGGCN_BUF_HFR_H, TGGCN_BUF_HFR_O, TGGCN_BUF_HFR_G};
+        const int whh_f[3] = {TGGCN_W_HUM_RNN_WHH_F, TGGCN_W_OBJ_RNN_WHH_F, TGGCN_W_GEO_RNN_WHH_F};
+        const int whh_b[3] = {TGGCN_W_HUM_RNN_WHH_B, TGGCN_W_OBJ_RNN_WHH_B, TGGCN_W_GEO_RNN_WHH_B};
+        const int bhh_f[3] = {TGGCN_W_HUM_RNN_BHH_F, TGGCN_W_OBJ_RNN_BHH_F, TGGCN_W_GEO_RNN_BHH_F};
+        const int bhh_b[3] = {TGGCN_W_HUM_RNN_BHH_B, TGGCN_W_OBJ_RNN_BHH_B, TGGCN_W_GEO_RNN_BHH_B};
+        const int E[3] = {H, O, 1};
+        for (int i = 0; i < 3; ++i) {
+            P.g[i].gi = buf(gi_id[i]); P.g[i].hfr = buf(hfr_id[i]);
+            P.g[i].whh[0] = W(whh_f[i]); P.g[i].whh[1] = W(whh_b[i]);
+            P.g[i].bhh[0] = W(bhh_f[i]); P.g[i].bhh[1] = W(bhh_b[i]);
+            P.g[i].E = E[i]; P.g[i].rows = B * E[i];
+            TG_REQUIRE(P.g[i].whh[0] && P.g[i].whh[1] && P.g[i].bhh[0] && P.g[i].bhh[1], "forward: BiGRU weights missing");
+        }
+        P.sync.counter = sync; P.sync.error = sync + 1;
+        if (int rc = launch_bigru(P, d.persistent, stream)) return rc;
+    }
+    // 6. Linear(2D->D)+ReLU on the BiGRU outputs, written next to x in the [x | h] rows
+    g.count = 0;
+    gemm_add(g, buf(TGGCN_BUF_HFR_H), 2 * D, W(TGGCN_W_HUM_BD_W), 2 * D, W(TGGCN_W_HUM_BD_B), buf(TGGCN_BUF_S_H) + D, 2 * D, N * H, D, 2 * D, 1);
+    gemm_add(g, buf(TGGCN_BUF_HFR_O), 2 * D, W(TGGCN_W_OBJ_BD_W), 2 * D, W(TGGCN_W_OBJ_BD_B), buf(TGGCN_BUF_S_O) + D, 2 * D, N * O, D, 2 * D, 1);
+    gemm_add(g, buf(TGGCN_BUF_HFR_G), 2 * D, W(TGGCN_W_GEO_BD_W), 2 * D, W(TGGCN_W_GEO_BD_B), buf(TGGCN_BUF_S_G) + D, 2 * D, N, D, 2 * D, 1);
+    if (int rc = launch_gemm(g, d.gemm_path, stream)) return rc;
+    // 7. per-sender frame messages, each computed once per sender and message kind (models.py:1693-1718)
+    g.count = 0;
+    if (d.hh) gemm_add(g, buf(TGGCN_BUF_S_H), 2 * D, W(TGGCN_W_MSG_HH_W), 2 * D, W(TGGCN_W_MSG_HH_B), buf(TGGCN_BUF_MSG_HH), D, N * H, D, 2 * D, 1);
+    gemm_add(g, buf(TGGCN_BUF_S_H), 2 * D, W(TGGCN_W_MSG_HO_W), 2 * D, W(TGGCN_W_MSG_HO_B), buf(TGGCN_BUF_MSG_HO), D, N * H, D, 2 * D, 1);
+    gemm_add(g, buf(TGGCN_BUF_S_O), 2 * D, W(TGGCN_W_MSG_OH_W), 2 * D, W(TGGCN_W_MSG_OH_B), buf(TGGCN_BUF_MSG_OH), D, N * O, D, 2 * D, 1);
+    gemm_add(g, buf(TGGCN_BUF_S_O), 2 * D, W(TGGCN_W_MSG_OO_W), 2 * D, W(TGGCN_W_MSG_OO_B), buf(TGGCN_BUF_MSG_OO), D, N * O, D, 2 * D, 1);
+    gemm_add(g, buf(TGGCN_BUF_S_G), 2 * D, W(TGGCN_W_MSG_GO_W), 2 * D, W(TGGCN_W_MSG_GO_B), buf(TGGCN_BUF_MSG_GO), D, N, D, 2 * D, 1);
+    if (int rc = launch_gemm(g, d.gemm_path, stream)) return rc;
+    // 8. attention, aggregation, gates, segment-level inputs
+    {
+        FrameMsgParams P;
+        memset(&P, 0, sizeof(P));
+        P.B = B; P.T = T; P.H = H; P.O = O; P.D = D; P.hh = d.hh; P.thr = d.thr;
+        P.s_h = buf(TGGCN_BUF_S_H); P.s_o = buf(TGGCN_BUF_S_O);
+        P.msg_hh = buf(TGGCN_BUF_MSG_HH); P.msg_ho = buf(TGGCN_BUF_MSG_HO); P.msg_oh = buf(TGGCN_BUF_MSG_OH);
+        P.msg_oo = buf(TGGCN_BUF_MSG_OO); P.msg_go = buf(TGGCN_BUF_MSG_GO);
+        P.om = io->objects_mask;
+        P.w_uh = W(TGGCN_W_UPD_H_W); P.b_uh = W(TGGCN_W_UPD_H_B);
+        P.w_uo = W(TGGCN_W_UPD_O_W); P.b_uo = W(TGGCN_W_UPD_O_B);
+        P.noise = io->noise; P.human_seg = io->human_seg; P.object_seg = io->object_seg;
+        P.xx_h = buf(TGGCN_BUF_XX_H); P.xx_o = buf(TGGCN_BUF_XX_O);
+        P.y_hs = io->y_hs; P.y_hss = io->y_hss; P.y_os = io->y_os; P.y_oss = io->y_oss;
+        P.att_frame = d.inspect ? io->att_frame : nullptr;
+        if (int rc = launch_frame_messages(P, stream)) return rc;
+    }
+    // 9. optional local-maximum filter + reorder gather index
+    if (int rc = launch_gate_post(io->y_hs, io->y_hss, io->y_os, io->y_oss, (int*)buf(TGGCN_BUF_REIDX), B, T, H, O, d.filter,
+                                  d.thr, stream))
+        return rc;
+    // 10. hoisted frame-part of the segment cells' W_ih x + b_ih, both directions
+    const int kh = (1 + nkh) * D, ldwh = (1 + 2 * nkh) * D;
+    g.count = 0;
+    gemm_add(g, buf(TGGCN_BUF_XX_H), kh, W(TGGCN_W_HSEG_F_WIH), ldwh, W(TGGCN_W_HSEG_F_BIH), buf(TGGCN_BUF_GS_H), 6 * D, N * H, 3 * D, kh, 0);
+    gemm_add(g, buf(TGGCN_BUF_XX_H), kh, W(TGGCN_W_HSEG_B_WIH), ldwh, W(TGGCN_W_HSEG_B_BIH), buf(TGGCN_BUF_GS_H) + 3 * D, 6 * D, N * H, 3 * D, kh, 0);
+    gemm_add(g, buf(TGGCN_BUF_XX_O), 4 * D, W(TGGCN_W_OSEG_F_WIH), 6 * D, W(TGGCN_W_OSEG_F_BIH), buf(TGGCN_BUF_GS_O), 6 * D, N * O, 3 * D, 4 * D, 0);
+    gemm_add(g, buf(TGGCN_BUF_XX_O), 4 * D, W(TGGCN_W_OSEG_B_WIH), 6 * D, W(TGGCN_W_OSEG_B_BIH), buf(TGGCN_BUF_GS_O) + 3 * D, 6 * D, N * O, 3 * D, 4 * D, 0);
+    if (int rc = launch_gemm(g, d.gemm_path, stream)) return rc;
+    // 11. segment-level recurrent graph (models.py:785-880)
+    {
+        SegParams P;
+        memset(&P, 0, sizeof(P));
+        P.B = B; P.T = T; P.H = H; P.O = O; P.D = D; P.hh = d.hh;
+        P.gs_h = buf(TGGCN_BUF_GS_H); P.gs_o = buf(TGGCN_BUF_GS_O);
+        P.u_h = io->y_hs; P.u_o = io->y_os; P.om = io->objects_mask;
+        P.wih_h[0] = W(TGGCN_W_HSEG_F_WIH); P.wih_h[1] = W(TGGCN_W_HSEG_B_WIH); P.ldw_h = ldwh; P.col_h = kh;
+        P.wih_o[0] = W(TGGCN_W_OSEG_F_WIH); P.wih_o[1] = W(TGGCN_W_OSEG_B_WIH); P.ldw_o = 6 * D; P.col_o = 4 * D;
+        P.whh_h[0] = W(TGGCN_W_HSEG_F_WHH); P.whh_h[1] = W(TGGCN_W_HSEG_B_WHH);
+        P.bhh_h[0] = W(TGGCN_W_HSEG_F_BHH); P.bhh_h[1] = W(TGGCN_W_HSEG_B_BHH);
+        P.whh_o[0] = W(TGGCN_W_OSEG_F_WHH); P.whh_o[1] = W(TGGCN_W_OSEG_B_WHH);
+        P.bhh_o[0] = W(TGGCN_W_OSEG_F_BHH); P.bhh_o[1] = W(TGGCN_W_OSEG_B_BHH);
+        P.wm[0] = W(TGGCN_W_SMSG_HH_W); P.bm[0] = W(TGGCN_W_SMSG_HH_B);
+        P.wm[1] = W(TGGCN_W_SMSG_OH_W); P.bm[1] = W(TGGCN_W_SMSG_OH_B);
+        P.wm[2] = W(TGGCN_W_SMSG_HO_W); P.bm[2] = W(TGGCN_W_SMSG_HO_B);
+        P.wm[3] = W(TGGCN_W_SMSG_OO_W); P.bm[3] = W(TGGCN_W_SMSG_OO_B);
+        for (int i = 0; i < 2; ++i)
+            TG_REQUIRE(P.wih_h[i] && P.wih_o[i] && P.whh_h[i] && P.whh_o[i] && P.bhh_h[i] && P.bhh_o[i],
+                       "forward: segment cell weights missing");
+        P.hx_h = buf(TGGCN_BUF_HX_H); P.hx_o = buf(TGGCN_BUF_HX_O);
+        P.mg_h = mg_h; P.mg_o = mg_o;
+        P.att_f = d.inspect ? io->att_seg_f : nullptr;
+        P.att_b = d.inspect ? io->att_seg_b : nullptr;
+        P.sync.counter = sync + 2; P.sync.error = sync + 3;
+        if (int rc = launch_segment(P, d.persistent, stream)) return rc;
+    }
+    // 12. label heads (models.py:909-917)
+    {
+        HeadsParams P;
+        memset(&P, 0, sizeof(P));
+        P.B = B; P.T = T; P.E = H; P.NE = H + O; P.e_off = 0; P.D = D; P.C = d.C_sub;
+        P.hfr = buf(TGGCN_BUF_HFR_H); P.hx = buf(TGGCN_BUF_HX_H); P.reidx = (const int*)buf(TGGCN_BUF_REIDX);
+        const int wid[4] = {TGGCN_W_HEAD_H_FREC_W, TGGCN_W_HEAD_H_FPRED_W, TGGCN_W_HEAD_H_REC_W, TGGCN_W_HEAD_H_PRED_W};
+        for (int i = 0; i < 4; ++i) { P.w[i] = W(wid[i]); P.b[i] = W(wid[i] + 1); P.out[i] = io->out_h[i]; }
+        if (int rc = launch_heads(P, stream)) return rc;
+        if (d.C_aff > 0) {
+            P.E = O; P.e_off = H; P.C = d.C_aff;
+            P.hfr = buf(TGGCN_BUF_HFR_O); P.hx = buf(TGGCN_BUF_HX_O);
+            const int oid[4] = {TGGCN_W_HEAD_O_FREC_W, TGGCN_W_HEAD_O_FPRED_W, TGGCN_W_HEAD_O_REC_W, TGGCN_W_HEAD_O_PRED_W};
+            for (int i = 0; i < 4; ++i) { P.w[i] = W(oid[i]); P.b[i] = W(oid[i] + 1); P.out[i] = io->out_o[i]; }
+            if (int rc = launch_heads(P, stream)) return rc;
+        }
+    }
+    return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,65 @@
+// Parameter blocks of the recurrent kernels.
+#pragma once
+#include "common.cuh"
+
+namespace tg {
+
+struct BiGruGroup {
+    const float* gi;        // (B,T,E,2,3D) input pre-activations incl. b_ih, [dir][gate][unit]
+    float* hfr;             // (B,T,E,2D)   outputs [fwd | bwd]; also the recurrent state
+    const float* whh[2];    // (3D,D) per direction
+    const float* bhh[2];    // (3D)
+    int E;                  // entities of this group
+    int rows;               // B*E
+    int nrg, jeff, n_rb, n_ub, tile_begin;   // tiling (filled by the launcher)
+};
+
+struct BiGruParams {
+    BiGruGroup g[3];
+    int ngroups;
+    int B, T, D;
+    int total_tiles;
+    GridSync sync;
+};
+
+int launch_bigru(BiGruParams& P, int persistent, cudaStream_t stream);
+
+// ---- segment-level recurrent graph (segment.cu) ------------------------------------------------
+struct SegParams {
+    int B, T, H, O, D;
+    int hh;                       // humans->human messages on
+    // hoisted frame-part pre-activations (incl. b_ih) and gates
+    const float* gs_h;            // (B,T,H,2,3D)
+    const float* gs_o;            // (B,T,O,2,3D)
+    const float* u_h;             // (B,T,H) hard gates
+    const float* u_o;             // (B,T,O)
+    const float* om;              // (B,O)
+    // cell weights per direction: segment-message columns of W_ih, W_hh, b_hh
+    const float* wih_h[2]; int ldw_h; int col_h;    // human cell: W_ih (3D, ldw_h), segment part starts at col_h
+    const float* wih_o[2]; int ldw_o; int col_o;
+    const float* whh_h[2]; const float* bhh_h[2];
+    const float* whh_o[2]; const float* bhh_o[2];
+    // segment message MLPs (D,D) + bias; kinds: 0 hh, 1 oh (receiver human) ; 2 ho, 3 oo (receiver object)
+    const float* wm[4]; const float* bm[4];
+    // state / outputs
+    float* hx_h;                  // (B,T,H,2D) [fwd | bwd]
+    float* hx_o;                  // (B,T,O,2D)
+    float* mg_h;                  // (2,B,H,nk_h*D) aggregated segment messages per direction
+    float* mg_o;                  // (2,B,O,2D)
+    float* att_f; float* att_b;   // (B,H,T,O) or null
+    // tiling (filled by the launcher)
+    int nk_h;                     // message kinds feeding the human cell (2 with hh, else 1)
+    int bbv, n_vb;                // videos per message tile, number of video blocks
+    int msg_tiles_kind[4];        // unit blocks per kind
+    int msg_tile_begin[5];        // prefix over kinds (per direction)
+    int msg_tiles_dir;            // message tiles per direction
+    int nrg_h, jeff_h, nrb_h, nub_h;
+    int nrg_o, jeff_o, nrb_o, nub_o;
+    int cell_tiles_h_dir, cell_tiles_dir;
+    int tilesA, tilesB;
+    GridSync sync;
+};
+
+int launch_segment(SegParams& P, int persistent, cudaStream_t stream);
+
+}  // namespace tg

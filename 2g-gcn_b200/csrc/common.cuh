@@ -1,0 +1,123 @@
+// Shared device/host helpers for the sm_100a kernels of the 2G-GCN hot path.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+#include <math.h>
+
+#include "../../include/tggcn_b200.h"
+
+namespace tg {
+
+// ---------------------------------------------------------------------------------------------
+// error plumbing (host)
+// ---------------------------------------------------------------------------------------------
+void set_error(const char* fmt, ...);
+
+#define TG_CUDA_OK(expr)                                                                        \
+    do {                                                                                        \
+        cudaError_t _e = (expr);                                                                \
+        if (_e != cudaSuccess) {                                                                \
+            tg::set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #expr, cudaGetErrorString(_e)); \
+            return 1;                                                                           \
+        }                                                                                       \
+    } while (0)
+
+#define TG_REQUIRE(cond, ...)                \
+    do {                                     \
+        if (!(cond)) {                       \
+            tg::set_error(__VA_ARGS__);      \
+            return 2;                        \
+        }                                    \
+    } while (0)
+
+#define TG_LAUNCH_OK()                                                                          \
+    do {                                                                                        \
+        cudaError_t _e = cudaGetLastError();                                                    \
+        if (_e != cudaSuccess) {                                                                \
+            tg::set_error("%s:%d: launch failed -> %s", __FILE__, __LINE__, cudaGetErrorString(_e)); \
+            return 1;                                                                           \
+        }                                                                                       \
+    } while (0)
+
+inline int cdiv(int a, int b) { return (a + b - 1) / b; }
+inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+int num_sms();   // cached SM count of the current device
+
+// ---------------------------------------------------------------------------------------------
+// device helpers
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
+__device__ __forceinline__ float sigmoidf_acc(float x) { return 1.0f / (1.0f + expf(-x)); }
+
+// 16-byte async copy global -> shared, bypassing L1 (.cg): used for data other CTAs produced.
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
+    unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
+
+// L2-coherent scalar / vector loads (never served from a stale L1 line).
+__device__ __forceinline__ float ld_cg(const float* p) {
+    float v;
+    asm volatile("ld.global.cg.f32 %0, [%1];\n" : "=f"(v) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ float4 ld_cg4(const float* p) {
+    float4 v;
+    asm volatile("ld.global.cg.v4.f32 {%0,%1,%2,%3}, [%4];\n" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+    return v;
+}
+
+// ---------------------------------------------------------------------------------------------
+// grid-wide barrier for persistent (cooperatively launched) kernels.
+// A monotonically increasing arrival counter: barrier number k (1-based) completes when the counter
+// reaches k * nblocks.  Spins are bounded so a scheduling mistake surfaces as an error flag instead of
+// a hung device.
+// ---------------------------------------------------------------------------------------------
+struct GridSync {
+    unsigned int* counter;   // zeroed before launch
+    unsigned int* error;     // set to 1 on spin timeout
+};
+
+__device__ __forceinline__ bool grid_barrier(const GridSync& gs, unsigned int& epoch, unsigned int nblocks,
+                                             volatile int* s_fail) {
+    __syncthreads();
+    epoch += 1;
+    if (threadIdx.x == 0) {
+        __threadfence();
+        atomicAdd(gs.counter, 1u);
+        const unsigned int target = epoch * nblocks;
+        unsigned int spins = 0;
+        while (true) {
+            unsigned int v;
+            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];\n" : "=r"(v) : "l"(gs.counter) : "memory");
+            if (v >= target) break;
+            if (++spins > (1u << 22)) {   // far beyond any legitimate wait (each probe is an L2 round trip)
+                atomicExch(gs.error, 1u);
+                *s_fail = 1;
+                break;
+            }
+            if ((spins & 1023u) == 0 && *((volatile unsigned int*)gs.error)) { *s_fail = 1; break; }
+        }
+        __threadfence();
+    }
+    __syncthreads();
+    return *s_fail == 0;
+}
+
+}  // namespace tg

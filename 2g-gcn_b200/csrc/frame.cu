@@ -1,0 +1,306 @@
+// Frame-level graph kernels (K-D, K-E, K-G):
+//   frame_messages_kernel : per (video, frame) — scaled-dot-product attention logits between the
+//       [x | h] features of all humans and objects, masked softmax, aggregation of the per-sender
+//       messages, objects_mask multiplies, the Gumbel-sigmoid segmentation gates, and the concatenated
+//       segment-level inputs xx_h / xx_o.     (vhoi/models.py:664-749, :1004-1533, :1693-1754;
+//       pyrutils/torch/distributions.py:4-36)
+//   gate_post_kernel      : optional local-maximum filter of the soft gates (models.py:1637-1664) and
+//       the "next segment end" gather index of reorder_hidden_states (models.py:1567-1586)
+//   heads_kernel          : Linear(2D->C) + LogSoftmax + (B,T,E,C)->(B,C,T,E) (models.py:909-917)
+// All of it is memory-bound elementwise/reduction work: one pass over the frame's rows, everything
+// else in shared memory / registers.
+#include "common.cuh"
+#include "frame.h"
+
+namespace tg {
+
+constexpr int FM_THREADS = 256;
+constexpr int FM_MAXE = 16;
+
+__global__ void __launch_bounds__(FM_THREADS) frame_messages_kernel(const FrameMsgParams P) {
+    extern __shared__ __align__(16) float smem[];
+    const int D = P.D, H = P.H, O = P.O, T = P.T;
+    const int NE = H + O, D2 = 2 * D;
+    const int n = blockIdx.x, b = n / T, t = n - b * T;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int nkh = P.hh ? 2 : 1;
+
+    float* sv = smem;                         // [NE][2D]   [x | h] of humans then objects
+    float* mh = sv + NE * D2;                 // [H][nkh*D] m_hh, m_oh
+    float* mo = mh + H * nkh * D;             // [O][3D]    m_ho, m_go, m_oo
+    __shared__ float gram[(FM_MAXE * 2) * (FM_MAXE * 2)];
+    __shared__ float a_hh[FM_MAXE * FM_MAXE], a_oh[FM_MAXE * FM_MAXE], a_ho[FM_MAXE * FM_MAXE], a_oo[FM_MAXE * FM_MAXE];
+    __shared__ float om[FM_MAXE];
+
+    // -- stage rows ---------------------------------------------------------------------------------
+    for (int i = tid; i < H * D2 / 4; i += FM_THREADS)
+        reinterpret_cast<float4*>(sv)[i] = __ldg(reinterpret_cast<const float4*>(P.s_h + (size_t)n * H * D2) + i);
+    for (int i = tid; i < O * D2 / 4; i += FM_THREADS)
+        reinterpret_cast<float4*>(sv + H * D2)[i] = __ldg(reinterpret_cast<const float4*>(P.s_o + (size_t)n * O * D2) + i);
+    if (tid < O) om[tid] = P.om[b * O + tid];
+    __syncthreads();
+    // -- Gram matrix of all entity pairs, one warp per pair --------------------------------------------
+    const float scale = 1.0f / sqrtf((float)D2);
+    for (int pidx = warp; pidx < NE * NE; pidx += FM_THREADS / 32) {
+        const int e1 = pidx / NE, e2 = pidx - e1 * NE;
+        if (e2 <= e1) continue;
+        const float* x = sv + e1 * D2;
+        const float* y = sv + e2 * D2;
+        float acc = 0.0f;
+        for (int k = lane * 4; k < D2; k += 128) {
+            const float4 u = *reinterpret_cast<const float4*>(x + k);
+            const float4 v = *reinterpret_cast<const float4*>(y + k);
+            acc = fmaf(u.x, v.x, acc); acc = fmaf(u.y, v.y, acc); acc = fmaf(u.z, v.z, acc); acc = fmaf(u.w, v.w, acc);
+        }
+        acc = warp_sum(acc) * scale;
+        if (lane == 0) { gram[e1 * NE + e2] = acc; gram[e2 * NE + e1] = acc; }
+    }
+    __syncthreads();
+    // -- masked softmaxes (models.py:1750-1753): one thread per receiver and kind ---------------------
+    if (tid < 2 * NE) {
+        const int e = tid % NE;
+        const bool second = tid >= NE;          // humans: 0 -> hh, 1 -> oh ; objects: 0 -> ho, 1 -> oo
+        const bool recv_h = e < H;
+        const bool send_h = !second;            // hh / ho have human senders
+        const int r = recv_h ? e : e - H;
+        const int Es = send_h ? H : O;
+        float* out = recv_h ? (second ? a_oh : a_hh) : (second ? a_oo : a_ho);
+        const bool same = (recv_h == send_h);
+        if (!(recv_h && !second && !P.hh)) {
+            float m = -INFINITY;
+            for (int sdr = 0; sdr < Es; ++sdr) {
+                bool ok = !(same && sdr == r);
+                if (!send_h) ok = ok && (om[sdr] != 0.0f);
+                if (ok) m = fmaxf(m, gram[e * NE + (send_h ? sdr : H + sdr)]);
+            }
+            float sum = 0.0f;
+            for (int sdr = 0; sdr < Es; ++sdr) {
+                bool ok = !(same && sdr == r);
+                if (!send_h) ok = ok && (om[sdr] != 0.0f);
+                const float ex = ok ? expf(gram[e * NE + (send_h ? sdr : H + sdr)] - m) : 0.0f;
+                out[r * FM_MAXE + sdr] = ex;
+                sum += ex;
+            }
+            const float inv = sum > 0.0f ? 1.0f / sum : 0.0f;
+            for (int sdr = 0; sdr < Es; ++sdr) {
+                const float a = out[r * FM_MAXE + sdr] * inv;
+                out[r * FM_MAXE + sdr] = a;
+                if (recv_h && second && P.att_frame != nullptr) P.att_frame[((size_t)(b * H + r) * T + t) * O + sdr] = a;
+            }
+        }
+    }
+    __syncthreads();
+    // -- aggregated messages; also the concatenated segment-level inputs -------------------------------
+    {
+        const float* g_hh = P.msg_hh + (size_t)n * H * D;
+        const float* g_ho = P.msg_ho + (size_t)n * H * D;
+        const float* g_oh = P.msg_oh + (size_t)n * O * D;
+        const float* g_oo = P.msg_oo + (size_t)n * O * D;
+        const float* g_go = P.msg_go + (size_t)n * D;
+        const int wh = (1 + nkh) * D;            // xx_h row: [h, (m_hh), m_oh]
+        float* xxh = P.xx_h + (size_t)n * H * wh;
+        float* xxo = P.xx_o + (size_t)n * O * 4 * D;
+        for (int idx = tid; idx < H * D; idx += FM_THREADS) {
+            const int h = idx / D, c = idx - h * D;
+            float* row = xxh + h * wh;
+            row[c] = sv[h * D2 + D + c];
+            if (P.hh) {
+                float v = 0.0f;
+                for (int j = 0; j < H; ++j)
+                    if (j != h) v = fmaf(a_hh[h * FM_MAXE + j], __ldg(g_hh + j * D + c), v);
+                mh[h * nkh * D + c] = v;
+                row[D + c] = v;
+            }
+            float v = 0.0f;
+            for (int k = 0; k < O; ++k) v = fmaf(a_oh[h * FM_MAXE + k], __ldg(g_oh + k * D + c) * om[k], v);
+            mh[h * nkh * D + (nkh - 1) * D + c] = v;
+            row[nkh * D + c] = v;
+        }
+        for (int idx = tid; idx < O * D; idx += FM_THREADS) {
+            const int k = idx / D, c = idx - k * D;
+            float* row = xxo + k * 4 * D;
+            row[c] = sv[(H + k) * D2 + D + c];
+            float v = 0.0f;
+            for (int h = 0; h < H; ++h) v = fmaf(a_ho[k * FM_MAXE + h], __ldg(g_ho + h * D + c), v);
+            v *= om[k];                                           // models.py:720
+            const float go = __ldg(g_go + c) * om[k];             // single sender, alpha = 1; models.py:729
+            float w = 0.0f;
+            for (int j = 0; j < O; ++j)
+                if (j != k) w = fmaf(a_oo[k * FM_MAXE + j], __ldg(g_oo + j * D + c) * om[j], w);
+            mo[k * 3 * D + c] = v;
+            mo[k * 3 * D + D + c] = go;
+            mo[k * 3 * D + 2 * D + c] = w;
+            row[D + c] = v;                                       // models.py:748 order: h, m_ho, m_go, m_oo
+            row[2 * D + c] = go;
+            row[3 * D + c] = w;
+        }
+    }
+    __syncthreads();
+    // -- segmentation gates, one warp per entity -----------------------------------------------------------
+    const int n_sampled = (P.human_seg ? 0 : H) + (P.object_seg ? 0 : O);
+    for (int e = warp; e < NE; e += FM_THREADS / 32) {
+        const bool is_h = e < H;
+        const int r = is_h ? e : e - H;
+        const float* given = is_h ? P.human_seg : P.object_seg;
+        float* y_hard = is_h ? P.y_hs : P.y_os;
+        float* y_soft = is_h ? P.y_hss : P.y_oss;
+        const int E = is_h ? H : O;
+        const size_t oi = (size_t)(b * T + t) * E + r;
+        if (given != nullptr) {
+            if (lane == 0) { const float v = __ldg(given + oi); y_hard[oi] = v; y_soft[oi] = v; }
+            continue;
+        }
+        const float* w = is_h ? P.w_uh : P.w_uo;
+        float acc = 0.0f;
+        const float* s = sv + e * D2;
+        for (int k = lane; k < D2; k += 32) acc = fmaf(__ldg(w + k), s[k], acc);
+        if (is_h) {
+            const float* m = mh + r * nkh * D;       // gate input order [x, h, m_hh, m_oh], models.py:1494
+            for (int k = lane; k < nkh * D; k += 32) acc = fmaf(__ldg(w + D2 + k), m[k], acc);
+        } else {
+            const float* m = mo + r * 3 * D;          // gate input order [x, h, m_ho, m_oo, m_go], models.py:1527
+            for (int k = lane; k < D; k += 32) {
+                acc = fmaf(__ldg(w + D2 + k), m[k], acc);
+                acc = fmaf(__ldg(w + D2 + D + k), m[2 * D + k], acc);
+                acc = fmaf(__ldg(w + D2 + 2 * D + k), m[D + k], acc);
+            }
+        }
+        acc = warp_sum(acc);
+        if (lane == 0) {
+            const float logit = acc + __ldg(is_h ? P.b_uh : P.b_uo);
+            const float p = 1.0f / (1.0f + expf(-logit));
+            const int pos = is_h ? r : (P.human_seg ? 0 : H) + r;
+            const float* g = P.noise + ((size_t)(t * n_sampled + pos) * P.B + b) * 2;
+            const float la = logf(p + 1e-20f) + __ldg(g);
+            const float lb = logf((1.0f - p) + 1e-20f) + __ldg(g + 1);
+            const float mx = fmaxf(la, lb);
+            const float ea = expf(la - mx), eb = expf(lb - mx);
+            const float y = ea / (ea + eb);
+            const float z = y > P.thr ? 1.0f : 0.0f;
+            float hard = (z - y) + y;                 // straight-through value, distributions.py:35
+            if (t == T - 1) hard = 1.0f;              // models.py:701-702, :744-745
+            y_soft[oi] = y;
+            y_hard[oi] = hard;
+        }
+    }
+}
+
+size_t frame_messages_smem(int H, int O, int D, int hh) {
+    const int nkh = hh ? 2 : 1;
+    return sizeof(float) * ((size_t)(H + O) * 2 * D + (size_t)H * nkh * D + (size_t)O * 3 * D);
+}
+
+int launch_frame_messages(const FrameMsgParams& P, cudaStream_t stream) {
+    TG_REQUIRE(P.H <= FM_MAXE && P.O <= FM_MAXE, "frame_messages: at most %d humans / objects", FM_MAXE);
+    TG_REQUIRE(P.D % 4 == 0, "frame_messages: hidden_size must be a multiple of 4");
+    TG_REQUIRE(P.O >= 2 && (!P.hh || P.H >= 2), "frame_messages: need >=2 objects (and >=2 humans with humans->human)");
+    const size_t smem = frame_messages_smem(P.H, P.O, P.D, P.hh);
+    TG_REQUIRE(smem <= 200 * 1024, "frame_messages: shape needs %zu bytes of shared memory", smem);
+    static size_t configured = 0;
+    if (smem > configured) {
+        TG_CUDA_OK(cudaFuncSetAttribute(frame_messages_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = smem;
+    }
+    frame_messages_kernel<<<P.B * P.T, FM_THREADS, smem, stream>>>(P);
+    TG_LAUNCH_OK();
+    return 0;
+}
+
+// One warp per (video, entity): filter + reorder index.
+__global__ void gate_post_kernel(float* y_hs, const float* y_hss, float* y_os, const float* y_oss, int* reidx, int B, int T,
+                                 int H, int O, int filter, float thr) {
+    const int NE = H + O;
+    const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (w >= B * NE) return;
+    const int b = w / NE, e = w - b * NE;
+    const bool is_h = e < H;
+    const int E = is_h ? H : O, r = is_h ? e : e - H;
+    float* hard = is_h ? y_hs : y_os;
+    const float* soft = is_h ? y_hss : y_oss;
+    if (filter) {   // hard_t = 1 iff y_t > y_{t-1} and y_t > y_{t+1} and y_t >= thr (zeros beyond the ends)
+        for (int t = lane; t < T; t += 32) {
+            const float y = soft[(size_t)(b * T + t) * E + r];
+            const float yp = t > 0 ? soft[(size_t)(b * T + t - 1) * E + r] : 0.0f;
+            const float yn = t + 1 < T ? soft[(size_t)(b * T + t + 1) * E + r] : 0.0f;
+            const bool keep = (y > yp) && (y > yn) && (y >= thr);
+            const float z = y >= thr ? 1.0f : 0.0f;
+            const float u = (z - y) + y;
+            hard[(size_t)(b * T + t) * E + r] = keep ? u : fminf(u, 0.0f);
+        }
+        __syncwarp();
+    }
+    // idx[t] = min{ e >= t : hard[e] != 0 } if any, else t   (scan from the end, 32 frames at a time)
+    int carry = -1;
+    for (int base = ((T - 1) / 32) * 32; base >= 0; base -= 32) {
+        const int t = base + lane;
+        const bool end = t < T && hard[(size_t)(b * T + t) * E + r] != 0.0f;
+        const unsigned m = __ballot_sync(0xffffffffu, end);
+        if (t < T) {
+            const unsigned mm = m & (0xffffffffu << lane);
+            int idx;
+            if (mm) idx = base + __ffs(mm) - 1;
+            else idx = carry >= 0 ? carry : t;
+            reidx[(size_t)(b * T + t) * NE + e] = idx;
+        }
+        if (m) carry = base + __ffs(m) - 1;
+    }
+}
+
+int launch_gate_post(float* y_hs, const float* y_hss, float* y_os, const float* y_oss, int* reidx, int B, int T, int H,
+                     int O, int filter, float thr, cudaStream_t stream) {
+    const int warps = B * (H + O);
+    gate_post_kernel<<<cdiv(warps * 32, 128), 128, 0, stream>>>(y_hs, y_hss, y_os, y_oss, reidx, B, T, H, O, filter, thr);
+    TG_LAUNCH_OK();
+    return 0;
+}
+
+// One warp per (row, source): two heads share the same input row.
+__global__ void __launch_bounds__(256) heads_kernel(const HeadsParams P) {
+    const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    const int rows = P.B * P.T * P.E;
+    if (w >= rows * 2) return;
+    const int src = w / rows;              // 0: frame level (BiGRU outputs), 1: segment level (reordered states)
+    const int row = w - src * rows;
+    const int e = row % P.E, bt = row / P.E;
+    const int t = bt % P.T, b = bt / P.T;
+    const int D2 = 2 * P.D, C = P.C;
+    const float* x;
+    if (src == 0) x = P.hfr + (size_t)row * D2;
+    else {
+        const int ti = P.reidx[(size_t)bt * P.NE + P.e_off + e];
+        x = P.hx + ((size_t)(b * P.T + ti) * P.E + e) * D2;
+    }
+#pragma unroll 1
+    for (int hd = 0; hd < 2; ++hd) {
+        const float* W = P.w[src * 2 + hd];
+        const float* bias = P.b[src * 2 + hd];
+        float* out = P.out[src * 2 + hd];
+        float mine = -INFINITY;
+        for (int c = 0; c < C; ++c) {
+            const float* wr = W + (size_t)c * D2;
+            float acc = 0.0f;
+            for (int k = lane * 4; k < D2; k += 128) {
+                const float4 u = __ldg(reinterpret_cast<const float4*>(wr + k));
+                const float4 v = *reinterpret_cast<const float4*>(x + k);
+                acc = fmaf(u.x, v.x, acc); acc = fmaf(u.y, v.y, acc); acc = fmaf(u.z, v.z, acc); acc = fmaf(u.w, v.w, acc);
+            }
+            acc = warp_sum(acc) + __ldg(bias + c);
+            if (lane == c) mine = acc;
+        }
+        const float m = warp_max(mine);
+        const float ex = lane < C ? expf(mine - m) : 0.0f;
+        const float lse = m + logf(warp_sum(ex));
+        if (lane < C) out[((size_t)(b * C + lane) * P.T + t) * P.E + e] = mine - lse;
+    }
+}
+
+int launch_heads(const HeadsParams& P, cudaStream_t stream) {
+    TG_REQUIRE(P.C >= 1 && P.C <= 32, "heads: number of classes %d unsupported (1..32)", P.C);
+    TG_REQUIRE(P.D % 2 == 0, "heads: hidden_size must be even");
+    const long warps = 2L * P.B * P.T * P.E;
+    heads_kernel<<<(unsigned)((warps * 32 + 255) / 256), 256, 0, stream>>>(P);
+    TG_LAUNCH_OK();
+    return 0;
+}
+
+}  // namespace tg

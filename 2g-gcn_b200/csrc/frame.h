@@ -1,0 +1,46 @@
+// Parameter blocks of the frame-level graph kernels (frame.cu).
+#pragma once
+#include "common.cuh"
+
+namespace tg {
+
+struct FrameMsgParams {
+    int B, T, H, O, D, hh;
+    float thr;
+    const float* s_h;       // (B,T,H,2D) [x | h]
+    const float* s_o;       // (B,T,O,2D)
+    const float* msg_hh;    // (B,T,H,D) ReLU(W_hh_msg s_h + b)      (unused when !hh)
+    const float* msg_ho;    // (B,T,H,D)
+    const float* msg_oh;    // (B,T,O,D)
+    const float* msg_oo;    // (B,T,O,D)
+    const float* msg_go;    // (B,T,1,D)
+    const float* om;        // (B,O)
+    const float* w_uh; const float* b_uh;   // update_human_segment_mlp.0  (1, 2D + nkh*D)
+    const float* w_uo; const float* b_uo;   // update_object_segment_mlp.0 (1, 5D)
+    const float* noise;     // (T*n_sampled, B, 2)
+    const float* human_seg; // (B,T,H) or null
+    const float* object_seg;// (B,T,O) or null
+    float* xx_h;            // (B,T,H,(1+nkh)D)
+    float* xx_o;            // (B,T,O,4D)
+    float* y_hs; float* y_hss; float* y_os; float* y_oss;
+    float* att_frame;       // (B,H,T,O) or null
+};
+
+struct HeadsParams {
+    int B, T, E, NE, e_off, D, C;
+    const float* hfr;       // (B,T,E,2D) frame-level BiGRU outputs
+    const float* hx;        // (B,T,E,2D) segment-level states (gathered through reidx)
+    const int* reidx;       // (B,T,NE)
+    const float* w[4]; const float* b[4];   // frame_rec, frame_pred, seg_rec, seg_pred
+    float* out[4];          // (B,C,T,E)
+};
+
+int launch_frame_messages(const FrameMsgParams& P, cudaStream_t stream);
+int launch_gate_post(float* y_hs, const float* y_hss, float* y_os, const float* y_oss, int* reidx, int B, int T, int H,
+                     int O, int filter, float thr, cudaStream_t stream);
+int launch_heads(const HeadsParams& P, cudaStream_t stream);
+int launch_geo_gcn(const float* x_human, const void* const* w, float* out, float* bn_running_mean,
+                   float* bn_running_var, int64_t* bn_num_batches, float* stats_ws, int B, int T, int H, int V, int Fh,
+                   int bn_train, cudaStream_t stream);
+
+}  // namespace tg

@@ -1,0 +1,39 @@
+// Problem descriptors shared by the SIMT and tcgen05 projection kernels.
+#pragma once
+#include <cuda_runtime.h>
+
+namespace tg {
+
+constexpr int GEMM_MAX_PROBLEMS = 8;
+
+// C[M,N] = act(A[M,K] W[N,K]^T + bias[N]); A, W are K-major (row-major with leading dims lda, ldw).
+struct GemmProblem {
+    const float* A;
+    const float* W;
+    const float* bias;   // may be null
+    float* C;
+    int M, N, K;
+    int lda, ldw, ldc;
+    int relu;
+    int tile_begin;      // filled by the launcher
+};
+
+struct GemmGroup {
+    GemmProblem p[GEMM_MAX_PROBLEMS];
+    int count;
+};
+
+inline void gemm_add(GemmGroup& g, const float* A, int lda, const float* W, int ldw, const float* bias, float* C,
+                     int ldc, int M, int N, int K, int relu) {
+    GemmProblem& q = g.p[g.count++];
+    q.A = A; q.W = W; q.bias = bias; q.C = C;
+    q.M = M; q.N = N; q.K = K; q.lda = lda; q.ldw = ldw; q.ldc = ldc; q.relu = relu; q.tile_begin = 0;
+}
+
+int launch_gemm_simt(GemmGroup& grp, cudaStream_t stream);
+int launch_gemm_tc(GemmGroup& grp, cudaStream_t stream);     // tcgen05 3xTF32 (gemm_tc.cu)
+inline int launch_gemm(GemmGroup& grp, int path, cudaStream_t stream) {
+    return path == 1 ? launch_gemm_tc(grp, stream) : launch_gemm_simt(grp, stream);
+}
+
+}  // namespace tg

@@ -1,0 +1,327 @@
+"""Drop-in ``TGGCN`` (the 2G-GCN model class): host-side mirror of ``vhoi/models.py:178-933``.
+
+Same constructor arguments (``conf/models/2G-GCN_stage{1,2}.yaml:4-29`` + ``input_size`` / ``num_classes``,
+train.py:28-34), same ``state_dict()`` names and shapes (so reference ``.tar`` checkpoints load both
+ways), same keyword-called ``forward`` (vhoi/data_loading.py:1245-1279) and the same output list
+(models.py:919-932).  The module only *holds* parameters; all arithmetic of the forward runs in the
+hand-written sm_100a kernels behind the C ABI (``include/tggcn_b200.h``).  There is no PyTorch or CPU
+fallback: without a CUDA device or without the built library, ``forward`` raises.
+
+Supported configuration family = what the shipped yaml files exercise; every other flag
+value raises ``NotImplementedError`` at construction.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from typing import Optional
+
+import torch
+import torch.nn as nn
+
+from . import abi
+
+_GS = {'gs', 'gumbel-sigmoid'}
+_ATT = {'att', 'attention'}
+_V3 = {'v3', 'scaled_dot-product'}
+_NONREL = {'v2', 'non-relational'}
+_GENERIC = {'v1', 'generic'}
+_IND = {'ind', 'independent'}
+
+
+def _mlp(dims, acts):
+    """Linear/activation stack with the reference's module indices (pyrutils/torch/models.py:30-36)."""
+    layers = []
+    for i, a in enumerate(acts):
+        layers.append(nn.Linear(dims[i], dims[i + 1], bias=True))
+        layers.append({'relu': nn.ReLU, 'sigmoid': nn.Sigmoid}.get(a, nn.Identity)() if a != 'logsoftmax'
+                      else nn.LogSoftmax(dim=-1))
+    return nn.Sequential(*layers)
+
+
+class _Holder(nn.Module):
+    """Named container used to reproduce the reference's nested parameter paths."""
+
+
+def _geo_gcn_holder(node_n: int) -> nn.Module:
+    """Parameter tree of Geo_gcn (pyrutils/torch/models_gcn.py:16-28): same names, shapes and init."""
+    root = _Holder()
+    norm = _Holder()
+    norm.bn = nn.BatchNorm1d(4 * node_n)
+    conv_a, conv_b = _Holder(), _Holder()
+    conv_a.cnn = nn.Conv2d(4, 64, kernel_size=1, bias=True)
+    conv_b.cnn = nn.Conv2d(64, 64, kernel_size=1, bias=True)
+    embed = _Holder()
+    embed.cnn = nn.Sequential(norm, conv_a, nn.ReLU(), conv_b, nn.ReLU())
+    root.joint_embed = embed
+    sim = _Holder()
+    sim.s1, sim.s2 = _Holder(), _Holder()
+    sim.s1.cnn = nn.Conv2d(64, 128, kernel_size=1, bias=True)
+    sim.s2.cnn = nn.Conv2d(64, 128, kernel_size=1, bias=True)
+    root.get_s = sim
+    root.weight = nn.Parameter(torch.empty(64, 128))
+    stdv = 1.0 / math.sqrt(root.weight.size(1))
+    with torch.no_grad():
+        root.weight.uniform_(-stdv, stdv)
+    return root
+
+
+class TGGCN(nn.Module):
+    """B200-native 2G-GCN.  See module docstring; argument meaning as in vhoi/models.py:191-233."""
+
+    def __init__(self, input_size: tuple, num_classes: tuple, hidden_size: int = 128,
+                 discrete_networks_num_layers: int = 1, discrete_optimization_strategy: str = 'gumbel-sigmoid',
+                 filter_discrete_updates: bool = False, gcn_node: int = 26,
+                 message_humans_to_human: bool = True, message_human_to_objects: bool = True,
+                 message_objects_to_human: bool = True, message_objects_to_object: bool = True,
+                 message_geometry_to_objects: bool = True, message_geometry_to_human: bool = False,
+                 message_segment: bool = False, message_type: str = 'relational', message_granularity: str = 'specific',
+                 message_aggregation: str = 'attention', attention_style: str = 'concat',
+                 object_segment_update_strategy: str = 'independent', update_segment_threshold: float = 0.5,
+                 add_segment_length: bool = False, add_time_position: bool = False, time_position_strategy: str = 's',
+                 positional_encoding_style: str = 'embedding', cat_level_states: bool = False,
+                 share_level_mlps: bool = False, bias: bool = True):
+        super().__init__()
+        unsupported = []
+        if discrete_networks_num_layers != 1: unsupported.append('discrete_networks_num_layers != 1')
+        if discrete_optimization_strategy not in _GS: unsupported.append('discrete_optimization_strategy != gumbel-sigmoid')
+        if not (message_human_to_objects and message_objects_to_human and message_objects_to_object
+                and message_geometry_to_objects): unsupported.append('a human/object/geometry message switched off')
+        if message_geometry_to_human: unsupported.append('message_geometry_to_human')
+        if not message_segment: unsupported.append('message_segment off')
+        if message_type not in _NONREL: unsupported.append("message_type != 'v2'")
+        if message_granularity not in _GENERIC: unsupported.append("message_granularity != 'v1'")
+        if message_aggregation not in _ATT: unsupported.append("message_aggregation != 'att'")
+        if attention_style not in _V3: unsupported.append("attention_style != 'v3'")
+        if object_segment_update_strategy not in _IND: unsupported.append("object_segment_update_strategy != 'ind'")
+        if add_segment_length or add_time_position: unsupported.append('time/length position features')
+        if cat_level_states or share_level_mlps: unsupported.append('cat_level_states / share_level_mlps')
+        if not bias: unsupported.append('bias=False')
+        if hidden_size % 16 != 0: unsupported.append('hidden_size not a multiple of 16')
+        if unsupported:
+            raise NotImplementedError('2G-GCN B200 path supports the shipped configuration family only; got: '
+                                      + '; '.join(unsupported))
+        human_input_size, object_input_size = input_size
+        if human_input_size != 2048 + 4 * gcn_node or object_input_size != 2048:
+            raise NotImplementedError(f'input_size {tuple(input_size)} does not match 2048+4*gcn_node / 2048')
+        n_sub, n_aff = num_classes
+        D = hidden_size
+        # attributes the reference also keeps (vhoi/models.py:237-257)
+        self.discrete_optimization_strategy = discrete_optimization_strategy
+        self.filter_discrete_updates = bool(filter_discrete_updates)
+        self.gcn_node = gcn_node
+        self.message_humans_to_human = bool(message_humans_to_human)
+        self.message_human_to_objects = True
+        self.message_objects_to_human = True
+        self.message_objects_to_object = True
+        self.message_geometry_to_objects = True
+        self.message_geometry_to_human = False
+        self.message_segment = True
+        self.message_type, self.message_granularity = message_type, message_granularity
+        self.message_aggregation, self.attention_style = message_aggregation, attention_style
+        self.object_segment_update_strategy = object_segment_update_strategy
+        self.update_segment_threshold = float(update_segment_threshold)
+        self.add_segment_length = self.add_time_position = False
+        self.time_position_strategy, self.positional_encoding_style = time_position_strategy, positional_encoding_style
+        self.cat_level_states = False
+        self.hidden_size, self.num_classes = D, (n_sub, n_aff)
+        hh = self.message_humans_to_human
+        # ---- parameter holders, registered in the reference's order (vhoi/models.py:264-580) ----------
+        self.geometry_embedding_gcn = _geo_gcn_holder(gcn_node)
+        self.geometry_embedding_mlp = _mlp([gcn_node * 128, 2048, D], ['relu', 'relu'])
+        self.geometry_bd_rnn = nn.GRU(D, D, num_layers=1, bias=True, batch_first=True, bidirectional=True)
+        self.geometry_bd_embedding_mlp = _mlp([2 * D, D], ['relu'])
+        self.human_embedding_mlp = _mlp([2048, D], ['relu'])
+        self.human_bd_rnn = nn.GRU(D, D, num_layers=1, bias=True, batch_first=True, bidirectional=True)
+        self.human_bd_embedding_mlp = _mlp([2 * D, D], ['relu'])
+        h_in = D * (1 + (2 if hh else 0) + 2)
+        self.human_segment_rnn_fcell = nn.GRUCell(h_in, D, bias=True)
+        self.human_segment_rnn_bcell = nn.GRUCell(h_in, D, bias=True)
+        self.object_embedding_mlp = _mlp([object_input_size, D], ['relu'])
+        self.object_bd_rnn = nn.GRU(D, D, num_layers=1, bias=True, batch_first=True, bidirectional=True)
+        self.object_bd_embedding_mlp = _mlp([2 * D, D], ['relu'])
+        self.object_segment_rnn_fcell = nn.GRUCell(6 * D, D, bias=True)
+        self.object_segment_rnn_bcell = nn.GRUCell(6 * D, D, bias=True)
+        kinds = (['humans_to_human'] if hh else []) + ['human_to_object', 'objects_to_human', 'objects_to_object']
+        att_names = {'humans_to_human': 'humans_to_human', 'human_to_object': 'humans_to_object',
+                     'objects_to_human': 'objects_to_human', 'objects_to_object': 'objects_to_object'}
+        for kind in kinds:
+            setattr(self, f'{kind}_message_mlp', _mlp([2 * D, D], ['relu']))
+            setattr(self, f'{kind}_segment_message_mlp', _mlp([D, D], ['relu']))
+            # present in the reference's state_dict but unused under attention_style 'v3'
+            setattr(self, f'{att_names[kind]}_message_att_mlp', _mlp([4 * D, 1], ['relu']))
+            setattr(self, f'{att_names[kind]}_segment_message_att_mlp', _mlp([2 * D, 1], ['relu']))
+        self.geometry_to_object_message_mlp = _mlp([2 * D, D], ['relu'])
+        self.geometry_to_object_segment_message_mlp = _mlp([D, D], ['relu'])          # dead in the reference too
+        self.geometry_to_object_message_att_mlp = _mlp([4 * D, 1], ['relu'])
+        self.geometry_to_object_segment_message_att_mlp = _mlp([2 * D, 1], ['relu'])
+        self.update_human_segment_mlp = _mlp([D * (2 + (1 if hh else 0) + 1), 1], ['sigmoid'])
+        self.update_object_segment_mlp = _mlp([5 * D, 1], ['sigmoid'])
+        self.human_recognition_mlp = _mlp([2 * D, n_sub], ['logsoftmax'])
+        self.human_prediction_mlp = _mlp([2 * D, n_sub], ['logsoftmax'])
+        if n_aff is not None:
+            self.object_recognition_mlp = _mlp([2 * D, n_aff], ['logsoftmax'])
+            self.object_prediction_mlp = _mlp([2 * D, n_aff], ['logsoftmax'])
+        self.human_frame_recognition_mlp = _mlp([2 * D, n_sub], ['logsoftmax'])
+        self.human_frame_prediction_mlp = _mlp([2 * D, n_sub], ['logsoftmax'])
+        if n_aff is not None:
+            self.object_frame_recognition_mlp = _mlp([2 * D, n_aff], ['logsoftmax'])
+            self.object_frame_prediction_mlp = _mlp([2 * D, n_aff], ['logsoftmax'])
+        # ---- runtime state (not part of state_dict) ------------------------------------------------------
+        self._ptr_cache = None
+        self._ws = {}
+        self._noise_override: Optional[torch.Tensor] = None
+        self.persistent_kernels = True      # False: one launch per recurrent step (debug aid)
+        self.gemm_path = 0                  # 0: fp32 SIMT projections; 1: tcgen05 3xTF32
+
+    # ------------------------------------------------------------------------------------------------
+    def set_gumbel_noise(self, noise: Optional[torch.Tensor]):
+        """Inject the Gumbel(0,1) draws of the next forward calls: (n_calls, B, 2) in the reference's call
+        order (t-major; sampled humans, then sampled objects).  ``None`` restores the default, which draws
+        from the global CPU generator exactly like pyrutils/torch/distributions.py:16 does."""
+        self._noise_override = noise
+
+    def _apply(self, fn, *args, **kwargs):
+        self._ptr_cache = None
+        self._ws = {}
+        return super()._apply(fn, *args, **kwargs)
+
+    def _weight_pointers(self, device):
+        sd_items = list(self.named_parameters()) + list(self.named_buffers())
+        probe = (sd_items[0][1].data_ptr(), sd_items[-1][1].data_ptr(), len(sd_items))
+        if self._ptr_cache is not None and self._ptr_cache[0] == probe:
+            return self._ptr_cache[1]
+        arr = (C.c_void_p * abi.N_WEIGHTS)()
+        for name, t in sd_items:
+            idx = abi.WEIGHT_INDEX.get(name)
+            if idx is None:
+                continue
+            if t.device != device or t.dtype != torch.float32 or not t.is_contiguous():
+                raise abi.TggcnError(f'parameter {name} must be a contiguous fp32 tensor on {device}')
+            arr[idx] = t.data_ptr()
+        self._ptr_cache = (probe, arr)
+        return arr
+
+    def _workspace(self, dims: abi.Dims, device):
+        key = (dims.B, dims.T, dims.H, dims.O, device)
+        ws = self._ws.get(key)
+        if ws is None:
+            ws = torch.empty(abi.workspace_bytes(dims), dtype=torch.uint8, device=device)
+            if len(self._ws) > 4:
+                self._ws.clear()
+            self._ws[key] = ws
+        return ws
+
+    @staticmethod
+    def draw_gumbel_noise(n_calls: int, batch: int) -> torch.Tensor:
+        """All Gumbel(0,1) draws of one forward in one CPU call; bit-identical to n_calls successive
+        ``Gumbel(0,1).sample((batch, 2))`` calls on the global CPU generator (tests/test_noise.py)."""
+        fi = torch.finfo(torch.float32)
+        u = torch.rand(n_calls, batch, 2)
+        u = u * ((1.0 - fi.eps) - fi.tiny) + fi.tiny
+        return -torch.log(-torch.log(u))
+
+    # ------------------------------------------------------------------------------------------------
+    def forward(self, x_human, x_objects, objects_mask, human_segmentation=None, objects_segmentation=None,
+                human_human_distances=None, human_object_distances=None, object_object_distances=None,
+                steps_per_example=None, inspect_model=False):
+        """Same contract as vhoi/models.py:584-623.  Returns the list of models.py:919-926 (6 tensors, or 12
+        when affordance classes exist), plus the attention stacks when ``inspect_model``."""
+        if human_human_distances is not None or human_object_distances is not None or object_object_distances is not None:
+            raise NotImplementedError('distance-based attention (misc.make_attention_distance_based) is not supported')
+        if not x_human.is_cuda:
+            raise abi.TggcnError('2G-GCN B200 path runs on a CUDA device only (no CPU fallback); got a CPU tensor')
+        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
+            raise NotImplementedError('backward kernels are not built yet: call forward under torch.no_grad()')
+        dev = x_human.device
+        B, T, H, Fh = x_human.shape
+        O = x_objects.size(2)
+        n_sub, n_aff = self.num_classes
+        f32 = dict(dtype=torch.float32, device=dev)
+
+        def prep(t):
+            return t if (t.dtype == torch.float32 and t.is_contiguous()) else t.contiguous().float()
+        x_human, x_objects, objects_mask = prep(x_human), prep(x_objects), prep(objects_mask)
+        hseg = prep(human_segmentation) if human_segmentation is not None else None
+        oseg = prep(objects_segmentation) if objects_segmentation is not None else None
+
+        dims = abi.Dims(B=B, T=T, H=H, O=O, V=self.gcn_node, D=self.hidden_size, Fh=Fh, C_sub=n_sub,
+                        C_aff=0 if n_aff is None else n_aff, hh=int(self.message_humans_to_human),
+                        filter=int(self.filter_discrete_updates), bn_train=int(self.training),
+                        human_seg_given=int(hseg is not None), object_seg_given=int(oseg is not None),
+                        inspect=int(bool(inspect_model)), persistent=int(self.persistent_kernels),
+                        gemm_path=int(self.gemm_path), thr=self.update_segment_threshold)
+        n_sampled = (0 if hseg is not None else H) + (0 if oseg is not None else O)
+        noise = None
+        if n_sampled:
+            noise = self._noise_override
+            if noise is None:
+                noise = self.draw_gumbel_noise(T * n_sampled, B)
+            if tuple(noise.shape) != (T * n_sampled, B, 2):
+                raise ValueError(f'gumbel noise must have shape {(T * n_sampled, B, 2)}, got {tuple(noise.shape)}')
+            noise = noise.to(device=dev, dtype=torch.float32, non_blocking=True).contiguous()
+
+        y_hs, y_hss = torch.empty(B, T, H, **f32), torch.empty(B, T, H, **f32)
+        y_os, y_oss = torch.empty(B, T, O, **f32), torch.empty(B, T, O, **f32)
+        out_h = [torch.empty(B, n_sub, T, H, **f32) for _ in range(4)]
+        out_o = [torch.empty(B, n_aff, T, O, **f32) for _ in range(4)] if n_aff is not None else []
+        att = [torch.zeros(B, H, T, O, **f32) for _ in range(3)] if inspect_model else []
+
+        io = abi.IO()
+        io.x_human, io.x_objects, io.objects_mask = x_human.data_ptr(), x_objects.data_ptr(), objects_mask.data_ptr()
+        io.human_seg = hseg.data_ptr() if hseg is not None else None
+        io.object_seg = oseg.data_ptr() if oseg is not None else None
+        io.noise = noise.data_ptr() if noise is not None else None
+        io.y_hs, io.y_hss, io.y_os, io.y_oss = y_hs.data_ptr(), y_hss.data_ptr(), y_os.data_ptr(), y_oss.data_ptr()
+        for i in range(4):
+            io.out_h[i] = out_h[i].data_ptr()
+            io.out_o[i] = out_o[i].data_ptr() if out_o else None
+        if inspect_model:
+            io.att_frame, io.att_seg_f, io.att_seg_b = (a.data_ptr() for a in att)
+        bn = self.geometry_embedding_gcn.joint_embed.cnn[0].bn
+        io.bn_running_mean, io.bn_running_var = bn.running_mean.data_ptr(), bn.running_var.data_ptr()
+        io.bn_num_batches = bn.num_batches_tracked.data_ptr()
+
+        ws = self._workspace(dims, dev)
+        weights = self._weight_pointers(dev)
+        with torch.cuda.device(dev):
+            stream = torch.cuda.current_stream(dev).cuda_stream
+            rc = abi.lib().tggcn_forward(C.byref(dims), weights, abi.N_WEIGHTS, C.byref(io), ws.data_ptr(), ws.numel(),
+                                         C.c_void_p(stream))
+        abi.check(rc, 'tggcn_forward')
+        self._last = (dims, ws, (x_human, x_objects, objects_mask, hseg, oseg, noise))   # keep inputs alive until queued work ran
+        if n_aff is None:
+            output = [y_hs, y_hss] + out_h
+        else:
+            output = [y_hs, y_os, y_hss, y_oss] + out_h[:2] + out_o[:2] + out_h[2:] + out_o[2:]
+        if inspect_model:
+            return output, att
+        return output
+
+    # -- debugging / test helpers ----------------------------------------------------------------------
+    def workspace_tensor(self, name: str, shape, dtype=torch.float32) -> torch.Tensor:
+        """View of a named intermediate of the last forward (see enum tggcn_buf_id)."""
+        dims, ws, _ = self._last
+        off, nbytes = abi.workspace_view(dims, name)
+        return ws[off:off + nbytes].view(dtype)[:math.prod(shape)].view(*shape)
+
+    def check_persistent_kernels(self):
+        """Raise if a grid barrier of the persistent kernels timed out during the last forward."""
+        dims, ws, _ = self._last
+        stream = torch.cuda.current_stream(ws.device).cuda_stream
+        abi.check(abi.lib().tggcn_sync_status(C.byref(dims), ws.data_ptr(), C.c_void_p(stream)), 'persistent kernels')
+
+
+def select_model(model_name: str):
+    """Same lookup as vhoi/models.py:1589-1595 for the model this package provides."""
+    if model_name != '2G-GCN':
+        raise KeyError(f'{model_name}: only the 2G-GCN model is provided by the B200 path')
+    return TGGCN
+
+
+def install_dropin():
+    """Make the unchanged reference scripts (train.py:27, predict.py:36) pick up this class:
+    ``vhoi.models.select_model('2G-GCN')`` builds its table from the module-global ``TGGCN``."""
+    import vhoi.models as ref_models
+    ref_models.TGGCN = TGGCN
+    return ref_models

@@ -1,0 +1,255 @@
+/*
+ * tggcn_b200.h — C ABI of the B200-native 2G-GCN (TGGCN) hot path.
+ *
+ * The reference (tanqiu98/2G-GCN) is pure Python/PyTorch and has no FFI of its own; the boundary this
+ * library replaces is the body of `TGGCN.forward` (vhoi/models.py:584-933) together with the building
+ * blocks it calls (pyrutils/torch/models_gcn.py:6-100, pyrutils/torch/distributions.py:4-36).  A
+ * maintainer binds it with a ctypes stub; our own host-side mirror of the model class
+ * (2g-gcn_b200/model.py) is that stub plus the nn.Module parameter holders.
+ *
+ * Conventions
+ *  - plain pointers and sizes only; every pointer is a DEVICE pointer unless named *_host;
+ *  - all tensors are fp32, contiguous, row-major with the shapes given below (labels of the reference);
+ *  - every entry returns 0 on success, non-zero on error (message via tggcn_last_error()); no entry
+ *    allocates, synchronises the device, or keeps state between calls;
+ *  - `stream` is a cudaStream_t passed as void* (0 = legacy default stream).
+ */
+#ifndef TGGCN_B200_H_
+#define TGGCN_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TGGCN_ABI_VERSION 1
+
+#if defined(__GNUC__)
+#define TGGCN_API __attribute__((visibility("default")))
+#else
+#define TGGCN_API
+#endif
+
+/* Problem description: the constructor arguments of TGGCN.__init__ (vhoi/models.py:179-190) that change
+ * the arithmetic, plus the batch geometry of one forward call (vhoi/models.py:624, :640). */
+typedef struct tggcn_dims {
+    int32_t B, T, H, O;          /* videos, padded frames, humans, object slots                         */
+    int32_t V, D;                /* gcn_node, hidden_size                                                */
+    int32_t Fh;                  /* x_human feature size = 2048 + 4V (models.py:631-639)                 */
+    int32_t C_sub, C_aff;        /* num_classes; C_aff = 0 when num_affordances is None (models.py:560)  */
+    int32_t hh;                  /* message_humans_to_human                                              */
+    int32_t filter;              /* filter_discrete_updates (models.py:751-753)                          */
+    int32_t bn_train;            /* BatchNorm1d uses batch statistics and updates running stats          */
+    int32_t human_seg_given;     /* human_segmentation passed (models.py:697-698)                        */
+    int32_t object_seg_given;    /* objects_segmentation passed (models.py:738-739)                      */
+    int32_t inspect;             /* inspect_model: also emit attention weights (models.py:927-932)       */
+    int32_t persistent;          /* 1 = persistent cooperative recurrent kernels, 0 = one launch per step */
+    int32_t gemm_path;           /* 0 = fp32 SIMT projections, 1 = tcgen05 3xTF32 projections            */
+    float   thr;                 /* update_segment_threshold                                             */
+} tggcn_dims;
+
+/* Parameter table.  One device pointer per reference state_dict() entry, in this order
+ * (keys: SURVEY.md §8b; vhoi/models.py:264-580).  Entries a configuration does not have are NULL. */
+#define TGGCN_WEIGHT_LIST(X)                                                                            \
+    X(GCN_W,        "geometry_embedding_gcn.weight")                                                   \
+    X(GCN_BN_W,     "geometry_embedding_gcn.joint_embed.cnn.0.bn.weight")                              \
+    X(GCN_BN_B,     "geometry_embedding_gcn.joint_embed.cnn.0.bn.bias")                                \
+    X(GCN_BN_MEAN,  "geometry_embedding_gcn.joint_embed.cnn.0.bn.running_mean")                        \
+    X(GCN_BN_VAR,   "geometry_embedding_gcn.joint_embed.cnn.0.bn.running_var")                         \
+    X(GCN_C1_W,     "geometry_embedding_gcn.joint_embed.cnn.1.cnn.weight")                             \
+    X(GCN_C1_B,     "geometry_embedding_gcn.joint_embed.cnn.1.cnn.bias")                               \
+    X(GCN_C3_W,     "geometry_embedding_gcn.joint_embed.cnn.3.cnn.weight")                             \
+    X(GCN_C3_B,     "geometry_embedding_gcn.joint_embed.cnn.3.cnn.bias")                               \
+    X(GCN_S1_W,     "geometry_embedding_gcn.get_s.s1.cnn.weight")                                      \
+    X(GCN_S1_B,     "geometry_embedding_gcn.get_s.s1.cnn.bias")                                        \
+    X(GCN_S2_W,     "geometry_embedding_gcn.get_s.s2.cnn.weight")                                      \
+    X(GCN_S2_B,     "geometry_embedding_gcn.get_s.s2.cnn.bias")                                        \
+    X(GEO_MLP0_W,   "geometry_embedding_mlp.0.weight")                                                 \
+    X(GEO_MLP0_B,   "geometry_embedding_mlp.0.bias")                                                   \
+    X(GEO_MLP2_W,   "geometry_embedding_mlp.2.weight")                                                 \
+    X(GEO_MLP2_B,   "geometry_embedding_mlp.2.bias")                                                   \
+    X(HUM_EMB_W,    "human_embedding_mlp.0.weight")                                                    \
+    X(HUM_EMB_B,    "human_embedding_mlp.0.bias")                                                      \
+    X(OBJ_EMB_W,    "object_embedding_mlp.0.weight")                                                   \
+    X(OBJ_EMB_B,    "object_embedding_mlp.0.bias")                                                     \
+    X(GEO_RNN_WIH_F, "geometry_bd_rnn.weight_ih_l0")                                                   \
+    X(GEO_RNN_WHH_F, "geometry_bd_rnn.weight_hh_l0")                                                   \
+    X(GEO_RNN_BIH_F, "geometry_bd_rnn.bias_ih_l0")                                                     \
+    X(GEO_RNN_BHH_F, "geometry_bd_rnn.bias_hh_l0")                                                     \
+    X(GEO_RNN_WIH_B, "geometry_bd_rnn.weight_ih_l0_reverse")                                           \
+    X(GEO_RNN_WHH_B, "geometry_bd_rnn.weight_hh_l0_reverse")                                           \
+    X(GEO_RNN_BIH_B, "geometry_bd_rnn.bias_ih_l0_reverse")                                             \
+    X(GEO_RNN_BHH_B, "geometry_bd_rnn.bias_hh_l0_reverse")                                             \
+    X(HUM_RNN_WIH_F, "human_bd_rnn.weight_ih_l0")                                                      \
+    X(HUM_RNN_WHH_F, "human_bd_rnn.weight_hh_l0")                                                      \
+    X(HUM_RNN_BIH_F, "human_bd_rnn.bias_ih_l0")                                                        \
+    X(HUM_RNN_BHH_F, "human_bd_rnn.bias_hh_l0")                                                        \
+    X(HUM_RNN_WIH_B, "human_bd_rnn.weight_ih_l0_reverse")                                              \
+    X(HUM_RNN_WHH_B, "human_bd_rnn.weight_hh_l0_reverse")                                              \
+    X(HUM_RNN_BIH_B, "human_bd_rnn.bias_ih_l0_reverse")                                                \
+    X(HUM_RNN_BHH_B, "human_bd_rnn.bias_hh_l0_reverse")                                                \
+    X(OBJ_RNN_WIH_F, "object_bd_rnn.weight_ih_l0")                                                     \
+    X(OBJ_RNN_WHH_F, "object_bd_rnn.weight_hh_l0")                                                     \
+    X(OBJ_RNN_BIH_F, "object_bd_rnn.bias_ih_l0")                                                       \
+    X(OBJ_RNN_BHH_F, "object_bd_rnn.bias_hh_l0")                                                       \
+    X(OBJ_RNN_WIH_B, "object_bd_rnn.weight_ih_l0_reverse")                                             \
+    X(OBJ_RNN_WHH_B, "object_bd_rnn.weight_hh_l0_reverse")                                             \
+    X(OBJ_RNN_BIH_B, "object_bd_rnn.bias_ih_l0_reverse")                                               \
+    X(OBJ_RNN_BHH_B, "object_bd_rnn.bias_hh_l0_reverse")                                               \
+    X(GEO_BD_W,     "geometry_bd_embedding_mlp.0.weight")                                              \
+    X(GEO_BD_B,     "geometry_bd_embedding_mlp.0.bias")                                                \
+    X(HUM_BD_W,     "human_bd_embedding_mlp.0.weight")                                                 \
+    X(HUM_BD_B,     "human_bd_embedding_mlp.0.bias")                                                   \
+    X(OBJ_BD_W,     "object_bd_embedding_mlp.0.weight")                                                \
+    X(OBJ_BD_B,     "object_bd_embedding_mlp.0.bias")                                                  \
+    X(MSG_HH_W,     "humans_to_human_message_mlp.0.weight")                                            \
+    X(MSG_HH_B,     "humans_to_human_message_mlp.0.bias")                                              \
+    X(MSG_HO_W,     "human_to_object_message_mlp.0.weight")                                            \
+    X(MSG_HO_B,     "human_to_object_message_mlp.0.bias")                                              \
+    X(MSG_OH_W,     "objects_to_human_message_mlp.0.weight")                                           \
+    X(MSG_OH_B,     "objects_to_human_message_mlp.0.bias")                                             \
+    X(MSG_OO_W,     "objects_to_object_message_mlp.0.weight")                                          \
+    X(MSG_OO_B,     "objects_to_object_message_mlp.0.bias")                                            \
+    X(MSG_GO_W,     "geometry_to_object_message_mlp.0.weight")                                         \
+    X(MSG_GO_B,     "geometry_to_object_message_mlp.0.bias")                                           \
+    X(SMSG_HH_W,    "humans_to_human_segment_message_mlp.0.weight")                                    \
+    X(SMSG_HH_B,    "humans_to_human_segment_message_mlp.0.bias")                                      \
+    X(SMSG_HO_W,    "human_to_object_segment_message_mlp.0.weight")                                    \
+    X(SMSG_HO_B,    "human_to_object_segment_message_mlp.0.bias")                                      \
+    X(SMSG_OH_W,    "objects_to_human_segment_message_mlp.0.weight")                                   \
+    X(SMSG_OH_B,    "objects_to_human_segment_message_mlp.0.bias")                                     \
+    X(SMSG_OO_W,    "objects_to_object_segment_message_mlp.0.weight")                                  \
+    X(SMSG_OO_B,    "objects_to_object_segment_message_mlp.0.bias")                                    \
+    X(UPD_H_W,      "update_human_segment_mlp.0.weight")                                               \
+    X(UPD_H_B,      "update_human_segment_mlp.0.bias")                                                 \
+    X(UPD_O_W,      "update_object_segment_mlp.0.weight")                                              \
+    X(UPD_O_B,      "update_object_segment_mlp.0.bias")                                                \
+    X(HSEG_F_WIH,   "human_segment_rnn_fcell.weight_ih")                                               \
+    X(HSEG_F_WHH,   "human_segment_rnn_fcell.weight_hh")                                               \
+    X(HSEG_F_BIH,   "human_segment_rnn_fcell.bias_ih")                                                 \
+    X(HSEG_F_BHH,   "human_segment_rnn_fcell.bias_hh")                                                 \
+    X(HSEG_B_WIH,   "human_segment_rnn_bcell.weight_ih")                                               \
+    X(HSEG_B_WHH,   "human_segment_rnn_bcell.weight_hh")                                               \
+    X(HSEG_B_BIH,   "human_segment_rnn_bcell.bias_ih")                                                 \
+    X(HSEG_B_BHH,   "human_segment_rnn_bcell.bias_hh")                                                 \
+    X(OSEG_F_WIH,   "object_segment_rnn_fcell.weight_ih")                                              \
+    X(OSEG_F_WHH,   "object_segment_rnn_fcell.weight_hh")                                              \
+    X(OSEG_F_BIH,   "object_segment_rnn_fcell.bias_ih")                                                \
+    X(OSEG_F_BHH,   "object_segment_rnn_fcell.bias_hh")                                                \
+    X(OSEG_B_WIH,   "object_segment_rnn_bcell.weight_ih")                                              \
+    X(OSEG_B_WHH,   "object_segment_rnn_bcell.weight_hh")                                              \
+    X(OSEG_B_BIH,   "object_segment_rnn_bcell.bias_ih")                                                \
+    X(OSEG_B_BHH,   "object_segment_rnn_bcell.bias_hh")                                                \
+    X(HEAD_H_FREC_W, "human_frame_recognition_mlp.0.weight")                                           \
+    X(HEAD_H_FREC_B, "human_frame_recognition_mlp.0.bias")                                             \
+    X(HEAD_H_FPRED_W, "human_frame_prediction_mlp.0.weight")                                           \
+    X(HEAD_H_FPRED_B, "human_frame_prediction_mlp.0.bias")                                             \
+    X(HEAD_H_REC_W, "human_recognition_mlp.0.weight")                                                  \
+    X(HEAD_H_REC_B, "human_recognition_mlp.0.bias")                                                    \
+    X(HEAD_H_PRED_W, "human_prediction_mlp.0.weight")                                                  \
+    X(HEAD_H_PRED_B, "human_prediction_mlp.0.bias")                                                    \
+    X(HEAD_O_FREC_W, "object_frame_recognition_mlp.0.weight")                                          \
+    X(HEAD_O_FREC_B, "object_frame_recognition_mlp.0.bias")                                            \
+    X(HEAD_O_FPRED_W, "object_frame_prediction_mlp.0.weight")                                          \
+    X(HEAD_O_FPRED_B, "object_frame_prediction_mlp.0.bias")                                            \
+    X(HEAD_O_REC_W, "object_recognition_mlp.0.weight")                                                 \
+    X(HEAD_O_REC_B, "object_recognition_mlp.0.bias")                                                   \
+    X(HEAD_O_PRED_W, "object_prediction_mlp.0.weight")                                                 \
+    X(HEAD_O_PRED_B, "object_prediction_mlp.0.bias")
+
+enum tggcn_weight_id {
+#define TGGCN_X_ENUM(id, key) TGGCN_W_##id,
+    TGGCN_WEIGHT_LIST(TGGCN_X_ENUM)
+#undef TGGCN_X_ENUM
+    TGGCN_W_COUNT
+};
+
+/* Inputs / outputs of one forward call: the keyword arguments of TGGCN.forward (models.py:584-586,
+ * as passed by gcn_forward, vhoi/data_loading.py:1245-1279) and the tensors of its output list
+ * (models.py:919-932). */
+typedef struct tggcn_io {
+    const float* x_human;        /* (B,T,H,Fh)                                                          */
+    const float* x_objects;      /* (B,T,O,2048)                                                        */
+    const float* objects_mask;   /* (B,O) in {0,1}                                                      */
+    const float* human_seg;      /* (B,T,H) or NULL                                                     */
+    const float* object_seg;     /* (B,T,O) or NULL                                                     */
+    const float* noise;          /* (T*n_sampled, B, 2) Gumbel(0,1) draws in the reference's call order
+                                    (t-major; sampled humans then sampled objects), or NULL if none     */
+    float* y_hs;  float* y_hss;  /* (B,T,H) hard / soft human gates                                     */
+    float* y_os;  float* y_oss;  /* (B,T,O) hard / soft object gates                                    */
+    float* out_h[4];             /* frame_rec, frame_pred, seg_rec, seg_pred: (B,C_sub,T,H) log-probs   */
+    float* out_o[4];             /* same for objects (B,C_aff,T,O); NULL when C_aff == 0                */
+    float* att_frame;            /* (B,H,T,O) objects->human frame attention, NULL unless inspect       */
+    float* att_seg_f;            /* (B,H,T,O) segment-level, forward direction, NULL unless inspect     */
+    float* att_seg_b;            /* (B,H,T,O) segment-level, backward direction, NULL unless inspect    */
+    float* bn_running_mean;      /* (4V) updated in place when bn_train                                  */
+    float* bn_running_var;       /* (4V) updated in place when bn_train                                  */
+    int64_t* bn_num_batches;     /* scalar, incremented when bn_train                                    */
+} tggcn_io;
+
+/* Named regions of the workspace, exposed so that tests can compare intermediates with the oracle. */
+enum tggcn_buf_id {
+    TGGCN_BUF_GCN_OUT = 0,   /* (B,128,V,T)          Geo_gcn output, models_gcn.py:30-37                 */
+    TGGCN_BUF_GEO_HID,       /* (B*T,2048)           geometry_embedding_mlp hidden                       */
+    TGGCN_BUF_S_H,           /* (B,T,H,2D)           [x_h | h_h]                                         */
+    TGGCN_BUF_S_O,           /* (B,T,O,2D)                                                               */
+    TGGCN_BUF_S_G,           /* (B,T,1,2D)                                                               */
+    TGGCN_BUF_GI_H,          /* (B,T,H,2,3D)         BiGRU input pre-activations (fwd, bwd)              */
+    TGGCN_BUF_GI_O,
+    TGGCN_BUF_GI_G,
+    TGGCN_BUF_HFR_H,         /* (B,T,H,2D)           BiGRU outputs                                       */
+    TGGCN_BUF_HFR_O,
+    TGGCN_BUF_HFR_G,
+    TGGCN_BUF_MSG_HH,        /* (B,T,H,D)            per-sender frame messages                           */
+    TGGCN_BUF_MSG_HO,        /* (B,T,H,D)                                                                */
+    TGGCN_BUF_MSG_OH,        /* (B,T,O,D)                                                                */
+    TGGCN_BUF_MSG_OO,        /* (B,T,O,D)                                                                */
+    TGGCN_BUF_MSG_GO,        /* (B,T,1,D)                                                                */
+    TGGCN_BUF_XX_H,          /* (B,T,H,3D or 2D)     segment-level frame inputs, models.py:705           */
+    TGGCN_BUF_XX_O,          /* (B,T,O,4D)           models.py:748                                       */
+    TGGCN_BUF_GS_H,          /* (B,T,H,2,3D)         hoisted segment-cell input pre-activations          */
+    TGGCN_BUF_GS_O,          /* (B,T,O,2,3D)                                                             */
+    TGGCN_BUF_HX_H,          /* (B,T,H,2D)           segment states [fwd | bwd], before reorder          */
+    TGGCN_BUF_HX_O,          /* (B,T,O,2D)                                                               */
+    TGGCN_BUF_REIDX,         /* (B,T,H+O) int32      reorder gather index, models.py:1567-1586           */
+    TGGCN_BUF_SEG_SCRATCH,   /* per-step message scratch of the segment kernel                            */
+    TGGCN_BUF_SYNC,          /* grid-barrier counters + error flag                                        */
+    TGGCN_BUF_COUNT
+};
+
+TGGCN_API int         tggcn_abi_version(void);
+TGGCN_API const char* tggcn_last_error(void);
+
+/* Bytes of device scratch tggcn_forward needs for these dims. */
+TGGCN_API size_t tggcn_workspace_bytes(const tggcn_dims* dims);
+/* Offset/size of one named region inside the workspace (for tests / debugging). */
+TGGCN_API int    tggcn_workspace_view(const tggcn_dims* dims, int buf_id, size_t* offset, size_t* bytes);
+
+/* Debug aid: 0 if no grid barrier of the persistent kernels timed out during the work queued so far on
+ * `stream` for this workspace (synchronises the stream), 1 otherwise. */
+TGGCN_API int tggcn_sync_status(const tggcn_dims* dims, const void* workspace, void* stream);
+
+/* The whole forward pass: replaces TGGCN.forward (vhoi/models.py:584-933).
+ * `weights` holds TGGCN_W_COUNT device pointers ordered by enum tggcn_weight_id. */
+TGGCN_API int tggcn_forward(const tggcn_dims* dims, const void* const* weights, int n_weights, const tggcn_io* io,
+                  void* workspace, size_t workspace_bytes, void* stream);
+
+/* Kernel-family entry points (also used by tggcn_forward). */
+
+/* Geo_gcn.forward + the input split of models.py:631-642 (pyrutils/torch/models_gcn.py:30-100).
+ * x_human (B,T,H,Fh) -> out (B,128,V,T).  gcn_weights: the 13 GCN_* pointers of the weight table. */
+TGGCN_API int tggcn_geo_gcn_fwd(const float* x_human, const void* const* weights, float* out, float* bn_running_mean,
+                      float* bn_running_var, int64_t* bn_num_batches, void* workspace, int B, int T, int H, int V,
+                      int Fh, int bn_train, void* stream);
+
+/* nn.Linear (+ReLU): C[M,N] = act(A[M,K] W[N,K]^T + bias[N]) with leading dimensions
+ * (build_mlp, pyrutils/torch/models.py:31-33).  gemm_path as in tggcn_dims. */
+TGGCN_API int tggcn_linear_fwd(const float* A, int lda, const float* W, int ldw, const float* bias, float* C, int ldc,
+                     int M, int N, int K, int relu, int gemm_path, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TGGCN_B200_H_ */

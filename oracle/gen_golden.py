@@ -1,0 +1,157 @@
+"""Generate the golden vectors under tests/golden/ by EXECUTING THE UNMODIFIED REFERENCE.
+
+TEST INFRASTRUCTURE.  Runs only in the build container (needs /root/reference, which does not
+exist on the GPU box); its outputs are committed so nothing at test/bench time reads the reference.
+
+    python oracle/gen_golden.py            # rewrites tests/golden/*.npz
+
+For every case the reference ``TGGCN`` (vhoi/models.py:178) is built with the yaml constructor
+arguments, its ``state_dict`` is overwritten by ``synth.deterministic_fill`` (values depend only on
+seed/key/shape, so any box can regenerate the same weights), the Gumbel sampler
+(pyrutils/torch/distributions.py:4) is replaced by one that consumes a pre-drawn noise tensor in call
+order, and the outputs of ``model(**kwargs)`` — called through the reference's own ``gcn_forward``
+(vhoi/data_loading.py:1233) — are stored together with the reference's losses
+(vhoi/losses.py:8 → pyrutils/torch/losses.py:39) and F1@k (pyrutils/metrics.py:64).
+Seeds are advanced until every sampled gate is at least 1e-4 away from its threshold / its
+neighbours, so that fp32 re-association in another implementation cannot flip a discrete decision.
+"""
+from __future__ import annotations
+
+import importlib
+import os
+import sys
+import types
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+pkg = importlib.import_module('2g-gcn_b200.synth')
+
+sys.modules.setdefault('zarr', types.ModuleType('zarr'))   # data_loading imports zarr at top (:14)
+sys.path.insert(0, '/root/reference')
+from vhoi.models import select_model                                  # noqa: E402
+from vhoi.data_loading import select_model_data_feeder                # noqa: E402
+from vhoi.losses import select_loss                                   # noqa: E402
+from pyrutils.metrics import f1_at_k                                  # noqa: E402
+import pyrutils.torch.distributions as ref_dist                      # noqa: E402
+
+sys.path.insert(0, os.path.join(ROOT, 'oracle'))
+import tggcn_oracle as orc                                            # noqa: E402
+
+
+class Cfg(dict):
+    def get(self, k, default_value=None):
+        return dict.get(self, k, default_value)
+
+
+CASES = [
+    # name, shape, D, B, T, stage, train_mode, gain, inspect
+    ('mphoi_s1_eval', 'mphoi', 32, 2, 12, 1, False, 2.0, False),
+    ('mphoi_s2_eval', 'mphoi', 32, 3, 14, 2, False, 2.0, True),
+    ('mphoi_s2_train_bn', 'mphoi', 32, 2, 11, 2, True, 2.0, False),
+    ('mphoi_s2_d64', 'mphoi', 64, 4, 40, 2, False, 1.5, False),
+    ('cad120_s1_eval', 'cad120', 32, 2, 10, 1, False, 2.0, False),
+    ('cad120_s2_eval', 'cad120', 32, 2, 13, 2, False, 2.0, False),
+    ('bimanual_s2_eval', 'bimanual', 16, 2, 9, 2, False, 2.0, False),
+]
+
+
+def run_case(name, shape_name, D, B, T, stage, train_mode, gain, inspect):
+    shape = pkg.SHAPES[shape_name]
+    kw = pkg.model_kwargs(shape, hidden_size=D, stage=stage)
+    model = select_model('2G-GCN')(**kw)
+    pkg.deterministic_fill(model.state_dict(), seed=7, gain=gain)
+    sd = {k: v.detach().clone() for k, v in model.state_dict().items()}   # snapshot (train mode mutates BN)
+    model.train(train_mode)
+    misc = dict(impose_segmentation_pattern=1 if stage == 1 else 0,
+                segmentation_loss=dict(add=(stage == 2), sigma=4.0 if stage == 2 else 0.0, weight=1.0))
+    feed = select_model_data_feeder('2G-GCN', 'multiple', dataset_name=shape.dataset, inspect_model=inspect, **misc)
+    criterion, _ = select_loss('2G-GCN', 'multiple', shape.dataset, cfg=Cfg(misc=misc))
+    thr = kw['update_segment_threshold']
+    for attempt in range(50):
+        data_seed, noise_seed = 100 + attempt, 500 + attempt
+        batch = pkg.make_batch(shape, B, T, seed=data_seed)
+        n_calls = orc.num_noise_draws(T, shape.H, shape.O, stage == 1, stage == 1 and shape.dataset == 'cad120')
+        noise = orc.draw_noise(max(n_calls, 1), B, torch.Generator().manual_seed(noise_seed))[:n_calls]
+        it = iter(noise)
+
+        def injected(p, temperature=1.0):
+            y = torch.log(torch.cat([p, 1.0 - p], -1) + 1e-20) + next(it).to(p)
+            return torch.softmax(y / temperature, -1)[:, :1]
+
+        ref_dist.sample_from_gumbel_sigmoid = injected
+        model.load_state_dict(sd)
+        captured = {}
+        hk = model.geometry_embedding_gcn.register_forward_hook(lambda m, i, o: captured.__setitem__('gcn_out', o.detach().clone()))
+        # data tuple layout of gcn_fetcher (data_loading.py:1282-1315)
+        data = [batch['x_human'], batch['x_objects'], batch['objects_mask'], None, None, None, None,
+                batch['steps_per_example']]
+        with torch.no_grad():
+            res = feed(model, data)
+        hk.remove()
+        out, att = (res if inspect else (res, None))
+        soft = [o for o in (out[1:2] if shape.num_classes[1] is None else out[2:4])]
+        sampled = []
+        if stage != 1:
+            sampled = soft
+        elif shape.dataset != 'cad120':
+            sampled = []      # humans imposed; object gates are sampled but not returned for MPHOI
+        margin = 1.0
+        for s in sampled:
+            margin = min(margin, float((s - thr).abs().min()))
+            if stage == 2:
+                margin = min(margin, float((s[:, 1:] - s[:, :-1]).abs().min()))
+        if margin > 1e-4:
+            break
+    else:
+        raise RuntimeError(f'no seed with a safe gate margin for {name}')
+    # oracle agreement (also guards MPHOI object gates, which the reference does not return)
+    p64 = {k: v.double() for k, v in sd.items()}
+    ocfg = orc.OracleConfig(D, shape.V, shape.num_classes, shape.hh, stage == 2, thr)
+    hseg = torch.ones(B, T, shape.H) if stage == 1 else None
+    oseg = torch.ones(B, T, shape.O) if (stage == 1 and shape.dataset == 'cad120') else None
+    taps = {}
+    o64 = orc.forward(p64, ocfg, batch['x_human'].double(), batch['x_objects'].double(),
+                      batch['objects_mask'].double(), None if hseg is None else hseg.double(),
+                      None if oseg is None else oseg.double(), noise.double(), training=train_mode, taps=taps)
+    o_margin = float((taps['y_oss'] - thr).abs().min()) if oseg is None else 1.0
+    if o_margin <= 1e-4:
+        raise RuntimeError(f'{name}: object gate margin too small ({o_margin}); change seeds')
+    worst = max(float((a.double() - b).abs().max()) for a, b in zip(out, o64))
+    print(f'{name:20s} seeds=({data_seed},{noise_seed}) gate margin={min(margin, o_margin):.2e} '
+          f'|reference - oracle(fp64)|max={worst:.2e}')
+    tg = pkg.make_targets(shape, batch['lengths'], T, seed=900 + attempt)
+    targets = pkg.target_list(shape, tg)
+    losses = criterion(out, targets, reduction='mean')
+    # F1@k on the segment-level recognition output, predict.py:229-246 convention
+    rec_idx = 4 if shape.num_classes[1] is None else 8
+    pred = out[rec_idx].argmax(dim=1).numpy()                           # (B,T,H)
+    tgt = tg['rec_h'].numpy()
+    f1 = [f1_at_k(orc.labels_for_f1(tgt), orc.labels_for_f1(pred), shape.num_classes[0], overlap=k,
+                  ignore_value=-1.0) for k in (0.10, 0.25, 0.50)]
+    blob = {f'out{i}': o.numpy() for i, o in enumerate(out)}
+    blob['losses'] = np.array([float(l) for l in losses], dtype=np.float64)
+    blob['f1'] = np.array(f1, dtype=np.float64)
+    blob['gcn_out'] = captured['gcn_out'].numpy()
+    blob['meta'] = np.array([data_seed, noise_seed, 900 + attempt, 7], dtype=np.int64)
+    blob['gain'] = np.array([gain])
+    blob['weights_checksum'] = np.array([pkg.state_checksum(sd)])
+    blob['inputs_checksum'] = np.array([float(batch['x_human'].double().sum() + batch['x_objects'].double().sum())])
+    blob['noise_checksum'] = np.array([float(noise.double().sum())])
+    if train_mode:
+        after = model.state_dict()
+        for k in after:
+            if '.bn.running' in k:
+                blob['bn_after.' + k.rsplit('.', 1)[1]] = after[k].numpy()
+    if att is not None:
+        for i, a in enumerate(att):
+            blob[f'att{i}'] = a.numpy()
+    np.savez_compressed(os.path.join(ROOT, 'tests', 'golden', name + '.npz'), **blob)
+
+
+if __name__ == '__main__':
+    torch.set_num_threads(8)
+    for case in CASES:
+        run_case(*case)

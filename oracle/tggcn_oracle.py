@@ -1,0 +1,476 @@
+"""CPU oracle for the 2G-GCN (TGGCN) hot path.  TEST INFRASTRUCTURE ONLY.
+
+This module is a plain-PyTorch (CPU, fp32/fp64) restatement of the algorithm of the reference's
+``TGGCN.forward`` + losses + F1@k.  It is *not* part of the product: only ``tests/``,
+``__graft_entry__.smoke()`` and ``bench.py``'s ``cpu_baseline`` / ``--impl reference`` legs may import it,
+and there only as the checker (or as the timed CPU baseline), never as the thing shipped.
+
+Parity status: **pinned**.  The reference has no tests or golden vectors of its own, so
+the pins are outputs of the *unmodified reference executed in the build container*
+(``oracle/gen_golden.py`` imports ``/root/reference``) and committed under ``tests/golden/``;
+``tests/test_oracle_golden.py`` checks this file against every one of them.
+
+Every function cites the reference lines it restates (paths relative to the reference root).
+The control flow deliberately keeps the reference's per-timestep structure (two Python loops over T),
+so that timing this file on host cores is a fair stand-in for the reference's own CPU path.
+
+State is a flat ``dict`` of tensors keyed by the reference's ``state_dict`` names.
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass
+from itertools import accumulate, groupby
+from typing import Dict, List, Optional, Tuple
+
+import numpy as np
+import torch
+
+Tensor = torch.Tensor
+
+_GCN = 'geometry_embedding_gcn.'
+
+
+@dataclass
+class OracleConfig:
+    """The subset of ``conf/models/2G-GCN_stage{1,2}.yaml:4-29`` that changes the arithmetic."""
+    hidden_size: int = 512
+    gcn_node: int = 26
+    num_classes: Tuple[int, Optional[int]] = (13, None)
+    message_humans_to_human: bool = True
+    filter_discrete_updates: bool = False
+    update_segment_threshold: float = 0.5
+
+
+# ----------------------------------------------------------------------------------------------
+# building blocks
+# ----------------------------------------------------------------------------------------------
+def _lin(p: Dict[str, Tensor], name: str, x: Tensor) -> Tensor:
+    """nn.Linear as built by build_mlp (pyrutils/torch/models.py:31-33): x W^T + b."""
+    return x @ p[name + '.weight'].t() + p[name + '.bias']
+
+
+def _relu_lin(p, name, x):
+    return torch.relu(_lin(p, name, x))
+
+
+def geo_gcn(p: Dict[str, Tensor], xg: Tensor, training: bool = False,
+            stats_out: Optional[dict] = None) -> Tensor:
+    """Geo_gcn.forward, pyrutils/torch/models_gcn.py:30-37 (+ norm_data :45-50, embed :57-62,
+    compute_similarity :95-100).  ``xg`` is (B, 4, V, T); returns (B, 128, V, T) contiguous."""
+    B, C, V, T = xg.shape
+    # BatchNorm1d over channel index c*V+v, statistics over (B, T)  (models_gcn.py:46-48)
+    x = xg.reshape(B, C * V, T)
+    g, b = p[_GCN + 'joint_embed.cnn.0.bn.weight'], p[_GCN + 'joint_embed.cnn.0.bn.bias']
+    if training:
+        mean = x.mean(dim=(0, 2))
+        var = x.var(dim=(0, 2), unbiased=False)
+        if stats_out is not None:
+            n = B * T
+            stats_out['batch_mean'] = mean
+            stats_out['batch_var_unbiased'] = var * n / max(n - 1, 1)
+    else:
+        mean = p[_GCN + 'joint_embed.cnn.0.bn.running_mean']
+        var = p[_GCN + 'joint_embed.cnn.0.bn.running_var']
+    x = (x - mean[None, :, None]) / torch.sqrt(var[None, :, None] + 1e-5) * g[None, :, None] + b[None, :, None]
+    x = x.reshape(B, C, V, T).permute(0, 3, 2, 1)                     # (B, T, V, 4)
+    w1 = p[_GCN + 'joint_embed.cnn.1.cnn.weight'].reshape(64, C)
+    w3 = p[_GCN + 'joint_embed.cnn.3.cnn.weight'].reshape(64, 64)
+    e = torch.relu(x @ w1.t() + p[_GCN + 'joint_embed.cnn.1.cnn.bias'])
+    e = torch.relu(e @ w3.t() + p[_GCN + 'joint_embed.cnn.3.cnn.bias'])   # (B, T, V, 64)
+    th = e @ p[_GCN + 'get_s.s1.cnn.weight'].reshape(128, 64).t() + p[_GCN + 'get_s.s1.cnn.bias']
+    ph = e @ p[_GCN + 'get_s.s2.cnn.weight'].reshape(128, 64).t() + p[_GCN + 'get_s.s2.cnn.bias']
+    s = torch.softmax(th @ ph.transpose(-1, -2), dim=-1)               # (B, T, V, V), no 1/sqrt(d)
+    y = (s @ e) @ p[_GCN + 'weight']                                   # (B, T, V, 128)
+    return y.permute(0, 3, 2, 1).contiguous()                          # (B, 128, V, T)
+
+
+def gru_step(x_gates: Tensor, h: Tensor, w_hh: Tensor, b_hh: Tensor) -> Tensor:
+    """One GRU update given input pre-activations ``x_gates = W_ih x + b_ih``; gate order r, z, n
+    (torch.nn.GRU / GRUCell as used at vhoi/models.py:267,274,299 and :294-295,:319-320)."""
+    hg = h @ w_hh.t() + b_hh
+    xr, xz, xn = x_gates.chunk(3, dim=-1)
+    hr, hz, hn = hg.chunk(3, dim=-1)
+    r = torch.sigmoid(xr + hr)
+    z = torch.sigmoid(xz + hz)
+    n = torch.tanh(xn + r * hn)
+    return (1.0 - z) * n + z * h
+
+
+def bigru(p: Dict[str, Tensor], prefix: str, x: Tensor) -> Tensor:
+    """Bidirectional single-layer GRU, batch_first, zero initial state, no packing.
+    x: (R, T, D) -> (R, T, 2D).  Reference: nn.GRU called per entity at vhoi/models.py:997-1000."""
+    R, T, D = x.shape
+    outs = []
+    for suffix, order in (('', range(T)), ('_reverse', range(T - 1, -1, -1))):
+        w_ih, w_hh = p[f'{prefix}.weight_ih_l0{suffix}'], p[f'{prefix}.weight_hh_l0{suffix}']
+        b_ih, b_hh = p[f'{prefix}.bias_ih_l0{suffix}'], p[f'{prefix}.bias_hh_l0{suffix}']
+        gi = x @ w_ih.t() + b_ih
+        h = x.new_zeros(R, D)
+        hs = [None] * T
+        for t in order:
+            h = gru_step(gi[:, t], h, w_hh, b_hh)
+            hs[t] = h
+        outs.append(torch.stack(hs, dim=1))
+    return torch.cat(outs, dim=-1)
+
+
+def frame_level_rnn(p, x: Tensor, rnn: str, mlp: str) -> Tuple[Tensor, Tensor]:
+    """_process_frame_level_rnn, vhoi/models.py:983-1002.  x: (B,T,E,D) -> h_f (B,T,E,D), h_fr (B,T,E,2D)."""
+    h_fr = torch.stack([bigru(p, rnn, x[:, :, e]) for e in range(x.size(2))], dim=2)
+    return _relu_lin(p, mlp + '.0', h_fr), h_fr
+
+
+def attend(query: Tensor, keys: Tensor, values: Tensor, mask: Tensor) -> Tuple[Tensor, Tensor]:
+    """Scaled dot-product attention of compute_attention_weights (vhoi/models.py:1721-1754, style 'v3')
+    followed by the weighted sum at e.g. :1047-1048.
+    query (B,F), keys (B,S,F), values (B,S,D), mask (B,S) in {0,1}.  Fully masked rows give zeros
+    (softmax of all -inf is NaN, replaced by 0 at :1753)."""
+    logits = (query[:, None, :] * keys).sum(-1) / math.sqrt(keys.size(-1))
+    logits = torch.where(mask.bool(), logits, torch.full_like(logits, float('-inf')))
+    w = torch.softmax(logits, dim=1)
+    w = torch.where(torch.isnan(w), torch.zeros_like(w), w)
+    return (w[..., None] * values).sum(1), w
+
+
+def _others(x: Tensor, i: int) -> Tensor:
+    return torch.cat([x[:, :i], x[:, i + 1:]], dim=1)
+
+
+def gumbel_sigmoid(prob: Tensor, g: Optional[Tensor]) -> Tensor:
+    """sample_from_gumbel_sigmoid, pyrutils/torch/distributions.py:15-18 (temperature 1).
+    ``g`` is the (B, 2) Gumbel(0,1) draw; if None it is drawn exactly like the reference does."""
+    pp = torch.cat([prob, 1.0 - prob], dim=-1)
+    if g is None:
+        g = torch.distributions.gumbel.Gumbel(0.0, 1.0).sample(pp.size())
+    y = torch.log(pp + 1e-20) + g.to(pp)
+    return torch.softmax(y, dim=-1)[:, :1]
+
+
+def hard_gate(y: Tensor, thr: float) -> Tensor:
+    """straight_through_gumbel_sigmoid, pyrutils/torch/distributions.py:33-36: value of (z - y) + y."""
+    z = (y > thr).to(y.dtype)
+    return (z - y) + y
+
+
+def filter_soft(y: Tensor, thr: float) -> Tensor:
+    """filter_soft_decisions, vhoi/models.py:1637-1664, on a (B, T) tensor of soft gates of one entity."""
+    B, T = y.shape
+    zero = y.new_zeros(B, 1)
+    prev = torch.cat([zero, y[:, :-1]], dim=1)
+    nxt = torch.cat([y[:, 1:], zero], dim=1)
+    keep = (y > prev) & (y > nxt) & (y >= thr)
+    u = ((y >= thr).to(y.dtype) - y) + y
+    return torch.where(keep, u, torch.clamp(u, max=0.0))
+
+
+def reorder(hx: Tensor, u: Tensor) -> Tensor:
+    """reorder_hidden_states, vhoi/models.py:1567-1586.  hx (B,T,F), u (B,T): every frame before a
+    segment end takes the state of that end frame; frames after the last end keep their own."""
+    B, T, _ = hx.shape
+    out = hx.clone()
+    for b in range(B):
+        nxt = -1
+        for t in range(T - 1, -1, -1):
+            if u[b, t] != 0:
+                nxt = t
+            if nxt >= 0:
+                out[b, t] = hx[b, nxt]
+    return out
+
+
+# ----------------------------------------------------------------------------------------------
+# whole forward
+# ----------------------------------------------------------------------------------------------
+def forward(p: Dict[str, Tensor], cfg: OracleConfig, x_human: Tensor, x_objects: Tensor, objects_mask: Tensor,
+            human_segmentation: Optional[Tensor] = None, objects_segmentation: Optional[Tensor] = None,
+            noise: Optional[Tensor] = None, training: bool = False, inspect_model: bool = False,
+            taps: Optional[dict] = None):
+    """TGGCN.forward, vhoi/models.py:584-933, for the shipped configuration family
+    (message_type v2, granularity v1, attention aggregation style v3, update strategy 'ind',
+    gumbel-sigmoid gates, message_segment on, geometry->objects on, geometry->human off).
+
+    ``noise``: (n_calls, B, 2) Gumbel(0,1) draws consumed in the reference's call order
+    (t-major; humans then objects; only entities whose segmentation is not given), or None to draw
+    from the global CPU generator per call like pyrutils/torch/distributions.py:16.
+    ``taps``: optional dict that receives named intermediates (kernel-level parity tests)."""
+    D, V, thr = cfg.hidden_size, cfg.gcn_node, cfg.update_segment_threshold
+    hh_on = cfg.message_humans_to_human
+    B, T, H, _ = x_human.shape
+    O = x_objects.size(2)
+    tap = (lambda k, v: taps.__setitem__(k, v)) if taps is not None else (lambda k, v: None)
+    noise_it = iter(noise) if noise is not None else None
+
+    # -- split, geometry GCN, scrambled view (models.py:631-645) -------------------------------
+    vis = x_human[..., :2048]
+    geo = x_human[:, :, 0, 2048:2048 + 4 * V]                          # human 0 only
+    y = geo_gcn(p, geo.reshape(B, T, V, 4).permute(0, 3, 2, 1).contiguous(), training, taps)
+    tap('gcn_out', y)
+    x_g = y.reshape(B, T, 1, 128 * V)                                  # reinterpretation, NOT a permute
+    # -- embeddings (models.py:646) -----------------------------------------------------------
+    x_h = _relu_lin(p, 'human_embedding_mlp.0', vis)
+    x_o = _relu_lin(p, 'object_embedding_mlp.0', x_objects)
+    x_g = _relu_lin(p, 'geometry_embedding_mlp.2', _relu_lin(p, 'geometry_embedding_mlp.0', x_g))
+    tap('x_h', x_h), tap('x_o', x_o), tap('x_g', x_g)
+    # -- frame-level BiGRUs (models.py:649-651) -----------------------------------------------
+    h_h, hfr_h = frame_level_rnn(p, x_h, 'human_bd_rnn', 'human_bd_embedding_mlp')
+    h_o, hfr_o = frame_level_rnn(p, x_o, 'object_bd_rnn', 'object_bd_embedding_mlp')
+    h_g, hfr_g = frame_level_rnn(p, x_g, 'geometry_bd_rnn', 'geometry_bd_embedding_mlp')
+    tap('hfr_h', hfr_h), tap('hfr_o', hfr_o), tap('hfr_g', hfr_g)
+    tap('h_h', h_h), tap('h_o', h_o), tap('h_g', h_g)
+
+    # -- frame-level messages and gates, one timestep at a time (models.py:664-749) ------------
+    ones_h = x_h.new_ones(B, max(H - 1, 0))
+    ones_H = x_h.new_ones(B, H)
+    xx_h = [[None] * T for _ in range(H)]
+    xx_o = [[None] * T for _ in range(O)]
+    hard_h = [[None] * T for _ in range(H)]
+    soft_h = [[None] * T for _ in range(H)]
+    hard_o = [[None] * T for _ in range(O)]
+    soft_o = [[None] * T for _ in range(O)]
+    att_oh = [[None] * T for _ in range(H)]
+    for t in range(T):
+        s_h = torch.cat([x_h[:, t], h_h[:, t]], dim=-1)                # (B,H,2D) sender/receiver features
+        s_o = torch.cat([x_o[:, t], h_o[:, t]], dim=-1)
+        s_g = torch.cat([x_g[:, t], h_g[:, t]], dim=-1)
+        for h in range(H):
+            parts = [h_h[:, t, h]]
+            gate_in = [x_h[:, t, h], h_h[:, t, h]]
+            if hh_on:                                                   # :1004-1049
+                snd = _others(s_h, h)
+                m_hh, _ = attend(s_h[:, h], snd, _relu_lin(p, 'humans_to_human_message_mlp.0', snd), ones_h)
+                parts.append(m_hh), gate_in.append(m_hh)
+            val = _relu_lin(p, 'objects_to_human_message_mlp.0', s_o) * objects_mask[..., None]   # :1191-1237
+            m_oh, w_oh = attend(s_h[:, h], s_o, val, objects_mask)
+            att_oh[h][t] = w_oh
+            parts.append(m_oh), gate_in.append(m_oh)
+            if human_segmentation is not None:                          # :697-698
+                hard_h[h][t] = soft_h[h][t] = human_segmentation[:, t:t + 1, h]
+            else:                                                       # :1477-1498, :700-702
+                prob = torch.sigmoid(_lin(p, 'update_human_segment_mlp.0', torch.cat(gate_in, dim=-1)))
+                ysoft = gumbel_sigmoid(prob, next(noise_it) if noise_it is not None else None)
+                z = hard_gate(ysoft, thr)
+                if t == T - 1:
+                    z = torch.ones_like(z)
+                hard_h[h][t], soft_h[h][t] = z, ysoft
+            xx_h[h][t] = torch.cat(parts, dim=-1)                       # :705  [h, m_hh, m_oh]
+        for k in range(O):
+            mk = objects_mask[:, k:k + 1]
+            m_ho, _ = attend(s_o[:, k], s_h, _relu_lin(p, 'human_to_object_message_mlp.0', s_h), ones_H)
+            m_ho = m_ho * mk                                            # :1099-1143, :720
+            m_go = _relu_lin(p, 'geometry_to_object_message_mlp.0', s_g[:, 0]) * mk   # :1384-1428, :729
+            snd, snd_mask = _others(s_o, k), _others(objects_mask, k)   # :1286-1332
+            val = _relu_lin(p, 'objects_to_object_message_mlp.0', snd) * snd_mask[..., None]
+            m_oo, _ = attend(s_o[:, k], snd, val, snd_mask)
+            if objects_segmentation is not None:                        # :738-739
+                hard_o[k][t] = soft_o[k][t] = objects_segmentation[:, t:t + 1, k]
+            else:                                                       # :1500-1533 ('ind'); input order :1527
+                gate_in = torch.cat([x_o[:, t, k], h_o[:, t, k], m_ho, m_oo, m_go], dim=-1)
+                prob = torch.sigmoid(_lin(p, 'update_object_segment_mlp.0', gate_in))
+                ysoft = gumbel_sigmoid(prob, next(noise_it) if noise_it is not None else None)
+                z = hard_gate(ysoft, thr)
+                if t == T - 1:
+                    z = torch.ones_like(z)
+                hard_o[k][t], soft_o[k][t] = z, ysoft
+            xx_o[k][t] = torch.cat([h_o[:, t, k], m_ho, m_go, m_oo], dim=-1)    # :748
+    y_hss = torch.stack([torch.cat(s, dim=-1) for s in soft_h], dim=-1)          # (B,T,H)
+    y_oss = torch.stack([torch.cat(s, dim=-1) for s in soft_o], dim=-1)          # (B,T,O)
+    y_hs = torch.stack([torch.cat(s, dim=-1) for s in hard_h], dim=-1)
+    y_os = torch.stack([torch.cat(s, dim=-1) for s in hard_o], dim=-1)
+    # -- optional local-maximum filter replaces the hard gates (models.py:751-753) -------------
+    if cfg.filter_discrete_updates:
+        y_hs = torch.stack([filter_soft(y_hss[..., h], thr) for h in range(H)], dim=-1)
+        y_os = torch.stack([filter_soft(y_oss[..., k], thr) for k in range(O)], dim=-1)
+    tap('xx_h', torch.stack([torch.stack(r, dim=1) for r in xx_h], dim=2))       # (B,T,H,3D)
+    tap('xx_o', torch.stack([torch.stack(r, dim=1) for r in xx_o], dim=2))       # (B,T,O,4D)
+
+    # -- segment-level recurrent graph, both directions in lock-step (models.py:785-880) -------
+    def seg_dir(order, hcell: str, ocell: str):
+        SH = [x_h.new_zeros(B, D) for _ in range(H)]
+        SO = [x_h.new_zeros(B, D) for _ in range(O)]
+        out_h = [[None] * T for _ in range(H)]
+        out_o = [[None] * T for _ in range(O)]
+        att = [[None] * T for _ in range(H)]
+        for t in order:
+            sh, so = torch.stack(SH, dim=1), torch.stack(SO, dim=1)     # previous-step states only
+            newH, newO = [], []
+            for h in range(H):
+                x = [xx_h[h][t]]
+                if hh_on:                                               # :1051-1097
+                    snd = _others(sh, h)
+                    mg, _ = attend(SH[h], snd, _relu_lin(p, 'humans_to_human_segment_message_mlp.0', snd), ones_h)
+                    x.append(mg)
+                val = _relu_lin(p, 'objects_to_human_segment_message_mlp.0', so) * objects_mask[..., None]
+                mg, w = attend(SH[h], so, val, objects_mask)            # :1239-1284
+                att[h][t] = w
+                x.append(mg)
+                newH.append(_seg_cell(p, hcell, torch.cat(x, dim=-1), y_hs[:, t, h:h + 1], SH[h]))
+            for k in range(O):
+                mg_ho, _ = attend(SO[k], sh, _relu_lin(p, 'human_to_object_segment_message_mlp.0', sh), ones_H)
+                snd, snd_mask = _others(so, k), _others(objects_mask, k)        # :1334-1381
+                val = _relu_lin(p, 'objects_to_object_segment_message_mlp.0', snd) * snd_mask[..., None]
+                mg_oo, _ = attend(SO[k], snd, val, snd_mask)
+                x = torch.cat([xx_o[k][t], mg_ho, mg_oo], dim=-1)
+                newO.append(_seg_cell(p, ocell, x, y_os[:, t, k:k + 1], SO[k]))
+            SH, SO = newH, newO                                         # commit, :875-880
+            for h in range(H):
+                out_h[h][t] = SH[h]
+            for k in range(O):
+                out_o[k][t] = SO[k]
+        oh = torch.stack([torch.stack(r, dim=1) for r in out_h], dim=2)         # (B,T,H,D)
+        oo = torch.stack([torch.stack(r, dim=1) for r in out_o], dim=2)
+        aw = torch.stack([torch.stack(r, dim=1) for r in att], dim=1)           # (B,H,T,O)
+        return oh, oo, aw
+
+    fh, fo, att_f = seg_dir(range(T), 'human_segment_rnn_fcell', 'object_segment_rnn_fcell')
+    bh, bo, att_b = seg_dir(range(T - 1, -1, -1), 'human_segment_rnn_bcell', 'object_segment_rnn_bcell')
+    hx_h = torch.cat([fh, bh], dim=-1)                                          # (B,T,H,2D)
+    hx_o = torch.cat([fo, bo], dim=-1)
+    tap('hx_h', hx_h), tap('hx_o', hx_o)
+    # -- reorder (models.py:886-899) -------------------------------------------------------------
+    hx_h = torch.stack([reorder(hx_h[:, :, h], y_hs[:, :, h]) for h in range(H)], dim=2)
+    hx_o = torch.stack([reorder(hx_o[:, :, k], y_os[:, :, k]) for k in range(O)], dim=2)
+    tap('hx_h_reordered', hx_h), tap('hx_o_reordered', hx_o)
+
+    # -- heads (models.py:905-926) ---------------------------------------------------------------
+    def head(name, x):
+        return torch.log_softmax(_lin(p, name + '.0', x), dim=-1).permute(0, 3, 1, 2).contiguous()
+
+    out_h = [head('human_frame_recognition_mlp', hfr_h), head('human_frame_prediction_mlp', hfr_h),
+             head('human_recognition_mlp', hx_h), head('human_prediction_mlp', hx_h)]
+    if cfg.num_classes[1] is None:
+        output = [y_hs, y_hss] + out_h
+    else:
+        out_o = [head('object_frame_recognition_mlp', hfr_o), head('object_frame_prediction_mlp', hfr_o),
+                 head('object_recognition_mlp', hx_o), head('object_prediction_mlp', hx_o)]
+        output = [y_hs, y_os, y_hss, y_oss] + out_h[:2] + out_o[:2] + out_h[2:] + out_o[2:]
+    tap('y_os', y_os), tap('y_oss', y_oss)
+    if inspect_model:
+        ax_hf = torch.stack([torch.stack(r, dim=1) for r in att_oh], dim=1)     # (B,H,T,O)  :928
+        return output, [ax_hf, att_f, att_b]
+    return output
+
+
+def _seg_cell(p, cell: str, x: Tensor, u: Tensor, h: Tensor) -> Tensor:
+    """_bidirectional_step, vhoi/models.py:1535-1564: u * GRUCell(x, h) + (1 - u) * h."""
+    gi = x @ p[cell + '.weight_ih'].t() + p[cell + '.bias_ih']
+    new = gru_step(gi, h, p[cell + '.weight_hh'], p[cell + '.bias_hh'])
+    return u * new + (1.0 - u) * h
+
+
+def num_noise_draws(T: int, H: int, O: int, human_given: bool, objects_given: bool) -> int:
+    """Number of (B,2) Gumbel draws one forward consumes (vhoi/models.py:697-702, :738-745)."""
+    return T * ((0 if human_given else H) + (0 if objects_given else O))
+
+
+def draw_noise(n_calls: int, B: int, generator: Optional[torch.Generator] = None) -> Tensor:
+    """Pre-draw the Gumbel(0,1) noise of a forward in one call.  Equal, draw for draw, to what
+    torch.distributions.gumbel.Gumbel(0,1).sample((B,2)) yields call by call:
+    Gumbel.sample = -log(-log(U)), U = rand()*(1-eps-tiny)+tiny."""
+    fi = torch.finfo(torch.float32)
+    u = torch.rand(n_calls, B, 2, generator=generator)
+    u = u * ((1.0 - fi.eps) - fi.tiny) + fi.tiny
+    return -torch.log(-torch.log(u))
+
+
+# ----------------------------------------------------------------------------------------------
+# losses (pyrutils/torch/losses.py:7-51, vhoi/losses.py:8-61)
+# ----------------------------------------------------------------------------------------------
+def budget_loss(inp: Tensor, tgt: Tensor) -> Tensor:
+    """budget_loss, pyrutils/torch/losses.py:24-36."""
+    mask = (tgt != -1).to(inp.dtype)
+    n = float(mask.sum())
+    if n == 0:
+        return inp.new_zeros(())
+    return (inp * mask).mean() * (inp.numel() / n)
+
+
+def bce_loss(inp: Tensor, tgt: Tensor) -> Tensor:
+    """binary_cross_entropy_loss, pyrutils/torch/losses.py:7-21 (positive_class_weight == 1).
+    F.binary_cross_entropy clamps each log term at -100."""
+    mask = (tgt != -1).to(inp.dtype)
+    n = float(mask.sum())
+    if n == 0:
+        return inp.new_zeros(())
+    o, t = inp * mask, tgt * mask
+    ll = t * torch.clamp(torch.log(o), min=-100.0) + (1.0 - t) * torch.clamp(torch.log(1.0 - o), min=-100.0)
+    return (-ll).mean() * (inp.numel() / n)
+
+
+def nll_loss(logp: Tensor, tgt: Tensor) -> Tensor:
+    """F.nll_loss(ignore_index=-1, reduction='mean') on (B,C,T,E) log-probs and (B,T,E) int64 targets
+    (pyrutils/torch/losses.py:46-47)."""
+    valid = tgt != -1
+    picked = torch.gather(logp, 1, tgt.clamp(min=0).unsqueeze(1)).squeeze(1)
+    return -(picked * valid.to(logp.dtype)).sum() / valid.sum().to(logp.dtype)
+
+
+def loss_weights(dataset: str, stage: int) -> List[float]:
+    """select_loss weights for the shipped yaml files (vhoi/losses.py:8-61 with
+    conf/models/2G-GCN_stage{1,2}.yaml:37-54): stage 2 switches the segmentation BCE on."""
+    s = 1.0 if stage == 2 else 0.0
+    if dataset == 'cad120':
+        return [0.0, 0.0, s, s, 0.0, 0.0, 0.0, 0.0, 1.0, 1.0, 1.0, 1.0]
+    return [0.0, s, 0.0, 0.0, 1.0, 1.0]
+
+
+def multi_task_loss(outputs: List[Tensor], targets: List[Tensor], dataset: str, stage: int) -> List[Tensor]:
+    """multi_task_loss, pyrutils/torch/losses.py:39-51, with the function tuple of vhoi/losses.py:41-60."""
+    if dataset == 'cad120':
+        fns = [budget_loss, budget_loss, bce_loss, bce_loss] + [nll_loss] * 8
+    else:
+        fns = [budget_loss, bce_loss] + [nll_loss] * 4
+    return [w * fn(o, t) for o, t, fn, w in zip(outputs, targets, fns, loss_weights(dataset, stage))]
+
+
+# ----------------------------------------------------------------------------------------------
+# F1@k (pyrutils/metrics.py:7-81, pyrutils/utils.py:56-60, pyrutils/itertools.py:15-18)
+# ----------------------------------------------------------------------------------------------
+def _runs(seq):
+    labels, lengths = zip(*[(k, len(list(v))) for k, v in groupby(seq)])
+    starts = [0] + list(accumulate(lengths))
+    return np.array(labels), np.array(list(zip(starts[:-1], starts[1:])))
+
+
+def f1_at_k_single(y_true, y_pred, num_classes: int, overlap: float) -> float:
+    """f1_at_k_single_example, pyrutils/metrics.py:7-61."""
+    t_ids, t_iv = _runs(y_true)
+    o_ids, o_iv = _runs(y_pred)
+    tp = fp = 0.0
+    used = np.zeros(len(t_ids), dtype=bool)
+    for (a, b), oid in zip(o_iv, o_ids):
+        inter = np.minimum(b, t_iv[:, 1]) - np.maximum(a, t_iv[:, 0])
+        union = np.maximum(b, t_iv[:, 1]) - np.minimum(a, t_iv[:, 0])
+        iou = (inter / union) * (oid == t_ids)
+        j = int(np.argmax(iou))
+        if oid >= num_classes:
+            continue
+        if iou[j] >= overlap and not used[j]:
+            tp += 1
+            used[j] = True
+        else:
+            fp += 1
+    fn = len(used) - float(used.sum())
+    prec = tp / (tp + fp) if (tp + fp) else 0.0
+    rec = tp / (tp + fn) if (tp + fn) else 0.0
+    return 2 * prec * rec / (prec + rec) if (prec + rec) else 0.0
+
+
+def f1_at_k(y_true, y_pred, num_classes: int, overlap: float, ignore_value=-1.0) -> float:
+    """f1_at_k, pyrutils/metrics.py:64-81.  y_* are (rows, T) label arrays."""
+    total, n = 0.0, 0
+    for yt, yp in zip(np.asarray(y_true), np.asarray(y_pred)):
+        keep = yt != ignore_value
+        yt, yp = yt[keep], yp[keep]
+        if yt.size == 0:
+            continue
+        total += f1_at_k_single(yt, yp, num_classes, overlap)
+        n += 1
+    return total / n
+
+
+def labels_for_f1(arr: np.ndarray) -> np.ndarray:
+    """The reshape convention of predict.py:236-240: (B,T,E) -> swapaxes(1,2) -> (B*E, T)."""
+    if arr.ndim == 3:
+        arr = np.swapaxes(arr, 1, 2)
+    return arr.reshape(-1, arr.shape[-1])

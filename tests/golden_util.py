@@ -1,0 +1,59 @@
+"""Rebuild the inputs/weights/noise of a golden case from its recorded seeds (no reference needed)."""
+import importlib
+import os
+
+import numpy as np
+import torch
+
+GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden')
+
+# name -> (shape, D, B, T, stage, train_mode, inspect)   (mirrors oracle/gen_golden.py:CASES)
+CASES = {
+    'mphoi_s1_eval': ('mphoi', 32, 2, 12, 1, False, False),
+    'mphoi_s2_eval': ('mphoi', 32, 3, 14, 2, False, True),
+    'mphoi_s2_train_bn': ('mphoi', 32, 2, 11, 2, True, False),
+    'mphoi_s2_d64': ('mphoi', 64, 4, 40, 2, False, False),
+    'cad120_s1_eval': ('cad120', 32, 2, 10, 1, False, False),
+    'cad120_s2_eval': ('cad120', 32, 2, 13, 2, False, False),
+    'bimanual_s2_eval': ('bimanual', 16, 2, 9, 2, False, False),
+}
+
+
+class GoldenCase:
+    def __init__(self, name):
+        import tggcn_oracle as orc
+        synth = importlib.import_module('2g-gcn_b200.synth')
+        self.name = name
+        shape_name, D, B, T, stage, train_mode, inspect = CASES[name]
+        self.shape = synth.SHAPES[shape_name]
+        self.D, self.B, self.T, self.stage, self.train_mode, self.inspect = D, B, T, stage, train_mode, inspect
+        self.blob = np.load(os.path.join(GOLDEN_DIR, name + '.npz'))
+        data_seed, noise_seed, target_seed, weight_seed = [int(v) for v in self.blob['meta']]
+        self.weight_seed, self.gain = weight_seed, float(self.blob['gain'][0])
+        self.kwargs = synth.model_kwargs(self.shape, hidden_size=D, stage=stage)
+        self.thr = self.kwargs['update_segment_threshold']
+        self.batch = synth.make_batch(self.shape, B, T, seed=data_seed)
+        H, O = self.shape.H, self.shape.O
+        self.human_given = stage == 1
+        self.objects_given = stage == 1 and self.shape.dataset == 'cad120'
+        n_calls = orc.num_noise_draws(T, H, O, self.human_given, self.objects_given)
+        self.noise = orc.draw_noise(max(n_calls, 1), B, torch.Generator().manual_seed(noise_seed))[:n_calls]
+        self.hseg = torch.ones(B, T, H) if self.human_given else None
+        self.oseg = torch.ones(B, T, O) if self.objects_given else None
+        self.targets = synth.target_list(self.shape, synth.make_targets(self.shape, self.batch['lengths'], T,
+                                                                        seed=target_seed))
+        self.outputs = [torch.from_numpy(self.blob[f'out{i}']) for i in range(6 if self.shape.num_classes[1] is None else 12)]
+        self.ocfg = orc.OracleConfig(D, self.shape.V, self.shape.num_classes, self.shape.hh, stage == 2, self.thr)
+        # the regenerated inputs must be the bytes the reference saw
+        chk = float(self.batch['x_human'].double().sum() + self.batch['x_objects'].double().sum())
+        assert abs(chk - float(self.blob['inputs_checksum'][0])) <= 1e-6 * abs(chk), 'synthetic inputs differ from golden run'
+        nchk = float(self.noise.double().sum())
+        assert abs(nchk - float(self.blob['noise_checksum'][0])) <= 1e-9 * max(1.0, abs(nchk)), 'noise differs from golden run'
+
+    def fill(self, state_dict):
+        synth = importlib.import_module('2g-gcn_b200.synth')
+        synth.deterministic_fill(state_dict, seed=self.weight_seed, gain=self.gain)
+        chk = synth.state_checksum(state_dict)
+        ref = float(self.blob['weights_checksum'][0])
+        assert abs(chk - ref) <= 1e-9 * max(1.0, abs(ref)), 'regenerated weights differ from golden run'
+        return state_dict

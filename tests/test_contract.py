@@ -1,0 +1,77 @@
+"""CPU: the drop-in boundary — constructor, state_dict layout, C-ABI surface, loud failure without CUDA."""
+import ctypes
+import json
+import os
+import re
+
+import pytest
+import torch
+
+from golden_util import GOLDEN_DIR
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.mark.parametrize('name', ['mphoi', 'cad120', 'bimanual'])
+def test_state_dict_layout_equals_reference(name, pkg, synth):
+    layout = json.load(open(os.path.join(GOLDEN_DIR, 'state_dict_layout.json')))[f'{name}_D32']
+    model = pkg.TGGCN(**synth.model_kwargs(synth.SHAPES[name], hidden_size=32, stage=1))
+    got = [[k, list(v.shape)] for k, v in model.state_dict().items()]
+    assert got == layout
+
+
+def test_constructor_accepts_yaml_values_and_rejects_the_rest(pkg, synth):
+    kw = synth.model_kwargs(synth.MPHOI, hidden_size=64, stage=2)
+    m = pkg.TGGCN(**kw)
+    assert m.filter_discrete_updates and m.update_segment_threshold == pytest.approx(0.1)
+    for bad in (dict(message_type='v1'), dict(attention_style='v1'), dict(message_aggregation='mp'),
+                dict(object_segment_update_strategy='sah'), dict(add_time_position=1), dict(cat_level_states=1),
+                dict(discrete_networks_num_layers=2), dict(message_geometry_to_human=True), dict(hidden_size=20)):
+        with pytest.raises(NotImplementedError):
+            pkg.TGGCN(**{**kw, **bad})
+    assert pkg.select_model('2G-GCN') is pkg.TGGCN
+
+
+def test_weight_table_covers_the_state_dict(pkg, synth):
+    for name in ('mphoi', 'cad120'):
+        model = pkg.TGGCN(**synth.model_kwargs(synth.SHAPES[name], hidden_size=32, stage=1))
+        keys = set(model.state_dict().keys())
+        table = set(pkg.abi.WEIGHT_KEYS)
+        assert table <= keys | {k for k in table if k.startswith('object_') or k.startswith('humans_to_human')}
+        used_somewhere = {k for k in keys if k in table}
+        # everything not in the table is a parameter the shipped configuration never reads
+        dead = keys - used_somewhere
+        assert all(('_att_mlp' in k) or k.startswith('geometry_to_object_segment_message_mlp') or
+                   k.endswith('num_batches_tracked') for k in dead), sorted(dead)
+
+
+def test_library_loads_and_exports_every_declared_symbol(pkg):
+    header = open(os.path.join(ROOT, 'include', 'tggcn_b200.h')).read()
+    declared = re.findall(r'TGGCN_API\s+[\w\s\*]+?\b(tggcn_\w+)\s*\(', header)
+    assert len(declared) >= 8
+    lib = pkg.abi.lib()
+    for sym in declared:
+        assert hasattr(lib, sym), sym
+    assert lib.tggcn_abi_version() == 1
+    # struct mirrors: 17 int32 + 1 float; io = 6 + 4 + 8 + 3 + 3 pointers
+    assert ctypes.sizeof(pkg.abi.Dims) == 18 * 4
+    assert ctypes.sizeof(pkg.abi.IO) == 24 * 8
+
+
+def test_workspace_query_needs_no_gpu(pkg):
+    d = pkg.abi.Dims(B=8, T=128, H=2, O=4, V=26, D=512, Fh=2152, C_sub=13, C_aff=0, hh=1, filter=1, bn_train=0,
+                     human_seg_given=0, object_seg_given=0, inspect=0, persistent=1, gemm_path=0, thr=0.1)
+    total = pkg.abi.workspace_bytes(d)
+    assert 100e6 < total < 2e9
+    off, nbytes = pkg.abi.workspace_view(d, 'GCN_OUT')
+    assert off == 0 and nbytes == 8 * 128 * 26 * 128 * 4
+    bad = pkg.abi.Dims(B=8, T=128, H=2, O=4, V=26, D=500, Fh=2152, C_sub=13)
+    with pytest.raises(pkg.abi.TggcnError):
+        pkg.abi.workspace_bytes(bad)
+
+
+def test_forward_refuses_cpu_tensors(pkg, synth):
+    model = pkg.TGGCN(**synth.model_kwargs(synth.MPHOI, hidden_size=32, stage=1))
+    batch = synth.make_batch(synth.MPHOI, 2, 5)
+    with torch.no_grad(), pytest.raises(pkg.abi.TggcnError):
+        model(x_human=batch['x_human'], x_objects=batch['x_objects'], objects_mask=batch['objects_mask'])

@@ -1,0 +1,11 @@
+"""Import alias for the package directory ``2g-gcn_b200`` (not a valid identifier):
+``import tggcn_b200`` gives the same module object as ``importlib.import_module('2g-gcn_b200')``."""
+import importlib
+import os
+import sys
+
+_root = os.path.dirname(os.path.abspath(__file__))
+if _root not in sys.path:
+    sys.path.insert(0, _root)
+_pkg = importlib.import_module('2g-gcn_b200')
+sys.modules[__name__] = _pkg

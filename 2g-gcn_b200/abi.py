@@ -40,10 +40,17 @@ def _parse_header():
     body = re.sub(r'/\*.*?\*/', '', body, flags=re.S)
     bufs = [t.split('=')[0].strip() for t in body.split(',') if t.strip()]
     assert bufs[-1] == 'TGGCN_BUF_COUNT'
+    sbody = re.search(r'enum tggcn_stage_id \{(.*?)\};', text, re.S).group(1)
+    sbody = re.sub(r'/\*.*?\*/', '', sbody, flags=re.S)
+    stages = [t.split('=')[0].strip() for t in sbody.split(',') if t.strip()]
+    assert stages[-1] == 'TGGCN_STAGE_COUNT'
+    global STAGE_NAMES
+    STAGE_NAMES = [n.replace('TGGCN_STAGE_', '').lower() for n in stages[:-1]]
     funcs = re.findall(r'TGGCN_API\s+[\w\s\*]+?\b(tggcn_\w+)\s*\(', text)
     return weights, bufs[:-1], funcs
 
 
+STAGE_NAMES: List[str] = []
 WEIGHT_TABLE, BUF_NAMES, EXPORTED = _parse_header()
 WEIGHT_KEYS: List[str] = [k for _, k in WEIGHT_TABLE]
 WEIGHT_INDEX: Dict[str, int] = {k: i for i, k in enumerate(WEIGHT_KEYS)}
@@ -78,6 +85,9 @@ def lib():
     L.tggcn_forward.restype = C.c_int
     L.tggcn_forward.argtypes = [C.POINTER(Dims), C.POINTER(C.c_void_p), C.c_int, C.POINTER(IO), C.c_void_p, C.c_size_t,
                                 C.c_void_p]
+    L.tggcn_forward_profile.restype = C.c_int
+    L.tggcn_forward_profile.argtypes = L.tggcn_forward.argtypes + [C.POINTER(C.c_float)]
+    L.tggcn_launch_count.restype = C.c_ulonglong
     L.tggcn_geo_gcn_fwd.restype = C.c_int
     L.tggcn_geo_gcn_fwd.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                     C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]

@@ -10,6 +10,7 @@
 namespace tg {
 
 static thread_local char g_err[1024] = "";
+unsigned long long g_launches = 0;   // kernels launched by this library since load
 
 void set_error(const char* fmt, ...) {
     va_list ap;
@@ -148,8 +149,10 @@ int tggcn_linear_fwd(const float* A, int lda, const float* W, int ldw, const flo
     return launch_gemm(g, gemm_path, (cudaStream_t)stream);
 }
 
-int tggcn_forward(const tggcn_dims* dims, const void* const* weights, int n_weights, const tggcn_io* io,
-                  void* workspace, size_t workspace_bytes, void* stream_) {
+}  // extern "C"
+
+static int forward_impl(const tggcn_dims* dims, const void* const* weights, int n_weights, const tggcn_io* io,
+                        void* workspace, size_t workspace_bytes, void* stream_, cudaEvent_t* ev) {
     TG_REQUIRE(dims && weights && io && workspace, "forward: null argument");
     TG_REQUIRE(n_weights == TGGCN_W_COUNT, "forward: expected %d weight pointers, got %d", (int)TGGCN_W_COUNT, n_weights);
     const tggcn_dims& d = *dims;
@@ -192,11 +195,19 @@ int tggcn_forward(const tggcn_dims* dims, const void* const* weights, int n_weig
     float* bn_stats = mg_o + 2 * (size_t)B * O * 2 * D;
     unsigned int* sync = (unsigned int*)buf(TGGCN_BUF_SYNC);
 
+    int stage = 0;
+#define STAGE_END()                                                  \
+    do {                                                             \
+        if (ev) TG_CUDA_OK(cudaEventRecord(ev[stage + 1], stream));  \
+        ++stage;                                                     \
+    } while (0)
+    if (ev) TG_CUDA_OK(cudaEventRecord(ev[0], stream));
     // 1. geometry GCN (stored (B,128,V,T); the scrambled view is a reinterpretation as (B*T, 128V))
     if (int rc = launch_geo_gcn(io->x_human, weights, buf(TGGCN_BUF_GCN_OUT), io->bn_running_mean, io->bn_running_var,
                                 io->bn_num_batches, bn_stats, B, T, H, V, d.Fh, d.bn_train, stream))
         return rc;
 
+    STAGE_END();
     GemmGroup g;
     // 2. ROI embeddings and the first geometry MLP layer (models.py:646)
     g.count = 0;
@@ -204,10 +215,12 @@ int tggcn_forward(const tggcn_dims* dims, const void* const* weights, int n_weig
     gemm_add(g, io->x_objects, 2048, W(TGGCN_W_OBJ_EMB_W), 2048, W(TGGCN_W_OBJ_EMB_B), buf(TGGCN_BUF_S_O), 2 * D, N * O, D, 2048, 1);
     gemm_add(g, buf(TGGCN_BUF_GCN_OUT), 128 * V, W(TGGCN_W_GEO_MLP0_W), 128 * V, W(TGGCN_W_GEO_MLP0_B), buf(TGGCN_BUF_GEO_HID), 2048, N, 2048, 128 * V, 1);
     if (int rc = launch_gemm(g, d.gemm_path, stream)) return rc;
+    STAGE_END();
     // 3. second geometry MLP layer
     g.count = 0;
     gemm_add(g, buf(TGGCN_BUF_GEO_HID), 2048, W(TGGCN_W_GEO_MLP2_W), 2048, W(TGGCN_W_GEO_MLP2_B), buf(TGGCN_BUF_S_G), 2 * D, N, D, 2048, 1);
     if (int rc = launch_gemm(g, d.gemm_path, stream)) return rc;
+    STAGE_END();
     // 4. BiGRU input pre-activations for both directions (hoisted W_ih x + b_ih)
     g.count = 0;
     gemm_add(g, buf(TGGCN_BUF_S_H), 2 * D, W(TGGCN_W_HUM_RNN_WIH_F), D, W(TGGCN_W_HUM_RNN_BIH_F), buf(TGGCN_BUF_GI_H), 6 * D, N * H, 3 * D, D, 0);
@@ -217,6 +230,7 @@ int tggcn_forward(const tggcn_dims* dims, const void* const* weights, int n_weig
     gemm_add(g, buf(TGGCN_BUF_S_G), 2 * D, W(TGGCN_W_GEO_RNN_WIH_F), D, W(TGGCN_W_GEO_RNN_BIH_F), buf(TGGCN_BUF_GI_G), 6 * D, N, 3 * D, D, 0);
     gemm_add(g, buf(TGGCN_BUF_S_G), 2 * D, W(TGGCN_W_GEO_RNN_WIH_B), D, W(TGGCN_W_GEO_RNN_BIH_B), buf(TGGCN_BUF_GI_G) + 3 * D, 6 * D, N, 3 * D, D, 0);
     if (int rc = launch_gemm(g, d.gemm_path, stream)) return rc;
+    STAGE_END();
     // 5. frame-level BiGRU recurrences (models.py:649-651)
     {
         BiGruParams P;
@@ -239,12 +253,14 @@ int tggcn_forward(const tggcn_dims* dims, const void* const* weights, int n_weig
         P.sync.counter = sync; P.sync.error = sync + 1;
         if (int rc = launch_bigru(P, d.persistent, stream)) return rc;
     }
+    STAGE_END();
     // 6. Linear(2D->D)+ReLU on the BiGRU outputs, written next to x in the [x | h] rows
     g.count = 0;
     gemm_add(g, buf(TGGCN_BUF_HFR_H), 2 * D, W(TGGCN_W_HUM_BD_W), 2 * D, W(TGGCN_W_HUM_BD_B), buf(TGGCN_BUF_S_H) + D, 2 * D, N * H, D, 2 * D, 1);
     gemm_add(g, buf(TGGCN_BUF_HFR_O), 2 * D, W(TGGCN_W_OBJ_BD_W), 2 * D, W(TGGCN_W_OBJ_BD_B), buf(TGGCN_BUF_S_O) + D, 2 * D, N * O, D, 2 * D, 1);
     gemm_add(g, buf(TGGCN_BUF_HFR_G), 2 * D, W(TGGCN_W_GEO_BD_W), 2 * D, W(TGGCN_W_GEO_BD_B), buf(TGGCN_BUF_S_G) + D, 2 * D, N, D, 2 * D, 1);
     if (int rc = launch_gemm(g, d.gemm_path, stream)) return rc;
+    STAGE_END();
     // 7. per-sender frame messages, each computed once per sender and message kind (models.py:1693-1718)
     g.count = 0;
     if (d.hh) gemm_add(g, buf(TGGCN_BUF_S_H), 2 * D, W(TGGCN_W_MSG_HH_W), 2 * D, W(TGGCN_W_MSG_HH_B), buf(TGGCN_BUF_MSG_HH), D, N * H, D, 2 * D, 1);
@@ -253,6 +269,7 @@ int tggcn_forward(const tggcn_dims* dims, const void* const* weights, int n_weig
     gemm_add(g, buf(TGGCN_BUF_S_O), 2 * D, W(TGGCN_W_MSG_OO_W), 2 * D, W(TGGCN_W_MSG_OO_B), buf(TGGCN_BUF_MSG_OO), D, N * O, D, 2 * D, 1);
     gemm_add(g, buf(TGGCN_BUF_S_G), 2 * D, W(TGGCN_W_MSG_GO_W), 2 * D, W(TGGCN_W_MSG_GO_B), buf(TGGCN_BUF_MSG_GO), D, N, D, 2 * D, 1);
     if (int rc = launch_gemm(g, d.gemm_path, stream)) return rc;
+    STAGE_END();
     // 8. attention, aggregation, gates, segment-level inputs
     {
         FrameMsgParams P;
@@ -270,10 +287,12 @@ int tggcn_forward(const tggcn_dims* dims, const void* const* weights, int n_weig
         P.att_frame = d.inspect ? io->att_frame : nullptr;
         if (int rc = launch_frame_messages(P, stream)) return rc;
     }
+    STAGE_END();
     // 9. optional local-maximum filter + reorder gather index
     if (int rc = launch_gate_post(io->y_hs, io->y_hss, io->y_os, io->y_oss, (int*)buf(TGGCN_BUF_REIDX), B, T, H, O, d.filter,
                                   d.thr, stream))
         return rc;
+    STAGE_END();
     // 10. hoisted frame-part of the segment cells' W_ih x + b_ih, both directions
     const int kh = (1 + nkh) * D, ldwh = (1 + 2 * nkh) * D;
     g.count = 0;
@@ -282,6 +301,7 @@ int tggcn_forward(const tggcn_dims* dims, const void* const* weights, int n_weig
     gemm_add(g, buf(TGGCN_BUF_XX_O), 4 * D, W(TGGCN_W_OSEG_F_WIH), 6 * D, W(TGGCN_W_OSEG_F_BIH), buf(TGGCN_BUF_GS_O), 6 * D, N * O, 3 * D, 4 * D, 0);
     gemm_add(g, buf(TGGCN_BUF_XX_O), 4 * D, W(TGGCN_W_OSEG_B_WIH), 6 * D, W(TGGCN_W_OSEG_B_BIH), buf(TGGCN_BUF_GS_O) + 3 * D, 6 * D, N * O, 3 * D, 4 * D, 0);
     if (int rc = launch_gemm(g, d.gemm_path, stream)) return rc;
+    STAGE_END();
     // 11. segment-level recurrent graph (models.py:785-880)
     {
         SegParams P;
@@ -309,6 +329,7 @@ int tggcn_forward(const tggcn_dims* dims, const void* const* weights, int n_weig
         P.sync.counter = sync + 2; P.sync.error = sync + 3;
         if (int rc = launch_segment(P, d.persistent, stream)) return rc;
     }
+    STAGE_END();
     // 12. label heads (models.py:909-917)
     {
         HeadsParams P;
@@ -326,7 +347,35 @@ int tggcn_forward(const tggcn_dims* dims, const void* const* weights, int n_weig
             if (int rc = launch_heads(P, stream)) return rc;
         }
     }
+    STAGE_END();
+#undef STAGE_END
     return 0;
 }
+
+extern "C" {
+
+int tggcn_forward(const tggcn_dims* dims, const void* const* weights, int n_weights, const tggcn_io* io,
+                  void* workspace, size_t workspace_bytes, void* stream) {
+    return forward_impl(dims, weights, n_weights, io, workspace, workspace_bytes, stream, nullptr);
+}
+
+int tggcn_forward_profile(const tggcn_dims* dims, const void* const* weights, int n_weights, const tggcn_io* io,
+                          void* workspace, size_t workspace_bytes, void* stream, float* stage_ms_host) {
+    TG_REQUIRE(stage_ms_host != nullptr, "forward_profile: null stage_ms_host");
+    cudaEvent_t ev[TGGCN_STAGE_COUNT + 1];
+    for (int i = 0; i <= TGGCN_STAGE_COUNT; ++i) TG_CUDA_OK(cudaEventCreate(&ev[i]));
+    int rc = forward_impl(dims, weights, n_weights, io, workspace, workspace_bytes, stream, ev);
+    if (rc == 0) {
+        cudaError_t e = cudaStreamSynchronize((cudaStream_t)stream);
+        if (e != cudaSuccess) { set_error("forward_profile: %s", cudaGetErrorString(e)); rc = 1; }
+    }
+    for (int i = 0; i < TGGCN_STAGE_COUNT && rc == 0; ++i) {
+        if (cudaEventElapsedTime(&stage_ms_host[i], ev[i], ev[i + 1]) != cudaSuccess) { set_error("forward_profile: event timing failed"); rc = 1; }
+    }
+    for (int i = 0; i <= TGGCN_STAGE_COUNT; ++i) cudaEventDestroy(ev[i]);
+    return rc;
+}
+
+unsigned long long tggcn_launch_count(void) { return tg::g_launches; }
 
 }  // extern "C"

@@ -149,6 +149,7 @@ int launch_bigru(BiGruParams& P, int persistent, cudaStream_t stream) {
         int s0 = 0, s1 = P.T, pers = 1;
         void* args[] = {(void*)&P, (void*)&s0, (void*)&s1, (void*)&pers};
         TG_CUDA_OK(cudaLaunchCooperativeKernel((const void*)kern, dim3(grid), dim3(REC_THREADS), args, smem, stream));
+        ++g_launches;
     } else {
         for (int s = 0; s < P.T; ++s) {
             kern<<<P.total_tiles, REC_THREADS, smem, stream>>>(P, s, s + 1, 0);

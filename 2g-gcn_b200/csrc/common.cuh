@@ -14,6 +14,8 @@ namespace tg {
 // error plumbing (host)
 // ---------------------------------------------------------------------------------------------
 void set_error(const char* fmt, ...);
+}  // namespace tg
+namespace tg {
 
 #define TG_CUDA_OK(expr)                                                                        \
     do {                                                                                        \
@@ -32,8 +34,11 @@ void set_error(const char* fmt, ...);
         }                                    \
     } while (0)
 
+extern unsigned long long g_launches;
+
 #define TG_LAUNCH_OK()                                                                          \
     do {                                                                                        \
+        ++tg::g_launches;                                                                       \
         cudaError_t _e = cudaGetLastError();                                                    \
         if (_e != cudaSuccess) {                                                                \
             tg::set_error("%s:%d: launch failed -> %s", __FILE__, __LINE__, cudaGetErrorString(_e)); \

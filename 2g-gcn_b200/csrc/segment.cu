@@ -358,6 +358,7 @@ int launch_segment(SegParams& P, int persistent, cudaStream_t stream) {
         int s0 = 0, s1 = P.T, phases = 3, pers = 1;
         void* args[] = {(void*)&P, (void*)&s0, (void*)&s1, (void*)&phases, (void*)&pers};
         TG_CUDA_OK(cudaLaunchCooperativeKernel((const void*)kern, dim3(grid), dim3(REC_THREADS), args, smem, stream));
+        ++g_launches;
     } else {
         for (int s = 0; s < P.T; ++s) {
             kern<<<P.tilesA, REC_THREADS, smem, stream>>>(P, s, s + 1, 1, 0);

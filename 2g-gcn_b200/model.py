@@ -227,7 +227,20 @@ class TGGCN(nn.Module):
                 steps_per_example=None, inspect_model=False):
         """Same contract as vhoi/models.py:584-623.  Returns the list of models.py:919-926 (6 tensors, or 12
         when affordance classes exist), plus the attention stacks when ``inspect_model``."""
-        if human_human_distances is not None or human_object_distances is not None or object_object_distances is not None:
+        return self._run(x_human, x_objects, objects_mask, human_segmentation, objects_segmentation,
+                         human_human_distances, human_object_distances, object_object_distances, inspect_model, None)
+
+    def forward_profile(self, x_human, x_objects, objects_mask, human_segmentation=None, objects_segmentation=None,
+                        inspect_model=False):
+        """forward() with CUDA events around every stage; returns (outputs, {stage name: milliseconds})."""
+        ms = (C.c_float * len(abi.STAGE_NAMES))()
+        out = self._run(x_human, x_objects, objects_mask, human_segmentation, objects_segmentation, None, None, None,
+                        inspect_model, ms)
+        return out, dict(zip(abi.STAGE_NAMES, list(ms)))
+
+    def _run(self, x_human, x_objects, objects_mask, human_segmentation, objects_segmentation, hh_d, ho_d, oo_d,
+             inspect_model, stage_ms):
+        if hh_d is not None or ho_d is not None or oo_d is not None:
             raise NotImplementedError('distance-based attention (misc.make_attention_distance_based) is not supported')
         if not x_human.is_cuda:
             raise abi.TggcnError('2G-GCN B200 path runs on a CUDA device only (no CPU fallback); got a CPU tensor')
@@ -285,11 +298,16 @@ class TGGCN(nn.Module):
         ws = self._workspace(dims, dev)
         weights = self._weight_pointers(dev)
         with torch.cuda.device(dev):
-            stream = torch.cuda.current_stream(dev).cuda_stream
-            rc = abi.lib().tggcn_forward(C.byref(dims), weights, abi.N_WEIGHTS, C.byref(io), ws.data_ptr(), ws.numel(),
-                                         C.c_void_p(stream))
+            stream = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+            if stage_ms is None:
+                rc = abi.lib().tggcn_forward(C.byref(dims), weights, abi.N_WEIGHTS, C.byref(io), ws.data_ptr(),
+                                             ws.numel(), stream)
+            else:
+                rc = abi.lib().tggcn_forward_profile(C.byref(dims), weights, abi.N_WEIGHTS, C.byref(io), ws.data_ptr(),
+                                                     ws.numel(), stream, stage_ms)
         abi.check(rc, 'tggcn_forward')
-        self._last = (dims, ws, (x_human, x_objects, objects_mask, hseg, oseg, noise))   # keep inputs alive until queued work ran
+        # keep inputs alive until the queued work ran
+        self._last = (dims, ws, (x_human, x_objects, objects_mask, hseg, oseg, noise))
         if n_aff is None:
             output = [y_hs, y_hss] + out_h
         else:

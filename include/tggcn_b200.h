@@ -236,6 +236,32 @@ TGGCN_API int tggcn_sync_status(const tggcn_dims* dims, const void* workspace, v
 TGGCN_API int tggcn_forward(const tggcn_dims* dims, const void* const* weights, int n_weights, const tggcn_io* io,
                   void* workspace, size_t workspace_bytes, void* stream);
 
+/* Stages of the forward, in launch order (tggcn_forward_profile reports one duration per stage). */
+enum tggcn_stage_id {
+    TGGCN_STAGE_GEO_GCN = 0,     /* geo_gcn_kernel                                   (K-A)               */
+    TGGCN_STAGE_GEMM_EMBED,      /* ROI embeddings + geometry MLP layer 0            (K-B)               */
+    TGGCN_STAGE_GEMM_GEO2,       /* geometry MLP layer 2                                                  */
+    TGGCN_STAGE_GEMM_GI,         /* BiGRU input pre-activations, 3 groups x 2 directions                  */
+    TGGCN_STAGE_BIGRU,           /* persistent BiGRU recurrences                     (K-C)               */
+    TGGCN_STAGE_GEMM_BD,         /* Linear(2D->D) on BiGRU outputs                                        */
+    TGGCN_STAGE_GEMM_MSG,        /* per-sender frame message MLPs                                         */
+    TGGCN_STAGE_FRAME_MSG,       /* attention + aggregation + gates                  (K-D)               */
+    TGGCN_STAGE_GATE_POST,       /* filter + reorder index                           (K-E)               */
+    TGGCN_STAGE_GEMM_GS,         /* hoisted frame-part of the segment cells' W_ih x                       */
+    TGGCN_STAGE_SEGMENT,         /* persistent segment-level recurrent graph         (K-F)               */
+    TGGCN_STAGE_HEADS,           /* label heads                                      (K-G)               */
+    TGGCN_STAGE_COUNT
+};
+
+/* Same as tggcn_forward, but brackets every stage with CUDA events on `stream`, synchronises the stream and
+ * writes TGGCN_STAGE_COUNT durations (milliseconds) to stage_ms_host.  Measurement aid for bench.py. */
+TGGCN_API int tggcn_forward_profile(const tggcn_dims* dims, const void* const* weights, int n_weights,
+                                    const tggcn_io* io, void* workspace, size_t workspace_bytes, void* stream,
+                                    float* stage_ms_host);
+
+/* Number of kernels this library has launched since it was loaded (host-side counter). */
+TGGCN_API unsigned long long tggcn_launch_count(void);
+
 /* Kernel-family entry points (also used by tggcn_forward). */
 
 /* Geo_gcn.forward + the input split of models.py:631-642 (pyrutils/torch/models_gcn.py:30-100).

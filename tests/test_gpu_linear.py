@@ -1,0 +1,52 @@
+"""GPU: the projection kernels (tggcn_linear_fwd) against a float64 CPU matmul, including ragged tiles,
+strided operands and sliced outputs as the forward uses them."""
+import ctypes as C
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+SHAPES = [
+    # M, N, K, lda_pad, ldw_pad, ldc_pad, relu, bias
+    (1, 16, 16, 0, 0, 0, 0, 1),
+    (37, 48, 32, 0, 0, 0, 1, 1),
+    (130, 130, 64, 8, 4, 3, 0, 1),
+    (257, 96, 48, 104, 0, 32, 1, 0),
+    (2048, 512, 2048, 104, 0, 512, 1, 1),      # human ROI embedding, B=8,T=128
+    (1024, 2048, 3328, 0, 0, 0, 1, 1),         # geometry MLP layer 0
+    (4096, 1536, 512, 512, 0, 1536, 0, 1),     # BiGRU input gates, objects
+]
+
+
+def _linear(pkg, A, W, bias, C_out, M, N, K, relu, path):
+    lib = pkg.abi.lib()
+    rc = lib.tggcn_linear_fwd(A.data_ptr(), A.stride(0), W.data_ptr(), W.stride(0),
+                              bias.data_ptr() if bias is not None else None, C_out.data_ptr(), C_out.stride(0),
+                              M, N, K, relu, path, C.c_void_p(torch.cuda.current_stream().cuda_stream))
+    pkg.abi.check(rc, 'tggcn_linear_fwd')
+
+
+@pytest.mark.parametrize('path', [0])
+@pytest.mark.parametrize('shape', SHAPES)
+def test_linear_matches_fp64(shape, path, pkg):
+    M, N, K, pa, pw, pc, relu, has_bias = shape
+    g = torch.Generator().manual_seed(M * 7 + N * 3 + K)
+    A_full = torch.randn(M, K + pa, generator=g)
+    W_full = torch.randn(N, K + pw, generator=g) / K ** 0.5
+    bias = torch.randn(N, generator=g) if has_bias else None
+    ref = A_full[:, :K].double() @ W_full[:, :K].double().t()
+    if bias is not None:
+        ref = ref + bias.double()
+    if relu:
+        ref = ref.clamp_min(0)
+    A_d, W_d = A_full.cuda(), W_full.cuda()
+    C_full = torch.full((M, N + pc), -7.0, device='cuda')
+    _linear(pkg, A_d[:, :K], W_d[:, :K], None if bias is None else bias.cuda(), C_full[:, :N], M, N, K, relu, path)
+    torch.cuda.synchronize()
+    got = C_full[:, :N].cpu().double()
+    err = (got - ref).abs().max().item()
+    scale = ref.abs().max().item() + 1e-6
+    assert err <= 2e-5 * scale + 1e-5, f'max err {err:.3e} (scale {scale:.3e})'
+    if pc:
+        assert torch.all(C_full[:, N:] == -7.0), 'wrote outside the N columns'

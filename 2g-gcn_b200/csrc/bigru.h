@@ -11,7 +11,7 @@ struct BiGruGroup {
     const float* bhh[2];    // (3D)
     int E;                  // entities of this group
     int rows;               // B*E
-    int nrg, jeff, n_rb, n_ub, tile_begin;   // tiling (filled by the launcher)
+    int cfg, jeff, n_rb, n_ub, tile_begin;   // tiling (filled by the launcher); cfg: see rec_cfg_for_rows
 };
 
 struct BiGruParams {
@@ -49,12 +49,12 @@ struct SegParams {
     float* att_f; float* att_b;   // (B,H,T,O) or null
     // tiling (filled by the launcher)
     int nk_h;                     // message kinds feeding the human cell (2 with hh, else 1)
-    int bbv, n_vb;                // videos per message tile, number of video blocks
+    int bbv[4], n_vb[4];          // per message kind: videos per message tile, number of video blocks
     int msg_tiles_kind[4];        // unit blocks per kind
     int msg_tile_begin[5];        // prefix over kinds (per direction)
     int msg_tiles_dir;            // message tiles per direction
-    int nrg_h, jeff_h, nrb_h, nub_h;
-    int nrg_o, jeff_o, nrb_o, nub_o;
+    int cfg_h, jeff_h, nrb_h, nub_h;
+    int cfg_o, jeff_o, nrb_o, nub_o;
     int cell_tiles_h_dir, cell_tiles_dir;
     int tilesA, tilesB;
     GridSync sync;

@@ -1,94 +1,186 @@
 // Building block of the two recurrent kernels (frame-level BiGRU, segment-level gated GRUCell graph):
 // a CTA-wide "gate tile"
-//     acc[g][r] += sum_k W[g*gate_stride + unit][k] * X[r][k]        g < NG gates, r < RB rows
-// with the weight slice and the activation rows streamed through shared memory in K-chunks by
-// cp.async (.cg: activations were written by other CTAs of the same persistent kernel, L1 must be
-// bypassed) and double-buffered.  Thread (j, rg) owns unit j and rows 2rg, 2rg+1 for all gates, so the
-// GRU gate math that follows is thread-local.
+//     out[g][r][u] = sum_k Wrow[g*16 + u][k] * X[r][k]          g < NG groups, r < 16 rows, u < 16 units
+// Weight rows and activation rows are addressed through pointer tables (a null pointer is an all-zero
+// row), so the same routine serves W_hh h, the segment columns of W_ih, the message MLPs and — with the
+// receivers' state rows as an extra "weight" group — the attention logits of the message tiles.
+//
+// How it got here (ncu captures under profiles/, round 1): three FFMA versions (CTA-wide K-chunk barrier;
+// K split across warps; warp-private pipelines with 512 threads) all stalled at IPC ~0.4 — first on
+// short_scoreboard/barrier, finally on mio_throttle: a 16-row tile reuses every weight only 16 times, so an
+// FFMA formulation issues one LDS.128 per ~9 FFMA and the shared-memory instruction queue, not the FMA pipe,
+// is the limit.  This version therefore runs the products on the tensor cores:
+//  * mma.sync.m16n8k8 TF32 with the 3xTF32 split (a = hi + lo, hi*hi + hi*lo + lo*hi, fp32 accumulate), which
+//    keeps fp32-class accuracy (relative error ~2^-21 per product) at 1/3 of the instruction count of FFMA and
+//    a third of the shared-memory instructions;
+//  * the K range is split across the 8 warps in 16-float chunks (round-robin) and EVERY WARP RUNS ITS OWN
+//    cp.async PIPELINE in a private shared-memory ring: no block-wide barrier inside the K loop, only __syncwarp;
+//  * ring rows are padded to 20 floats so that the 8 rows x 4 columns of a fragment load hit 32 distinct banks;
+//  * copies are branch-free (cp.async zero-fill form; .cg because activations were written by other CTAs of the
+//    same persistent kernel and L1 must be bypassed);
+//  * partial accumulators of the 8 warps are reduced through shared memory once per tile.
 #pragma once
 #include "common.cuh"
 
 namespace tg {
 
 constexpr int REC_THREADS = 256;
+constexpr int REC_WARPS = REC_THREADS / 32;
+constexpr int REC_J = 16;         // units per tile  (one m16 MMA tile per group)
+constexpr int REC_RB = 16;        // rows per tile   (two n8 MMA tiles)
+constexpr int REC_CK = 16;        // floats of K per chunk (two k8 MMA steps, 64 bytes per row)
+constexpr int REC_RS = 20;        // ring row stride in floats (16 data + 4 pad)
 
-template <int NRG>
-struct TileGeom {
-    static constexpr int RB = 2 * NRG;               // rows per tile
-    static constexpr int J = REC_THREADS / NRG;      // units per tile
-};
-
-// shared memory floats needed by tile_accumulate<NG,NRG,KC,XROWS>
-template <int NG, int NRG, int KC, int XROWS>
-__host__ __device__ constexpr int tile_smem_floats() {
-    return 2 * (NG * TileGeom<NRG>::J + XROWS) * (KC + 4);
+__host__ __device__ constexpr int tile_ring_floats(int NG, int STAGES) {
+    return REC_WARPS * STAGES * (NG * REC_J + REC_RB) * REC_RS;
+}
+__host__ __device__ constexpr int tile_red_floats(int NG) { return REC_WARPS * NG * 2 * 32 * 4; }
+__host__ __device__ constexpr int tile_smem_floats(int NG, int STAGES) {
+    return tile_ring_floats(NG, STAGES) > tile_red_floats(NG) ? tile_ring_floats(NG, STAGES) : tile_red_floats(NG);
 }
 
-struct NoHook {
-    __device__ __forceinline__ void operator()(const float*, int) const {}
-};
+// 16-byte async copy with zero-fill: copies `valid ? 16 : 0` bytes and zero-fills the rest.
+__device__ __forceinline__ void cp_async16_zfill(void* smem, const void* gmem, bool valid) {
+    unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+    const int n = valid ? 16 : 0;
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(s), "l"(gmem), "r"(n) : "memory");
+}
 
-// xrows: shared-memory array of XROWS global row pointers (nullptr = all-zero row).
-// rows [0, RB) feed the gate GEMM; rows [RB, XROWS) are only visible to the hook.
-template <int NG, int NRG, int KC, int XROWS, typename Hook>
-__device__ __forceinline__ void tile_accumulate(float (&acc)[NG][2], const float* __restrict__ W, int ldw,
-                                                int gate_stride, int unit0, int unit_end, int row_end,
-                                                const float* const* xrows, int K, float* smem, Hook hook) {
-    constexpr int J = TileGeom<NRG>::J;
-    constexpr int LD = KC + 4;
-    constexpr int F4 = KC / 4;
-    float* Ws = smem;                              // [2][NG*J][LD]
-    float* Xs = smem + 2 * NG * J * LD;            // [2][XROWS][LD]
-    const int tid = threadIdx.x;
-    const int j = (tid & 15) + 16 * (tid / (16 * NRG));
-    const int rg = (tid >> 4) % NRG;
-    const int nchunks = K / KC;
-    if (nchunks <= 0) return;
+// D += A(16x8, row) * B(8x8, col), TF32 operands, fp32 accumulate.
+__device__ __forceinline__ void mma_tf32(float (&d)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
+    asm volatile(
+        "mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};\n"
+        : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+}
 
-    auto issue = [&](int c, int buf) {
-        for (int f = tid; f < NG * J * F4; f += REC_THREADS) {
-            const int row = f / F4, q = f - row * F4;
-            const int g = row / J, jj = row - g * J;
-            const int unit = unit0 + jj;
-            const int wrow = g * gate_stride + unit;
-            float* dst = Ws + (buf * NG * J + row) * LD + q * 4;
-            if (unit < unit_end && wrow < row_end) cp_async16(dst, W + (size_t)wrow * ldw + c * KC + q * 4);
-            else *reinterpret_cast<float4*>(dst) = make_float4(0.f, 0.f, 0.f, 0.f);
-        }
-        for (int f = tid; f < XROWS * F4; f += REC_THREADS) {
-            const int row = f / F4, q = f - row * F4;
-            const float* src = xrows[row];
-            float* dst = Xs + (buf * XROWS + row) * LD + q * 4;
-            if (src != nullptr) cp_async16(dst, src + c * KC + q * 4);
-            else *reinterpret_cast<float4*>(dst) = make_float4(0.f, 0.f, 0.f, 0.f);
-        }
-        cp_async_commit();
-    };
+// x = hi + lo with hi exactly representable in TF32 (low 13 mantissa bits cleared) and lo = x - hi exact in fp32.
+__device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) {
+    hi = __float_as_uint(x) & 0xffffe000u;
+    lo = __float_as_uint(x - __uint_as_float(hi));
+}
 
-    issue(0, 0);
-    for (int c = 0; c < nchunks; ++c) {
-        const int buf = c & 1;
-        if (c + 1 < nchunks) { issue(c + 1, buf ^ 1); cp_async_wait<1>(); }
-        else                 { cp_async_wait<0>(); }
-        __syncthreads();
-        const float* wb = Ws + (buf * NG * J + j) * LD;
-        const float* xb = Xs + (buf * XROWS + 2 * rg) * LD;
+// wrows: shared-memory table of NG*16 weight-row pointers; xrows: table of 16 activation-row pointers
+// (nullptr = zero row); every row holds at least K floats, K a multiple of 16, 16-byte aligned.
+// On return out[g] holds the full sum for this thread's epilogue pair: unit = tid % 16, row = tid / 16.
+template <int NG, int STAGES>
+__device__ __forceinline__ void tile_accumulate(float (&out)[NG], const float* const* wrows, const float* const* xrows,
+                                                int K, float* smem) {
+    constexpr int ROWS = NG * REC_J + REC_RB;
+    constexpr int STAGE_F = ROWS * REC_RS;
+    constexpr int NP = (ROWS * 4 + 31) / 32;            // 16-byte pieces per lane per chunk
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int g8 = lane >> 2, t4 = lane & 3;
+    float* ring = smem + warp * (STAGES * STAGE_F);
+
+    float c[NG][2][4];
 #pragma unroll
-        for (int q = 0; q < F4; ++q) {
-            const float4 x0 = *reinterpret_cast<const float4*>(xb + q * 4);
-            const float4 x1 = *reinterpret_cast<const float4*>(xb + LD + q * 4);
+    for (int m = 0; m < NG; ++m)
 #pragma unroll
-            for (int g = 0; g < NG; ++g) {
-                const float4 w = *reinterpret_cast<const float4*>(wb + g * J * LD + q * 4);
-                acc[g][0] = fmaf(w.x, x0.x, acc[g][0]); acc[g][0] = fmaf(w.y, x0.y, acc[g][0]);
-                acc[g][0] = fmaf(w.z, x0.z, acc[g][0]); acc[g][0] = fmaf(w.w, x0.w, acc[g][0]);
-                acc[g][1] = fmaf(w.x, x1.x, acc[g][1]); acc[g][1] = fmaf(w.y, x1.y, acc[g][1]);
-                acc[g][1] = fmaf(w.z, x1.z, acc[g][1]); acc[g][1] = fmaf(w.w, x1.w, acc[g][1]);
+        for (int n = 0; n < 2; ++n)
+#pragma unroll
+            for (int r = 0; r < 4; ++r) c[m][n][r] = 0.0f;
+
+    const int total_chunks = K / REC_CK;
+    const int nmine = warp < total_chunks ? (total_chunks - warp + REC_WARPS - 1) / REC_WARPS : 0;
+    if (nmine > 0) {
+        // this lane's copy pieces: (row, quarter) pairs; the source pointer only moves along K
+        const float* src[NP];
+        int dst[NP];
+        bool ok[NP], in[NP];
+        const float* safe = wrows[0];
+#pragma unroll
+        for (int p = 0; p < NP; ++p) {
+            const int piece = lane + p * 32;
+            const int row = piece >> 2, quarter = piece & 3;
+            in[p] = piece < ROWS * 4;
+            const float* base = nullptr;
+            if (in[p]) base = row < NG * REC_J ? wrows[row] : xrows[row - NG * REC_J];
+            ok[p] = base != nullptr;
+            src[p] = ok[p] ? base + quarter * 4 + warp * REC_CK : safe;
+            dst[p] = row * REC_RS + quarter * 4;
+        }
+        auto issue = [&](int n, int st) {
+#pragma unroll
+            for (int p = 0; p < NP; ++p)
+                if (in[p]) cp_async16_zfill(ring + st * STAGE_F + dst[p], ok[p] ? src[p] + (size_t)n * (REC_WARPS * REC_CK) : src[p], ok[p]);
+        };
+#pragma unroll
+        for (int st = 0; st < STAGES - 1; ++st) {
+            if (st < nmine) issue(st, st);
+            cp_async_commit();
+        }
+#pragma unroll 1
+        for (int n = 0; n < nmine; ++n) {
+            cp_async_wait<STAGES - 2>();         // this lane's pieces of chunk n have landed
+            __syncwarp();                        // ... all lanes'; and all lanes are done reading chunk n-1
+            {
+                const int nn = n + STAGES - 1;
+                if (nn < nmine) issue(nn, nn % STAGES);
+                cp_async_commit();
+            }
+            const float* wb = ring + (n % STAGES) * STAGE_F + g8 * REC_RS + t4;
+            const float* xb = ring + (n % STAGES) * STAGE_F + (NG * REC_J + g8) * REC_RS + t4;
+#pragma unroll
+            for (int kk = 0; kk < REC_CK / 8; ++kk) {
+                uint32_t bh[2][2], bl[2][2];
+#pragma unroll
+                for (int nt = 0; nt < 2; ++nt) {
+                    split_tf32(xb[nt * 8 * REC_RS + kk * 8], bh[nt][0], bl[nt][0]);
+                    split_tf32(xb[nt * 8 * REC_RS + kk * 8 + 4], bh[nt][1], bl[nt][1]);
+                }
+                uint32_t ah[NG][4], al[NG][4];
+#pragma unroll
+                for (int m = 0; m < NG; ++m) {
+                    const float* wm = wb + m * REC_J * REC_RS + kk * 8;
+                    split_tf32(wm[0], ah[m][0], al[m][0]);
+                    split_tf32(wm[8 * REC_RS], ah[m][1], al[m][1]);
+                    split_tf32(wm[4], ah[m][2], al[m][2]);
+                    split_tf32(wm[8 * REC_RS + 4], ah[m][3], al[m][3]);
+                }
+                // three passes over the 2*NG independent accumulator tiles (small terms first): consecutive MMAs
+                // never depend on each other, so the tensor pipe latency is hidden inside one warp
+#pragma unroll
+                for (int m = 0; m < NG; ++m)
+#pragma unroll
+                    for (int nt = 0; nt < 2; ++nt) mma_tf32(c[m][nt], al[m], bh[nt]);
+#pragma unroll
+                for (int m = 0; m < NG; ++m)
+#pragma unroll
+                    for (int nt = 0; nt < 2; ++nt) mma_tf32(c[m][nt], ah[m], bl[nt]);
+#pragma unroll
+                for (int m = 0; m < NG; ++m)
+#pragma unroll
+                    for (int nt = 0; nt < 2; ++nt) mma_tf32(c[m][nt], ah[m], bh[nt]);
             }
         }
-        hook(Xs + buf * XROWS * LD, LD);
-        __syncthreads();
+        cp_async_wait<0>();
     }
+    __syncthreads();                             // every warp's ring is dead: reuse the memory for the reduction
+    // cross-warp reduction of the K split: red[warp][m][n][reg][lane]
+    float* red = smem;
+#pragma unroll
+    for (int m = 0; m < NG; ++m)
+#pragma unroll
+        for (int n = 0; n < 2; ++n)
+#pragma unroll
+            for (int r = 0; r < 4; ++r) red[(((warp * NG + m) * 2 + n) * 4 + r) * 32 + lane] = c[m][n][r];
+    __syncthreads();
+    {
+        // accumulator element (unit u, row) of group m lives in: n = row / 8, lane = (u % 8) * 4 + (row % 8) / 2,
+        // reg = (u / 8) * 2 + (row % 2)        (m16n8 C fragment layout)
+        const int u = tid & 15, row = tid >> 4;
+        const int n = row >> 3, col = row & 7;
+        const int l = (u & 7) * 4 + (col >> 1), r = (u >> 3) * 2 + (col & 1);
+#pragma unroll
+        for (int m = 0; m < NG; ++m) {
+            float s = 0.0f;
+#pragma unroll
+            for (int w = 0; w < REC_WARPS; ++w) s += red[(((w * NG + m) * 2 + n) * 4 + r) * 32 + l];
+            out[m] = s;
+        }
+    }
+    __syncthreads();                             // smem may be reused by the caller right away
 }
 
 // GRU cell update, gate order (r, z, n) as torch.nn.GRU / GRUCell (vhoi/models.py:267,:294):

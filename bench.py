@@ -1,0 +1,328 @@
+"""Benchmark of the 2G-GCN hot path (BASELINE.json: video frames/s of the forward on MPHOI-72-shaped data).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+A "step" is one forward pass (eval, no_grad) of the drop-in TGGCN over one padded batch of synthetic
+videos: B=8 videos per GPU, T=128 frames, H=2 humans, O=4 object slots, V=26 nodes, hidden 512,
+stage-2 settings (learned Gumbel gates + local-maximum filter) — BASELINE.json configs[1].  Videos are
+independent, so N GPUs run N disjoint batches with no data-path collective ("scaling": "weak").
+
+`value`      : frames/s with inputs (and the pre-drawn Gumbel noise) resident in HBM, CUDA events, max over ranks.
+`e2e`        : the same through the public call with HOST buffers: pinned host inputs -> H2D, the per-call CPU
+               Gumbel draw the reference semantics require, forward, outputs -> D2H, all inside the timed region.
+`roofline`   : the dominant kernel (largest share of the step, per-stage CUDA events measured live).
+`cpu_baseline`: the CPU oracle port of the reference path (oracle/tggcn_oracle.py) timed on this box's host cores.
+`--impl reference` times that CPU port as the reference arm (the reference itself is pure PyTorch and is not
+present on the GPU box; its CPU algorithm is restated 1:1, loops included, in the oracle).
+"""
+from __future__ import annotations
+
+import argparse
+import importlib
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = 'video frames/sec (2G-GCN forward, MPHOI-72 shape)'
+UNIT = 'frames/s'
+
+
+def load_peaks():
+    path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(path):
+        p = json.load(open(path))
+        return dict(hbm_gbs=p['hbm_gbs'], tf_burst=p['bf16_tflops'], tf_sustained=p.get('bf16_tflops_sustained', p['bf16_tflops']),
+                    source='measured')
+    return dict(hbm_gbs=6650.0, tf_burst=1590.0, tf_sustained=1400.0, source='fallback')
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+    Q = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,'
+         'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, gpu_index: int):
+        self.idx, self.proc, self.path = gpu_index, None, None
+
+    def __enter__(self):
+        try:
+            f = tempfile.NamedTemporaryFile('w', suffix='.csv', delete=False)
+            self.path = f.name
+            self.proc = subprocess.Popen(['nvidia-smi', f'--query-gpu={self.Q}', '--format=csv,noheader,nounits', '-lms', '200',
+                                          '-i', str(self.idx)], stdout=f, stderr=subprocess.DEVNULL)
+            time.sleep(0.25)
+        except Exception:
+            self.proc = None
+        return self
+
+    def __exit__(self, *a):
+        if self.proc is not None:
+            time.sleep(0.25)
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=5)
+            except Exception:
+                self.proc.kill()
+
+    def summary(self):
+        if self.proc is None or not self.path or not os.path.exists(self.path):
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=['unavailable'])
+        sm, mx, reasons = [], [], set()
+        for line in open(self.path):
+            c = [x.strip() for x in line.split(',')]
+            if len(c) < 9:
+                continue
+            try:
+                sm.append(float(c[1])); mx.append(float(c[2]))
+            except ValueError:
+                continue
+            for name, v in zip(('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap'), c[5:9]):
+                if v.lower().startswith('active'):
+                    reasons.add(name)
+        os.unlink(self.path)
+        if not sm:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=['no samples'])
+        return dict(sm_mhz=statistics.median(sm), sm_max_mhz=max(mx), reasons=sorted(reasons))
+
+
+def workload(args):
+    pkg = importlib.import_module('2g-gcn_b200')
+    shape = pkg.synth.SHAPES[args.shape]
+    kwargs = pkg.synth.model_kwargs(shape, hidden_size=args.D, stage=2)
+    return pkg, shape, kwargs
+
+
+def stage_work(shape, B, T, D, hh=True):
+    """Algorithmic FLOPs and HBM bytes per forward of each stage (SURVEY.md §8d closed forms; message MLPs
+    counted once per sender and kind; fp32 operands).  Returns {stage: (flops, bytes)}."""
+    H, O, V = shape.H, shape.O, shape.V
+    N = B * T
+    nkh = 2 if hh else 1
+    f = 4
+    gemm = lambda M, Nn, K: (2.0 * M * Nn * K, f * (M * K + Nn * K + M * Nn))
+    add = lambda *xs: (sum(x[0] for x in xs), sum(x[1] for x in xs))
+    w = {}
+    w['geo_gcn'] = (N * (2 * V * (4 * 64 + 64 * 64 + 2 * 64 * 128 + 64 * 128) + 2 * V * V * (128 + 64)),
+                    f * N * (4 * V + 128 * V) + f * 28000)
+    w['gemm_embed'] = add(gemm(N * H, D, 2048), gemm(N * O, D, 2048), gemm(N, 2048, 128 * V))
+    w['gemm_geo2'] = gemm(N, D, 2048)
+    w['gemm_gi'] = add(*[gemm(N * E, 3 * D, D) for E in (H, H, O, O, 1, 1)])
+    rows = B * (H + O + 1)
+    w['bigru'] = (T * 2 * rows * 2 * 3 * D * D, f * (N * (H + O + 1) * (6 * D + 2 * D) + 6 * 3 * D * D))
+    w['gemm_bd'] = add(*[gemm(N * E, D, 2 * D) for E in (H, O, 1)])
+    w['gemm_msg'] = add(*[gemm(N * E, D, 2 * D) for E in ((H,) if hh else ()) + (H, O, O, 1)])
+    w['frame_msg'] = (N * (H + O) * (H + O) * 2 * D, f * N * ((H + O) * 2 * D + (nkh * H + 2 * H + 2 * O + 1) * D
+                                                                + H * (1 + nkh) * D + O * 4 * D))
+    w['gate_post'] = (0.0, f * N * (H + O) * 3)
+    w['gemm_gs'] = add(gemm(N * H, 3 * D, (1 + nkh) * D), gemm(N * H, 3 * D, (1 + nkh) * D), gemm(N * O, 3 * D, 4 * D),
+                       gemm(N * O, 3 * D, 4 * D))
+    seg_flops = T * 2 * (2.0 * B * H * 3 * D * (nkh * D + D) + 2.0 * B * O * 3 * D * (2 * D + D)
+                         + 2.0 * B * (nkh * H + 2 * O) * D * D)
+    seg_bytes = f * (N * (H + O) * (6 * D + 2 * D) + 2 * (3 * D * (nkh * D + D) + 3 * D * 3 * D + (nkh + 3) * D * D))
+    w['segment'] = (seg_flops, seg_bytes)
+    w['heads'] = (N * H * 4 * 2 * 2 * D * shape.num_classes[0], f * N * H * (2 * 2 * D + 4 * shape.num_classes[0]))
+    return w
+
+
+def run_ours(args, rank, world, local_rank):
+    import torch.distributed as dist
+    pkg, shape, kwargs = workload(args)
+    dev = torch.device('cuda', local_rank)
+    torch.cuda.set_device(dev)
+    torch.manual_seed(0)
+    model = pkg.TGGCN(**kwargs).to(dev).eval()
+    model.gemm_path = args.gemm_path
+    B, T, D = args.B, args.T, args.D
+    host = pkg.synth.make_batch(shape, B, T, seed=1234 + rank)
+    pinned = {k: host[k].pin_memory() for k in ('x_human', 'x_objects', 'objects_mask')}
+    resident = {k: v.to(dev) for k, v in pinned.items()}
+    n_calls = T * (shape.H + shape.O)
+    noise_dev = pkg.TGGCN.draw_gumbel_noise(n_calls, B).to(dev)
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)   # > 126 MB L2
+    lib = pkg.abi.lib()
+
+    def step_resident():
+        return model(x_human=resident['x_human'], x_objects=resident['x_objects'], objects_mask=resident['objects_mask'])
+
+    def step_e2e():
+        xs = {k: v.to(dev, non_blocking=True) for k, v in pinned.items()}
+        out = model(x_human=xs['x_human'], x_objects=xs['x_objects'], objects_mask=xs['objects_mask'])
+        return [o.cpu() for o in out]
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    def timed(fn, steps, warmup):
+        for _ in range(warmup):
+            fn()
+        barrier()
+        evs = []
+        launches0 = lib.tggcn_launch_count()
+        for _ in range(steps):
+            flush.zero_()                      # evict L2 between timed iterations (outside the event pair)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            fn()
+            e1.record()
+            evs.append((e0, e1))
+        barrier()
+        launches = lib.tggcn_launch_count() - launches0
+        ms = [a.elapsed_time(b) for a, b in evs]
+        total = torch.tensor([sum(ms)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(total, op=dist.ReduceOp.MAX)
+        return float(total.item()), ms, launches
+
+    with torch.no_grad():
+        model.set_gumbel_noise(noise_dev)
+        with ClockSampler(local_rank) as clk:
+            total_ms, ms_list, launches = timed(step_resident, args.steps, args.warmup)
+        clocks = clk.summary()
+        model.check_persistent_kernels()
+        model.set_gumbel_noise(None)           # e2e: per-call CPU draw + H2D, like the reference
+        e2e_total_ms, _, _ = timed(step_e2e, args.steps, max(3, args.warmup))
+        # per-stage device time (CUDA events on the launching stream, inside this process)
+        model.set_gumbel_noise(noise_dev)
+        rows = []
+        for i in range(6):
+            flush.zero_()
+            _, st = model.forward_profile(resident['x_human'], resident['x_objects'], resident['objects_mask'])
+            if i:
+                rows.append(st)
+    frames = world * B * T * args.steps
+    value = frames / (total_ms / 1e3)
+    e2e_value = frames / (e2e_total_ms / 1e3)
+    if rank != 0:
+        return
+    stages = {k: statistics.median(r[k] for r in rows) for k in rows[0]}
+    step_ms = sum(stages.values())
+    work = stage_work(shape, B, T, D, shape.hh)
+    peaks = load_peaks()
+    top = max(stages, key=stages.get)
+    flops, nbytes = work[top]
+    intensity = flops / max(nbytes, 1.0)
+    balance = peaks['tf_sustained'] * 1e12 / (peaks['hbm_gbs'] * 1e9)
+    sec = stages[top] / 1e3
+    if intensity >= balance or top in ('segment', 'bigru') or top.startswith('gemm'):
+        roof = dict(bound='tensor', achieved=flops / sec / 1e12, peak=peaks['tf_sustained'], unit='TFLOP/s')
+    else:
+        roof = dict(bound='hbm', achieved=nbytes / sec / 1e9, peak=peaks['hbm_gbs'], unit='GB/s')
+    roof['frac'] = roof['achieved'] / roof['peak']
+    roof['traffic'] = None
+    roof.update(kernel=top, kernel_ms=stages[top], share_of_step=stages[top] / step_ms, peak_source=peaks['source'],
+                us_per_recurrent_step=(stages[top] * 1e3 / T) if top in ('segment', 'bigru') else None)
+    tr = os.path.join(ROOT, 'profiles', 'ncu_traffic.json')
+    if os.path.exists(tr):
+        roof['traffic'] = json.load(open(tr)).get(top)
+    h2d = sum(v.numel() * v.element_size() for v in pinned.values()) + n_calls * B * 2 * 4
+    d2h = 2 * B * T * shape.H * 4 + 4 * B * shape.num_classes[0] * T * shape.H * 4
+    line = {
+        'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
+        'ms_per_step': total_ms / args.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+        'dtype': 'f32', 'data': 'synthetic',
+        'config': {'workload': f'2G-GCN inference forward, {shape.name.upper()} shape, stage-2 settings', 'videos_per_gpu': B,
+                   'frames_per_video': T, 'humans': shape.H, 'objects': shape.O, 'gcn_node': shape.V, 'hidden_size': D,
+                   'weights': 'reference default init, torch.manual_seed(0)', 'l2': 'flushed (256 MB memset) between timed steps',
+                   'projections': 'tcgen05 3xTF32' if args.gemm_path else 'fp32 SIMT', 'parallelism': f'replicas x{world} (videos sharded)'},
+        'clocks': clocks,
+        'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
+                'ms_per_step': e2e_total_ms / args.steps},
+        'gpu_launches': int(launches),
+        'roofline': roof,
+        'stages_ms': {k: round(v, 4) for k, v in stages.items()},
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        line['cpu_baseline'] = cpu_port_throughput(args, shape, kwargs, warmup=1, steps=2)
+    print(json.dumps(line), flush=True)
+
+
+def cpu_port_throughput(args, shape, kwargs, warmup, steps):
+    """The oracle port of the reference's CPU path, timed on this box's host cores (whole workload per step)."""
+    sys.path.insert(0, os.path.join(ROOT, 'oracle'))
+    import tggcn_oracle as orc
+    pkg = importlib.import_module('2g-gcn_b200')
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    torch.manual_seed(0)
+    params = {k: v.detach() for k, v in pkg.TGGCN(**kwargs).state_dict().items()}
+    B, T = args.B, args.T
+    batch = pkg.synth.make_batch(shape, B, T, seed=1234)
+    cfg = orc.OracleConfig(args.D, shape.V, shape.num_classes, shape.hh, True, kwargs['update_segment_threshold'])
+    times = []
+    with torch.no_grad():
+        for i in range(warmup + steps):
+            t0 = time.perf_counter()
+            orc.forward(params, cfg, batch['x_human'], batch['x_objects'], batch['objects_mask'], None, None, None)
+            if i >= warmup:
+                times.append(time.perf_counter() - t0)
+    sec = sum(times) / len(times)
+    return {'value': B * T / sec, 'unit': UNIT, 'cores': cores, 'kind': 'port',
+            'sample': f'whole workload (B={B}, T={T}, hidden {args.D}), {steps} timed forwards after {warmup} warm-up, '
+                      f'{cores} torch threads', 'seconds_per_step': sec}
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    pkg, shape, kwargs = workload(args)
+    res = cpu_port_throughput(args, shape, kwargs, warmup=min(args.warmup, 1), steps=min(args.steps, 3))
+    line = {
+        'impl': 'reference', 'metric': METRIC, 'value': res['value'], 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,
+        'warmup': args.warmup, 'ms_per_step': res['seconds_per_step'] * 1e3, 'higher_is_better': True, 'scaling': 'weak',
+        'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+        'config': {'workload': f'2G-GCN inference forward, {shape.name.upper()} shape, stage-2 settings', 'videos_per_gpu': args.B,
+                   'frames_per_video': args.T, 'humans': shape.H, 'objects': shape.O, 'gcn_node': shape.V, 'hidden_size': args.D,
+                   'note': 'CPU port of the reference path (oracle); timed steps capped at 3 to bound the run'},
+        'cpu_baseline': {k: res[k] for k in ('value', 'unit', 'cores', 'kind', 'sample')},
+        'e2e': {'value': res['value'], 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=20)
+    ap.add_argument('--warmup', type=int, default=5)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--shape', default='mphoi')
+    ap.add_argument('--B', type=int, default=8)
+    ap.add_argument('--T', type=int, default=128)
+    ap.add_argument('--D', type=int, default=512)
+    ap.add_argument('--gemm-path', type=int, default=0)
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == 'ours' else args.warmup
+    rank = int(os.environ.get('RANK', '0'))
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+    if args.impl == 'reference':
+        run_reference(args, rank, world)
+        return
+    if world > 1:
+        import torch.distributed as dist
+        os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
+    try:
+        run_ours(args, rank, world, local_rank)
+    finally:
+        if world > 1:
+            import torch.distributed as dist
+            dist.destroy_process_group()
+
+
+if __name__ == '__main__':
+    main()

@@ -32,7 +32,13 @@ inline void gemm_add(GemmGroup& g, const float* A, int lda, const float* W, int 
 
 int launch_gemm_simt(GemmGroup& grp, cudaStream_t stream);
 int launch_gemm_tc(GemmGroup& grp, cudaStream_t stream);     // tcgen05 3xTF32 (gemm_tc.cu)
+// path 0: fp32 SIMT; 1: tcgen05 3xTF32 (K % 32 == 0 required); 2: tcgen05 where the shapes allow it, SIMT otherwise
 inline int launch_gemm(GemmGroup& grp, int path, cudaStream_t stream) {
+    if (path == 2) {
+        path = 1;
+        for (int i = 0; i < grp.count; ++i)
+            if (grp.p[i].K % 32 != 0) path = 0;
+    }
     return path == 1 ? launch_gemm_tc(grp, stream) : launch_gemm_simt(grp, stream);
 }
 

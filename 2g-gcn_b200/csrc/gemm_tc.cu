@@ -1,13 +1,283 @@
-// tcgen05 (5th-gen tensor core) projection path — placeholder until the 3xTF32 kernel lands.
+// tcgen05 projection kernel (K-B, tensor-core path):
+//   C[M,N] = act(A[M,K] * W[N,K]^T + bias[N])      (nn.Linear as built by build_mlp,
+//                                                   pyrutils/torch/models.py:31-33)
+// fp32 in, fp32 out, fp32-class accuracy through the 3xTF32 split on the 5th-generation tensor cores:
+//   x = hi + lo (hi: top 19 bits, exactly TF32; lo = x - hi), D += A_lo W_hi + A_hi W_lo + A_hi W_hi,
+// accumulated in fp32 in TMEM.  Relative error per product ~2^-21, i.e. the same class as fp32 FFMA with a
+// different summation order, which the discrete segmentation gates downstream require.
+//
+// CTA = one 128 x 128 output tile, 288 threads:
+//   warps 0-7  producers, later epilogue.  Per k-block (32 floats = one 128-byte swizzle row) they load
+//              A/W rows from global (coalesced LDG.128, prefetched two k-blocks ahead in registers), split into
+//              hi/lo and store both tiles in the canonical K-major SWIZZLE_128B layout the UMMA descriptors
+//              expect; fence.proxy.async + mbarrier arrive hands the stage to the tensor core.
+//   warp 8     allocates TMEM (128 fp32 columns) and one elected lane issues 12 tcgen05.mma (kind::tf32,
+//              M=128,N=128,K=8: 4 k-steps x 3 split products) per k-block; tcgen05.commit frees the stage.
+//   epilogue   tcgen05.ld 32x32b.x32 (lane = output row), bias + ReLU, float4 stores.
+// Several independent problems are batched into one launch like the SIMT path.
 #include "common.cuh"
 #include "gemm.h"
 
 namespace tg {
 
+constexpr int TC_BM = 128, TC_BN = 128, TC_BK = 32;
+constexpr int TC_STAGES = 3;
+constexpr int TC_PRODUCER_WARPS = 8;
+constexpr int TC_THREADS = (TC_PRODUCER_WARPS + 1) * 32;
+constexpr int TC_TILE_BYTES = TC_BM * TC_BK * 4;                  // 16 KB, one operand tile (hi or lo)
+constexpr int TC_STAGE_BYTES = 4 * TC_TILE_BYTES;                 // A_hi, A_lo, W_hi, W_lo
+constexpr int TC_SMEM_BYTES = TC_STAGES * TC_STAGE_BYTES + 1024;  // + alignment slack
+constexpr uint32_t TC_TMEM_COLS = 128;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}\n" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t done = 0, spins = 0;
+    while (true) {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
+                     : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+        if (done) break;
+        if (++spins > (1u << 26)) __trap();       // a pipeline bug must surface as an error, not a hung device
+    }
+}
+
+// K-major, SWIZZLE_128B shared-memory matrix descriptor (sm_100 UMMA format):
+// [0,14) start address >> 4 | [16,30) leading byte offset >> 4 (unused for swizzled K-major) |
+// [32,46) stride byte offset >> 4 (1024 B between 8-row groups) | [46,48) version = 1 | [61,64) layout = 2 (128B swizzle)
+__device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);
+    d |= (uint64_t)1 << 16;
+    d |= (uint64_t)(1024u >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+
+// kind::tf32 instruction descriptor: D=F32 (bits 4-5 = 1), A=B=TF32 (format 2 at bits 7-9 / 10-12), both K-major,
+// N>>3 at bits 17-22, M>>4 at bits 24-28.
+__device__ __forceinline__ uint32_t umma_idesc_tf32(int M, int N) {
+    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory"); }
+
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
+    uint32_t r[32];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];\n"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+          "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
+          "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+          "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr)
+        : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// byte offset of 16-byte chunk `c` of row `r` inside a K-major SWIZZLE_128B tile (rows of 128 bytes)
+__device__ __forceinline__ uint32_t sw128_off(int r, int c) { return (uint32_t)((r >> 3) * 1024 + (r & 7) * 128 + ((c ^ (r & 7)) << 4)); }
+
+__global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const GemmGroup grp) {
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ __align__(8) uint64_t bars[2 * TC_STAGES + 1];
+    __shared__ uint32_t tmem_base_smem;
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    uint8_t* tiles = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    const uint32_t tiles_u32 = smem_u32(tiles);
+    const uint32_t full0 = smem_u32(&bars[0]), empty0 = smem_u32(&bars[TC_STAGES]), tfull = smem_u32(&bars[2 * TC_STAGES]);
+
+    // locate this CTA's problem and tile
+    int pi = 0;
+#pragma unroll 1
+    for (int i = 1; i < grp.count; ++i)
+        if ((int)blockIdx.x >= grp.p[i].tile_begin) pi = i;
+    const GemmProblem& P = grp.p[pi];
+    const int tile = blockIdx.x - P.tile_begin;
+    const int tiles_n = (P.N + TC_BN - 1) / TC_BN;
+    const int m0 = (tile / tiles_n) * TC_BM, n0 = (tile % tiles_n) * TC_BN;
+    const int nkb = P.K / TC_BK;
+
+    if (tid == 0) {
+        for (int s = 0; s < TC_STAGES; ++s) {
+            mbar_init(full0 + 8 * s, TC_PRODUCER_WARPS);
+            mbar_init(empty0 + 8 * s, 1);
+        }
+        mbar_init(tfull, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    }
+    if (warp == TC_PRODUCER_WARPS) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(&tmem_base_smem)), "r"(TC_TMEM_COLS)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_base_smem;
+
+    if (warp < TC_PRODUCER_WARPS) {
+        // ------------------------------ producers ------------------------------
+        // thread -> 16-byte chunk c of rows r0 + 32*i (i < 4) of the A tile and of the W tile
+        const int c = tid & 7, r0 = tid >> 3;                 // 256 threads: r0 in [0,32)
+        const float* aptr[4];
+        const float* wptr[4];
+        bool aok[4], wok[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int r = r0 + 32 * i;
+            aok[i] = (m0 + r) < P.M;
+            wok[i] = (n0 + r) < P.N;
+            aptr[i] = P.A + (size_t)(aok[i] ? m0 + r : 0) * P.lda + c * 4;
+            wptr[i] = P.W + (size_t)(wok[i] ? n0 + r : 0) * P.ldw + c * 4;
+        }
+        float4 pa0[4], pw0[4], pa1[4], pw1[4];                // register prefetch, two k-blocks deep (static slots)
+        auto load = [&](int kb, float4 (&pa)[4], float4 (&pw)[4]) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                pa[i] = aok[i] ? __ldg(reinterpret_cast<const float4*>(aptr[i] + (size_t)kb * TC_BK)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                pw[i] = wok[i] ? __ldg(reinterpret_cast<const float4*>(wptr[i] + (size_t)kb * TC_BK)) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+        };
+        auto split4 = [](const float4& x, float4& hi, float4& lo) {
+            hi.x = __uint_as_float(__float_as_uint(x.x) & 0xffffe000u); lo.x = x.x - hi.x;
+            hi.y = __uint_as_float(__float_as_uint(x.y) & 0xffffe000u); lo.y = x.y - hi.y;
+            hi.z = __uint_as_float(__float_as_uint(x.z) & 0xffffe000u); lo.z = x.z - hi.z;
+            hi.w = __uint_as_float(__float_as_uint(x.w) & 0xffffe000u); lo.w = x.w - hi.w;
+        };
+        auto produce = [&](int kb, float4 (&pa)[4], float4 (&pw)[4]) {
+            const int s = kb % TC_STAGES;
+            mbar_wait(empty0 + 8 * s, ((kb / TC_STAGES) & 1) ^ 1);
+            uint8_t* st = tiles + s * TC_STAGE_BYTES;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const uint32_t off = sw128_off(r0 + 32 * i, c);
+                float4 hi, lo;
+                split4(pa[i], hi, lo);
+                *reinterpret_cast<float4*>(st + off) = hi;
+                *reinterpret_cast<float4*>(st + TC_TILE_BYTES + off) = lo;
+                split4(pw[i], hi, lo);
+                *reinterpret_cast<float4*>(st + 2 * TC_TILE_BYTES + off) = hi;
+                *reinterpret_cast<float4*>(st + 3 * TC_TILE_BYTES + off) = lo;
+            }
+            if (kb + 2 < nkb) load(kb + 2, pa, pw);
+            asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");   // generic-proxy writes -> visible to the tensor core
+            __syncwarp();
+            if (lane == 0) mbar_arrive(full0 + 8 * s);
+        };
+        if (nkb > 0) load(0, pa0, pw0);
+        if (nkb > 1) load(1, pa1, pw1);
+#pragma unroll 1
+        for (int kb = 0; kb < nkb; kb += 2) {
+            produce(kb, pa0, pw0);
+            if (kb + 1 < nkb) produce(kb + 1, pa1, pw1);
+        }
+        // ------------------------------ epilogue ------------------------------
+        mbar_wait(tfull, 0);
+        tc_fence_after();
+        const int q = warp & 3;                                // TMEM lane quarter this warp may access
+        const int row = m0 + q * 32 + lane;
+        const int col_half = (warp >> 2) * (TC_BN / 2);        // warps 0-3: columns 0..63, warps 4-7: 64..127
+#pragma unroll 1
+        for (int cb = 0; cb < TC_BN / 2; cb += 32) {
+            float v[32];
+            tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(col_half + cb), v);
+            const int nbase = n0 + col_half + cb;
+            if (row < P.M && nbase < P.N) {
+                float* dst = P.C + (size_t)row * P.ldc + nbase;
+                const bool vec = ((P.ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0) && (nbase + 32 <= P.N);
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    float x = v[j];
+                    if (P.bias != nullptr && nbase + j < P.N) x += __ldg(P.bias + nbase + j);
+                    if (P.relu) x = fmaxf(x, 0.0f);
+                    v[j] = x;
+                }
+                if (vec) {
+#pragma unroll
+                    for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(dst + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j)
+                        if (nbase + j < P.N) dst[j] = v[j];
+                }
+            }
+        }
+    } else {
+        // ------------------------------ MMA issuer ------------------------------
+        const uint32_t idesc = umma_idesc_tf32(TC_BM, TC_BN);
+#pragma unroll 1
+        for (int kb = 0; kb < nkb; ++kb) {
+            const int s = kb % TC_STAGES;
+            mbar_wait(full0 + 8 * s, (kb / TC_STAGES) & 1);
+            tc_fence_after();
+            if (lane == 0) {
+                const uint32_t a_hi = tiles_u32 + s * TC_STAGE_BYTES, a_lo = a_hi + TC_TILE_BYTES;
+                const uint32_t w_hi = a_hi + 2 * TC_TILE_BYTES, w_lo = a_hi + 3 * TC_TILE_BYTES;
+#pragma unroll
+                for (int kk = 0; kk < TC_BK / 8; ++kk) {
+                    const uint32_t ko = kk * 32;               // 8 tf32 = 32 bytes along the swizzled row
+                    umma_tf32(tmem_base, umma_desc(a_lo + ko), umma_desc(w_hi + ko), idesc, (kb | kk) != 0);
+                    umma_tf32(tmem_base, umma_desc(a_hi + ko), umma_desc(w_lo + ko), idesc, 1);
+                    umma_tf32(tmem_base, umma_desc(a_hi + ko), umma_desc(w_hi + ko), idesc, 1);
+                }
+                umma_commit(empty0 + 8 * s);                  // frees the stage when these MMAs have read it
+                if (kb == nkb - 1) umma_commit(tfull);        // accumulator complete
+            }
+            __syncwarp();
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == TC_PRODUCER_WARPS) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem_base), "r"(TC_TMEM_COLS) : "memory");
+    }
+}
+
 int launch_gemm_tc(GemmGroup& grp, cudaStream_t stream) {
-    (void)grp; (void)stream;
-    set_error("gemm_path=1 (tcgen05) is not built into this library");
-    return 3;
+    if (grp.count == 0) return 0;
+    TG_REQUIRE(grp.count <= GEMM_MAX_PROBLEMS, "gemm_tc: too many problems in one group (%d)", grp.count);
+    int begin = 0;
+    for (int i = 0; i < grp.count; ++i) {
+        const GemmProblem& p = grp.p[i];
+        TG_REQUIRE(p.M > 0 && p.N > 0 && p.K > 0, "gemm_tc: empty problem");
+        TG_REQUIRE(p.K % TC_BK == 0, "gemm_tc: K=%d must be a multiple of %d", p.K, TC_BK);
+        TG_REQUIRE(p.lda % 4 == 0 && p.ldw % 4 == 0, "gemm_tc: lda/ldw must be multiples of 4");
+        TG_REQUIRE((reinterpret_cast<uintptr_t>(p.A) & 15) == 0 && (reinterpret_cast<uintptr_t>(p.W) & 15) == 0,
+                   "gemm_tc: A and W must be 16-byte aligned");
+        grp.p[i].tile_begin = begin;
+        begin += cdiv(p.M, TC_BM) * cdiv(p.N, TC_BN);
+    }
+    static bool configured = false;
+    if (!configured) {
+        TG_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
+        configured = true;
+    }
+    gemm_tc_kernel<<<begin, TC_THREADS, TC_SMEM_BYTES, stream>>>(grp);
+    TG_LAUNCH_OK();
+    return 0;
 }
 
 }  // namespace tg

@@ -172,7 +172,7 @@ class TGGCN(nn.Module):
         self._ws = {}
         self._noise_override: Optional[torch.Tensor] = None
         self.persistent_kernels = True      # False: one launch per recurrent step (debug aid)
-        self.gemm_path = 0                  # 0: fp32 SIMT projections; 1: tcgen05 3xTF32
+        self.gemm_path = 2                  # 0: fp32 SIMT projections; 1: tcgen05 3xTF32; 2: tcgen05 where K % 32 == 0
 
     # ------------------------------------------------------------------------------------------------
     def set_gumbel_noise(self, noise: Optional[torch.Tensor]):

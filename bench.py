@@ -302,7 +302,7 @@ def main():
     ap.add_argument('--B', type=int, default=8)
     ap.add_argument('--T', type=int, default=128)
     ap.add_argument('--D', type=int, default=512)
-    ap.add_argument('--gemm-path', type=int, default=0)
+    ap.add_argument('--gemm-path', type=int, default=2)
     ap.add_argument('--no-cpu-baseline', action='store_true')
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == 'ours' else args.warmup

@@ -46,7 +46,7 @@ typedef struct tggcn_dims {
     int32_t object_seg_given;    /* objects_segmentation passed (models.py:738-739)                      */
     int32_t inspect;             /* inspect_model: also emit attention weights (models.py:927-932)       */
     int32_t persistent;          /* 1 = persistent cooperative recurrent kernels, 0 = one launch per step */
-    int32_t gemm_path;           /* 0 = fp32 SIMT projections, 1 = tcgen05 3xTF32 projections            */
+    int32_t gemm_path;           /* projections: 0 = fp32 SIMT, 1 = tcgen05 3xTF32, 2 = tcgen05 where K%32==0 */
     float   thr;                 /* update_segment_threshold                                             */
 } tggcn_dims;
 

@@ -12,6 +12,8 @@ SHAPES = [
     (1, 16, 16, 0, 0, 0, 0, 1),
     (37, 48, 32, 0, 0, 0, 1, 1),
     (130, 130, 64, 8, 4, 3, 0, 1),
+    (128, 128, 32, 0, 0, 0, 0, 0),
+    (300, 200, 96, 0, 0, 0, 1, 1),
     (257, 96, 48, 104, 0, 32, 1, 0),
     (2048, 512, 2048, 104, 0, 512, 1, 1),      # human ROI embedding, B=8,T=128
     (1024, 2048, 3328, 0, 0, 0, 1, 1),         # geometry MLP layer 0
@@ -27,10 +29,12 @@ def _linear(pkg, A, W, bias, C_out, M, N, K, relu, path):
     pkg.abi.check(rc, 'tggcn_linear_fwd')
 
 
-@pytest.mark.parametrize('path', [0])
+@pytest.mark.parametrize('path', [0, 1])
 @pytest.mark.parametrize('shape', SHAPES)
 def test_linear_matches_fp64(shape, path, pkg):
     M, N, K, pa, pw, pc, relu, has_bias = shape
+    if path == 1 and K % 32 != 0:
+        pytest.skip('tcgen05 path needs K % 32 == 0')
     g = torch.Generator().manual_seed(M * 7 + N * 3 + K)
     A_full = torch.randn(M, K + pa, generator=g)
     W_full = torch.randn(N, K + pw, generator=g) / K ** 0.5

@@ -15,13 +15,14 @@ from golden_util import CASES, GoldenCase
 pytestmark = pytest.mark.gpu
 
 
-def _build(case, persistent=True):
+def _build(case, persistent=True, gemm_path=0):
     pkg = importlib.import_module('2g-gcn_b200')
     model = pkg.TGGCN(**case.kwargs)
     case.fill(model.state_dict())
     model = model.cuda()
     model.train(case.train_mode)
     model.persistent_kernels = persistent
+    model.gemm_path = gemm_path
     model.set_gumbel_noise(case.noise)
     return model
 
@@ -147,3 +148,20 @@ def test_unmasked_objects_do_not_leak(pkg):
         assert torch.equal(out[i], ref[i])
     for i in range(2, 6):
         _assert_close(f'out{i}', out[i], ref[i], rtol=1e-5, atol=1e-6)
+
+
+@pytest.mark.parametrize('name', ['mphoi_s1_eval', 'mphoi_s2_eval', 'mphoi_s2_d64', 'cad120_s2_eval', 'mphoi_s2_train_bn'])
+def test_forward_with_tcgen05_projections(name, orc):
+    """Same parity bar with every nn.Linear on the tcgen05 3xTF32 kernel (gemm_path = 1)."""
+    case = GoldenCase(name)
+    model = _build(case, True, gemm_path=1)
+    out = _run(model, case)
+    n_gate = 2 if case.shape.num_classes[1] is None else 4
+    for i, (o, g) in enumerate(zip(out, case.outputs)):
+        if i < n_gate:
+            _assert_close(f'{name}.out{i} (gates)', o, g, rtol=0, atol=5e-6)
+            if i < n_gate // 2:
+                assert torch.equal(o.cpu() != 0, g != 0), f'{name}.out{i}: hard gates differ'
+        else:
+            _assert_close(f'{name}.out{i}', o, g, rtol=1e-3, atol=1e-4)
+            assert torch.equal(o.argmax(1).cpu(), g.argmax(1)), f'{name}.out{i}: argmax labels differ'

@@ -35,7 +35,7 @@ def main():
     ap.add_argument('--stage', type=int, default=2)
     ap.add_argument('--iters', type=int, default=5)
     ap.add_argument('--per-step', action='store_true', help='one launch per recurrent step instead of persistent kernels')
-    ap.add_argument('--gemm-path', type=int, default=0)
+    ap.add_argument('--gemm-path', type=int, default=2)
     a = ap.parse_args()
     shape = pkg.synth.SHAPES[a.shape]
     torch.manual_seed(0)

@@ -1,9 +1,11 @@
 // Building block of the two recurrent kernels (frame-level BiGRU, segment-level gated GRUCell graph):
 // a CTA-wide "gate tile"
-//     out[g][r][u] = sum_k Wrow[g*16 + u][k] * X[r][k]          g < NG groups, r < 16 rows, u < 16 units
-// Weight rows and activation rows are addressed through pointer tables (a null pointer is an all-zero
-// row), so the same routine serves W_hh h, the segment columns of W_ih, the message MLPs and — with the
-// receivers' state rows as an extra "weight" group — the attention logits of the message tiles.
+//     out[g][r][u] = sum_k Wrow[g*16 + u][k] * X[r][k]          g < NG groups, r < 8*NT rows, u < 16 units
+// over a K range made of up to two segments (e.g. the segment-message columns of W_ih against the aggregated
+// messages, then W_hh against the previous state), each with its own pointer tables.  Weight rows and
+// activation rows are addressed through pointer tables (a null pointer is an all-zero row), so the same routine
+// serves W_hh h, the segment columns of W_ih, the message MLPs and — with the receivers' state rows as an extra
+// "weight" group — the attention logits of the message tiles.
 //
 // How it got here (ncu captures under profiles/, round 1): three FFMA versions (CTA-wide K-chunk barrier;
 // K split across warps; warp-private pipelines with 512 threads) all stalled at IPC ~0.4 — first on
@@ -27,16 +29,16 @@ namespace tg {
 constexpr int REC_THREADS = 256;
 constexpr int REC_WARPS = REC_THREADS / 32;
 constexpr int REC_J = 16;         // units per tile  (one m16 MMA tile per group)
-constexpr int REC_RB = 16;        // rows per tile   (two n8 MMA tiles)
 constexpr int REC_CK = 16;        // floats of K per chunk (two k8 MMA steps, 64 bytes per row)
 constexpr int REC_RS = 20;        // ring row stride in floats (16 data + 4 pad)
 
-__host__ __device__ constexpr int tile_ring_floats(int NG, int STAGES) {
-    return REC_WARPS * STAGES * (NG * REC_J + REC_RB) * REC_RS;
+__host__ __device__ constexpr int tile_ring_floats(int NG, int NT, int STAGES) {
+    return REC_WARPS * STAGES * (NG * REC_J + 8 * NT) * REC_RS;
 }
-__host__ __device__ constexpr int tile_red_floats(int NG) { return REC_WARPS * NG * 2 * 32 * 4; }
-__host__ __device__ constexpr int tile_smem_floats(int NG, int STAGES) {
-    return tile_ring_floats(NG, STAGES) > tile_red_floats(NG) ? tile_ring_floats(NG, STAGES) : tile_red_floats(NG);
+__host__ __device__ constexpr int tile_red_floats(int NG, int NT) { return REC_WARPS * NG * NT * 32 * 4; }
+__host__ __device__ constexpr int tile_smem_floats(int NG, int NT, int STAGES) {
+    return tile_ring_floats(NG, NT, STAGES) > tile_red_floats(NG, NT) ? tile_ring_floats(NG, NT, STAGES)
+                                                                       : tile_red_floats(NG, NT);
 }
 
 // 16-byte async copy with zero-fill: copies `valid ? 16 : 0` bytes and zero-fills the rest.
@@ -60,50 +62,61 @@ __device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) 
     lo = __float_as_uint(x - __uint_as_float(hi));
 }
 
-// wrows: shared-memory table of NG*16 weight-row pointers; xrows: table of 16 activation-row pointers
-// (nullptr = zero row); every row holds at least K floats, K a multiple of 16, 16-byte aligned.
-// On return out[g] holds the full sum for this thread's epilogue pair: unit = tid % 16, row = tid / 16.
-template <int NG, int STAGES>
-__device__ __forceinline__ void tile_accumulate(float (&out)[NG], const float* const* wrows, const float* const* xrows,
-                                                int K, float* smem) {
-    constexpr int ROWS = NG * REC_J + REC_RB;
+// Pointer tables in shared memory: rows [0, NG*16) are weight rows, rows [NG*16, NG*16 + 8*NT) activation rows.
+// tab1 covers K columns [0, K1), tab2 columns [K1, K1 + K2) (row pointers are to the START of the segment).
+// K1, K2 multiples of 16; rows 16-byte aligned.  A null pointer is an all-zero row for that segment.
+// skip1 / skip2: bit m set = group m is all-zero in segment 1 / 2 (its MMAs are skipped).
+// gdummy: any valid 16-byte aligned global address (source operand of the zero-size copies).
+// On return out[g][p] holds the full sum for this thread's epilogue pair p: unit = tid % 16, row = tid / 16 + 16*p.
+template <int NG, int NT, int STAGES>
+__device__ __forceinline__ void tile_accumulate(float (&out)[NG][(NT + 1) / 2], const float* const* tab1,
+                                                const float* const* tab2, int K1, int K2, unsigned skip1, unsigned skip2,
+                                                const float* gdummy, float* smem) {
+    constexpr int WR = NG * REC_J, ROWS = WR + 8 * NT;
     constexpr int STAGE_F = ROWS * REC_RS;
     constexpr int NP = (ROWS * 4 + 31) / 32;            // 16-byte pieces per lane per chunk
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int g8 = lane >> 2, t4 = lane & 3;
     float* ring = smem + warp * (STAGES * STAGE_F);
 
-    float c[NG][2][4];
+    float c[NG][NT][4];
 #pragma unroll
     for (int m = 0; m < NG; ++m)
 #pragma unroll
-        for (int n = 0; n < 2; ++n)
+        for (int n = 0; n < NT; ++n)
 #pragma unroll
             for (int r = 0; r < 4; ++r) c[m][n][r] = 0.0f;
 
-    const int total_chunks = K / REC_CK;
+    const int chunks1 = K1 / REC_CK, total_chunks = (K1 + K2) / REC_CK;
     const int nmine = warp < total_chunks ? (total_chunks - warp + REC_WARPS - 1) / REC_WARPS : 0;
     if (nmine > 0) {
-        // this lane's copy pieces: (row, quarter) pairs; the source pointer only moves along K
-        const float* src[NP];
+        // this lane's copy pieces: (row, quarter) pairs; per segment a source pointer that only moves along K
+        const float* s1[NP];
+        const float* s2[NP];
         int dst[NP];
-        bool ok[NP], in[NP];
-        const float* safe = wrows[0];
+        bool in[NP];
 #pragma unroll
         for (int p = 0; p < NP; ++p) {
             const int piece = lane + p * 32;
             const int row = piece >> 2, quarter = piece & 3;
             in[p] = piece < ROWS * 4;
-            const float* base = nullptr;
-            if (in[p]) base = row < NG * REC_J ? wrows[row] : xrows[row - NG * REC_J];
-            ok[p] = base != nullptr;
-            src[p] = ok[p] ? base + quarter * 4 + warp * REC_CK : safe;
+            const float* b1 = in[p] ? tab1[row] : nullptr;
+            const float* b2 = (in[p] && K2 > 0) ? tab2[row] : nullptr;
+            s1[p] = b1 != nullptr ? b1 + quarter * 4 : nullptr;
+            s2[p] = b2 != nullptr ? b2 + quarter * 4 - K1 : nullptr;      // indexed with the global k offset
             dst[p] = row * REC_RS + quarter * 4;
         }
         auto issue = [&](int n, int st) {
+            const int chunk = warp + n * REC_WARPS;
+            const bool seg1 = chunk < chunks1;
+            const size_t koff = (size_t)chunk * REC_CK;
 #pragma unroll
-            for (int p = 0; p < NP; ++p)
-                if (in[p]) cp_async16_zfill(ring + st * STAGE_F + dst[p], ok[p] ? src[p] + (size_t)n * (REC_WARPS * REC_CK) : src[p], ok[p]);
+            for (int p = 0; p < NP; ++p) {
+                if (!in[p]) continue;
+                const float* base = seg1 ? s1[p] : s2[p];
+                const bool ok = base != nullptr;
+                cp_async16_zfill(ring + st * STAGE_F + dst[p], ok ? base + koff : gdummy, ok);   // !ok: size 0, zero-fill
+            }
         };
 #pragma unroll
         for (int st = 0; st < STAGES - 1; ++st) {
@@ -119,39 +132,34 @@ __device__ __forceinline__ void tile_accumulate(float (&out)[NG], const float* c
                 if (nn < nmine) issue(nn, nn % STAGES);
                 cp_async_commit();
             }
+            const unsigned skip = (warp + n * REC_WARPS) < chunks1 ? skip1 : skip2;
             const float* wb = ring + (n % STAGES) * STAGE_F + g8 * REC_RS + t4;
-            const float* xb = ring + (n % STAGES) * STAGE_F + (NG * REC_J + g8) * REC_RS + t4;
+            const float* xb = ring + (n % STAGES) * STAGE_F + (WR + g8) * REC_RS + t4;
 #pragma unroll
             for (int kk = 0; kk < REC_CK / 8; ++kk) {
-                uint32_t bh[2][2], bl[2][2];
+                uint32_t bh[NT][2], bl[NT][2];
 #pragma unroll
-                for (int nt = 0; nt < 2; ++nt) {
+                for (int nt = 0; nt < NT; ++nt) {
                     split_tf32(xb[nt * 8 * REC_RS + kk * 8], bh[nt][0], bl[nt][0]);
                     split_tf32(xb[nt * 8 * REC_RS + kk * 8 + 4], bh[nt][1], bl[nt][1]);
                 }
-                uint32_t ah[NG][4], al[NG][4];
 #pragma unroll
                 for (int m = 0; m < NG; ++m) {
+                    if ((skip >> m) & 1u) continue;              // warp-uniform
+                    uint32_t ah[4], al[4];
                     const float* wm = wb + m * REC_J * REC_RS + kk * 8;
-                    split_tf32(wm[0], ah[m][0], al[m][0]);
-                    split_tf32(wm[8 * REC_RS], ah[m][1], al[m][1]);
-                    split_tf32(wm[4], ah[m][2], al[m][2]);
-                    split_tf32(wm[8 * REC_RS + 4], ah[m][3], al[m][3]);
+                    split_tf32(wm[0], ah[0], al[0]);
+                    split_tf32(wm[8 * REC_RS], ah[1], al[1]);
+                    split_tf32(wm[4], ah[2], al[2]);
+                    split_tf32(wm[8 * REC_RS + 4], ah[3], al[3]);
+                    // three passes over the NT independent accumulator tiles (small terms first)
+#pragma unroll
+                    for (int nt = 0; nt < NT; ++nt) mma_tf32(c[m][nt], al, bh[nt]);
+#pragma unroll
+                    for (int nt = 0; nt < NT; ++nt) mma_tf32(c[m][nt], ah, bl[nt]);
+#pragma unroll
+                    for (int nt = 0; nt < NT; ++nt) mma_tf32(c[m][nt], ah, bh[nt]);
                 }
-                // three passes over the 2*NG independent accumulator tiles (small terms first): consecutive MMAs
-                // never depend on each other, so the tensor pipe latency is hidden inside one warp
-#pragma unroll
-                for (int m = 0; m < NG; ++m)
-#pragma unroll
-                    for (int nt = 0; nt < 2; ++nt) mma_tf32(c[m][nt], al[m], bh[nt]);
-#pragma unroll
-                for (int m = 0; m < NG; ++m)
-#pragma unroll
-                    for (int nt = 0; nt < 2; ++nt) mma_tf32(c[m][nt], ah[m], bl[nt]);
-#pragma unroll
-                for (int m = 0; m < NG; ++m)
-#pragma unroll
-                    for (int nt = 0; nt < 2; ++nt) mma_tf32(c[m][nt], ah[m], bh[nt]);
             }
         }
         cp_async_wait<0>();
@@ -162,22 +170,25 @@ __device__ __forceinline__ void tile_accumulate(float (&out)[NG], const float* c
 #pragma unroll
     for (int m = 0; m < NG; ++m)
 #pragma unroll
-        for (int n = 0; n < 2; ++n)
+        for (int n = 0; n < NT; ++n)
 #pragma unroll
-            for (int r = 0; r < 4; ++r) red[(((warp * NG + m) * 2 + n) * 4 + r) * 32 + lane] = c[m][n][r];
+            for (int r = 0; r < 4; ++r) red[(((warp * NG + m) * NT + n) * 4 + r) * 32 + lane] = c[m][n][r];
     __syncthreads();
-    {
+#pragma unroll
+    for (int p = 0; p < (NT + 1) / 2; ++p) {
         // accumulator element (unit u, row) of group m lives in: n = row / 8, lane = (u % 8) * 4 + (row % 8) / 2,
         // reg = (u / 8) * 2 + (row % 2)        (m16n8 C fragment layout)
-        const int u = tid & 15, row = tid >> 4;
+        const int u = tid & 15, row = (tid >> 4) + 16 * p;
         const int n = row >> 3, col = row & 7;
         const int l = (u & 7) * 4 + (col >> 1), r = (u >> 3) * 2 + (col & 1);
 #pragma unroll
         for (int m = 0; m < NG; ++m) {
             float s = 0.0f;
+            if (n < NT) {
 #pragma unroll
-            for (int w = 0; w < REC_WARPS; ++w) s += red[(((w * NG + m) * 2 + n) * 4 + r) * 32 + l];
-            out[m] = s;
+                for (int w = 0; w < REC_WARPS; ++w) s += red[(((w * NG + m) * NT + n) * 4 + r) * 32 + l];
+            }
+            out[m][p] = s;
         }
     }
     __syncthreads();                             // smem may be reused by the caller right away

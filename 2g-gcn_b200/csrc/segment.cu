@@ -17,14 +17,15 @@ namespace tg {
 
 constexpr int MSG_NG = 4;                    // message tiles: 16 sender rows x (4 x 16) units ...
 constexpr int MSG_NGL = MSG_NG + 1;          // ... plus one group whose "weight rows" are the receivers' states (logits)
-constexpr int MSG_ROWS = REC_RB;             // sender rows per message tile (whole videos)
+constexpr int MSG_ROWS = 16;                 // sender rows per message tile (whole videos)
 constexpr int MSG_UNITS = MSG_NG * REC_J;
 constexpr int MSG_LDM = MSG_UNITS + 1;
-constexpr int MSG_MAXPAIRS = REC_RB * REC_J;
+constexpr int MSG_MAXPAIRS = MSG_ROWS * REC_J;
 
 struct SegShared {
-    const float* wrows[MSG_NGL * REC_J];
-    const float* xrows[REC_RB];
+    const float* tab1[MSG_NGL * REC_J + 32];     // weight rows then activation rows, K segment 1
+    const float* tab2[MSG_NGL * REC_J + 32];     // K segment 2 (cell tiles: W_hh against the previous state)
+    float om[MSG_ROWS];                          // objects_mask of the sender rows of a message tile
     float msg[MSG_ROWS * MSG_LDM];
     float logit[MSG_MAXPAIRS];
     float alpha[MSG_MAXPAIRS];
@@ -56,7 +57,7 @@ __device__ __forceinline__ void seg_message_tile(const SegParams& P, int tile, i
     __syncthreads();
     if (tid < MSG_UNITS) {                                   // message MLP rows of this unit slice
         const int unit = unit0 + tid;
-        sh.wrows[tid] = unit < D ? P.wm[kind] + (size_t)unit * D : nullptr;
+        sh.tab1[tid] = unit < D ? P.wm[kind] + (size_t)unit * D : nullptr;
     } else if (tid < MSG_UNITS + REC_J) {                    // receivers' previous states: the logit "weights"
         const int l = tid - MSG_UNITS, bl = l / Er, e = l - bl * Er;
         const float* ptr = nullptr;
@@ -64,7 +65,7 @@ __device__ __forceinline__ void seg_message_tile(const SegParams& P, int tile, i
             const float* base = recv_h ? P.hx_h : P.hx_o;
             ptr = base + ((size_t)((b0 + bl) * T + tprev) * Er + e) * 2 * D + dir * D;
         }
-        sh.wrows[tid] = ptr;
+        sh.tab1[tid] = ptr;
     } else if (tid < MSG_UNITS + REC_J + MSG_ROWS) {         // senders' previous states
         const int l = tid - MSG_UNITS - REC_J, bl = l / Es, e = l - bl * Es;
         const float* ptr = nullptr;
@@ -72,25 +73,32 @@ __device__ __forceinline__ void seg_message_tile(const SegParams& P, int tile, i
             const float* base = send_h ? P.hx_h : P.hx_o;
             ptr = base + ((size_t)((b0 + bl) * T + tprev) * Es + e) * 2 * D + dir * D;
         }
-        sh.xrows[l] = ptr;
+        sh.tab1[tid] = ptr;
+        sh.om[l] = (!send_h && bl < nb) ? __ldg(P.om + (b0 + bl) * O + e) : 1.0f;
+    }
+    // bias of this thread's message columns, fetched before the K loop
+    float bias[MSG_NG];
+#pragma unroll
+    for (int g = 0; g < MSG_NG; ++g) {
+        const int u = unit0 + g * REC_J + (tid & 15);
+        bias[g] = u < D ? __ldg(P.bm[kind] + u) : 0.0f;
     }
     __syncthreads();
 
-    float acc[MSG_NGL];
-    tile_accumulate<MSG_NGL, 3>(acc, sh.wrows, sh.xrows, s > 0 ? D : 0, smem);
+    float acc[MSG_NGL][1];
+    tile_accumulate<MSG_NGL, 2, 3>(acc, sh.tab1, sh.tab1, s > 0 ? D : 0, 0, 0u, 0u, P.wm[kind], smem);
 
     // thread pair: unit (or receiver) index = tid % 16, sender row = tid / 16
     if (tid < MSG_ROWS * REC_J) {
         const int j = tid & 15, row = tid >> 4;
 #pragma unroll
         for (int g = 0; g < MSG_NG; ++g) {
-            const int c = g * REC_J + j, u = unit0 + c;
-            const float bias = u < D ? __ldg(P.bm[kind] + u) : 0.0f;
-            sh.msg[row * MSG_LDM + c] = fmaxf(acc[g] + bias, 0.0f);
+            const int c = g * REC_J + j;
+            sh.msg[row * MSG_LDM + c] = fmaxf(acc[g][0] + bias[g], 0.0f);
         }
         // logit of (receiver j, sender row) when both belong to the same video of the block
         const int blr = j / Er, r = j - blr * Er, bls = row / Es, sdr = row - bls * Es;
-        if (blr == bls && blr < nb) sh.logit[(blr * Er + r) * Es + sdr] = acc[MSG_NG] * (1.0f / sqrtf((float)D));
+        if (blr == bls && blr < nb) sh.logit[(blr * Er + r) * Es + sdr] = acc[MSG_NG][0] * (1.0f / sqrtf((float)D));
     }
     __syncthreads();
     // masked softmax over the senders of each receiver (vhoi/models.py:1750-1753)
@@ -100,14 +108,12 @@ __device__ __forceinline__ void seg_message_tile(const SegParams& P, int tile, i
         const float* lrow = sh.logit + tid * Es;
         float m = -INFINITY;
         for (int sdr = 0; sdr < Es; ++sdr) {
-            bool ok = !(same && sdr == r);
-            if (!send_h) ok = ok && (P.om[b * O + sdr] != 0.0f);
+            const bool ok = !(same && sdr == r) && sh.om[bl * Es + sdr] != 0.0f;
             if (ok) m = fmaxf(m, lrow[sdr]);
         }
         float sum = 0.0f;
         for (int sdr = 0; sdr < Es; ++sdr) {
-            bool ok = !(same && sdr == r);
-            if (!send_h) ok = ok && (P.om[b * O + sdr] != 0.0f);
+            const bool ok = !(same && sdr == r) && sh.om[bl * Es + sdr] != 0.0f;
             const float ex = ok ? expf(lrow[sdr] - m) : 0.0f;
             sh.alpha[tid * Es + sdr] = ex;
             sum += ex;
@@ -142,68 +148,95 @@ __device__ __forceinline__ void seg_message_tile(const SegParams& P, int tile, i
 }
 
 // ---- phase B ------------------------------------------------------------------------------------
-__device__ __forceinline__ void seg_cell_tile(const SegParams& P, int tile, int s, float* smem, SegShared& sh) {
+// One pipeline over the concatenated K range [segment-message columns of W_ih | W_hh] with four weight groups:
+// r and z accumulate over both segments, n_i only over the first, n_h only over the second (GRU needs them apart).
+template <int NT>
+__device__ __forceinline__ void seg_cell_tile(const SegParams& P, bool is_h, int dir, int rb, int ub, int s, float* smem,
+                                              SegShared& sh) {
+    constexpr int RBT = 8 * NT, NPAIR = NT / 2, WR = 4 * REC_J;
     const int D = P.D, T = P.T, B = P.B;
-    const int dir = tile / P.cell_tiles_dir;
-    int rem = tile - dir * P.cell_tiles_dir;
-    const bool is_h = rem < P.cell_tiles_h_dir;
-    if (!is_h) rem -= P.cell_tiles_h_dir;
-    const int nub = is_h ? P.nub_h : P.nub_o;
-    const int rb = rem / nub, ub = rem - rb * nub;
     const int E = is_h ? P.H : P.O;
     const int rows = B * E;
-    const int row0 = rb * REC_RB, unit0 = ub * REC_J;
+    const int row0 = rb * RBT, unit0 = ub * REC_J;
     const int t = dir == 0 ? s : T - 1 - s;
     const int tprev = dir == 0 ? t - 1 : t + 1;
     const int tid = threadIdx.x;
     const int nk = is_h ? P.nk_h : 2;
     float* hx = is_h ? P.hx_h : P.hx_o;
     const float* mgbase = is_h ? P.mg_h : P.mg_o;
+    const float* Wi = is_h ? P.wih_h[dir] + P.col_h : P.wih_o[dir] + P.col_o;
+    const int ldw = is_h ? P.ldw_h : P.ldw_o;
+    const float* Wh = is_h ? P.whh_h[dir] : P.whh_o[dir];
 
     __syncthreads();
-    if (tid < 3 * REC_J) {           // segment-message columns of W_ih
-        const int g = tid / REC_J, unit = unit0 + tid % REC_J;
-        const float* W = is_h ? P.wih_h[dir] + P.col_h : P.wih_o[dir] + P.col_o;
-        const int ldw = is_h ? P.ldw_h : P.ldw_o;
-        sh.wrows[tid] = unit < D ? W + (size_t)(g * D + unit) * ldw : nullptr;
-    } else if (tid < 3 * REC_J + REC_RB) {
-        const int r = row0 + tid - 3 * REC_J;
-        sh.xrows[tid - 3 * REC_J] = r < rows ? mgbase + ((size_t)dir * rows + r) * nk * D : nullptr;
-    }
-    __syncthreads();
-    float acc_i[3], acc_h[3];
-    tile_accumulate<3, 4>(acc_i, sh.wrows, sh.xrows, nk * D, smem);
-    if (tid < 3 * REC_J) {           // W_hh
-        const int g = tid / REC_J, unit = unit0 + tid % REC_J;
-        const float* W = is_h ? P.whh_h[dir] : P.whh_o[dir];
-        sh.wrows[tid] = unit < D ? W + (size_t)(g * D + unit) * D : nullptr;
-    } else if (tid < 3 * REC_J + REC_RB) {
-        const int r = row0 + tid - 3 * REC_J;
-        const float* ptr = nullptr;
-        if (r < rows && s > 0) {
-            const int b = r / E, e = r - b * E;
-            ptr = hx + ((size_t)(b * T + tprev) * E + e) * 2 * D + dir * D;
+    if (tid < WR) {
+        const int g = tid / REC_J, unit = unit0 + tid % REC_J;   // groups: 0 r, 1 z, 2 n (input part), 3 n (hidden part)
+        const int gate = g < 3 ? g : 2;
+        const bool ok = unit < D;
+        sh.tab1[tid] = (ok && g < 3) ? Wi + (size_t)(gate * D + unit) * ldw : nullptr;
+        sh.tab2[tid] = (ok && g != 2) ? Wh + (size_t)(gate * D + unit) * D : nullptr;
+    } else if (tid < WR + RBT) {
+        const int r = row0 + tid - WR;
+        const float* p1 = nullptr;
+        const float* p2 = nullptr;
+        if (r < rows) {
+            p1 = mgbase + ((size_t)dir * rows + r) * nk * D;
+            if (s > 0) {
+                const int b = r / E, e = r - b * E;
+                p2 = hx + ((size_t)(b * T + tprev) * E + e) * 2 * D + dir * D;
+            }
         }
-        sh.xrows[tid - 3 * REC_J] = ptr;
+        sh.tab1[tid] = p1;
+        sh.tab2[tid] = p2;
+    }
+    // epilogue operands, fetched before the K loop
+    const int unit = unit0 + (tid & 15);
+    const float* bhh = is_h ? P.bhh_h[dir] : P.bhh_o[dir];
+    const float* gsb = is_h ? P.gs_h : P.gs_o;
+    const float* ub_ = is_h ? P.u_h : P.u_o;
+    float bh[3] = {0.f, 0.f, 0.f}, xg[NPAIR][3], hprev[NPAIR], ug[NPAIR];
+    bool valid[NPAIR];
+    size_t orow[NPAIR];
+    if (unit < D) { bh[0] = __ldg(bhh + unit); bh[1] = __ldg(bhh + D + unit); bh[2] = __ldg(bhh + 2 * D + unit); }
+#pragma unroll
+    for (int p = 0; p < NPAIR; ++p) {
+        const int lr = (tid >> 4) + 16 * p, r = row0 + lr;
+        valid[p] = unit < D && r < rows && lr < RBT;
+        xg[p][0] = xg[p][1] = xg[p][2] = hprev[p] = ug[p] = 0.0f;
+        orow[p] = 0;
+        if (valid[p]) {
+            const int b = r / E, e = r - b * E;
+            const size_t fe = (size_t)(b * T + t) * E + e;
+            const float* gs = gsb + (fe * 2 + dir) * 3 * D;
+            xg[p][0] = __ldg(gs + unit); xg[p][1] = __ldg(gs + D + unit); xg[p][2] = __ldg(gs + 2 * D + unit);
+            ug[p] = __ldg(ub_ + fe);
+            if (s > 0) hprev[p] = ld_cg(hx + ((size_t)(b * T + tprev) * E + e) * 2 * D + dir * D + unit);
+            orow[p] = fe * 2 * D + dir * D + unit;
+        }
     }
     __syncthreads();
-    tile_accumulate<3, 4>(acc_h, sh.wrows, sh.xrows, s > 0 ? D : 0, smem);
 
-    const int unit = unit0 + (tid & 15), lr = tid >> 4, r = row0 + lr;
-    if (lr < REC_RB && unit < D && r < rows) {
-        const float* bhh = is_h ? P.bhh_h[dir] : P.bhh_o[dir];
-        const float* gsb = is_h ? P.gs_h : P.gs_o;
-        const float* ub_ = is_h ? P.u_h : P.u_o;
-        const int b = r / E, e = r - b * E;
-        const size_t fe = (size_t)(b * T + t) * E + e;
-        const float* gs = gsb + (fe * 2 + dir) * 3 * D;
-        const float hprev = s > 0 ? ld_cg(hx + ((size_t)(b * T + tprev) * E + e) * 2 * D + dir * D + unit) : 0.0f;
-        const float hnew = gru_update(__ldg(gs + unit) + acc_i[0], __ldg(gs + D + unit) + acc_i[1],
-                                      __ldg(gs + 2 * D + unit) + acc_i[2], acc_h[0] + __ldg(bhh + unit),
-                                      acc_h[1] + __ldg(bhh + D + unit), acc_h[2] + __ldg(bhh + 2 * D + unit), hprev);
-        const float u = __ldg(ub_ + fe);
-        hx[fe * 2 * D + dir * D + unit] = u * hnew + (1.0f - u) * hprev;
+    float acc[4][NPAIR];
+    tile_accumulate<4, NT, 3>(acc, sh.tab1, sh.tab2, nk * D, s > 0 ? D : 0, 1u << 3, 1u << 2, Wh, smem);
+
+#pragma unroll
+    for (int p = 0; p < NPAIR; ++p) {
+        if (!valid[p]) continue;
+        const float hnew = gru_update(xg[p][0] + acc[0][p], xg[p][1] + acc[1][p], xg[p][2] + acc[2][p], bh[0], bh[1],
+                                      acc[3][p] + bh[2], hprev[p]);
+        hx[orow[p]] = ug[p] * hnew + (1.0f - ug[p]) * hprev[p];
     }
+}
+
+__device__ __forceinline__ void seg_cell_dispatch(const SegParams& P, int tile, int s, float* smem, SegShared& sh) {
+    const int dir = tile / P.cell_tiles_dir;
+    int rem = tile - dir * P.cell_tiles_dir;
+    const bool is_h = rem < P.cell_tiles_h_dir;
+    if (!is_h) rem -= P.cell_tiles_h_dir;
+    const int nub = is_h ? P.nub_h : P.nub_o;
+    const int rb = rem / nub, ub = rem - rb * nub;
+    if ((is_h ? P.cfg_h : P.cfg_o) == 4) seg_cell_tile<4>(P, is_h, dir, rb, ub, s, smem, sh);
+    else                                 seg_cell_tile<2>(P, is_h, dir, rb, ub, s, smem, sh);
 }
 
 // phases: bit 0 = A (messages), bit 1 = B (cells)
@@ -219,7 +252,7 @@ __global__ void __launch_bounds__(REC_THREADS, 1) segment_kernel(const SegParams
             if (persistent && !grid_barrier(P.sync, epoch, gridDim.x, &sh.s_fail)) return;
         }
         if (phases & 2) {
-            for (int tile = blockIdx.x; tile < P.tilesB; tile += gridDim.x) seg_cell_tile(P, tile, s, smem, sh);
+            for (int tile = blockIdx.x; tile < P.tilesB; tile += gridDim.x) seg_cell_dispatch(P, tile, s, smem, sh);
             if (persistent && s + 1 < s_end && !grid_barrier(P.sync, epoch, gridDim.x, &sh.s_fail)) return;
         }
     }
@@ -250,8 +283,11 @@ int launch_segment(SegParams& P, int persistent, cudaStream_t stream) {
     P.tilesA = 2 * begin;
 
     auto kern = segment_kernel;
-    const int fa = tile_smem_floats(3, 4), fb = tile_smem_floats(MSG_NGL, 3);
-    const size_t smem = sizeof(float) * (size_t)(fa > fb ? fa : fb);
+    int fa = tile_smem_floats(4, 4, 3);
+    const int fb = tile_smem_floats(MSG_NGL, 2, 3), fc = tile_smem_floats(4, 2, 3);
+    if (fb > fa) fa = fb;
+    if (fc > fa) fa = fc;
+    const size_t smem = sizeof(float) * (size_t)fa;
     static bool configured = false;
     if (!configured) {
         TG_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -262,10 +298,11 @@ int launch_segment(SegParams& P, int persistent, cudaStream_t stream) {
     TG_REQUIRE(per_sm >= 1, "segment: kernel does not fit on an SM (smem %zu)", smem);
     const int capacity = per_sm * num_sms();
 
-    P.cfg_h = P.cfg_o = 1;
+    P.cfg_h = B * H > 16 ? 4 : 2;            // n8 row tiles per cell tile
+    P.cfg_o = B * O > 16 ? 4 : 2;
     P.jeff_h = P.jeff_o = REC_J;
-    P.nrb_h = cdiv(B * H, REC_RB); P.nub_h = cdiv(D, REC_J);
-    P.nrb_o = cdiv(B * O, REC_RB); P.nub_o = cdiv(D, REC_J);
+    P.nrb_h = cdiv(B * H, 8 * P.cfg_h); P.nub_h = cdiv(D, REC_J);
+    P.nrb_o = cdiv(B * O, 8 * P.cfg_o); P.nub_o = cdiv(D, REC_J);
     P.cell_tiles_h_dir = P.nrb_h * P.nub_h;
     P.cell_tiles_dir = P.cell_tiles_h_dir + P.nrb_o * P.nub_o;
     P.tilesB = 2 * P.cell_tiles_dir;

@@ -1,0 +1,98 @@
+"""GPU: shapes beyond the golden cases — several row blocks / video blocks per recurrent tile grid, the
+BASELINE.json full-size workload through size-independent properties (batch-split consistency, determinism)."""
+import importlib
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _mk(shape_name, D, B, T, stage, seed=0, gain=1.5):
+    pkg = importlib.import_module('2g-gcn_b200')
+    shape = pkg.synth.SHAPES[shape_name]
+    kw = pkg.synth.model_kwargs(shape, hidden_size=D, stage=stage)
+    model = pkg.TGGCN(**kw)
+    pkg.synth.deterministic_fill(model.state_dict(), seed=11 + seed, gain=gain)
+    batch = pkg.synth.make_batch(shape, B, T, seed=77 + seed)
+    n_calls = T * (shape.H + shape.O) if stage == 2 else T * (shape.O if shape.dataset != 'cad120' else 0)
+    import tggcn_oracle as orc
+    noise = orc.draw_noise(max(n_calls, 1), B, torch.Generator().manual_seed(1000 + seed))[:n_calls]
+    return pkg, shape, kw, model, batch, noise
+
+
+def _fwd(model, batch, noise, sl=slice(None), hseg=None, oseg=None):
+    model.set_gumbel_noise(noise[:, sl] if noise.numel() else noise)
+    with torch.no_grad():
+        out = model(x_human=batch['x_human'][sl].cuda(), x_objects=batch['x_objects'][sl].cuda(),
+                    objects_mask=batch['objects_mask'][sl].cuda(),
+                    human_segmentation=None if hseg is None else hseg[sl].cuda(),
+                    objects_segmentation=None if oseg is None else oseg[sl].cuda())
+    torch.cuda.synchronize()
+    model.check_persistent_kernels()
+    return [o.cpu() for o in out]
+
+
+# (shape, D, B, T, stage, seed): seeds chosen on the CPU oracle so that every sampled gate is >2e-4 from a decision edge
+@pytest.mark.parametrize('cfg', [('cad120', 32, 13, 18, 2, 2), ('mphoi', 32, 20, 10, 2, 0), ('bimanual', 32, 7, 12, 2, 5),
+                                 ('cad120', 32, 9, 11, 1, 0), ('mphoi', 64, 11, 9, 1, 0)])
+def test_many_row_blocks_match_oracle(cfg, orc):
+    """B large enough that every recurrent phase has several row blocks and video blocks."""
+    shape_name, D, B, T, stage, seed = cfg
+    pkg, shape, kw, model, batch, noise = _mk(shape_name, D, B, T, stage, seed=seed)
+    params = {k: v.clone().double() if v.is_floating_point() else v.clone() for k, v in model.state_dict().items()}
+    hseg = torch.ones(B, T, shape.H) if stage == 1 else None
+    oseg = torch.ones(B, T, shape.O) if (stage == 1 and shape.dataset == 'cad120') else None
+    ocfg = orc.OracleConfig(D, shape.V, shape.num_classes, shape.hh, stage == 2, kw['update_segment_threshold'])
+    dd = lambda t: None if t is None else t.double()
+    ref = orc.forward(params, ocfg, dd(batch['x_human']), dd(batch['x_objects']), dd(batch['objects_mask']), dd(hseg),
+                      dd(oseg), dd(noise) if noise.numel() else None)
+    model = model.cuda().eval()
+    out = _fwd(model, batch, noise, hseg=hseg, oseg=oseg)
+    n_gate = 2 if shape.num_classes[1] is None else 4
+    thr = kw['update_segment_threshold']
+    for i, (o, r) in enumerate(zip(out, ref)):
+        r = r.float()
+        if i < n_gate // 2:          # hard gates: compare away from knife-edge decisions of the fp64 oracle
+            soft = ref[n_gate // 2 + i].float()
+            safe = (soft - thr).abs() > 1e-4
+            if stage == 2:
+                pad = torch.zeros_like(soft[:, :1])
+                safe &= ((soft - torch.cat([pad, soft[:, :-1]], 1)).abs() > 1e-4) & ((soft - torch.cat([soft[:, 1:], pad], 1)).abs() > 1e-4)
+            assert safe.float().mean() > 0.99
+            assert torch.equal((o != 0)[safe], (r != 0)[safe])
+            if not bool(safe.all()):
+                pytest.skip('a gate sits within 1e-4 of its threshold for this seed; remaining outputs not comparable')
+        elif i < n_gate:
+            torch.testing.assert_close(o, r, rtol=0, atol=5e-6)
+        else:
+            torch.testing.assert_close(o, r, rtol=1e-3, atol=1e-4)
+            assert torch.equal(o.argmax(1), r.argmax(1))
+
+
+def test_full_size_batch_split_consistency_and_determinism():
+    """BASELINE.json workload (MPHOI, B=8, T=128, hidden 512): videos are independent in eval mode, so running
+    the batch whole or as two halves must agree; two identical runs must agree bitwise."""
+    pkg, shape, kw, model, batch, noise = _mk('mphoi', 512, 8, 128, 2, gain=1.0)
+    model = model.cuda().eval()
+    whole = _fwd(model, batch, noise)
+    again = _fwd(model, batch, noise)
+    for a, b in zip(whole, again):
+        assert torch.equal(a, b)
+    lo = _fwd(model, batch, noise, slice(0, 4))
+    hi = _fwd(model, batch, noise, slice(4, 8))
+    thr = kw['update_segment_threshold']
+    soft = whole[1]
+    knife = (soft - thr).abs().min() < 1e-5
+    for i, w in enumerate(whole):
+        halves = torch.cat([lo[i], hi[i]], dim=0)
+        if i == 0:
+            if not knife:
+                assert torch.equal(w != 0, halves != 0)
+        elif i == 1:
+            torch.testing.assert_close(halves, w, rtol=0, atol=5e-6)
+        elif not knife:
+            torch.testing.assert_close(halves, w, rtol=1e-3, atol=1e-4)
+    for o in whole[2:]:          # every output row is a log-probability vector
+        torch.testing.assert_close(o.exp().sum(1), torch.ones_like(o[:, 0]), rtol=1e-4, atol=1e-4)
+    assert torch.isfinite(torch.stack([o.float().abs().max() for o in whole])).all()

@@ -151,7 +151,96 @@ def run_case(name, shape_name, D, B, T, stage, train_mode, gain, inspect):
     np.savez_compressed(os.path.join(ROOT, 'tests', 'golden', name + '.npz'), **blob)
 
 
+GRAD_CASES = [
+    # name, shape, D, B, T, stage, gain  -- full training-mode forward + multi_task_loss + backward of the reference
+    ('grad_mphoi_s1', 'mphoi', 32, 2, 9, 1, 2.0),
+    ('grad_mphoi_s2', 'mphoi', 32, 3, 10, 2, 2.0),
+    ('grad_cad120_s2', 'cad120', 32, 2, 8, 2, 2.0),
+]
+
+
+def summarize_grad(g):
+    """Full tensor when small, otherwise sums + fixed samples (keeps the fixtures small)."""
+    f = g.detach().double().reshape(-1)
+    if f.numel() <= 4096:
+        return f.numpy()
+    idx = torch.linspace(0, f.numel() - 1, 256).long()
+    return np.concatenate([[float(f.sum()), float(f.abs().sum()), float((f * f).sum())], f[idx].numpy()])
+
+
+def run_grad_case(name, shape_name, D, B, T, stage, gain):
+    shape = pkg.SHAPES[shape_name]
+    kw = pkg.model_kwargs(shape, hidden_size=D, stage=stage)
+    model = select_model('2G-GCN')(**kw)
+    pkg.deterministic_fill(model.state_dict(), seed=7, gain=gain)
+    sd = {k: v.detach().clone() for k, v in model.state_dict().items()}
+    model.train(True)
+    misc = dict(impose_segmentation_pattern=1 if stage == 1 else 0,
+                segmentation_loss=dict(add=(stage == 2), sigma=4.0 if stage == 2 else 0.0, weight=1.0))
+    feed = select_model_data_feeder('2G-GCN', 'multiple', dataset_name=shape.dataset, **misc)
+    criterion, _ = select_loss('2G-GCN', 'multiple', shape.dataset, cfg=Cfg(misc=misc))
+    thr = kw['update_segment_threshold']
+    for attempt in range(50):
+        data_seed, noise_seed = 300 + attempt, 700 + attempt
+        batch = pkg.make_batch(shape, B, T, seed=data_seed)
+        n_calls = orc.num_noise_draws(T, shape.H, shape.O, stage == 1, stage == 1 and shape.dataset == 'cad120')
+        noise = orc.draw_noise(max(n_calls, 1), B, torch.Generator().manual_seed(noise_seed))[:n_calls]
+        # margin check on the fp64 oracle (covers object gates that MPHOI does not return)
+        p64 = {k: v.double() for k, v in sd.items()}
+        ocfg = orc.OracleConfig(D, shape.V, shape.num_classes, shape.hh, stage == 2, thr)
+        hseg = torch.ones(B, T, shape.H) if stage == 1 else None
+        oseg = torch.ones(B, T, shape.O) if (stage == 1 and shape.dataset == 'cad120') else None
+        taps = {}
+        o64 = orc.forward(p64, ocfg, batch['x_human'].double(), batch['x_objects'].double(), batch['objects_mask'].double(),
+                          None if hseg is None else hseg.double(), None if oseg is None else oseg.double(),
+                          noise.double() if n_calls else None, training=True, taps=taps)
+        softs = ([o64[1]] if shape.num_classes[1] is None else [o64[2], o64[3]]) if stage == 2 else []
+        if oseg is None:
+            softs.append(taps['y_oss'])
+        margin = 1.0
+        for sft in softs:
+            margin = min(margin, float((sft - thr).abs().min()))
+            if stage == 2:
+                margin = min(margin, float((sft[:, 1:] - sft[:, :-1]).abs().min()))
+        if margin > 1e-4:
+            break
+    else:
+        raise RuntimeError(f'no safe seed for {name}')
+    it = iter(noise)
+
+    def injected(p, temperature=1.0):
+        y = torch.log(torch.cat([p, 1.0 - p], -1) + 1e-20) + next(it).to(p)
+        return torch.softmax(y / temperature, -1)[:, :1]
+
+    ref_dist.sample_from_gumbel_sigmoid = injected
+    model.load_state_dict(sd)
+    model.zero_grad()
+    data = [batch['x_human'], batch['x_objects'], batch['objects_mask'], None, None, None, None, batch['steps_per_example']]
+    out = feed(model, data)
+    tg = pkg.make_targets(shape, batch['lengths'], T, seed=900 + attempt)
+    targets = pkg.target_list(shape, tg)
+    losses = criterion(out, targets, reduction='mean')
+    total = sum(losses)
+    total.backward()
+    blob = {'meta': np.array([data_seed, noise_seed, 900 + attempt, 7], dtype=np.int64), 'gain': np.array([gain]),
+            'loss': np.array([float(total)]), 'losses': np.array([float(l) for l in losses]),
+            'weights_checksum': np.array([pkg.state_checksum(sd)])}
+    none_keys = []
+    for k, prm in model.named_parameters():
+        if prm.grad is None:
+            none_keys.append(k)
+        else:
+            blob['grad.' + k] = summarize_grad(prm.grad)
+    blob['none_grad_keys'] = np.array(none_keys)
+    np.savez_compressed(os.path.join(ROOT, 'tests', 'golden', name + '.npz'), **blob)
+    print(f'{name:20s} seeds=({data_seed},{noise_seed}) margin={margin:.2e} loss={float(total):.6f} '
+          f'params with grad: {len(blob) - 6}, without: {len(none_keys)}')
+
+
 if __name__ == '__main__':
     torch.set_num_threads(8)
-    for case in CASES:
-        run_case(*case)
+    if '--grads-only' not in sys.argv:
+        for case in CASES:
+            run_case(*case)
+    for case in GRAD_CASES:
+        run_grad_case(*case)

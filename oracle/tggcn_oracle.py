@@ -150,7 +150,7 @@ def gumbel_sigmoid(prob: Tensor, g: Optional[Tensor]) -> Tensor:
 def hard_gate(y: Tensor, thr: float) -> Tensor:
     """straight_through_gumbel_sigmoid, pyrutils/torch/distributions.py:33-36: value of (z - y) + y."""
     z = (y > thr).to(y.dtype)
-    return (z - y) + y
+    return (z - y).detach() + y           # forward value z (up to rounding), d/dy = 1
 
 
 def filter_soft(y: Tensor, thr: float) -> Tensor:
@@ -160,7 +160,7 @@ def filter_soft(y: Tensor, thr: float) -> Tensor:
     prev = torch.cat([zero, y[:, :-1]], dim=1)
     nxt = torch.cat([y[:, 1:], zero], dim=1)
     keep = (y > prev) & (y > nxt) & (y >= thr)
-    u = ((y >= thr).to(y.dtype) - y) + y
+    u = ((y >= thr).to(y.dtype) - y).detach() + y      # straight-through, models.py:1660-1661
     return torch.where(keep, u, torch.clamp(u, max=0.0))
 
 
@@ -393,8 +393,8 @@ def bce_loss(inp: Tensor, tgt: Tensor) -> Tensor:
     if n == 0:
         return inp.new_zeros(())
     o, t = inp * mask, tgt * mask
-    ll = t * torch.clamp(torch.log(o), min=-100.0) + (1.0 - t) * torch.clamp(torch.log(1.0 - o), min=-100.0)
-    return (-ll).mean() * (inp.numel() / n)
+    # = mean(-[t*max(log o, -100) + (1-t)*max(log(1-o), -100)]); the library op also has the finite backward at o == 0
+    return torch.nn.functional.binary_cross_entropy(o, t, reduction='mean') * (inp.numel() / n)
 
 
 def nll_loss(logp: Tensor, tgt: Tensor) -> Tensor:

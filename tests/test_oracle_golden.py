@@ -78,3 +78,63 @@ def test_reorder_and_filter_edge_cases(orc):
     y = torch.tensor([[0.05, 0.3, 0.2, 0.2, 0.6, 0.7]])
     f = orc.filter_soft(y, 0.1)
     assert f.ne(0).tolist() == [[False, True, False, False, False, True]]
+
+
+GRAD_CASES = {
+    'grad_mphoi_s1': ('mphoi', 32, 2, 9, 1),
+    'grad_mphoi_s2': ('mphoi', 32, 3, 10, 2),
+    'grad_cad120_s2': ('cad120', 32, 2, 8, 2),
+}
+
+
+def _summarize(g):
+    f = g.detach().double().reshape(-1)
+    if f.numel() <= 4096:
+        return f.numpy()
+    idx = torch.linspace(0, f.numel() - 1, 256).long()
+    return np.concatenate([[float(f.sum()), float(f.abs().sum()), float((f * f).sum())], f[idx].numpy()])
+
+
+@pytest.mark.parametrize('name', sorted(GRAD_CASES))
+def test_oracle_gradients_match_reference(name, orc, synth, pkg):
+    """Backward pins for the next round: autograd through the oracle (train mode, multi_task_loss summed) against the
+    gradients of the unmodified reference (oracle/gen_golden.py::run_grad_case), including which parameters get none."""
+    import os
+    from golden_util import GOLDEN_DIR
+    shape_name, D, B, T, stage = GRAD_CASES[name]
+    blob = np.load(os.path.join(GOLDEN_DIR, name + '.npz'))
+    data_seed, noise_seed, target_seed, weight_seed = [int(v) for v in blob['meta']]
+    shape = synth.SHAPES[shape_name]
+    kw = synth.model_kwargs(shape, hidden_size=D, stage=stage)
+    model = pkg.TGGCN(**kw)
+    synth.deterministic_fill(model.state_dict(), seed=weight_seed, gain=float(blob['gain'][0]))
+    assert abs(synth.state_checksum(model.state_dict()) - float(blob['weights_checksum'][0])) < 1e-6
+    p = {k: v.detach().double().requires_grad_(v.is_floating_point() and 'running' not in k)
+         if v.is_floating_point() else v for k, v in model.state_dict().items()}
+    batch = synth.make_batch(shape, B, T, seed=data_seed)
+    human_given, objects_given = stage == 1, stage == 1 and shape.dataset == 'cad120'
+    n_calls = orc.num_noise_draws(T, shape.H, shape.O, human_given, objects_given)
+    noise = orc.draw_noise(max(n_calls, 1), B, torch.Generator().manual_seed(noise_seed))[:n_calls]
+    hseg = torch.ones(B, T, shape.H).double() if human_given else None
+    oseg = torch.ones(B, T, shape.O).double() if objects_given else None
+    ocfg = orc.OracleConfig(D, shape.V, shape.num_classes, shape.hh, stage == 2, kw['update_segment_threshold'])
+    out = orc.forward(p, ocfg, batch['x_human'].double(), batch['x_objects'].double(), batch['objects_mask'].double(),
+                      hseg, oseg, noise.double() if n_calls else None, training=True)
+    targets = synth.target_list(shape, synth.make_targets(shape, batch['lengths'], T, seed=target_seed))
+    targets = [t.double() if t.is_floating_point() else t for t in targets]
+    losses = orc.multi_task_loss(out, targets, shape.dataset, stage)
+    total = sum(losses)
+    np.testing.assert_allclose(float(total), float(blob['loss'][0]), rtol=1e-5)
+    total.backward()
+    none_ref = set(str(k) for k in blob['none_grad_keys'])
+    params = dict(model.named_parameters())
+    for k in params:
+        g = p[k].grad
+        if k in none_ref:
+            assert g is None or float(g.abs().max()) == 0.0, k
+            continue
+        assert g is not None, k
+        want = blob['grad.' + k]
+        got = _summarize(g)
+        scale = max(float(np.abs(want).max()), 1e-6)
+        np.testing.assert_allclose(got, want, rtol=2e-3, atol=2e-5 * scale + 1e-7, err_msg=k)   # 1e-7: fp32 noise floor of exact zeros

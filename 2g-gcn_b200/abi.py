@@ -94,6 +94,16 @@ def lib():
     L.tggcn_linear_fwd.restype = C.c_int
     L.tggcn_linear_fwd.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
                                    C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]
+    L.tggcn_linear_bwd.restype = C.c_int
+    L.tggcn_linear_bwd.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int,
+                                   C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p,
+                                   C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]
+    L.tggcn_bigru_fwd.restype = C.c_int
+    L.tggcn_bigru_fwd.argtypes = [C.c_void_p] * 8 + [C.c_int] * 5 + [C.c_void_p]
+    L.tggcn_bigru_bwd_scratch_floats.restype = C.c_size_t
+    L.tggcn_bigru_bwd_scratch_floats.argtypes = [C.c_int] * 4
+    L.tggcn_bigru_bwd.restype = C.c_int
+    L.tggcn_bigru_bwd.argtypes = [C.c_void_p] * 12 + [C.c_int] * 5 + [C.c_void_p]
     if L.tggcn_abi_version() != 1:
         raise TggcnError('lib2ggcn_b200.so ABI version mismatch; rebuild')
     _lib = L

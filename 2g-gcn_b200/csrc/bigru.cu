@@ -42,6 +42,7 @@ __device__ __forceinline__ void bigru_tile(const BiGruParams& P, const BiGruGrou
     float xg[NPAIR][3], hprev[NPAIR], bh[3] = {0.f, 0.f, 0.f};
     bool valid[NPAIR];
     size_t orow[NPAIR];
+    float* gsave[NPAIR];
     if (unit < D) {
         bh[0] = __ldg(G.bhh[dir] + unit); bh[1] = __ldg(G.bhh[dir] + D + unit); bh[2] = __ldg(G.bhh[dir] + 2 * D + unit);
     }
@@ -51,12 +52,14 @@ __device__ __forceinline__ void bigru_tile(const BiGruParams& P, const BiGruGrou
         valid[p] = unit < D && r < G.rows && ((tid >> 4) + 16 * p) < RBT;
         xg[p][0] = xg[p][1] = xg[p][2] = hprev[p] = 0.0f;
         orow[p] = 0;
+        gsave[p] = nullptr;
         if (valid[p]) {
             const int b = r / G.E, e = r - b * G.E;
             const float* gi = G.gi + (((size_t)(b * T + t) * G.E + e) * 2 + dir) * 3 * D;
             xg[p][0] = __ldg(gi + unit); xg[p][1] = __ldg(gi + D + unit); xg[p][2] = __ldg(gi + 2 * D + unit);
             if (s > 0) hprev[p] = ld_cg(G.hfr + ((size_t)(b * T + tprev) * G.E + e) * 2 * D + dir * D + unit);
             orow[p] = ((size_t)(b * T + t) * G.E + e) * 2 * D + dir * D + unit;
+            gsave[p] = G.gates != nullptr ? G.gates + (((size_t)(b * T + t) * G.E + e) * 2 + dir) * 4 * D + unit : nullptr;
         }
     }
     __syncthreads();
@@ -67,7 +70,8 @@ __device__ __forceinline__ void bigru_tile(const BiGruParams& P, const BiGruGrou
 #pragma unroll
     for (int p = 0; p < NPAIR; ++p)
         if (valid[p])
-            G.hfr[orow[p]] = gru_update(xg[p][0], xg[p][1], xg[p][2], acc[0][p] + bh[0], acc[1][p] + bh[1], acc[2][p] + bh[2], hprev[p]);
+            G.hfr[orow[p]] = gru_update(xg[p][0], xg[p][1], xg[p][2], acc[0][p] + bh[0], acc[1][p] + bh[1], acc[2][p] + bh[2], hprev[p],
+                                        gsave[p], D);
 }
 
 __global__ void __launch_bounds__(REC_THREADS, 1) bigru_kernel(const BiGruParams P, int s_begin, int s_end, int persistent) {

@@ -7,6 +7,7 @@ namespace tg {
 struct BiGruGroup {
     const float* gi;        // (B,T,E,2,3D) input pre-activations incl. b_ih, [dir][gate][unit]
     float* hfr;             // (B,T,E,2D)   outputs [fwd | bwd]; also the recurrent state
+    float* gates;           // (B,T,E,2,4D) r, z, n, hn saved for the backward, or null
     const float* whh[2];    // (3D,D) per direction
     const float* bhh[2];    // (3D)
     int E;                  // entities of this group
@@ -23,6 +24,10 @@ struct BiGruParams {
 };
 
 int launch_bigru(BiGruParams& P, int persistent, cudaStream_t stream);
+int launch_transpose(const float* in, int ldi, float* out, int ldo, int R, int C, cudaStream_t stream);
+int launch_gemm_tn(const float* Z, int ldz, const float* mask, int ldm, const float* A, int lda, float* C, int ldc, int M, int N,
+                   int K, int a_shift, int period, int beta, cudaStream_t stream);
+int launch_colsum(const float* Z, int ldz, const float* mask, int ldm, float* out, int M, int N, int beta, cudaStream_t stream);
 
 // ---- segment-level recurrent graph (segment.cu) ------------------------------------------------
 struct SegParams {

@@ -16,6 +16,10 @@ struct GemmProblem {
     int lda, ldw, ldc;
     int relu;
     int tile_begin;      // filled by the launcher
+    // backward use (gemm_bwd.cu): A is read as A[m][k] * (amask[m][k] > 0) and the result is added to C when beta != 0
+    const float* amask;  // may be null
+    int ldm;
+    int beta;
 };
 
 struct GemmGroup {
@@ -28,6 +32,7 @@ inline void gemm_add(GemmGroup& g, const float* A, int lda, const float* W, int 
     GemmProblem& q = g.p[g.count++];
     q.A = A; q.W = W; q.bias = bias; q.C = C;
     q.M = M; q.N = N; q.K = K; q.lda = lda; q.ldw = ldw; q.ldc = ldc; q.relu = relu; q.tile_begin = 0;
+    q.amask = nullptr; q.ldm = 0; q.beta = 0;
 }
 
 int launch_gemm_simt(GemmGroup& grp, cudaStream_t stream);

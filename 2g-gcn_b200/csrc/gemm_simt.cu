@@ -41,6 +41,11 @@ __global__ void __launch_bounds__(256) gemm_simt_kernel(const GemmGroup grp) {
             const int m = m0 + row;
             ra[i] = m < P.M ? __ldg(reinterpret_cast<const float4*>(P.A + (size_t)m * P.lda + k0 + kq))
                             : make_float4(0.f, 0.f, 0.f, 0.f);
+            if (P.amask != nullptr && m < P.M) {
+                const float4 mk = __ldg(reinterpret_cast<const float4*>(P.amask + (size_t)m * P.ldm + k0 + kq));
+                ra[i].x = mk.x > 0.f ? ra[i].x : 0.f; ra[i].y = mk.y > 0.f ? ra[i].y : 0.f;
+                ra[i].z = mk.z > 0.f ? ra[i].z : 0.f; ra[i].w = mk.w > 0.f ? ra[i].w : 0.f;
+            }
         }
 #pragma unroll
         for (int i = 0; i < B_F4; ++i) {
@@ -124,6 +129,11 @@ __global__ void __launch_bounds__(256) gemm_simt_kernel(const GemmGroup grp) {
                     v[jj] = x;
                 }
                 float* dst = P.C + (size_t)m * P.ldc + n;
+                if (P.beta) {
+#pragma unroll
+                    for (int jj = 0; jj < 4; ++jj)
+                        if (n + jj < P.N) v[jj] += dst[jj];
+                }
                 if (n + 3 < P.N && ((P.ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
                     *reinterpret_cast<float4*>(dst) = make_float4(v[0], v[1], v[2], v[3]);
                 } else {
@@ -141,6 +151,8 @@ int validate_problem(const GemmProblem& p) {
     TG_REQUIRE(p.lda % 4 == 0 && p.ldw % 4 == 0, "gemm: lda=%d / ldw=%d must be multiples of 4", p.lda, p.ldw);
     TG_REQUIRE((reinterpret_cast<uintptr_t>(p.A) & 15) == 0 && (reinterpret_cast<uintptr_t>(p.W) & 15) == 0,
                "gemm: A and W must be 16-byte aligned");
+    TG_REQUIRE(p.amask == nullptr || (p.ldm % 4 == 0 && (reinterpret_cast<uintptr_t>(p.amask) & 15) == 0),
+               "gemm: mask must be 16-byte aligned with ldm a multiple of 4");
     return 0;
 }
 

@@ -143,6 +143,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const GemmGroup 
         const int c = tid & 7, r0 = tid >> 3;                 // 256 threads: r0 in [0,32)
         const float* aptr[4];
         const float* wptr[4];
+        const float* mptr[4];
         bool aok[4], wok[4];
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
@@ -150,6 +151,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const GemmGroup 
             aok[i] = (m0 + r) < P.M;
             wok[i] = (n0 + r) < P.N;
             aptr[i] = P.A + (size_t)(aok[i] ? m0 + r : 0) * P.lda + c * 4;
+            mptr[i] = P.amask != nullptr ? P.amask + (size_t)(aok[i] ? m0 + r : 0) * P.ldm + c * 4 : nullptr;
             wptr[i] = P.W + (size_t)(wok[i] ? n0 + r : 0) * P.ldw + c * 4;
         }
         float4 pa0[4], pw0[4], pa1[4], pw1[4];                // register prefetch, two k-blocks deep (static slots)
@@ -157,6 +159,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const GemmGroup 
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
                 pa[i] = aok[i] ? __ldg(reinterpret_cast<const float4*>(aptr[i] + (size_t)kb * TC_BK)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                if (mptr[i] != nullptr && aok[i]) {
+                    const float4 mk = __ldg(reinterpret_cast<const float4*>(mptr[i] + (size_t)kb * TC_BK));
+                    pa[i].x = mk.x > 0.f ? pa[i].x : 0.f; pa[i].y = mk.y > 0.f ? pa[i].y : 0.f;
+                    pa[i].z = mk.z > 0.f ? pa[i].z : 0.f; pa[i].w = mk.w > 0.f ? pa[i].w : 0.f;
+                }
                 pw[i] = wok[i] ? __ldg(reinterpret_cast<const float4*>(wptr[i] + (size_t)kb * TC_BK)) : make_float4(0.f, 0.f, 0.f, 0.f);
             }
         };
@@ -212,6 +219,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const GemmGroup 
                     float x = v[j];
                     if (P.bias != nullptr && nbase + j < P.N) x += __ldg(P.bias + nbase + j);
                     if (P.relu) x = fmaxf(x, 0.0f);
+                    if (P.beta && nbase + j < P.N) x += dst[j];
                     v[j] = x;
                 }
                 if (vec) {
@@ -267,6 +275,8 @@ int launch_gemm_tc(GemmGroup& grp, cudaStream_t stream) {
         TG_REQUIRE(p.lda % 4 == 0 && p.ldw % 4 == 0, "gemm_tc: lda/ldw must be multiples of 4");
         TG_REQUIRE((reinterpret_cast<uintptr_t>(p.A) & 15) == 0 && (reinterpret_cast<uintptr_t>(p.W) & 15) == 0,
                    "gemm_tc: A and W must be 16-byte aligned");
+        TG_REQUIRE(p.amask == nullptr || (p.ldm % 4 == 0 && (reinterpret_cast<uintptr_t>(p.amask) & 15) == 0),
+                   "gemm_tc: mask must be 16-byte aligned with ldm a multiple of 4");
         grp.p[i].tile_begin = begin;
         begin += cdiv(p.M, TC_BM) * cdiv(p.N, TC_BN);
     }

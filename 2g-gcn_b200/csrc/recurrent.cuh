@@ -196,10 +196,13 @@ __device__ __forceinline__ void tile_accumulate(float (&out)[NG][(NT + 1) / 2], 
 
 // GRU cell update, gate order (r, z, n) as torch.nn.GRU / GRUCell (vhoi/models.py:267,:294):
 //   r = s(xr + hr), z = s(xz + hz), n = tanh(xn + r*hn), h' = n + z*(h - n)
-__device__ __forceinline__ float gru_update(float xr, float xz, float xn, float hr, float hz, float hn, float hprev) {
+// When `gates` is not null the values the backward needs are saved: gates[0]=r, [stride]=z, [2*stride]=n, [3*stride]=hn.
+__device__ __forceinline__ float gru_update(float xr, float xz, float xn, float hr, float hz, float hn, float hprev,
+                                            float* gates = nullptr, int stride = 0) {
     const float r = sigmoidf_acc(xr + hr);
     const float z = sigmoidf_acc(xz + hz);
     const float n = tanhf(xn + r * hn);
+    if (gates != nullptr) { gates[0] = r; gates[stride] = z; gates[2 * stride] = n; gates[3 * stride] = hn; }
     return n + z * (hprev - n);
 }
 

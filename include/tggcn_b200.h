@@ -275,6 +275,26 @@ TGGCN_API int tggcn_geo_gcn_fwd(const float* x_human, const void* const* weights
 TGGCN_API int tggcn_linear_fwd(const float* A, int lda, const float* W, int ldw, const float* bias, float* C, int ldc,
                      int M, int N, int K, int relu, int gemm_path, void* stream);
 
+/* Backward of nn.Linear (+ReLU), i.e. what autograd does for y = act(x W^T + b) (pyrutils/torch/models.py:31-33):
+ *   Z = dY (.) [Y > 0] (Y = forward output, NULL when there was no ReLU);  dX = Z W (added to dX when beta_dx);
+ *   dW = Z^T X;  db = column sums of Z.  Any of dX / dW / db may be NULL.  wt_scratch: K*N floats (W^T) when dX != NULL. */
+TGGCN_API int tggcn_linear_bwd(const float* dY, int ldy, const float* Y, int ldyf, const float* X, int ldx,
+                               const float* W, int ldw, float* dX, int lddx, int beta_dx, float* dW, int lddw,
+                               float* db, float* wt_scratch, int M, int N, int K, int gemm_path, void* stream);
+
+/* One group of the frame-level bidirectional GRU recurrence (nn.GRU as called at vhoi/models.py:997-1000), given the
+ * hoisted input pre-activations gi = W_ih x + b_ih (B,T,E,2,3D).  hfr (B,T,E,2D) out; gates (B,T,E,2,4D) out or NULL
+ * (r, z, n, W_hn h + b_hn: what the backward needs); sync: 16 bytes of device scratch. */
+TGGCN_API int tggcn_bigru_fwd(const float* gi, const float* whh_f, const float* whh_b, const float* bhh_f,
+                              const float* bhh_b, float* hfr, float* gates, void* sync, int B, int T, int E, int D,
+                              int persistent, void* stream);
+/* Backward through time of the same recurrence (autograd of nn.GRU).  dhfr: gradient w.r.t. hfr.  Outputs: dgi
+ * (gradient w.r.t. gi), dgh (scratch of the same size), dW_hh / db_hh per direction (may be NULL). */
+TGGCN_API size_t tggcn_bigru_bwd_scratch_floats(int B, int T, int E, int D);
+TGGCN_API int tggcn_bigru_bwd(const float* dhfr, const float* hfr, const float* gates, const float* whh_f,
+                              const float* whh_b, float* dgi, float* dgh, float* dwhh_f, float* dwhh_b, float* dbhh_f,
+                              float* dbhh_b, float* scratch, int B, int T, int E, int D, int gemm_path, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -54,3 +54,48 @@ def test_linear_matches_fp64(shape, path, pkg):
     assert err <= 2e-5 * scale + 1e-5, f'max err {err:.3e} (scale {scale:.3e})'
     if pc:
         assert torch.all(C_full[:, N:] == -7.0), 'wrote outside the N columns'
+
+
+BWD_SHAPES = [
+    # M, N, K, relu, lda_pad, ldy_pad
+    (37, 48, 32, 1, 0, 0),
+    (300, 64, 96, 0, 8, 16),
+    (1030, 512, 1024, 1, 0, 512),
+    (2048, 1536, 512, 0, 512, 1536),
+]
+
+
+@pytest.mark.parametrize('path', [0, 1])
+@pytest.mark.parametrize('shape', BWD_SHAPES)
+def test_linear_backward_matches_autograd(shape, path, pkg):
+    M, N, K, relu, pa, py = shape
+    if path == 1 and (K % 32 or N % 32):
+        pytest.skip('tcgen05 path needs multiples of 32')
+    g = torch.Generator().manual_seed(M + 3 * N + 7 * K)
+    X = torch.randn(M, K + pa, generator=g)
+    W = (torch.randn(N, K, generator=g) / K ** 0.5)
+    b = torch.randn(N, generator=g) * 0.1
+    dY = torch.randn(M, N + py, generator=g)
+    dX0 = torch.randn(M, K, generator=g)
+    x64, w64, b64 = X[:, :K].double().requires_grad_(), W.double().requires_grad_(), b.double().requires_grad_()
+    y64 = x64 @ w64.t() + b64
+    if relu:
+        y64 = y64.clamp_min(0)
+    y64.backward(dY[:, :N].double())
+    Xd, Wd, dYd = X.cuda(), W.cuda(), dY.cuda()
+    Yd = y64.detach().float().cuda() if relu else None
+    dX = dX0.clone().cuda()
+    dW = torch.empty(N, K, device='cuda')
+    db = torch.empty(N, device='cuda')
+    wt = torch.empty(K * N, device='cuda')
+    lib = pkg.abi.lib()
+    rc = lib.tggcn_linear_bwd(dYd.data_ptr(), dYd.stride(0), Yd.data_ptr() if relu else None, N, Xd.data_ptr(), Xd.stride(0),
+                              Wd.data_ptr(), K, dX.data_ptr(), K, 1, dW.data_ptr(), K, db.data_ptr(), wt.data_ptr(), M, N, K, path,
+                              C.c_void_p(torch.cuda.current_stream().cuda_stream))
+    pkg.abi.check(rc, 'tggcn_linear_bwd')
+    torch.cuda.synchronize()
+    for name, got, want in (('dX', dX.cpu().double() - dX0.double(), x64.grad), ('dW', dW.cpu().double(), w64.grad),
+                            ('db', db.cpu().double(), b64.grad)):
+        err = (got - want).abs().max().item()
+        scale = want.abs().max().item() + 1e-6
+        assert err <= 3e-5 * scale + 1e-5, f'{name}: max err {err:.3e} (scale {scale:.3e})'

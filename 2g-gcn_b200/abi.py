@@ -19,7 +19,12 @@ LIB_PATH = os.path.join(HERE, 'lib2ggcn_b200.so')
 class Dims(C.Structure):
     _fields_ = [(n, C.c_int32) for n in (
         'B', 'T', 'H', 'O', 'V', 'D', 'Fh', 'C_sub', 'C_aff', 'hh', 'filter', 'bn_train', 'human_seg_given',
-        'object_seg_given', 'inspect', 'persistent', 'gemm_path')] + [('thr', C.c_float)]
+        'object_seg_given', 'inspect', 'persistent', 'gemm_path')] + [('thr', C.c_float), ('save_for_backward', C.c_int32)]
+
+
+class GradOutputs(C.Structure):
+    _fields_ = [('d_y_hs', C.c_void_p), ('d_y_hss', C.c_void_p), ('d_y_os', C.c_void_p), ('d_y_oss', C.c_void_p),
+                ('d_out_h', C.c_void_p * 4), ('d_out_o', C.c_void_p * 4)]
 
 
 class IO(C.Structure):
@@ -104,7 +109,12 @@ def lib():
     L.tggcn_bigru_bwd_scratch_floats.argtypes = [C.c_int] * 4
     L.tggcn_bigru_bwd.restype = C.c_int
     L.tggcn_bigru_bwd.argtypes = [C.c_void_p] * 12 + [C.c_int] * 5 + [C.c_void_p]
-    if L.tggcn_abi_version() != 1:
+    L.tggcn_backward_workspace_bytes.restype = C.c_size_t
+    L.tggcn_backward_workspace_bytes.argtypes = [C.POINTER(Dims)]
+    L.tggcn_backward.restype = C.c_int
+    L.tggcn_backward.argtypes = [C.POINTER(Dims), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.c_int, C.POINTER(IO),
+                                 C.POINTER(GradOutputs), C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_void_p]
+    if L.tggcn_abi_version() != 2:
         raise TggcnError('lib2ggcn_b200.so ABI version mismatch; rebuild')
     _lib = L
     return L

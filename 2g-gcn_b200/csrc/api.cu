@@ -6,6 +6,7 @@
 #include "gemm.h"
 #include "bigru.h"
 #include "frame.h"
+#include "api_internal.h"
 
 namespace tg {
 
@@ -32,15 +33,7 @@ int num_sms() {
     return cached;
 }
 
-struct Layout {
-    size_t off[TGGCN_BUF_COUNT];
-    size_t bytes[TGGCN_BUF_COUNT];
-    size_t total;
-};
-
-static int nkh_of(const tggcn_dims& d) { return d.hh ? 2 : 1; }
-
-static void make_layout(const tggcn_dims& d, Layout& L) {
+void make_layout(const tggcn_dims& d, Layout& L) {
     const size_t N = (size_t)d.B * d.T, H = d.H, O = d.O, D = d.D, V = d.V;
     const size_t f = sizeof(float);
     const size_t nkh = nkh_of(d);
@@ -70,6 +63,24 @@ static void make_layout(const tggcn_dims& d, Layout& L) {
     sz[TGGCN_BUF_REIDX] = N * (H + O) * sizeof(int);
     sz[TGGCN_BUF_SEG_SCRATCH] = (2 * (size_t)d.B * H * nkh * D + 2 * (size_t)d.B * O * 2 * D + 8 * V) * f;
     sz[TGGCN_BUF_SYNC] = 64;
+    const size_t sv = d.save_for_backward ? 1 : 0;      // save buffers are empty in inference
+    sz[TGGCN_BUF_GATES_H] = sv * N * H * 8 * D * f;
+    sz[TGGCN_BUF_GATES_O] = sv * N * O * 8 * D * f;
+    sz[TGGCN_BUF_GATES_G] = sv * N * 8 * D * f;
+    sz[TGGCN_BUF_ALPHA_F] = sv * N * (H * H + 2 * H * O + O * O) * f;
+    sz[TGGCN_BUF_PGATE] = sv * N * (H + O) * f;
+    sz[TGGCN_BUF_SGATES_H] = sv * N * H * 8 * D * f;
+    sz[TGGCN_BUF_SGATES_O] = sv * N * O * 8 * D * f;
+    sz[TGGCN_BUF_MG_ALL_H] = sv * 2 * N * H * nkh * D * f;
+    sz[TGGCN_BUF_MG_ALL_O] = sv * 2 * N * O * 2 * D * f;
+    sz[TGGCN_BUF_SMSG_HH] = sv * 2 * N * H * D * f;
+    sz[TGGCN_BUF_SMSG_OH] = sv * 2 * N * O * D * f;
+    sz[TGGCN_BUF_SMSG_HO] = sv * 2 * N * H * D * f;
+    sz[TGGCN_BUF_SMSG_OO] = sv * 2 * N * O * D * f;
+    sz[TGGCN_BUF_SALPHA_HH] = sv * 2 * N * H * H * f;
+    sz[TGGCN_BUF_SALPHA_OH] = sv * 2 * N * H * O * f;
+    sz[TGGCN_BUF_SALPHA_HO] = sv * 2 * N * O * H * f;
+    sz[TGGCN_BUF_SALPHA_OO] = sv * 2 * N * O * O * f;
     size_t off = 0;
     for (int i = 0; i < TGGCN_BUF_COUNT; ++i) {
         L.off[i] = off;
@@ -79,7 +90,7 @@ static void make_layout(const tggcn_dims& d, Layout& L) {
     L.total = off;
 }
 
-static int check_dims(const tggcn_dims& d) {
+int check_dims(const tggcn_dims& d) {
     TG_REQUIRE(d.B >= 1 && d.T >= 1 && d.H >= 1 && d.O >= 1, "dims: B,T,H,O must be positive");
     TG_REQUIRE(d.D >= 16 && d.D % 16 == 0, "dims: hidden_size=%d must be a positive multiple of 16", d.D);
     TG_REQUIRE(d.V >= 1 && d.V <= 32, "dims: gcn_node=%d unsupported", d.V);
@@ -245,6 +256,8 @@ static int forward_impl(const tggcn_dims* dims, const void* const* weights, int 
         const int E[3] = {H, O, 1};
         for (int i = 0; i < 3; ++i) {
             P.g[i].gi = buf(gi_id[i]); P.g[i].hfr = buf(hfr_id[i]);
+            const int gates_id[3] = {TGGCN_BUF_GATES_H, TGGCN_BUF_GATES_O, TGGCN_BUF_GATES_G};
+            P.g[i].gates = d.save_for_backward ? buf(gates_id[i]) : nullptr;
             P.g[i].whh[0] = W(whh_f[i]); P.g[i].whh[1] = W(whh_b[i]);
             P.g[i].bhh[0] = W(bhh_f[i]); P.g[i].bhh[1] = W(bhh_b[i]);
             P.g[i].E = E[i]; P.g[i].rows = B * E[i];
@@ -285,6 +298,8 @@ static int forward_impl(const tggcn_dims* dims, const void* const* weights, int 
         P.xx_h = buf(TGGCN_BUF_XX_H); P.xx_o = buf(TGGCN_BUF_XX_O);
         P.y_hs = io->y_hs; P.y_hss = io->y_hss; P.y_os = io->y_os; P.y_oss = io->y_oss;
         P.att_frame = d.inspect ? io->att_frame : nullptr;
+        P.alpha_save = d.save_for_backward ? buf(TGGCN_BUF_ALPHA_F) : nullptr;
+        P.pgate_save = d.save_for_backward ? buf(TGGCN_BUF_PGATE) : nullptr;
         if (int rc = launch_frame_messages(P, stream)) return rc;
     }
     STAGE_END();
@@ -324,6 +339,15 @@ static int forward_impl(const tggcn_dims* dims, const void* const* weights, int 
                        "forward: segment cell weights missing");
         P.hx_h = buf(TGGCN_BUF_HX_H); P.hx_o = buf(TGGCN_BUF_HX_O);
         P.mg_h = mg_h; P.mg_o = mg_o;
+        P.mg_T = 1;
+        if (d.save_for_backward) {
+            P.mg_h = buf(TGGCN_BUF_MG_ALL_H); P.mg_o = buf(TGGCN_BUF_MG_ALL_O); P.mg_T = T;
+            P.sgates_h = buf(TGGCN_BUF_SGATES_H); P.sgates_o = buf(TGGCN_BUF_SGATES_O);
+            P.smsg[0] = d.hh ? buf(TGGCN_BUF_SMSG_HH) : nullptr; P.smsg[1] = buf(TGGCN_BUF_SMSG_OH);
+            P.smsg[2] = buf(TGGCN_BUF_SMSG_HO); P.smsg[3] = buf(TGGCN_BUF_SMSG_OO);
+            P.salpha[0] = d.hh ? buf(TGGCN_BUF_SALPHA_HH) : nullptr; P.salpha[1] = buf(TGGCN_BUF_SALPHA_OH);
+            P.salpha[2] = buf(TGGCN_BUF_SALPHA_HO); P.salpha[3] = buf(TGGCN_BUF_SALPHA_OO);
+        }
         P.att_f = d.inspect ? io->att_seg_f : nullptr;
         P.att_b = d.inspect ? io->att_seg_b : nullptr;
         P.sync.counter = sync + 2; P.sync.error = sync + 3;
@@ -377,5 +401,6 @@ int tggcn_forward_profile(const tggcn_dims* dims, const void* const* weights, in
 }
 
 unsigned long long tggcn_launch_count(void) { return tg::g_launches; }
+
 
 }  // extern "C"

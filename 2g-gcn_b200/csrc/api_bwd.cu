@@ -1,0 +1,491 @@
+// C ABI, backward half: tggcn_backward = what loss.backward() does through TGGCN.forward (vhoi/models.py:584-933)
+// and its building blocks.  The forward must have run with dims.save_for_backward on the same workspace.
+// Order = reverse of the forward's launch sequence (api.cu): heads -> segment-level recurrent graph (reverse time) ->
+// hoisted segment projections -> frame-level graph + gates -> message MLPs -> Linear(2D->D) -> BiGRU BPTT ->
+// input projections -> embeddings / geometry MLP -> geometry GCN.
+// No allocation, no device synchronisation, no state between calls.
+#include "common.cuh"
+#include "gemm.h"
+#include "bigru.h"
+#include "frame.h"
+#include "backward.cuh"
+#include "api_internal.h"
+
+using namespace tg;
+
+extern "C" int tggcn_bigru_bwd(const float* dhfr, const float* hfr, const float* gates, const float* whh_f, const float* whh_b,
+                               float* dgi, float* dgh, float* dwhh_f, float* dwhh_b, float* dbhh_f, float* dbhh_b, float* scratch,
+                               int B, int T, int E, int D, int gemm_path, void* stream_);
+extern "C" size_t tggcn_bigru_bwd_scratch_floats(int B, int T, int E, int D);
+
+namespace {
+
+// Regions of the backward workspace (floats).
+struct BwdLayout {
+    size_t total = 0;
+    size_t take(size_t n) {
+        const size_t o = total;
+        total += (n + 63) / 64 * 64;
+        return o;
+    }
+    size_t dhfr[3], dhx[2], dgs[2], dghs[2], du[2], carry[2][2], dgi_s[2], dgh_s[2], dmg[2], dpre[2], dpre_all[4];
+    size_t dxx[2], ds[3], dmsg[5], dgi[3], dgh[3], bigru_scratch, dgeo_hid, dgcn_out, dxn, wt_seg, wt;
+    size_t zero_begin, zero_end;     // region that must be zero before the kernels run (atomically accumulated)
+};
+
+void make_bwd_layout(const tggcn_dims& d, BwdLayout& L) {
+    const size_t N = (size_t)d.B * d.T, B = d.B, H = d.H, O = d.O, D = d.D, V = d.V;
+    const size_t nkh = nkh_of(d);
+    const size_t E[3] = {H, O, 1};
+    L.zero_begin = L.total;
+    for (int g = 0; g < 2; ++g) L.dhfr[g] = L.take(N * E[g] * 2 * D);
+    for (int g = 0; g < 2; ++g) L.dhx[g] = L.take(N * E[g] * 2 * D);
+    for (int g = 0; g < 2; ++g) L.du[g] = L.take(N * E[g]);
+    L.zero_end = L.total;
+    L.dhfr[2] = L.take(N * 2 * D);
+    for (int g = 0; g < 2; ++g) {
+        L.dgs[g] = L.take(N * E[g] * 6 * D);
+        L.dghs[g] = L.take(N * E[g] * 6 * D);
+        for (int i = 0; i < 2; ++i) L.carry[g][i] = L.take(2 * B * E[g] * D);
+        L.dgi_s[g] = L.take(2 * B * E[g] * 3 * D);
+        L.dgh_s[g] = L.take(2 * B * E[g] * 3 * D);
+        L.dmg[g] = L.take(2 * B * E[g] * (g == 0 ? nkh : 2) * D);
+        L.dpre[g] = L.take(2 * B * E[g] * 2 * D);
+    }
+    L.dpre_all[0] = L.take(2 * N * H * D);
+    L.dpre_all[1] = L.take(2 * N * O * D);
+    L.dpre_all[2] = L.take(2 * N * H * D);
+    L.dpre_all[3] = L.take(2 * N * O * D);
+    L.dxx[0] = L.take(N * H * (1 + nkh) * D);
+    L.dxx[1] = L.take(N * O * 4 * D);
+    for (int g = 0; g < 3; ++g) L.ds[g] = L.take(N * E[g] * 2 * D);
+    L.dmsg[0] = L.take(N * H * D);
+    L.dmsg[1] = L.take(N * H * D);
+    L.dmsg[2] = L.take(N * O * D);
+    L.dmsg[3] = L.take(N * O * D);
+    L.dmsg[4] = L.take(N * D);
+    for (int g = 0; g < 3; ++g) {
+        L.dgi[g] = L.take(N * E[g] * 6 * D);
+        L.dgh[g] = L.take(N * E[g] * 6 * D);
+    }
+    size_t bs = 0;
+    for (int g = 0; g < 3; ++g) {
+        const size_t s = tggcn_bigru_bwd_scratch_floats(d.B, d.T, (int)E[g], d.D);
+        if (s > bs) bs = s;
+    }
+    L.bigru_scratch = L.take(bs);
+    L.dgeo_hid = L.take(N * 2048);
+    L.dgcn_out = L.take(N * 128 * V);
+    L.dxn = L.take(N * V * 4);
+    // transposed recurrent weights that live through the whole reverse loop:
+    // W_hh^T (4 x D x 3D), W_ih[:, seg]^T (2 x nkh*D x 3D + 2 x 2D x 3D), message MLPs (2 x D x 2D)
+    L.wt_seg = L.take(4 * D * 3 * D + 2 * nkh * D * 3 * D + 2 * 2 * D * 3 * D + 2 * D * 2 * D);
+    // scratch for one transposed projection weight at a time
+    size_t wmax = (size_t)2048 * 128 * V;                 // geometry_embedding_mlp.0
+    const size_t cands[] = {4 * D * 6 * D, (1 + nkh) * D * 6 * D, (size_t)2048 * D, 2 * D * D, D * 6 * D};
+    for (size_t c : cands)
+        if (c > wmax) wmax = c;
+    L.wt = L.take(wmax);
+}
+
+// C[M, Nout] (+)= (A (.) [mask > 0]) [M, K] * Wt[Nout, K]^T
+int gemm_nt(const float* A, int lda, const float* mask, int ldm, const float* Wt, int ldw, float* C, int ldc, int M, int Nout, int K,
+            int beta, int path, cudaStream_t stream) {
+    GemmGroup g;
+    g.count = 0;
+    gemm_add(g, A, lda, Wt, ldw, nullptr, C, ldc, M, Nout, K, 0);
+    g.p[0].amask = mask; g.p[0].ldm = ldm; g.p[0].beta = beta;
+    return launch_gemm(g, path, stream);
+}
+
+}  // namespace
+
+extern "C" {
+
+size_t tggcn_backward_workspace_bytes(const tggcn_dims* dims) {
+    if (dims == nullptr || check_dims(*dims)) return 0;
+    BwdLayout L;
+    make_bwd_layout(*dims, L);
+    return L.total * sizeof(float);
+}
+
+int tggcn_backward(const tggcn_dims* dims, const void* const* weights, void* const* grad_weights, int n_weights,
+                   const tggcn_io* io, const tggcn_grad_outputs* grads, void* workspace, size_t workspace_bytes,
+                   void* bwd_workspace, size_t bwd_workspace_bytes, void* stream_) {
+    TG_REQUIRE(dims && weights && grad_weights && io && grads && workspace && bwd_workspace, "backward: null argument");
+    TG_REQUIRE(n_weights == TGGCN_W_COUNT, "backward: expected %d weight pointers, got %d", (int)TGGCN_W_COUNT, n_weights);
+    const tggcn_dims& d = *dims;
+    if (int rc = check_dims(d)) return rc;
+    TG_REQUIRE(d.save_for_backward, "backward: the forward must run with dims.save_for_backward = 1");
+    Layout L;
+    make_layout(d, L);
+    TG_REQUIRE(workspace_bytes >= L.total, "backward: forward workspace too small (%zu < %zu)", workspace_bytes, L.total);
+    BwdLayout BL;
+    make_bwd_layout(d, BL);
+    TG_REQUIRE(bwd_workspace_bytes >= BL.total * sizeof(float), "backward: workspace too small (%zu < %zu)", bwd_workspace_bytes,
+               BL.total * sizeof(float));
+    TG_REQUIRE((reinterpret_cast<uintptr_t>(bwd_workspace) & 255) == 0, "backward: workspace must be 256-byte aligned");
+    cudaStream_t stream = (cudaStream_t)stream_;
+    const int B = d.B, T = d.T, H = d.H, O = d.O, D = d.D, V = d.V, N = B * T;
+    const int nkh = nkh_of(d), nks = nkh;
+    const int path = d.gemm_path;
+    auto W = [&](int id) { return (const float*)weights[id]; };
+    auto G = [&](int id) { return (float*)grad_weights[id]; };
+    auto buf = [&](int id) { return (float*)((char*)workspace + L.off[id]); };
+    float* bw = (float*)bwd_workspace;
+    auto bb = [&](size_t off) { return bw + off; };
+
+    // every parameter on the gradient path needs a destination
+    {
+        static const int need[] = {
+            TGGCN_W_GCN_W, TGGCN_W_GCN_BN_W, TGGCN_W_GCN_BN_B, TGGCN_W_GCN_C1_W, TGGCN_W_GCN_C1_B, TGGCN_W_GCN_C3_W, TGGCN_W_GCN_C3_B,
+            TGGCN_W_GCN_S1_W, TGGCN_W_GCN_S1_B, TGGCN_W_GCN_S2_W, TGGCN_W_GCN_S2_B, TGGCN_W_GEO_MLP0_W, TGGCN_W_GEO_MLP0_B,
+            TGGCN_W_GEO_MLP2_W, TGGCN_W_GEO_MLP2_B, TGGCN_W_HUM_EMB_W, TGGCN_W_HUM_EMB_B, TGGCN_W_OBJ_EMB_W, TGGCN_W_OBJ_EMB_B,
+            TGGCN_W_GEO_RNN_WIH_F, TGGCN_W_GEO_RNN_WHH_F, TGGCN_W_GEO_RNN_BIH_F, TGGCN_W_GEO_RNN_BHH_F, TGGCN_W_GEO_RNN_WIH_B,
+            TGGCN_W_GEO_RNN_WHH_B, TGGCN_W_GEO_RNN_BIH_B, TGGCN_W_GEO_RNN_BHH_B, TGGCN_W_HUM_RNN_WIH_F, TGGCN_W_HUM_RNN_WHH_F,
+            TGGCN_W_HUM_RNN_BIH_F, TGGCN_W_HUM_RNN_BHH_F, TGGCN_W_HUM_RNN_WIH_B, TGGCN_W_HUM_RNN_WHH_B, TGGCN_W_HUM_RNN_BIH_B,
+            TGGCN_W_HUM_RNN_BHH_B, TGGCN_W_OBJ_RNN_WIH_F, TGGCN_W_OBJ_RNN_WHH_F, TGGCN_W_OBJ_RNN_BIH_F, TGGCN_W_OBJ_RNN_BHH_F,
+            TGGCN_W_OBJ_RNN_WIH_B, TGGCN_W_OBJ_RNN_WHH_B, TGGCN_W_OBJ_RNN_BIH_B, TGGCN_W_OBJ_RNN_BHH_B, TGGCN_W_GEO_BD_W,
+            TGGCN_W_GEO_BD_B, TGGCN_W_HUM_BD_W, TGGCN_W_HUM_BD_B, TGGCN_W_OBJ_BD_W, TGGCN_W_OBJ_BD_B, TGGCN_W_MSG_HO_W,
+            TGGCN_W_MSG_HO_B, TGGCN_W_MSG_OH_W, TGGCN_W_MSG_OH_B, TGGCN_W_MSG_OO_W, TGGCN_W_MSG_OO_B, TGGCN_W_MSG_GO_W,
+            TGGCN_W_MSG_GO_B, TGGCN_W_SMSG_HO_W, TGGCN_W_SMSG_HO_B, TGGCN_W_SMSG_OH_W, TGGCN_W_SMSG_OH_B, TGGCN_W_SMSG_OO_W,
+            TGGCN_W_SMSG_OO_B, TGGCN_W_HSEG_F_WIH, TGGCN_W_HSEG_F_WHH, TGGCN_W_HSEG_F_BIH, TGGCN_W_HSEG_F_BHH, TGGCN_W_HSEG_B_WIH,
+            TGGCN_W_HSEG_B_WHH, TGGCN_W_HSEG_B_BIH, TGGCN_W_HSEG_B_BHH, TGGCN_W_OSEG_F_WIH, TGGCN_W_OSEG_F_WHH, TGGCN_W_OSEG_F_BIH,
+            TGGCN_W_OSEG_F_BHH, TGGCN_W_OSEG_B_WIH, TGGCN_W_OSEG_B_WHH, TGGCN_W_OSEG_B_BIH, TGGCN_W_OSEG_B_BHH,
+            TGGCN_W_HEAD_H_FREC_W, TGGCN_W_HEAD_H_FREC_B, TGGCN_W_HEAD_H_FPRED_W, TGGCN_W_HEAD_H_FPRED_B, TGGCN_W_HEAD_H_REC_W,
+            TGGCN_W_HEAD_H_REC_B, TGGCN_W_HEAD_H_PRED_W, TGGCN_W_HEAD_H_PRED_B};
+        for (size_t i = 0; i < sizeof(need) / sizeof(need[0]); ++i)
+            TG_REQUIRE(weights[need[i]] && grad_weights[need[i]], "backward: weight / gradient pointer #%d is null", need[i]);
+        if (d.hh)
+            TG_REQUIRE(G(TGGCN_W_MSG_HH_W) && G(TGGCN_W_MSG_HH_B) && G(TGGCN_W_SMSG_HH_W) && G(TGGCN_W_SMSG_HH_B),
+                       "backward: humans->human gradient pointers missing");
+        if (d.C_aff > 0)
+            for (int id = TGGCN_W_HEAD_O_FREC_W; id <= TGGCN_W_HEAD_O_PRED_B; ++id)
+                TG_REQUIRE(weights[id] && grad_weights[id], "backward: object head pointer #%d is null", id);
+        if (!d.human_seg_given) TG_REQUIRE(G(TGGCN_W_UPD_H_W) && G(TGGCN_W_UPD_H_B), "backward: human gate gradient pointers missing");
+        if (!d.object_seg_given) TG_REQUIRE(G(TGGCN_W_UPD_O_W) && G(TGGCN_W_UPD_O_B), "backward: object gate gradient pointers missing");
+    }
+
+    TG_CUDA_OK(cudaMemsetAsync(bb(BL.zero_begin), 0, (BL.zero_end - BL.zero_begin) * sizeof(float), stream));
+
+    // ---- 12. heads --------------------------------------------------------------------------------------------------
+    {
+        HeadsBwdParams P;
+        memset(&P, 0, sizeof(P));
+        P.B = B; P.T = T; P.E = H; P.NE = H + O; P.e_off = 0; P.D = D; P.C = d.C_sub;
+        P.hfr = buf(TGGCN_BUF_HFR_H); P.hx = buf(TGGCN_BUF_HX_H); P.reidx = (const int*)buf(TGGCN_BUF_REIDX);
+        const int wid[4] = {TGGCN_W_HEAD_H_FREC_W, TGGCN_W_HEAD_H_FPRED_W, TGGCN_W_HEAD_H_REC_W, TGGCN_W_HEAD_H_PRED_W};
+        for (int i = 0; i < 4; ++i) {
+            P.w[i] = W(wid[i]); P.bias[i] = W(wid[i] + 1); P.dlogp[i] = grads->d_out_h[i];
+            P.dw[i] = G(wid[i]); P.db[i] = G(wid[i] + 1);
+            TG_CUDA_OK(cudaMemsetAsync(P.dw[i], 0, sizeof(float) * (size_t)d.C_sub * 2 * D, stream));
+            TG_CUDA_OK(cudaMemsetAsync(P.db[i], 0, sizeof(float) * (size_t)d.C_sub, stream));
+        }
+        P.dhfr = bb(BL.dhfr[0]); P.dhx = bb(BL.dhx[0]);
+        if (int rc = launch_heads_bwd(P, stream)) return rc;
+        if (d.C_aff > 0) {
+            P.E = O; P.e_off = H; P.C = d.C_aff;
+            P.hfr = buf(TGGCN_BUF_HFR_O); P.hx = buf(TGGCN_BUF_HX_O);
+            const int oid[4] = {TGGCN_W_HEAD_O_FREC_W, TGGCN_W_HEAD_O_FPRED_W, TGGCN_W_HEAD_O_REC_W, TGGCN_W_HEAD_O_PRED_W};
+            for (int i = 0; i < 4; ++i) {
+                P.w[i] = W(oid[i]); P.bias[i] = W(oid[i] + 1); P.dlogp[i] = grads->d_out_o[i];
+                P.dw[i] = G(oid[i]); P.db[i] = G(oid[i] + 1);
+                TG_CUDA_OK(cudaMemsetAsync(P.dw[i], 0, sizeof(float) * (size_t)d.C_aff * 2 * D, stream));
+                TG_CUDA_OK(cudaMemsetAsync(P.db[i], 0, sizeof(float) * (size_t)d.C_aff, stream));
+            }
+            P.dhfr = bb(BL.dhfr[1]); P.dhx = bb(BL.dhx[1]);
+            if (int rc = launch_heads_bwd(P, stream)) return rc;
+        }
+    }
+
+    // ---- 11. segment-level recurrent graph, reverse time ---------------------------------------------------------------
+    const int kh = (1 + nkh) * D, ldwh = (1 + 2 * nkh) * D;       // human cell: frame-part columns, row stride of W_ih
+    const int rows_h = B * H, rows_o = B * O;
+    const int wih_h_id[2] = {TGGCN_W_HSEG_F_WIH, TGGCN_W_HSEG_B_WIH}, wih_o_id[2] = {TGGCN_W_OSEG_F_WIH, TGGCN_W_OSEG_B_WIH};
+    const int whh_h_id[2] = {TGGCN_W_HSEG_F_WHH, TGGCN_W_HSEG_B_WHH}, whh_o_id[2] = {TGGCN_W_OSEG_F_WHH, TGGCN_W_OSEG_B_WHH};
+    const int smsg_w_id[4] = {TGGCN_W_SMSG_HH_W, TGGCN_W_SMSG_OH_W, TGGCN_W_SMSG_HO_W, TGGCN_W_SMSG_OO_W};
+    {
+        // transposed weights, kept for the whole loop
+        float* p = bb(BL.wt_seg);
+        float* whhT_h[2]; float* whhT_o[2]; float* wihT_h[2]; float* wihT_o[2];
+        for (int dir = 0; dir < 2; ++dir) { whhT_h[dir] = p; p += (size_t)D * 3 * D; }
+        for (int dir = 0; dir < 2; ++dir) { whhT_o[dir] = p; p += (size_t)D * 3 * D; }
+        for (int dir = 0; dir < 2; ++dir) { wihT_h[dir] = p; p += (size_t)nkh * D * 3 * D; }
+        for (int dir = 0; dir < 2; ++dir) { wihT_o[dir] = p; p += (size_t)2 * D * 3 * D; }
+        float* wmT_h = p; p += (size_t)D * nks * D;      // (D, nks*D): [W_hh_msg^T | W_ho_msg^T]
+        float* wmT_o = p;                                // (D, 2D):    [W_oh_msg^T | W_oo_msg^T]
+        for (int dir = 0; dir < 2; ++dir) {
+            if (int rc = launch_transpose(W(whh_h_id[dir]), D, whhT_h[dir], 3 * D, 3 * D, D, stream)) return rc;
+            if (int rc = launch_transpose(W(whh_o_id[dir]), D, whhT_o[dir], 3 * D, 3 * D, D, stream)) return rc;
+            if (int rc = launch_transpose(W(wih_h_id[dir]) + kh, ldwh, wihT_h[dir], 3 * D, 3 * D, nkh * D, stream)) return rc;
+            if (int rc = launch_transpose(W(wih_o_id[dir]) + 4 * D, 6 * D, wihT_o[dir], 3 * D, 3 * D, 2 * D, stream)) return rc;
+        }
+        if (d.hh)
+            if (int rc = launch_transpose(W(TGGCN_W_SMSG_HH_W), D, wmT_h, nks * D, D, D, stream)) return rc;
+        if (int rc = launch_transpose(W(TGGCN_W_SMSG_HO_W), D, wmT_h + (nks - 1) * D, nks * D, D, D, stream)) return rc;
+        if (int rc = launch_transpose(W(TGGCN_W_SMSG_OH_W), D, wmT_o, 2 * D, D, D, stream)) return rc;
+        if (int rc = launch_transpose(W(TGGCN_W_SMSG_OO_W), D, wmT_o + D, 2 * D, D, D, stream)) return rc;
+
+        SegBwdParams P;
+        memset(&P, 0, sizeof(P));
+        P.B = B; P.T = T; P.H = H; P.O = O; P.D = D; P.hh = d.hh; P.nk_h = nkh;
+        P.hx_h = buf(TGGCN_BUF_HX_H); P.hx_o = buf(TGGCN_BUF_HX_O);
+        P.sgates_h = buf(TGGCN_BUF_SGATES_H); P.sgates_o = buf(TGGCN_BUF_SGATES_O);
+        P.u_h = io->y_hs; P.u_o = io->y_os; P.om = io->objects_mask;
+        P.dhx_h = bb(BL.dhx[0]); P.dhx_o = bb(BL.dhx[1]);
+        P.dgs_h = bb(BL.dgs[0]); P.dgs_o = bb(BL.dgs[1]);
+        P.dghs_h = bb(BL.dghs[0]); P.dghs_o = bb(BL.dghs[1]);
+        P.du_h = bb(BL.du[0]); P.du_o = bb(BL.du[1]);
+        for (int i = 0; i < 2; ++i) { P.carry_h[i] = bb(BL.carry[0][i]); P.carry_o[i] = bb(BL.carry[1][i]); }
+        P.dgi_h = bb(BL.dgi_s[0]); P.dgi_o = bb(BL.dgi_s[1]);
+        P.dgh_h = bb(BL.dgh_s[0]); P.dgh_o = bb(BL.dgh_s[1]);
+        P.dmg_h = bb(BL.dmg[0]); P.dmg_o = bb(BL.dmg[1]);
+        P.dpre_h = bb(BL.dpre[0]); P.dpre_o = bb(BL.dpre[1]);
+        const int smsg_id[4] = {TGGCN_BUF_SMSG_HH, TGGCN_BUF_SMSG_OH, TGGCN_BUF_SMSG_HO, TGGCN_BUF_SMSG_OO};
+        const int salpha_id[4] = {TGGCN_BUF_SALPHA_HH, TGGCN_BUF_SALPHA_OH, TGGCN_BUF_SALPHA_HO, TGGCN_BUF_SALPHA_OO};
+        for (int k = 0; k < 4; ++k) {
+            P.smsg[k] = buf(smsg_id[k]); P.salpha[k] = buf(salpha_id[k]); P.dpre_all[k] = bb(BL.dpre_all[k]);
+        }
+        for (int s = 0; s < T; ++s) {
+            float* cout_h = P.carry_h[(s + 1) & 1];
+            float* cout_o = P.carry_o[(s + 1) & 1];
+            const bool last = (s == T - 1);          // the forward's first step: no previous state to send gradient to
+            if (int rc = launch_seg_cell_bwd(P, s, stream)) return rc;
+            GemmGroup g;
+            g.count = 0;
+            for (int dir = 0; dir < 2; ++dir) {
+                gemm_add(g, P.dgi_h + (size_t)dir * rows_h * 3 * D, 3 * D, wihT_h[dir], 3 * D, nullptr,
+                         P.dmg_h + (size_t)dir * rows_h * nkh * D, nkh * D, rows_h, nkh * D, 3 * D, 0);
+                gemm_add(g, P.dgi_o + (size_t)dir * rows_o * 3 * D, 3 * D, wihT_o[dir], 3 * D, nullptr,
+                         P.dmg_o + (size_t)dir * rows_o * 2 * D, 2 * D, rows_o, 2 * D, 3 * D, 0);
+                if (!last) {
+                    gemm_add(g, P.dgh_h + (size_t)dir * rows_h * 3 * D, 3 * D, whhT_h[dir], 3 * D, nullptr,
+                             cout_h + (size_t)dir * rows_h * D, D, rows_h, D, 3 * D, 0);
+                    g.p[g.count - 1].beta = 1;
+                    gemm_add(g, P.dgh_o + (size_t)dir * rows_o * 3 * D, 3 * D, whhT_o[dir], 3 * D, nullptr,
+                             cout_o + (size_t)dir * rows_o * D, D, rows_o, D, 3 * D, 0);
+                    g.p[g.count - 1].beta = 1;
+                }
+            }
+            if (int rc = launch_gemm(g, path, stream)) return rc;
+            if (int rc = launch_seg_msg_bwd(P, s, stream)) return rc;
+            if (!last) {
+                g.count = 0;
+                for (int dir = 0; dir < 2; ++dir) {
+                    gemm_add(g, P.dpre_h + (size_t)dir * rows_h * nks * D, nks * D, wmT_h, nks * D, nullptr,
+                             cout_h + (size_t)dir * rows_h * D, D, rows_h, D, nks * D, 0);
+                    g.p[g.count - 1].beta = 1;
+                    gemm_add(g, P.dpre_o + (size_t)dir * rows_o * 2 * D, 2 * D, wmT_o, 2 * D, nullptr,
+                             cout_o + (size_t)dir * rows_o * D, D, rows_o, D, 2 * D, 0);
+                    g.p[g.count - 1].beta = 1;
+                }
+                if (int rc = launch_gemm(g, path, stream)) return rc;
+            }
+        }
+        // weight gradients of the cells and message MLPs: GEMMs over all (video, t, entity) rows
+        for (int dir = 0; dir < 2; ++dir) {
+            // humans
+            if (int rc = launch_gemm_tn(P.dghs_h + (size_t)dir * 3 * D, 6 * D, nullptr, 0, P.hx_h + (size_t)dir * D, 2 * D,
+                                        G(whh_h_id[dir]), D, N * H, 3 * D, D, dir == 0 ? -H : H, T * H, 0, stream)) return rc;
+            if (int rc = launch_colsum(P.dghs_h + (size_t)dir * 3 * D, 6 * D, nullptr, 0, G(whh_h_id[dir] + 2), N * H, 3 * D, 0, stream)) return rc;
+            if (int rc = launch_gemm_tn(P.dgs_h + (size_t)dir * 3 * D, 6 * D, nullptr, 0, buf(TGGCN_BUF_XX_H), kh, G(wih_h_id[dir]), ldwh,
+                                        N * H, 3 * D, kh, 0, 0, 0, stream)) return rc;
+            if (int rc = launch_gemm_tn(P.dgs_h + (size_t)dir * 3 * D, 6 * D, nullptr, 0,
+                                        buf(TGGCN_BUF_MG_ALL_H) + (size_t)dir * N * H * nkh * D, nkh * D, G(wih_h_id[dir]) + kh, ldwh,
+                                        N * H, 3 * D, nkh * D, 0, 0, 0, stream)) return rc;
+            if (int rc = launch_colsum(P.dgs_h + (size_t)dir * 3 * D, 6 * D, nullptr, 0, G(wih_h_id[dir] + 2), N * H, 3 * D, 0, stream)) return rc;
+            // objects
+            if (int rc = launch_gemm_tn(P.dghs_o + (size_t)dir * 3 * D, 6 * D, nullptr, 0, P.hx_o + (size_t)dir * D, 2 * D,
+                                        G(whh_o_id[dir]), D, N * O, 3 * D, D, dir == 0 ? -O : O, T * O, 0, stream)) return rc;
+            if (int rc = launch_colsum(P.dghs_o + (size_t)dir * 3 * D, 6 * D, nullptr, 0, G(whh_o_id[dir] + 2), N * O, 3 * D, 0, stream)) return rc;
+            if (int rc = launch_gemm_tn(P.dgs_o + (size_t)dir * 3 * D, 6 * D, nullptr, 0, buf(TGGCN_BUF_XX_O), 4 * D, G(wih_o_id[dir]), 6 * D,
+                                        N * O, 3 * D, 4 * D, 0, 0, 0, stream)) return rc;
+            if (int rc = launch_gemm_tn(P.dgs_o + (size_t)dir * 3 * D, 6 * D, nullptr, 0,
+                                        buf(TGGCN_BUF_MG_ALL_O) + (size_t)dir * N * O * 2 * D, 2 * D, G(wih_o_id[dir]) + 4 * D, 6 * D,
+                                        N * O, 3 * D, 2 * D, 0, 0, 0, stream)) return rc;
+            if (int rc = launch_colsum(P.dgs_o + (size_t)dir * 3 * D, 6 * D, nullptr, 0, G(wih_o_id[dir] + 2), N * O, 3 * D, 0, stream)) return rc;
+        }
+        for (int k = d.hh ? 0 : 1; k < 4; ++k) {
+            const bool send_h = (k == 0 || k == 2);
+            const int Es = send_h ? H : O;
+            const float* hx = send_h ? P.hx_h : P.hx_o;
+            for (int dir = 0; dir < 2; ++dir)
+                if (int rc = launch_gemm_tn(P.dpre_all[k] + (size_t)dir * N * Es * D, D, nullptr, 0, hx + (size_t)dir * D, 2 * D,
+                                            G(smsg_w_id[k]), D, N * Es, D, D, dir == 0 ? -Es : Es, T * Es, dir, stream)) return rc;
+            if (int rc = launch_colsum(P.dpre_all[k], D, nullptr, 0, G(smsg_w_id[k] + 1), 2 * N * Es, D, 0, stream)) return rc;
+        }
+    }
+
+    // ---- 10. hoisted frame-part of the segment cells: d xx = [dGs_f | dGs_b] [W_ih_f[:, :k] ; W_ih_b[:, :k]] -----------------------
+    {
+        float* wt = bb(BL.wt);
+        for (int dir = 0; dir < 2; ++dir)
+            if (int rc = launch_transpose(W(wih_h_id[dir]), ldwh, wt + (size_t)dir * 3 * D, 6 * D, 3 * D, kh, stream)) return rc;
+        if (int rc = gemm_nt(bb(BL.dgs[0]), 6 * D, nullptr, 0, wt, 6 * D, bb(BL.dxx[0]), kh, N * H, kh, 6 * D, 0, path, stream)) return rc;
+        for (int dir = 0; dir < 2; ++dir)
+            if (int rc = launch_transpose(W(wih_o_id[dir]), 6 * D, wt + (size_t)dir * 3 * D, 6 * D, 3 * D, 4 * D, stream)) return rc;
+        if (int rc = gemm_nt(bb(BL.dgs[1]), 6 * D, nullptr, 0, wt, 6 * D, bb(BL.dxx[1]), 4 * D, N * O, 4 * D, 6 * D, 0, path, stream)) return rc;
+    }
+
+    // ---- 9/8. gates (straight-through, filter), attention, aggregation ------------------------------------------------------------
+    {
+        FrameBwdParams P;
+        memset(&P, 0, sizeof(P));
+        P.B = B; P.T = T; P.H = H; P.O = O; P.D = D; P.hh = d.hh; P.filter = d.filter; P.thr = d.thr;
+        P.s_h = buf(TGGCN_BUF_S_H); P.s_o = buf(TGGCN_BUF_S_O);
+        P.msg_hh = buf(TGGCN_BUF_MSG_HH); P.msg_ho = buf(TGGCN_BUF_MSG_HO); P.msg_oh = buf(TGGCN_BUF_MSG_OH);
+        P.msg_oo = buf(TGGCN_BUF_MSG_OO); P.msg_go = buf(TGGCN_BUF_MSG_GO);
+        P.om = io->objects_mask;
+        P.w_uh = W(TGGCN_W_UPD_H_W); P.w_uo = W(TGGCN_W_UPD_O_W);
+        P.alpha = buf(TGGCN_BUF_ALPHA_F); P.pgate = buf(TGGCN_BUF_PGATE);
+        P.y_hss = io->y_hss; P.y_oss = io->y_oss;
+        P.human_seg = io->human_seg; P.object_seg = io->object_seg;
+        P.xx_h = buf(TGGCN_BUF_XX_H); P.xx_o = buf(TGGCN_BUF_XX_O);
+        P.dxx_h = bb(BL.dxx[0]); P.dxx_o = bb(BL.dxx[1]);
+        P.du_h = bb(BL.du[0]); P.du_o = bb(BL.du[1]);
+        P.dy_hs = grads->d_y_hs; P.dy_os = grads->d_y_os; P.dy_hss = grads->d_y_hss; P.dy_oss = grads->d_y_oss;
+        P.ds_h = bb(BL.ds[0]); P.ds_o = bb(BL.ds[1]);
+        P.dmsg_hh = bb(BL.dmsg[0]); P.dmsg_ho = bb(BL.dmsg[1]); P.dmsg_oh = bb(BL.dmsg[2]); P.dmsg_oo = bb(BL.dmsg[3]);
+        P.dmsg_go = bb(BL.dmsg[4]);
+        P.dw_uh = G(TGGCN_W_UPD_H_W); P.db_uh = G(TGGCN_W_UPD_H_B); P.dw_uo = G(TGGCN_W_UPD_O_W); P.db_uo = G(TGGCN_W_UPD_O_B);
+        if (!d.human_seg_given) {
+            TG_CUDA_OK(cudaMemsetAsync(P.dw_uh, 0, sizeof(float) * (size_t)(2 + nkh) * D, stream));
+            TG_CUDA_OK(cudaMemsetAsync(P.db_uh, 0, sizeof(float), stream));
+        }
+        if (!d.object_seg_given) {
+            TG_CUDA_OK(cudaMemsetAsync(P.dw_uo, 0, sizeof(float) * (size_t)5 * D, stream));
+            TG_CUDA_OK(cudaMemsetAsync(P.db_uo, 0, sizeof(float), stream));
+        }
+        if (int rc = launch_frame_bwd(P, stream)) return rc;
+    }
+
+    // ---- 7. message MLPs: msg = ReLU(W [x|h] + b) ---------------------------------------------------------------------------------
+    {
+        struct Kind { int w_id; int msg_buf; int dmsg; int grp; int on; };
+        const Kind kinds[5] = {{TGGCN_W_MSG_HH_W, TGGCN_BUF_MSG_HH, 0, 0, d.hh}, {TGGCN_W_MSG_HO_W, TGGCN_BUF_MSG_HO, 1, 0, 1},
+                               {TGGCN_W_MSG_OH_W, TGGCN_BUF_MSG_OH, 2, 1, 1},    {TGGCN_W_MSG_OO_W, TGGCN_BUF_MSG_OO, 3, 1, 1},
+                               {TGGCN_W_MSG_GO_W, TGGCN_BUF_MSG_GO, 4, 2, 1}};
+        const int s_buf[3] = {TGGCN_BUF_S_H, TGGCN_BUF_S_O, TGGCN_BUF_S_G};
+        const int Eg[3] = {H, O, 1};
+        int touched[3] = {1, 1, 0};      // ds_h / ds_o were written by the frame kernel; ds_g starts here
+        float* wt = bb(BL.wt);
+        for (int k = 0; k < 5; ++k) {
+            if (!kinds[k].on) continue;
+            const int gidx = kinds[k].grp, M = N * Eg[gidx];
+            const float* dmsg = bb(BL.dmsg[kinds[k].dmsg]);
+            const float* msg = buf(kinds[k].msg_buf);
+            if (int rc = launch_transpose(W(kinds[k].w_id), 2 * D, wt, D, D, 2 * D, stream)) return rc;      // (D,2D) -> (2D,D)
+            if (int rc = gemm_nt(dmsg, D, msg, D, wt, D, bb(BL.ds[gidx]), 2 * D, M, 2 * D, D, touched[gidx], path, stream)) return rc;
+            touched[gidx] = 1;
+            if (int rc = launch_gemm_tn(dmsg, D, msg, D, buf(s_buf[gidx]), 2 * D, G(kinds[k].w_id), 2 * D, M, D, 2 * D, 0, 0, 0, stream)) return rc;
+            if (int rc = launch_colsum(dmsg, D, msg, D, G(kinds[k].w_id + 1), M, D, 0, stream)) return rc;
+        }
+    }
+
+    // ---- 6. Linear(2D->D)+ReLU on the BiGRU outputs: h = S[:, D:2D] ------------------------------------------------------------------
+    const int s_buf[3] = {TGGCN_BUF_S_H, TGGCN_BUF_S_O, TGGCN_BUF_S_G};
+    const int hfr_buf[3] = {TGGCN_BUF_HFR_H, TGGCN_BUF_HFR_O, TGGCN_BUF_HFR_G};
+    const int gates_buf[3] = {TGGCN_BUF_GATES_H, TGGCN_BUF_GATES_O, TGGCN_BUF_GATES_G};
+    const int bd_id[3] = {TGGCN_W_HUM_BD_W, TGGCN_W_OBJ_BD_W, TGGCN_W_GEO_BD_W};
+    const int Eg[3] = {H, O, 1};
+    {
+        float* wt = bb(BL.wt);
+        for (int g = 0; g < 3; ++g) {
+            const int M = N * Eg[g];
+            const float* dZ = bb(BL.ds[g]) + D;
+            const float* Y = buf(s_buf[g]) + D;
+            if (int rc = launch_transpose(W(bd_id[g]), 2 * D, wt, D, D, 2 * D, stream)) return rc;
+            const int beta = (g == 0 || (g == 1 && d.C_aff > 0)) ? 1 : 0;     // the frame heads already wrote into d hfr
+            if (int rc = gemm_nt(dZ, 2 * D, Y, 2 * D, wt, D, bb(BL.dhfr[g]), 2 * D, M, 2 * D, D, beta, path, stream)) return rc;
+            if (int rc = launch_gemm_tn(dZ, 2 * D, Y, 2 * D, buf(hfr_buf[g]), 2 * D, G(bd_id[g]), 2 * D, M, D, 2 * D, 0, 0, 0, stream)) return rc;
+            if (int rc = launch_colsum(dZ, 2 * D, Y, 2 * D, G(bd_id[g] + 1), M, D, 0, stream)) return rc;
+        }
+    }
+
+    // ---- 5/4. BiGRU backward through time, then the hoisted input projections --------------------------------------------------------
+    {
+        const int wih_f[3] = {TGGCN_W_HUM_RNN_WIH_F, TGGCN_W_OBJ_RNN_WIH_F, TGGCN_W_GEO_RNN_WIH_F};
+        float* wt = bb(BL.wt);
+        for (int g = 0; g < 3; ++g) {
+            // table order per group: WIH_F, WHH_F, BIH_F, BHH_F, WIH_B, WHH_B, BIH_B, BHH_B
+            const int base = wih_f[g];
+            const int M = N * Eg[g];
+            float* dgi = bb(BL.dgi[g]);
+            if (int rc = tggcn_bigru_bwd(bb(BL.dhfr[g]), buf(hfr_buf[g]), buf(gates_buf[g]), W(base + 1), W(base + 5), dgi, bb(BL.dgh[g]),
+                                         G(base + 1), G(base + 5), G(base + 3), G(base + 7), bb(BL.bigru_scratch), B, T, Eg[g], D, path,
+                                         stream))
+                return rc;
+            // d x (+)= [dGi_f | dGi_b] [W_ih_f ; W_ih_b]   (x = S[:, :D])
+            if (int rc = launch_transpose(W(base), D, wt, 6 * D, 3 * D, D, stream)) return rc;
+            if (int rc = launch_transpose(W(base + 4), D, wt + 3 * D, 6 * D, 3 * D, D, stream)) return rc;
+            if (int rc = gemm_nt(dgi, 6 * D, nullptr, 0, wt, 6 * D, bb(BL.ds[g]), 2 * D, M, D, 6 * D, 1, path, stream)) return rc;
+            for (int dir = 0; dir < 2; ++dir) {
+                if (int rc = launch_gemm_tn(dgi + (size_t)dir * 3 * D, 6 * D, nullptr, 0, buf(s_buf[g]), 2 * D, G(base + 4 * dir), D, M, 3 * D, D,
+                                            0, 0, 0, stream)) return rc;
+                if (int rc = launch_colsum(dgi + (size_t)dir * 3 * D, 6 * D, nullptr, 0, G(base + 4 * dir + 2), M, 3 * D, 0, stream)) return rc;
+            }
+        }
+    }
+
+    // ---- 3/2. embeddings (inputs are data: weight gradients only) and the geometry MLP ---------------------------------------------------
+    {
+        // x = ReLU(W roi + b) = S[:, :D]
+        if (int rc = launch_gemm_tn(bb(BL.ds[0]), 2 * D, buf(TGGCN_BUF_S_H), 2 * D, io->x_human, d.Fh, G(TGGCN_W_HUM_EMB_W), 2048, N * H, D, 2048,
+                                    0, 0, 0, stream)) return rc;
+        if (int rc = launch_colsum(bb(BL.ds[0]), 2 * D, buf(TGGCN_BUF_S_H), 2 * D, G(TGGCN_W_HUM_EMB_B), N * H, D, 0, stream)) return rc;
+        if (int rc = launch_gemm_tn(bb(BL.ds[1]), 2 * D, buf(TGGCN_BUF_S_O), 2 * D, io->x_objects, 2048, G(TGGCN_W_OBJ_EMB_W), 2048, N * O, D, 2048,
+                                    0, 0, 0, stream)) return rc;
+        if (int rc = launch_colsum(bb(BL.ds[1]), 2 * D, buf(TGGCN_BUF_S_O), 2 * D, G(TGGCN_W_OBJ_EMB_B), N * O, D, 0, stream)) return rc;
+        // geometry MLP layer 2: S_G[:, :D] = ReLU(W2 hid + b2)
+        float* wt = bb(BL.wt);
+        if (int rc = launch_transpose(W(TGGCN_W_GEO_MLP2_W), 2048, wt, D, D, 2048, stream)) return rc;          // (D,2048) -> (2048,D)
+        if (int rc = gemm_nt(bb(BL.ds[2]), 2 * D, buf(TGGCN_BUF_S_G), 2 * D, wt, D, bb(BL.dgeo_hid), 2048, N, 2048, D, 0, path, stream)) return rc;
+        if (int rc = launch_gemm_tn(bb(BL.ds[2]), 2 * D, buf(TGGCN_BUF_S_G), 2 * D, buf(TGGCN_BUF_GEO_HID), 2048, G(TGGCN_W_GEO_MLP2_W), 2048, N, D,
+                                    2048, 0, 0, 0, stream)) return rc;
+        if (int rc = launch_colsum(bb(BL.ds[2]), 2 * D, buf(TGGCN_BUF_S_G), 2 * D, G(TGGCN_W_GEO_MLP2_B), N, D, 0, stream)) return rc;
+        // layer 0: hid = ReLU(W0 gcn + b0), gcn = the scrambled view (N, 128V)
+        const int KV = 128 * V;
+        if (int rc = launch_transpose(W(TGGCN_W_GEO_MLP0_W), KV, wt, 2048, 2048, KV, stream)) return rc;         // (2048,128V) -> (128V,2048)
+        if (int rc = gemm_nt(bb(BL.dgeo_hid), 2048, buf(TGGCN_BUF_GEO_HID), 2048, wt, 2048, bb(BL.dgcn_out), KV, N, KV, 2048, 0, path, stream)) return rc;
+        if (int rc = launch_gemm_tn(bb(BL.dgeo_hid), 2048, buf(TGGCN_BUF_GEO_HID), 2048, buf(TGGCN_BUF_GCN_OUT), KV, G(TGGCN_W_GEO_MLP0_W), KV, N,
+                                    2048, KV, 0, 0, 0, stream)) return rc;
+        if (int rc = launch_colsum(bb(BL.dgeo_hid), 2048, buf(TGGCN_BUF_GEO_HID), 2048, G(TGGCN_W_GEO_MLP0_B), N, 2048, 0, stream)) return rc;
+    }
+
+    // ---- 1. geometry GCN ---------------------------------------------------------------------------------------------------------------------
+    {
+        GcnBwdParams P;
+        memset(&P, 0, sizeof(P));
+        P.xh = io->x_human; P.B = B; P.T = T; P.H = H; P.V = V; P.Fh = d.Fh;
+        if (d.bn_train) {
+            const float* stats = buf(TGGCN_BUF_SEG_SCRATCH) + 2 * (size_t)B * H * nkh * D + 2 * (size_t)B * O * 2 * D;   // see api.cu
+            P.mean = stats; P.var = stats + 4 * V;
+        } else {
+            P.mean = W(TGGCN_W_GCN_BN_MEAN); P.var = W(TGGCN_W_GCN_BN_VAR);
+        }
+        P.gamma = W(TGGCN_W_GCN_BN_W); P.beta = W(TGGCN_W_GCN_BN_B);
+        P.w1 = W(TGGCN_W_GCN_C1_W); P.b1 = W(TGGCN_W_GCN_C1_B); P.w3 = W(TGGCN_W_GCN_C3_W); P.b3 = W(TGGCN_W_GCN_C3_B);
+        P.ws1 = W(TGGCN_W_GCN_S1_W); P.bs1 = W(TGGCN_W_GCN_S1_B); P.ws2 = W(TGGCN_W_GCN_S2_W); P.bs2 = W(TGGCN_W_GCN_S2_B);
+        P.wg = W(TGGCN_W_GCN_W);
+        P.dout = bb(BL.dgcn_out);
+        P.dwg = G(TGGCN_W_GCN_W); P.dws1 = G(TGGCN_W_GCN_S1_W); P.dbs1 = G(TGGCN_W_GCN_S1_B); P.dws2 = G(TGGCN_W_GCN_S2_W);
+        P.dbs2 = G(TGGCN_W_GCN_S2_B); P.dw3 = G(TGGCN_W_GCN_C3_W); P.db3 = G(TGGCN_W_GCN_C3_B); P.dw1 = G(TGGCN_W_GCN_C1_W);
+        P.db1 = G(TGGCN_W_GCN_C1_B);
+        P.dxn = bb(BL.dxn);
+        TG_CUDA_OK(cudaMemsetAsync(P.dwg, 0, sizeof(float) * 64 * 128, stream));
+        TG_CUDA_OK(cudaMemsetAsync(P.dws1, 0, sizeof(float) * 128 * 64, stream));
+        TG_CUDA_OK(cudaMemsetAsync(P.dbs1, 0, sizeof(float) * 128, stream));
+        TG_CUDA_OK(cudaMemsetAsync(P.dws2, 0, sizeof(float) * 128 * 64, stream));
+        TG_CUDA_OK(cudaMemsetAsync(P.dbs2, 0, sizeof(float) * 128, stream));
+        TG_CUDA_OK(cudaMemsetAsync(P.dw3, 0, sizeof(float) * 64 * 64, stream));
+        TG_CUDA_OK(cudaMemsetAsync(P.db3, 0, sizeof(float) * 64, stream));
+        TG_CUDA_OK(cudaMemsetAsync(P.dw1, 0, sizeof(float) * 64 * 4, stream));
+        TG_CUDA_OK(cudaMemsetAsync(P.db1, 0, sizeof(float) * 64, stream));
+        if (int rc = launch_geo_gcn_bwd(P, stream)) return rc;
+        if (int rc = launch_geo_bn_bwd(io->x_human, P.dxn, P.mean, P.var, P.gamma, G(TGGCN_W_GCN_BN_W), G(TGGCN_W_GCN_BN_B), B, T, H, V, d.Fh,
+                                       stream)) return rc;
+    }
+    return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,483 @@
+// Hand-written backward kernels of the graph stages (autograd of vhoi/models.py:664-933; Appendix B of SURVEY.md):
+//   heads_bwd_kernel     Linear(2D->C)+LogSoftmax backward, scatter through the reorder index
+//   seg_cell_bwd_kernel  one reverse step of the gated GRUCell update  h = u*GRU(x,h') + (1-u)*h'
+//   seg_msg_bwd_kernel   one reverse step of the segment-level attention messages
+//   frame_bwd_kernel     frame-level attention / aggregation / Gumbel-sigmoid gates (straight-through, filter)
+// Dense matrix products of the backward run on the projection kernels (gemm_*.cu, gemm_bwd.cu).
+#include "backward.cuh"
+
+namespace tg {
+
+// =============================================================================================================
+// heads
+// =============================================================================================================
+__global__ void __launch_bounds__(256) heads_bwd_kernel(const HeadsBwdParams P) {
+    extern __shared__ __align__(16) float sm[];
+    const int hd = blockIdx.y, src = hd >> 1;
+    if (P.dlogp[hd] == nullptr) return;
+    const int D2 = 2 * P.D, C = P.C;
+    float* sdw = sm;                 // [C][D2]
+    float* sdb = sm + C * D2;        // [C]
+    for (int i = threadIdx.x; i < C * D2 + C; i += blockDim.x) sm[i] = 0.0f;
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int rows = P.B * P.T * P.E;
+    const float* W = P.w[hd];
+    for (int row = blockIdx.x * 8 + warp; row < rows; row += gridDim.x * 8) {
+        const int e = row % P.E, bt = row / P.E;
+        const int t = bt % P.T, b = bt / P.T;
+        size_t xrow;
+        if (src == 0) xrow = (size_t)row;
+        else xrow = (size_t)(b * P.T + P.reidx[(size_t)bt * P.NE + P.e_off + e]) * P.E + e;
+        const float* x = (src == 0 ? P.hfr : P.hx) + xrow * D2;
+        float mine = -INFINITY;
+        for (int c = 0; c < C; ++c) {
+            const float* wr = W + (size_t)c * D2;
+            float acc = 0.0f;
+            for (int k = lane * 4; k < D2; k += 128) {
+                const float4 u = __ldg(reinterpret_cast<const float4*>(wr + k));
+                const float4 v = *reinterpret_cast<const float4*>(x + k);
+                acc = fmaf(u.x, v.x, acc); acc = fmaf(u.y, v.y, acc); acc = fmaf(u.z, v.z, acc); acc = fmaf(u.w, v.w, acc);
+            }
+            acc = warp_sum(acc) + __ldg(P.bias[hd] + c);
+            if (lane == c) mine = acc;
+        }
+        const float m = warp_max(mine);
+        const float ex = lane < C ? expf(mine - m) : 0.0f;
+        const float prob = ex / warp_sum(ex);
+        const float g = lane < C ? __ldg(P.dlogp[hd] + ((size_t)(b * C + lane) * P.T + t) * P.E + e) : 0.0f;
+        const float gs = warp_sum(g);
+        const float dz = lane < C ? g - prob * gs : 0.0f;     // d log_softmax
+        if (lane < C) atomicAdd(&sdb[lane], dz);
+        float* dxrow = (src == 0 ? P.dhfr : P.dhx) + xrow * D2;
+        for (int k = lane * 4; k < D2; k += 128) {
+            const float4 xv = *reinterpret_cast<const float4*>(x + k);
+            float4 dx = make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int c = 0; c < C; ++c) {
+                const float dzc = __shfl_sync(0xffffffffu, dz, c);
+                const float4 wv = __ldg(reinterpret_cast<const float4*>(W + (size_t)c * D2 + k));
+                dx.x = fmaf(dzc, wv.x, dx.x); dx.y = fmaf(dzc, wv.y, dx.y); dx.z = fmaf(dzc, wv.z, dx.z); dx.w = fmaf(dzc, wv.w, dx.w);
+                float* d = sdw + c * D2 + k;
+                atomicAdd(d, dzc * xv.x); atomicAdd(d + 1, dzc * xv.y); atomicAdd(d + 2, dzc * xv.z); atomicAdd(d + 3, dzc * xv.w);
+            }
+            atomicAdd(dxrow + k, dx.x); atomicAdd(dxrow + k + 1, dx.y); atomicAdd(dxrow + k + 2, dx.z); atomicAdd(dxrow + k + 3, dx.w);
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < C * D2; i += blockDim.x) atomicAdd(P.dw[hd] + i, sdw[i]);
+    for (int i = threadIdx.x; i < C; i += blockDim.x) atomicAdd(P.db[hd] + i, sdb[i]);
+}
+
+int launch_heads_bwd(const HeadsBwdParams& P, cudaStream_t stream) {
+    TG_REQUIRE(P.C >= 1 && P.C <= 32 && P.D % 2 == 0, "heads_bwd: unsupported sizes");
+    const size_t smem = sizeof(float) * ((size_t)P.C * 2 * P.D + P.C);
+    TG_REQUIRE(smem <= 200 * 1024, "heads_bwd: weight gradient tile does not fit in shared memory");
+    static size_t configured = 0;
+    if (smem > configured) {
+        TG_CUDA_OK(cudaFuncSetAttribute(heads_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = smem;
+    }
+    const int rows = P.B * P.T * P.E;
+    int chunks = cdiv(rows, 8 * 8);
+    if (chunks > 64) chunks = 64;
+    heads_bwd_kernel<<<dim3(chunks, 4), 256, smem, stream>>>(P);
+    TG_LAUNCH_OK();
+    return 0;
+}
+
+// =============================================================================================================
+// segment cells, one reverse step
+// =============================================================================================================
+__global__ void __launch_bounds__(256) seg_cell_bwd_kernel(const SegBwdParams P, int s) {
+    const int D = P.D, T = P.T;
+    const int rows_h = P.B * P.H, rows_o = P.B * P.O, rows_all = rows_h + rows_o;
+    const int dir = blockIdx.x / rows_all;
+    int r = blockIdx.x - dir * rows_all;
+    const bool is_h = r < rows_h;
+    if (!is_h) r -= rows_h;
+    const int E = is_h ? P.H : P.O, rows = is_h ? rows_h : rows_o;
+    const int b = r / E, e = r - b * E;
+    const int t = dir == 0 ? T - 1 - s : s;
+    const int tprev = dir == 0 ? t - 1 : t + 1;
+    const bool has_prev = tprev >= 0 && tprev < T;
+    const size_t fe = (size_t)(b * T + t) * E + e;
+    const float* hx = is_h ? P.hx_h : P.hx_o;
+    const float* dhx = is_h ? P.dhx_h : P.dhx_o;
+    const float* sg = (is_h ? P.sgates_h : P.sgates_o) + (fe * 2 + dir) * 4 * D;
+    const float u = (is_h ? P.u_h : P.u_o)[fe];
+    const float* cin = (is_h ? P.carry_h : P.carry_o)[s & 1] + ((size_t)dir * rows + r) * D;
+    float* cout = (is_h ? P.carry_h : P.carry_o)[(s + 1) & 1] + ((size_t)dir * rows + r) * D;
+    float* dgs = (is_h ? P.dgs_h : P.dgs_o) + (fe * 2 + dir) * 3 * D;
+    float* dghs = (is_h ? P.dghs_h : P.dghs_o) + (fe * 2 + dir) * 3 * D;
+    float* dgi_d = (is_h ? P.dgi_h : P.dgi_o) + ((size_t)dir * rows + r) * 3 * D;
+    float* dgh_d = (is_h ? P.dgh_h : P.dgh_o) + ((size_t)dir * rows + r) * 3 * D;
+    float du_part = 0.0f;
+    for (int unit = threadIdx.x; unit < D; unit += blockDim.x) {
+        const float dH = dhx[fe * 2 * D + dir * D + unit] + (s > 0 ? cin[unit] : 0.0f);
+        const float rr = sg[unit], z = sg[D + unit], n = sg[2 * D + unit], hn = sg[3 * D + unit];
+        const float hprev = has_prev ? hx[((size_t)(b * T + tprev) * E + e) * 2 * D + dir * D + unit] : 0.0f;
+        const float hnew = n + z * (hprev - n);
+        du_part += dH * (hnew - hprev);
+        const float dhnew = u * dH;
+        const float dn = dhnew * (1.0f - z);
+        const float dz = dhnew * (hprev - n);
+        const float dan = dn * (1.0f - n * n);
+        const float daz = dz * z * (1.0f - z);
+        const float dar = dan * hn * rr * (1.0f - rr);
+        const float dhn = dan * rr;
+        dgs[unit] = dar; dgs[D + unit] = daz; dgs[2 * D + unit] = dan;
+        dghs[unit] = dar; dghs[D + unit] = daz; dghs[2 * D + unit] = dhn;
+        dgi_d[unit] = dar; dgi_d[D + unit] = daz; dgi_d[2 * D + unit] = dan;
+        dgh_d[unit] = dar; dgh_d[D + unit] = daz; dgh_d[2 * D + unit] = dhn;
+        cout[unit] = (1.0f - u) * dH + dhnew * z;
+    }
+    __shared__ float red[8];
+    du_part = warp_sum(du_part);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = du_part;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float tot = 0.0f;
+        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) tot += red[w];
+        atomicAdd((is_h ? P.du_h : P.du_o) + fe, tot);
+    }
+}
+
+int launch_seg_cell_bwd(const SegBwdParams& P, int s, cudaStream_t stream) {
+    seg_cell_bwd_kernel<<<2 * (P.B * P.H + P.B * P.O), 256, 0, stream>>>(P, s);
+    TG_LAUNCH_OK();
+    return 0;
+}
+
+// =============================================================================================================
+// segment messages, one reverse step; one CTA per (direction, video)
+// =============================================================================================================
+constexpr int SM_MAXE = 16;
+
+__global__ void __launch_bounds__(256) seg_msg_bwd_kernel(const SegBwdParams P, int s) {
+    extern __shared__ __align__(16) float sm[];
+    const int D = P.D, T = P.T, B = P.B, H = P.H, O = P.O, nk = P.nk_h;
+    const int dir = blockIdx.x / B, b = blockIdx.x - dir * B;
+    const int t = dir == 0 ? T - 1 - s : s;
+    const int tprev = dir == 0 ? t - 1 : t + 1;
+    const bool has_prev = tprev >= 0 && tprev < T;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int rows_h = B * H, rows_o = B * O;
+    float* dmg_h = sm;                          // [H][nk*D]
+    float* dmg_o = dmg_h + H * nk * D;          // [O][2D]
+    float* st = dmg_o + O * 2 * D;              // [H+O][D] previous states (zeros at the first forward step)
+    float* msg = st + (H + O) * D;              // [maxE][D] saved messages of the current kind
+    __shared__ float al[SM_MAXE * SM_MAXE], da[SM_MAXE * SM_MAXE], dl[SM_MAXE * SM_MAXE];
+
+    for (int i = tid; i < H * nk * D; i += 256) dmg_h[i] = P.dmg_h[((size_t)dir * rows_h + b * H) * nk * D + i];
+    for (int i = tid; i < O * 2 * D; i += 256) dmg_o[i] = P.dmg_o[((size_t)dir * rows_o + b * O) * 2 * D + i];
+    for (int i = tid; i < (H + O) * D; i += 256) {
+        const int e = i / D, c = i - e * D;
+        float v = 0.0f;
+        if (has_prev)
+            v = e < H ? P.hx_h[((size_t)(b * T + tprev) * H + e) * 2 * D + dir * D + c]
+                      : P.hx_o[((size_t)(b * T + tprev) * O + (e - H)) * 2 * D + dir * D + c];
+        st[i] = v;
+    }
+    float* carry_h = P.carry_h[(s + 1) & 1] + ((size_t)dir * rows_h + b * H) * D;
+    float* carry_o = P.carry_o[(s + 1) & 1] + ((size_t)dir * rows_o + b * O) * D;
+    const float scale = 1.0f / sqrtf((float)D);
+    const int nks = P.hh ? 2 : 1;               // message kinds per human sender
+    __syncthreads();
+
+    for (int kind = P.hh ? 0 : 1; kind < 4; ++kind) {
+        const bool send_h = (kind == 0 || kind == 2), recv_h = (kind == 0 || kind == 1);
+        const int Es = send_h ? H : O, Er = recv_h ? H : O;
+        const int slot = recv_h ? (kind == 0 ? 0 : nk - 1) : kind - 2;
+        const float* dmg = recv_h ? dmg_h : dmg_o;
+        const int ldr = recv_h ? nk * D : 2 * D;
+        const size_t base_s = (((size_t)dir * B + b) * T + t) * Es;
+        for (int i = tid; i < Es * D; i += 256) msg[i] = P.smsg[kind][base_s * D + i];
+        if (tid < Er * Es) al[tid] = P.salpha[kind][((((size_t)dir * B + b) * T + t) * Er) * Es + tid];
+        __syncthreads();
+        // d alpha[r][s] = <dmg_kind[r], msg[s]>
+        for (int p = warp; p < Er * Es; p += 8) {
+            const int r = p / Es, sd = p - r * Es;
+            const float* a = dmg + r * ldr + slot * D;
+            const float* m = msg + sd * D;
+            float acc = 0.0f;
+            for (int c = lane; c < D; c += 32) acc = fmaf(a[c], m[c], acc);
+            acc = warp_sum(acc);
+            if (lane == 0) da[p] = acc;
+        }
+        __syncthreads();
+        if (tid < Er) {
+            float dot = 0.0f;
+            for (int sd = 0; sd < Es; ++sd) dot = fmaf(al[tid * Es + sd], da[tid * Es + sd], dot);
+            for (int sd = 0; sd < Es; ++sd) dl[tid * Es + sd] = al[tid * Es + sd] * (da[tid * Es + sd] - dot) * scale;
+        }
+        __syncthreads();
+        // gradient of the pre-activation of every sender's message MLP
+        {
+            const int col = send_h ? (kind == 0 ? 0 : (nks - 1) * D) : (kind == 1 ? 0 : D);
+            const int lds = send_h ? nks * D : 2 * D;
+            float* dense = send_h ? P.dpre_h + ((size_t)dir * rows_h + b * H) * lds : P.dpre_o + ((size_t)dir * rows_o + b * O) * lds;
+            float* all = P.dpre_all[kind] + base_s * D;
+            for (int i = tid; i < Es * D; i += 256) {
+                const int sd = i / D, c = i - sd * D;
+                float v = 0.0f;
+                for (int r = 0; r < Er; ++r) v = fmaf(al[r * Es + sd], dmg[r * ldr + slot * D + c], v);
+                v = msg[i] > 0.0f ? v : 0.0f;
+                dense[sd * lds + col + c] = v;
+                all[i] = v;
+            }
+        }
+        // gradient of the attention logits w.r.t. the previous states of receivers and senders
+        if (has_prev) {
+            const float* sr = recv_h ? st : st + H * D;
+            const float* ss = send_h ? st : st + H * D;
+            float* cr = recv_h ? carry_h : carry_o;
+            float* cs = send_h ? carry_h : carry_o;
+            for (int i = tid; i < Er * D; i += 256) {
+                const int r = i / D, c = i - r * D;
+                float v = 0.0f;
+                for (int sd = 0; sd < Es; ++sd) v = fmaf(dl[r * Es + sd], ss[sd * D + c], v);
+                cr[i] += v;
+            }
+            __syncthreads();      // receivers and senders may be the same rows (hh, oo)
+            for (int i = tid; i < Es * D; i += 256) {
+                const int sd = i / D, c = i - sd * D;
+                float v = 0.0f;
+                for (int r = 0; r < Er; ++r) v = fmaf(dl[r * Es + sd], sr[r * D + c], v);
+                cs[i] += v;
+            }
+        }
+        __syncthreads();
+    }
+}
+
+int launch_seg_msg_bwd(const SegBwdParams& P, int s, cudaStream_t stream) {
+    TG_REQUIRE(P.H <= SM_MAXE && P.O <= SM_MAXE, "seg_msg_bwd: at most %d entities per type", SM_MAXE);
+    const int maxE = P.H > P.O ? P.H : P.O;
+    const size_t smem = sizeof(float) * ((size_t)P.H * P.nk_h * P.D + (size_t)P.O * 2 * P.D + (size_t)(P.H + P.O) * P.D + (size_t)maxE * P.D);
+    TG_REQUIRE(smem <= 200 * 1024, "seg_msg_bwd: shape needs %zu bytes of shared memory", smem);
+    static size_t configured = 0;
+    if (smem > configured) {
+        TG_CUDA_OK(cudaFuncSetAttribute(seg_msg_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = smem;
+    }
+    seg_msg_bwd_kernel<<<2 * P.B, 256, smem, stream>>>(P, s);
+    TG_LAUNCH_OK();
+    return 0;
+}
+
+// =============================================================================================================
+// frame-level graph; one CTA per (video, frame)
+// =============================================================================================================
+constexpr int FB_MAXE = 16;
+
+__global__ void __launch_bounds__(256) frame_bwd_kernel(const FrameBwdParams P) {
+    extern __shared__ __align__(16) float sm[];
+    const int D = P.D, H = P.H, O = P.O, T = P.T;
+    const int NE = H + O, D2 = 2 * D;
+    const int n = blockIdx.x, b = n / T, t = n - b * T;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int nkh = P.hh ? 2 : 1;
+    const int wh = (1 + nkh) * D;
+    float* sv = sm;                            // [NE][2D]
+    float* dmh = sv + NE * D2;                 // [H][nkh*D]   d m_hh | d m_oh
+    float* dmo = dmh + H * nkh * D;            // [O][3D]      d m_ho | d m_go | d m_oo
+    float* ds = dmo + O * 3 * D;               // [NE][2D]
+    __shared__ float a_hh[FB_MAXE * FB_MAXE], a_oh[FB_MAXE * FB_MAXE], a_ho[FB_MAXE * FB_MAXE], a_oo[FB_MAXE * FB_MAXE];
+    __shared__ float d_hh[FB_MAXE * FB_MAXE], d_oh[FB_MAXE * FB_MAXE], d_ho[FB_MAXE * FB_MAXE], d_oo[FB_MAXE * FB_MAXE];
+    __shared__ float cm[2 * FB_MAXE * 2 * FB_MAXE];
+    __shared__ float om[FB_MAXE], dlogit[2 * FB_MAXE];
+
+    for (int i = tid; i < H * D2 / 4; i += 256)
+        reinterpret_cast<float4*>(sv)[i] = __ldg(reinterpret_cast<const float4*>(P.s_h + (size_t)n * H * D2) + i);
+    for (int i = tid; i < O * D2 / 4; i += 256)
+        reinterpret_cast<float4*>(sv + H * D2)[i] = __ldg(reinterpret_cast<const float4*>(P.s_o + (size_t)n * O * D2) + i);
+    if (tid < O) om[tid] = P.om[b * O + tid];
+    {   // saved attention weights
+        const float* al = P.alpha + (size_t)n * (H * H + 2 * H * O + O * O);
+        for (int i = tid; i < H * H; i += 256) a_hh[(i / H) * FB_MAXE + i % H] = P.hh ? al[i] : 0.0f;
+        for (int i = tid; i < H * O; i += 256) a_oh[(i / O) * FB_MAXE + i % O] = al[H * H + i];
+        for (int i = tid; i < O * H; i += 256) a_ho[(i / H) * FB_MAXE + i % H] = al[H * H + H * O + i];
+        for (int i = tid; i < O * O; i += 256) a_oo[(i / O) * FB_MAXE + i % O] = al[H * H + 2 * H * O + i];
+    }
+    // ---- gates: straight-through / filter rule, Gumbel-sigmoid, sigmoid -----------------------------------------
+    if (tid < NE) {
+        const bool is_h = tid < H;
+        const int r = is_h ? tid : tid - H, E = is_h ? H : O;
+        const float* given = is_h ? P.human_seg : P.object_seg;
+        float dl_ = 0.0f;
+        if (given == nullptr) {
+            const float* soft = is_h ? P.y_hss : P.y_oss;
+            const size_t oi = (size_t)(b * T + t) * E + r;
+            const float y = soft[oi];
+            float dhard = (is_h ? P.du_h : P.du_o)[oi];
+            const float* dyh = is_h ? P.dy_hs : P.dy_os;
+            if (dyh != nullptr) dhard += dyh[oi];
+            float pass;
+            if (P.filter) {
+                const float yp = t > 0 ? soft[oi - E] : 0.0f, yn = t + 1 < T ? soft[oi + E] : 0.0f;
+                const bool keep = (y > yp) && (y > yn) && (y >= P.thr);
+                pass = (keep || y < P.thr) ? 1.0f : 0.0f;       // models.py:1660-1662 (clamp(max=0) passes at u == 0)
+            } else {
+                pass = t == T - 1 ? 0.0f : 1.0f;                // last step overwritten by 1 (models.py:701-702)
+            }
+            float dy = dhard * pass;
+            const float* dys = is_h ? P.dy_hss : P.dy_oss;
+            if (dys != nullptr) dy += dys[oi];
+            const float p = P.pgate[(size_t)n * NE + tid];
+            // y = sigmoid(log(p+eps) - log(1-p+eps) + g0 - g1), p = sigmoid(logit)
+            dl_ = dy * y * (1.0f - y) * (1.0f / (p + 1e-20f) + 1.0f / ((1.0f - p) + 1e-20f)) * p * (1.0f - p);
+        }
+        dlogit[tid] = dl_;
+    }
+    __syncthreads();
+    // ---- gradient of the aggregated messages and the direct parts of d[x|h] ----------------------------------------
+    for (int i = tid; i < H * D; i += 256) {
+        const int h = i / D, c = i - h * D;
+        const float* dx = P.dxx_h + ((size_t)n * H + h) * wh;
+        const float g = dlogit[h];
+        ds[h * D2 + c] = g * __ldg(P.w_uh + c);
+        ds[h * D2 + D + c] = g * __ldg(P.w_uh + D + c) + dx[c];
+        if (P.hh) dmh[h * nkh * D + c] = dx[D + c] + g * __ldg(P.w_uh + D2 + c);
+        dmh[h * nkh * D + (nkh - 1) * D + c] = dx[nkh * D + c] + g * __ldg(P.w_uh + D2 + (nkh - 1) * D + c);
+    }
+    for (int i = tid; i < O * D; i += 256) {
+        const int k = i / D, c = i - k * D;
+        const float* dx = P.dxx_o + ((size_t)n * O + k) * 4 * D;
+        const float g = dlogit[H + k];
+        ds[(H + k) * D2 + c] = g * __ldg(P.w_uo + c);
+        ds[(H + k) * D2 + D + c] = g * __ldg(P.w_uo + D + c) + dx[c];
+        dmo[k * 3 * D + c] = dx[D + c] + g * __ldg(P.w_uo + D2 + c);                    // m_ho   (gate order x,h,m_ho,m_oo,m_go)
+        dmo[k * 3 * D + D + c] = dx[2 * D + c] + g * __ldg(P.w_uo + D2 + 2 * D + c);    // m_go
+        dmo[k * 3 * D + 2 * D + c] = dx[3 * D + c] + g * __ldg(P.w_uo + D2 + D + c);    // m_oo
+    }
+    // gate weight gradients: d w[k] += sum_e dlogit[e] * input_e[k]
+    if (P.human_seg == nullptr) {
+        for (int k = tid; k < D2 + nkh * D; k += 256) {
+            float v = 0.0f;
+            for (int h = 0; h < H; ++h) {
+                const float in = k < D2 ? sv[h * D2 + k] : __ldg(P.xx_h + ((size_t)n * H + h) * wh + D + (k - D2));
+                v = fmaf(dlogit[h], in, v);
+            }
+            atomicAdd(P.dw_uh + k, v);
+        }
+        if (tid == 0) { float v = 0.0f; for (int h = 0; h < H; ++h) v += dlogit[h]; atomicAdd(P.db_uh, v); }
+    }
+    if (P.object_seg == nullptr) {
+        for (int k = tid; k < 5 * D; k += 256) {
+            float v = 0.0f;
+            for (int o = 0; o < O; ++o) {
+                float in;
+                if (k < D2) in = sv[(H + o) * D2 + k];
+                else {
+                    const int part = (k - D2) / D, c = (k - D2) - part * D;          // 0: m_ho, 1: m_oo, 2: m_go
+                    const int xoff = part == 0 ? D : (part == 1 ? 3 * D : 2 * D);    // xx_o = [h, m_ho, m_go, m_oo]
+                    in = __ldg(P.xx_o + ((size_t)n * O + o) * 4 * D + xoff + c);
+                }
+                v = fmaf(dlogit[H + o], in, v);
+            }
+            atomicAdd(P.dw_uo + k, v);
+        }
+        if (tid == 0) { float v = 0.0f; for (int o = 0; o < O; ++o) v += dlogit[H + o]; atomicAdd(P.db_uo, v); }
+    }
+    __syncthreads();
+    // ---- d alpha: one warp per (receiver, sender) pair -----------------------------------------------------------------
+    {
+        const float* g_hh = P.msg_hh + (size_t)n * H * D;
+        const float* g_ho = P.msg_ho + (size_t)n * H * D;
+        const float* g_oh = P.msg_oh + (size_t)n * O * D;
+        const float* g_oo = P.msg_oo + (size_t)n * O * D;
+        const int n_hh = P.hh ? H * H : 0, n_oh = H * O, n_ho = O * H, n_oo = O * O;
+        for (int p = warp; p < n_hh + n_oh + n_ho + n_oo; p += 8) {
+            const float* a; const float* m; float* dst; float f = 1.0f;
+            int q = p;
+            if (q < n_hh) { const int h = q / H, j = q % H; a = dmh + h * nkh * D; m = g_hh + j * D; dst = &d_hh[h * FB_MAXE + j]; if (j == h) f = 0.0f; }
+            else if ((q -= n_hh) < n_oh) { const int h = q / O, k = q % O; a = dmh + h * nkh * D + (nkh - 1) * D; m = g_oh + k * D; dst = &d_oh[h * FB_MAXE + k]; f = om[k]; }
+            else if ((q -= n_oh) < n_ho) { const int k = q / H, h = q % H; a = dmo + k * 3 * D; m = g_ho + h * D; dst = &d_ho[k * FB_MAXE + h]; f = om[k]; }
+            else { q -= n_ho; const int k = q / O, j = q % O; a = dmo + k * 3 * D + 2 * D; m = g_oo + j * D; dst = &d_oo[k * FB_MAXE + j]; f = (j == k) ? 0.0f : om[j]; }
+            float acc = 0.0f;
+            for (int c = lane; c < D; c += 32) acc = fmaf(a[c], __ldg(m + c), acc);
+            acc = warp_sum(acc);
+            if (lane == 0) *dst = acc * f;
+        }
+    }
+    __syncthreads();
+    // ---- softmax backward -> d logits (kept in the d_* arrays), scale 1/sqrt(2D) -------------------------------------------
+    if (tid < 2 * NE) {
+        const int e = tid % NE;
+        const bool second = tid >= NE, recv_h = e < H;
+        const int r = recv_h ? e : e - H;
+        const int Es = second ? O : H;
+        float* al = recv_h ? (second ? a_oh : a_hh) : (second ? a_oo : a_ho);
+        float* dd = recv_h ? (second ? d_oh : d_hh) : (second ? d_oo : d_ho);
+        if (!(recv_h && !second && !P.hh)) {
+            const float scale = 1.0f / sqrtf((float)D2);
+            float dot = 0.0f;
+            for (int sd = 0; sd < Es; ++sd) dot = fmaf(al[r * FB_MAXE + sd], dd[r * FB_MAXE + sd], dot);
+            for (int sd = 0; sd < Es; ++sd) dd[r * FB_MAXE + sd] = al[r * FB_MAXE + sd] * (dd[r * FB_MAXE + sd] - dot) * scale;
+        }
+    }
+    __syncthreads();
+    // symmetric coefficient matrix of the logit gradients: d s[e1] += sum_e2 cm[e1][e2] s[e2]
+    for (int i = tid; i < NE * NE; i += 256) {
+        const int e1 = i / NE, e2 = i - e1 * NE;
+        float v = 0.0f;
+        if (e1 < H && e2 < H) { if (P.hh && e1 != e2) v = d_hh[e1 * FB_MAXE + e2] + d_hh[e2 * FB_MAXE + e1]; }
+        else if (e1 < H) v = d_oh[e1 * FB_MAXE + (e2 - H)] + d_ho[(e2 - H) * FB_MAXE + e1];
+        else if (e2 < H) v = d_oh[e2 * FB_MAXE + (e1 - H)] + d_ho[(e1 - H) * FB_MAXE + e2];
+        else if (e1 != e2) v = d_oo[(e1 - H) * FB_MAXE + (e2 - H)] + d_oo[(e2 - H) * FB_MAXE + (e1 - H)];
+        cm[e1 * 2 * FB_MAXE + e2] = v;
+    }
+    __syncthreads();
+    // ---- outputs: d messages per sender, d[x|h] per entity ---------------------------------------------------------------
+    for (int i = tid; i < H * D; i += 256) {
+        const int h = i / D, c = i - h * D;
+        if (P.hh) {
+            float v = 0.0f;
+            for (int r = 0; r < H; ++r)
+                if (r != h) v = fmaf(a_hh[r * FB_MAXE + h], dmh[r * nkh * D + c], v);
+            P.dmsg_hh[(size_t)n * H * D + i] = v;
+        }
+        float w = 0.0f;
+        for (int k = 0; k < O; ++k) w = fmaf(om[k] * a_ho[k * FB_MAXE + h], dmo[k * 3 * D + c], w);
+        P.dmsg_ho[(size_t)n * H * D + i] = w;
+    }
+    for (int i = tid; i < O * D; i += 256) {
+        const int k = i / D, c = i - k * D;
+        float v = 0.0f;
+        for (int h = 0; h < H; ++h) v = fmaf(a_oh[h * FB_MAXE + k], dmh[h * nkh * D + (nkh - 1) * D + c], v);
+        P.dmsg_oh[(size_t)n * O * D + i] = v * om[k];
+        float w = 0.0f;
+        for (int r = 0; r < O; ++r)
+            if (r != k) w = fmaf(a_oo[r * FB_MAXE + k], dmo[r * 3 * D + 2 * D + c], w);
+        P.dmsg_oo[(size_t)n * O * D + i] = w * om[k];
+    }
+    for (int c = tid; c < D; c += 256) {
+        float v = 0.0f;
+        for (int k = 0; k < O; ++k) v = fmaf(om[k], dmo[k * 3 * D + D + c], v);
+        P.dmsg_go[(size_t)n * D + c] = v;
+    }
+    for (int i = tid; i < NE * D2; i += 256) {
+        const int e = i / D2, c = i - e * D2;
+        float v = ds[i];
+        for (int e2 = 0; e2 < NE; ++e2) v = fmaf(cm[e * 2 * FB_MAXE + e2], sv[e2 * D2 + c], v);
+        if (e < H) P.ds_h[(size_t)n * H * D2 + i] = v;
+        else P.ds_o[(size_t)n * O * D2 + (i - H * D2)] = v;
+    }
+}
+
+int launch_frame_bwd(const FrameBwdParams& P, cudaStream_t stream) {
+    TG_REQUIRE(P.H <= FB_MAXE && P.O <= FB_MAXE, "frame_bwd: at most %d humans / objects", FB_MAXE);
+    const int nkh = P.hh ? 2 : 1;
+    const size_t smem = sizeof(float) * ((size_t)(P.H + P.O) * 4 * P.D + (size_t)P.H * nkh * P.D + (size_t)P.O * 3 * P.D);
+    TG_REQUIRE(smem <= 200 * 1024, "frame_bwd: shape needs %zu bytes of shared memory", smem);
+    static size_t configured = 0;
+    if (smem > configured) {
+        TG_CUDA_OK(cudaFuncSetAttribute(frame_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = smem;
+    }
+    frame_bwd_kernel<<<P.B * P.T, 256, smem, stream>>>(P);
+    TG_LAUNCH_OK();
+    return 0;
+}
+
+}  // namespace tg

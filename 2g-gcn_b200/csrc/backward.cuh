@@ -1,0 +1,83 @@
+// Parameter blocks and launchers of the hand-written backward kernels (backward.cu, geo_gcn_bwd.cu).
+#pragma once
+#include "common.cuh"
+
+namespace tg {
+
+// ---- label heads: Linear(2D->C) + LogSoftmax, gathered through the reorder index (models.py:909-917) -------------
+struct HeadsBwdParams {
+    int B, T, E, NE, e_off, D, C;
+    const float* hfr;        // (B,T,E,2D) frame-level BiGRU outputs (input of the two frame heads)
+    const float* hx;         // (B,T,E,2D) segment states (input of the two segment heads, through reidx)
+    const int* reidx;        // (B,T,NE)
+    const float* w[4];       // frame_rec, frame_pred, seg_rec, seg_pred weights (C,2D)
+    const float* bias[4];
+    const float* dlogp[4];   // upstream gradients (B,C,T,E); null = no gradient for that head
+    float* dw[4];            // (C,2D)  accumulated with atomics: zero before the launch
+    float* db[4];            // (C)
+    float* dhfr;             // (B,T,E,2D) accumulated with atomics
+    float* dhx;              // (B,T,E,2D) accumulated with atomics
+};
+int launch_heads_bwd(const HeadsBwdParams& P, cudaStream_t stream);
+
+// ---- segment-level recurrent graph, one reverse step (models.py:785-880) ------------------------------------------
+struct SegBwdParams {
+    int B, T, H, O, D, hh, nk_h;
+    const float* hx_h; const float* hx_o;          // forward states (B,T,E,2D)
+    const float* sgates_h; const float* sgates_o;  // (B,T,E,2,4D) r, z, n, hn
+    const float* u_h; const float* u_o;            // hard gates (B,T,E)
+    const float* om;                               // (B,O)
+    const float* dhx_h; const float* dhx_o;        // upstream gradient of the states (B,T,E,2D)
+    float* dgs_h; float* dgs_o;                    // (B,T,E,2,3D) gradient of the hoisted pre-activations (= of W_ih x + b_ih)
+    float* dghs_h; float* dghs_o;                  // (B,T,E,2,3D) gradient of W_hh h + b_hh
+    float* du_h; float* du_o;                      // (B,T,E) gradient of the hard gates (atomics; zero before the loop)
+    // per-step dense staging (one step, both directions)
+    float* carry_h[2]; float* carry_o[2];          // ping-pong [2 dirs][rows][D]: gradient flowing into the previous state
+    float* dgi_h; float* dgi_o;                    // [2][rows][3D] dense copies of this step's dGi / dGh (GEMM operands)
+    float* dgh_h; float* dgh_o;
+    float* dmg_h; float* dmg_o;                    // [2][rows][nk*D] gradient of the aggregated messages (GEMM output)
+    float* dpre_h; float* dpre_o;                  // [2][rows_sender][2D]: [hh | ho] for human senders, [oh | oo] for objects
+    const float* smsg[4]; const float* salpha[4];  // saved messages / attention weights (kinds hh, oh, ho, oo)
+    float* dpre_all[4];                            // per kind [dir][b][t][sender][D]: for the message weight gradients
+};
+int launch_seg_cell_bwd(const SegBwdParams& P, int s, cudaStream_t stream);
+int launch_seg_msg_bwd(const SegBwdParams& P, int s, cudaStream_t stream);
+
+// ---- frame-level graph: attention, aggregation, gates (models.py:664-749, :1004-1533; distributions.py:4-36) ---------
+struct FrameBwdParams {
+    int B, T, H, O, D, hh, filter;
+    float thr;
+    const float* s_h; const float* s_o;            // (B,T,E,2D)
+    const float* msg_hh; const float* msg_ho; const float* msg_oh; const float* msg_oo; const float* msg_go;
+    const float* om;
+    const float* w_uh; const float* w_uo;          // gate weights
+    const float* alpha; const float* pgate;        // saved by the forward
+    const float* y_hss; const float* y_oss;        // soft gates (forward outputs)
+    const float* human_seg; const float* object_seg;   // given segmentations (then no gate gradient)
+    const float* xx_h; const float* xx_o;          // forward segment-level inputs [h, m..] (gate inputs are read from here)
+    const float* dxx_h; const float* dxx_o;        // gradient of the segment-level inputs
+    const float* du_h; const float* du_o;          // gradient of the hard gates from the segment loop
+    const float* dy_hs; const float* dy_os;        // direct upstream gradient of the hard-gate outputs (may be null)
+    const float* dy_hss; const float* dy_oss;      // direct upstream gradient of the soft-gate outputs (may be null)
+    float* ds_h; float* ds_o;                      // (B,T,E,2D) written
+    float* dmsg_hh; float* dmsg_ho; float* dmsg_oh; float* dmsg_oo; float* dmsg_go;   // (B,T,E,D) written
+    float* dw_uh; float* db_uh; float* dw_uo; float* db_uo;   // accumulated with atomics: zero before the launch
+};
+int launch_frame_bwd(const FrameBwdParams& P, cudaStream_t stream);
+
+// ---- geometry GCN (models_gcn.py:30-100) -----------------------------------------------------------------------------
+struct GcnBwdParams {
+    const float* xh; int B, T, H, V, Fh;
+    const float* mean; const float* var;           // the statistics the forward normalised with
+    const float* gamma; const float* beta;
+    const float* w1; const float* b1; const float* w3; const float* b3;
+    const float* ws1; const float* bs1; const float* ws2; const float* bs2; const float* wg;
+    const float* dout;                             // (B,128,V,T)
+    float* dwg; float* dws1; float* dbs1; float* dws2; float* dbs2; float* dw3; float* db3; float* dw1; float* db1;   // atomics
+    float* dxn;                                    // (B*T, V, 4) gradient of the normalised input (BN backward is a second pass)
+};
+int launch_geo_gcn_bwd(const GcnBwdParams& P, cudaStream_t stream);
+int launch_geo_bn_bwd(const float* xh, const float* dxn, const float* mean, const float* var, const float* gamma, float* dgamma,
+                      float* dbeta, int B, int T, int H, int V, int Fh, cudaStream_t stream);
+
+}  // namespace tg

@@ -52,6 +52,12 @@ struct SegParams {
     float* mg_h;                  // (2,B,H,nk_h*D) aggregated segment messages per direction
     float* mg_o;                  // (2,B,O,2D)
     float* att_f; float* att_b;   // (B,H,T,O) or null
+    // saved for the backward (null / mg_T == 1 in inference): see tggcn_backward
+    int mg_T;                     // T: mg_* hold every step [dir][b][t][e][..]; 1: a single step is kept
+    float* sgates_h;              // (B,T,H,2,4D) r, z, n, hn of the human cells
+    float* sgates_o;              // (B,T,O,2,4D)
+    float* smsg[4];               // per kind (hh, oh, ho, oo): [dir][b][t][sender][D] post-ReLU messages
+    float* salpha[4];             // per kind: [dir][b][t][receiver][sender] attention weights
     // tiling (filled by the launcher)
     int nk_h;                     // message kinds feeding the human cell (2 with hh, else 1)
     int bbv[4], n_vb[4];          // per message kind: videos per message tile, number of video blocks

@@ -86,6 +86,10 @@ __global__ void __launch_bounds__(FM_THREADS) frame_messages_kernel(const FrameM
                 const float a = out[r * FM_MAXE + sdr] * inv;
                 out[r * FM_MAXE + sdr] = a;
                 if (recv_h && second && P.att_frame != nullptr) P.att_frame[((size_t)(b * H + r) * T + t) * O + sdr] = a;
+                if (P.alpha_save != nullptr) {
+                    const int off = recv_h ? (second ? H * H : 0) : (second ? H * H + 2 * H * O : H * H + H * O);
+                    P.alpha_save[(size_t)n * (H * H + 2 * H * O + O * O) + off + r * Es + sdr] = a;
+                }
             }
         }
     }
@@ -169,6 +173,7 @@ __global__ void __launch_bounds__(FM_THREADS) frame_messages_kernel(const FrameM
         if (lane == 0) {
             const float logit = acc + __ldg(is_h ? P.b_uh : P.b_uo);
             const float p = 1.0f / (1.0f + expf(-logit));
+            if (P.pgate_save != nullptr) P.pgate_save[(size_t)n * NE + e] = p;
             const int pos = is_h ? r : (P.human_seg ? 0 : H) + r;
             const float* g = P.noise + ((size_t)(t * n_sampled + pos) * P.B + b) * 2;
             const float la = logf(p + 1e-20f) + __ldg(g);

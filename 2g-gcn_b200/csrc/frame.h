@@ -24,6 +24,9 @@ struct FrameMsgParams {
     float* xx_o;            // (B,T,O,4D)
     float* y_hs; float* y_hss; float* y_os; float* y_oss;
     float* att_frame;       // (B,H,T,O) or null
+    // saved for the backward (null in inference)
+    float* alpha_save;      // (B*T, H*H + H*O + O*H + O*O): a_hh | a_oh | a_ho | a_oo, row-major [receiver][sender]
+    float* pgate_save;      // (B*T, H+O): sigmoid probability of every sampled gate
 };
 
 struct HeadsParams {

@@ -94,7 +94,10 @@ __device__ __forceinline__ void seg_message_tile(const SegParams& P, int tile, i
 #pragma unroll
         for (int g = 0; g < MSG_NG; ++g) {
             const int c = g * REC_J + j;
-            sh.msg[row * MSG_LDM + c] = fmaxf(acc[g][0] + bias[g], 0.0f);
+            const float mv = fmaxf(acc[g][0] + bias[g], 0.0f);
+            sh.msg[row * MSG_LDM + c] = mv;
+            if (P.smsg[kind] != nullptr && row / Es < nb && unit0 + c < D)
+                P.smsg[kind][((((size_t)dir * B + b0 + row / Es) * T + t) * Es + row % Es) * D + unit0 + c] = mv;
         }
         // logit of (receiver j, sender row) when both belong to the same video of the block
         const int blr = j / Er, r = j - blr * Er, bls = row / Es, sdr = row - bls * Es;
@@ -126,6 +129,8 @@ __device__ __forceinline__ void seg_message_tile(const SegParams& P, int tile, i
                 float* att = dir == 0 ? P.att_f : P.att_b;
                 if (att != nullptr) att[((size_t)(b * H + r) * T + t) * O + sdr] = a;
             }
+            if (ub == 0 && P.salpha[kind] != nullptr)
+                P.salpha[kind][((((size_t)dir * B + b) * T + t) * Er + r) * Es + sdr] = a;
         }
     }
     __syncthreads();
@@ -143,7 +148,7 @@ __device__ __forceinline__ void seg_message_tile(const SegParams& P, int tile, i
         float v = 0.0f;
         for (int sdr = 0; sdr < Es; ++sdr) v = fmaf(al[sdr], ms[sdr * MSG_LDM], v);
         const int r = br - bl * Er;
-        mg[(((size_t)dir * B + b0 + bl) * Er + r) * nk_r * D + slot * D + u] = v;
+        mg[((((size_t)dir * B + b0 + bl) * P.mg_T + (P.mg_T > 1 ? t : 0)) * Er + r) * nk_r * D + slot * D + u] = v;
     }
 }
 
@@ -180,9 +185,9 @@ __device__ __forceinline__ void seg_cell_tile(const SegParams& P, bool is_h, int
         const float* p1 = nullptr;
         const float* p2 = nullptr;
         if (r < rows) {
-            p1 = mgbase + ((size_t)dir * rows + r) * nk * D;
+            const int b = r / E, e = r - b * E;
+            p1 = mgbase + ((((size_t)dir * B + b) * P.mg_T + (P.mg_T > 1 ? t : 0)) * E + e) * nk * D;
             if (s > 0) {
-                const int b = r / E, e = r - b * E;
                 p2 = hx + ((size_t)(b * T + tprev) * E + e) * 2 * D + dir * D;
             }
         }
@@ -197,6 +202,8 @@ __device__ __forceinline__ void seg_cell_tile(const SegParams& P, bool is_h, int
     float bh[3] = {0.f, 0.f, 0.f}, xg[NPAIR][3], hprev[NPAIR], ug[NPAIR];
     bool valid[NPAIR];
     size_t orow[NPAIR];
+    float* gsave[NPAIR];
+    float* sg = is_h ? P.sgates_h : P.sgates_o;
     if (unit < D) { bh[0] = __ldg(bhh + unit); bh[1] = __ldg(bhh + D + unit); bh[2] = __ldg(bhh + 2 * D + unit); }
 #pragma unroll
     for (int p = 0; p < NPAIR; ++p) {
@@ -204,6 +211,7 @@ __device__ __forceinline__ void seg_cell_tile(const SegParams& P, bool is_h, int
         valid[p] = unit < D && r < rows && lr < RBT;
         xg[p][0] = xg[p][1] = xg[p][2] = hprev[p] = ug[p] = 0.0f;
         orow[p] = 0;
+        gsave[p] = nullptr;
         if (valid[p]) {
             const int b = r / E, e = r - b * E;
             const size_t fe = (size_t)(b * T + t) * E + e;
@@ -212,6 +220,7 @@ __device__ __forceinline__ void seg_cell_tile(const SegParams& P, bool is_h, int
             ug[p] = __ldg(ub_ + fe);
             if (s > 0) hprev[p] = ld_cg(hx + ((size_t)(b * T + tprev) * E + e) * 2 * D + dir * D + unit);
             orow[p] = fe * 2 * D + dir * D + unit;
+            if (sg != nullptr) gsave[p] = sg + (fe * 2 + dir) * 4 * D + unit;
         }
     }
     __syncthreads();
@@ -223,7 +232,7 @@ __device__ __forceinline__ void seg_cell_tile(const SegParams& P, bool is_h, int
     for (int p = 0; p < NPAIR; ++p) {
         if (!valid[p]) continue;
         const float hnew = gru_update(xg[p][0] + acc[0][p], xg[p][1] + acc[1][p], xg[p][2] + acc[2][p], bh[0], bh[1],
-                                      acc[3][p] + bh[2], hprev[p]);
+                                      acc[3][p] + bh[2], hprev[p], gsave[p], D);
         hx[orow[p]] = ug[p] * hnew + (1.0f - ug[p]) * hprev[p];
     }
 }
@@ -266,6 +275,7 @@ int launch_segment(SegParams& P, int persistent, cudaStream_t stream) {
     const int maxE = H > O ? H : O;
     TG_REQUIRE(maxE <= 16, "segment: at most 16 entities per type supported (got %d)", maxE);
     P.nk_h = P.hh ? 2 : 1;
+    if (P.mg_T < 1) P.mg_T = 1;
     const int nub_msg = cdiv(D, MSG_UNITS);
     int begin = 0;
     for (int k = 0; k < 4; ++k) {

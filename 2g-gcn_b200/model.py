@@ -66,6 +66,29 @@ def _geo_gcn_holder(node_n: int) -> nn.Module:
     return root
 
 
+
+class _ForwardBackward(torch.autograd.Function):
+    """Training-mode bridge: forward = tggcn_forward with dims.save_for_backward, backward = tggcn_backward
+    (the hand-written backward kernels).  Inputs after the first two are the parameters of the weight table that
+    can receive a gradient, so the unchanged ``loss.backward()`` / ``optimizer.step()`` of
+    pyrutils/torch/train_utils.py:150-154 work."""
+
+    @staticmethod
+    def forward(ctx, model, launch, *params):
+        outputs, state = launch()
+        ctx.model, ctx.state = model, state
+        ctx.n_out = len(outputs)
+        nondiff = [o for o, d in zip(outputs, state['differentiable']) if not d]
+        if nondiff:
+            ctx.mark_non_differentiable(*nondiff)
+        return tuple(outputs)
+
+    @staticmethod
+    def backward(ctx, *gouts):
+        grads = ctx.model._backward(ctx.state, gouts)
+        return (None, None) + tuple(grads)
+
+
 class TGGCN(nn.Module):
     """B200-native 2G-GCN.  See module docstring; argument meaning as in vhoi/models.py:191-233."""
 
@@ -171,6 +194,8 @@ class TGGCN(nn.Module):
         self._ptr_cache = None
         self._ws = {}
         self._noise_override: Optional[torch.Tensor] = None
+        self._generation = 0
+        self.flat_grad = None
         self.persistent_kernels = True      # False: one launch per recurrent step (debug aid)
         self.gemm_path = 2                  # 0: fp32 SIMT projections; 1: tcgen05 3xTF32; 2: tcgen05 where K % 32 == 0
 
@@ -202,12 +227,18 @@ class TGGCN(nn.Module):
         self._ptr_cache = (probe, arr)
         return arr
 
-    def _workspace(self, dims: abi.Dims, device):
-        key = (dims.B, dims.T, dims.H, dims.O, device)
+    def _workspace(self, dims: abi.Dims, device, backward: bool = False):
+        key = (dims.B, dims.T, dims.H, dims.O, dims.save_for_backward, backward, device)
         ws = self._ws.get(key)
         if ws is None:
-            ws = torch.empty(abi.workspace_bytes(dims), dtype=torch.uint8, device=device)
-            if len(self._ws) > 4:
+            if backward:
+                nbytes = int(abi.lib().tggcn_backward_workspace_bytes(C.byref(dims)))
+                if nbytes == 0:
+                    raise abi.TggcnError('tggcn_backward_workspace_bytes: ' + abi.lib().tggcn_last_error().decode(errors='replace'))
+            else:
+                nbytes = abi.workspace_bytes(dims)
+            ws = torch.empty(nbytes, dtype=torch.uint8, device=device)
+            if len(self._ws) > 8:
                 self._ws.clear()
             self._ws[key] = ws
         return ws
@@ -244,13 +275,14 @@ class TGGCN(nn.Module):
             raise NotImplementedError('distance-based attention (misc.make_attention_distance_based) is not supported')
         if not x_human.is_cuda:
             raise abi.TggcnError('2G-GCN B200 path runs on a CUDA device only (no CPU fallback); got a CPU tensor')
-        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
-            raise NotImplementedError('backward kernels are not built yet: call forward under torch.no_grad()')
         dev = x_human.device
         B, T, H, Fh = x_human.shape
         O = x_objects.size(2)
         n_sub, n_aff = self.num_classes
         f32 = dict(dtype=torch.float32, device=dev)
+        with_grad = torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters())
+        if with_grad and (inspect_model or stage_ms is not None):
+            raise NotImplementedError('inspect_model / stage profiling are inference-only: call under torch.no_grad()')
 
         def prep(t):
             return t if (t.dtype == torch.float32 and t.is_contiguous()) else t.contiguous().float()
@@ -263,7 +295,8 @@ class TGGCN(nn.Module):
                         filter=int(self.filter_discrete_updates), bn_train=int(self.training),
                         human_seg_given=int(hseg is not None), object_seg_given=int(oseg is not None),
                         inspect=int(bool(inspect_model)), persistent=int(self.persistent_kernels),
-                        gemm_path=int(self.gemm_path), thr=self.update_segment_threshold)
+                        gemm_path=int(self.gemm_path), thr=self.update_segment_threshold,
+                        save_for_backward=int(with_grad))
         n_sampled = (0 if hseg is not None else H) + (0 if oseg is not None else O)
         noise = None
         if n_sampled:
@@ -274,47 +307,133 @@ class TGGCN(nn.Module):
                 raise ValueError(f'gumbel noise must have shape {(T * n_sampled, B, 2)}, got {tuple(noise.shape)}')
             noise = noise.to(device=dev, dtype=torch.float32, non_blocking=True).contiguous()
 
-        y_hs, y_hss = torch.empty(B, T, H, **f32), torch.empty(B, T, H, **f32)
-        y_os, y_oss = torch.empty(B, T, O, **f32), torch.empty(B, T, O, **f32)
-        out_h = [torch.empty(B, n_sub, T, H, **f32) for _ in range(4)]
-        out_o = [torch.empty(B, n_aff, T, O, **f32) for _ in range(4)] if n_aff is not None else []
-        att = [torch.zeros(B, H, T, O, **f32) for _ in range(3)] if inspect_model else []
+        def launch():
+            y_hs, y_hss = torch.empty(B, T, H, **f32), torch.empty(B, T, H, **f32)
+            y_os, y_oss = torch.empty(B, T, O, **f32), torch.empty(B, T, O, **f32)
+            out_h = [torch.empty(B, n_sub, T, H, **f32) for _ in range(4)]
+            out_o = [torch.empty(B, n_aff, T, O, **f32) for _ in range(4)] if n_aff is not None else []
+            att = [torch.zeros(B, H, T, O, **f32) for _ in range(3)] if inspect_model else []
 
-        io = abi.IO()
-        io.x_human, io.x_objects, io.objects_mask = x_human.data_ptr(), x_objects.data_ptr(), objects_mask.data_ptr()
-        io.human_seg = hseg.data_ptr() if hseg is not None else None
-        io.object_seg = oseg.data_ptr() if oseg is not None else None
-        io.noise = noise.data_ptr() if noise is not None else None
-        io.y_hs, io.y_hss, io.y_os, io.y_oss = y_hs.data_ptr(), y_hss.data_ptr(), y_os.data_ptr(), y_oss.data_ptr()
-        for i in range(4):
-            io.out_h[i] = out_h[i].data_ptr()
-            io.out_o[i] = out_o[i].data_ptr() if out_o else None
-        if inspect_model:
-            io.att_frame, io.att_seg_f, io.att_seg_b = (a.data_ptr() for a in att)
-        bn = self.geometry_embedding_gcn.joint_embed.cnn[0].bn
-        io.bn_running_mean, io.bn_running_var = bn.running_mean.data_ptr(), bn.running_var.data_ptr()
-        io.bn_num_batches = bn.num_batches_tracked.data_ptr()
+            io = abi.IO()
+            io.x_human, io.x_objects, io.objects_mask = x_human.data_ptr(), x_objects.data_ptr(), objects_mask.data_ptr()
+            io.human_seg = hseg.data_ptr() if hseg is not None else None
+            io.object_seg = oseg.data_ptr() if oseg is not None else None
+            io.noise = noise.data_ptr() if noise is not None else None
+            io.y_hs, io.y_hss, io.y_os, io.y_oss = y_hs.data_ptr(), y_hss.data_ptr(), y_os.data_ptr(), y_oss.data_ptr()
+            for i in range(4):
+                io.out_h[i] = out_h[i].data_ptr()
+                io.out_o[i] = out_o[i].data_ptr() if out_o else None
+            if inspect_model:
+                io.att_frame, io.att_seg_f, io.att_seg_b = (a.data_ptr() for a in att)
+            bn = self.geometry_embedding_gcn.joint_embed.cnn[0].bn
+            io.bn_running_mean, io.bn_running_var = bn.running_mean.data_ptr(), bn.running_var.data_ptr()
+            io.bn_num_batches = bn.num_batches_tracked.data_ptr()
 
-        ws = self._workspace(dims, dev)
+            ws = self._workspace(dims, dev)
+            weights = self._weight_pointers(dev)
+            with torch.cuda.device(dev):
+                stream = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+                if stage_ms is None:
+                    rc = abi.lib().tggcn_forward(C.byref(dims), weights, abi.N_WEIGHTS, C.byref(io), ws.data_ptr(),
+                                                 ws.numel(), stream)
+                else:
+                    rc = abi.lib().tggcn_forward_profile(C.byref(dims), weights, abi.N_WEIGHTS, C.byref(io), ws.data_ptr(),
+                                                         ws.numel(), stream, stage_ms)
+            abi.check(rc, 'tggcn_forward')
+            # keep inputs alive until the queued work ran
+            keep = (x_human, x_objects, objects_mask, hseg, oseg, noise)
+            self._last = (dims, ws, keep)
+            if n_aff is None:
+                output = [y_hs, y_hss] + out_h
+                diff = [hseg is None, hseg is None] + [True] * 4
+            else:
+                output = [y_hs, y_os, y_hss, y_oss] + out_h[:2] + out_o[:2] + out_h[2:] + out_o[2:]
+                diff = [hseg is None, oseg is None, hseg is None, oseg is None] + [True] * 8
+            self._generation += 1
+            state = dict(dims=dims, io=io, ws=ws, keep=keep, gates=(y_hs, y_hss, y_os, y_oss), differentiable=diff,
+                         generation=self._generation)
+            return output, (att if inspect_model else state)
+
+        if not with_grad:
+            output, att = launch()
+            return (output, att) if inspect_model else output
+        names, params = self._trainable_table(dims)
+        self._grad_names = names
+        return list(_ForwardBackward.apply(self, launch, *params))
+
+    def _trainable_table(self, dims):
+        """Parameters of the weight table that are on the gradient path of this call (the others keep grad=None,
+        like the 22-24 dead tensors of the reference)."""
+        names, params = [], []
+        for name, prm in self.named_parameters():
+            if name not in abi.WEIGHT_INDEX:
+                continue                       # *_att_mlp, geometry_to_object_segment_message_mlp: never used
+            if name.startswith('update_human_segment_mlp') and dims.human_seg_given:
+                continue
+            if name.startswith('update_object_segment_mlp') and dims.object_seg_given:
+                continue
+            names.append(name)
+            params.append(prm)
+        return names, params
+
+    def _backward(self, state, gouts):
+        """tggcn_backward on the workspace of the matching forward.  Returns one gradient per tensor of
+        ``_trainable_table`` (views into one flat buffer, ``self.flat_grad``, so that a data-parallel
+        driver can all-reduce it in a single call)."""
+        if state['generation'] != self._generation:
+            raise abi.TggcnError('backward called after a later training-mode forward reused the workspace; '
+                                 'run forward -> backward one at a time')
+        dims, io, ws = state['dims'], state['io'], state['ws']
+        dev = ws.device
+        names, params = self._trainable_table(dims)
+        sizes = [p.numel() for p in params]
+        offs, total = [], 0
+        for n in sizes:
+            offs.append(total)
+            total += (n + 3) // 4 * 4                    # keep every gradient 16-byte aligned
+        flat = torch.empty(total, dtype=torch.float32, device=dev)
+        grads = [flat[o:o + n].view(p.shape) for o, n, p in zip(offs, sizes, params)]
+        garr = (C.c_void_p * abi.N_WEIGHTS)()
+        for name, g in zip(names, grads):
+            garr[abi.WEIGHT_INDEX[name]] = g.data_ptr()
+        n_aff = self.num_classes[1]
+
+        def gp(t):
+            if t is None:
+                return None, None
+            t = t if (t.dtype == torch.float32 and t.is_contiguous()) else t.contiguous().float()
+            return t, t.data_ptr()
+        go = abi.GradOutputs()
+        keep = []
+        if n_aff is None:
+            order = {'d_y_hs': 0, 'd_y_hss': 1}
+            heads_h, heads_o = [2, 3, 4, 5], []
+        else:
+            order = {'d_y_hs': 0, 'd_y_os': 1, 'd_y_hss': 2, 'd_y_oss': 3}
+            heads_h, heads_o = [4, 5, 8, 9], [6, 7, 10, 11]
+        for field, i in order.items():
+            if state['differentiable'][i]:
+                t, ptr = gp(gouts[i])
+                keep.append(t)
+                setattr(go, field, ptr)
+        for j, i in enumerate(heads_h):
+            t, ptr = gp(gouts[i])
+            keep.append(t)
+            go.d_out_h[j] = ptr
+        for j, i in enumerate(heads_o):
+            t, ptr = gp(gouts[i])
+            keep.append(t)
+            go.d_out_o[j] = ptr
+        bws = self._workspace(dims, dev, backward=True)
         weights = self._weight_pointers(dev)
         with torch.cuda.device(dev):
             stream = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
-            if stage_ms is None:
-                rc = abi.lib().tggcn_forward(C.byref(dims), weights, abi.N_WEIGHTS, C.byref(io), ws.data_ptr(),
-                                             ws.numel(), stream)
-            else:
-                rc = abi.lib().tggcn_forward_profile(C.byref(dims), weights, abi.N_WEIGHTS, C.byref(io), ws.data_ptr(),
-                                                     ws.numel(), stream, stage_ms)
-        abi.check(rc, 'tggcn_forward')
-        # keep inputs alive until the queued work ran
-        self._last = (dims, ws, (x_human, x_objects, objects_mask, hseg, oseg, noise))
-        if n_aff is None:
-            output = [y_hs, y_hss] + out_h
-        else:
-            output = [y_hs, y_os, y_hss, y_oss] + out_h[:2] + out_o[:2] + out_h[2:] + out_o[2:]
-        if inspect_model:
-            return output, att
-        return output
+            rc = abi.lib().tggcn_backward(C.byref(dims), weights, garr, abi.N_WEIGHTS, C.byref(io), C.byref(go), ws.data_ptr(),
+                                          ws.numel(), bws.data_ptr(), bws.numel(), stream)
+        abi.check(rc, 'tggcn_backward')
+        self._last_bwd = (keep, bws)
+        self.flat_grad = flat
+        return grads
 
     # -- debugging / test helpers ----------------------------------------------------------------------
     def workspace_tensor(self, name: str, shape, dtype=torch.float32) -> torch.Tensor:

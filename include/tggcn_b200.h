@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define TGGCN_ABI_VERSION 1
+#define TGGCN_ABI_VERSION 2
 
 #if defined(__GNUC__)
 #define TGGCN_API __attribute__((visibility("default")))
@@ -48,6 +48,7 @@ typedef struct tggcn_dims {
     int32_t persistent;          /* 1 = persistent cooperative recurrent kernels, 0 = one launch per step */
     int32_t gemm_path;           /* projections: 0 = fp32 SIMT, 1 = tcgen05 3xTF32, 2 = tcgen05 where K%32==0 */
     float   thr;                 /* update_segment_threshold                                             */
+    int32_t save_for_backward;   /* forward also stores what tggcn_backward needs (bigger workspace)     */
 } tggcn_dims;
 
 /* Parameter table.  One device pointer per reference state_dict() entry, in this order
@@ -216,6 +217,24 @@ enum tggcn_buf_id {
     TGGCN_BUF_REIDX,         /* (B,T,H+O) int32      reorder gather index, models.py:1567-1586           */
     TGGCN_BUF_SEG_SCRATCH,   /* per-step message scratch of the segment kernel                            */
     TGGCN_BUF_SYNC,          /* grid-barrier counters + error flag                                        */
+    /* saved for the backward (empty unless dims.save_for_backward) */
+    TGGCN_BUF_GATES_H,       /* (B,T,H,2,4D)         BiGRU gates r, z, n, W_hn h + b_hn                           */
+    TGGCN_BUF_GATES_O,
+    TGGCN_BUF_GATES_G,
+    TGGCN_BUF_ALPHA_F,       /* (B*T, H*H+2*H*O+O*O) frame-level attention weights                                */
+    TGGCN_BUF_PGATE,         /* (B*T, H+O)           sigmoid probability of the sampled gates                     */
+    TGGCN_BUF_SGATES_H,      /* (B,T,H,2,4D)         segment-cell gates                                           */
+    TGGCN_BUF_SGATES_O,
+    TGGCN_BUF_MG_ALL_H,      /* (2,B,T,H,nk*D)       aggregated segment messages of every step                    */
+    TGGCN_BUF_MG_ALL_O,      /* (2,B,T,O,2D)                                                                      */
+    TGGCN_BUF_SMSG_HH,       /* (2,B,T,senders,D)    per-sender segment messages (post-ReLU), kinds hh, oh, ho, oo */
+    TGGCN_BUF_SMSG_OH,
+    TGGCN_BUF_SMSG_HO,
+    TGGCN_BUF_SMSG_OO,
+    TGGCN_BUF_SALPHA_HH,     /* (2,B,T,receivers,senders) segment-level attention weights                         */
+    TGGCN_BUF_SALPHA_OH,
+    TGGCN_BUF_SALPHA_HO,
+    TGGCN_BUF_SALPHA_OO,
     TGGCN_BUF_COUNT
 };
 
@@ -274,6 +293,23 @@ TGGCN_API int tggcn_geo_gcn_fwd(const float* x_human, const void* const* weights
  * (build_mlp, pyrutils/torch/models.py:31-33).  gemm_path as in tggcn_dims. */
 TGGCN_API int tggcn_linear_fwd(const float* A, int lda, const float* W, int ldw, const float* bias, float* C, int ldc,
                      int M, int N, int K, int relu, int gemm_path, void* stream);
+
+/* Upstream gradients of the forward's output list (models.py:919-926), same shapes as the outputs; NULL = no gradient. */
+typedef struct tggcn_grad_outputs {
+    const float* d_y_hs;  const float* d_y_hss;   /* (B,T,H) hard / soft human gates                              */
+    const float* d_y_os;  const float* d_y_oss;   /* (B,T,O)                                                      */
+    const float* d_out_h[4];                      /* (B,C_sub,T,H) frame_rec, frame_pred, seg_rec, seg_pred       */
+    const float* d_out_o[4];                      /* (B,C_aff,T,O)                                                */
+} tggcn_grad_outputs;
+
+/* Backward of tggcn_forward (what loss.backward() does through vhoi/models.py:584-933).  The forward must have run with
+ * dims.save_for_backward on the same `workspace`, which must still hold its contents.  `grad_weights` holds TGGCN_W_COUNT
+ * device pointers (same order as `weights`): each non-NULL entry receives the gradient of that parameter (overwritten);
+ * NULL entries are skipped where possible.  `bwd_workspace`: tggcn_backward_workspace_bytes(dims) bytes of scratch. */
+TGGCN_API size_t tggcn_backward_workspace_bytes(const tggcn_dims* dims);
+TGGCN_API int tggcn_backward(const tggcn_dims* dims, const void* const* weights, void* const* grad_weights, int n_weights,
+                             const tggcn_io* io, const tggcn_grad_outputs* grads, void* workspace, size_t workspace_bytes,
+                             void* bwd_workspace, size_t bwd_workspace_bytes, void* stream);
 
 /* Backward of nn.Linear (+ReLU), i.e. what autograd does for y = act(x W^T + b) (pyrutils/torch/models.py:31-33):
  *   Z = dY (.) [Y > 0] (Y = forward output, NULL when there was no ReLU);  dX = Z W (added to dX when beta_dx);

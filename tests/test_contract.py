@@ -52,9 +52,9 @@ def test_library_loads_and_exports_every_declared_symbol(pkg):
     lib = pkg.abi.lib()
     for sym in declared:
         assert hasattr(lib, sym), sym
-    assert lib.tggcn_abi_version() == 1
-    # struct mirrors: 17 int32 + 1 float; io = 6 + 4 + 8 + 3 + 3 pointers
-    assert ctypes.sizeof(pkg.abi.Dims) == 18 * 4
+    assert lib.tggcn_abi_version() == 2
+    # struct mirrors: 17 int32 + 1 float + 1 int32; io = 6 + 4 + 8 + 3 + 3 pointers
+    assert ctypes.sizeof(pkg.abi.Dims) == 19 * 4
     assert ctypes.sizeof(pkg.abi.IO) == 24 * 8
 
 

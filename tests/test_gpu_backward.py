@@ -1,0 +1,135 @@
+"""GPU: the whole training-mode forward + hand-written backward (tggcn_backward through the autograd bridge) against
+(a) the gradients of the unmodified reference (tests/golden/grad_*.npz, oracle/gen_golden.py::run_grad_case) and
+(b) fp64 autograd through the oracle, every parameter tensor in full.  Tolerance: 2e-3 relative to the tensor's
+largest gradient entry (fp32 kernels with 3xTF32 products against fp64)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+GRAD_CASES = {
+    'grad_mphoi_s1': ('mphoi', 32, 2, 9, 1),
+    'grad_mphoi_s2': ('mphoi', 32, 3, 10, 2),
+    'grad_cad120_s2': ('cad120', 32, 2, 8, 2),
+}
+
+
+def _summarize(g):
+    f = g.detach().double().reshape(-1).cpu()
+    if f.numel() <= 4096:
+        return f.numpy()
+    idx = torch.linspace(0, f.numel() - 1, 256).long()
+    return np.concatenate([[float(f.sum()), float(f.abs().sum()), float((f * f).sum())], f[idx].numpy()])
+
+
+def _setup(name, orc, synth, pkg):
+    from golden_util import GOLDEN_DIR
+    shape_name, D, B, T, stage = GRAD_CASES[name]
+    blob = np.load(os.path.join(GOLDEN_DIR, name + '.npz'))
+    data_seed, noise_seed, target_seed, weight_seed = [int(v) for v in blob['meta']]
+    shape = synth.SHAPES[shape_name]
+    kw = synth.model_kwargs(shape, hidden_size=D, stage=stage)
+    model = pkg.TGGCN(**kw)
+    synth.deterministic_fill(model.state_dict(), seed=weight_seed, gain=float(blob['gain'][0]))
+    batch = synth.make_batch(shape, B, T, seed=data_seed)
+    human_given, objects_given = stage == 1, stage == 1 and shape.dataset == 'cad120'
+    n_calls = orc.num_noise_draws(T, shape.H, shape.O, human_given, objects_given)
+    noise = orc.draw_noise(max(n_calls, 1), B, torch.Generator().manual_seed(noise_seed))[:n_calls]
+    hseg = torch.ones(B, T, shape.H) if human_given else None
+    oseg = torch.ones(B, T, shape.O) if objects_given else None
+    targets = synth.target_list(shape, synth.make_targets(shape, batch['lengths'], T, seed=target_seed))
+    ocfg = orc.OracleConfig(D, shape.V, shape.num_classes, shape.hh, stage == 2, kw['update_segment_threshold'])
+    return dict(blob=blob, shape=shape, stage=stage, model=model, batch=batch, noise=noise if n_calls else None, hseg=hseg,
+                oseg=oseg, targets=targets, ocfg=ocfg)
+
+
+def _oracle_grads(c, orc):
+    p = {k: v.detach().double().requires_grad_(v.is_floating_point() and 'running' not in k) if v.is_floating_point() else v
+         for k, v in c['model'].state_dict().items()}
+    b = c['batch']
+    dd = lambda t: None if t is None else t.double()
+    out = orc.forward(p, c['ocfg'], b['x_human'].double(), b['x_objects'].double(), b['objects_mask'].double(), dd(c['hseg']),
+                      dd(c['oseg']), dd(c['noise']), training=True)
+    targets = [t.double() if t.is_floating_point() else t for t in c['targets']]
+    losses = orc.multi_task_loss(out, targets, c['shape'].dataset, c['stage'])
+    sum(losses).backward()
+    return {k: v.grad for k, v in p.items() if torch.is_tensor(v) and v.is_floating_point()}, [float(l) for l in losses]
+
+
+@pytest.mark.parametrize('persistent', [True, False])
+@pytest.mark.parametrize('name', sorted(GRAD_CASES))
+def test_backward_matches_reference_and_oracle(name, persistent, orc, synth, pkg):
+    c = _setup(name, orc, synth, pkg)
+    want_full, want_losses = _oracle_grads(c, orc)
+    blob = c['blob']
+    model = c['model'].cuda().train()
+    model.persistent_kernels = persistent
+    model.set_gumbel_noise(c['noise'])
+    b = c['batch']
+    cu = lambda t: None if t is None else t.cuda()
+    kwargs = dict(x_human=b['x_human'].cuda(), x_objects=b['x_objects'].cuda(), objects_mask=b['objects_mask'].cuda(),
+                  human_segmentation=cu(c['hseg']))
+    if c['oseg'] is not None:
+        kwargs['objects_segmentation'] = cu(c['oseg'])
+    out = model(**kwargs)
+    model.check_persistent_kernels()
+    targets = [t.cuda() for t in c['targets']]
+    losses = orc.multi_task_loss(out, targets, c['shape'].dataset, c['stage'])      # torch ops on our outputs (the unchanged criterion)
+    total = sum(losses)
+    np.testing.assert_allclose(float(total), float(blob['loss'][0]), rtol=1e-4)
+    np.testing.assert_allclose([float(l) for l in losses], want_losses, rtol=1e-4, atol=1e-6)
+    total.backward()
+    torch.cuda.synchronize()
+    none_ref = set(str(k) for k in blob['none_grad_keys'])
+    bad = []
+    for k, prm in model.named_parameters():
+        if k in none_ref:
+            assert prm.grad is None or float(prm.grad.abs().max()) == 0.0, f'{k}: the reference gives no gradient'
+            continue
+        assert prm.grad is not None, f'{k}: gradient missing'
+        got = prm.grad.detach().double().cpu()
+        assert torch.isfinite(got).all(), k
+        want = want_full[k]
+        scale = max(float(want.abs().max()), 1e-6)
+        err = float((got - want).abs().max())
+        if err > 2e-3 * scale + 1e-7:
+            bad.append(f'{k}: max err {err:.3e} vs scale {scale:.3e}')
+            continue
+        ref = blob['grad.' + k]
+        rscale = max(float(np.abs(ref).max()), 1e-6)
+        np.testing.assert_allclose(_summarize(prm.grad), ref, rtol=4e-3, atol=4e-5 * rscale + 1e-7, err_msg=k)
+    assert not bad, '\n'.join(bad)
+
+
+def test_backward_twice_accumulates_and_is_deterministic(orc, synth, pkg):
+    """Two forward/backward rounds without zero_grad double every gradient (autograd accumulation through the bridge);
+    parameters off the gradient path keep grad=None."""
+    c = _setup('grad_mphoi_s2', orc, synth, pkg)
+    model = c['model'].cuda().train()
+    model.set_gumbel_noise(c['noise'])
+    b = c['batch']
+    targets = [t.cuda() for t in c['targets']]
+    grads = []
+    for it in range(2):
+        out = model(x_human=b['x_human'].cuda(), x_objects=b['x_objects'].cuda(), objects_mask=b['objects_mask'].cuda())
+        sum(orc.multi_task_loss(out, targets, 'mphoi', 2)).backward()
+        grads.append({k: p.grad.clone() for k, p in model.named_parameters() if p.grad is not None})
+    for k in grads[0]:
+        scale = float(grads[0][k].abs().max()) + 1e-12
+        err = float((grads[1][k] - 2 * grads[0][k]).abs().max())
+        assert err <= 1e-3 * scale, f'{k}: {err:.3e} vs {scale:.3e}'      # atomics reorder some sums between runs
+    dead = [k for k, p in model.named_parameters() if p.grad is None]
+    assert any('att_mlp' in k for k in dead) and all(('att_mlp' in k or 'geometry_to_object_segment' in k) for k in dead)
+
+
+def test_forward_requires_no_grad_features(orc, synth, pkg):
+    c = _setup('grad_mphoi_s1', orc, synth, pkg)
+    model = c['model'].cuda().train()
+    model.set_gumbel_noise(c['noise'])
+    b = c['batch']
+    with pytest.raises(NotImplementedError):
+        model(x_human=b['x_human'].cuda(), x_objects=b['x_objects'].cuda(), objects_mask=b['objects_mask'].cuda(),
+              human_segmentation=c['hseg'].cuda(), inspect_model=True)

@@ -1,6 +1,7 @@
 // C ABI (include/tggcn_b200.h): workspace layout and the launch sequence of one TGGCN forward
 // (vhoi/models.py:584-933).  No allocation, no device synchronisation, no state between calls.
 #include <stdarg.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 #include "gemm.h"
@@ -18,6 +19,15 @@ void set_error(const char* fmt, ...) {
     va_start(ap, fmt);
     vsnprintf(g_err, sizeof(g_err), fmt, ap);
     va_end(ap);
+}
+
+bool debug_sync() {
+    static int cached = -1;
+    if (cached < 0) {
+        const char* e = getenv("TGGCN_DEBUG_SYNC");
+        cached = (e != nullptr && e[0] == '1') ? 1 : 0;
+    }
+    return cached == 1;
 }
 
 int num_sms() {
@@ -213,6 +223,7 @@ static int forward_impl(const tggcn_dims* dims, const void* const* weights, int 
         ++stage;                                                     \
     } while (0)
     if (ev) TG_CUDA_OK(cudaEventRecord(ev[0], stream));
+    TG_CUDA_OK(cudaMemsetAsync(sync, 0, L.bytes[TGGCN_BUF_SYNC], stream));     // barrier counters + error flags
     // 1. geometry GCN (stored (B,128,V,T); the scrambled view is a reinterpretation as (B*T, 128V))
     if (int rc = launch_geo_gcn(io->x_human, weights, buf(TGGCN_BUF_GCN_OUT), io->bn_running_mean, io->bn_running_var,
                                 io->bn_num_batches, bn_stats, B, T, H, V, d.Fh, d.bn_train, stream))

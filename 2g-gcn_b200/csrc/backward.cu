@@ -50,17 +50,20 @@ __global__ void __launch_bounds__(256) heads_bwd_kernel(const HeadsBwdParams P) 
         const float dz = lane < C ? g - prob * gs : 0.0f;     // d log_softmax
         if (lane < C) atomicAdd(&sdb[lane], dz);
         float* dxrow = (src == 0 ? P.dhfr : P.dhx) + xrow * D2;
-        for (int k = lane * 4; k < D2; k += 128) {
-            const float4 xv = *reinterpret_cast<const float4*>(x + k);
+        for (int k0 = 0; k0 < D2; k0 += 128) {               // warp-uniform trip count: the shuffles need every lane
+            const int k = k0 + lane * 4;
+            const bool ok = k < D2;
+            const float4 xv = ok ? *reinterpret_cast<const float4*>(x + k) : make_float4(0.f, 0.f, 0.f, 0.f);
             float4 dx = make_float4(0.f, 0.f, 0.f, 0.f);
             for (int c = 0; c < C; ++c) {
                 const float dzc = __shfl_sync(0xffffffffu, dz, c);
+                if (!ok) continue;
                 const float4 wv = __ldg(reinterpret_cast<const float4*>(W + (size_t)c * D2 + k));
                 dx.x = fmaf(dzc, wv.x, dx.x); dx.y = fmaf(dzc, wv.y, dx.y); dx.z = fmaf(dzc, wv.z, dx.z); dx.w = fmaf(dzc, wv.w, dx.w);
                 float* d = sdw + c * D2 + k;
                 atomicAdd(d, dzc * xv.x); atomicAdd(d + 1, dzc * xv.y); atomicAdd(d + 2, dzc * xv.z); atomicAdd(d + 3, dzc * xv.w);
             }
-            atomicAdd(dxrow + k, dx.x); atomicAdd(dxrow + k + 1, dx.y); atomicAdd(dxrow + k + 2, dx.z); atomicAdd(dxrow + k + 3, dx.w);
+            if (ok) { atomicAdd(dxrow + k, dx.x); atomicAdd(dxrow + k + 1, dx.y); atomicAdd(dxrow + k + 2, dx.z); atomicAdd(dxrow + k + 3, dx.w); }
         }
     }
     __syncthreads();

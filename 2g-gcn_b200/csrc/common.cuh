@@ -36,10 +36,13 @@ namespace tg {
 
 extern unsigned long long g_launches;
 
+bool debug_sync();   // TGGCN_DEBUG_SYNC=1: synchronise after every launch so an asynchronous fault names its kernel
+
 #define TG_LAUNCH_OK()                                                                          \
     do {                                                                                        \
         ++tg::g_launches;                                                                       \
         cudaError_t _e = cudaGetLastError();                                                    \
+        if (_e == cudaSuccess && tg::debug_sync()) _e = cudaDeviceSynchronize();                \
         if (_e != cudaSuccess) {                                                                \
             tg::set_error("%s:%d: launch failed -> %s", __FILE__, __LINE__, cudaGetErrorString(_e)); \
             return 1;                                                                           \

@@ -120,7 +120,7 @@ def test_backward_twice_accumulates_and_is_deterministic(orc, synth, pkg):
     for k in grads[0]:
         scale = float(grads[0][k].abs().max()) + 1e-12
         err = float((grads[1][k] - 2 * grads[0][k]).abs().max())
-        assert err <= 1e-3 * scale, f'{k}: {err:.3e} vs {scale:.3e}'      # atomics reorder some sums between runs
+        assert err <= 1e-3 * scale + 1e-7, f'{k}: {err:.3e} vs {scale:.3e}'      # atomics reorder some sums; 1e-7: exact-zero gradients
     dead = [k for k, p in model.named_parameters() if p.grad is None]
     assert any('att_mlp' in k for k in dead) and all(('att_mlp' in k or 'geometry_to_object_segment' in k) for k in dead)
 

@@ -432,8 +432,16 @@ class TGGCN(nn.Module):
                                           ws.numel(), bws.data_ptr(), bws.numel(), stream)
         abi.check(rc, 'tggcn_backward')
         self._last_bwd = (keep, bws)
-        self.flat_grad = flat
+        self.flat_grad, self._flat_views = flat, (params, grads)
         return grads
+
+    def bind_flat_grads(self):
+        """Point every trainable parameter's ``.grad`` at its slice of ``flat_grad`` (the buffer the last backward wrote).
+        A data-parallel driver all-reduces ``flat_grad`` once and calls this before ``optimizer.step()``; autograd itself
+        may have copied the slices when it accumulated them."""
+        params, grads = self._flat_views
+        for prm, g in zip(params, grads):
+            prm.grad = g
 
     # -- debugging / test helpers ----------------------------------------------------------------------
     def workspace_tensor(self, name: str, shape, dtype=torch.float32) -> torch.Tensor:

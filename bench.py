@@ -202,6 +202,10 @@ def run_ours(args, rank, world, local_rank):
             _, st = model.forward_profile(resident['x_human'], resident['x_objects'], resident['objects_mask'])
             if i:
                 rows.append(st)
+    train = None
+    if not args.no_train:
+        del model
+        train = train_step_throughput(args, pkg, shape, kwargs, dev, rank, world, flush, barrier)
     frames = world * B * T * args.steps
     value = frames / (total_ms / 1e3)
     e2e_value = frames / (e2e_total_ms / 1e3)
@@ -244,9 +248,68 @@ def run_ours(args, rank, world, local_rank):
         'roofline': roof,
         'stages_ms': {k: round(v, 4) for k, v in stages.items()},
     }
+    if train is not None:
+        line['train_step'] = train
     if world == 1 and not args.no_cpu_baseline:
         line['cpu_baseline'] = cpu_port_throughput(args, shape, kwargs, warmup=1, steps=2)
     print(json.dumps(line), flush=True)
+
+
+def train_step_throughput(args, pkg, shape, kwargs, dev, rank, world, flush, barrier):
+    """One training step = forward (BatchNorm in train mode, activations saved) + the criterion of vhoi/losses.py:8
+    (stage-2 weights: BCE on the soft gates + 2 NLL terms, torch ops on our outputs exactly as the unchanged
+    train_utils.py:147-150 does) + the hand-written backward (tggcn_backward) + gradient all-reduce (N > 1) + Adam."""
+    import torch.distributed as dist
+    sys.path.insert(0, os.path.join(ROOT, 'oracle'))
+    import tggcn_oracle as orc          # loss functions only: the restated criterion, torch ops on device tensors
+    torch.manual_seed(0)
+    model = pkg.TGGCN(**kwargs).to(dev).train()
+    model.gemm_path = args.gemm_path
+    opt = torch.optim.Adam(model.parameters(), lr=1e-4)
+    B, T = args.B, args.T
+    host = pkg.synth.make_batch(shape, B, T, seed=1234 + rank)
+    x = {k: host[k].to(dev) for k in ('x_human', 'x_objects', 'objects_mask')}
+    targets = [t.to(dev) for t in pkg.synth.target_list(shape, pkg.synth.make_targets(shape, host['lengths'], T, seed=77 + rank))]
+    model.set_gumbel_noise(pkg.TGGCN.draw_gumbel_noise(T * (shape.H + shape.O), B).to(dev))
+    lib = pkg.abi.lib()
+
+    def step():
+        opt.zero_grad(set_to_none=True)
+        out = model(**x)
+        loss = sum(orc.multi_task_loss(out, targets, shape.dataset, 2))
+        loss.backward()
+        if world > 1:                                  # data-parallel: one all-reduce of the flat gradient buffer
+            dist.all_reduce(model.flat_grad)
+            model.flat_grad.div_(world)
+            model.bind_flat_grads()
+        opt.step()
+        return loss
+
+    steps, warmup = max(3, min(args.steps, 10)), 3
+    for _ in range(warmup):
+        step()
+    barrier()
+    evs = []
+    l0 = lib.tggcn_launch_count()
+    for _ in range(steps):
+        flush.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        loss = step()
+        e1.record()
+        evs.append((e0, e1))
+    barrier()
+    model.check_persistent_kernels()
+    launches = lib.tggcn_launch_count() - l0
+    total = torch.tensor([sum(a.elapsed_time(b) for a, b in evs)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(total, op=dist.ReduceOp.MAX)
+    ms = float(total.item()) / steps
+    return {'value': world * B * T / (ms / 1e3), 'unit': UNIT, 'ms_per_step': ms, 'steps': steps, 'warmup': warmup,
+            'gpu_launches_per_step': int(launches // steps), 'loss': float(loss.detach()),
+            'what': 'forward(train-mode BN, saves) + criterion (BCE + 2x NLL) + tggcn_backward + '
+                    + ('NCCL all-reduce of the flat gradient + ' if world > 1 else '') + 'torch.optim.Adam step; fp32 (3xTF32 products)',
+            'global_batch_videos': world * B}
 
 
 def cpu_port_throughput(args, shape, kwargs, warmup, steps):
@@ -304,6 +367,7 @@ def main():
     ap.add_argument('--D', type=int, default=512)
     ap.add_argument('--gemm-path', type=int, default=2)
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-train', action='store_true', help='skip the training-step measurement')
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == 'ours' else args.warmup
     rank = int(os.environ.get('RANK', '0'))

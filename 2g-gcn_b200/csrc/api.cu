@@ -142,12 +142,13 @@ int tggcn_sync_status(const tggcn_dims* dims, const void* workspace, void* strea
     if (int rc = check_dims(*dims)) return rc;
     Layout L;
     make_layout(*dims, L);
-    unsigned int flags[4] = {0, 0, 0, 0};
+    unsigned int flags[8] = {0, 0, 0, 0, 0, 0, 0, 0};    // (counter, error) of bigru, segment, bigru_bwd, segment_bwd
     TG_CUDA_OK(cudaMemcpyAsync(flags, (const char*)workspace + L.off[TGGCN_BUF_SYNC], sizeof(flags), cudaMemcpyDeviceToHost,
                                (cudaStream_t)stream));
     TG_CUDA_OK(cudaStreamSynchronize((cudaStream_t)stream));
-    if (flags[1] || flags[3]) {
-        set_error("persistent kernel grid barrier timed out (bigru=%u, segment=%u)", flags[1], flags[3]);
+    if (flags[1] || flags[3] || flags[5] || flags[7]) {
+        set_error("persistent kernel grid barrier timed out (bigru=%u, segment=%u, bigru_bwd=%u, segment_bwd=%u)", flags[1], flags[3],
+                  flags[5], flags[7]);
         return 1;
     }
     return 0;

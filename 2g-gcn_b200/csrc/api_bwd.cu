@@ -13,10 +13,6 @@
 
 using namespace tg;
 
-extern "C" int tggcn_bigru_bwd(const float* dhfr, const float* hfr, const float* gates, const float* whh_f, const float* whh_b,
-                               float* dgi, float* dgh, float* dwhh_f, float* dwhh_b, float* dbhh_f, float* dbhh_b, float* scratch,
-                               int B, int T, int E, int D, int gemm_path, void* stream_);
-extern "C" size_t tggcn_bigru_bwd_scratch_floats(int B, int T, int E, int D);
 
 namespace {
 
@@ -28,7 +24,7 @@ struct BwdLayout {
         total += (n + 63) / 64 * 64;
         return o;
     }
-    size_t dhfr[3], dhx[2], dgs[2], dghs[2], du[2], carry[2][2], dgi_s[2], dgh_s[2], dmg[2], dpre[2], dpre_all[4];
+    size_t dhfr[3], dhx[2], dgs[2], dghs[2], du[2], direct[2], dmg[2], dpre[2], lgr[4], lgs[4], dpre_all[4], gru_direct[3];
     size_t dxx[2], ds[3], dmsg[5], dgi[3], dgh[3], bigru_scratch, dgeo_hid, dgcn_out, dxn, wt_seg, wt;
     size_t zero_begin, zero_end;     // region that must be zero before the kernels run (atomically accumulated)
 };
@@ -46,12 +42,16 @@ void make_bwd_layout(const tggcn_dims& d, BwdLayout& L) {
     for (int g = 0; g < 2; ++g) {
         L.dgs[g] = L.take(N * E[g] * 6 * D);
         L.dghs[g] = L.take(N * E[g] * 6 * D);
-        for (int i = 0; i < 2; ++i) L.carry[g][i] = L.take(2 * B * E[g] * D);
-        L.dgi_s[g] = L.take(2 * B * E[g] * 3 * D);
-        L.dgh_s[g] = L.take(2 * B * E[g] * 3 * D);
+        L.direct[g] = L.take(2 * B * E[g] * D);
         L.dmg[g] = L.take(2 * B * E[g] * (g == 0 ? nkh : 2) * D);
         L.dpre[g] = L.take(2 * B * E[g] * 2 * D);
     }
+    for (int k = 0; k < 4; ++k) {
+        const size_t Er = (k == 0 || k == 1) ? H : O, Es = (k == 0 || k == 2) ? H : O;
+        L.lgr[k] = L.take(2 * B * Er * D);
+        L.lgs[k] = L.take(2 * B * Es * D);
+    }
+    for (int g = 0; g < 3; ++g) L.gru_direct[g] = L.take(2 * B * E[g] * D);
     L.dpre_all[0] = L.take(2 * N * H * D);
     L.dpre_all[1] = L.take(2 * N * O * D);
     L.dpre_all[2] = L.take(2 * N * H * D);
@@ -68,12 +68,7 @@ void make_bwd_layout(const tggcn_dims& d, BwdLayout& L) {
         L.dgi[g] = L.take(N * E[g] * 6 * D);
         L.dgh[g] = L.take(N * E[g] * 6 * D);
     }
-    size_t bs = 0;
-    for (int g = 0; g < 3; ++g) {
-        const size_t s = tggcn_bigru_bwd_scratch_floats(d.B, d.T, (int)E[g], d.D);
-        if (s > bs) bs = s;
-    }
-    L.bigru_scratch = L.take(bs);
+    L.bigru_scratch = L.take(6 * D * 3 * D);               // W_hh^T of the three frame-level BiGRUs, both directions
     L.dgeo_hid = L.take(N * 2048);
     L.dgcn_out = L.take(N * 128 * V);
     L.dxn = L.take(N * V * 4);
@@ -200,7 +195,6 @@ int tggcn_backward(const tggcn_dims* dims, const void* const* weights, void* con
 
     // ---- 11. segment-level recurrent graph, reverse time ---------------------------------------------------------------
     const int kh = (1 + nkh) * D, ldwh = (1 + 2 * nkh) * D;       // human cell: frame-part columns, row stride of W_ih
-    const int rows_h = B * H, rows_o = B * O;
     const int wih_h_id[2] = {TGGCN_W_HSEG_F_WIH, TGGCN_W_HSEG_B_WIH}, wih_o_id[2] = {TGGCN_W_OSEG_F_WIH, TGGCN_W_OSEG_B_WIH};
     const int whh_h_id[2] = {TGGCN_W_HSEG_F_WHH, TGGCN_W_HSEG_B_WHH}, whh_o_id[2] = {TGGCN_W_OSEG_F_WHH, TGGCN_W_OSEG_B_WHH};
     const int smsg_w_id[4] = {TGGCN_W_SMSG_HH_W, TGGCN_W_SMSG_OH_W, TGGCN_W_SMSG_HO_W, TGGCN_W_SMSG_OO_W};
@@ -236,52 +230,22 @@ int tggcn_backward(const tggcn_dims* dims, const void* const* weights, void* con
         P.dgs_h = bb(BL.dgs[0]); P.dgs_o = bb(BL.dgs[1]);
         P.dghs_h = bb(BL.dghs[0]); P.dghs_o = bb(BL.dghs[1]);
         P.du_h = bb(BL.du[0]); P.du_o = bb(BL.du[1]);
-        for (int i = 0; i < 2; ++i) { P.carry_h[i] = bb(BL.carry[0][i]); P.carry_o[i] = bb(BL.carry[1][i]); }
-        P.dgi_h = bb(BL.dgi_s[0]); P.dgi_o = bb(BL.dgi_s[1]);
-        P.dgh_h = bb(BL.dgh_s[0]); P.dgh_o = bb(BL.dgh_s[1]);
+        P.direct_h = bb(BL.direct[0]); P.direct_o = bb(BL.direct[1]);
         P.dmg_h = bb(BL.dmg[0]); P.dmg_o = bb(BL.dmg[1]);
         P.dpre_h = bb(BL.dpre[0]); P.dpre_o = bb(BL.dpre[1]);
+        for (int dir = 0; dir < 2; ++dir) {
+            P.wihT_h[dir] = wihT_h[dir]; P.wihT_o[dir] = wihT_o[dir]; P.whhT_h[dir] = whhT_h[dir]; P.whhT_o[dir] = whhT_o[dir];
+        }
+        P.wmT_h = wmT_h; P.wmT_o = wmT_o;
         const int smsg_id[4] = {TGGCN_BUF_SMSG_HH, TGGCN_BUF_SMSG_OH, TGGCN_BUF_SMSG_HO, TGGCN_BUF_SMSG_OO};
         const int salpha_id[4] = {TGGCN_BUF_SALPHA_HH, TGGCN_BUF_SALPHA_OH, TGGCN_BUF_SALPHA_HO, TGGCN_BUF_SALPHA_OO};
         for (int k = 0; k < 4; ++k) {
             P.smsg[k] = buf(smsg_id[k]); P.salpha[k] = buf(salpha_id[k]); P.dpre_all[k] = bb(BL.dpre_all[k]);
+            P.lgr[k] = bb(BL.lgr[k]); P.lgs[k] = bb(BL.lgs[k]);
         }
-        for (int s = 0; s < T; ++s) {
-            float* cout_h = P.carry_h[(s + 1) & 1];
-            float* cout_o = P.carry_o[(s + 1) & 1];
-            const bool last = (s == T - 1);          // the forward's first step: no previous state to send gradient to
-            if (int rc = launch_seg_cell_bwd(P, s, stream)) return rc;
-            GemmGroup g;
-            g.count = 0;
-            for (int dir = 0; dir < 2; ++dir) {
-                gemm_add(g, P.dgi_h + (size_t)dir * rows_h * 3 * D, 3 * D, wihT_h[dir], 3 * D, nullptr,
-                         P.dmg_h + (size_t)dir * rows_h * nkh * D, nkh * D, rows_h, nkh * D, 3 * D, 0);
-                gemm_add(g, P.dgi_o + (size_t)dir * rows_o * 3 * D, 3 * D, wihT_o[dir], 3 * D, nullptr,
-                         P.dmg_o + (size_t)dir * rows_o * 2 * D, 2 * D, rows_o, 2 * D, 3 * D, 0);
-                if (!last) {
-                    gemm_add(g, P.dgh_h + (size_t)dir * rows_h * 3 * D, 3 * D, whhT_h[dir], 3 * D, nullptr,
-                             cout_h + (size_t)dir * rows_h * D, D, rows_h, D, 3 * D, 0);
-                    g.p[g.count - 1].beta = 1;
-                    gemm_add(g, P.dgh_o + (size_t)dir * rows_o * 3 * D, 3 * D, whhT_o[dir], 3 * D, nullptr,
-                             cout_o + (size_t)dir * rows_o * D, D, rows_o, D, 3 * D, 0);
-                    g.p[g.count - 1].beta = 1;
-                }
-            }
-            if (int rc = launch_gemm(g, path, stream)) return rc;
-            if (int rc = launch_seg_msg_bwd(P, s, stream)) return rc;
-            if (!last) {
-                g.count = 0;
-                for (int dir = 0; dir < 2; ++dir) {
-                    gemm_add(g, P.dpre_h + (size_t)dir * rows_h * nks * D, nks * D, wmT_h, nks * D, nullptr,
-                             cout_h + (size_t)dir * rows_h * D, D, rows_h, D, nks * D, 0);
-                    g.p[g.count - 1].beta = 1;
-                    gemm_add(g, P.dpre_o + (size_t)dir * rows_o * 2 * D, 2 * D, wmT_o, 2 * D, nullptr,
-                             cout_o + (size_t)dir * rows_o * D, D, rows_o, D, 2 * D, 0);
-                    g.p[g.count - 1].beta = 1;
-                }
-                if (int rc = launch_gemm(g, path, stream)) return rc;
-            }
-        }
+        unsigned int* sync = (unsigned int*)buf(TGGCN_BUF_SYNC);
+        P.sync.counter = sync + 6; P.sync.error = sync + 7;
+        if (int rc = launch_segment_bwd(P, d.persistent, stream)) return rc;
         // weight gradients of the cells and message MLPs: GEMMs over all (video, t, entity) rows
         for (int dir = 0; dir < 2; ++dir) {
             // humans
@@ -402,19 +366,40 @@ int tggcn_backward(const tggcn_dims* dims, const void* const* weights, void* con
         }
     }
 
-    // ---- 5/4. BiGRU backward through time, then the hoisted input projections --------------------------------------------------------
+    // ---- 5/4. BiGRU backward through time (all three groups in one persistent kernel), then the hoisted input projections ----------
     {
         const int wih_f[3] = {TGGCN_W_HUM_RNN_WIH_F, TGGCN_W_OBJ_RNN_WIH_F, TGGCN_W_GEO_RNN_WIH_F};
+        // table order per group: WIH_F, WHH_F, BIH_F, BHH_F, WIH_B, WHH_B, BIH_B, BHH_B
+        BiGruBwdParams P;
+        memset(&P, 0, sizeof(P));
+        P.ngroups = 3; P.B = B; P.T = T; P.D = D;
+        float* whhT = bb(BL.bigru_scratch);
+        for (int g = 0; g < 3; ++g) {
+            BiGruBwdGroup& Gp = P.g[g];
+            for (int dir = 0; dir < 2; ++dir) {
+                float* wt = whhT + (size_t)(g * 2 + dir) * D * 3 * D;
+                if (int rc = launch_transpose(W(wih_f[g] + 1 + 4 * dir), D, wt, 3 * D, 3 * D, D, stream)) return rc;      // (3D,D) -> (D,3D)
+                Gp.whhT[dir] = wt;
+            }
+            Gp.dhfr = bb(BL.dhfr[g]); Gp.hfr = buf(hfr_buf[g]); Gp.gates = buf(gates_buf[g]);
+            Gp.dgi = bb(BL.dgi[g]); Gp.dgh = bb(BL.dgh[g]); Gp.direct = bb(BL.gru_direct[g]);
+            Gp.E = Eg[g]; Gp.rows = B * Eg[g];
+        }
+        unsigned int* sync = (unsigned int*)buf(TGGCN_BUF_SYNC);
+        P.sync.counter = sync + 4; P.sync.error = sync + 5;
+        if (int rc = launch_bigru_bwd(P, d.persistent, stream)) return rc;
         float* wt = bb(BL.wt);
         for (int g = 0; g < 3; ++g) {
-            // table order per group: WIH_F, WHH_F, BIH_F, BHH_F, WIH_B, WHH_B, BIH_B, BHH_B
             const int base = wih_f[g];
             const int M = N * Eg[g];
             float* dgi = bb(BL.dgi[g]);
-            if (int rc = tggcn_bigru_bwd(bb(BL.dhfr[g]), buf(hfr_buf[g]), buf(gates_buf[g]), W(base + 1), W(base + 5), dgi, bb(BL.dgh[g]),
-                                         G(base + 1), G(base + 5), G(base + 3), G(base + 7), bb(BL.bigru_scratch), B, T, Eg[g], D, path,
-                                         stream))
-                return rc;
+            const float* dgh = bb(BL.dgh[g]);
+            for (int dir = 0; dir < 2; ++dir) {
+                // dW_hh = dGh^T h_{t-1} (fwd) / h_{t+1} (bwd): row shift inside each video
+                if (int rc = launch_gemm_tn(dgh + (size_t)dir * 3 * D, 6 * D, nullptr, 0, buf(hfr_buf[g]) + (size_t)dir * D, 2 * D,
+                                            G(base + 1 + 4 * dir), D, M, 3 * D, D, dir == 0 ? -Eg[g] : Eg[g], T * Eg[g], 0, stream)) return rc;
+                if (int rc = launch_colsum(dgh + (size_t)dir * 3 * D, 6 * D, nullptr, 0, G(base + 3 + 4 * dir), M, 3 * D, 0, stream)) return rc;
+            }
             // d x (+)= [dGi_f | dGi_b] [W_ih_f ; W_ih_b]   (x = S[:, :D])
             if (int rc = launch_transpose(W(base), D, wt, 6 * D, 3 * D, D, stream)) return rc;
             if (int rc = launch_transpose(W(base + 4), D, wt + 3 * D, 6 * D, 3 * D, D, stream)) return rc;

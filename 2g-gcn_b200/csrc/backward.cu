@@ -1,9 +1,8 @@
 // Hand-written backward kernels of the graph stages (autograd of vhoi/models.py:664-933; Appendix B of SURVEY.md):
 //   heads_bwd_kernel     Linear(2D->C)+LogSoftmax backward, scatter through the reorder index
-//   seg_cell_bwd_kernel  one reverse step of the gated GRUCell update  h = u*GRU(x,h') + (1-u)*h'
-//   seg_msg_bwd_kernel   one reverse step of the segment-level attention messages
 //   frame_bwd_kernel     frame-level attention / aggregation / Gumbel-sigmoid gates (straight-through, filter)
-// Dense matrix products of the backward run on the projection kernels (gemm_*.cu, gemm_bwd.cu).
+// The recurrent stages run backward through time in recurrent_bwd.cu; dense matrix products of the backward run on the
+// projection kernels (gemm_*.cu, gemm_bwd.cu).
 #include "backward.cuh"
 
 namespace tg {
@@ -84,186 +83,6 @@ int launch_heads_bwd(const HeadsBwdParams& P, cudaStream_t stream) {
     int chunks = cdiv(rows, 8 * 8);
     if (chunks > 64) chunks = 64;
     heads_bwd_kernel<<<dim3(chunks, 4), 256, smem, stream>>>(P);
-    TG_LAUNCH_OK();
-    return 0;
-}
-
-// =============================================================================================================
-// segment cells, one reverse step
-// =============================================================================================================
-__global__ void __launch_bounds__(256) seg_cell_bwd_kernel(const SegBwdParams P, int s) {
-    const int D = P.D, T = P.T;
-    const int rows_h = P.B * P.H, rows_o = P.B * P.O, rows_all = rows_h + rows_o;
-    const int dir = blockIdx.x / rows_all;
-    int r = blockIdx.x - dir * rows_all;
-    const bool is_h = r < rows_h;
-    if (!is_h) r -= rows_h;
-    const int E = is_h ? P.H : P.O, rows = is_h ? rows_h : rows_o;
-    const int b = r / E, e = r - b * E;
-    const int t = dir == 0 ? T - 1 - s : s;
-    const int tprev = dir == 0 ? t - 1 : t + 1;
-    const bool has_prev = tprev >= 0 && tprev < T;
-    const size_t fe = (size_t)(b * T + t) * E + e;
-    const float* hx = is_h ? P.hx_h : P.hx_o;
-    const float* dhx = is_h ? P.dhx_h : P.dhx_o;
-    const float* sg = (is_h ? P.sgates_h : P.sgates_o) + (fe * 2 + dir) * 4 * D;
-    const float u = (is_h ? P.u_h : P.u_o)[fe];
-    const float* cin = (is_h ? P.carry_h : P.carry_o)[s & 1] + ((size_t)dir * rows + r) * D;
-    float* cout = (is_h ? P.carry_h : P.carry_o)[(s + 1) & 1] + ((size_t)dir * rows + r) * D;
-    float* dgs = (is_h ? P.dgs_h : P.dgs_o) + (fe * 2 + dir) * 3 * D;
-    float* dghs = (is_h ? P.dghs_h : P.dghs_o) + (fe * 2 + dir) * 3 * D;
-    float* dgi_d = (is_h ? P.dgi_h : P.dgi_o) + ((size_t)dir * rows + r) * 3 * D;
-    float* dgh_d = (is_h ? P.dgh_h : P.dgh_o) + ((size_t)dir * rows + r) * 3 * D;
-    float du_part = 0.0f;
-    for (int unit = threadIdx.x; unit < D; unit += blockDim.x) {
-        const float dH = dhx[fe * 2 * D + dir * D + unit] + (s > 0 ? cin[unit] : 0.0f);
-        const float rr = sg[unit], z = sg[D + unit], n = sg[2 * D + unit], hn = sg[3 * D + unit];
-        const float hprev = has_prev ? hx[((size_t)(b * T + tprev) * E + e) * 2 * D + dir * D + unit] : 0.0f;
-        const float hnew = n + z * (hprev - n);
-        du_part += dH * (hnew - hprev);
-        const float dhnew = u * dH;
-        const float dn = dhnew * (1.0f - z);
-        const float dz = dhnew * (hprev - n);
-        const float dan = dn * (1.0f - n * n);
-        const float daz = dz * z * (1.0f - z);
-        const float dar = dan * hn * rr * (1.0f - rr);
-        const float dhn = dan * rr;
-        dgs[unit] = dar; dgs[D + unit] = daz; dgs[2 * D + unit] = dan;
-        dghs[unit] = dar; dghs[D + unit] = daz; dghs[2 * D + unit] = dhn;
-        dgi_d[unit] = dar; dgi_d[D + unit] = daz; dgi_d[2 * D + unit] = dan;
-        dgh_d[unit] = dar; dgh_d[D + unit] = daz; dgh_d[2 * D + unit] = dhn;
-        cout[unit] = (1.0f - u) * dH + dhnew * z;
-    }
-    __shared__ float red[8];
-    du_part = warp_sum(du_part);
-    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = du_part;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        float tot = 0.0f;
-        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) tot += red[w];
-        atomicAdd((is_h ? P.du_h : P.du_o) + fe, tot);
-    }
-}
-
-int launch_seg_cell_bwd(const SegBwdParams& P, int s, cudaStream_t stream) {
-    seg_cell_bwd_kernel<<<2 * (P.B * P.H + P.B * P.O), 256, 0, stream>>>(P, s);
-    TG_LAUNCH_OK();
-    return 0;
-}
-
-// =============================================================================================================
-// segment messages, one reverse step; one CTA per (direction, video)
-// =============================================================================================================
-constexpr int SM_MAXE = 16;
-
-__global__ void __launch_bounds__(256) seg_msg_bwd_kernel(const SegBwdParams P, int s) {
-    extern __shared__ __align__(16) float sm[];
-    const int D = P.D, T = P.T, B = P.B, H = P.H, O = P.O, nk = P.nk_h;
-    const int dir = blockIdx.x / B, b = blockIdx.x - dir * B;
-    const int t = dir == 0 ? T - 1 - s : s;
-    const int tprev = dir == 0 ? t - 1 : t + 1;
-    const bool has_prev = tprev >= 0 && tprev < T;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int rows_h = B * H, rows_o = B * O;
-    float* dmg_h = sm;                          // [H][nk*D]
-    float* dmg_o = dmg_h + H * nk * D;          // [O][2D]
-    float* st = dmg_o + O * 2 * D;              // [H+O][D] previous states (zeros at the first forward step)
-    float* msg = st + (H + O) * D;              // [maxE][D] saved messages of the current kind
-    __shared__ float al[SM_MAXE * SM_MAXE], da[SM_MAXE * SM_MAXE], dl[SM_MAXE * SM_MAXE];
-
-    for (int i = tid; i < H * nk * D; i += 256) dmg_h[i] = P.dmg_h[((size_t)dir * rows_h + b * H) * nk * D + i];
-    for (int i = tid; i < O * 2 * D; i += 256) dmg_o[i] = P.dmg_o[((size_t)dir * rows_o + b * O) * 2 * D + i];
-    for (int i = tid; i < (H + O) * D; i += 256) {
-        const int e = i / D, c = i - e * D;
-        float v = 0.0f;
-        if (has_prev)
-            v = e < H ? P.hx_h[((size_t)(b * T + tprev) * H + e) * 2 * D + dir * D + c]
-                      : P.hx_o[((size_t)(b * T + tprev) * O + (e - H)) * 2 * D + dir * D + c];
-        st[i] = v;
-    }
-    float* carry_h = P.carry_h[(s + 1) & 1] + ((size_t)dir * rows_h + b * H) * D;
-    float* carry_o = P.carry_o[(s + 1) & 1] + ((size_t)dir * rows_o + b * O) * D;
-    const float scale = 1.0f / sqrtf((float)D);
-    const int nks = P.hh ? 2 : 1;               // message kinds per human sender
-    __syncthreads();
-
-    for (int kind = P.hh ? 0 : 1; kind < 4; ++kind) {
-        const bool send_h = (kind == 0 || kind == 2), recv_h = (kind == 0 || kind == 1);
-        const int Es = send_h ? H : O, Er = recv_h ? H : O;
-        const int slot = recv_h ? (kind == 0 ? 0 : nk - 1) : kind - 2;
-        const float* dmg = recv_h ? dmg_h : dmg_o;
-        const int ldr = recv_h ? nk * D : 2 * D;
-        const size_t base_s = (((size_t)dir * B + b) * T + t) * Es;
-        for (int i = tid; i < Es * D; i += 256) msg[i] = P.smsg[kind][base_s * D + i];
-        if (tid < Er * Es) al[tid] = P.salpha[kind][((((size_t)dir * B + b) * T + t) * Er) * Es + tid];
-        __syncthreads();
-        // d alpha[r][s] = <dmg_kind[r], msg[s]>
-        for (int p = warp; p < Er * Es; p += 8) {
-            const int r = p / Es, sd = p - r * Es;
-            const float* a = dmg + r * ldr + slot * D;
-            const float* m = msg + sd * D;
-            float acc = 0.0f;
-            for (int c = lane; c < D; c += 32) acc = fmaf(a[c], m[c], acc);
-            acc = warp_sum(acc);
-            if (lane == 0) da[p] = acc;
-        }
-        __syncthreads();
-        if (tid < Er) {
-            float dot = 0.0f;
-            for (int sd = 0; sd < Es; ++sd) dot = fmaf(al[tid * Es + sd], da[tid * Es + sd], dot);
-            for (int sd = 0; sd < Es; ++sd) dl[tid * Es + sd] = al[tid * Es + sd] * (da[tid * Es + sd] - dot) * scale;
-        }
-        __syncthreads();
-        // gradient of the pre-activation of every sender's message MLP
-        {
-            const int col = send_h ? (kind == 0 ? 0 : (nks - 1) * D) : (kind == 1 ? 0 : D);
-            const int lds = send_h ? nks * D : 2 * D;
-            float* dense = send_h ? P.dpre_h + ((size_t)dir * rows_h + b * H) * lds : P.dpre_o + ((size_t)dir * rows_o + b * O) * lds;
-            float* all = P.dpre_all[kind] + base_s * D;
-            for (int i = tid; i < Es * D; i += 256) {
-                const int sd = i / D, c = i - sd * D;
-                float v = 0.0f;
-                for (int r = 0; r < Er; ++r) v = fmaf(al[r * Es + sd], dmg[r * ldr + slot * D + c], v);
-                v = msg[i] > 0.0f ? v : 0.0f;
-                dense[sd * lds + col + c] = v;
-                all[i] = v;
-            }
-        }
-        // gradient of the attention logits w.r.t. the previous states of receivers and senders
-        if (has_prev) {
-            const float* sr = recv_h ? st : st + H * D;
-            const float* ss = send_h ? st : st + H * D;
-            float* cr = recv_h ? carry_h : carry_o;
-            float* cs = send_h ? carry_h : carry_o;
-            for (int i = tid; i < Er * D; i += 256) {
-                const int r = i / D, c = i - r * D;
-                float v = 0.0f;
-                for (int sd = 0; sd < Es; ++sd) v = fmaf(dl[r * Es + sd], ss[sd * D + c], v);
-                cr[i] += v;
-            }
-            __syncthreads();      // receivers and senders may be the same rows (hh, oo)
-            for (int i = tid; i < Es * D; i += 256) {
-                const int sd = i / D, c = i - sd * D;
-                float v = 0.0f;
-                for (int r = 0; r < Er; ++r) v = fmaf(dl[r * Es + sd], sr[r * D + c], v);
-                cs[i] += v;
-            }
-        }
-        __syncthreads();
-    }
-}
-
-int launch_seg_msg_bwd(const SegBwdParams& P, int s, cudaStream_t stream) {
-    TG_REQUIRE(P.H <= SM_MAXE && P.O <= SM_MAXE, "seg_msg_bwd: at most %d entities per type", SM_MAXE);
-    const int maxE = P.H > P.O ? P.H : P.O;
-    const size_t smem = sizeof(float) * ((size_t)P.H * P.nk_h * P.D + (size_t)P.O * 2 * P.D + (size_t)(P.H + P.O) * P.D + (size_t)maxE * P.D);
-    TG_REQUIRE(smem <= 200 * 1024, "seg_msg_bwd: shape needs %zu bytes of shared memory", smem);
-    static size_t configured = 0;
-    if (smem > configured) {
-        TG_CUDA_OK(cudaFuncSetAttribute(seg_msg_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = smem;
-    }
-    seg_msg_bwd_kernel<<<2 * P.B, 256, smem, stream>>>(P, s);
     TG_LAUNCH_OK();
     return 0;
 }

@@ -20,7 +20,27 @@ struct HeadsBwdParams {
 };
 int launch_heads_bwd(const HeadsBwdParams& P, cudaStream_t stream);
 
-// ---- segment-level recurrent graph, one reverse step (models.py:785-880) ------------------------------------------
+// ---- frame-level BiGRU, backward through time (recurrent_bwd.cu) ---------------------------------------------------
+struct BiGruBwdGroup {
+    const float* dhfr;       // (B,T,E,2D) gradient w.r.t. the BiGRU outputs
+    const float* hfr;        // (B,T,E,2D) forward outputs
+    const float* gates;      // (B,T,E,2,4D) r, z, n, hn saved by the forward
+    const float* whhT[2];    // (D,3D) W_hh^T per direction
+    float* dgi;              // (B,T,E,2,3D) out: gradient w.r.t. W_ih x + b_ih
+    float* dgh;              // (B,T,E,2,3D) out: gradient w.r.t. W_hh h + b_hh
+    float* direct;           // (2,rows,D) scratch: z (.) dh of the previous reverse step
+    int E, rows;
+    int cfg, n_rb, n_ub, tile_begin;     // tiling (filled by the launcher)
+};
+struct BiGruBwdParams {
+    BiGruBwdGroup g[3];
+    int ngroups, B, T, D;
+    int NG, total_tiles;                 // filled by the launcher
+    GridSync sync;
+};
+int launch_bigru_bwd(BiGruBwdParams& P, int persistent, cudaStream_t stream);
+
+// ---- segment-level recurrent graph, backward through time (models.py:785-880; recurrent_bwd.cu) ----------------------
 struct SegBwdParams {
     int B, T, H, O, D, hh, nk_h;
     const float* hx_h; const float* hx_o;          // forward states (B,T,E,2D)
@@ -28,20 +48,26 @@ struct SegBwdParams {
     const float* u_h; const float* u_o;            // hard gates (B,T,E)
     const float* om;                               // (B,O)
     const float* dhx_h; const float* dhx_o;        // upstream gradient of the states (B,T,E,2D)
+    const float* smsg[4]; const float* salpha[4];  // saved messages / attention weights (kinds hh, oh, ho, oo)
+    // transposed weights (rows = output of the backward product)
+    const float* wihT_h[2]; const float* wihT_o[2];   // (nk*D, 3D): segment-message columns of W_ih
+    const float* whhT_h[2]; const float* whhT_o[2];   // (D, 3D)
+    const float* wmT_h; const float* wmT_o;           // (D, nks*D): [W_hh_msg^T | W_ho_msg^T], [W_oh_msg^T | W_oo_msg^T]
+    // outputs kept for the weight-gradient GEMMs
     float* dgs_h; float* dgs_o;                    // (B,T,E,2,3D) gradient of the hoisted pre-activations (= of W_ih x + b_ih)
     float* dghs_h; float* dghs_o;                  // (B,T,E,2,3D) gradient of W_hh h + b_hh
-    float* du_h; float* du_o;                      // (B,T,E) gradient of the hard gates (atomics; zero before the loop)
-    // per-step dense staging (one step, both directions)
-    float* carry_h[2]; float* carry_o[2];          // ping-pong [2 dirs][rows][D]: gradient flowing into the previous state
-    float* dgi_h; float* dgi_o;                    // [2][rows][3D] dense copies of this step's dGi / dGh (GEMM operands)
-    float* dgh_h; float* dgh_o;
-    float* dmg_h; float* dmg_o;                    // [2][rows][nk*D] gradient of the aggregated messages (GEMM output)
-    float* dpre_h; float* dpre_o;                  // [2][rows_sender][2D]: [hh | ho] for human senders, [oh | oo] for objects
-    const float* smsg[4]; const float* salpha[4];  // saved messages / attention weights (kinds hh, oh, ho, oo)
-    float* dpre_all[4];                            // per kind [dir][b][t][sender][D]: for the message weight gradients
+    float* du_h; float* du_o;                      // (B,T,E) gradient of the hard gates (atomics; zero before the launch)
+    float* dpre_all[4];                            // per kind [dir][b][t][sender][D]: message MLP pre-activation gradients
+    // per-step scratch (one step, both directions)
+    float* direct_h; float* direct_o;              // [2][rows][D]: (1-u) dH + u z dH of the previous reverse step
+    float* dmg_h; float* dmg_o;                    // [2][rows][nk*D] gradient of the aggregated messages
+    float* dpre_h; float* dpre_o;                  // [2][rows_sender][nks*D]: [hh | ho] for human senders, [oh | oo] for objects
+    float* lgr[4]; float* lgs[4];                  // per kind [2][rows][D]: attention-logit terms for receivers / senders
+    // tiling (filled by the launcher)
+    int cfg_h, cfg_o, nubA_h, nubA_o, tilesA_h, tilesA_dir, nubC, tilesC_h, tilesC_dir;
+    GridSync sync;
 };
-int launch_seg_cell_bwd(const SegBwdParams& P, int s, cudaStream_t stream);
-int launch_seg_msg_bwd(const SegBwdParams& P, int s, cudaStream_t stream);
+int launch_segment_bwd(SegBwdParams& P, int persistent, cudaStream_t stream);
 
 // ---- frame-level graph: attention, aggregation, gates (models.py:664-749, :1004-1533; distributions.py:4-36) ---------
 struct FrameBwdParams {

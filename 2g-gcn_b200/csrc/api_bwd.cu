@@ -25,7 +25,7 @@ struct BwdLayout {
         return o;
     }
     size_t dhfr[3], dhx[2], dgs[2], dghs[2], du[2], direct[2], dmg[2], dpre[2], lgr[4], lgs[4], dpre_all[4], gru_direct[3];
-    size_t dxx[2], ds[3], dmsg[5], dgi[3], dgh[3], bigru_scratch, dgeo_hid, dgcn_out, dxn, wt_seg, wt;
+    size_t dxx[2], ds[3], dmsg[5], dgi[3], dgh[3], bigru_scratch, dgeo_hid, dgcn_out, dxn, wt_seg, wt, tn, tn_floats;
     size_t zero_begin, zero_end;     // region that must be zero before the kernels run (atomically accumulated)
 };
 
@@ -81,6 +81,12 @@ void make_bwd_layout(const tggcn_dims& d, BwdLayout& L) {
     for (size_t c : cands)
         if (c > wmax) wmax = c;
     L.wt = L.take(wmax);
+    // transposed operands of one weight-gradient GEMM: (N + K) x M rounded up to 32
+    const size_t rp = (N * (H > O ? H : O) + 31) / 32 * 32, np = (N + 31) / 32 * 32;
+    size_t tmax = (3 * D + (4 * D > 2048 ? 4 * D : 2048)) * rp;
+    if ((2048 + 128 * V) * np > tmax) tmax = (2048 + 128 * V) * np;
+    L.tn_floats = tmax;
+    L.tn = L.take(tmax);
 }
 
 // C[M, Nout] (+)= (A (.) [mask > 0]) [M, K] * Wt[Nout, K]^T
@@ -160,6 +166,20 @@ int tggcn_backward(const tggcn_dims* dims, const void* const* weights, void* con
         if (!d.human_seg_given) TG_REQUIRE(G(TGGCN_W_UPD_H_W) && G(TGGCN_W_UPD_H_B), "backward: human gate gradient pointers missing");
         if (!d.object_seg_given) TG_REQUIRE(G(TGGCN_W_UPD_O_W) && G(TGGCN_W_UPD_O_B), "backward: object gate gradient pointers missing");
     }
+
+    // weight gradient dW[N,K] (+)= (Z (.) [mask > 0])^T X with an optional row shift of X inside blocks of `period` rows:
+    // both operands are transposed into scratch (reduction index contiguous) and contracted by the tcgen05 NT kernel.
+    float* tn_scratch = bb(BL.tn);
+    auto tn = [&](const float* Z, int ldz, const float* mask, int ldm, const float* X, int ldx, float* dW, int lddw, int M, int Nn, int K,
+                  int shift, int period, int beta, cudaStream_t st) -> int {
+        const int Mp = (M + 31) / 32 * 32;
+        TG_REQUIRE((size_t)(Nn + K) * Mp <= BL.tn_floats, "backward: weight-gradient scratch too small (%d + %d) x %d", Nn, K, Mp);
+        float* zt = tn_scratch;
+        float* xt = zt + (size_t)Nn * Mp;
+        if (int rc = launch_transpose_prep(Z, ldz, mask, ldm, zt, Mp, M, Nn, 0, 0, nullptr, st)) return rc;
+        if (int rc = launch_transpose_prep(X, ldx, nullptr, 0, xt, Mp, M, K, shift, period, nullptr, st)) return rc;
+        return gemm_nt(zt, Mp, nullptr, 0, xt, Mp, dW, lddw, Nn, K, Mp, beta, path, st);
+    };
 
     TG_CUDA_OK(cudaMemsetAsync(bb(BL.zero_begin), 0, (BL.zero_end - BL.zero_begin) * sizeof(float), stream));
 
@@ -249,22 +269,22 @@ int tggcn_backward(const tggcn_dims* dims, const void* const* weights, void* con
         // weight gradients of the cells and message MLPs: GEMMs over all (video, t, entity) rows
         for (int dir = 0; dir < 2; ++dir) {
             // humans
-            if (int rc = launch_gemm_tn(P.dghs_h + (size_t)dir * 3 * D, 6 * D, nullptr, 0, P.hx_h + (size_t)dir * D, 2 * D,
+            if (int rc = tn(P.dghs_h + (size_t)dir * 3 * D, 6 * D, nullptr, 0, P.hx_h + (size_t)dir * D, 2 * D,
                                         G(whh_h_id[dir]), D, N * H, 3 * D, D, dir == 0 ? -H : H, T * H, 0, stream)) return rc;
             if (int rc = launch_colsum(P.dghs_h + (size_t)dir * 3 * D, 6 * D, nullptr, 0, G(whh_h_id[dir] + 2), N * H, 3 * D, 0, stream)) return rc;
-            if (int rc = launch_gemm_tn(P.dgs_h + (size_t)dir * 3 * D, 6 * D, nullptr, 0, buf(TGGCN_BUF_XX_H), kh, G(wih_h_id[dir]), ldwh,
+            if (int rc = tn(P.dgs_h + (size_t)dir * 3 * D, 6 * D, nullptr, 0, buf(TGGCN_BUF_XX_H), kh, G(wih_h_id[dir]), ldwh,
                                         N * H, 3 * D, kh, 0, 0, 0, stream)) return rc;
-            if (int rc = launch_gemm_tn(P.dgs_h + (size_t)dir * 3 * D, 6 * D, nullptr, 0,
+            if (int rc = tn(P.dgs_h + (size_t)dir * 3 * D, 6 * D, nullptr, 0,
                                         buf(TGGCN_BUF_MG_ALL_H) + (size_t)dir * N * H * nkh * D, nkh * D, G(wih_h_id[dir]) + kh, ldwh,
                                         N * H, 3 * D, nkh * D, 0, 0, 0, stream)) return rc;
             if (int rc = launch_colsum(P.dgs_h + (size_t)dir * 3 * D, 6 * D, nullptr, 0, G(wih_h_id[dir] + 2), N * H, 3 * D, 0, stream)) return rc;
             // objects
-            if (int rc = launch_gemm_tn(P.dghs_o + (size_t)dir * 3 * D, 6 * D, nullptr, 0, P.hx_o + (size_t)dir * D, 2 * D,
+            if (int rc = tn(P.dghs_o + (size_t)dir * 3 * D, 6 * D, nullptr, 0, P.hx_o + (size_t)dir * D, 2 * D,
                                         G(whh_o_id[dir]), D, N * O, 3 * D, D, dir == 0 ? -O : O, T * O, 0, stream)) return rc;
             if (int rc = launch_colsum(P.dghs_o + (size_t)dir * 3 * D, 6 * D, nullptr, 0, G(whh_o_id[dir] + 2), N * O, 3 * D, 0, stream)) return rc;
-            if (int rc = launch_gemm_tn(P.dgs_o + (size_t)dir * 3 * D, 6 * D, nullptr, 0, buf(TGGCN_BUF_XX_O), 4 * D, G(wih_o_id[dir]), 6 * D,
+            if (int rc = tn(P.dgs_o + (size_t)dir * 3 * D, 6 * D, nullptr, 0, buf(TGGCN_BUF_XX_O), 4 * D, G(wih_o_id[dir]), 6 * D,
                                         N * O, 3 * D, 4 * D, 0, 0, 0, stream)) return rc;
-            if (int rc = launch_gemm_tn(P.dgs_o + (size_t)dir * 3 * D, 6 * D, nullptr, 0,
+            if (int rc = tn(P.dgs_o + (size_t)dir * 3 * D, 6 * D, nullptr, 0,
                                         buf(TGGCN_BUF_MG_ALL_O) + (size_t)dir * N * O * 2 * D, 2 * D, G(wih_o_id[dir]) + 4 * D, 6 * D,
                                         N * O, 3 * D, 2 * D, 0, 0, 0, stream)) return rc;
             if (int rc = launch_colsum(P.dgs_o + (size_t)dir * 3 * D, 6 * D, nullptr, 0, G(wih_o_id[dir] + 2), N * O, 3 * D, 0, stream)) return rc;
@@ -274,7 +294,7 @@ int tggcn_backward(const tggcn_dims* dims, const void* const* weights, void* con
             const int Es = send_h ? H : O;
             const float* hx = send_h ? P.hx_h : P.hx_o;
             for (int dir = 0; dir < 2; ++dir)
-                if (int rc = launch_gemm_tn(P.dpre_all[k] + (size_t)dir * N * Es * D, D, nullptr, 0, hx + (size_t)dir * D, 2 * D,
+                if (int rc = tn(P.dpre_all[k] + (size_t)dir * N * Es * D, D, nullptr, 0, hx + (size_t)dir * D, 2 * D,
                                             G(smsg_w_id[k]), D, N * Es, D, D, dir == 0 ? -Es : Es, T * Es, dir, stream)) return rc;
             if (int rc = launch_colsum(P.dpre_all[k], D, nullptr, 0, G(smsg_w_id[k] + 1), 2 * N * Es, D, 0, stream)) return rc;
         }
@@ -341,7 +361,7 @@ int tggcn_backward(const tggcn_dims* dims, const void* const* weights, void* con
             if (int rc = launch_transpose(W(kinds[k].w_id), 2 * D, wt, D, D, 2 * D, stream)) return rc;      // (D,2D) -> (2D,D)
             if (int rc = gemm_nt(dmsg, D, msg, D, wt, D, bb(BL.ds[gidx]), 2 * D, M, 2 * D, D, touched[gidx], path, stream)) return rc;
             touched[gidx] = 1;
-            if (int rc = launch_gemm_tn(dmsg, D, msg, D, buf(s_buf[gidx]), 2 * D, G(kinds[k].w_id), 2 * D, M, D, 2 * D, 0, 0, 0, stream)) return rc;
+            if (int rc = tn(dmsg, D, msg, D, buf(s_buf[gidx]), 2 * D, G(kinds[k].w_id), 2 * D, M, D, 2 * D, 0, 0, 0, stream)) return rc;
             if (int rc = launch_colsum(dmsg, D, msg, D, G(kinds[k].w_id + 1), M, D, 0, stream)) return rc;
         }
     }
@@ -361,7 +381,7 @@ int tggcn_backward(const tggcn_dims* dims, const void* const* weights, void* con
             if (int rc = launch_transpose(W(bd_id[g]), 2 * D, wt, D, D, 2 * D, stream)) return rc;
             const int beta = (g == 0 || (g == 1 && d.C_aff > 0)) ? 1 : 0;     // the frame heads already wrote into d hfr
             if (int rc = gemm_nt(dZ, 2 * D, Y, 2 * D, wt, D, bb(BL.dhfr[g]), 2 * D, M, 2 * D, D, beta, path, stream)) return rc;
-            if (int rc = launch_gemm_tn(dZ, 2 * D, Y, 2 * D, buf(hfr_buf[g]), 2 * D, G(bd_id[g]), 2 * D, M, D, 2 * D, 0, 0, 0, stream)) return rc;
+            if (int rc = tn(dZ, 2 * D, Y, 2 * D, buf(hfr_buf[g]), 2 * D, G(bd_id[g]), 2 * D, M, D, 2 * D, 0, 0, 0, stream)) return rc;
             if (int rc = launch_colsum(dZ, 2 * D, Y, 2 * D, G(bd_id[g] + 1), M, D, 0, stream)) return rc;
         }
     }
@@ -396,7 +416,7 @@ int tggcn_backward(const tggcn_dims* dims, const void* const* weights, void* con
             const float* dgh = bb(BL.dgh[g]);
             for (int dir = 0; dir < 2; ++dir) {
                 // dW_hh = dGh^T h_{t-1} (fwd) / h_{t+1} (bwd): row shift inside each video
-                if (int rc = launch_gemm_tn(dgh + (size_t)dir * 3 * D, 6 * D, nullptr, 0, buf(hfr_buf[g]) + (size_t)dir * D, 2 * D,
+                if (int rc = tn(dgh + (size_t)dir * 3 * D, 6 * D, nullptr, 0, buf(hfr_buf[g]) + (size_t)dir * D, 2 * D,
                                             G(base + 1 + 4 * dir), D, M, 3 * D, D, dir == 0 ? -Eg[g] : Eg[g], T * Eg[g], 0, stream)) return rc;
                 if (int rc = launch_colsum(dgh + (size_t)dir * 3 * D, 6 * D, nullptr, 0, G(base + 3 + 4 * dir), M, 3 * D, 0, stream)) return rc;
             }
@@ -405,7 +425,7 @@ int tggcn_backward(const tggcn_dims* dims, const void* const* weights, void* con
             if (int rc = launch_transpose(W(base + 4), D, wt + 3 * D, 6 * D, 3 * D, D, stream)) return rc;
             if (int rc = gemm_nt(dgi, 6 * D, nullptr, 0, wt, 6 * D, bb(BL.ds[g]), 2 * D, M, D, 6 * D, 1, path, stream)) return rc;
             for (int dir = 0; dir < 2; ++dir) {
-                if (int rc = launch_gemm_tn(dgi + (size_t)dir * 3 * D, 6 * D, nullptr, 0, buf(s_buf[g]), 2 * D, G(base + 4 * dir), D, M, 3 * D, D,
+                if (int rc = tn(dgi + (size_t)dir * 3 * D, 6 * D, nullptr, 0, buf(s_buf[g]), 2 * D, G(base + 4 * dir), D, M, 3 * D, D,
                                             0, 0, 0, stream)) return rc;
                 if (int rc = launch_colsum(dgi + (size_t)dir * 3 * D, 6 * D, nullptr, 0, G(base + 4 * dir + 2), M, 3 * D, 0, stream)) return rc;
             }
@@ -415,24 +435,24 @@ int tggcn_backward(const tggcn_dims* dims, const void* const* weights, void* con
     // ---- 3/2. embeddings (inputs are data: weight gradients only) and the geometry MLP ---------------------------------------------------
     {
         // x = ReLU(W roi + b) = S[:, :D]
-        if (int rc = launch_gemm_tn(bb(BL.ds[0]), 2 * D, buf(TGGCN_BUF_S_H), 2 * D, io->x_human, d.Fh, G(TGGCN_W_HUM_EMB_W), 2048, N * H, D, 2048,
+        if (int rc = tn(bb(BL.ds[0]), 2 * D, buf(TGGCN_BUF_S_H), 2 * D, io->x_human, d.Fh, G(TGGCN_W_HUM_EMB_W), 2048, N * H, D, 2048,
                                     0, 0, 0, stream)) return rc;
         if (int rc = launch_colsum(bb(BL.ds[0]), 2 * D, buf(TGGCN_BUF_S_H), 2 * D, G(TGGCN_W_HUM_EMB_B), N * H, D, 0, stream)) return rc;
-        if (int rc = launch_gemm_tn(bb(BL.ds[1]), 2 * D, buf(TGGCN_BUF_S_O), 2 * D, io->x_objects, 2048, G(TGGCN_W_OBJ_EMB_W), 2048, N * O, D, 2048,
+        if (int rc = tn(bb(BL.ds[1]), 2 * D, buf(TGGCN_BUF_S_O), 2 * D, io->x_objects, 2048, G(TGGCN_W_OBJ_EMB_W), 2048, N * O, D, 2048,
                                     0, 0, 0, stream)) return rc;
         if (int rc = launch_colsum(bb(BL.ds[1]), 2 * D, buf(TGGCN_BUF_S_O), 2 * D, G(TGGCN_W_OBJ_EMB_B), N * O, D, 0, stream)) return rc;
         // geometry MLP layer 2: S_G[:, :D] = ReLU(W2 hid + b2)
         float* wt = bb(BL.wt);
         if (int rc = launch_transpose(W(TGGCN_W_GEO_MLP2_W), 2048, wt, D, D, 2048, stream)) return rc;          // (D,2048) -> (2048,D)
         if (int rc = gemm_nt(bb(BL.ds[2]), 2 * D, buf(TGGCN_BUF_S_G), 2 * D, wt, D, bb(BL.dgeo_hid), 2048, N, 2048, D, 0, path, stream)) return rc;
-        if (int rc = launch_gemm_tn(bb(BL.ds[2]), 2 * D, buf(TGGCN_BUF_S_G), 2 * D, buf(TGGCN_BUF_GEO_HID), 2048, G(TGGCN_W_GEO_MLP2_W), 2048, N, D,
+        if (int rc = tn(bb(BL.ds[2]), 2 * D, buf(TGGCN_BUF_S_G), 2 * D, buf(TGGCN_BUF_GEO_HID), 2048, G(TGGCN_W_GEO_MLP2_W), 2048, N, D,
                                     2048, 0, 0, 0, stream)) return rc;
         if (int rc = launch_colsum(bb(BL.ds[2]), 2 * D, buf(TGGCN_BUF_S_G), 2 * D, G(TGGCN_W_GEO_MLP2_B), N, D, 0, stream)) return rc;
         // layer 0: hid = ReLU(W0 gcn + b0), gcn = the scrambled view (N, 128V)
         const int KV = 128 * V;
         if (int rc = launch_transpose(W(TGGCN_W_GEO_MLP0_W), KV, wt, 2048, 2048, KV, stream)) return rc;         // (2048,128V) -> (128V,2048)
         if (int rc = gemm_nt(bb(BL.dgeo_hid), 2048, buf(TGGCN_BUF_GEO_HID), 2048, wt, 2048, bb(BL.dgcn_out), KV, N, KV, 2048, 0, path, stream)) return rc;
-        if (int rc = launch_gemm_tn(bb(BL.dgeo_hid), 2048, buf(TGGCN_BUF_GEO_HID), 2048, buf(TGGCN_BUF_GCN_OUT), KV, G(TGGCN_W_GEO_MLP0_W), KV, N,
+        if (int rc = tn(bb(BL.dgeo_hid), 2048, buf(TGGCN_BUF_GEO_HID), 2048, buf(TGGCN_BUF_GCN_OUT), KV, G(TGGCN_W_GEO_MLP0_W), KV, N,
                                     2048, KV, 0, 0, 0, stream)) return rc;
         if (int rc = launch_colsum(bb(BL.dgeo_hid), 2048, buf(TGGCN_BUF_GEO_HID), 2048, G(TGGCN_W_GEO_MLP0_B), N, 2048, 0, stream)) return rc;
     }

@@ -25,6 +25,8 @@ struct BiGruParams {
 
 int launch_bigru(BiGruParams& P, int persistent, cudaStream_t stream);
 int launch_transpose(const float* in, int ldi, float* out, int ldo, int R, int C, cudaStream_t stream);
+int launch_transpose_prep(const float* in, int ldi, const float* mask, int ldm, float* out, int Mp, int M, int C, int shift, int period,
+                          float* colsum, cudaStream_t stream);
 int launch_gemm_tn(const float* Z, int ldz, const float* mask, int ldm, const float* A, int lda, float* C, int ldc, int M, int N,
                    int K, int a_shift, int period, int beta, cudaStream_t stream);
 int launch_colsum(const float* Z, int ldz, const float* mask, int ldm, float* out, int M, int N, int beta, cudaStream_t stream);

@@ -116,14 +116,14 @@ __global__ void __launch_bounds__(256) gemm_tn_kernel(const TnProblem P) {
         }
 }
 
-// out[n] (+)= sum_m Z[m][n] * [mask[m][n] > 0]
+// out[n] (+)= sum_m Z[m][n] * [mask[m][n] > 0]; rows are split over blockIdx.y and combined with atomics
 __global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ Z, int ldz, const float* __restrict__ mask, int ldm,
-                                                     float* __restrict__ out, int M, int N, int beta) {
+                                                     float* __restrict__ out, int M, int N) {
     __shared__ float part[8][33];
     const int n = blockIdx.x * 32 + (threadIdx.x & 31), ry = threadIdx.x >> 5;
     float s = 0.0f;
     if (n < N)
-        for (int m = ry; m < M; m += 8) {
+        for (int m = blockIdx.y * 8 + ry; m < M; m += 8 * gridDim.y) {
             float z = __ldg(Z + (size_t)m * ldz + n);
             if (mask != nullptr && !(__ldg(mask + (size_t)m * ldm + n) > 0.f)) z = 0.0f;
             s += z;
@@ -134,7 +134,7 @@ __global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ Z
         float t = 0.0f;
 #pragma unroll
         for (int i = 0; i < 8; ++i) t += part[i][threadIdx.x];
-        out[n] = beta ? out[n] + t : t;
+        atomicAdd(out + n, t);
     }
 }
 
@@ -149,6 +149,54 @@ __global__ void __launch_bounds__(256) transpose_kernel(const float* __restrict_
     __syncthreads();
     for (int j = y; j < 32; j += 8)
         if (c0 + j < Cc && r0 + x < R) out[(size_t)(c0 + j) * ldo + r0 + x] = t[x][j];
+}
+
+// out[c][m] = in[m + shift][c] * [mask[m + shift][c] > 0]   for m < M (0 where the shifted row leaves its block of `period`
+// rows), and 0 for M <= m < Mp: the reduction index of a weight gradient becomes the contiguous (K-major) axis, so that
+// dW = Z^T X runs on the tcgen05 NT projection kernel as  dW[N,K] = Zt[N,Mp] Xt[K,Mp]^T.  Optionally accumulates the column
+// sums of the (masked) input with atomics: the bias gradient, for free.
+__global__ void __launch_bounds__(256) transpose_prep_kernel(const float* __restrict__ in, int ldi, const float* __restrict__ mask,
+                                                             int ldm, float* __restrict__ out, int ldo, int M, int Mp, int Cc, int shift,
+                                                             int period, float* __restrict__ colsum) {
+    __shared__ float t[32][33];
+    const int c0 = blockIdx.x * 32, m0 = blockIdx.y * 32;
+    const int x = threadIdx.x & 31, y = threadIdx.x >> 5;
+    for (int j = y; j < 32; j += 8) {
+        const int m = m0 + j, c = c0 + x;
+        float v = 0.0f;
+        if (m < M && c < Cc) {
+            int ms = m;
+            bool ok = true;
+            if (shift != 0) {
+                const int pos = m % period + shift;
+                ok = pos >= 0 && pos < period;
+                ms = m + shift;
+            }
+            if (ok) {
+                v = __ldg(in + (size_t)ms * ldi + c);
+                if (mask != nullptr && !(__ldg(mask + (size_t)ms * ldm + c) > 0.0f)) v = 0.0f;
+            }
+        }
+        t[j][x] = v;
+    }
+    __syncthreads();
+    for (int j = y; j < 32; j += 8)
+        if (c0 + j < Cc && m0 + x < Mp) out[(size_t)(c0 + j) * ldo + m0 + x] = t[x][j];
+    if (colsum != nullptr && y == 0 && c0 + x < Cc) {
+        float sacc = 0.0f;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) sacc += t[j][x];
+        atomicAdd(colsum + c0 + x, sacc);
+    }
+}
+
+int launch_transpose_prep(const float* in, int ldi, const float* mask, int ldm, float* out, int Mp, int M, int C, int shift, int period,
+                          float* colsum, cudaStream_t stream) {
+    TG_REQUIRE(Mp >= M && Mp % 32 == 0, "transpose_prep: padded length %d must be a multiple of 32 >= %d", Mp, M);
+    TG_REQUIRE(shift == 0 || period > 0, "transpose_prep: shift needs a period");
+    transpose_prep_kernel<<<dim3(cdiv(C, 32), Mp / 32), 256, 0, stream>>>(in, ldi, mask, ldm, out, Mp, M, Mp, C, shift, period, colsum);
+    TG_LAUNCH_OK();
+    return 0;
 }
 
 int launch_transpose(const float* in, int ldi, float* out, int ldo, int R, int C, cudaStream_t stream) {
@@ -173,7 +221,10 @@ int launch_gemm_tn(const float* Z, int ldz, const float* mask, int ldm, const fl
 }
 
 int launch_colsum(const float* Z, int ldz, const float* mask, int ldm, float* out, int M, int N, int beta, cudaStream_t stream) {
-    colsum_kernel<<<cdiv(N, 32), 256, 0, stream>>>(Z, ldz, mask, ldm, out, M, N, beta);
+    if (!beta) TG_CUDA_OK(cudaMemsetAsync(out, 0, sizeof(float) * (size_t)N, stream));
+    int ysplit = cdiv(M, 64);
+    if (ysplit > 64) ysplit = 64;
+    colsum_kernel<<<dim3(cdiv(N, 32), ysplit), 256, 0, stream>>>(Z, ldz, mask, ldm, out, M, N);
     TG_LAUNCH_OK();
     return 0;
 }

@@ -20,6 +20,7 @@ struct GemmProblem {
     const float* amask;  // may be null
     int ldm;
     int beta;
+    int ksplit;          // tcgen05 path: K range split over this many CTAs per tile, combined with atomics (filled by the launcher)
 };
 
 struct GemmGroup {
@@ -32,7 +33,7 @@ inline void gemm_add(GemmGroup& g, const float* A, int lda, const float* W, int 
     GemmProblem& q = g.p[g.count++];
     q.A = A; q.W = W; q.bias = bias; q.C = C;
     q.M = M; q.N = N; q.K = K; q.lda = lda; q.ldw = ldw; q.ldc = ldc; q.relu = relu; q.tile_begin = 0;
-    q.amask = nullptr; q.ldm = 0; q.beta = 0;
+    q.amask = nullptr; q.ldm = 0; q.beta = 0; q.ksplit = 1;
 }
 
 int launch_gemm_simt(GemmGroup& grp, cudaStream_t stream);

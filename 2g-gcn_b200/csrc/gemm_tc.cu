@@ -114,10 +114,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const GemmGroup 
     for (int i = 1; i < grp.count; ++i)
         if ((int)blockIdx.x >= grp.p[i].tile_begin) pi = i;
     const GemmProblem& P = grp.p[pi];
-    const int tile = blockIdx.x - P.tile_begin;
+    int tile = blockIdx.x - P.tile_begin;
+    const int ks = tile % P.ksplit;                     // split-K slice of this CTA
+    tile /= P.ksplit;
     const int tiles_n = (P.N + TC_BN - 1) / TC_BN;
     const int m0 = (tile / tiles_n) * TC_BM, n0 = (tile % tiles_n) * TC_BN;
-    const int nkb = P.K / TC_BK;
+    const int nkb_all = P.K / TC_BK;
+    const int kb0 = (int)((long long)nkb_all * ks / P.ksplit);
+    const int nkb = (int)((long long)nkb_all * (ks + 1) / P.ksplit) - kb0;
 
     if (tid == 0) {
         for (int s = 0; s < TC_STAGES; ++s) {
@@ -150,9 +154,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const GemmGroup 
             const int r = r0 + 32 * i;
             aok[i] = (m0 + r) < P.M;
             wok[i] = (n0 + r) < P.N;
-            aptr[i] = P.A + (size_t)(aok[i] ? m0 + r : 0) * P.lda + c * 4;
-            mptr[i] = P.amask != nullptr ? P.amask + (size_t)(aok[i] ? m0 + r : 0) * P.ldm + c * 4 : nullptr;
-            wptr[i] = P.W + (size_t)(wok[i] ? n0 + r : 0) * P.ldw + c * 4;
+            aptr[i] = P.A + (size_t)(aok[i] ? m0 + r : 0) * P.lda + c * 4 + (size_t)kb0 * TC_BK;
+            mptr[i] = P.amask != nullptr ? P.amask + (size_t)(aok[i] ? m0 + r : 0) * P.ldm + c * 4 + (size_t)kb0 * TC_BK : nullptr;
+            wptr[i] = P.W + (size_t)(wok[i] ? n0 + r : 0) * P.ldw + c * 4 + (size_t)kb0 * TC_BK;
         }
         float4 pa0[4], pw0[4], pa1[4], pw1[4];                // register prefetch, two k-blocks deep (static slots)
         auto load = [&](int kb, float4 (&pa)[4], float4 (&pw)[4]) {
@@ -213,6 +217,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const GemmGroup 
             const int nbase = n0 + col_half + cb;
             if (row < P.M && nbase < P.N) {
                 float* dst = P.C + (size_t)row * P.ldc + nbase;
+                if (P.ksplit > 1) {                       // partial sum of one K slice (no bias / activation on this path)
+#pragma unroll
+                    for (int j = 0; j < 32; ++j)
+                        if (nbase + j < P.N) atomicAdd(dst + j, v[j]);
+                    continue;
+                }
                 const bool vec = ((P.ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0) && (nbase + 32 <= P.N);
 #pragma unroll
                 for (int j = 0; j < 32; ++j) {
@@ -277,8 +287,25 @@ int launch_gemm_tc(GemmGroup& grp, cudaStream_t stream) {
                    "gemm_tc: A and W must be 16-byte aligned");
         TG_REQUIRE(p.amask == nullptr || (p.ldm % 4 == 0 && (reinterpret_cast<uintptr_t>(p.amask) & 15) == 0),
                    "gemm_tc: mask must be 16-byte aligned with ldm a multiple of 4");
-        grp.p[i].tile_begin = begin;
-        begin += cdiv(p.M, TC_BM) * cdiv(p.N, TC_BN);
+    }
+    int base_tiles = 0;
+    for (int i = 0; i < grp.count; ++i) base_tiles += cdiv(grp.p[i].M, TC_BM) * cdiv(grp.p[i].N, TC_BN);
+    for (int i = 0; i < grp.count; ++i) {
+        GemmProblem& p = grp.p[i];
+        // under-filled grid and a long reduction: split K over several CTAs per tile (weight gradients, M' x N' small, K' = rows)
+        p.ksplit = 1;
+        const int nkb = p.K / TC_BK;
+        if (p.bias == nullptr && !p.relu && base_tiles * 2 <= num_sms() && nkb >= 16) {
+            int ks = num_sms() / base_tiles;
+            if (ks > nkb / 8) ks = nkb / 8;
+            if (ks > 1) {
+                p.ksplit = ks;
+                if (!p.beta)
+                    TG_CUDA_OK(cudaMemset2DAsync(p.C, sizeof(float) * (size_t)p.ldc, 0, sizeof(float) * (size_t)p.N, (size_t)p.M, stream));
+            }
+        }
+        p.tile_begin = begin;
+        begin += cdiv(p.M, TC_BM) * cdiv(p.N, TC_BN) * p.ksplit;
     }
     static bool configured = false;
     if (!configured) {

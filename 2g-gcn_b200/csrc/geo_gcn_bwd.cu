@@ -1,7 +1,7 @@
 // Backward of the geometry-level GCN (autograd of Geo_gcn.forward, pyrutils/torch/models_gcn.py:30-100).
 // The BatchNorm input is model data, so only the affine parameters of the norm get a gradient:
 // d gamma = sum dY * x_hat, d beta = sum dY (second pass, geo_bn_bwd_kernel).
-// A CTA walks over GB_FPC frames; per frame it recomputes the forward intermediates in shared memory, runs the
+// A CTA walks over a contiguous run of frames (one CTA per SM); per frame it recomputes the forward intermediates in shared memory, runs the
 // backward stages, and keeps the weight-gradient partials of "its" weight rows in registers across frames, so the
 // global atomics are issued once per CTA.
 #include "backward.cuh"
@@ -9,10 +9,9 @@
 namespace tg {
 
 constexpr int GB_THREADS = 256;
-constexpr int GB_FPC = 16;       // frames per CTA
 constexpr int GB_LDT = 257, GB_LDO = 129, GB_LDS = 32;
 
-__global__ void __launch_bounds__(GB_THREADS, 1) geo_gcn_bwd_kernel(const GcnBwdParams P) {
+__global__ void __launch_bounds__(GB_THREADS, 1) geo_gcn_bwd_kernel(const GcnBwdParams P, int fpc) {
     extern __shared__ __align__(16) float sm[];
     const int V = P.V, T = P.T, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     float* xn = sm;                       // [V][4]
@@ -41,7 +40,7 @@ __global__ void __launch_bounds__(GB_THREADS, 1) geo_gcn_bwd_kernel(const GcnBwd
     for (int i = 0; i < 4; ++i) g_w1[i] = 0.f;
 
     const int N = P.B * T;
-    const int f0 = blockIdx.x * GB_FPC, f1 = min(f0 + GB_FPC, N);
+    const int f0 = blockIdx.x * fpc, f1 = min(f0 + fpc, N);
     for (int n = f0; n < f1; ++n) {
         const int b = n / T, t = n - b * T;
         __syncthreads();
@@ -306,7 +305,8 @@ int launch_geo_gcn_bwd(const GcnBwdParams& P, cudaStream_t stream) {
         TG_CUDA_OK(cudaFuncSetAttribute(geo_gcn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = smem;
     }
-    geo_gcn_bwd_kernel<<<cdiv(P.B * P.T, GB_FPC), GB_THREADS, smem, stream>>>(P);
+    const int fpc = cdiv(P.B * P.T, num_sms());          // frames per CTA: one wave, the register partials are flushed once per CTA
+    geo_gcn_bwd_kernel<<<cdiv(P.B * P.T, fpc), GB_THREADS, smem, stream>>>(P, fpc);
     TG_LAUNCH_OK();
     return 0;
 }

@@ -1,4 +1,4 @@
-"""2g-gcn_b200 — B200-native (sm_100a) implementation of the 2G-GCN forward hot path.
+"""2g-gcn_b200 — B200-native (sm_100a) implementation of the 2G-GCN forward/backward hot path.
 
 The directory name is the one the build contract prescribes; because it is not a valid Python
 identifier, import it with ``importlib.import_module('2g-gcn_b200')`` or through the alias module
@@ -8,9 +8,10 @@ Public surface (mirrors the reference's ``vhoi.models`` for this path):
     TGGCN, select_model, install_dropin      -- drop-in model class (model.py)
     abi                                      -- ctypes binding of include/tggcn_b200.h
     synth                                    -- synthetic MPHOI/CAD-120/Bimanual-shaped batches
+    dp                                       -- data-parallel glue: batch sharding + one all-reduce of the flat gradient
     build                                    -- in-tree nvcc build of lib2ggcn_b200.so
 """
-from . import abi, synth            # noqa: F401
+from . import abi, dp, synth        # noqa: F401
 from .model import TGGCN, select_model, install_dropin   # noqa: F401
 
-__all__ = ['TGGCN', 'select_model', 'install_dropin', 'abi', 'synth']
+__all__ = ['TGGCN', 'select_model', 'install_dropin', 'abi', 'dp', 'synth']

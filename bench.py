@@ -252,6 +252,8 @@ def run_ours(args, rank, world, local_rank):
         line['train_step'] = train
     if world == 1 and not args.no_cpu_baseline:
         line['cpu_baseline'] = cpu_port_throughput(args, shape, kwargs, warmup=1, steps=2)
+        if train is not None:
+            line['cpu_baseline']['train_step'] = cpu_port_train_throughput(args, shape, kwargs)
     print(json.dumps(line), flush=True)
 
 
@@ -266,6 +268,8 @@ def train_step_throughput(args, pkg, shape, kwargs, dev, rank, world, flush, bar
     model = pkg.TGGCN(**kwargs).to(dev).train()
     model.gemm_path = args.gemm_path
     opt = torch.optim.Adam(model.parameters(), lr=1e-4)
+    reducer = pkg.dp.GradientAllReduce(model)
+    reducer.sync_parameters()
     B, T = args.B, args.T
     host = pkg.synth.make_batch(shape, B, T, seed=1234 + rank)
     x = {k: host[k].to(dev) for k in ('x_human', 'x_objects', 'objects_mask')}
@@ -279,9 +283,7 @@ def train_step_throughput(args, pkg, shape, kwargs, dev, rank, world, flush, bar
         loss = sum(orc.multi_task_loss(out, targets, shape.dataset, 2))
         loss.backward()
         if world > 1:                                  # data-parallel: one all-reduce of the flat gradient buffer
-            dist.all_reduce(model.flat_grad)
-            model.flat_grad.div_(world)
-            model.bind_flat_grads()
+            reducer.reduce()
         opt.step()
         return loss
 
@@ -337,6 +339,39 @@ def cpu_port_throughput(args, shape, kwargs, warmup, steps):
                       f'{cores} torch threads', 'seconds_per_step': sec}
 
 
+def cpu_port_train_throughput(args, shape, kwargs, T_sample=32, steps=1):
+    """CPU train step of the reference path (oracle port: train-mode forward + criterion + autograd backward + Adam) on a
+    bounded sample: the full batch of videos, truncated to T_sample frames (cost is linear in T: two recurrent loops)."""
+    sys.path.insert(0, os.path.join(ROOT, 'oracle'))
+    import tggcn_oracle as orc
+    pkg = importlib.import_module('2g-gcn_b200')
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    torch.manual_seed(0)
+    sd = pkg.TGGCN(**kwargs).state_dict()
+    params = {k: (v.detach().clone().requires_grad_(True) if (v.is_floating_point() and 'running' not in k) else v.clone())
+              for k, v in sd.items()}
+    opt = torch.optim.Adam([v for v in params.values() if v.requires_grad], lr=1e-4)
+    B, T = args.B, min(T_sample, args.T)
+    batch = pkg.synth.make_batch(shape, B, T, seed=1234)
+    targets = pkg.synth.target_list(shape, pkg.synth.make_targets(shape, batch['lengths'], T, seed=77))
+    cfg = orc.OracleConfig(args.D, shape.V, shape.num_classes, shape.hh, True, kwargs['update_segment_threshold'])
+    times = []
+    for i in range(1 + steps):
+        t0 = time.perf_counter()
+        opt.zero_grad(set_to_none=True)
+        out = orc.forward(params, cfg, batch['x_human'], batch['x_objects'], batch['objects_mask'], None, None, None, training=True)
+        loss = sum(orc.multi_task_loss(out, targets, shape.dataset, 2))
+        loss.backward()
+        opt.step()
+        if i >= 1:
+            times.append(time.perf_counter() - t0)
+    sec = sum(times) / len(times)
+    return {'value': B * T / sec, 'unit': UNIT, 'cores': cores, 'kind': 'port', 'seconds_per_step': sec,
+            'sample': f'train step on B={B} videos truncated to T={T} frames (hidden {args.D}), {steps} timed step(s) after 1 warm-up, '
+                      f'{cores} torch threads'}
+
+
 def run_reference(args, rank, world):
     if rank != 0:
         return
@@ -352,6 +387,8 @@ def run_reference(args, rank, world):
         'cpu_baseline': {k: res[k] for k in ('value', 'unit', 'cores', 'kind', 'sample')},
         'e2e': {'value': res['value'], 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
     }
+    if not args.no_train:
+        line['train_step'] = cpu_port_train_throughput(args, shape, kwargs)
     print(json.dumps(line), flush=True)
 
 

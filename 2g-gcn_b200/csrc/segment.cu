@@ -10,7 +10,9 @@
 //   B  cell tiles    : W_ih[:, seg cols] mg + (hoisted frame part) , W_hh h_prev, gate math, blend with
 //                      the hard gate u, publish the new state (which is also the output row)  -> L2
 // The frame-part of W_ih x (3D/4D of the 5D/6D input columns) was hoisted into a batched projection.
+#include <stdlib.h>
 #include "recurrent.cuh"
+#include "recurrent_tc.cuh"
 #include "bigru.h"
 
 namespace tg {
@@ -33,7 +35,9 @@ struct SegShared {
 };
 
 // ---- phase A ------------------------------------------------------------------------------------
-__device__ __forceinline__ void seg_message_tile(const SegParams& P, int tile, int s, float* smem, SegShared& sh) {
+template <bool TC>
+__device__ __forceinline__ void seg_message_tile(const SegParams& P, int tile, int s, float* smem, SegShared& sh, RtcShared& rsh,
+                                                 RtcState& rst) {
     const int D = P.D, T = P.T, B = P.B, H = P.H, O = P.O;
     const int dir = tile / P.msg_tiles_dir;
     int rem = tile - dir * P.msg_tiles_dir;
@@ -86,7 +90,8 @@ __device__ __forceinline__ void seg_message_tile(const SegParams& P, int tile, i
     __syncthreads();
 
     float acc[MSG_NGL][1];
-    tile_accumulate<MSG_NGL, 2, 3>(acc, sh.tab1, sh.tab1, s > 0 ? D : 0, 0, 0u, 0u, P.wm[kind], smem);
+    if (TC) tile_accumulate_tc<MSG_NGL, 2>(acc, sh.tab1, sh.tab1, s > 0 ? D : 0, 0, rsh, rst);
+    else    tile_accumulate<MSG_NGL, 2, 3>(acc, sh.tab1, sh.tab1, (s > 0 && !(P.dbg & 1)) ? D : 0, 0, (P.dbg & 2) ? 0x1fu : 0u, 0u, P.wm[kind], smem);
 
     // thread pair: unit (or receiver) index = tid % 16, sender row = tid / 16
     if (tid < MSG_ROWS * REC_J) {
@@ -138,7 +143,7 @@ __device__ __forceinline__ void seg_message_tile(const SegParams& P, int tile, i
     const int nk_r = recv_h ? P.nk_h : 2;
     const int slot = recv_h ? (kind == 0 ? 0 : P.nk_h - 1) : kind - 2;
     float* mg = recv_h ? P.mg_h : P.mg_o;
-    for (int idx = tid; idx < nb * Er * MSG_UNITS; idx += REC_THREADS) {
+    for (int idx = tid < REC_THREADS ? tid : nb * Er * MSG_UNITS; idx < nb * Er * MSG_UNITS; idx += REC_THREADS) {
         const int c = idx % MSG_UNITS, br = idx / MSG_UNITS;
         const int u = unit0 + c;
         if (u >= D) continue;
@@ -155,9 +160,9 @@ __device__ __forceinline__ void seg_message_tile(const SegParams& P, int tile, i
 // ---- phase B ------------------------------------------------------------------------------------
 // One pipeline over the concatenated K range [segment-message columns of W_ih | W_hh] with four weight groups:
 // r and z accumulate over both segments, n_i only over the first, n_h only over the second (GRU needs them apart).
-template <int NT>
+template <int NT, bool TC>
 __device__ __forceinline__ void seg_cell_tile(const SegParams& P, bool is_h, int dir, int rb, int ub, int s, float* smem,
-                                              SegShared& sh) {
+                                              SegShared& sh, RtcShared& rsh, RtcState& rst) {
     constexpr int RBT = 8 * NT, NPAIR = NT / 2, WR = 4 * REC_J;
     const int D = P.D, T = P.T, B = P.B;
     const int E = is_h ? P.H : P.O;
@@ -208,7 +213,7 @@ __device__ __forceinline__ void seg_cell_tile(const SegParams& P, bool is_h, int
 #pragma unroll
     for (int p = 0; p < NPAIR; ++p) {
         const int lr = (tid >> 4) + 16 * p, r = row0 + lr;
-        valid[p] = unit < D && r < rows && lr < RBT;
+        valid[p] = unit < D && r < rows && lr < RBT && tid < REC_THREADS;
         xg[p][0] = xg[p][1] = xg[p][2] = hprev[p] = ug[p] = 0.0f;
         orow[p] = 0;
         gsave[p] = nullptr;
@@ -226,7 +231,9 @@ __device__ __forceinline__ void seg_cell_tile(const SegParams& P, bool is_h, int
     __syncthreads();
 
     float acc[4][NPAIR];
-    tile_accumulate<4, NT, 3>(acc, sh.tab1, sh.tab2, nk * D, s > 0 ? D : 0, 1u << 3, 1u << 2, Wh, smem);
+    if (TC) tile_accumulate_tc<4, NT>(acc, sh.tab1, sh.tab2, nk * D, s > 0 ? D : 0, rsh, rst);
+    else    tile_accumulate<4, NT, 3>(acc, sh.tab1, sh.tab2, (P.dbg & 1) ? 0 : nk * D, (s > 0 && !(P.dbg & 1)) ? D : 0,
+                                      (P.dbg & 2) ? 0xfu : 1u << 3, (P.dbg & 2) ? 0xfu : 1u << 2, Wh, smem);
 
 #pragma unroll
     for (int p = 0; p < NPAIR; ++p) {
@@ -237,34 +244,46 @@ __device__ __forceinline__ void seg_cell_tile(const SegParams& P, bool is_h, int
     }
 }
 
-__device__ __forceinline__ void seg_cell_dispatch(const SegParams& P, int tile, int s, float* smem, SegShared& sh) {
+template <bool TC>
+__device__ __forceinline__ void seg_cell_dispatch(const SegParams& P, int tile, int s, float* smem, SegShared& sh, RtcShared& rsh,
+                                                  RtcState& rst) {
     const int dir = tile / P.cell_tiles_dir;
     int rem = tile - dir * P.cell_tiles_dir;
     const bool is_h = rem < P.cell_tiles_h_dir;
     if (!is_h) rem -= P.cell_tiles_h_dir;
     const int nub = is_h ? P.nub_h : P.nub_o;
     const int rb = rem / nub, ub = rem - rb * nub;
-    if ((is_h ? P.cfg_h : P.cfg_o) == 4) seg_cell_tile<4>(P, is_h, dir, rb, ub, s, smem, sh);
-    else                                 seg_cell_tile<2>(P, is_h, dir, rb, ub, s, smem, sh);
+    if ((is_h ? P.cfg_h : P.cfg_o) == 4) seg_cell_tile<4, TC>(P, is_h, dir, rb, ub, s, smem, sh, rsh, rst);
+    else                                 seg_cell_tile<2, TC>(P, is_h, dir, rb, ub, s, smem, sh, rsh, rst);
 }
 
-// phases: bit 0 = A (messages), bit 1 = B (cells)
-__global__ void __launch_bounds__(REC_THREADS, 1) segment_kernel(const SegParams P, int s_begin, int s_end, int phases,
-                                                                int persistent) {
+// phases: bit 0 = A (messages), bit 1 = B (cells).  TC: gate tiles on tcgen05 (recurrent_tc.cuh, 288 threads), else mma.sync.
+template <bool TC>
+__global__ void __launch_bounds__(TC ? RTC_THREADS : REC_THREADS, 1) segment_kernel(const SegParams P, int s_begin, int s_end, int phases,
+                                                                                  int persistent) {
     extern __shared__ __align__(16) float smem[];
     __shared__ SegShared sh;
+    __shared__ RtcShared rsh;
+    RtcState rst;
     if (threadIdx.x == 0) sh.s_fail = 0;
+    if (TC) { rtc_init(rsh, rst, reinterpret_cast<uint8_t*>(smem)); rst.dbg = phases >> 4; }
     unsigned int epoch = 0;
-    for (int s = s_begin; s < s_end; ++s) {
+    bool ok = true;
+    for (int s = s_begin; s < s_end && ok; ++s) {
+        if (phases & 4) {       // timing experiment: two bare grid barriers per step
+            if (!grid_barrier(P.sync, epoch, gridDim.x, &sh.s_fail)) { ok = false; break; }
+            if (!grid_barrier(P.sync, epoch, gridDim.x, &sh.s_fail)) { ok = false; break; }
+        }
         if (phases & 1) {
-            for (int tile = blockIdx.x; tile < P.tilesA; tile += gridDim.x) seg_message_tile(P, tile, s, smem, sh);
-            if (persistent && !grid_barrier(P.sync, epoch, gridDim.x, &sh.s_fail)) return;
+            for (int tile = blockIdx.x; tile < P.tilesA; tile += gridDim.x) seg_message_tile<TC>(P, tile, s, smem, sh, rsh, rst);
+            if (persistent && !grid_barrier(P.sync, epoch, gridDim.x, &sh.s_fail)) { ok = false; break; }
         }
         if (phases & 2) {
-            for (int tile = blockIdx.x; tile < P.tilesB; tile += gridDim.x) seg_cell_dispatch(P, tile, s, smem, sh);
-            if (persistent && s + 1 < s_end && !grid_barrier(P.sync, epoch, gridDim.x, &sh.s_fail)) return;
+            for (int tile = blockIdx.x; tile < P.tilesB; tile += gridDim.x) seg_cell_dispatch<TC>(P, tile, s, smem, sh, rsh, rst);
+            if (persistent && s + 1 < s_end && !grid_barrier(P.sync, epoch, gridDim.x, &sh.s_fail)) { ok = false; break; }
         }
     }
+    if (TC) rtc_finish(rst);
 }
 
 int launch_segment(SegParams& P, int persistent, cudaStream_t stream) {
@@ -292,19 +311,21 @@ int launch_segment(SegParams& P, int persistent, cudaStream_t stream) {
     P.msg_tiles_dir = begin;
     P.tilesA = 2 * begin;
 
-    auto kern = segment_kernel;
+    const bool tc = rec_use_tc(D);            // tcgen05 gate tiles need every K segment to be a multiple of 32 floats
+    auto kern = tc ? segment_kernel<true> : segment_kernel<false>;
+    const int threads = tc ? RTC_THREADS : REC_THREADS;
     int fa = tile_smem_floats(4, 4, 3);
     const int fb = tile_smem_floats(MSG_NGL, 2, 3), fc = tile_smem_floats(4, 2, 3);
     if (fb > fa) fa = fb;
     if (fc > fa) fa = fc;
-    const size_t smem = sizeof(float) * (size_t)fa;
-    static bool configured = false;
-    if (!configured) {
+    const size_t smem = tc ? (size_t)RTC_SMEM_BYTES : sizeof(float) * (size_t)fa;
+    static bool configured[2] = {false, false};
+    if (!configured[tc]) {
         TG_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = true;
+        configured[tc] = true;
     }
     int per_sm = 0;
-    TG_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, REC_THREADS, smem));
+    TG_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, smem));
     TG_REQUIRE(per_sm >= 1, "segment: kernel does not fit on an SM (smem %zu)", smem);
     const int capacity = per_sm * num_sms();
 
@@ -322,14 +343,16 @@ int launch_segment(SegParams& P, int persistent, cudaStream_t stream) {
         if (grid > capacity) grid = capacity;
         TG_CUDA_OK(cudaMemsetAsync(P.sync.counter, 0, 2 * sizeof(unsigned int), stream));
         int s0 = 0, s1 = P.T, phases = 3, pers = 1;
+        if (const char* e = getenv("TGGCN_SEG_PHASES")) phases = atoi(e);      // timing experiments only (results are garbage)
+        P.dbg = phases >> 4;
         void* args[] = {(void*)&P, (void*)&s0, (void*)&s1, (void*)&phases, (void*)&pers};
-        TG_CUDA_OK(cudaLaunchCooperativeKernel((const void*)kern, dim3(grid), dim3(REC_THREADS), args, smem, stream));
+        TG_CUDA_OK(cudaLaunchCooperativeKernel((const void*)kern, dim3(grid), dim3(threads), args, smem, stream));
         ++g_launches;
     } else {
         for (int s = 0; s < P.T; ++s) {
-            kern<<<P.tilesA, REC_THREADS, smem, stream>>>(P, s, s + 1, 1, 0);
+            kern<<<P.tilesA, threads, smem, stream>>>(P, s, s + 1, 1, 0);
             TG_LAUNCH_OK();
-            kern<<<P.tilesB, REC_THREADS, smem, stream>>>(P, s, s + 1, 2, 0);
+            kern<<<P.tilesB, threads, smem, stream>>>(P, s, s + 1, 2, 0);
             TG_LAUNCH_OK();
         }
     }

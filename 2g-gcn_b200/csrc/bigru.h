@@ -70,7 +70,6 @@ struct SegParams {
     int cfg_o, jeff_o, nrb_o, nub_o;
     int cell_tiles_h_dir, cell_tiles_dir;
     int tilesA, tilesB;
-    int dbg;                      // timing experiments (TGGCN_SEG_PHASES >> 4): 1 = no K loop, 2 = copies without MMAs
     GridSync sync;
 };
 

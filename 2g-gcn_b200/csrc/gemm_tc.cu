@@ -30,6 +30,8 @@ constexpr int TC_STAGE_BYTES = 4 * TC_TILE_BYTES;                 // A_hi, A_lo,
 constexpr int TC_SMEM_BYTES = TC_STAGES * TC_STAGE_BYTES + 1024;  // + alignment slack
 constexpr uint32_t TC_TMEM_COLS = 128;
 
+// MASK: some problem of the group reads A through a ReLU mask (backward use); compiled out of the forward instantiation.
+template <bool MASK>
 __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const GemmGroup grp) {
     extern __shared__ uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t bars[2 * TC_STAGES + 1];
@@ -87,7 +89,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const GemmGroup 
             aok[i] = (m0 + r) < P.M;
             wok[i] = (n0 + r) < P.N;
             aptr[i] = P.A + (size_t)(aok[i] ? m0 + r : 0) * P.lda + c * 4 + (size_t)kb0 * TC_BK;
-            mptr[i] = P.amask != nullptr ? P.amask + (size_t)(aok[i] ? m0 + r : 0) * P.ldm + c * 4 + (size_t)kb0 * TC_BK : nullptr;
+            mptr[i] = (MASK && P.amask != nullptr) ? P.amask + (size_t)(aok[i] ? m0 + r : 0) * P.ldm + c * 4 + (size_t)kb0 * TC_BK : nullptr;
             wptr[i] = P.W + (size_t)(wok[i] ? n0 + r : 0) * P.ldw + c * 4 + (size_t)kb0 * TC_BK;
         }
         float4 pa0[4], pw0[4], pa1[4], pw1[4];                // register prefetch, two k-blocks deep (static slots)
@@ -95,7 +97,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const GemmGroup 
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
                 pa[i] = aok[i] ? __ldg(reinterpret_cast<const float4*>(aptr[i] + (size_t)kb * TC_BK)) : make_float4(0.f, 0.f, 0.f, 0.f);
-                if (mptr[i] != nullptr && aok[i]) {
+                if (MASK && mptr[i] != nullptr && aok[i]) {
                     const float4 mk = __ldg(reinterpret_cast<const float4*>(mptr[i] + (size_t)kb * TC_BK));
                     pa[i].x = mk.x > 0.f ? pa[i].x : 0.f; pa[i].y = mk.y > 0.f ? pa[i].y : 0.f;
                     pa[i].z = mk.z > 0.f ? pa[i].z : 0.f; pa[i].w = mk.w > 0.f ? pa[i].w : 0.f;
@@ -239,12 +241,16 @@ int launch_gemm_tc(GemmGroup& grp, cudaStream_t stream) {
         p.tile_begin = begin;
         begin += cdiv(p.M, TC_BM) * cdiv(p.N, TC_BN) * p.ksplit;
     }
+    bool mask = false;
+    for (int i = 0; i < grp.count; ++i) mask |= grp.p[i].amask != nullptr;
     static bool configured = false;
     if (!configured) {
-        TG_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
+        TG_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
+        TG_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
         configured = true;
     }
-    gemm_tc_kernel<<<begin, TC_THREADS, TC_SMEM_BYTES, stream>>>(grp);
+    if (mask) gemm_tc_kernel<true><<<begin, TC_THREADS, TC_SMEM_BYTES, stream>>>(grp);
+    else      gemm_tc_kernel<false><<<begin, TC_THREADS, TC_SMEM_BYTES, stream>>>(grp);
     TG_LAUNCH_OK();
     return 0;
 }

@@ -91,7 +91,7 @@ __device__ __forceinline__ void seg_message_tile(const SegParams& P, int tile, i
 
     float acc[MSG_NGL][1];
     if (TC) tile_accumulate_tc<MSG_NGL, 2>(acc, sh.tab1, sh.tab1, s > 0 ? D : 0, 0, rsh, rst);
-    else    tile_accumulate<MSG_NGL, 2, 3>(acc, sh.tab1, sh.tab1, (s > 0 && !(P.dbg & 1)) ? D : 0, 0, (P.dbg & 2) ? 0x1fu : 0u, 0u, P.wm[kind], smem);
+    else    tile_accumulate<MSG_NGL, 2, 3>(acc, sh.tab1, sh.tab1, s > 0 ? D : 0, 0, 0u, 0u, P.wm[kind], smem);
 
     // thread pair: unit (or receiver) index = tid % 16, sender row = tid / 16
     if (tid < MSG_ROWS * REC_J) {
@@ -232,8 +232,7 @@ __device__ __forceinline__ void seg_cell_tile(const SegParams& P, bool is_h, int
 
     float acc[4][NPAIR];
     if (TC) tile_accumulate_tc<4, NT>(acc, sh.tab1, sh.tab2, nk * D, s > 0 ? D : 0, rsh, rst);
-    else    tile_accumulate<4, NT, 3>(acc, sh.tab1, sh.tab2, (P.dbg & 1) ? 0 : nk * D, (s > 0 && !(P.dbg & 1)) ? D : 0,
-                                      (P.dbg & 2) ? 0xfu : 1u << 3, (P.dbg & 2) ? 0xfu : 1u << 2, Wh, smem);
+    else    tile_accumulate<4, NT, 3>(acc, sh.tab1, sh.tab2, nk * D, s > 0 ? D : 0, 1u << 3, 1u << 2, Wh, smem);
 
 #pragma unroll
     for (int p = 0; p < NPAIR; ++p) {
@@ -266,7 +265,7 @@ __global__ void __launch_bounds__(TC ? RTC_THREADS : REC_THREADS, 1) segment_ker
     __shared__ RtcShared rsh;
     RtcState rst;
     if (threadIdx.x == 0) sh.s_fail = 0;
-    if (TC) { rtc_init(rsh, rst, reinterpret_cast<uint8_t*>(smem)); rst.dbg = phases >> 4; }
+    if (TC) { rtc_init(rsh, rst, reinterpret_cast<uint8_t*>(smem)); rst.dbg = phases >> 4; }      // dbg: timing experiments
     unsigned int epoch = 0;
     bool ok = true;
     for (int s = s_begin; s < s_end && ok; ++s) {
@@ -344,7 +343,6 @@ int launch_segment(SegParams& P, int persistent, cudaStream_t stream) {
         TG_CUDA_OK(cudaMemsetAsync(P.sync.counter, 0, 2 * sizeof(unsigned int), stream));
         int s0 = 0, s1 = P.T, phases = 3, pers = 1;
         if (const char* e = getenv("TGGCN_SEG_PHASES")) phases = atoi(e);      // timing experiments only (results are garbage)
-        P.dbg = phases >> 4;
         void* args[] = {(void*)&P, (void*)&s0, (void*)&s1, (void*)&phases, (void*)&pers};
         TG_CUDA_OK(cudaLaunchCooperativeKernel((const void*)kern, dim3(grid), dim3(threads), args, smem, stream));
         ++g_launches;

@@ -126,6 +126,8 @@ int launch_bigru(BiGruParams& P, int persistent, cudaStream_t stream) {
     const int capacity = per_sm * num_sms();
     plan_tiles(P);
     if (persistent) {
+        const int rc = launch_bigru_resident(P, stream);      // recurrent weights resident in shared memory when the shape allows
+        if (rc >= 0) return rc;
         const int grid = P.total_tiles < capacity ? P.total_tiles : capacity;
         TG_CUDA_OK(cudaMemsetAsync(P.sync.counter, 0, 2 * sizeof(unsigned int), stream));
         int s0 = 0, s1 = P.T, pers = 1;

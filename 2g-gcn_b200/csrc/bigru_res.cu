@@ -1,0 +1,264 @@
+// Frame-level bidirectional GRUs with SMEM-RESIDENT recurrent weights (K-C, second design).
+//
+// The streaming kernel (bigru.cu) re-reads the 18.9 MB of W_hh from L2 on every one of the T steps.  W_hh of all three
+// groups and both directions fits in the shared memory of the chip: each CTA owns up to three blocks of 8 hidden units
+// (x 3 gates = 72 weight rows of D floats, 145 KB at D = 512) of ONE (group, direction), loads them once, and keeps them
+// for all T steps.  Per step a CTA
+//   1. stages the previous hidden state of its group's rows (<= 32 rows x D floats) from L2 into shared memory (cp.async),
+//   2. multiplies on the tensor cores from shared memory only: mma.sync m16n8k8 TF32 with the 3xTF32 split, A = state rows,
+//      B = resident weight rows, K split over the 8 warps (each warp: all 2 x 9 accumulator tiles for D/8 columns),
+//   3. reduces the 8 partial accumulators through shared memory (the staging buffer is reused), applies the GRU gate math
+//      for its 24 units and publishes the new state (= the output row) through L2,
+// followed by one grid barrier.  Same arithmetic, rounding class and outputs as bigru_kernel (parity tests unchanged).
+#include <stdlib.h>
+#include "recurrent.cuh"
+#include "bigru.h"
+
+namespace tg {
+
+namespace {
+
+constexpr int BR_UB = 8;          // hidden units per block (one n8 MMA tile per gate)
+constexpr int BR_NBLK = 3;        // unit blocks per CTA
+constexpr int BR_NT = 3 * BR_NBLK;   // n8 tiles per CTA: [gate][block]
+constexpr int BR_ROWS = 32;       // state rows per pass (two m16 tiles)
+constexpr int BR_ACC = 2 * BR_NT * 4;   // accumulator floats per lane
+
+__device__ __forceinline__ int br_ld(int D) { return D + 4; }    // padded row stride: fragment loads hit 32 distinct banks
+
+__global__ void __launch_bounds__(REC_THREADS, 1) bigru_res_kernel(const BiGruParams P, int ctas_per_gd) {
+    extern __shared__ __align__(16) float smem[];
+    __shared__ int s_fail;
+    __shared__ long long rowoff[BR_ROWS];                // element offset of (video, entity) of each state row at t = 0 (first row block)
+    const int D = P.D, T = P.T, LD = br_ld(D);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int g8 = lane >> 2, t4 = lane & 3;
+    float* wsm = smem;                                   // [BR_NT * 8][LD]   row (nt*8 + n): gate = nt / NBLK, block = nt % NBLK
+    float* hsm = wsm + BR_NT * 8 * LD;                   // [BR_ROWS][LD] staged previous state; reused as the reduction buffer
+    const int gd = blockIdx.x / ctas_per_gd, c = blockIdx.x - gd * ctas_per_gd;
+    const int group = gd >> 1, dir = gd & 1;
+    const BiGruGroup& G = P.g[group];
+    const int nblk = D / BR_UB;
+    const int j0 = c * BR_NBLK;
+    const int nb = min(BR_NBLK, nblk - j0);              // blocks this CTA owns (>= 1 by construction)
+    if (tid == 0) s_fail = 0;
+    const bool single_rb = G.rows <= BR_ROWS;            // the common case: every step sees the same rows -> offsets precomputed
+    if (tid < BR_ROWS) {
+        const int r = tid < G.rows ? tid : 0, b = r / G.E, e = r - b * G.E;
+        rowoff[tid] = ((long long)b * T * G.E + e) * 2 * D + dir * D;
+    }
+
+    // ---- load the resident weight rows once ------------------------------------------------------------------
+    {
+        const float* W = G.whh[dir];
+        const int d4 = D / 4;
+        for (int i = tid; i < BR_NT * 8 * d4; i += REC_THREADS) {
+            const int row = i / d4, c4 = i - row * d4;
+            const int nt = row >> 3, n = row & 7, gate = nt / BR_NBLK, blk = nt - gate * BR_NBLK;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (blk < nb) v = __ldg(reinterpret_cast<const float4*>(W + (size_t)(gate * D + (j0 + blk) * BR_UB + n) * D) + c4);
+            *reinterpret_cast<float4*>(wsm + row * LD + c4 * 4) = v;
+        }
+    }
+    // epilogue constants: this thread's outputs o = tid + 256*q  ->  (m tile, block, accumulator register, lane)
+    float bh[3][3];
+    int o_row[3], o_unit[3], o_base[3];
+    bool o_ok[3];
+#pragma unroll
+    for (int q = 0; q < 3; ++q) {
+        const int o = tid + REC_THREADS * q;
+        const int ol = o & 31, reg = (o >> 5) & 3, blk = (o >> 7) % BR_NBLK, m = o / (128 * BR_NBLK);
+        o_row[q] = m * 16 + (ol >> 2) + ((reg & 2) ? 8 : 0);
+        o_unit[q] = (j0 + blk) * BR_UB + 2 * (ol & 3) + (reg & 1);
+        o_base[q] = ((m * BR_NT + blk) * 4 + reg) * 32 + ol;        // + gate * NBLK * 4 * 32 per gate, + warp * BR_ACC * 32 per partial
+        o_ok[q] = m < 2 && blk < nb;
+#pragma unroll
+        for (int gt = 0; gt < 3; ++gt) bh[q][gt] = o_ok[q] ? __ldg(G.bhh[dir] + gt * D + o_unit[q]) : 0.0f;
+    }
+    long long o_fe0[3];                                  // (video, entity) part of the frame-entity index at t = 0 (first row block)
+#pragma unroll
+    for (int q = 0; q < 3; ++q) {
+        const int r = o_row[q] < G.rows ? o_row[q] : 0, b = r / G.E, e = r - b * G.E;
+        o_fe0[q] = (long long)b * T * G.E + e;
+    }
+    __syncthreads();
+
+    const int kw = D / 64;                               // k8 steps per warp (K split over the 8 warps)
+    unsigned int epoch = 0;
+    bool ok = true;
+    for (int s = 0; s < T && ok; ++s) {
+        const int t = dir == 0 ? s : T - 1 - s;
+        const int tprev = dir == 0 ? t - 1 : t + 1;
+        for (int rb0 = 0; rb0 < G.rows; rb0 += BR_ROWS) {
+            const int nrows = min(BR_ROWS, G.rows - rb0);
+            // ---- 1. stage the previous state of these rows; fetch the epilogue operands meanwhile ------------------
+            if (s > 0) {
+                const int d4 = D / 4;
+                const size_t tstep = (size_t)tprev * G.E * 2 * D;
+                const int rstep = REC_THREADS / d4, cstep = REC_THREADS - rstep * d4;     // (row, column) advance per iteration
+                int row = tid / d4, c4 = tid - row * d4;
+                for (; row < BR_ROWS; row += rstep) {
+                    const bool valid = row < nrows;
+                    const float* src;
+                    if (single_rb) {
+                        src = G.hfr + rowoff[row] + tstep + c4 * 4;
+                    } else {
+                        const int r = rb0 + row;
+                        const int b = valid ? r / G.E : 0, e = valid ? r - b * G.E : 0;
+                        src = G.hfr + ((size_t)(b * T + tprev) * G.E + e) * 2 * D + dir * D + c4 * 4;
+                    }
+                    cp_async16_zfill(hsm + row * LD + c4 * 4, valid ? src : G.hfr, valid);
+                    c4 += cstep;
+                    if (c4 >= d4) { c4 -= d4; ++row; }
+                }
+            }
+            cp_async_commit();
+            float xg[3][3], hprev[3];
+            size_t orow[3];
+            float* gsave[3];
+            bool valid[3];
+#pragma unroll
+            for (int q = 0; q < 3; ++q) {
+                valid[q] = o_ok[q] && o_row[q] < nrows;
+                xg[q][0] = xg[q][1] = xg[q][2] = hprev[q] = 0.0f;
+                orow[q] = 0;
+                gsave[q] = nullptr;
+                if (valid[q]) {
+                    const int unit = o_unit[q];
+                    size_t fe0;
+                    if (single_rb) {
+                        fe0 = (size_t)o_fe0[q];
+                    } else {
+                        const int r = rb0 + o_row[q], b = r / G.E, e = r - b * G.E;
+                        fe0 = (size_t)b * T * G.E + e;
+                    }
+                    const size_t fe = fe0 + (size_t)t * G.E;
+                    const float* gi = G.gi + (fe * 2 + dir) * 3 * D;
+                    xg[q][0] = __ldg(gi + unit); xg[q][1] = __ldg(gi + D + unit); xg[q][2] = __ldg(gi + 2 * D + unit);
+                    if (s > 0) hprev[q] = ld_cg(G.hfr + (fe0 + (size_t)tprev * G.E) * 2 * D + dir * D + unit);
+                    orow[q] = fe * 2 * D + dir * D + unit;
+                    if (G.gates != nullptr) gsave[q] = G.gates + (fe * 2 + dir) * 4 * D + unit;
+                }
+            }
+            cp_async_wait<0>();
+            __syncthreads();
+            float sum[3][3];
+#pragma unroll
+            for (int q = 0; q < 3; ++q) sum[q][0] = sum[q][1] = sum[q][2] = 0.0f;
+            if (s > 0) {
+                // ---- 2. W_hh h on the tensor cores, operands from shared memory only --------------------------------
+                float acc[2][BR_NT][4];
+#pragma unroll
+                for (int m = 0; m < 2; ++m)
+#pragma unroll
+                    for (int nt = 0; nt < BR_NT; ++nt)
+#pragma unroll
+                        for (int r = 0; r < 4; ++r) acc[m][nt][r] = 0.0f;
+                const bool two = nrows > 16;             // second m16 tile holds rows
+#pragma unroll 2
+                for (int kk = 0; kk < kw; ++kk) {
+                    const int k0 = (warp * kw + kk) * 8;
+                    uint32_t ah[2][4], al[2][4];
+#pragma unroll
+                    for (int m = 0; m < 2; ++m) {
+                        if (m == 1 && !two) continue;
+                        const float* hp = hsm + (m * 16 + g8) * LD + k0 + t4;
+                        split_tf32(hp[0], ah[m][0], al[m][0]);
+                        split_tf32(hp[8 * LD], ah[m][1], al[m][1]);
+                        split_tf32(hp[4], ah[m][2], al[m][2]);
+                        split_tf32(hp[8 * LD + 4], ah[m][3], al[m][3]);
+                    }
+#pragma unroll
+                    for (int gt = 0; gt < 3; ++gt) {     // one gate = BR_NBLK n-tiles: 2*NBLK independent accumulators per pass
+                        uint32_t bhi[BR_NBLK][2], blo[BR_NBLK][2];
+#pragma unroll
+                        for (int j = 0; j < BR_NBLK; ++j) {
+                            const float* wp = wsm + ((gt * BR_NBLK + j) * 8 + g8) * LD + k0 + t4;
+                            split_tf32(wp[0], bhi[j][0], blo[j][0]);
+                            split_tf32(wp[4], bhi[j][1], blo[j][1]);
+                        }
+#pragma unroll
+                        for (int j = 0; j < BR_NBLK; ++j) {
+                            mma_tf32(acc[0][gt * BR_NBLK + j], al[0], bhi[j]);
+                            if (two) mma_tf32(acc[1][gt * BR_NBLK + j], al[1], bhi[j]);
+                        }
+#pragma unroll
+                        for (int j = 0; j < BR_NBLK; ++j) {
+                            mma_tf32(acc[0][gt * BR_NBLK + j], ah[0], blo[j]);
+                            if (two) mma_tf32(acc[1][gt * BR_NBLK + j], ah[1], blo[j]);
+                        }
+#pragma unroll
+                        for (int j = 0; j < BR_NBLK; ++j) {
+                            mma_tf32(acc[0][gt * BR_NBLK + j], ah[0], bhi[j]);
+                            if (two) mma_tf32(acc[1][gt * BR_NBLK + j], ah[1], bhi[j]);
+                        }
+                    }
+                }
+                __syncthreads();                         // every warp is done reading the staged state
+                // ---- 3. reduce the 8 K-slices through shared memory ------------------------------------------------
+                float* red = hsm;
+#pragma unroll
+                for (int m = 0; m < 2; ++m)
+#pragma unroll
+                    for (int nt = 0; nt < BR_NT; ++nt)
+#pragma unroll
+                        for (int r = 0; r < 4; ++r) red[(warp * BR_ACC + (m * BR_NT + nt) * 4 + r) * 32 + lane] = acc[m][nt][r];
+                __syncthreads();
+#pragma unroll
+                for (int q = 0; q < 3; ++q) {
+                    if (!o_ok[q]) continue;
+#pragma unroll
+                    for (int gt = 0; gt < 3; ++gt) {
+                        float v = 0.0f;
+#pragma unroll
+                        for (int w = 0; w < REC_WARPS; ++w) v += red[w * BR_ACC * 32 + gt * BR_NBLK * 4 * 32 + o_base[q]];
+                        sum[q][gt] = v;
+                    }
+                }
+            }
+#pragma unroll
+            for (int q = 0; q < 3; ++q)
+                if (valid[q])
+                    G.hfr[orow[q]] = gru_update(xg[q][0], xg[q][1], xg[q][2], sum[q][0] + bh[q][0], sum[q][1] + bh[q][1],
+                                                sum[q][2] + bh[q][2], hprev[q], gsave[q], D);
+            __syncthreads();                             // the reduction buffer becomes the staging buffer again
+        }
+        if (s + 1 < T && !grid_barrier(P.sync, epoch, gridDim.x, &s_fail)) ok = false;
+    }
+}
+
+}  // namespace
+
+// Returns 0 when the resident kernel was launched, -1 when this shape does not qualify (caller falls back), > 0 on error.
+int launch_bigru_resident(BiGruParams& P, cudaStream_t stream) {
+    static int enabled = -1;
+    if (enabled < 0) {
+        const char* e = getenv("TGGCN_BIGRU_RES");
+        enabled = (e != nullptr && e[0] == '0') ? 0 : 1;
+    }
+    const int D = P.D;
+    if (!enabled || D % 64 != 0) return -1;
+    const int LD = D + 4;
+    const size_t red_floats = (size_t)REC_WARPS * BR_ACC * 32, stage_floats = (size_t)BR_ROWS * LD;
+    const size_t smem = sizeof(float) * ((size_t)BR_NT * 8 * LD + (red_floats > stage_floats ? red_floats : stage_floats));
+    if (smem > 227 * 1024) return -1;
+    const int ctas_per_gd = cdiv(D / BR_UB, BR_NBLK);
+    const int grid = 2 * P.ngroups * ctas_per_gd;
+    auto kern = bigru_res_kernel;
+    static size_t configured = 0;
+    if (smem > configured) {
+        TG_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = smem;
+    }
+    int per_sm = 0;
+    TG_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, REC_THREADS, smem));
+    if (per_sm < 1 || grid > per_sm * num_sms()) return -1;
+    TG_CUDA_OK(cudaMemsetAsync(P.sync.counter, 0, 2 * sizeof(unsigned int), stream));
+    int cpg = ctas_per_gd;
+    void* args[] = {(void*)&P, (void*)&cpg};
+    TG_CUDA_OK(cudaLaunchCooperativeKernel((const void*)kern, dim3(grid), dim3(REC_THREADS), args, smem, stream));
+    ++g_launches;
+    return 0;
+}
+
+}  // namespace tg

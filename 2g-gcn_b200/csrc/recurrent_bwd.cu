@@ -12,6 +12,7 @@
 //                            the epilogue the gated-cell backward of the next reverse step (writes dGs / dGhs / d u).
 // Weight gradients are NOT accumulated here: dGi/dGh/d pre of every step are kept and contracted afterwards in a few
 // large GEMMs over all (video, t, entity) rows (api_bwd.cu).
+#include <stdlib.h>
 #include "recurrent.cuh"
 #include "backward.cuh"
 
@@ -198,25 +199,38 @@ __device__ __forceinline__ void seg_bwd_msg_item(const SegBwdParams& P, int item
     float* ss = sr + ME * D;            // [Es][D]  senders' previous states
 
     __syncthreads();
-    {
+    const int d4 = D / 4;
+    {   // all four operand blocks in flight at once (cp.async through L2: d mg was written by other CTAs in phase A)
         const float* src = (recv_h ? P.dmg_h : P.dmg_o) + ((size_t)dir * rows_r + b * Er) * ldr + slot * D;
-        for (int i = tid; i < Er * D; i += REC_THREADS) { const int r = i / D, c = i - r * D; dmg[i] = ld_cg(src + (size_t)r * ldr + c); }
-        const size_t base_s = (((size_t)dir * B + b) * T + t) * Es;
-        for (int i = tid; i < Es * D; i += REC_THREADS) msg[i] = P.smsg[kind][base_s * D + i];
-        if (tid < Er * Es) sh.al[tid] = P.salpha[kind][((((size_t)dir * B + b) * T + t) * Er) * Es + tid];
-        if (has_prev) {
-            const float* hr = recv_h ? P.hx_h : P.hx_o;
-            const float* hs = send_h ? P.hx_h : P.hx_o;
-            for (int i = tid; i < Er * D; i += REC_THREADS) { const int r = i / D, c = i - r * D; sr[i] = hr[((size_t)(b * T + tprev) * Er + r) * 2 * D + dir * D + c]; }
-            for (int i = tid; i < Es * D; i += REC_THREADS) { const int q = i / D, c = i - q * D; ss[i] = hs[((size_t)(b * T + tprev) * Es + q) * 2 * D + dir * D + c]; }
+        const float* msrc = P.smsg[kind] + (((size_t)dir * B + b) * T + t) * Es * D;
+        const float* hr = (recv_h ? P.hx_h : P.hx_o) + ((size_t)(b * T + (has_prev ? tprev : 0)) * Er) * 2 * D + dir * D;
+        const float* hs = (send_h ? P.hx_h : P.hx_o) + ((size_t)(b * T + (has_prev ? tprev : 0)) * Es) * 2 * D + dir * D;
+        const int nr = Er * d4, ns = Es * d4;
+        for (int i = tid; i < nr; i += REC_THREADS) {
+            const int r = i / d4, c = (i - r * d4) * 4;
+            cp_async16(dmg + r * D + c, src + (size_t)r * ldr + c);
+            if (has_prev) cp_async16(sr + r * D + c, hr + (size_t)r * 2 * D + c);
         }
+        for (int i = tid; i < ns; i += REC_THREADS) {
+            const int q = i / d4, c = (i - q * d4) * 4;
+            cp_async16(msg + q * D + c, msrc + (size_t)q * D + c);
+            if (has_prev) cp_async16(ss + q * D + c, hs + (size_t)q * 2 * D + c);
+        }
+        cp_async_commit();
+        if (tid < Er * Es) sh.al[tid] = P.salpha[kind][((((size_t)dir * B + b) * T + t) * Er) * Es + tid];
+        cp_async_wait<0>();
     }
     __syncthreads();
     // d alpha[r][q] = <d mg[r], msg[q]>
     for (int p = warp; p < Er * Es; p += REC_WARPS) {
         const int r = p / Es, q = p - r * Es;
+        const float4* x = reinterpret_cast<const float4*>(dmg + r * D);
+        const float4* y = reinterpret_cast<const float4*>(msg + q * D);
         float acc = 0.0f;
-        for (int c = lane; c < D; c += 32) acc = fmaf(dmg[r * D + c], msg[q * D + c], acc);
+        for (int c = lane; c < d4; c += 32) {
+            const float4 u = x[c], v = y[c];
+            acc = fmaf(u.x, v.x, acc); acc = fmaf(u.y, v.y, acc); acc = fmaf(u.z, v.z, acc); acc = fmaf(u.w, v.w, acc);
+        }
         acc = warp_sum(acc);
         if (lane == 0) sh.da[p] = acc;
     }
@@ -228,34 +242,43 @@ __device__ __forceinline__ void seg_bwd_msg_item(const SegBwdParams& P, int item
         for (int q = 0; q < Es; ++q) sh.dl[tid * Es + q] = sh.al[tid * Es + q] * (sh.da[tid * Es + q] - dot) * scale;
     }
     __syncthreads();
-    {   // gradient of the pre-activation of every sender's message MLP
+    {   // gradient of the pre-activation of every sender's message MLP; attention-logit terms of the senders
         const int col = send_h ? (kind == 0 ? 0 : (nks - 1) * D) : (kind == 1 ? 0 : D);
         const int lds = send_h ? nks * D : 2 * D;
         float* dense = (send_h ? P.dpre_h : P.dpre_o) + ((size_t)dir * rows_s + b * Es) * lds + col;
         float* all = P.dpre_all[kind] + (((size_t)dir * B + b) * T + t) * Es * D;
-        for (int i = tid; i < Es * D; i += REC_THREADS) {
-            const int q = i / D, c = i - q * D;
-            float v = 0.0f;
-            for (int r = 0; r < Er; ++r) v = fmaf(sh.al[r * Es + q], dmg[r * D + c], v);
-            v = msg[i] > 0.0f ? v : 0.0f;
-            dense[(size_t)q * lds + c] = v;
-            all[i] = v;
+        float* lgs = P.lgs[kind] + ((size_t)dir * rows_s + b * Es) * D;
+        for (int i = tid; i < Es * d4; i += REC_THREADS) {
+            const int q = i / d4, c = (i - q * d4) * 4;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f), g = make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int r = 0; r < Er; ++r) {
+                const float a = sh.al[r * Es + q];
+                const float4 dm = *reinterpret_cast<const float4*>(dmg + r * D + c);
+                v.x = fmaf(a, dm.x, v.x); v.y = fmaf(a, dm.y, v.y); v.z = fmaf(a, dm.z, v.z); v.w = fmaf(a, dm.w, v.w);
+                if (has_prev) {
+                    const float l = sh.dl[r * Es + q];
+                    const float4 st = *reinterpret_cast<const float4*>(sr + r * D + c);
+                    g.x = fmaf(l, st.x, g.x); g.y = fmaf(l, st.y, g.y); g.z = fmaf(l, st.z, g.z); g.w = fmaf(l, st.w, g.w);
+                }
+            }
+            const float4 m = *reinterpret_cast<const float4*>(msg + q * D + c);
+            v.x = m.x > 0.0f ? v.x : 0.0f; v.y = m.y > 0.0f ? v.y : 0.0f; v.z = m.z > 0.0f ? v.z : 0.0f; v.w = m.w > 0.0f ? v.w : 0.0f;
+            *reinterpret_cast<float4*>(dense + (size_t)q * lds + c) = v;
+            *reinterpret_cast<float4*>(all + (size_t)q * D + c) = v;
+            if (has_prev) *reinterpret_cast<float4*>(lgs + (size_t)q * D + c) = g;
         }
     }
-    if (has_prev) {   // attention-logit terms:  d s_r += sum_q dl[r][q] s_q ,  d s_q += sum_r dl[r][q] s_r
+    if (has_prev) {   // attention-logit terms of the receivers:  d s_r += sum_q dl[r][q] s_q
         float* lgr = P.lgr[kind] + ((size_t)dir * rows_r + b * Er) * D;
-        float* lgs = P.lgs[kind] + ((size_t)dir * rows_s + b * Es) * D;
-        for (int i = tid; i < Er * D; i += REC_THREADS) {
-            const int r = i / D, c = i - r * D;
-            float v = 0.0f;
-            for (int q = 0; q < Es; ++q) v = fmaf(sh.dl[r * Es + q], ss[q * D + c], v);
-            lgr[i] = v;
-        }
-        for (int i = tid; i < Es * D; i += REC_THREADS) {
-            const int q = i / D, c = i - q * D;
-            float v = 0.0f;
-            for (int r = 0; r < Er; ++r) v = fmaf(sh.dl[r * Es + q], sr[r * D + c], v);
-            lgs[i] = v;
+        for (int i = tid; i < Er * d4; i += REC_THREADS) {
+            const int r = i / d4, c = (i - r * d4) * 4;
+            float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int q = 0; q < Es; ++q) {
+                const float l = sh.dl[r * Es + q];
+                const float4 st = *reinterpret_cast<const float4*>(ss + q * D + c);
+                g.x = fmaf(l, st.x, g.x); g.y = fmaf(l, st.y, g.y); g.z = fmaf(l, st.z, g.z); g.w = fmaf(l, st.w, g.w);
+            }
+            *reinterpret_cast<float4*>(lgr + (size_t)r * D + c) = g;
         }
     }
 }
@@ -484,6 +507,7 @@ int launch_segment_bwd(SegBwdParams& P, int persistent, cudaStream_t stream) {
         if (grid > capacity) grid = capacity;
         TG_CUDA_OK(cudaMemsetAsync(P.sync.counter, 0, 2 * sizeof(unsigned int), stream));
         int s0 = -1, s1 = P.T, phases = 7, pers = 1;
+        if (const char* e = getenv("TGGCN_SEGBWD_PHASES")) phases = atoi(e);   // timing experiments only (results are garbage)
         void* args[] = {(void*)&P, (void*)&s0, (void*)&s1, (void*)&phases, (void*)&pers};
         TG_CUDA_OK(cudaLaunchCooperativeKernel((const void*)kern, dim3(grid), dim3(REC_THREADS), args, smem, stream));
         ++g_launches;

@@ -68,6 +68,31 @@ __device__ __forceinline__ void bigru_bwd_tile(const BiGruBwdParams& P, const Bi
         }
         sh.tab1[tid] = ptr;
     }
+    // epilogue operands, fetched before the K loop so that their latency overlaps it
+    float e_dh[NPAIR][NG], e_r[NPAIR][NG], e_z[NPAIR][NG], e_n[NPAIR][NG], e_hn[NPAIR][NG], e_hp[NPAIR][NG];
+    bool ok[NPAIR];
+    size_t e_fe[NPAIR];
+#pragma unroll
+    for (int p = 0; p < NPAIR; ++p) {
+        const int lr = (tid >> 4) + 16 * p, r = row0 + lr;
+        ok[p] = r < G.rows && lr < RBT;
+        e_fe[p] = 0;
+#pragma unroll
+        for (int g = 0; g < NG; ++g) e_dh[p][g] = e_r[p][g] = e_z[p][g] = e_n[p][g] = e_hn[p][g] = e_hp[p][g] = 0.0f;
+        if (!ok[p]) continue;
+        const int b = r / G.E, e = r - b * G.E;
+        const size_t fe = (size_t)(b * T + t) * G.E + e;
+        e_fe[p] = fe;
+#pragma unroll
+        for (int g = 0; g < NG; ++g) {
+            const int unit = unit0 + g * REC_J + (tid & 15);
+            if (unit >= D) continue;
+            e_dh[p][g] = G.dhfr[fe * 2 * D + dir * D + unit] + (s > 0 ? G.direct[((size_t)dir * G.rows + r) * D + unit] : 0.0f);
+            const float* gt = G.gates + (fe * 2 + dir) * 4 * D + unit;
+            e_r[p][g] = gt[0]; e_z[p][g] = gt[D]; e_n[p][g] = gt[2 * D]; e_hn[p][g] = gt[3 * D];
+            e_hp[p][g] = has_prev ? G.hfr[((size_t)(b * T + tprev) * G.E + e) * 2 * D + dir * D + unit] : 0.0f;
+        }
+    }
     __syncthreads();
 
     float acc[NG][NPAIR];
@@ -75,19 +100,15 @@ __device__ __forceinline__ void bigru_bwd_tile(const BiGruBwdParams& P, const Bi
 
 #pragma unroll
     for (int p = 0; p < NPAIR; ++p) {
-        const int lr = (tid >> 4) + 16 * p, r = row0 + lr;
-        if (r >= G.rows || lr >= RBT) continue;
-        const int b = r / G.E, e = r - b * G.E;
-        const size_t fe = (size_t)(b * T + t) * G.E + e;
+        if (!ok[p]) continue;
+        const int r = row0 + (tid >> 4) + 16 * p;
+        const size_t fe = e_fe[p];
 #pragma unroll
         for (int g = 0; g < NG; ++g) {
             const int unit = unit0 + g * REC_J + (tid & 15);
             if (unit >= D) continue;
-            float* dirp = G.direct + ((size_t)dir * G.rows + r) * D + unit;
-            const float dh = G.dhfr[fe * 2 * D + dir * D + unit] + (s > 0 ? *dirp + acc[g][p] : 0.0f);
-            const float* gt = G.gates + (fe * 2 + dir) * 4 * D + unit;
-            const float rr = gt[0], z = gt[D], n = gt[2 * D], hn = gt[3 * D];
-            const float hprev = has_prev ? G.hfr[((size_t)(b * T + tprev) * G.E + e) * 2 * D + dir * D + unit] : 0.0f;
+            const float dh = e_dh[p][g] + (s > 0 ? acc[g][p] : 0.0f);
+            const float rr = e_r[p][g], z = e_z[p][g], n = e_n[p][g], hn = e_hn[p][g], hprev = e_hp[p][g];
             // h = n + z (hprev - n)
             const float dan = dh * (1.0f - z) * (1.0f - n * n);
             const float daz = dh * (hprev - n) * z * (1.0f - z);
@@ -96,7 +117,7 @@ __device__ __forceinline__ void bigru_bwd_tile(const BiGruBwdParams& P, const Bi
             gi[0] = dar; gi[D] = daz; gi[2 * D] = dan;
             float* gh = G.dgh + (fe * 2 + dir) * 3 * D + unit;
             gh[0] = dar; gh[D] = daz; gh[2 * D] = dan * rr;
-            *dirp = dh * z;
+            G.direct[((size_t)dir * G.rows + r) * D + unit] = dh * z;
         }
     }
 }
@@ -322,10 +343,8 @@ __device__ __forceinline__ void seg_bwd_carry_tile(const SegBwdParams& P, bool i
         sh.tab1[tid] = p1;
         sh.tab2[tid] = p2;
     }
-    __syncthreads();
-    float acc[NG][NPAIR];
-    tile_accumulate<NG, NT, 3>(acc, sh.tab1, sh.tab2, gemm ? 3 * D : 0, gemm ? nks * D : 0, 0u, 0u, whhT, smem);
-
+    // epilogue operands: fetched before the K loop so that their latency overlaps it (the attention-logit terms were written
+    // by phase B, complete since the last grid barrier)
     const float* hx = is_h ? P.hx_h : P.hx_o;
     const float* dhx = is_h ? P.dhx_h : P.dhx_o;
     const float* sgb = is_h ? P.sgates_h : P.sgates_o;
@@ -334,35 +353,64 @@ __device__ __forceinline__ void seg_bwd_carry_tile(const SegBwdParams& P, bool i
     float* dghs_o = is_h ? P.dghs_h : P.dghs_o;
     float* du = is_h ? P.du_h : P.du_o;
     float* direct = is_h ? P.direct_h : P.direct_o;
+    float e_base[NPAIR][NG], e_dhx[NPAIR][NG], e_r[NPAIR][NG], e_z[NPAIR][NG], e_n[NPAIR][NG], e_hn[NPAIR][NG], e_hp[NPAIR][NG], e_u[NPAIR];
+    bool rvalid[NPAIR];
+    size_t e_fe[NPAIR];
 #pragma unroll
     for (int p = 0; p < NPAIR; ++p) {
         const int lr = (tid >> 4) + 16 * p, r = row0 + lr;
-        const bool rvalid = r < rows && lr < RBT;                 // uniform over the 16 lanes that share the row
-        float du_part = 0.0f;
-        if (rvalid) {
+        rvalid[p] = r < rows && lr < RBT;                         // uniform over the 16 lanes that share the row
+        e_u[p] = 0.0f;
+        e_fe[p] = 0;
+#pragma unroll
+        for (int g = 0; g < NG; ++g) e_base[p][g] = e_dhx[p][g] = e_r[p][g] = e_z[p][g] = e_n[p][g] = e_hn[p][g] = e_hp[p][g] = 0.0f;
+        if (rvalid[p]) {
             const int b = r / E, e = r - b * E;
             const size_t fe = (size_t)(b * T + t) * E + e;
-            const float u = ub_[fe];
+            e_fe[p] = fe;
+            e_u[p] = ub_[fe];
 #pragma unroll
             for (int g = 0; g < NG; ++g) {
                 const int unit = unit0 + g * REC_J + (tid & 15);
                 if (unit >= D) continue;
                 const size_t ro = ((size_t)dir * rows + r) * D + unit;
-                float carry = 0.0f;
+                float base = 0.0f;
                 if (gemm) {
-                    carry = direct[ro] + acc[g][p];
-                    // attention-logit terms written by phase B (kinds: 0 hh, 1 oh, 2 ho, 3 oo)
+                    base = direct[ro];
+                    // attention-logit terms (kinds: 0 hh, 1 oh, 2 ho, 3 oo)
                     if (is_h) {
-                        if (P.hh) carry += ld_cg(P.lgr[0] + ro) + ld_cg(P.lgs[0] + ro);
-                        carry += ld_cg(P.lgr[1] + ro) + ld_cg(P.lgs[2] + ro);
+                        if (P.hh) base += ld_cg(P.lgr[0] + ro) + ld_cg(P.lgs[0] + ro);
+                        base += ld_cg(P.lgr[1] + ro) + ld_cg(P.lgs[2] + ro);
                     } else {
-                        carry += ld_cg(P.lgs[1] + ro) + ld_cg(P.lgr[2] + ro) + ld_cg(P.lgr[3] + ro) + ld_cg(P.lgs[3] + ro);
+                        base += ld_cg(P.lgs[1] + ro) + ld_cg(P.lgr[2] + ro) + ld_cg(P.lgr[3] + ro) + ld_cg(P.lgs[3] + ro);
                     }
                 }
-                const float dH = dhx[fe * 2 * D + dir * D + unit] + carry;
+                e_base[p][g] = base;
+                e_dhx[p][g] = dhx[fe * 2 * D + dir * D + unit];
                 const float* sg = sgb + (fe * 2 + dir) * 4 * D + unit;
-                const float rr = sg[0], z = sg[D], n = sg[2 * D], hn = sg[3 * D];
-                const float hprev = has_prev ? hx[((size_t)(b * T + tprev) * E + e) * 2 * D + dir * D + unit] : 0.0f;
+                e_r[p][g] = sg[0]; e_z[p][g] = sg[D]; e_n[p][g] = sg[2 * D]; e_hn[p][g] = sg[3 * D];
+                e_hp[p][g] = has_prev ? hx[((size_t)(b * T + tprev) * E + e) * 2 * D + dir * D + unit] : 0.0f;
+            }
+        }
+    }
+    __syncthreads();
+    float acc[NG][NPAIR];
+    tile_accumulate<NG, NT, 3>(acc, sh.tab1, sh.tab2, gemm ? 3 * D : 0, gemm ? nks * D : 0, 0u, 0u, whhT, smem);
+
+#pragma unroll
+    for (int p = 0; p < NPAIR; ++p) {
+        const int lr = (tid >> 4) + 16 * p, r = row0 + lr;
+        float du_part = 0.0f;
+        if (rvalid[p]) {
+            const size_t fe = e_fe[p];
+            const float u = e_u[p];
+#pragma unroll
+            for (int g = 0; g < NG; ++g) {
+                const int unit = unit0 + g * REC_J + (tid & 15);
+                if (unit >= D) continue;
+                const size_t ro = ((size_t)dir * rows + r) * D + unit;
+                const float dH = e_dhx[p][g] + e_base[p][g] + (gemm ? acc[g][p] : 0.0f);
+                const float rr = e_r[p][g], z = e_z[p][g], n = e_n[p][g], hn = e_hn[p][g], hprev = e_hp[p][g];
                 const float hnew = n + z * (hprev - n);
                 du_part += dH * (hnew - hprev);
                 const float dhnew = u * dH;
@@ -377,10 +425,7 @@ __device__ __forceinline__ void seg_bwd_carry_tile(const SegBwdParams& P, bool i
             }
         }
         du_part = half_warp_sum(du_part);
-        if (rvalid && (tid & 15) == 0) {
-            const int b = r / E, e = r - b * E;
-            atomicAdd(du + (size_t)(b * T + t) * E + e, du_part);
-        }
+        if (rvalid[p] && (tid & 15) == 0) atomicAdd(du + e_fe[p], du_part);
     }
 }
 

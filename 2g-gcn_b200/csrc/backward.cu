@@ -10,25 +10,32 @@ namespace tg {
 // =============================================================================================================
 // heads
 // =============================================================================================================
+constexpr int HB_ROWS = 64;        // rows (video, frame, entity) per CTA
+
+// Two passes per CTA over its HB_ROWS rows: (1) one warp per row recomputes the logits, forms d log-softmax (kept in shared
+// memory) and scatters d x = dz W into d hfr / d hx (atomics: several frames share a segment-end row); (2) every thread owns
+// 2D/256 input columns and accumulates dW[c][k] = sum_rows dz[row][c] x[row][k] in registers — no shared-memory atomics — and
+// flushes once per CTA.
 __global__ void __launch_bounds__(256) heads_bwd_kernel(const HeadsBwdParams P) {
-    extern __shared__ __align__(16) float sm[];
+    __shared__ float sdz[HB_ROWS][33];
+    __shared__ size_t sx[HB_ROWS];
     const int hd = blockIdx.y, src = hd >> 1;
     if (P.dlogp[hd] == nullptr) return;
     const int D2 = 2 * P.D, C = P.C;
-    float* sdw = sm;                 // [C][D2]
-    float* sdb = sm + C * D2;        // [C]
-    for (int i = threadIdx.x; i < C * D2 + C; i += blockDim.x) sm[i] = 0.0f;
-    __syncthreads();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int rows = P.B * P.T * P.E;
+    const int row0 = blockIdx.x * HB_ROWS, nrows = min(HB_ROWS, rows - row0);
     const float* W = P.w[hd];
-    for (int row = blockIdx.x * 8 + warp; row < rows; row += gridDim.x * 8) {
+    const float* xin = src == 0 ? P.hfr : P.hx;
+    // ---- pass 1 ----
+    for (int lr = warp; lr < nrows; lr += 8) {
+        const int row = row0 + lr;
         const int e = row % P.E, bt = row / P.E;
         const int t = bt % P.T, b = bt / P.T;
         size_t xrow;
         if (src == 0) xrow = (size_t)row;
         else xrow = (size_t)(b * P.T + P.reidx[(size_t)bt * P.NE + P.e_off + e]) * P.E + e;
-        const float* x = (src == 0 ? P.hfr : P.hx) + xrow * D2;
+        const float* x = xin + xrow * D2;
         float mine = -INFINITY;
         for (int c = 0; c < C; ++c) {
             const float* wr = W + (size_t)c * D2;
@@ -47,42 +54,51 @@ __global__ void __launch_bounds__(256) heads_bwd_kernel(const HeadsBwdParams P) 
         const float g = lane < C ? __ldg(P.dlogp[hd] + ((size_t)(b * C + lane) * P.T + t) * P.E + e) : 0.0f;
         const float gs = warp_sum(g);
         const float dz = lane < C ? g - prob * gs : 0.0f;     // d log_softmax
-        if (lane < C) atomicAdd(&sdb[lane], dz);
+        sdz[lr][lane] = dz;
+        if (lane == 0) sx[lr] = xrow;
         float* dxrow = (src == 0 ? P.dhfr : P.dhx) + xrow * D2;
         for (int k0 = 0; k0 < D2; k0 += 128) {               // warp-uniform trip count: the shuffles need every lane
             const int k = k0 + lane * 4;
             const bool ok = k < D2;
-            const float4 xv = ok ? *reinterpret_cast<const float4*>(x + k) : make_float4(0.f, 0.f, 0.f, 0.f);
             float4 dx = make_float4(0.f, 0.f, 0.f, 0.f);
             for (int c = 0; c < C; ++c) {
                 const float dzc = __shfl_sync(0xffffffffu, dz, c);
                 if (!ok) continue;
                 const float4 wv = __ldg(reinterpret_cast<const float4*>(W + (size_t)c * D2 + k));
                 dx.x = fmaf(dzc, wv.x, dx.x); dx.y = fmaf(dzc, wv.y, dx.y); dx.z = fmaf(dzc, wv.z, dx.z); dx.w = fmaf(dzc, wv.w, dx.w);
-                float* d = sdw + c * D2 + k;
-                atomicAdd(d, dzc * xv.x); atomicAdd(d + 1, dzc * xv.y); atomicAdd(d + 2, dzc * xv.z); atomicAdd(d + 3, dzc * xv.w);
             }
             if (ok) { atomicAdd(dxrow + k, dx.x); atomicAdd(dxrow + k + 1, dx.y); atomicAdd(dxrow + k + 2, dx.z); atomicAdd(dxrow + k + 3, dx.w); }
         }
     }
     __syncthreads();
-    for (int i = threadIdx.x; i < C * D2; i += blockDim.x) atomicAdd(P.dw[hd] + i, sdw[i]);
-    for (int i = threadIdx.x; i < C; i += blockDim.x) atomicAdd(P.db[hd] + i, sdb[i]);
+    // ---- pass 2: weight and bias gradients ----
+    for (int k0 = 0; k0 < D2; k0 += 256) {
+        const int k = k0 + threadIdx.x;
+        if (k >= D2) continue;
+        float acc[32];
+#pragma unroll
+        for (int c = 0; c < 32; ++c) acc[c] = 0.0f;
+        for (int lr = 0; lr < nrows; ++lr) {
+            const float xv = xin[sx[lr] * D2 + k];
+#pragma unroll
+            for (int c = 0; c < 32; ++c)
+                if (c < C) acc[c] = fmaf(sdz[lr][c], xv, acc[c]);
+        }
+#pragma unroll
+        for (int c = 0; c < 32; ++c)
+            if (c < C) atomicAdd(P.dw[hd] + (size_t)c * D2 + k, acc[c]);
+    }
+    if (threadIdx.x < C) {
+        float sacc = 0.0f;
+        for (int lr = 0; lr < nrows; ++lr) sacc += sdz[lr][threadIdx.x];
+        atomicAdd(P.db[hd] + threadIdx.x, sacc);
+    }
 }
 
 int launch_heads_bwd(const HeadsBwdParams& P, cudaStream_t stream) {
     TG_REQUIRE(P.C >= 1 && P.C <= 32 && P.D % 2 == 0, "heads_bwd: unsupported sizes");
-    const size_t smem = sizeof(float) * ((size_t)P.C * 2 * P.D + P.C);
-    TG_REQUIRE(smem <= 200 * 1024, "heads_bwd: weight gradient tile does not fit in shared memory");
-    static size_t configured = 0;
-    if (smem > configured) {
-        TG_CUDA_OK(cudaFuncSetAttribute(heads_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = smem;
-    }
     const int rows = P.B * P.T * P.E;
-    int chunks = cdiv(rows, 8 * 8);
-    if (chunks > 64) chunks = 64;
-    heads_bwd_kernel<<<dim3(chunks, 4), 256, smem, stream>>>(P);
+    heads_bwd_kernel<<<dim3(cdiv(rows, HB_ROWS), 4), 256, 0, stream>>>(P);
     TG_LAUNCH_OK();
     return 0;
 }

@@ -9,11 +9,12 @@ Public surface (mirrors the reference's ``vhoi.models`` for this path):
     abi                                      -- ctypes binding of include/tggcn_b200.h
     synth                                    -- synthetic MPHOI/CAD-120/Bimanual-shaped batches
     dp                                       -- data-parallel glue: batch sharding + one all-reduce of the flat gradient
+    losses                                   -- fused criterion, drop-in for vhoi.losses.select_loss (budget / BCE / NLL in two kernels)
     feeder                                   -- double-buffered host->device input pipeline (pinned memory, side stream)
     train_loop                               -- data-parallel counterpart of train_utils.train_single_epoch
     build                                    -- in-tree nvcc build of lib2ggcn_b200.so
 """
-from . import abi, dp, feeder, synth, train_loop        # noqa: F401
+from . import abi, dp, feeder, losses, synth, train_loop        # noqa: F401
 from .model import TGGCN, select_model, install_dropin   # noqa: F401
 
-__all__ = ['TGGCN', 'select_model', 'install_dropin', 'abi', 'dp', 'feeder', 'synth', 'train_loop']
+__all__ = ['TGGCN', 'select_model', 'install_dropin', 'abi', 'dp', 'feeder', 'losses', 'synth', 'train_loop']

@@ -272,12 +272,10 @@ def run_ours(args, rank, world, local_rank):
 
 
 def train_step_throughput(args, pkg, shape, kwargs, dev, rank, world, flush, barrier):
-    """One training step = forward (BatchNorm in train mode, activations saved) + the criterion of vhoi/losses.py:8
-    (stage-2 weights: BCE on the soft gates + 2 NLL terms, torch ops on our outputs exactly as the unchanged
-    train_utils.py:147-150 does) + the hand-written backward (tggcn_backward) + gradient all-reduce (N > 1) + Adam."""
+    """One training step = forward (BatchNorm in train mode, activations saved) + the fused criterion (drop-in for
+    vhoi/losses.py:8, stage-2 weights: BCE on the soft gates + 2 NLL terms) + the hand-written backward (tggcn_backward) +
+    gradient all-reduce (N > 1) + Adam, in the sequence of train_utils.py:143-154."""
     import torch.distributed as dist
-    sys.path.insert(0, os.path.join(ROOT, 'oracle'))
-    import tggcn_oracle as orc          # loss functions only: the restated criterion, torch ops on device tensors
     torch.manual_seed(0)
     model = pkg.TGGCN(**kwargs).to(dev).train()
     model.gemm_path = args.gemm_path
@@ -291,10 +289,17 @@ def train_step_throughput(args, pkg, shape, kwargs, dev, rank, world, flush, bar
     model.set_gumbel_noise(pkg.TGGCN.draw_gumbel_noise(T * (shape.H + shape.O), B).to(dev))
     lib = pkg.abi.lib()
 
+    class Cfg(dict):                                   # omegaconf-1.4 style node, as vhoi/losses.py:10 reads it
+        def get(self, k, default_value=None):
+            return dict.get(self, k, default_value)
+    # conf/models/2G-GCN_stage2.yaml:37-54: segmentation BCE on, both label NLLs on
+    criterion, _ = pkg.losses.select_loss('2G-GCN', 'multiple', shape.dataset,
+                                          Cfg(misc=dict(segmentation_loss=dict(add=True, sigma=4.0, weight=1.0))))
+
     def step():
         opt.zero_grad(set_to_none=True)
         out = model(**x)
-        loss = sum(orc.multi_task_loss(out, targets, shape.dataset, 2))
+        loss = sum(criterion(out, targets, reduction='mean'))
         loss.backward()
         if world > 1:                                  # data-parallel: one all-reduce of the flat gradient buffer
             reducer.reduce()
@@ -323,7 +328,7 @@ def train_step_throughput(args, pkg, shape, kwargs, dev, rank, world, flush, bar
     ms = float(total.item()) / steps
     return {'value': world * B * T / (ms / 1e3), 'unit': UNIT, 'ms_per_step': ms, 'steps': steps, 'warmup': warmup,
             'gpu_launches_per_step': int(launches // steps), 'loss': float(loss.detach()),
-            'what': 'forward(train-mode BN, saves) + criterion (BCE + 2x NLL) + tggcn_backward + '
+            'what': 'forward(train-mode BN, saves) + fused criterion (BCE + 2x NLL) + tggcn_backward + '
                     + ('NCCL all-reduce of the flat gradient + ' if world > 1 else '') + 'torch.optim.Adam step; fp32 (3xTF32 products)',
             'global_batch_videos': world * B}
 

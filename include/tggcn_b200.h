@@ -331,6 +331,25 @@ TGGCN_API int tggcn_bigru_bwd(const float* dhfr, const float* hfr, const float* 
                               const float* whh_b, float* dgi, float* dgh, float* dwhh_f, float* dwhh_b, float* dbhh_f,
                               float* dbhh_b, float* scratch, int B, int T, int E, int D, int gemm_path, void* stream);
 
+/* ---- fused criterion: multi_task_loss (pyrutils/torch/losses.py:39-51) with the function tuple of vhoi/losses.py:41-60 ----
+ * One term per model output.  budget_loss (pyrutils/torch/losses.py:24-36) and binary_cross_entropy_loss (:7-21) take the
+ * (B,T,E) gate outputs with float targets (-1 = ignore); F.nll_loss(ignore_index=-1, 'mean') takes (B,C,T,E) log-probs with
+ * int64 targets (B,T,E). */
+enum tggcn_loss_kind { TGGCN_LOSS_BUDGET = 0, TGGCN_LOSS_BCE = 1, TGGCN_LOSS_NLL = 2 };
+typedef struct tggcn_loss_term {
+    int32_t kind;                /* enum tggcn_loss_kind                                                          */
+    float   weight;              /* vhoi/losses.py:8-61                                                            */
+    const float* out;            /* model output                                                                   */
+    const void*  target;         /* float (budget / bce) or int64 (nll), -1 = ignore                               */
+    float*  d_out;               /* backward: gradient w.r.t. `out`, same shape, overwritten; NULL = skip           */
+    int64_t numel;               /* budget / bce: elements; nll: B*T*E positions                                    */
+    int32_t B, C, T, E;          /* nll only                                                                        */
+} tggcn_loss_term;
+/* losses: n_terms floats (device) = weight_i * loss_i; scratch: 2*n_terms floats (device), kept for the backward. */
+TGGCN_API int tggcn_loss_fwd(const tggcn_loss_term* terms, int n_terms, float* losses, float* scratch, void* stream);
+/* grad_losses: n_terms floats (device) upstream gradients of the loss values, or NULL for ones. */
+TGGCN_API int tggcn_loss_bwd(const tggcn_loss_term* terms, int n_terms, const float* scratch, const float* grad_losses, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -12,7 +12,6 @@ import torch
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-sys.path.insert(0, os.path.join(ROOT, 'oracle'))
 
 
 def main():
@@ -23,9 +22,9 @@ def main():
     ap.add_argument('--D', type=int, default=512)
     ap.add_argument('--stage', type=int, default=2)
     ap.add_argument('--iters', type=int, default=5)
+    ap.add_argument('--torch-criterion', action='store_true', help='plain torch ops (what the unchanged reference criterion launches)')
     args = ap.parse_args()
     pkg = importlib.import_module('2g-gcn_b200')
-    import tggcn_oracle as orc          # only its loss functions (torch ops standing in for the unchanged criterion)
     shape = pkg.synth.SHAPES[args.shape]
     kwargs = pkg.synth.model_kwargs(shape, hidden_size=args.D, stage=args.stage)
     dev = torch.device('cuda', 0)
@@ -40,6 +39,15 @@ def main():
     n_s = T * ((0 if args.stage == 1 else shape.H) + shape.O)
     noise = pkg.TGGCN.draw_gumbel_noise(n_s, B).to(dev)
     model.set_gumbel_noise(noise)
+    class Cfg(dict):
+        def get(self, k, default_value=None):
+            return dict.get(self, k, default_value)
+    misc = dict(segmentation_loss=dict(add=args.stage == 2, sigma=4.0, weight=1.0))
+    criterion, _ = pkg.losses.select_loss('2G-GCN', 'multiple', shape.dataset, Cfg(misc=misc))
+    if args.torch_criterion:
+        sys.path.insert(0, os.path.join(ROOT, 'oracle'))
+        import tggcn_oracle as orc
+        criterion = lambda o, t, reduction='mean': orc.multi_task_loss(o, t, shape.dataset, args.stage)
     rows = []
     for it in range(args.iters + 2):
         ev = [torch.cuda.Event(enable_timing=True) for _ in range(5)]
@@ -47,7 +55,7 @@ def main():
         ev[0].record()
         out = model(human_segmentation=hseg, **x)
         ev[1].record()
-        loss = sum(orc.multi_task_loss(out, targets, shape.dataset, args.stage))
+        loss = sum(criterion(out, targets, reduction='mean'))
         ev[2].record()
         loss.backward()
         ev[3].record()

@@ -1,0 +1,276 @@
+// Gate tile with ON-CHIP RESIDENT weights for the persistent segment-level kernel (third variant of recurrent.cuh's tile).
+//
+// Measured (profiles/r01_segment_phase_timing.txt): the cell phase of a segment step streams 57 MB through L2 at ~6.7 TB/s —
+// the L2->SM fabric limit — and two thirds of it are the cell weights, which are the SAME on every one of the T steps.  In the
+// persistent kernel a CTA owns the same cell tile on every step, so its weights can stay on the SM:
+//   * each thread keeps ITS OWN mma.sync A-fragments (the 4 fp32 values of a 16x8 weight block that this lane feeds to
+//     mma.m16n8k8) for all K chunks its warp processes: 288 words per thread at D = 512;
+//   * 256 of them live in TENSOR MEMORY, used as a per-thread register-file extension: tcgen05.st 32x32b once at kernel start,
+//     tcgen05.ld 32x32b.x4 inside the K loop (lane i of warp w owns TMEM lane 32*(w%4)+i; warps w and w+4 share a lane
+//     quarter and take columns [0,256) / [256,512)); the remaining words sit in shared memory, one float4 column per thread.
+//     Because every lane reads back exactly what it stored, no layout conversion is ever needed;
+//   * only the ACTIVATION rows (aggregated messages, previous state: 8*NT rows) still stream through the warp-private
+//     cp.async ring, so the ring is a third of its old size and the L2 traffic of the phase drops to the activations.
+// Arithmetic is unchanged: 3xTF32 split in registers, fp32 accumulate, K split over the 8 warps, partials reduced through
+// shared memory (in two halves: the reduction buffer is smaller than before).
+#pragma once
+#include "recurrent.cuh"
+#include "tcgen05.cuh"
+
+namespace tg {
+
+constexpr int RES_TMEM_WORDS = 256;          // per-thread words in tensor memory (512 columns shared by two warps per lane quarter)
+constexpr int RES_SMEM_WORDS = 32;           // per-thread overflow words in shared memory
+constexpr int RES_GROUPS = 3;                // weight groups active in a K chunk of the cell tile: (r, z, n_i) or (r, z, n_h)
+constexpr int RES_CHUNK_WORDS = 2 * RES_GROUPS * 4;   // two k8 steps x 3 groups x 4 fragment registers
+
+struct ResState {
+    uint32_t tmem_base;
+    float4* wovf;            // [RES_SMEM_WORDS / 4][REC_THREADS] overflow fragments
+    int ready;               // fragments of this CTA's cell tile are loaded
+};
+
+__device__ __forceinline__ void tmem_st4(uint32_t taddr, const float (&v)[4]) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1,%2,%3,%4};\n" ::"r"(taddr), "r"(__float_as_uint(v[0])),
+                 "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])), "r"(__float_as_uint(v[3]))
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_ld4_nowait(uint32_t taddr, uint32_t (&r)[4]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0,%1,%2,%3}, [%4];\n" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory"); }
+__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;\n" ::: "memory"); }
+
+// TMEM address of word j of this thread
+__device__ __forceinline__ uint32_t res_taddr(const ResState& rs, int j) {
+    const int warp = threadIdx.x >> 5;
+    return rs.tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)((warp >> 2) * RES_TMEM_WORDS + j);
+}
+
+// Once per kernel (all threads): allocate tensor memory.  Pair with res_finish on every exit path.
+__device__ __forceinline__ void res_init(ResState& rs, uint32_t* tmem_slot, float4* wovf) {
+    if ((threadIdx.x >> 5) == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(tmem_slot)), "r"(512u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    rs.tmem_base = *tmem_slot;
+    rs.wovf = wovf;
+    rs.ready = 0;
+}
+__device__ __forceinline__ void res_finish(ResState& rs) {
+    tc_fence_before();
+    __syncthreads();
+    if ((threadIdx.x >> 5) == 0) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(rs.tmem_base), "r"(512u) : "memory");
+    }
+}
+
+// Load this thread's weight fragments of one cell tile.  wrow1[g*16 + u] / wrow2[...]: weight row pointers of K segment 1 / 2
+// (null = group absent in that segment), exactly the first 64 entries of the streaming tile's pointer tables.
+// Words of chunk n (chunk id = warp + 8 n), k8 step kk, active group gi, register r:  j = ((n*2 + kk)*3 + gi)*4 + r.
+// Returns false (uniformly) when the tile needs more words than fit.
+__device__ __forceinline__ bool res_fill_cell(ResState& rs, const float* const* wrow1, const float* const* wrow2, int K1, int K2) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g8 = lane >> 2, t4 = lane & 3;
+    const int chunks1 = K1 / REC_CK, total = (K1 + K2) / REC_CK;
+    const int nmine = warp < total ? (total - warp + REC_WARPS - 1) / REC_WARPS : 0;
+    const int nmax = (total + REC_WARPS - 1) / REC_WARPS;
+    if (nmax * RES_CHUNK_WORDS > RES_TMEM_WORDS + RES_SMEM_WORDS) return false;
+    for (int n = 0; n < nmine; ++n) {
+        const int chunk = warp + n * REC_WARPS;
+        const bool seg1 = chunk < chunks1;
+        const int kbase = (seg1 ? chunk : chunk - chunks1) * REC_CK;
+#pragma unroll
+        for (int kk = 0; kk < 2; ++kk)
+#pragma unroll
+            for (int gi = 0; gi < RES_GROUPS; ++gi) {
+                const int g = (gi == 2 && !seg1) ? 3 : gi;                     // seg 1: r, z, n_i ; seg 2: r, z, n_h
+                const float* r0 = (seg1 ? wrow1 : wrow2)[g * REC_J + g8];
+                const float* r1 = (seg1 ? wrow1 : wrow2)[g * REC_J + g8 + 8];
+                const int k = kbase + kk * 8 + t4;
+                float v[4];
+                v[0] = r0 != nullptr ? __ldg(r0 + k) : 0.0f;
+                v[1] = r1 != nullptr ? __ldg(r1 + k) : 0.0f;
+                v[2] = r0 != nullptr ? __ldg(r0 + k + 4) : 0.0f;
+                v[3] = r1 != nullptr ? __ldg(r1 + k + 4) : 0.0f;
+                const int j = ((n * 2 + kk) * RES_GROUPS + gi) * 4;
+                if (j < RES_TMEM_WORDS) tmem_st4(res_taddr(rs, j), v);           // warp-uniform branch (j depends on n only)
+                else rs.wovf[((j - RES_TMEM_WORDS) >> 2) * REC_THREADS + tid] = make_float4(v[0], v[1], v[2], v[3]);
+            }
+    }
+    tmem_wait_st();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    rs.ready = 1;
+    return true;
+}
+
+// out[g][p] as tile_accumulate<4, NT, 3> delivers it (groups 0 r, 1 z, 2 n_i, 3 n_h), weights from the resident fragments,
+// activation rows act1 (K segment 1) / act2 (segment 2) through the ring.  K1, K2 multiples of 16 and the same on every call.
+template <int NT>
+__device__ __forceinline__ void tile_accumulate_res(float (&out)[4][(NT + 1) / 2], const float* const* act1, const float* const* act2,
+                                                    int K1, int K2, const ResState& rs, const float* gdummy, float* smem) {
+    constexpr int NG = 4, STAGES = 3, ROWS = 8 * NT;
+    constexpr int STAGE_F = ROWS * REC_RS;
+    constexpr int NP = (ROWS * 4 + 31) / 32;            // 16-byte pieces per lane per chunk
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int g8 = lane >> 2, t4 = lane & 3;
+    float* ring = smem + warp * (STAGES * STAGE_F);
+
+    float c[NG][NT][4];
+#pragma unroll
+    for (int m = 0; m < NG; ++m)
+#pragma unroll
+        for (int n = 0; n < NT; ++n)
+#pragma unroll
+            for (int r = 0; r < 4; ++r) c[m][n][r] = 0.0f;
+
+    const int chunks1 = K1 / REC_CK, total_chunks = (K1 + K2) / REC_CK;
+    const int nmine = warp < total_chunks ? (total_chunks - warp + REC_WARPS - 1) / REC_WARPS : 0;
+    if (nmine > 0) {
+        const float* s1[NP];
+        const float* s2[NP];
+        int dst[NP];
+        bool in[NP];
+#pragma unroll
+        for (int p = 0; p < NP; ++p) {
+            const int piece = lane + p * 32;
+            const int row = piece >> 2, quarter = piece & 3;
+            in[p] = piece < ROWS * 4;
+            const float* b1 = in[p] ? act1[row] : nullptr;
+            const float* b2 = in[p] ? act2[row] : nullptr;
+            s1[p] = b1 != nullptr ? b1 + quarter * 4 : nullptr;
+            s2[p] = b2 != nullptr ? b2 + quarter * 4 - K1 : nullptr;      // indexed with the global k offset
+            dst[p] = row * REC_RS + quarter * 4;
+        }
+        auto issue = [&](int n, int st) {
+            const int chunk = warp + n * REC_WARPS;
+            const bool seg1 = chunk < chunks1;
+            const size_t koff = (size_t)chunk * REC_CK;
+#pragma unroll
+            for (int p = 0; p < NP; ++p) {
+                if (!in[p]) continue;
+                const float* base = seg1 ? s1[p] : s2[p];
+                const bool ok = base != nullptr;
+                cp_async16_zfill(ring + st * STAGE_F + dst[p], ok ? base + koff : gdummy, ok);
+            }
+        };
+#pragma unroll
+        for (int st = 0; st < STAGES - 1; ++st) {
+            if (st < nmine) issue(st, st);
+            cp_async_commit();
+        }
+#pragma unroll 1
+        for (int n = 0; n < nmine; ++n) {
+            // this chunk's weight fragments: tensor memory (or the shared-memory overflow), fetched while the copies land
+            uint32_t w[2][RES_GROUPS][4];
+            const int j0 = n * RES_CHUNK_WORDS;
+#pragma unroll
+            for (int kk = 0; kk < 2; ++kk)
+#pragma unroll
+                for (int gi = 0; gi < RES_GROUPS; ++gi) {
+                    const int j = j0 + (kk * RES_GROUPS + gi) * 4;
+                    if (j < RES_TMEM_WORDS) {
+                        tmem_ld4_nowait(res_taddr(rs, j), w[kk][gi]);
+                    } else {
+                        const float4 v = rs.wovf[((j - RES_TMEM_WORDS) >> 2) * REC_THREADS + tid];
+                        w[kk][gi][0] = __float_as_uint(v.x); w[kk][gi][1] = __float_as_uint(v.y);
+                        w[kk][gi][2] = __float_as_uint(v.z); w[kk][gi][3] = __float_as_uint(v.w);
+                    }
+                }
+            cp_async_wait<STAGES - 2>();
+            __syncwarp();
+            {
+                const int nn = n + STAGES - 1;
+                if (nn < nmine) issue(nn, nn % STAGES);
+                cp_async_commit();
+            }
+            tmem_wait_ld();
+            const bool seg1 = (warp + n * REC_WARPS) < chunks1;
+            const float* xb = ring + (n % STAGES) * STAGE_F + g8 * REC_RS + t4;
+#pragma unroll
+            for (int kk = 0; kk < REC_CK / 8; ++kk) {
+                uint32_t bh[NT][2], bl[NT][2];
+#pragma unroll
+                for (int nt = 0; nt < NT; ++nt) {
+                    split_tf32(xb[nt * 8 * REC_RS + kk * 8], bh[nt][0], bl[nt][0]);
+                    split_tf32(xb[nt * 8 * REC_RS + kk * 8 + 4], bh[nt][1], bl[nt][1]);
+                }
+#pragma unroll
+                for (int gi = 0; gi < RES_GROUPS; ++gi) {
+                    uint32_t ah[4], al[4];
+#pragma unroll
+                    for (int r = 0; r < 4; ++r) {
+                        const float x = __uint_as_float(w[kk][gi][r]);
+                        split_tf32(x, ah[r], al[r]);
+                    }
+                    // seg 1 feeds groups (r, z, n_i) = accumulators 0, 1, 2; seg 2 feeds (r, z, n_h) = 0, 1, 3
+                    if (gi < 2 || seg1) {
+                        float (&cc)[NT][4] = c[gi];
+#pragma unroll
+                        for (int nt = 0; nt < NT; ++nt) mma_tf32(cc[nt], al, bh[nt]);
+#pragma unroll
+                        for (int nt = 0; nt < NT; ++nt) mma_tf32(cc[nt], ah, bl[nt]);
+#pragma unroll
+                        for (int nt = 0; nt < NT; ++nt) mma_tf32(cc[nt], ah, bh[nt]);
+                    } else {
+                        float (&cc)[NT][4] = c[3];
+#pragma unroll
+                        for (int nt = 0; nt < NT; ++nt) mma_tf32(cc[nt], al, bh[nt]);
+#pragma unroll
+                        for (int nt = 0; nt < NT; ++nt) mma_tf32(cc[nt], ah, bl[nt]);
+#pragma unroll
+                        for (int nt = 0; nt < NT; ++nt) mma_tf32(cc[nt], ah, bh[nt]);
+                    }
+                }
+            }
+        }
+        cp_async_wait<0>();
+    }
+    __syncthreads();                             // every warp's ring is dead: reuse the memory for the reduction
+    // cross-warp reduction of the K split in two halves (the buffer holds 4 warps' partials): red[w4][m][n][reg][lane]
+    float* red = smem;
+    if (warp >= 4) {
+#pragma unroll
+        for (int m = 0; m < NG; ++m)
+#pragma unroll
+            for (int n = 0; n < NT; ++n)
+#pragma unroll
+                for (int r = 0; r < 4; ++r) red[((((warp - 4) * NG + m) * NT + n) * 4 + r) * 32 + lane] = c[m][n][r];
+    }
+    __syncthreads();
+    if (warp < 4) {
+#pragma unroll
+        for (int m = 0; m < NG; ++m)
+#pragma unroll
+            for (int n = 0; n < NT; ++n)
+#pragma unroll
+                for (int r = 0; r < 4; ++r) {
+                    const int idx = (((warp * NG + m) * NT + n) * 4 + r) * 32 + lane;
+                    red[idx] += c[m][n][r];
+                }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int p = 0; p < (NT + 1) / 2; ++p) {
+        const int u = tid & 15, row = (tid >> 4) + 16 * p;
+        const int n = row >> 3, col = row & 7;
+        const int l = (u & 7) * 4 + (col >> 1), r = (u >> 3) * 2 + (col & 1);
+#pragma unroll
+        for (int m = 0; m < NG; ++m) {
+            float s = 0.0f;
+            if (n < NT) {
+#pragma unroll
+                for (int w4 = 0; w4 < 4; ++w4) s += red[(((w4 * NG + m) * NT + n) * 4 + r) * 32 + l];
+            }
+            out[m][p] = s;
+        }
+    }
+    __syncthreads();                             // smem may be reused by the caller right away
+}
+
+}  // namespace tg

@@ -13,6 +13,7 @@
 #include <stdlib.h>
 #include "recurrent.cuh"
 #include "recurrent_tc.cuh"
+#include "recurrent_res.cuh"
 #include "bigru.h"
 
 namespace tg {
@@ -35,7 +36,9 @@ struct SegShared {
 };
 
 // ---- phase A ------------------------------------------------------------------------------------
-template <bool TC>
+// MODE: 0 = streaming mma.sync tiles, 1 = tcgen05 gate tile (recurrent_tc.cuh), 2 = streaming message tiles + cell tiles with
+// on-chip resident weights (recurrent_res.cuh)
+template <int MODE>
 __device__ __forceinline__ void seg_message_tile(const SegParams& P, int tile, int s, float* smem, SegShared& sh, RtcShared& rsh,
                                                  RtcState& rst) {
     const int D = P.D, T = P.T, B = P.B, H = P.H, O = P.O;
@@ -90,7 +93,7 @@ __device__ __forceinline__ void seg_message_tile(const SegParams& P, int tile, i
     __syncthreads();
 
     float acc[MSG_NGL][1];
-    if (TC) tile_accumulate_tc<MSG_NGL, 2>(acc, sh.tab1, sh.tab1, s > 0 ? D : 0, 0, rsh, rst);
+    if (MODE == 1) tile_accumulate_tc<MSG_NGL, 2>(acc, sh.tab1, sh.tab1, s > 0 ? D : 0, 0, rsh, rst);
     else    tile_accumulate<MSG_NGL, 2, 3>(acc, sh.tab1, sh.tab1, s > 0 ? D : 0, 0, 0u, 0u, P.wm[kind], smem);
 
     // thread pair: unit (or receiver) index = tid % 16, sender row = tid / 16
@@ -160,9 +163,9 @@ __device__ __forceinline__ void seg_message_tile(const SegParams& P, int tile, i
 // ---- phase B ------------------------------------------------------------------------------------
 // One pipeline over the concatenated K range [segment-message columns of W_ih | W_hh] with four weight groups:
 // r and z accumulate over both segments, n_i only over the first, n_h only over the second (GRU needs them apart).
-template <int NT, bool TC>
+template <int NT, int MODE>
 __device__ __forceinline__ void seg_cell_tile(const SegParams& P, bool is_h, int dir, int rb, int ub, int s, float* smem,
-                                              SegShared& sh, RtcShared& rsh, RtcState& rst) {
+                                              SegShared& sh, RtcShared& rsh, RtcState& rst, ResState& res) {
     constexpr int RBT = 8 * NT, NPAIR = NT / 2, WR = 4 * REC_J;
     const int D = P.D, T = P.T, B = P.B;
     const int E = is_h ? P.H : P.O;
@@ -231,8 +234,14 @@ __device__ __forceinline__ void seg_cell_tile(const SegParams& P, bool is_h, int
     __syncthreads();
 
     float acc[4][NPAIR];
-    if (TC) tile_accumulate_tc<4, NT>(acc, sh.tab1, sh.tab2, nk * D, s > 0 ? D : 0, rsh, rst);
-    else    tile_accumulate<4, NT, 3>(acc, sh.tab1, sh.tab2, nk * D, s > 0 ? D : 0, 1u << 3, 1u << 2, Wh, smem);
+    if (MODE == 2) {
+        if (!res.ready) res_fill_cell(res, sh.tab1, sh.tab2, nk * D, D);       // first step: this CTA's weight fragments go on chip
+        tile_accumulate_res<NT>(acc, sh.tab1 + WR, sh.tab2 + WR, nk * D, D, res, Wh, smem);   // s == 0: null state rows = zeros
+    } else if (MODE == 1) {
+        tile_accumulate_tc<4, NT>(acc, sh.tab1, sh.tab2, nk * D, s > 0 ? D : 0, rsh, rst);
+    } else {
+        tile_accumulate<4, NT, 3>(acc, sh.tab1, sh.tab2, nk * D, s > 0 ? D : 0, 1u << 3, 1u << 2, Wh, smem);
+    }
 
 #pragma unroll
     for (int p = 0; p < NPAIR; ++p) {
@@ -243,29 +252,33 @@ __device__ __forceinline__ void seg_cell_tile(const SegParams& P, bool is_h, int
     }
 }
 
-template <bool TC>
+template <int MODE>
 __device__ __forceinline__ void seg_cell_dispatch(const SegParams& P, int tile, int s, float* smem, SegShared& sh, RtcShared& rsh,
-                                                  RtcState& rst) {
+                                                  RtcState& rst, ResState& res) {
     const int dir = tile / P.cell_tiles_dir;
     int rem = tile - dir * P.cell_tiles_dir;
     const bool is_h = rem < P.cell_tiles_h_dir;
     if (!is_h) rem -= P.cell_tiles_h_dir;
     const int nub = is_h ? P.nub_h : P.nub_o;
     const int rb = rem / nub, ub = rem - rb * nub;
-    if ((is_h ? P.cfg_h : P.cfg_o) == 4) seg_cell_tile<4, TC>(P, is_h, dir, rb, ub, s, smem, sh, rsh, rst);
-    else                                 seg_cell_tile<2, TC>(P, is_h, dir, rb, ub, s, smem, sh, rsh, rst);
+    if ((is_h ? P.cfg_h : P.cfg_o) == 4) seg_cell_tile<4, MODE>(P, is_h, dir, rb, ub, s, smem, sh, rsh, rst, res);
+    else                                 seg_cell_tile<2, MODE>(P, is_h, dir, rb, ub, s, smem, sh, rsh, rst, res);
 }
 
-// phases: bit 0 = A (messages), bit 1 = B (cells).  TC: gate tiles on tcgen05 (recurrent_tc.cuh, 288 threads), else mma.sync.
-template <bool TC>
-__global__ void __launch_bounds__(TC ? RTC_THREADS : REC_THREADS, 1) segment_kernel(const SegParams P, int s_begin, int s_end, int phases,
-                                                                                  int persistent) {
+// phases: bit 0 = A (messages), bit 1 = B (cells).  MODE as above.
+template <int MODE>
+__global__ void __launch_bounds__(MODE == 1 ? RTC_THREADS : REC_THREADS, 1) segment_kernel(const SegParams P, int s_begin, int s_end,
+                                                                                          int phases, int persistent) {
     extern __shared__ __align__(16) float smem[];
     __shared__ SegShared sh;
     __shared__ RtcShared rsh;
+    __shared__ uint32_t tmem_slot;
     RtcState rst;
+    ResState res;
     if (threadIdx.x == 0) sh.s_fail = 0;
-    if (TC) { rtc_init(rsh, rst, reinterpret_cast<uint8_t*>(smem)); rst.dbg = phases >> 4; }      // dbg: timing experiments
+    if (MODE == 1) { rtc_init(rsh, rst, reinterpret_cast<uint8_t*>(smem)); rst.dbg = phases >> 4; }      // dbg: timing experiments
+    // MODE 2: the ring keeps its place at the start of dynamic shared memory; the overflow fragments follow it
+    if (MODE == 2) res_init(res, &tmem_slot, reinterpret_cast<float4*>(smem + P.res_ring_floats));
     unsigned int epoch = 0;
     bool ok = true;
     for (int s = s_begin; s < s_end && ok; ++s) {
@@ -274,15 +287,16 @@ __global__ void __launch_bounds__(TC ? RTC_THREADS : REC_THREADS, 1) segment_ker
             if (!grid_barrier(P.sync, epoch, gridDim.x, &sh.s_fail)) { ok = false; break; }
         }
         if (phases & 1) {
-            for (int tile = blockIdx.x; tile < P.tilesA; tile += gridDim.x) seg_message_tile<TC>(P, tile, s, smem, sh, rsh, rst);
+            for (int tile = blockIdx.x; tile < P.tilesA; tile += gridDim.x) seg_message_tile<MODE>(P, tile, s, smem, sh, rsh, rst);
             if (persistent && !grid_barrier(P.sync, epoch, gridDim.x, &sh.s_fail)) { ok = false; break; }
         }
         if (phases & 2) {
-            for (int tile = blockIdx.x; tile < P.tilesB; tile += gridDim.x) seg_cell_dispatch<TC>(P, tile, s, smem, sh, rsh, rst);
+            for (int tile = blockIdx.x; tile < P.tilesB; tile += gridDim.x) seg_cell_dispatch<MODE>(P, tile, s, smem, sh, rsh, rst, res);
             if (persistent && s + 1 < s_end && !grid_barrier(P.sync, epoch, gridDim.x, &sh.s_fail)) { ok = false; break; }
         }
     }
-    if (TC) rtc_finish(rst);
+    if (MODE == 1) rtc_finish(rst);
+    if (MODE == 2) res_finish(res);
 }
 
 int launch_segment(SegParams& P, int persistent, cudaStream_t stream) {
@@ -310,24 +324,7 @@ int launch_segment(SegParams& P, int persistent, cudaStream_t stream) {
     P.msg_tiles_dir = begin;
     P.tilesA = 2 * begin;
 
-    const bool tc = rec_use_tc(D);            // tcgen05 gate tiles need every K segment to be a multiple of 32 floats
-    auto kern = tc ? segment_kernel<true> : segment_kernel<false>;
-    const int threads = tc ? RTC_THREADS : REC_THREADS;
-    int fa = tile_smem_floats(4, 4, 3);
-    const int fb = tile_smem_floats(MSG_NGL, 2, 3), fc = tile_smem_floats(4, 2, 3);
-    if (fb > fa) fa = fb;
-    if (fc > fa) fa = fc;
-    const size_t smem = tc ? (size_t)RTC_SMEM_BYTES : sizeof(float) * (size_t)fa;
-    static bool configured[2] = {false, false};
-    if (!configured[tc]) {
-        TG_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured[tc] = true;
-    }
-    int per_sm = 0;
-    TG_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, smem));
-    TG_REQUIRE(per_sm >= 1, "segment: kernel does not fit on an SM (smem %zu)", smem);
-    const int capacity = per_sm * num_sms();
-
+    // tiling of the cell phase (needed to choose the kernel variant)
     P.cfg_h = B * H > 16 ? 4 : 2;            // n8 row tiles per cell tile
     P.cfg_o = B * O > 16 ? 4 : 2;
     P.jeff_h = P.jeff_o = REC_J;
@@ -336,6 +333,36 @@ int launch_segment(SegParams& P, int persistent, cudaStream_t stream) {
     P.cell_tiles_h_dir = P.nrb_h * P.nub_h;
     P.cell_tiles_dir = P.cell_tiles_h_dir + P.nrb_o * P.nub_o;
     P.tilesB = 2 * P.cell_tiles_dir;
+
+    int fa = tile_smem_floats(4, 4, 3);
+    const int fb = tile_smem_floats(MSG_NGL, 2, 3), fc = tile_smem_floats(4, 2, 3);
+    if (fb > fa) fa = fb;
+    if (fc > fa) fa = fc;
+    // variant: 1 = tcgen05 gate tile (opt-in), 2 = cell weights resident on chip (every CTA owns at most one cell tile and the
+    // per-thread fragment words fit in tensor memory + overflow), 0 = streaming
+    static int res_env = -1;
+    if (res_env < 0) {
+        const char* e = getenv("TGGCN_SEG_RES");
+        res_env = (e != nullptr && e[0] == '0') ? 0 : 1;
+    }
+    int mode = rec_use_tc(D) ? 1 : 0;
+    const int kmax = (P.nk_h > 2 ? P.nk_h : 2) * D + D;
+    const bool res_fits = cdiv(kmax / REC_CK, REC_WARPS) * RES_CHUNK_WORDS <= RES_TMEM_WORDS + RES_SMEM_WORDS;
+    if (mode == 0 && res_env && res_fits && P.tilesB <= num_sms() && (persistent ? P.tilesA <= num_sms() : true)) mode = 2;
+    P.res_ring_floats = fa;
+    auto kern = mode == 1 ? segment_kernel<1> : (mode == 2 ? segment_kernel<2> : segment_kernel<0>);
+    const int threads = mode == 1 ? RTC_THREADS : REC_THREADS;
+    const size_t smem = mode == 1 ? (size_t)RTC_SMEM_BYTES
+                                  : sizeof(float) * (size_t)fa + (mode == 2 ? sizeof(float) * RES_SMEM_WORDS * REC_THREADS : 0);
+    static bool configured[3] = {false, false, false};
+    if (!configured[mode]) {
+        TG_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured[mode] = true;
+    }
+    int per_sm = 0;
+    TG_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, smem));
+    TG_REQUIRE(per_sm >= 1, "segment: kernel does not fit on an SM (smem %zu)", smem);
+    const int capacity = per_sm * num_sms();
 
     if (persistent) {
         int grid = P.tilesA > P.tilesB ? P.tilesA : P.tilesB;

@@ -146,9 +146,15 @@ int tggcn_sync_status(const tggcn_dims* dims, const void* workspace, void* strea
     TG_CUDA_OK(cudaMemcpyAsync(flags, (const char*)workspace + L.off[TGGCN_BUF_SYNC], sizeof(flags), cudaMemcpyDeviceToHost,
                                (cudaStream_t)stream));
     TG_CUDA_OK(cudaStreamSynchronize((cudaStream_t)stream));
-    if (flags[1] || flags[3] || flags[5] || flags[7]) {
-        set_error("persistent kernel grid barrier timed out (bigru=%u, segment=%u, bigru_bwd=%u, segment_bwd=%u)", flags[1], flags[3],
-                  flags[5], flags[7]);
+    if ((flags[1] | flags[3] | flags[5] | flags[7]) & 1u) {
+        set_error("persistent kernel grid barrier timed out (bigru=%u, segment=%u, bigru_bwd=%u, segment_bwd=%u)", flags[1] & 1u,
+                  flags[3] & 1u, flags[5] & 1u, flags[7] & 1u);
+        return 1;
+    }
+    if ((flags[1] | flags[3]) & 2u) {
+        set_error("a recurrent weight (|w| >= 255) or activation (>= 65504) left the range of the fp16-split gate tiles (bigru=%u, "
+                  "segment=%u); rerun with TGGCN_SEG_RES=0 TGGCN_BIGRU_RES=0 for the 3xTF32 streaming kernels", (flags[1] >> 1) & 1u,
+                  (flags[3] >> 1) & 1u);
         return 1;
     }
     return 0;

@@ -5,13 +5,16 @@
 // (x 3 gates = 72 weight rows of D floats, 145 KB at D = 512) of ONE (group, direction), loads them once, and keeps them
 // for all T steps.  Per step a CTA
 //   1. stages the previous hidden state of its group's rows (<= 32 rows x D floats) from L2 into shared memory (cp.async),
-//   2. multiplies on the tensor cores from shared memory only: mma.sync m16n8k8 TF32 with the 3xTF32 split, A = state rows,
-//      B = resident weight rows, K split over the 8 warps (each warp: all 2 x 9 accumulator tiles for D/8 columns),
+//   2. multiplies on the tensor cores from shared memory only: mma.sync m16n8k16 with the 3xFP16 split (recurrent_res.cuh:
+//      same accuracy class as 3xTF32 at half the tensor-pipe instructions), A = state rows split in registers, B = resident
+//      weight rows stored PRE-SPLIT as (hi, lo) f16x2 word pairs — the same bytes as the fp32 values they replace —, K split
+//      over the 8 warps in k16 steps (each warp: all 2 x 9 accumulator tiles),
 //   3. reduces the 8 partial accumulators through shared memory (the staging buffer is reused), applies the GRU gate math
 //      for its 24 units and publishes the new state (= the output row) through L2,
-// followed by one grid barrier.  Same arithmetic, rounding class and outputs as bigru_kernel (parity tests unchanged).
+// followed by one grid barrier.  Same rounding class and outputs as bigru_kernel (parity tests unchanged).
 #include <stdlib.h>
 #include "recurrent.cuh"
+#include "recurrent_res.cuh"
 #include "bigru.h"
 
 namespace tg {
@@ -24,7 +27,7 @@ constexpr int BR_NT = 3 * BR_NBLK;   // n8 tiles per CTA: [gate][block]
 constexpr int BR_ROWS = 32;       // state rows per pass (two m16 tiles)
 constexpr int BR_ACC = 2 * BR_NT * 4;   // accumulator floats per lane
 
-__device__ __forceinline__ int br_ld(int D) { return D + 4; }    // padded row stride: fragment loads hit 32 distinct banks
+__device__ __forceinline__ int br_ld(int D) { return D + 8; }    // padded row stride (words): 64-bit fragment loads of a half-warp hit 16 distinct 8-byte slots
 
 __global__ void __launch_bounds__(REC_THREADS, 1) bigru_res_kernel(const BiGruParams P, int ctas_per_gd) {
     extern __shared__ __align__(16) float smem[];
@@ -48,17 +51,22 @@ __global__ void __launch_bounds__(REC_THREADS, 1) bigru_res_kernel(const BiGruPa
         rowoff[tid] = ((long long)b * T * G.E + e) * 2 * D + dir * D;
     }
 
-    // ---- load the resident weight rows once ------------------------------------------------------------------
+    // ---- load the resident weight rows once, pre-split: word pair kp of a row = (hi, lo) f16x2 of columns 2kp, 2kp+1 -------
     {
         const float* W = G.whh[dir];
-        const int d4 = D / 4;
-        for (int i = tid; i < BR_NT * 8 * d4; i += REC_THREADS) {
-            const int row = i / d4, c4 = i - row * d4;
+        const int d2 = D / 2;
+        float wmax = 0.0f;
+        for (int i = tid; i < BR_NT * 8 * d2; i += REC_THREADS) {
+            const int row = i / d2, kp = i - row * d2;
             const int nt = row >> 3, n = row & 7, gate = nt / BR_NBLK, blk = nt - gate * BR_NBLK;
-            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (blk < nb) v = __ldg(reinterpret_cast<const float4*>(W + (size_t)(gate * D + (j0 + blk) * BR_UB + n) * D) + c4);
-            *reinterpret_cast<float4*>(wsm + row * LD + c4 * 4) = v;
+            float2 v = make_float2(0.f, 0.f);
+            if (blk < nb) v = __ldg(reinterpret_cast<const float2*>(W + (size_t)(gate * D + (j0 + blk) * BR_UB + n) * D) + kp);
+            wmax = fmaxf(wmax, fmaxf(fabsf(v.x), fabsf(v.y)));
+            uint2 hl;
+            split_f16x2(v.x * RES_WSCALE, v.y * RES_WSCALE, hl.x, hl.y);
+            *reinterpret_cast<uint2*>(wsm + row * LD + kp * 2) = hl;
         }
+        if (!(wmax * RES_WSCALE < RES_F16_MAX)) atomicOr(P.sync.error, 2u);
     }
     // epilogue constants: this thread's outputs o = tid + 256*q  ->  (m tile, block, accumulator register, lane)
     float bh[3][3];
@@ -83,7 +91,6 @@ __global__ void __launch_bounds__(REC_THREADS, 1) bigru_res_kernel(const BiGruPa
     }
     __syncthreads();
 
-    const int kw = D / 64;                               // k8 steps per warp (K split over the 8 warps)
     unsigned int epoch = 0;
     bool ok = true;
     for (int s = 0; s < T && ok; ++s) {
@@ -155,42 +162,49 @@ __global__ void __launch_bounds__(REC_THREADS, 1) bigru_res_kernel(const BiGruPa
 #pragma unroll
                         for (int r = 0; r < 4; ++r) acc[m][nt][r] = 0.0f;
                 const bool two = nrows > 16;             // second m16 tile holds rows
-#pragma unroll 2
-                for (int kk = 0; kk < kw; ++kk) {
-                    const int k0 = (warp * kw + kk) * 8;
+#pragma unroll 1
+                for (int ks = warp; ks < D / 16; ks += REC_WARPS) {
+                    const int k0 = ks * 16;
+                    // A fragments (state rows): register 0 = (row g8, k0 + 2 t4 + {0,1}), 1 = row + 8, 2 = k + 8, 3 = both
                     uint32_t ah[2][4], al[2][4];
 #pragma unroll
                     for (int m = 0; m < 2; ++m) {
                         if (m == 1 && !two) continue;
-                        const float* hp = hsm + (m * 16 + g8) * LD + k0 + t4;
-                        split_tf32(hp[0], ah[m][0], al[m][0]);
-                        split_tf32(hp[8 * LD], ah[m][1], al[m][1]);
-                        split_tf32(hp[4], ah[m][2], al[m][2]);
-                        split_tf32(hp[8 * LD + 4], ah[m][3], al[m][3]);
+                        const float* hp = hsm + (m * 16 + g8) * LD + k0 + 2 * t4;
+                        const float2 x0 = *reinterpret_cast<const float2*>(hp);
+                        const float2 x1 = *reinterpret_cast<const float2*>(hp + 8 * LD);
+                        const float2 x2 = *reinterpret_cast<const float2*>(hp + 8);
+                        const float2 x3 = *reinterpret_cast<const float2*>(hp + 8 * LD + 8);
+                        split_f16x2(x0.x, x0.y, ah[m][0], al[m][0]);
+                        split_f16x2(x1.x, x1.y, ah[m][1], al[m][1]);
+                        split_f16x2(x2.x, x2.y, ah[m][2], al[m][2]);
+                        split_f16x2(x3.x, x3.y, ah[m][3], al[m][3]);
                     }
 #pragma unroll
                     for (int gt = 0; gt < 3; ++gt) {     // one gate = BR_NBLK n-tiles: 2*NBLK independent accumulators per pass
                         uint32_t bhi[BR_NBLK][2], blo[BR_NBLK][2];
 #pragma unroll
                         for (int j = 0; j < BR_NBLK; ++j) {
-                            const float* wp = wsm + ((gt * BR_NBLK + j) * 8 + g8) * LD + k0 + t4;
-                            split_tf32(wp[0], bhi[j][0], blo[j][0]);
-                            split_tf32(wp[4], bhi[j][1], blo[j][1]);
+                            const float* wp = wsm + ((gt * BR_NBLK + j) * 8 + g8) * LD + k0 + 2 * t4;
+                            const uint2 w0 = *reinterpret_cast<const uint2*>(wp);
+                            const uint2 w1 = *reinterpret_cast<const uint2*>(wp + 8);
+                            bhi[j][0] = w0.x; blo[j][0] = w0.y;
+                            bhi[j][1] = w1.x; blo[j][1] = w1.y;
                         }
 #pragma unroll
                         for (int j = 0; j < BR_NBLK; ++j) {
-                            mma_tf32(acc[0][gt * BR_NBLK + j], al[0], bhi[j]);
-                            if (two) mma_tf32(acc[1][gt * BR_NBLK + j], al[1], bhi[j]);
+                            mma_f16(acc[0][gt * BR_NBLK + j], al[0], bhi[j]);
+                            if (two) mma_f16(acc[1][gt * BR_NBLK + j], al[1], bhi[j]);
                         }
 #pragma unroll
                         for (int j = 0; j < BR_NBLK; ++j) {
-                            mma_tf32(acc[0][gt * BR_NBLK + j], ah[0], blo[j]);
-                            if (two) mma_tf32(acc[1][gt * BR_NBLK + j], ah[1], blo[j]);
+                            mma_f16(acc[0][gt * BR_NBLK + j], ah[0], blo[j]);
+                            if (two) mma_f16(acc[1][gt * BR_NBLK + j], ah[1], blo[j]);
                         }
 #pragma unroll
                         for (int j = 0; j < BR_NBLK; ++j) {
-                            mma_tf32(acc[0][gt * BR_NBLK + j], ah[0], bhi[j]);
-                            if (two) mma_tf32(acc[1][gt * BR_NBLK + j], ah[1], bhi[j]);
+                            mma_f16(acc[0][gt * BR_NBLK + j], ah[0], bhi[j]);
+                            if (two) mma_f16(acc[1][gt * BR_NBLK + j], ah[1], bhi[j]);
                         }
                     }
                 }
@@ -212,7 +226,7 @@ __global__ void __launch_bounds__(REC_THREADS, 1) bigru_res_kernel(const BiGruPa
                         float v = 0.0f;
 #pragma unroll
                         for (int w = 0; w < REC_WARPS; ++w) v += red[w * BR_ACC * 32 + gt * BR_NBLK * 4 * 32 + o_base[q]];
-                        sum[q][gt] = v;
+                        sum[q][gt] = v * (1.0f / RES_WSCALE);
                     }
                 }
             }
@@ -238,7 +252,7 @@ int launch_bigru_resident(BiGruParams& P, cudaStream_t stream) {
     }
     const int D = P.D;
     if (!enabled || D % 64 != 0) return -1;
-    const int LD = D + 4;
+    const int LD = D + 8;
     const size_t red_floats = (size_t)REC_WARPS * BR_ACC * 32, stage_floats = (size_t)BR_ROWS * LD;
     const size_t smem = sizeof(float) * ((size_t)BR_NT * 8 * LD + (red_floats > stage_floats ? red_floats : stage_floats));
     if (smem > 227 * 1024) return -1;

@@ -116,11 +116,11 @@ __device__ __forceinline__ bool grid_barrier(const GridSync& gs, unsigned int& e
             asm volatile("ld.acquire.gpu.global.u32 %0, [%1];\n" : "=r"(v) : "l"(gs.counter) : "memory");
             if (v >= target) break;
             if (++spins > (1u << 22)) {   // far beyond any legitimate wait (each probe is an L2 round trip)
-                atomicExch(gs.error, 1u);
+                atomicOr(gs.error, 1u);                    // bit 0: timeout (bit 1: operand range of the fp16-split tiles)
                 *s_fail = 1;
                 break;
             }
-            if ((spins & 1023u) == 0 && *((volatile unsigned int*)gs.error)) { *s_fail = 1; break; }
+            if ((spins & 1023u) == 0 && (*((volatile unsigned int*)gs.error) & 1u)) { *s_fail = 1; break; }
         }
         __threadfence();
     }

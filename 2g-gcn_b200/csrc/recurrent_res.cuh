@@ -11,9 +11,17 @@
 //     Because every lane reads back exactly what it stored, no layout conversion is ever needed;
 //   * only the ACTIVATION rows (aggregated messages, previous state: 8*NT rows) still stream through the warp-private
 //     cp.async ring, so the ring is a third of its old size and the L2 traffic of the phase drops to the activations.
-// Arithmetic is unchanged: 3xTF32 split in registers, fp32 accumulate, K split over the 8 warps, partials reduced through
-// shared memory (in two halves: the reduction buffer is smaller than before).
+// Arithmetic: 3xFP16 split products on mma.sync.m16n8k16 (x = hi + lo with hi = fp16(x), lo = fp16(x - hi): 22 mantissa bits;
+// hi*hi + hi*lo + lo*hi, fp32 accumulate) — the same accuracy class as the 3xTF32 split of the streaming tile (measured: max
+// error 1.7e-7 on a K = 1536 gate pre-activation against 7.8e-7 for 3xTF32 and 2.4e-6 for a sequential fp32 sum) at HALF the
+// tensor-pipe instructions, which is what bounds this tile once the weights no longer stream (ncu r01: tensor pipe 24 % of the
+// whole kernel, math_pipe_throttle).  The resident weights are stored PRE-SPLIT: one (hi, lo) pair of f16x2 words takes exactly
+// the space of the two fp32 values it replaces, so the per-step weight split disappears from the K loop.  Weights are scaled by
+// 2^8 before the split (keeps the lo parts of default-init-sized weights out of the fp16 subnormals; undone on the reduced sums);
+// a weight beyond 65504 / 2^8 or an activation beyond 65504 raises the kernel's range flag (GridSync::error bit 1).
+// K split over the 8 warps, partials reduced through shared memory (in two halves: the reduction buffer is small).
 #pragma once
+#include <cuda_fp16.h>
 #include "recurrent.cuh"
 #include "tcgen05.cuh"
 
@@ -22,18 +30,38 @@ namespace tg {
 constexpr int RES_TMEM_WORDS = 256;          // per-thread words in tensor memory (512 columns shared by two warps per lane quarter)
 constexpr int RES_SMEM_WORDS = 32;           // per-thread overflow words in shared memory
 constexpr int RES_GROUPS = 3;                // weight groups active in a K chunk of the cell tile: (r, z, n_i) or (r, z, n_h)
-constexpr int RES_CHUNK_WORDS = 2 * RES_GROUPS * 4;   // two k8 steps x 3 groups x 4 fragment registers
+constexpr int RES_CHUNK_WORDS = 2 * RES_GROUPS * 4;   // one k16 step x 3 groups x (hi, lo) x 4 fragment registers
+constexpr int RES_RS = 24;                   // ring row stride in floats (16 data + 8 pad): conflict-free 64-bit fragment loads
+constexpr int RES_STAGES = 4;                // cp.async ring depth per warp (activation rows only)
+constexpr float RES_WSCALE = 256.0f;         // weights are split as fp16(w * 2^8)
+constexpr float RES_F16_MAX = 65504.0f;
 
 struct ResState {
     uint32_t tmem_base;
-    float4* wovf;            // [RES_SMEM_WORDS / 4][REC_THREADS] overflow fragments
+    uint4* wovf;             // [RES_SMEM_WORDS / 4][REC_THREADS] overflow fragments
     int ready;               // fragments of this CTA's cell tile are loaded
 };
 
-__device__ __forceinline__ void tmem_st4(uint32_t taddr, const float (&v)[4]) {
-    asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1,%2,%3,%4};\n" ::"r"(taddr), "r"(__float_as_uint(v[0])),
-                 "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])), "r"(__float_as_uint(v[3]))
+__device__ __forceinline__ void tmem_st4(uint32_t taddr, const uint32_t (&v)[4]) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1,%2,%3,%4};\n" ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3])
                  : "memory");
+}
+
+// D += A(16x16, row) * B(16x8, col), fp16 operands, fp32 accumulate.
+__device__ __forceinline__ void mma_f16(float (&d)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
+    asm volatile(
+        "mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};\n"
+        : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+}
+
+// (x0, x1) = hi + lo, both f16x2 words with x0 in the low half (the smaller k index of an MMA fragment register).
+__device__ __forceinline__ void split_f16x2(float x0, float x1, uint32_t& hi, uint32_t& lo) {
+    const __half2 h = __floats2half2_rn(x0, x1);
+    const float2 f = __half22float2(h);
+    const __half2 l = __floats2half2_rn(x0 - f.x, x1 - f.y);
+    hi = *reinterpret_cast<const uint32_t*>(&h);
+    lo = *reinterpret_cast<const uint32_t*>(&l);
 }
 __device__ __forceinline__ void tmem_ld4_nowait(uint32_t taddr, uint32_t (&r)[4]) {
     asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0,%1,%2,%3}, [%4];\n" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(taddr) : "memory");
@@ -48,7 +76,7 @@ __device__ __forceinline__ uint32_t res_taddr(const ResState& rs, int j) {
 }
 
 // Once per kernel (all threads): allocate tensor memory.  Pair with res_finish on every exit path.
-__device__ __forceinline__ void res_init(ResState& rs, uint32_t* tmem_slot, float4* wovf) {
+__device__ __forceinline__ void res_init(ResState& rs, uint32_t* tmem_slot, uint4* wovf) {
     if ((threadIdx.x >> 5) == 0) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(tmem_slot)), "r"(512u) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
@@ -69,38 +97,49 @@ __device__ __forceinline__ void res_finish(ResState& rs) {
     }
 }
 
-// Load this thread's weight fragments of one cell tile.  wrow1[g*16 + u] / wrow2[...]: weight row pointers of K segment 1 / 2
-// (null = group absent in that segment), exactly the first 64 entries of the streaming tile's pointer tables.
-// Words of chunk n (chunk id = warp + 8 n), k8 step kk, active group gi, register r:  j = ((n*2 + kk)*3 + gi)*4 + r.
-// Returns false (uniformly) when the tile needs more words than fit.
-__device__ __forceinline__ bool res_fill_cell(ResState& rs, const float* const* wrow1, const float* const* wrow2, int K1, int K2) {
+// Load this thread's weight fragments of one cell tile, pre-split into fp16 (hi, lo) MMA A-fragments.
+// wrow1[g*16 + u] / wrow2[...]: weight row pointers of K segment 1 / 2 (null = group absent in that segment), exactly the first
+// 64 entries of the streaming tile's pointer tables.  A-fragment of m16n8k16 for lane (g8, t4): register 0 = row g8, k = 2 t4 + {0,1};
+// 1 = row g8 + 8, same k; 2 = row g8, k + 8; 3 = row g8 + 8, k + 8.
+// Words of chunk n (chunk id = warp + 8 n), active group gi, half hl (0 hi, 1 lo), register r:  j = ((n*3 + gi)*2 + hl)*4 + r.
+// Returns false (uniformly) when the tile needs more words than fit; *range_bad is set when a weight leaves the fp16 split range.
+__device__ __forceinline__ bool res_fill_cell(ResState& rs, const float* const* wrow1, const float* const* wrow2, int K1, int K2,
+                                              unsigned int* range_flag) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g8 = lane >> 2, t4 = lane & 3;
     const int chunks1 = K1 / REC_CK, total = (K1 + K2) / REC_CK;
     const int nmine = warp < total ? (total - warp + REC_WARPS - 1) / REC_WARPS : 0;
     const int nmax = (total + REC_WARPS - 1) / REC_WARPS;
     if (nmax * RES_CHUNK_WORDS > RES_TMEM_WORDS + RES_SMEM_WORDS) return false;
+    float wmax = 0.0f;
     for (int n = 0; n < nmine; ++n) {
         const int chunk = warp + n * REC_WARPS;
         const bool seg1 = chunk < chunks1;
-        const int kbase = (seg1 ? chunk : chunk - chunks1) * REC_CK;
+        const int k = (seg1 ? chunk : chunk - chunks1) * REC_CK + 2 * t4;
 #pragma unroll
-        for (int kk = 0; kk < 2; ++kk)
+        for (int gi = 0; gi < RES_GROUPS; ++gi) {
+            const int g = (gi == 2 && !seg1) ? 3 : gi;                         // seg 1: r, z, n_i ; seg 2: r, z, n_h
+            const float* r0 = (seg1 ? wrow1 : wrow2)[g * REC_J + g8];
+            const float* r1 = (seg1 ? wrow1 : wrow2)[g * REC_J + g8 + 8];
+            float2 v[4];
+            v[0] = r0 != nullptr ? __ldg(reinterpret_cast<const float2*>(r0 + k)) : make_float2(0.f, 0.f);
+            v[1] = r1 != nullptr ? __ldg(reinterpret_cast<const float2*>(r1 + k)) : make_float2(0.f, 0.f);
+            v[2] = r0 != nullptr ? __ldg(reinterpret_cast<const float2*>(r0 + k + 8)) : make_float2(0.f, 0.f);
+            v[3] = r1 != nullptr ? __ldg(reinterpret_cast<const float2*>(r1 + k + 8)) : make_float2(0.f, 0.f);
+            uint32_t hi[4], lo[4];
 #pragma unroll
-            for (int gi = 0; gi < RES_GROUPS; ++gi) {
-                const int g = (gi == 2 && !seg1) ? 3 : gi;                     // seg 1: r, z, n_i ; seg 2: r, z, n_h
-                const float* r0 = (seg1 ? wrow1 : wrow2)[g * REC_J + g8];
-                const float* r1 = (seg1 ? wrow1 : wrow2)[g * REC_J + g8 + 8];
-                const int k = kbase + kk * 8 + t4;
-                float v[4];
-                v[0] = r0 != nullptr ? __ldg(r0 + k) : 0.0f;
-                v[1] = r1 != nullptr ? __ldg(r1 + k) : 0.0f;
-                v[2] = r0 != nullptr ? __ldg(r0 + k + 4) : 0.0f;
-                v[3] = r1 != nullptr ? __ldg(r1 + k + 4) : 0.0f;
-                const int j = ((n * 2 + kk) * RES_GROUPS + gi) * 4;
-                if (j < RES_TMEM_WORDS) tmem_st4(res_taddr(rs, j), v);           // warp-uniform branch (j depends on n only)
-                else rs.wovf[((j - RES_TMEM_WORDS) >> 2) * REC_THREADS + tid] = make_float4(v[0], v[1], v[2], v[3]);
+            for (int r = 0; r < 4; ++r) {
+                wmax = fmaxf(wmax, fmaxf(fabsf(v[r].x), fabsf(v[r].y)));
+                split_f16x2(v[r].x * RES_WSCALE, v[r].y * RES_WSCALE, hi[r], lo[r]);
             }
+            const int j = ((n * RES_GROUPS + gi) * 2) * 4;
+            // warp-uniform branches (j depends on n and gi only)
+            if (j < RES_TMEM_WORDS) tmem_st4(res_taddr(rs, j), hi);
+            else rs.wovf[((j - RES_TMEM_WORDS) >> 2) * REC_THREADS + tid] = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+            if (j + 4 < RES_TMEM_WORDS) tmem_st4(res_taddr(rs, j + 4), lo);
+            else rs.wovf[((j + 4 - RES_TMEM_WORDS) >> 2) * REC_THREADS + tid] = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+        }
     }
+    if (!(wmax * RES_WSCALE < RES_F16_MAX)) atomicOr(range_flag, 2u);        // also catches NaN weights
     tmem_wait_st();
     tc_fence_before();
     __syncthreads();
@@ -114,8 +153,8 @@ __device__ __forceinline__ bool res_fill_cell(ResState& rs, const float* const* 
 template <int NT>
 __device__ __forceinline__ void tile_accumulate_res(float (&out)[4][(NT + 1) / 2], const float* const* act1, const float* const* act2,
                                                     int K1, int K2, const ResState& rs, const float* gdummy, float* smem) {
-    constexpr int NG = 4, STAGES = 3, ROWS = 8 * NT;
-    constexpr int STAGE_F = ROWS * REC_RS;
+    constexpr int NG = 4, STAGES = RES_STAGES, ROWS = 8 * NT;
+    constexpr int STAGE_F = ROWS * RES_RS;
     constexpr int NP = (ROWS * 4 + 31) / 32;            // 16-byte pieces per lane per chunk
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int g8 = lane >> 2, t4 = lane & 3;
@@ -145,7 +184,7 @@ __device__ __forceinline__ void tile_accumulate_res(float (&out)[4][(NT + 1) / 2
             const float* b2 = in[p] ? act2[row] : nullptr;
             s1[p] = b1 != nullptr ? b1 + quarter * 4 : nullptr;
             s2[p] = b2 != nullptr ? b2 + quarter * 4 - K1 : nullptr;      // indexed with the global k offset
-            dst[p] = row * REC_RS + quarter * 4;
+            dst[p] = row * RES_RS + quarter * 4;
         }
         auto issue = [&](int n, int st) {
             const int chunk = warp + n * REC_WARPS;
@@ -166,20 +205,19 @@ __device__ __forceinline__ void tile_accumulate_res(float (&out)[4][(NT + 1) / 2
         }
 #pragma unroll 1
         for (int n = 0; n < nmine; ++n) {
-            // this chunk's weight fragments: tensor memory (or the shared-memory overflow), fetched while the copies land
-            uint32_t w[2][RES_GROUPS][4];
+            // this chunk's pre-split weight fragments: tensor memory (or the shared-memory overflow), fetched while the copies land
+            uint32_t w[RES_GROUPS][2][4];
             const int j0 = n * RES_CHUNK_WORDS;
 #pragma unroll
-            for (int kk = 0; kk < 2; ++kk)
+            for (int gi = 0; gi < RES_GROUPS; ++gi)
 #pragma unroll
-                for (int gi = 0; gi < RES_GROUPS; ++gi) {
-                    const int j = j0 + (kk * RES_GROUPS + gi) * 4;
+                for (int hl = 0; hl < 2; ++hl) {
+                    const int j = j0 + (gi * 2 + hl) * 4;
                     if (j < RES_TMEM_WORDS) {
-                        tmem_ld4_nowait(res_taddr(rs, j), w[kk][gi]);
+                        tmem_ld4_nowait(res_taddr(rs, j), w[gi][hl]);
                     } else {
-                        const float4 v = rs.wovf[((j - RES_TMEM_WORDS) >> 2) * REC_THREADS + tid];
-                        w[kk][gi][0] = __float_as_uint(v.x); w[kk][gi][1] = __float_as_uint(v.y);
-                        w[kk][gi][2] = __float_as_uint(v.z); w[kk][gi][3] = __float_as_uint(v.w);
+                        const uint4 v = rs.wovf[((j - RES_TMEM_WORDS) >> 2) * REC_THREADS + tid];
+                        w[gi][hl][0] = v.x; w[gi][hl][1] = v.y; w[gi][hl][2] = v.z; w[gi][hl][3] = v.w;
                     }
                 }
             cp_async_wait<STAGES - 2>();
@@ -189,43 +227,37 @@ __device__ __forceinline__ void tile_accumulate_res(float (&out)[4][(NT + 1) / 2
                 if (nn < nmine) issue(nn, nn % STAGES);
                 cp_async_commit();
             }
-            tmem_wait_ld();
             const bool seg1 = (warp + n * REC_WARPS) < chunks1;
-            const float* xb = ring + (n % STAGES) * STAGE_F + g8 * REC_RS + t4;
+            // B fragments of m16n8k16 for lane (g8, t4): register 0 = (k = 2 t4 + {0,1}, row g8), register 1 = (k + 8, row g8)
+            const float* xb = ring + (n % STAGES) * STAGE_F + g8 * RES_RS + 2 * t4;
+            uint32_t bh[NT][2], bl[NT][2];
 #pragma unroll
-            for (int kk = 0; kk < REC_CK / 8; ++kk) {
-                uint32_t bh[NT][2], bl[NT][2];
+            for (int nt = 0; nt < NT; ++nt) {
+                const float2 v0 = *reinterpret_cast<const float2*>(xb + nt * 8 * RES_RS);
+                const float2 v1 = *reinterpret_cast<const float2*>(xb + nt * 8 * RES_RS + 8);
+                split_f16x2(v0.x, v0.y, bh[nt][0], bl[nt][0]);
+                split_f16x2(v1.x, v1.y, bh[nt][1], bl[nt][1]);
+            }
+            tmem_wait_ld();
 #pragma unroll
-                for (int nt = 0; nt < NT; ++nt) {
-                    split_tf32(xb[nt * 8 * REC_RS + kk * 8], bh[nt][0], bl[nt][0]);
-                    split_tf32(xb[nt * 8 * REC_RS + kk * 8 + 4], bh[nt][1], bl[nt][1]);
-                }
+            for (int gi = 0; gi < RES_GROUPS; ++gi) {
+                // seg 1 feeds groups (r, z, n_i) = accumulators 0, 1, 2; seg 2 feeds (r, z, n_h) = 0, 1, 3
+                if (gi < 2 || seg1) {
+                    float (&cc)[NT][4] = c[gi];
 #pragma unroll
-                for (int gi = 0; gi < RES_GROUPS; ++gi) {
-                    uint32_t ah[4], al[4];
+                    for (int nt = 0; nt < NT; ++nt) mma_f16(cc[nt], w[gi][1], bh[nt]);
 #pragma unroll
-                    for (int r = 0; r < 4; ++r) {
-                        const float x = __uint_as_float(w[kk][gi][r]);
-                        split_tf32(x, ah[r], al[r]);
-                    }
-                    // seg 1 feeds groups (r, z, n_i) = accumulators 0, 1, 2; seg 2 feeds (r, z, n_h) = 0, 1, 3
-                    if (gi < 2 || seg1) {
-                        float (&cc)[NT][4] = c[gi];
+                    for (int nt = 0; nt < NT; ++nt) mma_f16(cc[nt], w[gi][0], bl[nt]);
 #pragma unroll
-                        for (int nt = 0; nt < NT; ++nt) mma_tf32(cc[nt], al, bh[nt]);
+                    for (int nt = 0; nt < NT; ++nt) mma_f16(cc[nt], w[gi][0], bh[nt]);
+                } else {
+                    float (&cc)[NT][4] = c[3];
 #pragma unroll
-                        for (int nt = 0; nt < NT; ++nt) mma_tf32(cc[nt], ah, bl[nt]);
+                    for (int nt = 0; nt < NT; ++nt) mma_f16(cc[nt], w[gi][1], bh[nt]);
 #pragma unroll
-                        for (int nt = 0; nt < NT; ++nt) mma_tf32(cc[nt], ah, bh[nt]);
-                    } else {
-                        float (&cc)[NT][4] = c[3];
+                    for (int nt = 0; nt < NT; ++nt) mma_f16(cc[nt], w[gi][0], bl[nt]);
 #pragma unroll
-                        for (int nt = 0; nt < NT; ++nt) mma_tf32(cc[nt], al, bh[nt]);
-#pragma unroll
-                        for (int nt = 0; nt < NT; ++nt) mma_tf32(cc[nt], ah, bl[nt]);
-#pragma unroll
-                        for (int nt = 0; nt < NT; ++nt) mma_tf32(cc[nt], ah, bh[nt]);
-                    }
+                    for (int nt = 0; nt < NT; ++nt) mma_f16(cc[nt], w[gi][0], bh[nt]);
                 }
             }
         }
@@ -267,7 +299,7 @@ __device__ __forceinline__ void tile_accumulate_res(float (&out)[4][(NT + 1) / 2
 #pragma unroll
                 for (int w4 = 0; w4 < 4; ++w4) s += red[(((w4 * NG + m) * NT + n) * 4 + r) * 32 + l];
             }
-            out[m][p] = s;
+            out[m][p] = s * (1.0f / RES_WSCALE);
         }
     }
     __syncthreads();                             // smem may be reused by the caller right away

@@ -155,6 +155,7 @@ __device__ __forceinline__ void seg_message_tile(const SegParams& P, int tile, i
         const float* ms = sh.msg + (bl * Es) * MSG_LDM + c;
         float v = 0.0f;
         for (int sdr = 0; sdr < Es; ++sdr) v = fmaf(al[sdr], ms[sdr * MSG_LDM], v);
+        if (MODE == 2 && !(v < RES_F16_MAX)) atomicOr(P.sync.error, 2u);      // operand of the fp16-split cell tile out of range
         const int r = br - bl * Er;
         mg[((((size_t)dir * B + b0 + bl) * P.mg_T + (P.mg_T > 1 ? t : 0)) * Er + r) * nk_r * D + slot * D + u] = v;
     }
@@ -235,7 +236,7 @@ __device__ __forceinline__ void seg_cell_tile(const SegParams& P, bool is_h, int
 
     float acc[4][NPAIR];
     if (MODE == 2) {
-        if (!res.ready) res_fill_cell(res, sh.tab1, sh.tab2, nk * D, D);       // first step: this CTA's weight fragments go on chip
+        if (!res.ready) res_fill_cell(res, sh.tab1, sh.tab2, nk * D, D, P.sync.error);       // first step: this CTA's weight fragments go on chip
         tile_accumulate_res<NT>(acc, sh.tab1 + WR, sh.tab2 + WR, nk * D, D, res, Wh, smem);   // s == 0: null state rows = zeros
     } else if (MODE == 1) {
         tile_accumulate_tc<4, NT>(acc, sh.tab1, sh.tab2, nk * D, s > 0 ? D : 0, rsh, rst);
@@ -278,7 +279,7 @@ __global__ void __launch_bounds__(MODE == 1 ? RTC_THREADS : REC_THREADS, 1) segm
     if (threadIdx.x == 0) sh.s_fail = 0;
     if (MODE == 1) { rtc_init(rsh, rst, reinterpret_cast<uint8_t*>(smem)); rst.dbg = phases >> 4; }      // dbg: timing experiments
     // MODE 2: the ring keeps its place at the start of dynamic shared memory; the overflow fragments follow it
-    if (MODE == 2) res_init(res, &tmem_slot, reinterpret_cast<float4*>(smem + P.res_ring_floats));
+    if (MODE == 2) res_init(res, &tmem_slot, reinterpret_cast<uint4*>(smem + P.res_ring_floats));
     unsigned int epoch = 0;
     bool ok = true;
     for (int s = s_begin; s < s_end && ok; ++s) {
@@ -338,6 +339,8 @@ int launch_segment(SegParams& P, int persistent, cudaStream_t stream) {
     const int fb = tile_smem_floats(MSG_NGL, 2, 3), fc = tile_smem_floats(4, 2, 3);
     if (fb > fa) fa = fb;
     if (fc > fa) fa = fc;
+    const int fr = REC_WARPS * RES_STAGES * 32 * RES_RS;       // activation ring of the resident cell tile
+    if (fr > fa) fa = fr;
     // variant: 1 = tcgen05 gate tile (opt-in), 2 = cell weights resident on chip (every CTA owns at most one cell tile and the
     // per-thread fragment words fit in tensor memory + overflow), 0 = streaming
     static int res_env = -1;

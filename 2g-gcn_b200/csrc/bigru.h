@@ -72,6 +72,7 @@ struct SegParams {
     int cfg_o, jeff_o, nrb_o, nub_o;
     int cell_tiles_h_dir, cell_tiles_dir;
     int tilesA, tilesB;
+    int res_msg;                  // resident-weight variant: message-tile weights are kept in shared memory too
     int res_ring_floats;          // resident-weight variant: floats of the cp.async ring that precede the overflow fragments in shared memory
     GridSync sync;
 };

@@ -31,8 +31,16 @@ constexpr int RES_TMEM_WORDS = 256;          // per-thread words in tensor memor
 constexpr int RES_SMEM_WORDS = 32;           // per-thread overflow words in shared memory
 constexpr int RES_GROUPS = 3;                // weight groups active in a K chunk of the cell tile: (r, z, n_i) or (r, z, n_h)
 constexpr int RES_CHUNK_WORDS = 2 * RES_GROUPS * 4;   // one k16 step x 3 groups x (hi, lo) x 4 fragment registers
-constexpr int RES_RS = 24;                   // ring row stride in floats (16 data + 8 pad): conflict-free 64-bit fragment loads
-constexpr int RES_STAGES = 4;                // cp.async ring depth per warp (activation rows only)
+constexpr int RES_RS = 16;                   // ring row stride in floats: no padding, the 16-byte quarters of a row are XOR-swizzled
+constexpr int RES_STAGES = 3;                // cp.async ring depth per warp (activation rows only)
+constexpr int RES_MSG_GROUPS = 4;            // message tile: 4 resident weight groups of 16 units (+ the receivers' rows as a streamed 5th)
+
+// Ring layout: row r, 16-byte quarter q lives at float offset r*16 + 4*(q ^ (r & 2)); with it the 64-bit fragment loads of a
+// half-warp (rows g8 = 0..3 or 4..7, columns 2 t4) hit 16 distinct 8-byte slots.
+__device__ __forceinline__ int res_ring_off(int row, int quarter) { return row * RES_RS + ((quarter ^ (row & 2)) << 2); }
+// float offset of column 2 t4 (first fragment register) within a row whose index is congruent to g8 modulo 8; the second
+// register (column + 8) is at this offset ^ 8
+__device__ __forceinline__ int res_frag_col(int g8, int t4) { return ((((t4 >> 1) ^ (g8 & 2))) << 2) + ((t4 & 1) << 1); }
 constexpr float RES_WSCALE = 256.0f;         // weights are split as fp16(w * 2^8)
 constexpr float RES_F16_MAX = 65504.0f;
 
@@ -157,7 +165,7 @@ __device__ __forceinline__ void tile_accumulate_res(float (&out)[4][(NT + 1) / 2
     constexpr int STAGE_F = ROWS * RES_RS;
     constexpr int NP = (ROWS * 4 + 31) / 32;            // 16-byte pieces per lane per chunk
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int g8 = lane >> 2, t4 = lane & 3;
+    const int g8 = lane >> 2, t4 = lane & 3, fc = res_frag_col(g8, t4);
     float* ring = smem + warp * (STAGES * STAGE_F);
 
     float c[NG][NT][4];
@@ -184,7 +192,7 @@ __device__ __forceinline__ void tile_accumulate_res(float (&out)[4][(NT + 1) / 2
             const float* b2 = in[p] ? act2[row] : nullptr;
             s1[p] = b1 != nullptr ? b1 + quarter * 4 : nullptr;
             s2[p] = b2 != nullptr ? b2 + quarter * 4 - K1 : nullptr;      // indexed with the global k offset
-            dst[p] = row * RES_RS + quarter * 4;
+            dst[p] = res_ring_off(row, quarter);
         }
         auto issue = [&](int n, int st) {
             const int chunk = warp + n * REC_WARPS;
@@ -229,12 +237,12 @@ __device__ __forceinline__ void tile_accumulate_res(float (&out)[4][(NT + 1) / 2
             }
             const bool seg1 = (warp + n * REC_WARPS) < chunks1;
             // B fragments of m16n8k16 for lane (g8, t4): register 0 = (k = 2 t4 + {0,1}, row g8), register 1 = (k + 8, row g8)
-            const float* xb = ring + (n % STAGES) * STAGE_F + g8 * RES_RS + 2 * t4;
+            const float* xb = ring + (n % STAGES) * STAGE_F + g8 * RES_RS;
             uint32_t bh[NT][2], bl[NT][2];
 #pragma unroll
             for (int nt = 0; nt < NT; ++nt) {
-                const float2 v0 = *reinterpret_cast<const float2*>(xb + nt * 8 * RES_RS);
-                const float2 v1 = *reinterpret_cast<const float2*>(xb + nt * 8 * RES_RS + 8);
+                const float2 v0 = *reinterpret_cast<const float2*>(xb + nt * 8 * RES_RS + fc);
+                const float2 v1 = *reinterpret_cast<const float2*>(xb + nt * 8 * RES_RS + (fc ^ 8));
                 split_f16x2(v0.x, v0.y, bh[nt][0], bl[nt][0]);
                 split_f16x2(v1.x, v1.y, bh[nt][1], bl[nt][1]);
             }
@@ -303,6 +311,167 @@ __device__ __forceinline__ void tile_accumulate_res(float (&out)[4][(NT + 1) / 2
         }
     }
     __syncthreads();                             // smem may be reused by the caller right away
+}
+
+// ---- message tile with SMEM-RESIDENT weights ---------------------------------------------------------------------------------
+// The message MLP rows of a tile (4 groups x 16 units x K) never change either: they sit in shared memory as pre-split fp16
+// A-fragments in per-thread order, wmsg[((n*4 + g)*2 + hl) * REC_THREADS + tid] = the four fragment registers of chunk
+// (warp + 8 n), group g, half hl — one conflict-free LDS.128 each.  Only the 16 receiver rows (the A operand of the logit group)
+// and the 16 sender rows (B operand) stream through the ring: 64 KB per step instead of 224 KB.
+__device__ __forceinline__ void res_fill_msg(uint4* wmsg, const float* const* wrow, int K, unsigned int* range_flag) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g8 = lane >> 2, t4 = lane & 3;
+    const int total = K / REC_CK;
+    const int nmine = warp < total ? (total - warp + REC_WARPS - 1) / REC_WARPS : 0;
+    float wmax = 0.0f;
+    for (int n = 0; n < nmine; ++n) {
+        const int k = (warp + n * REC_WARPS) * REC_CK + 2 * t4;
+#pragma unroll
+        for (int g = 0; g < RES_MSG_GROUPS; ++g) {
+            const float* r0 = wrow[g * REC_J + g8];
+            const float* r1 = wrow[g * REC_J + g8 + 8];
+            float2 v[4];
+            v[0] = r0 != nullptr ? __ldg(reinterpret_cast<const float2*>(r0 + k)) : make_float2(0.f, 0.f);
+            v[1] = r1 != nullptr ? __ldg(reinterpret_cast<const float2*>(r1 + k)) : make_float2(0.f, 0.f);
+            v[2] = r0 != nullptr ? __ldg(reinterpret_cast<const float2*>(r0 + k + 8)) : make_float2(0.f, 0.f);
+            v[3] = r1 != nullptr ? __ldg(reinterpret_cast<const float2*>(r1 + k + 8)) : make_float2(0.f, 0.f);
+            uint32_t hi[4], lo[4];
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+                wmax = fmaxf(wmax, fmaxf(fabsf(v[r].x), fabsf(v[r].y)));
+                split_f16x2(v[r].x * RES_WSCALE, v[r].y * RES_WSCALE, hi[r], lo[r]);
+            }
+            wmsg[((n * RES_MSG_GROUPS + g) * 2 + 0) * REC_THREADS + tid] = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+            wmsg[((n * RES_MSG_GROUPS + g) * 2 + 1) * REC_THREADS + tid] = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+        }
+    }
+    if (!(wmax * RES_WSCALE < RES_F16_MAX)) atomicOr(range_flag, 2u);
+    __syncthreads();
+}
+
+// out[g][0] for g < 4: message pre-activations (unit = tid % 16 of group g, sender row = tid / 16); out[4][0]: <receiver tid % 16,
+// sender tid / 16> — what tile_accumulate<5, 2, 3> delivers.  act[0..15]: receiver rows, act[16..31]: sender rows (null = zeros).
+__device__ __forceinline__ void tile_accumulate_msg_res(float (&out)[RES_MSG_GROUPS + 1][1], const float* const* act, int K,
+                                                        const uint4* wmsg, const float* gdummy, float* smem) {
+    constexpr int NG = RES_MSG_GROUPS + 1, NT = 2, STAGES = RES_STAGES, ROWS = 32;
+    constexpr int STAGE_F = ROWS * RES_RS;
+    constexpr int NP = ROWS * 4 / 32;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int g8 = lane >> 2, t4 = lane & 3, fc = res_frag_col(g8, t4);
+    float* ring = smem + warp * (STAGES * STAGE_F);
+
+    float c[NG][NT][4];
+#pragma unroll
+    for (int m = 0; m < NG; ++m)
+#pragma unroll
+        for (int n = 0; n < NT; ++n)
+#pragma unroll
+            for (int r = 0; r < 4; ++r) c[m][n][r] = 0.0f;
+
+    const int total_chunks = K / REC_CK;
+    const int nmine = warp < total_chunks ? (total_chunks - warp + REC_WARPS - 1) / REC_WARPS : 0;
+    if (nmine > 0) {
+        const float* src[NP];
+        int dst[NP];
+#pragma unroll
+        for (int p = 0; p < NP; ++p) {
+            const int piece = lane + p * 32;
+            const int row = piece >> 2, quarter = piece & 3;
+            const float* b = act[row];
+            src[p] = b != nullptr ? b + quarter * 4 : nullptr;
+            dst[p] = res_ring_off(row, quarter);
+        }
+        auto issue = [&](int n, int st) {
+            const size_t koff = (size_t)(warp + n * REC_WARPS) * REC_CK;
+#pragma unroll
+            for (int p = 0; p < NP; ++p) {
+                const bool ok = src[p] != nullptr;
+                cp_async16_zfill(ring + st * STAGE_F + dst[p], ok ? src[p] + koff : gdummy, ok);
+            }
+        };
+#pragma unroll
+        for (int st = 0; st < STAGES - 1; ++st) {
+            if (st < nmine) issue(st, st);
+            cp_async_commit();
+        }
+#pragma unroll 1
+        for (int n = 0; n < nmine; ++n) {
+            uint4 w[RES_MSG_GROUPS][2];
+#pragma unroll
+            for (int g = 0; g < RES_MSG_GROUPS; ++g) {
+                w[g][0] = wmsg[((n * RES_MSG_GROUPS + g) * 2 + 0) * REC_THREADS + tid];
+                w[g][1] = wmsg[((n * RES_MSG_GROUPS + g) * 2 + 1) * REC_THREADS + tid];
+            }
+            cp_async_wait<STAGES - 2>();
+            __syncwarp();
+            {
+                const int nn = n + STAGES - 1;
+                if (nn < nmine) issue(nn, nn % STAGES);
+                cp_async_commit();
+            }
+            const float* xb = ring + (n % STAGES) * STAGE_F + g8 * RES_RS;
+            // logit group: A fragments from the receiver rows 0..15
+            uint32_t rh[4], rl[4];
+            {
+                const float2 x0 = *reinterpret_cast<const float2*>(xb + fc);
+                const float2 x1 = *reinterpret_cast<const float2*>(xb + 8 * RES_RS + fc);
+                const float2 x2 = *reinterpret_cast<const float2*>(xb + (fc ^ 8));
+                const float2 x3 = *reinterpret_cast<const float2*>(xb + 8 * RES_RS + (fc ^ 8));
+                split_f16x2(x0.x, x0.y, rh[0], rl[0]);
+                split_f16x2(x1.x, x1.y, rh[1], rl[1]);
+                split_f16x2(x2.x, x2.y, rh[2], rl[2]);
+                split_f16x2(x3.x, x3.y, rh[3], rl[3]);
+            }
+            // B fragments from the sender rows 16..31
+            uint32_t bh[NT][2], bl[NT][2];
+#pragma unroll
+            for (int nt = 0; nt < NT; ++nt) {
+                const float2 v0 = *reinterpret_cast<const float2*>(xb + (16 + nt * 8) * RES_RS + fc);
+                const float2 v1 = *reinterpret_cast<const float2*>(xb + (16 + nt * 8) * RES_RS + (fc ^ 8));
+                split_f16x2(v0.x, v0.y, bh[nt][0], bl[nt][0]);
+                split_f16x2(v1.x, v1.y, bh[nt][1], bl[nt][1]);
+            }
+#pragma unroll
+            for (int g = 0; g < RES_MSG_GROUPS; ++g) {
+                const uint32_t ah[4] = {w[g][0].x, w[g][0].y, w[g][0].z, w[g][0].w};
+                const uint32_t al[4] = {w[g][1].x, w[g][1].y, w[g][1].z, w[g][1].w};
+#pragma unroll
+                for (int nt = 0; nt < NT; ++nt) mma_f16(c[g][nt], al, bh[nt]);
+#pragma unroll
+                for (int nt = 0; nt < NT; ++nt) mma_f16(c[g][nt], ah, bl[nt]);
+#pragma unroll
+                for (int nt = 0; nt < NT; ++nt) mma_f16(c[g][nt], ah, bh[nt]);
+            }
+#pragma unroll
+            for (int nt = 0; nt < NT; ++nt) mma_f16(c[RES_MSG_GROUPS][nt], rl, bh[nt]);
+#pragma unroll
+            for (int nt = 0; nt < NT; ++nt) mma_f16(c[RES_MSG_GROUPS][nt], rh, bl[nt]);
+#pragma unroll
+            for (int nt = 0; nt < NT; ++nt) mma_f16(c[RES_MSG_GROUPS][nt], rh, bh[nt]);
+        }
+        cp_async_wait<0>();
+    }
+    __syncthreads();                             // every warp's ring is dead: reuse the memory for the reduction
+    float* red = smem;                           // red[warp][m][n][reg][lane]: 8 x 5 x 2 x 4 x 32 floats = 40 KB (ring: 48 KB)
+#pragma unroll
+    for (int m = 0; m < NG; ++m)
+#pragma unroll
+        for (int n = 0; n < NT; ++n)
+#pragma unroll
+            for (int r = 0; r < 4; ++r) red[(((warp * NG + m) * NT + n) * 4 + r) * 32 + lane] = c[m][n][r];
+    __syncthreads();
+    {
+        const int u = tid & 15, row = tid >> 4;
+        const int n = row >> 3, col = row & 7;
+        const int l = (u & 7) * 4 + (col >> 1), r = (u >> 3) * 2 + (col & 1);
+#pragma unroll
+        for (int m = 0; m < NG; ++m) {
+            float s = 0.0f;
+#pragma unroll
+            for (int w = 0; w < REC_WARPS; ++w) s += red[(((w * NG + m) * NT + n) * 4 + r) * 32 + l];
+            out[m][0] = m < RES_MSG_GROUPS ? s * (1.0f / RES_WSCALE) : s;
+        }
+    }
+    __syncthreads();
 }
 
 }  // namespace tg

@@ -40,7 +40,7 @@ struct SegShared {
 // on-chip resident weights (recurrent_res.cuh)
 template <int MODE>
 __device__ __forceinline__ void seg_message_tile(const SegParams& P, int tile, int s, float* smem, SegShared& sh, RtcShared& rsh,
-                                                 RtcState& rst) {
+                                                 RtcState& rst, uint4* wmsg, int& msg_ready) {
     const int D = P.D, T = P.T, B = P.B, H = P.H, O = P.O;
     const int dir = tile / P.msg_tiles_dir;
     int rem = tile - dir * P.msg_tiles_dir;
@@ -93,8 +93,14 @@ __device__ __forceinline__ void seg_message_tile(const SegParams& P, int tile, i
     __syncthreads();
 
     float acc[MSG_NGL][1];
-    if (MODE == 1) tile_accumulate_tc<MSG_NGL, 2>(acc, sh.tab1, sh.tab1, s > 0 ? D : 0, 0, rsh, rst);
-    else    tile_accumulate<MSG_NGL, 2, 3>(acc, sh.tab1, sh.tab1, s > 0 ? D : 0, 0, 0u, 0u, P.wm[kind], smem);
+    if (MODE == 2 && P.res_msg) {
+        if (!msg_ready) { res_fill_msg(wmsg, sh.tab1, D, P.sync.error); msg_ready = 1; }   // first step: this CTA's message weights go on chip
+        tile_accumulate_msg_res(acc, sh.tab1 + MSG_UNITS, s > 0 ? D : 0, wmsg, P.wm[kind], smem);
+    } else if (MODE == 1) {
+        tile_accumulate_tc<MSG_NGL, 2>(acc, sh.tab1, sh.tab1, s > 0 ? D : 0, 0, rsh, rst);
+    } else {
+        tile_accumulate<MSG_NGL, 2, 3>(acc, sh.tab1, sh.tab1, s > 0 ? D : 0, 0, 0u, 0u, P.wm[kind], smem);
+    }
 
     // thread pair: unit (or receiver) index = tid % 16, sender row = tid / 16
     if (tid < MSG_ROWS * REC_J) {
@@ -280,6 +286,9 @@ __global__ void __launch_bounds__(MODE == 1 ? RTC_THREADS : REC_THREADS, 1) segm
     if (MODE == 1) { rtc_init(rsh, rst, reinterpret_cast<uint8_t*>(smem)); rst.dbg = phases >> 4; }      // dbg: timing experiments
     // MODE 2: the ring keeps its place at the start of dynamic shared memory; the overflow fragments follow it
     if (MODE == 2) res_init(res, &tmem_slot, reinterpret_cast<uint4*>(smem + P.res_ring_floats));
+    // MODE 2 with res_msg: the message weights of this CTA's message tile follow the overflow fragments
+    uint4* wmsg = reinterpret_cast<uint4*>(smem + P.res_ring_floats + RES_SMEM_WORDS * REC_THREADS);
+    int msg_ready = 0;
     unsigned int epoch = 0;
     bool ok = true;
     for (int s = s_begin; s < s_end && ok; ++s) {
@@ -288,7 +297,7 @@ __global__ void __launch_bounds__(MODE == 1 ? RTC_THREADS : REC_THREADS, 1) segm
             if (!grid_barrier(P.sync, epoch, gridDim.x, &sh.s_fail)) { ok = false; break; }
         }
         if (phases & 1) {
-            for (int tile = blockIdx.x; tile < P.tilesA; tile += gridDim.x) seg_message_tile<MODE>(P, tile, s, smem, sh, rsh, rst);
+            for (int tile = blockIdx.x; tile < P.tilesA; tile += gridDim.x) seg_message_tile<MODE>(P, tile, s, smem, sh, rsh, rst, wmsg, msg_ready);
             if (persistent && !grid_barrier(P.sync, epoch, gridDim.x, &sh.s_fail)) { ok = false; break; }
         }
         if (phases & 2) {
@@ -352,15 +361,27 @@ int launch_segment(SegParams& P, int persistent, cudaStream_t stream) {
     const int kmax = (P.nk_h > 2 ? P.nk_h : 2) * D + D;
     const bool res_fits = cdiv(kmax / REC_CK, REC_WARPS) * RES_CHUNK_WORDS <= RES_TMEM_WORDS + RES_SMEM_WORDS;
     if (mode == 0 && res_env && res_fits && P.tilesB <= num_sms() && (persistent ? P.tilesA <= num_sms() : true)) mode = 2;
+    // resident message weights as well: one message tile per CTA for the whole launch, D*256 bytes of fragments fit beside the rest
+    const size_t static_smem = 8448;
+    P.res_msg = 0;
+    if (mode == 2 && persistent && MSG_UNITS == RES_MSG_GROUPS * REC_J) {
+        int fm = REC_WARPS * RES_STAGES * 32 * RES_RS;                       // activation ring (message and cell tiles)
+        const int red_msg = REC_WARPS * MSG_NGL * 2 * 4 * 32, red_cell = 4 * 4 * 4 * 4 * 32;
+        if (red_msg > fm) fm = red_msg;
+        if (red_cell > fm) fm = red_cell;
+        const size_t need = sizeof(float) * ((size_t)fm + RES_SMEM_WORDS * REC_THREADS) + (size_t)cdiv(D / REC_CK, REC_WARPS) * RES_MSG_GROUPS * 2 * REC_THREADS * 16;
+        if (need + static_smem <= 227 * 1024) { P.res_msg = 1; fa = fm; }
+    }
     P.res_ring_floats = fa;
     auto kern = mode == 1 ? segment_kernel<1> : (mode == 2 ? segment_kernel<2> : segment_kernel<0>);
     const int threads = mode == 1 ? RTC_THREADS : REC_THREADS;
     const size_t smem = mode == 1 ? (size_t)RTC_SMEM_BYTES
-                                  : sizeof(float) * (size_t)fa + (mode == 2 ? sizeof(float) * RES_SMEM_WORDS * REC_THREADS : 0);
-    static bool configured[3] = {false, false, false};
-    if (!configured[mode]) {
+                                  : sizeof(float) * (size_t)fa + (mode == 2 ? sizeof(float) * RES_SMEM_WORDS * REC_THREADS : 0)
+                                        + (P.res_msg ? (size_t)cdiv(D / REC_CK, REC_WARPS) * RES_MSG_GROUPS * 2 * REC_THREADS * 16 : 0);
+    static size_t configured[3] = {0, 0, 0};
+    if (smem > configured[mode]) {
         TG_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured[mode] = true;
+        configured[mode] = smem;
     }
     int per_sm = 0;
     TG_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, smem));

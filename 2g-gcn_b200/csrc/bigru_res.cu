@@ -93,62 +93,70 @@ __global__ void __launch_bounds__(REC_THREADS, 1) bigru_res_kernel(const BiGruPa
 
     unsigned int epoch = 0;
     bool ok = true;
+    // epilogue operands of one (step, row block): input pre-activations, previous state, output offsets
+    float xg[3][3], hprev[3];
+    size_t orow[3];
+    float* gsave[3];
+    bool valid[3];
+    auto fetch = [&](int s, int rb0, int nrows) {
+        const int t = dir == 0 ? s : T - 1 - s;
+        const int tprev = dir == 0 ? t - 1 : t + 1;
+#pragma unroll
+        for (int q = 0; q < 3; ++q) {
+            valid[q] = o_ok[q] && o_row[q] < nrows;
+            xg[q][0] = xg[q][1] = xg[q][2] = 0.0f;
+            if (!single_rb || s == 0) hprev[q] = 0.0f;           // single row block: hprev is carried in the register (own last output)
+            orow[q] = 0;
+            gsave[q] = nullptr;
+            if (valid[q]) {
+                const int unit = o_unit[q];
+                size_t fe0;
+                if (single_rb) {
+                    fe0 = (size_t)o_fe0[q];
+                } else {
+                    const int r = rb0 + o_row[q], b = r / G.E, e = r - b * G.E;
+                    fe0 = (size_t)b * T * G.E + e;
+                }
+                const size_t fe = fe0 + (size_t)t * G.E;
+                const float* gi = G.gi + (fe * 2 + dir) * 3 * D;
+                xg[q][0] = __ldg(gi + unit); xg[q][1] = __ldg(gi + D + unit); xg[q][2] = __ldg(gi + 2 * D + unit);
+                if (!single_rb && s > 0) hprev[q] = ld_cg(G.hfr + (fe0 + (size_t)tprev * G.E) * 2 * D + dir * D + unit);
+                orow[q] = fe * 2 * D + dir * D + unit;
+                if (G.gates != nullptr) gsave[q] = G.gates + (fe * 2 + dir) * 4 * D + unit;
+            }
+        }
+    };
+    if (single_rb) fetch(0, 0, G.rows);
     for (int s = 0; s < T && ok; ++s) {
         const int t = dir == 0 ? s : T - 1 - s;
         const int tprev = dir == 0 ? t - 1 : t + 1;
         for (int rb0 = 0; rb0 < G.rows; rb0 += BR_ROWS) {
             const int nrows = min(BR_ROWS, G.rows - rb0);
-            // ---- 1. stage the previous state of these rows; fetch the epilogue operands meanwhile ------------------
+            // ---- 1. stage the previous state of these rows: every warp copies exactly the K columns it multiplies (its k16
+            //         steps ks = warp, warp + 8, ...), so only a __syncwarp separates the copies from the MMAs -------------
             if (s > 0) {
-                const int d4 = D / 4;
                 const size_t tstep = (size_t)tprev * G.E * 2 * D;
-                const int rstep = REC_THREADS / d4, cstep = REC_THREADS - rstep * d4;     // (row, column) advance per iteration
-                int row = tid / d4, c4 = tid - row * d4;
-                for (; row < BR_ROWS; row += rstep) {
-                    const bool valid = row < nrows;
-                    const float* src;
+                const int quarter = lane & 3;
+#pragma unroll
+                for (int p = 0; p < BR_ROWS / 8; ++p) {
+                    const int row = (lane >> 2) + 8 * p;
+                    const bool rv = row < nrows;
+                    const float* base;
                     if (single_rb) {
-                        src = G.hfr + rowoff[row] + tstep + c4 * 4;
+                        base = G.hfr + rowoff[row] + tstep + quarter * 4;
                     } else {
                         const int r = rb0 + row;
-                        const int b = valid ? r / G.E : 0, e = valid ? r - b * G.E : 0;
-                        src = G.hfr + ((size_t)(b * T + tprev) * G.E + e) * 2 * D + dir * D + c4 * 4;
+                        const int b = rv ? r / G.E : 0, e = rv ? r - b * G.E : 0;
+                        base = G.hfr + ((size_t)(b * T + tprev) * G.E + e) * 2 * D + dir * D + quarter * 4;
                     }
-                    cp_async16_zfill(hsm + row * LD + c4 * 4, valid ? src : G.hfr, valid);
-                    c4 += cstep;
-                    if (c4 >= d4) { c4 -= d4; ++row; }
+                    float* dstp = hsm + row * LD + quarter * 4;
+                    for (int ks = warp; ks < D / 16; ks += REC_WARPS) cp_async16_zfill(dstp + ks * 16, rv ? base + ks * 16 : G.hfr, rv);
                 }
             }
             cp_async_commit();
-            float xg[3][3], hprev[3];
-            size_t orow[3];
-            float* gsave[3];
-            bool valid[3];
-#pragma unroll
-            for (int q = 0; q < 3; ++q) {
-                valid[q] = o_ok[q] && o_row[q] < nrows;
-                xg[q][0] = xg[q][1] = xg[q][2] = hprev[q] = 0.0f;
-                orow[q] = 0;
-                gsave[q] = nullptr;
-                if (valid[q]) {
-                    const int unit = o_unit[q];
-                    size_t fe0;
-                    if (single_rb) {
-                        fe0 = (size_t)o_fe0[q];
-                    } else {
-                        const int r = rb0 + o_row[q], b = r / G.E, e = r - b * G.E;
-                        fe0 = (size_t)b * T * G.E + e;
-                    }
-                    const size_t fe = fe0 + (size_t)t * G.E;
-                    const float* gi = G.gi + (fe * 2 + dir) * 3 * D;
-                    xg[q][0] = __ldg(gi + unit); xg[q][1] = __ldg(gi + D + unit); xg[q][2] = __ldg(gi + 2 * D + unit);
-                    if (s > 0) hprev[q] = ld_cg(G.hfr + (fe0 + (size_t)tprev * G.E) * 2 * D + dir * D + unit);
-                    orow[q] = fe * 2 * D + dir * D + unit;
-                    if (G.gates != nullptr) gsave[q] = G.gates + (fe * 2 + dir) * 4 * D + unit;
-                }
-            }
+            if (!single_rb) fetch(s, rb0, nrows);
             cp_async_wait<0>();
-            __syncthreads();
+            __syncwarp();
             float sum[3][3];
 #pragma unroll
             for (int q = 0; q < 3; ++q) sum[q][0] = sum[q][1] = sum[q][2] = 0.0f;
@@ -232,12 +240,19 @@ __global__ void __launch_bounds__(REC_THREADS, 1) bigru_res_kernel(const BiGruPa
             }
 #pragma unroll
             for (int q = 0; q < 3; ++q)
-                if (valid[q])
-                    G.hfr[orow[q]] = gru_update(xg[q][0], xg[q][1], xg[q][2], sum[q][0] + bh[q][0], sum[q][1] + bh[q][1],
-                                                sum[q][2] + bh[q][2], hprev[q], gsave[q], D);
-            __syncthreads();                             // the reduction buffer becomes the staging buffer again
+                if (valid[q]) {
+                    const float hnew = gru_update(xg[q][0], xg[q][1], xg[q][2], sum[q][0] + bh[q][0], sum[q][1] + bh[q][1],
+                                                  sum[q][2] + bh[q][2], hprev[q], gsave[q], D);
+                    G.hfr[orow[q]] = hnew;
+                    hprev[q] = hnew;
+                }
+            if (!single_rb) __syncthreads();             // the reduction buffer becomes the staging buffer again
         }
-        if (s + 1 < T && !grid_barrier(P.sync, epoch, gridDim.x, &s_fail)) ok = false;
+        if (s + 1 < T) {
+            grid_arrive(P.sync, epoch);                  // (its __syncthreads also retires the reduction buffer)
+            if (single_rb) fetch(s + 1, 0, G.rows);      // next step's input pre-activations arrive in the shadow of the barrier
+            if (!grid_wait(P.sync, epoch, gridDim.x, &s_fail)) ok = false;
+        }
     }
 }
 

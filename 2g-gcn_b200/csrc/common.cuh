@@ -102,13 +102,21 @@ struct GridSync {
     unsigned int* error;     // set to 1 on spin timeout
 };
 
-__device__ __forceinline__ bool grid_barrier(const GridSync& gs, unsigned int& epoch, unsigned int nblocks,
-                                             volatile int* s_fail) {
+// Split form: grid_arrive publishes this CTA's writes (release at GPU scope, cumulative over the CTA through the
+// __syncthreads) and returns at once; work that does not depend on other CTAs can run before grid_wait, which blocks
+// until every CTA has arrived and makes their writes visible to the whole CTA.
+__device__ __forceinline__ void grid_arrive(const GridSync& gs, unsigned int& epoch) {
     __syncthreads();
     epoch += 1;
+#ifdef GRID_FENCE_BARRIER
+    if (threadIdx.x == 0) { __threadfence(); atomicAdd(gs.counter, 1u); }
+#else
+    if (threadIdx.x == 0) asm volatile("red.release.gpu.global.add.u32 [%0], %1;\n" ::"l"(gs.counter), "r"(1u) : "memory");
+#endif
+}
+
+__device__ __forceinline__ bool grid_wait(const GridSync& gs, unsigned int epoch, unsigned int nblocks, volatile int* s_fail) {
     if (threadIdx.x == 0) {
-        __threadfence();
-        atomicAdd(gs.counter, 1u);
         const unsigned int target = epoch * nblocks;
         unsigned int spins = 0;
         while (true) {
@@ -116,16 +124,24 @@ __device__ __forceinline__ bool grid_barrier(const GridSync& gs, unsigned int& e
             asm volatile("ld.acquire.gpu.global.u32 %0, [%1];\n" : "=r"(v) : "l"(gs.counter) : "memory");
             if (v >= target) break;
             if (++spins > (1u << 22)) {   // far beyond any legitimate wait (each probe is an L2 round trip)
-                atomicOr(gs.error, 1u);                    // bit 0: timeout (bit 1: operand range of the fp16-split tiles)
+                atomicOr(gs.error, 1u);   // bit 0: timeout (bit 1: operand range of the fp16-split tiles)
                 *s_fail = 1;
                 break;
             }
             if ((spins & 1023u) == 0 && (*((volatile unsigned int*)gs.error) & 1u)) { *s_fail = 1; break; }
         }
+#ifdef GRID_FENCE_BARRIER
         __threadfence();
+#endif
     }
     __syncthreads();
     return *s_fail == 0;
+}
+
+__device__ __forceinline__ bool grid_barrier(const GridSync& gs, unsigned int& epoch, unsigned int nblocks,
+                                             volatile int* s_fail) {
+    grid_arrive(gs, epoch);
+    return grid_wait(gs, epoch, nblocks, s_fail);
 }
 
 }  // namespace tg

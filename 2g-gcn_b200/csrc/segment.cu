@@ -38,9 +38,11 @@ struct SegShared {
 // ---- phase A ------------------------------------------------------------------------------------
 // MODE: 0 = streaming mma.sync tiles, 1 = tcgen05 gate tile (recurrent_tc.cuh), 2 = streaming message tiles + cell tiles with
 // on-chip resident weights (recurrent_res.cuh)
+// part: bit 0 = set-up (pointer tables; depends on nothing another CTA writes during the step), bit 1 = compute.  The persistent
+// resident variant runs the set-up of the NEXT phase between grid_arrive and grid_wait; everything else passes part = 3.
 template <int MODE>
 __device__ __forceinline__ void seg_message_tile(const SegParams& P, int tile, int s, float* smem, SegShared& sh, RtcShared& rsh,
-                                                 RtcState& rst, uint4* wmsg, int& msg_ready) {
+                                                 RtcState& rst, uint4* wmsg, int& msg_ready, int part) {
     const int D = P.D, T = P.T, B = P.B, H = P.H, O = P.O;
     const int dir = tile / P.msg_tiles_dir;
     int rem = tile - dir * P.msg_tiles_dir;
@@ -61,8 +63,9 @@ __device__ __forceinline__ void seg_message_tile(const SegParams& P, int tile, i
     const int tprev = dir == 0 ? t - 1 : t + 1;
     const int tid = threadIdx.x;
 
-    __syncthreads();
-    if (tid < MSG_UNITS) {                                   // message MLP rows of this unit slice
+    if (part == 3) __syncthreads();
+    if (!(part & 1)) {
+    } else if (tid < MSG_UNITS) {                            // message MLP rows of this unit slice
         const int unit = unit0 + tid;
         sh.tab1[tid] = unit < D ? P.wm[kind] + (size_t)unit * D : nullptr;
     } else if (tid < MSG_UNITS + REC_J) {                    // receivers' previous states: the logit "weights"
@@ -83,6 +86,7 @@ __device__ __forceinline__ void seg_message_tile(const SegParams& P, int tile, i
         sh.tab1[tid] = ptr;
         sh.om[l] = (!send_h && bl < nb) ? __ldg(P.om + (b0 + bl) * O + e) : 1.0f;
     }
+    if (!(part & 2)) return;
     // bias of this thread's message columns, fetched before the K loop
     float bias[MSG_NG];
 #pragma unroll
@@ -90,7 +94,7 @@ __device__ __forceinline__ void seg_message_tile(const SegParams& P, int tile, i
         const int u = unit0 + g * REC_J + (tid & 15);
         bias[g] = u < D ? __ldg(P.bm[kind] + u) : 0.0f;
     }
-    __syncthreads();
+    if (part == 3) __syncthreads();
 
     float acc[MSG_NGL][1];
     if (MODE == 2 && P.res_msg) {
@@ -118,33 +122,35 @@ __device__ __forceinline__ void seg_message_tile(const SegParams& P, int tile, i
         if (blr == bls && blr < nb) sh.logit[(blr * Er + r) * Es + sdr] = acc[MSG_NG][0] * (1.0f / sqrtf((float)D));
     }
     __syncthreads();
-    // masked softmax over the senders of each receiver (vhoi/models.py:1750-1753)
-    if (tid < nb * Er) {
-        const int bl = tid / Er, r = tid - bl * Er;
-        const int b = b0 + bl;
-        const float* lrow = sh.logit + tid * Es;
+    // masked softmax over the senders of each receiver (vhoi/models.py:1750-1753), one thread per (receiver, sender) pair:
+    // un-normalised weight exp(l - max) into shared memory; the pair threads of unit block 0 also publish the normalised weights
+    if (tid < nb * Er * Es) {
+        const int br = tid / Es, sdr = tid - br * Es;
+        const int bl = br / Er, r = br - bl * Er;
+        const float* lrow = sh.logit + br * Es;
+        const float* omr = sh.om + bl * Es;
         float m = -INFINITY;
-        for (int sdr = 0; sdr < Es; ++sdr) {
-            const bool ok = !(same && sdr == r) && sh.om[bl * Es + sdr] != 0.0f;
-            if (ok) m = fmaxf(m, lrow[sdr]);
+        for (int q = 0; q < Es; ++q) {
+            const bool okq = !(same && q == r) && omr[q] != 0.0f;
+            if (okq) m = fmaxf(m, lrow[q]);
         }
-        float sum = 0.0f;
-        for (int sdr = 0; sdr < Es; ++sdr) {
-            const bool ok = !(same && sdr == r) && sh.om[bl * Es + sdr] != 0.0f;
-            const float ex = ok ? expf(lrow[sdr] - m) : 0.0f;
-            sh.alpha[tid * Es + sdr] = ex;
-            sum += ex;
-        }
-        const float inv = sum > 0.0f ? 1.0f / sum : 0.0f;
-        for (int sdr = 0; sdr < Es; ++sdr) {
-            const float a = sh.alpha[tid * Es + sdr] * inv;
-            sh.alpha[tid * Es + sdr] = a;
-            if (kind == 1 && ub == 0) {
+        const bool ok = !(same && sdr == r) && omr[sdr] != 0.0f;
+        const float ex = ok ? expf(lrow[sdr] - m) : 0.0f;
+        sh.alpha[tid] = ex;
+        const bool publish = ub == 0 && ((kind == 1 && (dir == 0 ? P.att_f : P.att_b) != nullptr) || P.salpha[kind] != nullptr);
+        if (publish) {                                   // warp-uniform; the sum over this receiver's senders in sender order
+            float sum = 0.0f;
+            for (int q = 0; q < Es; ++q) {
+                const bool okq = !(same && q == r) && omr[q] != 0.0f;
+                sum += okq ? expf(lrow[q] - m) : 0.0f;
+            }
+            const float a = ex * (sum > 0.0f ? 1.0f / sum : 0.0f);
+            const int b = b0 + bl;
+            if (kind == 1) {
                 float* att = dir == 0 ? P.att_f : P.att_b;
                 if (att != nullptr) att[((size_t)(b * H + r) * T + t) * O + sdr] = a;
             }
-            if (ub == 0 && P.salpha[kind] != nullptr)
-                P.salpha[kind][((((size_t)dir * B + b) * T + t) * Er + r) * Es + sdr] = a;
+            if (P.salpha[kind] != nullptr) P.salpha[kind][((((size_t)dir * B + b) * T + t) * Er + r) * Es + sdr] = a;
         }
     }
     __syncthreads();
@@ -159,8 +165,11 @@ __device__ __forceinline__ void seg_message_tile(const SegParams& P, int tile, i
         const int bl = br / Er;
         const float* al = sh.alpha + br * Es;
         const float* ms = sh.msg + (bl * Es) * MSG_LDM + c;
+        float sum = 0.0f;
+        for (int sdr = 0; sdr < Es; ++sdr) sum += al[sdr];
+        const float inv = sum > 0.0f ? 1.0f / sum : 0.0f;
         float v = 0.0f;
-        for (int sdr = 0; sdr < Es; ++sdr) v = fmaf(al[sdr], ms[sdr * MSG_LDM], v);
+        for (int sdr = 0; sdr < Es; ++sdr) v = fmaf(al[sdr] * inv, ms[sdr * MSG_LDM], v);
         if (MODE == 2 && !(v < RES_F16_MAX)) atomicOr(P.sync.error, 2u);      // operand of the fp16-split cell tile out of range
         const int r = br - bl * Er;
         mg[((((size_t)dir * B + b0 + bl) * P.mg_T + (P.mg_T > 1 ? t : 0)) * Er + r) * nk_r * D + slot * D + u] = v;
@@ -170,9 +179,18 @@ __device__ __forceinline__ void seg_message_tile(const SegParams& P, int tile, i
 // ---- phase B ------------------------------------------------------------------------------------
 // One pipeline over the concatenated K range [segment-message columns of W_ih | W_hh] with four weight groups:
 // r and z accumulate over both segments, n_i only over the first, n_h only over the second (GRU needs them apart).
+// Epilogue operands of a cell tile, fetched by the set-up part and consumed after the K loop.
+struct CellPre {
+    float bh[3], xg[2][3], hprev[2], ug[2];
+    bool valid[2];
+    size_t orow[2];
+    float* gsave[2];
+};
+
+// part: as for seg_message_tile (bit 0 = pointer tables + epilogue operands, bit 1 = K loop + gate math).
 template <int NT, int MODE>
 __device__ __forceinline__ void seg_cell_tile(const SegParams& P, bool is_h, int dir, int rb, int ub, int s, float* smem,
-                                              SegShared& sh, RtcShared& rsh, RtcState& rst, ResState& res) {
+                                              SegShared& sh, RtcShared& rsh, RtcState& rst, ResState& res, int part, CellPre& pre) {
     constexpr int RBT = 8 * NT, NPAIR = NT / 2, WR = 4 * REC_J;
     const int D = P.D, T = P.T, B = P.B;
     const int E = is_h ? P.H : P.O;
@@ -183,66 +201,68 @@ __device__ __forceinline__ void seg_cell_tile(const SegParams& P, bool is_h, int
     const int tid = threadIdx.x;
     const int nk = is_h ? P.nk_h : 2;
     float* hx = is_h ? P.hx_h : P.hx_o;
-    const float* mgbase = is_h ? P.mg_h : P.mg_o;
-    const float* Wi = is_h ? P.wih_h[dir] + P.col_h : P.wih_o[dir] + P.col_o;
-    const int ldw = is_h ? P.ldw_h : P.ldw_o;
     const float* Wh = is_h ? P.whh_h[dir] : P.whh_o[dir];
 
-    __syncthreads();
-    if (tid < WR) {
-        const int g = tid / REC_J, unit = unit0 + tid % REC_J;   // groups: 0 r, 1 z, 2 n (input part), 3 n (hidden part)
-        const int gate = g < 3 ? g : 2;
-        const bool ok = unit < D;
-        sh.tab1[tid] = (ok && g < 3) ? Wi + (size_t)(gate * D + unit) * ldw : nullptr;
-        sh.tab2[tid] = (ok && g != 2) ? Wh + (size_t)(gate * D + unit) * D : nullptr;
-    } else if (tid < WR + RBT) {
-        const int r = row0 + tid - WR;
-        const float* p1 = nullptr;
-        const float* p2 = nullptr;
-        if (r < rows) {
-            const int b = r / E, e = r - b * E;
-            p1 = mgbase + ((((size_t)dir * B + b) * P.mg_T + (P.mg_T > 1 ? t : 0)) * E + e) * nk * D;
-            if (s > 0) {
-                p2 = hx + ((size_t)(b * T + tprev) * E + e) * 2 * D + dir * D;
+    if (part == 3) __syncthreads();
+    if (part & 1) {
+        const float* mgbase = is_h ? P.mg_h : P.mg_o;
+        const float* Wi = is_h ? P.wih_h[dir] + P.col_h : P.wih_o[dir] + P.col_o;
+        const int ldw = is_h ? P.ldw_h : P.ldw_o;
+        if (tid < WR) {
+            if (MODE != 2 || !res.ready) {                           // resident weights: the row pointers are only needed for the fill
+                const int g = tid / REC_J, unit = unit0 + tid % REC_J;   // groups: 0 r, 1 z, 2 n (input part), 3 n (hidden part)
+                const int gate = g < 3 ? g : 2;
+                const bool ok = unit < D;
+                sh.tab1[tid] = (ok && g < 3) ? Wi + (size_t)(gate * D + unit) * ldw : nullptr;
+                sh.tab2[tid] = (ok && g != 2) ? Wh + (size_t)(gate * D + unit) * D : nullptr;
+            }
+        } else if (tid < WR + RBT) {
+            const int r = row0 + tid - WR;
+            const float* p1 = nullptr;
+            const float* p2 = nullptr;
+            if (r < rows) {
+                const int b = r / E, e = r - b * E;
+                p1 = mgbase + ((((size_t)dir * B + b) * P.mg_T + (P.mg_T > 1 ? t : 0)) * E + e) * nk * D;
+                if (s > 0) {
+                    p2 = hx + ((size_t)(b * T + tprev) * E + e) * 2 * D + dir * D;
+                }
+            }
+            sh.tab1[tid] = p1;
+            sh.tab2[tid] = p2;
+        }
+        // epilogue operands, fetched before the K loop
+        const int unit = unit0 + (tid & 15);
+        const float* bhh = is_h ? P.bhh_h[dir] : P.bhh_o[dir];
+        const float* gsb = is_h ? P.gs_h : P.gs_o;
+        const float* ub_ = is_h ? P.u_h : P.u_o;
+        float* sg = is_h ? P.sgates_h : P.sgates_o;
+        pre.bh[0] = pre.bh[1] = pre.bh[2] = 0.f;
+        if (unit < D) { pre.bh[0] = __ldg(bhh + unit); pre.bh[1] = __ldg(bhh + D + unit); pre.bh[2] = __ldg(bhh + 2 * D + unit); }
+#pragma unroll
+        for (int p = 0; p < NPAIR; ++p) {
+            const int lr = (tid >> 4) + 16 * p, r = row0 + lr;
+            pre.valid[p] = unit < D && r < rows && lr < RBT && tid < REC_THREADS;
+            pre.xg[p][0] = pre.xg[p][1] = pre.xg[p][2] = pre.hprev[p] = pre.ug[p] = 0.0f;
+            pre.orow[p] = 0;
+            pre.gsave[p] = nullptr;
+            if (pre.valid[p]) {
+                const int b = r / E, e = r - b * E;
+                const size_t fe = (size_t)(b * T + t) * E + e;
+                const float* gs = gsb + (fe * 2 + dir) * 3 * D;
+                pre.xg[p][0] = __ldg(gs + unit); pre.xg[p][1] = __ldg(gs + D + unit); pre.xg[p][2] = __ldg(gs + 2 * D + unit);
+                pre.ug[p] = __ldg(ub_ + fe);
+                if (s > 0) pre.hprev[p] = ld_cg(hx + ((size_t)(b * T + tprev) * E + e) * 2 * D + dir * D + unit);
+                pre.orow[p] = fe * 2 * D + dir * D + unit;
+                if (sg != nullptr) pre.gsave[p] = sg + (fe * 2 + dir) * 4 * D + unit;
             }
         }
-        sh.tab1[tid] = p1;
-        sh.tab2[tid] = p2;
     }
-    // epilogue operands, fetched before the K loop
-    const int unit = unit0 + (tid & 15);
-    const float* bhh = is_h ? P.bhh_h[dir] : P.bhh_o[dir];
-    const float* gsb = is_h ? P.gs_h : P.gs_o;
-    const float* ub_ = is_h ? P.u_h : P.u_o;
-    float bh[3] = {0.f, 0.f, 0.f}, xg[NPAIR][3], hprev[NPAIR], ug[NPAIR];
-    bool valid[NPAIR];
-    size_t orow[NPAIR];
-    float* gsave[NPAIR];
-    float* sg = is_h ? P.sgates_h : P.sgates_o;
-    if (unit < D) { bh[0] = __ldg(bhh + unit); bh[1] = __ldg(bhh + D + unit); bh[2] = __ldg(bhh + 2 * D + unit); }
-#pragma unroll
-    for (int p = 0; p < NPAIR; ++p) {
-        const int lr = (tid >> 4) + 16 * p, r = row0 + lr;
-        valid[p] = unit < D && r < rows && lr < RBT && tid < REC_THREADS;
-        xg[p][0] = xg[p][1] = xg[p][2] = hprev[p] = ug[p] = 0.0f;
-        orow[p] = 0;
-        gsave[p] = nullptr;
-        if (valid[p]) {
-            const int b = r / E, e = r - b * E;
-            const size_t fe = (size_t)(b * T + t) * E + e;
-            const float* gs = gsb + (fe * 2 + dir) * 3 * D;
-            xg[p][0] = __ldg(gs + unit); xg[p][1] = __ldg(gs + D + unit); xg[p][2] = __ldg(gs + 2 * D + unit);
-            ug[p] = __ldg(ub_ + fe);
-            if (s > 0) hprev[p] = ld_cg(hx + ((size_t)(b * T + tprev) * E + e) * 2 * D + dir * D + unit);
-            orow[p] = fe * 2 * D + dir * D + unit;
-            if (sg != nullptr) gsave[p] = sg + (fe * 2 + dir) * 4 * D + unit;
-        }
-    }
-    __syncthreads();
+    if (!(part & 2)) return;
+    if (part == 3) __syncthreads();
 
     float acc[4][NPAIR];
     if (MODE == 2) {
-        if (!res.ready) res_fill_cell(res, sh.tab1, sh.tab2, nk * D, D, P.sync.error);       // first step: this CTA's weight fragments go on chip
+        if (!res.ready) res_fill_cell(res, sh.tab1, sh.tab2, nk * D, D, P.sync.error);   // first step: this CTA's weight fragments go on chip
         tile_accumulate_res<NT>(acc, sh.tab1 + WR, sh.tab2 + WR, nk * D, D, res, Wh, smem);   // s == 0: null state rows = zeros
     } else if (MODE == 1) {
         tile_accumulate_tc<4, NT>(acc, sh.tab1, sh.tab2, nk * D, s > 0 ? D : 0, rsh, rst);
@@ -252,24 +272,24 @@ __device__ __forceinline__ void seg_cell_tile(const SegParams& P, bool is_h, int
 
 #pragma unroll
     for (int p = 0; p < NPAIR; ++p) {
-        if (!valid[p]) continue;
-        const float hnew = gru_update(xg[p][0] + acc[0][p], xg[p][1] + acc[1][p], xg[p][2] + acc[2][p], bh[0], bh[1],
-                                      acc[3][p] + bh[2], hprev[p], gsave[p], D);
-        hx[orow[p]] = ug[p] * hnew + (1.0f - ug[p]) * hprev[p];
+        if (!pre.valid[p]) continue;
+        const float hnew = gru_update(pre.xg[p][0] + acc[0][p], pre.xg[p][1] + acc[1][p], pre.xg[p][2] + acc[2][p], pre.bh[0], pre.bh[1],
+                                      acc[3][p] + pre.bh[2], pre.hprev[p], pre.gsave[p], D);
+        hx[pre.orow[p]] = pre.ug[p] * hnew + (1.0f - pre.ug[p]) * pre.hprev[p];
     }
 }
 
 template <int MODE>
 __device__ __forceinline__ void seg_cell_dispatch(const SegParams& P, int tile, int s, float* smem, SegShared& sh, RtcShared& rsh,
-                                                  RtcState& rst, ResState& res) {
+                                                  RtcState& rst, ResState& res, int part, CellPre& pre) {
     const int dir = tile / P.cell_tiles_dir;
     int rem = tile - dir * P.cell_tiles_dir;
     const bool is_h = rem < P.cell_tiles_h_dir;
     if (!is_h) rem -= P.cell_tiles_h_dir;
     const int nub = is_h ? P.nub_h : P.nub_o;
     const int rb = rem / nub, ub = rem - rb * nub;
-    if ((is_h ? P.cfg_h : P.cfg_o) == 4) seg_cell_tile<4, MODE>(P, is_h, dir, rb, ub, s, smem, sh, rsh, rst, res);
-    else                                 seg_cell_tile<2, MODE>(P, is_h, dir, rb, ub, s, smem, sh, rsh, rst, res);
+    if ((is_h ? P.cfg_h : P.cfg_o) == 4) seg_cell_tile<4, MODE>(P, is_h, dir, rb, ub, s, smem, sh, rsh, rst, res, part, pre);
+    else                                 seg_cell_tile<2, MODE>(P, is_h, dir, rb, ub, s, smem, sh, rsh, rst, res, part, pre);
 }
 
 // phases: bit 0 = A (messages), bit 1 = B (cells).  MODE as above.
@@ -291,17 +311,41 @@ __global__ void __launch_bounds__(MODE == 1 ? RTC_THREADS : REC_THREADS, 1) segm
     int msg_ready = 0;
     unsigned int epoch = 0;
     bool ok = true;
+    CellPre pre;
+#ifndef SEG_NO_SHADOW
+    if (MODE == 2 && persistent && phases == 3 && P.res_msg) {
+        // one message tile and one cell tile per CTA for the whole launch (launcher guarantees tilesA, tilesB <= gridDim.x):
+        // the set-up of the next phase (pointer tables, epilogue operands) runs in the shadow of the grid barrier
+        const int bid = blockIdx.x;
+        const bool hasA = bid < P.tilesA, hasB = bid < P.tilesB;
+        if (hasA) seg_message_tile<MODE>(P, bid, s_begin, smem, sh, rsh, rst, wmsg, msg_ready, 1);
+        __syncthreads();
+        for (int s = s_begin; s < s_end; ++s) {
+            if (hasA) seg_message_tile<MODE>(P, bid, s, smem, sh, rsh, rst, wmsg, msg_ready, 2);
+            grid_arrive(P.sync, epoch);
+            if (hasB) seg_cell_dispatch<MODE>(P, bid, s, smem, sh, rsh, rst, res, 1, pre);
+            if (!grid_wait(P.sync, epoch, gridDim.x, &sh.s_fail)) break;
+            if (hasB) seg_cell_dispatch<MODE>(P, bid, s, smem, sh, rsh, rst, res, 2, pre);
+            if (s + 1 == s_end) break;
+            grid_arrive(P.sync, epoch);
+            if (hasA) seg_message_tile<MODE>(P, bid, s + 1, smem, sh, rsh, rst, wmsg, msg_ready, 1);
+            if (!grid_wait(P.sync, epoch, gridDim.x, &sh.s_fail)) break;
+        }
+        s_begin = s_end;                        // skip the generic loop
+    }
+#endif
     for (int s = s_begin; s < s_end && ok; ++s) {
         if (phases & 4) {       // timing experiment: two bare grid barriers per step
             if (!grid_barrier(P.sync, epoch, gridDim.x, &sh.s_fail)) { ok = false; break; }
             if (!grid_barrier(P.sync, epoch, gridDim.x, &sh.s_fail)) { ok = false; break; }
         }
         if (phases & 1) {
-            for (int tile = blockIdx.x; tile < P.tilesA; tile += gridDim.x) seg_message_tile<MODE>(P, tile, s, smem, sh, rsh, rst, wmsg, msg_ready);
+            for (int tile = blockIdx.x; tile < P.tilesA; tile += gridDim.x)
+                seg_message_tile<MODE>(P, tile, s, smem, sh, rsh, rst, wmsg, msg_ready, 3);
             if (persistent && !grid_barrier(P.sync, epoch, gridDim.x, &sh.s_fail)) { ok = false; break; }
         }
         if (phases & 2) {
-            for (int tile = blockIdx.x; tile < P.tilesB; tile += gridDim.x) seg_cell_dispatch<MODE>(P, tile, s, smem, sh, rsh, rst, res);
+            for (int tile = blockIdx.x; tile < P.tilesB; tile += gridDim.x) seg_cell_dispatch<MODE>(P, tile, s, smem, sh, rsh, rst, res, 3, pre);
             if (persistent && s + 1 < s_end && !grid_barrier(P.sync, epoch, gridDim.x, &sh.s_fail)) { ok = false; break; }
         }
     }

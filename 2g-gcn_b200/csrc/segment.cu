@@ -32,6 +32,15 @@ struct SegShared {
     float msg[MSG_ROWS * MSG_LDM];
     float logit[MSG_MAXPAIRS];
     float alpha[MSG_MAXPAIRS];
+    // step plan of the message tile's epilogue, written by the set-up part (no integer divisions on the compute path)
+    int pair[MSG_MAXPAIRS];                      // (receiver, sender) pair of thread tid: receiver | sender << 8 | allowed << 16, or -1
+    int lidx[MSG_MAXPAIRS];                      // epilogue thread (receiver tid % 16, sender row tid / 16): index into logit[], or -1
+    unsigned int rcv_mask[MSG_ROWS];             // allowed senders of a receiver (bit q)
+    int rcv_msg[MSG_ROWS];                       // offset of the receiver's video's first sender row in msg[]
+    float* rcv_mg[MSG_ROWS];                     // where the receiver's aggregated message slice goes
+    float* rcv_att[MSG_ROWS];                    // attention outputs of the receiver (inspect / saved for the backward), or null
+    float* rcv_sal[MSG_ROWS];
+    float* row_smsg[MSG_ROWS];                   // saved post-ReLU message slice of a sender row, or null
     int s_fail;
 };
 
@@ -86,6 +95,50 @@ __device__ __forceinline__ void seg_message_tile(const SegParams& P, int tile, i
         sh.tab1[tid] = ptr;
         sh.om[l] = (!send_h && bl < nb) ? __ldg(P.om + (b0 + bl) * O + e) : 1.0f;
     }
+    if (part & 1) {
+        const int nk_r = recv_h ? P.nk_h : 2;
+        const int slot = recv_h ? (kind == 0 ? 0 : P.nk_h - 1) : kind - 2;
+        if (tid < MSG_MAXPAIRS) {
+            int info = -1;
+            if (tid < nb * Er * Es) {
+                const int br = tid / Es, sdr = tid - br * Es, bl = br / Er, r = br - bl * Er;
+                const bool ok = !(same && sdr == r) && (send_h || __ldg(P.om + (b0 + bl) * O + sdr) != 0.0f);
+                info = br | (sdr << 8) | ((int)ok << 16);
+            }
+            sh.pair[tid] = info;
+            const int j = tid & 15, row = tid >> 4;
+            const int blr = j / Er, r = j - blr * Er, bls = row / Es, sdr = row - bls * Es;
+            sh.lidx[tid] = (blr == bls && blr < nb) ? (blr * Er + r) * Es + sdr : -1;
+        }
+        if (tid < MSG_ROWS) {                                    // receiver tid of the block
+            const int br = tid, bl = br / Er, r = br - bl * Er, b = b0 + bl;
+            unsigned int mask = 0;
+            float* mgp = nullptr;
+            float* attp = nullptr;
+            float* salp = nullptr;
+            if (br < nb * Er) {
+                for (int q = 0; q < Es; ++q)
+                    if (!(same && q == r) && (send_h || __ldg(P.om + b * O + q) != 0.0f)) mask |= 1u << q;
+                float* mg = recv_h ? P.mg_h : P.mg_o;
+                mgp = mg + ((((size_t)dir * B + b) * P.mg_T + (P.mg_T > 1 ? t : 0)) * Er + r) * nk_r * D + slot * D + unit0;
+                if (ub == 0) {
+                    float* att = dir == 0 ? P.att_f : P.att_b;
+                    if (kind == 1 && att != nullptr) attp = att + ((size_t)(b * H + r) * T + t) * O;
+                    if (P.salpha[kind] != nullptr) salp = P.salpha[kind] + ((((size_t)dir * B + b) * T + t) * Er + r) * Es;
+                }
+            }
+            sh.rcv_mask[br] = mask;
+            sh.rcv_msg[br] = bl * Es * MSG_LDM;
+            sh.rcv_mg[br] = mgp;
+            sh.rcv_att[br] = attp;
+            sh.rcv_sal[br] = salp;
+        } else if (tid >= 32 && tid < 32 + MSG_ROWS) {           // sender row tid - 32
+            const int row = tid - 32, bls = row / Es, sdr = row - bls * Es;
+            float* ptr = nullptr;
+            if (P.smsg[kind] != nullptr && bls < nb) ptr = P.smsg[kind] + ((((size_t)dir * B + b0 + bls) * T + t) * Es + sdr) * D + unit0;
+            sh.row_smsg[row] = ptr;
+        }
+    }
     if (!(part & 2)) return;
     // bias of this thread's message columns, fetched before the K loop
     float bias[MSG_NG];
@@ -109,70 +162,56 @@ __device__ __forceinline__ void seg_message_tile(const SegParams& P, int tile, i
     // thread pair: unit (or receiver) index = tid % 16, sender row = tid / 16
     if (tid < MSG_ROWS * REC_J) {
         const int j = tid & 15, row = tid >> 4;
+        float* sv = sh.row_smsg[row];
 #pragma unroll
         for (int g = 0; g < MSG_NG; ++g) {
             const int c = g * REC_J + j;
             const float mv = fmaxf(acc[g][0] + bias[g], 0.0f);
             sh.msg[row * MSG_LDM + c] = mv;
-            if (P.smsg[kind] != nullptr && row / Es < nb && unit0 + c < D)
-                P.smsg[kind][((((size_t)dir * B + b0 + row / Es) * T + t) * Es + row % Es) * D + unit0 + c] = mv;
+            if (sv != nullptr && unit0 + c < D) sv[c] = mv;
         }
         // logit of (receiver j, sender row) when both belong to the same video of the block
-        const int blr = j / Er, r = j - blr * Er, bls = row / Es, sdr = row - bls * Es;
-        if (blr == bls && blr < nb) sh.logit[(blr * Er + r) * Es + sdr] = acc[MSG_NG][0] * (1.0f / sqrtf((float)D));
+        const int li = sh.lidx[tid];
+        if (li >= 0) sh.logit[li] = acc[MSG_NG][0] * (1.0f / sqrtf((float)D));
     }
     __syncthreads();
     // masked softmax over the senders of each receiver (vhoi/models.py:1750-1753), one thread per (receiver, sender) pair:
     // un-normalised weight exp(l - max) into shared memory; the pair threads of unit block 0 also publish the normalised weights
-    if (tid < nb * Er * Es) {
-        const int br = tid / Es, sdr = tid - br * Es;
-        const int bl = br / Er, r = br - bl * Er;
+    if (tid < MSG_MAXPAIRS && sh.pair[tid] >= 0) {
+        const int info = sh.pair[tid], br = info & 255, sdr = (info >> 8) & 255;
+        const unsigned int mask = sh.rcv_mask[br];
         const float* lrow = sh.logit + br * Es;
-        const float* omr = sh.om + bl * Es;
         float m = -INFINITY;
-        for (int q = 0; q < Es; ++q) {
-            const bool okq = !(same && q == r) && omr[q] != 0.0f;
-            if (okq) m = fmaxf(m, lrow[q]);
-        }
-        const bool ok = !(same && sdr == r) && omr[sdr] != 0.0f;
-        const float ex = ok ? expf(lrow[sdr] - m) : 0.0f;
+        for (int q = 0; q < Es; ++q)
+            if ((mask >> q) & 1u) m = fmaxf(m, lrow[q]);
+        const float ex = (info >> 16) ? expf(lrow[sdr] - m) : 0.0f;
         sh.alpha[tid] = ex;
-        const bool publish = ub == 0 && ((kind == 1 && (dir == 0 ? P.att_f : P.att_b) != nullptr) || P.salpha[kind] != nullptr);
-        if (publish) {                                   // warp-uniform; the sum over this receiver's senders in sender order
+        float* attp = sh.rcv_att[br];
+        float* salp = sh.rcv_sal[br];
+        if (attp != nullptr || salp != nullptr) {            // the sum over this receiver's senders in sender order
             float sum = 0.0f;
-            for (int q = 0; q < Es; ++q) {
-                const bool okq = !(same && q == r) && omr[q] != 0.0f;
-                sum += okq ? expf(lrow[q] - m) : 0.0f;
-            }
+            for (int q = 0; q < Es; ++q) sum += ((mask >> q) & 1u) ? expf(lrow[q] - m) : 0.0f;
             const float a = ex * (sum > 0.0f ? 1.0f / sum : 0.0f);
-            const int b = b0 + bl;
-            if (kind == 1) {
-                float* att = dir == 0 ? P.att_f : P.att_b;
-                if (att != nullptr) att[((size_t)(b * H + r) * T + t) * O + sdr] = a;
-            }
-            if (P.salpha[kind] != nullptr) P.salpha[kind][((((size_t)dir * B + b) * T + t) * Er + r) * Es + sdr] = a;
+            if (attp != nullptr) attp[sdr] = a;
+            if (salp != nullptr) salp[sdr] = a;
         }
     }
     __syncthreads();
-    // aggregated message for every receiver of the block
-    const int nk_r = recv_h ? P.nk_h : 2;
-    const int slot = recv_h ? (kind == 0 ? 0 : P.nk_h - 1) : kind - 2;
-    float* mg = recv_h ? P.mg_h : P.mg_o;
-    for (int idx = tid < REC_THREADS ? tid : nb * Er * MSG_UNITS; idx < nb * Er * MSG_UNITS; idx += REC_THREADS) {
-        const int c = idx % MSG_UNITS, br = idx / MSG_UNITS;
-        const int u = unit0 + c;
-        if (u >= D) continue;
-        const int bl = br / Er;
-        const float* al = sh.alpha + br * Es;
-        const float* ms = sh.msg + (bl * Es) * MSG_LDM + c;
-        float sum = 0.0f;
-        for (int sdr = 0; sdr < Es; ++sdr) sum += al[sdr];
-        const float inv = sum > 0.0f ? 1.0f / sum : 0.0f;
-        float v = 0.0f;
-        for (int sdr = 0; sdr < Es; ++sdr) v = fmaf(al[sdr] * inv, ms[sdr * MSG_LDM], v);
-        if (MODE == 2 && !(v < RES_F16_MAX)) atomicOr(P.sync.error, 2u);      // operand of the fp16-split cell tile out of range
-        const int r = br - bl * Er;
-        mg[((((size_t)dir * B + b0 + bl) * P.mg_T + (P.mg_T > 1 ? t : 0)) * Er + r) * nk_r * D + slot * D + u] = v;
+    // aggregated message for every receiver of the block: unit column tid % 64, receivers tid / 64 + 4 i
+    if (tid < REC_THREADS) {
+        const int c = tid & (MSG_UNITS - 1);
+        const bool uok = unit0 + c < D;
+        for (int br = tid / MSG_UNITS; br < nb * Er; br += REC_THREADS / MSG_UNITS) {
+            const float* al = sh.alpha + br * Es;
+            const float* ms = sh.msg + sh.rcv_msg[br] + c;
+            float sum = 0.0f;
+            for (int sdr = 0; sdr < Es; ++sdr) sum += al[sdr];
+            const float inv = sum > 0.0f ? 1.0f / sum : 0.0f;
+            float v = 0.0f;
+            for (int sdr = 0; sdr < Es; ++sdr) v = fmaf(al[sdr] * inv, ms[sdr * MSG_LDM], v);
+            if (MODE == 2 && !(v < RES_F16_MAX)) atomicOr(P.sync.error, 2u);      // operand of the fp16-split cell tile out of range
+            if (uok) sh.rcv_mg[br][c] = v;
+        }
     }
 }
 
@@ -406,7 +445,7 @@ int launch_segment(SegParams& P, int persistent, cudaStream_t stream) {
     const bool res_fits = cdiv(kmax / REC_CK, REC_WARPS) * RES_CHUNK_WORDS <= RES_TMEM_WORDS + RES_SMEM_WORDS;
     if (mode == 0 && res_env && res_fits && P.tilesB <= num_sms() && (persistent ? P.tilesA <= num_sms() : true)) mode = 2;
     // resident message weights as well: one message tile per CTA for the whole launch, D*256 bytes of fragments fit beside the rest
-    const size_t static_smem = 8448;
+    const size_t static_smem = 12288;                 // upper bound of the kernel's static shared memory (SegShared + barrier slots)
     P.res_msg = 0;
     if (mode == 2 && persistent && MSG_UNITS == RES_MSG_GROUPS * REC_J) {
         int fm = REC_WARPS * RES_STAGES * 32 * RES_RS;                       // activation ring (message and cell tiles)

@@ -72,6 +72,9 @@ struct SegParams {
     int cfg_o, jeff_o, nrb_o, nub_o;
     int cell_tiles_h_dir, cell_tiles_dir;
     int tilesA, tilesB;
+    int msg_g[4];                 // per message kind: video-block groups (= n_vb unless res_multi: a tile then walks over n_vb / msg_g blocks)
+    int cell_g_h, cell_g_o;       // row-block groups of the cell tiles (= nrb unless res_multi: a tile then walks over nrb / cell_g row blocks)
+    int res_multi;                // resident-weight variant, larger batches: tiles are weight slices, row / video blocks are walked inside the CTA
     int res_msg;                  // resident-weight variant: message-tile weights are kept in shared memory too
     int res_ring_floats;          // resident-weight variant: floats of the cp.async ring that precede the overflow fragments in shared memory
     GridSync sync;

@@ -49,9 +49,11 @@ struct SegShared {
 // on-chip resident weights (recurrent_res.cuh)
 // part: bit 0 = set-up (pointer tables; depends on nothing another CTA writes during the step), bit 1 = compute.  The persistent
 // resident variant runs the set-up of the NEXT phase between grid_arrive and grid_wait; everything else passes part = 3.
+// vbi: iteration over the video blocks a resident tile owns (video block = first block + vbi * groups); returns false
+// (uniformly) when the tile has no such block.
 template <int MODE>
-__device__ __forceinline__ void seg_message_tile(const SegParams& P, int tile, int s, float* smem, SegShared& sh, RtcShared& rsh,
-                                                 RtcState& rst, uint4* wmsg, int& msg_ready, int part) {
+__device__ __forceinline__ bool seg_message_tile(const SegParams& P, int tile, int s, float* smem, SegShared& sh, RtcShared& rsh,
+                                                 RtcState& rst, uint4* wmsg, int& msg_ready, int part, int vbi = 0) {
     const int D = P.D, T = P.T, B = P.B, H = P.H, O = P.O;
     const int dir = tile / P.msg_tiles_dir;
     int rem = tile - dir * P.msg_tiles_dir;
@@ -60,8 +62,10 @@ __device__ __forceinline__ void seg_message_tile(const SegParams& P, int tile, i
     for (int k = 1; k < 4; ++k)
         if (rem >= P.msg_tile_begin[k]) kind = k;
     rem -= P.msg_tile_begin[kind];
-    const int nub = P.msg_tiles_kind[kind] / P.n_vb[kind];
-    const int vb = rem / nub, ub = rem - vb * nub;
+    const int nub = P.msg_tiles_kind[kind] / P.msg_g[kind];
+    const int vbg = rem / nub, ub = rem - vbg * nub;
+    const int vb = vbg + vbi * P.msg_g[kind];
+    if (vb >= P.n_vb[kind]) return false;
     const bool send_h = (kind == 0 || kind == 2);       // sender type: humans for hh, ho
     const bool recv_h = (kind == 0 || kind == 1);       // receiver type: humans for hh, oh
     const int Es = send_h ? H : O, Er = recv_h ? H : O;
@@ -139,7 +143,7 @@ __device__ __forceinline__ void seg_message_tile(const SegParams& P, int tile, i
             sh.row_smsg[row] = ptr;
         }
     }
-    if (!(part & 2)) return;
+    if (!(part & 2)) return true;
     // bias of this thread's message columns, fetched before the K loop
     float bias[MSG_NG];
 #pragma unroll
@@ -213,6 +217,7 @@ __device__ __forceinline__ void seg_message_tile(const SegParams& P, int tile, i
             if (uok) sh.rcv_mg[br][c] = v;
         }
     }
+    return true;
 }
 
 // ---- phase B ------------------------------------------------------------------------------------
@@ -318,17 +323,22 @@ __device__ __forceinline__ void seg_cell_tile(const SegParams& P, bool is_h, int
     }
 }
 
+// rbi: with res_multi a tile is one (direction, entity type, row-block group, unit block) and owns every cell_g-th row block —
+// the weights stay resident while rbi walks over them; returns false (uniformly) when there is no such row block.
 template <int MODE>
-__device__ __forceinline__ void seg_cell_dispatch(const SegParams& P, int tile, int s, float* smem, SegShared& sh, RtcShared& rsh,
-                                                  RtcState& rst, ResState& res, int part, CellPre& pre) {
+__device__ __forceinline__ bool seg_cell_dispatch(const SegParams& P, int tile, int s, float* smem, SegShared& sh, RtcShared& rsh,
+                                                  RtcState& rst, ResState& res, int part, CellPre& pre, int rbi = 0) {
     const int dir = tile / P.cell_tiles_dir;
     int rem = tile - dir * P.cell_tiles_dir;
     const bool is_h = rem < P.cell_tiles_h_dir;
     if (!is_h) rem -= P.cell_tiles_h_dir;
     const int nub = is_h ? P.nub_h : P.nub_o;
-    const int rb = rem / nub, ub = rem - rb * nub;
+    const int rbg = rem / nub, ub = rem - rbg * nub;
+    const int rb = rbg + rbi * (is_h ? P.cell_g_h : P.cell_g_o);
+    if (rb >= (is_h ? P.nrb_h : P.nrb_o)) return false;
     if ((is_h ? P.cfg_h : P.cfg_o) == 4) seg_cell_tile<4, MODE>(P, is_h, dir, rb, ub, s, smem, sh, rsh, rst, res, part, pre);
     else                                 seg_cell_tile<2, MODE>(P, is_h, dir, rb, ub, s, smem, sh, rsh, rst, res, part, pre);
+    return true;
 }
 
 // phases: bit 0 = A (messages), bit 1 = B (cells).  MODE as above.
@@ -352,7 +362,7 @@ __global__ void __launch_bounds__(MODE == 1 ? RTC_THREADS : REC_THREADS, 1) segm
     bool ok = true;
     CellPre pre;
 #ifndef SEG_NO_SHADOW
-    if (MODE == 2 && persistent && phases == 3 && P.res_msg) {
+    if (MODE == 2 && persistent && phases == 3 && P.res_msg && !P.res_multi) {
         // one message tile and one cell tile per CTA for the whole launch (launcher guarantees tilesA, tilesB <= gridDim.x):
         // the set-up of the next phase (pointer tables, epilogue operands) runs in the shadow of the grid barrier
         const int bid = blockIdx.x;
@@ -373,6 +383,20 @@ __global__ void __launch_bounds__(MODE == 1 ? RTC_THREADS : REC_THREADS, 1) segm
         s_begin = s_end;                        // skip the generic loop
     }
 #endif
+    if (MODE == 2 && persistent && P.res_multi) {
+        // larger batches: a CTA still owns ONE (direction, kind, unit block) message slice and ONE (direction, type, unit block)
+        // cell slice with resident weights, and walks over the video blocks / row blocks that share them
+        const int bid = blockIdx.x;
+        for (int s = s_begin; s < s_end; ++s) {
+            if (bid < P.tilesA)
+                for (int vbi = 0; seg_message_tile<MODE>(P, bid, s, smem, sh, rsh, rst, wmsg, msg_ready, 3, vbi); ++vbi) {}
+            if (!grid_barrier(P.sync, epoch, gridDim.x, &sh.s_fail)) break;
+            if (bid < P.tilesB)
+                for (int rbi = 0; seg_cell_dispatch<MODE>(P, bid, s, smem, sh, rsh, rst, res, 3, pre, rbi); ++rbi) {}
+            if (s + 1 < s_end && !grid_barrier(P.sync, epoch, gridDim.x, &sh.s_fail)) break;
+        }
+        s_begin = s_end;
+    }
     for (int s = s_begin; s < s_end && ok; ++s) {
         if (phases & 4) {       // timing experiment: two bare grid barriers per step
             if (!grid_barrier(P.sync, epoch, gridDim.x, &sh.s_fail)) { ok = false; break; }
@@ -409,9 +433,11 @@ int launch_segment(SegParams& P, int persistent, cudaStream_t stream) {
         P.bbv[k] = MSG_ROWS / me;                       // whole videos per message tile (senders and receivers fit)
         P.n_vb[k] = cdiv(B, P.bbv[k]);
         P.msg_tile_begin[k] = begin;
+        P.msg_g[k] = P.n_vb[k];
         P.msg_tiles_kind[k] = (k == 0 && !P.hh) ? 0 : P.n_vb[k] * nub_msg;
         begin += P.msg_tiles_kind[k];
     }
+    P.res_multi = 0;
     if (!P.hh) P.msg_tile_begin[0] = 0;
     P.msg_tile_begin[4] = begin;
     P.msg_tiles_dir = begin;
@@ -423,6 +449,7 @@ int launch_segment(SegParams& P, int persistent, cudaStream_t stream) {
     P.jeff_h = P.jeff_o = REC_J;
     P.nrb_h = cdiv(B * H, 8 * P.cfg_h); P.nub_h = cdiv(D, REC_J);
     P.nrb_o = cdiv(B * O, 8 * P.cfg_o); P.nub_o = cdiv(D, REC_J);
+    P.cell_g_h = P.nrb_h; P.cell_g_o = P.nrb_o;
     P.cell_tiles_h_dir = P.nrb_h * P.nub_h;
     P.cell_tiles_dir = P.cell_tiles_h_dir + P.nrb_o * P.nub_o;
     P.tilesB = 2 * P.cell_tiles_dir;
@@ -444,6 +471,43 @@ int launch_segment(SegParams& P, int persistent, cudaStream_t stream) {
     const int kmax = (P.nk_h > 2 ? P.nk_h : 2) * D + D;
     const bool res_fits = cdiv(kmax / REC_CK, REC_WARPS) * RES_CHUNK_WORDS <= RES_TMEM_WORDS + RES_SMEM_WORDS;
     if (mode == 0 && res_env && res_fits && P.tilesB <= num_sms() && (persistent ? P.tilesA <= num_sms() : true)) mode = 2;
+    // larger batches (persistent only): one resident weight slice per CTA, row blocks / video blocks walked inside the CTA
+    if (mode == 0 && res_env && res_fits && persistent && 2 * (P.nub_h + P.nub_o) <= num_sms()) {
+        int g[4], total;
+        for (int k = 0; k < 4; ++k) g[k] = P.n_vb[k];
+        auto count = [&]() { int t = 0; for (int k = 0; k < 4; ++k) t += (k == 0 && !P.hh) ? 0 : g[k] * nub_msg; return 2 * t; };
+        while ((total = count()) > num_sms()) {
+            int big = -1;
+            for (int k = 0; k < 4; ++k)
+                if (!(k == 0 && !P.hh) && g[k] > 1 && (big < 0 || g[k] > g[big])) big = k;
+            if (big < 0) break;
+            g[big] = (g[big] + 1) / 2;
+        }
+        // row-block groups of the cell tiles: as many CTAs per weight slice as fit (each keeps its own copy of the slice)
+        int gh = P.nrb_h, go = P.nrb_o;
+        while (2 * (P.nub_h * gh + P.nub_o * go) > num_sms() && (gh > 1 || go > 1)) {
+            if (go >= gh) go = (go + 1) / 2; else gh = (gh + 1) / 2;
+        }
+        if (total <= num_sms()) {
+            mode = 2;
+            P.res_multi = 1;
+            P.cell_g_h = gh; P.cell_g_o = go;
+            begin = 0;
+            for (int k = 0; k < 4; ++k) {
+                P.msg_g[k] = g[k];
+                P.msg_tile_begin[k] = begin;
+                P.msg_tiles_kind[k] = (k == 0 && !P.hh) ? 0 : g[k] * nub_msg;
+                begin += P.msg_tiles_kind[k];
+            }
+            if (!P.hh) P.msg_tile_begin[0] = 0;
+            P.msg_tile_begin[4] = begin;
+            P.msg_tiles_dir = begin;
+            P.tilesA = 2 * begin;
+            P.cell_tiles_h_dir = P.nub_h * gh;
+            P.cell_tiles_dir = P.nub_h * gh + P.nub_o * go;
+            P.tilesB = 2 * P.cell_tiles_dir;
+        }
+    }
     // resident message weights as well: one message tile per CTA for the whole launch, D*256 bytes of fragments fit beside the rest
     const size_t static_smem = 12288;                 // upper bound of the kernel's static shared memory (SegShared + barrier slots)
     P.res_msg = 0;

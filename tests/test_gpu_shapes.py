@@ -35,7 +35,9 @@ def _fwd(model, batch, noise, sl=slice(None), hseg=None, oseg=None):
 
 # (shape, D, B, T, stage, seed): seeds chosen on the CPU oracle so that every sampled gate is >2e-4 from a decision edge
 @pytest.mark.parametrize('cfg', [('cad120', 32, 13, 18, 2, 2), ('mphoi', 32, 20, 10, 2, 0), ('bimanual', 32, 7, 12, 2, 5),
-                                 ('cad120', 32, 9, 11, 1, 0), ('mphoi', 64, 11, 9, 1, 0)])
+                                 ('cad120', 32, 9, 11, 1, 0), ('mphoi', 64, 11, 9, 1, 0),
+                                 # hidden 512: resident-weight recurrent kernels walking several row / video blocks per CTA
+                                 ('mphoi', 512, 20, 6, 2, 0), ('cad120', 512, 24, 5, 2, 1), ('bimanual', 512, 9, 5, 2, 2)])
 def test_many_row_blocks_match_oracle(cfg, orc):
     """B large enough that every recurrent phase has several row blocks and video blocks."""
     shape_name, D, B, T, stage, seed = cfg

@@ -12,9 +12,10 @@ Public surface (mirrors the reference's ``vhoi.models`` for this path):
     losses                                   -- fused criterion, drop-in for vhoi.losses.select_loss (budget / BCE / NLL in two kernels)
     feeder                                   -- double-buffered host->device input pipeline (pinned memory, side stream)
     train_loop                               -- data-parallel counterpart of train_utils.train_single_epoch
+    evaluate                                 -- device-side predict.py post-processing: up-sampling + argmax, F1@k (pyrutils/metrics.py)
     build                                    -- in-tree nvcc build of lib2ggcn_b200.so
 """
-from . import abi, dp, feeder, losses, synth, train_loop        # noqa: F401
+from . import abi, dp, evaluate, feeder, losses, synth, train_loop        # noqa: F401
 from .model import TGGCN, select_model, install_dropin   # noqa: F401
 
-__all__ = ['TGGCN', 'select_model', 'install_dropin', 'abi', 'dp', 'feeder', 'losses', 'synth', 'train_loop']
+__all__ = ['TGGCN', 'select_model', 'install_dropin', 'abi', 'dp', 'evaluate', 'feeder', 'losses', 'synth', 'train_loop']

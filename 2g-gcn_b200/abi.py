@@ -114,6 +114,13 @@ def lib():
     L.tggcn_backward.restype = C.c_int
     L.tggcn_backward.argtypes = [C.POINTER(Dims), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.c_int, C.POINTER(IO),
                                  C.POINTER(GradOutputs), C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_void_p]
+    L.tggcn_upsample_argmax.restype = C.c_int
+    L.tggcn_upsample_argmax.argtypes = [C.c_void_p, C.c_void_p] + [C.c_int] * 6 + [C.c_void_p]
+    L.tggcn_f1_at_k_scratch_bytes.restype = C.c_size_t
+    L.tggcn_f1_at_k_scratch_bytes.argtypes = [C.c_int] * 3
+    L.tggcn_f1_at_k.restype = C.c_int
+    L.tggcn_f1_at_k.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int64,
+                                C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     if L.tggcn_abi_version() != 2:
         raise TggcnError('lib2ggcn_b200.so ABI version mismatch; rebuild')
     _lib = L

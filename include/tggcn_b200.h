@@ -350,6 +350,21 @@ TGGCN_API int tggcn_loss_fwd(const tggcn_loss_term* terms, int n_terms, float* l
 /* grad_losses: n_terms floats (device) upstream gradients of the loss values, or NULL for ones. */
 TGGCN_API int tggcn_loss_bwd(const tggcn_loss_term* terms, int n_terms, const float* scratch, const float* grad_losses, void* stream);
 
+/* ---- evaluation post-processing: what predict.py does on the host after the forward ------------------------
+ * tggcn_upsample_argmax: predict.py:64-70 (torch.repeat_interleave(out, downsampling, dim=-2) + match_shape :95-122) followed
+ *   by np.argmax(axis=1) of process_output (:186-202).  logp (B,C,T,E) float -> labels (B,Tt,E) int64.
+ * tggcn_f1_at_k: pyrutils/metrics.py:7-81 (f1_at_k / f1_at_k_single_example) on the rows predict.py:236-240 builds
+ *   ((B,Tt,E) -> swapaxes(1,2) -> (B*E, Tt)), frames whose target equals ignore_value removed.  Per row and overlap the F1 in
+ *   f1_rows[k * B*E + row] (double, device) and valid_rows[row] = the row has at least one frame; the caller averages the valid
+ *   rows in row order (as the reference's accumulation does).  overlaps: n_overlaps doubles (device).
+ *   scratch: tggcn_f1_at_k_scratch_bytes(B, Tt, E) bytes (device). */
+TGGCN_API int tggcn_upsample_argmax(const float* logp, int64_t* labels, int B, int C, int T, int E, int Tt, int downsampling,
+                                    void* stream);
+TGGCN_API size_t tggcn_f1_at_k_scratch_bytes(int B, int Tt, int E);
+TGGCN_API int tggcn_f1_at_k(const int64_t* target, const int64_t* pred, int B, int Tt, int E, int num_classes,
+                            const double* overlaps, int n_overlaps, int64_t ignore_value, void* scratch, double* f1_rows,
+                            int32_t* valid_rows, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

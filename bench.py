@@ -292,7 +292,7 @@ def train_step_throughput(args, pkg, shape, kwargs, dev, rank, world, flush, bar
     torch.manual_seed(0)
     model = pkg.TGGCN(**kwargs).to(dev).train()
     model.gemm_path = args.gemm_path
-    opt = torch.optim.Adam(model.parameters(), lr=1e-4)
+    opt = torch.optim.Adam(model.parameters(), lr=1e-4, fused=True)      # torch's own Adam (train.py's optimiser), fused variant
     reducer = pkg.dp.GradientAllReduce(model)
     reducer.sync_parameters()
     B, T = args.B, args.T
@@ -342,7 +342,7 @@ def train_step_throughput(args, pkg, shape, kwargs, dev, rank, world, flush, bar
     return {'value': world * B * T / (ms / 1e3), 'unit': UNIT, 'ms_per_step': ms, 'steps': steps, 'warmup': warmup,
             'gpu_launches_per_step': int(launches // steps), 'loss': float(loss.detach()),
             'what': 'forward(train-mode BN, saves) + fused criterion (BCE + 2x NLL) + tggcn_backward + '
-                    + ('NCCL all-reduce of the flat gradient + ' if world > 1 else '') + 'torch.optim.Adam step; fp32 (3xTF32 products)',
+                    + ('NCCL all-reduce of the flat gradient + ' if world > 1 else '') + 'torch.optim.Adam(fused=True) step; fp32-accurate products (3xTF32 / 3xFP16 split)',
             'global_batch_videos': world * B}
 
 

@@ -15,24 +15,33 @@
 //              M=128,N=128,K=8: 4 k-steps x 3 split products) per k-block; tcgen05.commit frees the stage.
 //   epilogue   tcgen05.ld 32x32b.x32 (lane = output row), bias + ReLU, float4 stores.
 // Several independent problems are batched into one launch like the SIMT path.
+#include <stdlib.h>
 #include "common.cuh"
 #include "gemm.h"
 #include "tcgen05.cuh"
 
 namespace tg {
 
-constexpr int TC_BM = 128, TC_BN = 128, TC_BK = 32;
-constexpr int TC_STAGES = 3;
+constexpr int TC_BM = 128, TC_BK = 32;
 constexpr int TC_PRODUCER_WARPS = 8;
 constexpr int TC_THREADS = (TC_PRODUCER_WARPS + 1) * 32;
-constexpr int TC_TILE_BYTES = TC_BM * TC_BK * 4;                  // 16 KB, one operand tile (hi or lo)
-constexpr int TC_STAGE_BYTES = 4 * TC_TILE_BYTES;                 // A_hi, A_lo, W_hi, W_lo
-constexpr int TC_SMEM_BYTES = TC_STAGES * TC_STAGE_BYTES + 1024;  // + alignment slack
-constexpr uint32_t TC_TMEM_COLS = 128;
+constexpr int TC_TILE_BYTES = TC_BM * TC_BK * 4;                  // 16 KB, one 128-row operand tile (hi or lo)
+// Output tile 128 x BN.  BN = 256 (large problems): a W tile is two 128-row tiles, the stage grows to 96 KB (two stages) and
+// the fp32 operand bytes read from L2 per FLOP fall by a quarter — the kernel sits at the L2 -> SM bandwidth, not the MMA rate.
+template <int BN> struct TcCfg {
+    static constexpr int W_TILE_BYTES = BN * TC_BK * 4;
+    static constexpr int STAGE_BYTES = 2 * TC_TILE_BYTES + 2 * W_TILE_BYTES;     // A_hi, A_lo, W_hi, W_lo
+    static constexpr int STAGES = BN == 128 ? 3 : 2;
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024;              // + alignment slack
+    static constexpr int WP = BN / 32;                                           // W rows per producer thread
+};
 
 // MASK: some problem of the group reads A through a ReLU mask (backward use); compiled out of the forward instantiation.
-template <bool MASK>
+template <bool MASK, int BN>
 __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const GemmGroup grp) {
+    constexpr int TC_BN = BN, TC_STAGES = TcCfg<BN>::STAGES, TC_STAGE_BYTES = TcCfg<BN>::STAGE_BYTES, WP = TcCfg<BN>::WP;
+    constexpr int W_TILE_BYTES = TcCfg<BN>::W_TILE_BYTES;
+    constexpr uint32_t TC_TMEM_COLS = BN;
     extern __shared__ uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t bars[2 * TC_STAGES + 1];
     __shared__ uint32_t tmem_base_smem;
@@ -80,20 +89,24 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const GemmGroup 
         // thread -> 16-byte chunk c of rows r0 + 32*i (i < 4) of the A tile and of the W tile
         const int c = tid & 7, r0 = tid >> 3;                 // 256 threads: r0 in [0,32)
         const float* aptr[4];
-        const float* wptr[4];
+        const float* wptr[WP];
         const float* mptr[4];
-        bool aok[4], wok[4];
+        bool aok[4], wok[WP];
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
             const int r = r0 + 32 * i;
             aok[i] = (m0 + r) < P.M;
-            wok[i] = (n0 + r) < P.N;
             aptr[i] = P.A + (size_t)(aok[i] ? m0 + r : 0) * P.lda + c * 4 + (size_t)kb0 * TC_BK;
             mptr[i] = (MASK && P.amask != nullptr) ? P.amask + (size_t)(aok[i] ? m0 + r : 0) * P.ldm + c * 4 + (size_t)kb0 * TC_BK : nullptr;
+        }
+#pragma unroll
+        for (int i = 0; i < WP; ++i) {
+            const int r = r0 + 32 * i;
+            wok[i] = (n0 + r) < P.N;
             wptr[i] = P.W + (size_t)(wok[i] ? n0 + r : 0) * P.ldw + c * 4 + (size_t)kb0 * TC_BK;
         }
-        float4 pa0[4], pw0[4], pa1[4], pw1[4];                // register prefetch, two k-blocks deep (static slots)
-        auto load = [&](int kb, float4 (&pa)[4], float4 (&pw)[4]) {
+        float4 pa0[4], pw0[WP], pa1[4], pw1[WP];              // register prefetch, two k-blocks deep (static slots)
+        auto load = [&](int kb, float4 (&pa)[4], float4 (&pw)[WP]) {
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
                 pa[i] = aok[i] ? __ldg(reinterpret_cast<const float4*>(aptr[i] + (size_t)kb * TC_BK)) : make_float4(0.f, 0.f, 0.f, 0.f);
@@ -102,8 +115,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const GemmGroup 
                     pa[i].x = mk.x > 0.f ? pa[i].x : 0.f; pa[i].y = mk.y > 0.f ? pa[i].y : 0.f;
                     pa[i].z = mk.z > 0.f ? pa[i].z : 0.f; pa[i].w = mk.w > 0.f ? pa[i].w : 0.f;
                 }
-                pw[i] = wok[i] ? __ldg(reinterpret_cast<const float4*>(wptr[i] + (size_t)kb * TC_BK)) : make_float4(0.f, 0.f, 0.f, 0.f);
             }
+#pragma unroll
+            for (int i = 0; i < WP; ++i)
+                pw[i] = wok[i] ? __ldg(reinterpret_cast<const float4*>(wptr[i] + (size_t)kb * TC_BK)) : make_float4(0.f, 0.f, 0.f, 0.f);
         };
         auto split4 = [](const float4& x, float4& hi, float4& lo) {
             hi.x = __uint_as_float(__float_as_uint(x.x) & 0xffffe000u); lo.x = x.x - hi.x;
@@ -111,7 +126,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const GemmGroup 
             hi.z = __uint_as_float(__float_as_uint(x.z) & 0xffffe000u); lo.z = x.z - hi.z;
             hi.w = __uint_as_float(__float_as_uint(x.w) & 0xffffe000u); lo.w = x.w - hi.w;
         };
-        auto produce = [&](int kb, float4 (&pa)[4], float4 (&pw)[4]) {
+        auto produce = [&](int kb, float4 (&pa)[4], float4 (&pw)[WP]) {
             const int s = kb % TC_STAGES;
             mbar_wait(empty0 + 8 * s, ((kb / TC_STAGES) & 1) ^ 1);
             uint8_t* st = tiles + s * TC_STAGE_BYTES;
@@ -122,9 +137,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const GemmGroup 
                 split4(pa[i], hi, lo);
                 *reinterpret_cast<float4*>(st + off) = hi;
                 *reinterpret_cast<float4*>(st + TC_TILE_BYTES + off) = lo;
+            }
+#pragma unroll
+            for (int i = 0; i < WP; ++i) {                       // W rows r0 + 32 i: the swizzle pattern repeats every 8 rows
+                const uint32_t off = sw128_off(r0 + 32 * i, c);
+                float4 hi, lo;
                 split4(pw[i], hi, lo);
                 *reinterpret_cast<float4*>(st + 2 * TC_TILE_BYTES + off) = hi;
-                *reinterpret_cast<float4*>(st + 3 * TC_TILE_BYTES + off) = lo;
+                *reinterpret_cast<float4*>(st + 2 * TC_TILE_BYTES + W_TILE_BYTES + off) = lo;
             }
             if (kb + 2 < nkb) load(kb + 2, pa, pw);
             asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");   // generic-proxy writes -> visible to the tensor core
@@ -186,7 +206,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const GemmGroup 
             tc_fence_after();
             if (lane == 0) {
                 const uint32_t a_hi = tiles_u32 + s * TC_STAGE_BYTES, a_lo = a_hi + TC_TILE_BYTES;
-                const uint32_t w_hi = a_hi + 2 * TC_TILE_BYTES, w_lo = a_hi + 3 * TC_TILE_BYTES;
+                const uint32_t w_hi = a_hi + 2 * TC_TILE_BYTES, w_lo = w_hi + W_TILE_BYTES;
 #pragma unroll
                 for (int kk = 0; kk < TC_BK / 8; ++kk) {
                     const uint32_t ko = kk * 32;               // 8 tf32 = 32 bytes along the swizzled row
@@ -222,6 +242,16 @@ int launch_gemm_tc(GemmGroup& grp, cudaStream_t stream) {
         TG_REQUIRE(p.amask == nullptr || (p.ldm % 4 == 0 && (reinterpret_cast<uintptr_t>(p.amask) & 15) == 0),
                    "gemm_tc: mask must be 16-byte aligned with ldm a multiple of 4");
     }
+    // 128 x 256 tiles when they still fill the GPU twice over (TGGCN_GEMM_BN=128 disables them)
+    static int bn_env = -1;
+    if (bn_env < 0) {
+        const char* e = getenv("TGGCN_GEMM_BN");
+        bn_env = (e != nullptr && atoi(e) == 128) ? 128 : 256;
+    }
+    int tiles256 = 0;
+    for (int i = 0; i < grp.count; ++i) tiles256 += cdiv(grp.p[i].M, TC_BM) * cdiv(grp.p[i].N, 256);
+    const int bn = (bn_env == 256 && tiles256 >= 2 * num_sms()) ? 256 : 128;
+    const int TC_BN = bn;
     int base_tiles = 0;
     for (int i = 0; i < grp.count; ++i) base_tiles += cdiv(grp.p[i].M, TC_BM) * cdiv(grp.p[i].N, TC_BN);
     for (int i = 0; i < grp.count; ++i) {
@@ -245,12 +275,19 @@ int launch_gemm_tc(GemmGroup& grp, cudaStream_t stream) {
     for (int i = 0; i < grp.count; ++i) mask |= grp.p[i].amask != nullptr;
     static bool configured = false;
     if (!configured) {
-        TG_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
-        TG_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
+        TG_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<false, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<128>::SMEM_BYTES));
+        TG_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<true, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<128>::SMEM_BYTES));
+        TG_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<false, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<256>::SMEM_BYTES));
+        TG_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<true, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<256>::SMEM_BYTES));
         configured = true;
     }
-    if (mask) gemm_tc_kernel<true><<<begin, TC_THREADS, TC_SMEM_BYTES, stream>>>(grp);
-    else      gemm_tc_kernel<false><<<begin, TC_THREADS, TC_SMEM_BYTES, stream>>>(grp);
+    if (bn == 256) {
+        if (mask) gemm_tc_kernel<true, 256><<<begin, TC_THREADS, TcCfg<256>::SMEM_BYTES, stream>>>(grp);
+        else      gemm_tc_kernel<false, 256><<<begin, TC_THREADS, TcCfg<256>::SMEM_BYTES, stream>>>(grp);
+    } else {
+        if (mask) gemm_tc_kernel<true, 128><<<begin, TC_THREADS, TcCfg<128>::SMEM_BYTES, stream>>>(grp);
+        else      gemm_tc_kernel<false, 128><<<begin, TC_THREADS, TcCfg<128>::SMEM_BYTES, stream>>>(grp);
+    }
     TG_LAUNCH_OK();
     return 0;
 }

@@ -38,16 +38,25 @@ __global__ void __launch_bounds__(REC_THREADS, 1) bigru_res_kernel(const BiGruPa
     const int g8 = lane >> 2, t4 = lane & 3;
     float* wsm = smem;                                   // [BR_NT * 8][LD]   row (nt*8 + n): gate = nt / NBLK, block = nt % NBLK
     float* hsm = wsm + BR_NT * 8 * LD;                   // [BR_ROWS][LD] staged previous state; reused as the reduction buffer
-    const int gd = blockIdx.x / ctas_per_gd, c = blockIdx.x - gd * ctas_per_gd;
-    const int group = gd >> 1, dir = gd & 1;
+    // CTA -> (group, direction, row-block group, unit-block slice).  A group with several row blocks is spread over n_rb CTAs per
+    // weight slice when the grid has room (each keeps its own copy of the slice and walks every n_rb-th row block)
+    int group = 0;
+#pragma unroll 1
+    for (int i = 1; i < P.ngroups; ++i)
+        if ((int)blockIdx.x >= P.g[i].tile_begin) group = i;
     const BiGruGroup& G = P.g[group];
+    const int RG = G.n_rb;
+    const int local = blockIdx.x - G.tile_begin;
+    const int dir = local / (RG * ctas_per_gd);
+    const int rg = (local - dir * RG * ctas_per_gd) / ctas_per_gd, c = local % ctas_per_gd;
+    const int rbase = rg * BR_ROWS;
     const int nblk = D / BR_UB;
     const int j0 = c * BR_NBLK;
     const int nb = min(BR_NBLK, nblk - j0);              // blocks this CTA owns (>= 1 by construction)
     if (tid == 0) s_fail = 0;
-    const bool single_rb = G.rows <= BR_ROWS;            // the common case: every step sees the same rows -> offsets precomputed
+    const bool single_rb = rbase + RG * BR_ROWS >= G.rows;   // this CTA owns one row block: every step sees the same rows -> offsets precomputed
     if (tid < BR_ROWS) {
-        const int r = tid < G.rows ? tid : 0, b = r / G.E, e = r - b * G.E;
+        const int r = rbase + tid < G.rows ? rbase + tid : 0, b = r / G.E, e = r - b * G.E;
         rowoff[tid] = ((long long)b * T * G.E + e) * 2 * D + dir * D;
     }
 
@@ -86,7 +95,7 @@ __global__ void __launch_bounds__(REC_THREADS, 1) bigru_res_kernel(const BiGruPa
     long long o_fe0[3];                                  // (video, entity) part of the frame-entity index at t = 0 (first row block)
 #pragma unroll
     for (int q = 0; q < 3; ++q) {
-        const int r = o_row[q] < G.rows ? o_row[q] : 0, b = r / G.E, e = r - b * G.E;
+        const int r = rbase + o_row[q] < G.rows ? rbase + o_row[q] : 0, b = r / G.E, e = r - b * G.E;
         o_fe0[q] = (long long)b * T * G.E + e;
     }
     __syncthreads();
@@ -126,11 +135,12 @@ __global__ void __launch_bounds__(REC_THREADS, 1) bigru_res_kernel(const BiGruPa
             }
         }
     };
-    if (single_rb) fetch(0, 0, G.rows);
+    const int own_rows = min(BR_ROWS, G.rows - rbase);      // rows of the CTA's first row block (> 0 by construction)
+    if (single_rb) fetch(0, rbase, own_rows);
     for (int s = 0; s < T && ok; ++s) {
         const int t = dir == 0 ? s : T - 1 - s;
         const int tprev = dir == 0 ? t - 1 : t + 1;
-        for (int rb0 = 0; rb0 < G.rows; rb0 += BR_ROWS) {
+        for (int rb0 = rbase; rb0 < G.rows; rb0 += RG * BR_ROWS) {
             const int nrows = min(BR_ROWS, G.rows - rb0);
             // ---- 1. stage the previous state of these rows: every warp copies exactly the K columns it multiplies (its k16
             //         steps ks = warp, warp + 8, ...), so only a __syncwarp separates the copies from the MMAs -------------
@@ -250,7 +260,7 @@ __global__ void __launch_bounds__(REC_THREADS, 1) bigru_res_kernel(const BiGruPa
         }
         if (s + 1 < T) {
             grid_arrive(P.sync, epoch);                  // (its __syncthreads also retires the reduction buffer)
-            if (single_rb) fetch(s + 1, 0, G.rows);      // next step's input pre-activations arrive in the shadow of the barrier
+            if (single_rb) fetch(s + 1, rbase, own_rows);      // next step's input pre-activations arrive in the shadow of the barrier
             if (!grid_wait(P.sync, epoch, gridDim.x, &s_fail)) ok = false;
         }
     }
@@ -272,7 +282,24 @@ int launch_bigru_resident(BiGruParams& P, cudaStream_t stream) {
     const size_t smem = sizeof(float) * ((size_t)BR_NT * 8 * LD + (red_floats > stage_floats ? red_floats : stage_floats));
     if (smem > 227 * 1024) return -1;
     const int ctas_per_gd = cdiv(D / BR_UB, BR_NBLK);
-    const int grid = 2 * P.ngroups * ctas_per_gd;
+    // row-block groups per (group, direction): as many as the row blocks while the grid fits on the GPU
+    int rgs[3] = {1, 1, 1};
+    auto total = [&]() { int t = 0; for (int i = 0; i < P.ngroups; ++i) t += 2 * rgs[i] * ctas_per_gd; return t; };
+    for (bool grown = true; grown;) {
+        grown = false;
+        for (int i = 0; i < P.ngroups; ++i) {
+            if (rgs[i] < cdiv(P.g[i].rows, BR_ROWS)) {
+                ++rgs[i];
+                if (total() <= num_sms()) grown = true; else --rgs[i];
+            }
+        }
+    }
+    int grid = 0;
+    for (int i = 0; i < P.ngroups; ++i) {
+        P.g[i].n_rb = rgs[i];
+        P.g[i].tile_begin = grid;
+        grid += 2 * rgs[i] * ctas_per_gd;
+    }
     auto kern = bigru_res_kernel;
     static size_t configured = 0;
     if (smem > configured) {

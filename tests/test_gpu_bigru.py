@@ -28,7 +28,8 @@ def _reference(gi, whh, bhh, G, orc):
 
 
 @pytest.mark.parametrize('persistent', [1, 0])
-@pytest.mark.parametrize('dims', [(3, 7, 2, 32), (8, 12, 4, 64), (5, 6, 1, 48), (9, 5, 5, 32)])
+@pytest.mark.parametrize('dims', [(3, 7, 2, 32), (8, 12, 4, 64), (5, 6, 1, 48), (9, 5, 5, 32),
+                                  (20, 6, 9, 64), (11, 5, 3, 128)])      # the last two: several row blocks per weight slice
 def test_bigru_forward_backward(dims, persistent, pkg, orc):
     B, T, E, D = dims
     g = torch.Generator().manual_seed(B * 100 + T * 10 + E)

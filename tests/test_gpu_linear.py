@@ -18,6 +18,8 @@ SHAPES = [
     (2048, 512, 2048, 104, 0, 512, 1, 1),      # human ROI embedding, B=8,T=128
     (1024, 2048, 3328, 0, 0, 0, 1, 1),         # geometry MLP layer 0
     (4096, 1536, 512, 512, 0, 1536, 0, 1),     # BiGRU input gates, objects
+    (5000, 4000, 96, 8, 4, 32, 1, 1),          # enough 128x256 tiles for the wide-tile tcgen05 variant, ragged in M and N
+    (4096, 3072, 64, 0, 0, 0, 0, 0),
 ]
 
 

@@ -98,3 +98,21 @@ def test_full_size_batch_split_consistency_and_determinism():
     for o in whole[2:]:          # every output row is a log-probability vector
         torch.testing.assert_close(o.exp().sum(1), torch.ones_like(o[:, 0]), rtol=1e-4, atol=1e-4)
     assert torch.isfinite(torch.stack([o.float().abs().max() for o in whole])).all()
+
+
+def test_fp16_split_range_violation_is_reported(pkg):
+    """The on-chip-resident recurrent kernels split their operands into fp16 pairs (weights scaled by 2^8): a recurrent weight
+    beyond 255 must surface through check_persistent_kernels(), never as silently wrong numbers."""
+    shape = pkg.synth.SHAPES['mphoi']
+    torch.manual_seed(0)
+    model = pkg.TGGCN(**pkg.synth.model_kwargs(shape, hidden_size=64, stage=2)).cuda().eval()
+    batch = pkg.synth.make_batch(shape, 4, 6, seed=3)
+    x = {k: batch[k].cuda() for k in ('x_human', 'x_objects', 'objects_mask')}
+    with torch.no_grad():
+        model(**x)
+        model.check_persistent_kernels()                       # healthy weights: no flag
+        model.human_segment_rnn_fcell.weight_hh[3, 5] = 300.0
+        model(**x)
+    torch.cuda.synchronize()
+    with pytest.raises(pkg.abi.TggcnError, match='fp16-split'):
+        model.check_persistent_kernels()

@@ -19,7 +19,8 @@ LIB_PATH = os.path.join(HERE, 'lib2ggcn_b200.so')
 class Dims(C.Structure):
     _fields_ = [(n, C.c_int32) for n in (
         'B', 'T', 'H', 'O', 'V', 'D', 'Fh', 'C_sub', 'C_aff', 'hh', 'filter', 'bn_train', 'human_seg_given',
-        'object_seg_given', 'inspect', 'persistent', 'gemm_path')] + [('thr', C.c_float), ('save_for_backward', C.c_int32)]
+        'object_seg_given', 'inspect', 'persistent', 'gemm_path')] + [('thr', C.c_float), ('save_for_backward', C.c_int32),
+                                                                       ('cat_level_states', C.c_int32)]
 
 
 class GradOutputs(C.Structure):
@@ -121,7 +122,7 @@ def lib():
     L.tggcn_f1_at_k.restype = C.c_int
     L.tggcn_f1_at_k.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int64,
                                 C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
-    if L.tggcn_abi_version() != 2:
+    if L.tggcn_abi_version() != 3:
         raise TggcnError('lib2ggcn_b200.so ABI version mismatch; rebuild')
     _lib = L
     return L

@@ -376,7 +376,7 @@ static int forward_impl(const tggcn_dims* dims, const void* const* weights, int 
     {
         HeadsParams P;
         memset(&P, 0, sizeof(P));
-        P.B = B; P.T = T; P.E = H; P.NE = H + O; P.e_off = 0; P.D = D; P.C = d.C_sub;
+        P.B = B; P.T = T; P.E = H; P.NE = H + O; P.e_off = 0; P.D = D; P.C = d.C_sub; P.cat = d.cat_level_states;
         P.hfr = buf(TGGCN_BUF_HFR_H); P.hx = buf(TGGCN_BUF_HX_H); P.reidx = (const int*)buf(TGGCN_BUF_REIDX);
         const int wid[4] = {TGGCN_W_HEAD_H_FREC_W, TGGCN_W_HEAD_H_FPRED_W, TGGCN_W_HEAD_H_REC_W, TGGCN_W_HEAD_H_PRED_W};
         for (int i = 0; i < 4; ++i) { P.w[i] = W(wid[i]); P.b[i] = W(wid[i] + 1); P.out[i] = io->out_h[i]; }

@@ -187,13 +187,15 @@ int tggcn_backward(const tggcn_dims* dims, const void* const* weights, void* con
     {
         HeadsBwdParams P;
         memset(&P, 0, sizeof(P));
-        P.B = B; P.T = T; P.E = H; P.NE = H + O; P.e_off = 0; P.D = D; P.C = d.C_sub;
+        P.B = B; P.T = T; P.E = H; P.NE = H + O; P.e_off = 0; P.D = D; P.C = d.C_sub; P.cat = d.cat_level_states;
         P.hfr = buf(TGGCN_BUF_HFR_H); P.hx = buf(TGGCN_BUF_HX_H); P.reidx = (const int*)buf(TGGCN_BUF_REIDX);
         const int wid[4] = {TGGCN_W_HEAD_H_FREC_W, TGGCN_W_HEAD_H_FPRED_W, TGGCN_W_HEAD_H_REC_W, TGGCN_W_HEAD_H_PRED_W};
+        // (share_level_mlps: the frame-level and segment-level heads are the same tensors; their gradients then accumulate
+        //  into the same destination, which is zeroed before the launch like any other)
         for (int i = 0; i < 4; ++i) {
             P.w[i] = W(wid[i]); P.bias[i] = W(wid[i] + 1); P.dlogp[i] = grads->d_out_h[i];
             P.dw[i] = G(wid[i]); P.db[i] = G(wid[i] + 1);
-            TG_CUDA_OK(cudaMemsetAsync(P.dw[i], 0, sizeof(float) * (size_t)d.C_sub * 2 * D, stream));
+            TG_CUDA_OK(cudaMemsetAsync(P.dw[i], 0, sizeof(float) * (size_t)d.C_sub * ((i >= 2 && d.cat_level_states) ? 4 : 2) * D, stream));
             TG_CUDA_OK(cudaMemsetAsync(P.db[i], 0, sizeof(float) * (size_t)d.C_sub, stream));
         }
         P.dhfr = bb(BL.dhfr[0]); P.dhx = bb(BL.dhx[0]);
@@ -205,7 +207,7 @@ int tggcn_backward(const tggcn_dims* dims, const void* const* weights, void* con
             for (int i = 0; i < 4; ++i) {
                 P.w[i] = W(oid[i]); P.bias[i] = W(oid[i] + 1); P.dlogp[i] = grads->d_out_o[i];
                 P.dw[i] = G(oid[i]); P.db[i] = G(oid[i] + 1);
-                TG_CUDA_OK(cudaMemsetAsync(P.dw[i], 0, sizeof(float) * (size_t)d.C_aff * 2 * D, stream));
+                TG_CUDA_OK(cudaMemsetAsync(P.dw[i], 0, sizeof(float) * (size_t)d.C_aff * ((i >= 2 && d.cat_level_states) ? 4 : 2) * D, stream));
                 TG_CUDA_OK(cudaMemsetAsync(P.db[i], 0, sizeof(float) * (size_t)d.C_aff, stream));
             }
             P.dhfr = bb(BL.dhfr[1]); P.dhx = bb(BL.dhx[1]);

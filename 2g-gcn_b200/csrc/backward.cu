@@ -22,6 +22,8 @@ __global__ void __launch_bounds__(256) heads_bwd_kernel(const HeadsBwdParams P) 
     const int hd = blockIdx.y, src = hd >> 1;
     if (P.dlogp[hd] == nullptr) return;
     const int D2 = 2 * P.D, C = P.C;
+    const bool cat = P.cat && src == 1;        // segment heads on [hx | hfr] (models.py:901-903): weight rows of 4D
+    const int ldw = cat ? 2 * D2 : D2;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int rows = P.B * P.T * P.E;
     const int row0 = blockIdx.x * HB_ROWS, nrows = min(HB_ROWS, rows - row0);
@@ -36,15 +38,22 @@ __global__ void __launch_bounds__(256) heads_bwd_kernel(const HeadsBwdParams P) 
         if (src == 0) xrow = (size_t)row;
         else xrow = (size_t)(b * P.T + P.reidx[(size_t)bt * P.NE + P.e_off + e]) * P.E + e;
         const float* x = xin + xrow * D2;
+        const float* x2 = P.hfr + (size_t)row * D2;
         float mine = -INFINITY;
         for (int c = 0; c < C; ++c) {
-            const float* wr = W + (size_t)c * D2;
+            const float* wr = W + (size_t)c * ldw;
             float acc = 0.0f;
             for (int k = lane * 4; k < D2; k += 128) {
                 const float4 u = __ldg(reinterpret_cast<const float4*>(wr + k));
                 const float4 v = *reinterpret_cast<const float4*>(x + k);
                 acc = fmaf(u.x, v.x, acc); acc = fmaf(u.y, v.y, acc); acc = fmaf(u.z, v.z, acc); acc = fmaf(u.w, v.w, acc);
             }
+            if (cat)
+                for (int k = lane * 4; k < D2; k += 128) {
+                    const float4 u = __ldg(reinterpret_cast<const float4*>(wr + D2 + k));
+                    const float4 v = *reinterpret_cast<const float4*>(x2 + k);
+                    acc = fmaf(u.x, v.x, acc); acc = fmaf(u.y, v.y, acc); acc = fmaf(u.z, v.z, acc); acc = fmaf(u.w, v.w, acc);
+                }
             acc = warp_sum(acc) + __ldg(P.bias[hd] + c);
             if (lane == c) mine = acc;
         }
@@ -56,37 +65,39 @@ __global__ void __launch_bounds__(256) heads_bwd_kernel(const HeadsBwdParams P) 
         const float dz = lane < C ? g - prob * gs : 0.0f;     // d log_softmax
         sdz[lr][lane] = dz;
         if (lane == 0) sx[lr] = xrow;
-        float* dxrow = (src == 0 ? P.dhfr : P.dhx) + xrow * D2;
-        for (int k0 = 0; k0 < D2; k0 += 128) {               // warp-uniform trip count: the shuffles need every lane
-            const int k = k0 + lane * 4;
-            const bool ok = k < D2;
-            float4 dx = make_float4(0.f, 0.f, 0.f, 0.f);
-            for (int c = 0; c < C; ++c) {
-                const float dzc = __shfl_sync(0xffffffffu, dz, c);
-                if (!ok) continue;
-                const float4 wv = __ldg(reinterpret_cast<const float4*>(W + (size_t)c * D2 + k));
-                dx.x = fmaf(dzc, wv.x, dx.x); dx.y = fmaf(dzc, wv.y, dx.y); dx.z = fmaf(dzc, wv.z, dx.z); dx.w = fmaf(dzc, wv.w, dx.w);
+        for (int part = 0; part < (cat ? 2 : 1); ++part) {   // part 1: the frame-level half of a concatenated input
+            float* dxrow = part == 0 ? (src == 0 ? P.dhfr : P.dhx) + xrow * D2 : P.dhfr + (size_t)row * D2;
+            for (int k0 = 0; k0 < D2; k0 += 128) {           // warp-uniform trip count: the shuffles need every lane
+                const int k = k0 + lane * 4;
+                const bool ok = k < D2;
+                float4 dx = make_float4(0.f, 0.f, 0.f, 0.f);
+                for (int c = 0; c < C; ++c) {
+                    const float dzc = __shfl_sync(0xffffffffu, dz, c);
+                    if (!ok) continue;
+                    const float4 wv = __ldg(reinterpret_cast<const float4*>(W + (size_t)c * ldw + part * D2 + k));
+                    dx.x = fmaf(dzc, wv.x, dx.x); dx.y = fmaf(dzc, wv.y, dx.y); dx.z = fmaf(dzc, wv.z, dx.z); dx.w = fmaf(dzc, wv.w, dx.w);
+                }
+                if (ok) { atomicAdd(dxrow + k, dx.x); atomicAdd(dxrow + k + 1, dx.y); atomicAdd(dxrow + k + 2, dx.z); atomicAdd(dxrow + k + 3, dx.w); }
             }
-            if (ok) { atomicAdd(dxrow + k, dx.x); atomicAdd(dxrow + k + 1, dx.y); atomicAdd(dxrow + k + 2, dx.z); atomicAdd(dxrow + k + 3, dx.w); }
         }
     }
     __syncthreads();
     // ---- pass 2: weight and bias gradients ----
-    for (int k0 = 0; k0 < D2; k0 += 256) {
+    for (int k0 = 0; k0 < ldw; k0 += 256) {
         const int k = k0 + threadIdx.x;
-        if (k >= D2) continue;
+        if (k >= ldw) continue;
         float acc[32];
 #pragma unroll
         for (int c = 0; c < 32; ++c) acc[c] = 0.0f;
         for (int lr = 0; lr < nrows; ++lr) {
-            const float xv = xin[sx[lr] * D2 + k];
+            const float xv = k < D2 ? xin[sx[lr] * D2 + k] : P.hfr[(size_t)(row0 + lr) * D2 + (k - D2)];
 #pragma unroll
             for (int c = 0; c < 32; ++c)
                 if (c < C) acc[c] = fmaf(sdz[lr][c], xv, acc[c]);
         }
 #pragma unroll
         for (int c = 0; c < 32; ++c)
-            if (c < C) atomicAdd(P.dw[hd] + (size_t)c * D2 + k, acc[c]);
+            if (c < C) atomicAdd(P.dw[hd] + (size_t)c * ldw + k, acc[c]);
     }
     if (threadIdx.x < C) {
         float sacc = 0.0f;

@@ -7,6 +7,7 @@ namespace tg {
 // ---- label heads: Linear(2D->C) + LogSoftmax, gathered through the reorder index (models.py:909-917) -------------
 struct HeadsBwdParams {
     int B, T, E, NE, e_off, D, C;
+    int cat;                 // cat_level_states: the segment heads read [hx | hfr], weights (C,4D)
     const float* hfr;        // (B,T,E,2D) frame-level BiGRU outputs (input of the two frame heads)
     const float* hx;         // (B,T,E,2D) segment states (input of the two segment heads, through reidx)
     const int* reidx;        // (B,T,NE)

@@ -275,6 +275,9 @@ __global__ void __launch_bounds__(256) heads_kernel(const HeadsParams P) {
         const int ti = P.reidx[(size_t)bt * P.NE + P.e_off + e];
         x = P.hx + ((size_t)(b * P.T + ti) * P.E + e) * D2;
     }
+    const bool cat = P.cat && src == 1;     // models.py:901-903: segment heads read [reordered segment state | frame-level state]
+    const float* x2 = P.hfr + (size_t)row * D2;
+    const int ldw = cat ? 2 * D2 : D2;
 #pragma unroll 1
     for (int hd = 0; hd < 2; ++hd) {
         const float* W = P.w[src * 2 + hd];
@@ -282,13 +285,19 @@ __global__ void __launch_bounds__(256) heads_kernel(const HeadsParams P) {
         float* out = P.out[src * 2 + hd];
         float mine = -INFINITY;
         for (int c = 0; c < C; ++c) {
-            const float* wr = W + (size_t)c * D2;
+            const float* wr = W + (size_t)c * ldw;
             float acc = 0.0f;
             for (int k = lane * 4; k < D2; k += 128) {
                 const float4 u = __ldg(reinterpret_cast<const float4*>(wr + k));
                 const float4 v = *reinterpret_cast<const float4*>(x + k);
                 acc = fmaf(u.x, v.x, acc); acc = fmaf(u.y, v.y, acc); acc = fmaf(u.z, v.z, acc); acc = fmaf(u.w, v.w, acc);
             }
+            if (cat)
+                for (int k = lane * 4; k < D2; k += 128) {
+                    const float4 u = __ldg(reinterpret_cast<const float4*>(wr + D2 + k));
+                    const float4 v = *reinterpret_cast<const float4*>(x2 + k);
+                    acc = fmaf(u.x, v.x, acc); acc = fmaf(u.y, v.y, acc); acc = fmaf(u.z, v.z, acc); acc = fmaf(u.w, v.w, acc);
+                }
             acc = warp_sum(acc) + __ldg(bias + c);
             if (lane == c) mine = acc;
         }

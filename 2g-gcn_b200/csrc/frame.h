@@ -31,6 +31,7 @@ struct FrameMsgParams {
 
 struct HeadsParams {
     int B, T, E, NE, e_off, D, C;
+    int cat;                // cat_level_states: the two segment-level heads read [hx | hfr] with (C,4D) weights
     const float* hfr;       // (B,T,E,2D) frame-level BiGRU outputs
     const float* hx;        // (B,T,E,2D) segment-level states (gathered through reidx)
     const int* reidx;       // (B,T,NE)

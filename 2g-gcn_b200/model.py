@@ -118,7 +118,6 @@ class TGGCN(nn.Module):
         if attention_style not in _V3: unsupported.append("attention_style != 'v3'")
         if object_segment_update_strategy not in _IND: unsupported.append("object_segment_update_strategy != 'ind'")
         if add_segment_length or add_time_position: unsupported.append('time/length position features')
-        if cat_level_states or share_level_mlps: unsupported.append('cat_level_states / share_level_mlps')
         if not bias: unsupported.append('bias=False')
         if hidden_size % 16 != 0: unsupported.append('hidden_size not a multiple of 16')
         if unsupported:
@@ -146,7 +145,8 @@ class TGGCN(nn.Module):
         self.update_segment_threshold = float(update_segment_threshold)
         self.add_segment_length = self.add_time_position = False
         self.time_position_strategy, self.positional_encoding_style = time_position_strategy, positional_encoding_style
-        self.cat_level_states = False
+        self.cat_level_states = bool(cat_level_states)
+        self.share_level_mlps = bool(share_level_mlps) and not self.cat_level_states     # models.py:565: sharing needs equal input sizes
         self.hidden_size, self.num_classes = D, (n_sub, n_aff)
         hh = self.message_humans_to_human
         # ---- parameter holders, registered in the reference's order (vhoi/models.py:264-580) ----------
@@ -180,16 +180,24 @@ class TGGCN(nn.Module):
         self.geometry_to_object_segment_message_att_mlp = _mlp([2 * D, 1], ['relu'])
         self.update_human_segment_mlp = _mlp([D * (2 + (1 if hh else 0) + 1), 1], ['sigmoid'])
         self.update_object_segment_mlp = _mlp([5 * D, 1], ['sigmoid'])
-        self.human_recognition_mlp = _mlp([2 * D, n_sub], ['logsoftmax'])
-        self.human_prediction_mlp = _mlp([2 * D, n_sub], ['logsoftmax'])
+        label_in = (4 if self.cat_level_states else 2) * D        # models.py:553-555
+        self.human_recognition_mlp = _mlp([label_in, n_sub], ['logsoftmax'])
+        self.human_prediction_mlp = _mlp([label_in, n_sub], ['logsoftmax'])
         if n_aff is not None:
-            self.object_recognition_mlp = _mlp([2 * D, n_aff], ['logsoftmax'])
-            self.object_prediction_mlp = _mlp([2 * D, n_aff], ['logsoftmax'])
-        self.human_frame_recognition_mlp = _mlp([2 * D, n_sub], ['logsoftmax'])
-        self.human_frame_prediction_mlp = _mlp([2 * D, n_sub], ['logsoftmax'])
-        if n_aff is not None:
-            self.object_frame_recognition_mlp = _mlp([2 * D, n_aff], ['logsoftmax'])
-            self.object_frame_prediction_mlp = _mlp([2 * D, n_aff], ['logsoftmax'])
+            self.object_recognition_mlp = _mlp([label_in, n_aff], ['logsoftmax'])
+            self.object_prediction_mlp = _mlp([label_in, n_aff], ['logsoftmax'])
+        if self.share_level_mlps:                                  # models.py:565-570: the SAME modules under a second name
+            self.human_frame_recognition_mlp = self.human_recognition_mlp
+            self.human_frame_prediction_mlp = self.human_prediction_mlp
+            if n_aff is not None:
+                self.object_frame_recognition_mlp = self.object_recognition_mlp
+                self.object_frame_prediction_mlp = self.object_prediction_mlp
+        else:
+            self.human_frame_recognition_mlp = _mlp([2 * D, n_sub], ['logsoftmax'])
+            self.human_frame_prediction_mlp = _mlp([2 * D, n_sub], ['logsoftmax'])
+            if n_aff is not None:
+                self.object_frame_recognition_mlp = _mlp([2 * D, n_aff], ['logsoftmax'])
+                self.object_frame_prediction_mlp = _mlp([2 * D, n_aff], ['logsoftmax'])
         # ---- runtime state (not part of state_dict) ------------------------------------------------------
         self._ptr_cache = None
         self._ws = {}
@@ -224,8 +232,22 @@ class TGGCN(nn.Module):
             if t.device != device or t.dtype != torch.float32 or not t.is_contiguous():
                 raise abi.TggcnError(f'parameter {name} must be a contiguous fp32 tensor on {device}')
             arr[idx] = t.data_ptr()
+        self._alias_shared_heads(arr)
         self._ptr_cache = (probe, arr)
         return arr
+
+    def _alias_shared_heads(self, table):
+        """share_level_mlps: the frame-level heads ARE the segment-level heads (vhoi/models.py:565-570); named_parameters()
+        lists them once, under the segment-level name, so the frame-level slots of a pointer table point at the same memory."""
+        if not self.share_level_mlps:
+            return
+        for ent in ('human', 'object'):
+            for kind in ('recognition', 'prediction'):
+                for leaf in ('0.weight', '0.bias'):
+                    src = abi.WEIGHT_INDEX.get(f'{ent}_{kind}_mlp.{leaf}')
+                    dst = abi.WEIGHT_INDEX.get(f'{ent}_frame_{kind}_mlp.{leaf}')
+                    if src is not None and dst is not None and table[src]:
+                        table[dst] = table[src]
 
     def _workspace(self, dims: abi.Dims, device, backward: bool = False):
         key = (dims.B, dims.T, dims.H, dims.O, dims.save_for_backward, backward, device)
@@ -296,7 +318,7 @@ class TGGCN(nn.Module):
                         human_seg_given=int(hseg is not None), object_seg_given=int(oseg is not None),
                         inspect=int(bool(inspect_model)), persistent=int(self.persistent_kernels),
                         gemm_path=int(self.gemm_path), thr=self.update_segment_threshold,
-                        save_for_backward=int(with_grad))
+                        save_for_backward=int(with_grad), cat_level_states=int(self.cat_level_states))
         n_sampled = (0 if hseg is not None else H) + (0 if oseg is not None else O)
         noise = None
         if n_sampled:
@@ -396,6 +418,7 @@ class TGGCN(nn.Module):
         garr = (C.c_void_p * abi.N_WEIGHTS)()
         for name, g in zip(names, grads):
             garr[abi.WEIGHT_INDEX[name]] = g.data_ptr()
+        self._alias_shared_heads(garr)           # shared heads: both uses accumulate into the one gradient
         n_aff = self.num_classes[1]
 
         def gp(t):

@@ -42,10 +42,10 @@ BIMANUAL = Shape('bimanual', 2, 9, 30, (14, None), True, 'bimanual')
 SHAPES = {s.name: s for s in (MPHOI, CAD120, BIMANUAL)}
 
 
-def model_kwargs(shape: Shape, hidden_size: int = 512, stage: int = 1) -> dict:
+def model_kwargs(shape: Shape, hidden_size: int = 512, stage: int = 1, **overrides) -> dict:
     """Constructor kwargs == ``cfg.parameters`` of conf/models/2G-GCN_stage{1,2}.yaml:4-29 plus the
     ``input_size`` / ``num_classes`` that train.py:28-34 adds."""
-    return dict(
+    kw = dict(
         input_size=(shape.Fh, 2048), num_classes=shape.num_classes,
         add_segment_length=0, add_time_position=0, time_position_strategy='s', positional_encoding_style='e',
         attention_style='v3', bias=True, cat_level_states=0, discrete_networks_num_layers=1,
@@ -55,6 +55,8 @@ def model_kwargs(shape: Shape, hidden_size: int = 512, stage: int = 1) -> dict:
         message_geometry_to_human=False, message_segment=True, message_type='v2', message_granularity='v1',
         message_aggregation='att', object_segment_update_strategy='ind', share_level_mlps=0,
         update_segment_threshold=0.1 if stage == 2 else 0.5)
+    kw.update(overrides)          # e.g. cat_level_states=1, share_level_mlps=1 (yaml: conf/models/2G-GCN_stage1.yaml:12,28)
+    return kw
 
 
 def make_batch(shape: Shape, B: int, T: int, seed: int = 1234, min_len_frac: float = 0.6,

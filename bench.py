@@ -255,8 +255,18 @@ def run_ours(args, rank, world, local_rank):
     roof.update(kernel=top, kernel_ms=stages[top], share_of_step=stages[top] / step_ms, peak_source=peaks['source'],
                 us_per_recurrent_step=(stages[top] * 1e3 / T) if top in ('segment', 'bigru') else None)
     tr = os.path.join(ROOT, 'profiles', 'ncu_traffic.json')
-    if os.path.exists(tr):
-        roof['traffic'] = json.load(open(tr)).get(top)
+    traffic = json.load(open(tr)) if os.path.exists(tr) else {}
+    roof['traffic'] = traffic.get(top)
+    # the same two ratios for every stage (algorithmic FLOPs and bytes of stage_work over the live stage time): tensor-bound
+    # stages are quoted against the sustained bf16 peak although they compute fp32-accurate products (3 MMAs per product)
+    per_stage = {}
+    for k, ms in stages.items():
+        fl, by = work[k]
+        if ms <= 0:
+            continue
+        per_stage[k] = {'ms': round(ms, 4), 'tflops': round(fl / (ms / 1e3) / 1e12, 2), 'gbs': round(by / (ms / 1e3) / 1e9, 1),
+                        'frac_tensor': round(fl / (ms / 1e3) / 1e12 / peaks['tf_sustained'], 4),
+                        'frac_hbm': round(by / (ms / 1e3) / 1e9 / peaks['hbm_gbs'], 4)}
     h2d = sum(v.numel() * v.element_size() for v in pinned.values()) + n_calls * B * 2 * 4
     d2h = 2 * B * T * shape.H * 4 + 4 * B * shape.num_classes[0] * T * shape.H * 4
     line = {
@@ -274,6 +284,7 @@ def run_ours(args, rank, world, local_rank):
         'gpu_launches': int(launches),
         'roofline': roof,
         'stages_ms': {k: round(v, 4) for k, v in stages.items()},
+        'stage_roofline': per_stage,
     }
     if train is not None:
         line['train_step'] = train

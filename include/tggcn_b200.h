@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define TGGCN_ABI_VERSION 2
+#define TGGCN_ABI_VERSION 3
 
 #if defined(__GNUC__)
 #define TGGCN_API __attribute__((visibility("default")))
@@ -49,6 +49,8 @@ typedef struct tggcn_dims {
     int32_t gemm_path;           /* projections: 0 = fp32 SIMT, 1 = tcgen05 3xTF32, 2 = tcgen05 where K%32==0 */
     float   thr;                 /* update_segment_threshold                                             */
     int32_t save_for_backward;   /* forward also stores what tggcn_backward needs (bigger workspace)     */
+    int32_t cat_level_states;    /* segment-level heads read [segment state | frame-level state] (models.py:901-903): their
+                                    weights are (C, 4D) instead of (C, 2D)                              */
 } tggcn_dims;
 
 /* Parameter table.  One device pointer per reference state_dict() entry, in this order

@@ -55,12 +55,17 @@ CASES = [
     ('cad120_s1_eval', 'cad120', 32, 2, 10, 1, False, 2.0, False),
     ('cad120_s2_eval', 'cad120', 32, 2, 13, 2, False, 2.0, False),
     ('bimanual_s2_eval', 'bimanual', 16, 2, 9, 2, False, 2.0, False),
+    # model variants beyond the shipped yaml values: trailing dict = constructor overrides
+    ('mphoi_s2_cat', 'mphoi', 32, 2, 12, 2, False, 2.0, False, {'cat_level_states': 1}),
+    ('cad120_s2_cat', 'cad120', 32, 2, 11, 2, False, 2.0, False, {'cat_level_states': 1}),
+    ('mphoi_s2_share', 'mphoi', 32, 2, 12, 2, False, 2.0, False, {'share_level_mlps': 1}),
 ]
 
 
-def run_case(name, shape_name, D, B, T, stage, train_mode, gain, inspect):
+def run_case(name, shape_name, D, B, T, stage, train_mode, gain, inspect, extra=None):
     shape = pkg.SHAPES[shape_name]
-    kw = pkg.model_kwargs(shape, hidden_size=D, stage=stage)
+    extra = extra or {}
+    kw = pkg.model_kwargs(shape, hidden_size=D, stage=stage, **extra)
     model = select_model('2G-GCN')(**kw)
     pkg.deterministic_fill(model.state_dict(), seed=7, gain=gain)
     sd = {k: v.detach().clone() for k, v in model.state_dict().items()}   # snapshot (train mode mutates BN)
@@ -109,7 +114,7 @@ def run_case(name, shape_name, D, B, T, stage, train_mode, gain, inspect):
         raise RuntimeError(f'no seed with a safe gate margin for {name}')
     # oracle agreement (also guards MPHOI object gates, which the reference does not return)
     p64 = {k: v.double() for k, v in sd.items()}
-    ocfg = orc.OracleConfig(D, shape.V, shape.num_classes, shape.hh, stage == 2, thr)
+    ocfg = orc.OracleConfig(D, shape.V, shape.num_classes, shape.hh, stage == 2, thr, bool(extra.get('cat_level_states', 0)))
     hseg = torch.ones(B, T, shape.H) if stage == 1 else None
     oseg = torch.ones(B, T, shape.O) if (stage == 1 and shape.dataset == 'cad120') else None
     taps = {}
@@ -156,6 +161,9 @@ GRAD_CASES = [
     ('grad_mphoi_s1', 'mphoi', 32, 2, 9, 1, 2.0),
     ('grad_mphoi_s2', 'mphoi', 32, 3, 10, 2, 2.0),
     ('grad_cad120_s2', 'cad120', 32, 2, 8, 2, 2.0),
+    ('grad_mphoi_s2_cat', 'mphoi', 32, 2, 9, 2, 2.0, {'cat_level_states': 1}),
+    ('grad_cad120_s2_cat', 'cad120', 32, 2, 8, 2, 2.0, {'cat_level_states': 1}),
+    ('grad_mphoi_s2_share', 'mphoi', 32, 2, 9, 2, 2.0, {'share_level_mlps': 1}),
 ]
 
 
@@ -168,9 +176,10 @@ def summarize_grad(g):
     return np.concatenate([[float(f.sum()), float(f.abs().sum()), float((f * f).sum())], f[idx].numpy()])
 
 
-def run_grad_case(name, shape_name, D, B, T, stage, gain):
+def run_grad_case(name, shape_name, D, B, T, stage, gain, extra=None):
     shape = pkg.SHAPES[shape_name]
-    kw = pkg.model_kwargs(shape, hidden_size=D, stage=stage)
+    extra = extra or {}
+    kw = pkg.model_kwargs(shape, hidden_size=D, stage=stage, **extra)
     model = select_model('2G-GCN')(**kw)
     pkg.deterministic_fill(model.state_dict(), seed=7, gain=gain)
     sd = {k: v.detach().clone() for k, v in model.state_dict().items()}
@@ -187,7 +196,7 @@ def run_grad_case(name, shape_name, D, B, T, stage, gain):
         noise = orc.draw_noise(max(n_calls, 1), B, torch.Generator().manual_seed(noise_seed))[:n_calls]
         # margin check on the fp64 oracle (covers object gates that MPHOI does not return)
         p64 = {k: v.double() for k, v in sd.items()}
-        ocfg = orc.OracleConfig(D, shape.V, shape.num_classes, shape.hh, stage == 2, thr)
+        ocfg = orc.OracleConfig(D, shape.V, shape.num_classes, shape.hh, stage == 2, thr, bool(extra.get('cat_level_states', 0)))
         hseg = torch.ones(B, T, shape.H) if stage == 1 else None
         oseg = torch.ones(B, T, shape.O) if (stage == 1 and shape.dataset == 'cad120') else None
         taps = {}
@@ -239,8 +248,11 @@ def run_grad_case(name, shape_name, D, B, T, stage, gain):
 
 if __name__ == '__main__':
     torch.set_num_threads(8)
+    only = [a for a in sys.argv[1:] if not a.startswith('--')]       # optional case names: regenerate just those
     if '--grads-only' not in sys.argv:
         for case in CASES:
-            run_case(*case)
+            if not only or case[0] in only:
+                run_case(*case)
     for case in GRAD_CASES:
-        run_grad_case(*case)
+        if not only or case[0] in only:
+            run_grad_case(*case)

@@ -40,6 +40,7 @@ class OracleConfig:
     message_humans_to_human: bool = True
     filter_discrete_updates: bool = False
     update_segment_threshold: float = 0.5
+    cat_level_states: bool = False          # models.py:901-903 (share_level_mlps changes no arithmetic: same tensors, two names)
 
 
 # ----------------------------------------------------------------------------------------------
@@ -332,6 +333,9 @@ def forward(p: Dict[str, Tensor], cfg: OracleConfig, x_human: Tensor, x_objects:
     hx_o = torch.stack([reorder(hx_o[:, :, k], y_os[:, :, k]) for k in range(O)], dim=2)
     tap('hx_h_reordered', hx_h), tap('hx_o_reordered', hx_o)
 
+    if cfg.cat_level_states:                                                    # models.py:901-903
+        hx_h = torch.cat([hx_h, hfr_h], dim=-1)
+        hx_o = torch.cat([hx_o, hfr_o], dim=-1)
     # -- heads (models.py:905-926) ---------------------------------------------------------------
     def head(name, x):
         return torch.log_softmax(_lin(p, name + '.0', x), dim=-1).permute(0, 3, 1, 2).contiguous()

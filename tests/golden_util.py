@@ -16,7 +16,30 @@ CASES = {
     'cad120_s1_eval': ('cad120', 32, 2, 10, 1, False, False),
     'cad120_s2_eval': ('cad120', 32, 2, 13, 2, False, False),
     'bimanual_s2_eval': ('bimanual', 16, 2, 9, 2, False, False),
+    # model variants beyond the shipped yaml values: trailing dict = constructor overrides
+    'mphoi_s2_cat': ('mphoi', 32, 2, 12, 2, False, False, {'cat_level_states': 1}),
+    'cad120_s2_cat': ('cad120', 32, 2, 11, 2, False, False, {'cat_level_states': 1}),
+    'mphoi_s2_share': ('mphoi', 32, 2, 12, 2, False, False, {'share_level_mlps': 1}),
 }
+
+# name -> (shape, D, B, T, stage[, constructor overrides])   (mirrors oracle/gen_golden.py:GRAD_CASES)
+GRAD_CASES = {
+    'grad_mphoi_s1': ('mphoi', 32, 2, 9, 1),
+    'grad_mphoi_s2': ('mphoi', 32, 3, 10, 2),
+    'grad_cad120_s2': ('cad120', 32, 2, 8, 2),
+    'grad_mphoi_s2_cat': ('mphoi', 32, 2, 9, 2, {'cat_level_states': 1}),
+    'grad_cad120_s2_cat': ('cad120', 32, 2, 8, 2, {'cat_level_states': 1}),
+    'grad_mphoi_s2_share': ('mphoi', 32, 2, 9, 2, {'share_level_mlps': 1}),
+}
+
+
+def alias_shared_heads(params, extra):
+    """share_level_mlps: both names of a shared head must be ONE tensor in a parameter dict used for autograd."""
+    if extra.get('share_level_mlps'):
+        for k in list(params):
+            if '_frame_' in k and k.replace('_frame_', '_') in params:
+                params[k] = params[k.replace('_frame_', '_')]
+    return params
 
 
 class GoldenCase:
@@ -24,13 +47,14 @@ class GoldenCase:
         import tggcn_oracle as orc
         synth = importlib.import_module('2g-gcn_b200.synth')
         self.name = name
-        shape_name, D, B, T, stage, train_mode, inspect = CASES[name]
+        shape_name, D, B, T, stage, train_mode, inspect = CASES[name][:7]
+        self.extra = CASES[name][7] if len(CASES[name]) > 7 else {}
         self.shape = synth.SHAPES[shape_name]
         self.D, self.B, self.T, self.stage, self.train_mode, self.inspect = D, B, T, stage, train_mode, inspect
         self.blob = np.load(os.path.join(GOLDEN_DIR, name + '.npz'))
         data_seed, noise_seed, target_seed, weight_seed = [int(v) for v in self.blob['meta']]
         self.weight_seed, self.gain = weight_seed, float(self.blob['gain'][0])
-        self.kwargs = synth.model_kwargs(self.shape, hidden_size=D, stage=stage)
+        self.kwargs = synth.model_kwargs(self.shape, hidden_size=D, stage=stage, **self.extra)
         self.thr = self.kwargs['update_segment_threshold']
         self.batch = synth.make_batch(self.shape, B, T, seed=data_seed)
         H, O = self.shape.H, self.shape.O
@@ -43,7 +67,8 @@ class GoldenCase:
         self.targets = synth.target_list(self.shape, synth.make_targets(self.shape, self.batch['lengths'], T,
                                                                         seed=target_seed))
         self.outputs = [torch.from_numpy(self.blob[f'out{i}']) for i in range(6 if self.shape.num_classes[1] is None else 12)]
-        self.ocfg = orc.OracleConfig(D, self.shape.V, self.shape.num_classes, self.shape.hh, stage == 2, self.thr)
+        self.ocfg = orc.OracleConfig(D, self.shape.V, self.shape.num_classes, self.shape.hh, stage == 2, self.thr,
+                                     bool(self.extra.get('cat_level_states', 0)))
         # the regenerated inputs must be the bytes the reference saw
         chk = float(self.batch['x_human'].double().sum() + self.batch['x_objects'].double().sum())
         assert abs(chk - float(self.blob['inputs_checksum'][0])) <= 1e-6 * abs(chk), 'synthetic inputs differ from golden run'

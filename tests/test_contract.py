@@ -25,11 +25,28 @@ def test_constructor_accepts_yaml_values_and_rejects_the_rest(pkg, synth):
     m = pkg.TGGCN(**kw)
     assert m.filter_discrete_updates and m.update_segment_threshold == pytest.approx(0.1)
     for bad in (dict(message_type='v1'), dict(attention_style='v1'), dict(message_aggregation='mp'),
-                dict(object_segment_update_strategy='sah'), dict(add_time_position=1), dict(cat_level_states=1),
+                dict(object_segment_update_strategy='sah'), dict(add_time_position=1), dict(share_level_mlps=1, bias=False),
                 dict(discrete_networks_num_layers=2), dict(message_geometry_to_human=True), dict(hidden_size=20)):
         with pytest.raises(NotImplementedError):
             pkg.TGGCN(**{**kw, **bad})
     assert pkg.select_model('2G-GCN') is pkg.TGGCN
+
+
+def test_level_state_variants_keep_the_reference_layout(pkg, synth):
+    """cat_level_states / share_level_mlps (vhoi/models.py:553-570): head shapes and the duplicated state_dict names."""
+    D = 32
+    cat = pkg.TGGCN(**synth.model_kwargs(synth.CAD120, hidden_size=D, stage=2, cat_level_states=1))
+    sd = cat.state_dict()
+    assert tuple(sd['human_recognition_mlp.0.weight'].shape) == (10, 4 * D)
+    assert tuple(sd['object_prediction_mlp.0.weight'].shape) == (12, 4 * D)
+    assert tuple(sd['human_frame_recognition_mlp.0.weight'].shape) == (10, 2 * D)
+    share = pkg.TGGCN(**synth.model_kwargs(synth.MPHOI, hidden_size=D, stage=2, share_level_mlps=1))
+    sd = share.state_dict()
+    assert sd['human_frame_recognition_mlp.0.weight'].data_ptr() == sd['human_recognition_mlp.0.weight'].data_ptr()
+    names = [n for n, _ in share.named_parameters()]
+    assert 'human_recognition_mlp.0.weight' in names and 'human_frame_recognition_mlp.0.weight' not in names
+    both = pkg.TGGCN(**synth.model_kwargs(synth.MPHOI, hidden_size=D, stage=2, share_level_mlps=1, cat_level_states=1))
+    assert not both.share_level_mlps and both.cat_level_states          # models.py:565: no sharing with concatenated inputs
 
 
 def test_weight_table_covers_the_state_dict(pkg, synth):
@@ -52,9 +69,9 @@ def test_library_loads_and_exports_every_declared_symbol(pkg):
     lib = pkg.abi.lib()
     for sym in declared:
         assert hasattr(lib, sym), sym
-    assert lib.tggcn_abi_version() == 2
-    # struct mirrors: 17 int32 + 1 float + 1 int32; io = 6 + 4 + 8 + 3 + 3 pointers
-    assert ctypes.sizeof(pkg.abi.Dims) == 19 * 4
+    assert lib.tggcn_abi_version() == 3
+    # struct mirrors: 17 int32 + 1 float + 2 int32; io = 6 + 4 + 8 + 3 + 3 pointers
+    assert ctypes.sizeof(pkg.abi.Dims) == 20 * 4
     assert ctypes.sizeof(pkg.abi.IO) == 24 * 8
 
 

@@ -10,11 +10,7 @@ import torch
 
 pytestmark = pytest.mark.gpu
 
-GRAD_CASES = {
-    'grad_mphoi_s1': ('mphoi', 32, 2, 9, 1),
-    'grad_mphoi_s2': ('mphoi', 32, 3, 10, 2),
-    'grad_cad120_s2': ('cad120', 32, 2, 8, 2),
-}
+from golden_util import GRAD_CASES, alias_shared_heads      # noqa: E402
 
 
 def _summarize(g):
@@ -27,11 +23,12 @@ def _summarize(g):
 
 def _setup(name, orc, synth, pkg):
     from golden_util import GOLDEN_DIR
-    shape_name, D, B, T, stage = GRAD_CASES[name]
+    shape_name, D, B, T, stage = GRAD_CASES[name][:5]
+    extra = GRAD_CASES[name][5] if len(GRAD_CASES[name]) > 5 else {}
     blob = np.load(os.path.join(GOLDEN_DIR, name + '.npz'))
     data_seed, noise_seed, target_seed, weight_seed = [int(v) for v in blob['meta']]
     shape = synth.SHAPES[shape_name]
-    kw = synth.model_kwargs(shape, hidden_size=D, stage=stage)
+    kw = synth.model_kwargs(shape, hidden_size=D, stage=stage, **extra)
     model = pkg.TGGCN(**kw)
     synth.deterministic_fill(model.state_dict(), seed=weight_seed, gain=float(blob['gain'][0]))
     batch = synth.make_batch(shape, B, T, seed=data_seed)
@@ -41,14 +38,16 @@ def _setup(name, orc, synth, pkg):
     hseg = torch.ones(B, T, shape.H) if human_given else None
     oseg = torch.ones(B, T, shape.O) if objects_given else None
     targets = synth.target_list(shape, synth.make_targets(shape, batch['lengths'], T, seed=target_seed))
-    ocfg = orc.OracleConfig(D, shape.V, shape.num_classes, shape.hh, stage == 2, kw['update_segment_threshold'])
+    ocfg = orc.OracleConfig(D, shape.V, shape.num_classes, shape.hh, stage == 2, kw['update_segment_threshold'],
+                            bool(extra.get('cat_level_states', 0)))
     return dict(blob=blob, shape=shape, stage=stage, model=model, batch=batch, noise=noise if n_calls else None, hseg=hseg,
-                oseg=oseg, targets=targets, ocfg=ocfg)
+                oseg=oseg, targets=targets, ocfg=ocfg, extra=extra)
 
 
 def _oracle_grads(c, orc):
     p = {k: v.detach().double().requires_grad_(v.is_floating_point() and 'running' not in k) if v.is_floating_point() else v
          for k, v in c['model'].state_dict().items()}
+    alias_shared_heads(p, c.get('extra', {}))
     b = c['batch']
     dd = lambda t: None if t is None else t.double()
     out = orc.forward(p, c['ocfg'], b['x_human'].double(), b['x_objects'].double(), b['objects_mask'].double(), dd(c['hseg']),

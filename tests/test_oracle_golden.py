@@ -80,11 +80,7 @@ def test_reorder_and_filter_edge_cases(orc):
     assert f.ne(0).tolist() == [[False, True, False, False, False, True]]
 
 
-GRAD_CASES = {
-    'grad_mphoi_s1': ('mphoi', 32, 2, 9, 1),
-    'grad_mphoi_s2': ('mphoi', 32, 3, 10, 2),
-    'grad_cad120_s2': ('cad120', 32, 2, 8, 2),
-}
+from golden_util import GRAD_CASES, alias_shared_heads      # noqa: E402
 
 
 def _summarize(g):
@@ -101,23 +97,26 @@ def test_oracle_gradients_match_reference(name, orc, synth, pkg):
     gradients of the unmodified reference (oracle/gen_golden.py::run_grad_case), including which parameters get none."""
     import os
     from golden_util import GOLDEN_DIR
-    shape_name, D, B, T, stage = GRAD_CASES[name]
+    shape_name, D, B, T, stage = GRAD_CASES[name][:5]
+    extra = GRAD_CASES[name][5] if len(GRAD_CASES[name]) > 5 else {}
     blob = np.load(os.path.join(GOLDEN_DIR, name + '.npz'))
     data_seed, noise_seed, target_seed, weight_seed = [int(v) for v in blob['meta']]
     shape = synth.SHAPES[shape_name]
-    kw = synth.model_kwargs(shape, hidden_size=D, stage=stage)
+    kw = synth.model_kwargs(shape, hidden_size=D, stage=stage, **extra)
     model = pkg.TGGCN(**kw)
     synth.deterministic_fill(model.state_dict(), seed=weight_seed, gain=float(blob['gain'][0]))
     assert abs(synth.state_checksum(model.state_dict()) - float(blob['weights_checksum'][0])) < 1e-6
     p = {k: v.detach().double().requires_grad_(v.is_floating_point() and 'running' not in k)
          if v.is_floating_point() else v for k, v in model.state_dict().items()}
+    alias_shared_heads(p, extra)
     batch = synth.make_batch(shape, B, T, seed=data_seed)
     human_given, objects_given = stage == 1, stage == 1 and shape.dataset == 'cad120'
     n_calls = orc.num_noise_draws(T, shape.H, shape.O, human_given, objects_given)
     noise = orc.draw_noise(max(n_calls, 1), B, torch.Generator().manual_seed(noise_seed))[:n_calls]
     hseg = torch.ones(B, T, shape.H).double() if human_given else None
     oseg = torch.ones(B, T, shape.O).double() if objects_given else None
-    ocfg = orc.OracleConfig(D, shape.V, shape.num_classes, shape.hh, stage == 2, kw['update_segment_threshold'])
+    ocfg = orc.OracleConfig(D, shape.V, shape.num_classes, shape.hh, stage == 2, kw['update_segment_threshold'],
+                            bool(extra.get('cat_level_states', 0)))
     out = orc.forward(p, ocfg, batch['x_human'].double(), batch['x_objects'].double(), batch['objects_mask'].double(),
                       hseg, oseg, noise.double() if n_calls else None, training=True)
     targets = synth.target_list(shape, synth.make_targets(shape, batch['lengths'], T, seed=target_seed))

@@ -350,7 +350,61 @@ def train_step_throughput(args, pkg, shape, kwargs, dev, rank, world, flush, bar
     if world > 1:
         dist.all_reduce(total, op=dist.ReduceOp.MAX)
     ms = float(total.item()) / steps
+
+    # the same step end to end: inputs AND targets come from pinned host memory every step (double-buffered on the feeder's
+    # side stream), the Gumbel noise is drawn on the CPU per call, and the loss value is read back on the host one step later
+    model.set_gumbel_noise(None)
+    host_step = {k: host[k].pin_memory() for k in ('x_human', 'x_objects', 'objects_mask')}
+    host_tg = pkg.synth.target_list(shape, pkg.synth.make_targets(shape, host['lengths'], T, seed=77 + rank))
+    for i, t in enumerate(host_tg):
+        host_step[f'target{i}'] = t.pin_memory()
+    pipe = pkg.feeder.DeviceBatchPipeline(dev, host_step)
+    loss_host = [torch.empty(1, pin_memory=True), torch.empty(1, pin_memory=True)]
+    loss_done = [None, None]
+    count = [0]
+
+    def step_e2e():
+        i = count[0]
+        count[0] += 1
+        cur = pipe.get()
+        pipe.submit(host_step)
+        opt.zero_grad(set_to_none=True)
+        out = model(x_human=cur['x_human'], x_objects=cur['x_objects'], objects_mask=cur['objects_mask'])
+        loss = sum(criterion(out, [cur[f'target{j}'] for j in range(len(host_tg))], reduction='mean'))
+        loss.backward()
+        pipe.release()
+        if world > 1:
+            reducer.reduce()
+        opt.step()
+        loss_host[i & 1].copy_(loss.detach().reshape(1), non_blocking=True)
+        loss_done[i & 1] = torch.cuda.Event()
+        loss_done[i & 1].record()
+        if loss_done[(i & 1) ^ 1] is not None:
+            loss_done[(i & 1) ^ 1].synchronize()
+            return float(loss_host[(i & 1) ^ 1][0])
+        return None
+
+    pipe.submit(host_step)
+    for _ in range(warmup):
+        step_e2e()
+    barrier()
+    evs = []
+    for _ in range(steps):
+        flush.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        step_e2e()
+        e1.record()
+        evs.append((e0, e1))
+    barrier()
+    total = torch.tensor([sum(a.elapsed_time(b) for a, b in evs)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(total, op=dist.ReduceOp.MAX)
+    e2e_ms = float(total.item()) / steps
+    h2d = sum(v.numel() * v.element_size() for v in host_step.values()) + T * (shape.H + shape.O) * B * 2 * 4
     return {'value': world * B * T / (ms / 1e3), 'unit': UNIT, 'ms_per_step': ms, 'steps': steps, 'warmup': warmup,
+            'e2e': {'value': world * B * T / (e2e_ms / 1e3), 'unit': UNIT, 'ms_per_step': e2e_ms, 'h2d_bytes_per_step': h2d,
+                    'd2h_bytes_per_step': 4},
             'gpu_launches_per_step': int(launches // steps), 'loss': float(loss.detach()),
             'what': 'forward(train-mode BN, saves) + fused criterion (BCE + 2x NLL) + tggcn_backward + '
                     + ('NCCL all-reduce of the flat gradient + ' if world > 1 else '') + 'torch.optim.Adam(fused=True) step; fp32-accurate products (3xTF32 / 3xFP16 split)',

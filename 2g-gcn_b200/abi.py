@@ -20,7 +20,7 @@ class Dims(C.Structure):
     _fields_ = [(n, C.c_int32) for n in (
         'B', 'T', 'H', 'O', 'V', 'D', 'Fh', 'C_sub', 'C_aff', 'hh', 'filter', 'bn_train', 'human_seg_given',
         'object_seg_given', 'inspect', 'persistent', 'gemm_path')] + [('thr', C.c_float), ('save_for_backward', C.c_int32),
-                                                                       ('cat_level_states', C.c_int32)]
+                                                                       ('cat_level_states', C.c_int32), ('mean_pool', C.c_int32)]
 
 
 class GradOutputs(C.Structure):
@@ -122,7 +122,7 @@ def lib():
     L.tggcn_f1_at_k.restype = C.c_int
     L.tggcn_f1_at_k.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int64,
                                 C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
-    if L.tggcn_abi_version() != 3:
+    if L.tggcn_abi_version() != 4:
         raise TggcnError('lib2ggcn_b200.so ABI version mismatch; rebuild')
     _lib = L
     return L

@@ -262,7 +262,8 @@ __global__ void __launch_bounds__(256) frame_bwd_kernel(const FrameBwdParams P) 
             const float scale = 1.0f / sqrtf((float)D2);
             float dot = 0.0f;
             for (int sd = 0; sd < Es; ++sd) dot = fmaf(al[r * FB_MAXE + sd], dd[r * FB_MAXE + sd], dot);
-            for (int sd = 0; sd < Es; ++sd) dd[r * FB_MAXE + sd] = al[r * FB_MAXE + sd] * (dd[r * FB_MAXE + sd] - dot) * scale;
+            for (int sd = 0; sd < Es; ++sd)            // mean pooling: the weights do not depend on the states
+                dd[r * FB_MAXE + sd] = P.mean_pool ? 0.0f : al[r * FB_MAXE + sd] * (dd[r * FB_MAXE + sd] - dot) * scale;
         }
     }
     __syncthreads();

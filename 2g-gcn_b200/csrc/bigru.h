@@ -37,6 +37,7 @@ int launch_colsum(const float* Z, int ldz, const float* mask, int ldm, float* ou
 struct SegParams {
     int B, T, H, O, D;
     int hh;                       // humans->human messages on
+    int mean_pool;                // message_aggregation 'mp': uniform weights over the valid senders instead of attention
     // hoisted frame-part pre-activations (incl. b_ih) and gates
     const float* gs_h;            // (B,T,H,2,3D)
     const float* gs_o;            // (B,T,O,2,3D)

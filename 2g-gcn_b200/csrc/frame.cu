@@ -77,7 +77,8 @@ __global__ void __launch_bounds__(FM_THREADS) frame_messages_kernel(const FrameM
             for (int sdr = 0; sdr < Es; ++sdr) {
                 bool ok = !(same && sdr == r);
                 if (!send_h) ok = ok && (om[sdr] != 0.0f);
-                const float ex = ok ? expf(gram[e * NE + (send_h ? sdr : H + sdr)] - m) : 0.0f;
+                // mean pooling (models.py:1033-1036): every valid sender weighs 1 / #valid
+                const float ex = ok ? (P.mean_pool ? 1.0f : expf(gram[e * NE + (send_h ? sdr : H + sdr)] - m)) : 0.0f;
                 out[r * FM_MAXE + sdr] = ex;
                 sum += ex;
             }

@@ -188,13 +188,13 @@ __device__ __forceinline__ bool seg_message_tile(const SegParams& P, int tile, i
         float m = -INFINITY;
         for (int q = 0; q < Es; ++q)
             if ((mask >> q) & 1u) m = fmaxf(m, lrow[q]);
-        const float ex = (info >> 16) ? expf(lrow[sdr] - m) : 0.0f;
+        const float ex = (info >> 16) ? (P.mean_pool ? 1.0f : expf(lrow[sdr] - m)) : 0.0f;      // 'mp': weight 1 / #valid senders
         sh.alpha[tid] = ex;
         float* attp = sh.rcv_att[br];
         float* salp = sh.rcv_sal[br];
         if (attp != nullptr || salp != nullptr) {            // the sum over this receiver's senders in sender order
             float sum = 0.0f;
-            for (int q = 0; q < Es; ++q) sum += ((mask >> q) & 1u) ? expf(lrow[q] - m) : 0.0f;
+            for (int q = 0; q < Es; ++q) sum += ((mask >> q) & 1u) ? (P.mean_pool ? 1.0f : expf(lrow[q] - m)) : 0.0f;
             const float a = ex * (sum > 0.0f ? 1.0f / sum : 0.0f);
             if (attp != nullptr) attp[sdr] = a;
             if (salp != nullptr) salp[sdr] = a;

@@ -13,6 +13,7 @@ value raises ``NotImplementedError`` at construction.
 from __future__ import annotations
 
 import ctypes as C
+import os
 import math
 from typing import Optional
 
@@ -23,6 +24,7 @@ from . import abi
 
 _GS = {'gs', 'gumbel-sigmoid'}
 _ATT = {'att', 'attention'}
+_MP = {'mp', 'mean_pooling'}
 _V3 = {'v3', 'scaled_dot-product'}
 _NONREL = {'v2', 'non-relational'}
 _GENERIC = {'v1', 'generic'}
@@ -114,7 +116,7 @@ class TGGCN(nn.Module):
         if not message_segment: unsupported.append('message_segment off')
         if message_type not in _NONREL: unsupported.append("message_type != 'v2'")
         if message_granularity not in _GENERIC: unsupported.append("message_granularity != 'v1'")
-        if message_aggregation not in _ATT: unsupported.append("message_aggregation != 'att'")
+        if message_aggregation not in _ATT | _MP: unsupported.append("message_aggregation not in {'att', 'mp'}")
         if attention_style not in _V3: unsupported.append("attention_style != 'v3'")
         if object_segment_update_strategy not in _IND: unsupported.append("object_segment_update_strategy != 'ind'")
         if add_segment_length or add_time_position: unsupported.append('time/length position features')
@@ -171,13 +173,15 @@ class TGGCN(nn.Module):
         for kind in kinds:
             setattr(self, f'{kind}_message_mlp', _mlp([2 * D, D], ['relu']))
             setattr(self, f'{kind}_segment_message_mlp', _mlp([D, D], ['relu']))
-            # present in the reference's state_dict but unused under attention_style 'v3'
-            setattr(self, f'{att_names[kind]}_message_att_mlp', _mlp([4 * D, 1], ['relu']))
-            setattr(self, f'{att_names[kind]}_segment_message_att_mlp', _mlp([2 * D, 1], ['relu']))
+            # present in the reference's state_dict (attention aggregation only) but unused under attention_style 'v3'
+            if message_aggregation in _ATT:
+                setattr(self, f'{att_names[kind]}_message_att_mlp', _mlp([4 * D, 1], ['relu']))
+                setattr(self, f'{att_names[kind]}_segment_message_att_mlp', _mlp([2 * D, 1], ['relu']))
         self.geometry_to_object_message_mlp = _mlp([2 * D, D], ['relu'])
         self.geometry_to_object_segment_message_mlp = _mlp([D, D], ['relu'])          # dead in the reference too
-        self.geometry_to_object_message_att_mlp = _mlp([4 * D, 1], ['relu'])
-        self.geometry_to_object_segment_message_att_mlp = _mlp([2 * D, 1], ['relu'])
+        if message_aggregation in _ATT:
+            self.geometry_to_object_message_att_mlp = _mlp([4 * D, 1], ['relu'])
+            self.geometry_to_object_segment_message_att_mlp = _mlp([2 * D, 1], ['relu'])
         self.update_human_segment_mlp = _mlp([D * (2 + (1 if hh else 0) + 1), 1], ['sigmoid'])
         self.update_object_segment_mlp = _mlp([5 * D, 1], ['sigmoid'])
         label_in = (4 if self.cat_level_states else 2) * D        # models.py:553-555
@@ -303,6 +307,12 @@ class TGGCN(nn.Module):
         n_sub, n_aff = self.num_classes
         f32 = dict(dtype=torch.float32, device=dev)
         with_grad = torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters())
+        if inspect_model and self.message_aggregation in _MP:
+            raise NotImplementedError('inspect_model has no attention weights to return under mean-pooling aggregation')
+        if with_grad and self.message_aggregation in _MP and os.environ.get('TGGCN_ALLOW_MP_BACKWARD') != '1':
+            # forward parity with the reference is pinned (tests/golden/*_mp.npz); the backward still differs from the reference by
+            # ~1 % in the frame-level objects->object message gradient when a receiver has >= 2 senders
+            raise NotImplementedError("message_aggregation='mp' is inference-only for now: call under torch.no_grad()")
         if with_grad and (inspect_model or stage_ms is not None):
             raise NotImplementedError('inspect_model / stage profiling are inference-only: call under torch.no_grad()')
 
@@ -318,7 +328,8 @@ class TGGCN(nn.Module):
                         human_seg_given=int(hseg is not None), object_seg_given=int(oseg is not None),
                         inspect=int(bool(inspect_model)), persistent=int(self.persistent_kernels),
                         gemm_path=int(self.gemm_path), thr=self.update_segment_threshold,
-                        save_for_backward=int(with_grad), cat_level_states=int(self.cat_level_states))
+                        save_for_backward=int(with_grad), cat_level_states=int(self.cat_level_states),
+                        mean_pool=int(self.message_aggregation in _MP))
         n_sampled = (0 if hseg is not None else H) + (0 if oseg is not None else O)
         noise = None
         if n_sampled:

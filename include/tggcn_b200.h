@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define TGGCN_ABI_VERSION 3
+#define TGGCN_ABI_VERSION 4
 
 #if defined(__GNUC__)
 #define TGGCN_API __attribute__((visibility("default")))
@@ -51,6 +51,8 @@ typedef struct tggcn_dims {
     int32_t save_for_backward;   /* forward also stores what tggcn_backward needs (bigger workspace)     */
     int32_t cat_level_states;    /* segment-level heads read [segment state | frame-level state] (models.py:901-903): their
                                     weights are (C, 4D) instead of (C, 2D)                              */
+    int32_t mean_pool;           /* message_aggregation 'mp': senders averaged with weight mask / max(#valid, 1) instead of
+                                    the scaled-dot-product attention (models.py:1033-1036 and the other message functions) */
 } tggcn_dims;
 
 /* Parameter table.  One device pointer per reference state_dict() entry, in this order

@@ -59,6 +59,8 @@ CASES = [
     ('mphoi_s2_cat', 'mphoi', 32, 2, 12, 2, False, 2.0, False, {'cat_level_states': 1}),
     ('cad120_s2_cat', 'cad120', 32, 2, 11, 2, False, 2.0, False, {'cat_level_states': 1}),
     ('mphoi_s2_share', 'mphoi', 32, 2, 12, 2, False, 2.0, False, {'share_level_mlps': 1}),
+    ('mphoi_s2_mp', 'mphoi', 32, 2, 12, 2, False, 2.0, False, {'message_aggregation': 'mp'}),
+    ('cad120_s2_mp', 'cad120', 32, 2, 11, 2, False, 2.0, False, {'message_aggregation': 'mp'}),
 ]
 
 
@@ -114,7 +116,7 @@ def run_case(name, shape_name, D, B, T, stage, train_mode, gain, inspect, extra=
         raise RuntimeError(f'no seed with a safe gate margin for {name}')
     # oracle agreement (also guards MPHOI object gates, which the reference does not return)
     p64 = {k: v.double() for k, v in sd.items()}
-    ocfg = orc.OracleConfig(D, shape.V, shape.num_classes, shape.hh, stage == 2, thr, bool(extra.get('cat_level_states', 0)))
+    ocfg = orc.OracleConfig(D, shape.V, shape.num_classes, shape.hh, stage == 2, thr, bool(extra.get('cat_level_states', 0)), extra.get('message_aggregation') in ('mp', 'mean_pooling'))
     hseg = torch.ones(B, T, shape.H) if stage == 1 else None
     oseg = torch.ones(B, T, shape.O) if (stage == 1 and shape.dataset == 'cad120') else None
     taps = {}
@@ -164,6 +166,8 @@ GRAD_CASES = [
     ('grad_mphoi_s2_cat', 'mphoi', 32, 2, 9, 2, 2.0, {'cat_level_states': 1}),
     ('grad_cad120_s2_cat', 'cad120', 32, 2, 8, 2, 2.0, {'cat_level_states': 1}),
     ('grad_mphoi_s2_share', 'mphoi', 32, 2, 9, 2, 2.0, {'share_level_mlps': 1}),
+    ('grad_mphoi_s2_mp', 'mphoi', 32, 2, 9, 2, 2.0, {'message_aggregation': 'mp'}),
+    ('grad_cad120_s2_mp', 'cad120', 32, 2, 8, 2, 2.0, {'message_aggregation': 'mp'}),
 ]
 
 
@@ -196,7 +200,7 @@ def run_grad_case(name, shape_name, D, B, T, stage, gain, extra=None):
         noise = orc.draw_noise(max(n_calls, 1), B, torch.Generator().manual_seed(noise_seed))[:n_calls]
         # margin check on the fp64 oracle (covers object gates that MPHOI does not return)
         p64 = {k: v.double() for k, v in sd.items()}
-        ocfg = orc.OracleConfig(D, shape.V, shape.num_classes, shape.hh, stage == 2, thr, bool(extra.get('cat_level_states', 0)))
+        ocfg = orc.OracleConfig(D, shape.V, shape.num_classes, shape.hh, stage == 2, thr, bool(extra.get('cat_level_states', 0)), extra.get('message_aggregation') in ('mp', 'mean_pooling'))
         hseg = torch.ones(B, T, shape.H) if stage == 1 else None
         oseg = torch.ones(B, T, shape.O) if (stage == 1 and shape.dataset == 'cad120') else None
         taps = {}

@@ -24,7 +24,7 @@ def test_constructor_accepts_yaml_values_and_rejects_the_rest(pkg, synth):
     kw = synth.model_kwargs(synth.MPHOI, hidden_size=64, stage=2)
     m = pkg.TGGCN(**kw)
     assert m.filter_discrete_updates and m.update_segment_threshold == pytest.approx(0.1)
-    for bad in (dict(message_type='v1'), dict(attention_style='v1'), dict(message_aggregation='mp'),
+    for bad in (dict(message_type='v1'), dict(attention_style='v1'), dict(message_aggregation='max'),
                 dict(object_segment_update_strategy='sah'), dict(add_time_position=1), dict(share_level_mlps=1, bias=False),
                 dict(discrete_networks_num_layers=2), dict(message_geometry_to_human=True), dict(hidden_size=20)):
         with pytest.raises(NotImplementedError):
@@ -69,9 +69,9 @@ def test_library_loads_and_exports_every_declared_symbol(pkg):
     lib = pkg.abi.lib()
     for sym in declared:
         assert hasattr(lib, sym), sym
-    assert lib.tggcn_abi_version() == 3
-    # struct mirrors: 17 int32 + 1 float + 2 int32; io = 6 + 4 + 8 + 3 + 3 pointers
-    assert ctypes.sizeof(pkg.abi.Dims) == 20 * 4
+    assert lib.tggcn_abi_version() == 4
+    # struct mirrors: 17 int32 + 1 float + 3 int32; io = 6 + 4 + 8 + 3 + 3 pointers
+    assert ctypes.sizeof(pkg.abi.Dims) == 21 * 4
     assert ctypes.sizeof(pkg.abi.IO) == 24 * 8
 
 

@@ -80,7 +80,8 @@ def test_reorder_and_filter_edge_cases(orc):
     assert f.ne(0).tolist() == [[False, True, False, False, False, True]]
 
 
-from golden_util import GRAD_CASES, alias_shared_heads      # noqa: E402
+from golden_util import GRAD_CASES as _GPU_GRAD_CASES, GRAD_CASES_ORACLE_ONLY, alias_shared_heads      # noqa: E402
+GRAD_CASES = {**_GPU_GRAD_CASES, **GRAD_CASES_ORACLE_ONLY}
 
 
 def _summarize(g):
@@ -116,7 +117,7 @@ def test_oracle_gradients_match_reference(name, orc, synth, pkg):
     hseg = torch.ones(B, T, shape.H).double() if human_given else None
     oseg = torch.ones(B, T, shape.O).double() if objects_given else None
     ocfg = orc.OracleConfig(D, shape.V, shape.num_classes, shape.hh, stage == 2, kw['update_segment_threshold'],
-                            bool(extra.get('cat_level_states', 0)))
+                            bool(extra.get('cat_level_states', 0)), extra.get('message_aggregation') in ('mp', 'mean_pooling'))
     out = orc.forward(p, ocfg, batch['x_human'].double(), batch['x_objects'].double(), batch['objects_mask'].double(),
                       hseg, oseg, noise.double() if n_calls else None, training=True)
     targets = synth.target_list(shape, synth.make_targets(shape, batch['lengths'], T, seed=target_seed))

@@ -171,6 +171,32 @@ GRAD_CASES = [
 ]
 
 
+# Under mean pooling every sender weighs 1/n, so a message pre-activation that sits within rounding distance of zero (a ReLU
+# knife edge: implementations with a different summation order disagree on its sign) shifts the gradient of its MLP visibly —
+# with attention such a sender usually carries a negligible weight.  Found on grad_cad120_s2_mp, seed 300: one
+# objects_to_object_message_mlp pre-activation of 5.3e-7 flipped under the GPU's 3xTF32 product and moved the bias gradient by
+# 0.7 %.  For these cases the seed search therefore also demands a margin on EVERY ReLU pre-activation of the oracle forward.
+RELU_STABLE_CASES = {'grad_mphoi_s2_mp', 'grad_cad120_s2_mp'}
+
+
+def _relu_margin(p64, ocfg, batch, hseg, oseg, noise, n_calls):
+    worst = [float('inf')]
+    orig = orc._relu_lin
+
+    def spy(pp, name, x):
+        pre = orc._lin(pp, name, x)
+        worst[0] = min(worst[0], float(pre.abs().min()))
+        return torch.relu(pre)
+    orc._relu_lin = spy
+    try:
+        orc.forward(p64, ocfg, batch['x_human'].double(), batch['x_objects'].double(), batch['objects_mask'].double(),
+                    None if hseg is None else hseg.double(), None if oseg is None else oseg.double(),
+                    noise.double() if n_calls else None, training=True)
+    finally:
+        orc._relu_lin = orig
+    return worst[0]
+
+
 def summarize_grad(g):
     """Full tensor when small, otherwise sums + fixed samples (keeps the fixtures small)."""
     f = g.detach().double().reshape(-1)
@@ -215,7 +241,7 @@ def run_grad_case(name, shape_name, D, B, T, stage, gain, extra=None):
             margin = min(margin, float((sft - thr).abs().min()))
             if stage == 2:
                 margin = min(margin, float((sft[:, 1:] - sft[:, :-1]).abs().min()))
-        if margin > 1e-4:
+        if margin > 1e-4 and (name not in RELU_STABLE_CASES or _relu_margin(p64, ocfg, batch, hseg, oseg, noise, n_calls) > 2e-5):
             break
     else:
         raise RuntimeError(f'no safe seed for {name}')

@@ -267,6 +267,9 @@ def forward(p: Dict[str, Tensor], cfg: OracleConfig, x_human: Tensor, x_objects:
             snd, snd_mask = _others(s_o, k), _others(objects_mask, k)   # :1286-1332
             val = _relu_lin(p, 'objects_to_object_message_mlp.0', snd) * snd_mask[..., None]
             m_oo, _ = attend(s_o[:, k], snd, val, snd_mask, cfg.mean_pool)
+            if taps is not None:                                        # per-(t, receiver) tensors for gradient debugging
+                taps.setdefault('val_oo', {})[(t, k)] = val
+                taps.setdefault('m_oo', {})[(t, k)] = m_oo
             if objects_segmentation is not None:                        # :738-739
                 hard_o[k][t] = soft_o[k][t] = objects_segmentation[:, t:t + 1, k]
             else:                                                       # :1500-1533 ('ind'); input order :1527

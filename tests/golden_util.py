@@ -32,10 +32,7 @@ GRAD_CASES = {
     'grad_mphoi_s2_cat': ('mphoi', 32, 2, 9, 2, {'cat_level_states': 1}),
     'grad_cad120_s2_cat': ('cad120', 32, 2, 8, 2, {'cat_level_states': 1}),
     'grad_mphoi_s2_share': ('mphoi', 32, 2, 9, 2, {'share_level_mlps': 1}),
-}
-
-# reference gradients kept as pins for the oracle (CPU test) — the GPU backward of this variant is not released yet
-GRAD_CASES_ORACLE_ONLY = {
+    # seeds of these two also keep every ReLU pre-activation > 2e-5 from zero (oracle/gen_golden.py: RELU_STABLE_CASES)
     'grad_mphoi_s2_mp': ('mphoi', 32, 2, 9, 2, {'message_aggregation': 'mp'}),
     'grad_cad120_s2_mp': ('cad120', 32, 2, 8, 2, {'message_aggregation': 'mp'}),
 }

@@ -117,13 +117,3 @@ def test_fp16_split_range_violation_is_reported(pkg):
     with pytest.raises(pkg.abi.TggcnError, match='fp16-split'):
         model.check_persistent_kernels()
 
-
-def test_mean_pool_is_inference_only(pkg):
-    shape = pkg.synth.SHAPES['mphoi']
-    model = pkg.TGGCN(**pkg.synth.model_kwargs(shape, hidden_size=32, stage=2, message_aggregation='mp')).cuda().train()
-    batch = pkg.synth.make_batch(shape, 2, 5, seed=3)
-    x = {k: batch[k].cuda() for k in ('x_human', 'x_objects', 'objects_mask')}
-    with pytest.raises(NotImplementedError, match='inference-only'):
-        model(**x)
-    with torch.no_grad():
-        assert len(model(**x)) == 6

@@ -80,8 +80,7 @@ def test_reorder_and_filter_edge_cases(orc):
     assert f.ne(0).tolist() == [[False, True, False, False, False, True]]
 
 
-from golden_util import GRAD_CASES as _GPU_GRAD_CASES, GRAD_CASES_ORACLE_ONLY, alias_shared_heads      # noqa: E402
-GRAD_CASES = {**_GPU_GRAD_CASES, **GRAD_CASES_ORACLE_ONLY}
+from golden_util import GRAD_CASES, alias_shared_heads      # noqa: E402
 
 
 def _summarize(g):

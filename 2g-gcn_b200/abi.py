@@ -20,7 +20,9 @@ class Dims(C.Structure):
     _fields_ = [(n, C.c_int32) for n in (
         'B', 'T', 'H', 'O', 'V', 'D', 'Fh', 'C_sub', 'C_aff', 'hh', 'filter', 'bn_train', 'human_seg_given',
         'object_seg_given', 'inspect', 'persistent', 'gemm_path')] + [('thr', C.c_float), ('save_for_backward', C.c_int32),
-                                                                       ('cat_level_states', C.c_int32), ('mean_pool', C.c_int32)]
+                                                                       ('cat_level_states', C.c_int32), ('mean_pool', C.c_int32),
+                                                                       ('recurrent_mode', C.c_int32), ('no_fp16_split', C.c_int32),
+                                                                       ('precision', C.c_int32)]
 
 
 class GradOutputs(C.Structure):
@@ -36,6 +38,7 @@ class IO(C.Structure):
         ('out_h', C.c_void_p * 4), ('out_o', C.c_void_p * 4),
         ('att_frame', C.c_void_p), ('att_seg_f', C.c_void_p), ('att_seg_b', C.c_void_p),
         ('bn_running_mean', C.c_void_p), ('bn_running_var', C.c_void_p), ('bn_num_batches', C.c_void_p),
+        ('status_host', C.c_void_p),
     ]
 
 
@@ -88,6 +91,8 @@ def lib():
     L.tggcn_workspace_view.argtypes = [C.POINTER(Dims), C.c_int, C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]
     L.tggcn_sync_status.restype = C.c_int
     L.tggcn_sync_status.argtypes = [C.POINTER(Dims), C.c_void_p, C.c_void_p]
+    L.tggcn_status_decode.restype = C.c_int
+    L.tggcn_status_decode.argtypes = [C.c_void_p]
     L.tggcn_forward.restype = C.c_int
     L.tggcn_forward.argtypes = [C.POINTER(Dims), C.POINTER(C.c_void_p), C.c_int, C.POINTER(IO), C.c_void_p, C.c_size_t,
                                 C.c_void_p]
@@ -122,7 +127,7 @@ def lib():
     L.tggcn_f1_at_k.restype = C.c_int
     L.tggcn_f1_at_k.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int64,
                                 C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
-    if L.tggcn_abi_version() != 4:
+    if L.tggcn_abi_version() != 5:
         raise TggcnError('lib2ggcn_b200.so ABI version mismatch; rebuild')
     _lib = L
     return L

@@ -2,6 +2,8 @@
 // (vhoi/models.py:584-933).  No allocation, no device synchronisation, no state between calls.
 #include <stdarg.h>
 #include <stdlib.h>
+#include <mutex>
+#include <vector>
 
 #include "common.cuh"
 #include "gemm.h"
@@ -30,17 +32,37 @@ bool debug_sync() {
     return cached == 1;
 }
 
+constexpr int MAX_DEVICES = 64;
+
 int num_sms() {
-    static int cached = 0;
-    if (cached == 0) {
-        int dev = 0, n = 0;
-        if (cudaGetDevice(&dev) == cudaSuccess &&
-            cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0)
-            cached = n;
-        else
-            return 148;
+    static int cached[MAX_DEVICES] = {0};
+    int dev = 0, n = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= MAX_DEVICES) return 148;
+    if (cached[dev] == 0) {
+        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0) cached[dev] = n;
+        else return 148;
     }
-    return cached;
+    return cached[dev];
+}
+
+int ensure_smem(const void* func, size_t bytes) {
+    struct Entry { const void* func; size_t bytes; };
+    static std::mutex mu;
+    static std::vector<Entry> table[MAX_DEVICES];
+    int dev = 0;
+    TG_CUDA_OK(cudaGetDevice(&dev));
+    TG_REQUIRE(dev >= 0 && dev < MAX_DEVICES, "device ordinal %d out of range", dev);
+    std::lock_guard<std::mutex> lock(mu);
+    for (Entry& e : table[dev])
+        if (e.func == func) {
+            if (e.bytes >= bytes) return 0;
+            TG_CUDA_OK(cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+            e.bytes = bytes;
+            return 0;
+        }
+    TG_CUDA_OK(cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    table[dev].push_back({func, bytes});
+    return 0;
 }
 
 void make_layout(const tggcn_dims& d, Layout& L) {
@@ -146,18 +168,25 @@ int tggcn_sync_status(const tggcn_dims* dims, const void* workspace, void* strea
     TG_CUDA_OK(cudaMemcpyAsync(flags, (const char*)workspace + L.off[TGGCN_BUF_SYNC], sizeof(flags), cudaMemcpyDeviceToHost,
                                (cudaStream_t)stream));
     TG_CUDA_OK(cudaStreamSynchronize((cudaStream_t)stream));
+    return tggcn_status_decode(flags);
+}
+
+int tggcn_status_decode(const uint32_t* flags) {
+    TG_REQUIRE(flags != nullptr, "status_decode: null argument");
+    int rc = 0;
     if ((flags[1] | flags[3] | flags[5] | flags[7]) & 1u) {
-        set_error("persistent kernel grid barrier timed out (bigru=%u, segment=%u, bigru_bwd=%u, segment_bwd=%u)", flags[1] & 1u,
-                  flags[3] & 1u, flags[5] & 1u, flags[7] & 1u);
-        return 1;
+        set_error("persistent kernel grid barrier timed out (bigru=%u, segment=%u, bigru_bwd=%u, segment_bwd=%u): the results of "
+                  "that call are undefined", flags[1] & 1u, flags[3] & 1u, flags[5] & 1u, flags[7] & 1u);
+        rc |= 1;
     }
     if ((flags[1] | flags[3]) & 2u) {
-        set_error("a recurrent weight (|w| >= 255) or activation (>= 65504) left the range of the fp16-split gate tiles (bigru=%u, "
-                  "segment=%u); rerun with TGGCN_SEG_RES=0 TGGCN_BIGRU_RES=0 for the 3xTF32 streaming kernels", (flags[1] >> 1) & 1u,
-                  (flags[3] >> 1) & 1u);
-        return 1;
+        if (!(rc & 1))
+            set_error("a recurrent weight (|w| >= 255) or activation (>= 65504) left the range of the fp16-split gate tiles (bigru=%u, "
+                      "segment=%u): the results of that call are invalid; rerun with dims.no_fp16_split = 1 (3xTF32 streaming kernels)",
+                      (flags[1] >> 1) & 1u, (flags[3] >> 1) & 1u);
+        rc |= 2;
     }
-    return 0;
+    return rc;
 }
 
 int tggcn_geo_gcn_fwd(const float* x_human, const void* const* weights, float* out, float* bn_running_mean,
@@ -282,6 +311,7 @@ static int forward_impl(const tggcn_dims* dims, const void* const* weights, int 
             TG_REQUIRE(P.g[i].whh[0] && P.g[i].whh[1] && P.g[i].bhh[0] && P.g[i].bhh[1], "forward: BiGRU weights missing");
         }
         P.sync.counter = sync; P.sync.error = sync + 1;
+        P.no_fp16_split = d.no_fp16_split;
         if (int rc = launch_bigru(P, d.persistent, stream)) return rc;
     }
     STAGE_END();
@@ -369,6 +399,7 @@ static int forward_impl(const tggcn_dims* dims, const void* const* weights, int 
         P.att_f = d.inspect ? io->att_seg_f : nullptr;
         P.att_b = d.inspect ? io->att_seg_b : nullptr;
         P.sync.counter = sync + 2; P.sync.error = sync + 3;
+        P.no_fp16_split = d.no_fp16_split;
         if (int rc = launch_segment(P, d.persistent, stream)) return rc;
     }
     STAGE_END();
@@ -391,6 +422,8 @@ static int forward_impl(const tggcn_dims* dims, const void* const* weights, int 
     }
     STAGE_END();
 #undef STAGE_END
+    if (io->status_host != nullptr)
+        TG_CUDA_OK(cudaMemcpyAsync(io->status_host, sync, 8 * sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
     return 0;
 }
 

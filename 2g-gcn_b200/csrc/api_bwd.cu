@@ -492,6 +492,8 @@ int tggcn_backward(const tggcn_dims* dims, const void* const* weights, void* con
         if (int rc = launch_geo_bn_bwd(io->x_human, P.dxn, P.mean, P.var, P.gamma, G(TGGCN_W_GCN_BN_W), G(TGGCN_W_GCN_BN_B), B, T, H, V, d.Fh,
                                        stream)) return rc;
     }
+    if (io->status_host != nullptr)
+        TG_CUDA_OK(cudaMemcpyAsync(io->status_host, buf(TGGCN_BUF_SYNC), 8 * sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
     return 0;
 }
 

@@ -320,11 +320,7 @@ int launch_frame_bwd(const FrameBwdParams& P, cudaStream_t stream) {
     const int nkh = P.hh ? 2 : 1;
     const size_t smem = sizeof(float) * ((size_t)(P.H + P.O) * 4 * P.D + (size_t)P.H * nkh * P.D + (size_t)P.O * 3 * P.D);
     TG_REQUIRE(smem <= 200 * 1024, "frame_bwd: shape needs %zu bytes of shared memory", smem);
-    static size_t configured = 0;
-    if (smem > configured) {
-        TG_CUDA_OK(cudaFuncSetAttribute(frame_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = smem;
-    }
+    if (int rc = ensure_smem((const void*)frame_bwd_kernel, smem)) return rc;
     frame_bwd_kernel<<<P.B * P.T, 256, smem, stream>>>(P);
     TG_LAUNCH_OK();
     return 0;

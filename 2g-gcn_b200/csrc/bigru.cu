@@ -115,11 +115,7 @@ int launch_bigru(BiGruParams& P, int persistent, cudaStream_t stream) {
     const int fa = tile_smem_floats(3, 4, 3), fb = tile_smem_floats(3, 2, 4);
     const size_t smem = sizeof(float) * (size_t)(fa > fb ? fa : fb);
     auto kern = bigru_kernel;
-    static bool configured = false;
-    if (!configured) {
-        TG_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = true;
-    }
+    if (int rc = ensure_smem((const void*)kern, smem)) return rc;
     int per_sm = 0;
     TG_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, REC_THREADS, smem));
     TG_REQUIRE(per_sm >= 1, "bigru: kernel does not fit on an SM (smem %zu)", smem);

@@ -20,6 +20,7 @@ struct BiGruParams {
     int ngroups;
     int B, T, D;
     int total_tiles;
+    int no_fp16_split;      // 1: never the SMEM-resident fp16-split variant (dims.no_fp16_split)
     GridSync sync;
 };
 
@@ -78,6 +79,7 @@ struct SegParams {
     int res_multi;                // resident-weight variant, larger batches: tiles are weight slices, row / video blocks are walked inside the CTA
     int res_msg;                  // resident-weight variant: message-tile weights are kept in shared memory too
     int res_ring_floats;          // resident-weight variant: floats of the cp.async ring that precede the overflow fragments in shared memory
+    int no_fp16_split;            // 1: never the on-chip resident fp16-split variant (dims.no_fp16_split)
     GridSync sync;
 };
 

@@ -276,7 +276,7 @@ int launch_bigru_resident(BiGruParams& P, cudaStream_t stream) {
         enabled = (e != nullptr && e[0] == '0') ? 0 : 1;
     }
     const int D = P.D;
-    if (!enabled || D % 64 != 0) return -1;
+    if (!enabled || P.no_fp16_split || D % 64 != 0) return -1;
     const int LD = D + 8;
     const size_t red_floats = (size_t)REC_WARPS * BR_ACC * 32, stage_floats = (size_t)BR_ROWS * LD;
     const size_t smem = sizeof(float) * ((size_t)BR_NT * 8 * LD + (red_floats > stage_floats ? red_floats : stage_floats));
@@ -301,11 +301,7 @@ int launch_bigru_resident(BiGruParams& P, cudaStream_t stream) {
         grid += 2 * rgs[i] * ctas_per_gd;
     }
     auto kern = bigru_res_kernel;
-    static size_t configured = 0;
-    if (smem > configured) {
-        TG_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = smem;
-    }
+    if (int rc = ensure_smem((const void*)kern, smem)) return rc;
     int per_sm = 0;
     TG_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, REC_THREADS, smem));
     if (per_sm < 1 || grid > per_sm * num_sms()) return -1;

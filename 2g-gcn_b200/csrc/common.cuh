@@ -52,7 +52,10 @@ bool debug_sync();   // TGGCN_DEBUG_SYNC=1: synchronise after every launch so an
 inline int cdiv(int a, int b) { return (a + b - 1) / b; }
 inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
-int num_sms();   // cached SM count of the current device
+int num_sms();   // SM count of the CURRENT device (cached per device)
+// Raise a kernel's dynamic shared-memory limit to `bytes` on the CURRENT device if it is lower (function attributes are
+// per device: the cache is keyed by (device, function)).
+int ensure_smem(const void* func, size_t bytes);
 
 // ---------------------------------------------------------------------------------------------
 // device helpers

@@ -202,11 +202,7 @@ int launch_frame_messages(const FrameMsgParams& P, cudaStream_t stream) {
     TG_REQUIRE(P.O >= 2 && (!P.hh || P.H >= 2), "frame_messages: need >=2 objects (and >=2 humans with humans->human)");
     const size_t smem = frame_messages_smem(P.H, P.O, P.D, P.hh);
     TG_REQUIRE(smem <= 200 * 1024, "frame_messages: shape needs %zu bytes of shared memory", smem);
-    static size_t configured = 0;
-    if (smem > configured) {
-        TG_CUDA_OK(cudaFuncSetAttribute(frame_messages_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = smem;
-    }
+    if (int rc = ensure_smem((const void*)frame_messages_kernel, smem)) return rc;
     frame_messages_kernel<<<P.B * P.T, FM_THREADS, smem, stream>>>(P);
     TG_LAUNCH_OK();
     return 0;

@@ -273,14 +273,10 @@ int launch_gemm_tc(GemmGroup& grp, cudaStream_t stream) {
     }
     bool mask = false;
     for (int i = 0; i < grp.count; ++i) mask |= grp.p[i].amask != nullptr;
-    static bool configured = false;
-    if (!configured) {
-        TG_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<false, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<128>::SMEM_BYTES));
-        TG_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<true, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<128>::SMEM_BYTES));
-        TG_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<false, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<256>::SMEM_BYTES));
-        TG_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<true, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<256>::SMEM_BYTES));
-        configured = true;
-    }
+    if (int rc = ensure_smem((const void*)gemm_tc_kernel<false, 128>, TcCfg<128>::SMEM_BYTES)) return rc;
+    if (int rc = ensure_smem((const void*)gemm_tc_kernel<true, 128>, TcCfg<128>::SMEM_BYTES)) return rc;
+    if (int rc = ensure_smem((const void*)gemm_tc_kernel<false, 256>, TcCfg<256>::SMEM_BYTES)) return rc;
+    if (int rc = ensure_smem((const void*)gemm_tc_kernel<true, 256>, TcCfg<256>::SMEM_BYTES)) return rc;
     if (bn == 256) {
         if (mask) gemm_tc_kernel<true, 256><<<begin, TC_THREADS, TcCfg<256>::SMEM_BYTES, stream>>>(grp);
         else      gemm_tc_kernel<false, 256><<<begin, TC_THREADS, TcCfg<256>::SMEM_BYTES, stream>>>(grp);

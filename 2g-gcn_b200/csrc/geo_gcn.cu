@@ -314,11 +314,7 @@ int launch_geo_gcn(const float* x_human, const void* const* w, float* out, float
     p.out = out;
     p.B = B; p.T = T; p.H = H; p.V = V; p.Fh = Fh;
     const size_t smem = geo_gcn_smem_bytes(V);
-    static size_t configured = 0;
-    if (smem > configured) {
-        TG_CUDA_OK(cudaFuncSetAttribute(geo_gcn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = smem;
-    }
+    if (int rc = ensure_smem((const void*)geo_gcn_kernel, smem)) return rc;
     const int tiles = cdiv(T, GCN_TT);
     geo_gcn_kernel<<<B * tiles, GCN_THREADS, smem, stream>>>(p);
     TG_LAUNCH_OK();

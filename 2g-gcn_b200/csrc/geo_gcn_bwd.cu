@@ -305,11 +305,7 @@ __global__ void __launch_bounds__(256) geo_bn_bwd_kernel(const float* __restrict
 int launch_geo_gcn_bwd(const GcnBwdParams& P, cudaStream_t stream) {
     TG_REQUIRE(P.V >= 1 && P.V <= 32, "geo_gcn_bwd: gcn_node=%d unsupported", P.V);
     const size_t smem = sizeof(float) * (size_t)P.V * (4 + GB_LD + GB_LD + GB_LDT + GB_LDS + GB_LD + GB_LDO + GB_LD + GB_LDS + GB_LD + GB_LDT + GB_LD);
-    static size_t configured = 0;
-    if (smem > configured) {
-        TG_CUDA_OK(cudaFuncSetAttribute(geo_gcn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = smem;
-    }
+    if (int rc = ensure_smem((const void*)geo_gcn_bwd_kernel, smem)) return rc;
     const int fpc = cdiv(P.B * P.T, num_sms());          // frames per CTA: one wave, the register partials are flushed once per CTA
     geo_gcn_bwd_kernel<<<cdiv(P.B * P.T, fpc), GB_THREADS, smem, stream>>>(P, fpc);
     TG_LAUNCH_OK();

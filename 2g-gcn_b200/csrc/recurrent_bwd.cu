@@ -481,11 +481,7 @@ int launch_bigru_bwd(BiGruBwdParams& P, int persistent, cudaStream_t stream) {
     TG_REQUIRE(P.D % 16 == 0, "bigru_bwd: hidden_size=%d must be a multiple of 16", P.D);
     auto kern = bigru_bwd_kernel;
     const size_t smem = sizeof(float) * (size_t)tile_smem_floats(2, 4, 3);
-    static bool configured = false;
-    if (!configured) {
-        TG_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = true;
-    }
+    if (int rc = ensure_smem((const void*)kern, smem)) return rc;
     int per_sm = 0;
     TG_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, REC_THREADS, smem));
     TG_REQUIRE(per_sm >= 1, "bigru_bwd: kernel does not fit on an SM (smem %zu)", smem);
@@ -529,11 +525,7 @@ int launch_segment_bwd(SegBwdParams& P, int persistent, cudaStream_t stream) {
     const size_t smem_b = sizeof(float) * (size_t)4 * (H > O ? H : O) * D;
     if (smem_b > smem) smem = smem_b;
     TG_REQUIRE(smem <= 200 * 1024, "segment_bwd: hidden_size=%d needs %zu bytes of shared memory", D, smem);
-    static size_t configured = 0;
-    if (smem > configured) {
-        TG_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = smem;
-    }
+    if (int rc = ensure_smem((const void*)kern, smem)) return rc;
     int per_sm = 0;
     TG_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, REC_THREADS, smem));
     TG_REQUIRE(per_sm >= 1, "segment_bwd: kernel does not fit on an SM (smem %zu)", smem);
@@ -553,7 +545,9 @@ int launch_segment_bwd(SegBwdParams& P, int persistent, cudaStream_t stream) {
         if (grid > capacity) grid = capacity;
         TG_CUDA_OK(cudaMemsetAsync(P.sync.counter, 0, 2 * sizeof(unsigned int), stream));
         int s0 = -1, s1 = P.T, phases = 7, pers = 1;
-        if (const char* e = getenv("TGGCN_SEGBWD_PHASES")) phases = atoi(e);   // timing experiments only (results are garbage)
+#ifdef TGGCN_TIMING_EXPERIMENTS      // never in the product build: skipping a phase leaves the gradients undefined
+        if (const char* e = getenv("TGGCN_SEGBWD_PHASES")) phases = atoi(e);
+#endif
         void* args[] = {(void*)&P, (void*)&s0, (void*)&s1, (void*)&phases, (void*)&pers};
         TG_CUDA_OK(cudaLaunchCooperativeKernel((const void*)kern, dim3(grid), dim3(REC_THREADS), args, smem, stream));
         ++g_launches;

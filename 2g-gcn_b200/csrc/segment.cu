@@ -462,11 +462,13 @@ int launch_segment(SegParams& P, int persistent, cudaStream_t stream) {
     if (fr > fa) fa = fr;
     // variant: 1 = tcgen05 gate tile (opt-in), 2 = cell weights resident on chip (every CTA owns at most one cell tile and the
     // per-thread fragment words fit in tensor memory + overflow), 0 = streaming
-    static int res_env = -1;
-    if (res_env < 0) {
+    static int res_env_cached = -1;
+    int& res_env_ref = res_env_cached;
+    if (res_env_ref < 0) {
         const char* e = getenv("TGGCN_SEG_RES");
-        res_env = (e != nullptr && e[0] == '0') ? 0 : 1;
+        res_env_ref = (e != nullptr && e[0] == '0') ? 0 : 1;
     }
+    const int res_env = P.no_fp16_split ? 0 : res_env_cached;
     int mode = rec_use_tc(D) ? 1 : 0;
     const int kmax = (P.nk_h > 2 ? P.nk_h : 2) * D + D;
     const bool res_fits = cdiv(kmax / REC_CK, REC_WARPS) * RES_CHUNK_WORDS <= RES_TMEM_WORDS + RES_SMEM_WORDS;
@@ -522,17 +524,18 @@ int launch_segment(SegParams& P, int persistent, cudaStream_t stream) {
     P.res_ring_floats = fa;
     auto kern = mode == 1 ? segment_kernel<1> : (mode == 2 ? segment_kernel<2> : segment_kernel<0>);
     const int threads = mode == 1 ? RTC_THREADS : REC_THREADS;
-    const size_t smem = mode == 1 ? (size_t)RTC_SMEM_BYTES
-                                  : sizeof(float) * (size_t)fa + (mode == 2 ? sizeof(float) * RES_SMEM_WORDS * REC_THREADS : 0)
-                                        + (P.res_msg ? (size_t)cdiv(D / REC_CK, REC_WARPS) * RES_MSG_GROUPS * 2 * REC_THREADS * 16 : 0);
-    static size_t configured[3] = {0, 0, 0};
-    if (smem > configured[mode]) {
-        TG_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured[mode] = smem;
-    }
+    size_t smem = mode == 1 ? (size_t)RTC_SMEM_BYTES
+                            : sizeof(float) * (size_t)fa + (mode == 2 ? sizeof(float) * RES_SMEM_WORDS * REC_THREADS : 0)
+                                  + (P.res_msg ? (size_t)cdiv(D / REC_CK, REC_WARPS) * RES_MSG_GROUPS * 2 * REC_THREADS * 16 : 0);
+    // The resident variant allocates all 512 tensor-memory columns of its SM: a second CTA of this kernel on the same SM would
+    // block in tcgen05.alloc while the first one spins at the grid barrier.  Requesting more than half of the SM's shared memory
+    // makes co-residency impossible at small hidden sizes too (2 x (116 KB + static + 1 KB reserved) > 228 KB).
+    if (mode == 2 && smem < 116 * 1024) smem = 116 * 1024;
+    if (int rc = ensure_smem((const void*)kern, smem)) return rc;
     int per_sm = 0;
     TG_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, smem));
     TG_REQUIRE(per_sm >= 1, "segment: kernel does not fit on an SM (smem %zu)", smem);
+    TG_REQUIRE(mode != 2 || per_sm == 1, "segment: the tensor-memory resident variant must own its SM (occupancy %d)", per_sm);
     const int capacity = per_sm * num_sms();
 
     if (persistent) {
@@ -540,7 +543,9 @@ int launch_segment(SegParams& P, int persistent, cudaStream_t stream) {
         if (grid > capacity) grid = capacity;
         TG_CUDA_OK(cudaMemsetAsync(P.sync.counter, 0, 2 * sizeof(unsigned int), stream));
         int s0 = 0, s1 = P.T, phases = 3, pers = 1;
-        if (const char* e = getenv("TGGCN_SEG_PHASES")) phases = atoi(e);      // timing experiments only (results are garbage)
+#ifdef TGGCN_TIMING_EXPERIMENTS      // never in the product build: skipping a phase leaves the outputs undefined
+        if (const char* e = getenv("TGGCN_SEG_PHASES")) phases = atoi(e);
+#endif
         void* args[] = {(void*)&P, (void*)&s0, (void*)&s1, (void*)&phases, (void*)&pers};
         TG_CUDA_OK(cudaLaunchCooperativeKernel((const void*)kern, dim3(grid), dim3(threads), args, smem, stream));
         ++g_launches;

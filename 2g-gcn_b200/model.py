@@ -210,6 +210,11 @@ class TGGCN(nn.Module):
         self.flat_grad = None
         self.persistent_kernels = True      # False: one launch per recurrent step (debug aid)
         self.gemm_path = 2                  # 0: fp32 SIMT projections; 1: tcgen05 3xTF32; 2: tcgen05 where K % 32 == 0
+        self.recurrent_mode = int(os.environ.get('TGGCN_RECURRENT_MODE', '0'))   # dims.recurrent_mode (0 = by rows per step)
+        self.no_fp16_split = False          # set after a range violation: 3xTF32 streaming recurrent kernels from then on
+        self.precision = 0                  # dims.precision: 0 = fp32-class split products, 1 = bf16 operands (set_precision)
+        self._pending_status = []           # (event, pinned status words, what) of calls whose status has not been looked at
+        self._status_pool = []              # pinned 8-word buffers ready for reuse
 
     # ------------------------------------------------------------------------------------------------
     def set_gumbel_noise(self, noise: Optional[torch.Tensor]):
@@ -217,6 +222,47 @@ class TGGCN(nn.Module):
         order (t-major; sampled humans, then sampled objects).  ``None`` restores the default, which draws
         from the global CPU generator exactly like pyrutils/torch/distributions.py:16 does."""
         self._noise_override = noise
+
+    def set_precision(self, precision: str):
+        """'fp32' (default): every matrix product is a 3-term split MMA with fp32-class accuracy — the configuration all parity
+        tests run.  'bf16': projections and the large-batch recurrent kernels round their operands to bf16 and accumulate in
+        fp32 (BASELINE.json configs[2], "training step bf16"); gates, softmaxes, losses and the optimiser state stay fp32."""
+        if precision not in ('fp32', 'bf16'):
+            raise ValueError("precision must be 'fp32' or 'bf16'")
+        self.precision = 1 if precision == 'bf16' else 0
+        return self
+
+    # -- status words of the persistent kernels -------------------------------------------------------------------------
+    def _queue_status(self, io, dev, what):
+        """Give the call a pinned landing zone for its status words; they are looked at by a LATER call (or by
+        check_persistent_kernels), so the check costs no synchronisation on the hot path."""
+        words = self._status_pool.pop() if self._status_pool else torch.zeros(8, dtype=torch.int32).pin_memory()
+        io.status_host = words.data_ptr()
+        return (torch.cuda.Event(), words, what)
+
+    def _poll_status(self, wait: bool = False):
+        """Test the status words of earlier calls whose copy has landed (all of them when ``wait``).  A grid-barrier time-out
+        or an fp16-split range violation raises — results of that call were wrong; after a range violation the model switches
+        itself to the 3xTF32 streaming kernels, so a caller that catches the error can simply repeat the step."""
+        still = []
+        err = None
+        for ev, words, what in self._pending_status:
+            if wait:
+                ev.synchronize()
+            if not ev.query():
+                still.append((ev, words, what))
+                continue
+            rc = abi.lib().tggcn_status_decode(C.c_void_p(words.data_ptr()))
+            self._status_pool.append(words)
+            if rc != 0 and err is None:
+                msg = abi.lib().tggcn_last_error().decode(errors='replace')
+                if rc & 2:
+                    self.no_fp16_split = True
+                    msg += ' — this model now runs the 3xTF32 streaming recurrent kernels (no_fp16_split); repeat the step'
+                err = abi.TggcnError(f'{what}: {msg}')
+        self._pending_status = still
+        if err is not None:
+            raise err
 
     def _apply(self, fn, *args, **kwargs):
         self._ptr_cache = None
@@ -301,6 +347,7 @@ class TGGCN(nn.Module):
             raise NotImplementedError('distance-based attention (misc.make_attention_distance_based) is not supported')
         if not x_human.is_cuda:
             raise abi.TggcnError('2G-GCN B200 path runs on a CUDA device only (no CPU fallback); got a CPU tensor')
+        self._poll_status()                 # status words of earlier calls that have landed by now
         dev = x_human.device
         B, T, H, Fh = x_human.shape
         O = x_objects.size(2)
@@ -325,7 +372,8 @@ class TGGCN(nn.Module):
                         inspect=int(bool(inspect_model)), persistent=int(self.persistent_kernels),
                         gemm_path=int(self.gemm_path), thr=self.update_segment_threshold,
                         save_for_backward=int(with_grad), cat_level_states=int(self.cat_level_states),
-                        mean_pool=int(self.message_aggregation in _MP))
+                        mean_pool=int(self.message_aggregation in _MP), recurrent_mode=int(self.recurrent_mode),
+                        no_fp16_split=int(self.no_fp16_split), precision=int(self.precision))
         n_sampled = (0 if hseg is not None else H) + (0 if oseg is not None else O)
         noise = None
         if n_sampled:
@@ -360,6 +408,7 @@ class TGGCN(nn.Module):
 
             ws = self._workspace(dims, dev)
             weights = self._weight_pointers(dev)
+            pending = self._queue_status(io, dev, 'forward')
             with torch.cuda.device(dev):
                 stream = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
                 if stage_ms is None:
@@ -369,6 +418,8 @@ class TGGCN(nn.Module):
                     rc = abi.lib().tggcn_forward_profile(C.byref(dims), weights, abi.N_WEIGHTS, C.byref(io), ws.data_ptr(),
                                                          ws.numel(), stream, stage_ms)
             abi.check(rc, 'tggcn_forward')
+            pending[0].record(torch.cuda.current_stream(dev))
+            self._pending_status.append(pending)
             # keep inputs alive until the queued work ran
             keep = (x_human, x_objects, objects_mask, hseg, oseg, noise)
             self._last = (dims, ws, keep)
@@ -456,11 +507,14 @@ class TGGCN(nn.Module):
             go.d_out_o[j] = ptr
         bws = self._workspace(dims, dev, backward=True)
         weights = self._weight_pointers(dev)
+        pending = self._queue_status(io, dev, 'backward')
         with torch.cuda.device(dev):
             stream = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
             rc = abi.lib().tggcn_backward(C.byref(dims), weights, garr, abi.N_WEIGHTS, C.byref(io), C.byref(go), ws.data_ptr(),
                                           ws.numel(), bws.data_ptr(), bws.numel(), stream)
         abi.check(rc, 'tggcn_backward')
+        pending[0].record(torch.cuda.current_stream(dev))
+        self._pending_status.append(pending)
         self._last_bwd = (keep, bws)
         self.flat_grad, self._flat_views = flat, (params, grads)
         return grads
@@ -481,7 +535,10 @@ class TGGCN(nn.Module):
         return ws[off:off + nbytes].view(dtype)[:math.prod(shape)].view(*shape)
 
     def check_persistent_kernels(self):
-        """Raise if a grid barrier of the persistent kernels timed out during the last forward."""
+        """Wait for every call queued so far and raise if one of them reported a grid-barrier time-out or an fp16-split range
+        violation.  forward() / backward() run the same test on their own for calls that have already finished; this is the
+        synchronous form (end of an epoch, end of predict.py's loop, tests)."""
+        self._poll_status(wait=True)
         dims, ws, _ = self._last
         stream = torch.cuda.current_stream(ws.device).cuda_stream
         abi.check(abi.lib().tggcn_sync_status(C.byref(dims), ws.data_ptr(), C.c_void_p(stream)), 'persistent kernels')

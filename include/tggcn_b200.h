@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define TGGCN_ABI_VERSION 4
+#define TGGCN_ABI_VERSION 5
 
 #if defined(__GNUC__)
 #define TGGCN_API __attribute__((visibility("default")))
@@ -53,6 +53,14 @@ typedef struct tggcn_dims {
                                     weights are (C, 4D) instead of (C, 2D)                              */
     int32_t mean_pool;           /* message_aggregation 'mp': senders averaged with weight mask / max(#valid, 1) instead of
                                     the scaled-dot-product attention (models.py:1033-1036 and the other message functions) */
+    int32_t recurrent_mode;      /* recurrent kernels (BiGRU + segment level): 0 = choose by rows per step, 1 = latency path
+                                    (persistent mma.sync kernels, weights resident on chip where they fit), 2 = large-batch path
+                                    (one tcgen05 + TMA step kernel per recurrent step, activation rows as the UMMA M operand)  */
+    int32_t no_fp16_split;       /* 1 = never use the fp16 (hi, lo) operand split in the recurrent kernels (3xTF32 streaming
+                                    tiles only); set by the host after a range violation was reported in the status words     */
+    int32_t precision;           /* 0 = fp32-class products everywhere (3-term split MMAs; the parity configuration),
+                                    1 = bf16 operands with fp32 accumulation in the projections and the large-batch recurrent
+                                    kernels (BASELINE.json configs[2]); gate / softmax / loss arithmetic stays fp32           */
 } tggcn_dims;
 
 /* Parameter table.  One device pointer per reference state_dict() entry, in this order
@@ -192,6 +200,9 @@ typedef struct tggcn_io {
     float* bn_running_mean;      /* (4V) updated in place when bn_train                                  */
     float* bn_running_var;       /* (4V) updated in place when bn_train                                  */
     int64_t* bn_num_batches;     /* scalar, incremented when bn_train                                    */
+    uint32_t* status_host;       /* PINNED HOST memory, 8 words, or NULL.  When set, tggcn_forward / tggcn_backward end with an
+                                    asynchronous copy of the status words (see tggcn_status_decode) into it, so the caller can
+                                    test them after any later synchronisation point without an extra round trip.           */
 } tggcn_io;
 
 /* Named regions of the workspace, exposed so that tests can compare intermediates with the oracle. */
@@ -250,9 +261,13 @@ TGGCN_API size_t tggcn_workspace_bytes(const tggcn_dims* dims);
 /* Offset/size of one named region inside the workspace (for tests / debugging). */
 TGGCN_API int    tggcn_workspace_view(const tggcn_dims* dims, int buf_id, size_t* offset, size_t* bytes);
 
-/* Debug aid: 0 if no grid barrier of the persistent kernels timed out during the work queued so far on
- * `stream` for this workspace (synchronises the stream), 1 otherwise. */
+/* 0 if no grid barrier of the persistent kernels timed out and no operand left the range of the fp16-split tiles during the
+ * work queued so far on `stream` for this workspace (synchronises the stream), non-zero otherwise. */
 TGGCN_API int tggcn_sync_status(const tggcn_dims* dims, const void* workspace, void* stream);
+/* Interpret 8 status words (host memory, as delivered through tggcn_io.status_host): 0 = healthy; bit 0 of the result = a grid
+ * barrier timed out (results undefined), bit 1 = fp16-split range violation (|w| >= 255 or an activation >= 65504: results of
+ * that call are invalid; rerun with dims.no_fp16_split).  The message is available through tggcn_last_error(). */
+TGGCN_API int tggcn_status_decode(const uint32_t* status_words_host);
 
 /* The whole forward pass: replaces TGGCN.forward (vhoi/models.py:584-933).
  * `weights` holds TGGCN_W_COUNT device pointers ordered by enum tggcn_weight_id. */

@@ -61,7 +61,13 @@ CASES = [
     ('mphoi_s2_share', 'mphoi', 32, 2, 12, 2, False, 2.0, False, {'share_level_mlps': 1}),
     ('mphoi_s2_mp', 'mphoi', 32, 2, 12, 2, False, 2.0, False, {'message_aggregation': 'mp'}),
     ('cad120_s2_mp', 'cad120', 32, 2, 11, 2, False, 2.0, False, {'message_aggregation': 'mp'}),
+    # the benchmarked configuration itself (BASELINE.json configs[1]: MPHOI, B=8, T=128, hidden 512, stage-2 settings)
+    ('mphoi_s2_d512_full', 'mphoi', 512, 8, 128, 2, False, 1.0, False),
 ]
+
+# Decision margin demanded of a case's seeds.  6144 gates at the full size leave no seed with 1e-4 everywhere; the CUDA path
+# reproduces soft gates to ~1e-6, so 2e-5 still keeps every discrete decision off the knife edge.
+CASE_MARGIN = {'mphoi_s2_d512_full': 2e-5, 'grad_mphoi_s2_d512': 2e-5}
 
 
 def run_case(name, shape_name, D, B, T, stage, train_mode, gain, inspect, extra=None):
@@ -82,6 +88,18 @@ def run_case(name, shape_name, D, B, T, stage, train_mode, gain, inspect, extra=
         batch = pkg.make_batch(shape, B, T, seed=data_seed)
         n_calls = orc.num_noise_draws(T, shape.H, shape.O, stage == 1, stage == 1 and shape.dataset == 'cad120')
         noise = orc.draw_noise(max(n_calls, 1), B, torch.Generator().manual_seed(noise_seed))[:n_calls]
+        if name in CASE_MARGIN and not train_mode:
+            # big cases: pre-screen both human and object gates on the oracle's early exit before paying for the reference
+            with torch.no_grad():
+                _, s_h, _, s_o = orc.forward({k: v.double() for k, v in sd.items()},
+                                             orc.OracleConfig(D, shape.V, shape.num_classes, shape.hh, stage == 2, thr),
+                                             batch['x_human'].double(), batch['x_objects'].double(), batch['objects_mask'].double(),
+                                             None, None, noise.double(), gates_only=True)
+            pre = 1.0
+            for sft in (s_h, s_o):
+                pre = min(pre, float((sft - thr).abs().min()), float((sft[:, 1:] - sft[:, :-1]).abs().min()))
+            if pre <= CASE_MARGIN[name]:
+                continue
         it = iter(noise)
 
         def injected(p, temperature=1.0):
@@ -110,7 +128,7 @@ def run_case(name, shape_name, D, B, T, stage, train_mode, gain, inspect, extra=
             margin = min(margin, float((s - thr).abs().min()))
             if stage == 2:
                 margin = min(margin, float((s[:, 1:] - s[:, :-1]).abs().min()))
-        if margin > 1e-4:
+        if margin > CASE_MARGIN.get(name, 1e-4):
             break
     else:
         raise RuntimeError(f'no seed with a safe gate margin for {name}')
@@ -124,7 +142,7 @@ def run_case(name, shape_name, D, B, T, stage, train_mode, gain, inspect, extra=
                       batch['objects_mask'].double(), None if hseg is None else hseg.double(),
                       None if oseg is None else oseg.double(), noise.double(), training=train_mode, taps=taps)
     o_margin = float((taps['y_oss'] - thr).abs().min()) if oseg is None else 1.0
-    if o_margin <= 1e-4:
+    if o_margin <= CASE_MARGIN.get(name, 1e-4):
         raise RuntimeError(f'{name}: object gate margin too small ({o_margin}); change seeds')
     worst = max(float((a.double() - b).abs().max()) for a, b in zip(out, o64))
     print(f'{name:20s} seeds=({data_seed},{noise_seed}) gate margin={min(margin, o_margin):.2e} '
@@ -141,7 +159,8 @@ def run_case(name, shape_name, D, B, T, stage, train_mode, gain, inspect, extra=
     blob = {f'out{i}': o.numpy() for i, o in enumerate(out)}
     blob['losses'] = np.array([float(l) for l in losses], dtype=np.float64)
     blob['f1'] = np.array(f1, dtype=np.float64)
-    blob['gcn_out'] = captured['gcn_out'].numpy()
+    if name not in CASE_MARGIN:          # 13.6 MB at the full size; the small cases pin the GCN output
+        blob['gcn_out'] = captured['gcn_out'].numpy()
     blob['meta'] = np.array([data_seed, noise_seed, 900 + attempt, 7], dtype=np.int64)
     blob['gain'] = np.array([gain])
     blob['weights_checksum'] = np.array([pkg.state_checksum(sd)])
@@ -168,6 +187,8 @@ GRAD_CASES = [
     ('grad_mphoi_s2_share', 'mphoi', 32, 2, 9, 2, 2.0, {'share_level_mlps': 1}),
     ('grad_mphoi_s2_mp', 'mphoi', 32, 2, 9, 2, 2.0, {'message_aggregation': 'mp'}),
     ('grad_cad120_s2_mp', 'cad120', 32, 2, 8, 2, 2.0, {'message_aggregation': 'mp'}),
+    # hidden 512 (the benchmarked width), T = 32: the D=512 BPTT and split-K weight-gradient paths against the reference itself
+    ('grad_mphoi_s2_d512', 'mphoi', 512, 8, 32, 2, 1.0),
 ]
 
 
@@ -241,7 +262,7 @@ def run_grad_case(name, shape_name, D, B, T, stage, gain, extra=None):
             margin = min(margin, float((sft - thr).abs().min()))
             if stage == 2:
                 margin = min(margin, float((sft[:, 1:] - sft[:, :-1]).abs().min()))
-        if margin > 1e-4 and (name not in RELU_STABLE_CASES or _relu_margin(p64, ocfg, batch, hseg, oseg, noise, n_calls) > 2e-5):
+        if margin > CASE_MARGIN.get(name, 1e-4) and (name not in RELU_STABLE_CASES or _relu_margin(p64, ocfg, batch, hseg, oseg, noise, n_calls) > 2e-5):
             break
     else:
         raise RuntimeError(f'no safe seed for {name}')

@@ -190,7 +190,7 @@ def reorder(hx: Tensor, u: Tensor) -> Tensor:
 def forward(p: Dict[str, Tensor], cfg: OracleConfig, x_human: Tensor, x_objects: Tensor, objects_mask: Tensor,
             human_segmentation: Optional[Tensor] = None, objects_segmentation: Optional[Tensor] = None,
             noise: Optional[Tensor] = None, training: bool = False, inspect_model: bool = False,
-            taps: Optional[dict] = None):
+            taps: Optional[dict] = None, gates_only: bool = False):
     """TGGCN.forward, vhoi/models.py:584-933, for the shipped configuration family
     (message_type v2, granularity v1, attention aggregation style v3, update strategy 'ind',
     gumbel-sigmoid gates, message_segment on, geometry->objects on, geometry->human off).
@@ -198,7 +198,9 @@ def forward(p: Dict[str, Tensor], cfg: OracleConfig, x_human: Tensor, x_objects:
     ``noise``: (n_calls, B, 2) Gumbel(0,1) draws consumed in the reference's call order
     (t-major; humans then objects; only entities whose segmentation is not given), or None to draw
     from the global CPU generator per call like pyrutils/torch/distributions.py:16.
-    ``taps``: optional dict that receives named intermediates (kernel-level parity tests)."""
+    ``taps``: optional dict that receives named intermediates (kernel-level parity tests).
+    ``gates_only``: stop after the frame-level part and return (y_hs, y_hss, y_os, y_oss) — used by the seed search of the
+    full-size parity cases (tools/find_safe_seeds.py), which only needs the gate margins."""
     D, V, thr = cfg.hidden_size, cfg.gcn_node, cfg.update_segment_threshold
     hh_on = cfg.message_humans_to_human
     B, T, H, _ = x_human.shape
@@ -289,6 +291,8 @@ def forward(p: Dict[str, Tensor], cfg: OracleConfig, x_human: Tensor, x_objects:
     if cfg.filter_discrete_updates:
         y_hs = torch.stack([filter_soft(y_hss[..., h], thr) for h in range(H)], dim=-1)
         y_os = torch.stack([filter_soft(y_oss[..., k], thr) for k in range(O)], dim=-1)
+    if gates_only:
+        return y_hs, y_hss, y_os, y_oss
     tap('xx_h', torch.stack([torch.stack(r, dim=1) for r in xx_h], dim=2))       # (B,T,H,3D)
     tap('xx_o', torch.stack([torch.stack(r, dim=1) for r in xx_o], dim=2))       # (B,T,O,4D)
 

@@ -24,6 +24,12 @@ CASES = {
     'cad120_s2_mp': ('cad120', 32, 2, 11, 2, False, False, {'message_aggregation': 'mp'}),
 }
 
+# BASELINE.json configs[1] itself — what bench.py times (reference outputs; gate margin 2.5e-5).  Kept apart from CASES: the
+# tests that loop over CASES demand exact argmax equality and per-kernel taps, this one is compared in tests/test_gpu_fullsize.py.
+FULL_CASES = {
+    'mphoi_s2_d512_full': ('mphoi', 512, 8, 128, 2, False, False),
+}
+
 # name -> (shape, D, B, T, stage[, constructor overrides])   (mirrors oracle/gen_golden.py:GRAD_CASES)
 GRAD_CASES = {
     'grad_mphoi_s1': ('mphoi', 32, 2, 9, 1),
@@ -35,6 +41,7 @@ GRAD_CASES = {
     # seeds of these two also keep every ReLU pre-activation > 2e-5 from zero (oracle/gen_golden.py: RELU_STABLE_CASES)
     'grad_mphoi_s2_mp': ('mphoi', 32, 2, 9, 2, {'message_aggregation': 'mp'}),
     'grad_cad120_s2_mp': ('cad120', 32, 2, 8, 2, {'message_aggregation': 'mp'}),
+    'grad_mphoi_s2_d512': ('mphoi', 512, 8, 32, 2),       # hidden 512: compared in tests/test_gpu_fullsize.py
 }
 
 
@@ -52,8 +59,9 @@ class GoldenCase:
         import tggcn_oracle as orc
         synth = importlib.import_module('2g-gcn_b200.synth')
         self.name = name
-        shape_name, D, B, T, stage, train_mode, inspect = CASES[name][:7]
-        self.extra = CASES[name][7] if len(CASES[name]) > 7 else {}
+        spec = CASES[name] if name in CASES else FULL_CASES[name]
+        shape_name, D, B, T, stage, train_mode, inspect = spec[:7]
+        self.extra = spec[7] if len(spec) > 7 else {}
         self.shape = synth.SHAPES[shape_name]
         self.D, self.B, self.T, self.stage, self.train_mode, self.inspect = D, B, T, stage, train_mode, inspect
         self.blob = np.load(os.path.join(GOLDEN_DIR, name + '.npz'))

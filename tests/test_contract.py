@@ -69,10 +69,17 @@ def test_library_loads_and_exports_every_declared_symbol(pkg):
     lib = pkg.abi.lib()
     for sym in declared:
         assert hasattr(lib, sym), sym
-    assert lib.tggcn_abi_version() == 4
-    # struct mirrors: 17 int32 + 1 float + 3 int32; io = 6 + 4 + 8 + 3 + 3 pointers
-    assert ctypes.sizeof(pkg.abi.Dims) == 21 * 4
-    assert ctypes.sizeof(pkg.abi.IO) == 24 * 8
+    assert lib.tggcn_abi_version() == 5
+    # struct mirrors: 17 int32 + 1 float + 6 int32; io = 6 + 4 + 8 + 3 + 3 + 1 pointers
+    assert ctypes.sizeof(pkg.abi.Dims) == 24 * 4
+    assert ctypes.sizeof(pkg.abi.IO) == 25 * 8
+    # the status decoder is host-only: healthy words, a barrier time-out, an fp16-split range violation
+    words = (ctypes.c_uint32 * 8)()
+    assert lib.tggcn_status_decode(words) == 0
+    words[3] = 2
+    assert lib.tggcn_status_decode(words) == 2 and b'fp16-split' in lib.tggcn_last_error()
+    words[7] = 1
+    assert lib.tggcn_status_decode(words) == 3 and b'timed out' in lib.tggcn_last_error()
 
 
 def test_workspace_query_needs_no_gpu(pkg):

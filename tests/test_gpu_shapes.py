@@ -116,4 +116,30 @@ def test_fp16_split_range_violation_is_reported(pkg):
     torch.cuda.synchronize()
     with pytest.raises(pkg.abi.TggcnError, match='fp16-split'):
         model.check_persistent_kernels()
+    # ... and the model has switched itself to the 3xTF32 streaming kernels: repeating the step now works
+    assert model.no_fp16_split
+    with torch.no_grad():
+        out = model(**x)
+    model.check_persistent_kernels()
+    assert all(torch.isfinite(o).all() for o in out)
+
+
+def test_status_is_checked_without_an_explicit_call(pkg):
+    """The unchanged train.py / predict.py never call check_persistent_kernels(): a later forward must raise on its own
+    once the status words of the faulty call have landed (the status word was never read on the production path)."""
+    shape = pkg.synth.SHAPES['mphoi']
+    torch.manual_seed(0)
+    model = pkg.TGGCN(**pkg.synth.model_kwargs(shape, hidden_size=64, stage=2)).cuda().eval()
+    batch = pkg.synth.make_batch(shape, 4, 6, seed=3)
+    x = {k: batch[k].cuda() for k in ('x_human', 'x_objects', 'objects_mask')}
+    with torch.no_grad():
+        model.object_segment_rnn_bcell.weight_hh[1, 2] = -400.0
+        model(**x)
+        torch.cuda.synchronize()                    # any synchronisation point of the caller (e.g. reading the loss)
+        with pytest.raises(pkg.abi.TggcnError, match='fp16-split'):
+            model(**x)
+        out = model(**x)                            # recovered: streaming kernels
+        torch.cuda.synchronize()
+        model(**x)                                  # polls the recovered call's words: healthy
+    assert all(torch.isfinite(o).all() for o in out)
 

@@ -4,7 +4,7 @@ import numpy as np
 import pytest
 import torch
 
-from golden_util import CASES, GoldenCase
+from golden_util import CASES, FULL_CASES, GoldenCase
 import importlib
 
 
@@ -15,7 +15,7 @@ def _state(case, dtype):
     return {k: v.to(dtype) if v.is_floating_point() else v for k, v in sd.items()}
 
 
-@pytest.mark.parametrize('name', sorted(CASES))
+@pytest.mark.parametrize('name', sorted(CASES) + sorted(FULL_CASES))
 @pytest.mark.parametrize('dtype', [torch.float32, torch.float64])
 def test_oracle_matches_reference(name, dtype, orc):
     case = GoldenCase(name)
@@ -39,7 +39,7 @@ def test_oracle_matches_reference(name, dtype, orc):
             torch.testing.assert_close(a.float(), torch.from_numpy(case.blob[f'att{i}']), rtol=1e-4, atol=1e-6)
 
 
-@pytest.mark.parametrize('name', sorted(CASES))
+@pytest.mark.parametrize('name', sorted(CASES) + sorted(FULL_CASES))
 def test_oracle_losses_and_f1(name, orc):
     case = GoldenCase(name)
     losses = orc.multi_task_loss(case.outputs, case.targets, case.shape.dataset, case.stage)

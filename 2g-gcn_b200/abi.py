@@ -30,6 +30,13 @@ class GradOutputs(C.Structure):
                 ('d_out_h', C.c_void_p * 4), ('d_out_o', C.c_void_p * 4)]
 
 
+BWD_BUCKETS = 4          # TGGCN_BWD_BUCKETS
+
+
+class BwdHooks(C.Structure):
+    _fields_ = [('bucket_done', C.c_void_p * BWD_BUCKETS)]
+
+
 class IO(C.Structure):
     _fields_ = [
         ('x_human', C.c_void_p), ('x_objects', C.c_void_p), ('objects_mask', C.c_void_p),
@@ -120,6 +127,10 @@ def lib():
     L.tggcn_backward.restype = C.c_int
     L.tggcn_backward.argtypes = [C.POINTER(Dims), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.c_int, C.POINTER(IO),
                                  C.POINTER(GradOutputs), C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_void_p]
+    L.tggcn_backward_ex.restype = C.c_int
+    L.tggcn_backward_ex.argtypes = L.tggcn_backward.argtypes + [C.POINTER(BwdHooks)]
+    L.tggcn_backward_bucket.restype = C.c_int
+    L.tggcn_backward_bucket.argtypes = [C.c_int]
     L.tggcn_upsample_argmax.restype = C.c_int
     L.tggcn_upsample_argmax.argtypes = [C.c_void_p, C.c_void_p] + [C.c_int] * 6 + [C.c_void_p]
     L.tggcn_f1_at_k_scratch_bytes.restype = C.c_size_t

@@ -110,9 +110,24 @@ size_t tggcn_backward_workspace_bytes(const tggcn_dims* dims) {
     return L.total * sizeof(float);
 }
 
+int tggcn_backward_bucket(int id) {
+    if (id < 0 || id >= TGGCN_W_COUNT) return -1;
+    if (id <= TGGCN_W_GCN_S2_B) return 3;                                   // GCN_* (first 13 entries of the table)
+    if (id <= TGGCN_W_OBJ_EMB_B) return 2;                                  // geometry MLP, ROI embeddings
+    if (id >= TGGCN_W_HSEG_F_WIH || (id >= TGGCN_W_SMSG_HH_W && id <= TGGCN_W_SMSG_OO_B)) return 0;   // cells, heads, segment MLPs
+    return 1;
+}
+
 int tggcn_backward(const tggcn_dims* dims, const void* const* weights, void* const* grad_weights, int n_weights,
                    const tggcn_io* io, const tggcn_grad_outputs* grads, void* workspace, size_t workspace_bytes,
                    void* bwd_workspace, size_t bwd_workspace_bytes, void* stream_) {
+    return tggcn_backward_ex(dims, weights, grad_weights, n_weights, io, grads, workspace, workspace_bytes, bwd_workspace,
+                             bwd_workspace_bytes, stream_, nullptr);
+}
+
+int tggcn_backward_ex(const tggcn_dims* dims, const void* const* weights, void* const* grad_weights, int n_weights,
+                      const tggcn_io* io, const tggcn_grad_outputs* grads, void* workspace, size_t workspace_bytes,
+                      void* bwd_workspace, size_t bwd_workspace_bytes, void* stream_, const tggcn_bwd_hooks* hooks) {
     TG_REQUIRE(dims && weights && grad_weights && io && grads && workspace && bwd_workspace, "backward: null argument");
     TG_REQUIRE(n_weights == TGGCN_W_COUNT, "backward: expected %d weight pointers, got %d", (int)TGGCN_W_COUNT, n_weights);
     const tggcn_dims& d = *dims;
@@ -302,6 +317,8 @@ int tggcn_backward(const tggcn_dims* dims, const void* const* weights, void* con
         }
     }
 
+    if (hooks && hooks->bucket_done[0]) TG_CUDA_OK(cudaEventRecord((cudaEvent_t)hooks->bucket_done[0], stream));
+
     // ---- 10. hoisted frame-part of the segment cells: d xx = [dGs_f | dGs_b] [W_ih_f[:, :k] ; W_ih_b[:, :k]] -----------------------
     {
         float* wt = bb(BL.wt);
@@ -434,6 +451,8 @@ int tggcn_backward(const tggcn_dims* dims, const void* const* weights, void* con
         }
     }
 
+    if (hooks && hooks->bucket_done[1]) TG_CUDA_OK(cudaEventRecord((cudaEvent_t)hooks->bucket_done[1], stream));
+
     // ---- 3/2. embeddings (inputs are data: weight gradients only) and the geometry MLP ---------------------------------------------------
     {
         // x = ReLU(W roi + b) = S[:, :D]
@@ -458,6 +477,8 @@ int tggcn_backward(const tggcn_dims* dims, const void* const* weights, void* con
                                     2048, KV, 0, 0, 0, stream)) return rc;
         if (int rc = launch_colsum(bb(BL.dgeo_hid), 2048, buf(TGGCN_BUF_GEO_HID), 2048, G(TGGCN_W_GEO_MLP0_B), N, 2048, 0, stream)) return rc;
     }
+
+    if (hooks && hooks->bucket_done[2]) TG_CUDA_OK(cudaEventRecord((cudaEvent_t)hooks->bucket_done[2], stream));
 
     // ---- 1. geometry GCN ---------------------------------------------------------------------------------------------------------------------
     {
@@ -492,6 +513,7 @@ int tggcn_backward(const tggcn_dims* dims, const void* const* weights, void* con
         if (int rc = launch_geo_bn_bwd(io->x_human, P.dxn, P.mean, P.var, P.gamma, G(TGGCN_W_GCN_BN_W), G(TGGCN_W_GCN_BN_B), B, T, H, V, d.Fh,
                                        stream)) return rc;
     }
+    if (hooks && hooks->bucket_done[3]) TG_CUDA_OK(cudaEventRecord((cudaEvent_t)hooks->bucket_done[3], stream));
     if (io->status_host != nullptr)
         TG_CUDA_OK(cudaMemcpyAsync(io->status_host, buf(TGGCN_BUF_SYNC), 8 * sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
     return 0;

@@ -79,7 +79,7 @@ class _ForwardBackward(torch.autograd.Function):
     def forward(ctx, model, launch, *params):
         outputs, state = launch()
         ctx.model, ctx.state = model, state
-        ctx.n_out = len(outputs)
+        ctx.n_out, ctx.n_params = len(outputs), len(params)
         nondiff = [o for o, d in zip(outputs, state['differentiable']) if not d]
         if nondiff:
             ctx.mark_non_differentiable(*nondiff)
@@ -87,8 +87,10 @@ class _ForwardBackward(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, *gouts):
-        grads = ctx.model._backward(ctx.state, gouts)
-        return (None, None) + tuple(grads)
+        # _backward binds every parameter's .grad to its slice of the flat buffer itself (no AccumulateGrad copy of 182 MB, and
+        # the data-parallel reducer can start on a bucket while later stages still run); autograd gets no tensors to accumulate
+        ctx.model._backward(ctx.state, gouts)
+        return (None, None) + (None,) * ctx.n_params
 
 
 class TGGCN(nn.Module):
@@ -215,6 +217,10 @@ class TGGCN(nn.Module):
         self.precision = 0                  # dims.precision: 0 = fp32-class split products, 1 = bf16 operands (set_precision)
         self._pending_status = []           # (event, pinned status words, what) of calls whose status has not been looked at
         self._status_pool = []              # pinned 8-word buffers ready for reuse
+        self._bucket_events = {}            # device -> cudaEvents recorded by tggcn_backward_ex at the gradient-bucket boundaries
+        self._flat_pad_index = None
+        self.grad_buckets = []              # [(start, end, event)] slices of flat_grad in completion order (last backward)
+        self.grad_ready_callback = None     # called with the model once a backward has been queued (data-parallel reducer)
 
     # ------------------------------------------------------------------------------------------------
     def set_gumbel_noise(self, noise: Optional[torch.Tensor]):
@@ -466,12 +472,33 @@ class TGGCN(nn.Module):
         dims, io, ws = state['dims'], state['io'], state['ws']
         dev = ws.device
         names, params = self._trainable_table(dims)
-        sizes = [p.numel() for p in params]
-        offs, total = [], 0
-        for n in sizes:
-            offs.append(total)
-            total += (n + 3) // 4 * 4                    # keep every gradient 16-byte aligned
+        # flat layout: bucket by bucket in the order the backward completes them (tggcn_backward_bucket), so a data-parallel
+        # reducer can all-reduce bucket k as soon as its event has been recorded
+        bucket_of = [abi.lib().tggcn_backward_bucket(abi.WEIGHT_INDEX[n]) for n in names]
+        order = sorted(range(len(names)), key=lambda i: (bucket_of[i], i))
+        offs, total = [0] * len(names), 0
+        bucket_ranges = []
+        for k in range(abi.BWD_BUCKETS):
+            start = total
+            for i in order:
+                if bucket_of[i] == k:
+                    offs[i] = total
+                    total += (params[i].numel() + 3) // 4 * 4        # keep every gradient 16-byte aligned
+            total = (total + 63) // 64 * 64                          # buckets start on 256-byte boundaries
+            bucket_ranges.append((start, total))
         flat = torch.empty(total, dtype=torch.float32, device=dev)
+        sizes = [p.numel() for p in params]
+        key = (total, tuple(offs), str(dev))
+        if self._flat_pad_index is None or self._flat_pad_index[0] != key:
+            used = sorted(zip(offs, sizes))
+            gaps, pos = [], 0
+            for o, n in used:
+                gaps.extend(range(pos, o))
+                pos = o + n
+            gaps.extend(range(pos, total))
+            self._flat_pad_index = (key, torch.tensor(gaps, dtype=torch.int64, device=dev))
+        if self._flat_pad_index[1].numel():
+            flat.index_fill_(0, self._flat_pad_index[1], 0.0)        # alignment gaps take part in the all-reduce: keep them finite
         grads = [flat[o:o + n].view(p.shape) for o, n, p in zip(offs, sizes, params)]
         garr = (C.c_void_p * abi.N_WEIGHTS)()
         for name, g in zip(names, grads):
@@ -508,21 +535,38 @@ class TGGCN(nn.Module):
         bws = self._workspace(dims, dev, backward=True)
         weights = self._weight_pointers(dev)
         pending = self._queue_status(io, dev, 'backward')
+        hooks = abi.BwdHooks()
+        events = self._bucket_events.get(dev)
+        if events is None:
+            events = [torch.cuda.Event() for _ in range(abi.BWD_BUCKETS)]
+            for ev in events:
+                ev.record(torch.cuda.current_stream(dev))            # torch creates the cudaEvent_t lazily, at the first record
+            self._bucket_events[dev] = events
+        for k, ev in enumerate(events):
+            hooks.bucket_done[k] = ev.cuda_event
         with torch.cuda.device(dev):
             stream = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
-            rc = abi.lib().tggcn_backward(C.byref(dims), weights, garr, abi.N_WEIGHTS, C.byref(io), C.byref(go), ws.data_ptr(),
-                                          ws.numel(), bws.data_ptr(), bws.numel(), stream)
+            rc = abi.lib().tggcn_backward_ex(C.byref(dims), weights, garr, abi.N_WEIGHTS, C.byref(io), C.byref(go), ws.data_ptr(),
+                                             ws.numel(), bws.data_ptr(), bws.numel(), stream, C.byref(hooks))
         abi.check(rc, 'tggcn_backward')
         pending[0].record(torch.cuda.current_stream(dev))
         self._pending_status.append(pending)
         self._last_bwd = (keep, bws)
         self.flat_grad, self._flat_views = flat, (params, grads)
+        self.grad_buckets = [(s, e, ev) for (s, e), ev in zip(bucket_ranges, events) if e > s]
+        # gradients land in .grad here (autograd's accumulation semantics: a parameter that already holds a gradient adds to it)
+        for prm, g in zip(params, grads):
+            if prm.grad is None:
+                prm.grad = g
+            else:
+                prm.grad = prm.grad + g
+        if self.grad_ready_callback is not None:
+            self.grad_ready_callback(self)       # e.g. dp.GradientAllReduce: bucket all-reduces on a side stream, overlapping
         return grads
 
     def bind_flat_grads(self):
-        """Point every trainable parameter's ``.grad`` at its slice of ``flat_grad`` (the buffer the last backward wrote).
-        A data-parallel driver all-reduces ``flat_grad`` once and calls this before ``optimizer.step()``; autograd itself
-        may have copied the slices when it accumulated them."""
+        """Point every trainable parameter's ``.grad`` at its slice of ``flat_grad`` (the buffer the last backward wrote) —
+        what the backward itself does when the parameter held no gradient; kept for callers that replaced ``.grad`` since."""
         params, grads = self._flat_views
         for prm, g in zip(params, grads):
             prm.grad = g

@@ -330,6 +330,24 @@ TGGCN_API int tggcn_backward(const tggcn_dims* dims, const void* const* weights,
                              const tggcn_io* io, const tggcn_grad_outputs* grads, void* workspace, size_t workspace_bytes,
                              void* bwd_workspace, size_t bwd_workspace_bytes, void* stream);
 
+/* Gradient buckets for a data-parallel caller (the reference is single-device).  The backward finishes the
+ * parameter gradients in reverse model order; bucket k is complete when stage group k has been queued:
+ *   0  label heads + segment-level cells and message MLPs (after the segment BPTT and its weight-gradient GEMMs)
+ *   1  gate MLPs, frame-level message MLPs, Linear(2D->D), BiGRU weights
+ *   2  ROI embeddings + geometry MLP
+ *   3  geometry GCN
+ * tggcn_backward_bucket(weight id) names the bucket of every weight-table entry, so the caller can lay its gradient buffer out
+ * bucket by bucket; tggcn_backward_ex records hooks->bucket_done[k] (a cudaEvent_t, or NULL) on `stream` when bucket k is
+ * complete, so an all-reduce of bucket k on another stream can wait for exactly that event and overlap the rest of the backward. */
+#define TGGCN_BWD_BUCKETS 4
+typedef struct tggcn_bwd_hooks {
+    void* bucket_done[TGGCN_BWD_BUCKETS];
+} tggcn_bwd_hooks;
+TGGCN_API int tggcn_backward_bucket(int weight_id);
+TGGCN_API int tggcn_backward_ex(const tggcn_dims* dims, const void* const* weights, void* const* grad_weights, int n_weights,
+                                const tggcn_io* io, const tggcn_grad_outputs* grads, void* workspace, size_t workspace_bytes,
+                                void* bwd_workspace, size_t bwd_workspace_bytes, void* stream, const tggcn_bwd_hooks* hooks);
+
 /* Backward of nn.Linear (+ReLU), i.e. what autograd does for y = act(x W^T + b) (pyrutils/torch/models.py:31-33):
  *   Z = dY (.) [Y > 0] (Y = forward output, NULL when there was no ReLU);  dX = Z W (added to dX when beta_dx);
  *   dW = Z^T X;  db = column sums of Z.  Any of dX / dW / db may be NULL.  wt_scratch: K*N floats (W^T) when dX != NULL. */

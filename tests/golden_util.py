@@ -41,7 +41,13 @@ GRAD_CASES = {
     # seeds of these two also keep every ReLU pre-activation > 2e-5 from zero (oracle/gen_golden.py: RELU_STABLE_CASES)
     'grad_mphoi_s2_mp': ('mphoi', 32, 2, 9, 2, {'message_aggregation': 'mp'}),
     'grad_cad120_s2_mp': ('cad120', 32, 2, 8, 2, {'message_aggregation': 'mp'}),
-    'grad_mphoi_s2_d512': ('mphoi', 512, 8, 32, 2),       # hidden 512: compared in tests/test_gpu_fullsize.py
+}
+
+# hidden 512 (the benchmarked width), T = 32.  Kept apart from GRAD_CASES: the reference's own fp32 autograd carries summation
+# noise of ~3e-4 of a tensor's largest entry at this size, so tests/test_gpu_fullsize.py compares it with a matching tolerance
+# (the tight check at this size is the fp64 oracle, same file).
+FULL_GRAD_CASES = {
+    'grad_mphoi_s2_d512': ('mphoi', 512, 8, 32, 2),
 }
 
 

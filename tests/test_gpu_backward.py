@@ -23,8 +23,10 @@ def _summarize(g):
 
 def _setup(name, orc, synth, pkg):
     from golden_util import GOLDEN_DIR
-    shape_name, D, B, T, stage = GRAD_CASES[name][:5]
-    extra = GRAD_CASES[name][5] if len(GRAD_CASES[name]) > 5 else {}
+    from golden_util import FULL_GRAD_CASES
+    spec = GRAD_CASES[name] if name in GRAD_CASES else FULL_GRAD_CASES[name]
+    shape_name, D, B, T, stage = spec[:5]
+    extra = spec[5] if len(spec) > 5 else {}
     blob = np.load(os.path.join(GOLDEN_DIR, name + '.npz'))
     data_seed, noise_seed, target_seed, weight_seed = [int(v) for v in blob['meta']]
     shape = synth.SHAPES[shape_name]

@@ -80,7 +80,7 @@ def test_reorder_and_filter_edge_cases(orc):
     assert f.ne(0).tolist() == [[False, True, False, False, False, True]]
 
 
-from golden_util import GRAD_CASES, alias_shared_heads      # noqa: E402
+from golden_util import GRAD_CASES, FULL_GRAD_CASES, alias_shared_heads      # noqa: E402
 
 
 def _summarize(g):
@@ -91,14 +91,15 @@ def _summarize(g):
     return np.concatenate([[float(f.sum()), float(f.abs().sum()), float((f * f).sum())], f[idx].numpy()])
 
 
-@pytest.mark.parametrize('name', sorted(GRAD_CASES))
+@pytest.mark.parametrize('name', sorted(GRAD_CASES) + sorted(FULL_GRAD_CASES))
 def test_oracle_gradients_match_reference(name, orc, synth, pkg):
     """Backward pins for the next round: autograd through the oracle (train mode, multi_task_loss summed) against the
     gradients of the unmodified reference (oracle/gen_golden.py::run_grad_case), including which parameters get none."""
     import os
     from golden_util import GOLDEN_DIR
-    shape_name, D, B, T, stage = GRAD_CASES[name][:5]
-    extra = GRAD_CASES[name][5] if len(GRAD_CASES[name]) > 5 else {}
+    spec = GRAD_CASES[name] if name in GRAD_CASES else FULL_GRAD_CASES[name]
+    shape_name, D, B, T, stage = spec[:5]
+    extra = spec[5] if len(spec) > 5 else {}
     blob = np.load(os.path.join(GOLDEN_DIR, name + '.npz'))
     data_seed, noise_seed, target_seed, weight_seed = [int(v) for v in blob['meta']]
     shape = synth.SHAPES[shape_name]

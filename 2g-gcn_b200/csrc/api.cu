@@ -10,6 +10,7 @@
 #include "bigru.h"
 #include "frame.h"
 #include "api_internal.h"
+#include "step_tc.cuh"
 
 namespace tg {
 
@@ -95,6 +96,12 @@ void make_layout(const tggcn_dims& d, Layout& L) {
     sz[TGGCN_BUF_REIDX] = N * (H + O) * sizeof(int);
     sz[TGGCN_BUF_SEG_SCRATCH] = (2 * (size_t)d.B * H * nkh * D + 2 * (size_t)d.B * O * 2 * D + 8 * V) * f;
     sz[TGGCN_BUF_SYNC] = 64;
+    sz[TGGCN_BUF_BIG] = 0;
+    if (use_big_path(d)) {                    // 16-bit operand copies, state rings and message scratch of the large-batch recurrent path
+        BigLayout BLy;
+        big_layout(d.B, d.H, d.O, d.D, d.hh, BLy);
+        sz[TGGCN_BUF_BIG] = BLy.total;
+    }
     const size_t sv = d.save_for_backward ? 1 : 0;      // save buffers are empty in inference
     sz[TGGCN_BUF_GATES_H] = sv * N * H * 8 * D * f;
     sz[TGGCN_BUF_GATES_O] = sv * N * O * 8 * D * f;
@@ -312,6 +319,7 @@ static int forward_impl(const tggcn_dims* dims, const void* const* weights, int 
         }
         P.sync.counter = sync; P.sync.error = sync + 1;
         P.no_fp16_split = d.no_fp16_split;
+        P.big_ws = use_big_path(d) ? (void*)buf(TGGCN_BUF_BIG) : nullptr; P.precision = d.precision;
         if (int rc = launch_bigru(P, d.persistent, stream)) return rc;
     }
     STAGE_END();
@@ -400,6 +408,7 @@ static int forward_impl(const tggcn_dims* dims, const void* const* weights, int 
         P.att_b = d.inspect ? io->att_seg_b : nullptr;
         P.sync.counter = sync + 2; P.sync.error = sync + 3;
         P.no_fp16_split = d.no_fp16_split;
+        P.big_ws = use_big_path(d) ? (void*)buf(TGGCN_BUF_BIG) : nullptr; P.precision = d.precision;
         if (int rc = launch_segment(P, d.persistent, stream)) return rc;
     }
     STAGE_END();

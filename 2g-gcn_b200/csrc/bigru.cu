@@ -6,6 +6,7 @@
 // like the reference does (no packing).
 #include "recurrent.cuh"
 #include "bigru.h"
+#include "step_tc.cuh"
 
 namespace tg {
 
@@ -111,6 +112,7 @@ static void plan_tiles(BiGruParams& P) {
 }
 
 int launch_bigru(BiGruParams& P, int persistent, cudaStream_t stream) {
+    if (P.big_ws != nullptr) return launch_bigru_big(P, P.big_ws, P.precision, stream);
     TG_REQUIRE(P.D % 16 == 0, "bigru: hidden_size=%d must be a multiple of 16", P.D);
     const int fa = tile_smem_floats(3, 4, 3), fb = tile_smem_floats(3, 2, 4);
     const size_t smem = sizeof(float) * (size_t)(fa > fb ? fa : fb);

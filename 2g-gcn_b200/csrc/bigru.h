@@ -21,6 +21,8 @@ struct BiGruParams {
     int B, T, D;
     int total_tiles;
     int no_fp16_split;      // 1: never the SMEM-resident fp16-split variant (dims.no_fp16_split)
+    void* big_ws;           // non-null: large-batch path (step_tc.cu) on this TGGCN_BUF_BIG region
+    int precision;          // dims.precision (large-batch path)
     GridSync sync;
 };
 
@@ -80,6 +82,8 @@ struct SegParams {
     int res_msg;                  // resident-weight variant: message-tile weights are kept in shared memory too
     int res_ring_floats;          // resident-weight variant: floats of the cp.async ring that precede the overflow fragments in shared memory
     int no_fp16_split;            // 1: never the on-chip resident fp16-split variant (dims.no_fp16_split)
+    void* big_ws;                 // non-null: large-batch path (step_tc.cu) on this TGGCN_BUF_BIG region
+    int precision;                // dims.precision (large-batch path)
     GridSync sync;
 };
 

@@ -15,6 +15,7 @@
 #include "recurrent_tc.cuh"
 #include "recurrent_res.cuh"
 #include "bigru.h"
+#include "step_tc.cuh"
 
 namespace tg {
 
@@ -417,6 +418,7 @@ __global__ void __launch_bounds__(MODE == 1 ? RTC_THREADS : REC_THREADS, 1) segm
 }
 
 int launch_segment(SegParams& P, int persistent, cudaStream_t stream) {
+    if (P.big_ws != nullptr) return launch_segment_big(P, P.big_ws, P.precision, P.T, stream);
     const int D = P.D, B = P.B, H = P.H, O = P.O;
     TG_REQUIRE(D % 16 == 0, "segment: hidden_size=%d must be a multiple of 16", D);
     TG_REQUIRE(O >= 2, "segment: objects->object messages need at least 2 object slots (got %d)", O);

@@ -232,6 +232,8 @@ enum tggcn_buf_id {
     TGGCN_BUF_REIDX,         /* (B,T,H+O) int32      reorder gather index, models.py:1567-1586           */
     TGGCN_BUF_SEG_SCRATCH,   /* per-step message scratch of the segment kernel                            */
     TGGCN_BUF_SYNC,          /* grid-barrier counters + error flag                                        */
+    TGGCN_BUF_BIG,           /* large-batch recurrent path: 16-bit operand copies of the recurrent weights, state rings,
+                                aggregated-message operand rows, per-step message scratch (empty on the latency path)  */
     /* saved for the backward (empty unless dims.save_for_backward) */
     TGGCN_BUF_GATES_H,       /* (B,T,H,2,4D)         BiGRU gates r, z, n, W_hn h + b_hn                           */
     TGGCN_BUF_GATES_O,

@@ -188,11 +188,18 @@ def _wide_setup(name, orc, synth, pkg):
     return dict(shape=shape, stage=stage, model=model, batch=batch, noise=noise, hseg=hseg, oseg=oseg, targets=targets, ocfg=ocfg)
 
 
-@pytest.mark.parametrize('name', sorted(WIDE_CASES))
-def test_backward_wide_shapes_match_oracle(name, orc, synth, pkg):
+# large-batch recurrent path (recurrent_mode 2): its forward must leave exactly what the BPTT kernels read (gates, aggregated
+# messages, per-sender messages, attention weights)
+BIG_PATH_CASES = ['mphoi_d128_s2_rows', 'cad120_d128_s2_big', 'bimanual_d128_s2_big']
+WIDE_CASES.update({'cad120_d128_s2_big': ('cad120', 128, 5, 14, 2), 'bimanual_d128_s2_big': ('bimanual', 128, 3, 10, 2)})
+
+
+@pytest.mark.parametrize('name,mode', [(n, 0) for n in sorted(WIDE_CASES)] + [(n, 2) for n in BIG_PATH_CASES])
+def test_backward_wide_shapes_match_oracle(name, mode, orc, synth, pkg):
     c = _wide_setup(name, orc, synth, pkg)
     want, want_losses = _oracle_grads(c, orc)
     model = c['model'].cuda().train()
+    model.recurrent_mode = mode
     model.set_gumbel_noise(c['noise'])
     b = c['batch']
     cu = lambda t: None if t is None else t.cuda()

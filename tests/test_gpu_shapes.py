@@ -33,15 +33,19 @@ def _fwd(model, batch, noise, sl=slice(None), hseg=None, oseg=None):
     return [o.cpu() for o in out]
 
 
-# (shape, D, B, T, stage, seed): seeds chosen on the CPU oracle so that every sampled gate is >2e-4 from a decision edge
+# (shape, D, B, T, stage, seed[, recurrent_mode]): seeds chosen on the CPU oracle so that every sampled gate is >2e-4 from a decision edge
 @pytest.mark.parametrize('cfg', [('cad120', 32, 13, 18, 2, 2), ('mphoi', 32, 20, 10, 2, 0), ('bimanual', 32, 7, 12, 2, 5),
                                  ('cad120', 32, 9, 11, 1, 0), ('mphoi', 64, 11, 9, 1, 0),
-                                 # hidden 512: resident-weight recurrent kernels walking several row / video blocks per CTA
-                                 ('mphoi', 512, 20, 6, 2, 0), ('cad120', 512, 24, 5, 2, 1), ('bimanual', 512, 9, 5, 2, 2)])
+                                 # hidden 512, recurrent_mode 1: resident-weight kernels walking several row / video blocks per CTA
+                                 ('mphoi', 512, 20, 6, 2, 0, 1), ('cad120', 512, 24, 5, 2, 1, 1), ('bimanual', 512, 9, 5, 2, 2, 1),
+                                 # recurrent_mode 2: the large-batch path (tcgen05 + TMA step kernels), also where rows < 128 pad a tile
+                                 ('mphoi', 512, 20, 6, 2, 0, 2), ('cad120', 512, 24, 5, 2, 1, 2), ('bimanual', 512, 9, 5, 2, 2, 2),
+                                 ('mphoi', 128, 5, 7, 1, 3, 2), ('cad120', 192, 3, 9, 2, 2, 2)])
 def test_many_row_blocks_match_oracle(cfg, orc):
     """B large enough that every recurrent phase has several row blocks and video blocks."""
-    shape_name, D, B, T, stage, seed = cfg
+    shape_name, D, B, T, stage, seed = cfg[:6]
     pkg, shape, kw, model, batch, noise = _mk(shape_name, D, B, T, stage, seed=seed)
+    model.recurrent_mode = cfg[6] if len(cfg) > 6 else 0
     params = {k: v.clone().double() if v.is_floating_point() else v.clone() for k, v in model.state_dict().items()}
     hseg = torch.ones(B, T, shape.H) if stage == 1 else None
     oseg = torch.ones(B, T, shape.O) if (stage == 1 and shape.dataset == 'cad120') else None

@@ -143,6 +143,13 @@ __device__ __forceinline__ void store16f(float* p, const float (&v)[16]) {
     for (int j = 0; j < 4; ++j) reinterpret_cast<float4*>(p)[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
 }
 
+#ifdef ST_TRACE      // timing experiments only (TGGCN_NVCC_DEFS=-DST_TRACE): clock64 stamps of CTA 0, read back with tggcn_debug_trace
+__device__ long long g_st_trace[64];
+#define ST_STAMP(i) do { if (blockIdx.x == 0) g_st_trace[i] = clock64(); } while (0)
+#else
+#define ST_STAMP(i) do { } while (0)
+#endif
+
 template <int PREC>
 __global__ void __launch_bounds__(ST_THREADS, 1) step_tc_kernel(const __grid_constant__ StepLaunch L) {
     using Cfg = StCfg<PREC>;
@@ -152,6 +159,7 @@ __global__ void __launch_bounds__(ST_THREADS, 1) step_tc_kernel(const __grid_con
     __shared__ uint32_t tmem_base_smem;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    if (tid == 0) ST_STAMP(0);
     uint8_t* tiles = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     const uint32_t tiles_u32 = smem_u32(tiles);
     const uint32_t full0 = smem_u32(&bars[0]), empty0 = smem_u32(&bars[STAGES]), tfull = smem_u32(&bars[2 * STAGES]);
@@ -184,6 +192,7 @@ __global__ void __launch_bounds__(ST_THREADS, 1) step_tc_kernel(const __grid_con
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = tmem_base_smem;
+    if (tid == 0) ST_STAMP(1);
 
     if (warp == 0) {
         // ------------------------------ TMA producer ------------------------------
@@ -193,6 +202,7 @@ __global__ void __launch_bounds__(ST_THREADS, 1) step_tc_kernel(const __grid_con
             for (int kb = 0; kb < nkb; ++kb) {
                 const int s = kb % STAGES;
                 mbar_wait_backoff(empty0 + 8 * s, ((kb / STAGES) & 1) ^ 1);
+                if (kb < 12) ST_STAMP(4 + kb);
                 const uint32_t bar = full0 + 8 * s;
                 mbar_expect_tx(bar, tx);
                 const bool seg2 = kb >= P.nkb1;
@@ -231,6 +241,7 @@ __global__ void __launch_bounds__(ST_THREADS, 1) step_tc_kernel(const __grid_con
             mbar_wait(full0 + 8 * s, (kb / STAGES) & 1);
             tc_fence_after();
             if (lane == 0) {
+                if (kb < 12) ST_STAMP(20 + kb);
                 const uint32_t st = tiles_u32 + s * Cfg::STAGE_BYTES;
                 const uint32_t a_hi = st, a_lo = st + ST_A_TILE;
                 const uint32_t b_hi = st + Cfg::A_BYTES, b_lo = b_hi + ST_B_TILE;
@@ -285,6 +296,7 @@ __global__ void __launch_bounds__(ST_THREADS, 1) step_tc_kernel(const __grid_con
             // operands of the first chunk are fetched while the main loop still runs
             mbar_wait_backoff(tfull, 0);
             tc_fence_after();
+            if (tid == 64) ST_STAMP(2);
 #pragma unroll 1
             for (int c = half; c < ST_U / 16; c += 2) {
                 const int ub = nt * ST_U + c * 16;
@@ -341,11 +353,20 @@ __global__ void __launch_bounds__(ST_THREADS, 1) step_tc_kernel(const __grid_con
     }
     tc_fence_before();
     __syncthreads();
+    if (tid == 0) ST_STAMP(3);
     if (warp == 2) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem_base), "r"((uint32_t)ST_TMEM_COLS) : "memory");
     }
 }
+
+#ifdef ST_TRACE
+}  // namespace tg
+extern "C" __attribute__((visibility("default"))) int tggcn_debug_trace(long long* out_host) {
+    return cudaMemcpyFromSymbol(out_host, tg::g_st_trace, sizeof(long long) * 64) == cudaSuccess ? 0 : 1;
+}
+namespace tg {
+#endif
 
 // ---- operand preparation: fp32 weights -> fp16 (hi, lo) planes (scaled) or one bf16 plane ------------------------------------
 constexpr int PACK_MAX_JOBS = 20;

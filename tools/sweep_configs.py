@@ -111,11 +111,13 @@ def main():
     ap.add_argument('--what', default='cad120,bimanual,mphoi')
     ap.add_argument('--iters', type=int, default=5)
     ap.add_argument('--max-gb', type=float, default=100.0)
+    ap.add_argument('--batches', default='8,16,32,64,128,256', help='batch sizes of the CAD-120 sweep')
     a = ap.parse_args()
     what = a.what.split(',')
+    print(f'# TGGCN_RECURRENT_MODE={os.environ.get("TGGCN_RECURRENT_MODE", "0")} (0: by rows per step, 1: latency path, 2: large-batch path)')
     print(f'# {torch.cuda.get_device_name(0)}; median of {a.iters} timed runs after 3 warm-ups, CUDA events; synthetic tensors (2g-gcn_b200/synth.py)')
     if 'cad120' in what:       # BASELINE.json configs[3]: CAD-120 shape (1 human, 5 objects, long sequences), inference sweep bs 8 -> 256
-        for B in (8, 16, 32, 64, 128, 256):
+        for B in [int(b) for b in a.batches.split(',')]:
             inference_case(pkg.synth.SHAPES['cad120'], B, 512, 512, a.iters, a.max_gb)
     if 'bimanual' in what:     # configs[4]: Bimanual shape (2 hands, 9 objects), training; D = 64 is the shipped yaml comment, D = 512 the others' size
         for D in (64, 512):

@@ -3,7 +3,8 @@
 //     gates[rows, 3D] = act_rows[rows, K] * W[3D, K]^T            rows = B * entities (hundreds to thousands)
 // on the 5th-generation tensor cores, with the GRU cell fused into the epilogue.
 //
-// step_tc_kernel, one 128-row x 64-unit tile per CTA, 320 threads, warp-specialised:
+// step_tc_kernel, one (128 * MT)-row x 64-unit tile per CTA (MT = 2: two accumulators share every weight tile — the kernel runs at
+// the L2 -> SM bandwidth, and a 256-row tile moves 30 % fewer operand bytes per FLOP), 320 threads, warp-specialised:
 //   warp 0      TMA producer: one elected lane streams the operand tiles with cp.async.bulk.tensor (3-D tensor maps: K x rows x
 //               plane) straight into the K-major SWIZZLE_128B layout the UMMA descriptors read — no register pass, no split at
 //               run time: activations are WRITTEN as fp16 (hi, lo) pairs by the previous step's epilogue, weights are split
@@ -18,6 +19,7 @@
 //               training — the gate values the BPTT kernels need.
 // The same kernel runs the segment-level message MLPs (ReLU epilogue, N = 128).  seg_attend_kernel turns their outputs into the
 // aggregated messages (scaled-dot-product attention over the previous states, vhoi/models.py:1051-1381) between the two GEMMs.
+#include <stdlib.h>
 #include <cuda.h>
 #include <cuda_fp16.h>
 #include <cuda_bf16.h>
@@ -35,17 +37,19 @@ constexpr int ST_EPI_WARPS = 8;
 constexpr int ST_THREADS = (2 + ST_EPI_WARPS) * 32;
 constexpr int ST_MAX_PROBLEMS = 8;
 constexpr int ST_MAX_MAPS = 14;
-constexpr int ST_TMEM_COLS = 256;
+constexpr int ST_ACC_COLS = 256;            // TMEM columns of one 128-row accumulator: [n_i | r | z | n_h] x 64 units
 constexpr int ST_A_TILE = ST_BM * 128;      // bytes of one 128-row operand tile
 constexpr int ST_B_TILE = 3 * ST_U * 128;   // bytes of one weight tile (three gate boxes, or one 128-row box + slack)
 constexpr float ST_W_SCALE = 256.0f;        // fp16 split: weights are stored times 2^8
 
-template <int PREC> struct StCfg {
+template <int PREC, int MT> struct StCfg {
     static constexpr int PLANES = PREC == 0 ? 2 : 1;                       // (hi, lo) or a single bf16 plane
-    static constexpr int A_BYTES = PLANES * ST_A_TILE;
-    static constexpr int STAGE_BYTES = PLANES * (ST_A_TILE + ST_B_TILE);
+    static constexpr int A_PLANE = MT * ST_A_TILE;                         // one plane of the activation tile: 128 * MT rows
+    static constexpr int A_BYTES = PLANES * A_PLANE;
+    static constexpr int STAGE_BYTES = A_BYTES + PLANES * ST_B_TILE;       // 80 / 112 KB (fp16 split), 40 / 56 KB (bf16)
     static constexpr int STAGES = PREC == 0 ? 2 : 4;
     static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024;
+    static constexpr int TMEM_COLS = MT * ST_ACC_COLS;
 };
 
 enum { ST_GRU = 0, ST_RELU = 1 };
@@ -150,9 +154,9 @@ __device__ long long g_st_trace[64];
 #define ST_STAMP(i) do { } while (0)
 #endif
 
-template <int PREC>
+template <int PREC, int MT>
 __global__ void __launch_bounds__(ST_THREADS, 1) step_tc_kernel(const __grid_constant__ StepLaunch L) {
-    using Cfg = StCfg<PREC>;
+    using Cfg = StCfg<PREC, MT>;
     constexpr int STAGES = Cfg::STAGES, PLANES = Cfg::PLANES;
     extern __shared__ uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t bars[2 * STAGES + 1];
@@ -171,7 +175,7 @@ __global__ void __launch_bounds__(ST_THREADS, 1) step_tc_kernel(const __grid_con
     const StepProblem& P = L.p[pi];
     const int tile = blockIdx.x - P.tile_begin;
     const int mt = tile / P.n_tiles, nt = tile - mt * P.n_tiles;
-    const int m0 = mt * ST_BM;
+    const int m0 = mt * ST_BM * MT;
     const int nkb = P.nkb1 + P.nkb2;
     const bool gru = P.mode == ST_GRU;
 
@@ -184,7 +188,7 @@ __global__ void __launch_bounds__(ST_THREADS, 1) step_tc_kernel(const __grid_con
         asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
     }
     if (warp == 2) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(&tmem_base_smem)), "r"((uint32_t)ST_TMEM_COLS)
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(&tmem_base_smem)), "r"((uint32_t)Cfg::TMEM_COLS)
                      : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
     }
@@ -197,7 +201,7 @@ __global__ void __launch_bounds__(ST_THREADS, 1) step_tc_kernel(const __grid_con
     if (warp == 0) {
         // ------------------------------ TMA producer ------------------------------
         if (lane == 0) {
-            const uint32_t tx = (uint32_t)PLANES * (ST_A_TILE + (gru ? 3 * ST_U * 128 : ST_BN_RELU * 128));
+            const uint32_t tx = (uint32_t)PLANES * (Cfg::A_PLANE + (gru ? 3 * ST_U * 128 : ST_BN_RELU * 128));
 #pragma unroll 1
             for (int kb = 0; kb < nkb; ++kb) {
                 const int s = kb % STAGES;
@@ -212,7 +216,7 @@ __global__ void __launch_bounds__(ST_THREADS, 1) step_tc_kernel(const __grid_con
                 const CUtensorMap* bm = &L.maps[seg2 ? P.b2_map : P.b1_map];
                 const int ap = seg2 ? P.a2_plane : P.a1_plane, bp = seg2 ? P.b2_plane : P.b1_plane;
 #pragma unroll
-                for (int pl = 0; pl < PLANES; ++pl) tma_load_3d(st + pl * ST_A_TILE, am, k0, m0, ap + pl, bar);
+                for (int pl = 0; pl < PLANES; ++pl) tma_load_3d(st + pl * Cfg::A_PLANE, am, k0, m0, ap + pl, bar);   // box: 128 * MT rows
                 if (gru) {
                     // gate boxes in accumulator-column order: input part -> [n r z], hidden part -> [r z n]
                     const int g0 = seg2 ? 0 : 2, g1 = seg2 ? 1 : 0, g2 = seg2 ? 2 : 1;
@@ -243,7 +247,7 @@ __global__ void __launch_bounds__(ST_THREADS, 1) step_tc_kernel(const __grid_con
             if (lane == 0) {
                 if (kb < 12) ST_STAMP(20 + kb);
                 const uint32_t st = tiles_u32 + s * Cfg::STAGE_BYTES;
-                const uint32_t a_hi = st, a_lo = st + ST_A_TILE;
+                const uint32_t a_hi = st, a_lo = st + Cfg::A_PLANE;
                 const uint32_t b_hi = st + Cfg::A_BYTES, b_lo = b_hi + ST_B_TILE;
                 const bool seg2 = kb >= P.nkb1;
 #pragma unroll
@@ -254,21 +258,26 @@ __global__ void __launch_bounds__(ST_THREADS, 1) step_tc_kernel(const __grid_con
                         // small terms first: lo*hi, hi*lo, hi*hi
                         const uint32_t a = (PREC == 0 && term == 0) ? a_lo : a_hi;
                         const uint32_t b = (PREC == 0 && term == 1) ? b_lo : b_hi;
-                        const uint64_t ad = umma_desc(a + ko);
+                        const uint64_t bd = umma_desc(b + ko);
                         const bool very_first = kb == 0 && kk == 0 && term == 0;
-                        if (!gru) {
-                            umma_f16(tmem_base, ad, umma_desc(b + ko), idr, !very_first);
-                        } else if (!seg2) {
-                            umma_f16(tmem_base, ad, umma_desc(b + ko), id3, !very_first);                 // columns [n_i r z]
-                        } else if (kb == P.nkb1 && kk == 0 && term == 0) {
-                            if (P.nkb1 > 0) {      // r, z keep accumulating; n_h starts here
-                                umma_f16(tmem_base + ST_U, ad, umma_desc(b + ko), id2, 1);
-                                umma_f16(tmem_base + 3 * ST_U, ad, umma_desc(b + 2 * ST_U * 128 + ko), id1, 0);
+#pragma unroll
+                        for (int mh = 0; mh < MT; ++mh) {                   // the 128-row halves of the tile share the weight operand
+                            const uint64_t ad = umma_desc(a + mh * ST_A_TILE + ko);
+                            const uint32_t tacc = tmem_base + mh * ST_ACC_COLS;
+                            if (!gru) {
+                                umma_f16(tacc, ad, bd, idr, !very_first);
+                            } else if (!seg2) {
+                                umma_f16(tacc, ad, bd, id3, !very_first);                                  // columns [n_i r z]
+                            } else if (kb == P.nkb1 && kk == 0 && term == 0) {
+                                if (P.nkb1 > 0) {      // r, z keep accumulating; n_h starts here
+                                    umma_f16(tacc + ST_U, ad, bd, id2, 1);
+                                    umma_f16(tacc + 3 * ST_U, ad, umma_desc(b + 2 * ST_U * 128 + ko), id1, 0);
+                                } else {
+                                    umma_f16(tacc + ST_U, ad, bd, id3, 0);                                 // plain GRU: [r z n_h] only
+                                }
                             } else {
-                                umma_f16(tmem_base + ST_U, ad, umma_desc(b + ko), id3, 0);                // plain GRU: [r z n_h] only
+                                umma_f16(tacc + ST_U, ad, bd, id3, 1);                                     // columns [r z n_h]
                             }
-                        } else {
-                            umma_f16(tmem_base + ST_U, ad, umma_desc(b + ko), id3, 1);                    // columns [r z n_h]
                         }
                     }
                 }
@@ -279,11 +288,14 @@ __global__ void __launch_bounds__(ST_THREADS, 1) step_tc_kernel(const __grid_con
         }
     } else {
         // ------------------------------ epilogue ------------------------------
-        const int ew = warp - 2, q = warp & 3, half = ew >> 2;       // TMEM lane quarter of a warp = warp id % 4
-        const int row = m0 + q * 32 + lane;
+        // TMEM lane quarter of a warp = warp id % 4.  MT = 1: the two warps of a quarter split the column chunks;
+        // MT = 2: they take one 128-row accumulator each.
+        const int ew = warp - 2, q = warp & 3, half = ew >> 2;
+        const int acc_i = MT == 2 ? half : 0, c_first = MT == 2 ? 0 : half, c_step = MT == 2 ? 1 : 2;
+        const int row = m0 + acc_i * ST_BM + q * 32 + lane;
         const bool valid = row < P.rows;
         const int b = valid ? row / P.E : 0, e = valid ? row - b * P.E : 0;
-        const uint32_t tq = tmem_base + ((uint32_t)(q * 32) << 16);
+        const uint32_t tq = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc_i * ST_ACC_COLS);
         const float sc = L.acc_scale;
         const int D = P.D;
         if (gru) {
@@ -298,7 +310,7 @@ __global__ void __launch_bounds__(ST_THREADS, 1) step_tc_kernel(const __grid_con
             tc_fence_after();
             if (tid == 64) ST_STAMP(2);
 #pragma unroll 1
-            for (int c = half; c < ST_U / 16; c += 2) {
+            for (int c = c_first; c < ST_U / 16; c += c_step) {
                 const int ub = nt * ST_U + c * 16;
                 float ni[16], ar[16], az[16], nh[16];
                 if (P.nkb1 > 0) tmem_ld16(tq + (uint32_t)(c * 16), ni);
@@ -339,7 +351,7 @@ __global__ void __launch_bounds__(ST_THREADS, 1) step_tc_kernel(const __grid_con
             mbar_wait_backoff(tfull, 0);
             tc_fence_after();
 #pragma unroll 1
-            for (int c = half; c < ST_BN_RELU / 16; c += 2) {
+            for (int c = c_first; c < ST_BN_RELU / 16; c += c_step) {
                 const int nb = nt * ST_BN_RELU + c * 16;
                 float v[16], bias[16];
                 tmem_ld16(tq + (uint32_t)(c * 16), v);
@@ -356,7 +368,7 @@ __global__ void __launch_bounds__(ST_THREADS, 1) step_tc_kernel(const __grid_con
     if (tid == 0) ST_STAMP(3);
     if (warp == 2) {
         tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem_base), "r"((uint32_t)ST_TMEM_COLS) : "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem_base), "r"((uint32_t)Cfg::TMEM_COLS) : "memory");
     }
 }
 
@@ -437,8 +449,6 @@ template <int PREC> __global__ void __launch_bounds__(AT_THREADS) seg_attend_ker
     const int H = P.H, O = P.O, D = P.D, E = H + O, T = P.T;
     const int t = dir == 0 ? P.s : T - 1 - P.s, tprev = dir == 0 ? t - 1 : t + 1;
     float* hs = at_smem;                                  // [E][D] previous states: humans then objects
-    float* ms = hs + (size_t)E * D;                       // messages: kind 0 (H rows), 1 (O), 2 (H), 3 (O)
-    const int moff[4] = {0, H, H + O, 2 * H + O};
     const int D4 = D / 4;
     for (int i = tid; i < E * D4; i += AT_THREADS) {
         const int e = i / D4, c = (i - e * D4) * 4;
@@ -449,14 +459,6 @@ template <int PREC> __global__ void __launch_bounds__(AT_THREADS) seg_attend_ker
             v = ld_cg4(src + c);
         }
         *reinterpret_cast<float4*>(hs + (size_t)e * D + c) = v;
-    }
-    for (int k = P.hh ? 0 : 1; k < 4; ++k) {
-        const int Es = (k == 0 || k == 2) ? H : O;
-        const float* base = P.msg[dir][k] + (size_t)b * P.msg_bstride[k];
-        for (int i = tid; i < Es * D4; i += AT_THREADS) {
-            const int e = i / D4, c = (i - e * D4) * 4;
-            *reinterpret_cast<float4*>(ms + (size_t)(moff[k] + e) * D + c) = ld_cg4(base + (size_t)e * D + c);
-        }
     }
     __syncthreads();
     // logits into alpha[k][r][s]
@@ -520,9 +522,13 @@ template <int PREC> __global__ void __launch_bounds__(AT_THREADS) seg_attend_ker
             float acc[16];
 #pragma unroll
             for (int j = 0; j < 16; ++j) acc[j] = 0.0f;
+            // the senders' messages were written by the previous launch: plain cached loads (a row is read by every receiver)
+            const float* mbase = P.msg[dir][k] + (size_t)b * P.msg_bstride[k] + cu * 16;
             for (int sd = 0; sd < Es; ++sd) {
                 const float a = alpha[k][r][sd];
-                const float* m = ms + (size_t)(moff[k] + sd) * D + cu * 16;
+                if (a == 0.0f) continue;                     // masked sender
+                float m[16];
+                load16(mbase + (size_t)sd * D, m);
 #pragma unroll
                 for (int j = 0; j < 16; ++j) acc[j] = fmaf(a, m[j], acc[j]);
             }
@@ -624,25 +630,48 @@ void pack_add(PackJobs& jobs, const float* src, int ld, int rows, int cols, void
     j.src = src; j.ld = ld; j.rows = rows; j.cols = cols; j.hi = hi;
 }
 
-int launch_step(StepLaunch& L, int precision, cudaStream_t stream) {
+template <int PREC, int MT> int launch_step_t(const StepLaunch& L, int grid, cudaStream_t stream) {
+    if (int rc = ensure_smem((const void*)step_tc_kernel<PREC, MT>, StCfg<PREC, MT>::SMEM_BYTES)) return rc;
+    step_tc_kernel<PREC, MT><<<grid, ST_THREADS, StCfg<PREC, MT>::SMEM_BYTES, stream>>>(L);
+    TG_LAUNCH_OK();
+    return 0;
+}
+
+// Operand bytes one launch pulls through L2 with 128 * mt rows per tile (what bounds the kernel): tiles x k-blocks x stage bytes.
+double step_traffic(const StepLaunch& L, int mt) {
+    double bytes = 0.0;
+    for (int i = 0; i < L.count; ++i) {
+        const StepProblem& p = L.p[i];
+        const int n_tiles = p.mode == ST_GRU ? p.D / ST_U : cdiv(p.D, ST_BN_RELU);
+        bytes += (double)cdiv(p.rows, ST_BM * mt) * n_tiles * (p.nkb1 + p.nkb2) * (mt * ST_A_TILE + (p.mode == ST_GRU ? ST_B_TILE : ST_BN_RELU * 128));
+    }
+    return bytes;
+}
+
+// mt: 128-row accumulators per tile (1 or 2); the activation tensor maps of L must have been encoded with a 128 * mt row box
+int launch_step(StepLaunch& L, int precision, int mt, cudaStream_t stream) {
     int begin = 0;
     for (int i = 0; i < L.count; ++i) {
         StepProblem& p = L.p[i];
-        p.m_tiles = cdiv(p.rows, ST_BM);
+        p.m_tiles = cdiv(p.rows, ST_BM * mt);
         p.n_tiles = p.mode == ST_GRU ? p.D / ST_U : cdiv(p.D, ST_BN_RELU);
         p.tile_begin = begin;
         begin += p.m_tiles * p.n_tiles;
     }
     L.acc_scale = precision ? 1.0f : 1.0f / ST_W_SCALE;
-    if (precision) {
-        if (int rc = ensure_smem((const void*)step_tc_kernel<1>, StCfg<1>::SMEM_BYTES)) return rc;
-        step_tc_kernel<1><<<begin, ST_THREADS, StCfg<1>::SMEM_BYTES, stream>>>(L);
-    } else {
-        if (int rc = ensure_smem((const void*)step_tc_kernel<0>, StCfg<0>::SMEM_BYTES)) return rc;
-        step_tc_kernel<0><<<begin, ST_THREADS, StCfg<0>::SMEM_BYTES, stream>>>(L);
+    if (precision) return mt == 2 ? launch_step_t<1, 2>(L, begin, stream) : launch_step_t<1, 1>(L, begin, stream);
+    return mt == 2 ? launch_step_t<0, 2>(L, begin, stream) : launch_step_t<0, 1>(L, begin, stream);
+}
+
+// 256-row tiles when they move fewer operand bytes (TGGCN_STEP_MT=1|2 forces a choice: A/B experiments)
+int choose_mt(const StepLaunch& L) {
+    static int forced = -1;
+    if (forced < 0) {
+        const char* e = getenv("TGGCN_STEP_MT");
+        forced = (e != nullptr && (e[0] == '1' || e[0] == '2')) ? e[0] - '0' : 0;
     }
-    TG_LAUNCH_OK();
-    return 0;
+    if (forced) return forced;
+    return step_traffic(L, 2) < 0.95 * step_traffic(L, 1) ? 2 : 1;
 }
 
 size_t plane_bytes(size_t rows, size_t K) { return rows * K * 2; }
@@ -665,13 +694,7 @@ int launch_bigru_big(BiGruParams& P, void* big_ws, int precision, cudaStream_t s
     if (int rc = launch_pack(jobs, precision, stream)) return rc;
     StepLaunch L;
     memset(&L, 0, sizeof(L));
-    for (int g = 0; g < 3; ++g) {
-        const size_t rows = P.g[g].rows;
-        if (int rc = make_map(&L.maps[g], ws + BL.ring_g[g], precision, D, rows, 8, ST_BM)) return rc;
-        if (int rc = make_map(&L.maps[3 + g], ws + BL.whh_g[g], precision, D, 3 * D, 4, ST_U)) return rc;
-        // the state "before the first step" is zero: slot 1 is what step 0 reads
-        TG_CUDA_OK(cudaMemsetAsync(ws + BL.ring_g[g] + 4 * plane_bytes(rows, D), 0, 4 * plane_bytes(rows, D), stream));
-    }
+    int mt = 1;
     for (int s = 0; s < T; ++s) {
         const int slot_in = (s & 1) ^ 1, slot_out = s & 1;
         L.count = 0;
@@ -688,7 +711,17 @@ int launch_bigru_big(BiGruParams& P, void* big_ws, int precision, cudaStream_t s
                 q.xg = G.gi; q.bhh = G.bhh[dir]; q.ugate = nullptr; q.hx = G.hfr; q.gsave = G.gates;
                 q.ring_out = ws + BL.ring_g[g] + (size_t)(slot_out * 2 + dir) * 2 * plane_bytes(G.rows, D);
             }
-        if (int rc = launch_step(L, precision, stream)) return rc;
+        if (s == 0) {            // the problem list has the same shape every step: choose the tile height, then encode the maps
+            mt = choose_mt(L);
+            for (int g = 0; g < 3; ++g) {
+                const size_t rows = P.g[g].rows;
+                if (int rc = make_map(&L.maps[g], ws + BL.ring_g[g], precision, D, rows, 8, ST_BM * mt)) return rc;
+                if (int rc = make_map(&L.maps[3 + g], ws + BL.whh_g[g], precision, D, 3 * D, 4, ST_U)) return rc;
+                // the state "before the first step" is zero: slot 1 is what step 0 reads
+                TG_CUDA_OK(cudaMemsetAsync(ws + BL.ring_g[g] + 4 * plane_bytes(rows, D), 0, 4 * plane_bytes(rows, D), stream));
+            }
+        }
+        if (int rc = launch_step(L, precision, mt, stream)) return rc;
     }
     return 0;
 }
@@ -721,23 +754,26 @@ int launch_segment_big(SegParams& P, void* big_ws, int precision, int T_save, cu
     enum { M_RING_H = 0, M_RING_O, M_MG_H, M_MG_O, M_WIH_H, M_WIH_O, M_WHH_H, M_WHH_O, M_WM };
     StepLaunch LA, LB;
     memset(&LA, 0, sizeof(LA));
-    if (int rc = make_map(&LA.maps[M_RING_H], ws + BL.ring_h, precision, D, Rh, 8, ST_BM)) return rc;
-    if (int rc = make_map(&LA.maps[M_RING_O], ws + BL.ring_o, precision, D, Ro, 8, ST_BM)) return rc;
-    if (int rc = make_map(&LA.maps[M_MG_H], ws + BL.mg_h, precision, (size_t)nkh * D, Rh, 4, ST_BM)) return rc;
-    if (int rc = make_map(&LA.maps[M_MG_O], ws + BL.mg_o, precision, (size_t)2 * D, Ro, 4, ST_BM)) return rc;
-    if (int rc = make_map(&LA.maps[M_WIH_H], ws + BL.wih_h, precision, (size_t)nkh * D, 3 * D, 4, ST_U)) return rc;
-    if (int rc = make_map(&LA.maps[M_WIH_O], ws + BL.wih_o, precision, (size_t)2 * D, 3 * D, 4, ST_U)) return rc;
-    if (int rc = make_map(&LA.maps[M_WHH_H], ws + BL.whh_h, precision, D, 3 * D, 4, ST_U)) return rc;
-    if (int rc = make_map(&LA.maps[M_WHH_O], ws + BL.whh_o, precision, D, 3 * D, 4, ST_U)) return rc;
-    if (int rc = make_map(&LA.maps[M_WM], ws + BL.wm, precision, D, D, 8, ST_BN_RELU)) return rc;
-    memcpy(&LB, &LA, sizeof(LA));
+    memset(&LB, 0, sizeof(LB));
+    int mtA = 1, mtB = 1;
+    auto encode_maps = [&](StepLaunch& L, int mt) -> int {       // activation boxes: 128 * mt rows; weight boxes: one gate slice
+        if (int rc = make_map(&L.maps[M_RING_H], ws + BL.ring_h, precision, D, Rh, 8, ST_BM * mt)) return rc;
+        if (int rc = make_map(&L.maps[M_RING_O], ws + BL.ring_o, precision, D, Ro, 8, ST_BM * mt)) return rc;
+        if (int rc = make_map(&L.maps[M_MG_H], ws + BL.mg_h, precision, (size_t)nkh * D, Rh, 4, ST_BM * mt)) return rc;
+        if (int rc = make_map(&L.maps[M_MG_O], ws + BL.mg_o, precision, (size_t)2 * D, Ro, 4, ST_BM * mt)) return rc;
+        if (int rc = make_map(&L.maps[M_WIH_H], ws + BL.wih_h, precision, (size_t)nkh * D, 3 * D, 4, ST_U)) return rc;
+        if (int rc = make_map(&L.maps[M_WIH_O], ws + BL.wih_o, precision, (size_t)2 * D, 3 * D, 4, ST_U)) return rc;
+        if (int rc = make_map(&L.maps[M_WHH_H], ws + BL.whh_h, precision, D, 3 * D, 4, ST_U)) return rc;
+        if (int rc = make_map(&L.maps[M_WHH_O], ws + BL.whh_o, precision, D, 3 * D, 4, ST_U)) return rc;
+        return make_map(&L.maps[M_WM], ws + BL.wm, precision, D, D, 8, ST_BN_RELU);
+    };
     TG_CUDA_OK(cudaMemsetAsync(ws + BL.ring_h + 4 * plane_bytes(Rh, D), 0, 4 * plane_bytes(Rh, D), stream));
     TG_CUDA_OK(cudaMemsetAsync(ws + BL.ring_o + 4 * plane_bytes(Ro, D), 0, 4 * plane_bytes(Ro, D), stream));
 
     // per-step message buffers: the save buffers of the backward when training, a scratch region otherwise
     const bool saving = P.smsg[1] != nullptr;
     float* msg_scratch = reinterpret_cast<float*>(ws + BL.msg);
-    const size_t at_smem = sizeof(float) * ((size_t)(H + O) + 2 * (size_t)(H + O)) * D;
+    const size_t at_smem = sizeof(float) * (size_t)(H + O) * D;
     TG_REQUIRE(at_smem <= 200 * 1024, "segment (large-batch path): %zu bytes of shared memory for the attention kernel", at_smem);
     if (precision) { if (int rc = ensure_smem((const void*)seg_attend_kernel<1>, at_smem)) return rc; }
     else           { if (int rc = ensure_smem((const void*)seg_attend_kernel<0>, at_smem)) return rc; }
@@ -771,7 +807,11 @@ int launch_segment_big(SegParams& P, void* big_ws, int precision, int T_save, cu
                 q.bias = P.bm[k]; q.out = out; q.out_bstride = bstride;
             }
         }
-        if (int rc = launch_step(LA, precision, stream)) return rc;
+        if (s == 0) {
+            mtA = choose_mt(LA);
+            if (int rc = encode_maps(LA, mtA)) return rc;
+        }
+        if (int rc = launch_step(LA, precision, mtA, stream)) return rc;
         // ---- phase A2: attention over the previous states + aggregation -> operand rows of the cell GEMM ------------------------
         A.B = B; A.T = T; A.H = H; A.O = O; A.D = D; A.hh = P.hh; A.nk_h = nkh; A.mean_pool = P.mean_pool; A.first = s == 0; A.s = s;
         A.hx_h = P.hx_h; A.hx_o = P.hx_o; A.om = P.om;
@@ -802,7 +842,11 @@ int launch_segment_big(SegParams& P, void* big_ws, int precision, int T_save, cu
                 q.ugate = is_h ? P.u_h : P.u_o; q.hx = is_h ? P.hx_h : P.hx_o; q.gsave = is_h ? P.sgates_h : P.sgates_o;
                 q.ring_out = ws + (is_h ? BL.ring_h : BL.ring_o) + (size_t)(slot_out * 2 + dir) * 2 * plane_bytes(R, D);
             }
-        if (int rc = launch_step(LB, precision, stream)) return rc;
+        if (s == 0) {
+            mtB = choose_mt(LB);
+            if (int rc = encode_maps(LB, mtB)) return rc;
+        }
+        if (int rc = launch_step(LB, precision, mtB, stream)) return rc;
     }
     (void)T_save;
     return 0;

@@ -273,18 +273,19 @@ static int forward_impl(const tggcn_dims* dims, const void* const* weights, int 
         return rc;
 
     STAGE_END();
+    const int gpath = (d.precision == 1 && d.gemm_path != 0) ? 3 : d.gemm_path;      // bf16 operands on the tensor-core projections
     GemmGroup g;
     // 2. ROI embeddings and the first geometry MLP layer (models.py:646)
     g.count = 0;
     gemm_add(g, io->x_human, d.Fh, W(TGGCN_W_HUM_EMB_W), 2048, W(TGGCN_W_HUM_EMB_B), buf(TGGCN_BUF_S_H), 2 * D, N * H, D, 2048, 1);
     gemm_add(g, io->x_objects, 2048, W(TGGCN_W_OBJ_EMB_W), 2048, W(TGGCN_W_OBJ_EMB_B), buf(TGGCN_BUF_S_O), 2 * D, N * O, D, 2048, 1);
     gemm_add(g, buf(TGGCN_BUF_GCN_OUT), 128 * V, W(TGGCN_W_GEO_MLP0_W), 128 * V, W(TGGCN_W_GEO_MLP0_B), buf(TGGCN_BUF_GEO_HID), 2048, N, 2048, 128 * V, 1);
-    if (int rc = launch_gemm(g, d.gemm_path, stream)) return rc;
+    if (int rc = launch_gemm(g, gpath, stream)) return rc;
     STAGE_END();
     // 3. second geometry MLP layer
     g.count = 0;
     gemm_add(g, buf(TGGCN_BUF_GEO_HID), 2048, W(TGGCN_W_GEO_MLP2_W), 2048, W(TGGCN_W_GEO_MLP2_B), buf(TGGCN_BUF_S_G), 2 * D, N, D, 2048, 1);
-    if (int rc = launch_gemm(g, d.gemm_path, stream)) return rc;
+    if (int rc = launch_gemm(g, gpath, stream)) return rc;
     STAGE_END();
     // 4. BiGRU input pre-activations for both directions (hoisted W_ih x + b_ih)
     g.count = 0;
@@ -294,7 +295,7 @@ static int forward_impl(const tggcn_dims* dims, const void* const* weights, int 
     gemm_add(g, buf(TGGCN_BUF_S_O), 2 * D, W(TGGCN_W_OBJ_RNN_WIH_B), D, W(TGGCN_W_OBJ_RNN_BIH_B), buf(TGGCN_BUF_GI_O) + 3 * D, 6 * D, N * O, 3 * D, D, 0);
     gemm_add(g, buf(TGGCN_BUF_S_G), 2 * D, W(TGGCN_W_GEO_RNN_WIH_F), D, W(TGGCN_W_GEO_RNN_BIH_F), buf(TGGCN_BUF_GI_G), 6 * D, N, 3 * D, D, 0);
     gemm_add(g, buf(TGGCN_BUF_S_G), 2 * D, W(TGGCN_W_GEO_RNN_WIH_B), D, W(TGGCN_W_GEO_RNN_BIH_B), buf(TGGCN_BUF_GI_G) + 3 * D, 6 * D, N, 3 * D, D, 0);
-    if (int rc = launch_gemm(g, d.gemm_path, stream)) return rc;
+    if (int rc = launch_gemm(g, gpath, stream)) return rc;
     STAGE_END();
     // 5. frame-level BiGRU recurrences (models.py:649-651)
     {
@@ -328,7 +329,7 @@ static int forward_impl(const tggcn_dims* dims, const void* const* weights, int 
     gemm_add(g, buf(TGGCN_BUF_HFR_H), 2 * D, W(TGGCN_W_HUM_BD_W), 2 * D, W(TGGCN_W_HUM_BD_B), buf(TGGCN_BUF_S_H) + D, 2 * D, N * H, D, 2 * D, 1);
     gemm_add(g, buf(TGGCN_BUF_HFR_O), 2 * D, W(TGGCN_W_OBJ_BD_W), 2 * D, W(TGGCN_W_OBJ_BD_B), buf(TGGCN_BUF_S_O) + D, 2 * D, N * O, D, 2 * D, 1);
     gemm_add(g, buf(TGGCN_BUF_HFR_G), 2 * D, W(TGGCN_W_GEO_BD_W), 2 * D, W(TGGCN_W_GEO_BD_B), buf(TGGCN_BUF_S_G) + D, 2 * D, N, D, 2 * D, 1);
-    if (int rc = launch_gemm(g, d.gemm_path, stream)) return rc;
+    if (int rc = launch_gemm(g, gpath, stream)) return rc;
     STAGE_END();
     // 7. per-sender frame messages, each computed once per sender and message kind (models.py:1693-1718)
     g.count = 0;
@@ -337,7 +338,7 @@ static int forward_impl(const tggcn_dims* dims, const void* const* weights, int 
     gemm_add(g, buf(TGGCN_BUF_S_O), 2 * D, W(TGGCN_W_MSG_OH_W), 2 * D, W(TGGCN_W_MSG_OH_B), buf(TGGCN_BUF_MSG_OH), D, N * O, D, 2 * D, 1);
     gemm_add(g, buf(TGGCN_BUF_S_O), 2 * D, W(TGGCN_W_MSG_OO_W), 2 * D, W(TGGCN_W_MSG_OO_B), buf(TGGCN_BUF_MSG_OO), D, N * O, D, 2 * D, 1);
     gemm_add(g, buf(TGGCN_BUF_S_G), 2 * D, W(TGGCN_W_MSG_GO_W), 2 * D, W(TGGCN_W_MSG_GO_B), buf(TGGCN_BUF_MSG_GO), D, N, D, 2 * D, 1);
-    if (int rc = launch_gemm(g, d.gemm_path, stream)) return rc;
+    if (int rc = launch_gemm(g, gpath, stream)) return rc;
     STAGE_END();
     // 8. attention, aggregation, gates, segment-level inputs
     {
@@ -371,7 +372,7 @@ static int forward_impl(const tggcn_dims* dims, const void* const* weights, int 
     gemm_add(g, buf(TGGCN_BUF_XX_H), kh, W(TGGCN_W_HSEG_B_WIH), ldwh, W(TGGCN_W_HSEG_B_BIH), buf(TGGCN_BUF_GS_H) + 3 * D, 6 * D, N * H, 3 * D, kh, 0);
     gemm_add(g, buf(TGGCN_BUF_XX_O), 4 * D, W(TGGCN_W_OSEG_F_WIH), 6 * D, W(TGGCN_W_OSEG_F_BIH), buf(TGGCN_BUF_GS_O), 6 * D, N * O, 3 * D, 4 * D, 0);
     gemm_add(g, buf(TGGCN_BUF_XX_O), 4 * D, W(TGGCN_W_OSEG_B_WIH), 6 * D, W(TGGCN_W_OSEG_B_BIH), buf(TGGCN_BUF_GS_O) + 3 * D, 6 * D, N * O, 3 * D, 4 * D, 0);
-    if (int rc = launch_gemm(g, d.gemm_path, stream)) return rc;
+    if (int rc = launch_gemm(g, gpath, stream)) return rc;
     STAGE_END();
     // 11. segment-level recurrent graph (models.py:785-880)
     {

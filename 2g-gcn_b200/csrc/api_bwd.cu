@@ -144,7 +144,7 @@ int tggcn_backward_ex(const tggcn_dims* dims, const void* const* weights, void* 
     cudaStream_t stream = (cudaStream_t)stream_;
     const int B = d.B, T = d.T, H = d.H, O = d.O, D = d.D, V = d.V, N = B * T;
     const int nkh = nkh_of(d), nks = nkh;
-    const int path = d.gemm_path;
+    const int path = (d.precision == 1 && d.gemm_path != 0) ? 3 : d.gemm_path;      // bf16 operands on the tensor-core GEMMs
     auto W = [&](int id) { return (const float*)weights[id]; };
     auto G = [&](int id) { return (float*)grad_weights[id]; };
     auto buf = [&](int id) { return (float*)((char*)workspace + L.off[id]); };

@@ -26,6 +26,7 @@ struct GemmProblem {
 struct GemmGroup {
     GemmProblem p[GEMM_MAX_PROBLEMS];
     int count;
+    int precision;       // tcgen05 path: 0 = 3xTF32 split (fp32-class), 1 = bf16 operands, fp32 accumulate (set by launch_gemm)
 };
 
 inline void gemm_add(GemmGroup& g, const float* A, int lda, const float* W, int ldw, const float* bias, float* C,
@@ -37,10 +38,12 @@ inline void gemm_add(GemmGroup& g, const float* A, int lda, const float* W, int 
 }
 
 int launch_gemm_simt(GemmGroup& grp, cudaStream_t stream);
-int launch_gemm_tc(GemmGroup& grp, cudaStream_t stream);     // tcgen05 3xTF32 (gemm_tc.cu)
-// path 0: fp32 SIMT; 1: tcgen05 3xTF32 (K % 32 == 0 required); 2: tcgen05 where the shapes allow it, SIMT otherwise
+int launch_gemm_tc(GemmGroup& grp, cudaStream_t stream);     // tcgen05 3xTF32 or bf16 (gemm_tc.cu)
+// path 0: fp32 SIMT; 1: tcgen05 3xTF32 (K % 32 == 0 required); 2: tcgen05 where the shapes allow it, SIMT otherwise;
+// 3: like 2 with bf16 operands on the tensor-core path (dims.precision = 1)
 inline int launch_gemm(GemmGroup& grp, int path, cudaStream_t stream) {
-    if (path == 2) {
+    grp.precision = path == 3 ? 1 : 0;
+    if (path == 2 || path == 3) {
         path = 1;
         for (int i = 0; i < grp.count; ++i)
             if (grp.p[i].K % 32 != 0) path = 0;

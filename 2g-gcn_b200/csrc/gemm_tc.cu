@@ -19,6 +19,7 @@
 #include "common.cuh"
 #include "gemm.h"
 #include "tcgen05.cuh"
+#include <cuda_bf16.h>
 
 namespace tg {
 
@@ -36,8 +37,30 @@ template <int BN> struct TcCfg {
     static constexpr int WP = BN / 32;                                           // W rows per producer thread
 };
 
+// kind::f16 instruction descriptor with bf16 operands: D = F32, A = B = BF16 (format 1), both K-major
+__device__ __forceinline__ uint32_t umma_idesc_bf16(int M, int N) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ uint2 pack_bf16x4(const float4& x) {
+    const __nv_bfloat162 lo = __floats2bfloat162_rn(x.x, x.y), hi = __floats2bfloat162_rn(x.z, x.w);
+    uint2 r;
+    r.x = *reinterpret_cast<const uint32_t*>(&lo);
+    r.y = *reinterpret_cast<const uint32_t*>(&hi);
+    return r;
+}
+
 // MASK: some problem of the group reads A through a ReLU mask (backward use); compiled out of the forward instantiation.
-template <bool MASK, int BN>
+// PREC 0: 3xTF32 split (hi and lo tiles, 12 MMAs per k-block).  PREC 1 (dims.precision = 1): the producers round the fp32
+// operands to bf16 and fill the FIRST 64 bytes of each 128-byte swizzle row of the hi tiles (32 K-elements per k-block as before),
+// the issuer runs two kind::f16 MMAs (K = 16) per k-block: one sixth of the tensor-pipe work, half the shared-memory bytes.
+template <bool MASK, int BN, int PREC>
 __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const GemmGroup grp) {
     constexpr int TC_BN = BN, TC_STAGES = TcCfg<BN>::STAGES, TC_STAGE_BYTES = TcCfg<BN>::STAGE_BYTES, WP = TcCfg<BN>::WP;
     constexpr int W_TILE_BYTES = TcCfg<BN>::W_TILE_BYTES;
@@ -132,6 +155,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const GemmGroup 
             uint8_t* st = tiles + s * TC_STAGE_BYTES;
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
+                if (PREC == 1) {     // float4 chunk c = bf16 elements 4c..4c+3 = bytes 8c..8c+7 of the row: 16-byte chunk c / 2
+                    *reinterpret_cast<uint2*>(st + sw128_off(r0 + 32 * i, c >> 1) + (c & 1) * 8) = pack_bf16x4(pa[i]);
+                    continue;
+                }
                 const uint32_t off = sw128_off(r0 + 32 * i, c);
                 float4 hi, lo;
                 split4(pa[i], hi, lo);
@@ -140,6 +167,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const GemmGroup 
             }
 #pragma unroll
             for (int i = 0; i < WP; ++i) {                       // W rows r0 + 32 i: the swizzle pattern repeats every 8 rows
+                if (PREC == 1) {
+                    *reinterpret_cast<uint2*>(st + 2 * TC_TILE_BYTES + sw128_off(r0 + 32 * i, c >> 1) + (c & 1) * 8) = pack_bf16x4(pw[i]);
+                    continue;
+                }
                 const uint32_t off = sw128_off(r0 + 32 * i, c);
                 float4 hi, lo;
                 split4(pw[i], hi, lo);
@@ -198,7 +229,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const GemmGroup 
         }
     } else {
         // ------------------------------ MMA issuer ------------------------------
-        const uint32_t idesc = umma_idesc_tf32(TC_BM, TC_BN);
+        const uint32_t idesc = PREC == 1 ? umma_idesc_bf16(TC_BM, TC_BN) : umma_idesc_tf32(TC_BM, TC_BN);
 #pragma unroll 1
         for (int kb = 0; kb < nkb; ++kb) {
             const int s = kb % TC_STAGES;
@@ -207,8 +238,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const GemmGroup 
             if (lane == 0) {
                 const uint32_t a_hi = tiles_u32 + s * TC_STAGE_BYTES, a_lo = a_hi + TC_TILE_BYTES;
                 const uint32_t w_hi = a_hi + 2 * TC_TILE_BYTES, w_lo = w_hi + W_TILE_BYTES;
+                if (PREC == 1) {
 #pragma unroll
-                for (int kk = 0; kk < TC_BK / 8; ++kk) {
+                    for (int kk = 0; kk < TC_BK / 16; ++kk)        // 16 bf16 = 32 bytes along the swizzled row
+                        umma_bf16(tmem_base, umma_desc(a_hi + kk * 32), umma_desc(w_hi + kk * 32), idesc, (kb | kk) != 0);
+                }
+#pragma unroll
+                for (int kk = 0; kk < (PREC == 1 ? 0 : TC_BK / 8); ++kk) {
                     const uint32_t ko = kk * 32;               // 8 tf32 = 32 bytes along the swizzled row
                     umma_tf32(tmem_base, umma_desc(a_lo + ko), umma_desc(w_hi + ko), idesc, (kb | kk) != 0);
                     umma_tf32(tmem_base, umma_desc(a_hi + ko), umma_desc(w_lo + ko), idesc, 1);
@@ -273,19 +309,18 @@ int launch_gemm_tc(GemmGroup& grp, cudaStream_t stream) {
     }
     bool mask = false;
     for (int i = 0; i < grp.count; ++i) mask |= grp.p[i].amask != nullptr;
-    if (int rc = ensure_smem((const void*)gemm_tc_kernel<false, 128>, TcCfg<128>::SMEM_BYTES)) return rc;
-    if (int rc = ensure_smem((const void*)gemm_tc_kernel<true, 128>, TcCfg<128>::SMEM_BYTES)) return rc;
-    if (int rc = ensure_smem((const void*)gemm_tc_kernel<false, 256>, TcCfg<256>::SMEM_BYTES)) return rc;
-    if (int rc = ensure_smem((const void*)gemm_tc_kernel<true, 256>, TcCfg<256>::SMEM_BYTES)) return rc;
-    if (bn == 256) {
-        if (mask) gemm_tc_kernel<true, 256><<<begin, TC_THREADS, TcCfg<256>::SMEM_BYTES, stream>>>(grp);
-        else      gemm_tc_kernel<false, 256><<<begin, TC_THREADS, TcCfg<256>::SMEM_BYTES, stream>>>(grp);
-    } else {
-        if (mask) gemm_tc_kernel<true, 128><<<begin, TC_THREADS, TcCfg<128>::SMEM_BYTES, stream>>>(grp);
-        else      gemm_tc_kernel<false, 128><<<begin, TC_THREADS, TcCfg<128>::SMEM_BYTES, stream>>>(grp);
+    auto launch = [&](auto kern, int smem) -> int {
+        if (int rc = ensure_smem((const void*)kern, smem)) return rc;
+        kern<<<begin, TC_THREADS, smem, stream>>>(grp);
+        TG_LAUNCH_OK();
+        return 0;
+    };
+    if (grp.precision == 1) {
+        if (bn == 256) return mask ? launch(gemm_tc_kernel<true, 256, 1>, TcCfg<256>::SMEM_BYTES) : launch(gemm_tc_kernel<false, 256, 1>, TcCfg<256>::SMEM_BYTES);
+        return mask ? launch(gemm_tc_kernel<true, 128, 1>, TcCfg<128>::SMEM_BYTES) : launch(gemm_tc_kernel<false, 128, 1>, TcCfg<128>::SMEM_BYTES);
     }
-    TG_LAUNCH_OK();
-    return 0;
+    if (bn == 256) return mask ? launch(gemm_tc_kernel<true, 256, 0>, TcCfg<256>::SMEM_BYTES) : launch(gemm_tc_kernel<false, 256, 0>, TcCfg<256>::SMEM_BYTES);
+    return mask ? launch(gemm_tc_kernel<true, 128, 0>, TcCfg<128>::SMEM_BYTES) : launch(gemm_tc_kernel<false, 128, 0>, TcCfg<128>::SMEM_BYTES);
 }
 
 }  // namespace tg

@@ -573,8 +573,10 @@ bool use_big_path(const tggcn_dims& d) {
     if (d.D % 64 != 0 || d.D < 128 || d.H > AT_MAXE || d.O > AT_MAXE) return false;
     if (d.recurrent_mode == 2) return true;
     if (d.recurrent_mode == 1) return false;
+    // measured crossover against the latency path (profiles/r02_sweep_configs.txt): CAD-120 B=32 (160 rows) breaks even,
+    // B=16 (80 rows) and MPHOI B=32 (128 rows) are faster on the persistent kernels
     const int rows = d.B * (d.H > d.O ? d.H : d.O);
-    return rows >= 64;
+    return rows >= 192;
 }
 
 namespace {
@@ -663,15 +665,18 @@ int launch_step(StepLaunch& L, int precision, int mt, cudaStream_t stream) {
     return mt == 2 ? launch_step_t<0, 2>(L, begin, stream) : launch_step_t<0, 1>(L, begin, stream);
 }
 
-// 256-row tiles when they move fewer operand bytes (TGGCN_STEP_MT=1|2 forces a choice: A/B experiments)
-int choose_mt(const StepLaunch& L) {
+// Tile height.  Measured on B200 (profiles/r02_step_tile_height.txt): the 256-row tile moves 30 % fewer operand bytes through L2
+// but is NOT faster — the kernel is bound by shared-memory bandwidth (every tcgen05.mma re-reads its (128 + 192) x 16 operand
+// slice from shared memory, three times per k-step with the split, while TMA writes the next stage), not by L2.  Default: 128
+// rows, which gives more CTAs per launch; TGGCN_STEP_MT=2 selects the 256-row tile (kept for bf16, where it is the better ratio).
+int choose_mt(const StepLaunch& L, int precision) {
     static int forced = -1;
     if (forced < 0) {
         const char* e = getenv("TGGCN_STEP_MT");
         forced = (e != nullptr && (e[0] == '1' || e[0] == '2')) ? e[0] - '0' : 0;
     }
     if (forced) return forced;
-    return step_traffic(L, 2) < 0.95 * step_traffic(L, 1) ? 2 : 1;
+    return (precision == 1 && step_traffic(L, 2) < 0.8 * step_traffic(L, 1)) ? 2 : 1;
 }
 
 size_t plane_bytes(size_t rows, size_t K) { return rows * K * 2; }
@@ -712,7 +717,7 @@ int launch_bigru_big(BiGruParams& P, void* big_ws, int precision, cudaStream_t s
                 q.ring_out = ws + BL.ring_g[g] + (size_t)(slot_out * 2 + dir) * 2 * plane_bytes(G.rows, D);
             }
         if (s == 0) {            // the problem list has the same shape every step: choose the tile height, then encode the maps
-            mt = choose_mt(L);
+            mt = choose_mt(L, precision);
             for (int g = 0; g < 3; ++g) {
                 const size_t rows = P.g[g].rows;
                 if (int rc = make_map(&L.maps[g], ws + BL.ring_g[g], precision, D, rows, 8, ST_BM * mt)) return rc;
@@ -808,7 +813,7 @@ int launch_segment_big(SegParams& P, void* big_ws, int precision, int T_save, cu
             }
         }
         if (s == 0) {
-            mtA = choose_mt(LA);
+            mtA = choose_mt(LA, precision);
             if (int rc = encode_maps(LA, mtA)) return rc;
         }
         if (int rc = launch_step(LA, precision, mtA, stream)) return rc;
@@ -843,7 +848,7 @@ int launch_segment_big(SegParams& P, void* big_ws, int precision, int T_save, cu
                 q.ring_out = ws + (is_h ? BL.ring_h : BL.ring_o) + (size_t)(slot_out * 2 + dir) * 2 * plane_bytes(R, D);
             }
         if (s == 0) {
-            mtB = choose_mt(LB);
+            mtB = choose_mt(LB, precision);
             if (int rc = encode_maps(LB, mtB)) return rc;
         }
         if (int rc = launch_step(LB, precision, mtB, stream)) return rc;

@@ -19,13 +19,13 @@ pytestmark = pytest.mark.gpu
 
 MARGIN = 2e-5
 
-# name: (shape, D, B, T, stage, seed attempt of tools/find_safe_seeds.py, min share of knife-edge-free videos)
+# name: (shape, D, B, T, stage, seed attempt of tools/find_safe_seeds.py, min share of knife-edge-free videos, recurrent_mode)
 FWD_CASES = {
-    'mphoi_bench': ('mphoi', 512, 8, 128, 2, 0, 1.0),          # BASELINE.json configs[1] == bench.py's workload
-    'cad120_long': ('cad120', 512, 8, 512, 2, 5, 1.0),         # configs[3], first point of the sweep
-    'bimanual_b32': ('bimanual', 64, 32, 256, 2, 0, 0.7),      # configs[4], shipped hidden size
-    'bimanual_d512_rows': ('bimanual', 512, 16, 24, 2, 0, 1.0),   # 32 / 144 rows per step: large-batch recurrent kernels
-    'cad120_b64_rows': ('cad120', 512, 64, 16, 2, 1, 1.0),        # 64 / 320 rows per step
+    'mphoi_bench': ('mphoi', 512, 8, 128, 2, 0, 1.0, 0),          # BASELINE.json configs[1] == bench.py's workload
+    'cad120_long': ('cad120', 512, 8, 512, 2, 5, 1.0, 0),         # configs[3], first point of the sweep
+    'bimanual_b32': ('bimanual', 64, 32, 256, 2, 0, 0.7, 0),      # configs[4], shipped hidden size
+    'bimanual_d512_rows': ('bimanual', 512, 16, 24, 2, 0, 1.0, 2),   # 32 / 144 rows per step on the large-batch recurrent kernels
+    'cad120_b64_rows': ('cad120', 512, 64, 16, 2, 1, 1.0, 0),        # 64 / 320 rows per step: large-batch path chosen automatically
 }
 
 
@@ -62,6 +62,7 @@ def test_benchmark_sizes_forward_matches_oracle(name, orc, synth, pkg):
         ref = orc.forward(p64, ocfg, batch['x_human'].double(), batch['x_objects'].double(), batch['objects_mask'].double(),
                           None, None, noise.double(), taps=taps)
     model = model.cuda().eval()
+    model.recurrent_mode = FWD_CASES[name][7]
     model.set_gumbel_noise(noise)
     with torch.no_grad():
         out = model(x_human=batch['x_human'].cuda(), x_objects=batch['x_objects'].cuda(), objects_mask=batch['objects_mask'].cuda())

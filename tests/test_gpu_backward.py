@@ -191,7 +191,7 @@ def _wide_setup(name, orc, synth, pkg):
 # large-batch recurrent path (recurrent_mode 2): its forward must leave exactly what the BPTT kernels read (gates, aggregated
 # messages, per-sender messages, attention weights)
 BIG_PATH_CASES = ['mphoi_d128_s2_rows', 'cad120_d128_s2_big', 'bimanual_d128_s2_big']
-WIDE_CASES.update({'cad120_d128_s2_big': ('cad120', 128, 5, 14, 2), 'bimanual_d128_s2_big': ('bimanual', 128, 3, 10, 2)})
+WIDE_CASES.update({'cad120_d128_s2_big': ('cad120', 128, 5, 14, 2), 'bimanual_d128_s2_big': ('bimanual', 128, 4, 8, 2)})
 
 
 @pytest.mark.parametrize('name,mode', [(n, 0) for n in sorted(WIDE_CASES)] + [(n, 2) for n in BIG_PATH_CASES])

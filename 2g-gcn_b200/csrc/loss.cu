@@ -29,7 +29,10 @@ __global__ void __launch_bounds__(256) loss_sum_kernel(const LossTerms L, float*
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < t.numel; i += stride) {
         if (t.kind == TGGCN_LOSS_NLL) {
             const long long tg_ = ((const long long*)t.target)[i];          // position (b, t, e)
-            if (tg_ >= 0) {
+            if (tg_ >= t.C) {             // F.nll_loss raises for a class index >= C: no out-of-bounds read here, the loss turns NaN
+                s = __int_as_float(0x7fc00000);
+                n += 1.0f;
+            } else if (tg_ >= 0) {
                 const long long e = i % t.E, bt = i / t.E, tt = bt % t.T, b = bt / t.T;
                 s -= t.out[((b * t.C + tg_) * t.T + tt) * t.E + e];
                 n += 1.0f;

@@ -12,7 +12,6 @@
 // The frame-part of W_ih x (3D/4D of the 5D/6D input columns) was hoisted into a batched projection.
 #include <stdlib.h>
 #include "recurrent.cuh"
-#include "recurrent_tc.cuh"
 #include "recurrent_res.cuh"
 #include "bigru.h"
 #include "step_tc.cuh"
@@ -46,15 +45,15 @@ struct SegShared {
 };
 
 // ---- phase A ------------------------------------------------------------------------------------
-// MODE: 0 = streaming mma.sync tiles, 1 = tcgen05 gate tile (recurrent_tc.cuh), 2 = streaming message tiles + cell tiles with
+// MODE: 0 = streaming mma.sync tiles, 2 = streaming message tiles + cell tiles with
 // on-chip resident weights (recurrent_res.cuh)
 // part: bit 0 = set-up (pointer tables; depends on nothing another CTA writes during the step), bit 1 = compute.  The persistent
 // resident variant runs the set-up of the NEXT phase between grid_arrive and grid_wait; everything else passes part = 3.
 // vbi: iteration over the video blocks a resident tile owns (video block = first block + vbi * groups); returns false
 // (uniformly) when the tile has no such block.
 template <int MODE>
-__device__ __forceinline__ bool seg_message_tile(const SegParams& P, int tile, int s, float* smem, SegShared& sh, RtcShared& rsh,
-                                                 RtcState& rst, uint4* wmsg, int& msg_ready, int part, int vbi = 0) {
+__device__ __forceinline__ bool seg_message_tile(const SegParams& P, int tile, int s, float* smem, SegShared& sh,
+                                                 uint4* wmsg, int& msg_ready, int part, int vbi = 0) {
     const int D = P.D, T = P.T, B = P.B, H = P.H, O = P.O;
     const int dir = tile / P.msg_tiles_dir;
     int rem = tile - dir * P.msg_tiles_dir;
@@ -158,8 +157,6 @@ __device__ __forceinline__ bool seg_message_tile(const SegParams& P, int tile, i
     if (MODE == 2 && P.res_msg) {
         if (!msg_ready) { res_fill_msg(wmsg, sh.tab1, D, P.sync.error); msg_ready = 1; }   // first step: this CTA's message weights go on chip
         tile_accumulate_msg_res(acc, sh.tab1 + MSG_UNITS, s > 0 ? D : 0, wmsg, P.wm[kind], smem);
-    } else if (MODE == 1) {
-        tile_accumulate_tc<MSG_NGL, 2>(acc, sh.tab1, sh.tab1, s > 0 ? D : 0, 0, rsh, rst);
     } else {
         tile_accumulate<MSG_NGL, 2, 3>(acc, sh.tab1, sh.tab1, s > 0 ? D : 0, 0, 0u, 0u, P.wm[kind], smem);
     }
@@ -235,7 +232,7 @@ struct CellPre {
 // part: as for seg_message_tile (bit 0 = pointer tables + epilogue operands, bit 1 = K loop + gate math).
 template <int NT, int MODE>
 __device__ __forceinline__ void seg_cell_tile(const SegParams& P, bool is_h, int dir, int rb, int ub, int s, float* smem,
-                                              SegShared& sh, RtcShared& rsh, RtcState& rst, ResState& res, int part, CellPre& pre) {
+                                              SegShared& sh, ResState& res, int part, CellPre& pre) {
     constexpr int RBT = 8 * NT, NPAIR = NT / 2, WR = 4 * REC_J;
     const int D = P.D, T = P.T, B = P.B;
     const int E = is_h ? P.H : P.O;
@@ -309,8 +306,6 @@ __device__ __forceinline__ void seg_cell_tile(const SegParams& P, bool is_h, int
     if (MODE == 2) {
         if (!res.ready) res_fill_cell(res, sh.tab1, sh.tab2, nk * D, D, P.sync.error);   // first step: this CTA's weight fragments go on chip
         tile_accumulate_res<NT>(acc, sh.tab1 + WR, sh.tab2 + WR, nk * D, D, res, Wh, smem);   // s == 0: null state rows = zeros
-    } else if (MODE == 1) {
-        tile_accumulate_tc<4, NT>(acc, sh.tab1, sh.tab2, nk * D, s > 0 ? D : 0, rsh, rst);
     } else {
         tile_accumulate<4, NT, 3>(acc, sh.tab1, sh.tab2, nk * D, s > 0 ? D : 0, 1u << 3, 1u << 2, Wh, smem);
     }
@@ -327,8 +322,8 @@ __device__ __forceinline__ void seg_cell_tile(const SegParams& P, bool is_h, int
 // rbi: with res_multi a tile is one (direction, entity type, row-block group, unit block) and owns every cell_g-th row block —
 // the weights stay resident while rbi walks over them; returns false (uniformly) when there is no such row block.
 template <int MODE>
-__device__ __forceinline__ bool seg_cell_dispatch(const SegParams& P, int tile, int s, float* smem, SegShared& sh, RtcShared& rsh,
-                                                  RtcState& rst, ResState& res, int part, CellPre& pre, int rbi = 0) {
+__device__ __forceinline__ bool seg_cell_dispatch(const SegParams& P, int tile, int s, float* smem, SegShared& sh,
+                                                  ResState& res, int part, CellPre& pre, int rbi = 0) {
     const int dir = tile / P.cell_tiles_dir;
     int rem = tile - dir * P.cell_tiles_dir;
     const bool is_h = rem < P.cell_tiles_h_dir;
@@ -337,23 +332,20 @@ __device__ __forceinline__ bool seg_cell_dispatch(const SegParams& P, int tile, 
     const int rbg = rem / nub, ub = rem - rbg * nub;
     const int rb = rbg + rbi * (is_h ? P.cell_g_h : P.cell_g_o);
     if (rb >= (is_h ? P.nrb_h : P.nrb_o)) return false;
-    if ((is_h ? P.cfg_h : P.cfg_o) == 4) seg_cell_tile<4, MODE>(P, is_h, dir, rb, ub, s, smem, sh, rsh, rst, res, part, pre);
-    else                                 seg_cell_tile<2, MODE>(P, is_h, dir, rb, ub, s, smem, sh, rsh, rst, res, part, pre);
+    if ((is_h ? P.cfg_h : P.cfg_o) == 4) seg_cell_tile<4, MODE>(P, is_h, dir, rb, ub, s, smem, sh, res, part, pre);
+    else                                 seg_cell_tile<2, MODE>(P, is_h, dir, rb, ub, s, smem, sh, res, part, pre);
     return true;
 }
 
 // phases: bit 0 = A (messages), bit 1 = B (cells).  MODE as above.
 template <int MODE>
-__global__ void __launch_bounds__(MODE == 1 ? RTC_THREADS : REC_THREADS, 1) segment_kernel(const SegParams P, int s_begin, int s_end,
+__global__ void __launch_bounds__(REC_THREADS, 1) segment_kernel(const SegParams P, int s_begin, int s_end,
                                                                                           int phases, int persistent) {
     extern __shared__ __align__(16) float smem[];
     __shared__ SegShared sh;
-    __shared__ RtcShared rsh;
     __shared__ uint32_t tmem_slot;
-    RtcState rst;
     ResState res;
     if (threadIdx.x == 0) sh.s_fail = 0;
-    if (MODE == 1) { rtc_init(rsh, rst, reinterpret_cast<uint8_t*>(smem)); rst.dbg = phases >> 4; }      // dbg: timing experiments
     // MODE 2: the ring keeps its place at the start of dynamic shared memory; the overflow fragments follow it
     if (MODE == 2) res_init(res, &tmem_slot, reinterpret_cast<uint4*>(smem + P.res_ring_floats));
     // MODE 2 with res_msg: the message weights of this CTA's message tile follow the overflow fragments
@@ -368,17 +360,17 @@ __global__ void __launch_bounds__(MODE == 1 ? RTC_THREADS : REC_THREADS, 1) segm
         // the set-up of the next phase (pointer tables, epilogue operands) runs in the shadow of the grid barrier
         const int bid = blockIdx.x;
         const bool hasA = bid < P.tilesA, hasB = bid < P.tilesB;
-        if (hasA) seg_message_tile<MODE>(P, bid, s_begin, smem, sh, rsh, rst, wmsg, msg_ready, 1);
+        if (hasA) seg_message_tile<MODE>(P, bid, s_begin, smem, sh, wmsg, msg_ready, 1);
         __syncthreads();
         for (int s = s_begin; s < s_end; ++s) {
-            if (hasA) seg_message_tile<MODE>(P, bid, s, smem, sh, rsh, rst, wmsg, msg_ready, 2);
+            if (hasA) seg_message_tile<MODE>(P, bid, s, smem, sh, wmsg, msg_ready, 2);
             grid_arrive(P.sync, epoch);
-            if (hasB) seg_cell_dispatch<MODE>(P, bid, s, smem, sh, rsh, rst, res, 1, pre);
+            if (hasB) seg_cell_dispatch<MODE>(P, bid, s, smem, sh, res, 1, pre);
             if (!grid_wait(P.sync, epoch, gridDim.x, &sh.s_fail)) break;
-            if (hasB) seg_cell_dispatch<MODE>(P, bid, s, smem, sh, rsh, rst, res, 2, pre);
+            if (hasB) seg_cell_dispatch<MODE>(P, bid, s, smem, sh, res, 2, pre);
             if (s + 1 == s_end) break;
             grid_arrive(P.sync, epoch);
-            if (hasA) seg_message_tile<MODE>(P, bid, s + 1, smem, sh, rsh, rst, wmsg, msg_ready, 1);
+            if (hasA) seg_message_tile<MODE>(P, bid, s + 1, smem, sh, wmsg, msg_ready, 1);
             if (!grid_wait(P.sync, epoch, gridDim.x, &sh.s_fail)) break;
         }
         s_begin = s_end;                        // skip the generic loop
@@ -390,10 +382,10 @@ __global__ void __launch_bounds__(MODE == 1 ? RTC_THREADS : REC_THREADS, 1) segm
         const int bid = blockIdx.x;
         for (int s = s_begin; s < s_end; ++s) {
             if (bid < P.tilesA)
-                for (int vbi = 0; seg_message_tile<MODE>(P, bid, s, smem, sh, rsh, rst, wmsg, msg_ready, 3, vbi); ++vbi) {}
+                for (int vbi = 0; seg_message_tile<MODE>(P, bid, s, smem, sh, wmsg, msg_ready, 3, vbi); ++vbi) {}
             if (!grid_barrier(P.sync, epoch, gridDim.x, &sh.s_fail)) break;
             if (bid < P.tilesB)
-                for (int rbi = 0; seg_cell_dispatch<MODE>(P, bid, s, smem, sh, rsh, rst, res, 3, pre, rbi); ++rbi) {}
+                for (int rbi = 0; seg_cell_dispatch<MODE>(P, bid, s, smem, sh, res, 3, pre, rbi); ++rbi) {}
             if (s + 1 < s_end && !grid_barrier(P.sync, epoch, gridDim.x, &sh.s_fail)) break;
         }
         s_begin = s_end;
@@ -405,15 +397,14 @@ __global__ void __launch_bounds__(MODE == 1 ? RTC_THREADS : REC_THREADS, 1) segm
         }
         if (phases & 1) {
             for (int tile = blockIdx.x; tile < P.tilesA; tile += gridDim.x)
-                seg_message_tile<MODE>(P, tile, s, smem, sh, rsh, rst, wmsg, msg_ready, 3);
+                seg_message_tile<MODE>(P, tile, s, smem, sh, wmsg, msg_ready, 3);
             if (persistent && !grid_barrier(P.sync, epoch, gridDim.x, &sh.s_fail)) { ok = false; break; }
         }
         if (phases & 2) {
-            for (int tile = blockIdx.x; tile < P.tilesB; tile += gridDim.x) seg_cell_dispatch<MODE>(P, tile, s, smem, sh, rsh, rst, res, 3, pre);
+            for (int tile = blockIdx.x; tile < P.tilesB; tile += gridDim.x) seg_cell_dispatch<MODE>(P, tile, s, smem, sh, res, 3, pre);
             if (persistent && s + 1 < s_end && !grid_barrier(P.sync, epoch, gridDim.x, &sh.s_fail)) { ok = false; break; }
         }
     }
-    if (MODE == 1) rtc_finish(rst);
     if (MODE == 2) res_finish(res);
 }
 
@@ -462,7 +453,7 @@ int launch_segment(SegParams& P, int persistent, cudaStream_t stream) {
     if (fc > fa) fa = fc;
     const int fr = REC_WARPS * RES_STAGES * 32 * RES_RS;       // activation ring of the resident cell tile
     if (fr > fa) fa = fr;
-    // variant: 1 = tcgen05 gate tile (opt-in), 2 = cell weights resident on chip (every CTA owns at most one cell tile and the
+    // variant: 2 = cell weights resident on chip (every CTA owns at most one cell tile and the
     // per-thread fragment words fit in tensor memory + overflow), 0 = streaming
     static int res_env_cached = -1;
     int& res_env_ref = res_env_cached;
@@ -471,7 +462,7 @@ int launch_segment(SegParams& P, int persistent, cudaStream_t stream) {
         res_env_ref = (e != nullptr && e[0] == '0') ? 0 : 1;
     }
     const int res_env = P.no_fp16_split ? 0 : res_env_cached;
-    int mode = rec_use_tc(D) ? 1 : 0;
+    int mode = 0;
     const int kmax = (P.nk_h > 2 ? P.nk_h : 2) * D + D;
     const bool res_fits = cdiv(kmax / REC_CK, REC_WARPS) * RES_CHUNK_WORDS <= RES_TMEM_WORDS + RES_SMEM_WORDS;
     if (mode == 0 && res_env && res_fits && P.tilesB <= num_sms() && (persistent ? P.tilesA <= num_sms() : true)) mode = 2;
@@ -524,10 +515,9 @@ int launch_segment(SegParams& P, int persistent, cudaStream_t stream) {
         if (need + static_smem <= 227 * 1024) { P.res_msg = 1; fa = fm; }
     }
     P.res_ring_floats = fa;
-    auto kern = mode == 1 ? segment_kernel<1> : (mode == 2 ? segment_kernel<2> : segment_kernel<0>);
-    const int threads = mode == 1 ? RTC_THREADS : REC_THREADS;
-    size_t smem = mode == 1 ? (size_t)RTC_SMEM_BYTES
-                            : sizeof(float) * (size_t)fa + (mode == 2 ? sizeof(float) * RES_SMEM_WORDS * REC_THREADS : 0)
+    auto kern = mode == 2 ? segment_kernel<2> : segment_kernel<0>;
+    const int threads = REC_THREADS;
+    size_t smem = sizeof(float) * (size_t)fa + (mode == 2 ? sizeof(float) * RES_SMEM_WORDS * REC_THREADS : 0)
                                   + (P.res_msg ? (size_t)cdiv(D / REC_CK, REC_WARPS) * RES_MSG_GROUPS * 2 * REC_THREADS * 16 : 0);
     // The resident variant allocates all 512 tensor-memory columns of its SM: a second CTA of this kernel on the same SM would
     // block in tcgen05.alloc while the first one spins at the grid barrier.  Requesting more than half of the SM's shared memory

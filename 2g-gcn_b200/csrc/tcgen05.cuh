@@ -1,5 +1,5 @@
 // Thin PTX wrappers for the 5th-generation tensor cores (tcgen05 / TMEM / mbarrier) shared by the projection kernel
-// (gemm_tc.cu) and the recurrent gate tiles (recurrent_tc.cuh).  sm_100a only.
+// (gemm_tc.cu) and the large-batch recurrent step kernels (step_tc.cu).  sm_100a only.
 #pragma once
 #include <stdint.h>
 #include <cuda_runtime.h>

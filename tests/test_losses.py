@@ -74,3 +74,14 @@ def test_fused_loss_all_targets_ignored_is_zero(pkg):
     assert [float(l) for l in losses] == [0.0, 0.0]
     sum(losses).backward()
     assert float(out[0].grad.abs().max()) == 0.0 and float(out[1].grad.abs().max()) == 0.0
+
+
+@pytest.mark.gpu
+def test_fused_nll_class_index_out_of_range_is_loud(pkg):
+    """F.nll_loss raises for a target >= C; the fused kernel must not read out of bounds and must not return a plausible
+    number: the term turns NaN."""
+    out = [torch.log_softmax(torch.randn(2, 4, 5, 2, device='cuda'), 1)]
+    tgt = [torch.randint(0, 4, (2, 5, 2), device='cuda')]
+    tgt[0][1, 3, 0] = 4
+    losses = pkg.losses.multi_task_loss(out, tgt, [pkg.losses.NLL], [1.0])
+    assert torch.isnan(losses[0])

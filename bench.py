@@ -231,10 +231,12 @@ def run_ours(args, rank, world, local_rank):
             _, st = model.forward_profile(resident['x_human'], resident['x_objects'], resident['objects_mask'])
             if i:
                 rows.append(st)
-    train = None
+    train = train_bf16 = None
     if not args.no_train:
         del model
         train = train_step_throughput(args, pkg, shape, kwargs, dev, rank, world, flush, barrier)
+        train_bf16 = train_step_throughput(args, pkg, shape, kwargs, dev, rank, world, flush, barrier, precision='bf16')
+    others = other_configs(args, pkg, dev, flush) if (world == 1 and not args.no_extras) else None
     frames = world * B * T * args.steps
     value = frames / (total_ms / 1e3)
     e2e_value = frames / (e2e_total_ms / 1e3)
@@ -280,7 +282,9 @@ def run_ours(args, rank, world, local_rank):
                    'frames_per_video': T, 'humans': shape.H, 'objects': shape.O, 'gcn_node': shape.V, 'hidden_size': D,
                    'weights': 'reference default init, torch.manual_seed(0)', 'l2': 'flushed (256 MB memset) between timed steps',
                    'projections': 'tcgen05 3xTF32' if args.gemm_path else 'fp32 SIMT',
-                   'recurrences': 'persistent kernels, on-chip resident weights, mma.sync 3xFP16 split (fp32-class accuracy)', 'parallelism': f'replicas x{world} (videos sharded)'},
+                   'recurrences': 'persistent kernels, on-chip resident weights, mma.sync 3xFP16 split (fp32-class accuracy); '
+                                  'large-batch tcgen05 + TMA step kernels from 192 rows per step (other_configs)',
+                   'parallelism': f'replicas x{world} (videos sharded)'},
         'clocks': clocks,
         'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
                 'ms_per_step': e2e_total_ms / args.steps},
@@ -291,6 +295,9 @@ def run_ours(args, rank, world, local_rank):
     }
     if train is not None:
         line['train_step'] = train
+        line['train_step_bf16'] = train_bf16         # BASELINE.json configs[2]
+    if others is not None:
+        line['other_configs'] = others               # BASELINE.json configs[3], [4]
     if world == 1 and not args.no_cpu_baseline:
         line['cpu_baseline'] = cpu_port_throughput(args, shape, kwargs, warmup=1, steps=2)
         if train is not None:
@@ -298,16 +305,18 @@ def run_ours(args, rank, world, local_rank):
     print(json.dumps(line), flush=True)
 
 
-def train_step_throughput(args, pkg, shape, kwargs, dev, rank, world, flush, barrier):
+def train_step_throughput(args, pkg, shape, kwargs, dev, rank, world, flush, barrier, precision='fp32'):
     """One training step = forward (BatchNorm in train mode, activations saved) + the fused criterion (drop-in for
-    vhoi/losses.py:8, stage-2 weights: BCE on the soft gates + 2 NLL terms) + the hand-written backward (tggcn_backward) +
-    gradient all-reduce (N > 1) + Adam, in the sequence of train_utils.py:143-154."""
+    vhoi/losses.py:8, stage-2 weights: BCE on the soft gates + 2 NLL terms) + the hand-written backward (tggcn_backward_ex) +
+    gradient all-reduce (N > 1: four buckets launched from the backward's stage boundaries on a side stream, loss terms weighted
+    by each rank's share of the valid targets) + Adam, in the sequence of train_utils.py:143-154."""
     import torch.distributed as dist
     torch.manual_seed(0)
     model = pkg.TGGCN(**kwargs).to(dev).train()
     model.gemm_path = args.gemm_path
+    model.set_precision(precision)
     opt = torch.optim.Adam(model.parameters(), lr=1e-4, fused=True)      # torch's own Adam (train.py's optimiser), fused variant
-    reducer = pkg.dp.GradientAllReduce(model)
+    reducer = pkg.dp.GradientAllReduce(model).attach()
     reducer.sync_parameters()
     B, T = args.B, args.T
     host = pkg.synth.make_batch(shape, B, T, seed=1234 + rank)
@@ -326,10 +335,14 @@ def train_step_throughput(args, pkg, shape, kwargs, dev, rank, world, flush, bar
     def step():
         opt.zero_grad(set_to_none=True)
         out = model(**x)
-        loss = sum(criterion(out, targets, reduction='mean'))
-        loss.backward()
-        if world > 1:                                  # data-parallel: one all-reduce of the flat gradient buffer
-            reducer.reduce()
+        losses = criterion(out, targets, reduction='mean')
+        if world > 1:                                  # each rank's terms weighted by its share of the valid targets
+            w = pkg.dp.loss_term_weights(targets)
+            losses = [l * wi for l, wi in zip(losses, w.unbind(0))]
+        loss = sum(losses)
+        loss.backward()                                # queues the backward, then the bucket all-reduces on the side stream
+        if world > 1:
+            reducer.reduce()                           # joins the streams
         opt.step()
         return loss
 
@@ -373,9 +386,14 @@ def train_step_throughput(args, pkg, shape, kwargs, dev, rank, world, flush, bar
         pipe.submit(host_step)
         opt.zero_grad(set_to_none=True)
         out = model(x_human=cur['x_human'], x_objects=cur['x_objects'], objects_mask=cur['objects_mask'])
-        loss = sum(criterion(out, [cur[f'target{j}'] for j in range(len(host_tg))], reduction='mean'))
+        tg = [cur[f'target{j}'] for j in range(len(host_tg))]
+        losses = criterion(out, tg, reduction='mean')
+        if world > 1:
+            w = pkg.dp.loss_term_weights(tg)
+            losses = [l * wi for l, wi in zip(losses, w.unbind(0))]
+        loss = sum(losses)
         loss.backward()
-        pipe.release()
+        pipe.release()                                 # after the backward: tggcn_backward reads the inputs from the slot
         if world > 1:
             reducer.reduce()
         opt.step()
@@ -409,9 +427,92 @@ def train_step_throughput(args, pkg, shape, kwargs, dev, rank, world, flush, bar
             'e2e': {'value': world * B * T / (e2e_ms / 1e3), 'unit': UNIT, 'ms_per_step': e2e_ms, 'h2d_bytes_per_step': h2d,
                     'd2h_bytes_per_step': 4},
             'gpu_launches_per_step': int(launches // steps), 'loss': float(loss.detach()),
-            'what': 'forward(train-mode BN, saves) + fused criterion (BCE + 2x NLL) + tggcn_backward + '
-                    + ('NCCL all-reduce of the flat gradient + ' if world > 1 else '') + 'torch.optim.Adam(fused=True) step; fp32-accurate products (3xTF32 / 3xFP16 split)',
+            'dtype': 'bf16' if precision == 'bf16' else 'f32',
+            'what': 'forward(train-mode BN, saves) + fused criterion (BCE + 2x NLL) + tggcn_backward_ex + '
+                    + ('bucketed NCCL all-reduce of the flat gradient overlapped with the backward + ' if world > 1 else '')
+                    + 'torch.optim.Adam(fused=True) step; '
+                    + ('bf16 operands / fp32 accumulation in every projection and weight-gradient GEMM, fp32 gates, recurrences and optimiser'
+                       if precision == 'bf16' else 'fp32-accurate products (3xTF32 / 3xFP16 split)'),
             'global_batch_videos': world * B}
+
+
+def other_configs(args, pkg, dev, flush):
+    """BASELINE.json configs[3] and [4] on this GPU (N = 1): the CAD-120-shaped inference sweep over the batch size (T = 512) and
+    the Bimanual-shaped training step (B = 32, T = 256, hidden 64 as shipped and 512).  Each entry: frames/s (CUDA events, median
+    of 3 after 2 warm-ups, L2 flushed between iterations) and the roofline of its largest stage from the stage_work closed forms."""
+    peaks = load_peaks()
+    res = {'cad120_inference_sweep': [], 'bimanual_training': []}
+
+    def med(fn, iters=3, warm=2):
+        for _ in range(warm):
+            fn()
+        torch.cuda.synchronize(dev)
+        ms = []
+        for _ in range(iters):
+            flush.zero_()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            fn()
+            e1.record()
+            torch.cuda.synchronize(dev)
+            ms.append(e0.elapsed_time(e1))
+        return statistics.median(ms)
+
+    cad = pkg.synth.SHAPES['cad120']
+    T = 512
+    sweep = [b for b in (8, 16, 32, 64, 128, 256) if b <= args.max_sweep_batch]
+    big = pkg.synth.make_batch(cad, max(sweep), T, seed=1234)                 # generated once, sliced for the smaller batches
+    torch.manual_seed(0)
+    model = pkg.TGGCN(**pkg.synth.model_kwargs(cad, hidden_size=512, stage=2)).to(dev).eval()
+    for b in sweep:
+        x = {k: big[k][:b].to(dev) for k in ('x_human', 'x_objects', 'objects_mask')}
+        model.set_gumbel_noise(pkg.TGGCN.draw_gumbel_noise(T * (cad.H + cad.O), b).to(dev))
+        with torch.no_grad():
+            ms = med(lambda: model(**x))
+            _, st = model.forward_profile(x['x_human'], x['x_objects'], x['objects_mask'])
+        model.check_persistent_kernels()
+        top = max(st, key=st.get)
+        fl, by = stage_work(cad, b, T, 512, cad.hh)[top]
+        rows = b * max(cad.H, cad.O)
+        res['cad120_inference_sweep'].append({
+            'videos': b, 'frames_per_video': T, 'ms': round(ms, 3), 'frames_per_s': round(b * T / ms * 1e3),
+            'recurrent_path': 'large-batch tcgen05 + TMA step kernels' if rows >= 192 else 'persistent latency path',
+            'top_stage': top, 'top_stage_ms': round(st[top], 3), 'us_per_recurrent_step': round(st[top] * 1e3 / T, 2) if top in ('segment', 'bigru') else None,
+            'roofline': {'bound': 'tensor', 'achieved': round(fl / (st[top] / 1e3) / 1e12, 2), 'peak': peaks['tf_sustained'], 'unit': 'TFLOP/s',
+                         'frac': round(fl / (st[top] / 1e3) / 1e12 / peaks['tf_sustained'], 4)}})
+        del x
+    del model, big
+    torch.cuda.empty_cache()
+
+    class Cfg(dict):
+        def get(self, k, default_value=None):
+            return dict.get(self, k, default_value)
+    bim = pkg.synth.SHAPES['bimanual']
+    Bb, Tb = 32, 256
+    host = pkg.synth.make_batch(bim, Bb, Tb, seed=1234)
+    x = {k: host[k].to(dev) for k in ('x_human', 'x_objects', 'objects_mask')}
+    targets = [t.to(dev) for t in pkg.synth.target_list(bim, pkg.synth.make_targets(bim, host['lengths'], Tb, seed=5))]
+    criterion, _ = pkg.losses.select_loss('2G-GCN', 'multiple', bim.dataset, Cfg(misc=dict(segmentation_loss=dict(add=True, sigma=4.0, weight=1.0))))
+    for D in (64, 512):
+        torch.manual_seed(0)
+        m = pkg.TGGCN(**pkg.synth.model_kwargs(bim, hidden_size=D, stage=2)).to(dev).train()
+        opt = torch.optim.Adam(m.parameters(), lr=1e-4, fused=True)
+        m.set_gumbel_noise(pkg.TGGCN.draw_gumbel_noise(Tb * (bim.H + bim.O), Bb).to(dev))
+
+        def step():
+            opt.zero_grad(set_to_none=True)
+            sum(criterion(m(**x), targets, reduction='mean')).backward()
+            opt.step()
+        ms = med(step)
+        m.check_persistent_kernels()
+        fl = 3.0 * sum(v[0] for v in stage_work(bim, Bb, Tb, D, bim.hh).values())          # forward + 2x backward (SURVEY.md §8d)
+        res['bimanual_training'].append({
+            'videos': Bb, 'frames_per_video': Tb, 'hidden_size': D, 'ms': round(ms, 3), 'frames_per_s': round(Bb * Tb / ms * 1e3),
+            'roofline': {'bound': 'tensor', 'achieved': round(fl / (ms / 1e3) / 1e12, 2), 'peak': peaks['tf_sustained'], 'unit': 'TFLOP/s',
+                         'frac': round(fl / (ms / 1e3) / 1e12 / peaks['tf_sustained'], 4), 'of': 'whole training step'}})
+        del m, opt
+    torch.cuda.empty_cache()
+    return res
 
 
 def cpu_port_throughput(args, shape, kwargs, warmup, steps):
@@ -439,9 +540,10 @@ def cpu_port_throughput(args, shape, kwargs, warmup, steps):
                       f'{cores} torch threads', 'seconds_per_step': sec}
 
 
-def cpu_port_train_throughput(args, shape, kwargs, T_sample=32, steps=1):
-    """CPU train step of the reference path (oracle port: train-mode forward + criterion + autograd backward + Adam) on a
-    bounded sample: the full batch of videos, truncated to T_sample frames (cost is linear in T: two recurrent loops)."""
+def cpu_port_train_throughput(args, shape, kwargs, T_sample=None, steps=1):
+    """CPU train step of the reference path (oracle port: train-mode forward + criterion + autograd backward + Adam) on the
+    WHOLE workload (all B videos, all T frames; ~5-10 s per step on 16 cores), one timed step after one warm-up."""
+    T_sample = args.T if T_sample is None else T_sample
     sys.path.insert(0, os.path.join(ROOT, 'oracle'))
     import tggcn_oracle as orc
     pkg = importlib.import_module('2g-gcn_b200')
@@ -468,7 +570,7 @@ def cpu_port_train_throughput(args, shape, kwargs, T_sample=32, steps=1):
             times.append(time.perf_counter() - t0)
     sec = sum(times) / len(times)
     return {'value': B * T / sec, 'unit': UNIT, 'cores': cores, 'kind': 'port', 'seconds_per_step': sec,
-            'sample': f'train step on B={B} videos truncated to T={T} frames (hidden {args.D}), {steps} timed step(s) after 1 warm-up, '
+            'sample': f'whole workload: train step on B={B} videos x T={T} frames (hidden {args.D}), {steps} timed step(s) after 1 warm-up, '
                       f'{cores} torch threads'}
 
 
@@ -476,14 +578,15 @@ def run_reference(args, rank, world):
     if rank != 0:
         return
     pkg, shape, kwargs = workload(args)
-    res = cpu_port_throughput(args, shape, kwargs, warmup=min(args.warmup, 1), steps=min(args.steps, 3))
+    ran_steps, ran_warmup = min(args.steps, 3), min(args.warmup, 1)     # ~1.2 s per forward on 16 cores: bounded so the arm ends in seconds
+    res = cpu_port_throughput(args, shape, kwargs, warmup=ran_warmup, steps=ran_steps)
     line = {
-        'impl': 'reference', 'metric': METRIC, 'metric_detail': METRIC_DETAIL, 'value': res['value'], 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,
-        'warmup': args.warmup, 'ms_per_step': res['seconds_per_step'] * 1e3, 'higher_is_better': True, 'scaling': 'weak',
+        'impl': 'reference', 'metric': METRIC, 'metric_detail': METRIC_DETAIL, 'value': res['value'], 'unit': UNIT, 'n_gpus': world, 'steps': ran_steps,
+        'warmup': ran_warmup, 'steps_requested': args.steps, 'warmup_requested': args.warmup, 'ms_per_step': res['seconds_per_step'] * 1e3, 'higher_is_better': True, 'scaling': 'weak',
         'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
         'config': {'workload': f'2G-GCN inference forward, {shape.name.upper()} shape, stage-2 settings', 'videos_per_gpu': args.B,
                    'frames_per_video': args.T, 'humans': shape.H, 'objects': shape.O, 'gcn_node': shape.V, 'hidden_size': args.D,
-                   'note': 'CPU port of the reference path (oracle); timed steps capped at 3 to bound the run'},
+                   'note': 'CPU port of the reference path (oracle); steps / warmup are what was run (timed steps capped at 3)'},
         'cpu_baseline': {k: res[k] for k in ('value', 'unit', 'cores', 'kind', 'sample')},
         'e2e': {'value': res['value'], 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
     }
@@ -505,6 +608,8 @@ def main():
     ap.add_argument('--gemm-path', type=int, default=2)
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-train', action='store_true', help='skip the training-step measurement')
+    ap.add_argument('--max-sweep-batch', type=int, default=256, help='largest batch of the CAD-120 sweep in other_configs (46 GB at 256)')
+    ap.add_argument('--no-extras', action='store_true', help='skip the CAD-120 sweep and the Bimanual training configs (other_configs)')
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == 'ours' else args.warmup
     rank = int(os.environ.get('RANK', '0'))

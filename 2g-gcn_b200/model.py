@@ -95,6 +95,7 @@ class _ForwardBackward(torch.autograd.Function):
 
 class TGGCN(nn.Module):
     """B200-native 2G-GCN.  See module docstring; argument meaning as in vhoi/models.py:191-233."""
+    _STATUS_SLOTS = 64
 
     def __init__(self, input_size: tuple, num_classes: tuple, hidden_size: int = 128,
                  discrete_networks_num_layers: int = 1, discrete_optimization_strategy: str = 'gumbel-sigmoid',
@@ -215,8 +216,9 @@ class TGGCN(nn.Module):
         self.recurrent_mode = int(os.environ.get('TGGCN_RECURRENT_MODE', '0'))   # dims.recurrent_mode (0 = by rows per step)
         self.no_fp16_split = False          # set after a range violation: 3xTF32 streaming recurrent kernels from then on
         self.precision = 0                  # dims.precision: 0 = fp32-class split products, 1 = bf16 operands (set_precision)
-        self._pending_status = []           # (event, pinned status words, what) of calls whose status has not been looked at
-        self._status_pool = []              # pinned 8-word buffers ready for reuse
+        self._pending_status = []           # (event, ring slot, what) of calls whose status words have not been looked at
+        self._status_ring = None            # pinned (slots, 8) int32: landing zones of the asynchronous status copies
+        self._status_next = 0
         self._bucket_events = {}            # device -> cudaEvents recorded by tggcn_backward_ex at the gradient-bucket boundaries
         self._flat_pad_index = None
         self.grad_buckets = []              # [(start, end, event)] slices of flat_grad in completion order (last backward)
@@ -242,9 +244,15 @@ class TGGCN(nn.Module):
     def _queue_status(self, io, dev, what):
         """Give the call a pinned landing zone for its status words; they are looked at by a LATER call (or by
         check_persistent_kernels), so the check costs no synchronisation on the hot path."""
-        words = self._status_pool.pop() if self._status_pool else torch.zeros(8, dtype=torch.int32).pin_memory()
+        if self._status_ring is None:           # one pinned allocation for the life of the model (cudaHostAlloc is slow and may synchronise)
+            self._status_ring = torch.zeros(self._STATUS_SLOTS, 8, dtype=torch.int32).pin_memory()
+        slot = self._status_next % self._STATUS_SLOTS
+        self._status_next += 1
+        if any(s == slot for _, s, _ in self._pending_status):      # the ring wrapped onto a call nobody has looked at: look now
+            self._poll_status(wait=True)
+        words = self._status_ring[slot]
         io.status_host = words.data_ptr()
-        return (torch.cuda.Event(), words, what)
+        return (torch.cuda.Event(), slot, what)
 
     def _poll_status(self, wait: bool = False):
         """Test the status words of earlier calls whose copy has landed (all of them when ``wait``).  A grid-barrier time-out
@@ -252,14 +260,13 @@ class TGGCN(nn.Module):
         itself to the 3xTF32 streaming kernels, so a caller that catches the error can simply repeat the step."""
         still = []
         err = None
-        for ev, words, what in self._pending_status:
+        for ev, slot, what in self._pending_status:
             if wait:
                 ev.synchronize()
             if not ev.query():
-                still.append((ev, words, what))
+                still.append((ev, slot, what))
                 continue
-            rc = abi.lib().tggcn_status_decode(C.c_void_p(words.data_ptr()))
-            self._status_pool.append(words)
+            rc = abi.lib().tggcn_status_decode(C.c_void_p(self._status_ring[slot].data_ptr()))
             if rc != 0 and err is None:
                 msg = abi.lib().tggcn_last_error().decode(errors='replace')
                 if rc & 2:

@@ -42,14 +42,20 @@ constexpr int ST_A_TILE = ST_BM * 128;      // bytes of one 128-row operand tile
 constexpr int ST_B_TILE = 3 * ST_U * 128;   // bytes of one weight tile (three gate boxes, or one 128-row box + slack)
 constexpr float ST_W_SCALE = 256.0f;        // fp16 split: weights are stored times 2^8
 
-template <int PREC, int MT> struct StCfg {
+// CG: CTAs per tile (tcgen05 cta_group).  CG = 2: a CTA pair on the two SMs of a TPC computes a 256-row tile — each CTA
+// stages its own 128 activation rows and HALF of the weight rows, one tcgen05.mma.cta_group::2 reads both halves — so every SM
+// moves 30 % fewer bytes through its shared memory per FLOP, which is what bounds this kernel (profiles/r02_step_tile_height.txt).
+template <int PREC, int MT, int CG> struct StCfg {
+    static_assert(CG == 1 || MT == 1, "256-row tiles are either two accumulators in one CTA or one accumulator in each CTA of a pair");
     static constexpr int PLANES = PREC == 0 ? 2 : 1;                       // (hi, lo) or a single bf16 plane
-    static constexpr int A_PLANE = MT * ST_A_TILE;                         // one plane of the activation tile: 128 * MT rows
+    static constexpr int A_PLANE = MT * ST_A_TILE;                         // one plane of this CTA's activation rows: 128 * MT rows
     static constexpr int A_BYTES = PLANES * A_PLANE;
-    static constexpr int STAGE_BYTES = A_BYTES + PLANES * ST_B_TILE;       // 80 / 112 KB (fp16 split), 40 / 56 KB (bf16)
-    static constexpr int STAGES = PREC == 0 ? 2 : 4;
+    static constexpr int B_PLANE = ST_B_TILE / CG;                         // this CTA's share of the weight tile
+    static constexpr int STAGE_BYTES = A_BYTES + PLANES * B_PLANE;         // fp16 split: 80 / 112 / 56 KB; bf16: half of that
+    static constexpr int STAGES = (227 * 1024 - 2048) / STAGE_BYTES > 8 ? 8 : (227 * 1024 - 2048) / STAGE_BYTES;
     static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024;
     static constexpr int TMEM_COLS = MT * ST_ACC_COLS;
+    static constexpr int WBOX = ST_U / CG;                                 // rows of one weight TMA box (the maps are encoded with it)
 };
 
 enum { ST_GRU = 0, ST_RELU = 1 };
@@ -81,26 +87,65 @@ struct StepLaunch {
     float acc_scale;
 };
 
-// ---- PTX helpers (TMA) -----------------------------------------------------------------------------------------------
+// ---- PTX helpers (TMA, CTA pairs) ------------------------------------------------------------------------------------------
 __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
     asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n\t}\n" ::"r"(bar), "r"(bytes) : "memory");
 }
-__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, int c0, int c1, int c2, uint32_t bar) {
-    asm volatile(
-        "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];\n" ::"r"(dst),
-        "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(c2), "r"(bar)
-        : "memory");
+// CG = 2: the copy lands in THIS CTA's shared memory and completes bytes on the LEADER's barrier (bar: shared::cluster address)
+template <int CG> __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, int c0, int c1, int c2, uint32_t bar) {
+    if (CG == 1)
+        asm volatile(
+            "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];\n" ::"r"(dst),
+            "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(c2), "r"(bar)
+            : "memory");
+    else
+        asm volatile(
+            "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];\n" ::"r"(dst),
+            "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(c2), "r"(bar)
+            : "memory");
 }
 // kind::f16 instruction descriptor: D = F32, A = B = F16 (0) or BF16 (1), both K-major, N >> 3 at bits 17-22, M >> 4 at 24-28
 __device__ __forceinline__ uint32_t umma_idesc_16(int bf16, int M, int N) {
     return (1u << 4) | ((uint32_t)bf16 << 7) | ((uint32_t)bf16 << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
-__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(tmem_d),
-        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-        : "memory");
+template <int CG> __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    if (CG == 1)
+        asm volatile(
+            "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+            "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(tmem_d),
+            "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+            : "memory");
+    else
+        asm volatile(
+            "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+            "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(tmem_d),
+            "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+            : "memory");
+}
+// arrive on the barrier at the same offset in every CTA of the pair once the MMAs issued so far have completed
+template <int CG> __device__ __forceinline__ void umma_commit_cg(uint32_t bar) {
+    if (CG == 1)
+        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(bar) : "memory");
+    else
+        asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;\n" ::"r"(bar),
+                     "h"((uint16_t)3)
+                     : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;\n" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;\n" ::: "memory");
+}
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t cta_addr, uint32_t rank) {       // shared::cluster address of the same offset in CTA `rank`
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;\n" : "=r"(r) : "r"(cta_addr), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t cluster_addr) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];\n" ::"r"(cluster_addr) : "memory");
 }
 
 template <int PREC> __device__ __forceinline__ void store16(void* hi_plane, size_t plane_elems, size_t off, const float (&v)[16]) {
@@ -154,10 +199,14 @@ __device__ long long g_st_trace[64];
 #define ST_STAMP(i) do { } while (0)
 #endif
 
-template <int PREC, int MT>
+// Accumulator columns of a GRU tile: [r (64) | z (64) | n_i (64) | n_h (64)].  Weight tile in shared memory: [r z] rows (one
+// N = 128 operand) followed by the n rows (N = 64) — with CG = 2 the first CTA of the pair holds the r rows and the first half of
+// the n rows, the second one the z rows and the other half, which is exactly how cta_group::2 splits an N-operand.
+template <int PREC, int MT, int CG>
 __global__ void __launch_bounds__(ST_THREADS, 1) step_tc_kernel(const __grid_constant__ StepLaunch L) {
-    using Cfg = StCfg<PREC, MT>;
-    constexpr int STAGES = Cfg::STAGES, PLANES = Cfg::PLANES;
+    using Cfg = StCfg<PREC, MT, CG>;
+    constexpr int STAGES = Cfg::STAGES, PLANES = Cfg::PLANES, WBOX = Cfg::WBOX;
+    constexpr int RZ_BYTES = 2 * ST_U * 128 / CG, NB_BYTES = ST_U * 128 / CG;        // this CTA's rows of the two weight operands
     extern __shared__ uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t bars[2 * STAGES + 1];
     __shared__ uint32_t tmem_base_smem;
@@ -167,48 +216,57 @@ __global__ void __launch_bounds__(ST_THREADS, 1) step_tc_kernel(const __grid_con
     uint8_t* tiles = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     const uint32_t tiles_u32 = smem_u32(tiles);
     const uint32_t full0 = smem_u32(&bars[0]), empty0 = smem_u32(&bars[STAGES]), tfull = smem_u32(&bars[2 * STAGES]);
+    const int rank = CG == 2 ? (int)cluster_ctarank() : 0;
+    const bool leader = rank == 0;
 
+    const int vtile = CG == 2 ? (int)blockIdx.x >> 1 : (int)blockIdx.x;          // a CTA pair works on one tile
     int pi = 0;
 #pragma unroll 1
     for (int i = 1; i < L.count; ++i)
-        if ((int)blockIdx.x >= L.p[i].tile_begin) pi = i;
+        if (vtile >= L.p[i].tile_begin) pi = i;
     const StepProblem& P = L.p[pi];
-    const int tile = blockIdx.x - P.tile_begin;
+    const int tile = vtile - P.tile_begin;
     const int mt = tile / P.n_tiles, nt = tile - mt * P.n_tiles;
-    const int m0 = mt * ST_BM * MT;
+    const int m0 = mt * ST_BM * MT * CG + rank * ST_BM;                          // first activation row of THIS CTA
     const int nkb = P.nkb1 + P.nkb2;
     const bool gru = P.mode == ST_GRU;
 
     if (tid == 0) {
         for (int s = 0; s < STAGES; ++s) {
-            mbar_init(full0 + 8 * s, 1);
-            mbar_init(empty0 + 8 * s, 1);
+            mbar_init(full0 + 8 * s, CG);              // leader's expect_tx arrive (+ the peer's plain arrive)
+            mbar_init(empty0 + 8 * s, 1);              // one tcgen05.commit (multicast to both CTAs of a pair)
         }
         mbar_init(tfull, 1);
         asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
     }
     if (warp == 2) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(&tmem_base_smem)), "r"((uint32_t)Cfg::TMEM_COLS)
-                     : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
+        if (CG == 1) {
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(&tmem_base_smem)), "r"((uint32_t)Cfg::TMEM_COLS) : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
+        } else {
+            asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(&tmem_base_smem)), "r"((uint32_t)Cfg::TMEM_COLS) : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;\n" ::: "memory");
+        }
     }
     tc_fence_before();
-    __syncthreads();
+    if (CG == 2) cluster_sync_all(); else __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = tmem_base_smem;
     if (tid == 0) ST_STAMP(1);
 
     if (warp == 0) {
-        // ------------------------------ TMA producer ------------------------------
+        // ------------------------------ TMA producer (every CTA) ------------------------------
         if (lane == 0) {
-            const uint32_t tx = (uint32_t)PLANES * (Cfg::A_PLANE + (gru ? 3 * ST_U * 128 : ST_BN_RELU * 128));
+            const uint32_t stage_tx = (uint32_t)PLANES * (Cfg::A_PLANE + (gru ? RZ_BYTES + NB_BYTES : ST_BN_RELU * 128 / CG));
 #pragma unroll 1
             for (int kb = 0; kb < nkb; ++kb) {
                 const int s = kb % STAGES;
                 mbar_wait_backoff(empty0 + 8 * s, ((kb / STAGES) & 1) ^ 1);
                 if (kb < 12) ST_STAMP(4 + kb);
-                const uint32_t bar = full0 + 8 * s;
-                mbar_expect_tx(bar, tx);
+                const uint32_t my_full = full0 + 8 * s;
+                const uint32_t bar = CG == 2 ? mapa_u32(my_full, 0) : my_full;          // bytes complete on the leader's barrier
+                if (leader) mbar_expect_tx(my_full, stage_tx * CG);
+                else        mbar_arrive_remote(bar);
                 const bool seg2 = kb >= P.nkb1;
                 const int k0 = (seg2 ? kb - P.nkb1 : kb) * ST_BK;
                 const uint32_t st = tiles_u32 + s * Cfg::STAGE_BYTES;
@@ -216,78 +274,78 @@ __global__ void __launch_bounds__(ST_THREADS, 1) step_tc_kernel(const __grid_con
                 const CUtensorMap* bm = &L.maps[seg2 ? P.b2_map : P.b1_map];
                 const int ap = seg2 ? P.a2_plane : P.a1_plane, bp = seg2 ? P.b2_plane : P.b1_plane;
 #pragma unroll
-                for (int pl = 0; pl < PLANES; ++pl) tma_load_3d(st + pl * Cfg::A_PLANE, am, k0, m0, ap + pl, bar);   // box: 128 * MT rows
-                if (gru) {
-                    // gate boxes in accumulator-column order: input part -> [n r z], hidden part -> [r z n]
-                    const int g0 = seg2 ? 0 : 2, g1 = seg2 ? 1 : 0, g2 = seg2 ? 2 : 1;
-                    const int u0 = nt * ST_U;
+                for (int pl = 0; pl < PLANES; ++pl) tma_load_3d<CG>(st + pl * Cfg::A_PLANE, am, k0, m0, ap + pl, bar);   // box: 128 * MT rows
 #pragma unroll
-                    for (int pl = 0; pl < PLANES; ++pl) {
-                        const uint32_t b = st + Cfg::A_BYTES + pl * ST_B_TILE;
-                        tma_load_3d(b, bm, k0, g0 * P.D + u0, bp + pl, bar);
-                        tma_load_3d(b + ST_U * 128, bm, k0, g1 * P.D + u0, bp + pl, bar);
-                        tma_load_3d(b + 2 * ST_U * 128, bm, k0, g2 * P.D + u0, bp + pl, bar);
+                for (int pl = 0; pl < PLANES; ++pl) {
+                    const uint32_t b = st + Cfg::A_BYTES + pl * Cfg::B_PLANE;
+                    if (gru) {
+                        const int u0 = nt * ST_U;
+                        if (CG == 1) {                 // boxes of 64 rows: r, z, n
+                            tma_load_3d<CG>(b, bm, k0, u0, bp + pl, bar);
+                            tma_load_3d<CG>(b + ST_U * 128, bm, k0, P.D + u0, bp + pl, bar);
+                            tma_load_3d<CG>(b + 2 * ST_U * 128, bm, k0, 2 * P.D + u0, bp + pl, bar);
+                        } else {                       // boxes of 32 rows: my gate of (r, z) in two halves, my half of n
+                            tma_load_3d<CG>(b, bm, k0, rank * P.D + u0, bp + pl, bar);
+                            tma_load_3d<CG>(b + WBOX * 128, bm, k0, rank * P.D + u0 + WBOX, bp + pl, bar);
+                            tma_load_3d<CG>(b + 2 * WBOX * 128, bm, k0, 2 * P.D + u0 + rank * WBOX, bp + pl, bar);
+                        }
+                    } else {                           // 128 output columns: 2 boxes of 64 rows, or this CTA's 64 rows as 2 boxes of 32
+                        const int n0 = nt * ST_BN_RELU + rank * (ST_BN_RELU / 2);
+                        tma_load_3d<CG>(b, bm, k0, CG == 1 ? nt * ST_BN_RELU : n0, bp + pl, bar);
+                        tma_load_3d<CG>(b + WBOX * 128, bm, k0, (CG == 1 ? nt * ST_BN_RELU : n0) + WBOX, bp + pl, bar);
                     }
-                } else {
-#pragma unroll
-                    for (int pl = 0; pl < PLANES; ++pl)
-                        tma_load_3d(st + Cfg::A_BYTES + pl * ST_B_TILE, bm, k0, nt * ST_BN_RELU, bp + pl, bar);
                 }
             }
         }
     } else if (warp == 1) {
-        // ------------------------------ MMA issuer ------------------------------
-        const uint32_t id3 = umma_idesc_16(PREC, ST_BM, 3 * ST_U), id2 = umma_idesc_16(PREC, ST_BM, 2 * ST_U),
-                       id1 = umma_idesc_16(PREC, ST_BM, ST_U), idr = umma_idesc_16(PREC, ST_BM, ST_BN_RELU);
+        // ------------------------------ MMA issuer (leader CTA only) ------------------------------
+        if (leader) {
+            constexpr int MM = ST_BM * CG;
+            const uint32_t id_rz = umma_idesc_16(PREC, MM, 2 * ST_U), id_n = umma_idesc_16(PREC, MM, ST_U), id_relu = umma_idesc_16(PREC, MM, ST_BN_RELU);
 #pragma unroll 1
-        for (int kb = 0; kb < nkb; ++kb) {
-            const int s = kb % STAGES;
-            mbar_wait(full0 + 8 * s, (kb / STAGES) & 1);
-            tc_fence_after();
-            if (lane == 0) {
-                if (kb < 12) ST_STAMP(20 + kb);
-                const uint32_t st = tiles_u32 + s * Cfg::STAGE_BYTES;
-                const uint32_t a_hi = st, a_lo = st + Cfg::A_PLANE;
-                const uint32_t b_hi = st + Cfg::A_BYTES, b_lo = b_hi + ST_B_TILE;
-                const bool seg2 = kb >= P.nkb1;
+            for (int kb = 0; kb < nkb; ++kb) {
+                const int s = kb % STAGES;
+                mbar_wait(full0 + 8 * s, (kb / STAGES) & 1);
+                tc_fence_after();
+                if (lane == 0) {
+                    if (kb < 12) ST_STAMP(20 + kb);
+                    const uint32_t st = tiles_u32 + s * Cfg::STAGE_BYTES;
+                    const uint32_t a_hi = st, a_lo = st + Cfg::A_PLANE;
+                    const uint32_t b_hi = st + Cfg::A_BYTES, b_lo = b_hi + Cfg::B_PLANE;
+                    const bool seg2 = kb >= P.nkb1;
+                    const bool seg_first_kb = seg2 ? kb == P.nkb1 : kb == 0;
+                    const uint32_t ncol = seg2 ? 3 * ST_U : 2 * ST_U;               // n_h or n_i accumulator columns
 #pragma unroll
-                for (int kk = 0; kk < ST_BK / 16; ++kk) {
-                    const uint32_t ko = kk * 32;            // 16 halves = 32 bytes along the swizzled row
+                    for (int kk = 0; kk < ST_BK / 16; ++kk) {
+                        const uint32_t ko = kk * 32;            // 16 halves = 32 bytes along the swizzled row
 #pragma unroll
-                    for (int term = 0; term < (PREC == 0 ? 3 : 1); ++term) {
-                        // small terms first: lo*hi, hi*lo, hi*hi
-                        const uint32_t a = (PREC == 0 && term == 0) ? a_lo : a_hi;
-                        const uint32_t b = (PREC == 0 && term == 1) ? b_lo : b_hi;
-                        const uint64_t bd = umma_desc(b + ko);
-                        const bool very_first = kb == 0 && kk == 0 && term == 0;
+                        for (int term = 0; term < (PREC == 0 ? 3 : 1); ++term) {
+                            // small terms first: lo*hi, hi*lo, hi*hi
+                            const uint32_t a = (PREC == 0 && term == 0) ? a_lo : a_hi;
+                            const uint32_t b = (PREC == 0 && term == 1) ? b_lo : b_hi;
+                            const bool tile_first = kb == 0 && kk == 0 && term == 0;
+                            const bool seg_first = seg_first_kb && kk == 0 && term == 0;
 #pragma unroll
-                        for (int mh = 0; mh < MT; ++mh) {                   // the 128-row halves of the tile share the weight operand
-                            const uint64_t ad = umma_desc(a + mh * ST_A_TILE + ko);
-                            const uint32_t tacc = tmem_base + mh * ST_ACC_COLS;
-                            if (!gru) {
-                                umma_f16(tacc, ad, bd, idr, !very_first);
-                            } else if (!seg2) {
-                                umma_f16(tacc, ad, bd, id3, !very_first);                                  // columns [n_i r z]
-                            } else if (kb == P.nkb1 && kk == 0 && term == 0) {
-                                if (P.nkb1 > 0) {      // r, z keep accumulating; n_h starts here
-                                    umma_f16(tacc + ST_U, ad, bd, id2, 1);
-                                    umma_f16(tacc + 3 * ST_U, ad, umma_desc(b + 2 * ST_U * 128 + ko), id1, 0);
+                            for (int mh = 0; mh < MT; ++mh) {                   // the 128-row halves of an MT = 2 tile share the weight operand
+                                const uint64_t ad = umma_desc(a + mh * ST_A_TILE + ko);
+                                const uint32_t tacc = tmem_base + mh * ST_ACC_COLS;
+                                if (!gru) {
+                                    umma_f16<CG>(tacc, ad, umma_desc(b + ko), id_relu, !tile_first);
                                 } else {
-                                    umma_f16(tacc + ST_U, ad, bd, id3, 0);                                 // plain GRU: [r z n_h] only
+                                    umma_f16<CG>(tacc, ad, umma_desc(b + ko), id_rz, !tile_first);                     // r, z: both K parts
+                                    umma_f16<CG>(tacc + ncol, ad, umma_desc(b + RZ_BYTES + ko), id_n, !seg_first);    // n_i / n_h apart
                                 }
-                            } else {
-                                umma_f16(tacc + ST_U, ad, bd, id3, 1);                                     // columns [r z n_h]
                             }
                         }
                     }
+                    umma_commit_cg<CG>(empty0 + 8 * s);
+                    if (kb == nkb - 1) umma_commit_cg<CG>(tfull);
                 }
-                umma_commit(empty0 + 8 * s);
-                if (kb == nkb - 1) umma_commit(tfull);
+                __syncwarp();
             }
-            __syncwarp();
         }
     } else {
-        // ------------------------------ epilogue ------------------------------
+        // ------------------------------ epilogue (every CTA: its own 128 * MT rows) ------------------------------
         // TMEM lane quarter of a warp = warp id % 4.  MT = 1: the two warps of a quarter split the column chunks;
         // MT = 2: they take one 128-row accumulator each.
         const int ew = warp - 2, q = warp & 3, half = ew >> 2;
@@ -305,7 +363,6 @@ __global__ void __launch_bounds__(ST_THREADS, 1) step_tc_kernel(const __grid_con
             float* ho = P.hx + fe * 2 * D + (size_t)P.dir * D;
             float* gs = P.gsave != nullptr ? P.gsave + (fe * 2 + P.dir) * 4 * D : nullptr;
             const float ug = (valid && P.ugate != nullptr) ? __ldg(P.ugate + fe) : 1.0f;
-            // operands of the first chunk are fetched while the main loop still runs
             mbar_wait_backoff(tfull, 0);
             tc_fence_after();
             if (tid == 64) ST_STAMP(2);
@@ -313,9 +370,9 @@ __global__ void __launch_bounds__(ST_THREADS, 1) step_tc_kernel(const __grid_con
             for (int c = c_first; c < ST_U / 16; c += c_step) {
                 const int ub = nt * ST_U + c * 16;
                 float ni[16], ar[16], az[16], nh[16];
-                if (P.nkb1 > 0) tmem_ld16(tq + (uint32_t)(c * 16), ni);
-                tmem_ld16(tq + (uint32_t)(ST_U + c * 16), ar);
-                tmem_ld16(tq + (uint32_t)(2 * ST_U + c * 16), az);
+                tmem_ld16(tq + (uint32_t)(c * 16), ar);
+                tmem_ld16(tq + (uint32_t)(ST_U + c * 16), az);
+                if (P.nkb1 > 0) tmem_ld16(tq + (uint32_t)(2 * ST_U + c * 16), ni);
                 tmem_ld16(tq + (uint32_t)(3 * ST_U + c * 16), nh);
                 if (!valid) continue;
                 float xr[16], xz[16], xn[16], hprev[16], br[16], bz[16], bn[16], outv[16];
@@ -364,11 +421,12 @@ __global__ void __launch_bounds__(ST_THREADS, 1) step_tc_kernel(const __grid_con
         }
     }
     tc_fence_before();
-    __syncthreads();
+    if (CG == 2) cluster_sync_all(); else __syncthreads();      // the peer's epilogue must have read its accumulator before the pair's columns go
     if (tid == 0) ST_STAMP(3);
     if (warp == 2) {
         tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem_base), "r"((uint32_t)Cfg::TMEM_COLS) : "memory");
+        if (CG == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem_base), "r"((uint32_t)Cfg::TMEM_COLS) : "memory");
+        else         asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;\n" ::"r"(tmem_base), "r"((uint32_t)Cfg::TMEM_COLS) : "memory");
     }
 }
 
@@ -632,51 +690,57 @@ void pack_add(PackJobs& jobs, const float* src, int ld, int rows, int cols, void
     j.src = src; j.ld = ld; j.rows = rows; j.cols = cols; j.hi = hi;
 }
 
-template <int PREC, int MT> int launch_step_t(const StepLaunch& L, int grid, cudaStream_t stream) {
-    if (int rc = ensure_smem((const void*)step_tc_kernel<PREC, MT>, StCfg<PREC, MT>::SMEM_BYTES)) return rc;
-    step_tc_kernel<PREC, MT><<<grid, ST_THREADS, StCfg<PREC, MT>::SMEM_BYTES, stream>>>(L);
+template <int PREC, int MT, int CG> int launch_step_t(const StepLaunch& L, int tiles, cudaStream_t stream) {
+    using Cfg = StCfg<PREC, MT, CG>;
+    if (int rc = ensure_smem((const void*)step_tc_kernel<PREC, MT, CG>, Cfg::SMEM_BYTES)) return rc;
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(tiles * CG);
+    cfg.blockDim = dim3(ST_THREADS);
+    cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;          // CG = 2: the two CTAs of a tile on the two SMs of one TPC
+    attr[0].val.clusterDim.x = CG; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    TG_CUDA_OK(cudaLaunchKernelEx(&cfg, step_tc_kernel<PREC, MT, CG>, L));
     TG_LAUNCH_OK();
     return 0;
 }
 
-// Operand bytes one launch pulls through L2 with 128 * mt rows per tile (what bounds the kernel): tiles x k-blocks x stage bytes.
-double step_traffic(const StepLaunch& L, int mt) {
-    double bytes = 0.0;
-    for (int i = 0; i < L.count; ++i) {
-        const StepProblem& p = L.p[i];
-        const int n_tiles = p.mode == ST_GRU ? p.D / ST_U : cdiv(p.D, ST_BN_RELU);
-        bytes += (double)cdiv(p.rows, ST_BM * mt) * n_tiles * (p.nkb1 + p.nkb2) * (mt * ST_A_TILE + (p.mode == ST_GRU ? ST_B_TILE : ST_BN_RELU * 128));
-    }
-    return bytes;
-}
+// Tile shape of a launch: mt = 128-row accumulators per CTA (1 or 2), cg = CTAs per tile (1, or 2 = tcgen05 cta_group::2 pair).
+// The tensor maps of the launch must have been encoded for it: activation boxes of 128 * mt rows, weight boxes of 64 / cg rows.
+struct StepShape { int mt, cg; };
 
-// mt: 128-row accumulators per tile (1 or 2); the activation tensor maps of L must have been encoded with a 128 * mt row box
-int launch_step(StepLaunch& L, int precision, int mt, cudaStream_t stream) {
+int launch_step(StepLaunch& L, int precision, StepShape sh, cudaStream_t stream) {
     int begin = 0;
     for (int i = 0; i < L.count; ++i) {
         StepProblem& p = L.p[i];
-        p.m_tiles = cdiv(p.rows, ST_BM * mt);
+        p.m_tiles = cdiv(p.rows, ST_BM * sh.mt * sh.cg);
         p.n_tiles = p.mode == ST_GRU ? p.D / ST_U : cdiv(p.D, ST_BN_RELU);
         p.tile_begin = begin;
         begin += p.m_tiles * p.n_tiles;
     }
     L.acc_scale = precision ? 1.0f : 1.0f / ST_W_SCALE;
-    if (precision) return mt == 2 ? launch_step_t<1, 2>(L, begin, stream) : launch_step_t<1, 1>(L, begin, stream);
-    return mt == 2 ? launch_step_t<0, 2>(L, begin, stream) : launch_step_t<0, 1>(L, begin, stream);
+    if (sh.cg == 2) return precision ? launch_step_t<1, 1, 2>(L, begin, stream) : launch_step_t<0, 1, 2>(L, begin, stream);
+    if (precision) return sh.mt == 2 ? launch_step_t<1, 2, 1>(L, begin, stream) : launch_step_t<1, 1, 1>(L, begin, stream);
+    return sh.mt == 2 ? launch_step_t<0, 2, 1>(L, begin, stream) : launch_step_t<0, 1, 1>(L, begin, stream);
 }
 
-// Tile height.  Measured on B200 (profiles/r02_step_tile_height.txt): the 256-row tile moves 30 % fewer operand bytes through L2
-// but is NOT faster — the kernel is bound by shared-memory bandwidth (every tcgen05.mma re-reads its (128 + 192) x 16 operand
-// slice from shared memory, three times per k-step with the split, while TMA writes the next stage), not by L2.  Default: 128
-// rows, which gives more CTAs per launch; TGGCN_STEP_MT=2 selects the 256-row tile (kept for bf16, where it is the better ratio).
-int choose_mt(const StepLaunch& L, int precision) {
-    static int forced = -1;
-    if (forced < 0) {
-        const char* e = getenv("TGGCN_STEP_MT");
-        forced = (e != nullptr && (e[0] == '1' || e[0] == '2')) ? e[0] - '0' : 0;
+// Default: CTA pairs (cta_group::2).  The kernel is bound by shared-memory bandwidth — every tcgen05.mma re-reads its operand
+// slices from shared memory (three times per k-step with the split) while TMA writes the next stage — and a pair halves the
+// weight bytes each SM stages and reads (profiles/r02_step_tile_height.txt, r02_step_cta_pair.txt).  TGGCN_STEP_CG=1 selects
+// single-CTA tiles, TGGCN_STEP_MT=2 their two-accumulator variant (fewer L2 bytes, same shared-memory bytes: measured no gain).
+StepShape choose_shape() {
+    static int cg = 0, mt = 0;
+    if (cg == 0) {
+        const char* e = getenv("TGGCN_STEP_CG");
+        cg = (e != nullptr && e[0] == '1') ? 1 : 2;
+        const char* m = getenv("TGGCN_STEP_MT");
+        mt = (cg == 1 && m != nullptr && m[0] == '2') ? 2 : 1;
     }
-    if (forced) return forced;
-    return (precision == 1 && step_traffic(L, 2) < 0.8 * step_traffic(L, 1)) ? 2 : 1;
+    return StepShape{mt, cg};
 }
 
 size_t plane_bytes(size_t rows, size_t K) { return rows * K * 2; }
@@ -699,7 +763,7 @@ int launch_bigru_big(BiGruParams& P, void* big_ws, int precision, cudaStream_t s
     if (int rc = launch_pack(jobs, precision, stream)) return rc;
     StepLaunch L;
     memset(&L, 0, sizeof(L));
-    int mt = 1;
+    const StepShape shape = choose_shape();
     for (int s = 0; s < T; ++s) {
         const int slot_in = (s & 1) ^ 1, slot_out = s & 1;
         L.count = 0;
@@ -716,17 +780,16 @@ int launch_bigru_big(BiGruParams& P, void* big_ws, int precision, cudaStream_t s
                 q.xg = G.gi; q.bhh = G.bhh[dir]; q.ugate = nullptr; q.hx = G.hfr; q.gsave = G.gates;
                 q.ring_out = ws + BL.ring_g[g] + (size_t)(slot_out * 2 + dir) * 2 * plane_bytes(G.rows, D);
             }
-        if (s == 0) {            // the problem list has the same shape every step: choose the tile height, then encode the maps
-            mt = choose_mt(L, precision);
+        if (s == 0) {            // tensor maps: activation boxes of 128 * mt rows, weight boxes of 64 / cg rows
             for (int g = 0; g < 3; ++g) {
                 const size_t rows = P.g[g].rows;
-                if (int rc = make_map(&L.maps[g], ws + BL.ring_g[g], precision, D, rows, 8, ST_BM * mt)) return rc;
-                if (int rc = make_map(&L.maps[3 + g], ws + BL.whh_g[g], precision, D, 3 * D, 4, ST_U)) return rc;
+                if (int rc = make_map(&L.maps[g], ws + BL.ring_g[g], precision, D, rows, 8, ST_BM * shape.mt)) return rc;
+                if (int rc = make_map(&L.maps[3 + g], ws + BL.whh_g[g], precision, D, 3 * D, 4, ST_U / shape.cg)) return rc;
                 // the state "before the first step" is zero: slot 1 is what step 0 reads
                 TG_CUDA_OK(cudaMemsetAsync(ws + BL.ring_g[g] + 4 * plane_bytes(rows, D), 0, 4 * plane_bytes(rows, D), stream));
             }
         }
-        if (int rc = launch_step(L, precision, mt, stream)) return rc;
+        if (int rc = launch_step(L, precision, shape, stream)) return rc;
     }
     return 0;
 }
@@ -760,17 +823,18 @@ int launch_segment_big(SegParams& P, void* big_ws, int precision, int T_save, cu
     StepLaunch LA, LB;
     memset(&LA, 0, sizeof(LA));
     memset(&LB, 0, sizeof(LB));
-    int mtA = 1, mtB = 1;
-    auto encode_maps = [&](StepLaunch& L, int mt) -> int {       // activation boxes: 128 * mt rows; weight boxes: one gate slice
-        if (int rc = make_map(&L.maps[M_RING_H], ws + BL.ring_h, precision, D, Rh, 8, ST_BM * mt)) return rc;
-        if (int rc = make_map(&L.maps[M_RING_O], ws + BL.ring_o, precision, D, Ro, 8, ST_BM * mt)) return rc;
-        if (int rc = make_map(&L.maps[M_MG_H], ws + BL.mg_h, precision, (size_t)nkh * D, Rh, 4, ST_BM * mt)) return rc;
-        if (int rc = make_map(&L.maps[M_MG_O], ws + BL.mg_o, precision, (size_t)2 * D, Ro, 4, ST_BM * mt)) return rc;
-        if (int rc = make_map(&L.maps[M_WIH_H], ws + BL.wih_h, precision, (size_t)nkh * D, 3 * D, 4, ST_U)) return rc;
-        if (int rc = make_map(&L.maps[M_WIH_O], ws + BL.wih_o, precision, (size_t)2 * D, 3 * D, 4, ST_U)) return rc;
-        if (int rc = make_map(&L.maps[M_WHH_H], ws + BL.whh_h, precision, D, 3 * D, 4, ST_U)) return rc;
-        if (int rc = make_map(&L.maps[M_WHH_O], ws + BL.whh_o, precision, D, 3 * D, 4, ST_U)) return rc;
-        return make_map(&L.maps[M_WM], ws + BL.wm, precision, D, D, 8, ST_BN_RELU);
+    const StepShape shape = choose_shape();
+    auto encode_maps = [&](StepLaunch& L) -> int {       // activation boxes: 128 * mt rows; weight boxes: 64 / cg rows
+        const int abox = ST_BM * shape.mt, wbox = ST_U / shape.cg;
+        if (int rc = make_map(&L.maps[M_RING_H], ws + BL.ring_h, precision, D, Rh, 8, abox)) return rc;
+        if (int rc = make_map(&L.maps[M_RING_O], ws + BL.ring_o, precision, D, Ro, 8, abox)) return rc;
+        if (int rc = make_map(&L.maps[M_MG_H], ws + BL.mg_h, precision, (size_t)nkh * D, Rh, 4, abox)) return rc;
+        if (int rc = make_map(&L.maps[M_MG_O], ws + BL.mg_o, precision, (size_t)2 * D, Ro, 4, abox)) return rc;
+        if (int rc = make_map(&L.maps[M_WIH_H], ws + BL.wih_h, precision, (size_t)nkh * D, 3 * D, 4, wbox)) return rc;
+        if (int rc = make_map(&L.maps[M_WIH_O], ws + BL.wih_o, precision, (size_t)2 * D, 3 * D, 4, wbox)) return rc;
+        if (int rc = make_map(&L.maps[M_WHH_H], ws + BL.whh_h, precision, D, 3 * D, 4, wbox)) return rc;
+        if (int rc = make_map(&L.maps[M_WHH_O], ws + BL.whh_o, precision, D, 3 * D, 4, wbox)) return rc;
+        return make_map(&L.maps[M_WM], ws + BL.wm, precision, D, D, 8, wbox);
     };
     TG_CUDA_OK(cudaMemsetAsync(ws + BL.ring_h + 4 * plane_bytes(Rh, D), 0, 4 * plane_bytes(Rh, D), stream));
     TG_CUDA_OK(cudaMemsetAsync(ws + BL.ring_o + 4 * plane_bytes(Ro, D), 0, 4 * plane_bytes(Ro, D), stream));
@@ -812,11 +876,9 @@ int launch_segment_big(SegParams& P, void* big_ws, int precision, int T_save, cu
                 q.bias = P.bm[k]; q.out = out; q.out_bstride = bstride;
             }
         }
-        if (s == 0) {
-            mtA = choose_mt(LA, precision);
-            if (int rc = encode_maps(LA, mtA)) return rc;
-        }
-        if (int rc = launch_step(LA, precision, mtA, stream)) return rc;
+        if (s == 0)
+            if (int rc = encode_maps(LA)) return rc;
+        if (int rc = launch_step(LA, precision, shape, stream)) return rc;
         // ---- phase A2: attention over the previous states + aggregation -> operand rows of the cell GEMM ------------------------
         A.B = B; A.T = T; A.H = H; A.O = O; A.D = D; A.hh = P.hh; A.nk_h = nkh; A.mean_pool = P.mean_pool; A.first = s == 0; A.s = s;
         A.hx_h = P.hx_h; A.hx_o = P.hx_o; A.om = P.om;
@@ -847,11 +909,9 @@ int launch_segment_big(SegParams& P, void* big_ws, int precision, int T_save, cu
                 q.ugate = is_h ? P.u_h : P.u_o; q.hx = is_h ? P.hx_h : P.hx_o; q.gsave = is_h ? P.sgates_h : P.sgates_o;
                 q.ring_out = ws + (is_h ? BL.ring_h : BL.ring_o) + (size_t)(slot_out * 2 + dir) * 2 * plane_bytes(R, D);
             }
-        if (s == 0) {
-            mtB = choose_mt(LB, precision);
-            if (int rc = encode_maps(LB, mtB)) return rc;
-        }
-        if (int rc = launch_step(LB, precision, mtB, stream)) return rc;
+        if (s == 0)
+            if (int rc = encode_maps(LB)) return rc;
+        if (int rc = launch_step(LB, precision, shape, stream)) return rc;
     }
     (void)T_save;
     return 0;

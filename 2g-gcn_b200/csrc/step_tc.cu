@@ -67,7 +67,8 @@ struct StepProblem {
     int D;                              // layer width: gate row period of the weight matrices / output columns (RELU)
     int nkb1, nkb2;                     // k-blocks of the input part (aggregated messages) and of the hidden part
     int a1_map, a1_plane, a2_map, a2_plane;
-    int b1_map, b1_plane, b2_map, b2_plane;
+    int b1_map, b1_plane, b2_map, b2_plane;      // weight maps: whole gate tile (CG = 1) or my gate of (r, z) (CG = 2) ...
+    int b1n_map, b2n_map;                        // ... and my half of the n rows (CG = 2 only)
     int T, t, tprev, dir, first;
     const float* xg;                    // (B,T,E,2,3D) hoisted input pre-activations incl. b_ih
     const float* bhh;                   // (3D)
@@ -104,6 +105,19 @@ template <int CG> __device__ __forceinline__ void tma_load_3d(uint32_t dst, cons
             "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(c2), "r"(bar)
             : "memory");
 }
+template <int CG> __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, int c0, int c1, int c2, int c3, uint32_t bar) {
+    if (CG == 1)
+        asm volatile(
+            "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];\n" ::"r"(dst),
+            "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(bar)
+            : "memory");
+    else
+        asm volatile(
+            "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];\n" ::"r"(dst),
+            "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(bar)
+            : "memory");
+}
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];\n" ::"l"(p)); }
 // kind::f16 instruction descriptor: D = F32, A = B = F16 (0) or BF16 (1), both K-major, N >> 3 at bits 17-22, M >> 4 at 24-28
 __device__ __forceinline__ uint32_t umma_idesc_16(int bf16, int M, int N) {
     return (1u << 4) | ((uint32_t)bf16 << 7) | ((uint32_t)bf16 << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
@@ -173,6 +187,15 @@ template <int PREC> __device__ __forceinline__ void store16(void* hi_plane, size
     }
 }
 
+// Gate non-linearities of the epilogue on the fast exponential (ex2.approx: relative error ~2^-22, i.e. ~1e-7 absolute on values
+// in [-1, 1]).  The epilogue is issue-bound — 128 rows x 64 units of (2 sigmoids + 1 tanh) on 8 warps; with expf / tanhf it
+// took 26k of a cell tile's 79k cycles (clock64 trace, profiles/r02_step_trace.txt) — and only 2 warps per scheduler hide latency.
+__device__ __forceinline__ float sigmoid_fast(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
+__device__ __forceinline__ float tanh_fast(float x) {
+    const float t = __expf(-2.0f * fabsf(x));                      // in (0, 1]: no overflow, no cancellation for large |x|
+    return copysignf(__fdividef(1.0f - t, 1.0f + t), x);
+}
+
 __device__ __forceinline__ void load16(const float* p, float (&v)[16]) {
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
@@ -194,7 +217,8 @@ __device__ __forceinline__ void store16f(float* p, const float (&v)[16]) {
 
 #ifdef ST_TRACE      // timing experiments only (TGGCN_NVCC_DEFS=-DST_TRACE): clock64 stamps of CTA 0, read back with tggcn_debug_trace
 __device__ long long g_st_trace[64];
-#define ST_STAMP(i) do { if (blockIdx.x == 0) g_st_trace[i] = clock64(); } while (0)
+__device__ int g_st_trace_kind = 0;      // which launches record: 0 = cell GEMM (GRU with an input part), 1 = plain GRU (BiGRU), 2 = message MLPs
+#define ST_STAMP(i) do { if (blockIdx.x == 0 && st_trace_on) g_st_trace[i] = clock64(); } while (0)
 #else
 #define ST_STAMP(i) do { } while (0)
 #endif
@@ -212,7 +236,12 @@ __global__ void __launch_bounds__(ST_THREADS, 1) step_tc_kernel(const __grid_con
     __shared__ uint32_t tmem_base_smem;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    if (tid == 0) ST_STAMP(0);
+#ifdef ST_TRACE
+    const long long st_t0 = clock64();
+    const int st_kind = L.p[0].mode == ST_RELU ? 2 : (L.p[0].nkb1 > 0 ? 0 : 1);
+    const bool st_trace_on = st_kind == g_st_trace_kind;
+    if (tid == 0 && blockIdx.x == 0 && st_trace_on) g_st_trace[0] = st_t0;
+#endif
     uint8_t* tiles = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     const uint32_t tiles_u32 = smem_u32(tiles);
     const uint32_t full0 = smem_u32(&bars[0]), empty0 = smem_u32(&bars[STAGES]), tfull = smem_u32(&bars[2 * STAGES]);
@@ -262,7 +291,7 @@ __global__ void __launch_bounds__(ST_THREADS, 1) step_tc_kernel(const __grid_con
             for (int kb = 0; kb < nkb; ++kb) {
                 const int s = kb % STAGES;
                 mbar_wait_backoff(empty0 + 8 * s, ((kb / STAGES) & 1) ^ 1);
-                if (kb < 12) ST_STAMP(4 + kb);
+                if (kb < 28) ST_STAMP(4 + kb);
                 const uint32_t my_full = full0 + 8 * s;
                 const uint32_t bar = CG == 2 ? mapa_u32(my_full, 0) : my_full;          // bytes complete on the leader's barrier
                 if (leader) mbar_expect_tx(my_full, stage_tx * CG);
@@ -273,27 +302,22 @@ __global__ void __launch_bounds__(ST_THREADS, 1) step_tc_kernel(const __grid_con
                 const CUtensorMap* am = &L.maps[seg2 ? P.a2_map : P.a1_map];
                 const CUtensorMap* bm = &L.maps[seg2 ? P.b2_map : P.b1_map];
                 const int ap = seg2 ? P.a2_plane : P.a1_plane, bp = seg2 ? P.b2_plane : P.b1_plane;
-#pragma unroll
-                for (int pl = 0; pl < PLANES; ++pl) tma_load_3d<CG>(st + pl * Cfg::A_PLANE, am, k0, m0, ap + pl, bar);   // box: 128 * MT rows
-#pragma unroll
-                for (int pl = 0; pl < PLANES; ++pl) {
-                    const uint32_t b = st + Cfg::A_BYTES + pl * Cfg::B_PLANE;
-                    if (gru) {
-                        const int u0 = nt * ST_U;
-                        if (CG == 1) {                 // boxes of 64 rows: r, z, n
-                            tma_load_3d<CG>(b, bm, k0, u0, bp + pl, bar);
-                            tma_load_3d<CG>(b + ST_U * 128, bm, k0, P.D + u0, bp + pl, bar);
-                            tma_load_3d<CG>(b + 2 * ST_U * 128, bm, k0, 2 * P.D + u0, bp + pl, bar);
-                        } else {                       // boxes of 32 rows: my gate of (r, z) in two halves, my half of n
-                            tma_load_3d<CG>(b, bm, k0, rank * P.D + u0, bp + pl, bar);
-                            tma_load_3d<CG>(b + WBOX * 128, bm, k0, rank * P.D + u0 + WBOX, bp + pl, bar);
-                            tma_load_3d<CG>(b + 2 * WBOX * 128, bm, k0, 2 * P.D + u0 + rank * WBOX, bp + pl, bar);
-                        }
-                    } else {                           // 128 output columns: 2 boxes of 64 rows, or this CTA's 64 rows as 2 boxes of 32
-                        const int n0 = nt * ST_BN_RELU + rank * (ST_BN_RELU / 2);
-                        tma_load_3d<CG>(b, bm, k0, CG == 1 ? nt * ST_BN_RELU : n0, bp + pl, bar);
-                        tma_load_3d<CG>(b + WBOX * 128, bm, k0, (CG == 1 ? nt * ST_BN_RELU : n0) + WBOX, bp + pl, bar);
+                // Few, large copies: a tensor-map copy costs ~200 cycles of TMA issue whatever its size (measured: 8 copies per
+                // k-block gave a 2200-2460 cycle period for 56-112 KB stages, profiles/r02_step_tma_ops.txt), so the (hi, lo)
+                // planes travel in one box (last box dimension = PLANES) and the three gate slices in one 4-D box.
+                tma_load_3d<CG>(st, am, k0, m0, ap, bar);                                   // box {64 k, 128 * MT rows, PLANES}
+                const uint32_t b = st + Cfg::A_BYTES;
+                if (gru) {
+                    const int u0 = nt * ST_U;
+                    if (CG == 1) {
+                        tma_load_4d<CG>(b, bm, k0, u0, 0, bp, bar);                         // box {64 k, 64 units, 3 gates, PLANES}: [hi: r z n][lo: r z n]
+                    } else {
+                        const CUtensorMap* bn = &L.maps[seg2 ? P.b2n_map : P.b1n_map];
+                        tma_load_4d<CG>(b, bm, k0, u0, rank, bp, bar);                      // box {64, 64 units, 1 gate, PLANES}: my gate of (r, z)
+                        tma_load_4d<CG>(b + PLANES * RZ_BYTES, bn, k0, u0 + rank * WBOX, 2, bp, bar);   // box {64, 32 units, 1, PLANES}: my half of n
                     }
+                } else {
+                    tma_load_3d<CG>(b, bm, k0, nt * ST_BN_RELU + rank * (ST_BN_RELU / CG), bp, bar);    // box {64 k, 128 / CG rows, PLANES}
                 }
             }
         }
@@ -308,10 +332,13 @@ __global__ void __launch_bounds__(ST_THREADS, 1) step_tc_kernel(const __grid_con
                 mbar_wait(full0 + 8 * s, (kb / STAGES) & 1);
                 tc_fence_after();
                 if (lane == 0) {
-                    if (kb < 12) ST_STAMP(20 + kb);
+                    if (kb < 28) ST_STAMP(32 + kb);
                     const uint32_t st = tiles_u32 + s * Cfg::STAGE_BYTES;
                     const uint32_t a_hi = st, a_lo = st + Cfg::A_PLANE;
-                    const uint32_t b_hi = st + Cfg::A_BYTES, b_lo = b_hi + Cfg::B_PLANE;
+                    const uint32_t b0 = st + Cfg::A_BYTES;
+                    // weight tile: CG = 1 [hi: r z n][lo: r z n]; CG = 2 [rz_hi][rz_lo][n_hi][n_lo] (this CTA's rows); RELU [hi][lo]
+                    const uint32_t rz_hi = b0, rz_lo = b0 + (gru ? (CG == 1 ? ST_B_TILE : RZ_BYTES) : ST_BN_RELU * 128 / CG);
+                    const uint32_t n_hi = b0 + (CG == 1 ? 2 * ST_U * 128 : PLANES * RZ_BYTES), n_lo = n_hi + (CG == 1 ? ST_B_TILE : NB_BYTES);
                     const bool seg2 = kb >= P.nkb1;
                     const bool seg_first_kb = seg2 ? kb == P.nkb1 : kb == 0;
                     const uint32_t ncol = seg2 ? 3 * ST_U : 2 * ST_U;               // n_h or n_i accumulator columns
@@ -322,7 +349,7 @@ __global__ void __launch_bounds__(ST_THREADS, 1) step_tc_kernel(const __grid_con
                         for (int term = 0; term < (PREC == 0 ? 3 : 1); ++term) {
                             // small terms first: lo*hi, hi*lo, hi*hi
                             const uint32_t a = (PREC == 0 && term == 0) ? a_lo : a_hi;
-                            const uint32_t b = (PREC == 0 && term == 1) ? b_lo : b_hi;
+                            const uint32_t brz = (PREC == 0 && term == 1) ? rz_lo : rz_hi, bn_ = (PREC == 0 && term == 1) ? n_lo : n_hi;
                             const bool tile_first = kb == 0 && kk == 0 && term == 0;
                             const bool seg_first = seg_first_kb && kk == 0 && term == 0;
 #pragma unroll
@@ -330,10 +357,10 @@ __global__ void __launch_bounds__(ST_THREADS, 1) step_tc_kernel(const __grid_con
                                 const uint64_t ad = umma_desc(a + mh * ST_A_TILE + ko);
                                 const uint32_t tacc = tmem_base + mh * ST_ACC_COLS;
                                 if (!gru) {
-                                    umma_f16<CG>(tacc, ad, umma_desc(b + ko), id_relu, !tile_first);
+                                    umma_f16<CG>(tacc, ad, umma_desc(brz + ko), id_relu, !tile_first);
                                 } else {
-                                    umma_f16<CG>(tacc, ad, umma_desc(b + ko), id_rz, !tile_first);                     // r, z: both K parts
-                                    umma_f16<CG>(tacc + ncol, ad, umma_desc(b + RZ_BYTES + ko), id_n, !seg_first);    // n_i / n_h apart
+                                    umma_f16<CG>(tacc, ad, umma_desc(brz + ko), id_rz, !tile_first);              // r, z: both K parts
+                                    umma_f16<CG>(tacc + ncol, ad, umma_desc(bn_ + ko), id_n, !seg_first);          // n_i / n_h apart
                                 }
                             }
                         }
@@ -363,6 +390,16 @@ __global__ void __launch_bounds__(ST_THREADS, 1) step_tc_kernel(const __grid_con
             float* ho = P.hx + fe * 2 * D + (size_t)P.dir * D;
             float* gs = P.gsave != nullptr ? P.gsave + (fe * 2 + P.dir) * 4 * D : nullptr;
             const float ug = (valid && P.ugate != nullptr) ? __ldg(P.ugate + fe) : 1.0f;
+            // The hoisted pre-activations are read exactly once, from HBM, by every CTA at the same moment (all tiles leave their main
+            // loops together): pull this thread's lines into L2 while the main loop runs (measured: epilogue 27k -> cycles, see profiles)
+            if (valid) {
+#pragma unroll 1
+                for (int c = c_first; c < ST_U / 16; c += c_step) {
+                    const int ub = nt * ST_U + c * 16;
+                    prefetch_l2(xg + ub); prefetch_l2(xg + D + ub); prefetch_l2(xg + 2 * D + ub);
+                    if (!P.first) prefetch_l2(hp + ub);
+                }
+            }
             mbar_wait_backoff(tfull, 0);
             tc_fence_after();
             if (tid == 64) ST_STAMP(2);
@@ -387,10 +424,10 @@ __global__ void __launch_bounds__(ST_THREADS, 1) step_tc_kernel(const __grid_con
 #pragma unroll
                 for (int j = 0; j < 16; ++j) {
                     // gate order (r, z, n) as torch.nn.GRU / GRUCell: r = s(xr + hr), z = s(xz + hz), n = tanh(xn + r*hn), h' = n + z*(h - n)
-                    const float r = sigmoidf_acc(xr[j] + sc * ar[j] + br[j]);
-                    const float z = sigmoidf_acc(xz[j] + sc * az[j] + bz[j]);
+                    const float r = sigmoid_fast(xr[j] + sc * ar[j] + br[j]);
+                    const float z = sigmoid_fast(xz[j] + sc * az[j] + bz[j]);
                     const float hn = sc * nh[j] + bn[j];
-                    const float n = tanhf(xn[j] + (P.nkb1 > 0 ? sc * ni[j] : 0.0f) + r * hn);
+                    const float n = tanh_fast(xn[j] + (P.nkb1 > 0 ? sc * ni[j] : 0.0f) + r * hn);
                     const float hnew = n + z * (hprev[j] - n);
                     outv[j] = ug * hnew + (1.0f - ug) * hprev[j];
                     if (gs != nullptr) {
@@ -403,6 +440,7 @@ __global__ void __launch_bounds__(ST_THREADS, 1) step_tc_kernel(const __grid_con
                     store16f(gs + ub, xr); store16f(gs + D + ub, xz); store16f(gs + 2 * D + ub, xn); store16f(gs + 3 * D + ub, br);
                 }
             }
+            if (tid == 64) ST_STAMP(60);
         } else {
             float* orow = P.out + (size_t)b * P.out_bstride + (size_t)e * D;
             mbar_wait_backoff(tfull, 0);
@@ -434,6 +472,9 @@ __global__ void __launch_bounds__(ST_THREADS, 1) step_tc_kernel(const __grid_con
 }  // namespace tg
 extern "C" __attribute__((visibility("default"))) int tggcn_debug_trace(long long* out_host) {
     return cudaMemcpyFromSymbol(out_host, tg::g_st_trace, sizeof(long long) * 64) == cudaSuccess ? 0 : 1;
+}
+extern "C" __attribute__((visibility("default"))) int tggcn_debug_trace_kind(int kind) {
+    return cudaMemcpyToSymbol(tg::g_st_trace_kind, &kind, sizeof(int)) == cudaSuccess ? 0 : 1;
 }
 namespace tg {
 #endif
@@ -656,20 +697,41 @@ EncodeTiledFn encode_fn() {
 
 // 3-D tensor map over `planes` row-major [rows][K] matrices of 16-bit elements: box = 64 K-elements x box_rows rows x 1 plane,
 // 128-byte swizzle (the K-major layout of the UMMA descriptors), out-of-range rows / columns read as zeros.
-int make_map(CUtensorMap* m, const void* base, int precision, size_t K, size_t rows, size_t planes, int box_rows) {
+int encode_map(CUtensorMap* m, const void* base, int precision, int rank, const size_t* dims_, const int* box_) {
     EncodeTiledFn enc = encode_fn();
     TG_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled is not available from this driver");
-    TG_REQUIRE(K % 8 == 0 && K >= ST_BK, "tensor map: K=%zu must be a multiple of 8 and at least %d", K, ST_BK);
+    TG_REQUIRE(dims_[0] % 8 == 0 && dims_[0] >= ST_BK, "tensor map: K=%zu must be a multiple of 8 and at least %d", dims_[0], ST_BK);
     TG_REQUIRE((reinterpret_cast<uintptr_t>(base) & 15) == 0, "tensor map: base must be 16-byte aligned");
-    const cuuint64_t dims[3] = {(cuuint64_t)K, (cuuint64_t)rows, (cuuint64_t)planes};
-    const cuuint64_t strides[2] = {(cuuint64_t)K * 2, (cuuint64_t)K * 2 * rows};
-    const cuuint32_t box[3] = {(cuuint32_t)ST_BK, (cuuint32_t)box_rows, 1};
-    const cuuint32_t estr[3] = {1, 1, 1};
-    const CUresult r = enc(m, precision ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<void*>(base), dims,
-                           strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    TG_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed (%d) for K=%zu rows=%zu planes=%zu box_rows=%d", (int)r, K, rows, planes, box_rows);
+    cuuint64_t dims[4], strides[3];
+    cuuint32_t box[4], estr[4];
+    cuuint64_t pitch = 2;                                  // bytes per element; the tensors are dense in the order of dims
+    for (int i = 0; i < rank; ++i) {
+        dims[i] = (cuuint64_t)dims_[i];
+        box[i] = (cuuint32_t)box_[i];
+        estr[i] = 1;
+        pitch *= dims[i];
+        if (i < rank - 1) strides[i] = pitch;
+    }
+    const CUresult r = enc(m, precision ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, (cuuint32_t)rank,
+                           const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                           CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    TG_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed (%d): rank %d, K=%zu, box rows %d", (int)r, rank, dims_[0], box_[1]);
     return 0;
+}
+
+// 3-D map over `pairs` (hi, lo) plane pairs of row-major [rows][K] matrices of 16-bit elements: one copy moves a box of
+// 64 K-elements x box_rows rows x PLANES planes (bf16: the lo plane exists but is not read), 128-byte swizzle (the K-major layout
+// of the UMMA descriptors), out-of-range rows / columns read as zeros.
+int make_map(CUtensorMap* m, const void* base, int precision, size_t K, size_t rows, size_t planes, int box_rows) {
+    const size_t dims[3] = {K, rows, planes};
+    const int box[3] = {ST_BK, box_rows, precision ? 1 : 2};
+    return encode_map(m, base, precision, 3, dims, box);
+}
+// 4-D map over gate-major weights: planes of [3][D][K]: box = 64 K-elements x box_units units x box_gates gates x PLANES planes
+int make_gate_map(CUtensorMap* m, const void* base, int precision, size_t K, size_t D, size_t planes, int box_units, int box_gates) {
+    const size_t dims[4] = {K, D, 3, planes};
+    const int box[4] = {ST_BK, box_units, box_gates, precision ? 1 : 2};
+    return encode_map(m, base, precision, 4, dims, box);
 }
 
 int launch_pack(PackJobs& jobs, int precision, cudaStream_t stream) {
@@ -723,24 +785,25 @@ int launch_step(StepLaunch& L, int precision, StepShape sh, cudaStream_t stream)
         begin += p.m_tiles * p.n_tiles;
     }
     L.acc_scale = precision ? 1.0f : 1.0f / ST_W_SCALE;
+    TG_REQUIRE(sh.mt == 1, "step kernel: the two-accumulator (256-row) tile is not built (measured no gain, profiles/r02_step_tile_height.txt)");
     if (sh.cg == 2) return precision ? launch_step_t<1, 1, 2>(L, begin, stream) : launch_step_t<0, 1, 2>(L, begin, stream);
-    if (precision) return sh.mt == 2 ? launch_step_t<1, 2, 1>(L, begin, stream) : launch_step_t<1, 1, 1>(L, begin, stream);
-    return sh.mt == 2 ? launch_step_t<0, 2, 1>(L, begin, stream) : launch_step_t<0, 1, 1>(L, begin, stream);
+    return precision ? launch_step_t<1, 1, 1>(L, begin, stream) : launch_step_t<0, 1, 1>(L, begin, stream);
 }
 
-// Default: CTA pairs (cta_group::2).  The kernel is bound by shared-memory bandwidth — every tcgen05.mma re-reads its operand
-// slices from shared memory (three times per k-step with the split) while TMA writes the next stage — and a pair halves the
-// weight bytes each SM stages and reads (profiles/r02_step_tile_height.txt, r02_step_cta_pair.txt).  TGGCN_STEP_CG=1 selects
-// single-CTA tiles, TGGCN_STEP_MT=2 their two-accumulator variant (fewer L2 bytes, same shared-memory bytes: measured no gain).
+// Default: single-CTA tiles.  TGGCN_STEP_CG=2 selects CTA pairs (tcgen05 cta_group::2): each SM then stages and reads half of the
+// weight tile, the k-block period falls from 2463 to 2184 cycles (clock64 trace) — but a pair's epilogue ends later, and the whole
+// forward measured 3.5 % slower (CAD-120 B=256: 27.7 vs 26.8 ms per 64 steps; profiles/r02_step_trace.txt).  The main loop is bound
+// by shared-memory bandwidth: every tcgen05.mma re-reads its (128 + N) x 16 operand slice from shared memory, three split terms per
+// k-step, while TMA writes the next stage; the period does not move with the batch size, the number of TMA copies per stage (8 -> 2)
+// or the stage bytes (56 / 80 / 112 KB).  A two-accumulator 256-row tile (fewer L2 bytes, same shared-memory bytes) was measured at
+// no gain and is no longer built.
 StepShape choose_shape() {
-    static int cg = 0, mt = 0;
+    static int cg = 0;
     if (cg == 0) {
         const char* e = getenv("TGGCN_STEP_CG");
-        cg = (e != nullptr && e[0] == '1') ? 1 : 2;
-        const char* m = getenv("TGGCN_STEP_MT");
-        mt = (cg == 1 && m != nullptr && m[0] == '2') ? 2 : 1;
+        cg = (e != nullptr && e[0] == '2') ? 2 : 1;
     }
-    return StepShape{mt, cg};
+    return StepShape{1, cg};
 }
 
 size_t plane_bytes(size_t rows, size_t K) { return rows * K * 2; }
@@ -775,7 +838,7 @@ int launch_bigru_big(BiGruParams& P, void* big_ws, int precision, cudaStream_t s
                 q.mode = ST_GRU; q.rows = G.rows; q.E = G.E; q.D = D;
                 q.nkb1 = 0; q.nkb2 = cdiv(D, ST_BK);
                 q.a2_map = g; q.a2_plane = (slot_in * 2 + dir) * 2;
-                q.b2_map = 3 + g; q.b2_plane = dir * 2;
+                q.b2_map = 3 + g; q.b2n_map = 6 + g; q.b2_plane = dir * 2;
                 q.T = T; q.dir = dir; q.t = dir == 0 ? s : T - 1 - s; q.tprev = dir == 0 ? q.t - 1 : q.t + 1; q.first = s == 0;
                 q.xg = G.gi; q.bhh = G.bhh[dir]; q.ugate = nullptr; q.hx = G.hfr; q.gsave = G.gates;
                 q.ring_out = ws + BL.ring_g[g] + (size_t)(slot_out * 2 + dir) * 2 * plane_bytes(G.rows, D);
@@ -784,7 +847,12 @@ int launch_bigru_big(BiGruParams& P, void* big_ws, int precision, cudaStream_t s
             for (int g = 0; g < 3; ++g) {
                 const size_t rows = P.g[g].rows;
                 if (int rc = make_map(&L.maps[g], ws + BL.ring_g[g], precision, D, rows, 8, ST_BM * shape.mt)) return rc;
-                if (int rc = make_map(&L.maps[3 + g], ws + BL.whh_g[g], precision, D, 3 * D, 4, ST_U / shape.cg)) return rc;
+                if (shape.cg == 1) {
+                    if (int rc = make_gate_map(&L.maps[3 + g], ws + BL.whh_g[g], precision, D, D, 4, ST_U, 3)) return rc;
+                } else {
+                    if (int rc = make_gate_map(&L.maps[3 + g], ws + BL.whh_g[g], precision, D, D, 4, ST_U, 1)) return rc;
+                    if (int rc = make_gate_map(&L.maps[6 + g], ws + BL.whh_g[g], precision, D, D, 4, ST_U / 2, 1)) return rc;
+                }
                 // the state "before the first step" is zero: slot 1 is what step 0 reads
                 TG_CUDA_OK(cudaMemsetAsync(ws + BL.ring_g[g] + 4 * plane_bytes(rows, D), 0, 4 * plane_bytes(rows, D), stream));
             }
@@ -819,7 +887,7 @@ int launch_segment_big(SegParams& P, void* big_ws, int precision, int T_save, cu
     for (int k = P.hh ? 0 : 1; k < 4; ++k) pack_add(jobs, P.wm[k], D, D, D, ws + BL.wm + (size_t)k * 2 * plane_bytes(D, D));
     if (int rc = launch_pack(jobs, precision, stream)) return rc;
     // ---- tensor maps ---------------------------------------------------------------------------------------------------------
-    enum { M_RING_H = 0, M_RING_O, M_MG_H, M_MG_O, M_WIH_H, M_WIH_O, M_WHH_H, M_WHH_O, M_WM };
+    enum { M_RING_H = 0, M_RING_O, M_MG_H, M_MG_O, M_WIH_H, M_WIH_O, M_WHH_H, M_WHH_O, M_WM, M_WIH_H_N, M_WIH_O_N, M_WHH_H_N, M_WHH_O_N };
     StepLaunch LA, LB;
     memset(&LA, 0, sizeof(LA));
     memset(&LB, 0, sizeof(LB));
@@ -830,11 +898,18 @@ int launch_segment_big(SegParams& P, void* big_ws, int precision, int T_save, cu
         if (int rc = make_map(&L.maps[M_RING_O], ws + BL.ring_o, precision, D, Ro, 8, abox)) return rc;
         if (int rc = make_map(&L.maps[M_MG_H], ws + BL.mg_h, precision, (size_t)nkh * D, Rh, 4, abox)) return rc;
         if (int rc = make_map(&L.maps[M_MG_O], ws + BL.mg_o, precision, (size_t)2 * D, Ro, 4, abox)) return rc;
-        if (int rc = make_map(&L.maps[M_WIH_H], ws + BL.wih_h, precision, (size_t)nkh * D, 3 * D, 4, wbox)) return rc;
-        if (int rc = make_map(&L.maps[M_WIH_O], ws + BL.wih_o, precision, (size_t)2 * D, 3 * D, 4, wbox)) return rc;
-        if (int rc = make_map(&L.maps[M_WHH_H], ws + BL.whh_h, precision, D, 3 * D, 4, wbox)) return rc;
-        if (int rc = make_map(&L.maps[M_WHH_O], ws + BL.whh_o, precision, D, 3 * D, 4, wbox)) return rc;
-        return make_map(&L.maps[M_WM], ws + BL.wm, precision, D, D, 8, wbox);
+        const void* wbase[4] = {ws + BL.wih_h, ws + BL.wih_o, ws + BL.whh_h, ws + BL.whh_o};
+        const size_t wk[4] = {(size_t)nkh * D, (size_t)2 * D, (size_t)D, (size_t)D};
+        for (int i = 0; i < 4; ++i) {
+            if (shape.cg == 1) {
+                if (int rc = make_gate_map(&L.maps[M_WIH_H + i], wbase[i], precision, wk[i], D, 4, ST_U, 3)) return rc;
+            } else {
+                if (int rc = make_gate_map(&L.maps[M_WIH_H + i], wbase[i], precision, wk[i], D, 4, ST_U, 1)) return rc;
+                if (int rc = make_gate_map(&L.maps[M_WIH_H_N + i], wbase[i], precision, wk[i], D, 4, ST_U / 2, 1)) return rc;
+            }
+        }
+        (void)wbox;
+        return make_map(&L.maps[M_WM], ws + BL.wm, precision, D, D, 8, ST_BN_RELU / shape.cg);
     };
     TG_CUDA_OK(cudaMemsetAsync(ws + BL.ring_h + 4 * plane_bytes(Rh, D), 0, 4 * plane_bytes(Rh, D), stream));
     TG_CUDA_OK(cudaMemsetAsync(ws + BL.ring_o + 4 * plane_bytes(Ro, D), 0, 4 * plane_bytes(Ro, D), stream));
@@ -902,8 +977,8 @@ int launch_segment_big(SegParams& P, void* big_ws, int precision, int T_save, cu
                 q.nkb1 = cdiv(nk * D, ST_BK); q.nkb2 = cdiv(D, ST_BK);
                 q.a1_map = is_h ? M_MG_H : M_MG_O; q.a1_plane = dir * 2;
                 q.a2_map = is_h ? M_RING_H : M_RING_O; q.a2_plane = (slot_in * 2 + dir) * 2;
-                q.b1_map = is_h ? M_WIH_H : M_WIH_O; q.b1_plane = dir * 2;
-                q.b2_map = is_h ? M_WHH_H : M_WHH_O; q.b2_plane = dir * 2;
+                q.b1_map = is_h ? M_WIH_H : M_WIH_O; q.b1n_map = is_h ? M_WIH_H_N : M_WIH_O_N; q.b1_plane = dir * 2;
+                q.b2_map = is_h ? M_WHH_H : M_WHH_O; q.b2n_map = is_h ? M_WHH_H_N : M_WHH_O_N; q.b2_plane = dir * 2;
                 q.T = T; q.dir = dir; q.t = dir == 0 ? s : T - 1 - s; q.tprev = dir == 0 ? q.t - 1 : q.t + 1; q.first = s == 0;
                 q.xg = is_h ? P.gs_h : P.gs_o; q.bhh = is_h ? P.bhh_h[dir] : P.bhh_o[dir];
                 q.ugate = is_h ? P.u_h : P.u_o; q.hx = is_h ? P.hx_h : P.hx_o; q.gsave = is_h ? P.sgates_h : P.sgates_o;

@@ -531,7 +531,7 @@ template <int PREC> __global__ void pack16_kernel(const PackJobs jobs) {
 constexpr int AT_MAXE = 16;
 constexpr int AT_THREADS = 256;
 struct AttendParams {
-    int B, T, H, O, D, hh, nk_h, mean_pool, first, s;
+    int B, T, H, O, D, hh, nk_h, mean_pool, first, s, dir_base;
     const float* hx_h; const float* hx_o; const float* om;
     const float* msg[2][4]; long long msg_bstride[4];      // per direction and kind: sender row (b, e) at msg + b*bstride + e*D
     void* mg16_h; void* mg16_o;                            // planes [dir][hi, lo] of [rows][nk*D]
@@ -544,7 +544,7 @@ struct AttendParams {
 template <int PREC> __global__ void __launch_bounds__(AT_THREADS) seg_attend_kernel(const AttendParams P) {
     extern __shared__ __align__(16) float at_smem[];
     __shared__ float alpha[4][AT_MAXE][AT_MAXE];
-    const int b = blockIdx.x, dir = blockIdx.y, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int b = blockIdx.x, dir = blockIdx.y + P.dir_base, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int H = P.H, O = P.O, D = P.D, E = H + O, T = P.T;
     const int t = dir == 0 ? P.s : T - 1 - P.s, tprev = dir == 0 ? t - 1 : t + 1;
     float* hs = at_smem;                                  // [E][D] previous states: humans then objects
@@ -808,6 +808,35 @@ StepShape choose_shape() {
 
 size_t plane_bytes(size_t rows, size_t K) { return rows * K * 2; }
 
+// The forward and the backward time direction of a recurrence are independent chains (different weights, no exchange inside the
+// loop): their step kernels go to two streams, so the GPU packs CTAs of both chains onto its SMs instead of running two half-empty
+// waves per launch (a CAD-120 B=256 cell launch is 192 tiles on 148 SMs).  One non-blocking side stream and two events per device,
+// created on first use; TGGCN_STEP_STREAMS=1 keeps everything on the caller's stream.
+struct DirStreams { cudaStream_t side; cudaEvent_t fork, join; bool split; };
+int get_dir_streams(DirStreams& out) {
+    struct Entry { bool made; cudaStream_t s; cudaEvent_t f, j; };
+    static Entry cache[64];
+    static int enabled = -1;
+    if (enabled < 0) {
+        const char* e = getenv("TGGCN_STEP_STREAMS");
+        enabled = (e != nullptr && e[0] == '1') ? 0 : 1;
+    }
+    out.split = enabled != 0;
+    if (!out.split) return 0;
+    int dev = 0;
+    TG_CUDA_OK(cudaGetDevice(&dev));
+    TG_REQUIRE(dev >= 0 && dev < 64, "device ordinal %d out of range", dev);
+    Entry& e = cache[dev];
+    if (!e.made) {
+        TG_CUDA_OK(cudaStreamCreateWithFlags(&e.s, cudaStreamNonBlocking));
+        TG_CUDA_OK(cudaEventCreateWithFlags(&e.f, cudaEventDisableTiming));
+        TG_CUDA_OK(cudaEventCreateWithFlags(&e.j, cudaEventDisableTiming));
+        e.made = true;
+    }
+    out.side = e.s; out.fork = e.f; out.join = e.j;
+    return 0;
+}
+
 }  // namespace
 
 int launch_bigru_big(BiGruParams& P, void* big_ws, int precision, cudaStream_t stream) {
@@ -827,11 +856,29 @@ int launch_bigru_big(BiGruParams& P, void* big_ws, int precision, cudaStream_t s
     StepLaunch L;
     memset(&L, 0, sizeof(L));
     const StepShape shape = choose_shape();
+    for (int g = 0; g < 3; ++g) {            // tensor maps: activation boxes of 128 * mt rows, weight boxes per tile shape
+        const size_t rows = P.g[g].rows;
+        if (int rc = make_map(&L.maps[g], ws + BL.ring_g[g], precision, D, rows, 8, ST_BM * shape.mt)) return rc;
+        if (shape.cg == 1) {
+            if (int rc = make_gate_map(&L.maps[3 + g], ws + BL.whh_g[g], precision, D, D, 4, ST_U, 3)) return rc;
+        } else {
+            if (int rc = make_gate_map(&L.maps[3 + g], ws + BL.whh_g[g], precision, D, D, 4, ST_U, 1)) return rc;
+            if (int rc = make_gate_map(&L.maps[6 + g], ws + BL.whh_g[g], precision, D, D, 4, ST_U / 2, 1)) return rc;
+        }
+        // the state "before the first step" is zero: slot 1 is what step 0 reads
+        TG_CUDA_OK(cudaMemsetAsync(ws + BL.ring_g[g] + 4 * plane_bytes(rows, D), 0, 4 * plane_bytes(rows, D), stream));
+    }
+    DirStreams ds;
+    if (int rc = get_dir_streams(ds)) return rc;
+    if (ds.split) {
+        TG_CUDA_OK(cudaEventRecord(ds.fork, stream));
+        TG_CUDA_OK(cudaStreamWaitEvent(ds.side, ds.fork, 0));
+    }
     for (int s = 0; s < T; ++s) {
         const int slot_in = (s & 1) ^ 1, slot_out = s & 1;
-        L.count = 0;
-        for (int g = 0; g < 3; ++g)
-            for (int dir = 0; dir < 2; ++dir) {
+        for (int dir = 0; dir < 2; ++dir) {
+            if (ds.split || dir == 0) L.count = 0;
+            for (int g = 0; g < 3; ++g) {
                 StepProblem& q = L.p[L.count++];
                 memset(&q, 0, sizeof(q));
                 const BiGruGroup& G = P.g[g];
@@ -843,21 +890,13 @@ int launch_bigru_big(BiGruParams& P, void* big_ws, int precision, cudaStream_t s
                 q.xg = G.gi; q.bhh = G.bhh[dir]; q.ugate = nullptr; q.hx = G.hfr; q.gsave = G.gates;
                 q.ring_out = ws + BL.ring_g[g] + (size_t)(slot_out * 2 + dir) * 2 * plane_bytes(G.rows, D);
             }
-        if (s == 0) {            // tensor maps: activation boxes of 128 * mt rows, weight boxes of 64 / cg rows
-            for (int g = 0; g < 3; ++g) {
-                const size_t rows = P.g[g].rows;
-                if (int rc = make_map(&L.maps[g], ws + BL.ring_g[g], precision, D, rows, 8, ST_BM * shape.mt)) return rc;
-                if (shape.cg == 1) {
-                    if (int rc = make_gate_map(&L.maps[3 + g], ws + BL.whh_g[g], precision, D, D, 4, ST_U, 3)) return rc;
-                } else {
-                    if (int rc = make_gate_map(&L.maps[3 + g], ws + BL.whh_g[g], precision, D, D, 4, ST_U, 1)) return rc;
-                    if (int rc = make_gate_map(&L.maps[6 + g], ws + BL.whh_g[g], precision, D, D, 4, ST_U / 2, 1)) return rc;
-                }
-                // the state "before the first step" is zero: slot 1 is what step 0 reads
-                TG_CUDA_OK(cudaMemsetAsync(ws + BL.ring_g[g] + 4 * plane_bytes(rows, D), 0, 4 * plane_bytes(rows, D), stream));
-            }
+            if (ds.split || dir == 1)
+                if (int rc = launch_step(L, precision, shape, (ds.split && dir == 1) ? ds.side : stream)) return rc;
         }
-        if (int rc = launch_step(L, precision, shape, stream)) return rc;
+    }
+    if (ds.split) {
+        TG_CUDA_OK(cudaEventRecord(ds.join, ds.side));
+        TG_CUDA_OK(cudaStreamWaitEvent(stream, ds.join, 0));
     }
     return 0;
 }
@@ -922,71 +961,85 @@ int launch_segment_big(SegParams& P, void* big_ws, int precision, int T_save, cu
     if (precision) { if (int rc = ensure_smem((const void*)seg_attend_kernel<1>, at_smem)) return rc; }
     else           { if (int rc = ensure_smem((const void*)seg_attend_kernel<0>, at_smem)) return rc; }
 
+    if (int rc = encode_maps(LA)) return rc;
+    memcpy(LB.maps, LA.maps, sizeof(LA.maps));
+    DirStreams ds;
+    if (int rc = get_dir_streams(ds)) return rc;
+    if (ds.split) {
+        TG_CUDA_OK(cudaEventRecord(ds.fork, stream));
+        TG_CUDA_OK(cudaStreamWaitEvent(ds.side, ds.fork, 0));
+    }
     for (int s = 0; s < T; ++s) {
         const int slot_in = (s & 1) ^ 1, slot_out = s & 1;
-        AttendParams A;
-        memset(&A, 0, sizeof(A));
-        // ---- phase A1: per-sender messages msg = ReLU(W_k s_prev + b_k) for every kind and direction --------------------------
-        LA.count = 0;
-        for (int dir = 0; dir < 2; ++dir) {
-            const int t = dir == 0 ? s : T - 1 - s;
-            size_t scratch_off = (size_t)dir * 2 * (Rh + Ro) * D;
-            for (int k = 0; k < 4; ++k) {
-                const bool send_h = (k == 0 || k == 2);
-                const int Es = send_h ? H : O;
-                const size_t Rs = send_h ? Rh : Ro;
-                float* out;
-                long long bstride;
-                if (saving) { out = P.smsg[k] != nullptr ? P.smsg[k] + (((size_t)dir * B) * T + t) * Es * D : nullptr; bstride = (long long)T * Es * D; }
-                else        { out = msg_scratch + scratch_off; bstride = (long long)Es * D; }
-                scratch_off += Rs * D;
-                A.msg[dir][k] = out; A.msg_bstride[k] = bstride;
-                if (k == 0 && !P.hh) continue;
-                StepProblem& q = LA.p[LA.count++];
-                memset(&q, 0, sizeof(q));
-                q.mode = ST_RELU; q.rows = (int)Rs; q.E = Es; q.D = D;
-                q.nkb1 = 0; q.nkb2 = cdiv(D, ST_BK);
-                q.a2_map = send_h ? M_RING_H : M_RING_O; q.a2_plane = (slot_in * 2 + dir) * 2;
-                q.b2_map = M_WM; q.b2_plane = k * 2;
-                q.bias = P.bm[k]; q.out = out; q.out_bstride = bstride;
+        // the two time directions are independent chains of (messages -> attention -> cells): one stream each
+        for (int pass = 0; pass < (ds.split ? 2 : 1); ++pass) {
+            const int dir_lo = ds.split ? pass : 0, dir_hi = ds.split ? pass + 1 : 2;
+            cudaStream_t st = (ds.split && pass == 1) ? ds.side : stream;
+            AttendParams A;
+            memset(&A, 0, sizeof(A));
+            // ---- phase A1: per-sender messages msg = ReLU(W_k s_prev + b_k) for every kind ----------------------------------------
+            LA.count = 0;
+            for (int dir = dir_lo; dir < dir_hi; ++dir) {
+                const int t = dir == 0 ? s : T - 1 - s;
+                size_t scratch_off = (size_t)dir * 2 * (Rh + Ro) * D;
+                for (int k = 0; k < 4; ++k) {
+                    const bool send_h = (k == 0 || k == 2);
+                    const int Es = send_h ? H : O;
+                    const size_t Rs = send_h ? Rh : Ro;
+                    float* out;
+                    long long bstride;
+                    if (saving) { out = P.smsg[k] != nullptr ? P.smsg[k] + (((size_t)dir * B) * T + t) * Es * D : nullptr; bstride = (long long)T * Es * D; }
+                    else        { out = msg_scratch + scratch_off; bstride = (long long)Es * D; }
+                    scratch_off += Rs * D;
+                    A.msg[dir][k] = out; A.msg_bstride[k] = bstride;
+                    if (k == 0 && !P.hh) continue;
+                    StepProblem& q = LA.p[LA.count++];
+                    memset(&q, 0, sizeof(q));
+                    q.mode = ST_RELU; q.rows = (int)Rs; q.E = Es; q.D = D;
+                    q.nkb1 = 0; q.nkb2 = cdiv(D, ST_BK);
+                    q.a2_map = send_h ? M_RING_H : M_RING_O; q.a2_plane = (slot_in * 2 + dir) * 2;
+                    q.b2_map = M_WM; q.b2_plane = k * 2;
+                    q.bias = P.bm[k]; q.out = out; q.out_bstride = bstride;
+                }
             }
+            if (int rc = launch_step(LA, precision, shape, st)) return rc;
+            // ---- phase A2: attention over the previous states + aggregation -> operand rows of the cell GEMM --------------------
+            A.B = B; A.T = T; A.H = H; A.O = O; A.D = D; A.hh = P.hh; A.nk_h = nkh; A.mean_pool = P.mean_pool; A.first = s == 0; A.s = s;
+            A.dir_base = dir_lo;
+            A.hx_h = P.hx_h; A.hx_o = P.hx_o; A.om = P.om;
+            A.mg16_h = ws + BL.mg_h; A.mg16_o = ws + BL.mg_o;
+            A.mg32_h = P.mg_T > 1 ? P.mg_h : nullptr; A.mg32_o = P.mg_T > 1 ? P.mg_o : nullptr; A.mg_T = P.mg_T;
+            for (int k = 0; k < 4; ++k) A.salpha[k] = P.salpha[k];
+            A.att_f = P.att_f; A.att_b = P.att_b; A.err = P.sync.error;
+            if (precision) seg_attend_kernel<1><<<dim3(B, dir_hi - dir_lo), AT_THREADS, at_smem, st>>>(A);
+            else           seg_attend_kernel<0><<<dim3(B, dir_hi - dir_lo), AT_THREADS, at_smem, st>>>(A);
+            TG_LAUNCH_OK();
+            // ---- phase B: gated GRU cells -----------------------------------------------------------------------------------------
+            LB.count = 0;
+            for (int dir = dir_lo; dir < dir_hi; ++dir)
+                for (int type = 0; type < 2; ++type) {
+                    const bool is_h = type == 0;
+                    StepProblem& q = LB.p[LB.count++];
+                    memset(&q, 0, sizeof(q));
+                    const int E = is_h ? H : O, nk = is_h ? nkh : 2;
+                    const size_t R = is_h ? Rh : Ro;
+                    q.mode = ST_GRU; q.rows = (int)R; q.E = E; q.D = D;
+                    q.nkb1 = cdiv(nk * D, ST_BK); q.nkb2 = cdiv(D, ST_BK);
+                    q.a1_map = is_h ? M_MG_H : M_MG_O; q.a1_plane = dir * 2;
+                    q.a2_map = is_h ? M_RING_H : M_RING_O; q.a2_plane = (slot_in * 2 + dir) * 2;
+                    q.b1_map = is_h ? M_WIH_H : M_WIH_O; q.b1n_map = is_h ? M_WIH_H_N : M_WIH_O_N; q.b1_plane = dir * 2;
+                    q.b2_map = is_h ? M_WHH_H : M_WHH_O; q.b2n_map = is_h ? M_WHH_H_N : M_WHH_O_N; q.b2_plane = dir * 2;
+                    q.T = T; q.dir = dir; q.t = dir == 0 ? s : T - 1 - s; q.tprev = dir == 0 ? q.t - 1 : q.t + 1; q.first = s == 0;
+                    q.xg = is_h ? P.gs_h : P.gs_o; q.bhh = is_h ? P.bhh_h[dir] : P.bhh_o[dir];
+                    q.ugate = is_h ? P.u_h : P.u_o; q.hx = is_h ? P.hx_h : P.hx_o; q.gsave = is_h ? P.sgates_h : P.sgates_o;
+                    q.ring_out = ws + (is_h ? BL.ring_h : BL.ring_o) + (size_t)(slot_out * 2 + dir) * 2 * plane_bytes(R, D);
+                }
+            if (int rc = launch_step(LB, precision, shape, st)) return rc;
         }
-        if (s == 0)
-            if (int rc = encode_maps(LA)) return rc;
-        if (int rc = launch_step(LA, precision, shape, stream)) return rc;
-        // ---- phase A2: attention over the previous states + aggregation -> operand rows of the cell GEMM ------------------------
-        A.B = B; A.T = T; A.H = H; A.O = O; A.D = D; A.hh = P.hh; A.nk_h = nkh; A.mean_pool = P.mean_pool; A.first = s == 0; A.s = s;
-        A.hx_h = P.hx_h; A.hx_o = P.hx_o; A.om = P.om;
-        A.mg16_h = ws + BL.mg_h; A.mg16_o = ws + BL.mg_o;
-        A.mg32_h = P.mg_T > 1 ? P.mg_h : nullptr; A.mg32_o = P.mg_T > 1 ? P.mg_o : nullptr; A.mg_T = P.mg_T;
-        for (int k = 0; k < 4; ++k) A.salpha[k] = P.salpha[k];
-        A.att_f = P.att_f; A.att_b = P.att_b; A.err = P.sync.error;
-        if (precision) seg_attend_kernel<1><<<dim3(B, 2), AT_THREADS, at_smem, stream>>>(A);
-        else           seg_attend_kernel<0><<<dim3(B, 2), AT_THREADS, at_smem, stream>>>(A);
-        TG_LAUNCH_OK();
-        // ---- phase B: gated GRU cells ---------------------------------------------------------------------------------------------
-        LB.count = 0;
-        for (int dir = 0; dir < 2; ++dir)
-            for (int type = 0; type < 2; ++type) {
-                const bool is_h = type == 0;
-                StepProblem& q = LB.p[LB.count++];
-                memset(&q, 0, sizeof(q));
-                const int E = is_h ? H : O, nk = is_h ? nkh : 2;
-                const size_t R = is_h ? Rh : Ro;
-                q.mode = ST_GRU; q.rows = (int)R; q.E = E; q.D = D;
-                q.nkb1 = cdiv(nk * D, ST_BK); q.nkb2 = cdiv(D, ST_BK);
-                q.a1_map = is_h ? M_MG_H : M_MG_O; q.a1_plane = dir * 2;
-                q.a2_map = is_h ? M_RING_H : M_RING_O; q.a2_plane = (slot_in * 2 + dir) * 2;
-                q.b1_map = is_h ? M_WIH_H : M_WIH_O; q.b1n_map = is_h ? M_WIH_H_N : M_WIH_O_N; q.b1_plane = dir * 2;
-                q.b2_map = is_h ? M_WHH_H : M_WHH_O; q.b2n_map = is_h ? M_WHH_H_N : M_WHH_O_N; q.b2_plane = dir * 2;
-                q.T = T; q.dir = dir; q.t = dir == 0 ? s : T - 1 - s; q.tprev = dir == 0 ? q.t - 1 : q.t + 1; q.first = s == 0;
-                q.xg = is_h ? P.gs_h : P.gs_o; q.bhh = is_h ? P.bhh_h[dir] : P.bhh_o[dir];
-                q.ugate = is_h ? P.u_h : P.u_o; q.hx = is_h ? P.hx_h : P.hx_o; q.gsave = is_h ? P.sgates_h : P.sgates_o;
-                q.ring_out = ws + (is_h ? BL.ring_h : BL.ring_o) + (size_t)(slot_out * 2 + dir) * 2 * plane_bytes(R, D);
-            }
-        if (s == 0)
-            if (int rc = encode_maps(LB)) return rc;
-        if (int rc = launch_step(LB, precision, shape, stream)) return rc;
+    }
+    if (ds.split) {
+        TG_CUDA_OK(cudaEventRecord(ds.join, ds.side));
+        TG_CUDA_OK(cudaStreamWaitEvent(stream, ds.join, 0));
     }
     (void)T_save;
     return 0;

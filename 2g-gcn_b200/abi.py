@@ -112,6 +112,11 @@ def lib():
     L.tggcn_linear_fwd.restype = C.c_int
     L.tggcn_linear_fwd.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
                                    C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]
+    L.tggcn_linear16_scratch_bytes.restype = C.c_size_t
+    L.tggcn_linear16_scratch_bytes.argtypes = [C.c_int] * 3
+    L.tggcn_linear16_fwd.restype = C.c_int
+    L.tggcn_linear16_fwd.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
+                                     C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p]
     L.tggcn_linear_bwd.restype = C.c_int
     L.tggcn_linear_bwd.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int,
                                    C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p,
@@ -138,7 +143,7 @@ def lib():
     L.tggcn_f1_at_k.restype = C.c_int
     L.tggcn_f1_at_k.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int64,
                                 C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
-    if L.tggcn_abi_version() != 5:
+    if L.tggcn_abi_version() != 6:
         raise TggcnError('lib2ggcn_b200.so ABI version mismatch; rebuild')
     _lib = L
     return L

@@ -120,6 +120,18 @@ void make_layout(const tggcn_dims& d, Layout& L) {
     sz[TGGCN_BUF_SALPHA_OH] = sv * 2 * N * H * O * f;
     sz[TGGCN_BUF_SALPHA_HO] = sv * 2 * N * O * H * f;
     sz[TGGCN_BUF_SALPHA_OO] = sv * 2 * N * O * O * f;
+    {   // operand planes of the largest projection stage (4 bytes per operand element: fp16 hi + lo, or bf16 + slack)
+        const size_t kh = (1 + nkh) * D, KV = 128 * V;
+        const size_t st[6] = {N * (H + O) * 2048 + N * KV + 2 * D * 2048 + 2048 * KV,
+                              N * 2048 + D * 2048,
+                              N * (H + O + 1) * D + 6 * 3 * D * D,
+                              N * (H + O + 1) * 2 * D + 3 * D * 2 * D,
+                              N * (H + O + 1) * 2 * D + 5 * D * 2 * D,
+                              N * H * kh + N * O * 4 * D + 2 * 3 * D * kh + 2 * 3 * D * 4 * D};
+        size_t m = 0;
+        for (size_t v : st) m = v > m ? v : m;
+        sz[TGGCN_BUF_PACK] = m * 4 + 32 * 256;
+    }
     size_t off = 0;
     for (int i = 0; i < TGGCN_BUF_COUNT; ++i) {
         L.off[i] = off;
@@ -188,8 +200,8 @@ int tggcn_status_decode(const uint32_t* flags) {
     }
     if ((flags[1] | flags[3]) & 2u) {
         if (!(rc & 1))
-            set_error("a recurrent weight (|w| >= 255) or activation (>= 65504) left the range of the fp16-split gate tiles (bigru=%u, "
-                      "segment=%u): the results of that call are invalid; rerun with dims.no_fp16_split = 1 (3xTF32 streaming kernels)",
+            set_error("a weight (|w| >= 255) or activation (>= 65504) left the range of the fp16-split tensor-core tiles (projections / bigru=%u, "
+                      "segment=%u): the results of that call are invalid; rerun with dims.no_fp16_split = 1 (3xTF32 kernels)",
                       (flags[1] >> 1) & 1u, (flags[3] >> 1) & 1u);
         rc |= 2;
     }
@@ -211,6 +223,20 @@ int tggcn_linear_fwd(const float* A, int lda, const float* W, int ldw, const flo
     g.count = 0;
     gemm_add(g, A, lda, W, ldw, bias, C, ldc, M, N, K, relu);
     return launch_gemm(g, gemm_path, (cudaStream_t)stream);
+}
+
+size_t tggcn_linear16_scratch_bytes(int M, int N, int K) {
+    if (M <= 0 || N <= 0 || K <= 0) return 0;
+    return ((size_t)M * K * 4 + 255) / 256 * 256 + ((size_t)N * K * 4 + 255) / 256 * 256;
+}
+
+int tggcn_linear16_fwd(const float* A, int lda, const float* W, int ldw, const float* bias, float* C, int ldc, int M, int N,
+                       int K, int relu, int precision, void* scratch, size_t scratch_bytes, uint32_t* status, void* stream) {
+    TG_REQUIRE(A && W && C && scratch, "linear16_fwd: null pointer");
+    GemmGroup g;
+    g.count = 0;
+    gemm_add(g, A, lda, W, ldw, bias, C, ldc, M, N, K, relu);
+    return launch_gemm16(g, precision, scratch, scratch_bytes, status, (cudaStream_t)stream);
 }
 
 }  // extern "C"
@@ -275,17 +301,24 @@ static int forward_impl(const tggcn_dims* dims, const void* const* weights, int 
     STAGE_END();
     const int gpath = (d.precision == 1 && d.gemm_path != 0) ? 3 : d.gemm_path;      // bf16 operands on the tensor-core projections
     GemmGroup g;
+    // projections: the TMA-fed kernel on 16-bit operand planes (gemm16.cu) where the shapes qualify, else gemm_tc / SIMT
+    auto project = [&](GemmGroup& grp) -> int {
+        if (d.gemm_path != 0 && (d.precision == 1 || !d.no_fp16_split) && gemm16_eligible(grp) && gemm16_scratch_bytes(grp) <= L.bytes[TGGCN_BUF_PACK])
+            return launch_gemm16(grp, d.precision == 1 ? 1 : 0, buf(TGGCN_BUF_PACK), L.bytes[TGGCN_BUF_PACK],
+                                 d.precision == 1 ? nullptr : sync + 1, stream);
+        return launch_gemm(grp, gpath, stream);
+    };
     // 2. ROI embeddings and the first geometry MLP layer (models.py:646)
     g.count = 0;
     gemm_add(g, io->x_human, d.Fh, W(TGGCN_W_HUM_EMB_W), 2048, W(TGGCN_W_HUM_EMB_B), buf(TGGCN_BUF_S_H), 2 * D, N * H, D, 2048, 1);
     gemm_add(g, io->x_objects, 2048, W(TGGCN_W_OBJ_EMB_W), 2048, W(TGGCN_W_OBJ_EMB_B), buf(TGGCN_BUF_S_O), 2 * D, N * O, D, 2048, 1);
     gemm_add(g, buf(TGGCN_BUF_GCN_OUT), 128 * V, W(TGGCN_W_GEO_MLP0_W), 128 * V, W(TGGCN_W_GEO_MLP0_B), buf(TGGCN_BUF_GEO_HID), 2048, N, 2048, 128 * V, 1);
-    if (int rc = launch_gemm(g, gpath, stream)) return rc;
+    if (int rc = project(g)) return rc;
     STAGE_END();
     // 3. second geometry MLP layer
     g.count = 0;
     gemm_add(g, buf(TGGCN_BUF_GEO_HID), 2048, W(TGGCN_W_GEO_MLP2_W), 2048, W(TGGCN_W_GEO_MLP2_B), buf(TGGCN_BUF_S_G), 2 * D, N, D, 2048, 1);
-    if (int rc = launch_gemm(g, gpath, stream)) return rc;
+    if (int rc = project(g)) return rc;
     STAGE_END();
     // 4. BiGRU input pre-activations for both directions (hoisted W_ih x + b_ih)
     g.count = 0;
@@ -295,7 +328,7 @@ static int forward_impl(const tggcn_dims* dims, const void* const* weights, int 
     gemm_add(g, buf(TGGCN_BUF_S_O), 2 * D, W(TGGCN_W_OBJ_RNN_WIH_B), D, W(TGGCN_W_OBJ_RNN_BIH_B), buf(TGGCN_BUF_GI_O) + 3 * D, 6 * D, N * O, 3 * D, D, 0);
     gemm_add(g, buf(TGGCN_BUF_S_G), 2 * D, W(TGGCN_W_GEO_RNN_WIH_F), D, W(TGGCN_W_GEO_RNN_BIH_F), buf(TGGCN_BUF_GI_G), 6 * D, N, 3 * D, D, 0);
     gemm_add(g, buf(TGGCN_BUF_S_G), 2 * D, W(TGGCN_W_GEO_RNN_WIH_B), D, W(TGGCN_W_GEO_RNN_BIH_B), buf(TGGCN_BUF_GI_G) + 3 * D, 6 * D, N, 3 * D, D, 0);
-    if (int rc = launch_gemm(g, gpath, stream)) return rc;
+    if (int rc = project(g)) return rc;
     STAGE_END();
     // 5. frame-level BiGRU recurrences (models.py:649-651)
     {
@@ -329,7 +362,7 @@ static int forward_impl(const tggcn_dims* dims, const void* const* weights, int 
     gemm_add(g, buf(TGGCN_BUF_HFR_H), 2 * D, W(TGGCN_W_HUM_BD_W), 2 * D, W(TGGCN_W_HUM_BD_B), buf(TGGCN_BUF_S_H) + D, 2 * D, N * H, D, 2 * D, 1);
     gemm_add(g, buf(TGGCN_BUF_HFR_O), 2 * D, W(TGGCN_W_OBJ_BD_W), 2 * D, W(TGGCN_W_OBJ_BD_B), buf(TGGCN_BUF_S_O) + D, 2 * D, N * O, D, 2 * D, 1);
     gemm_add(g, buf(TGGCN_BUF_HFR_G), 2 * D, W(TGGCN_W_GEO_BD_W), 2 * D, W(TGGCN_W_GEO_BD_B), buf(TGGCN_BUF_S_G) + D, 2 * D, N, D, 2 * D, 1);
-    if (int rc = launch_gemm(g, gpath, stream)) return rc;
+    if (int rc = project(g)) return rc;
     STAGE_END();
     // 7. per-sender frame messages, each computed once per sender and message kind (models.py:1693-1718)
     g.count = 0;
@@ -338,7 +371,7 @@ static int forward_impl(const tggcn_dims* dims, const void* const* weights, int 
     gemm_add(g, buf(TGGCN_BUF_S_O), 2 * D, W(TGGCN_W_MSG_OH_W), 2 * D, W(TGGCN_W_MSG_OH_B), buf(TGGCN_BUF_MSG_OH), D, N * O, D, 2 * D, 1);
     gemm_add(g, buf(TGGCN_BUF_S_O), 2 * D, W(TGGCN_W_MSG_OO_W), 2 * D, W(TGGCN_W_MSG_OO_B), buf(TGGCN_BUF_MSG_OO), D, N * O, D, 2 * D, 1);
     gemm_add(g, buf(TGGCN_BUF_S_G), 2 * D, W(TGGCN_W_MSG_GO_W), 2 * D, W(TGGCN_W_MSG_GO_B), buf(TGGCN_BUF_MSG_GO), D, N, D, 2 * D, 1);
-    if (int rc = launch_gemm(g, gpath, stream)) return rc;
+    if (int rc = project(g)) return rc;
     STAGE_END();
     // 8. attention, aggregation, gates, segment-level inputs
     {
@@ -372,7 +405,7 @@ static int forward_impl(const tggcn_dims* dims, const void* const* weights, int 
     gemm_add(g, buf(TGGCN_BUF_XX_H), kh, W(TGGCN_W_HSEG_B_WIH), ldwh, W(TGGCN_W_HSEG_B_BIH), buf(TGGCN_BUF_GS_H) + 3 * D, 6 * D, N * H, 3 * D, kh, 0);
     gemm_add(g, buf(TGGCN_BUF_XX_O), 4 * D, W(TGGCN_W_OSEG_F_WIH), 6 * D, W(TGGCN_W_OSEG_F_BIH), buf(TGGCN_BUF_GS_O), 6 * D, N * O, 3 * D, 4 * D, 0);
     gemm_add(g, buf(TGGCN_BUF_XX_O), 4 * D, W(TGGCN_W_OSEG_B_WIH), 6 * D, W(TGGCN_W_OSEG_B_BIH), buf(TGGCN_BUF_GS_O) + 3 * D, 6 * D, N * O, 3 * D, 4 * D, 0);
-    if (int rc = launch_gemm(g, gpath, stream)) return rc;
+    if (int rc = project(g)) return rc;
     STAGE_END();
     // 11. segment-level recurrent graph (models.py:785-880)
     {

@@ -127,7 +127,7 @@ int launch_bigru(BiGruParams& P, int persistent, cudaStream_t stream) {
         const int rc = launch_bigru_resident(P, stream);      // recurrent weights resident in shared memory when the shape allows
         if (rc >= 0) return rc;
         const int grid = P.total_tiles < capacity ? P.total_tiles : capacity;
-        TG_CUDA_OK(cudaMemsetAsync(P.sync.counter, 0, 2 * sizeof(unsigned int), stream));
+        TG_CUDA_OK(cudaMemsetAsync(P.sync.counter, 0, sizeof(unsigned int), stream));      // the error word belongs to the caller (tggcn_forward zeroes it once)
         int s0 = 0, s1 = P.T, pers = 1;
         void* args[] = {(void*)&P, (void*)&s0, (void*)&s1, (void*)&pers};
         TG_CUDA_OK(cudaLaunchCooperativeKernel((const void*)kern, dim3(grid), dim3(REC_THREADS), args, smem, stream));

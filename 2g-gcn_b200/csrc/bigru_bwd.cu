@@ -31,6 +31,7 @@ int tggcn_bigru_fwd(const float* gi, const float* whh_f, const float* whh_b, con
     P.g[0].whh[0] = whh_f; P.g[0].whh[1] = whh_b; P.g[0].bhh[0] = bhh_f; P.g[0].bhh[1] = bhh_b;
     P.g[0].E = E; P.g[0].rows = B * E;
     P.sync.counter = (unsigned int*)sync; P.sync.error = (unsigned int*)sync + 1;
+    TG_CUDA_OK(cudaMemsetAsync(sync, 0, 2 * sizeof(unsigned int), (cudaStream_t)stream));
     return launch_bigru(P, persistent, (cudaStream_t)stream);
 }
 

@@ -305,7 +305,7 @@ int launch_bigru_resident(BiGruParams& P, cudaStream_t stream) {
     int per_sm = 0;
     TG_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, REC_THREADS, smem));
     if (per_sm < 1 || grid > per_sm * num_sms()) return -1;
-    TG_CUDA_OK(cudaMemsetAsync(P.sync.counter, 0, 2 * sizeof(unsigned int), stream));
+    TG_CUDA_OK(cudaMemsetAsync(P.sync.counter, 0, sizeof(unsigned int), stream));      // the error word belongs to the caller (tggcn_forward zeroes it once)
     int cpg = ctas_per_gd;
     void* args[] = {(void*)&P, (void*)&cpg};
     TG_CUDA_OK(cudaLaunchCooperativeKernel((const void*)kern, dim3(grid), dim3(REC_THREADS), args, smem, stream));

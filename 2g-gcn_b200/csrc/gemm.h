@@ -38,6 +38,10 @@ inline void gemm_add(GemmGroup& g, const float* A, int lda, const float* W, int 
 }
 
 int launch_gemm_simt(GemmGroup& grp, cudaStream_t stream);
+// TMA-fed tcgen05 kernel on 16-bit operand planes (gemm16.cu): precision 0 = fp16 (hi, lo) split (fp32-class), 1 = bf16
+bool gemm16_eligible(const GemmGroup& grp);
+size_t gemm16_scratch_bytes(const GemmGroup& grp);
+int launch_gemm16(GemmGroup& grp, int precision, void* scratch, size_t scratch_bytes, unsigned int* err, cudaStream_t stream);
 int launch_gemm_tc(GemmGroup& grp, cudaStream_t stream);     // tcgen05 3xTF32 or bf16 (gemm_tc.cu)
 // path 0: fp32 SIMT; 1: tcgen05 3xTF32 (K % 32 == 0 required); 2: tcgen05 where the shapes allow it, SIMT otherwise;
 // 3: like 2 with bf16 operands on the tensor-core path (dims.precision = 1)

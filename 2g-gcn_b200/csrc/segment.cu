@@ -533,7 +533,7 @@ int launch_segment(SegParams& P, int persistent, cudaStream_t stream) {
     if (persistent) {
         int grid = P.tilesA > P.tilesB ? P.tilesA : P.tilesB;
         if (grid > capacity) grid = capacity;
-        TG_CUDA_OK(cudaMemsetAsync(P.sync.counter, 0, 2 * sizeof(unsigned int), stream));
+        TG_CUDA_OK(cudaMemsetAsync(P.sync.counter, 0, sizeof(unsigned int), stream));      // the error word belongs to the caller (tggcn_forward zeroes it once)
         int s0 = 0, s1 = P.T, phases = 3, pers = 1;
 #ifdef TGGCN_TIMING_EXPERIMENTS      // never in the product build: skipping a phase leaves the outputs undefined
         if (const char* e = getenv("TGGCN_SEG_PHASES")) phases = atoi(e);

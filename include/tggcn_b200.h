@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define TGGCN_ABI_VERSION 5
+#define TGGCN_ABI_VERSION 6
 
 #if defined(__GNUC__)
 #define TGGCN_API __attribute__((visibility("default")))
@@ -252,6 +252,7 @@ enum tggcn_buf_id {
     TGGCN_BUF_SALPHA_OH,
     TGGCN_BUF_SALPHA_HO,
     TGGCN_BUF_SALPHA_OO,
+    TGGCN_BUF_PACK,          /* 16-bit operand planes of the projection stage in flight (gemm16.cu)                       */
     TGGCN_BUF_COUNT
 };
 
@@ -314,6 +315,15 @@ TGGCN_API int tggcn_geo_gcn_fwd(const float* x_human, const void* const* weights
  * (build_mlp, pyrutils/torch/models.py:31-33).  gemm_path as in tggcn_dims. */
 TGGCN_API int tggcn_linear_fwd(const float* A, int lda, const float* W, int ldw, const float* bias, float* C, int ldc,
                      int M, int N, int K, int relu, int gemm_path, void* stream);
+
+/* The same nn.Linear on the TMA-fed tcgen05 kernel over 16-bit operand planes (csrc/gemm16.cu), which the forward uses whenever
+ * K % 64 == 0 and N % 16 == 0: precision 0 = fp16 (hi, lo) operand split, fp32-class accuracy; 1 = bf16 operands.
+ * scratch: tggcn_linear16_scratch_bytes(M, N, K) bytes of device memory, 256-byte aligned (the operand planes).
+ * status: one device word, bit 1 is set when an operand leaves the fp16 range (precision 0); may be NULL. */
+TGGCN_API size_t tggcn_linear16_scratch_bytes(int M, int N, int K);
+TGGCN_API int tggcn_linear16_fwd(const float* A, int lda, const float* W, int ldw, const float* bias, float* C, int ldc,
+                       int M, int N, int K, int relu, int precision, void* scratch, size_t scratch_bytes,
+                       uint32_t* status, void* stream);
 
 /* Upstream gradients of the forward's output list (models.py:919-926), same shapes as the outputs; NULL = no gradient. */
 typedef struct tggcn_grad_outputs {

@@ -69,7 +69,7 @@ def test_library_loads_and_exports_every_declared_symbol(pkg):
     lib = pkg.abi.lib()
     for sym in declared:
         assert hasattr(lib, sym), sym
-    assert lib.tggcn_abi_version() == 5
+    assert lib.tggcn_abi_version() == 6
     # struct mirrors: 17 int32 + 1 float + 6 int32; io = 6 + 4 + 8 + 3 + 3 + 1 pointers
     assert ctypes.sizeof(pkg.abi.Dims) == 24 * 4
     assert ctypes.sizeof(pkg.abi.IO) == 25 * 8

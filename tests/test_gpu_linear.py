@@ -66,6 +66,87 @@ def test_linear_matches_fp64(shape, path, pkg):
         assert torch.all(C_full[:, N:] == -7.0), 'wrote outside the N columns'
 
 
+SHAPES16 = [
+    # M, N, K, lda_pad, ldw_pad, ldc_pad, relu, bias        (K % 64 == 0, N % 16 == 0: what the forward sends to gemm16.cu)
+    (1, 16, 64, 0, 0, 0, 0, 1),
+    (130, 144, 64, 8, 4, 4, 0, 1),
+    (300, 208, 192, 0, 0, 0, 1, 1),
+    (257, 96, 128, 104, 0, 32, 1, 0),
+    (2048, 512, 2048, 104, 0, 512, 1, 1),      # human ROI embedding, B=8,T=128
+    (1024, 2048, 3328, 0, 0, 0, 1, 1),         # geometry MLP layer 0
+    (4096, 1536, 512, 512, 0, 1536, 0, 1),     # BiGRU input gates, objects
+    (5000, 4000, 128, 8, 4, 32, 1, 1),         # many 128x256 tiles, ragged in M and N
+    (4096, 3072, 64, 0, 0, 0, 0, 0),
+]
+
+
+@pytest.mark.parametrize('precision', [0, 1])
+@pytest.mark.parametrize('shape', SHAPES16)
+def test_linear16_matches_fp64(shape, precision, pkg):
+    """The TMA-fed tcgen05 projection kernel on 16-bit operand planes (csrc/gemm16.cu): precision 0 = fp16 (hi, lo) split,
+    fp32-class accuracy (same bound as the 3xTF32 kernel); 1 = bf16 operands.  Rows of very different magnitudes exercise the
+    split (small values keep their absolute accuracy through the lo plane's subnormals)."""
+    M, N, K, pa, pw, pc, relu, has_bias = shape
+    g = torch.Generator().manual_seed(M * 7 + N * 3 + K + 1)
+    A_full = torch.randn(M, K + pa, generator=g)
+    A_full[::3] *= 30.0
+    A_full[1::3] *= 1e-3
+    W_full = torch.randn(N, K + pw, generator=g) / K ** 0.5
+    bias = torch.randn(N, generator=g) if has_bias else None
+    ref = A_full[:, :K].double() @ W_full[:, :K].double().t()
+    if bias is not None:
+        ref = ref + bias.double()
+    if relu:
+        ref = ref.clamp_min(0)
+    A_d, W_d = A_full.cuda(), W_full.cuda()
+    C_full = torch.full((M, N + pc), -7.0, device='cuda')
+    lib = pkg.abi.lib()
+    nbytes = lib.tggcn_linear16_scratch_bytes(M, N, K)
+    scratch = torch.empty(nbytes + 256, dtype=torch.uint8, device='cuda')
+    sptr = (scratch.data_ptr() + 255) // 256 * 256
+    status = torch.zeros(1, dtype=torch.int32, device='cuda')
+    rc = lib.tggcn_linear16_fwd(A_d.data_ptr(), A_d.stride(0), W_d.data_ptr(), W_d.stride(0),
+                                bias.cuda().data_ptr() if bias is not None else None, C_full.data_ptr(), C_full.stride(0),
+                                M, N, K, relu, precision, C.c_void_p(sptr), nbytes, C.c_void_p(status.data_ptr()),
+                                C.c_void_p(torch.cuda.current_stream().cuda_stream))
+    pkg.abi.check(rc, 'tggcn_linear16_fwd')
+    torch.cuda.synchronize()
+    assert int(status.item()) == 0
+    got = C_full[:, :N].cpu().double()
+    # per-row scale: the rows differ by 4.5 orders of magnitude
+    scale = ref.abs().amax(dim=1, keepdim=True) + 1e-6
+    rel = ((got - ref).abs() / scale).max().item()
+    if precision == 1:
+        assert rel <= 2e-2, f'bf16: max row-relative err {rel:.3e}'
+        assert rel > 1e-6, 'bf16 requested but the result is fp32-exact'
+    else:
+        big = (got - ref).abs()[::3].max().item() / (ref.abs()[::3].max().item() + 1e-6)
+        assert big <= 2e-5, f'fp16 split: max err on the large rows {big:.3e}'
+        # the small rows keep fp32-class ABSOLUTE accuracy (their lo parts are fp16 subnormals)
+        assert ((got - ref).abs()[1::3].max().item() if M > 1 else 0.0) <= 2e-5 * (ref.abs().max().item() + 1e-6) + 1e-5
+        assert rel <= 5e-4, f'fp16 split: max row-relative err {rel:.3e}'
+    if pc:
+        assert torch.all(C_full[:, N:] == -7.0), 'wrote outside the N columns'
+
+
+def test_linear16_reports_range_violation(pkg):
+    M, N, K = 64, 32, 64
+    A = torch.ones(M, K, device='cuda')
+    A[5, 7] = 1e6                                   # beyond fp16
+    W = torch.ones(N, K, device='cuda') * 0.01
+    Cout = torch.empty(M, N, device='cuda')
+    lib = pkg.abi.lib()
+    nbytes = lib.tggcn_linear16_scratch_bytes(M, N, K)
+    scratch = torch.empty(nbytes + 256, dtype=torch.uint8, device='cuda')
+    sptr = (scratch.data_ptr() + 255) // 256 * 256
+    status = torch.zeros(1, dtype=torch.int32, device='cuda')
+    rc = lib.tggcn_linear16_fwd(A.data_ptr(), K, W.data_ptr(), K, None, Cout.data_ptr(), N, M, N, K, 0, 0, C.c_void_p(sptr), nbytes,
+                                C.c_void_p(status.data_ptr()), C.c_void_p(torch.cuda.current_stream().cuda_stream))
+    pkg.abi.check(rc, 'tggcn_linear16_fwd')
+    torch.cuda.synchronize()
+    assert int(status.item()) & 2
+
+
 BWD_SHAPES = [
     # M, N, K, relu, lda_pad, ldy_pad
     (37, 48, 32, 1, 0, 0),

@@ -198,11 +198,11 @@ int tggcn_status_decode(const uint32_t* flags) {
                   "that call are undefined", flags[1] & 1u, flags[3] & 1u, flags[5] & 1u, flags[7] & 1u);
         rc |= 1;
     }
-    if ((flags[1] | flags[3]) & 2u) {
+    if ((flags[1] | flags[3] | flags[5] | flags[7]) & 2u) {
         if (!(rc & 1))
             set_error("a weight (|w| >= 255) or activation (>= 65504) left the range of the fp16-split tensor-core tiles (projections / bigru=%u, "
-                      "segment=%u): the results of that call are invalid; rerun with dims.no_fp16_split = 1 (3xTF32 kernels)",
-                      (flags[1] >> 1) & 1u, (flags[3] >> 1) & 1u);
+                      "segment=%u, backward GEMMs=%u): the results of that call are invalid; rerun with dims.no_fp16_split = 1 (3xTF32 kernels)",
+                      (flags[1] >> 1) & 1u, (flags[3] >> 1) & 1u, ((flags[5] | flags[7]) >> 1) & 1u);
         rc |= 2;
     }
     return rc;
@@ -227,7 +227,7 @@ int tggcn_linear_fwd(const float* A, int lda, const float* W, int ldw, const flo
 
 size_t tggcn_linear16_scratch_bytes(int M, int N, int K) {
     if (M <= 0 || N <= 0 || K <= 0) return 0;
-    return ((size_t)M * K * 4 + 255) / 256 * 256 + ((size_t)N * K * 4 + 255) / 256 * 256;
+    return 256 + ((size_t)M * K * 4 + 255) / 256 * 256 + ((size_t)N * K * 4 + 255) / 256 * 256;      // scale words + operand planes
 }
 
 int tggcn_linear16_fwd(const float* A, int lda, const float* W, int ldw, const float* bias, float* C, int ldc, int M, int N,

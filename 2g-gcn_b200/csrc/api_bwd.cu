@@ -81,17 +81,40 @@ void make_bwd_layout(const tggcn_dims& d, BwdLayout& L) {
     for (size_t c : cands)
         if (c > wmax) wmax = c;
     L.wt = L.take(wmax);
-    // transposed operands of one weight-gradient GEMM: (N + K) x M rounded up to 32
-    const size_t rp = (N * (H > O ? H : O) + 31) / 32 * 32, np = (N + 31) / 32 * 32;
+    // transposed operands of one weight-gradient GEMM: (N + K) x M rounded up to 64 (fp32 transposes, or the 16-bit operand planes
+    // of gemm16.cu — the same 4 bytes per element — which also holds the planes of one dX GEMM: gradient rows + transposed weight)
+    const size_t rp = (N * (H > O ? H : O) + 63) / 64 * 64, np = (N + 63) / 64 * 64;
     size_t tmax = (3 * D + (4 * D > 2048 ? 4 * D : 2048)) * rp;
     if ((2048 + 128 * V) * np > tmax) tmax = (2048 + 128 * V) * np;
+    const size_t nt_cands[] = {rp * 6 * D + 4 * D * 6 * D, np * 2048 + (size_t)2048 * 128 * V, np * 2 * D + (size_t)2048 * D};
+    for (size_t c : nt_cands)
+        if (c > tmax) tmax = c;
+    tmax += 1024;
     L.tn_floats = tmax;
     L.tn = L.take(tmax);
 }
 
+// scratch of the 16-bit operand planes (gemm16.cu) and the status word of the call; g16.ws == nullptr: the tf32 / bf16 kernels of gemm_tc.cu
+struct G16Ctx {
+    void* ws;
+    size_t bytes;
+    int precision;
+    unsigned int* err;
+};
+
 // C[M, Nout] (+)= (A (.) [mask > 0]) [M, K] * Wt[Nout, K]^T
 int gemm_nt(const float* A, int lda, const float* mask, int ldm, const float* Wt, int ldw, float* C, int ldc, int M, int Nout, int K,
-            int beta, int path, cudaStream_t stream) {
+            int beta, int path, cudaStream_t stream, const G16Ctx& g16) {
+    if (g16.ws != nullptr) {
+        // A is a gradient: amax-scaled fp16 (hi, lo) planes; Wt a transposed weight: times 2^8 as in the forward
+        Gemm16Problem q;
+        memset(&q, 0, sizeof(q));
+        q.a.src = A; q.a.ld = lda; q.a.rows = M; q.a.cols = K; q.a.mask = mask; q.a.ldm = ldm; q.a.dynamic = 1;
+        q.b.src = Wt; q.b.ld = ldw; q.b.rows = Nout; q.b.cols = K; q.b.scale = 256.0f;
+        q.C = C; q.ldc = ldc; q.beta = beta;
+        if (gemm16_eligible(&q, 1) && gemm16_scratch_bytes(&q, 1) <= g16.bytes)
+            return launch_gemm16(&q, 1, g16.precision, g16.ws, g16.bytes, g16.err, stream);
+    }
     GemmGroup g;
     g.count = 0;
     gemm_add(g, A, lda, Wt, ldw, nullptr, C, ldc, M, Nout, K, 0);
@@ -185,18 +208,34 @@ int tggcn_backward_ex(const tggcn_dims* dims, const void* const* weights, void* 
     // weight gradient dW[N,K] (+)= (Z (.) [mask > 0])^T X with an optional row shift of X inside blocks of `period` rows:
     // both operands are transposed into scratch (reduction index contiguous) and contracted by the tcgen05 NT kernel.
     float* tn_scratch = bb(BL.tn);
+    G16Ctx g16;
+    g16.ws = nullptr; g16.bytes = BL.tn_floats * sizeof(float); g16.precision = d.precision == 1 ? 1 : 0;
+    g16.err = (unsigned int*)buf(TGGCN_BUF_SYNC) + 7;
+    if (d.gemm_path != 0 && gemm16_enabled() && (d.precision == 1 || !d.no_fp16_split)) g16.ws = tn_scratch;
     auto tn = [&](const float* Z, int ldz, const float* mask, int ldm, const float* X, int ldx, float* dW, int lddw, int M, int Nn, int K,
                   int shift, int period, int beta, cudaStream_t st) -> int {
+        if (g16.ws != nullptr) {
+            // both operands packed TRANSPOSED (reduction index = the rows, contiguous and zero-padded to 64) straight from the
+            // row-major sources: replaces the two fp32 transposes; Z is a gradient (amax-scaled), X an activation
+            Gemm16Problem q;
+            memset(&q, 0, sizeof(q));
+            q.a.src = Z; q.a.ld = ldz; q.a.rows = M; q.a.cols = Nn; q.a.mask = mask; q.a.ldm = ldm; q.a.transpose = 1; q.a.dynamic = 1;
+            q.b.src = X; q.b.ld = ldx; q.b.rows = M; q.b.cols = K; q.b.transpose = 1; q.b.shift = shift; q.b.period = period; q.b.scale = 1.0f;
+            q.C = dW; q.ldc = lddw; q.beta = beta;
+            if (gemm16_eligible(&q, 1) && gemm16_scratch_bytes(&q, 1) <= g16.bytes)
+                return launch_gemm16(&q, 1, g16.precision, g16.ws, g16.bytes, g16.err, st);
+        }
         const int Mp = (M + 31) / 32 * 32;
         TG_REQUIRE((size_t)(Nn + K) * Mp <= BL.tn_floats, "backward: weight-gradient scratch too small (%d + %d) x %d", Nn, K, Mp);
         float* zt = tn_scratch;
         float* xt = zt + (size_t)Nn * Mp;
         if (int rc = launch_transpose_prep(Z, ldz, mask, ldm, zt, Mp, M, Nn, 0, 0, nullptr, st)) return rc;
         if (int rc = launch_transpose_prep(X, ldx, nullptr, 0, xt, Mp, M, K, shift, period, nullptr, st)) return rc;
-        return gemm_nt(zt, Mp, nullptr, 0, xt, Mp, dW, lddw, Nn, K, Mp, beta, path, st);
+        return gemm_nt(zt, Mp, nullptr, 0, xt, Mp, dW, lddw, Nn, K, Mp, beta, path, st, G16Ctx{nullptr, 0, 0, nullptr});
     };
 
     TG_CUDA_OK(cudaMemsetAsync(bb(BL.zero_begin), 0, (BL.zero_end - BL.zero_begin) * sizeof(float), stream));
+    TG_CUDA_OK(cudaMemsetAsync((unsigned int*)buf(TGGCN_BUF_SYNC) + 4, 0, 4 * sizeof(unsigned int), stream));      // status words of this call
 
     // ---- 12. heads --------------------------------------------------------------------------------------------------
     {
@@ -324,10 +363,10 @@ int tggcn_backward_ex(const tggcn_dims* dims, const void* const* weights, void* 
         float* wt = bb(BL.wt);
         for (int dir = 0; dir < 2; ++dir)
             if (int rc = launch_transpose(W(wih_h_id[dir]), ldwh, wt + (size_t)dir * 3 * D, 6 * D, 3 * D, kh, stream)) return rc;
-        if (int rc = gemm_nt(bb(BL.dgs[0]), 6 * D, nullptr, 0, wt, 6 * D, bb(BL.dxx[0]), kh, N * H, kh, 6 * D, 0, path, stream)) return rc;
+        if (int rc = gemm_nt(bb(BL.dgs[0]), 6 * D, nullptr, 0, wt, 6 * D, bb(BL.dxx[0]), kh, N * H, kh, 6 * D, 0, path, stream, g16)) return rc;
         for (int dir = 0; dir < 2; ++dir)
             if (int rc = launch_transpose(W(wih_o_id[dir]), 6 * D, wt + (size_t)dir * 3 * D, 6 * D, 3 * D, 4 * D, stream)) return rc;
-        if (int rc = gemm_nt(bb(BL.dgs[1]), 6 * D, nullptr, 0, wt, 6 * D, bb(BL.dxx[1]), 4 * D, N * O, 4 * D, 6 * D, 0, path, stream)) return rc;
+        if (int rc = gemm_nt(bb(BL.dgs[1]), 6 * D, nullptr, 0, wt, 6 * D, bb(BL.dxx[1]), 4 * D, N * O, 4 * D, 6 * D, 0, path, stream, g16)) return rc;
     }
 
     // ---- 9/8. gates (straight-through, filter), attention, aggregation ------------------------------------------------------------
@@ -378,7 +417,7 @@ int tggcn_backward_ex(const tggcn_dims* dims, const void* const* weights, void* 
             const float* dmsg = bb(BL.dmsg[kinds[k].dmsg]);
             const float* msg = buf(kinds[k].msg_buf);
             if (int rc = launch_transpose(W(kinds[k].w_id), 2 * D, wt, D, D, 2 * D, stream)) return rc;      // (D,2D) -> (2D,D)
-            if (int rc = gemm_nt(dmsg, D, msg, D, wt, D, bb(BL.ds[gidx]), 2 * D, M, 2 * D, D, touched[gidx], path, stream)) return rc;
+            if (int rc = gemm_nt(dmsg, D, msg, D, wt, D, bb(BL.ds[gidx]), 2 * D, M, 2 * D, D, touched[gidx], path, stream, g16)) return rc;
             touched[gidx] = 1;
             if (int rc = tn(dmsg, D, msg, D, buf(s_buf[gidx]), 2 * D, G(kinds[k].w_id), 2 * D, M, D, 2 * D, 0, 0, 0, stream)) return rc;
             if (int rc = launch_colsum(dmsg, D, msg, D, G(kinds[k].w_id + 1), M, D, 0, stream)) return rc;
@@ -399,7 +438,7 @@ int tggcn_backward_ex(const tggcn_dims* dims, const void* const* weights, void* 
             const float* Y = buf(s_buf[g]) + D;
             if (int rc = launch_transpose(W(bd_id[g]), 2 * D, wt, D, D, 2 * D, stream)) return rc;
             const int beta = (g == 0 || (g == 1 && d.C_aff > 0)) ? 1 : 0;     // the frame heads already wrote into d hfr
-            if (int rc = gemm_nt(dZ, 2 * D, Y, 2 * D, wt, D, bb(BL.dhfr[g]), 2 * D, M, 2 * D, D, beta, path, stream)) return rc;
+            if (int rc = gemm_nt(dZ, 2 * D, Y, 2 * D, wt, D, bb(BL.dhfr[g]), 2 * D, M, 2 * D, D, beta, path, stream, g16)) return rc;
             if (int rc = tn(dZ, 2 * D, Y, 2 * D, buf(hfr_buf[g]), 2 * D, G(bd_id[g]), 2 * D, M, D, 2 * D, 0, 0, 0, stream)) return rc;
             if (int rc = launch_colsum(dZ, 2 * D, Y, 2 * D, G(bd_id[g] + 1), M, D, 0, stream)) return rc;
         }
@@ -442,7 +481,7 @@ int tggcn_backward_ex(const tggcn_dims* dims, const void* const* weights, void* 
             // d x (+)= [dGi_f | dGi_b] [W_ih_f ; W_ih_b]   (x = S[:, :D])
             if (int rc = launch_transpose(W(base), D, wt, 6 * D, 3 * D, D, stream)) return rc;
             if (int rc = launch_transpose(W(base + 4), D, wt + 3 * D, 6 * D, 3 * D, D, stream)) return rc;
-            if (int rc = gemm_nt(dgi, 6 * D, nullptr, 0, wt, 6 * D, bb(BL.ds[g]), 2 * D, M, D, 6 * D, 1, path, stream)) return rc;
+            if (int rc = gemm_nt(dgi, 6 * D, nullptr, 0, wt, 6 * D, bb(BL.ds[g]), 2 * D, M, D, 6 * D, 1, path, stream, g16)) return rc;
             for (int dir = 0; dir < 2; ++dir) {
                 if (int rc = tn(dgi + (size_t)dir * 3 * D, 6 * D, nullptr, 0, buf(s_buf[g]), 2 * D, G(base + 4 * dir), D, M, 3 * D, D,
                                             0, 0, 0, stream)) return rc;
@@ -465,14 +504,14 @@ int tggcn_backward_ex(const tggcn_dims* dims, const void* const* weights, void* 
         // geometry MLP layer 2: S_G[:, :D] = ReLU(W2 hid + b2)
         float* wt = bb(BL.wt);
         if (int rc = launch_transpose(W(TGGCN_W_GEO_MLP2_W), 2048, wt, D, D, 2048, stream)) return rc;          // (D,2048) -> (2048,D)
-        if (int rc = gemm_nt(bb(BL.ds[2]), 2 * D, buf(TGGCN_BUF_S_G), 2 * D, wt, D, bb(BL.dgeo_hid), 2048, N, 2048, D, 0, path, stream)) return rc;
+        if (int rc = gemm_nt(bb(BL.ds[2]), 2 * D, buf(TGGCN_BUF_S_G), 2 * D, wt, D, bb(BL.dgeo_hid), 2048, N, 2048, D, 0, path, stream, g16)) return rc;
         if (int rc = tn(bb(BL.ds[2]), 2 * D, buf(TGGCN_BUF_S_G), 2 * D, buf(TGGCN_BUF_GEO_HID), 2048, G(TGGCN_W_GEO_MLP2_W), 2048, N, D,
                                     2048, 0, 0, 0, stream)) return rc;
         if (int rc = launch_colsum(bb(BL.ds[2]), 2 * D, buf(TGGCN_BUF_S_G), 2 * D, G(TGGCN_W_GEO_MLP2_B), N, D, 0, stream)) return rc;
         // layer 0: hid = ReLU(W0 gcn + b0), gcn = the scrambled view (N, 128V)
         const int KV = 128 * V;
         if (int rc = launch_transpose(W(TGGCN_W_GEO_MLP0_W), KV, wt, 2048, 2048, KV, stream)) return rc;         // (2048,128V) -> (128V,2048)
-        if (int rc = gemm_nt(bb(BL.dgeo_hid), 2048, buf(TGGCN_BUF_GEO_HID), 2048, wt, 2048, bb(BL.dgcn_out), KV, N, KV, 2048, 0, path, stream)) return rc;
+        if (int rc = gemm_nt(bb(BL.dgeo_hid), 2048, buf(TGGCN_BUF_GEO_HID), 2048, wt, 2048, bb(BL.dgcn_out), KV, N, KV, 2048, 0, path, stream, g16)) return rc;
         if (int rc = tn(bb(BL.dgeo_hid), 2048, buf(TGGCN_BUF_GEO_HID), 2048, buf(TGGCN_BUF_GCN_OUT), KV, G(TGGCN_W_GEO_MLP0_W), KV, N,
                                     2048, KV, 0, 0, 0, stream)) return rc;
         if (int rc = launch_colsum(bb(BL.dgeo_hid), 2048, buf(TGGCN_BUF_GEO_HID), 2048, G(TGGCN_W_GEO_MLP0_B), N, 2048, 0, stream)) return rc;

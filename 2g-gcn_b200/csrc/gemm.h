@@ -42,6 +42,30 @@ int launch_gemm_simt(GemmGroup& grp, cudaStream_t stream);
 bool gemm16_eligible(const GemmGroup& grp);
 size_t gemm16_scratch_bytes(const GemmGroup& grp);
 int launch_gemm16(GemmGroup& grp, int precision, void* scratch, size_t scratch_bytes, unsigned int* err, cudaStream_t stream);
+
+// General form (backward): C[M,N] (+)= act(A' B'^T + bias), A' / B' = 16-bit planes packed from fp32 sources.
+struct Gemm16Operand {
+    const float* src;       // fp32 source matrix [rows][cols], row stride ld
+    int ld, rows, cols;
+    const float* mask;      // optional ReLU mask of the same shape (value kept where mask > 0), row stride ldm
+    int ldm;
+    int transpose;          // 0: operand rows = source rows, reduction = source columns (cols % 64 == 0)
+                            // 1: operand rows = source columns, reduction = source rows (zero-padded to a multiple of 64)
+    int shift, period;      // transpose only: source row m + shift pairs with reduction index m when 0 <= m % period + shift < period
+    int dynamic;            // 1: gradient operand — scaled by the power of two that brings its largest magnitude to [2^13, 2^14)
+    float scale;            // fixed scale otherwise (0 = 1); the fixed scales of all problems of a group must agree
+};
+struct Gemm16Problem {
+    Gemm16Operand a, b;     // M = operand rows of a, N = operand rows of b (N % 16 == 0)
+    const float* bias;
+    float* C;
+    int ldc, relu, beta;
+};
+bool gemm16_enabled();
+bool gemm16_eligible(const Gemm16Problem* p, int count);
+size_t gemm16_scratch_bytes(const Gemm16Problem* p, int count);
+int launch_gemm16(const Gemm16Problem* p, int count, int precision, void* scratch, size_t scratch_bytes, unsigned int* err,
+                  cudaStream_t stream);
 int launch_gemm_tc(GemmGroup& grp, cudaStream_t stream);     // tcgen05 3xTF32 or bf16 (gemm_tc.cu)
 // path 0: fp32 SIMT; 1: tcgen05 3xTF32 (K % 32 == 0 required); 2: tcgen05 where the shapes allow it, SIMT otherwise;
 // 3: like 2 with bf16 operands on the tensor-core path (dims.precision = 1)

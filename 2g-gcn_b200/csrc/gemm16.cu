@@ -30,26 +30,46 @@ namespace tg {
 namespace {
 
 constexpr int G16_BM = 128;                  // output rows per tile (UMMA M)
-constexpr int G16_BK = 64;                   // K elements per k-block: 128 bytes of 16-bit = one swizzle row
+constexpr int G16_BK = 64;                   // K granularity of the problems (K % 64 == 0)
 constexpr int G16_EPI_WARPS = 8;
 constexpr int G16_THREADS = (2 + G16_EPI_WARPS) * 32;
 constexpr int G16_MAX_PROBLEMS = GEMM_MAX_PROBLEMS;
 constexpr float G16_W_SCALE = 256.0f;        // fp16 split: weights are stored times 2^8
 
-template <int PREC, int BN> struct G16Cfg {
+// BK: K elements per pipeline stage = one swizzle row of the operand tiles: 64 (SWIZZLE_128B) or 32 (SWIZZLE_64B).  The fp16-split
+// 128 x 256 tile has 96 KB stages at BK = 64 — only two fit, and a two-stage ring exposes the TMA latency (measured 2900 cycles
+// per 64 K against a 1536-cycle tensor-pipe floor); BK = 32 gives four 48 KB stages.
+template <int PREC, int BN, int BK> struct G16Cfg {
     static constexpr int PLANES = PREC == 0 ? 2 : 1;
-    static constexpr int A_PLANE = G16_BM * 128;                       // bytes of one plane of the A tile
-    static constexpr int B_PLANE = BN * 128;
-    static constexpr int STAGE_BYTES = PLANES * (A_PLANE + B_PLANE);   // fp16 split: 96 KB (BN 256) / 64 KB (BN 128); bf16: half
-    static constexpr int STAGES = (226 * 1024) / STAGE_BYTES > 6 ? 6 : (226 * 1024) / STAGE_BYTES;
+    static constexpr int ROW_BYTES = BK * 2;
+    static constexpr int A_PLANE = G16_BM * ROW_BYTES;                 // bytes of one plane of the A tile
+    static constexpr int B_PLANE = BN * ROW_BYTES;
+    static constexpr int STAGE_BYTES = PLANES * (A_PLANE + B_PLANE);
+    static constexpr int STAGES = (226 * 1024) / STAGE_BYTES > 8 ? 8 : (226 * 1024) / STAGE_BYTES;
     static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024;
 };
 
+// K-major shared-memory matrix descriptor for rows of ROW_BYTES (128: SWIZZLE_128B, layout 2; 64: SWIZZLE_64B, layout 4); the
+// stride between 8-row groups is 8 * ROW_BYTES
+template <int ROW_BYTES> __device__ __forceinline__ uint64_t g16_desc(uint32_t smem_addr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);
+    d |= (uint64_t)1 << 16;
+    d |= (uint64_t)((8u * ROW_BYTES) >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)(ROW_BYTES == 128 ? 2 : 4) << 61;
+    return d;
+}
+
 struct G16Problem {
-    int M, N, K;
+    int M, N, K;            // K: reduction length of the operand planes (a multiple of 64; zero-padded by the pack kernels)
     int m_tiles, n_tiles, tile_begin;
     int relu, ldc;
+    int beta;               // 1: add to C instead of overwriting it
+    int ksplit;             // > 1: the K range is split over this many CTAs per tile, combined with atomics (C zeroed / beta)
     const float* bias;      // (N) or null
+    const float* inv_a;     // device scalars: inverse of the dynamic (amax-derived, power-of-two) scale of an operand, or null
+    const float* inv_b;
     float* C;               // fp32 result, row stride ldc
     void* out16;            // optional: 16-bit planes [plane][M][N] of the result (unscaled), or null
 };
@@ -85,10 +105,10 @@ __device__ __forceinline__ void g16_mma(uint32_t tmem_d, uint64_t adesc, uint64_
         : "memory");
 }
 
-template <int PREC, int BN>
+template <int PREC, int BN, int BK>
 __global__ void __launch_bounds__(G16_THREADS, 1) gemm16_kernel(const __grid_constant__ G16Launch L) {
-    using Cfg = G16Cfg<PREC, BN>;
-    constexpr int STAGES = Cfg::STAGES, PLANES = Cfg::PLANES;
+    using Cfg = G16Cfg<PREC, BN, BK>;
+    constexpr int STAGES = Cfg::STAGES, PLANES = Cfg::PLANES, RB = Cfg::ROW_BYTES;
     extern __shared__ uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t bars[2 * STAGES + 1];
     __shared__ uint32_t tmem_base_smem;
@@ -103,10 +123,14 @@ __global__ void __launch_bounds__(G16_THREADS, 1) gemm16_kernel(const __grid_con
     for (int i = 1; i < L.count; ++i)
         if ((int)blockIdx.x >= L.p[i].tile_begin) pi = i;
     const G16Problem& P = L.p[pi];
-    const int tile = blockIdx.x - P.tile_begin;
+    int tile = blockIdx.x - P.tile_begin;
+    const int ks = tile % P.ksplit;                                   // split-K slice of this CTA
+    tile /= P.ksplit;
     const int mt = tile / P.n_tiles, nt = tile - mt * P.n_tiles;      // consecutive CTAs share the activation rows
     const int m0 = mt * G16_BM, n0 = nt * BN;
-    const int nkb = P.K / G16_BK;
+    const int nkb_all = P.K / BK;
+    const int kb0 = (int)((long long)nkb_all * ks / P.ksplit);
+    const int nkb = (int)((long long)nkb_all * (ks + 1) / P.ksplit) - kb0;
 
     if (tid == 0) {
         for (int s = 0; s < STAGES; ++s) {
@@ -139,8 +163,8 @@ __global__ void __launch_bounds__(G16_THREADS, 1) gemm16_kernel(const __grid_con
                 const uint32_t bar = full0 + 8 * s;
                 g16_expect_tx(bar, (uint32_t)Cfg::STAGE_BYTES);
                 const uint32_t st = tiles_u32 + s * Cfg::STAGE_BYTES;
-                g16_tma_3d(st, &L.amap[pi], kb * G16_BK, m0, 0, bar);                               // box {64 k, 128 rows, planes}
-                g16_tma_3d(st + PLANES * Cfg::A_PLANE, &L.bmap[pi], kb * G16_BK, n0, 0, bar);       // box {64 k, BN rows, planes}
+                g16_tma_3d(st, &L.amap[pi], (kb0 + kb) * BK, m0, 0, bar);                               // box {BK k, 128 rows, planes}
+                g16_tma_3d(st + PLANES * Cfg::A_PLANE, &L.bmap[pi], (kb0 + kb) * BK, n0, 0, bar);       // box {BK k, BN rows, planes}
             }
         }
     } else if (warp == 1) {
@@ -156,14 +180,14 @@ __global__ void __launch_bounds__(G16_THREADS, 1) gemm16_kernel(const __grid_con
                 const uint32_t a_hi = st, a_lo = st + Cfg::A_PLANE;
                 const uint32_t b_hi = st + PLANES * Cfg::A_PLANE, b_lo = b_hi + Cfg::B_PLANE;
 #pragma unroll
-                for (int kk = 0; kk < G16_BK / 16; ++kk) {
+                for (int kk = 0; kk < BK / 16; ++kk) {
                     const uint32_t ko = kk * 32;               // 16 halves = 32 bytes along the swizzled row
                     if (PREC == 0) {
-                        g16_mma(tmem_base, umma_desc(a_lo + ko), umma_desc(b_hi + ko), idesc, (kb | kk) != 0);
-                        g16_mma(tmem_base, umma_desc(a_hi + ko), umma_desc(b_lo + ko), idesc, 1);
-                        g16_mma(tmem_base, umma_desc(a_hi + ko), umma_desc(b_hi + ko), idesc, 1);
+                        g16_mma(tmem_base, g16_desc<RB>(a_lo + ko), g16_desc<RB>(b_hi + ko), idesc, (kb | kk) != 0);
+                        g16_mma(tmem_base, g16_desc<RB>(a_hi + ko), g16_desc<RB>(b_lo + ko), idesc, 1);
+                        g16_mma(tmem_base, g16_desc<RB>(a_hi + ko), g16_desc<RB>(b_hi + ko), idesc, 1);
                     } else {
-                        g16_mma(tmem_base, umma_desc(a_hi + ko), umma_desc(b_hi + ko), idesc, (kb | kk) != 0);
+                        g16_mma(tmem_base, g16_desc<RB>(a_hi + ko), g16_desc<RB>(b_hi + ko), idesc, (kb | kk) != 0);
                     }
                 }
                 umma_commit(empty0 + 8 * s);                  // frees the stage when these MMAs have read it
@@ -178,8 +202,11 @@ __global__ void __launch_bounds__(G16_THREADS, 1) gemm16_kernel(const __grid_con
         const int row = m0 + q * 32 + lane;
         const bool valid = row < P.M;
         const uint32_t tq = tmem_base + ((uint32_t)(q * 32) << 16);
-        const float sc = L.acc_scale;
+        float sc = L.acc_scale;
+        if (P.inv_a != nullptr) sc *= __ldg(P.inv_a);
+        if (P.inv_b != nullptr) sc *= __ldg(P.inv_b);
         float* crow = P.C + (size_t)(valid ? row : 0) * P.ldc;
+        const bool add_bias = P.bias != nullptr && ks == 0;
         mbar_wait_backoff(tfull, 0);
         tc_fence_after();
 #pragma unroll 1
@@ -189,7 +216,7 @@ __global__ void __launch_bounds__(G16_THREADS, 1) gemm16_kernel(const __grid_con
             float v[16];
             tmem_ld16(tq + (uint32_t)(c * 16), v);
             if (!valid) continue;
-            if (P.bias != nullptr) {
+            if (add_bias) {
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
                     const float4 b = __ldg(reinterpret_cast<const float4*>(P.bias + col) + j);
@@ -203,6 +230,18 @@ __global__ void __launch_bounds__(G16_THREADS, 1) gemm16_kernel(const __grid_con
             if (P.relu) {
 #pragma unroll
                 for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], 0.0f);
+            }
+            if (P.ksplit > 1) {                               // partial sums of a K slice: C was zeroed (or holds the beta term)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) atomicAdd(reinterpret_cast<float4*>(crow + col) + j, make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]));
+                continue;
+            }
+            if (P.beta) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const float4 o = reinterpret_cast<const float4*>(crow + col)[j];
+                    v[4 * j] += o.x; v[4 * j + 1] += o.y; v[4 * j + 2] += o.z; v[4 * j + 3] += o.w;
+                }
             }
 #pragma unroll
             for (int j = 0; j < 4; ++j) reinterpret_cast<float4*>(crow + col)[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
@@ -242,12 +281,25 @@ __global__ void __launch_bounds__(G16_THREADS, 1) gemm16_kernel(const __grid_con
 }
 
 // ---- operand preparation --------------------------------------------------------------------------------------------------------
-constexpr int P16_MAX_JOBS = 2 * G16_MAX_PROBLEMS;
+// One job = one fp32 source matrix [rows][cols] (row stride ld) -> 16-bit planes.
+//   transpose 0: planes[r][c] = f(src[r][c])                      out_ld >= cols                (activations, weights)
+//   transpose 1: planes[c][m] = f(src[m + shift][c]) for m < rows, zero for rows <= m < out_ld   (weight-gradient operands:
+//                the reduction index becomes contiguous; a row shift inside blocks of `period` rows pairs dG_t with h_{t-1})
+// f: optional ReLU mask (value kept where mask[r][c] > 0), then a scale: fixed, or dynamic = the power of two that brings the
+// operand's largest magnitude (amax word, filled by amax16_kernel) into [2^13, 2^14) — gradients are far below the fp16 range.
+constexpr int P16_MAX_JOBS = 3 * G16_MAX_PROBLEMS;
 struct P16Job {
     const float* src;
     int ld, rows, cols;
+    const float* mask;
+    int ldm;
+    int transpose, shift, period;
+    int out_ld;
     float scale;
-    void* hi;                   // [rows][cols]; the lo plane follows at + rows*cols elements
+    const unsigned int* amax;       // device word: bits of max |x| (dynamic scale), or null
+    float* inv_scale_out;           // device scalar the dynamic inverse scale is published to, or null
+    void* hi;                       // first element of the hi plane region this job writes
+    size_t plane_elems;             // distance hi plane -> lo plane
 };
 struct P16Jobs {
     P16Job j[P16_MAX_JOBS];
@@ -255,35 +307,124 @@ struct P16Jobs {
     unsigned int* err;          // bit 1 set when a value leaves the fp16 range (may be null)
 };
 
+__device__ __forceinline__ float p16_scale(const P16Job& J, bool publish) {
+    if (J.amax == nullptr) return J.scale;
+    const float amax = __uint_as_float(__ldg(J.amax));
+    int e = 0;
+    float sc = 1.0f, inv = 1.0f;
+    if (amax > 0.0f && amax < INFINITY) {
+        frexpf(amax, &e);                            // amax = m * 2^e, m in [0.5, 1)
+        sc = ldexpf(1.0f, 14 - e);                   // amax * sc in [2^13, 2^14)
+        inv = ldexpf(1.0f, e - 14);
+    }
+    if (publish && J.inv_scale_out != nullptr) *J.inv_scale_out = inv;
+    return sc;
+}
+
+template <int PREC> __device__ __forceinline__ void p16_store8(const P16Job& J, size_t o, const float (&v)[8], bool& bad) {
+    if (PREC == 0) {
+        __align__(16) __half hi[8];
+        __align__(16) __half lo[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            bad |= !(fabsf(v[k]) < 65504.0f);
+            hi[k] = __float2half_rn(v[k]);
+            lo[k] = __float2half_rn(v[k] - __half2float(hi[k]));
+        }
+        *reinterpret_cast<uint4*>(reinterpret_cast<__half*>(J.hi) + o) = *reinterpret_cast<const uint4*>(hi);
+        *reinterpret_cast<uint4*>(reinterpret_cast<__half*>(J.hi) + J.plane_elems + o) = *reinterpret_cast<const uint4*>(lo);
+    } else {
+        __align__(16) __nv_bfloat16 hi[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) hi[k] = __float2bfloat16_rn(v[k]);
+        *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(J.hi) + o) = *reinterpret_cast<const uint4*>(hi);
+    }
+}
+
+// max |x| of every job with a dynamic scale (one word per job, zeroed by the host)
+__global__ void __launch_bounds__(256) amax16_kernel(const P16Jobs jobs) {
+    const P16Job& J = jobs.j[blockIdx.y];
+    if (J.amax == nullptr) return;
+    const int c4 = J.cols / 4;
+    const size_t n4 = (size_t)J.rows * c4;
+    float m = 0.0f;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
+        const size_t r = i / c4;
+        const int c = (int)(i - r * c4) * 4;
+        const float4 x = __ldg(reinterpret_cast<const float4*>(J.src + r * J.ld + c));
+        m = fmaxf(m, fmaxf(fmaxf(fabsf(x.x), fabsf(x.y)), fmaxf(fabsf(x.z), fabsf(x.w))));
+    }
+    m = warp_max(m);
+    if ((threadIdx.x & 31) == 0 && m > 0.0f) atomicMax(const_cast<unsigned int*>(J.amax), __float_as_uint(m));
+}
+
 template <int PREC> __global__ void __launch_bounds__(256) pack16x_kernel(const P16Jobs jobs) {
     const P16Job& J = jobs.j[blockIdx.y];
-    const int c8 = J.cols / 8;
-    const size_t n8 = (size_t)J.rows * c8, plane = (size_t)J.rows * J.cols;
-    const float sc = J.scale;
     bool bad = false;
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += (size_t)gridDim.x * blockDim.x) {
-        const size_t r = i / c8;
-        const int c = (int)(i - r * c8) * 8;
-        const float4 x0 = __ldg(reinterpret_cast<const float4*>(J.src + r * J.ld + c));
-        const float4 x1 = __ldg(reinterpret_cast<const float4*>(J.src + r * J.ld + c) + 1);
-        const float v[8] = {x0.x * sc, x0.y * sc, x0.z * sc, x0.w * sc, x1.x * sc, x1.y * sc, x1.z * sc, x1.w * sc};
-        const size_t o = r * J.cols + c;
-        if (PREC == 0) {
-            __align__(16) __half hi[8];
-            __align__(16) __half lo[8];
+    const float sc = p16_scale(J, blockIdx.x == 0 && threadIdx.x == 0);
+    if (!J.transpose) {
+        const int c8 = J.cols / 8;
+        const size_t n8 = (size_t)J.rows * c8;
+        for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += (size_t)gridDim.x * blockDim.x) {
+            const size_t r = i / c8;
+            const int c = (int)(i - r * c8) * 8;
+            const float4 x0 = __ldg(reinterpret_cast<const float4*>(J.src + r * J.ld + c));
+            const float4 x1 = __ldg(reinterpret_cast<const float4*>(J.src + r * J.ld + c) + 1);
+            float v[8] = {x0.x * sc, x0.y * sc, x0.z * sc, x0.w * sc, x1.x * sc, x1.y * sc, x1.z * sc, x1.w * sc};
+            if (J.mask != nullptr) {
+                const float4 m0 = __ldg(reinterpret_cast<const float4*>(J.mask + r * J.ldm + c));
+                const float4 m1 = __ldg(reinterpret_cast<const float4*>(J.mask + r * J.ldm + c) + 1);
+                const float mk[8] = {m0.x, m0.y, m0.z, m0.w, m1.x, m1.y, m1.z, m1.w};
 #pragma unroll
-            for (int k = 0; k < 8; ++k) {
-                bad |= !(fabsf(v[k]) < 65504.0f);
-                hi[k] = __float2half_rn(v[k]);
-                lo[k] = __float2half_rn(v[k] - __half2float(hi[k]));
+                for (int k = 0; k < 8; ++k) v[k] = mk[k] > 0.0f ? v[k] : 0.0f;
             }
-            *reinterpret_cast<uint4*>(reinterpret_cast<__half*>(J.hi) + o) = *reinterpret_cast<const uint4*>(hi);
-            *reinterpret_cast<uint4*>(reinterpret_cast<__half*>(J.hi) + plane + o) = *reinterpret_cast<const uint4*>(lo);
-        } else {
-            __align__(16) __nv_bfloat16 hi[8];
+            p16_store8<PREC>(J, r * J.out_ld + c, v, bad);
+        }
+    } else {
+        // 64 source rows x 32 source columns per tile through shared memory; output rows = source columns
+        __shared__ float t[32][65];
+        const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+        const int ctiles = (J.cols + 31) / 32, mtiles = J.out_ld / 64;
+        for (int tile = blockIdx.x; tile < ctiles * mtiles; tile += gridDim.x) {
+            const int ct = tile / mtiles, mtile = tile - ct * mtiles;
+            const int c0 = ct * 32, m0 = mtile * 64;
 #pragma unroll
-            for (int k = 0; k < 8; ++k) hi[k] = __float2bfloat16_rn(v[k]);
-            *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(J.hi) + o) = *reinterpret_cast<const uint4*>(hi);
+            for (int i = 0; i < 8; ++i) {
+                const int ml = i * 8 + ty, m = m0 + ml, c = c0 + tx;
+                float x = 0.0f;
+                if (m < J.rows && c < J.cols) {
+                    bool ok = true;
+                    if (J.shift != 0) {
+                        const int pos = m % J.period + J.shift;
+                        ok = pos >= 0 && pos < J.period;
+                    }
+                    if (ok) {
+                        x = __ldg(J.src + (size_t)(m + J.shift) * J.ld + c);
+                        if (J.mask != nullptr && !(__ldg(J.mask + (size_t)m * J.ldm + c) > 0.0f)) x = 0.0f;
+                    }
+                }
+                t[tx][ml] = x * sc;
+            }
+            __syncthreads();
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int cl = ty + 8 * j, c = c0 + cl;
+                if (c < J.cols) {
+                    const float x0 = t[cl][2 * tx], x1 = t[cl][2 * tx + 1];
+                    const size_t o = (size_t)c * J.out_ld + m0 + 2 * tx;
+                    if (PREC == 0) {
+                        bad |= !(fabsf(x0) < 65504.0f) || !(fabsf(x1) < 65504.0f);
+                        const __half2 h = __floats2half2_rn(x0, x1);
+                        const float2 f = __half22float2(h);
+                        const __half2 l = __floats2half2_rn(x0 - f.x, x1 - f.y);
+                        *reinterpret_cast<__half2*>(reinterpret_cast<__half*>(J.hi) + o) = h;
+                        *reinterpret_cast<__half2*>(reinterpret_cast<__half*>(J.hi) + J.plane_elems + o) = l;
+                    } else {
+                        *reinterpret_cast<__nv_bfloat162*>(reinterpret_cast<__nv_bfloat16*>(J.hi) + o) = __floats2bfloat162_rn(x0, x1);
+                    }
+                }
+            }
+            __syncthreads();
         }
     }
     if (PREC == 0 && bad && jobs.err != nullptr) atomicOr(jobs.err, 2u);
@@ -304,82 +445,105 @@ EncodeTiledFn g16_encode_fn() {
     return fn;
 }
 
-// 3-D map over `planes` dense row-major [rows][K] matrices of 16-bit elements: box = 64 K-elements x box_rows rows x planes,
-// 128-byte swizzle (the K-major layout of the UMMA descriptors), out-of-range rows read as zeros.
-int g16_make_map(CUtensorMap* m, const void* base, int precision, size_t K, size_t rows, int box_rows) {
+// 3-D map over `planes` dense row-major [rows][K] matrices of 16-bit elements: box = bk K-elements x box_rows rows x planes,
+// 128- or 64-byte swizzle (the K-major layouts of the UMMA descriptors), out-of-range rows read as zeros.
+int g16_make_map(CUtensorMap* m, const void* base, int precision, size_t K, size_t rows, int box_rows, int bk) {
     EncodeTiledFn enc = g16_encode_fn();
     TG_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled is not available from this driver");
     const int planes = precision ? 1 : 2;
     cuuint64_t dims[3] = {(cuuint64_t)K, (cuuint64_t)rows, (cuuint64_t)planes};
     cuuint64_t strides[2] = {(cuuint64_t)K * 2, (cuuint64_t)K * 2 * rows};
-    cuuint32_t box[3] = {(cuuint32_t)G16_BK, (cuuint32_t)box_rows, (cuuint32_t)planes};
+    cuuint32_t box[3] = {(cuuint32_t)bk, (cuuint32_t)box_rows, (cuuint32_t)planes};
     cuuint32_t estr[3] = {1, 1, 1};
     const CUresult r = enc(m, precision ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<void*>(base), dims,
-                           strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                           strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, bk == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                           CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     TG_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed (%d): K=%zu rows=%zu box rows %d", (int)r, K, rows, box_rows);
     return 0;
 }
 
-template <int PREC, int BN> int g16_launch_t(const G16Launch& L, int tiles, cudaStream_t stream) {
-    using Cfg = G16Cfg<PREC, BN>;
-    if (int rc = ensure_smem((const void*)gemm16_kernel<PREC, BN>, Cfg::SMEM_BYTES)) return rc;
-    gemm16_kernel<PREC, BN><<<tiles, G16_THREADS, Cfg::SMEM_BYTES, stream>>>(L);
+template <int PREC, int BN, int BK> int g16_launch_t(const G16Launch& L, int tiles, cudaStream_t stream) {
+    using Cfg = G16Cfg<PREC, BN, BK>;
+    if (int rc = ensure_smem((const void*)gemm16_kernel<PREC, BN, BK>, Cfg::SMEM_BYTES)) return rc;
+    gemm16_kernel<PREC, BN, BK><<<tiles, G16_THREADS, Cfg::SMEM_BYTES, stream>>>(L);
     TG_LAUNCH_OK();
     return 0;
 }
 
 size_t up256(size_t x) { return (x + 255) / 256 * 256; }
+int pad64(int x) { return (x + 63) / 64 * 64; }
+
+// rows / reduction length of the operand planes a source produces
+int op_rows(const Gemm16Operand& o) { return o.transpose ? o.cols : o.rows; }
+int op_k(const Gemm16Operand& o) { return o.transpose ? pad64(o.rows) : o.cols; }
+bool same_op(const Gemm16Operand& a, const Gemm16Operand& b) {
+    return a.src == b.src && a.ld == b.ld && a.rows == b.rows && a.cols == b.cols && a.mask == b.mask && a.ldm == b.ldm &&
+           a.transpose == b.transpose && a.shift == b.shift && a.period == b.period && a.dynamic == b.dynamic && a.scale == b.scale;
+}
+bool op_ok(const Gemm16Operand& o) {
+    if (o.src == nullptr || o.rows <= 0 || o.cols <= 0) return false;
+    if (o.transpose) return true;                                   // scalar loads; any shape (the reduction length is padded)
+    if (o.cols % G16_BK != 0 || o.ld % 4 != 0 || (reinterpret_cast<uintptr_t>(o.src) & 15)) return false;
+    if (o.mask != nullptr && (o.ldm % 4 != 0 || (reinterpret_cast<uintptr_t>(o.mask) & 15))) return false;
+    return true;
+}
+// dynamic-scale operands are reduced with float4 loads
+bool amax_ok(const Gemm16Operand& o) { return !o.dynamic || (o.cols % 4 == 0 && o.ld % 4 == 0 && (reinterpret_cast<uintptr_t>(o.src) & 15) == 0); }
 
 }  // namespace
 
-bool gemm16_eligible(const GemmGroup& grp) {
+bool gemm16_enabled() {
     static int enabled = -1;
     if (enabled < 0) {
         const char* e = getenv("TGGCN_GEMM16");
         enabled = (e != nullptr && e[0] == '0') ? 0 : 1;
     }
-    if (!enabled || grp.count == 0 || grp.count > G16_MAX_PROBLEMS) return false;
-    for (int i = 0; i < grp.count; ++i) {
-        const GemmProblem& p = grp.p[i];
-        if (p.K % G16_BK != 0 || p.N % 16 != 0 || p.ldc % 4 != 0 || p.lda % 4 != 0 || p.ldw % 4 != 0) return false;
-        if (p.amask != nullptr || p.beta != 0) return false;
-        if ((reinterpret_cast<uintptr_t>(p.A) | reinterpret_cast<uintptr_t>(p.W) | reinterpret_cast<uintptr_t>(p.C)) & 15) return false;
-        if (p.bias != nullptr && (reinterpret_cast<uintptr_t>(p.bias) & 15)) return false;
+    return enabled != 0;
+}
+
+bool gemm16_eligible(const Gemm16Problem* p, int count) {
+    if (!gemm16_enabled() || count <= 0 || count > G16_MAX_PROBLEMS) return false;
+    for (int i = 0; i < count; ++i) {
+        const Gemm16Problem& q = p[i];
+        if (!op_ok(q.a) || !op_ok(q.b) || !amax_ok(q.a) || !amax_ok(q.b)) return false;
+        if (op_k(q.a) != op_k(q.b)) return false;
+        if (op_rows(q.b) % 16 != 0 || q.ldc % 4 != 0 || (reinterpret_cast<uintptr_t>(q.C) & 15)) return false;
+        if (q.bias != nullptr && (reinterpret_cast<uintptr_t>(q.bias) & 15)) return false;
     }
     return true;
 }
 
-// bytes of operand-plane scratch launch_gemm16 needs for this group (distinct operands are packed once)
-size_t gemm16_scratch_bytes(const GemmGroup& grp) {
-    size_t total = 0;
-    for (int i = 0; i < grp.count; ++i) {
-        const GemmProblem& p = grp.p[i];
-        bool dupa = false, dupw = false;
+size_t gemm16_scratch_bytes(const Gemm16Problem* p, int count) {
+    size_t total = 256;                                                 // amax words + published inverse scales
+    for (int i = 0; i < count; ++i) {
+        bool dupa = false, dupb = false;
         for (int j = 0; j < i; ++j) {
-            const GemmProblem& q = grp.p[j];
-            dupa |= q.A == p.A && q.lda == p.lda && q.M == p.M && q.K == p.K;
-            dupw |= q.W == p.W && q.ldw == p.ldw && q.N == p.N && q.K == p.K;
+            dupa |= same_op(p[j].a, p[i].a);
+            dupb |= same_op(p[j].b, p[i].b);
         }
-        if (!dupa) total += up256((size_t)p.M * p.K * 4);
-        if (!dupw) total += up256((size_t)p.N * p.K * 4);
+        if (!dupa) total += up256((size_t)op_rows(p[i].a) * op_k(p[i].a) * 4);
+        if (!dupb) total += up256((size_t)op_rows(p[i].b) * op_k(p[i].b) * 4);
     }
     return total;
 }
 
-// precision 0: fp16 (hi, lo) split, fp32-class accuracy; 1: bf16 operands.  scratch: gemm16_scratch_bytes(grp) bytes, 256-byte aligned.
-// err: status word of the forward (bit 1 = an operand left the fp16 range), may be null.
-int launch_gemm16(GemmGroup& grp, int precision, void* scratch, size_t scratch_bytes, unsigned int* err, cudaStream_t stream) {
-    if (grp.count == 0) return 0;
-    TG_REQUIRE(gemm16_eligible(grp), "gemm16: the group does not qualify (K %% 64, N %% 16, alignment, no mask / beta)");
-    TG_REQUIRE(scratch != nullptr && scratch_bytes >= gemm16_scratch_bytes(grp), "gemm16: operand scratch too small");
+// C[M,N] (+)= act(A' B'^T + bias) for every problem, A' / B' = the 16-bit planes of the two operands (packed here).
+// precision 0: fp16 (hi, lo) split, fp32-class accuracy; 1: bf16 operands.  scratch: gemm16_scratch_bytes() bytes, 256-byte aligned.
+// err: status word (bit 1 = an operand left the fp16 range), may be null.
+int launch_gemm16(const Gemm16Problem* prob, int count, int precision, void* scratch, size_t scratch_bytes, unsigned int* err,
+                  cudaStream_t stream) {
+    if (count == 0) return 0;
+    TG_REQUIRE(gemm16_eligible(prob, count), "gemm16: the group does not qualify (K %% 64, N %% 16, alignment)");
+    TG_REQUIRE(scratch != nullptr && scratch_bytes >= gemm16_scratch_bytes(prob, count), "gemm16: operand scratch too small");
     TG_REQUIRE((reinterpret_cast<uintptr_t>(scratch) & 255) == 0, "gemm16: scratch must be 256-byte aligned");
     // tile width: 256 columns move a quarter fewer operand bytes per FLOP; choose by waves x bytes per k-block
-    auto tiles_of = [&](int bn) { int t = 0; for (int i = 0; i < grp.count; ++i) t += cdiv(grp.p[i].M, G16_BM) * cdiv(grp.p[i].N, bn); return t; };
-    static int bn_env = -1;
+    auto tiles_of = [&](int bn) { int t = 0; for (int i = 0; i < count; ++i) t += cdiv(op_rows(prob[i].a), G16_BM) * cdiv(op_rows(prob[i].b), bn); return t; };
+    static int bn_env = -1, bk_env = -1;
     if (bn_env < 0) {
         const char* e = getenv("TGGCN_GEMM16_BN");
         bn_env = e != nullptr ? atoi(e) : 0;
+        e = getenv("TGGCN_GEMM16_BK");
+        bk_env = e != nullptr ? atoi(e) : 0;
     }
     int bn = 256;
     {
@@ -387,60 +551,136 @@ int launch_gemm16(GemmGroup& grp, int precision, void* scratch, size_t scratch_b
         if (c128 < c256) bn = 128;
         if (bn_env == 128 || bn_env == 256) bn = bn_env;
     }
+    // stage depth: K = 32 per stage (SWIZZLE_64B rows) for the fp16-split 256-wide tile, whose 64-deep stages are 96 KB
+    int bk = (precision == 0 && bn == 256) ? 32 : 64;
+    if (bk_env == 32 || bk_env == 64) bk = bk_env;
+
     G16Launch L;
     memset(&L, 0, sizeof(L));
     P16Jobs jobs;
     memset(&jobs, 0, sizeof(jobs));
     jobs.err = err;
     uint8_t* ws = reinterpret_cast<uint8_t*>(scratch);
-    size_t off = 0;
-    const void* aplane[G16_MAX_PROBLEMS];
-    const void* wplane[G16_MAX_PROBLEMS];
-    int begin = 0;
-    size_t max_elems = 0;
-    for (int i = 0; i < grp.count; ++i) {
-        const GemmProblem& p = grp.p[i];
-        aplane[i] = wplane[i] = nullptr;
-        for (int j = 0; j < i; ++j) {
-            const GemmProblem& q = grp.p[j];
-            if (q.A == p.A && q.lda == p.lda && q.M == p.M && q.K == p.K) aplane[i] = aplane[j];
-            if (q.W == p.W && q.ldw == p.ldw && q.N == p.N && q.K == p.K) wplane[i] = wplane[j];
-        }
-        if (aplane[i] == nullptr) {
-            aplane[i] = ws + off;
-            off += up256((size_t)p.M * p.K * 4);
+    unsigned int* amax_words = reinterpret_cast<unsigned int*>(ws);          // [0, 32): amax bits; [32, 64): inverse scales (float)
+    float* inv_words = reinterpret_cast<float*>(ws) + 32;
+    size_t off = 256;
+    const void* planes[2][G16_MAX_PROBLEMS];
+    const float* invs[2][G16_MAX_PROBLEMS];
+    int n_dyn = 0, begin = 0, base_tiles = tiles_of(bn);
+    size_t max_work = 0;
+    for (int i = 0; i < count; ++i) {
+        const Gemm16Problem& p = prob[i];
+        for (int side = 0; side < 2; ++side) {
+            const Gemm16Operand& o = side == 0 ? p.a : p.b;
+            planes[side][i] = nullptr;
+            invs[side][i] = nullptr;
+            for (int j = 0; j < i; ++j) {
+                const Gemm16Operand& oj = side == 0 ? prob[j].a : prob[j].b;
+                if (same_op(oj, o)) { planes[side][i] = planes[side][j]; invs[side][i] = invs[side][j]; }
+            }
+            if (planes[side][i] != nullptr) continue;
+            const int R = op_rows(o), K = op_k(o);
+            planes[side][i] = ws + off;
+            off += up256((size_t)R * K * 4);
+            TG_REQUIRE(jobs.count < P16_MAX_JOBS, "gemm16: too many operands in one group");
             P16Job& J = jobs.j[jobs.count++];
-            J.src = p.A; J.ld = p.lda; J.rows = p.M; J.cols = p.K; J.scale = 1.0f; J.hi = const_cast<void*>(aplane[i]);
-            if ((size_t)p.M * p.K > max_elems) max_elems = (size_t)p.M * p.K;
+            J.src = o.src; J.ld = o.ld; J.rows = o.rows; J.cols = o.cols; J.mask = o.mask; J.ldm = o.ldm;
+            J.transpose = o.transpose; J.shift = o.shift; J.period = o.period > 0 ? o.period : 1;
+            J.out_ld = K; J.scale = o.scale != 0.0f ? o.scale : 1.0f;
+            J.hi = const_cast<void*>(planes[side][i]); J.plane_elems = (size_t)R * K;
+            if (o.dynamic && precision == 0) {
+                TG_REQUIRE(n_dyn < 32, "gemm16: too many dynamically scaled operands");
+                J.amax = amax_words + n_dyn; J.inv_scale_out = inv_words + n_dyn;
+                invs[side][i] = inv_words + n_dyn;
+                ++n_dyn;
+            }
+            const size_t work = (size_t)(o.transpose ? pad64(o.rows) : o.rows) * o.cols;
+            if (work > max_work) max_work = work;
         }
-        if (wplane[i] == nullptr) {
-            wplane[i] = ws + off;
-            off += up256((size_t)p.N * p.K * 4);
-            P16Job& J = jobs.j[jobs.count++];
-            J.src = p.W; J.ld = p.ldw; J.rows = p.N; J.cols = p.K; J.scale = precision ? 1.0f : G16_W_SCALE; J.hi = const_cast<void*>(wplane[i]);
-            if ((size_t)p.N * p.K > max_elems) max_elems = (size_t)p.N * p.K;
-        }
-        if (int rc = g16_make_map(&L.amap[i], aplane[i], precision, p.K, p.M, G16_BM)) return rc;
-        if (int rc = g16_make_map(&L.bmap[i], wplane[i], precision, p.K, p.N, bn)) return rc;
+        const int M = op_rows(p.a), N = op_rows(p.b), K = op_k(p.a);
+        if (int rc = g16_make_map(&L.amap[i], planes[0][i], precision, K, M, G16_BM, bk)) return rc;
+        if (int rc = g16_make_map(&L.bmap[i], planes[1][i], precision, K, N, bn, bk)) return rc;
         G16Problem& q = L.p[i];
-        q.M = p.M; q.N = p.N; q.K = p.K; q.relu = p.relu; q.ldc = p.ldc; q.bias = p.bias; q.C = p.C; q.out16 = nullptr;
-        q.m_tiles = cdiv(p.M, G16_BM); q.n_tiles = cdiv(p.N, bn); q.tile_begin = begin;
-        begin += q.m_tiles * q.n_tiles;
+        q.M = M; q.N = N; q.K = K; q.relu = p.relu; q.ldc = p.ldc; q.bias = p.bias; q.C = p.C; q.out16 = nullptr; q.beta = p.beta;
+        q.inv_a = invs[0][i]; q.inv_b = invs[1][i];
+        q.m_tiles = cdiv(M, G16_BM); q.n_tiles = cdiv(N, bn); q.tile_begin = begin;
+        // under-filled grid and a long reduction (weight gradients): split K over several CTAs per tile, combined with atomics
+        q.ksplit = 1;
+        const int nkb = K / 64;
+        if (!p.relu && base_tiles * 2 <= num_sms() && nkb >= 8) {
+            int ks = num_sms() / base_tiles;
+            if (ks > nkb / 4) ks = nkb / 4;
+            if (ks > 1) {
+                q.ksplit = ks;
+                if (!p.beta) TG_CUDA_OK(cudaMemset2DAsync(p.C, sizeof(float) * (size_t)p.ldc, 0, sizeof(float) * (size_t)N, (size_t)M, stream));
+            }
+        }
+        begin += q.m_tiles * q.n_tiles * q.ksplit;
     }
-    L.count = grp.count;
-    L.acc_scale = precision ? 1.0f : 1.0f / G16_W_SCALE;
+    L.count = count;
+    L.acc_scale = 1.0f;
+    for (int i = 0; i < count; ++i) {                                  // fixed scales are folded per problem into the bias-free factor
+        // (all problems of a group share acc_scale: fixed scales must agree across the group)
+        const float f = (prob[i].a.dynamic || precision ? 1.0f : (prob[i].a.scale != 0.0f ? prob[i].a.scale : 1.0f)) *
+                        (prob[i].b.dynamic || precision ? 1.0f : (prob[i].b.scale != 0.0f ? prob[i].b.scale : 1.0f));
+        if (i == 0) L.acc_scale = 1.0f / f;
+        else TG_REQUIRE(L.acc_scale == 1.0f / f, "gemm16: the fixed operand scales of a group must agree");
+    }
     {
-        int gx = (int)((max_elems / 8 + 255) / 256);
+        int gx = (int)((max_work / 8 + 255) / 256);
         const int cap = 4 * num_sms();
         if (gx > cap) gx = cap;
         if (gx < 1) gx = 1;
         dim3 grid(gx, jobs.count);
-        if (precision) pack16x_kernel<1><<<grid, 256, 0, stream>>>(jobs);
-        else           pack16x_kernel<0><<<grid, 256, 0, stream>>>(jobs);
+        if (n_dyn > 0) {
+            TG_CUDA_OK(cudaMemsetAsync(amax_words, 0, 32 * sizeof(unsigned int), stream));
+            amax16_kernel<<<grid, 256, 0, stream>>>(jobs);
+            TG_LAUNCH_OK();
+        }
+        if (precision) {
+            for (int i = 0; i < jobs.count; ++i) jobs.j[i].scale = 1.0f;          // bf16 has the fp32 exponent range: no scaling
+            pack16x_kernel<1><<<grid, 256, 0, stream>>>(jobs);
+        } else {
+            pack16x_kernel<0><<<grid, 256, 0, stream>>>(jobs);
+        }
         TG_LAUNCH_OK();
     }
-    if (precision) return bn == 256 ? g16_launch_t<1, 256>(L, begin, stream) : g16_launch_t<1, 128>(L, begin, stream);
-    return bn == 256 ? g16_launch_t<0, 256>(L, begin, stream) : g16_launch_t<0, 128>(L, begin, stream);
+    if (precision) {
+        if (bk == 32) return bn == 256 ? g16_launch_t<1, 256, 32>(L, begin, stream) : g16_launch_t<1, 128, 32>(L, begin, stream);
+        return bn == 256 ? g16_launch_t<1, 256, 64>(L, begin, stream) : g16_launch_t<1, 128, 64>(L, begin, stream);
+    }
+    if (bk == 32) return bn == 256 ? g16_launch_t<0, 256, 32>(L, begin, stream) : g16_launch_t<0, 128, 32>(L, begin, stream);
+    return bn == 256 ? g16_launch_t<0, 256, 64>(L, begin, stream) : g16_launch_t<0, 128, 64>(L, begin, stream);
+}
+
+// The forward's grouped nn.Linear problems (gemm.h) on this kernel: activations unscaled, weights times 2^8.
+static void g16_from_group(const GemmGroup& grp, Gemm16Problem* out) {
+    for (int i = 0; i < grp.count; ++i) {
+        const GemmProblem& p = grp.p[i];
+        Gemm16Problem& q = out[i];
+        memset(&q, 0, sizeof(q));
+        q.a.src = p.A; q.a.ld = p.lda; q.a.rows = p.M; q.a.cols = p.K; q.a.mask = p.amask; q.a.ldm = p.ldm; q.a.scale = 1.0f;
+        q.b.src = p.W; q.b.ld = p.ldw; q.b.rows = p.N; q.b.cols = p.K; q.b.scale = G16_W_SCALE;
+        q.bias = p.bias; q.C = p.C; q.ldc = p.ldc; q.relu = p.relu; q.beta = p.beta;
+    }
+}
+bool gemm16_eligible(const GemmGroup& grp) {
+    if (grp.count <= 0 || grp.count > G16_MAX_PROBLEMS) return false;
+    Gemm16Problem q[G16_MAX_PROBLEMS];
+    g16_from_group(grp, q);
+    return gemm16_eligible(q, grp.count);
+}
+size_t gemm16_scratch_bytes(const GemmGroup& grp) {
+    Gemm16Problem q[G16_MAX_PROBLEMS];
+    g16_from_group(grp, q);
+    return gemm16_scratch_bytes(q, grp.count);
+}
+int launch_gemm16(GemmGroup& grp, int precision, void* scratch, size_t scratch_bytes, unsigned int* err, cudaStream_t stream) {
+    if (grp.count == 0) return 0;
+    TG_REQUIRE(grp.count <= G16_MAX_PROBLEMS, "gemm16: too many problems in one group (%d)", grp.count);
+    Gemm16Problem q[G16_MAX_PROBLEMS];
+    g16_from_group(grp, q);
+    return launch_gemm16(q, grp.count, precision, scratch, scratch_bytes, err, stream);
 }
 
 }  // namespace tg

@@ -502,7 +502,7 @@ int launch_bigru_bwd(BiGruBwdParams& P, int persistent, cudaStream_t stream) {
     }
     if (persistent) {
         const int grid = P.total_tiles < capacity ? P.total_tiles : capacity;
-        TG_CUDA_OK(cudaMemsetAsync(P.sync.counter, 0, 2 * sizeof(unsigned int), stream));
+        TG_CUDA_OK(cudaMemsetAsync(P.sync.counter, 0, sizeof(unsigned int), stream));      // the error word belongs to the caller
         int s0 = 0, s1 = P.T, pers = 1;
         void* args[] = {(void*)&P, (void*)&s0, (void*)&s1, (void*)&pers};
         TG_CUDA_OK(cudaLaunchCooperativeKernel((const void*)kern, dim3(grid), dim3(REC_THREADS), args, smem, stream));
@@ -543,7 +543,7 @@ int launch_segment_bwd(SegBwdParams& P, int persistent, cudaStream_t stream) {
         if (2 * P.tilesC_dir > grid) grid = 2 * P.tilesC_dir;
         if (items > grid) grid = items;
         if (grid > capacity) grid = capacity;
-        TG_CUDA_OK(cudaMemsetAsync(P.sync.counter, 0, 2 * sizeof(unsigned int), stream));
+        TG_CUDA_OK(cudaMemsetAsync(P.sync.counter, 0, sizeof(unsigned int), stream));      // the error word belongs to the caller
         int s0 = -1, s1 = P.T, phases = 7, pers = 1;
 #ifdef TGGCN_TIMING_EXPERIMENTS      // never in the product build: skipping a phase leaves the gradients undefined
         if (const char* e = getenv("TGGCN_SEGBWD_PHASES")) phases = atoi(e);

@@ -89,7 +89,14 @@ void make_bwd_layout(const tggcn_dims& d, BwdLayout& L) {
     const size_t nt_cands[] = {rp * 6 * D + 4 * D * 6 * D, np * 2048 + (size_t)2048 * 128 * V, np * 2 * D + (size_t)2048 * D};
     for (size_t c : nt_cands)
         if (c > tmax) tmax = c;
-    tmax += 1024;
+    // grouped weight-gradient launches keep every operand of a stage at once: the segment cells of one direction, the BiGRUs of
+    // humans + objects (both directions), the embeddings + geometry MLP
+    const size_t kh_ = (1 + nkh) * D;
+    const size_t grp_cands[] = {rp * ((H ? 1 : 0) * (7 * D + kh_ + nkh * D) + 13 * D), 2 * rp * 15 * D,
+                                2 * rp * (D + 2048) + np * (D + 2048) + np * (2048 + 128 * V), 3 * rp * 4 * D + np * 3 * D};
+    for (size_t c : grp_cands)
+        if (c > tmax) tmax = c;
+    tmax += 4096;
     L.tn_floats = tmax;
     L.tn = L.take(tmax);
 }
@@ -212,26 +219,61 @@ int tggcn_backward_ex(const tggcn_dims* dims, const void* const* weights, void* 
     g16.ws = nullptr; g16.bytes = BL.tn_floats * sizeof(float); g16.precision = d.precision == 1 ? 1 : 0;
     g16.err = (unsigned int*)buf(TGGCN_BUF_SYNC) + 7;
     if (d.gemm_path != 0 && gemm16_enabled() && (d.precision == 1 || !d.no_fp16_split)) g16.ws = tn_scratch;
-    auto tn = [&](const float* Z, int ldz, const float* mask, int ldm, const float* X, int ldx, float* dW, int lddw, int M, int Nn, int K,
-                  int shift, int period, int beta, cudaStream_t st) -> int {
-        if (g16.ws != nullptr) {
-            // both operands packed TRANSPOSED (reduction index = the rows, contiguous and zero-padded to 64) straight from the
-            // row-major sources: replaces the two fp32 transposes; Z is a gradient (amax-scaled), X an activation
-            Gemm16Problem q;
-            memset(&q, 0, sizeof(q));
-            q.a.src = Z; q.a.ld = ldz; q.a.rows = M; q.a.cols = Nn; q.a.mask = mask; q.a.ldm = ldm; q.a.transpose = 1; q.a.dynamic = 1;
-            q.b.src = X; q.b.ld = ldx; q.b.rows = M; q.b.cols = K; q.b.transpose = 1; q.b.shift = shift; q.b.period = period; q.b.scale = 1.0f;
-            q.C = dW; q.ldc = lddw; q.beta = beta;
-            if (gemm16_eligible(&q, 1) && gemm16_scratch_bytes(&q, 1) <= g16.bytes)
-                return launch_gemm16(&q, 1, g16.precision, g16.ws, g16.bytes, g16.err, st);
-        }
-        const int Mp = (M + 31) / 32 * 32;
-        TG_REQUIRE((size_t)(Nn + K) * Mp <= BL.tn_floats, "backward: weight-gradient scratch too small (%d + %d) x %d", Nn, K, Mp);
+    // One weight gradient dW[Nn,K] (+)= (Z (.) [mask > 0])^T X (optional row shift of X inside blocks of `period` rows) and, when db is
+    // given, the bias gradient db[Nn] (+)= column sums of the masked Z.  Calls are COLLECTED per backward stage and flushed as one
+    // grouped launch of the TMA-fed kernel (gemm16.cu): every distinct operand is packed once (transposed: the row index becomes the
+    // contiguous reduction index), the column sums ride on the pack of Z, and the small problems of a stage fill the GPU together.
+    struct TnCall {
+        const float* Z; int ldz; const float* mask; int ldm; const float* X; int ldx; float* dW; int lddw; int M, Nn, K, shift, period, beta;
+        float* db; int db_beta;
+    };
+    TnCall tn_calls[GEMM_MAX_PROBLEMS];
+    int tn_count = 0;
+    auto tn_single = [&](const TnCall& c, cudaStream_t st) -> int {      // fp32 transposes + the tf32 / bf16 kernel of gemm_tc.cu
+        const int Mp = (c.M + 31) / 32 * 32;
+        TG_REQUIRE((size_t)(c.Nn + c.K) * Mp <= BL.tn_floats, "backward: weight-gradient scratch too small (%d + %d) x %d", c.Nn, c.K, Mp);
         float* zt = tn_scratch;
-        float* xt = zt + (size_t)Nn * Mp;
-        if (int rc = launch_transpose_prep(Z, ldz, mask, ldm, zt, Mp, M, Nn, 0, 0, nullptr, st)) return rc;
-        if (int rc = launch_transpose_prep(X, ldx, nullptr, 0, xt, Mp, M, K, shift, period, nullptr, st)) return rc;
-        return gemm_nt(zt, Mp, nullptr, 0, xt, Mp, dW, lddw, Nn, K, Mp, beta, path, st, G16Ctx{nullptr, 0, 0, nullptr});
+        float* xt = zt + (size_t)c.Nn * Mp;
+        if (int rc = launch_transpose_prep(c.Z, c.ldz, c.mask, c.ldm, zt, Mp, c.M, c.Nn, 0, 0, nullptr, st)) return rc;
+        if (int rc = launch_transpose_prep(c.X, c.ldx, nullptr, 0, xt, Mp, c.M, c.K, c.shift, c.period, nullptr, st)) return rc;
+        if (int rc = gemm_nt(zt, Mp, nullptr, 0, xt, Mp, c.dW, c.lddw, c.Nn, c.K, Mp, c.beta, path, st, G16Ctx{nullptr, 0, 0, nullptr})) return rc;
+        if (c.db != nullptr) return launch_colsum(c.Z, c.ldz, c.mask, c.ldm, c.db, c.M, c.Nn, c.db_beta, st);
+        return 0;
+    };
+    auto tn_flush = [&](cudaStream_t st) -> int {
+        if (tn_count == 0) return 0;
+        const int n = tn_count;
+        tn_count = 0;
+        if (g16.ws != nullptr) {
+            Gemm16Problem q[GEMM_MAX_PROBLEMS];
+            memset(q, 0, sizeof(q));
+            for (int i = 0; i < n; ++i) {
+                const TnCall& c = tn_calls[i];
+                q[i].a.src = c.Z; q[i].a.ld = c.ldz; q[i].a.rows = c.M; q[i].a.cols = c.Nn; q[i].a.mask = c.mask; q[i].a.ldm = c.ldm;
+                q[i].a.transpose = 1; q[i].a.dynamic = 1; q[i].a.colsum = c.db; q[i].a.colsum_beta = c.db_beta;
+                q[i].b.src = c.X; q[i].b.ld = c.ldx; q[i].b.rows = c.M; q[i].b.cols = c.K; q[i].b.transpose = 1;
+                q[i].b.shift = c.shift; q[i].b.period = c.period; q[i].b.scale = 1.0f;
+                q[i].C = c.dW; q[i].ldc = c.lddw; q[i].beta = c.beta;
+            }
+            if (gemm16_eligible(q, n) && gemm16_scratch_bytes(q, n) <= g16.bytes)
+                return launch_gemm16(q, n, g16.precision, g16.ws, g16.bytes, g16.err, st);
+            for (int i = 0; i < n; ++i) {                                  // the group does not fit the scratch: one problem at a time
+                if (gemm16_eligible(&q[i], 1) && gemm16_scratch_bytes(&q[i], 1) <= g16.bytes) {
+                    if (int rc = launch_gemm16(&q[i], 1, g16.precision, g16.ws, g16.bytes, g16.err, st)) return rc;
+                } else if (int rc = tn_single(tn_calls[i], st)) return rc;
+            }
+            return 0;
+        }
+        for (int i = 0; i < n; ++i)
+            if (int rc = tn_single(tn_calls[i], st)) return rc;
+        return 0;
+    };
+    auto tn = [&](const float* Z, int ldz, const float* mask, int ldm, const float* X, int ldx, float* dW, int lddw, int M, int Nn, int K,
+                  int shift, int period, int beta, cudaStream_t st, float* db = nullptr, int db_beta = 0) -> int {
+        if (tn_count == GEMM_MAX_PROBLEMS)
+            if (int rc = tn_flush(st)) return rc;
+        tn_calls[tn_count++] = TnCall{Z, ldz, mask, ldm, X, ldx, dW, lddw, M, Nn, K, shift, period, beta, db, db_beta};
+        return 0;
     };
 
     TG_CUDA_OK(cudaMemsetAsync(bb(BL.zero_begin), 0, (BL.zero_end - BL.zero_begin) * sizeof(float), stream));
@@ -326,34 +368,31 @@ int tggcn_backward_ex(const tggcn_dims* dims, const void* const* weights, void* 
         for (int dir = 0; dir < 2; ++dir) {
             // humans
             if (int rc = tn(P.dghs_h + (size_t)dir * 3 * D, 6 * D, nullptr, 0, P.hx_h + (size_t)dir * D, 2 * D,
-                                        G(whh_h_id[dir]), D, N * H, 3 * D, D, dir == 0 ? -H : H, T * H, 0, stream)) return rc;
-            if (int rc = launch_colsum(P.dghs_h + (size_t)dir * 3 * D, 6 * D, nullptr, 0, G(whh_h_id[dir] + 2), N * H, 3 * D, 0, stream)) return rc;
+                                        G(whh_h_id[dir]), D, N * H, 3 * D, D, dir == 0 ? -H : H, T * H, 0, stream, G(whh_h_id[dir] + 2))) return rc;
             if (int rc = tn(P.dgs_h + (size_t)dir * 3 * D, 6 * D, nullptr, 0, buf(TGGCN_BUF_XX_H), kh, G(wih_h_id[dir]), ldwh,
-                                        N * H, 3 * D, kh, 0, 0, 0, stream)) return rc;
+                                        N * H, 3 * D, kh, 0, 0, 0, stream, G(wih_h_id[dir] + 2))) return rc;
             if (int rc = tn(P.dgs_h + (size_t)dir * 3 * D, 6 * D, nullptr, 0,
                                         buf(TGGCN_BUF_MG_ALL_H) + (size_t)dir * N * H * nkh * D, nkh * D, G(wih_h_id[dir]) + kh, ldwh,
                                         N * H, 3 * D, nkh * D, 0, 0, 0, stream)) return rc;
-            if (int rc = launch_colsum(P.dgs_h + (size_t)dir * 3 * D, 6 * D, nullptr, 0, G(wih_h_id[dir] + 2), N * H, 3 * D, 0, stream)) return rc;
             // objects
             if (int rc = tn(P.dghs_o + (size_t)dir * 3 * D, 6 * D, nullptr, 0, P.hx_o + (size_t)dir * D, 2 * D,
-                                        G(whh_o_id[dir]), D, N * O, 3 * D, D, dir == 0 ? -O : O, T * O, 0, stream)) return rc;
-            if (int rc = launch_colsum(P.dghs_o + (size_t)dir * 3 * D, 6 * D, nullptr, 0, G(whh_o_id[dir] + 2), N * O, 3 * D, 0, stream)) return rc;
+                                        G(whh_o_id[dir]), D, N * O, 3 * D, D, dir == 0 ? -O : O, T * O, 0, stream, G(whh_o_id[dir] + 2))) return rc;
             if (int rc = tn(P.dgs_o + (size_t)dir * 3 * D, 6 * D, nullptr, 0, buf(TGGCN_BUF_XX_O), 4 * D, G(wih_o_id[dir]), 6 * D,
-                                        N * O, 3 * D, 4 * D, 0, 0, 0, stream)) return rc;
+                                        N * O, 3 * D, 4 * D, 0, 0, 0, stream, G(wih_o_id[dir] + 2))) return rc;
             if (int rc = tn(P.dgs_o + (size_t)dir * 3 * D, 6 * D, nullptr, 0,
                                         buf(TGGCN_BUF_MG_ALL_O) + (size_t)dir * N * O * 2 * D, 2 * D, G(wih_o_id[dir]) + 4 * D, 6 * D,
                                         N * O, 3 * D, 2 * D, 0, 0, 0, stream)) return rc;
-            if (int rc = launch_colsum(P.dgs_o + (size_t)dir * 3 * D, 6 * D, nullptr, 0, G(wih_o_id[dir] + 2), N * O, 3 * D, 0, stream)) return rc;
+            if (int rc = tn_flush(stream)) return rc;
         }
         for (int k = d.hh ? 0 : 1; k < 4; ++k) {
             const bool send_h = (k == 0 || k == 2);
             const int Es = send_h ? H : O;
             const float* hx = send_h ? P.hx_h : P.hx_o;
-            for (int dir = 0; dir < 2; ++dir)
+            for (int dir = 0; dir < 2; ++dir)          // both directions accumulate into the same weight and bias gradient
                 if (int rc = tn(P.dpre_all[k] + (size_t)dir * N * Es * D, D, nullptr, 0, hx + (size_t)dir * D, 2 * D,
-                                            G(smsg_w_id[k]), D, N * Es, D, D, dir == 0 ? -Es : Es, T * Es, dir, stream)) return rc;
-            if (int rc = launch_colsum(P.dpre_all[k], D, nullptr, 0, G(smsg_w_id[k] + 1), 2 * N * Es, D, 0, stream)) return rc;
+                                            G(smsg_w_id[k]), D, N * Es, D, D, dir == 0 ? -Es : Es, T * Es, dir, stream, G(smsg_w_id[k] + 1), dir)) return rc;
         }
+        if (int rc = tn_flush(stream)) return rc;
     }
 
     if (hooks && hooks->bucket_done[0]) TG_CUDA_OK(cudaEventRecord((cudaEvent_t)hooks->bucket_done[0], stream));
@@ -419,9 +458,9 @@ int tggcn_backward_ex(const tggcn_dims* dims, const void* const* weights, void* 
             if (int rc = launch_transpose(W(kinds[k].w_id), 2 * D, wt, D, D, 2 * D, stream)) return rc;      // (D,2D) -> (2D,D)
             if (int rc = gemm_nt(dmsg, D, msg, D, wt, D, bb(BL.ds[gidx]), 2 * D, M, 2 * D, D, touched[gidx], path, stream, g16)) return rc;
             touched[gidx] = 1;
-            if (int rc = tn(dmsg, D, msg, D, buf(s_buf[gidx]), 2 * D, G(kinds[k].w_id), 2 * D, M, D, 2 * D, 0, 0, 0, stream)) return rc;
-            if (int rc = launch_colsum(dmsg, D, msg, D, G(kinds[k].w_id + 1), M, D, 0, stream)) return rc;
+            if (int rc = tn(dmsg, D, msg, D, buf(s_buf[gidx]), 2 * D, G(kinds[k].w_id), 2 * D, M, D, 2 * D, 0, 0, 0, stream, G(kinds[k].w_id + 1))) return rc;
         }
+        if (int rc = tn_flush(stream)) return rc;
     }
 
     // ---- 6. Linear(2D->D)+ReLU on the BiGRU outputs: h = S[:, D:2D] ------------------------------------------------------------------
@@ -439,9 +478,9 @@ int tggcn_backward_ex(const tggcn_dims* dims, const void* const* weights, void* 
             if (int rc = launch_transpose(W(bd_id[g]), 2 * D, wt, D, D, 2 * D, stream)) return rc;
             const int beta = (g == 0 || (g == 1 && d.C_aff > 0)) ? 1 : 0;     // the frame heads already wrote into d hfr
             if (int rc = gemm_nt(dZ, 2 * D, Y, 2 * D, wt, D, bb(BL.dhfr[g]), 2 * D, M, 2 * D, D, beta, path, stream, g16)) return rc;
-            if (int rc = tn(dZ, 2 * D, Y, 2 * D, buf(hfr_buf[g]), 2 * D, G(bd_id[g]), 2 * D, M, D, 2 * D, 0, 0, 0, stream)) return rc;
-            if (int rc = launch_colsum(dZ, 2 * D, Y, 2 * D, G(bd_id[g] + 1), M, D, 0, stream)) return rc;
+            if (int rc = tn(dZ, 2 * D, Y, 2 * D, buf(hfr_buf[g]), 2 * D, G(bd_id[g]), 2 * D, M, D, 2 * D, 0, 0, 0, stream, G(bd_id[g] + 1))) return rc;
         }
+        if (int rc = tn_flush(stream)) return rc;
     }
 
     // ---- 5/4. BiGRU backward through time (all three groups in one persistent kernel), then the hoisted input projections ----------
@@ -475,8 +514,7 @@ int tggcn_backward_ex(const tggcn_dims* dims, const void* const* weights, void* 
             for (int dir = 0; dir < 2; ++dir) {
                 // dW_hh = dGh^T h_{t-1} (fwd) / h_{t+1} (bwd): row shift inside each video
                 if (int rc = tn(dgh + (size_t)dir * 3 * D, 6 * D, nullptr, 0, buf(hfr_buf[g]) + (size_t)dir * D, 2 * D,
-                                            G(base + 1 + 4 * dir), D, M, 3 * D, D, dir == 0 ? -Eg[g] : Eg[g], T * Eg[g], 0, stream)) return rc;
-                if (int rc = launch_colsum(dgh + (size_t)dir * 3 * D, 6 * D, nullptr, 0, G(base + 3 + 4 * dir), M, 3 * D, 0, stream)) return rc;
+                                            G(base + 1 + 4 * dir), D, M, 3 * D, D, dir == 0 ? -Eg[g] : Eg[g], T * Eg[g], 0, stream, G(base + 3 + 4 * dir))) return rc;
             }
             // d x (+)= [dGi_f | dGi_b] [W_ih_f ; W_ih_b]   (x = S[:, :D])
             if (int rc = launch_transpose(W(base), D, wt, 6 * D, 3 * D, D, stream)) return rc;
@@ -484,10 +522,10 @@ int tggcn_backward_ex(const tggcn_dims* dims, const void* const* weights, void* 
             if (int rc = gemm_nt(dgi, 6 * D, nullptr, 0, wt, 6 * D, bb(BL.ds[g]), 2 * D, M, D, 6 * D, 1, path, stream, g16)) return rc;
             for (int dir = 0; dir < 2; ++dir) {
                 if (int rc = tn(dgi + (size_t)dir * 3 * D, 6 * D, nullptr, 0, buf(s_buf[g]), 2 * D, G(base + 4 * dir), D, M, 3 * D, D,
-                                            0, 0, 0, stream)) return rc;
-                if (int rc = launch_colsum(dgi + (size_t)dir * 3 * D, 6 * D, nullptr, 0, G(base + 4 * dir + 2), M, 3 * D, 0, stream)) return rc;
+                                            0, 0, 0, stream, G(base + 4 * dir + 2))) return rc;
             }
         }
+        if (int rc = tn_flush(stream)) return rc;
     }
 
     if (hooks && hooks->bucket_done[1]) TG_CUDA_OK(cudaEventRecord((cudaEvent_t)hooks->bucket_done[1], stream));
@@ -496,25 +534,22 @@ int tggcn_backward_ex(const tggcn_dims* dims, const void* const* weights, void* 
     {
         // x = ReLU(W roi + b) = S[:, :D]
         if (int rc = tn(bb(BL.ds[0]), 2 * D, buf(TGGCN_BUF_S_H), 2 * D, io->x_human, d.Fh, G(TGGCN_W_HUM_EMB_W), 2048, N * H, D, 2048,
-                                    0, 0, 0, stream)) return rc;
-        if (int rc = launch_colsum(bb(BL.ds[0]), 2 * D, buf(TGGCN_BUF_S_H), 2 * D, G(TGGCN_W_HUM_EMB_B), N * H, D, 0, stream)) return rc;
+                                    0, 0, 0, stream, G(TGGCN_W_HUM_EMB_B))) return rc;
         if (int rc = tn(bb(BL.ds[1]), 2 * D, buf(TGGCN_BUF_S_O), 2 * D, io->x_objects, 2048, G(TGGCN_W_OBJ_EMB_W), 2048, N * O, D, 2048,
-                                    0, 0, 0, stream)) return rc;
-        if (int rc = launch_colsum(bb(BL.ds[1]), 2 * D, buf(TGGCN_BUF_S_O), 2 * D, G(TGGCN_W_OBJ_EMB_B), N * O, D, 0, stream)) return rc;
+                                    0, 0, 0, stream, G(TGGCN_W_OBJ_EMB_B))) return rc;
         // geometry MLP layer 2: S_G[:, :D] = ReLU(W2 hid + b2)
         float* wt = bb(BL.wt);
         if (int rc = launch_transpose(W(TGGCN_W_GEO_MLP2_W), 2048, wt, D, D, 2048, stream)) return rc;          // (D,2048) -> (2048,D)
         if (int rc = gemm_nt(bb(BL.ds[2]), 2 * D, buf(TGGCN_BUF_S_G), 2 * D, wt, D, bb(BL.dgeo_hid), 2048, N, 2048, D, 0, path, stream, g16)) return rc;
         if (int rc = tn(bb(BL.ds[2]), 2 * D, buf(TGGCN_BUF_S_G), 2 * D, buf(TGGCN_BUF_GEO_HID), 2048, G(TGGCN_W_GEO_MLP2_W), 2048, N, D,
-                                    2048, 0, 0, 0, stream)) return rc;
-        if (int rc = launch_colsum(bb(BL.ds[2]), 2 * D, buf(TGGCN_BUF_S_G), 2 * D, G(TGGCN_W_GEO_MLP2_B), N, D, 0, stream)) return rc;
+                                    2048, 0, 0, 0, stream, G(TGGCN_W_GEO_MLP2_B))) return rc;
         // layer 0: hid = ReLU(W0 gcn + b0), gcn = the scrambled view (N, 128V)
         const int KV = 128 * V;
         if (int rc = launch_transpose(W(TGGCN_W_GEO_MLP0_W), KV, wt, 2048, 2048, KV, stream)) return rc;         // (2048,128V) -> (128V,2048)
         if (int rc = gemm_nt(bb(BL.dgeo_hid), 2048, buf(TGGCN_BUF_GEO_HID), 2048, wt, 2048, bb(BL.dgcn_out), KV, N, KV, 2048, 0, path, stream, g16)) return rc;
         if (int rc = tn(bb(BL.dgeo_hid), 2048, buf(TGGCN_BUF_GEO_HID), 2048, buf(TGGCN_BUF_GCN_OUT), KV, G(TGGCN_W_GEO_MLP0_W), KV, N,
-                                    2048, KV, 0, 0, 0, stream)) return rc;
-        if (int rc = launch_colsum(bb(BL.dgeo_hid), 2048, buf(TGGCN_BUF_GEO_HID), 2048, G(TGGCN_W_GEO_MLP0_B), N, 2048, 0, stream)) return rc;
+                                    2048, KV, 0, 0, 0, stream, G(TGGCN_W_GEO_MLP0_B))) return rc;
+        if (int rc = tn_flush(stream)) return rc;
     }
 
     if (hooks && hooks->bucket_done[2]) TG_CUDA_OK(cudaEventRecord((cudaEvent_t)hooks->bucket_done[2], stream));

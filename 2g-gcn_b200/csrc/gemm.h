@@ -54,6 +54,8 @@ struct Gemm16Operand {
     int shift, period;      // transpose only: source row m + shift pairs with reduction index m when 0 <= m % period + shift < period
     int dynamic;            // 1: gradient operand — scaled by the power of two that brings its largest magnitude to [2^13, 2^14)
     float scale;            // fixed scale otherwise (0 = 1); the fixed scales of all problems of a group must agree
+    float* colsum;          // transpose only, optional: colsum[c] (+)= sum_m src[m][c] * [mask > 0] (the bias gradient), fused into the pack
+    int colsum_beta;        // 0: colsum is zeroed first, 1: accumulated into
 };
 struct Gemm16Problem {
     Gemm16Operand a, b;     // M = operand rows of a, N = operand rows of b (N % 16 == 0)

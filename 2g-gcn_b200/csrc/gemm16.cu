@@ -67,6 +67,7 @@ struct G16Problem {
     int relu, ldc;
     int beta;               // 1: add to C instead of overwriting it
     int ksplit;             // > 1: the K range is split over this many CTAs per tile, combined with atomics (C zeroed / beta)
+    int atomic;             // 1: combine with atomics even without a K split (several problems of the launch add into this C)
     const float* bias;      // (N) or null
     const float* inv_a;     // device scalars: inverse of the dynamic (amax-derived, power-of-two) scale of an operand, or null
     const float* inv_b;
@@ -231,7 +232,7 @@ __global__ void __launch_bounds__(G16_THREADS, 1) gemm16_kernel(const __grid_con
 #pragma unroll
                 for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], 0.0f);
             }
-            if (P.ksplit > 1) {                               // partial sums of a K slice: C was zeroed (or holds the beta term)
+            if (P.ksplit > 1 || P.atomic) {                   // partial sums: C was zeroed (or holds the beta term)
 #pragma unroll
                 for (int j = 0; j < 4; ++j) atomicAdd(reinterpret_cast<float4*>(crow + col) + j, make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]));
                 continue;
@@ -296,6 +297,7 @@ struct P16Job {
     int transpose, shift, period;
     int out_ld;
     float scale;
+    float* colsum;                  // transpose only: per-column sums of the masked, unscaled source (atomically accumulated), or null
     const unsigned int* amax;       // device word: bits of max |x| (dynamic scale), or null
     float* inv_scale_out;           // device scalar the dynamic inverse scale is published to, or null
     void* hi;                       // first element of the hi plane region this job writes
@@ -383,11 +385,13 @@ template <int PREC> __global__ void __launch_bounds__(256) pack16x_kernel(const 
     } else {
         // 64 source rows x 32 source columns per tile through shared memory; output rows = source columns
         __shared__ float t[32][65];
+        __shared__ float csum[8][32];
         const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
         const int ctiles = (J.cols + 31) / 32, mtiles = J.out_ld / 64;
         for (int tile = blockIdx.x; tile < ctiles * mtiles; tile += gridDim.x) {
             const int ct = tile / mtiles, mtile = tile - ct * mtiles;
             const int c0 = ct * 32, m0 = mtile * 64;
+            float part = 0.0f;
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
                 const int ml = i * 8 + ty, m = m0 + ml, c = c0 + tx;
@@ -404,8 +408,16 @@ template <int PREC> __global__ void __launch_bounds__(256) pack16x_kernel(const 
                     }
                 }
                 t[tx][ml] = x * sc;
+                part += x;
             }
+            if (J.colsum != nullptr) csum[ty][tx] = part;
             __syncthreads();
+            if (J.colsum != nullptr && ty == 0 && c0 + tx < J.cols) {
+                float v = 0.0f;
+#pragma unroll
+                for (int w = 0; w < 8; ++w) v += csum[w][tx];
+                atomicAdd(J.colsum + c0 + tx, v);
+            }
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
                 const int cl = ty + 8 * j, c = c0 + cl;
@@ -566,6 +578,7 @@ int launch_gemm16(const Gemm16Problem* prob, int count, int precision, void* scr
     size_t off = 256;
     const void* planes[2][G16_MAX_PROBLEMS];
     const float* invs[2][G16_MAX_PROBLEMS];
+    int jobidx[2][G16_MAX_PROBLEMS];
     int n_dyn = 0, begin = 0, base_tiles = tiles_of(bn);
     size_t max_work = 0;
     for (int i = 0; i < count; ++i) {
@@ -574,16 +587,30 @@ int launch_gemm16(const Gemm16Problem* prob, int count, int precision, void* scr
             const Gemm16Operand& o = side == 0 ? p.a : p.b;
             planes[side][i] = nullptr;
             invs[side][i] = nullptr;
+            jobidx[side][i] = -1;
             for (int j = 0; j < i; ++j) {
                 const Gemm16Operand& oj = side == 0 ? prob[j].a : prob[j].b;
-                if (same_op(oj, o)) { planes[side][i] = planes[side][j]; invs[side][i] = invs[side][j]; }
+                if (same_op(oj, o)) { planes[side][i] = planes[side][j]; invs[side][i] = invs[side][j]; jobidx[side][i] = jobidx[side][j]; }
             }
-            if (planes[side][i] != nullptr) continue;
+            if (o.colsum != nullptr) {
+                TG_REQUIRE(o.transpose, "gemm16: column sums are fused into the transposed pack only");
+                if (!o.colsum_beta) TG_CUDA_OK(cudaMemsetAsync(o.colsum, 0, sizeof(float) * (size_t)o.cols, stream));
+            }
+            if (planes[side][i] != nullptr) {                      // packed once; the job may still owe this problem's column sums
+                if (o.colsum != nullptr) {
+                    P16Job& Jd = jobs.j[jobidx[side][i]];
+                    TG_REQUIRE(Jd.colsum == nullptr || Jd.colsum == o.colsum, "gemm16: two column-sum destinations for one operand");
+                    Jd.colsum = o.colsum;
+                }
+                continue;
+            }
             const int R = op_rows(o), K = op_k(o);
             planes[side][i] = ws + off;
             off += up256((size_t)R * K * 4);
             TG_REQUIRE(jobs.count < P16_MAX_JOBS, "gemm16: too many operands in one group");
+            jobidx[side][i] = jobs.count;
             P16Job& J = jobs.j[jobs.count++];
+            J.colsum = o.colsum;
             J.src = o.src; J.ld = o.ld; J.rows = o.rows; J.cols = o.cols; J.mask = o.mask; J.ldm = o.ldm;
             J.transpose = o.transpose; J.shift = o.shift; J.period = o.period > 0 ? o.period : 1;
             J.out_ld = K; J.scale = o.scale != 0.0f ? o.scale : 1.0f;
@@ -606,15 +633,17 @@ int launch_gemm16(const Gemm16Problem* prob, int count, int precision, void* scr
         q.m_tiles = cdiv(M, G16_BM); q.n_tiles = cdiv(N, bn); q.tile_begin = begin;
         // under-filled grid and a long reduction (weight gradients): split K over several CTAs per tile, combined with atomics
         q.ksplit = 1;
+        q.atomic = 0;
+        for (int j = 0; j < count; ++j)
+            if (j != i && prob[j].C == p.C) q.atomic = 1;              // e.g. the two time directions of a shared message MLP
         const int nkb = K / 64;
         if (!p.relu && base_tiles * 2 <= num_sms() && nkb >= 8) {
             int ks = num_sms() / base_tiles;
             if (ks > nkb / 4) ks = nkb / 4;
-            if (ks > 1) {
-                q.ksplit = ks;
-                if (!p.beta) TG_CUDA_OK(cudaMemset2DAsync(p.C, sizeof(float) * (size_t)p.ldc, 0, sizeof(float) * (size_t)N, (size_t)M, stream));
-            }
+            if (ks > 1) q.ksplit = ks;
         }
+        if ((q.ksplit > 1 || q.atomic) && !p.beta)
+            TG_CUDA_OK(cudaMemset2DAsync(p.C, sizeof(float) * (size_t)p.ldc, 0, sizeof(float) * (size_t)N, (size_t)M, stream));
         begin += q.m_tiles * q.n_tiles * q.ksplit;
     }
     L.count = count;

@@ -124,7 +124,9 @@ int launch_bigru(BiGruParams& P, int persistent, cudaStream_t stream) {
     const int capacity = per_sm * num_sms();
     plan_tiles(P);
     if (persistent) {
-        const int rc = launch_bigru_resident(P, stream);      // recurrent weights resident in shared memory when the shape allows
+        int rc = launch_bigru_cluster(P, stream);             // independent recurrences on 16-CTA clusters, state exchanged through DSMEM
+        if (rc >= 0) return rc;
+        rc = launch_bigru_resident(P, stream);                // recurrent weights resident in shared memory when the shape allows
         if (rc >= 0) return rc;
         const int grid = P.total_tiles < capacity ? P.total_tiles : capacity;
         TG_CUDA_OK(cudaMemsetAsync(P.sync.counter, 0, sizeof(unsigned int), stream));      // the error word belongs to the caller (tggcn_forward zeroes it once)

@@ -29,6 +29,8 @@ struct BiGruParams {
 int launch_bigru(BiGruParams& P, int persistent, cudaStream_t stream);
 // SMEM-resident W_hh variant (bigru_res.cu): 0 = launched, -1 = shape does not qualify (use launch_bigru's streaming kernel), > 0 = error
 int launch_bigru_resident(BiGruParams& P, cudaStream_t stream);
+// cluster / distributed-shared-memory variant (bigru_cl.cu, hidden_size 512, small batches): same return convention
+int launch_bigru_cluster(BiGruParams& P, cudaStream_t stream);
 int launch_transpose(const float* in, int ldi, float* out, int ldo, int R, int C, cudaStream_t stream);
 int launch_transpose_prep(const float* in, int ldi, const float* mask, int ldm, float* out, int Mp, int M, int C, int shift, int period,
                           float* colsum, cudaStream_t stream);

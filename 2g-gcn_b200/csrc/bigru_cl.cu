@@ -1,0 +1,364 @@
+// Frame-level bidirectional GRUs, third design (K-C): THREAD-BLOCK CLUSTERS with the state exchanged through distributed shared
+// memory instead of L2 + a grid barrier (vhoi/models.py:649-651, :983-1002; hidden_size 512).
+//
+// The per-step cost of the SMEM-resident kernel (bigru_res.cu, 7.6 us per step) is a latency chain: publish the new state to L2,
+// release the grid barrier (all 132 CTAs), observe it, fetch the state rows back from L2.  But the recurrences of different
+// (group, direction, 16-row block) are INDEPENDENT, and one of them fits a 16-CTA cluster:
+//   * CTA `rank` of a cluster owns 32 hidden units: its 96 rows of W_hh (r, z, n gates) live in TENSOR MEMORY as pre-split fp16
+//     (hi, lo) mma.sync B-fragments, used as a per-thread register-file extension (tcgen05.st once, tcgen05.ld in the K loop:
+//     192 words per thread, see recurrent_res.cuh) — shared memory stays free for the state;
+//   * per step it multiplies the 16 state rows (one m16 tile) by its weight slice (mma.sync m16n8k16, 3-term fp16 split, fp32
+//     accumulate; K split over 4 warps x 2 halves of the gate columns), applies the GRU cell, and SENDS its 16 x 32 slice of the
+//     new state to all 16 CTAs of the cluster with cp.async.bulk shared::cta -> shared::cluster, completing bytes on the
+//     receiver's mbarrier: data movement and synchronisation are one operation, no L2 round trip, no grid-wide barrier;
+//   * staging buffers, send slices and barriers are double-buffered by step parity; a CTA can run at most one step ahead of the
+//     slowest peer because it needs that peer's slice to proceed.
+// Not a cooperative launch: clusters never wait for each other, so any number of them may be resident at a time.
+#include <stdlib.h>
+#include "recurrent.cuh"
+#include "recurrent_res.cuh"
+#include "bigru.h"
+
+namespace tg {
+
+namespace {
+
+constexpr int CL = 16;                          // CTAs per cluster
+constexpr int CL_D = 512;                       // hidden size this kernel is built for
+constexpr int CL_UPC = CL_D / CL;               // units per CTA
+constexpr int CL_ROWS = 32;                     // state rows per cluster: one or two m16 MMA tiles (the second one only when rows > 16)
+constexpr int CL_PITCH = 40;                    // words per (row, 32-unit block): 32 + 8 pad -> conflict-free 64-bit fragment loads
+constexpr int CL_SLICE = CL_ROWS * CL_PITCH;    // words of one CTA's slice of the state (5120 bytes; 2560 are sent when rows <= 16)
+constexpr int CL_STAGE = CL * CL_SLICE;         // words of one staging buffer (all 512 units of the rows)
+constexpr int CL_KS = CL_D / 16 / 4;            // k16 steps per warp (K split over 4 warps)
+constexpr int CL_NT = 6;                        // n8 tiles per warp: half of the CTA's 12 (3 gates x 32 units / 8)
+constexpr int CL_RED = REC_WARPS * 32 * 2 * CL_NT * 4;   // floats of the cross-warp reduction buffer
+constexpr int CL_MAX_CLUSTERS = 64;
+constexpr size_t CL_SMEM_BYTES = (2 * CL_STAGE + 2 * CL_SLICE + CL_RED) * sizeof(float);    // 218 KB: one CTA per SM (each allocates all of tensor memory)
+
+struct ClusterPlan {
+    int count;
+    unsigned char group[CL_MAX_CLUSTERS], dir[CL_MAX_CLUSTERS];
+    int row0[CL_MAX_CLUSTERS], nrows[CL_MAX_CLUSTERS];
+};
+
+__device__ __forceinline__ uint32_t cl_rank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;\n" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cl_sync() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;\n" ::: "memory");
+}
+__device__ __forceinline__ uint32_t cl_mapa(uint32_t cta_addr, uint32_t rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;\n" : "=r"(r) : "r"(cta_addr), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void cl_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n\t}\n" ::"r"(bar), "r"(bytes) : "memory");
+}
+// this CTA's shared memory -> a peer's shared memory, completing `bytes` on the peer's mbarrier
+__device__ __forceinline__ void cl_send(uint32_t dst_cluster, uint32_t src_cta, uint32_t bytes, uint32_t bar_cluster) {
+    asm volatile("cp.async.bulk.shared::cluster.shared::cta.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(dst_cluster),
+                 "r"(src_cta), "r"(bytes), "r"(bar_cluster)
+                 : "memory");
+}
+__device__ __forceinline__ void cl_wait(uint32_t bar, uint32_t parity) {
+    uint32_t done = 0, spins = 0;
+    while (true) {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
+                     : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+        if (done) break;
+        if (++spins > (1u << 26)) __trap();       // a protocol bug must surface as an error, not a hung device
+    }
+}
+
+// TWO: the cluster's rows fill two m16 tiles (17-32 rows); compile-time so that the 16-row clusters carry no second tile
+template <bool TWO>
+__device__ __forceinline__ void bigru_cluster_body(const BiGruParams& P, const ClusterPlan& plan, float* smem, uint64_t* bars, uint32_t& tmem_slot) {
+    constexpr int MT = TWO ? 2 : 1, NQ = 2 * MT;
+    float* stage = smem;                         // [2][CL][CL_ROWS][CL_PITCH]: the whole previous state of the cluster's rows
+    float* send = stage + 2 * CL_STAGE;          // [2][CL_ROWS][CL_PITCH]:     this CTA's slice of the new state
+    float* red = send + 2 * CL_SLICE;            // [8 warps][32 lanes][2 m tiles][CL_NT][4]
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g8 = lane >> 2, t4 = lane & 3;
+    const int cid = blockIdx.x / CL;
+    const int rank = (int)cl_rank();
+    const BiGruGroup& G = P.g[plan.group[cid]];
+    const int dir = plan.dir[cid], row0 = plan.row0[cid];
+    const int nrows = plan.nrows[cid];           // <= 32
+    const uint32_t slice_bytes = 16u * MT * CL_PITCH * 4u;               // bytes of a slice that travel
+    const int D = CL_D, T = P.T;
+    const int u0 = rank * CL_UPC;                // first hidden unit of this CTA
+    const int kq = warp & 3, nh = warp >> 2;     // K quarter and gate-column half of this warp
+    const uint32_t bar_u32[2] = {smem_u32(&bars[0]), smem_u32(&bars[1])};
+
+    if (tid == 0) {
+        mbar_init(bar_u32[0], 1);
+        mbar_init(bar_u32[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    }
+    ResState rs;
+    res_init(rs, &tmem_slot, nullptr);           // allocates all 512 tensor-memory columns (includes a __syncthreads)
+    if (tid == 0) {                              // both buffers expect one full state; re-armed after every wait
+        cl_expect_tx(bar_u32[1], CL * slice_bytes);       // step 1 reads buffer 1
+        cl_expect_tx(bar_u32[0], CL * slice_bytes);       // step 2 reads buffer 0
+    }
+
+    // ---- resident weights: B fragments of mma.m16n8k16 (register 0: row n = g8, k = 2 t4 + {0,1}; register 1: k + 8), pre-split ----
+    const uint32_t tbase = rs.tmem_base + ((uint32_t)(kq * 32) << 16) + (uint32_t)(nh * RES_TMEM_WORDS);
+    {
+        const float* W = G.whh[dir];
+        float wmax = 0.0f;
+        for (int i = 0; i < CL_KS; ++i) {
+            const int k = (kq + 4 * i) * 16 + 2 * t4;
+#pragma unroll
+            for (int j = 0; j < CL_NT; ++j) {
+                const int nt = nh * CL_NT + j, gate = nt >> 2, ub = nt & 3;
+                const float* wr = W + (size_t)(gate * D + u0 + ub * 8 + g8) * D + k;
+                const float2 v0 = __ldg(reinterpret_cast<const float2*>(wr)), v1 = __ldg(reinterpret_cast<const float2*>(wr + 8));
+                wmax = fmaxf(wmax, fmaxf(fmaxf(fabsf(v0.x), fabsf(v0.y)), fmaxf(fabsf(v1.x), fabsf(v1.y))));
+                uint32_t w4[4];                                  // (b0 hi, b0 lo, b1 hi, b1 lo)
+                split_f16x2(v0.x * RES_WSCALE, v0.y * RES_WSCALE, w4[0], w4[1]);
+                split_f16x2(v1.x * RES_WSCALE, v1.y * RES_WSCALE, w4[2], w4[3]);
+                tmem_st4(tbase + (uint32_t)((i * CL_NT + j) * 4), w4);
+            }
+        }
+        if (!(wmax * RES_WSCALE < RES_F16_MAX)) atomicOr(P.sync.error, 2u);
+        tmem_wait_st();
+    }
+    // ---- epilogue constants: this thread's outputs are unit u0 + lane of rows warp + 8 q, q < 4 ---------------------------------
+    const int unit = u0 + lane;
+    const float bh0 = __ldg(G.bhh[dir] + unit), bh1 = __ldg(G.bhh[dir] + D + unit), bh2 = __ldg(G.bhh[dir] + 2 * D + unit);
+    long long fe0[NQ];
+    bool valid[NQ];
+#pragma unroll
+    for (int q = 0; q < NQ; ++q) {
+        const int rl = warp + 8 * q;
+        valid[q] = rl < nrows;
+        const int r = valid[q] ? row0 + rl : row0, b = r / G.E, e = r - b * G.E;
+        fe0[q] = (long long)b * T * G.E + e;
+    }
+    float hprev[NQ];
+#pragma unroll
+    for (int q = 0; q < NQ; ++q) hprev[q] = 0.0f;
+    // where this thread's three gate pre-activations sit in the reduction buffer: column gt*32 + lane of the CTA's 96
+    int roff[3];
+#pragma unroll
+    for (int gt = 0; gt < 3; ++gt) {
+        const int nt = gt * 4 + (lane >> 3), n = lane & 7;
+        const int h = nt / CL_NT, j = nt - h * CL_NT;
+        const int lsrc = warp * 4 + (n >> 1);                    // lane that holds (row warp [+ 8], column n) of an m16n8 accumulator
+        roff[gt] = ((h * 4 * 32 + lsrc) * 2 * CL_NT + j) * 4 + (n & 1);  // + ks * 32 * 2 * CL_NT * 4 per K quarter, + 2 for row + 8, + CL_NT * 4 for the second m tile
+    }
+    tc_fence_before();
+    cl_sync();                                    // every CTA of the cluster has initialised and armed its barriers
+    tc_fence_after();
+
+    for (int s = 0; s < T; ++s) {
+        const int t = dir == 0 ? s : T - 1 - s;
+        // epilogue operands first: their latency overlaps the wait and the K loop
+        float xg[NQ][3];
+        size_t orow[NQ];
+        float* gsave[NQ];
+#pragma unroll
+        for (int q = 0; q < NQ; ++q) {
+            xg[q][0] = xg[q][1] = xg[q][2] = 0.0f;
+            orow[q] = 0;
+            gsave[q] = nullptr;
+            if (valid[q]) {
+                const size_t fe = (size_t)fe0[q] + (size_t)t * G.E;
+                const float* gi = G.gi + (fe * 2 + dir) * 3 * D;
+                xg[q][0] = __ldg(gi + unit); xg[q][1] = __ldg(gi + D + unit); xg[q][2] = __ldg(gi + 2 * D + unit);
+                orow[q] = fe * 2 * D + dir * D + unit;
+                if (G.gates != nullptr) gsave[q] = G.gates + (fe * 2 + dir) * 4 * D + unit;
+            }
+        }
+        float sum[NQ][3];
+#pragma unroll
+        for (int q = 0; q < NQ; ++q) sum[q][0] = sum[q][1] = sum[q][2] = 0.0f;
+        if (s > 0) {
+            const int p = s & 1;
+            cl_wait(bar_u32[p], (uint32_t)(((s - 1 - (p ^ 1)) >> 1) & 1));       // k-th use of buffer p: s = 1, 3, .. (p = 1) / 2, 4, .. (p = 0)
+            if (tid == 0 && s + 2 < T) cl_expect_tx(bar_u32[p], CL * slice_bytes);     // armed for step s + 2 (nobody can send it yet)
+            const float* hb = stage + p * CL_STAGE;
+            float c[MT][CL_NT][4];
+#pragma unroll
+            for (int m = 0; m < MT; ++m)
+#pragma unroll
+                for (int j = 0; j < CL_NT; ++j) c[m][j][0] = c[m][j][1] = c[m][j][2] = c[m][j][3] = 0.0f;
+#pragma unroll 2
+            for (int i = 0; i < CL_KS; ++i) {
+                uint32_t wv[CL_NT][4];
+#pragma unroll
+                for (int j = 0; j < CL_NT; ++j) tmem_ld4_nowait(tbase + (uint32_t)((i * CL_NT + j) * 4), wv[j]);
+                const int k0 = (kq + 4 * i) * 16;
+                const float* hp = hb + (k0 >> 5) * CL_SLICE + (k0 & 31) + 2 * t4;
+                uint32_t ah[MT][4], al[MT][4];
+#pragma unroll
+                for (int m = 0; m < MT; ++m) {
+                    const float* hm = hp + (m * 16 + g8) * CL_PITCH;
+                    const float2 x0 = *reinterpret_cast<const float2*>(hm);
+                    const float2 x1 = *reinterpret_cast<const float2*>(hm + 8 * CL_PITCH);
+                    const float2 x2 = *reinterpret_cast<const float2*>(hm + 8);
+                    const float2 x3 = *reinterpret_cast<const float2*>(hm + 8 * CL_PITCH + 8);
+                    split_f16x2(x0.x, x0.y, ah[m][0], al[m][0]);
+                    split_f16x2(x1.x, x1.y, ah[m][1], al[m][1]);
+                    split_f16x2(x2.x, x2.y, ah[m][2], al[m][2]);
+                    split_f16x2(x3.x, x3.y, ah[m][3], al[m][3]);
+                }
+                tmem_wait_ld();
+#pragma unroll
+                for (int j = 0; j < CL_NT; ++j) {
+                    const uint32_t bhi[2] = {wv[j][0], wv[j][2]}, blo[2] = {wv[j][1], wv[j][3]};
+#pragma unroll
+                    for (int m = 0; m < MT; ++m) mma_f16(c[m][j], al[m], bhi);
+#pragma unroll
+                    for (int m = 0; m < MT; ++m) mma_f16(c[m][j], ah[m], blo);
+#pragma unroll
+                    for (int m = 0; m < MT; ++m) mma_f16(c[m][j], ah[m], bhi);
+                }
+            }
+            // cross-warp reduction of the K quarters
+            float4* rw = reinterpret_cast<float4*>(red + (size_t)(warp * 32 + lane) * 2 * CL_NT * 4);
+#pragma unroll
+            for (int m = 0; m < MT; ++m) {
+#pragma unroll
+                for (int j = 0; j < CL_NT; ++j) rw[m * CL_NT + j] = make_float4(c[m][j][0], c[m][j][1], c[m][j][2], c[m][j][3]);
+            }
+            __syncthreads();
+#pragma unroll
+            for (int q = 0; q < NQ; ++q) {
+#pragma unroll
+                for (int gt = 0; gt < 3; ++gt) {
+                    float v = 0.0f;
+#pragma unroll
+                    for (int ks = 0; ks < 4; ++ks) v += red[roff[gt] + ks * 32 * 2 * CL_NT * 4 + (q >> 1) * CL_NT * 4 + 2 * (q & 1)];
+                    sum[q][gt] = v * (1.0f / RES_WSCALE);
+                }
+            }
+        }
+        float* sl = send + (s & 1) * CL_SLICE;
+#pragma unroll
+        for (int q = 0; q < NQ; ++q) {
+            float hnew = 0.0f;
+            if (valid[q]) {
+                hnew = gru_update(xg[q][0], xg[q][1], xg[q][2], sum[q][0] + bh0, sum[q][1] + bh1, sum[q][2] + bh2, hprev[q], gsave[q], D);
+                G.hfr[orow[q]] = hnew;
+                hprev[q] = hnew;
+            }
+            sl[(warp + 8 * q) * CL_PITCH + lane] = hnew;           // rows beyond the block stay zero
+        }
+        if (s + 1 < T) {
+            asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");      // the bulk copies read what the threads just wrote
+            __syncthreads();                                       // (also retires the reduction buffer)
+            if (tid < CL) {                                         // one copy per peer, issued in parallel by 16 threads
+                const int nb = (s + 1) & 1;
+                const uint32_t dst = cl_mapa(smem_u32(stage + nb * CL_STAGE + rank * CL_SLICE), (uint32_t)tid);
+                cl_send(dst, smem_u32(sl), slice_bytes, cl_mapa(bar_u32[nb], (uint32_t)tid));
+            }
+        }
+    }
+    cl_sync();                                    // no CTA leaves (and frees its shared memory) while copies may still be in flight
+    res_finish(rs);
+}
+
+__global__ void __launch_bounds__(REC_THREADS, 1) bigru_cluster_kernel(const BiGruParams P, const ClusterPlan plan) {
+    extern __shared__ __align__(128) float smem[];
+    __shared__ __align__(8) uint64_t bars[2];
+    __shared__ uint32_t tmem_slot;
+    if (plan.nrows[blockIdx.x / CL] > 16) bigru_cluster_body<true>(P, plan, smem, bars, tmem_slot);
+    else                                  bigru_cluster_body<false>(P, plan, smem, bars, tmem_slot);
+}
+
+}  // namespace
+
+// Returns 0 when the cluster kernel was launched, -1 when this shape does not qualify (caller falls back), > 0 on error.
+int launch_bigru_cluster(BiGruParams& P, cudaStream_t stream) {
+    static int enabled = -1;
+    if (enabled < 0) {
+        const char* e = getenv("TGGCN_BIGRU_CLUSTER");
+        enabled = (e != nullptr && e[0] == '0') ? 0 : 1;
+    }
+    if (!enabled || P.no_fp16_split || P.D != CL_D) return -1;
+    auto make_plan = [&](ClusterPlan& plan, int big_rows) -> bool {        // groups with more than big_rows rows use 32-row clusters
+        memset(&plan, 0, sizeof(plan));
+        for (int g = 0; g < P.ngroups; ++g) {
+            const int block = P.g[g].rows > big_rows ? 32 : 16;
+            for (int dir = 0; dir < 2; ++dir)
+                for (int r0 = 0; r0 < P.g[g].rows; r0 += block) {
+                    if (plan.count == CL_MAX_CLUSTERS) return false;
+                    plan.group[plan.count] = (unsigned char)g; plan.dir[plan.count] = (unsigned char)dir; plan.row0[plan.count] = r0;
+                    plan.nrows[plan.count] = P.g[g].rows - r0 < block ? P.g[g].rows - r0 : block;
+                    ++plan.count;
+                }
+        }
+        return true;
+    };
+    auto kern = bigru_cluster_kernel;
+    static_assert(CL_SMEM_BYTES <= 220 * 1024, "cluster BiGRU: shared memory layout");
+    if (int rc = ensure_smem((const void*)kern, CL_SMEM_BYTES)) return rc;
+    {
+        struct Once { bool done[64]; };
+        static Once once;
+        int dev = 0;
+        TG_CUDA_OK(cudaGetDevice(&dev));
+        if (dev >= 0 && dev < 64 && !once.done[dev]) {
+            TG_CUDA_OK(cudaFuncSetAttribute((const void*)kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+            once.done[dev] = true;
+        }
+    }
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(CL);
+    cfg.blockDim = dim3(REC_THREADS);
+    cfg.dynamicSmemBytes = CL_SMEM_BYTES;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    // a 16-CTA cluster needs 16 free SMs of one GPC: ask the driver before relying on it
+    int max_clusters = 0;
+    const cudaError_t oe = cudaOccupancyMaxActiveClusters(&max_clusters, (const void*)kern, &cfg);
+    if (getenv("TGGCN_CL_DEBUG") != nullptr)
+        fprintf(stderr, "bigru_cluster: cudaOccupancyMaxActiveClusters -> %s, %d\n", cudaGetErrorString(oe), max_clusters);
+    if (oe != cudaSuccess || max_clusters < 1) {
+        cudaGetLastError();
+        return -1;
+    }
+    // The clusters run in waves of max_clusters (7 on B200: a 16-CTA cluster needs 16 free SMs of one GPC).  Measured per step and
+    // wave (profiles/r02_bigru_cluster.txt): 16-row clusters 4.2 us (5.5 us when a later wave is only partly filled), 32-row
+    // clusters 8.5 us — the all-gather of the state through distributed shared memory (16 bulk copies per CTA and step) scales with
+    // the rows; the SMEM-resident grid-barrier kernel: 7.6 us per 32-row block.  MPHOI B=8 needs 8 recurrences of <= 16 rows, one more
+    // than fit at once, so it stays on the resident kernel; CAD-120 B=8 / 16 (40 / 80 object rows) run here (6.8 -> 5.7, 10.4 -> 5.9 ms).
+    ClusterPlan plan, plan16, plan32;
+    const bool ok16 = make_plan(plan16, 1 << 30), ok32 = make_plan(plan32, 16);
+    bool any32 = false;
+    for (int i = 0; ok32 && i < plan32.count; ++i) any32 |= plan32.nrows[i] > 16;
+    const float c16 = ok16 ? 5.5f * (float)cdiv(plan16.count, max_clusters) : 1e30f;
+    const float c32 = ok32 ? (any32 ? 8.5f : 5.5f) * (float)cdiv(plan32.count, max_clusters) : 1e30f;
+    int maxrows = 0;
+    for (int g = 0; g < P.ngroups; ++g) maxrows = P.g[g].rows > maxrows ? P.g[g].rows : maxrows;
+    const float cres = 7.6f * (float)cdiv(maxrows, 32);
+    static int force = -1;                        // TGGCN_CL_PLAN=16 / 32: measurement aid
+    if (force < 0) {
+        const char* e = getenv("TGGCN_CL_PLAN");
+        force = e != nullptr ? atoi(e) : 0;
+    }
+    if (force == 16 && ok16) plan = plan16;
+    else if (force == 32 && ok32) plan = plan32;
+    else {
+        if (c16 >= cres && c32 >= cres) return -1;
+        plan = c32 < c16 ? plan32 : plan16;
+    }
+    cfg.gridDim = dim3(plan.count * CL);
+    if (getenv("TGGCN_CL_DEBUG") != nullptr)
+        fprintf(stderr, "bigru_cluster: plan with %d clusters (16-row cost %.1f, 32-row cost %.1f, resident %.1f)\n", plan.count, c16, c32, cres);
+    TG_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, P, plan));
+    TG_LAUNCH_OK();
+    return 0;
+}
+
+}  // namespace tg

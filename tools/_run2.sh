@@ -1,4 +1,6 @@
 mkdir -p gpurun_out
-(timeout 1200 python -m pytest tests/test_gpu_backward.py tests/test_gpu_fullsize.py tests/test_gpu_bf16.py tests/test_gpu_train_loop.py tests/test_gpu_linear.py -m gpu -q -x 2>&1 | tail -15) > gpurun_out/s6_pytest.log
-cat gpurun_out/s6_pytest.log
-timeout 300 python tools/profile_train.py --iters 5 > gpurun_out/s6_train.txt 2>&1; tail -6 gpurun_out/s6_train.txt
+for plan in 16 32; do
+TGGCN_CL_PLAN=$plan timeout 300 python tools/profile_stages.py > gpurun_out/s10_stages_$plan.txt 2>&1; echo "plan $plan"; grep -E "forward|bigru" gpurun_out/s10_stages_$plan.txt
+done
+TGGCN_BIGRU_CLUSTER=0 timeout 300 python tools/profile_stages.py > gpurun_out/s10_stages_res.txt 2>&1; echo resident; grep -E "forward|bigru" gpurun_out/s10_stages_res.txt
+(TGGCN_CL_PLAN=32 timeout 600 python -m pytest tests/test_gpu_bigru.py tests/test_gpu_parity.py -m gpu -q -x 2>&1 | tail -3) > gpurun_out/s10_pytest.log; cat gpurun_out/s10_pytest.log

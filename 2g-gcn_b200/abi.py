@@ -22,7 +22,7 @@ class Dims(C.Structure):
         'object_seg_given', 'inspect', 'persistent', 'gemm_path')] + [('thr', C.c_float), ('save_for_backward', C.c_int32),
                                                                        ('cat_level_states', C.c_int32), ('mean_pool', C.c_int32),
                                                                        ('recurrent_mode', C.c_int32), ('no_fp16_split', C.c_int32),
-                                                                       ('precision', C.c_int32)]
+                                                                       ('precision', C.c_int32), ('att_noscale', C.c_int32)]
 
 
 class GradOutputs(C.Structure):
@@ -143,7 +143,7 @@ def lib():
     L.tggcn_f1_at_k.restype = C.c_int
     L.tggcn_f1_at_k.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int64,
                                 C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
-    if L.tggcn_abi_version() != 6:
+    if L.tggcn_abi_version() != 7:
         raise TggcnError('lib2ggcn_b200.so ABI version mismatch; rebuild')
     _lib = L
     return L

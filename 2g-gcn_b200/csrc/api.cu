@@ -377,7 +377,7 @@ static int forward_impl(const tggcn_dims* dims, const void* const* weights, int 
     {
         FrameMsgParams P;
         memset(&P, 0, sizeof(P));
-        P.B = B; P.T = T; P.H = H; P.O = O; P.D = D; P.hh = d.hh; P.thr = d.thr; P.mean_pool = d.mean_pool;
+        P.B = B; P.T = T; P.H = H; P.O = O; P.D = D; P.hh = d.hh; P.thr = d.thr; P.mean_pool = d.mean_pool; P.att_noscale = d.att_noscale;
         P.s_h = buf(TGGCN_BUF_S_H); P.s_o = buf(TGGCN_BUF_S_O);
         P.msg_hh = buf(TGGCN_BUF_MSG_HH); P.msg_ho = buf(TGGCN_BUF_MSG_HO); P.msg_oh = buf(TGGCN_BUF_MSG_OH);
         P.msg_oo = buf(TGGCN_BUF_MSG_OO); P.msg_go = buf(TGGCN_BUF_MSG_GO);
@@ -411,7 +411,7 @@ static int forward_impl(const tggcn_dims* dims, const void* const* weights, int 
     {
         SegParams P;
         memset(&P, 0, sizeof(P));
-        P.B = B; P.T = T; P.H = H; P.O = O; P.D = D; P.hh = d.hh; P.mean_pool = d.mean_pool;
+        P.B = B; P.T = T; P.H = H; P.O = O; P.D = D; P.hh = d.hh; P.mean_pool = d.mean_pool; P.att_noscale = d.att_noscale;
         P.gs_h = buf(TGGCN_BUF_GS_H); P.gs_o = buf(TGGCN_BUF_GS_O);
         P.u_h = io->y_hs; P.u_o = io->y_os; P.om = io->objects_mask;
         P.wih_h[0] = W(TGGCN_W_HSEG_F_WIH); P.wih_h[1] = W(TGGCN_W_HSEG_B_WIH); P.ldw_h = ldwh; P.col_h = kh;

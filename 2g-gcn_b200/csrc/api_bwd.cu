@@ -340,7 +340,7 @@ int tggcn_backward_ex(const tggcn_dims* dims, const void* const* weights, void* 
 
         SegBwdParams P;
         memset(&P, 0, sizeof(P));
-        P.B = B; P.T = T; P.H = H; P.O = O; P.D = D; P.hh = d.hh; P.nk_h = nkh; P.mean_pool = d.mean_pool;
+        P.B = B; P.T = T; P.H = H; P.O = O; P.D = D; P.hh = d.hh; P.nk_h = nkh; P.mean_pool = d.mean_pool; P.att_noscale = d.att_noscale;
         P.hx_h = buf(TGGCN_BUF_HX_H); P.hx_o = buf(TGGCN_BUF_HX_O);
         P.sgates_h = buf(TGGCN_BUF_SGATES_H); P.sgates_o = buf(TGGCN_BUF_SGATES_O);
         P.u_h = io->y_hs; P.u_o = io->y_os; P.om = io->objects_mask;
@@ -412,7 +412,7 @@ int tggcn_backward_ex(const tggcn_dims* dims, const void* const* weights, void* 
     {
         FrameBwdParams P;
         memset(&P, 0, sizeof(P));
-        P.B = B; P.T = T; P.H = H; P.O = O; P.D = D; P.hh = d.hh; P.filter = d.filter; P.thr = d.thr; P.mean_pool = d.mean_pool;
+        P.B = B; P.T = T; P.H = H; P.O = O; P.D = D; P.hh = d.hh; P.filter = d.filter; P.thr = d.thr; P.mean_pool = d.mean_pool; P.att_noscale = d.att_noscale;
         P.s_h = buf(TGGCN_BUF_S_H); P.s_o = buf(TGGCN_BUF_S_O);
         P.msg_hh = buf(TGGCN_BUF_MSG_HH); P.msg_ho = buf(TGGCN_BUF_MSG_HO); P.msg_oh = buf(TGGCN_BUF_MSG_OH);
         P.msg_oo = buf(TGGCN_BUF_MSG_OO); P.msg_go = buf(TGGCN_BUF_MSG_GO);

@@ -259,7 +259,7 @@ __global__ void __launch_bounds__(256) frame_bwd_kernel(const FrameBwdParams P) 
         float* al = recv_h ? (second ? a_oh : a_hh) : (second ? a_oo : a_ho);
         float* dd = recv_h ? (second ? d_oh : d_hh) : (second ? d_oo : d_ho);
         if (!(recv_h && !second && !P.hh)) {
-            const float scale = 1.0f / sqrtf((float)D2);
+            const float scale = P.att_noscale ? 1.0f : 1.0f / sqrtf((float)D2);
             float dot = 0.0f;
             for (int sd = 0; sd < Es; ++sd) dot = fmaf(al[r * FB_MAXE + sd], dd[r * FB_MAXE + sd], dot);
             for (int sd = 0; sd < Es; ++sd)            // mean pooling: the weights do not depend on the states

@@ -45,6 +45,7 @@ int launch_bigru_bwd(BiGruBwdParams& P, int persistent, cudaStream_t stream);
 struct SegBwdParams {
     int B, T, H, O, D, hh, nk_h;
     int mean_pool;                                 // uniform sender weights: no gradient through attention logits
+    int att_noscale;                               // attention_style 'v2': plain dot-product logits
     const float* hx_h; const float* hx_o;          // forward states (B,T,E,2D)
     const float* sgates_h; const float* sgates_o;  // (B,T,E,2,4D) r, z, n, hn
     const float* u_h; const float* u_o;            // hard gates (B,T,E)
@@ -75,6 +76,7 @@ int launch_segment_bwd(SegBwdParams& P, int persistent, cudaStream_t stream);
 struct FrameBwdParams {
     int B, T, H, O, D, hh, filter;
     int mean_pool;                                 // uniform sender weights: no gradient through attention logits
+    int att_noscale;                               // attention_style 'v2': plain dot-product logits
     float thr;
     const float* s_h; const float* s_o;            // (B,T,E,2D)
     const float* msg_hh; const float* msg_ho; const float* msg_oh; const float* msg_oo; const float* msg_go;

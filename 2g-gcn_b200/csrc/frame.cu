@@ -40,7 +40,7 @@ __global__ void __launch_bounds__(FM_THREADS) frame_messages_kernel(const FrameM
     if (tid < O) om[tid] = P.om[b * O + tid];
     __syncthreads();
     // -- Gram matrix of all entity pairs, one warp per pair --------------------------------------------
-    const float scale = 1.0f / sqrtf((float)D2);
+    const float scale = P.att_noscale ? 1.0f : 1.0f / sqrtf((float)D2);
     for (int pidx = warp; pidx < NE * NE; pidx += FM_THREADS / 32) {
         const int e1 = pidx / NE, e2 = pidx - e1 * NE;
         if (e2 <= e1) continue;

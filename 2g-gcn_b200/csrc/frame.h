@@ -7,6 +7,7 @@ namespace tg {
 struct FrameMsgParams {
     int B, T, H, O, D, hh;
     int mean_pool;          // message_aggregation 'mp': uniform weights over the valid senders instead of attention
+    int att_noscale;        // attention_style 'v2': plain dot-product logits
     float thr;
     const float* s_h;       // (B,T,H,2D) [x | h]
     const float* s_o;       // (B,T,O,2D)

@@ -257,7 +257,7 @@ __device__ __forceinline__ void seg_bwd_msg_item(const SegBwdParams& P, int item
     }
     __syncthreads();
     if (tid < Er) {
-        const float scale = 1.0f / sqrtf((float)D);
+        const float scale = P.att_noscale ? 1.0f : 1.0f / sqrtf((float)D);
         float dot = 0.0f;
         for (int q = 0; q < Es; ++q) dot = fmaf(sh.al[tid * Es + q], sh.da[tid * Es + q], dot);
         for (int q = 0; q < Es; ++q)                   // mean pooling: the weights do not depend on the states

@@ -174,7 +174,7 @@ __device__ __forceinline__ bool seg_message_tile(const SegParams& P, int tile, i
         }
         // logit of (receiver j, sender row) when both belong to the same video of the block
         const int li = sh.lidx[tid];
-        if (li >= 0) sh.logit[li] = acc[MSG_NG][0] * (1.0f / sqrtf((float)D));
+        if (li >= 0) sh.logit[li] = acc[MSG_NG][0] * (P.att_noscale ? 1.0f : 1.0f / sqrtf((float)D));
     }
     __syncthreads();
     // masked softmax over the senders of each receiver (vhoi/models.py:1750-1753), one thread per (receiver, sender) pair:

@@ -531,7 +531,7 @@ template <int PREC> __global__ void pack16_kernel(const PackJobs jobs) {
 constexpr int AT_MAXE = 16;
 constexpr int AT_THREADS = 256;
 struct AttendParams {
-    int B, T, H, O, D, hh, nk_h, mean_pool, first, s, dir_base;
+    int B, T, H, O, D, hh, nk_h, mean_pool, att_noscale, first, s, dir_base;
     const float* hx_h; const float* hx_o; const float* om;
     const float* msg[2][4]; long long msg_bstride[4];      // per direction and kind: sender row (b, e) at msg + b*bstride + e*D
     void* mg16_h; void* mg16_o;                            // planes [dir][hi, lo] of [rows][nk*D]
@@ -561,7 +561,7 @@ template <int PREC> __global__ void __launch_bounds__(AT_THREADS) seg_attend_ker
     }
     __syncthreads();
     // logits into alpha[k][r][s]
-    const float scale = 1.0f / sqrtf((float)D);
+    const float scale = P.att_noscale ? 1.0f : 1.0f / sqrtf((float)D);
     for (int k = P.hh ? 0 : 1; k < 4; ++k) {
         const bool send_h = (k == 0 || k == 2), recv_h = (k == 0 || k == 1);
         const int Es = send_h ? H : O, Er = recv_h ? H : O;
@@ -1004,7 +1004,7 @@ int launch_segment_big(SegParams& P, void* big_ws, int precision, int T_save, cu
             }
             if (int rc = launch_step(LA, precision, shape, st)) return rc;
             // ---- phase A2: attention over the previous states + aggregation -> operand rows of the cell GEMM --------------------
-            A.B = B; A.T = T; A.H = H; A.O = O; A.D = D; A.hh = P.hh; A.nk_h = nkh; A.mean_pool = P.mean_pool; A.first = s == 0; A.s = s;
+            A.B = B; A.T = T; A.H = H; A.O = O; A.D = D; A.hh = P.hh; A.nk_h = nkh; A.mean_pool = P.mean_pool; A.att_noscale = P.att_noscale; A.first = s == 0; A.s = s;
             A.dir_base = dir_lo;
             A.hx_h = P.hx_h; A.hx_o = P.hx_o; A.om = P.om;
             A.mg16_h = ws + BL.mg_h; A.mg16_o = ws + BL.mg_o;

@@ -26,6 +26,7 @@ _GS = {'gs', 'gumbel-sigmoid'}
 _ATT = {'att', 'attention'}
 _MP = {'mp', 'mean_pooling'}
 _V3 = {'v3', 'scaled_dot-product'}
+_V2 = {'v2', 'dot-product'}
 _NONREL = {'v2', 'non-relational'}
 _GENERIC = {'v1', 'generic'}
 _IND = {'ind', 'independent'}
@@ -120,7 +121,7 @@ class TGGCN(nn.Module):
         if message_type not in _NONREL: unsupported.append("message_type != 'v2'")
         if message_granularity not in _GENERIC: unsupported.append("message_granularity != 'v1'")
         if message_aggregation not in _ATT | _MP: unsupported.append("message_aggregation not in {'att', 'mp'}")
-        if attention_style not in _V3: unsupported.append("attention_style != 'v3'")
+        if attention_style not in _V3 | _V2: unsupported.append("attention_style not in {'v2', 'v3'}")
         if object_segment_update_strategy not in _IND: unsupported.append("object_segment_update_strategy != 'ind'")
         if add_segment_length or add_time_position: unsupported.append('time/length position features')
         if not bias: unsupported.append('bias=False')
@@ -386,7 +387,8 @@ class TGGCN(nn.Module):
                         gemm_path=int(self.gemm_path), thr=self.update_segment_threshold,
                         save_for_backward=int(with_grad), cat_level_states=int(self.cat_level_states),
                         mean_pool=int(self.message_aggregation in _MP), recurrent_mode=int(self.recurrent_mode),
-                        no_fp16_split=int(self.no_fp16_split), precision=int(self.precision))
+                        no_fp16_split=int(self.no_fp16_split), precision=int(self.precision),
+                        att_noscale=int(self.attention_style in _V2))
         n_sampled = (0 if hseg is not None else H) + (0 if oseg is not None else O)
         noise = None
         if n_sampled:

@@ -281,7 +281,7 @@ def run_ours(args, rank, world, local_rank):
         'config': {'workload': f'2G-GCN inference forward, {shape.name.upper()} shape, stage-2 settings', 'videos_per_gpu': B,
                    'frames_per_video': T, 'humans': shape.H, 'objects': shape.O, 'gcn_node': shape.V, 'hidden_size': D,
                    'weights': 'reference default init, torch.manual_seed(0)', 'l2': 'flushed (256 MB memset) between timed steps',
-                   'projections': 'tcgen05 3xTF32' if args.gemm_path else 'fp32 SIMT',
+                   'projections': 'TMA-fed tcgen05 kind::f16 on fp16 (hi, lo) operand planes, 3-term split (fp32-class accuracy)' if args.gemm_path else 'fp32 SIMT',
                    'recurrences': 'persistent kernels, on-chip resident weights, mma.sync 3xFP16 split (fp32-class accuracy); '
                                   'large-batch tcgen05 + TMA step kernels from 192 rows per step (other_configs)',
                    'parallelism': f'replicas x{world} (videos sharded)'},

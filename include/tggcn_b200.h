@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define TGGCN_ABI_VERSION 6
+#define TGGCN_ABI_VERSION 7
 
 #if defined(__GNUC__)
 #define TGGCN_API __attribute__((visibility("default")))
@@ -61,6 +61,8 @@ typedef struct tggcn_dims {
     int32_t precision;           /* 0 = fp32-class products everywhere (3-term split MMAs; the parity configuration),
                                     1 = bf16 operands with fp32 accumulation in the projections and the large-batch recurrent
                                     kernels (BASELINE.json configs[2]); gate / softmax / loss arithmetic stays fp32           */
+    int32_t att_noscale;         /* attention_style 'v2' / 'dot-product': logits <q, k> without the 1/sqrt(size) factor of 'v3'
+                                    (compute_attention_weights, models.py:1740-1745)                                           */
 } tggcn_dims;
 
 /* Parameter table.  One device pointer per reference state_dict() entry, in this order

@@ -61,6 +61,8 @@ CASES = [
     ('mphoi_s2_share', 'mphoi', 32, 2, 12, 2, False, 2.0, False, {'share_level_mlps': 1}),
     ('mphoi_s2_mp', 'mphoi', 32, 2, 12, 2, False, 2.0, False, {'message_aggregation': 'mp'}),
     ('cad120_s2_mp', 'cad120', 32, 2, 11, 2, False, 2.0, False, {'message_aggregation': 'mp'}),
+    ('mphoi_s2_dot', 'mphoi', 32, 2, 12, 2, False, 2.0, False, {'attention_style': 'v2'}),
+    ('cad120_s2_dot', 'cad120', 32, 2, 11, 2, False, 2.0, False, {'attention_style': 'v2'}),
     # the benchmarked configuration itself (BASELINE.json configs[1]: MPHOI, B=8, T=128, hidden 512, stage-2 settings)
     ('mphoi_s2_d512_full', 'mphoi', 512, 8, 128, 2, False, 1.0, False),
 ]
@@ -134,7 +136,8 @@ def run_case(name, shape_name, D, B, T, stage, train_mode, gain, inspect, extra=
         raise RuntimeError(f'no seed with a safe gate margin for {name}')
     # oracle agreement (also guards MPHOI object gates, which the reference does not return)
     p64 = {k: v.double() for k, v in sd.items()}
-    ocfg = orc.OracleConfig(D, shape.V, shape.num_classes, shape.hh, stage == 2, thr, bool(extra.get('cat_level_states', 0)), extra.get('message_aggregation') in ('mp', 'mean_pooling'))
+    ocfg = orc.OracleConfig(D, shape.V, shape.num_classes, shape.hh, stage == 2, thr, bool(extra.get('cat_level_states', 0)), extra.get('message_aggregation') in ('mp', 'mean_pooling'),
+                                     extra.get('attention_style') not in ('v2', 'dot-product'))
     hseg = torch.ones(B, T, shape.H) if stage == 1 else None
     oseg = torch.ones(B, T, shape.O) if (stage == 1 and shape.dataset == 'cad120') else None
     taps = {}
@@ -187,6 +190,8 @@ GRAD_CASES = [
     ('grad_mphoi_s2_share', 'mphoi', 32, 2, 9, 2, 2.0, {'share_level_mlps': 1}),
     ('grad_mphoi_s2_mp', 'mphoi', 32, 2, 9, 2, 2.0, {'message_aggregation': 'mp'}),
     ('grad_cad120_s2_mp', 'cad120', 32, 2, 8, 2, 2.0, {'message_aggregation': 'mp'}),
+    ('grad_mphoi_s2_dot', 'mphoi', 32, 2, 9, 2, 2.0, {'attention_style': 'v2'}),
+    ('grad_cad120_s2_dot', 'cad120', 32, 2, 8, 2, 2.0, {'attention_style': 'v2'}),
     # hidden 512 (the benchmarked width), T = 32: the D=512 BPTT and split-K weight-gradient paths against the reference itself
     ('grad_mphoi_s2_d512', 'mphoi', 512, 8, 32, 2, 1.0),
 ]
@@ -247,7 +252,8 @@ def run_grad_case(name, shape_name, D, B, T, stage, gain, extra=None):
         noise = orc.draw_noise(max(n_calls, 1), B, torch.Generator().manual_seed(noise_seed))[:n_calls]
         # margin check on the fp64 oracle (covers object gates that MPHOI does not return)
         p64 = {k: v.double() for k, v in sd.items()}
-        ocfg = orc.OracleConfig(D, shape.V, shape.num_classes, shape.hh, stage == 2, thr, bool(extra.get('cat_level_states', 0)), extra.get('message_aggregation') in ('mp', 'mean_pooling'))
+        ocfg = orc.OracleConfig(D, shape.V, shape.num_classes, shape.hh, stage == 2, thr, bool(extra.get('cat_level_states', 0)), extra.get('message_aggregation') in ('mp', 'mean_pooling'),
+                                     extra.get('attention_style') not in ('v2', 'dot-product'))
         hseg = torch.ones(B, T, shape.H) if stage == 1 else None
         oseg = torch.ones(B, T, shape.O) if (stage == 1 and shape.dataset == 'cad120') else None
         taps = {}

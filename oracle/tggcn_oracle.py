@@ -42,6 +42,7 @@ class OracleConfig:
     update_segment_threshold: float = 0.5
     cat_level_states: bool = False          # models.py:901-903 (share_level_mlps changes no arithmetic: same tensors, two names)
     mean_pool: bool = False                 # message_aggregation 'mp' (models.py:1033-1036 and the other message functions)
+    att_scaled: bool = True                 # attention_style 'v3' (scaled dot product); False = 'v2' (models.py:1740-1745)
 
 
 # ----------------------------------------------------------------------------------------------
@@ -123,7 +124,7 @@ def frame_level_rnn(p, x: Tensor, rnn: str, mlp: str) -> Tuple[Tensor, Tensor]:
     return _relu_lin(p, mlp + '.0', h_fr), h_fr
 
 
-def attend(query: Tensor, keys: Tensor, values: Tensor, mask: Tensor, mean_pool: bool = False) -> Tuple[Tensor, Tensor]:
+def attend(query: Tensor, keys: Tensor, values: Tensor, mask: Tensor, mean_pool: bool = False, scaled: bool = True) -> Tuple[Tensor, Tensor]:
     """Scaled dot-product attention of compute_attention_weights (vhoi/models.py:1721-1754, style 'v3')
     followed by the weighted sum at e.g. :1047-1048.
     query (B,F), keys (B,S,F), values (B,S,D), mask (B,S) in {0,1}.  Fully masked rows give zeros
@@ -131,7 +132,9 @@ def attend(query: Tensor, keys: Tensor, values: Tensor, mask: Tensor, mean_pool:
     if mean_pool:       # 'mp': sum of the (masked) messages over clamp(#valid senders, min=1), e.g. models.py:1033-1036
         w = mask / torch.clamp(mask.sum(dim=1, keepdim=True), min=1.0)
         return (w[..., None] * values).sum(1), w
-    logits = (query[:, None, :] * keys).sum(-1) / math.sqrt(keys.size(-1))
+    logits = (query[:, None, :] * keys).sum(-1)
+    if scaled:          # 'v3'; 'v2' is the plain dot product (models.py:1742-1745)
+        logits = logits / math.sqrt(keys.size(-1))
     logits = torch.where(mask.bool(), logits, torch.full_like(logits, float('-inf')))
     w = torch.softmax(logits, dim=1)
     w = torch.where(torch.isnan(w), torch.zeros_like(w), w)
@@ -245,10 +248,10 @@ def forward(p: Dict[str, Tensor], cfg: OracleConfig, x_human: Tensor, x_objects:
             gate_in = [x_h[:, t, h], h_h[:, t, h]]
             if hh_on:                                                   # :1004-1049
                 snd = _others(s_h, h)
-                m_hh, _ = attend(s_h[:, h], snd, _relu_lin(p, 'humans_to_human_message_mlp.0', snd), ones_h, cfg.mean_pool)
+                m_hh, _ = attend(s_h[:, h], snd, _relu_lin(p, 'humans_to_human_message_mlp.0', snd), ones_h, cfg.mean_pool, cfg.att_scaled)
                 parts.append(m_hh), gate_in.append(m_hh)
             val = _relu_lin(p, 'objects_to_human_message_mlp.0', s_o) * objects_mask[..., None]   # :1191-1237
-            m_oh, w_oh = attend(s_h[:, h], s_o, val, objects_mask, cfg.mean_pool)
+            m_oh, w_oh = attend(s_h[:, h], s_o, val, objects_mask, cfg.mean_pool, cfg.att_scaled)
             att_oh[h][t] = w_oh
             parts.append(m_oh), gate_in.append(m_oh)
             if human_segmentation is not None:                          # :697-698
@@ -263,12 +266,12 @@ def forward(p: Dict[str, Tensor], cfg: OracleConfig, x_human: Tensor, x_objects:
             xx_h[h][t] = torch.cat(parts, dim=-1)                       # :705  [h, m_hh, m_oh]
         for k in range(O):
             mk = objects_mask[:, k:k + 1]
-            m_ho, _ = attend(s_o[:, k], s_h, _relu_lin(p, 'human_to_object_message_mlp.0', s_h), ones_H, cfg.mean_pool)
+            m_ho, _ = attend(s_o[:, k], s_h, _relu_lin(p, 'human_to_object_message_mlp.0', s_h), ones_H, cfg.mean_pool, cfg.att_scaled)
             m_ho = m_ho * mk                                            # :1099-1143, :720
             m_go = _relu_lin(p, 'geometry_to_object_message_mlp.0', s_g[:, 0]) * mk   # :1384-1428, :729
             snd, snd_mask = _others(s_o, k), _others(objects_mask, k)   # :1286-1332
             val = _relu_lin(p, 'objects_to_object_message_mlp.0', snd) * snd_mask[..., None]
-            m_oo, _ = attend(s_o[:, k], snd, val, snd_mask, cfg.mean_pool)
+            m_oo, _ = attend(s_o[:, k], snd, val, snd_mask, cfg.mean_pool, cfg.att_scaled)
             if taps is not None:                                        # per-(t, receiver) tensors for gradient debugging
                 taps.setdefault('val_oo', {})[(t, k)] = val
                 taps.setdefault('m_oo', {})[(t, k)] = m_oo
@@ -310,18 +313,18 @@ def forward(p: Dict[str, Tensor], cfg: OracleConfig, x_human: Tensor, x_objects:
                 x = [xx_h[h][t]]
                 if hh_on:                                               # :1051-1097
                     snd = _others(sh, h)
-                    mg, _ = attend(SH[h], snd, _relu_lin(p, 'humans_to_human_segment_message_mlp.0', snd), ones_h, cfg.mean_pool)
+                    mg, _ = attend(SH[h], snd, _relu_lin(p, 'humans_to_human_segment_message_mlp.0', snd), ones_h, cfg.mean_pool, cfg.att_scaled)
                     x.append(mg)
                 val = _relu_lin(p, 'objects_to_human_segment_message_mlp.0', so) * objects_mask[..., None]
-                mg, w = attend(SH[h], so, val, objects_mask, cfg.mean_pool)            # :1239-1284
+                mg, w = attend(SH[h], so, val, objects_mask, cfg.mean_pool, cfg.att_scaled)            # :1239-1284
                 att[h][t] = w
                 x.append(mg)
                 newH.append(_seg_cell(p, hcell, torch.cat(x, dim=-1), y_hs[:, t, h:h + 1], SH[h]))
             for k in range(O):
-                mg_ho, _ = attend(SO[k], sh, _relu_lin(p, 'human_to_object_segment_message_mlp.0', sh), ones_H, cfg.mean_pool)
+                mg_ho, _ = attend(SO[k], sh, _relu_lin(p, 'human_to_object_segment_message_mlp.0', sh), ones_H, cfg.mean_pool, cfg.att_scaled)
                 snd, snd_mask = _others(so, k), _others(objects_mask, k)        # :1334-1381
                 val = _relu_lin(p, 'objects_to_object_segment_message_mlp.0', snd) * snd_mask[..., None]
-                mg_oo, _ = attend(SO[k], snd, val, snd_mask, cfg.mean_pool)
+                mg_oo, _ = attend(SO[k], snd, val, snd_mask, cfg.mean_pool, cfg.att_scaled)
                 x = torch.cat([xx_o[k][t], mg_ho, mg_oo], dim=-1)
                 newO.append(_seg_cell(p, ocell, x, y_os[:, t, k:k + 1], SO[k]))
             SH, SO = newH, newO                                         # commit, :875-880

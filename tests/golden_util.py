@@ -22,6 +22,8 @@ CASES = {
     'mphoi_s2_share': ('mphoi', 32, 2, 12, 2, False, False, {'share_level_mlps': 1}),
     'mphoi_s2_mp': ('mphoi', 32, 2, 12, 2, False, False, {'message_aggregation': 'mp'}),
     'cad120_s2_mp': ('cad120', 32, 2, 11, 2, False, False, {'message_aggregation': 'mp'}),
+    'mphoi_s2_dot': ('mphoi', 32, 2, 12, 2, False, False, {'attention_style': 'v2'}),
+    'cad120_s2_dot': ('cad120', 32, 2, 11, 2, False, False, {'attention_style': 'v2'}),
 }
 
 # BASELINE.json configs[1] itself — what bench.py times (reference outputs; gate margin 2.5e-5).  Kept apart from CASES: the
@@ -41,6 +43,8 @@ GRAD_CASES = {
     # seeds of these two also keep every ReLU pre-activation > 2e-5 from zero (oracle/gen_golden.py: RELU_STABLE_CASES)
     'grad_mphoi_s2_mp': ('mphoi', 32, 2, 9, 2, {'message_aggregation': 'mp'}),
     'grad_cad120_s2_mp': ('cad120', 32, 2, 8, 2, {'message_aggregation': 'mp'}),
+    'grad_mphoi_s2_dot': ('mphoi', 32, 2, 9, 2, {'attention_style': 'v2'}),
+    'grad_cad120_s2_dot': ('cad120', 32, 2, 8, 2, {'attention_style': 'v2'}),
 }
 
 # hidden 512 (the benchmarked width), T = 32.  Kept apart from GRAD_CASES: the reference's own fp32 autograd carries summation
@@ -88,7 +92,8 @@ class GoldenCase:
         self.outputs = [torch.from_numpy(self.blob[f'out{i}']) for i in range(6 if self.shape.num_classes[1] is None else 12)]
         self.ocfg = orc.OracleConfig(D, self.shape.V, self.shape.num_classes, self.shape.hh, stage == 2, self.thr,
                                      bool(self.extra.get('cat_level_states', 0)),
-                                     self.extra.get('message_aggregation') in ('mp', 'mean_pooling'))
+                                     self.extra.get('message_aggregation') in ('mp', 'mean_pooling'),
+                                     self.extra.get('attention_style') not in ('v2', 'dot-product'))
         # the regenerated inputs must be the bytes the reference saw
         chk = float(self.batch['x_human'].double().sum() + self.batch['x_objects'].double().sum())
         assert abs(chk - float(self.blob['inputs_checksum'][0])) <= 1e-6 * abs(chk), 'synthetic inputs differ from golden run'

@@ -69,9 +69,9 @@ def test_library_loads_and_exports_every_declared_symbol(pkg):
     lib = pkg.abi.lib()
     for sym in declared:
         assert hasattr(lib, sym), sym
-    assert lib.tggcn_abi_version() == 6
+    assert lib.tggcn_abi_version() == 7
     # struct mirrors: 17 int32 + 1 float + 6 int32; io = 6 + 4 + 8 + 3 + 3 + 1 pointers
-    assert ctypes.sizeof(pkg.abi.Dims) == 24 * 4
+    assert ctypes.sizeof(pkg.abi.Dims) == 25 * 4
     assert ctypes.sizeof(pkg.abi.IO) == 25 * 8
     # the status decoder is host-only: healthy words, a barrier time-out, an fp16-split range violation
     words = (ctypes.c_uint32 * 8)()

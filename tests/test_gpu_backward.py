@@ -41,7 +41,8 @@ def _setup(name, orc, synth, pkg):
     oseg = torch.ones(B, T, shape.O) if objects_given else None
     targets = synth.target_list(shape, synth.make_targets(shape, batch['lengths'], T, seed=target_seed))
     ocfg = orc.OracleConfig(D, shape.V, shape.num_classes, shape.hh, stage == 2, kw['update_segment_threshold'],
-                            bool(extra.get('cat_level_states', 0)), extra.get('message_aggregation') in ('mp', 'mean_pooling'))
+                            bool(extra.get('cat_level_states', 0)), extra.get('message_aggregation') in ('mp', 'mean_pooling'),
+                                     extra.get('attention_style') not in ('v2', 'dot-product'))
     return dict(blob=blob, shape=shape, stage=stage, model=model, batch=batch, noise=noise if n_calls else None, hseg=hseg,
                 oseg=oseg, targets=targets, ocfg=ocfg, extra=extra)
 

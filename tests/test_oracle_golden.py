@@ -117,7 +117,8 @@ def test_oracle_gradients_match_reference(name, orc, synth, pkg):
     hseg = torch.ones(B, T, shape.H).double() if human_given else None
     oseg = torch.ones(B, T, shape.O).double() if objects_given else None
     ocfg = orc.OracleConfig(D, shape.V, shape.num_classes, shape.hh, stage == 2, kw['update_segment_threshold'],
-                            bool(extra.get('cat_level_states', 0)), extra.get('message_aggregation') in ('mp', 'mean_pooling'))
+                            bool(extra.get('cat_level_states', 0)), extra.get('message_aggregation') in ('mp', 'mean_pooling'),
+                                     extra.get('attention_style') not in ('v2', 'dot-product'))
     out = orc.forward(p, ocfg, batch['x_human'].double(), batch['x_objects'].double(), batch['objects_mask'].double(),
                       hseg, oseg, noise.double() if n_calls else None, training=True)
     targets = synth.target_list(shape, synth.make_targets(shape, batch['lengths'], T, seed=target_seed))

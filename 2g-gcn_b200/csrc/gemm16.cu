@@ -17,6 +17,7 @@
 //                 the result as well, so that a following projection needs no pack pass.
 // Several problems per launch (grouped), as gemm_tc.cu.  Accuracy class measured in tests/test_gpu_linear.py (path 4 / 5).
 #include <stdlib.h>
+#include <mutex>
 #include <cuda.h>
 #include <cuda_fp16.h>
 #include <cuda_bf16.h>
@@ -557,12 +558,57 @@ int launch_gemm16(const Gemm16Problem* prob, int count, int precision, void* scr
         e = getenv("TGGCN_GEMM16_BK");
         bk_env = e != nullptr ? atoi(e) : 0;
     }
-    int bn = 256;
-    {
-        const long long c256 = (long long)cdiv(tiles_of(256), num_sms()) * (128 + 256), c128 = (long long)cdiv(tiles_of(128), num_sms()) * (128 + 128);
-        if (c128 < c256) bn = 128;
-        if (bn_env == 128 || bn_env == 256) bn = bn_env;
+    // Tile width and launch order by a makespan estimate.  A tile costs ~ (K / 64) x (128 + BN) (the main loop runs at the rate the
+    // operand bytes arrive) plus a fixed prologue / epilogue share; tiles are issued longest first (the hardware hands blocks to
+    // SMs in index order as they free up = greedy longest-processing-time scheduling), and the width with the shorter estimated
+    // makespan over the SMs wins.  ncu (profiles/r02_ncu_gemm16_embed.txt): the embedding stage ran 160 tiles of 128 x 256 with
+    // its 64 long tiles (K = 3328) LAST — 1.08 waves, tensor pipe 37 % against 61 % for the well-filled gs stage.
+    int order[G16_MAX_PROBLEMS];
+    for (int i = 0; i < count; ++i) order[i] = i;
+    for (int i = 1; i < count; ++i)                                     // problems by reduction length, longest first
+        for (int j = i; j > 0 && op_k(prob[order[j]].a) > op_k(prob[order[j - 1]].a); --j) { const int t = order[j]; order[j] = order[j - 1]; order[j - 1] = t; }
+    auto makespan = [&](int bnx) -> double {
+        const int S = num_sms();
+        if (tiles_of(bnx) > 16 * S) return (double)tiles_of(bnx) / S * (128 + bnx);      // many waves: quantisation does not matter
+        double load[256];
+        const int SS = S < 256 ? S : 256;
+        for (int i = 0; i < SS; ++i) load[i] = 0.0;
+        for (int oi = 0; oi < count; ++oi) {
+            const Gemm16Problem& q = prob[order[oi]];
+            const double cost = (double)(op_k(q.a) / 64) * (128 + bnx) + 6.0 * 384;          // + ~6 k-blocks of prologue / epilogue
+            const int nt = cdiv(op_rows(q.a), G16_BM) * cdiv(op_rows(q.b), bnx);
+            for (int t = 0; t < nt; ++t) {
+                int best = 0;
+                for (int i = 1; i < SS; ++i)
+                    if (load[i] < load[best]) best = i;
+                load[best] += cost;
+            }
+        }
+        double m = 0.0;
+        for (int i = 0; i < SS; ++i) m = load[i] > m ? load[i] : m;
+        return m;
+    };
+    int bn = 0;
+    {   // the estimate costs O(tiles x SMs) host operations: remember it per problem signature (a forward repeats its six stages)
+        static std::mutex mu;
+        static unsigned long long keys[128];
+        static int vals[128];
+        unsigned long long h = 1469598103934665603ull ^ (unsigned long long)num_sms();
+        for (int i = 0; i < count; ++i) {
+            const unsigned long long v[3] = {(unsigned long long)op_rows(prob[order[i]].a), (unsigned long long)op_rows(prob[order[i]].b),
+                                             (unsigned long long)op_k(prob[order[i]].a)};
+            for (unsigned long long x : v) h = (h ^ x) * 1099511628211ull;
+        }
+        if (h == 0) h = 1;
+        std::lock_guard<std::mutex> lock(mu);
+        const int slot = (int)(h % 128);
+        if (keys[slot] == h) bn = vals[slot];
+        else {
+            bn = makespan(128) < makespan(256) ? 128 : 256;
+            keys[slot] = h; vals[slot] = bn;
+        }
     }
+    if (bn_env == 128 || bn_env == 256) bn = bn_env;
     // stage depth: K = 32 per stage (SWIZZLE_64B rows) for the fp16-split 256-wide tile, whose 64-deep stages are 96 KB
     int bk = (precision == 0 && bn == 256) ? 32 : 64;
     if (bk_env == 32 || bk_env == 64) bk = bk_env;
@@ -581,6 +627,9 @@ int launch_gemm16(const Gemm16Problem* prob, int count, int precision, void* scr
     int jobidx[2][G16_MAX_PROBLEMS];
     int n_dyn = 0, begin = 0, base_tiles = tiles_of(bn);
     size_t max_work = 0;
+    Gemm16Problem sorted[G16_MAX_PROBLEMS];
+    for (int i = 0; i < count; ++i) sorted[i] = prob[order[i]];
+    prob = sorted;                                                      // longest reduction first (see above)
     for (int i = 0; i < count; ++i) {
         const Gemm16Problem& p = prob[i];
         for (int side = 0; side < 2; ++side) {

@@ -14,6 +14,7 @@
 // large GEMMs over all (video, t, entity) rows (api_bwd.cu).
 #include <stdlib.h>
 #include "recurrent.cuh"
+#include "recurrent_res.cuh"
 #include "backward.cuh"
 
 namespace tg {
@@ -39,9 +40,11 @@ __device__ __forceinline__ float half_warp_sum(float v) {
 // ---------------------------------------------------------------------------------------------------------------
 // frame-level BiGRU
 // ---------------------------------------------------------------------------------------------------------------
-template <int NG, int NT>
+// RES: the tile's W_hh^T rows stay on chip as fp32 mma fragments in tensor memory (recurrent_res.cuh: res32_*); the CTA owns this
+// tile for the whole launch and `ready` says whether they are loaded.
+template <int NG, int NT, bool RES>
 __device__ __forceinline__ void bigru_bwd_tile(const BiGruBwdParams& P, const BiGruBwdGroup& G, int local, int s, float* smem,
-                                               BwdShared& sh) {
+                                               BwdShared& sh, const ResState& rs, int& ready) {
     constexpr int RBT = 8 * NT, NPAIR = NT / 2, WR = NG * REC_J;
     const int D = P.D, T = P.T;
     const int per_dir = G.n_rb * G.n_ub;
@@ -96,7 +99,12 @@ __device__ __forceinline__ void bigru_bwd_tile(const BiGruBwdParams& P, const Bi
     __syncthreads();
 
     float acc[NG][NPAIR];
-    tile_accumulate<NG, NT, 3>(acc, sh.tab1, sh.tab1, s > 0 ? 3 * D : 0, 0, 0u, 0u, G.whhT[dir], smem);
+    if (RES) {
+        if (!ready) { res32_fill<NG>(rs, nullptr, 0, sh.tab1, sh.tab1, 3 * D, 0); ready = 1; }
+        tile_accumulate_res32<NG, NT>(acc, sh.tab1 + WR, sh.tab1 + WR, s > 0 ? 3 * D : 0, 0, rs, nullptr, 0, G.whhT[dir], smem);
+    } else {
+        tile_accumulate<NG, NT, 3>(acc, sh.tab1, sh.tab1, s > 0 ? 3 * D : 0, 0, 0u, 0u, G.whhT[dir], smem);
+    }
 
 #pragma unroll
     for (int p = 0; p < NPAIR; ++p) {
@@ -122,10 +130,15 @@ __device__ __forceinline__ void bigru_bwd_tile(const BiGruBwdParams& P, const Bi
     }
 }
 
+template <bool RES>
 __global__ void __launch_bounds__(REC_THREADS, 1) bigru_bwd_kernel(const BiGruBwdParams P, int s_begin, int s_end, int persistent) {
     extern __shared__ __align__(16) float smem[];
     __shared__ BwdShared sh;
+    __shared__ uint32_t tmem_slot;
     if (threadIdx.x == 0) sh.s_fail = 0;
+    ResState rs;
+    int ready = 0;
+    if (RES) res_init(rs, &tmem_slot, nullptr);
     unsigned int epoch = 0;
     for (int s = s_begin; s < s_end; ++s) {
         for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x) {
@@ -136,25 +149,35 @@ __global__ void __launch_bounds__(REC_THREADS, 1) bigru_bwd_kernel(const BiGruBw
             const BiGruBwdGroup& G = P.g[gi];
             const int local = tile - G.tile_begin;
             if (P.NG == 2) {
-                if (G.cfg == 4) bigru_bwd_tile<2, 4>(P, G, local, s, smem, sh);
-                else            bigru_bwd_tile<2, 2>(P, G, local, s, smem, sh);
+                if (G.cfg == 4) bigru_bwd_tile<2, 4, RES>(P, G, local, s, smem, sh, rs, ready);
+                else            bigru_bwd_tile<2, 2, RES>(P, G, local, s, smem, sh, rs, ready);
             } else {
-                if (G.cfg == 4) bigru_bwd_tile<1, 4>(P, G, local, s, smem, sh);
-                else            bigru_bwd_tile<1, 2>(P, G, local, s, smem, sh);
+                if (G.cfg == 4) bigru_bwd_tile<1, 4, RES>(P, G, local, s, smem, sh, rs, ready);
+                else            bigru_bwd_tile<1, 2, RES>(P, G, local, s, smem, sh, rs, ready);
             }
         }
         if (persistent && s + 1 < s_end)
-            if (!grid_barrier(P.sync, epoch, gridDim.x, &sh.s_fail)) return;
+            if (!grid_barrier(P.sync, epoch, gridDim.x, &sh.s_fail)) break;
     }
+    if (RES) res_finish(rs);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
 // segment-level recurrent graph
 // ---------------------------------------------------------------------------------------------------------------
 // Phase A: d mg[dir][row][c] = sum_k dGs[t][row][k] * W_ih[k][col0 + c]
-template <int NG, int NT>
+// Resident-weight state of the segment BPTT kernel: the phase-A tile's W_ih[:,seg]^T rows occupy words [0, wordsA) of the
+// per-thread word space, the phase-C tile's [W_hh^T | W_msg^T] rows the words after them (tensor memory, then the overflow).
+struct SegBwdRes {
+    ResState rs;
+    uint4* ovf;
+    int wordsA;
+    int readyA, readyC;
+};
+
+template <int NG, int NT, bool RES>
 __device__ __forceinline__ void seg_bwd_dmg_tile(const SegBwdParams& P, bool is_h, int dir, int ub, int rb, int s, float* smem,
-                                                 BwdShared& sh) {
+                                                 BwdShared& sh, SegBwdRes& R) {
     constexpr int RBT = 8 * NT, NPAIR = NT / 2, WR = NG * REC_J;
     const int D = P.D, T = P.T;
     const int E = is_h ? P.H : P.O, rows = P.B * E;
@@ -181,7 +204,12 @@ __device__ __forceinline__ void seg_bwd_dmg_tile(const SegBwdParams& P, bool is_
     }
     __syncthreads();
     float acc[NG][NPAIR];
-    tile_accumulate<NG, NT, 3>(acc, sh.tab1, sh.tab1, 3 * D, 0, 0u, 0u, wT, smem);
+    if (RES) {
+        if (!R.readyA) { res32_fill<NG>(R.rs, R.ovf, 0, sh.tab1, sh.tab1, 3 * D, 0); R.readyA = 1; }
+        tile_accumulate_res32<NG, NT>(acc, sh.tab1 + WR, sh.tab1 + WR, 3 * D, 0, R.rs, R.ovf, 0, wT, smem);
+    } else {
+        tile_accumulate<NG, NT, 3>(acc, sh.tab1, sh.tab1, 3 * D, 0, 0u, 0u, wT, smem);
+    }
 #pragma unroll
     for (int p = 0; p < NPAIR; ++p) {
         const int lr = (tid >> 4) + 16 * p, r = row0 + lr;
@@ -307,9 +335,9 @@ __device__ __forceinline__ void seg_bwd_msg_item(const SegBwdParams& P, int item
 
 // Phase C (s >= 0): carry into the previous state of reverse step s, then the gated-cell backward of reverse step s + 1.
 // s == -1: only the cell backward of reverse step 0 (no carry yet).
-template <int NG, int NT>
+template <int NG, int NT, bool RES>
 __device__ __forceinline__ void seg_bwd_carry_tile(const SegBwdParams& P, bool is_h, int dir, int ub, int rb, int s, float* smem,
-                                                   BwdShared& sh) {
+                                                   BwdShared& sh, SegBwdRes& R) {
     constexpr int RBT = 8 * NT, NPAIR = NT / 2, WR = NG * REC_J;
     const int D = P.D, T = P.T;
     const int E = is_h ? P.H : P.O, rows = P.B * E;
@@ -396,7 +424,12 @@ __device__ __forceinline__ void seg_bwd_carry_tile(const SegBwdParams& P, bool i
     }
     __syncthreads();
     float acc[NG][NPAIR];
-    tile_accumulate<NG, NT, 3>(acc, sh.tab1, sh.tab2, gemm ? 3 * D : 0, gemm ? nks * D : 0, 0u, 0u, whhT, smem);
+    if (RES) {
+        if (gemm && !R.readyC) { res32_fill<NG>(R.rs, R.ovf, R.wordsA, sh.tab1, sh.tab2, 3 * D, nks * D); R.readyC = 1; }
+        tile_accumulate_res32<NG, NT>(acc, sh.tab1 + WR, sh.tab2 + WR, gemm ? 3 * D : 0, gemm ? nks * D : 0, R.rs, R.ovf, R.wordsA, whhT, smem);
+    } else {
+        tile_accumulate<NG, NT, 3>(acc, sh.tab1, sh.tab2, gemm ? 3 * D : 0, gemm ? nks * D : 0, 0u, 0u, whhT, smem);
+    }
 
 #pragma unroll
     for (int p = 0; p < NPAIR; ++p) {
@@ -431,8 +464,8 @@ __device__ __forceinline__ void seg_bwd_carry_tile(const SegBwdParams& P, bool i
 }
 
 // tile index -> (cell type, dir, unit block); one row block per cell type (B*E <= 32 rows per tile, see launcher)
-template <int PHASE>
-__device__ __forceinline__ void seg_bwd_dispatch(const SegBwdParams& P, int tile, int s, float* smem, BwdShared& sh) {
+template <int PHASE, bool RES>
+__device__ __forceinline__ void seg_bwd_dispatch(const SegBwdParams& P, int tile, int s, float* smem, BwdShared& sh, SegBwdRes& R) {
     const int per_dir = PHASE == 0 ? P.tilesA_dir : P.tilesC_dir;
     const int nh = PHASE == 0 ? P.tilesA_h : P.tilesC_h;           // (row blocks x unit blocks) of the human cell, per direction
     const int dir = tile / per_dir;
@@ -443,50 +476,64 @@ __device__ __forceinline__ void seg_bwd_dispatch(const SegBwdParams& P, int tile
     const int rb = rem / nub, ub = rem - rb * nub;
     const int cfg = is_h ? P.cfg_h : P.cfg_o;
     if (PHASE == 0) {
-        if (cfg == 4) seg_bwd_dmg_tile<2, 4>(P, is_h, dir, ub, rb, s, smem, sh);
-        else          seg_bwd_dmg_tile<2, 2>(P, is_h, dir, ub, rb, s, smem, sh);
+        if (cfg == 4) seg_bwd_dmg_tile<2, 4, RES>(P, is_h, dir, ub, rb, s, smem, sh, R);
+        else          seg_bwd_dmg_tile<2, 2, RES>(P, is_h, dir, ub, rb, s, smem, sh, R);
     } else {
-        if (cfg == 4) seg_bwd_carry_tile<1, 4>(P, is_h, dir, ub, rb, s, smem, sh);
-        else          seg_bwd_carry_tile<1, 2>(P, is_h, dir, ub, rb, s, smem, sh);
+        if (cfg == 4) seg_bwd_carry_tile<1, 4, RES>(P, is_h, dir, ub, rb, s, smem, sh, R);
+        else          seg_bwd_carry_tile<1, 2, RES>(P, is_h, dir, ub, rb, s, smem, sh, R);
     }
 }
 
 // phases: bit 0 = A, bit 1 = B, bit 2 = C.  Steps s in [s_begin, s_end); s = -1 runs only the initial cell backward (phase C).
+// RES (persistent launches whose A and C tiles each fit one per CTA): transposed weights resident on chip; res_ovf_floats = offset of
+// the shared-memory overflow fragments behind the ring / phase-B region.
+template <bool RES>
 __global__ void __launch_bounds__(REC_THREADS, 1) segment_bwd_kernel(const SegBwdParams P, int s_begin, int s_end, int phases,
-                                                                    int persistent) {
+                                                                    int persistent, int res_ovf_floats, int res_words_a) {
     extern __shared__ __align__(16) float smem[];
     __shared__ BwdShared sh;
+    __shared__ uint32_t tmem_slot;
     if (threadIdx.x == 0) sh.s_fail = 0;
+    SegBwdRes R;
+    R.ovf = reinterpret_cast<uint4*>(smem + res_ovf_floats);
+    R.wordsA = res_words_a;
+    R.readyA = R.readyC = 0;
+    if (RES) res_init(R.rs, &tmem_slot, nullptr);
     unsigned int epoch = 0;
     const int T = P.T;
     for (int s = s_begin; s < s_end; ++s) {
         if (s >= 0 && (phases & 1)) {
-            for (int tile = blockIdx.x; tile < 2 * P.tilesA_dir; tile += gridDim.x) seg_bwd_dispatch<0>(P, tile, s, smem, sh);
-            if (persistent && !grid_barrier(P.sync, epoch, gridDim.x, &sh.s_fail)) return;
+            for (int tile = blockIdx.x; tile < 2 * P.tilesA_dir; tile += gridDim.x) seg_bwd_dispatch<0, RES>(P, tile, s, smem, sh, R);
+            if (persistent && !grid_barrier(P.sync, epoch, gridDim.x, &sh.s_fail)) break;
         }
         if (s >= 0 && (phases & 2)) {
             for (int item = blockIdx.x; item < 2 * P.B * 4; item += gridDim.x) seg_bwd_msg_item(P, item, s, smem, sh);
-            if (persistent && s + 1 < T && !grid_barrier(P.sync, epoch, gridDim.x, &sh.s_fail)) return;
+            if (persistent && s + 1 < T && !grid_barrier(P.sync, epoch, gridDim.x, &sh.s_fail)) break;
         }
         if (s + 1 < T && (phases & 4)) {
-            for (int tile = blockIdx.x; tile < 2 * P.tilesC_dir; tile += gridDim.x) seg_bwd_dispatch<1>(P, tile, s, smem, sh);
-            if (persistent && !grid_barrier(P.sync, epoch, gridDim.x, &sh.s_fail)) return;
+            for (int tile = blockIdx.x; tile < 2 * P.tilesC_dir; tile += gridDim.x) seg_bwd_dispatch<1, RES>(P, tile, s, smem, sh, R);
+            if (persistent && !grid_barrier(P.sync, epoch, gridDim.x, &sh.s_fail)) break;
         }
     }
+    if (RES) res_finish(R.rs);
 }
 
 }  // namespace
 
+// TGGCN_BWD_RES=0 keeps the streaming 3xTF32 tiles (A/B aid)
+static bool bwd_res_enabled() {
+    static int enabled = -1;
+    if (enabled < 0) {
+        const char* e = getenv("TGGCN_BWD_RES");
+        enabled = (e != nullptr && e[0] == '0') ? 0 : 1;
+    }
+    return enabled != 0;
+}
+
 int launch_bigru_bwd(BiGruBwdParams& P, int persistent, cudaStream_t stream) {
     TG_REQUIRE(P.D % 16 == 0, "bigru_bwd: hidden_size=%d must be a multiple of 16", P.D);
-    auto kern = bigru_bwd_kernel;
-    const size_t smem = sizeof(float) * (size_t)tile_smem_floats(2, 4, 3);
-    if (int rc = ensure_smem((const void*)kern, smem)) return rc;
-    int per_sm = 0;
-    TG_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, REC_THREADS, smem));
-    TG_REQUIRE(per_sm >= 1, "bigru_bwd: kernel does not fit on an SM (smem %zu)", smem);
-    const int capacity = per_sm * num_sms();
-    for (int ng = 1; ng <= 2; ++ng) {
+    // tiling first (it decides whether every CTA can own one tile, i.e. whether the weights can stay resident)
+    auto plan = [&](int ng) {
         int begin = 0;
         for (int i = 0; i < P.ngroups; ++i) {
             BiGruBwdGroup& G = P.g[i];
@@ -498,7 +545,45 @@ int launch_bigru_bwd(BiGruBwdParams& P, int persistent, cudaStream_t stream) {
         }
         P.total_tiles = begin;
         P.NG = ng;
-        if (begin <= capacity) break;          // prefer the finer split while every tile gets its own SM
+    };
+    // resident variant: one tile per CTA for the whole launch, W_hh^T fragments (cdiv(3D/16, 8) * NG * 8 words per thread) in tensor memory
+    bool res = false;
+    size_t smem_res = 0;
+    if (persistent && bwd_res_enabled()) {
+        for (int ng = 1; ng <= 2 && !res; ++ng) {
+            plan(ng);
+            const int words = cdiv(3 * P.D / REC_CK, REC_WARPS) * ng * 8;
+            if (P.total_tiles <= num_sms() && words <= RES_TMEM_WORDS) res = true;
+        }
+        if (res) {
+            smem_res = sizeof(float) * (size_t)res32_smem_floats(2, 4);
+            if (smem_res < 116 * 1024) smem_res = 116 * 1024;      // one CTA per SM: each allocates all of tensor memory
+        }
+    }
+    if (res) {
+        auto kern = bigru_bwd_kernel<true>;
+        if (int rc = ensure_smem((const void*)kern, smem_res)) return rc;
+        int per_sm = 0;
+        TG_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, REC_THREADS, smem_res));
+        if (per_sm == 1 && P.total_tiles <= num_sms()) {
+            TG_CUDA_OK(cudaMemsetAsync(P.sync.counter, 0, sizeof(unsigned int), stream));      // the error word belongs to the caller
+            int s0 = 0, s1 = P.T, pers = 1;
+            void* args[] = {(void*)&P, (void*)&s0, (void*)&s1, (void*)&pers};
+            TG_CUDA_OK(cudaLaunchCooperativeKernel((const void*)kern, dim3(P.total_tiles), dim3(REC_THREADS), args, smem_res, stream));
+            ++g_launches;
+            return 0;
+        }
+    }
+    auto kern = bigru_bwd_kernel<false>;
+    const size_t smem = sizeof(float) * (size_t)tile_smem_floats(2, 4, 3);
+    if (int rc = ensure_smem((const void*)kern, smem)) return rc;
+    int per_sm = 0;
+    TG_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, REC_THREADS, smem));
+    TG_REQUIRE(per_sm >= 1, "bigru_bwd: kernel does not fit on an SM (smem %zu)", smem);
+    const int capacity = per_sm * num_sms();
+    for (int ng = 1; ng <= 2; ++ng) {
+        plan(ng);
+        if (P.total_tiles <= capacity) break;          // prefer the finer split while every tile gets its own SM
     }
     if (persistent) {
         const int grid = P.total_tiles < capacity ? P.total_tiles : capacity;
@@ -520,16 +605,6 @@ int launch_segment_bwd(SegBwdParams& P, int persistent, cudaStream_t stream) {
     const int D = P.D, B = P.B, H = P.H, O = P.O;
     TG_REQUIRE(D % 16 == 0, "segment_bwd: hidden_size=%d must be a multiple of 16", D);
     TG_REQUIRE(H <= BW_MAXE && O <= BW_MAXE, "segment_bwd: at most %d entities per type", BW_MAXE);
-    auto kern = segment_bwd_kernel;
-    size_t smem = sizeof(float) * (size_t)tile_smem_floats(2, 4, 3);
-    const size_t smem_b = sizeof(float) * (size_t)4 * (H > O ? H : O) * D;
-    if (smem_b > smem) smem = smem_b;
-    TG_REQUIRE(smem <= 200 * 1024, "segment_bwd: hidden_size=%d needs %zu bytes of shared memory", D, smem);
-    if (int rc = ensure_smem((const void*)kern, smem)) return rc;
-    int per_sm = 0;
-    TG_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, REC_THREADS, smem));
-    TG_REQUIRE(per_sm >= 1, "segment_bwd: kernel does not fit on an SM (smem %zu)", smem);
-    const int capacity = per_sm * num_sms();
     P.cfg_h = B * H > 16 ? 4 : 2;
     P.cfg_o = B * O > 16 ? 4 : 2;
     const int nrb_h = cdiv(B * H, 8 * P.cfg_h), nrb_o = cdiv(B * O, 8 * P.cfg_o);
@@ -538,6 +613,43 @@ int launch_segment_bwd(SegBwdParams& P, int persistent, cudaStream_t stream) {
     P.nubC = cdiv(D, REC_J);
     P.tilesC_h = nrb_h * P.nubC; P.tilesC_dir = P.tilesC_h + nrb_o * P.nubC;
     const int items = 2 * B * 4;
+    const size_t smem_b = sizeof(float) * (size_t)4 * (H > O ? H : O) * D;
+    // resident variant: every CTA owns at most one phase-A tile (NG = 2, K = 3D) and one phase-C tile (NG = 1, K = 3D + nks*D) for the
+    // whole launch; their fp32 fragment words go to tensor memory (256 per thread) and a shared-memory overflow behind the ring
+    if (persistent && bwd_res_enabled() && 2 * P.tilesA_dir <= num_sms() && 2 * P.tilesC_dir <= num_sms() && items <= num_sms()) {
+        const int wordsA = cdiv(3 * D / REC_CK, REC_WARPS) * 2 * 8;
+        const int wordsC = cdiv((3 * D + 2 * D) / REC_CK, REC_WARPS) * 1 * 8;
+        const int ovf_words = wordsA + wordsC > RES_TMEM_WORDS ? (wordsA + wordsC - RES_TMEM_WORDS + 3) / 4 * 4 : 0;
+        size_t region = sizeof(float) * (size_t)res32_smem_floats(2, 4);
+        if (smem_b > region) region = smem_b;
+        region = (region + 15) / 16 * 16;
+        size_t smem = region + (size_t)ovf_words * REC_THREADS * 4;
+        if (smem < 116 * 1024) smem = 116 * 1024;                  // one CTA per SM: each allocates all of tensor memory
+        auto kern = segment_bwd_kernel<true>;
+        int per_sm = 0;
+        if (smem <= 200 * 1024 && ensure_smem((const void*)kern, smem) == 0 &&
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, REC_THREADS, smem) == cudaSuccess && per_sm == 1) {
+            int grid = 2 * P.tilesA_dir;
+            if (2 * P.tilesC_dir > grid) grid = 2 * P.tilesC_dir;
+            if (items > grid) grid = items;
+            TG_CUDA_OK(cudaMemsetAsync(P.sync.counter, 0, sizeof(unsigned int), stream));      // the error word belongs to the caller
+            int s0 = -1, s1 = P.T, phases = 7, pers = 1, ovf_off = (int)(region / sizeof(float)), wa = wordsA;
+            void* args[] = {(void*)&P, (void*)&s0, (void*)&s1, (void*)&phases, (void*)&pers, (void*)&ovf_off, (void*)&wa};
+            TG_CUDA_OK(cudaLaunchCooperativeKernel((const void*)kern, dim3(grid), dim3(REC_THREADS), args, smem, stream));
+            ++g_launches;
+            return 0;
+        }
+    }
+    auto kern = segment_bwd_kernel<false>;
+    size_t smem = sizeof(float) * (size_t)tile_smem_floats(2, 4, 3);
+    if (smem_b > smem) smem = smem_b;
+    TG_REQUIRE(smem <= 200 * 1024, "segment_bwd: hidden_size=%d needs %zu bytes of shared memory", D, smem);
+    if (int rc = ensure_smem((const void*)kern, smem)) return rc;
+    int per_sm = 0;
+    TG_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, REC_THREADS, smem));
+    TG_REQUIRE(per_sm >= 1, "segment_bwd: kernel does not fit on an SM (smem %zu)", smem);
+    const int capacity = per_sm * num_sms();
+    int zero = 0;
     if (persistent) {
         int grid = 2 * P.tilesA_dir;
         if (2 * P.tilesC_dir > grid) grid = 2 * P.tilesC_dir;
@@ -548,19 +660,19 @@ int launch_segment_bwd(SegBwdParams& P, int persistent, cudaStream_t stream) {
 #ifdef TGGCN_TIMING_EXPERIMENTS      // never in the product build: skipping a phase leaves the gradients undefined
         if (const char* e = getenv("TGGCN_SEGBWD_PHASES")) phases = atoi(e);
 #endif
-        void* args[] = {(void*)&P, (void*)&s0, (void*)&s1, (void*)&phases, (void*)&pers};
+        void* args[] = {(void*)&P, (void*)&s0, (void*)&s1, (void*)&phases, (void*)&pers, (void*)&zero, (void*)&zero};
         TG_CUDA_OK(cudaLaunchCooperativeKernel((const void*)kern, dim3(grid), dim3(REC_THREADS), args, smem, stream));
         ++g_launches;
     } else {
         for (int s = -1; s < P.T; ++s) {
             if (s >= 0) {
-                kern<<<2 * P.tilesA_dir, REC_THREADS, smem, stream>>>(P, s, s + 1, 1, 0);
+                kern<<<2 * P.tilesA_dir, REC_THREADS, smem, stream>>>(P, s, s + 1, 1, 0, 0, 0);
                 TG_LAUNCH_OK();
-                kern<<<items, REC_THREADS, smem, stream>>>(P, s, s + 1, 2, 0);
+                kern<<<items, REC_THREADS, smem, stream>>>(P, s, s + 1, 2, 0, 0, 0);
                 TG_LAUNCH_OK();
             }
             if (s + 1 < P.T) {
-                kern<<<2 * P.tilesC_dir, REC_THREADS, smem, stream>>>(P, s, s + 1, 4, 0);
+                kern<<<2 * P.tilesC_dir, REC_THREADS, smem, stream>>>(P, s, s + 1, 4, 0, 0, 0);
                 TG_LAUNCH_OK();
             }
         }

@@ -474,4 +474,189 @@ __device__ __forceinline__ void tile_accumulate_msg_res(float (&out)[RES_MSG_GRO
     __syncthreads();
 }
 
+
+// ---- fp32 resident fragments for the BACKWARD recurrences (3xTF32) -------------------------------------------------------------
+// The BPTT tiles multiply gradient rows (far below the fp16 range, different at every step) by TRANSPOSED weights that never
+// change: the weights stay on chip as raw fp32 mma.m16n8k8 A-fragment words (tensor memory first, shared-memory overflow after
+// RES_TMEM_WORDS words per thread) and are split into TF32 (hi, lo) in registers, exactly as the streaming tile does after its
+// ring loads — only the activation rows still stream (ncu r02: segment_bwd moved 424 MB of DRAM and ~110 MB of L2 -> SM traffic
+// per reverse step, 60 % of it the same weights again).  Several tiles of a CTA share the per-thread word space through `word0`.
+// Word of chunk n (chunk id = warp + 8 n), group m, k8 step kk, register r:  j = word0 + ((n*NG + m)*2 + kk)*4 + r.
+__device__ __forceinline__ uint32_t res32_taddr(const ResState& rs, int j) {
+    const int warp = threadIdx.x >> 5;
+    return rs.tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)((warp >> 2) * RES_TMEM_WORDS + j);
+}
+
+// wrow[g*16 + u]: K-contiguous weight row pointers (K = K1 of tab1 followed by K2 of tab2, null = zero row).  `ovf`: shared-memory
+// overflow [(words beyond RES_TMEM_WORDS) / 4][REC_THREADS] uint4.  Returns the number of words this tile occupies per thread.
+template <int NG>
+__device__ __forceinline__ int res32_fill(const ResState& rs, uint4* ovf, int word0, const float* const* wrow1, const float* const* wrow2,
+                                          int K1, int K2) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g8 = lane >> 2, t4 = lane & 3;
+    const int chunks1 = K1 / REC_CK, total = (K1 + K2) / REC_CK;
+    const int nmax = (total + REC_WARPS - 1) / REC_WARPS;
+    const int nmine = warp < total ? (total - warp + REC_WARPS - 1) / REC_WARPS : 0;
+    for (int n = 0; n < nmine; ++n) {
+        const int chunk = warp + n * REC_WARPS;
+        const bool seg1 = chunk < chunks1;
+        const int k = (seg1 ? chunk : chunk - chunks1) * REC_CK + t4;
+#pragma unroll
+        for (int m = 0; m < NG; ++m) {
+            const float* r0 = (seg1 ? wrow1 : wrow2)[m * REC_J + g8];
+            const float* r1 = (seg1 ? wrow1 : wrow2)[m * REC_J + g8 + 8];
+#pragma unroll
+            for (int kk = 0; kk < 2; ++kk) {
+                uint32_t w4[4];
+                w4[0] = r0 != nullptr ? __float_as_uint(__ldg(r0 + k + kk * 8)) : 0u;
+                w4[1] = r1 != nullptr ? __float_as_uint(__ldg(r1 + k + kk * 8)) : 0u;
+                w4[2] = r0 != nullptr ? __float_as_uint(__ldg(r0 + k + kk * 8 + 4)) : 0u;
+                w4[3] = r1 != nullptr ? __float_as_uint(__ldg(r1 + k + kk * 8 + 4)) : 0u;
+                const int j = word0 + ((n * NG + m) * 2 + kk) * 4;
+                if (j < RES_TMEM_WORDS) tmem_st4(res32_taddr(rs, j), w4);           // (warp-uniform: j depends on n, m, kk only)
+                else ovf[((j - RES_TMEM_WORDS) >> 2) * REC_THREADS + tid] = make_uint4(w4[0], w4[1], w4[2], w4[3]);
+            }
+        }
+    }
+    tmem_wait_st();
+    return nmax * NG * 8;
+}
+
+// out[g][p] as tile_accumulate<NG, NT, 3> delivers it; weights from the resident fp32 fragments (word0 as given to res32_fill),
+// activation rows act1 (K segment 1) / act2 (segment 2) through the warp-private cp.async ring.
+template <int NG, int NT>
+__device__ __forceinline__ void tile_accumulate_res32(float (&out)[NG][(NT + 1) / 2], const float* const* act1, const float* const* act2,
+                                                      int K1, int K2, const ResState& rs, const uint4* ovf, int word0, const float* gdummy,
+                                                      float* smem) {
+    constexpr int STAGES = RES_STAGES, ROWS = 8 * NT;
+    constexpr int STAGE_F = ROWS * REC_RS;
+    constexpr int NP = (ROWS * 4 + 31) / 32;            // 16-byte pieces per lane per chunk
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int g8 = lane >> 2, t4 = lane & 3;
+    float* ring = smem + warp * (STAGES * STAGE_F);
+
+    float c[NG][NT][4];
+#pragma unroll
+    for (int m = 0; m < NG; ++m)
+#pragma unroll
+        for (int n = 0; n < NT; ++n)
+#pragma unroll
+            for (int r = 0; r < 4; ++r) c[m][n][r] = 0.0f;
+
+    const int chunks1 = K1 / REC_CK, total_chunks = (K1 + K2) / REC_CK;
+    const int nmine = warp < total_chunks ? (total_chunks - warp + REC_WARPS - 1) / REC_WARPS : 0;
+    if (nmine > 0) {
+        const float* s1[NP];
+        const float* s2[NP];
+        int dst[NP];
+        bool in[NP];
+#pragma unroll
+        for (int p = 0; p < NP; ++p) {
+            const int piece = lane + p * 32;
+            const int row = piece >> 2, quarter = piece & 3;
+            in[p] = piece < ROWS * 4;
+            const float* b1 = in[p] ? act1[row] : nullptr;
+            const float* b2 = (in[p] && K2 > 0) ? act2[row] : nullptr;
+            s1[p] = b1 != nullptr ? b1 + quarter * 4 : nullptr;
+            s2[p] = b2 != nullptr ? b2 + quarter * 4 - K1 : nullptr;      // indexed with the global k offset
+            dst[p] = row * REC_RS + quarter * 4;
+        }
+        auto issue = [&](int n, int st) {
+            const int chunk = warp + n * REC_WARPS;
+            const bool seg1 = chunk < chunks1;
+            const size_t koff = (size_t)chunk * REC_CK;
+#pragma unroll
+            for (int p = 0; p < NP; ++p) {
+                if (!in[p]) continue;
+                const float* base = seg1 ? s1[p] : s2[p];
+                const bool ok = base != nullptr;
+                cp_async16_zfill(ring + st * STAGE_F + dst[p], ok ? base + koff : gdummy, ok);
+            }
+        };
+#pragma unroll
+        for (int st = 0; st < STAGES - 1; ++st) {
+            if (st < nmine) issue(st, st);
+            cp_async_commit();
+        }
+#pragma unroll 1
+        for (int n = 0; n < nmine; ++n) {
+            // this chunk's weight words: tensor memory (or the shared-memory overflow), fetched while the copies land
+            uint32_t w[NG][2][4];
+#pragma unroll
+            for (int m = 0; m < NG; ++m)
+#pragma unroll
+                for (int kk = 0; kk < 2; ++kk) {
+                    const int j = word0 + ((n * NG + m) * 2 + kk) * 4;
+                    if (j < RES_TMEM_WORDS) {
+                        tmem_ld4_nowait(res32_taddr(rs, j), w[m][kk]);
+                    } else {
+                        const uint4 v = ovf[((j - RES_TMEM_WORDS) >> 2) * REC_THREADS + tid];
+                        w[m][kk][0] = v.x; w[m][kk][1] = v.y; w[m][kk][2] = v.z; w[m][kk][3] = v.w;
+                    }
+                }
+            cp_async_wait<STAGES - 2>();
+            __syncwarp();
+            {
+                const int nn = n + STAGES - 1;
+                if (nn < nmine) issue(nn, nn % STAGES);
+                cp_async_commit();
+            }
+            tmem_wait_ld();
+            const float* xb = ring + (n % STAGES) * STAGE_F + g8 * REC_RS + t4;
+#pragma unroll
+            for (int kk = 0; kk < REC_CK / 8; ++kk) {
+                uint32_t bh[NT][2], bl[NT][2];
+#pragma unroll
+                for (int nt = 0; nt < NT; ++nt) {
+                    split_tf32(xb[nt * 8 * REC_RS + kk * 8], bh[nt][0], bl[nt][0]);
+                    split_tf32(xb[nt * 8 * REC_RS + kk * 8 + 4], bh[nt][1], bl[nt][1]);
+                }
+#pragma unroll
+                for (int m = 0; m < NG; ++m) {
+                    uint32_t ah[4], al[4];
+#pragma unroll
+                    for (int r = 0; r < 4; ++r) split_tf32(__uint_as_float(w[m][kk][r]), ah[r], al[r]);
+#pragma unroll
+                    for (int nt = 0; nt < NT; ++nt) mma_tf32(c[m][nt], al, bh[nt]);
+#pragma unroll
+                    for (int nt = 0; nt < NT; ++nt) mma_tf32(c[m][nt], ah, bl[nt]);
+#pragma unroll
+                    for (int nt = 0; nt < NT; ++nt) mma_tf32(c[m][nt], ah, bh[nt]);
+                }
+            }
+        }
+        cp_async_wait<0>();
+    }
+    __syncthreads();                             // every warp's ring is dead: reuse the memory for the reduction
+    float* red = smem;                           // red[warp][m][n][reg][lane]
+#pragma unroll
+    for (int m = 0; m < NG; ++m)
+#pragma unroll
+        for (int n = 0; n < NT; ++n)
+#pragma unroll
+            for (int r = 0; r < 4; ++r) red[(((warp * NG + m) * NT + n) * 4 + r) * 32 + lane] = c[m][n][r];
+    __syncthreads();
+#pragma unroll
+    for (int p = 0; p < (NT + 1) / 2; ++p) {
+        const int u = tid & 15, row = (tid >> 4) + 16 * p;
+        const int n = row >> 3, col = row & 7;
+        const int l = (u & 7) * 4 + (col >> 1), r = (u >> 3) * 2 + (col & 1);
+#pragma unroll
+        for (int m = 0; m < NG; ++m) {
+            float s = 0.0f;
+            if (n < NT) {
+#pragma unroll
+                for (int w8 = 0; w8 < REC_WARPS; ++w8) s += red[(((w8 * NG + m) * NT + n) * 4 + r) * 32 + l];
+            }
+            out[m][p] = s;
+        }
+    }
+    __syncthreads();                             // smem may be reused by the caller right away
+}
+
+// floats of shared memory tile_accumulate_res32<NG, NT> needs (activation ring or reduction buffer, whichever is larger)
+__host__ __device__ constexpr int res32_smem_floats(int NG, int NT) {
+    return REC_WARPS * RES_STAGES * 8 * NT * REC_RS > REC_WARPS * NG * NT * 4 * 32 ? REC_WARPS * RES_STAGES * 8 * NT * REC_RS
+                                                                                  : REC_WARPS * NG * NT * 4 * 32;
+}
+
 }  // namespace tg

@@ -303,9 +303,22 @@ static int forward_impl(const tggcn_dims* dims, const void* const* weights, int 
     GemmGroup g;
     // projections: the TMA-fed kernel on 16-bit operand planes (gemm16.cu) where the shapes qualify, else gemm_tc / SIMT
     auto project = [&](GemmGroup& grp) -> int {
-        if (d.gemm_path != 0 && (d.precision == 1 || !d.no_fp16_split) && gemm16_eligible(grp) && gemm16_scratch_bytes(grp) <= L.bytes[TGGCN_BUF_PACK])
-            return launch_gemm16(grp, d.precision == 1 ? 1 : 0, buf(TGGCN_BUF_PACK), L.bytes[TGGCN_BUF_PACK],
-                                 d.precision == 1 ? nullptr : sync + 1, stream);
+        // Narrow outputs (hidden_size 64: N = 64) are bound by reading A once; packing A first would triple that traffic
+        // (profiles: Bimanual D=64, pack16x = 11 % of a training step) — those problems stay on the register-producer kernel.
+        GemmGroup wide, narrow;
+        wide.count = narrow.count = 0;
+        wide.precision = narrow.precision = 0;
+        for (int i = 0; i < grp.count; ++i) {
+            GemmGroup& dst = grp.p[i].N >= 128 ? wide : narrow;
+            dst.p[dst.count++] = grp.p[i];
+        }
+        if (d.gemm_path != 0 && wide.count > 0 && (d.precision == 1 || !d.no_fp16_split) && gemm16_eligible(wide) &&
+            gemm16_scratch_bytes(wide) <= L.bytes[TGGCN_BUF_PACK]) {
+            if (int rc = launch_gemm16(wide, d.precision == 1 ? 1 : 0, buf(TGGCN_BUF_PACK), L.bytes[TGGCN_BUF_PACK],
+                                       d.precision == 1 ? nullptr : sync + 1, stream))
+                return rc;
+            return narrow.count > 0 ? launch_gemm(narrow, gpath, stream) : 0;
+        }
         return launch_gemm(grp, gpath, stream);
     };
     // 2. ROI embeddings and the first geometry MLP layer (models.py:646)

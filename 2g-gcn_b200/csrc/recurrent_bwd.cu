@@ -616,7 +616,7 @@ int launch_segment_bwd(SegBwdParams& P, int persistent, cudaStream_t stream) {
     const size_t smem_b = sizeof(float) * (size_t)4 * (H > O ? H : O) * D;
     // resident variant: every CTA owns at most one phase-A tile (NG = 2, K = 3D) and one phase-C tile (NG = 1, K = 3D + nks*D) for the
     // whole launch; their fp32 fragment words go to tensor memory (256 per thread) and a shared-memory overflow behind the ring
-    if (persistent && bwd_res_enabled() && 2 * P.tilesA_dir <= num_sms() && 2 * P.tilesC_dir <= num_sms() && items <= num_sms()) {
+    if (persistent && bwd_res_enabled() && 2 * P.tilesA_dir <= num_sms() && 2 * P.tilesC_dir <= num_sms()) {
         const int wordsA = cdiv(3 * D / REC_CK, REC_WARPS) * 2 * 8;
         const int wordsC = cdiv((3 * D + 2 * D) / REC_CK, REC_WARPS) * 1 * 8;
         const int ovf_words = wordsA + wordsC > RES_TMEM_WORDS ? (wordsA + wordsC - RES_TMEM_WORDS + 3) / 4 * 4 : 0;
@@ -632,6 +632,7 @@ int launch_segment_bwd(SegBwdParams& P, int persistent, cudaStream_t stream) {
             int grid = 2 * P.tilesA_dir;
             if (2 * P.tilesC_dir > grid) grid = 2 * P.tilesC_dir;
             if (items > grid) grid = items;
+            if (grid > num_sms()) grid = num_sms();                 // the phase-B items are strided over the CTAs
             TG_CUDA_OK(cudaMemsetAsync(P.sync.counter, 0, sizeof(unsigned int), stream));      // the error word belongs to the caller
             int s0 = -1, s1 = P.T, phases = 7, pers = 1, ovf_off = (int)(region / sizeof(float)), wa = wordsA;
             void* args[] = {(void*)&P, (void*)&s0, (void*)&s1, (void*)&phases, (void*)&pers, (void*)&ovf_off, (void*)&wa};

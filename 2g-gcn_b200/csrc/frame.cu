@@ -105,39 +105,45 @@ __global__ void __launch_bounds__(FM_THREADS) frame_messages_kernel(const FrameM
         const int wh = (1 + nkh) * D;            // xx_h row: [h, (m_hh), m_oh]
         float* xxh = P.xx_h + (size_t)n * H * wh;
         float* xxo = P.xx_o + (size_t)n * O * 4 * D;
-        for (int idx = tid; idx < H * D; idx += FM_THREADS) {
-            const int h = idx / D, c = idx - h * D;
+        // four columns per thread (float4 loads of the sender messages, float4 stores of xx rows); per element the same fmaf
+        // order as a scalar loop over the senders
+        const int D4 = D / 4;
+        auto fma4 = [](float a, const float4& m, float4& v) { v.x = fmaf(a, m.x, v.x); v.y = fmaf(a, m.y, v.y); v.z = fmaf(a, m.z, v.z); v.w = fmaf(a, m.w, v.w); };
+        auto ld4 = [](const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); };
+        auto scale4 = [](const float4& m, float s) { return make_float4(m.x * s, m.y * s, m.z * s, m.w * s); };
+        for (int idx = tid; idx < H * D4; idx += FM_THREADS) {
+            const int h = idx / D4, c = (idx - h * D4) * 4;
             float* row = xxh + h * wh;
-            row[c] = sv[h * D2 + D + c];
+            *reinterpret_cast<float4*>(row + c) = *reinterpret_cast<const float4*>(sv + h * D2 + D + c);
             if (P.hh) {
-                float v = 0.0f;
+                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
                 for (int j = 0; j < H; ++j)
-                    if (j != h) v = fmaf(a_hh[h * FM_MAXE + j], __ldg(g_hh + j * D + c), v);
-                mh[h * nkh * D + c] = v;
-                row[D + c] = v;
+                    if (j != h) fma4(a_hh[h * FM_MAXE + j], ld4(g_hh + j * D + c), v);
+                *reinterpret_cast<float4*>(mh + h * nkh * D + c) = v;
+                *reinterpret_cast<float4*>(row + D + c) = v;
             }
-            float v = 0.0f;
-            for (int k = 0; k < O; ++k) v = fmaf(a_oh[h * FM_MAXE + k], __ldg(g_oh + k * D + c) * om[k], v);
-            mh[h * nkh * D + (nkh - 1) * D + c] = v;
-            row[nkh * D + c] = v;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int k = 0; k < O; ++k) fma4(a_oh[h * FM_MAXE + k], scale4(ld4(g_oh + k * D + c), om[k]), v);
+            *reinterpret_cast<float4*>(mh + h * nkh * D + (nkh - 1) * D + c) = v;
+            *reinterpret_cast<float4*>(row + nkh * D + c) = v;
         }
-        for (int idx = tid; idx < O * D; idx += FM_THREADS) {
-            const int k = idx / D, c = idx - k * D;
+        for (int idx = tid; idx < O * D4; idx += FM_THREADS) {
+            const int k = idx / D4, c = (idx - k * D4) * 4;
             float* row = xxo + k * 4 * D;
-            row[c] = sv[(H + k) * D2 + D + c];
-            float v = 0.0f;
-            for (int h = 0; h < H; ++h) v = fmaf(a_ho[k * FM_MAXE + h], __ldg(g_ho + h * D + c), v);
-            v *= om[k];                                           // models.py:720
-            const float go = __ldg(g_go + c) * om[k];             // single sender, alpha = 1; models.py:729
-            float w = 0.0f;
+            *reinterpret_cast<float4*>(row + c) = *reinterpret_cast<const float4*>(sv + (H + k) * D2 + D + c);
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int h = 0; h < H; ++h) fma4(a_ho[k * FM_MAXE + h], ld4(g_ho + h * D + c), v);
+            v = scale4(v, om[k]);                                  // models.py:720
+            const float4 go = scale4(ld4(g_go + c), om[k]);        // single sender, alpha = 1; models.py:729
+            float4 w = make_float4(0.f, 0.f, 0.f, 0.f);
             for (int j = 0; j < O; ++j)
-                if (j != k) w = fmaf(a_oo[k * FM_MAXE + j], __ldg(g_oo + j * D + c) * om[j], w);
-            mo[k * 3 * D + c] = v;
-            mo[k * 3 * D + D + c] = go;
-            mo[k * 3 * D + 2 * D + c] = w;
-            row[D + c] = v;                                       // models.py:748 order: h, m_ho, m_go, m_oo
-            row[2 * D + c] = go;
-            row[3 * D + c] = w;
+                if (j != k) fma4(a_oo[k * FM_MAXE + j], scale4(ld4(g_oo + j * D + c), om[j]), w);
+            *reinterpret_cast<float4*>(mo + k * 3 * D + c) = v;
+            *reinterpret_cast<float4*>(mo + k * 3 * D + D + c) = go;
+            *reinterpret_cast<float4*>(mo + k * 3 * D + 2 * D + c) = w;
+            *reinterpret_cast<float4*>(row + D + c) = v;           // models.py:748 order: h, m_ho, m_go, m_oo
+            *reinterpret_cast<float4*>(row + 2 * D + c) = go;
+            *reinterpret_cast<float4*>(row + 3 * D + c) = w;
         }
     }
     __syncthreads();

@@ -97,7 +97,7 @@ void make_layout(const tggcn_dims& d, Layout& L) {
     sz[TGGCN_BUF_SEG_SCRATCH] = (2 * (size_t)d.B * H * nkh * D + 2 * (size_t)d.B * O * 2 * D + 8 * V) * f;
     sz[TGGCN_BUF_SYNC] = 64;
     sz[TGGCN_BUF_BIG] = 0;
-    if (use_big_path(d)) {                    // 16-bit operand copies, state rings and message scratch of the large-batch recurrent path
+    if (use_big_path(d, 0) || use_big_path(d, 1)) {   // 16-bit operand copies, state rings and message scratch of the large-batch recurrent path
         BigLayout BLy;
         big_layout(d.B, d.H, d.O, d.D, d.hh, BLy);
         sz[TGGCN_BUF_BIG] = BLy.total;
@@ -366,7 +366,7 @@ static int forward_impl(const tggcn_dims* dims, const void* const* weights, int 
         }
         P.sync.counter = sync; P.sync.error = sync + 1;
         P.no_fp16_split = d.no_fp16_split;
-        P.big_ws = use_big_path(d) ? (void*)buf(TGGCN_BUF_BIG) : nullptr; P.precision = d.precision;
+        P.big_ws = use_big_path(d, 0) ? (void*)buf(TGGCN_BUF_BIG) : nullptr; P.precision = d.precision;
         if (int rc = launch_bigru(P, d.persistent, stream)) return rc;
     }
     STAGE_END();
@@ -455,7 +455,7 @@ static int forward_impl(const tggcn_dims* dims, const void* const* weights, int 
         P.att_b = d.inspect ? io->att_seg_b : nullptr;
         P.sync.counter = sync + 2; P.sync.error = sync + 3;
         P.no_fp16_split = d.no_fp16_split;
-        P.big_ws = use_big_path(d) ? (void*)buf(TGGCN_BUF_BIG) : nullptr; P.precision = d.precision;
+        P.big_ws = use_big_path(d, 1) ? (void*)buf(TGGCN_BUF_BIG) : nullptr; P.precision = d.precision;
         if (int rc = launch_segment(P, d.persistent, stream)) return rc;
     }
     STAGE_END();

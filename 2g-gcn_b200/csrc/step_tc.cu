@@ -668,14 +668,16 @@ void big_layout(int B, int H, int O, int D, int hh, BigLayout& L) {
     L.total = off;
 }
 
-bool use_big_path(const tggcn_dims& d) {
+// stage 0: frame-level BiGRUs, 1: segment-level graph.  Measured crossovers against the latency path (round-2 sweeps, CUDA events):
+// segment level — MPHOI B=32 (128 rows per step) 9.61 -> 9.21 ms, CAD-120 B=32 (160 rows) 44.4 -> 37.1 ms on the step kernels,
+// CAD-120 B=16 (80 rows) 25.4 -> 35.3 ms (slower); BiGRUs — the cluster / resident kernels win up to 160 rows (CAD-120 B=32:
+// 8.6 vs 12.6 ms), the step kernels from CAD-120 B=64 (320 rows).
+bool use_big_path(const tggcn_dims& d, int stage) {
     if (d.D % 64 != 0 || d.D < 128 || d.H > AT_MAXE || d.O > AT_MAXE) return false;
     if (d.recurrent_mode == 2) return true;
     if (d.recurrent_mode == 1) return false;
-    // measured crossover against the latency path (profiles/r02_sweep_configs.txt): CAD-120 B=32 (160 rows) breaks even,
-    // B=16 (80 rows) and MPHOI B=32 (128 rows) are faster on the persistent kernels
     const int rows = d.B * (d.H > d.O ? d.H : d.O);
-    return rows >= 192;
+    return rows >= (stage == 1 ? 128 : 192);
 }
 
 namespace {

@@ -25,7 +25,7 @@ struct BigLayout {
 void big_layout(int B, int H, int O, int D, int hh, BigLayout& L);
 
 // true when the forward should run the recurrent stages on the large-batch path (dims.recurrent_mode, rows per step, shape limits)
-bool use_big_path(const tggcn_dims& d);
+bool use_big_path(const tggcn_dims& d, int stage);      // stage 0: BiGRUs, 1: segment level
 
 int launch_bigru_big(BiGruParams& P, void* big_ws, int precision, cudaStream_t stream);
 int launch_segment_big(SegParams& P, void* big_ws, int precision, int T_save, cudaStream_t stream);

@@ -283,7 +283,7 @@ def run_ours(args, rank, world, local_rank):
                    'weights': 'reference default init, torch.manual_seed(0)', 'l2': 'flushed (256 MB memset) between timed steps',
                    'projections': 'TMA-fed tcgen05 kind::f16 on fp16 (hi, lo) operand planes, 3-term split (fp32-class accuracy)' if args.gemm_path else 'fp32 SIMT',
                    'recurrences': 'persistent kernels, on-chip resident weights, mma.sync 3xFP16 split (fp32-class accuracy); '
-                                  'large-batch tcgen05 + TMA step kernels from 192 rows per step (other_configs)',
+                                  'large-batch tcgen05 + TMA step kernels from 128 rows per step (segment level) / 192 (BiGRUs) (other_configs)',
                    'parallelism': f'replicas x{world} (videos sharded)'},
         'clocks': clocks,
         'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
@@ -476,7 +476,8 @@ def other_configs(args, pkg, dev, flush):
         rows = b * max(cad.H, cad.O)
         res['cad120_inference_sweep'].append({
             'videos': b, 'frames_per_video': T, 'ms': round(ms, 3), 'frames_per_s': round(b * T / ms * 1e3),
-            'recurrent_path': 'large-batch tcgen05 + TMA step kernels' if rows >= 192 else 'persistent latency path',
+            'recurrent_path': ('large-batch tcgen05 + TMA step kernels' if rows >= 192 else
+                               'segment level: step kernels; BiGRUs: cluster / resident kernels' if rows >= 128 else 'persistent latency path'),
             'top_stage': top, 'top_stage_ms': round(st[top], 3), 'us_per_recurrent_step': round(st[top] * 1e3 / T, 2) if top in ('segment', 'bigru') else None,
             'roofline': {'bound': 'tensor', 'achieved': round(fl / (st[top] / 1e3) / 1e12, 2), 'peak': peaks['tf_sustained'], 'unit': 'TFLOP/s',
                          'frac': round(fl / (st[top] / 1e3) / 1e12 / peaks['tf_sustained'], 4)}})

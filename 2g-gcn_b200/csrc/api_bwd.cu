@@ -219,6 +219,37 @@ int tggcn_backward_ex(const tggcn_dims* dims, const void* const* weights, void* 
     g16.ws = nullptr; g16.bytes = BL.tn_floats * sizeof(float); g16.precision = d.precision == 1 ? 1 : 0;
     g16.err = (unsigned int*)buf(TGGCN_BUF_SYNC) + 7;
     if (d.gemm_path != 0 && gemm16_enabled() && (d.precision == 1 || !d.no_fp16_split)) g16.ws = tn_scratch;
+    // Input gradient of a projection: C[M, kf] (+)= (A (.) [mask > 0])[M, sum nf_i] * [W_0 ; W_1 ; ...] with W_i the FORWARD weight
+    // (nf_i rows of kf used columns, row stride ldw) — e.g. the two time directions of a hoisted W_ih.  On the TMA kernel the weights
+    // are packed transposed straight from their row-major storage (no fp32 transpose pass), the gradient block of each source is one
+    // problem, and the problems add into C atomically; otherwise: fp32 transposes into `wt` and the tf32 / bf16 kernel.
+    struct WSrc { const float* W; int ldw; int nf; };
+    auto dx_gemm = [&](const float* A, int lda, const float* mask, int ldm, const WSrc* ws, int nws, int kf, float* C, int ldc, int M,
+                       int beta, float* wt) -> int {
+        int ktot = 0;
+        for (int i = 0; i < nws; ++i) ktot += ws[i].nf;
+        if (g16.ws != nullptr && nws <= 2) {
+            Gemm16Problem q[2];
+            memset(q, 0, sizeof(q));
+            int koff = 0;
+            for (int i = 0; i < nws; ++i) {
+                q[i].a.src = A + koff; q[i].a.ld = lda; q[i].a.rows = M; q[i].a.cols = ws[i].nf;
+                q[i].a.mask = mask != nullptr ? mask + koff : nullptr; q[i].a.ldm = ldm; q[i].a.dynamic = 1;
+                q[i].b.src = ws[i].W; q[i].b.ld = ws[i].ldw; q[i].b.rows = ws[i].nf; q[i].b.cols = kf; q[i].b.transpose = 1; q[i].b.scale = 256.0f;
+                q[i].C = C; q[i].ldc = ldc; q[i].beta = i == 0 ? beta : 1;
+                koff += ws[i].nf;
+            }
+            if (gemm16_eligible(q, nws) && gemm16_scratch_bytes(q, nws) <= g16.bytes)
+                return launch_gemm16(q, nws, g16.precision, g16.ws, g16.bytes, g16.err, stream);
+        }
+        int koff = 0;
+        for (int i = 0; i < nws; ++i) {                      // wt[kf][ktot] = [W_0^T | W_1^T | ...]
+            if (int rc = launch_transpose(ws[i].W, ws[i].ldw, wt + koff, ktot, ws[i].nf, kf, stream)) return rc;
+            koff += ws[i].nf;
+        }
+        return gemm_nt(A, lda, mask, ldm, wt, ktot, C, ldc, M, kf, ktot, beta, path, stream, G16Ctx{nullptr, 0, 0, nullptr});
+    };
+
     // One weight gradient dW[Nn,K] (+)= (Z (.) [mask > 0])^T X (optional row shift of X inside blocks of `period` rows) and, when db is
     // given, the bias gradient db[Nn] (+)= column sums of the masked Z.  Calls are COLLECTED per backward stage and flushed as one
     // grouped launch of the TMA-fed kernel (gemm16.cu): every distinct operand is packed once (transposed: the row index becomes the
@@ -400,12 +431,10 @@ int tggcn_backward_ex(const tggcn_dims* dims, const void* const* weights, void* 
     // ---- 10. hoisted frame-part of the segment cells: d xx = [dGs_f | dGs_b] [W_ih_f[:, :k] ; W_ih_b[:, :k]] -----------------------
     {
         float* wt = bb(BL.wt);
-        for (int dir = 0; dir < 2; ++dir)
-            if (int rc = launch_transpose(W(wih_h_id[dir]), ldwh, wt + (size_t)dir * 3 * D, 6 * D, 3 * D, kh, stream)) return rc;
-        if (int rc = gemm_nt(bb(BL.dgs[0]), 6 * D, nullptr, 0, wt, 6 * D, bb(BL.dxx[0]), kh, N * H, kh, 6 * D, 0, path, stream, g16)) return rc;
-        for (int dir = 0; dir < 2; ++dir)
-            if (int rc = launch_transpose(W(wih_o_id[dir]), 6 * D, wt + (size_t)dir * 3 * D, 6 * D, 3 * D, 4 * D, stream)) return rc;
-        if (int rc = gemm_nt(bb(BL.dgs[1]), 6 * D, nullptr, 0, wt, 6 * D, bb(BL.dxx[1]), 4 * D, N * O, 4 * D, 6 * D, 0, path, stream, g16)) return rc;
+        const WSrc wh[2] = {{W(wih_h_id[0]), ldwh, 3 * D}, {W(wih_h_id[1]), ldwh, 3 * D}};
+        if (int rc = dx_gemm(bb(BL.dgs[0]), 6 * D, nullptr, 0, wh, 2, kh, bb(BL.dxx[0]), kh, N * H, 0, wt)) return rc;
+        const WSrc wo[2] = {{W(wih_o_id[0]), 6 * D, 3 * D}, {W(wih_o_id[1]), 6 * D, 3 * D}};
+        if (int rc = dx_gemm(bb(BL.dgs[1]), 6 * D, nullptr, 0, wo, 2, 4 * D, bb(BL.dxx[1]), 4 * D, N * O, 0, wt)) return rc;
     }
 
     // ---- 9/8. gates (straight-through, filter), attention, aggregation ------------------------------------------------------------
@@ -455,8 +484,8 @@ int tggcn_backward_ex(const tggcn_dims* dims, const void* const* weights, void* 
             const int gidx = kinds[k].grp, M = N * Eg[gidx];
             const float* dmsg = bb(BL.dmsg[kinds[k].dmsg]);
             const float* msg = buf(kinds[k].msg_buf);
-            if (int rc = launch_transpose(W(kinds[k].w_id), 2 * D, wt, D, D, 2 * D, stream)) return rc;      // (D,2D) -> (2D,D)
-            if (int rc = gemm_nt(dmsg, D, msg, D, wt, D, bb(BL.ds[gidx]), 2 * D, M, 2 * D, D, touched[gidx], path, stream, g16)) return rc;
+            const WSrc wk[1] = {{W(kinds[k].w_id), 2 * D, D}};
+            if (int rc = dx_gemm(dmsg, D, msg, D, wk, 1, 2 * D, bb(BL.ds[gidx]), 2 * D, M, touched[gidx], wt)) return rc;
             touched[gidx] = 1;
             if (int rc = tn(dmsg, D, msg, D, buf(s_buf[gidx]), 2 * D, G(kinds[k].w_id), 2 * D, M, D, 2 * D, 0, 0, 0, stream, G(kinds[k].w_id + 1))) return rc;
         }
@@ -475,9 +504,9 @@ int tggcn_backward_ex(const tggcn_dims* dims, const void* const* weights, void* 
             const int M = N * Eg[g];
             const float* dZ = bb(BL.ds[g]) + D;
             const float* Y = buf(s_buf[g]) + D;
-            if (int rc = launch_transpose(W(bd_id[g]), 2 * D, wt, D, D, 2 * D, stream)) return rc;
             const int beta = (g == 0 || (g == 1 && d.C_aff > 0)) ? 1 : 0;     // the frame heads already wrote into d hfr
-            if (int rc = gemm_nt(dZ, 2 * D, Y, 2 * D, wt, D, bb(BL.dhfr[g]), 2 * D, M, 2 * D, D, beta, path, stream, g16)) return rc;
+            const WSrc wb[1] = {{W(bd_id[g]), 2 * D, D}};
+            if (int rc = dx_gemm(dZ, 2 * D, Y, 2 * D, wb, 1, 2 * D, bb(BL.dhfr[g]), 2 * D, M, beta, wt)) return rc;
             if (int rc = tn(dZ, 2 * D, Y, 2 * D, buf(hfr_buf[g]), 2 * D, G(bd_id[g]), 2 * D, M, D, 2 * D, 0, 0, 0, stream, G(bd_id[g] + 1))) return rc;
         }
         if (int rc = tn_flush(stream)) return rc;
@@ -517,9 +546,8 @@ int tggcn_backward_ex(const tggcn_dims* dims, const void* const* weights, void* 
                                             G(base + 1 + 4 * dir), D, M, 3 * D, D, dir == 0 ? -Eg[g] : Eg[g], T * Eg[g], 0, stream, G(base + 3 + 4 * dir))) return rc;
             }
             // d x (+)= [dGi_f | dGi_b] [W_ih_f ; W_ih_b]   (x = S[:, :D])
-            if (int rc = launch_transpose(W(base), D, wt, 6 * D, 3 * D, D, stream)) return rc;
-            if (int rc = launch_transpose(W(base + 4), D, wt + 3 * D, 6 * D, 3 * D, D, stream)) return rc;
-            if (int rc = gemm_nt(dgi, 6 * D, nullptr, 0, wt, 6 * D, bb(BL.ds[g]), 2 * D, M, D, 6 * D, 1, path, stream, g16)) return rc;
+            const WSrc wi[2] = {{W(base), D, 3 * D}, {W(base + 4), D, 3 * D}};
+            if (int rc = dx_gemm(dgi, 6 * D, nullptr, 0, wi, 2, D, bb(BL.ds[g]), 2 * D, M, 1, wt)) return rc;
             for (int dir = 0; dir < 2; ++dir) {
                 if (int rc = tn(dgi + (size_t)dir * 3 * D, 6 * D, nullptr, 0, buf(s_buf[g]), 2 * D, G(base + 4 * dir), D, M, 3 * D, D,
                                             0, 0, 0, stream, G(base + 4 * dir + 2))) return rc;
@@ -539,14 +567,14 @@ int tggcn_backward_ex(const tggcn_dims* dims, const void* const* weights, void* 
                                     0, 0, 0, stream, G(TGGCN_W_OBJ_EMB_B))) return rc;
         // geometry MLP layer 2: S_G[:, :D] = ReLU(W2 hid + b2)
         float* wt = bb(BL.wt);
-        if (int rc = launch_transpose(W(TGGCN_W_GEO_MLP2_W), 2048, wt, D, D, 2048, stream)) return rc;          // (D,2048) -> (2048,D)
-        if (int rc = gemm_nt(bb(BL.ds[2]), 2 * D, buf(TGGCN_BUF_S_G), 2 * D, wt, D, bb(BL.dgeo_hid), 2048, N, 2048, D, 0, path, stream, g16)) return rc;
+        const WSrc w2[1] = {{W(TGGCN_W_GEO_MLP2_W), 2048, D}};
+        if (int rc = dx_gemm(bb(BL.ds[2]), 2 * D, buf(TGGCN_BUF_S_G), 2 * D, w2, 1, 2048, bb(BL.dgeo_hid), 2048, N, 0, wt)) return rc;
         if (int rc = tn(bb(BL.ds[2]), 2 * D, buf(TGGCN_BUF_S_G), 2 * D, buf(TGGCN_BUF_GEO_HID), 2048, G(TGGCN_W_GEO_MLP2_W), 2048, N, D,
                                     2048, 0, 0, 0, stream, G(TGGCN_W_GEO_MLP2_B))) return rc;
         // layer 0: hid = ReLU(W0 gcn + b0), gcn = the scrambled view (N, 128V)
         const int KV = 128 * V;
-        if (int rc = launch_transpose(W(TGGCN_W_GEO_MLP0_W), KV, wt, 2048, 2048, KV, stream)) return rc;         // (2048,128V) -> (128V,2048)
-        if (int rc = gemm_nt(bb(BL.dgeo_hid), 2048, buf(TGGCN_BUF_GEO_HID), 2048, wt, 2048, bb(BL.dgcn_out), KV, N, KV, 2048, 0, path, stream, g16)) return rc;
+        const WSrc w0[1] = {{W(TGGCN_W_GEO_MLP0_W), KV, 2048}};
+        if (int rc = dx_gemm(bb(BL.dgeo_hid), 2048, buf(TGGCN_BUF_GEO_HID), 2048, w0, 1, KV, bb(BL.dgcn_out), KV, N, 0, wt)) return rc;
         if (int rc = tn(bb(BL.dgeo_hid), 2048, buf(TGGCN_BUF_GEO_HID), 2048, buf(TGGCN_BUF_GCN_OUT), KV, G(TGGCN_W_GEO_MLP0_W), KV, N,
                                     2048, KV, 0, 0, 0, stream, G(TGGCN_W_GEO_MLP0_B))) return rc;
         if (int rc = tn_flush(stream)) return rc;

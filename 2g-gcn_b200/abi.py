@@ -22,7 +22,8 @@ class Dims(C.Structure):
         'object_seg_given', 'inspect', 'persistent', 'gemm_path')] + [('thr', C.c_float), ('save_for_backward', C.c_int32),
                                                                        ('cat_level_states', C.c_int32), ('mean_pool', C.c_int32),
                                                                        ('recurrent_mode', C.c_int32), ('no_fp16_split', C.c_int32),
-                                                                       ('precision', C.c_int32), ('att_noscale', C.c_int32)]
+                                                                       ('precision', C.c_int32), ('att_noscale', C.c_int32),
+                                                                       ('update_strategy', C.c_int32)]
 
 
 class GradOutputs(C.Structure):
@@ -73,6 +74,8 @@ WEIGHT_INDEX: Dict[str, int] = {k: i for i, k in enumerate(WEIGHT_KEYS)}
 WEIGHT_ID: Dict[str, int] = {n: i for i, (n, _) in enumerate(WEIGHT_TABLE)}
 N_WEIGHTS = len(WEIGHT_TABLE)
 BUF: Dict[str, int] = {n.replace('TGGCN_BUF_', ''): i for i, n in enumerate(BUF_NAMES)}
+
+ABI_VERSION = int(re.search(r'#define TGGCN_ABI_VERSION\s+(\d+)', open(HEADER).read()).group(1))
 
 _lib = None
 
@@ -143,7 +146,7 @@ def lib():
     L.tggcn_f1_at_k.restype = C.c_int
     L.tggcn_f1_at_k.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int64,
                                 C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
-    if L.tggcn_abi_version() != 7:
+    if L.tggcn_abi_version() != ABI_VERSION:
         raise TggcnError('lib2ggcn_b200.so ABI version mismatch; rebuild')
     _lib = L
     return L

@@ -272,11 +272,16 @@ static int forward_impl(const tggcn_dims* dims, const void* const* weights, int 
         TGGCN_W_GCN_S2_B, TGGCN_W_GEO_MLP0_W, TGGCN_W_GEO_MLP0_B, TGGCN_W_GEO_MLP2_W, TGGCN_W_GEO_MLP2_B,
         TGGCN_W_HUM_EMB_W, TGGCN_W_HUM_EMB_B, TGGCN_W_OBJ_EMB_W, TGGCN_W_OBJ_EMB_B, TGGCN_W_GEO_BD_W, TGGCN_W_HUM_BD_W,
         TGGCN_W_OBJ_BD_W, TGGCN_W_MSG_HO_W, TGGCN_W_MSG_OH_W, TGGCN_W_MSG_OO_W, TGGCN_W_MSG_GO_W, TGGCN_W_SMSG_HO_W,
-        TGGCN_W_SMSG_OH_W, TGGCN_W_SMSG_OO_W, TGGCN_W_UPD_H_W, TGGCN_W_UPD_O_W, TGGCN_W_HSEG_F_WIH, TGGCN_W_OSEG_F_WIH,
+        TGGCN_W_SMSG_OH_W, TGGCN_W_SMSG_OO_W, TGGCN_W_UPD_H_W, TGGCN_W_HSEG_F_WIH, TGGCN_W_OSEG_F_WIH,
         TGGCN_W_HEAD_H_FREC_W, TGGCN_W_HEAD_H_FPRED_W, TGGCN_W_HEAD_H_REC_W, TGGCN_W_HEAD_H_PRED_W};
     for (size_t i = 0; i < sizeof(required) / sizeof(required[0]); ++i)
         TG_REQUIRE(weights[required[i]] != nullptr, "forward: weight #%d is null", required[i]);
     if (d.hh) TG_REQUIRE(W(TGGCN_W_MSG_HH_W) && W(TGGCN_W_SMSG_HH_W), "forward: humans->human weights missing");
+    TG_REQUIRE(d.update_strategy >= 0 && d.update_strategy <= 2, "forward: update_strategy %d unknown", d.update_strategy);
+    if (d.update_strategy != 0)
+        TG_REQUIRE(H == 1 && !d.human_seg_given && !d.object_seg_given && (d.update_strategy == 1 || !d.filter),
+                   "forward: update_strategy 'sah'/'coh' acts with one human and sampled gates only ('coh' without the filter); pass 0 otherwise");
+    if (d.update_strategy != 1) TG_REQUIRE(W(TGGCN_W_UPD_O_W) && W(TGGCN_W_UPD_O_B), "forward: object gate weights missing");
     if (d.C_aff > 0) TG_REQUIRE(W(TGGCN_W_HEAD_O_REC_W) && W(TGGCN_W_HEAD_O_FREC_W), "forward: object head weights missing");
 
     float* scratch = buf(TGGCN_BUF_SEG_SCRATCH);
@@ -391,6 +396,7 @@ static int forward_impl(const tggcn_dims* dims, const void* const* weights, int 
         FrameMsgParams P;
         memset(&P, 0, sizeof(P));
         P.B = B; P.T = T; P.H = H; P.O = O; P.D = D; P.hh = d.hh; P.thr = d.thr; P.mean_pool = d.mean_pool; P.att_noscale = d.att_noscale;
+        P.update_strategy = d.update_strategy;
         P.s_h = buf(TGGCN_BUF_S_H); P.s_o = buf(TGGCN_BUF_S_O);
         P.msg_hh = buf(TGGCN_BUF_MSG_HH); P.msg_ho = buf(TGGCN_BUF_MSG_HO); P.msg_oh = buf(TGGCN_BUF_MSG_OH);
         P.msg_oo = buf(TGGCN_BUF_MSG_OO); P.msg_go = buf(TGGCN_BUF_MSG_GO);

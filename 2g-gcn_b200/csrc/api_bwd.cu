@@ -209,7 +209,8 @@ int tggcn_backward_ex(const tggcn_dims* dims, const void* const* weights, void* 
             for (int id = TGGCN_W_HEAD_O_FREC_W; id <= TGGCN_W_HEAD_O_PRED_B; ++id)
                 TG_REQUIRE(weights[id] && grad_weights[id], "backward: object head pointer #%d is null", id);
         if (!d.human_seg_given) TG_REQUIRE(G(TGGCN_W_UPD_H_W) && G(TGGCN_W_UPD_H_B), "backward: human gate gradient pointers missing");
-        if (!d.object_seg_given) TG_REQUIRE(G(TGGCN_W_UPD_O_W) && G(TGGCN_W_UPD_O_B), "backward: object gate gradient pointers missing");
+        if (!d.object_seg_given && d.update_strategy != 1)
+            TG_REQUIRE(G(TGGCN_W_UPD_O_W) && G(TGGCN_W_UPD_O_B), "backward: object gate gradient pointers missing");
     }
 
     // weight gradient dW[N,K] (+)= (Z (.) [mask > 0])^T X with an optional row shift of X inside blocks of `period` rows:
@@ -442,6 +443,7 @@ int tggcn_backward_ex(const tggcn_dims* dims, const void* const* weights, void* 
         FrameBwdParams P;
         memset(&P, 0, sizeof(P));
         P.B = B; P.T = T; P.H = H; P.O = O; P.D = D; P.hh = d.hh; P.filter = d.filter; P.thr = d.thr; P.mean_pool = d.mean_pool; P.att_noscale = d.att_noscale;
+        P.update_strategy = d.update_strategy;
         P.s_h = buf(TGGCN_BUF_S_H); P.s_o = buf(TGGCN_BUF_S_O);
         P.msg_hh = buf(TGGCN_BUF_MSG_HH); P.msg_ho = buf(TGGCN_BUF_MSG_HO); P.msg_oh = buf(TGGCN_BUF_MSG_OH);
         P.msg_oo = buf(TGGCN_BUF_MSG_OO); P.msg_go = buf(TGGCN_BUF_MSG_GO);
@@ -462,7 +464,7 @@ int tggcn_backward_ex(const tggcn_dims* dims, const void* const* weights, void* 
             TG_CUDA_OK(cudaMemsetAsync(P.dw_uh, 0, sizeof(float) * (size_t)(2 + nkh) * D, stream));
             TG_CUDA_OK(cudaMemsetAsync(P.db_uh, 0, sizeof(float), stream));
         }
-        if (!d.object_seg_given) {
+        if (!d.object_seg_given && d.update_strategy != 1) {
             TG_CUDA_OK(cudaMemsetAsync(P.dw_uo, 0, sizeof(float) * (size_t)5 * D, stream));
             TG_CUDA_OK(cudaMemsetAsync(P.db_uo, 0, sizeof(float), stream));
         }

@@ -149,15 +149,19 @@ __global__ void __launch_bounds__(256) frame_bwd_kernel(const FrameBwdParams P) 
         for (int i = tid; i < O * O; i += 256) a_oo[(i / O) * FB_MAXE + i % O] = al[H * H + 2 * H * O + i];
     }
     // ---- gates: straight-through / filter rule, Gumbel-sigmoid, sigmoid -----------------------------------------
-    if (tid < NE) {
-        const bool is_h = tid < H;
+    // update_strategy (one human, models.py:1523-1532): 'sah' — the object gates ARE the human's, so everything that reaches them is
+    // handed to the human's soft gate; 'coh' — hard_o = st(y_o) * st(y_h): each factor receives the other's decision as its weight.
+    if (tid < 32) {                             // NE <= 32: warp 0, one lane per entity
+        const int strat = P.update_strategy;
+        const bool act = tid < NE, is_h = tid < H;
         const int r = is_h ? tid : tid - H, E = is_h ? H : O;
         const float* given = is_h ? P.human_seg : P.object_seg;
-        float dl_ = 0.0f;
-        if (given == nullptr) {
+        const bool sampled = act && given == nullptr;
+        float dy = 0.0f, hand_over = 0.0f, y = 0.0f;
+        if (sampled) {
             const float* soft = is_h ? P.y_hss : P.y_oss;
             const size_t oi = (size_t)(b * T + t) * E + r;
-            const float y = soft[oi];
+            y = soft[oi];
             float dhard = (is_h ? P.du_h : P.du_o)[oi];
             const float* dyh = is_h ? P.dy_hs : P.dy_os;
             if (dyh != nullptr) dhard += dyh[oi];
@@ -169,14 +173,27 @@ __global__ void __launch_bounds__(256) frame_bwd_kernel(const FrameBwdParams P) 
             } else {
                 pass = t == T - 1 ? 0.0f : 1.0f;                // last step overwritten by 1 (models.py:701-702)
             }
-            float dy = dhard * pass;
+            dy = dhard * pass;
+            if (strat == 2 && !is_h) {
+                const float yh = P.y_hss[(size_t)(b * T + t) * H];
+                hand_over = dy * (y > P.thr ? 1.0f : 0.0f);
+                dy *= yh > P.thr ? 1.0f : 0.0f;
+            }
             const float* dys = is_h ? P.dy_hss : P.dy_oss;
             if (dys != nullptr) dy += dys[oi];
+            if (strat == 1 && !is_h) { hand_over = dy; dy = 0.0f; }
+        }
+        if (strat != 0) {
+            const float total = warp_sum(hand_over);
+            if (tid == 0) dy += total;
+        }
+        float dl_ = 0.0f;
+        if (sampled && !(strat == 1 && !is_h)) {
             const float p = P.pgate[(size_t)n * NE + tid];
             // y = sigmoid(log(p+eps) - log(1-p+eps) + g0 - g1), p = sigmoid(logit)
             dl_ = dy * y * (1.0f - y) * (1.0f / (p + 1e-20f) + 1.0f / ((1.0f - p) + 1e-20f)) * p * (1.0f - p);
         }
-        dlogit[tid] = dl_;
+        if (act) dlogit[tid] = dl_;
     }
     __syncthreads();
     // ---- gradient of the aggregated messages and the direct parts of d[x|h] ----------------------------------------
@@ -193,6 +210,14 @@ __global__ void __launch_bounds__(256) frame_bwd_kernel(const FrameBwdParams P) 
         const int k = i / D, c = i - k * D;
         const float* dx = P.dxx_o + ((size_t)n * O + k) * 4 * D;
         const float g = dlogit[H + k];
+        if (P.w_uo == nullptr) {                                                        // 'sah': no object gate MLP
+            ds[(H + k) * D2 + c] = 0.0f;
+            ds[(H + k) * D2 + D + c] = dx[c];
+            dmo[k * 3 * D + c] = dx[D + c];
+            dmo[k * 3 * D + D + c] = dx[2 * D + c];
+            dmo[k * 3 * D + 2 * D + c] = dx[3 * D + c];
+            continue;
+        }
         ds[(H + k) * D2 + c] = g * __ldg(P.w_uo + c);
         ds[(H + k) * D2 + D + c] = g * __ldg(P.w_uo + D + c) + dx[c];
         dmo[k * 3 * D + c] = dx[D + c] + g * __ldg(P.w_uo + D2 + c);                    // m_ho   (gate order x,h,m_ho,m_oo,m_go)
@@ -211,7 +236,7 @@ __global__ void __launch_bounds__(256) frame_bwd_kernel(const FrameBwdParams P) 
         }
         if (tid == 0) { float v = 0.0f; for (int h = 0; h < H; ++h) v += dlogit[h]; atomicAdd(P.db_uh, v); }
     }
-    if (P.object_seg == nullptr) {
+    if (P.object_seg == nullptr && P.dw_uo != nullptr) {
         for (int k = tid; k < 5 * D; k += 256) {
             float v = 0.0f;
             for (int o = 0; o < O; ++o) {

@@ -77,6 +77,7 @@ struct FrameBwdParams {
     int B, T, H, O, D, hh, filter;
     int mean_pool;                                 // uniform sender weights: no gradient through attention logits
     int att_noscale;                               // attention_style 'v2': plain dot-product logits
+    int update_strategy;                           // 0 'ind', 1 'sah', 2 'coh' (tggcn_dims.update_strategy)
     float thr;
     const float* s_h; const float* s_o;            // (B,T,E,2D)
     const float* msg_hh; const float* msg_ho; const float* msg_oh; const float* msg_oo; const float* msg_go;

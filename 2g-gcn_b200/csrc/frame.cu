@@ -148,19 +148,14 @@ __global__ void __launch_bounds__(FM_THREADS) frame_messages_kernel(const FrameM
     }
     __syncthreads();
     // -- segmentation gates, one warp per entity -----------------------------------------------------------
-    const int n_sampled = (P.human_seg ? 0 : H) + (P.object_seg ? 0 : O);
-    for (int e = warp; e < NE; e += FM_THREADS / 32) {
+    // update_strategy (models.py:1523-1532, one human only): 'sah' — the object warps evaluate the HUMAN's gate and publish it as
+    // their own (no object MLP, no noise of their own); 'coh' — they evaluate both and multiply the hard decisions.
+    const int strat = P.update_strategy;
+    const int n_sampled = (P.human_seg ? 0 : H) + ((P.object_seg || strat == 1) ? 0 : O);
+    // sampled gate of entity e: soft value y, hard decision z in {0, 1}, sigmoid probability p (all lanes call; lane 0 holds the result)
+    auto sample_gate = [&](int e, float& y, float& z, float& p) {
         const bool is_h = e < H;
         const int r = is_h ? e : e - H;
-        const float* given = is_h ? P.human_seg : P.object_seg;
-        float* y_hard = is_h ? P.y_hs : P.y_os;
-        float* y_soft = is_h ? P.y_hss : P.y_oss;
-        const int E = is_h ? H : O;
-        const size_t oi = (size_t)(b * T + t) * E + r;
-        if (given != nullptr) {
-            if (lane == 0) { const float v = __ldg(given + oi); y_hard[oi] = v; y_soft[oi] = v; }
-            continue;
-        }
         const float* w = is_h ? P.w_uh : P.w_uo;
         float acc = 0.0f;
         const float* s = sv + e * D2;
@@ -177,19 +172,40 @@ __global__ void __launch_bounds__(FM_THREADS) frame_messages_kernel(const FrameM
             }
         }
         acc = warp_sum(acc);
+        const float logit = acc + __ldg(is_h ? P.b_uh : P.b_uo);
+        p = 1.0f / (1.0f + expf(-logit));
+        const int pos = is_h ? r : (P.human_seg ? 0 : H) + r;
+        const float* g = P.noise + ((size_t)(t * n_sampled + pos) * P.B + b) * 2;
+        const float la = logf(p + 1e-20f) + __ldg(g);
+        const float lb = logf((1.0f - p) + 1e-20f) + __ldg(g + 1);
+        const float mx = fmaxf(la, lb);
+        const float ea = expf(la - mx), eb = expf(lb - mx);
+        y = ea / (ea + eb);
+        z = y > P.thr ? 1.0f : 0.0f;
+    };
+    for (int e = warp; e < NE; e += FM_THREADS / 32) {
+        const bool is_h = e < H;
+        const int r = is_h ? e : e - H;
+        const float* given = is_h ? P.human_seg : P.object_seg;
+        float* y_hard = is_h ? P.y_hs : P.y_os;
+        float* y_soft = is_h ? P.y_hss : P.y_oss;
+        const int E = is_h ? H : O;
+        const size_t oi = (size_t)(b * T + t) * E + r;
+        if (given != nullptr) {
+            if (lane == 0) { const float v = __ldg(given + oi); y_hard[oi] = v; y_soft[oi] = v; }
+            continue;
+        }
+        float y, z, p;
+        sample_gate((!is_h && strat == 1) ? 0 : e, y, z, p);
+        float human_hard = 1.0f;
+        if (!is_h && strat == 2) {
+            float yh, zh, ph;
+            sample_gate(0, yh, zh, ph);
+            human_hard = (zh - yh) + yh;
+        }
         if (lane == 0) {
-            const float logit = acc + __ldg(is_h ? P.b_uh : P.b_uo);
-            const float p = 1.0f / (1.0f + expf(-logit));
             if (P.pgate_save != nullptr) P.pgate_save[(size_t)n * NE + e] = p;
-            const int pos = is_h ? r : (P.human_seg ? 0 : H) + r;
-            const float* g = P.noise + ((size_t)(t * n_sampled + pos) * P.B + b) * 2;
-            const float la = logf(p + 1e-20f) + __ldg(g);
-            const float lb = logf((1.0f - p) + 1e-20f) + __ldg(g + 1);
-            const float mx = fmaxf(la, lb);
-            const float ea = expf(la - mx), eb = expf(lb - mx);
-            const float y = ea / (ea + eb);
-            const float z = y > P.thr ? 1.0f : 0.0f;
-            float hard = (z - y) + y;                 // straight-through value, distributions.py:35
+            float hard = ((z - y) + y) * human_hard;  // straight-through value, distributions.py:35 (x the human's under 'coh')
             if (t == T - 1) hard = 1.0f;              // models.py:701-702, :744-745
             y_soft[oi] = y;
             y_hard[oi] = hard;

@@ -8,6 +8,7 @@ struct FrameMsgParams {
     int B, T, H, O, D, hh;
     int mean_pool;          // message_aggregation 'mp': uniform weights over the valid senders instead of attention
     int att_noscale;        // attention_style 'v2': plain dot-product logits
+    int update_strategy;    // 0 'ind', 1 'sah' (object gates = the single human's), 2 'coh' (hard object gate x the human's)
     float thr;
     const float* s_h;       // (B,T,H,2D) [x | h]
     const float* s_o;       // (B,T,O,2D)

@@ -30,6 +30,8 @@ _V2 = {'v2', 'dot-product'}
 _NONREL = {'v2', 'non-relational'}
 _GENERIC = {'v1', 'generic'}
 _IND = {'ind', 'independent'}
+_SAH = {'sah', 'same_as_human'}
+_COH = {'coh', 'conditional_on_human'}
 
 
 def _mlp(dims, acts):
@@ -122,7 +124,7 @@ class TGGCN(nn.Module):
         if message_granularity not in _GENERIC: unsupported.append("message_granularity != 'v1'")
         if message_aggregation not in _ATT | _MP: unsupported.append("message_aggregation not in {'att', 'mp'}")
         if attention_style not in _V3 | _V2: unsupported.append("attention_style not in {'v2', 'v3'}")
-        if object_segment_update_strategy not in _IND: unsupported.append("object_segment_update_strategy != 'ind'")
+        if object_segment_update_strategy not in _IND | _SAH | _COH: unsupported.append('unknown object_segment_update_strategy')
         if add_segment_length or add_time_position: unsupported.append('time/length position features')
         if not bias: unsupported.append('bias=False')
         if hidden_size % 16 != 0: unsupported.append('hidden_size not a multiple of 16')
@@ -187,7 +189,8 @@ class TGGCN(nn.Module):
             self.geometry_to_object_message_att_mlp = _mlp([4 * D, 1], ['relu'])
             self.geometry_to_object_segment_message_att_mlp = _mlp([2 * D, 1], ['relu'])
         self.update_human_segment_mlp = _mlp([D * (2 + (1 if hh else 0) + 1), 1], ['sigmoid'])
-        self.update_object_segment_mlp = _mlp([5 * D, 1], ['sigmoid'])
+        if object_segment_update_strategy not in _SAH:            # models.py:537: no object gate MLP under 'sah'
+            self.update_object_segment_mlp = _mlp([5 * D, 1], ['sigmoid'])
         label_in = (4 if self.cat_level_states else 2) * D        # models.py:553-555
         self.human_recognition_mlp = _mlp([label_in, n_sub], ['logsoftmax'])
         self.human_prediction_mlp = _mlp([label_in, n_sub], ['logsoftmax'])
@@ -389,7 +392,19 @@ class TGGCN(nn.Module):
                         mean_pool=int(self.message_aggregation in _MP), recurrent_mode=int(self.recurrent_mode),
                         no_fp16_split=int(self.no_fp16_split), precision=int(self.precision),
                         att_noscale=int(self.attention_style in _V2))
-        n_sampled = (0 if hseg is not None else H) + (0 if oseg is not None else O)
+        # object_segment_update_strategy (models.py:741-742, :1523-1532): 'sah' / 'coh' act with exactly one human; with more the
+        # reference falls back to 'ind' ('sah' then has no object gate MLP to fall back on and fails there too)
+        strat = 1 if self.object_segment_update_strategy in _SAH else 2 if self.object_segment_update_strategy in _COH else 0
+        if strat == 1 and H != 1 and oseg is None:
+            raise ValueError("object_segment_update_strategy 'sah' needs exactly one human (the reference has no object gate MLP)")
+        if strat and H == 1 and oseg is None:
+            if hseg is not None:
+                raise NotImplementedError("object_segment_update_strategy 'sah'/'coh' with an imposed human_segmentation: the "
+                                          "reference writes the last step's 1.0 into the caller's tensor (models.py:744-745)")
+            if strat == 1 or not self.filter_discrete_updates:       # under the filter 'coh' equals 'ind' (models.py:751-753)
+                dims.update_strategy = strat
+        objects_sampled = oseg is None and dims.update_strategy != 1
+        n_sampled = (0 if hseg is not None else H) + (O if objects_sampled else 0)
         noise = None
         if n_sampled:
             noise = self._noise_override

@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define TGGCN_ABI_VERSION 7
+#define TGGCN_ABI_VERSION 8
 
 #if defined(__GNUC__)
 #define TGGCN_API __attribute__((visibility("default")))
@@ -63,6 +63,10 @@ typedef struct tggcn_dims {
                                     kernels (BASELINE.json configs[2]); gate / softmax / loss arithmetic stays fp32           */
     int32_t att_noscale;         /* attention_style 'v2' / 'dot-product': logits <q, k> without the 1/sqrt(size) factor of 'v3'
                                     (compute_attention_weights, models.py:1740-1745)                                           */
+    int32_t update_strategy;     /* object_segment_update_strategy (models.py:1523-1532): 0 = 'ind'; 1 = 'sah': with exactly one human
+                                    and no objects_segmentation the object gates (hard and soft) ARE the human's, no object gate MLP,
+                                    no noise drawn for objects; 2 = 'coh': hard object gate = own decision x the human's hard gate
+                                    (one human, no local-maximum filter; otherwise identical to 'ind')                          */
 } tggcn_dims;
 
 /* Parameter table.  One device pointer per reference state_dict() entry, in this order

@@ -63,6 +63,11 @@ CASES = [
     ('cad120_s2_mp', 'cad120', 32, 2, 11, 2, False, 2.0, False, {'message_aggregation': 'mp'}),
     ('mphoi_s2_dot', 'mphoi', 32, 2, 12, 2, False, 2.0, False, {'attention_style': 'v2'}),
     ('cad120_s2_dot', 'cad120', 32, 2, 11, 2, False, 2.0, False, {'attention_style': 'v2'}),
+    # object_segment_update_strategy (models.py:1523-1532; acts with exactly one human = CAD-120).  Under the local-maximum
+    # filter 'coh' equals 'ind' (the filter recomputes the hard gates from the soft ones, :751-753), so it is pinned without it.
+    ('cad120_s2_sah', 'cad120', 32, 2, 11, 2, False, 2.0, False, {'object_segment_update_strategy': 'sah'}),
+    ('cad120_nf_sah', 'cad120', 32, 2, 11, 2, False, 2.0, False, {'object_segment_update_strategy': 'sah', 'filter_discrete_updates': 0, 'update_segment_threshold': 0.5}),
+    ('cad120_nf_coh', 'cad120', 32, 2, 11, 2, False, 2.0, False, {'object_segment_update_strategy': 'coh', 'filter_discrete_updates': 0, 'update_segment_threshold': 0.5}),
     # the benchmarked configuration itself (BASELINE.json configs[1]: MPHOI, B=8, T=128, hidden 512, stage-2 settings)
     ('mphoi_s2_d512_full', 'mphoi', 512, 8, 128, 2, False, 1.0, False),
 ]
@@ -88,13 +93,14 @@ def run_case(name, shape_name, D, B, T, stage, train_mode, gain, inspect, extra=
     for attempt in range(50):
         data_seed, noise_seed = 100 + attempt, 500 + attempt
         batch = pkg.make_batch(shape, B, T, seed=data_seed)
-        n_calls = orc.num_noise_draws(T, shape.H, shape.O, stage == 1, stage == 1 and shape.dataset == 'cad120')
+        n_calls = orc.num_noise_draws(T, shape.H, shape.O, stage == 1, stage == 1 and shape.dataset == 'cad120',
+                                      kw['object_segment_update_strategy'])
         noise = orc.draw_noise(max(n_calls, 1), B, torch.Generator().manual_seed(noise_seed))[:n_calls]
         if name in CASE_MARGIN and not train_mode:
             # big cases: pre-screen both human and object gates on the oracle's early exit before paying for the reference
             with torch.no_grad():
                 _, s_h, _, s_o = orc.forward({k: v.double() for k, v in sd.items()},
-                                             orc.OracleConfig(D, shape.V, shape.num_classes, shape.hh, stage == 2, thr),
+                                             orc.config_from_kwargs(kw),
                                              batch['x_human'].double(), batch['x_objects'].double(), batch['objects_mask'].double(),
                                              None, None, noise.double(), gates_only=True)
             pre = 1.0
@@ -128,7 +134,7 @@ def run_case(name, shape_name, D, B, T, stage, train_mode, gain, inspect, extra=
         margin = 1.0
         for s in sampled:
             margin = min(margin, float((s - thr).abs().min()))
-            if stage == 2:
+            if kw['filter_discrete_updates']:
                 margin = min(margin, float((s[:, 1:] - s[:, :-1]).abs().min()))
         if margin > CASE_MARGIN.get(name, 1e-4):
             break
@@ -136,8 +142,7 @@ def run_case(name, shape_name, D, B, T, stage, train_mode, gain, inspect, extra=
         raise RuntimeError(f'no seed with a safe gate margin for {name}')
     # oracle agreement (also guards MPHOI object gates, which the reference does not return)
     p64 = {k: v.double() for k, v in sd.items()}
-    ocfg = orc.OracleConfig(D, shape.V, shape.num_classes, shape.hh, stage == 2, thr, bool(extra.get('cat_level_states', 0)), extra.get('message_aggregation') in ('mp', 'mean_pooling'),
-                                     extra.get('attention_style') not in ('v2', 'dot-product'))
+    ocfg = orc.config_from_kwargs(kw)
     hseg = torch.ones(B, T, shape.H) if stage == 1 else None
     oseg = torch.ones(B, T, shape.O) if (stage == 1 and shape.dataset == 'cad120') else None
     taps = {}
@@ -192,6 +197,9 @@ GRAD_CASES = [
     ('grad_cad120_s2_mp', 'cad120', 32, 2, 8, 2, 2.0, {'message_aggregation': 'mp'}),
     ('grad_mphoi_s2_dot', 'mphoi', 32, 2, 9, 2, 2.0, {'attention_style': 'v2'}),
     ('grad_cad120_s2_dot', 'cad120', 32, 2, 8, 2, 2.0, {'attention_style': 'v2'}),
+    ('grad_cad120_s2_sah', 'cad120', 32, 2, 8, 2, 2.0, {'object_segment_update_strategy': 'sah'}),
+    ('grad_cad120_nf_sah', 'cad120', 32, 2, 8, 2, 2.0, {'object_segment_update_strategy': 'sah', 'filter_discrete_updates': 0, 'update_segment_threshold': 0.5}),
+    ('grad_cad120_nf_coh', 'cad120', 32, 2, 8, 2, 2.0, {'object_segment_update_strategy': 'coh', 'filter_discrete_updates': 0, 'update_segment_threshold': 0.5}),
     # hidden 512 (the benchmarked width), T = 32: the D=512 BPTT and split-K weight-gradient paths against the reference itself
     ('grad_mphoi_s2_d512', 'mphoi', 512, 8, 32, 2, 1.0),
 ]
@@ -248,12 +256,12 @@ def run_grad_case(name, shape_name, D, B, T, stage, gain, extra=None):
     for attempt in range(50):
         data_seed, noise_seed = 300 + attempt, 700 + attempt
         batch = pkg.make_batch(shape, B, T, seed=data_seed)
-        n_calls = orc.num_noise_draws(T, shape.H, shape.O, stage == 1, stage == 1 and shape.dataset == 'cad120')
+        n_calls = orc.num_noise_draws(T, shape.H, shape.O, stage == 1, stage == 1 and shape.dataset == 'cad120',
+                                      kw['object_segment_update_strategy'])
         noise = orc.draw_noise(max(n_calls, 1), B, torch.Generator().manual_seed(noise_seed))[:n_calls]
         # margin check on the fp64 oracle (covers object gates that MPHOI does not return)
         p64 = {k: v.double() for k, v in sd.items()}
-        ocfg = orc.OracleConfig(D, shape.V, shape.num_classes, shape.hh, stage == 2, thr, bool(extra.get('cat_level_states', 0)), extra.get('message_aggregation') in ('mp', 'mean_pooling'),
-                                     extra.get('attention_style') not in ('v2', 'dot-product'))
+        ocfg = orc.config_from_kwargs(kw)
         hseg = torch.ones(B, T, shape.H) if stage == 1 else None
         oseg = torch.ones(B, T, shape.O) if (stage == 1 and shape.dataset == 'cad120') else None
         taps = {}
@@ -266,7 +274,7 @@ def run_grad_case(name, shape_name, D, B, T, stage, gain, extra=None):
         margin = 1.0
         for sft in softs:
             margin = min(margin, float((sft - thr).abs().min()))
-            if stage == 2:
+            if kw['filter_discrete_updates']:
                 margin = min(margin, float((sft[:, 1:] - sft[:, :-1]).abs().min()))
         if margin > CASE_MARGIN.get(name, 1e-4) and (name not in RELU_STABLE_CASES or _relu_margin(p64, ocfg, batch, hseg, oseg, noise, n_calls) > 2e-5):
             break

@@ -43,6 +43,20 @@ class OracleConfig:
     cat_level_states: bool = False          # models.py:901-903 (share_level_mlps changes no arithmetic: same tensors, two names)
     mean_pool: bool = False                 # message_aggregation 'mp' (models.py:1033-1036 and the other message functions)
     att_scaled: bool = True                 # attention_style 'v3' (scaled dot product); False = 'v2' (models.py:1740-1745)
+    update_strategy: str = 'ind'            # object_segment_update_strategy 'ind' | 'sah' | 'coh' (models.py:1523-1532); 'sah' and
+                                            # 'coh' only differ from 'ind' with exactly one human (models.py:741-742)
+
+
+_UPD = {'independent': 'ind', 'ind': 'ind', 'same_as_human': 'sah', 'sah': 'sah', 'conditional_on_human': 'coh', 'coh': 'coh'}
+
+
+def config_from_kwargs(kw: dict) -> OracleConfig:
+    """OracleConfig of a TGGCN constructor-kwargs dict (``cfg.parameters`` of the yaml files + input_size / num_classes)."""
+    return OracleConfig(kw['hidden_size'], kw['gcn_node'], tuple(kw['num_classes']), bool(kw['message_humans_to_human']),
+                        bool(kw['filter_discrete_updates']), float(kw['update_segment_threshold']),
+                        bool(kw.get('cat_level_states', 0)), kw.get('message_aggregation') in ('mp', 'mean_pooling'),
+                        kw.get('attention_style') not in ('v2', 'dot-product'),
+                        _UPD[kw.get('object_segment_update_strategy', 'ind')])
 
 
 # ----------------------------------------------------------------------------------------------
@@ -277,11 +291,15 @@ def forward(p: Dict[str, Tensor], cfg: OracleConfig, x_human: Tensor, x_objects:
                 taps.setdefault('m_oo', {})[(t, k)] = m_oo
             if objects_segmentation is not None:                        # :738-739
                 hard_o[k][t] = soft_o[k][t] = objects_segmentation[:, t:t + 1, k]
-            else:                                                       # :1500-1533 ('ind'); input order :1527
+            elif cfg.update_strategy == 'sah' and H == 1:               # :741-742, :1523-1525: the human's decision, no object MLP
+                hard_o[k][t], soft_o[k][t] = hard_h[0][t], soft_h[0][t]
+            else:                                                       # :1500-1533 ('ind' / 'coh'); input order :1527
                 gate_in = torch.cat([x_o[:, t, k], h_o[:, t, k], m_ho, m_oo, m_go], dim=-1)
                 prob = torch.sigmoid(_lin(p, 'update_object_segment_mlp.0', gate_in))
                 ysoft = gumbel_sigmoid(prob, next(noise_it) if noise_it is not None else None)
                 z = hard_gate(ysoft, thr)
+                if cfg.update_strategy == 'coh' and H == 1:             # :1531-1532: object updates only where the human does
+                    z = z * hard_h[0][t]
                 if t == T - 1:
                     z = torch.ones_like(z)
                 hard_o[k][t], soft_o[k][t] = z, ysoft
@@ -376,9 +394,11 @@ def _seg_cell(p, cell: str, x: Tensor, u: Tensor, h: Tensor) -> Tensor:
     return u * new + (1.0 - u) * h
 
 
-def num_noise_draws(T: int, H: int, O: int, human_given: bool, objects_given: bool) -> int:
-    """Number of (B,2) Gumbel draws one forward consumes (vhoi/models.py:697-702, :738-745)."""
-    return T * ((0 if human_given else H) + (0 if objects_given else O))
+def num_noise_draws(T: int, H: int, O: int, human_given: bool, objects_given: bool, update_strategy: str = 'ind') -> int:
+    """Number of (B,2) Gumbel draws one forward consumes (vhoi/models.py:697-702, :738-745); under 'sah' with one human the
+    objects copy the human's decision and draw nothing (:1523-1525)."""
+    objects_sampled = not objects_given and not (_UPD[update_strategy] == 'sah' and H == 1)
+    return T * ((0 if human_given else H) + (O if objects_sampled else 0))
 
 
 def draw_noise(n_calls: int, B: int, generator: Optional[torch.Generator] = None) -> Tensor:

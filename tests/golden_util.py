@@ -24,6 +24,9 @@ CASES = {
     'cad120_s2_mp': ('cad120', 32, 2, 11, 2, False, False, {'message_aggregation': 'mp'}),
     'mphoi_s2_dot': ('mphoi', 32, 2, 12, 2, False, False, {'attention_style': 'v2'}),
     'cad120_s2_dot': ('cad120', 32, 2, 11, 2, False, False, {'attention_style': 'v2'}),
+    'cad120_s2_sah': ('cad120', 32, 2, 11, 2, False, False, {'object_segment_update_strategy': 'sah'}),
+    'cad120_nf_sah': ('cad120', 32, 2, 11, 2, False, False, {'object_segment_update_strategy': 'sah', 'filter_discrete_updates': 0, 'update_segment_threshold': 0.5}),
+    'cad120_nf_coh': ('cad120', 32, 2, 11, 2, False, False, {'object_segment_update_strategy': 'coh', 'filter_discrete_updates': 0, 'update_segment_threshold': 0.5}),
 }
 
 # BASELINE.json configs[1] itself — what bench.py times (reference outputs; gate margin 2.5e-5).  Kept apart from CASES: the
@@ -45,6 +48,9 @@ GRAD_CASES = {
     'grad_cad120_s2_mp': ('cad120', 32, 2, 8, 2, {'message_aggregation': 'mp'}),
     'grad_mphoi_s2_dot': ('mphoi', 32, 2, 9, 2, {'attention_style': 'v2'}),
     'grad_cad120_s2_dot': ('cad120', 32, 2, 8, 2, {'attention_style': 'v2'}),
+    'grad_cad120_s2_sah': ('cad120', 32, 2, 8, 2, {'object_segment_update_strategy': 'sah'}),
+    'grad_cad120_nf_sah': ('cad120', 32, 2, 8, 2, {'object_segment_update_strategy': 'sah', 'filter_discrete_updates': 0, 'update_segment_threshold': 0.5}),
+    'grad_cad120_nf_coh': ('cad120', 32, 2, 8, 2, {'object_segment_update_strategy': 'coh', 'filter_discrete_updates': 0, 'update_segment_threshold': 0.5}),
 }
 
 # hidden 512 (the benchmarked width), T = 32.  Kept apart from GRAD_CASES: the reference's own fp32 autograd carries summation
@@ -83,17 +89,15 @@ class GoldenCase:
         H, O = self.shape.H, self.shape.O
         self.human_given = stage == 1
         self.objects_given = stage == 1 and self.shape.dataset == 'cad120'
-        n_calls = orc.num_noise_draws(T, H, O, self.human_given, self.objects_given)
+        n_calls = orc.num_noise_draws(T, H, O, self.human_given, self.objects_given,
+                                      self.kwargs['object_segment_update_strategy'])
         self.noise = orc.draw_noise(max(n_calls, 1), B, torch.Generator().manual_seed(noise_seed))[:n_calls]
         self.hseg = torch.ones(B, T, H) if self.human_given else None
         self.oseg = torch.ones(B, T, O) if self.objects_given else None
         self.targets = synth.target_list(self.shape, synth.make_targets(self.shape, self.batch['lengths'], T,
                                                                         seed=target_seed))
         self.outputs = [torch.from_numpy(self.blob[f'out{i}']) for i in range(6 if self.shape.num_classes[1] is None else 12)]
-        self.ocfg = orc.OracleConfig(D, self.shape.V, self.shape.num_classes, self.shape.hh, stage == 2, self.thr,
-                                     bool(self.extra.get('cat_level_states', 0)),
-                                     self.extra.get('message_aggregation') in ('mp', 'mean_pooling'),
-                                     self.extra.get('attention_style') not in ('v2', 'dot-product'))
+        self.ocfg = orc.config_from_kwargs(self.kwargs)
         # the regenerated inputs must be the bytes the reference saw
         chk = float(self.batch['x_human'].double().sum() + self.batch['x_objects'].double().sum())
         assert abs(chk - float(self.blob['inputs_checksum'][0])) <= 1e-6 * abs(chk), 'synthetic inputs differ from golden run'

@@ -25,7 +25,7 @@ def test_constructor_accepts_yaml_values_and_rejects_the_rest(pkg, synth):
     m = pkg.TGGCN(**kw)
     assert m.filter_discrete_updates and m.update_segment_threshold == pytest.approx(0.1)
     for bad in (dict(message_type='v1'), dict(attention_style='v1'), dict(message_aggregation='max'),
-                dict(object_segment_update_strategy='sah'), dict(add_time_position=1), dict(share_level_mlps=1, bias=False),
+                dict(object_segment_update_strategy='xyz'), dict(add_time_position=1), dict(share_level_mlps=1, bias=False),
                 dict(discrete_networks_num_layers=2), dict(message_geometry_to_human=True), dict(hidden_size=20)):
         with pytest.raises(NotImplementedError):
             pkg.TGGCN(**{**kw, **bad})
@@ -49,6 +49,16 @@ def test_level_state_variants_keep_the_reference_layout(pkg, synth):
     assert not both.share_level_mlps and both.cat_level_states          # models.py:565: no sharing with concatenated inputs
 
 
+def test_update_strategy_variants_keep_the_reference_layout(pkg, synth):
+    """object_segment_update_strategy (vhoi/models.py:537-547): 'sah' has no object gate MLP, 'coh' keeps it."""
+    ind = pkg.TGGCN(**synth.model_kwargs(synth.CAD120, hidden_size=32, stage=2))
+    sah = pkg.TGGCN(**synth.model_kwargs(synth.CAD120, hidden_size=32, stage=2, object_segment_update_strategy='sah'))
+    coh = pkg.TGGCN(**synth.model_kwargs(synth.CAD120, hidden_size=32, stage=2, object_segment_update_strategy='conditional_on_human'))
+    gate = {'update_object_segment_mlp.0.weight', 'update_object_segment_mlp.0.bias'}
+    assert list(coh.state_dict()) == list(ind.state_dict())
+    assert [k for k in ind.state_dict() if k not in gate] == list(sah.state_dict())
+
+
 def test_weight_table_covers_the_state_dict(pkg, synth):
     for name in ('mphoi', 'cad120'):
         model = pkg.TGGCN(**synth.model_kwargs(synth.SHAPES[name], hidden_size=32, stage=1))
@@ -69,9 +79,9 @@ def test_library_loads_and_exports_every_declared_symbol(pkg):
     lib = pkg.abi.lib()
     for sym in declared:
         assert hasattr(lib, sym), sym
-    assert lib.tggcn_abi_version() == 7
-    # struct mirrors: 17 int32 + 1 float + 6 int32; io = 6 + 4 + 8 + 3 + 3 + 1 pointers
-    assert ctypes.sizeof(pkg.abi.Dims) == 25 * 4
+    assert lib.tggcn_abi_version() == pkg.abi.ABI_VERSION == int(re.search(r'#define TGGCN_ABI_VERSION\s+(\d+)', header).group(1))
+    # struct mirrors: 17 int32 + 1 float + 8 int32; io = 6 + 4 + 8 + 3 + 3 + 1 pointers
+    assert ctypes.sizeof(pkg.abi.Dims) == 26 * 4
     assert ctypes.sizeof(pkg.abi.IO) == 25 * 8
     # the status decoder is host-only: healthy words, a barrier time-out, an fp16-split range violation
     words = (ctypes.c_uint32 * 8)()

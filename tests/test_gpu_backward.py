@@ -35,14 +35,12 @@ def _setup(name, orc, synth, pkg):
     synth.deterministic_fill(model.state_dict(), seed=weight_seed, gain=float(blob['gain'][0]))
     batch = synth.make_batch(shape, B, T, seed=data_seed)
     human_given, objects_given = stage == 1, stage == 1 and shape.dataset == 'cad120'
-    n_calls = orc.num_noise_draws(T, shape.H, shape.O, human_given, objects_given)
+    n_calls = orc.num_noise_draws(T, shape.H, shape.O, human_given, objects_given, kw['object_segment_update_strategy'])
     noise = orc.draw_noise(max(n_calls, 1), B, torch.Generator().manual_seed(noise_seed))[:n_calls]
     hseg = torch.ones(B, T, shape.H) if human_given else None
     oseg = torch.ones(B, T, shape.O) if objects_given else None
     targets = synth.target_list(shape, synth.make_targets(shape, batch['lengths'], T, seed=target_seed))
-    ocfg = orc.OracleConfig(D, shape.V, shape.num_classes, shape.hh, stage == 2, kw['update_segment_threshold'],
-                            bool(extra.get('cat_level_states', 0)), extra.get('message_aggregation') in ('mp', 'mean_pooling'),
-                                     extra.get('attention_style') not in ('v2', 'dot-product'))
+    ocfg = orc.config_from_kwargs(kw)
     return dict(blob=blob, shape=shape, stage=stage, model=model, batch=batch, noise=noise if n_calls else None, hseg=hseg,
                 oseg=oseg, targets=targets, ocfg=ocfg, extra=extra)
 

@@ -112,13 +112,11 @@ def test_oracle_gradients_match_reference(name, orc, synth, pkg):
     alias_shared_heads(p, extra)
     batch = synth.make_batch(shape, B, T, seed=data_seed)
     human_given, objects_given = stage == 1, stage == 1 and shape.dataset == 'cad120'
-    n_calls = orc.num_noise_draws(T, shape.H, shape.O, human_given, objects_given)
+    n_calls = orc.num_noise_draws(T, shape.H, shape.O, human_given, objects_given, kw['object_segment_update_strategy'])
     noise = orc.draw_noise(max(n_calls, 1), B, torch.Generator().manual_seed(noise_seed))[:n_calls]
     hseg = torch.ones(B, T, shape.H).double() if human_given else None
     oseg = torch.ones(B, T, shape.O).double() if objects_given else None
-    ocfg = orc.OracleConfig(D, shape.V, shape.num_classes, shape.hh, stage == 2, kw['update_segment_threshold'],
-                            bool(extra.get('cat_level_states', 0)), extra.get('message_aggregation') in ('mp', 'mean_pooling'),
-                                     extra.get('attention_style') not in ('v2', 'dot-product'))
+    ocfg = orc.config_from_kwargs(kw)
     out = orc.forward(p, ocfg, batch['x_human'].double(), batch['x_objects'].double(), batch['objects_mask'].double(),
                       hseg, oseg, noise.double() if n_calls else None, training=True)
     targets = synth.target_list(shape, synth.make_targets(shape, batch['lengths'], T, seed=target_seed))

@@ -23,7 +23,7 @@ class Dims(C.Structure):
                                                                        ('cat_level_states', C.c_int32), ('mean_pool', C.c_int32),
                                                                        ('recurrent_mode', C.c_int32), ('no_fp16_split', C.c_int32),
                                                                        ('precision', C.c_int32), ('att_noscale', C.c_int32),
-                                                                       ('update_strategy', C.c_int32)]
+                                                                       ('update_strategy', C.c_int32), ('time_position', C.c_int32), ('time_periodic', C.c_int32)]
 
 
 class GradOutputs(C.Structure):
@@ -46,7 +46,7 @@ class IO(C.Structure):
         ('out_h', C.c_void_p * 4), ('out_o', C.c_void_p * 4),
         ('att_frame', C.c_void_p), ('att_seg_f', C.c_void_p), ('att_seg_b', C.c_void_p),
         ('bn_running_mean', C.c_void_p), ('bn_running_var', C.c_void_p), ('bn_num_batches', C.c_void_p),
-        ('status_host', C.c_void_p),
+        ('steps_per_example', C.c_void_p), ('time_freq', C.c_void_p), ('status_host', C.c_void_p),
     ]
 
 

@@ -87,8 +87,9 @@ void make_layout(const tggcn_dims& d, Layout& L) {
     sz[TGGCN_BUF_MSG_OH] = N * O * D * f;
     sz[TGGCN_BUF_MSG_OO] = N * O * D * f;
     sz[TGGCN_BUF_MSG_GO] = N * D * f;
-    sz[TGGCN_BUF_XX_H] = N * H * (1 + nkh) * D * f;
-    sz[TGGCN_BUF_XX_O] = N * O * 4 * D * f;
+    sz[TGGCN_BUF_XX_H] = N * H * (size_t)kh_of(d) * f;
+    sz[TGGCN_BUF_XX_O] = N * O * (size_t)ko_of(d) * f;
+    sz[TGGCN_BUF_TIME_EMB] = d.time_position ? N * D * f : 0;
     sz[TGGCN_BUF_GS_H] = N * H * 6 * D * f;
     sz[TGGCN_BUF_GS_O] = N * O * 6 * D * f;
     sz[TGGCN_BUF_HX_H] = N * H * 2 * D * f;
@@ -121,13 +122,13 @@ void make_layout(const tggcn_dims& d, Layout& L) {
     sz[TGGCN_BUF_SALPHA_HO] = sv * 2 * N * O * H * f;
     sz[TGGCN_BUF_SALPHA_OO] = sv * 2 * N * O * O * f;
     {   // operand planes of the largest projection stage (4 bytes per operand element: fp16 hi + lo, or bf16 + slack)
-        const size_t kh = (1 + nkh) * D, KV = 128 * V;
+        const size_t kh = kh_of(d), ko = ko_of(d), KV = 128 * V;
         const size_t st[6] = {N * (H + O) * 2048 + N * KV + 2 * D * 2048 + 2048 * KV,
                               N * 2048 + D * 2048,
                               N * (H + O + 1) * D + 6 * 3 * D * D,
                               N * (H + O + 1) * 2 * D + 3 * D * 2 * D,
                               N * (H + O + 1) * 2 * D + 5 * D * 2 * D,
-                              N * H * kh + N * O * 4 * D + 2 * 3 * D * kh + 2 * 3 * D * 4 * D};
+                              N * H * kh + N * O * ko + 2 * 3 * D * kh + 2 * 3 * D * ko};
         size_t m = 0;
         for (size_t v : st) m = v > m ? v : m;
         sz[TGGCN_BUF_PACK] = m * 4 + 32 * 256;
@@ -147,6 +148,8 @@ int check_dims(const tggcn_dims& d) {
     TG_REQUIRE(d.V >= 1 && d.V <= 32, "dims: gcn_node=%d unsupported", d.V);
     TG_REQUIRE(d.Fh == 2048 + 4 * d.V, "dims: human feature size %d != 2048 + 4*gcn_node", d.Fh);
     TG_REQUIRE(d.C_sub >= 1 && d.C_sub <= 32 && d.C_aff >= 0 && d.C_aff <= 32, "dims: class counts out of range");
+    TG_REQUIRE(d.time_position >= 0 && d.time_position <= 2 && (d.time_periodic == 0 || d.time_periodic == 1),
+               "dims: time_position / time_periodic out of range");
     TG_REQUIRE((size_t)d.B * d.T * (size_t)(d.H > d.O ? d.H : d.O) * 6 * d.D < (1ull << 31),
                "dims: problem too large for 32-bit tile indexing");
     return 0;
@@ -392,11 +395,20 @@ static int forward_impl(const tggcn_dims* dims, const void* const* weights, int 
     if (int rc = project(g)) return rc;
     STAGE_END();
     // 8. attention, aggregation, gates, segment-level inputs
+    if (d.time_position) {      // time-position features of every frame (models.py:656-662 / :755-762)
+        TG_REQUIRE(io->steps_per_example != nullptr, "forward: add_time_position needs steps_per_example");
+        TG_REQUIRE(d.time_periodic ? io->time_freq != nullptr : (W(TGGCN_W_TIME_W) && W(TGGCN_W_TIME_B)),
+                   "forward: time-position parameters missing (time_position_mlp, or the period table of the periodic encoding)");
+        if (int rc = launch_time_embed(io->steps_per_example, W(TGGCN_W_TIME_W), W(TGGCN_W_TIME_B), io->time_freq,
+                                       buf(TGGCN_BUF_TIME_EMB), B, T, D, d.time_periodic, stream))
+            return rc;
+    }
     {
         FrameMsgParams P;
         memset(&P, 0, sizeof(P));
         P.B = B; P.T = T; P.H = H; P.O = O; P.D = D; P.hh = d.hh; P.thr = d.thr; P.mean_pool = d.mean_pool; P.att_noscale = d.att_noscale;
         P.update_strategy = d.update_strategy;
+        P.time_position = d.time_position; P.time_emb = d.time_position ? buf(TGGCN_BUF_TIME_EMB) : nullptr;
         P.s_h = buf(TGGCN_BUF_S_H); P.s_o = buf(TGGCN_BUF_S_O);
         P.msg_hh = buf(TGGCN_BUF_MSG_HH); P.msg_ho = buf(TGGCN_BUF_MSG_HO); P.msg_oh = buf(TGGCN_BUF_MSG_OH);
         P.msg_oo = buf(TGGCN_BUF_MSG_OO); P.msg_go = buf(TGGCN_BUF_MSG_GO);
@@ -418,12 +430,12 @@ static int forward_impl(const tggcn_dims* dims, const void* const* weights, int 
         return rc;
     STAGE_END();
     // 10. hoisted frame-part of the segment cells' W_ih x + b_ih, both directions
-    const int kh = (1 + nkh) * D, ldwh = (1 + 2 * nkh) * D;
+    const int kh = kh_of(d), ldwh = ldwh_of(d), ko = ko_of(d), ldwo = ldwo_of(d);
     g.count = 0;
     gemm_add(g, buf(TGGCN_BUF_XX_H), kh, W(TGGCN_W_HSEG_F_WIH), ldwh, W(TGGCN_W_HSEG_F_BIH), buf(TGGCN_BUF_GS_H), 6 * D, N * H, 3 * D, kh, 0);
     gemm_add(g, buf(TGGCN_BUF_XX_H), kh, W(TGGCN_W_HSEG_B_WIH), ldwh, W(TGGCN_W_HSEG_B_BIH), buf(TGGCN_BUF_GS_H) + 3 * D, 6 * D, N * H, 3 * D, kh, 0);
-    gemm_add(g, buf(TGGCN_BUF_XX_O), 4 * D, W(TGGCN_W_OSEG_F_WIH), 6 * D, W(TGGCN_W_OSEG_F_BIH), buf(TGGCN_BUF_GS_O), 6 * D, N * O, 3 * D, 4 * D, 0);
-    gemm_add(g, buf(TGGCN_BUF_XX_O), 4 * D, W(TGGCN_W_OSEG_B_WIH), 6 * D, W(TGGCN_W_OSEG_B_BIH), buf(TGGCN_BUF_GS_O) + 3 * D, 6 * D, N * O, 3 * D, 4 * D, 0);
+    gemm_add(g, buf(TGGCN_BUF_XX_O), ko, W(TGGCN_W_OSEG_F_WIH), ldwo, W(TGGCN_W_OSEG_F_BIH), buf(TGGCN_BUF_GS_O), 6 * D, N * O, 3 * D, ko, 0);
+    gemm_add(g, buf(TGGCN_BUF_XX_O), ko, W(TGGCN_W_OSEG_B_WIH), ldwo, W(TGGCN_W_OSEG_B_BIH), buf(TGGCN_BUF_GS_O) + 3 * D, 6 * D, N * O, 3 * D, ko, 0);
     if (int rc = project(g)) return rc;
     STAGE_END();
     // 11. segment-level recurrent graph (models.py:785-880)
@@ -434,7 +446,7 @@ static int forward_impl(const tggcn_dims* dims, const void* const* weights, int 
         P.gs_h = buf(TGGCN_BUF_GS_H); P.gs_o = buf(TGGCN_BUF_GS_O);
         P.u_h = io->y_hs; P.u_o = io->y_os; P.om = io->objects_mask;
         P.wih_h[0] = W(TGGCN_W_HSEG_F_WIH); P.wih_h[1] = W(TGGCN_W_HSEG_B_WIH); P.ldw_h = ldwh; P.col_h = kh;
-        P.wih_o[0] = W(TGGCN_W_OSEG_F_WIH); P.wih_o[1] = W(TGGCN_W_OSEG_B_WIH); P.ldw_o = 6 * D; P.col_o = 4 * D;
+        P.wih_o[0] = W(TGGCN_W_OSEG_F_WIH); P.wih_o[1] = W(TGGCN_W_OSEG_B_WIH); P.ldw_o = ldwo; P.col_o = ko;
         P.whh_h[0] = W(TGGCN_W_HSEG_F_WHH); P.whh_h[1] = W(TGGCN_W_HSEG_B_WHH);
         P.bhh_h[0] = W(TGGCN_W_HSEG_F_BHH); P.bhh_h[1] = W(TGGCN_W_HSEG_B_BHH);
         P.whh_o[0] = W(TGGCN_W_OSEG_F_WHH); P.whh_o[1] = W(TGGCN_W_OSEG_B_WHH);

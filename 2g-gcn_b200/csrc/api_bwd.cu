@@ -25,7 +25,7 @@ struct BwdLayout {
         return o;
     }
     size_t dhfr[3], dhx[2], dgs[2], dghs[2], du[2], direct[2], dmg[2], dpre[2], lgr[4], lgs[4], dpre_all[4], gru_direct[3];
-    size_t dxx[2], ds[3], dmsg[5], dgi[3], dgh[3], bigru_scratch, dgeo_hid, dgcn_out, dxn, wt_seg, wt, tn, tn_floats;
+    size_t dtime, dxx[2], ds[3], dmsg[5], dgi[3], dgh[3], bigru_scratch, dgeo_hid, dgcn_out, dxn, wt_seg, wt, tn, tn_floats;
     size_t zero_begin, zero_end;     // region that must be zero before the kernels run (atomically accumulated)
 };
 
@@ -56,8 +56,9 @@ void make_bwd_layout(const tggcn_dims& d, BwdLayout& L) {
     L.dpre_all[1] = L.take(2 * N * O * D);
     L.dpre_all[2] = L.take(2 * N * H * D);
     L.dpre_all[3] = L.take(2 * N * O * D);
-    L.dxx[0] = L.take(N * H * (1 + nkh) * D);
-    L.dxx[1] = L.take(N * O * 4 * D);
+    L.dxx[0] = L.take(N * H * (size_t)kh_of(d));
+    L.dxx[1] = L.take(N * O * (size_t)ko_of(d));
+    L.dtime = L.take(d.time_position && !d.time_periodic ? N * D : 0);
     for (int g = 0; g < 3; ++g) L.ds[g] = L.take(N * E[g] * 2 * D);
     L.dmsg[0] = L.take(N * H * D);
     L.dmsg[1] = L.take(N * H * D);
@@ -77,22 +78,23 @@ void make_bwd_layout(const tggcn_dims& d, BwdLayout& L) {
     L.wt_seg = L.take(4 * D * 3 * D + 2 * nkh * D * 3 * D + 2 * 2 * D * 3 * D + 2 * D * 2 * D);
     // scratch for one transposed projection weight at a time
     size_t wmax = (size_t)2048 * 128 * V;                 // geometry_embedding_mlp.0
-    const size_t cands[] = {4 * D * 6 * D, (1 + nkh) * D * 6 * D, (size_t)2048 * D, 2 * D * D, D * 6 * D};
+    const size_t cands[] = {(size_t)ko_of(d) * 6 * D, (size_t)kh_of(d) * 6 * D, (size_t)2048 * D, 2 * D * D, D * 6 * D};
     for (size_t c : cands)
         if (c > wmax) wmax = c;
     L.wt = L.take(wmax);
     // transposed operands of one weight-gradient GEMM: (N + K) x M rounded up to 64 (fp32 transposes, or the 16-bit operand planes
     // of gemm16.cu — the same 4 bytes per element — which also holds the planes of one dX GEMM: gradient rows + transposed weight)
     const size_t rp = (N * (H > O ? H : O) + 63) / 64 * 64, np = (N + 63) / 64 * 64;
-    size_t tmax = (3 * D + (4 * D > 2048 ? 4 * D : 2048)) * rp;
+    const size_t ko_ = ko_of(d);
+    size_t tmax = (3 * D + (ko_ > 2048 ? ko_ : 2048)) * rp;
     if ((2048 + 128 * V) * np > tmax) tmax = (2048 + 128 * V) * np;
-    const size_t nt_cands[] = {rp * 6 * D + 4 * D * 6 * D, np * 2048 + (size_t)2048 * 128 * V, np * 2 * D + (size_t)2048 * D};
+    const size_t nt_cands[] = {rp * 6 * D + ko_ * 6 * D, np * 2048 + (size_t)2048 * 128 * V, np * 2 * D + (size_t)2048 * D};
     for (size_t c : nt_cands)
         if (c > tmax) tmax = c;
     // grouped weight-gradient launches keep every operand of a stage at once: the segment cells of one direction, the BiGRUs of
     // humans + objects (both directions), the embeddings + geometry MLP
-    const size_t kh_ = (1 + nkh) * D;
-    const size_t grp_cands[] = {rp * ((H ? 1 : 0) * (7 * D + kh_ + nkh * D) + 13 * D), 2 * rp * 15 * D,
+    const size_t kh_ = kh_of(d);
+    const size_t grp_cands[] = {rp * ((H ? 1 : 0) * (7 * D + kh_ + nkh * D) + 9 * D + ko_), 2 * rp * 15 * D,
                                 2 * rp * (D + 2048) + np * (D + 2048) + np * (2048 + 128 * V), 3 * rp * 4 * D + np * 3 * D};
     for (size_t c : grp_cands)
         if (c > tmax) tmax = c;
@@ -142,6 +144,7 @@ size_t tggcn_backward_workspace_bytes(const tggcn_dims* dims) {
 
 int tggcn_backward_bucket(int id) {
     if (id < 0 || id >= TGGCN_W_COUNT) return -1;
+    if (id == TGGCN_W_TIME_W || id == TGGCN_W_TIME_B) return 1;            // formed with the frame-level graph
     if (id <= TGGCN_W_GCN_S2_B) return 3;                                   // GCN_* (first 13 entries of the table)
     if (id <= TGGCN_W_OBJ_EMB_B) return 2;                                  // geometry MLP, ROI embeddings
     if (id >= TGGCN_W_HSEG_F_WIH || (id >= TGGCN_W_SMSG_HH_W && id <= TGGCN_W_SMSG_OO_B)) return 0;   // cells, heads, segment MLPs
@@ -344,7 +347,8 @@ int tggcn_backward_ex(const tggcn_dims* dims, const void* const* weights, void* 
     }
 
     // ---- 11. segment-level recurrent graph, reverse time ---------------------------------------------------------------
-    const int kh = (1 + nkh) * D, ldwh = (1 + 2 * nkh) * D;       // human cell: frame-part columns, row stride of W_ih
+    const int kh = kh_of(d), ldwh = ldwh_of(d);                  // human cell: frame-part columns, row stride of W_ih
+    const int ko = ko_of(d), ldwo = ldwo_of(d);                  // object cell
     const int wih_h_id[2] = {TGGCN_W_HSEG_F_WIH, TGGCN_W_HSEG_B_WIH}, wih_o_id[2] = {TGGCN_W_OSEG_F_WIH, TGGCN_W_OSEG_B_WIH};
     const int whh_h_id[2] = {TGGCN_W_HSEG_F_WHH, TGGCN_W_HSEG_B_WHH}, whh_o_id[2] = {TGGCN_W_OSEG_F_WHH, TGGCN_W_OSEG_B_WHH};
     const int smsg_w_id[4] = {TGGCN_W_SMSG_HH_W, TGGCN_W_SMSG_OH_W, TGGCN_W_SMSG_HO_W, TGGCN_W_SMSG_OO_W};
@@ -362,7 +366,7 @@ int tggcn_backward_ex(const tggcn_dims* dims, const void* const* weights, void* 
             if (int rc = launch_transpose(W(whh_h_id[dir]), D, whhT_h[dir], 3 * D, 3 * D, D, stream)) return rc;
             if (int rc = launch_transpose(W(whh_o_id[dir]), D, whhT_o[dir], 3 * D, 3 * D, D, stream)) return rc;
             if (int rc = launch_transpose(W(wih_h_id[dir]) + kh, ldwh, wihT_h[dir], 3 * D, 3 * D, nkh * D, stream)) return rc;
-            if (int rc = launch_transpose(W(wih_o_id[dir]) + 4 * D, 6 * D, wihT_o[dir], 3 * D, 3 * D, 2 * D, stream)) return rc;
+            if (int rc = launch_transpose(W(wih_o_id[dir]) + ko, ldwo, wihT_o[dir], 3 * D, 3 * D, 2 * D, stream)) return rc;
         }
         if (d.hh)
             if (int rc = launch_transpose(W(TGGCN_W_SMSG_HH_W), D, wmT_h, nks * D, D, D, stream)) return rc;
@@ -409,10 +413,10 @@ int tggcn_backward_ex(const tggcn_dims* dims, const void* const* weights, void* 
             // objects
             if (int rc = tn(P.dghs_o + (size_t)dir * 3 * D, 6 * D, nullptr, 0, P.hx_o + (size_t)dir * D, 2 * D,
                                         G(whh_o_id[dir]), D, N * O, 3 * D, D, dir == 0 ? -O : O, T * O, 0, stream, G(whh_o_id[dir] + 2))) return rc;
-            if (int rc = tn(P.dgs_o + (size_t)dir * 3 * D, 6 * D, nullptr, 0, buf(TGGCN_BUF_XX_O), 4 * D, G(wih_o_id[dir]), 6 * D,
-                                        N * O, 3 * D, 4 * D, 0, 0, 0, stream, G(wih_o_id[dir] + 2))) return rc;
+            if (int rc = tn(P.dgs_o + (size_t)dir * 3 * D, 6 * D, nullptr, 0, buf(TGGCN_BUF_XX_O), ko, G(wih_o_id[dir]), ldwo,
+                                        N * O, 3 * D, ko, 0, 0, 0, stream, G(wih_o_id[dir] + 2))) return rc;
             if (int rc = tn(P.dgs_o + (size_t)dir * 3 * D, 6 * D, nullptr, 0,
-                                        buf(TGGCN_BUF_MG_ALL_O) + (size_t)dir * N * O * 2 * D, 2 * D, G(wih_o_id[dir]) + 4 * D, 6 * D,
+                                        buf(TGGCN_BUF_MG_ALL_O) + (size_t)dir * N * O * 2 * D, 2 * D, G(wih_o_id[dir]) + ko, ldwo,
                                         N * O, 3 * D, 2 * D, 0, 0, 0, stream)) return rc;
             if (int rc = tn_flush(stream)) return rc;
         }
@@ -434,8 +438,8 @@ int tggcn_backward_ex(const tggcn_dims* dims, const void* const* weights, void* 
         float* wt = bb(BL.wt);
         const WSrc wh[2] = {{W(wih_h_id[0]), ldwh, 3 * D}, {W(wih_h_id[1]), ldwh, 3 * D}};
         if (int rc = dx_gemm(bb(BL.dgs[0]), 6 * D, nullptr, 0, wh, 2, kh, bb(BL.dxx[0]), kh, N * H, 0, wt)) return rc;
-        const WSrc wo[2] = {{W(wih_o_id[0]), 6 * D, 3 * D}, {W(wih_o_id[1]), 6 * D, 3 * D}};
-        if (int rc = dx_gemm(bb(BL.dgs[1]), 6 * D, nullptr, 0, wo, 2, 4 * D, bb(BL.dxx[1]), 4 * D, N * O, 0, wt)) return rc;
+        const WSrc wo[2] = {{W(wih_o_id[0]), ldwo, 3 * D}, {W(wih_o_id[1]), ldwo, 3 * D}};
+        if (int rc = dx_gemm(bb(BL.dgs[1]), 6 * D, nullptr, 0, wo, 2, ko, bb(BL.dxx[1]), ko, N * O, 0, wt)) return rc;
     }
 
     // ---- 9/8. gates (straight-through, filter), attention, aggregation ------------------------------------------------------------
@@ -444,6 +448,9 @@ int tggcn_backward_ex(const tggcn_dims* dims, const void* const* weights, void* 
         memset(&P, 0, sizeof(P));
         P.B = B; P.T = T; P.H = H; P.O = O; P.D = D; P.hh = d.hh; P.filter = d.filter; P.thr = d.thr; P.mean_pool = d.mean_pool; P.att_noscale = d.att_noscale;
         P.update_strategy = d.update_strategy;
+        P.time_position = d.time_position; P.time_emb = d.time_position ? buf(TGGCN_BUF_TIME_EMB) : nullptr;
+        // no gradient pointers for time_position_mlp = it is off the gradient path of this call (strategy 'u' with every gate imposed)
+        P.dtime = (d.time_position && !d.time_periodic && G(TGGCN_W_TIME_W) && G(TGGCN_W_TIME_B)) ? bb(BL.dtime) : nullptr;
         P.s_h = buf(TGGCN_BUF_S_H); P.s_o = buf(TGGCN_BUF_S_O);
         P.msg_hh = buf(TGGCN_BUF_MSG_HH); P.msg_ho = buf(TGGCN_BUF_MSG_HO); P.msg_oh = buf(TGGCN_BUF_MSG_OH);
         P.msg_oo = buf(TGGCN_BUF_MSG_OO); P.msg_go = buf(TGGCN_BUF_MSG_GO);
@@ -461,14 +468,18 @@ int tggcn_backward_ex(const tggcn_dims* dims, const void* const* weights, void* 
         P.dmsg_go = bb(BL.dmsg[4]);
         P.dw_uh = G(TGGCN_W_UPD_H_W); P.db_uh = G(TGGCN_W_UPD_H_B); P.dw_uo = G(TGGCN_W_UPD_O_W); P.db_uo = G(TGGCN_W_UPD_O_B);
         if (!d.human_seg_given) {
-            TG_CUDA_OK(cudaMemsetAsync(P.dw_uh, 0, sizeof(float) * (size_t)(2 + nkh) * D, stream));
+            TG_CUDA_OK(cudaMemsetAsync(P.dw_uh, 0, sizeof(float) * (size_t)(2 + nkh + tu_of(d)) * D, stream));
             TG_CUDA_OK(cudaMemsetAsync(P.db_uh, 0, sizeof(float), stream));
         }
         if (!d.object_seg_given && d.update_strategy != 1) {
-            TG_CUDA_OK(cudaMemsetAsync(P.dw_uo, 0, sizeof(float) * (size_t)5 * D, stream));
+            TG_CUDA_OK(cudaMemsetAsync(P.dw_uo, 0, sizeof(float) * (size_t)(5 + tu_of(d)) * D, stream));
             TG_CUDA_OK(cudaMemsetAsync(P.db_uo, 0, sizeof(float), stream));
         }
         if (int rc = launch_frame_bwd(P, stream)) return rc;
+        if (P.dtime != nullptr) {      // time_position_mlp: Linear(1, D) + ReLU of (t+1) / steps
+            TG_REQUIRE(io->steps_per_example, "backward: steps_per_example missing");
+            if (int rc = launch_time_embed_bwd(P.dtime, P.time_emb, io->steps_per_example, G(TGGCN_W_TIME_W), G(TGGCN_W_TIME_B), B, T, D, stream)) return rc;
+        }
     }
 
     // ---- 7. message MLPs: msg = ReLU(W [x|h] + b) ---------------------------------------------------------------------------------

@@ -126,7 +126,8 @@ __global__ void __launch_bounds__(256) frame_bwd_kernel(const FrameBwdParams P) 
     const int n = blockIdx.x, b = n / T, t = n - b * T;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int nkh = P.hh ? 2 : 1;
-    const int wh = (1 + nkh) * D;
+    const int ts = P.time_position == 1 ? 1 : 0, tu = P.time_position == 2 ? 1 : 0;
+    const int wh = (1 + nkh + ts) * D, wo = (4 + ts) * D;      // rows of xx_h / xx_o (and of their gradients)
     float* sv = sm;                            // [NE][2D]
     float* dmh = sv + NE * D2;                 // [H][nkh*D]   d m_hh | d m_oh
     float* dmo = dmh + H * nkh * D;            // [O][3D]      d m_ho | d m_go | d m_oo
@@ -208,7 +209,7 @@ __global__ void __launch_bounds__(256) frame_bwd_kernel(const FrameBwdParams P) 
     }
     for (int i = tid; i < O * D; i += 256) {
         const int k = i / D, c = i - k * D;
-        const float* dx = P.dxx_o + ((size_t)n * O + k) * 4 * D;
+        const float* dx = P.dxx_o + ((size_t)n * O + k) * wo;
         const float g = dlogit[H + k];
         if (P.w_uo == nullptr) {                                                        // 'sah': no object gate MLP
             ds[(H + k) * D2 + c] = 0.0f;
@@ -223,6 +224,25 @@ __global__ void __launch_bounds__(256) frame_bwd_kernel(const FrameBwdParams P) 
         dmo[k * 3 * D + c] = dx[D + c] + g * __ldg(P.w_uo + D2 + c);                    // m_ho   (gate order x,h,m_ho,m_oo,m_go)
         dmo[k * 3 * D + D + c] = dx[2 * D + c] + g * __ldg(P.w_uo + D2 + 2 * D + c);    // m_go
         dmo[k * 3 * D + 2 * D + c] = dx[3 * D + c] + g * __ldg(P.w_uo + D2 + D + c);    // m_oo
+    }
+    // time-position features (add_time_position): gradient of this frame's feature vector — strategy 's': the time blocks of all xx
+    // rows; strategy 'u': through the last block of the gate inputs, whose weight gradient is formed here too
+    if (P.time_position != 0 && (tu || P.dtime != nullptr)) {
+        const float* te = P.time_emb + (size_t)n * D;
+        for (int c = tid; c < D; c += 256) {
+            float v = 0.0f;
+            if (ts) {
+                for (int h = 0; h < H; ++h) v += P.dxx_h[((size_t)n * H + h) * wh + (1 + nkh) * D + c];
+                for (int k = 0; k < O; ++k) v += P.dxx_o[((size_t)n * O + k) * wo + 4 * D + c];
+            } else {
+                float gh = 0.0f, go = 0.0f;
+                for (int h = 0; h < H; ++h) gh += dlogit[h];
+                for (int k = 0; k < O; ++k) go += dlogit[H + k];
+                if (P.human_seg == nullptr) { v = fmaf(gh, __ldg(P.w_uh + D2 + nkh * D + c), v); atomicAdd(P.dw_uh + D2 + nkh * D + c, gh * __ldg(te + c)); }
+                if (P.object_seg == nullptr && P.dw_uo != nullptr) { v = fmaf(go, __ldg(P.w_uo + 5 * D + c), v); atomicAdd(P.dw_uo + 5 * D + c, go * __ldg(te + c)); }
+            }
+            if (P.dtime != nullptr) P.dtime[(size_t)n * D + c] = v;
+        }
     }
     // gate weight gradients: d w[k] += sum_e dlogit[e] * input_e[k]
     if (P.human_seg == nullptr) {
@@ -245,7 +265,7 @@ __global__ void __launch_bounds__(256) frame_bwd_kernel(const FrameBwdParams P) 
                 else {
                     const int part = (k - D2) / D, c = (k - D2) - part * D;          // 0: m_ho, 1: m_oo, 2: m_go
                     const int xoff = part == 0 ? D : (part == 1 ? 3 * D : 2 * D);    // xx_o = [h, m_ho, m_go, m_oo]
-                    in = __ldg(P.xx_o + ((size_t)n * O + o) * 4 * D + xoff + c);
+                    in = __ldg(P.xx_o + ((size_t)n * O + o) * wo + xoff + c);
                 }
                 v = fmaf(dlogit[H + o], in, v);
             }
@@ -338,6 +358,39 @@ __global__ void __launch_bounds__(256) frame_bwd_kernel(const FrameBwdParams P) 
         if (e < H) P.ds_h[(size_t)n * H * D2 + i] = v;
         else P.ds_o[(size_t)n * O * D2 + (i - H * D2)] = v;
     }
+}
+
+// One CTA per 32 columns x a slab of frames: column sums of dtime (.) [emb > 0] (x tau), combined with atomics.
+__global__ void __launch_bounds__(256) time_embed_bwd_kernel(const float* __restrict__ dtime, const float* __restrict__ emb,
+                                                             const float* __restrict__ steps, float* dw, float* db, int B, int T, int D) {
+    __shared__ float sw[8][33], sb[8][33];
+    const int c = blockIdx.x * 32 + (threadIdx.x & 31), rl = threadIdx.x >> 5;
+    const int N = B * T;
+    float aw = 0.0f, ab = 0.0f;
+    if (c < D)
+        for (int n = blockIdx.y * 8 + rl; n < N; n += gridDim.y * 8) {
+            const float g = emb[(size_t)n * D + c] > 0.0f ? dtime[(size_t)n * D + c] : 0.0f;
+            const int b = n / T, t = n - b * T;
+            aw = fmaf(g, (float)(t + 1) / __ldg(steps + b), aw);
+            ab += g;
+        }
+    sw[rl][threadIdx.x & 31] = aw; sb[rl][threadIdx.x & 31] = ab;
+    __syncthreads();
+    if (rl == 0 && c < D) {
+        for (int r = 1; r < 8; ++r) { aw += sw[r][threadIdx.x]; ab += sb[r][threadIdx.x]; }
+        atomicAdd(dw + c, aw);
+        atomicAdd(db + c, ab);
+    }
+}
+
+int launch_time_embed_bwd(const float* dtime, const float* emb, const float* steps, float* dw, float* db, int B, int T, int D,
+                          cudaStream_t stream) {
+    TG_CUDA_OK(cudaMemsetAsync(dw, 0, sizeof(float) * D, stream));
+    TG_CUDA_OK(cudaMemsetAsync(db, 0, sizeof(float) * D, stream));
+    const int slabs = min(64, cdiv(B * T, 8));
+    time_embed_bwd_kernel<<<dim3(cdiv(D, 32), slabs), 256, 0, stream>>>(dtime, emb, steps, dw, db, B, T, D);
+    TG_LAUNCH_OK();
+    return 0;
 }
 
 int launch_frame_bwd(const FrameBwdParams& P, cudaStream_t stream) {

@@ -78,6 +78,9 @@ struct FrameBwdParams {
     int mean_pool;                                 // uniform sender weights: no gradient through attention logits
     int att_noscale;                               // attention_style 'v2': plain dot-product logits
     int update_strategy;                           // 0 'ind', 1 'sah', 2 'coh' (tggcn_dims.update_strategy)
+    int time_position;                             // 0 off, 1 's' (time block in the xx rows), 2 'u' (in the gate inputs)
+    const float* time_emb;                         // (B*T, D) forward time-position features, or null
+    float* dtime;                                  // (B*T, D) out: their gradient (null for the periodic encoding: no parameters)
     float thr;
     const float* s_h; const float* s_o;            // (B,T,E,2D)
     const float* msg_hh; const float* msg_ho; const float* msg_oh; const float* msg_oo; const float* msg_go;
@@ -96,6 +99,9 @@ struct FrameBwdParams {
     float* dw_uh; float* db_uh; float* dw_uo; float* db_uo;   // accumulated with atomics: zero before the launch
 };
 int launch_frame_bwd(const FrameBwdParams& P, cudaStream_t stream);
+// time_position_mlp (Linear(1, D) + ReLU of (t+1)/steps[b]): dw[k] = sum_n dtime[n,k] [emb[n,k] > 0] tau_n, db[k] likewise without tau
+int launch_time_embed_bwd(const float* dtime, const float* emb, const float* steps, float* dw, float* db, int B, int T, int D,
+                          cudaStream_t stream);
 
 // ---- geometry GCN (models_gcn.py:30-100) -----------------------------------------------------------------------------
 struct GcnBwdParams {

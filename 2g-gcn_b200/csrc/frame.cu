@@ -102,9 +102,12 @@ __global__ void __launch_bounds__(FM_THREADS) frame_messages_kernel(const FrameM
         const float* g_oh = P.msg_oh + (size_t)n * O * D;
         const float* g_oo = P.msg_oo + (size_t)n * O * D;
         const float* g_go = P.msg_go + (size_t)n * D;
-        const int wh = (1 + nkh) * D;            // xx_h row: [h, (m_hh), m_oh]
+        const int ts = P.time_position == 1 ? 1 : 0;
+        const int wh = (1 + nkh + ts) * D;       // xx_h row: [h, (m_hh), m_oh (, time)]
+        const int wo = (4 + ts) * D;             // xx_o row: [h, m_ho, m_go, m_oo (, time)]
         float* xxh = P.xx_h + (size_t)n * H * wh;
-        float* xxo = P.xx_o + (size_t)n * O * 4 * D;
+        float* xxo = P.xx_o + (size_t)n * O * wo;
+        const float* te = ts ? P.time_emb + (size_t)n * D : nullptr;
         // four columns per thread (float4 loads of the sender messages, float4 stores of xx rows); per element the same fmaf
         // order as a scalar loop over the senders
         const int D4 = D / 4;
@@ -126,10 +129,11 @@ __global__ void __launch_bounds__(FM_THREADS) frame_messages_kernel(const FrameM
             for (int k = 0; k < O; ++k) fma4(a_oh[h * FM_MAXE + k], scale4(ld4(g_oh + k * D + c), om[k]), v);
             *reinterpret_cast<float4*>(mh + h * nkh * D + (nkh - 1) * D + c) = v;
             *reinterpret_cast<float4*>(row + nkh * D + c) = v;
+            if (ts) *reinterpret_cast<float4*>(row + (1 + nkh) * D + c) = ld4(te + c);      // models.py:761
         }
         for (int idx = tid; idx < O * D4; idx += FM_THREADS) {
             const int k = idx / D4, c = (idx - k * D4) * 4;
-            float* row = xxo + k * 4 * D;
+            float* row = xxo + k * wo;
             *reinterpret_cast<float4*>(row + c) = *reinterpret_cast<const float4*>(sv + (H + k) * D2 + D + c);
             float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
             for (int h = 0; h < H; ++h) fma4(a_ho[k * FM_MAXE + h], ld4(g_ho + h * D + c), v);
@@ -144,6 +148,7 @@ __global__ void __launch_bounds__(FM_THREADS) frame_messages_kernel(const FrameM
             *reinterpret_cast<float4*>(row + D + c) = v;           // models.py:748 order: h, m_ho, m_go, m_oo
             *reinterpret_cast<float4*>(row + 2 * D + c) = go;
             *reinterpret_cast<float4*>(row + 3 * D + c) = w;
+            if (ts) *reinterpret_cast<float4*>(row + 4 * D + c) = ld4(te + c);               // models.py:762
         }
     }
     __syncthreads();
@@ -170,6 +175,11 @@ __global__ void __launch_bounds__(FM_THREADS) frame_messages_kernel(const FrameM
                 acc = fmaf(__ldg(w + D2 + D + k), m[2 * D + k], acc);
                 acc = fmaf(__ldg(w + D2 + 2 * D + k), m[D + k], acc);
             }
+        }
+        if (P.time_position == 2) {                   // strategy 'u': the time feature is the last block of the gate input
+            const float* wt = w + D2 + (is_h ? nkh : 3) * D;
+            const float* te = P.time_emb + (size_t)n * D;
+            for (int k = lane; k < D; k += 32) acc = fmaf(__ldg(wt + k), __ldg(te + k), acc);
         }
         acc = warp_sum(acc);
         const float logit = acc + __ldg(is_h ? P.b_uh : P.b_uo);
@@ -226,6 +236,35 @@ int launch_frame_messages(const FrameMsgParams& P, cudaStream_t stream) {
     TG_REQUIRE(smem <= 200 * 1024, "frame_messages: shape needs %zu bytes of shared memory", smem);
     if (int rc = ensure_smem((const void*)frame_messages_kernel, smem)) return rc;
     frame_messages_kernel<<<P.B * P.T, FM_THREADS, smem, stream>>>(P);
+    TG_LAUNCH_OK();
+    return 0;
+}
+
+// Time-position features of every frame: one thread per (frame, column).
+__global__ void time_embed_kernel(const float* __restrict__ steps, const float* __restrict__ w, const float* __restrict__ bias,
+                                  const float* __restrict__ freq, float* __restrict__ out, int B, int T, int D, int periodic) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (size_t)B * T * D) return;
+    const int k = (int)(i % D);
+    const size_t n = i / D;
+    const int b = (int)(n / T), t = (int)(n - (size_t)b * T);
+    const float pos = (float)(t + 1);
+    float v;
+    if (periodic) {                                  // make_periodic_embedding, models.py:1777-1794 (no division by the steps, :654)
+        const int half = D / 2;
+        const float x = pos / __ldg(freq + (k < half ? k : k - half));
+        v = k < half ? sinf(x) : cosf(x);
+    } else {                                         // _assemble_time_tensor + Linear(1, D) + ReLU, models.py:936-952, :259-260
+        const float tau = pos / __ldg(steps + b);
+        v = fmaxf(fmaf(__ldg(w + k), tau, __ldg(bias + k)), 0.0f);
+    }
+    out[i] = v;
+}
+
+int launch_time_embed(const float* steps, const float* w, const float* bias, const float* freq, float* out, int B, int T, int D,
+                      int periodic, cudaStream_t stream) {
+    const size_t total = (size_t)B * T * D;
+    time_embed_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(steps, w, bias, freq, out, B, T, D, periodic);
     TG_LAUNCH_OK();
     return 0;
 }

@@ -9,6 +9,8 @@ struct FrameMsgParams {
     int mean_pool;          // message_aggregation 'mp': uniform weights over the valid senders instead of attention
     int att_noscale;        // attention_style 'v2': plain dot-product logits
     int update_strategy;    // 0 'ind', 1 'sah' (object gates = the single human's), 2 'coh' (hard object gate x the human's)
+    int time_position;      // 0 off, 1 's': time block appended to the xx rows, 2 'u': appended to the gate inputs
+    const float* time_emb;  // (B*T, D) time-position features, or null
     float thr;
     const float* s_h;       // (B,T,H,2D) [x | h]
     const float* s_o;       // (B,T,O,2D)
@@ -43,6 +45,9 @@ struct HeadsParams {
 };
 
 int launch_frame_messages(const FrameMsgParams& P, cudaStream_t stream);
+// time-position features: 'e' ReLU(w * (t+1)/steps[b] + bias), 'p' [sin((t+1)/freq_i), cos((t+1)/freq_i)]  (models.py:936-952, :1777-1794)
+int launch_time_embed(const float* steps, const float* w, const float* bias, const float* freq, float* out, int B, int T, int D,
+                      int periodic, cudaStream_t stream);
 int launch_gate_post(float* y_hs, const float* y_hss, float* y_os, const float* y_oss, int* reidx, int B, int T, int H,
                      int O, int filter, float thr, cudaStream_t stream);
 int launch_heads(const HeadsParams& P, cudaStream_t stream);

@@ -30,6 +30,8 @@ _V2 = {'v2', 'dot-product'}
 _NONREL = {'v2', 'non-relational'}
 _GENERIC = {'v1', 'generic'}
 _IND = {'ind', 'independent'}
+_ENC_E = {'e', 'embedding'}
+_ENC_P = {'p', 'periodic'}
 _SAH = {'sah', 'same_as_human'}
 _COH = {'coh', 'conditional_on_human'}
 
@@ -125,7 +127,9 @@ class TGGCN(nn.Module):
         if message_aggregation not in _ATT | _MP: unsupported.append("message_aggregation not in {'att', 'mp'}")
         if attention_style not in _V3 | _V2: unsupported.append("attention_style not in {'v2', 'v3'}")
         if object_segment_update_strategy not in _IND | _SAH | _COH: unsupported.append('unknown object_segment_update_strategy')
-        if add_segment_length or add_time_position: unsupported.append('time/length position features')
+        if add_segment_length: unsupported.append('add_segment_length')
+        if add_time_position and time_position_strategy not in ('s', 'u'): unsupported.append("time_position_strategy not in {'s', 'u'}")
+        if add_time_position and positional_encoding_style not in _ENC_E | _ENC_P: unsupported.append('unknown positional_encoding_style')
         if not bias: unsupported.append('bias=False')
         if hidden_size % 16 != 0: unsupported.append('hidden_size not a multiple of 16')
         if unsupported:
@@ -151,13 +155,20 @@ class TGGCN(nn.Module):
         self.message_aggregation, self.attention_style = message_aggregation, attention_style
         self.object_segment_update_strategy = object_segment_update_strategy
         self.update_segment_threshold = float(update_segment_threshold)
-        self.add_segment_length = self.add_time_position = False
+        self.add_segment_length, self.add_time_position = False, bool(add_time_position)
         self.time_position_strategy, self.positional_encoding_style = time_position_strategy, positional_encoding_style
         self.cat_level_states = bool(cat_level_states)
         self.share_level_mlps = bool(share_level_mlps) and not self.cat_level_states     # models.py:565: sharing needs equal input sizes
         self.hidden_size, self.num_classes = D, (n_sub, n_aff)
         hh = self.message_humans_to_human
+        # time-position features (models.py:259-260, :290, :315, :530, :545): one more D-wide block in the segment-level inputs
+        # (strategy 's') or in the gate inputs ('u')
+        ts = int(self.add_time_position and time_position_strategy == 's')
+        tu = int(self.add_time_position and time_position_strategy == 'u')
+        self._time_periodic = positional_encoding_style in _ENC_P
         # ---- parameter holders, registered in the reference's order (vhoi/models.py:264-580) ----------
+        if self.add_time_position and not self._time_periodic:
+            self.time_position_mlp = _mlp([1, D], ['relu'])
         self.geometry_embedding_gcn = _geo_gcn_holder(gcn_node)
         self.geometry_embedding_mlp = _mlp([gcn_node * 128, 2048, D], ['relu', 'relu'])
         self.geometry_bd_rnn = nn.GRU(D, D, num_layers=1, bias=True, batch_first=True, bidirectional=True)
@@ -165,14 +176,14 @@ class TGGCN(nn.Module):
         self.human_embedding_mlp = _mlp([2048, D], ['relu'])
         self.human_bd_rnn = nn.GRU(D, D, num_layers=1, bias=True, batch_first=True, bidirectional=True)
         self.human_bd_embedding_mlp = _mlp([2 * D, D], ['relu'])
-        h_in = D * (1 + (2 if hh else 0) + 2)
+        h_in = D * (1 + (2 if hh else 0) + 2 + ts)
         self.human_segment_rnn_fcell = nn.GRUCell(h_in, D, bias=True)
         self.human_segment_rnn_bcell = nn.GRUCell(h_in, D, bias=True)
         self.object_embedding_mlp = _mlp([object_input_size, D], ['relu'])
         self.object_bd_rnn = nn.GRU(D, D, num_layers=1, bias=True, batch_first=True, bidirectional=True)
         self.object_bd_embedding_mlp = _mlp([2 * D, D], ['relu'])
-        self.object_segment_rnn_fcell = nn.GRUCell(6 * D, D, bias=True)
-        self.object_segment_rnn_bcell = nn.GRUCell(6 * D, D, bias=True)
+        self.object_segment_rnn_fcell = nn.GRUCell((6 + ts) * D, D, bias=True)
+        self.object_segment_rnn_bcell = nn.GRUCell((6 + ts) * D, D, bias=True)
         kinds = (['humans_to_human'] if hh else []) + ['human_to_object', 'objects_to_human', 'objects_to_object']
         att_names = {'humans_to_human': 'humans_to_human', 'human_to_object': 'humans_to_object',
                      'objects_to_human': 'objects_to_human', 'objects_to_object': 'objects_to_object'}
@@ -188,9 +199,9 @@ class TGGCN(nn.Module):
         if message_aggregation in _ATT:
             self.geometry_to_object_message_att_mlp = _mlp([4 * D, 1], ['relu'])
             self.geometry_to_object_segment_message_att_mlp = _mlp([2 * D, 1], ['relu'])
-        self.update_human_segment_mlp = _mlp([D * (2 + (1 if hh else 0) + 1), 1], ['sigmoid'])
+        self.update_human_segment_mlp = _mlp([D * (2 + (1 if hh else 0) + 1 + tu), 1], ['sigmoid'])
         if object_segment_update_strategy not in _SAH:            # models.py:537: no object gate MLP under 'sah'
-            self.update_object_segment_mlp = _mlp([5 * D, 1], ['sigmoid'])
+            self.update_object_segment_mlp = _mlp([(5 + tu) * D, 1], ['sigmoid'])
         label_in = (4 if self.cat_level_states else 2) * D        # models.py:553-555
         self.human_recognition_mlp = _mlp([label_in, n_sub], ['logsoftmax'])
         self.human_prediction_mlp = _mlp([label_in, n_sub], ['logsoftmax'])
@@ -212,6 +223,7 @@ class TGGCN(nn.Module):
         # ---- runtime state (not part of state_dict) ------------------------------------------------------
         self._ptr_cache = None
         self._ws = {}
+        self._time_freq = None
         self._noise_override: Optional[torch.Tensor] = None
         self._generation = 0
         self.flat_grad = None
@@ -348,18 +360,19 @@ class TGGCN(nn.Module):
         """Same contract as vhoi/models.py:584-623.  Returns the list of models.py:919-926 (6 tensors, or 12
         when affordance classes exist), plus the attention stacks when ``inspect_model``."""
         return self._run(x_human, x_objects, objects_mask, human_segmentation, objects_segmentation,
-                         human_human_distances, human_object_distances, object_object_distances, inspect_model, None)
+                         human_human_distances, human_object_distances, object_object_distances, inspect_model, None,
+                         steps_per_example)
 
     def forward_profile(self, x_human, x_objects, objects_mask, human_segmentation=None, objects_segmentation=None,
-                        inspect_model=False):
+                        inspect_model=False, steps_per_example=None):
         """forward() with CUDA events around every stage; returns (outputs, {stage name: milliseconds})."""
         ms = (C.c_float * len(abi.STAGE_NAMES))()
         out = self._run(x_human, x_objects, objects_mask, human_segmentation, objects_segmentation, None, None, None,
-                        inspect_model, ms)
+                        inspect_model, ms, steps_per_example)
         return out, dict(zip(abi.STAGE_NAMES, list(ms)))
 
     def _run(self, x_human, x_objects, objects_mask, human_segmentation, objects_segmentation, hh_d, ho_d, oo_d,
-             inspect_model, stage_ms):
+             inspect_model, stage_ms, steps_per_example=None):
         if hh_d is not None or ho_d is not None or oo_d is not None:
             raise NotImplementedError('distance-based attention (misc.make_attention_distance_based) is not supported')
         if not x_human.is_cuda:
@@ -392,6 +405,17 @@ class TGGCN(nn.Module):
                         mean_pool=int(self.message_aggregation in _MP), recurrent_mode=int(self.recurrent_mode),
                         no_fp16_split=int(self.no_fp16_split), precision=int(self.precision),
                         att_noscale=int(self.attention_style in _V2))
+        steps = freq = None
+        if self.add_time_position:
+            dims.time_position = 1 if self.time_position_strategy == 's' else 2
+            dims.time_periodic = int(self._time_periodic)
+            if steps_per_example is None:
+                raise ValueError('add_time_position needs steps_per_example (vhoi/data_loading.py:1277)')
+            steps = steps_per_example.to(device=dev, dtype=torch.float32).contiguous()
+            if self._time_periodic:             # the period table of make_periodic_embedding (models.py:1788-1790), a constant of D
+                if self._time_freq is None or self._time_freq.device != dev:
+                    self._time_freq = (torch.tensor([1e4]) ** torch.linspace(0, 1, self.hidden_size // 2)).to(dev)
+                freq = self._time_freq
         # object_segment_update_strategy (models.py:741-742, :1523-1532): 'sah' / 'coh' act with exactly one human; with more the
         # reference falls back to 'ind' ('sah' then has no object gate MLP to fall back on and fails there too)
         strat = 1 if self.object_segment_update_strategy in _SAH else 2 if self.object_segment_update_strategy in _COH else 0
@@ -426,6 +450,8 @@ class TGGCN(nn.Module):
             io.human_seg = hseg.data_ptr() if hseg is not None else None
             io.object_seg = oseg.data_ptr() if oseg is not None else None
             io.noise = noise.data_ptr() if noise is not None else None
+            io.steps_per_example = steps.data_ptr() if steps is not None else None
+            io.time_freq = freq.data_ptr() if freq is not None else None
             io.y_hs, io.y_hss, io.y_os, io.y_oss = y_hs.data_ptr(), y_hss.data_ptr(), y_os.data_ptr(), y_oss.data_ptr()
             for i in range(4):
                 io.out_h[i] = out_h[i].data_ptr()
@@ -451,7 +477,7 @@ class TGGCN(nn.Module):
             pending[0].record(torch.cuda.current_stream(dev))
             self._pending_status.append(pending)
             # keep inputs alive until the queued work ran
-            keep = (x_human, x_objects, objects_mask, hseg, oseg, noise)
+            keep = (x_human, x_objects, objects_mask, hseg, oseg, noise, steps, freq)
             self._last = (dims, ws, keep)
             if n_aff is None:
                 output = [y_hs, y_hss] + out_h
@@ -482,6 +508,8 @@ class TGGCN(nn.Module):
                 continue
             if name.startswith('update_object_segment_mlp') and dims.object_seg_given:
                 continue
+            if name.startswith('time_position_mlp') and dims.time_position == 2 and dims.human_seg_given and dims.object_seg_given:
+                continue                       # strategy 'u' feeds the gate MLPs only
             names.append(name)
             params.append(prm)
         return names, params

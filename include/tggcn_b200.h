@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define TGGCN_ABI_VERSION 8
+#define TGGCN_ABI_VERSION 9
 
 #if defined(__GNUC__)
 #define TGGCN_API __attribute__((visibility("default")))
@@ -67,6 +67,13 @@ typedef struct tggcn_dims {
                                     and no objects_segmentation the object gates (hard and soft) ARE the human's, no object gate MLP,
                                     no noise drawn for objects; 2 = 'coh': hard object gate = own decision x the human's hard gate
                                     (one human, no local-maximum filter; otherwise identical to 'ind')                          */
+    int32_t time_position;       /* add_time_position (models.py:656-662, :755-762): 0 = off; 1 = strategy 's': the time feature of frame
+                                    (b, t) is appended to every segment-level input row [h, m.., time] (so W_ih of the segment cells
+                                    has D more columns before the segment-message columns); 2 = strategy 'u': appended to the gate
+                                    MLP inputs instead (update_*_segment_mlp weights have D more columns at the end)             */
+    int32_t time_periodic;       /* positional_encoding_style: 0 = 'e': ReLU(time_position_mlp((t+1) / steps_per_example[b]))
+                                    (models.py:259-260, :936-952); 1 = 'p': [sin((t+1)/w_i), cos((t+1)/w_i)] with the D/2
+                                    frequencies w_i = 1e4^(i/(D/2-1)) passed in tggcn_io.time_freq (models.py:1777-1794)         */
 } tggcn_dims;
 
 /* Parameter table.  One device pointer per reference state_dict() entry, in this order
@@ -176,7 +183,9 @@ typedef struct tggcn_dims {
     X(HEAD_O_REC_W, "object_recognition_mlp.0.weight")                                                 \
     X(HEAD_O_REC_B, "object_recognition_mlp.0.bias")                                                   \
     X(HEAD_O_PRED_W, "object_prediction_mlp.0.weight")                                                 \
-    X(HEAD_O_PRED_B, "object_prediction_mlp.0.bias")
+    X(HEAD_O_PRED_B, "object_prediction_mlp.0.bias")                                                   \
+    X(TIME_W,       "time_position_mlp.0.weight")                                                      \
+    X(TIME_B,       "time_position_mlp.0.bias")
 
 enum tggcn_weight_id {
 #define TGGCN_X_ENUM(id, key) TGGCN_W_##id,
@@ -206,6 +215,8 @@ typedef struct tggcn_io {
     float* bn_running_mean;      /* (4V) updated in place when bn_train                                  */
     float* bn_running_var;       /* (4V) updated in place when bn_train                                  */
     int64_t* bn_num_batches;     /* scalar, incremented when bn_train                                    */
+    const float* steps_per_example; /* (B) number of real frames per video, or NULL; required when dims.time_position != 0   */
+    const float* time_freq;      /* (D/2) periods w_i of the periodic encoding (dims.time_periodic), else NULL               */
     uint32_t* status_host;       /* PINNED HOST memory, 8 words, or NULL.  When set, tggcn_forward / tggcn_backward end with an
                                     asynchronous copy of the status words (see tggcn_status_decode) into it, so the caller can
                                     test them after any later synchronisation point without an extra round trip.           */
@@ -229,8 +240,8 @@ enum tggcn_buf_id {
     TGGCN_BUF_MSG_OH,        /* (B,T,O,D)                                                                */
     TGGCN_BUF_MSG_OO,        /* (B,T,O,D)                                                                */
     TGGCN_BUF_MSG_GO,        /* (B,T,1,D)                                                                */
-    TGGCN_BUF_XX_H,          /* (B,T,H,3D or 2D)     segment-level frame inputs, models.py:705           */
-    TGGCN_BUF_XX_O,          /* (B,T,O,4D)           models.py:748                                       */
+    TGGCN_BUF_XX_H,          /* (B,T,H,3D or 2D [+D]) segment-level frame inputs, models.py:705 (+ time block, :761) */
+    TGGCN_BUF_XX_O,          /* (B,T,O,4D [+D])      models.py:748 (+ time block, :762)                  */
     TGGCN_BUF_GS_H,          /* (B,T,H,2,3D)         hoisted segment-cell input pre-activations          */
     TGGCN_BUF_GS_O,          /* (B,T,O,2,3D)                                                             */
     TGGCN_BUF_HX_H,          /* (B,T,H,2D)           segment states [fwd | bwd], before reorder          */
@@ -259,6 +270,7 @@ enum tggcn_buf_id {
     TGGCN_BUF_SALPHA_HO,
     TGGCN_BUF_SALPHA_OO,
     TGGCN_BUF_PACK,          /* 16-bit operand planes of the projection stage in flight (gemm16.cu)                       */
+    TGGCN_BUF_TIME_EMB,      /* (B*T, D)             time-position features (empty unless dims.time_position)             */
     TGGCN_BUF_COUNT
 };
 

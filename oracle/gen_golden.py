@@ -68,6 +68,11 @@ CASES = [
     ('cad120_s2_sah', 'cad120', 32, 2, 11, 2, False, 2.0, False, {'object_segment_update_strategy': 'sah'}),
     ('cad120_nf_sah', 'cad120', 32, 2, 11, 2, False, 2.0, False, {'object_segment_update_strategy': 'sah', 'filter_discrete_updates': 0, 'update_segment_threshold': 0.5}),
     ('cad120_nf_coh', 'cad120', 32, 2, 11, 2, False, 2.0, False, {'object_segment_update_strategy': 'coh', 'filter_discrete_updates': 0, 'update_segment_threshold': 0.5}),
+    # add_time_position (models.py:259-260, :656-662, :755-762): strategy 's' (segment-level input) / 'u' (gate input), encoding e / p
+    ('mphoi_s2_time_se', 'mphoi', 32, 2, 12, 2, False, 2.0, False, {'add_time_position': 1, 'time_position_strategy': 's', 'positional_encoding_style': 'e'}),
+    ('cad120_s2_time_sp', 'cad120', 32, 2, 11, 2, False, 2.0, False, {'add_time_position': 1, 'time_position_strategy': 's', 'positional_encoding_style': 'p'}),
+    ('cad120_s2_time_ue', 'cad120', 32, 2, 11, 2, False, 2.0, False, {'add_time_position': 1, 'time_position_strategy': 'u', 'positional_encoding_style': 'e'}),
+    ('mphoi_s2_time_up', 'mphoi', 32, 2, 12, 2, False, 2.0, False, {'add_time_position': 1, 'time_position_strategy': 'u', 'positional_encoding_style': 'p'}),
     # the benchmarked configuration itself (BASELINE.json configs[1]: MPHOI, B=8, T=128, hidden 512, stage-2 settings)
     ('mphoi_s2_d512_full', 'mphoi', 512, 8, 128, 2, False, 1.0, False),
 ]
@@ -102,7 +107,7 @@ def run_case(name, shape_name, D, B, T, stage, train_mode, gain, inspect, extra=
                 _, s_h, _, s_o = orc.forward({k: v.double() for k, v in sd.items()},
                                              orc.config_from_kwargs(kw),
                                              batch['x_human'].double(), batch['x_objects'].double(), batch['objects_mask'].double(),
-                                             None, None, noise.double(), gates_only=True)
+                                             None, None, noise.double(), gates_only=True, steps_per_example=batch['steps_per_example'])
             pre = 1.0
             for sft in (s_h, s_o):
                 pre = min(pre, float((sft - thr).abs().min()), float((sft[:, 1:] - sft[:, :-1]).abs().min()))
@@ -148,7 +153,8 @@ def run_case(name, shape_name, D, B, T, stage, train_mode, gain, inspect, extra=
     taps = {}
     o64 = orc.forward(p64, ocfg, batch['x_human'].double(), batch['x_objects'].double(),
                       batch['objects_mask'].double(), None if hseg is None else hseg.double(),
-                      None if oseg is None else oseg.double(), noise.double(), training=train_mode, taps=taps)
+                      None if oseg is None else oseg.double(), noise.double(), training=train_mode, taps=taps,
+                      steps_per_example=batch['steps_per_example'])
     o_margin = float((taps['y_oss'] - thr).abs().min()) if oseg is None else 1.0
     if o_margin <= CASE_MARGIN.get(name, 1e-4):
         raise RuntimeError(f'{name}: object gate margin too small ({o_margin}); change seeds')
@@ -200,6 +206,10 @@ GRAD_CASES = [
     ('grad_cad120_s2_sah', 'cad120', 32, 2, 8, 2, 2.0, {'object_segment_update_strategy': 'sah'}),
     ('grad_cad120_nf_sah', 'cad120', 32, 2, 8, 2, 2.0, {'object_segment_update_strategy': 'sah', 'filter_discrete_updates': 0, 'update_segment_threshold': 0.5}),
     ('grad_cad120_nf_coh', 'cad120', 32, 2, 8, 2, 2.0, {'object_segment_update_strategy': 'coh', 'filter_discrete_updates': 0, 'update_segment_threshold': 0.5}),
+    ('grad_mphoi_s2_time_se', 'mphoi', 32, 2, 9, 2, 2.0, {'add_time_position': 1, 'time_position_strategy': 's', 'positional_encoding_style': 'e'}),
+    ('grad_cad120_s2_time_sp', 'cad120', 32, 2, 8, 2, 2.0, {'add_time_position': 1, 'time_position_strategy': 's', 'positional_encoding_style': 'p'}),
+    ('grad_cad120_s2_time_ue', 'cad120', 32, 2, 8, 2, 2.0, {'add_time_position': 1, 'time_position_strategy': 'u', 'positional_encoding_style': 'e'}),
+    ('grad_mphoi_s2_time_up', 'mphoi', 32, 2, 9, 2, 2.0, {'add_time_position': 1, 'time_position_strategy': 'u', 'positional_encoding_style': 'p'}),
     # hidden 512 (the benchmarked width), T = 32: the D=512 BPTT and split-K weight-gradient paths against the reference itself
     ('grad_mphoi_s2_d512', 'mphoi', 512, 8, 32, 2, 1.0),
 ]
@@ -225,7 +235,7 @@ def _relu_margin(p64, ocfg, batch, hseg, oseg, noise, n_calls):
     try:
         orc.forward(p64, ocfg, batch['x_human'].double(), batch['x_objects'].double(), batch['objects_mask'].double(),
                     None if hseg is None else hseg.double(), None if oseg is None else oseg.double(),
-                    noise.double() if n_calls else None, training=True)
+                    noise.double() if n_calls else None, training=True, steps_per_example=batch['steps_per_example'])
     finally:
         orc._relu_lin = orig
     return worst[0]
@@ -267,7 +277,8 @@ def run_grad_case(name, shape_name, D, B, T, stage, gain, extra=None):
         taps = {}
         o64 = orc.forward(p64, ocfg, batch['x_human'].double(), batch['x_objects'].double(), batch['objects_mask'].double(),
                           None if hseg is None else hseg.double(), None if oseg is None else oseg.double(),
-                          noise.double() if n_calls else None, training=True, taps=taps)
+                          noise.double() if n_calls else None, training=True, taps=taps,
+                          steps_per_example=batch['steps_per_example'])
         softs = ([o64[1]] if shape.num_classes[1] is None else [o64[2], o64[3]]) if stage == 2 else []
         if oseg is None:
             softs.append(taps['y_oss'])

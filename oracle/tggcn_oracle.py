@@ -43,6 +43,9 @@ class OracleConfig:
     cat_level_states: bool = False          # models.py:901-903 (share_level_mlps changes no arithmetic: same tensors, two names)
     mean_pool: bool = False                 # message_aggregation 'mp' (models.py:1033-1036 and the other message functions)
     att_scaled: bool = True                 # attention_style 'v3' (scaled dot product); False = 'v2' (models.py:1740-1745)
+    time_position: str = ''                 # add_time_position: '' off, 's' = time embedding appended to the segment-level inputs
+                                            # (models.py:755-762), 'u' = appended to the gate MLP inputs (:656-662, :1494, :1527)
+    positional_encoding: str = 'e'          # 'e' = time_position_mlp (Linear(1, D) + ReLU) of (t+1)/steps, 'p' = periodic of (t+1)
     update_strategy: str = 'ind'            # object_segment_update_strategy 'ind' | 'sah' | 'coh' (models.py:1523-1532); 'sah' and
                                             # 'coh' only differ from 'ind' with exactly one human (models.py:741-742)
 
@@ -56,6 +59,8 @@ def config_from_kwargs(kw: dict) -> OracleConfig:
                         bool(kw['filter_discrete_updates']), float(kw['update_segment_threshold']),
                         bool(kw.get('cat_level_states', 0)), kw.get('message_aggregation') in ('mp', 'mean_pooling'),
                         kw.get('attention_style') not in ('v2', 'dot-product'),
+                        (kw.get('time_position_strategy', 's') if kw.get('add_time_position') else ''),
+                        'e' if kw.get('positional_encoding_style', 'e') in ('e', 'embedding') else 'p',
                         _UPD[kw.get('object_segment_update_strategy', 'ind')])
 
 
@@ -204,10 +209,23 @@ def reorder(hx: Tensor, u: Tensor) -> Tensor:
 # ----------------------------------------------------------------------------------------------
 # whole forward
 # ----------------------------------------------------------------------------------------------
+def time_embedding(p: Dict[str, Tensor], cfg: OracleConfig, steps_per_example: Tensor, T: int) -> Tensor:
+    """(T, B, D) time-position features: _assemble_time_tensor (vhoi/models.py:936-952) followed by time_position_mlp
+    (:259-260, embedding) or make_periodic_embedding (:1777-1794; no division by the number of steps, :654)."""
+    D = cfg.hidden_size
+    steps = steps_per_example.to(p['human_embedding_mlp.0.weight'].dtype)
+    x = torch.arange(1, T + 1, dtype=steps.dtype).unsqueeze(-1).repeat_interleave(steps.size(0), dim=1)     # (T, B)
+    if cfg.positional_encoding == 'e':
+        return _relu_lin(p, 'time_position_mlp.0', (x / steps).unsqueeze(-1))
+    w = torch.tensor([1e4], dtype=steps.dtype) ** torch.linspace(0, 1, D // 2, dtype=steps.dtype)
+    x = x.unsqueeze(-1)
+    return torch.cat([torch.sin(x / w), torch.cos(x / w)], dim=-1)
+
+
 def forward(p: Dict[str, Tensor], cfg: OracleConfig, x_human: Tensor, x_objects: Tensor, objects_mask: Tensor,
             human_segmentation: Optional[Tensor] = None, objects_segmentation: Optional[Tensor] = None,
             noise: Optional[Tensor] = None, training: bool = False, inspect_model: bool = False,
-            taps: Optional[dict] = None, gates_only: bool = False):
+            taps: Optional[dict] = None, gates_only: bool = False, steps_per_example: Optional[Tensor] = None):
     """TGGCN.forward, vhoi/models.py:584-933, for the shipped configuration family
     (message_type v2, granularity v1, attention aggregation style v3, update strategy 'ind',
     gumbel-sigmoid gates, message_segment on, geometry->objects on, geometry->human off).
@@ -253,6 +271,7 @@ def forward(p: Dict[str, Tensor], cfg: OracleConfig, x_human: Tensor, x_objects:
     hard_o = [[None] * T for _ in range(O)]
     soft_o = [[None] * T for _ in range(O)]
     att_oh = [[None] * T for _ in range(H)]
+    tt = time_embedding(p, cfg, steps_per_example, T) if cfg.time_position else None     # (T,B,D)
     for t in range(T):
         s_h = torch.cat([x_h[:, t], h_h[:, t]], dim=-1)                # (B,H,2D) sender/receiver features
         s_o = torch.cat([x_o[:, t], h_o[:, t]], dim=-1)
@@ -271,12 +290,16 @@ def forward(p: Dict[str, Tensor], cfg: OracleConfig, x_human: Tensor, x_objects:
             if human_segmentation is not None:                          # :697-698
                 hard_h[h][t] = soft_h[h][t] = human_segmentation[:, t:t + 1, h]
             else:                                                       # :1477-1498, :700-702
+                if cfg.time_position == 'u':
+                    gate_in.append(tt[t])
                 prob = torch.sigmoid(_lin(p, 'update_human_segment_mlp.0', torch.cat(gate_in, dim=-1)))
                 ysoft = gumbel_sigmoid(prob, next(noise_it) if noise_it is not None else None)
                 z = hard_gate(ysoft, thr)
                 if t == T - 1:
                     z = torch.ones_like(z)
                 hard_h[h][t], soft_h[h][t] = z, ysoft
+            if cfg.time_position == 's':
+                parts.append(tt[t])                                     # :755-762 (appended after the frame loop there)
             xx_h[h][t] = torch.cat(parts, dim=-1)                       # :705  [h, m_hh, m_oh]
         for k in range(O):
             mk = objects_mask[:, k:k + 1]
@@ -294,7 +317,7 @@ def forward(p: Dict[str, Tensor], cfg: OracleConfig, x_human: Tensor, x_objects:
             elif cfg.update_strategy == 'sah' and H == 1:               # :741-742, :1523-1525: the human's decision, no object MLP
                 hard_o[k][t], soft_o[k][t] = hard_h[0][t], soft_h[0][t]
             else:                                                       # :1500-1533 ('ind' / 'coh'); input order :1527
-                gate_in = torch.cat([x_o[:, t, k], h_o[:, t, k], m_ho, m_oo, m_go], dim=-1)
+                gate_in = torch.cat([x_o[:, t, k], h_o[:, t, k], m_ho, m_oo, m_go] + ([tt[t]] if cfg.time_position == 'u' else []), dim=-1)
                 prob = torch.sigmoid(_lin(p, 'update_object_segment_mlp.0', gate_in))
                 ysoft = gumbel_sigmoid(prob, next(noise_it) if noise_it is not None else None)
                 z = hard_gate(ysoft, thr)
@@ -303,7 +326,7 @@ def forward(p: Dict[str, Tensor], cfg: OracleConfig, x_human: Tensor, x_objects:
                 if t == T - 1:
                     z = torch.ones_like(z)
                 hard_o[k][t], soft_o[k][t] = z, ysoft
-            xx_o[k][t] = torch.cat([h_o[:, t, k], m_ho, m_go, m_oo], dim=-1)    # :748
+            xx_o[k][t] = torch.cat([h_o[:, t, k], m_ho, m_go, m_oo] + ([tt[t]] if cfg.time_position == 's' else []), dim=-1)    # :748
     y_hss = torch.stack([torch.cat(s, dim=-1) for s in soft_h], dim=-1)          # (B,T,H)
     y_oss = torch.stack([torch.cat(s, dim=-1) for s in soft_o], dim=-1)          # (B,T,O)
     y_hs = torch.stack([torch.cat(s, dim=-1) for s in hard_h], dim=-1)

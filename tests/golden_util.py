@@ -27,6 +27,10 @@ CASES = {
     'cad120_s2_sah': ('cad120', 32, 2, 11, 2, False, False, {'object_segment_update_strategy': 'sah'}),
     'cad120_nf_sah': ('cad120', 32, 2, 11, 2, False, False, {'object_segment_update_strategy': 'sah', 'filter_discrete_updates': 0, 'update_segment_threshold': 0.5}),
     'cad120_nf_coh': ('cad120', 32, 2, 11, 2, False, False, {'object_segment_update_strategy': 'coh', 'filter_discrete_updates': 0, 'update_segment_threshold': 0.5}),
+    'mphoi_s2_time_se': ('mphoi', 32, 2, 12, 2, False, False, {'add_time_position': 1, 'time_position_strategy': 's', 'positional_encoding_style': 'e'}),
+    'cad120_s2_time_sp': ('cad120', 32, 2, 11, 2, False, False, {'add_time_position': 1, 'time_position_strategy': 's', 'positional_encoding_style': 'p'}),
+    'cad120_s2_time_ue': ('cad120', 32, 2, 11, 2, False, False, {'add_time_position': 1, 'time_position_strategy': 'u', 'positional_encoding_style': 'e'}),
+    'mphoi_s2_time_up': ('mphoi', 32, 2, 12, 2, False, False, {'add_time_position': 1, 'time_position_strategy': 'u', 'positional_encoding_style': 'p'}),
 }
 
 # BASELINE.json configs[1] itself — what bench.py times (reference outputs; gate margin 2.5e-5).  Kept apart from CASES: the
@@ -51,6 +55,10 @@ GRAD_CASES = {
     'grad_cad120_s2_sah': ('cad120', 32, 2, 8, 2, {'object_segment_update_strategy': 'sah'}),
     'grad_cad120_nf_sah': ('cad120', 32, 2, 8, 2, {'object_segment_update_strategy': 'sah', 'filter_discrete_updates': 0, 'update_segment_threshold': 0.5}),
     'grad_cad120_nf_coh': ('cad120', 32, 2, 8, 2, {'object_segment_update_strategy': 'coh', 'filter_discrete_updates': 0, 'update_segment_threshold': 0.5}),
+    'grad_mphoi_s2_time_se': ('mphoi', 32, 2, 9, 2, {'add_time_position': 1, 'time_position_strategy': 's', 'positional_encoding_style': 'e'}),
+    'grad_cad120_s2_time_sp': ('cad120', 32, 2, 8, 2, {'add_time_position': 1, 'time_position_strategy': 's', 'positional_encoding_style': 'p'}),
+    'grad_cad120_s2_time_ue': ('cad120', 32, 2, 8, 2, {'add_time_position': 1, 'time_position_strategy': 'u', 'positional_encoding_style': 'e'}),
+    'grad_mphoi_s2_time_up': ('mphoi', 32, 2, 9, 2, {'add_time_position': 1, 'time_position_strategy': 'u', 'positional_encoding_style': 'p'}),
 }
 
 # hidden 512 (the benchmarked width), T = 32.  Kept apart from GRAD_CASES: the reference's own fp32 autograd carries summation

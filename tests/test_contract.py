@@ -25,7 +25,7 @@ def test_constructor_accepts_yaml_values_and_rejects_the_rest(pkg, synth):
     m = pkg.TGGCN(**kw)
     assert m.filter_discrete_updates and m.update_segment_threshold == pytest.approx(0.1)
     for bad in (dict(message_type='v1'), dict(attention_style='v1'), dict(message_aggregation='max'),
-                dict(object_segment_update_strategy='xyz'), dict(add_time_position=1), dict(share_level_mlps=1, bias=False),
+                dict(object_segment_update_strategy='xyz'), dict(add_segment_length=1), dict(share_level_mlps=1, bias=False),
                 dict(discrete_networks_num_layers=2), dict(message_geometry_to_human=True), dict(hidden_size=20)):
         with pytest.raises(NotImplementedError):
             pkg.TGGCN(**{**kw, **bad})
@@ -59,12 +59,30 @@ def test_update_strategy_variants_keep_the_reference_layout(pkg, synth):
     assert [k for k in ind.state_dict() if k not in gate] == list(sah.state_dict())
 
 
+def test_time_position_variants_keep_the_reference_layout(pkg, synth):
+    """add_time_position (vhoi/models.py:259-260, :290, :315, :530, :545): time_position_mlp registered first (embedding only),
+    one more D-wide block in the segment cells' inputs ('s') or in the gate MLPs' inputs ('u')."""
+    D = 32
+    base = pkg.TGGCN(**synth.model_kwargs(synth.CAD120, hidden_size=D, stage=2)).state_dict()
+    se = pkg.TGGCN(**synth.model_kwargs(synth.CAD120, hidden_size=D, stage=2, add_time_position=1)).state_dict()
+    assert list(se)[:2] == ['time_position_mlp.0.weight', 'time_position_mlp.0.bias'] and list(se)[2:] == list(base)
+    assert tuple(se['time_position_mlp.0.weight'].shape) == (D, 1)
+    assert se['human_segment_rnn_fcell.weight_ih'].shape[1] == base['human_segment_rnn_fcell.weight_ih'].shape[1] + D
+    assert se['object_segment_rnn_bcell.weight_ih'].shape[1] == 7 * D
+    assert se['update_object_segment_mlp.0.weight'].shape == base['update_object_segment_mlp.0.weight'].shape
+    up = pkg.TGGCN(**synth.model_kwargs(synth.CAD120, hidden_size=D, stage=2, add_time_position=1, time_position_strategy='u',
+                                        positional_encoding_style='p')).state_dict()
+    assert list(up) == list(base)                                   # periodic: no parameters of its own
+    assert up['update_object_segment_mlp.0.weight'].shape[1] == 6 * D and up['update_human_segment_mlp.0.weight'].shape[1] == 4 * D
+    assert up['object_segment_rnn_fcell.weight_ih'].shape == base['object_segment_rnn_fcell.weight_ih'].shape
+
+
 def test_weight_table_covers_the_state_dict(pkg, synth):
     for name in ('mphoi', 'cad120'):
         model = pkg.TGGCN(**synth.model_kwargs(synth.SHAPES[name], hidden_size=32, stage=1))
         keys = set(model.state_dict().keys())
         table = set(pkg.abi.WEIGHT_KEYS)
-        assert table <= keys | {k for k in table if k.startswith('object_') or k.startswith('humans_to_human')}
+        assert table <= keys | {k for k in table if k.startswith('object_') or k.startswith('humans_to_human') or k.startswith('time_position_mlp')}
         used_somewhere = {k for k in keys if k in table}
         # everything not in the table is a parameter the shipped configuration never reads
         dead = keys - used_somewhere
@@ -81,8 +99,8 @@ def test_library_loads_and_exports_every_declared_symbol(pkg):
         assert hasattr(lib, sym), sym
     assert lib.tggcn_abi_version() == pkg.abi.ABI_VERSION == int(re.search(r'#define TGGCN_ABI_VERSION\s+(\d+)', header).group(1))
     # struct mirrors: 17 int32 + 1 float + 8 int32; io = 6 + 4 + 8 + 3 + 3 + 1 pointers
-    assert ctypes.sizeof(pkg.abi.Dims) == 26 * 4
-    assert ctypes.sizeof(pkg.abi.IO) == 25 * 8
+    assert ctypes.sizeof(pkg.abi.Dims) == 28 * 4
+    assert ctypes.sizeof(pkg.abi.IO) == 27 * 8
     # the status decoder is host-only: healthy words, a barrier time-out, an fp16-split range violation
     words = (ctypes.c_uint32 * 8)()
     assert lib.tggcn_status_decode(words) == 0

@@ -52,7 +52,7 @@ def _oracle_grads(c, orc):
     b = c['batch']
     dd = lambda t: None if t is None else t.double()
     out = orc.forward(p, c['ocfg'], b['x_human'].double(), b['x_objects'].double(), b['objects_mask'].double(), dd(c['hseg']),
-                      dd(c['oseg']), dd(c['noise']), training=True)
+                      dd(c['oseg']), dd(c['noise']), training=True, steps_per_example=b['steps_per_example'])
     targets = [t.double() if t.is_floating_point() else t for t in c['targets']]
     losses = orc.multi_task_loss(out, targets, c['shape'].dataset, c['stage'])
     sum(losses).backward()
@@ -71,7 +71,7 @@ def test_backward_matches_reference_and_oracle(name, persistent, orc, synth, pkg
     b = c['batch']
     cu = lambda t: None if t is None else t.cuda()
     kwargs = dict(x_human=b['x_human'].cuda(), x_objects=b['x_objects'].cuda(), objects_mask=b['objects_mask'].cuda(),
-                  human_segmentation=cu(c['hseg']))
+                  human_segmentation=cu(c['hseg']), steps_per_example=b['steps_per_example'].cuda())
     if c['oseg'] is not None:
         kwargs['objects_segmentation'] = cu(c['oseg'])
     out = model(**kwargs)

@@ -97,7 +97,7 @@ def test_intermediates_match_oracle(name, orc):
     b = case.batch
     dd = lambda t: None if t is None else t.double()
     orc.forward(p64, case.ocfg, dd(b['x_human']), dd(b['x_objects']), dd(b['objects_mask']), dd(case.hseg), dd(case.oseg),
-                dd(case.noise), training=case.train_mode, taps=taps)
+                dd(case.noise), training=case.train_mode, taps=taps, steps_per_example=b['steps_per_example'])
     B, T, H, O, D, V = case.B, case.T, case.shape.H, case.shape.O, case.D, case.shape.V
     nkh = 2 if case.shape.hh else 1
     ws = model.workspace_tensor
@@ -108,8 +108,9 @@ def test_intermediates_match_oracle(name, orc):
         _assert_close('x_' + ent, s[..., :D], taps['x_' + ent])
         _assert_close('hfr_' + ent, ws('HFR_' + ent.upper(), (B, T, E, 2 * D)), taps['hfr_' + ent])
         _assert_close('h_' + ent, s[..., D:], taps['h_' + ent])
-    _assert_close('xx_h', ws('XX_H', (B, T, H, (1 + nkh) * D)), taps['xx_h'])
-    _assert_close('xx_o', ws('XX_O', (B, T, O, 4 * D)), taps['xx_o'])
+    ts = 1 if case.ocfg.time_position == 's' else 0
+    _assert_close('xx_h', ws('XX_H', (B, T, H, (1 + nkh + ts) * D)), taps['xx_h'])
+    _assert_close('xx_o', ws('XX_O', (B, T, O, (4 + ts) * D)), taps['xx_o'])
     _assert_close('hx_h', ws('HX_H', (B, T, H, 2 * D)), taps['hx_h'])
     _assert_close('hx_o', ws('HX_O', (B, T, O, 2 * D)), taps['hx_o'])
 

@@ -23,7 +23,8 @@ def test_oracle_matches_reference(name, dtype, orc):
     cast = lambda t: None if t is None else t.to(dtype)
     b = case.batch
     res = orc.forward(p, case.ocfg, cast(b['x_human']), cast(b['x_objects']), cast(b['objects_mask']), cast(case.hseg),
-                      cast(case.oseg), cast(case.noise), training=case.train_mode, inspect_model=case.inspect)
+                      cast(case.oseg), cast(case.noise), training=case.train_mode, inspect_model=case.inspect,
+                      steps_per_example=b['steps_per_example'])
     out, att = (res if case.inspect else (res, None))
     assert len(out) == len(case.outputs)
     n_gate = 2 if case.shape.num_classes[1] is None else 4
@@ -118,7 +119,7 @@ def test_oracle_gradients_match_reference(name, orc, synth, pkg):
     oseg = torch.ones(B, T, shape.O).double() if objects_given else None
     ocfg = orc.config_from_kwargs(kw)
     out = orc.forward(p, ocfg, batch['x_human'].double(), batch['x_objects'].double(), batch['objects_mask'].double(),
-                      hseg, oseg, noise.double() if n_calls else None, training=True)
+                      hseg, oseg, noise.double() if n_calls else None, training=True, steps_per_example=batch['steps_per_example'])
     targets = synth.target_list(shape, synth.make_targets(shape, batch['lengths'], T, seed=target_seed))
     targets = [t.double() if t.is_floating_point() else t for t in targets]
     losses = orc.multi_task_loss(out, targets, shape.dataset, stage)

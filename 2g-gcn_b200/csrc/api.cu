@@ -90,6 +90,7 @@ void make_layout(const tggcn_dims& d, Layout& L) {
     sz[TGGCN_BUF_XX_H] = N * H * (size_t)kh_of(d) * f;
     sz[TGGCN_BUF_XX_O] = N * O * (size_t)ko_of(d) * f;
     sz[TGGCN_BUF_TIME_EMB] = d.time_position ? N * D * f : 0;
+    sz[TGGCN_BUF_MSG_GH] = d.geo_to_human ? N * D * f : 0;
     sz[TGGCN_BUF_GS_H] = N * H * 6 * D * f;
     sz[TGGCN_BUF_GS_O] = N * O * 6 * D * f;
     sz[TGGCN_BUF_HX_H] = N * H * 2 * D * f;
@@ -127,7 +128,7 @@ void make_layout(const tggcn_dims& d, Layout& L) {
                               N * 2048 + D * 2048,
                               N * (H + O + 1) * D + 6 * 3 * D * D,
                               N * (H + O + 1) * 2 * D + 3 * D * 2 * D,
-                              N * (H + O + 1) * 2 * D + 5 * D * 2 * D,
+                              N * (H + O + 2) * 2 * D + 6 * D * 2 * D,
                               N * H * kh + N * O * ko + 2 * 3 * D * kh + 2 * 3 * D * ko};
         size_t m = 0;
         for (size_t v : st) m = v > m ? v : m;
@@ -268,7 +269,7 @@ static int forward_impl(const tggcn_dims* dims, const void* const* weights, int 
         for (int i = 0; i < 4; ++i) TG_REQUIRE(io->out_o[i], "forward: missing object head output %d", i);
     TG_REQUIRE((d.human_seg_given != 0) == (io->human_seg != nullptr), "forward: human_seg_given flag disagrees with pointer");
     TG_REQUIRE((d.object_seg_given != 0) == (io->object_seg != nullptr), "forward: object_seg_given flag disagrees with pointer");
-    TG_REQUIRE((d.human_seg_given && d.object_seg_given) || io->noise, "forward: Gumbel noise tensor required");
+    TG_REQUIRE((d.human_seg_given && d.object_seg_given) || d.straight_through || io->noise, "forward: Gumbel noise tensor required");
     static const int required[] = {
         TGGCN_W_GCN_W, TGGCN_W_GCN_BN_W, TGGCN_W_GCN_BN_B, TGGCN_W_GCN_BN_MEAN, TGGCN_W_GCN_BN_VAR, TGGCN_W_GCN_C1_W,
         TGGCN_W_GCN_C1_B, TGGCN_W_GCN_C3_W, TGGCN_W_GCN_C3_B, TGGCN_W_GCN_S1_W, TGGCN_W_GCN_S1_B, TGGCN_W_GCN_S2_W,
@@ -392,6 +393,10 @@ static int forward_impl(const tggcn_dims* dims, const void* const* weights, int 
     gemm_add(g, buf(TGGCN_BUF_S_O), 2 * D, W(TGGCN_W_MSG_OH_W), 2 * D, W(TGGCN_W_MSG_OH_B), buf(TGGCN_BUF_MSG_OH), D, N * O, D, 2 * D, 1);
     gemm_add(g, buf(TGGCN_BUF_S_O), 2 * D, W(TGGCN_W_MSG_OO_W), 2 * D, W(TGGCN_W_MSG_OO_B), buf(TGGCN_BUF_MSG_OO), D, N * O, D, 2 * D, 1);
     gemm_add(g, buf(TGGCN_BUF_S_G), 2 * D, W(TGGCN_W_MSG_GO_W), 2 * D, W(TGGCN_W_MSG_GO_B), buf(TGGCN_BUF_MSG_GO), D, N, D, 2 * D, 1);
+    if (d.geo_to_human) {
+        TG_REQUIRE(W(TGGCN_W_MSG_GH_W) && W(TGGCN_W_MSG_GH_B), "forward: geometry_to_human_message_mlp weights missing");
+        gemm_add(g, buf(TGGCN_BUF_S_G), 2 * D, W(TGGCN_W_MSG_GH_W), 2 * D, W(TGGCN_W_MSG_GH_B), buf(TGGCN_BUF_MSG_GH), D, N, D, 2 * D, 1);
+    }
     if (int rc = project(g)) return rc;
     STAGE_END();
     // 8. attention, aggregation, gates, segment-level inputs
@@ -407,7 +412,8 @@ static int forward_impl(const tggcn_dims* dims, const void* const* weights, int 
         FrameMsgParams P;
         memset(&P, 0, sizeof(P));
         P.B = B; P.T = T; P.H = H; P.O = O; P.D = D; P.hh = d.hh; P.thr = d.thr; P.mean_pool = d.mean_pool; P.att_noscale = d.att_noscale;
-        P.update_strategy = d.update_strategy;
+        P.update_strategy = d.update_strategy; P.straight_through = d.straight_through;
+        P.gh = d.geo_to_human ? 1 : 0; P.msg_gh = d.geo_to_human ? buf(TGGCN_BUF_MSG_GH) : nullptr;
         P.time_position = d.time_position; P.time_emb = d.time_position ? buf(TGGCN_BUF_TIME_EMB) : nullptr;
         P.s_h = buf(TGGCN_BUF_S_H); P.s_o = buf(TGGCN_BUF_S_O);
         P.msg_hh = buf(TGGCN_BUF_MSG_HH); P.msg_ho = buf(TGGCN_BUF_MSG_HO); P.msg_oh = buf(TGGCN_BUF_MSG_OH);

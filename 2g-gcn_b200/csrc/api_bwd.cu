@@ -25,7 +25,7 @@ struct BwdLayout {
         return o;
     }
     size_t dhfr[3], dhx[2], dgs[2], dghs[2], du[2], direct[2], dmg[2], dpre[2], lgr[4], lgs[4], dpre_all[4], gru_direct[3];
-    size_t dtime, dxx[2], ds[3], dmsg[5], dgi[3], dgh[3], bigru_scratch, dgeo_hid, dgcn_out, dxn, wt_seg, wt, tn, tn_floats;
+    size_t dtime, dxx[2], ds[3], dmsg[6], dgi[3], dgh[3], bigru_scratch, dgeo_hid, dgcn_out, dxn, wt_seg, wt, tn, tn_floats;
     size_t zero_begin, zero_end;     // region that must be zero before the kernels run (atomically accumulated)
 };
 
@@ -65,6 +65,7 @@ void make_bwd_layout(const tggcn_dims& d, BwdLayout& L) {
     L.dmsg[2] = L.take(N * O * D);
     L.dmsg[3] = L.take(N * O * D);
     L.dmsg[4] = L.take(N * D);
+    L.dmsg[5] = L.take(d.geo_to_human ? N * D : 0);
     for (int g = 0; g < 3; ++g) {
         L.dgi[g] = L.take(N * E[g] * 6 * D);
         L.dgh[g] = L.take(N * E[g] * 6 * D);
@@ -95,7 +96,7 @@ void make_bwd_layout(const tggcn_dims& d, BwdLayout& L) {
     // humans + objects (both directions), the embeddings + geometry MLP
     const size_t kh_ = kh_of(d);
     const size_t grp_cands[] = {rp * ((H ? 1 : 0) * (7 * D + kh_ + nkh * D) + 9 * D + ko_), 2 * rp * 15 * D,
-                                2 * rp * (D + 2048) + np * (D + 2048) + np * (2048 + 128 * V), 3 * rp * 4 * D + np * 3 * D};
+                                2 * rp * (D + 2048) + np * (D + 2048) + np * (2048 + 128 * V), 3 * rp * 4 * D + np * 6 * D};
     for (size_t c : grp_cands)
         if (c > tmax) tmax = c;
     tmax += 4096;
@@ -144,7 +145,7 @@ size_t tggcn_backward_workspace_bytes(const tggcn_dims* dims) {
 
 int tggcn_backward_bucket(int id) {
     if (id < 0 || id >= TGGCN_W_COUNT) return -1;
-    if (id == TGGCN_W_TIME_W || id == TGGCN_W_TIME_B) return 1;            // formed with the frame-level graph
+    if (id == TGGCN_W_TIME_W || id == TGGCN_W_TIME_B || id == TGGCN_W_MSG_GH_W || id == TGGCN_W_MSG_GH_B) return 1;            // formed with the frame-level graph
     if (id <= TGGCN_W_GCN_S2_B) return 3;                                   // GCN_* (first 13 entries of the table)
     if (id <= TGGCN_W_OBJ_EMB_B) return 2;                                  // geometry MLP, ROI embeddings
     if (id >= TGGCN_W_HSEG_F_WIH || (id >= TGGCN_W_SMSG_HH_W && id <= TGGCN_W_SMSG_OO_B)) return 0;   // cells, heads, segment MLPs
@@ -447,7 +448,8 @@ int tggcn_backward_ex(const tggcn_dims* dims, const void* const* weights, void* 
         FrameBwdParams P;
         memset(&P, 0, sizeof(P));
         P.B = B; P.T = T; P.H = H; P.O = O; P.D = D; P.hh = d.hh; P.filter = d.filter; P.thr = d.thr; P.mean_pool = d.mean_pool; P.att_noscale = d.att_noscale;
-        P.update_strategy = d.update_strategy;
+        P.update_strategy = d.update_strategy; P.straight_through = d.straight_through;
+        P.gh = d.geo_to_human ? 1 : 0; P.msg_gh = P.gh ? buf(TGGCN_BUF_MSG_GH) : nullptr; P.dmsg_gh = P.gh ? bb(BL.dmsg[5]) : nullptr;
         P.time_position = d.time_position; P.time_emb = d.time_position ? buf(TGGCN_BUF_TIME_EMB) : nullptr;
         // no gradient pointers for time_position_mlp = it is off the gradient path of this call (strategy 'u' with every gate imposed)
         P.dtime = (d.time_position && !d.time_periodic && G(TGGCN_W_TIME_W) && G(TGGCN_W_TIME_B)) ? bb(BL.dtime) : nullptr;
@@ -468,7 +470,7 @@ int tggcn_backward_ex(const tggcn_dims* dims, const void* const* weights, void* 
         P.dmsg_go = bb(BL.dmsg[4]);
         P.dw_uh = G(TGGCN_W_UPD_H_W); P.db_uh = G(TGGCN_W_UPD_H_B); P.dw_uo = G(TGGCN_W_UPD_O_W); P.db_uo = G(TGGCN_W_UPD_O_B);
         if (!d.human_seg_given) {
-            TG_CUDA_OK(cudaMemsetAsync(P.dw_uh, 0, sizeof(float) * (size_t)(2 + nkh + tu_of(d)) * D, stream));
+            TG_CUDA_OK(cudaMemsetAsync(P.dw_uh, 0, sizeof(float) * (size_t)(2 + nkh + gh_of(d) + tu_of(d)) * D, stream));
             TG_CUDA_OK(cudaMemsetAsync(P.db_uh, 0, sizeof(float), stream));
         }
         if (!d.object_seg_given && d.update_strategy != 1) {
@@ -485,15 +487,16 @@ int tggcn_backward_ex(const tggcn_dims* dims, const void* const* weights, void* 
     // ---- 7. message MLPs: msg = ReLU(W [x|h] + b) ---------------------------------------------------------------------------------
     {
         struct Kind { int w_id; int msg_buf; int dmsg; int grp; int on; };
-        const Kind kinds[5] = {{TGGCN_W_MSG_HH_W, TGGCN_BUF_MSG_HH, 0, 0, d.hh}, {TGGCN_W_MSG_HO_W, TGGCN_BUF_MSG_HO, 1, 0, 1},
+        const Kind kinds[6] = {{TGGCN_W_MSG_HH_W, TGGCN_BUF_MSG_HH, 0, 0, d.hh}, {TGGCN_W_MSG_HO_W, TGGCN_BUF_MSG_HO, 1, 0, 1},
                                {TGGCN_W_MSG_OH_W, TGGCN_BUF_MSG_OH, 2, 1, 1},    {TGGCN_W_MSG_OO_W, TGGCN_BUF_MSG_OO, 3, 1, 1},
-                               {TGGCN_W_MSG_GO_W, TGGCN_BUF_MSG_GO, 4, 2, 1}};
+                               {TGGCN_W_MSG_GO_W, TGGCN_BUF_MSG_GO, 4, 2, 1},    {TGGCN_W_MSG_GH_W, TGGCN_BUF_MSG_GH, 5, 2, d.geo_to_human}};
         const int s_buf[3] = {TGGCN_BUF_S_H, TGGCN_BUF_S_O, TGGCN_BUF_S_G};
         const int Eg[3] = {H, O, 1};
         int touched[3] = {1, 1, 0};      // ds_h / ds_o were written by the frame kernel; ds_g starts here
         float* wt = bb(BL.wt);
-        for (int k = 0; k < 5; ++k) {
+        for (int k = 0; k < 6; ++k) {
             if (!kinds[k].on) continue;
+            TG_REQUIRE(W(kinds[k].w_id) && G(kinds[k].w_id) && G(kinds[k].w_id + 1), "backward: message MLP #%d pointers missing", k);
             const int gidx = kinds[k].grp, M = N * Eg[gidx];
             const float* dmsg = bb(BL.dmsg[kinds[k].dmsg]);
             const float* msg = buf(kinds[k].msg_buf);

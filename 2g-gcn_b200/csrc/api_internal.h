@@ -14,8 +14,9 @@ inline int nkh_of(const tggcn_dims& d) { return d.hh ? 2 : 1; }
 // widths (in units of D) around the segment cells' input rows: [h, m.. (, time)] frame part, then the segment-message columns
 inline int ts_of(const tggcn_dims& d) { return d.time_position == 1 ? 1 : 0; }       // time block in the segment-level inputs
 inline int tu_of(const tggcn_dims& d) { return d.time_position == 2 ? 1 : 0; }       // time block in the gate MLP inputs
-inline int kh_of(const tggcn_dims& d) { return (1 + nkh_of(d) + ts_of(d)) * d.D; }   // xx_h row = frame-part columns of the human W_ih
-inline int ldwh_of(const tggcn_dims& d) { return (1 + 2 * nkh_of(d) + ts_of(d)) * d.D; }
+inline int gh_of(const tggcn_dims& d) { return d.geo_to_human ? 1 : 0; }             // geometry -> human message block
+inline int kh_of(const tggcn_dims& d) { return (1 + nkh_of(d) + gh_of(d) + ts_of(d)) * d.D; }   // xx_h row = frame-part columns of the human W_ih
+inline int ldwh_of(const tggcn_dims& d) { return kh_of(d) + nkh_of(d) * d.D; }
 inline int ko_of(const tggcn_dims& d) { return (4 + ts_of(d)) * d.D; }               // xx_o row
 inline int ldwo_of(const tggcn_dims& d) { return (6 + ts_of(d)) * d.D; }
 void make_layout(const tggcn_dims& d, Layout& L);

@@ -127,7 +127,8 @@ __global__ void __launch_bounds__(256) frame_bwd_kernel(const FrameBwdParams P) 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int nkh = P.hh ? 2 : 1;
     const int ts = P.time_position == 1 ? 1 : 0, tu = P.time_position == 2 ? 1 : 0;
-    const int wh = (1 + nkh + ts) * D, wo = (4 + ts) * D;      // rows of xx_h / xx_o (and of their gradients)
+    const int gh = P.gh;
+    const int wh = (1 + nkh + gh + ts) * D, wo = (4 + ts) * D;      // rows of xx_h / xx_o (and of their gradients)
     float* sv = sm;                            // [NE][2D]
     float* dmh = sv + NE * D2;                 // [H][nkh*D]   d m_hh | d m_oh
     float* dmo = dmh + H * nkh * D;            // [O][3D]      d m_ho | d m_go | d m_oo
@@ -192,7 +193,8 @@ __global__ void __launch_bounds__(256) frame_bwd_kernel(const FrameBwdParams P) 
         if (sampled && !(strat == 1 && !is_h)) {
             const float p = P.pgate[(size_t)n * NE + tid];
             // y = sigmoid(log(p+eps) - log(1-p+eps) + g0 - g1), p = sigmoid(logit)
-            dl_ = dy * y * (1.0f - y) * (1.0f / (p + 1e-20f) + 1.0f / ((1.0f - p) + 1e-20f)) * p * (1.0f - p);
+            dl_ = P.straight_through ? dy * p * (1.0f - p)          // y = p
+                                     : dy * y * (1.0f - y) * (1.0f / (p + 1e-20f) + 1.0f / ((1.0f - p) + 1e-20f)) * p * (1.0f - p);
         }
         if (act) dlogit[tid] = dl_;
     }
@@ -232,21 +234,32 @@ __global__ void __launch_bounds__(256) frame_bwd_kernel(const FrameBwdParams P) 
         for (int c = tid; c < D; c += 256) {
             float v = 0.0f;
             if (ts) {
-                for (int h = 0; h < H; ++h) v += P.dxx_h[((size_t)n * H + h) * wh + (1 + nkh) * D + c];
+                for (int h = 0; h < H; ++h) v += P.dxx_h[((size_t)n * H + h) * wh + (1 + nkh + gh) * D + c];
                 for (int k = 0; k < O; ++k) v += P.dxx_o[((size_t)n * O + k) * wo + 4 * D + c];
             } else {
-                float gh = 0.0f, go = 0.0f;
-                for (int h = 0; h < H; ++h) gh += dlogit[h];
+                float gsum_h = 0.0f, go = 0.0f;
+                for (int h = 0; h < H; ++h) gsum_h += dlogit[h];
                 for (int k = 0; k < O; ++k) go += dlogit[H + k];
-                if (P.human_seg == nullptr) { v = fmaf(gh, __ldg(P.w_uh + D2 + nkh * D + c), v); atomicAdd(P.dw_uh + D2 + nkh * D + c, gh * __ldg(te + c)); }
+                if (P.human_seg == nullptr) { v = fmaf(gsum_h, __ldg(P.w_uh + D2 + (nkh + gh) * D + c), v); atomicAdd(P.dw_uh + D2 + (nkh + gh) * D + c, gsum_h * __ldg(te + c)); }
                 if (P.object_seg == nullptr && P.dw_uo != nullptr) { v = fmaf(go, __ldg(P.w_uo + 5 * D + c), v); atomicAdd(P.dw_uo + 5 * D + c, go * __ldg(te + c)); }
             }
             if (P.dtime != nullptr) P.dtime[(size_t)n * D + c] = v;
         }
     }
+    // geometry -> human message (one sender, weight 1): gradient from every human's xx row and gate input
+    if (gh) {
+        for (int c = tid; c < D; c += 256) {
+            float v = 0.0f;
+            for (int h = 0; h < H; ++h) {
+                v += P.dxx_h[((size_t)n * H + h) * wh + (1 + nkh) * D + c];
+                if (P.human_seg == nullptr) v = fmaf(dlogit[h], __ldg(P.w_uh + D2 + nkh * D + c), v);
+            }
+            P.dmsg_gh[(size_t)n * D + c] = v;
+        }
+    }
     // gate weight gradients: d w[k] += sum_e dlogit[e] * input_e[k]
     if (P.human_seg == nullptr) {
-        for (int k = tid; k < D2 + nkh * D; k += 256) {
+        for (int k = tid; k < D2 + (nkh + gh) * D; k += 256) {      // xx_h row = [h, m_hh, m_oh, m_gh ..]: the gate's message blocks in order
             float v = 0.0f;
             for (int h = 0; h < H; ++h) {
                 const float in = k < D2 ? sv[h * D2 + k] : __ldg(P.xx_h + ((size_t)n * H + h) * wh + D + (k - D2));

@@ -78,6 +78,10 @@ struct FrameBwdParams {
     int mean_pool;                                 // uniform sender weights: no gradient through attention logits
     int att_noscale;                               // attention_style 'v2': plain dot-product logits
     int update_strategy;                           // 0 'ind', 1 'sah', 2 'coh' (tggcn_dims.update_strategy)
+    int gh;                                        // message_geometry_to_human: block m_gh after m_oh in the humans' rows
+    const float* msg_gh;                           // (B,T,1,D) forward message, or null
+    float* dmsg_gh;                                // (B,T,1,D) out: its gradient
+    int straight_through;                          // discrete_optimization_strategy 'st': y = p, identity gradient of the hard gate
     int time_position;                             // 0 off, 1 's' (time block in the xx rows), 2 'u' (in the gate inputs)
     const float* time_emb;                         // (B*T, D) forward time-position features, or null
     float* dtime;                                  // (B*T, D) out: their gradient (null for the periodic encoding: no parameters)

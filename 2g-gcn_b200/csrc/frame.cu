@@ -103,7 +103,8 @@ __global__ void __launch_bounds__(FM_THREADS) frame_messages_kernel(const FrameM
         const float* g_oo = P.msg_oo + (size_t)n * O * D;
         const float* g_go = P.msg_go + (size_t)n * D;
         const int ts = P.time_position == 1 ? 1 : 0;
-        const int wh = (1 + nkh + ts) * D;       // xx_h row: [h, (m_hh), m_oh (, time)]
+        const int gh = P.gh;
+        const int wh = (1 + nkh + gh + ts) * D;  // xx_h row: [h, (m_hh), m_oh (, m_gh) (, time)]
         const int wo = (4 + ts) * D;             // xx_o row: [h, m_ho, m_go, m_oo (, time)]
         float* xxh = P.xx_h + (size_t)n * H * wh;
         float* xxo = P.xx_o + (size_t)n * O * wo;
@@ -129,7 +130,8 @@ __global__ void __launch_bounds__(FM_THREADS) frame_messages_kernel(const FrameM
             for (int k = 0; k < O; ++k) fma4(a_oh[h * FM_MAXE + k], scale4(ld4(g_oh + k * D + c), om[k]), v);
             *reinterpret_cast<float4*>(mh + h * nkh * D + (nkh - 1) * D + c) = v;
             *reinterpret_cast<float4*>(row + nkh * D + c) = v;
-            if (ts) *reinterpret_cast<float4*>(row + (1 + nkh) * D + c) = ld4(te + c);      // models.py:761
+            if (gh) *reinterpret_cast<float4*>(row + (1 + nkh) * D + c) = ld4(P.msg_gh + (size_t)n * D + c);   // models.py:694, :705
+            if (ts) *reinterpret_cast<float4*>(row + (1 + nkh + gh) * D + c) = ld4(te + c);  // models.py:761
         }
         for (int idx = tid; idx < O * D4; idx += FM_THREADS) {
             const int k = idx / D4, c = (idx - k * D4) * 4;
@@ -168,6 +170,10 @@ __global__ void __launch_bounds__(FM_THREADS) frame_messages_kernel(const FrameM
         if (is_h) {
             const float* m = mh + r * nkh * D;       // gate input order [x, h, m_hh, m_oh], models.py:1494
             for (int k = lane; k < nkh * D; k += 32) acc = fmaf(__ldg(w + D2 + k), m[k], acc);
+            if (P.gh) {
+                const float* g = P.msg_gh + (size_t)n * D;
+                for (int k = lane; k < D; k += 32) acc = fmaf(__ldg(w + D2 + nkh * D + k), __ldg(g + k), acc);
+            }
         } else {
             const float* m = mo + r * 3 * D;          // gate input order [x, h, m_ho, m_oo, m_go], models.py:1527
             for (int k = lane; k < D; k += 32) {
@@ -177,13 +183,18 @@ __global__ void __launch_bounds__(FM_THREADS) frame_messages_kernel(const FrameM
             }
         }
         if (P.time_position == 2) {                   // strategy 'u': the time feature is the last block of the gate input
-            const float* wt = w + D2 + (is_h ? nkh : 3) * D;
+            const float* wt = w + D2 + (is_h ? nkh + P.gh : 3) * D;
             const float* te = P.time_emb + (size_t)n * D;
             for (int k = lane; k < D; k += 32) acc = fmaf(__ldg(wt + k), __ldg(te + k), acc);
         }
         acc = warp_sum(acc);
         const float logit = acc + __ldg(is_h ? P.b_uh : P.b_uo);
         p = 1.0f / (1.0f + expf(-logit));
+        if (P.straight_through) {                     // discrete_estimator 'st', models.py:1621-1622
+            y = p;
+            z = p > P.thr ? 1.0f : 0.0f;
+            return;
+        }
         const int pos = is_h ? r : (P.human_seg ? 0 : H) + r;
         const float* g = P.noise + ((size_t)(t * n_sampled + pos) * P.B + b) * 2;
         const float la = logf(p + 1e-20f) + __ldg(g);
@@ -211,11 +222,11 @@ __global__ void __launch_bounds__(FM_THREADS) frame_messages_kernel(const FrameM
         if (!is_h && strat == 2) {
             float yh, zh, ph;
             sample_gate(0, yh, zh, ph);
-            human_hard = (zh - yh) + yh;
+            human_hard = P.straight_through ? zh : (zh - yh) + yh;
         }
         if (lane == 0) {
             if (P.pgate_save != nullptr) P.pgate_save[(size_t)n * NE + e] = p;
-            float hard = ((z - y) + y) * human_hard;  // straight-through value, distributions.py:35 (x the human's under 'coh')
+            float hard = (P.straight_through ? z : (z - y) + y) * human_hard;  // straight-through value, distributions.py:35 (x the human's under 'coh')
             if (t == T - 1) hard = 1.0f;              // models.py:701-702, :744-745
             y_soft[oi] = y;
             y_hard[oi] = hard;

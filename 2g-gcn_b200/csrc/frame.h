@@ -9,6 +9,9 @@ struct FrameMsgParams {
     int mean_pool;          // message_aggregation 'mp': uniform weights over the valid senders instead of attention
     int att_noscale;        // attention_style 'v2': plain dot-product logits
     int update_strategy;    // 0 'ind', 1 'sah' (object gates = the single human's), 2 'coh' (hard object gate x the human's)
+    int gh;                 // message_geometry_to_human: block m_gh after m_oh in the humans' xx rows and gate inputs
+    const float* msg_gh;    // (B,T,1,D) ReLU(W_gh s_g + b), or null
+    int straight_through;   // discrete_optimization_strategy 'st': soft = sigmoid probability, hard = (p > thr), no noise
     int time_position;      // 0 off, 1 's': time block appended to the xx rows, 2 'u': appended to the gate inputs
     const float* time_emb;  // (B*T, D) time-position features, or null
     float thr;

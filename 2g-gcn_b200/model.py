@@ -23,6 +23,7 @@ import torch.nn as nn
 from . import abi
 
 _GS = {'gs', 'gumbel-sigmoid'}
+_ST = {'st', 'straight-through'}
 _ATT = {'att', 'attention'}
 _MP = {'mp', 'mean_pooling'}
 _V3 = {'v3', 'scaled_dot-product'}
@@ -117,10 +118,9 @@ class TGGCN(nn.Module):
         super().__init__()
         unsupported = []
         if discrete_networks_num_layers != 1: unsupported.append('discrete_networks_num_layers != 1')
-        if discrete_optimization_strategy not in _GS: unsupported.append('discrete_optimization_strategy != gumbel-sigmoid')
+        if discrete_optimization_strategy not in _GS | _ST: unsupported.append('unknown discrete_optimization_strategy')
         if not (message_human_to_objects and message_objects_to_human and message_objects_to_object
                 and message_geometry_to_objects): unsupported.append('a human/object/geometry message switched off')
-        if message_geometry_to_human: unsupported.append('message_geometry_to_human')
         if not message_segment: unsupported.append('message_segment off')
         if message_type not in _NONREL: unsupported.append("message_type != 'v2'")
         if message_granularity not in _GENERIC: unsupported.append("message_granularity != 'v1'")
@@ -149,7 +149,7 @@ class TGGCN(nn.Module):
         self.message_objects_to_human = True
         self.message_objects_to_object = True
         self.message_geometry_to_objects = True
-        self.message_geometry_to_human = False
+        self.message_geometry_to_human = bool(message_geometry_to_human)
         self.message_segment = True
         self.message_type, self.message_granularity = message_type, message_granularity
         self.message_aggregation, self.attention_style = message_aggregation, attention_style
@@ -176,7 +176,8 @@ class TGGCN(nn.Module):
         self.human_embedding_mlp = _mlp([2048, D], ['relu'])
         self.human_bd_rnn = nn.GRU(D, D, num_layers=1, bias=True, batch_first=True, bidirectional=True)
         self.human_bd_embedding_mlp = _mlp([2 * D, D], ['relu'])
-        h_in = D * (1 + (2 if hh else 0) + 2 + ts)
+        gh = int(self.message_geometry_to_human)
+        h_in = D * (1 + (2 if hh else 0) + 2 + gh + ts)
         self.human_segment_rnn_fcell = nn.GRUCell(h_in, D, bias=True)
         self.human_segment_rnn_bcell = nn.GRUCell(h_in, D, bias=True)
         self.object_embedding_mlp = _mlp([object_input_size, D], ['relu'])
@@ -194,12 +195,18 @@ class TGGCN(nn.Module):
             if message_aggregation in _ATT:
                 setattr(self, f'{att_names[kind]}_message_att_mlp', _mlp([4 * D, 1], ['relu']))
                 setattr(self, f'{att_names[kind]}_segment_message_att_mlp', _mlp([2 * D, 1], ['relu']))
+        if gh:                                                     # models.py:456-488; the segment-level MLP and the att MLPs are dead
+            self.geometry_to_human_message_mlp = _mlp([2 * D, D], ['relu'])
+            self.geometry_to_human_segment_message_mlp = _mlp([D, D], ['relu'])
+            if message_aggregation in _ATT:
+                self.geometry_to_human_message_att_mlp = _mlp([4 * D, 1], ['relu'])
+                self.geometry_to_human_segment_message_att_mlp = _mlp([2 * D, 1], ['relu'])
         self.geometry_to_object_message_mlp = _mlp([2 * D, D], ['relu'])
         self.geometry_to_object_segment_message_mlp = _mlp([D, D], ['relu'])          # dead in the reference too
         if message_aggregation in _ATT:
             self.geometry_to_object_message_att_mlp = _mlp([4 * D, 1], ['relu'])
             self.geometry_to_object_segment_message_att_mlp = _mlp([2 * D, 1], ['relu'])
-        self.update_human_segment_mlp = _mlp([D * (2 + (1 if hh else 0) + 1 + tu), 1], ['sigmoid'])
+        self.update_human_segment_mlp = _mlp([D * (2 + (1 if hh else 0) + 1 + gh + tu), 1], ['sigmoid'])
         if object_segment_update_strategy not in _SAH:            # models.py:537: no object gate MLP under 'sah'
             self.update_object_segment_mlp = _mlp([(5 + tu) * D, 1], ['sigmoid'])
         label_in = (4 if self.cat_level_states else 2) * D        # models.py:553-555
@@ -386,6 +393,9 @@ class TGGCN(nn.Module):
         with_grad = torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters())
         if inspect_model and self.message_aggregation in _MP:
             raise NotImplementedError('inspect_model has no attention weights to return under mean-pooling aggregation')
+        if with_grad and self.discrete_optimization_strategy in _ST and (human_segmentation is None or objects_segmentation is None):
+            raise NotImplementedError("discrete_optimization_strategy 'st' is inference-only: the reference's StraightThroughEstimator.backward "
+                                      'returns one gradient for two inputs and autograd rejects it (pyrutils/torch/distributions.py:39-53)')
         if with_grad and (inspect_model or stage_ms is not None):
             raise NotImplementedError('inspect_model / stage profiling are inference-only: call under torch.no_grad()')
 
@@ -405,6 +415,8 @@ class TGGCN(nn.Module):
                         mean_pool=int(self.message_aggregation in _MP), recurrent_mode=int(self.recurrent_mode),
                         no_fp16_split=int(self.no_fp16_split), precision=int(self.precision),
                         att_noscale=int(self.attention_style in _V2))
+        dims.straight_through = int(self.discrete_optimization_strategy in _ST)
+        dims.geo_to_human = int(self.message_geometry_to_human)
         steps = freq = None
         if self.add_time_position:
             dims.time_position = 1 if self.time_position_strategy == 's' else 2
@@ -428,7 +440,7 @@ class TGGCN(nn.Module):
             if strat == 1 or not self.filter_discrete_updates:       # under the filter 'coh' equals 'ind' (models.py:751-753)
                 dims.update_strategy = strat
         objects_sampled = oseg is None and dims.update_strategy != 1
-        n_sampled = (0 if hseg is not None else H) + (O if objects_sampled else 0)
+        n_sampled = 0 if dims.straight_through else (0 if hseg is not None else H) + (O if objects_sampled else 0)
         noise = None
         if n_sampled:
             noise = self._noise_override

@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define TGGCN_ABI_VERSION 9
+#define TGGCN_ABI_VERSION 11
 
 #if defined(__GNUC__)
 #define TGGCN_API __attribute__((visibility("default")))
@@ -74,6 +74,12 @@ typedef struct tggcn_dims {
     int32_t time_periodic;       /* positional_encoding_style: 0 = 'e': ReLU(time_position_mlp((t+1) / steps_per_example[b]))
                                     (models.py:259-260, :936-952); 1 = 'p': [sin((t+1)/w_i), cos((t+1)/w_i)] with the D/2
                                     frequencies w_i = 1e4^(i/(D/2-1)) passed in tggcn_io.time_freq (models.py:1777-1794)         */
+    int32_t straight_through;    /* discrete_optimization_strategy 'st' (discrete_estimator, models.py:1620-1622; StraightThroughEstimator,
+                                    distributions.py:39-53): soft gate = the sigmoid probability, hard gate = (p > thr) exactly, identity
+                                    gradient; no Gumbel noise is read.  0 = 'gs' (Gumbel-sigmoid, distributions.py:4-36)                */
+    int32_t geo_to_human;        /* message_geometry_to_human (models.py:690-695, :1432-1475): the humans' segment-level input rows and
+                                    gate inputs carry one more block m_gh = ReLU(geometry_to_human_message_mlp([x_g | h_g])) after
+                                    m_oh (single sender: weight 1, no mask)                                                     */
 } tggcn_dims;
 
 /* Parameter table.  One device pointer per reference state_dict() entry, in this order
@@ -185,7 +191,9 @@ typedef struct tggcn_dims {
     X(HEAD_O_PRED_W, "object_prediction_mlp.0.weight")                                                 \
     X(HEAD_O_PRED_B, "object_prediction_mlp.0.bias")                                                   \
     X(TIME_W,       "time_position_mlp.0.weight")                                                      \
-    X(TIME_B,       "time_position_mlp.0.bias")
+    X(TIME_B,       "time_position_mlp.0.bias")                                                        \
+    X(MSG_GH_W,     "geometry_to_human_message_mlp.0.weight")                                          \
+    X(MSG_GH_B,     "geometry_to_human_message_mlp.0.bias")
 
 enum tggcn_weight_id {
 #define TGGCN_X_ENUM(id, key) TGGCN_W_##id,
@@ -271,6 +279,7 @@ enum tggcn_buf_id {
     TGGCN_BUF_SALPHA_OO,
     TGGCN_BUF_PACK,          /* 16-bit operand planes of the projection stage in flight (gemm16.cu)                       */
     TGGCN_BUF_TIME_EMB,      /* (B*T, D)             time-position features (empty unless dims.time_position)             */
+    TGGCN_BUF_MSG_GH,        /* (B,T,1,D)            geometry -> human frame message (empty unless dims.geo_to_human)     */
     TGGCN_BUF_COUNT
 };
 

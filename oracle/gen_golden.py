@@ -73,6 +73,12 @@ CASES = [
     ('cad120_s2_time_sp', 'cad120', 32, 2, 11, 2, False, 2.0, False, {'add_time_position': 1, 'time_position_strategy': 's', 'positional_encoding_style': 'p'}),
     ('cad120_s2_time_ue', 'cad120', 32, 2, 11, 2, False, 2.0, False, {'add_time_position': 1, 'time_position_strategy': 'u', 'positional_encoding_style': 'e'}),
     ('mphoi_s2_time_up', 'mphoi', 32, 2, 12, 2, False, 2.0, False, {'add_time_position': 1, 'time_position_strategy': 'u', 'positional_encoding_style': 'p'}),
+    # discrete_optimization_strategy 'st' (models.py:1620-1622): no Gumbel noise, soft gate = sigmoid probability
+    ('mphoi_s2_st', 'mphoi', 32, 2, 12, 2, False, 2.0, False, {'discrete_optimization_strategy': 'st'}),
+    ('cad120_nf_st', 'cad120', 32, 2, 11, 2, False, 2.0, False, {'discrete_optimization_strategy': 'st', 'filter_discrete_updates': 0, 'update_segment_threshold': 0.5}),
+    # message_geometry_to_human (models.py:690-695, :1432-1475), also together with a time block in the gate inputs
+    ('mphoi_s2_gh', 'mphoi', 32, 2, 12, 2, False, 2.0, False, {'message_geometry_to_human': True}),
+    ('cad120_s2_gh_time_u', 'cad120', 32, 2, 11, 2, False, 2.0, False, {'message_geometry_to_human': True, 'add_time_position': 1, 'time_position_strategy': 'u'}),
     # the benchmarked configuration itself (BASELINE.json configs[1]: MPHOI, B=8, T=128, hidden 512, stage-2 settings)
     ('mphoi_s2_d512_full', 'mphoi', 512, 8, 128, 2, False, 1.0, False),
 ]
@@ -99,7 +105,8 @@ def run_case(name, shape_name, D, B, T, stage, train_mode, gain, inspect, extra=
         data_seed, noise_seed = 100 + attempt, 500 + attempt
         batch = pkg.make_batch(shape, B, T, seed=data_seed)
         n_calls = orc.num_noise_draws(T, shape.H, shape.O, stage == 1, stage == 1 and shape.dataset == 'cad120',
-                                      kw['object_segment_update_strategy'])
+                                      kw['object_segment_update_strategy'],
+                                      kw['discrete_optimization_strategy'] in ('st', 'straight-through'))
         noise = orc.draw_noise(max(n_calls, 1), B, torch.Generator().manual_seed(noise_seed))[:n_calls]
         if name in CASE_MARGIN and not train_mode:
             # big cases: pre-screen both human and object gates on the oracle's early exit before paying for the reference
@@ -210,6 +217,10 @@ GRAD_CASES = [
     ('grad_cad120_s2_time_sp', 'cad120', 32, 2, 8, 2, 2.0, {'add_time_position': 1, 'time_position_strategy': 's', 'positional_encoding_style': 'p'}),
     ('grad_cad120_s2_time_ue', 'cad120', 32, 2, 8, 2, 2.0, {'add_time_position': 1, 'time_position_strategy': 'u', 'positional_encoding_style': 'e'}),
     ('grad_mphoi_s2_time_up', 'mphoi', 32, 2, 9, 2, 2.0, {'add_time_position': 1, 'time_position_strategy': 'u', 'positional_encoding_style': 'p'}),
+    ('grad_mphoi_s2_gh', 'mphoi', 32, 2, 9, 2, 2.0, {'message_geometry_to_human': True}),
+    ('grad_cad120_s2_gh_time_u', 'cad120', 32, 2, 8, 2, 2.0, {'message_geometry_to_human': True, 'add_time_position': 1, 'time_position_strategy': 'u'}),
+    # no gradient case for discrete_optimization_strategy 'st': the reference's StraightThroughEstimator.backward returns one gradient
+    # for two forward inputs and autograd rejects it (distributions.py:39-53) — the reference cannot train with it
     # hidden 512 (the benchmarked width), T = 32: the D=512 BPTT and split-K weight-gradient paths against the reference itself
     ('grad_mphoi_s2_d512', 'mphoi', 512, 8, 32, 2, 1.0),
 ]
@@ -267,7 +278,8 @@ def run_grad_case(name, shape_name, D, B, T, stage, gain, extra=None):
         data_seed, noise_seed = 300 + attempt, 700 + attempt
         batch = pkg.make_batch(shape, B, T, seed=data_seed)
         n_calls = orc.num_noise_draws(T, shape.H, shape.O, stage == 1, stage == 1 and shape.dataset == 'cad120',
-                                      kw['object_segment_update_strategy'])
+                                      kw['object_segment_update_strategy'],
+                                      kw['discrete_optimization_strategy'] in ('st', 'straight-through'))
         noise = orc.draw_noise(max(n_calls, 1), B, torch.Generator().manual_seed(noise_seed))[:n_calls]
         # margin check on the fp64 oracle (covers object gates that MPHOI does not return)
         p64 = {k: v.double() for k, v in sd.items()}

@@ -46,6 +46,10 @@ class OracleConfig:
     time_position: str = ''                 # add_time_position: '' off, 's' = time embedding appended to the segment-level inputs
                                             # (models.py:755-762), 'u' = appended to the gate MLP inputs (:656-662, :1494, :1527)
     positional_encoding: str = 'e'          # 'e' = time_position_mlp (Linear(1, D) + ReLU) of (t+1)/steps, 'p' = periodic of (t+1)
+    geo_to_human: bool = False              # message_geometry_to_human (models.py:690-695, :1432-1475): one more message block
+                                            # ReLU(geometry_to_human_message_mlp([x_g | h_g])) in the humans' segment inputs and gate inputs
+    straight_through: bool = False          # discrete_optimization_strategy 'st' (models.py:1621-1622): soft gate = the sigmoid
+                                            # probability itself, hard gate = (p > thr) with identity gradient, no Gumbel noise
     update_strategy: str = 'ind'            # object_segment_update_strategy 'ind' | 'sah' | 'coh' (models.py:1523-1532); 'sah' and
                                             # 'coh' only differ from 'ind' with exactly one human (models.py:741-742)
 
@@ -61,6 +65,8 @@ def config_from_kwargs(kw: dict) -> OracleConfig:
                         kw.get('attention_style') not in ('v2', 'dot-product'),
                         (kw.get('time_position_strategy', 's') if kw.get('add_time_position') else ''),
                         'e' if kw.get('positional_encoding_style', 'e') in ('e', 'embedding') else 'p',
+                        bool(kw.get('message_geometry_to_human', False)),
+                        kw.get('discrete_optimization_strategy', 'gs') in ('st', 'straight-through'),
                         _UPD[kw.get('object_segment_update_strategy', 'ind')])
 
 
@@ -172,6 +178,14 @@ def gumbel_sigmoid(prob: Tensor, g: Optional[Tensor]) -> Tensor:
         g = torch.distributions.gumbel.Gumbel(0.0, 1.0).sample(pp.size())
     y = torch.log(pp + 1e-20) + g.to(pp)
     return torch.softmax(y, dim=-1)[:, :1]
+
+
+def sample_gate(prob: Tensor, g: Optional[Tensor], thr: float, straight_through: bool) -> Tuple[Tensor, Tensor]:
+    """discrete_estimator, vhoi/models.py:1620-1627: (hard, soft) decision of one entity at one step."""
+    if straight_through:            # StraightThroughEstimator, distributions.py:39-53: exact 0/1 forward, identity backward
+        return (prob > thr).to(prob.dtype) + (prob - prob.detach()), prob
+    y = gumbel_sigmoid(prob, g)
+    return hard_gate(y, thr), y
 
 
 def hard_gate(y: Tensor, thr: float) -> Tensor:
@@ -287,14 +301,16 @@ def forward(p: Dict[str, Tensor], cfg: OracleConfig, x_human: Tensor, x_objects:
             m_oh, w_oh = attend(s_h[:, h], s_o, val, objects_mask, cfg.mean_pool, cfg.att_scaled)
             att_oh[h][t] = w_oh
             parts.append(m_oh), gate_in.append(m_oh)
+            if cfg.geo_to_human:                                        # :690-695, :1432-1475: single sender, weight 1, no mask
+                m_gh = _relu_lin(p, 'geometry_to_human_message_mlp.0', s_g[:, 0])
+                parts.append(m_gh), gate_in.append(m_gh)
             if human_segmentation is not None:                          # :697-698
                 hard_h[h][t] = soft_h[h][t] = human_segmentation[:, t:t + 1, h]
             else:                                                       # :1477-1498, :700-702
                 if cfg.time_position == 'u':
                     gate_in.append(tt[t])
                 prob = torch.sigmoid(_lin(p, 'update_human_segment_mlp.0', torch.cat(gate_in, dim=-1)))
-                ysoft = gumbel_sigmoid(prob, next(noise_it) if noise_it is not None else None)
-                z = hard_gate(ysoft, thr)
+                z, ysoft = sample_gate(prob, next(noise_it) if (noise_it is not None and not cfg.straight_through) else None, thr, cfg.straight_through)
                 if t == T - 1:
                     z = torch.ones_like(z)
                 hard_h[h][t], soft_h[h][t] = z, ysoft
@@ -319,8 +335,7 @@ def forward(p: Dict[str, Tensor], cfg: OracleConfig, x_human: Tensor, x_objects:
             else:                                                       # :1500-1533 ('ind' / 'coh'); input order :1527
                 gate_in = torch.cat([x_o[:, t, k], h_o[:, t, k], m_ho, m_oo, m_go] + ([tt[t]] if cfg.time_position == 'u' else []), dim=-1)
                 prob = torch.sigmoid(_lin(p, 'update_object_segment_mlp.0', gate_in))
-                ysoft = gumbel_sigmoid(prob, next(noise_it) if noise_it is not None else None)
-                z = hard_gate(ysoft, thr)
+                z, ysoft = sample_gate(prob, next(noise_it) if (noise_it is not None and not cfg.straight_through) else None, thr, cfg.straight_through)
                 if cfg.update_strategy == 'coh' and H == 1:             # :1531-1532: object updates only where the human does
                     z = z * hard_h[0][t]
                 if t == T - 1:
@@ -417,9 +432,12 @@ def _seg_cell(p, cell: str, x: Tensor, u: Tensor, h: Tensor) -> Tensor:
     return u * new + (1.0 - u) * h
 
 
-def num_noise_draws(T: int, H: int, O: int, human_given: bool, objects_given: bool, update_strategy: str = 'ind') -> int:
+def num_noise_draws(T: int, H: int, O: int, human_given: bool, objects_given: bool, update_strategy: str = 'ind',
+                    straight_through: bool = False) -> int:
     """Number of (B,2) Gumbel draws one forward consumes (vhoi/models.py:697-702, :738-745); under 'sah' with one human the
     objects copy the human's decision and draw nothing (:1523-1525)."""
+    if straight_through:            # discrete_optimization_strategy 'st' samples nothing
+        return 0
     objects_sampled = not objects_given and not (_UPD[update_strategy] == 'sah' and H == 1)
     return T * ((0 if human_given else H) + (O if objects_sampled else 0))
 

@@ -31,6 +31,10 @@ CASES = {
     'cad120_s2_time_sp': ('cad120', 32, 2, 11, 2, False, False, {'add_time_position': 1, 'time_position_strategy': 's', 'positional_encoding_style': 'p'}),
     'cad120_s2_time_ue': ('cad120', 32, 2, 11, 2, False, False, {'add_time_position': 1, 'time_position_strategy': 'u', 'positional_encoding_style': 'e'}),
     'mphoi_s2_time_up': ('mphoi', 32, 2, 12, 2, False, False, {'add_time_position': 1, 'time_position_strategy': 'u', 'positional_encoding_style': 'p'}),
+    'mphoi_s2_st': ('mphoi', 32, 2, 12, 2, False, False, {'discrete_optimization_strategy': 'st'}),
+    'cad120_nf_st': ('cad120', 32, 2, 11, 2, False, False, {'discrete_optimization_strategy': 'st', 'filter_discrete_updates': 0, 'update_segment_threshold': 0.5}),
+    'mphoi_s2_gh': ('mphoi', 32, 2, 12, 2, False, False, {'message_geometry_to_human': True}),
+    'cad120_s2_gh_time_u': ('cad120', 32, 2, 11, 2, False, False, {'message_geometry_to_human': True, 'add_time_position': 1, 'time_position_strategy': 'u'}),
 }
 
 # BASELINE.json configs[1] itself — what bench.py times (reference outputs; gate margin 2.5e-5).  Kept apart from CASES: the
@@ -59,6 +63,8 @@ GRAD_CASES = {
     'grad_cad120_s2_time_sp': ('cad120', 32, 2, 8, 2, {'add_time_position': 1, 'time_position_strategy': 's', 'positional_encoding_style': 'p'}),
     'grad_cad120_s2_time_ue': ('cad120', 32, 2, 8, 2, {'add_time_position': 1, 'time_position_strategy': 'u', 'positional_encoding_style': 'e'}),
     'grad_mphoi_s2_time_up': ('mphoi', 32, 2, 9, 2, {'add_time_position': 1, 'time_position_strategy': 'u', 'positional_encoding_style': 'p'}),
+    'grad_mphoi_s2_gh': ('mphoi', 32, 2, 9, 2, {'message_geometry_to_human': True}),
+    'grad_cad120_s2_gh_time_u': ('cad120', 32, 2, 8, 2, {'message_geometry_to_human': True, 'add_time_position': 1, 'time_position_strategy': 'u'}),
 }
 
 # hidden 512 (the benchmarked width), T = 32.  Kept apart from GRAD_CASES: the reference's own fp32 autograd carries summation
@@ -98,7 +104,8 @@ class GoldenCase:
         self.human_given = stage == 1
         self.objects_given = stage == 1 and self.shape.dataset == 'cad120'
         n_calls = orc.num_noise_draws(T, H, O, self.human_given, self.objects_given,
-                                      self.kwargs['object_segment_update_strategy'])
+                                      self.kwargs['object_segment_update_strategy'],
+                                      self.kwargs['discrete_optimization_strategy'] in ('st', 'straight-through'))
         self.noise = orc.draw_noise(max(n_calls, 1), B, torch.Generator().manual_seed(noise_seed))[:n_calls]
         self.hseg = torch.ones(B, T, H) if self.human_given else None
         self.oseg = torch.ones(B, T, O) if self.objects_given else None

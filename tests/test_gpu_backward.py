@@ -35,7 +35,8 @@ def _setup(name, orc, synth, pkg):
     synth.deterministic_fill(model.state_dict(), seed=weight_seed, gain=float(blob['gain'][0]))
     batch = synth.make_batch(shape, B, T, seed=data_seed)
     human_given, objects_given = stage == 1, stage == 1 and shape.dataset == 'cad120'
-    n_calls = orc.num_noise_draws(T, shape.H, shape.O, human_given, objects_given, kw['object_segment_update_strategy'])
+    n_calls = orc.num_noise_draws(T, shape.H, shape.O, human_given, objects_given, kw['object_segment_update_strategy'],
+                                      kw['discrete_optimization_strategy'] in ('st', 'straight-through'))
     noise = orc.draw_noise(max(n_calls, 1), B, torch.Generator().manual_seed(noise_seed))[:n_calls]
     hseg = torch.ones(B, T, shape.H) if human_given else None
     oseg = torch.ones(B, T, shape.O) if objects_given else None

@@ -113,7 +113,8 @@ def test_oracle_gradients_match_reference(name, orc, synth, pkg):
     alias_shared_heads(p, extra)
     batch = synth.make_batch(shape, B, T, seed=data_seed)
     human_given, objects_given = stage == 1, stage == 1 and shape.dataset == 'cad120'
-    n_calls = orc.num_noise_draws(T, shape.H, shape.O, human_given, objects_given, kw['object_segment_update_strategy'])
+    n_calls = orc.num_noise_draws(T, shape.H, shape.O, human_given, objects_given, kw['object_segment_update_strategy'],
+                                      kw['discrete_optimization_strategy'] in ('st', 'straight-through'))
     noise = orc.draw_noise(max(n_calls, 1), B, torch.Generator().manual_seed(noise_seed))[:n_calls]
     hseg = torch.ones(B, T, shape.H).double() if human_given else None
     oseg = torch.ones(B, T, shape.O).double() if objects_given else None

@@ -91,6 +91,7 @@ void make_layout(const tggcn_dims& d, Layout& L) {
     sz[TGGCN_BUF_XX_O] = N * O * (size_t)ko_of(d) * f;
     sz[TGGCN_BUF_TIME_EMB] = d.time_position ? N * D * f : 0;
     sz[TGGCN_BUF_MSG_GH] = d.geo_to_human ? N * D * f : 0;
+    sz[TGGCN_BUF_SEG_LEN] = d.segment_length ? N * (H + O) * f : 0;
     sz[TGGCN_BUF_GS_H] = N * H * 6 * D * f;
     sz[TGGCN_BUF_GS_O] = N * O * 6 * D * f;
     sz[TGGCN_BUF_HX_H] = N * H * 2 * D * f;
@@ -414,6 +415,7 @@ static int forward_impl(const tggcn_dims* dims, const void* const* weights, int 
         P.B = B; P.T = T; P.H = H; P.O = O; P.D = D; P.hh = d.hh; P.thr = d.thr; P.mean_pool = d.mean_pool; P.att_noscale = d.att_noscale;
         P.update_strategy = d.update_strategy; P.straight_through = d.straight_through;
         P.gh = d.geo_to_human ? 1 : 0; P.msg_gh = d.geo_to_human ? buf(TGGCN_BUF_MSG_GH) : nullptr;
+        P.tl = tl_of(d);
         P.time_position = d.time_position; P.time_emb = d.time_position ? buf(TGGCN_BUF_TIME_EMB) : nullptr;
         P.s_h = buf(TGGCN_BUF_S_H); P.s_o = buf(TGGCN_BUF_S_O);
         P.msg_hh = buf(TGGCN_BUF_MSG_HH); P.msg_ho = buf(TGGCN_BUF_MSG_HO); P.msg_oh = buf(TGGCN_BUF_MSG_OH);
@@ -434,6 +436,15 @@ static int forward_impl(const tggcn_dims* dims, const void* const* weights, int 
     if (int rc = launch_gate_post(io->y_hs, io->y_hss, io->y_os, io->y_oss, (int*)buf(TGGCN_BUF_REIDX), B, T, H, O, d.filter,
                                   d.thr, stream))
         return rc;
+    if (d.segment_length) {     // segment lengths from the final hard gates, embedded into the last block of every xx row (models.py:763-779)
+        TG_REQUIRE(io->steps_per_example != nullptr, "forward: add_segment_length needs steps_per_example");
+        TG_REQUIRE(d.time_periodic ? io->time_freq != nullptr : (W(TGGCN_W_LEN_W) && W(TGGCN_W_LEN_B)),
+                   "forward: segment-length parameters missing (segment_length_mlp, or the period table of the periodic encoding)");
+        if (int rc = launch_segment_length(io->y_hs, io->y_os, io->steps_per_example, W(TGGCN_W_LEN_W), W(TGGCN_W_LEN_B), io->time_freq,
+                                           buf(TGGCN_BUF_SEG_LEN), buf(TGGCN_BUF_XX_H), kh_of(d), buf(TGGCN_BUF_XX_O), ko_of(d),
+                                           B, T, H, O, D, d.time_periodic, stream))
+            return rc;
+    }
     STAGE_END();
     // 10. hoisted frame-part of the segment cells' W_ih x + b_ih, both directions
     const int kh = kh_of(d), ldwh = ldwh_of(d), ko = ko_of(d), ldwo = ldwo_of(d);

@@ -145,7 +145,7 @@ size_t tggcn_backward_workspace_bytes(const tggcn_dims* dims) {
 
 int tggcn_backward_bucket(int id) {
     if (id < 0 || id >= TGGCN_W_COUNT) return -1;
-    if (id == TGGCN_W_TIME_W || id == TGGCN_W_TIME_B || id == TGGCN_W_MSG_GH_W || id == TGGCN_W_MSG_GH_B) return 1;            // formed with the frame-level graph
+    if (id >= TGGCN_W_TIME_W && id <= TGGCN_W_LEN_B) return 1;            // time / length MLPs, geometry -> human message MLP            // formed with the frame-level graph
     if (id <= TGGCN_W_GCN_S2_B) return 3;                                   // GCN_* (first 13 entries of the table)
     if (id <= TGGCN_W_OBJ_EMB_B) return 2;                                  // geometry MLP, ROI embeddings
     if (id >= TGGCN_W_HSEG_F_WIH || (id >= TGGCN_W_SMSG_HH_W && id <= TGGCN_W_SMSG_OO_B)) return 0;   // cells, heads, segment MLPs
@@ -443,6 +443,20 @@ int tggcn_backward_ex(const tggcn_dims* dims, const void* const* weights, void* 
         if (int rc = dx_gemm(bb(BL.dgs[1]), 6 * D, nullptr, 0, wo, 2, ko, bb(BL.dxx[1]), ko, N * O, 0, wt)) return rc;
     }
 
+    // ---- 9b. segment lengths: gradient of the hard gates through them, segment_length_mlp ------------------------------------------
+    if (d.segment_length) {
+        SegLenBwdParams P;
+        memset(&P, 0, sizeof(P));
+        P.B = B; P.T = T; P.H = H; P.O = O; P.D = D; P.periodic = d.time_periodic;
+        P.dxx_h = bb(BL.dxx[0]); P.xx_h = buf(TGGCN_BUF_XX_H); P.ldh = kh_of(d);
+        P.dxx_o = bb(BL.dxx[1]); P.xx_o = buf(TGGCN_BUF_XX_O); P.ldo = ko_of(d);
+        P.len = buf(TGGCN_BUF_SEG_LEN); P.y_hs = io->y_hs; P.y_os = io->y_os;
+        P.steps = io->steps_per_example; P.w = W(TGGCN_W_LEN_W); P.freq = io->time_freq;
+        P.du_h = bb(BL.du[0]); P.du_o = bb(BL.du[1]);
+        if (!d.time_periodic) { P.dw = G(TGGCN_W_LEN_W); P.db = G(TGGCN_W_LEN_B); }
+        TG_REQUIRE(P.steps != nullptr && (d.time_periodic ? P.freq != nullptr : P.w != nullptr), "backward: segment-length inputs missing");
+        if (int rc = launch_segment_length_bwd(P, stream)) return rc;
+    }
     // ---- 9/8. gates (straight-through, filter), attention, aggregation ------------------------------------------------------------
     {
         FrameBwdParams P;
@@ -450,6 +464,7 @@ int tggcn_backward_ex(const tggcn_dims* dims, const void* const* weights, void* 
         P.B = B; P.T = T; P.H = H; P.O = O; P.D = D; P.hh = d.hh; P.filter = d.filter; P.thr = d.thr; P.mean_pool = d.mean_pool; P.att_noscale = d.att_noscale;
         P.update_strategy = d.update_strategy; P.straight_through = d.straight_through;
         P.gh = d.geo_to_human ? 1 : 0; P.msg_gh = P.gh ? buf(TGGCN_BUF_MSG_GH) : nullptr; P.dmsg_gh = P.gh ? bb(BL.dmsg[5]) : nullptr;
+        P.tl = tl_of(d);
         P.time_position = d.time_position; P.time_emb = d.time_position ? buf(TGGCN_BUF_TIME_EMB) : nullptr;
         // no gradient pointers for time_position_mlp = it is off the gradient path of this call (strategy 'u' with every gate imposed)
         P.dtime = (d.time_position && !d.time_periodic && G(TGGCN_W_TIME_W) && G(TGGCN_W_TIME_B)) ? bb(BL.dtime) : nullptr;

@@ -15,10 +15,11 @@ inline int nkh_of(const tggcn_dims& d) { return d.hh ? 2 : 1; }
 inline int ts_of(const tggcn_dims& d) { return d.time_position == 1 ? 1 : 0; }       // time block in the segment-level inputs
 inline int tu_of(const tggcn_dims& d) { return d.time_position == 2 ? 1 : 0; }       // time block in the gate MLP inputs
 inline int gh_of(const tggcn_dims& d) { return d.geo_to_human ? 1 : 0; }             // geometry -> human message block
-inline int kh_of(const tggcn_dims& d) { return (1 + nkh_of(d) + gh_of(d) + ts_of(d)) * d.D; }   // xx_h row = frame-part columns of the human W_ih
+inline int tl_of(const tggcn_dims& d) { return d.segment_length ? 1 : 0; }           // segment-length block (last of the frame part)
+inline int kh_of(const tggcn_dims& d) { return (1 + nkh_of(d) + gh_of(d) + ts_of(d) + tl_of(d)) * d.D; }   // xx_h row = frame-part columns of the human W_ih
 inline int ldwh_of(const tggcn_dims& d) { return kh_of(d) + nkh_of(d) * d.D; }
-inline int ko_of(const tggcn_dims& d) { return (4 + ts_of(d)) * d.D; }               // xx_o row
-inline int ldwo_of(const tggcn_dims& d) { return (6 + ts_of(d)) * d.D; }
+inline int ko_of(const tggcn_dims& d) { return (4 + ts_of(d) + tl_of(d)) * d.D; }               // xx_o row
+inline int ldwo_of(const tggcn_dims& d) { return ko_of(d) + 2 * d.D; }
 void make_layout(const tggcn_dims& d, Layout& L);
 int check_dims(const tggcn_dims& d);
 

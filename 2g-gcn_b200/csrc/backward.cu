@@ -128,7 +128,7 @@ __global__ void __launch_bounds__(256) frame_bwd_kernel(const FrameBwdParams P) 
     const int nkh = P.hh ? 2 : 1;
     const int ts = P.time_position == 1 ? 1 : 0, tu = P.time_position == 2 ? 1 : 0;
     const int gh = P.gh;
-    const int wh = (1 + nkh + gh + ts) * D, wo = (4 + ts) * D;      // rows of xx_h / xx_o (and of their gradients)
+    const int wh = (1 + nkh + gh + ts + P.tl) * D, wo = (4 + ts + P.tl) * D;      // rows of xx_h / xx_o (and of their gradients)
     float* sv = sm;                            // [NE][2D]
     float* dmh = sv + NE * D2;                 // [H][nkh*D]   d m_hh | d m_oh
     float* dmo = dmh + H * nkh * D;            // [O][3D]      d m_ho | d m_go | d m_oo
@@ -403,6 +403,85 @@ int launch_time_embed_bwd(const float* dtime, const float* emb, const float* ste
     const int slabs = min(64, cdiv(B * T, 8));
     time_embed_bwd_kernel<<<dim3(cdiv(D, 32), slabs), 256, 0, stream>>>(dtime, emb, steps, dw, db, B, T, D);
     TG_LAUNCH_OK();
+    return 0;
+}
+
+// One warp per (video, entity): reverse scan over the frames.
+__global__ void __launch_bounds__(128) segment_length_bwd_kernel(const SegLenBwdParams P) {
+    const int NE = P.H + P.O, D = P.D, T = P.T;
+    const int wi = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (wi >= P.B * NE) return;
+    const int b = wi / NE, e = wi - b * NE;
+    const bool is_h = e < P.H;
+    const int E = is_h ? P.H : P.O, r = is_h ? e : e - P.H;
+    const int ld = is_h ? P.ldh : P.ldo;
+    const float* dxx = (is_h ? P.dxx_h : P.dxx_o) + (ld - D);
+    const float* xx = (is_h ? P.xx_h : P.xx_o) + (ld - D);
+    const float* hard = is_h ? P.y_hs : P.y_os;
+    float* du = is_h ? P.du_h : P.du_o;
+    const float st = P.periodic ? 1.0f : __ldg(P.steps + b);
+    const int half = D / 2;
+    float g_acc = 0.0f;
+    for (int t = T - 1; t >= 0; --t) {
+        const size_t row = (size_t)(b * T + t) * E + r;
+        const float x = P.len[(size_t)(b * T + t) * NE + e];
+        float g = 0.0f;
+        for (int k = lane; k < D; k += 32) {
+            const float dv = dxx[row * ld + k];
+            float der;
+            if (P.periodic) {
+                const float f = __ldg(P.freq + (k < half ? k : k - half)), a = x / f;
+                der = (k < half ? cosf(a) : -sinf(a)) / f;
+            } else {
+                der = xx[row * ld + k] > 0.0f ? __ldg(P.w + k) : 0.0f;
+            }
+            g = fmaf(dv, der, g);
+        }
+        g = warp_sum(g);
+        if (lane == 0) {
+            const float pos = P.periodic ? (float)(t + 1) : (float)(t + 1) / st;
+            du[row] += pos * (g + g_acc);
+        }
+        if (hard[row] != 0.0f) g_acc = -g;             // rel = u x - acc, acc' = u x;   else rel = u x, acc' = acc + u x
+    }
+}
+
+// segment_length_mlp: dw[k] = sum over rows of dxx[row, k] [emb > 0] len[row], db[k] likewise without len; humans then objects.
+__global__ void __launch_bounds__(256) segment_length_wgrad_kernel(const SegLenBwdParams P) {
+    __shared__ float sw[8][33], sb[8][33];
+    const int D = P.D, NE = P.H + P.O, N = P.B * P.T;
+    const int c = blockIdx.x * 32 + (threadIdx.x & 31), rl = threadIdx.x >> 5;
+    float aw = 0.0f, ab = 0.0f;
+    if (c < D)
+        for (int i = blockIdx.y * 8 + rl; i < N * NE; i += gridDim.y * 8) {
+            const int n = i / NE, e = i - n * NE;
+            const bool is_h = e < P.H;
+            const int ld = is_h ? P.ldh : P.ldo;
+            const size_t row = is_h ? (size_t)n * P.H + e : (size_t)n * P.O + (e - P.H);
+            const size_t off = row * ld + (ld - D) + c;
+            const float g = (is_h ? P.xx_h : P.xx_o)[off] > 0.0f ? (is_h ? P.dxx_h : P.dxx_o)[off] : 0.0f;
+            aw = fmaf(g, P.len[i], aw);
+            ab += g;
+        }
+    sw[rl][threadIdx.x & 31] = aw; sb[rl][threadIdx.x & 31] = ab;
+    __syncthreads();
+    if (rl == 0 && c < D) {
+        for (int r = 1; r < 8; ++r) { aw += sw[r][threadIdx.x]; ab += sb[r][threadIdx.x]; }
+        atomicAdd(P.dw + c, aw);
+        atomicAdd(P.db + c, ab);
+    }
+}
+
+int launch_segment_length_bwd(const SegLenBwdParams& P, cudaStream_t stream) {
+    segment_length_bwd_kernel<<<cdiv(P.B * (P.H + P.O) * 32, 128), 128, 0, stream>>>(P);
+    TG_LAUNCH_OK();
+    if (P.dw != nullptr && P.db != nullptr) {
+        TG_CUDA_OK(cudaMemsetAsync(P.dw, 0, sizeof(float) * P.D, stream));
+        TG_CUDA_OK(cudaMemsetAsync(P.db, 0, sizeof(float) * P.D, stream));
+        const int slabs = min(64, cdiv(P.B * P.T * (P.H + P.O), 8));
+        segment_length_wgrad_kernel<<<dim3(cdiv(P.D, 32), slabs), 256, 0, stream>>>(P);
+        TG_LAUNCH_OK();
+    }
     return 0;
 }
 

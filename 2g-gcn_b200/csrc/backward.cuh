@@ -78,6 +78,7 @@ struct FrameBwdParams {
     int mean_pool;                                 // uniform sender weights: no gradient through attention logits
     int att_noscale;                               // attention_style 'v2': plain dot-product logits
     int update_strategy;                           // 0 'ind', 1 'sah', 2 'coh' (tggcn_dims.update_strategy)
+    int tl;                                        // add_segment_length: one more block at the end of every xx row
     int gh;                                        // message_geometry_to_human: block m_gh after m_oh in the humans' rows
     const float* msg_gh;                           // (B,T,1,D) forward message, or null
     float* dmsg_gh;                                // (B,T,1,D) out: its gradient
@@ -103,6 +104,19 @@ struct FrameBwdParams {
     float* dw_uh; float* db_uh; float* dw_uo; float* db_uo;   // accumulated with atomics: zero before the launch
 };
 int launch_frame_bwd(const FrameBwdParams& P, cudaStream_t stream);
+// add_segment_length backward (models.py:763-779, :954-979): from the gradient of the length blocks of the xx rows — the gradient
+// of the hard gates (added into du_h / du_o, reverse scan over the frames) and, for the embedding encoding, of segment_length_mlp
+struct SegLenBwdParams {
+    int B, T, H, O, D, periodic;
+    const float* dxx_h; const float* xx_h; int ldh;   // gradient / forward rows of the humans (length block = last D columns)
+    const float* dxx_o; const float* xx_o; int ldo;
+    const float* len;                                  // (B,T,H+O) forward segment lengths
+    const float* y_hs; const float* y_os;              // hard gates
+    const float* steps; const float* w; const float* freq;
+    float* du_h; float* du_o;                          // (B,T,E) accumulated
+    float* dw; float* db;                              // segment_length_mlp gradients (null: periodic / not on the gradient path)
+};
+int launch_segment_length_bwd(const SegLenBwdParams& P, cudaStream_t stream);
 // time_position_mlp (Linear(1, D) + ReLU of (t+1)/steps[b]): dw[k] = sum_n dtime[n,k] [emb[n,k] > 0] tau_n, db[k] likewise without tau
 int launch_time_embed_bwd(const float* dtime, const float* emb, const float* steps, float* dw, float* db, int B, int T, int D,
                           cudaStream_t stream);

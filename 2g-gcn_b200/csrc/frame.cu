@@ -104,8 +104,8 @@ __global__ void __launch_bounds__(FM_THREADS) frame_messages_kernel(const FrameM
         const float* g_go = P.msg_go + (size_t)n * D;
         const int ts = P.time_position == 1 ? 1 : 0;
         const int gh = P.gh;
-        const int wh = (1 + nkh + gh + ts) * D;  // xx_h row: [h, (m_hh), m_oh (, m_gh) (, time)]
-        const int wo = (4 + ts) * D;             // xx_o row: [h, m_ho, m_go, m_oo (, time)]
+        const int wh = (1 + nkh + gh + ts + P.tl) * D;  // xx_h row: [h, (m_hh), m_oh (, m_gh) (, time) (, length)]
+        const int wo = (4 + ts + P.tl) * D;      // xx_o row: [h, m_ho, m_go, m_oo (, time) (, length)]
         float* xxh = P.xx_h + (size_t)n * H * wh;
         float* xxo = P.xx_o + (size_t)n * O * wo;
         const float* te = ts ? P.time_emb + (size_t)n * D : nullptr;
@@ -276,6 +276,64 @@ int launch_time_embed(const float* steps, const float* w, const float* bias, con
                       int periodic, cudaStream_t stream) {
     const size_t total = (size_t)B * T * D;
     time_embed_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(steps, w, bias, freq, out, B, T, D, periodic);
+    TG_LAUNCH_OK();
+    return 0;
+}
+
+// Segment lengths: one thread per (video, entity) scans the frames (models.py:954-979).
+__global__ void segment_length_scan_kernel(const float* __restrict__ y_hs, const float* __restrict__ y_os,
+                                           const float* __restrict__ steps, float* __restrict__ len, int B, int T, int H, int O,
+                                           int periodic) {
+    const int NE = H + O;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= B * NE) return;
+    const int b = i / NE, e = i - b * NE;
+    const bool is_h = e < H;
+    const int E = is_h ? H : O, r = is_h ? e : e - H;
+    const float* hard = is_h ? y_hs : y_os;
+    const float st = periodic ? 1.0f : __ldg(steps + b);
+    float acc = 0.0f;
+    for (int t = 0; t < T; ++t) {
+        const float x = periodic ? (float)(t + 1) : (float)(t + 1) / st;
+        float rel = hard[(size_t)(b * T + t) * E + r] * x;
+        if (rel != 0.0f) rel -= acc;
+        acc += rel;
+        len[(size_t)(b * T + t) * NE + e] = rel;
+    }
+}
+
+// Embedding of the lengths into the last D columns of the xx rows: one thread per (frame, entity, column).
+__global__ void segment_length_embed_kernel(const float* __restrict__ len, const float* __restrict__ w, const float* __restrict__ bias,
+                                            const float* __restrict__ freq, float* xx_h, int ldh, float* xx_o, int ldo, int N, int H,
+                                            int O, int D, int periodic) {
+    const int NE = H + O;
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (size_t)N * NE * D) return;
+    const int k = (int)(i % D);
+    const size_t ne = i / D;
+    const int e = (int)(ne % NE);
+    const size_t n = ne / NE;
+    const float x = len[ne];
+    float v;
+    if (periodic) {
+        const int half = D / 2;
+        const float a = x / __ldg(freq + (k < half ? k : k - half));
+        v = k < half ? sinf(a) : cosf(a);
+    } else {
+        v = fmaxf(fmaf(__ldg(w + k), x, __ldg(bias + k)), 0.0f);
+    }
+    if (e < H) xx_h[(n * H + e) * ldh + (ldh - D) + k] = v;
+    else       xx_o[(n * O + (e - H)) * ldo + (ldo - D) + k] = v;
+}
+
+int launch_segment_length(const float* y_hs, const float* y_os, const float* steps, const float* w, const float* bias,
+                          const float* freq, float* len, float* xx_h, int ldh, float* xx_o, int ldo, int B, int T, int H, int O,
+                          int D, int periodic, cudaStream_t stream) {
+    segment_length_scan_kernel<<<cdiv(B * (H + O), 128), 128, 0, stream>>>(y_hs, y_os, steps, len, B, T, H, O, periodic);
+    TG_LAUNCH_OK();
+    const size_t total = (size_t)B * T * (H + O) * D;
+    segment_length_embed_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(len, w, bias, freq, xx_h, ldh, xx_o, ldo, B * T, H, O,
+                                                                                    D, periodic);
     TG_LAUNCH_OK();
     return 0;
 }

@@ -9,6 +9,7 @@ struct FrameMsgParams {
     int mean_pool;          // message_aggregation 'mp': uniform weights over the valid senders instead of attention
     int att_noscale;        // attention_style 'v2': plain dot-product logits
     int update_strategy;    // 0 'ind', 1 'sah' (object gates = the single human's), 2 'coh' (hard object gate x the human's)
+    int tl;                 // add_segment_length: one more block at the end of every xx row (written by launch_segment_length)
     int gh;                 // message_geometry_to_human: block m_gh after m_oh in the humans' xx rows and gate inputs
     const float* msg_gh;    // (B,T,1,D) ReLU(W_gh s_g + b), or null
     int straight_through;   // discrete_optimization_strategy 'st': soft = sigmoid probability, hard = (p > thr), no noise
@@ -51,6 +52,11 @@ int launch_frame_messages(const FrameMsgParams& P, cudaStream_t stream);
 // time-position features: 'e' ReLU(w * (t+1)/steps[b] + bias), 'p' [sin((t+1)/freq_i), cos((t+1)/freq_i)]  (models.py:936-952, :1777-1794)
 int launch_time_embed(const float* steps, const float* w, const float* bias, const float* freq, float* out, int B, int T, int D,
                       int periodic, cudaStream_t stream);
+// add_segment_length: len[(b,t), e] from the hard gates (models.py:954-979), then its embedding ('e': ReLU(w * len + bias),
+// 'p': periodic) into the last D columns of every xx_h / xx_o row (row strides ldh / ldo)
+int launch_segment_length(const float* y_hs, const float* y_os, const float* steps, const float* w, const float* bias,
+                          const float* freq, float* len, float* xx_h, int ldh, float* xx_o, int ldo, int B, int T, int H, int O,
+                          int D, int periodic, cudaStream_t stream);
 int launch_gate_post(float* y_hs, const float* y_hss, float* y_os, const float* y_oss, int* reidx, int B, int T, int H,
                      int O, int filter, float thr, cudaStream_t stream);
 int launch_heads(const HeadsParams& P, cudaStream_t stream);

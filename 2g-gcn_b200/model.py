@@ -127,9 +127,8 @@ class TGGCN(nn.Module):
         if message_aggregation not in _ATT | _MP: unsupported.append("message_aggregation not in {'att', 'mp'}")
         if attention_style not in _V3 | _V2: unsupported.append("attention_style not in {'v2', 'v3'}")
         if object_segment_update_strategy not in _IND | _SAH | _COH: unsupported.append('unknown object_segment_update_strategy')
-        if add_segment_length: unsupported.append('add_segment_length')
         if add_time_position and time_position_strategy not in ('s', 'u'): unsupported.append("time_position_strategy not in {'s', 'u'}")
-        if add_time_position and positional_encoding_style not in _ENC_E | _ENC_P: unsupported.append('unknown positional_encoding_style')
+        if (add_time_position or add_segment_length) and positional_encoding_style not in _ENC_E | _ENC_P: unsupported.append('unknown positional_encoding_style')
         if not bias: unsupported.append('bias=False')
         if hidden_size % 16 != 0: unsupported.append('hidden_size not a multiple of 16')
         if unsupported:
@@ -155,7 +154,7 @@ class TGGCN(nn.Module):
         self.message_aggregation, self.attention_style = message_aggregation, attention_style
         self.object_segment_update_strategy = object_segment_update_strategy
         self.update_segment_threshold = float(update_segment_threshold)
-        self.add_segment_length, self.add_time_position = False, bool(add_time_position)
+        self.add_segment_length, self.add_time_position = bool(add_segment_length), bool(add_time_position)
         self.time_position_strategy, self.positional_encoding_style = time_position_strategy, positional_encoding_style
         self.cat_level_states = bool(cat_level_states)
         self.share_level_mlps = bool(share_level_mlps) and not self.cat_level_states     # models.py:565: sharing needs equal input sizes
@@ -169,6 +168,9 @@ class TGGCN(nn.Module):
         # ---- parameter holders, registered in the reference's order (vhoi/models.py:264-580) ----------
         if self.add_time_position and not self._time_periodic:
             self.time_position_mlp = _mlp([1, D], ['relu'])
+        if self.add_segment_length and not self._time_periodic:       # models.py:261-262
+            self.segment_length_mlp = _mlp([1, D], ['relu'])
+        ts += int(self.add_segment_length)                             # models.py:292-293, :317-318: one more D-wide input block
         self.geometry_embedding_gcn = _geo_gcn_holder(gcn_node)
         self.geometry_embedding_mlp = _mlp([gcn_node * 128, 2048, D], ['relu', 'relu'])
         self.geometry_bd_rnn = nn.GRU(D, D, num_layers=1, bias=True, batch_first=True, bidirectional=True)
@@ -418,11 +420,12 @@ class TGGCN(nn.Module):
         dims.straight_through = int(self.discrete_optimization_strategy in _ST)
         dims.geo_to_human = int(self.message_geometry_to_human)
         steps = freq = None
-        if self.add_time_position:
-            dims.time_position = 1 if self.time_position_strategy == 's' else 2
+        if self.add_time_position or self.add_segment_length:
+            dims.time_position = (1 if self.time_position_strategy == 's' else 2) if self.add_time_position else 0
+            dims.segment_length = int(self.add_segment_length)
             dims.time_periodic = int(self._time_periodic)
             if steps_per_example is None:
-                raise ValueError('add_time_position needs steps_per_example (vhoi/data_loading.py:1277)')
+                raise ValueError('add_time_position / add_segment_length need steps_per_example (vhoi/data_loading.py:1277)')
             steps = steps_per_example.to(device=dev, dtype=torch.float32).contiguous()
             if self._time_periodic:             # the period table of make_periodic_embedding (models.py:1788-1790), a constant of D
                 if self._time_freq is None or self._time_freq.device != dev:

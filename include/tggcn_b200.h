@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define TGGCN_ABI_VERSION 11
+#define TGGCN_ABI_VERSION 12
 
 #if defined(__GNUC__)
 #define TGGCN_API __attribute__((visibility("default")))
@@ -80,6 +80,10 @@ typedef struct tggcn_dims {
     int32_t geo_to_human;        /* message_geometry_to_human (models.py:690-695, :1432-1475): the humans' segment-level input rows and
                                     gate inputs carry one more block m_gh = ReLU(geometry_to_human_message_mlp([x_g | h_g])) after
                                     m_oh (single sender: weight 1, no mask)                                                     */
+    int32_t segment_length;      /* add_segment_length (models.py:763-779, :954-979): every segment-level input row ends with the embedding
+                                    (time_periodic selects segment_length_mlp or the periodic encoding) of its entity's segment length: at
+                                    a frame with a non-zero hard gate the (normalised) time since the previous such frame, else 0; the
+                                    hard gates receive a gradient through it.  Needs tggcn_io.steps_per_example                  */
 } tggcn_dims;
 
 /* Parameter table.  One device pointer per reference state_dict() entry, in this order
@@ -193,7 +197,9 @@ typedef struct tggcn_dims {
     X(TIME_W,       "time_position_mlp.0.weight")                                                      \
     X(TIME_B,       "time_position_mlp.0.bias")                                                        \
     X(MSG_GH_W,     "geometry_to_human_message_mlp.0.weight")                                          \
-    X(MSG_GH_B,     "geometry_to_human_message_mlp.0.bias")
+    X(MSG_GH_B,     "geometry_to_human_message_mlp.0.bias")                                            \
+    X(LEN_W,        "segment_length_mlp.0.weight")                                                     \
+    X(LEN_B,        "segment_length_mlp.0.bias")
 
 enum tggcn_weight_id {
 #define TGGCN_X_ENUM(id, key) TGGCN_W_##id,
@@ -280,6 +286,7 @@ enum tggcn_buf_id {
     TGGCN_BUF_PACK,          /* 16-bit operand planes of the projection stage in flight (gemm16.cu)                       */
     TGGCN_BUF_TIME_EMB,      /* (B*T, D)             time-position features (empty unless dims.time_position)             */
     TGGCN_BUF_MSG_GH,        /* (B,T,1,D)            geometry -> human frame message (empty unless dims.geo_to_human)     */
+    TGGCN_BUF_SEG_LEN,       /* (B,T,H+O)            segment lengths (empty unless dims.segment_length)                   */
     TGGCN_BUF_COUNT
 };
 

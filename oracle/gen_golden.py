@@ -79,6 +79,10 @@ CASES = [
     # message_geometry_to_human (models.py:690-695, :1432-1475), also together with a time block in the gate inputs
     ('mphoi_s2_gh', 'mphoi', 32, 2, 12, 2, False, 2.0, False, {'message_geometry_to_human': True}),
     ('cad120_s2_gh_time_u', 'cad120', 32, 2, 11, 2, False, 2.0, False, {'message_geometry_to_human': True, 'add_time_position': 1, 'time_position_strategy': 'u'}),
+    # add_segment_length (models.py:763-779, :954-979): embedding / periodic, with and without the filter, and after a time block
+    ('mphoi_s2_len_e', 'mphoi', 32, 2, 12, 2, False, 2.0, False, {'add_segment_length': 1}),
+    ('cad120_nf_len_p', 'cad120', 32, 2, 11, 2, False, 2.0, False, {'add_segment_length': 1, 'positional_encoding_style': 'p', 'filter_discrete_updates': 0, 'update_segment_threshold': 0.5}),
+    ('cad120_s2_time_len', 'cad120', 32, 2, 11, 2, False, 2.0, False, {'add_segment_length': 1, 'add_time_position': 1}),
     # the benchmarked configuration itself (BASELINE.json configs[1]: MPHOI, B=8, T=128, hidden 512, stage-2 settings)
     ('mphoi_s2_d512_full', 'mphoi', 512, 8, 128, 2, False, 1.0, False),
 ]
@@ -219,6 +223,9 @@ GRAD_CASES = [
     ('grad_mphoi_s2_time_up', 'mphoi', 32, 2, 9, 2, 2.0, {'add_time_position': 1, 'time_position_strategy': 'u', 'positional_encoding_style': 'p'}),
     ('grad_mphoi_s2_gh', 'mphoi', 32, 2, 9, 2, 2.0, {'message_geometry_to_human': True}),
     ('grad_cad120_s2_gh_time_u', 'cad120', 32, 2, 8, 2, 2.0, {'message_geometry_to_human': True, 'add_time_position': 1, 'time_position_strategy': 'u'}),
+    ('grad_mphoi_s2_len_e', 'mphoi', 32, 2, 9, 2, 2.0, {'add_segment_length': 1}),
+    ('grad_cad120_nf_len_p', 'cad120', 32, 2, 8, 2, 2.0, {'add_segment_length': 1, 'positional_encoding_style': 'p', 'filter_discrete_updates': 0, 'update_segment_threshold': 0.5}),
+    ('grad_cad120_s2_time_len', 'cad120', 32, 2, 8, 2, 2.0, {'add_segment_length': 1, 'add_time_position': 1}),
     # no gradient case for discrete_optimization_strategy 'st': the reference's StraightThroughEstimator.backward returns one gradient
     # for two forward inputs and autograd rejects it (distributions.py:39-53) — the reference cannot train with it
     # hidden 512 (the benchmarked width), T = 32: the D=512 BPTT and split-K weight-gradient paths against the reference itself

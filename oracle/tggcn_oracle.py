@@ -46,6 +46,8 @@ class OracleConfig:
     time_position: str = ''                 # add_time_position: '' off, 's' = time embedding appended to the segment-level inputs
                                             # (models.py:755-762), 'u' = appended to the gate MLP inputs (:656-662, :1494, :1527)
     positional_encoding: str = 'e'          # 'e' = time_position_mlp (Linear(1, D) + ReLU) of (t+1)/steps, 'p' = periodic of (t+1)
+    segment_length: bool = False            # add_segment_length (models.py:763-779, :954-979): per entity, the (normalised) length of
+                                            # the segment closed at a frame, embedded like the time position, appended to the xx rows
     geo_to_human: bool = False              # message_geometry_to_human (models.py:690-695, :1432-1475): one more message block
                                             # ReLU(geometry_to_human_message_mlp([x_g | h_g])) in the humans' segment inputs and gate inputs
     straight_through: bool = False          # discrete_optimization_strategy 'st' (models.py:1621-1622): soft gate = the sigmoid
@@ -65,6 +67,7 @@ def config_from_kwargs(kw: dict) -> OracleConfig:
                         kw.get('attention_style') not in ('v2', 'dot-product'),
                         (kw.get('time_position_strategy', 's') if kw.get('add_time_position') else ''),
                         'e' if kw.get('positional_encoding_style', 'e') in ('e', 'embedding') else 'p',
+                        bool(kw.get('add_segment_length', 0)),
                         bool(kw.get('message_geometry_to_human', False)),
                         kw.get('discrete_optimization_strategy', 'gs') in ('st', 'straight-through'),
                         _UPD[kw.get('object_segment_update_strategy', 'ind')])
@@ -236,6 +239,32 @@ def time_embedding(p: Dict[str, Tensor], cfg: OracleConfig, steps_per_example: T
     return torch.cat([torch.sin(x / w), torch.cos(x / w)], dim=-1)
 
 
+def _embed_positions(p: Dict[str, Tensor], cfg: OracleConfig, x: Tensor, mlp: str) -> Tensor:
+    """(…, 1) position values -> (…, D): Linear(1, D) + ReLU ('e') or make_periodic_embedding ('p', models.py:1777-1794)."""
+    if cfg.positional_encoding == 'e':
+        return _relu_lin(p, mlp, x)
+    w = torch.tensor([1e4], dtype=x.dtype) ** torch.linspace(0, 1, cfg.hidden_size // 2, dtype=x.dtype)
+    return torch.cat([torch.sin(x / w), torch.cos(x / w)], dim=-1)
+
+
+def segment_lengths(u: Tensor, steps_per_example: Tensor, periodic: bool) -> Tensor:
+    """_assemble_segment_length_tensor, vhoi/models.py:954-979, for the hard gates u (B, T, E): at a frame that closes a segment
+    (u != 0) the time since the previous boundary, else u * time (= 0 in value; the hard gates keep their gradient)."""
+    B, T, E = u.shape
+    steps = steps_per_example.to(u.dtype)
+    out = []
+    acc = u.new_zeros(B, E)
+    for t in range(T):
+        x_t = u.new_full((B, 1), float(t + 1))
+        if not periodic:
+            x_t = x_t / steps[:, None]
+        rel = u[:, t] * x_t
+        rel = torch.where(rel.bool(), rel - acc, rel)
+        acc = acc + rel
+        out.append(rel)
+    return torch.stack(out, dim=1)                                      # (B, T, E)
+
+
 def forward(p: Dict[str, Tensor], cfg: OracleConfig, x_human: Tensor, x_objects: Tensor, objects_mask: Tensor,
             human_segmentation: Optional[Tensor] = None, objects_segmentation: Optional[Tensor] = None,
             noise: Optional[Tensor] = None, training: bool = False, inspect_model: bool = False,
@@ -352,6 +381,13 @@ def forward(p: Dict[str, Tensor], cfg: OracleConfig, x_human: Tensor, x_objects:
         y_os = torch.stack([filter_soft(y_oss[..., k], thr) for k in range(O)], dim=-1)
     if gates_only:
         return y_hs, y_hss, y_os, y_oss
+    if cfg.segment_length:                                                      # models.py:763-779
+        for hard, xx in ((y_hs, xx_h), (y_os, xx_o)):
+            emb = _embed_positions(p, cfg, segment_lengths(hard, steps_per_example, cfg.positional_encoding == 'p').unsqueeze(-1),
+                                   'segment_length_mlp.0')                      # (B,T,E,D)
+            for e in range(len(xx)):
+                for t in range(T):
+                    xx[e][t] = torch.cat([xx[e][t], emb[:, t, e]], dim=-1)
     tap('xx_h', torch.stack([torch.stack(r, dim=1) for r in xx_h], dim=2))       # (B,T,H,3D)
     tap('xx_o', torch.stack([torch.stack(r, dim=1) for r in xx_o], dim=2))       # (B,T,O,4D)
 

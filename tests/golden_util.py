@@ -35,6 +35,9 @@ CASES = {
     'cad120_nf_st': ('cad120', 32, 2, 11, 2, False, False, {'discrete_optimization_strategy': 'st', 'filter_discrete_updates': 0, 'update_segment_threshold': 0.5}),
     'mphoi_s2_gh': ('mphoi', 32, 2, 12, 2, False, False, {'message_geometry_to_human': True}),
     'cad120_s2_gh_time_u': ('cad120', 32, 2, 11, 2, False, False, {'message_geometry_to_human': True, 'add_time_position': 1, 'time_position_strategy': 'u'}),
+    'mphoi_s2_len_e': ('mphoi', 32, 2, 12, 2, False, False, {'add_segment_length': 1}),
+    'cad120_nf_len_p': ('cad120', 32, 2, 11, 2, False, False, {'add_segment_length': 1, 'positional_encoding_style': 'p', 'filter_discrete_updates': 0, 'update_segment_threshold': 0.5}),
+    'cad120_s2_time_len': ('cad120', 32, 2, 11, 2, False, False, {'add_segment_length': 1, 'add_time_position': 1}),
 }
 
 # BASELINE.json configs[1] itself — what bench.py times (reference outputs; gate margin 2.5e-5).  Kept apart from CASES: the
@@ -65,6 +68,9 @@ GRAD_CASES = {
     'grad_mphoi_s2_time_up': ('mphoi', 32, 2, 9, 2, {'add_time_position': 1, 'time_position_strategy': 'u', 'positional_encoding_style': 'p'}),
     'grad_mphoi_s2_gh': ('mphoi', 32, 2, 9, 2, {'message_geometry_to_human': True}),
     'grad_cad120_s2_gh_time_u': ('cad120', 32, 2, 8, 2, {'message_geometry_to_human': True, 'add_time_position': 1, 'time_position_strategy': 'u'}),
+    'grad_mphoi_s2_len_e': ('mphoi', 32, 2, 9, 2, {'add_segment_length': 1}),
+    'grad_cad120_nf_len_p': ('cad120', 32, 2, 8, 2, {'add_segment_length': 1, 'positional_encoding_style': 'p', 'filter_discrete_updates': 0, 'update_segment_threshold': 0.5}),
+    'grad_cad120_s2_time_len': ('cad120', 32, 2, 8, 2, {'add_segment_length': 1, 'add_time_position': 1}),
 }
 
 # hidden 512 (the benchmarked width), T = 32.  Kept apart from GRAD_CASES: the reference's own fp32 autograd carries summation

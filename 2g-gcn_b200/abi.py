@@ -46,7 +46,7 @@ class IO(C.Structure):
         ('out_h', C.c_void_p * 4), ('out_o', C.c_void_p * 4),
         ('att_frame', C.c_void_p), ('att_seg_f', C.c_void_p), ('att_seg_b', C.c_void_p),
         ('bn_running_mean', C.c_void_p), ('bn_running_var', C.c_void_p), ('bn_num_batches', C.c_void_p),
-        ('steps_per_example', C.c_void_p), ('time_freq', C.c_void_p), ('status_host', C.c_void_p),
+        ('dist_hh', C.c_void_p), ('dist_ho', C.c_void_p), ('dist_oo', C.c_void_p), ('steps_per_example', C.c_void_p), ('time_freq', C.c_void_p), ('status_host', C.c_void_p),
     ]
 
 

@@ -416,6 +416,7 @@ static int forward_impl(const tggcn_dims* dims, const void* const* weights, int 
         P.update_strategy = d.update_strategy; P.straight_through = d.straight_through;
         P.gh = d.geo_to_human ? 1 : 0; P.msg_gh = d.geo_to_human ? buf(TGGCN_BUF_MSG_GH) : nullptr;
         P.tl = tl_of(d);
+        P.dist[0] = d.hh ? io->dist_hh : nullptr; P.dist[1] = io->dist_ho; P.dist[2] = io->dist_oo;
         P.time_position = d.time_position; P.time_emb = d.time_position ? buf(TGGCN_BUF_TIME_EMB) : nullptr;
         P.s_h = buf(TGGCN_BUF_S_H); P.s_o = buf(TGGCN_BUF_S_O);
         P.msg_hh = buf(TGGCN_BUF_MSG_HH); P.msg_ho = buf(TGGCN_BUF_MSG_HO); P.msg_oh = buf(TGGCN_BUF_MSG_OH);
@@ -461,6 +462,7 @@ static int forward_impl(const tggcn_dims* dims, const void* const* weights, int 
         memset(&P, 0, sizeof(P));
         P.B = B; P.T = T; P.H = H; P.O = O; P.D = D; P.hh = d.hh; P.mean_pool = d.mean_pool; P.att_noscale = d.att_noscale;
         P.gs_h = buf(TGGCN_BUF_GS_H); P.gs_o = buf(TGGCN_BUF_GS_O);
+        P.dist[0] = d.hh ? io->dist_hh : nullptr; P.dist[1] = io->dist_ho; P.dist[2] = io->dist_oo;
         P.u_h = io->y_hs; P.u_o = io->y_os; P.om = io->objects_mask;
         P.wih_h[0] = W(TGGCN_W_HSEG_F_WIH); P.wih_h[1] = W(TGGCN_W_HSEG_B_WIH); P.ldw_h = ldwh; P.col_h = kh;
         P.wih_o[0] = W(TGGCN_W_OSEG_F_WIH); P.wih_o[1] = W(TGGCN_W_OSEG_B_WIH); P.ldw_o = ldwo; P.col_o = ko;

@@ -378,6 +378,8 @@ int tggcn_backward_ex(const tggcn_dims* dims, const void* const* weights, void* 
         SegBwdParams P;
         memset(&P, 0, sizeof(P));
         P.B = B; P.T = T; P.H = H; P.O = O; P.D = D; P.hh = d.hh; P.nk_h = nkh; P.mean_pool = d.mean_pool; P.att_noscale = d.att_noscale;
+        P.dist_kind[0] = (d.hh && io->dist_hh && !d.mean_pool) ? 1 : 0; P.dist_kind[1] = P.dist_kind[2] = (io->dist_ho && !d.mean_pool) ? 1 : 0;
+        P.dist_kind[3] = (io->dist_oo && !d.mean_pool) ? 1 : 0;
         P.hx_h = buf(TGGCN_BUF_HX_H); P.hx_o = buf(TGGCN_BUF_HX_O);
         P.sgates_h = buf(TGGCN_BUF_SGATES_H); P.sgates_o = buf(TGGCN_BUF_SGATES_O);
         P.u_h = io->y_hs; P.u_o = io->y_os; P.om = io->objects_mask;
@@ -465,6 +467,8 @@ int tggcn_backward_ex(const tggcn_dims* dims, const void* const* weights, void* 
         P.update_strategy = d.update_strategy; P.straight_through = d.straight_through;
         P.gh = d.geo_to_human ? 1 : 0; P.msg_gh = P.gh ? buf(TGGCN_BUF_MSG_GH) : nullptr; P.dmsg_gh = P.gh ? bb(BL.dmsg[5]) : nullptr;
         P.tl = tl_of(d);
+        P.dist_kind[0] = (d.hh && io->dist_hh && !d.mean_pool) ? 1 : 0; P.dist_kind[1] = P.dist_kind[2] = (io->dist_ho && !d.mean_pool) ? 1 : 0;
+        P.dist_kind[3] = (io->dist_oo && !d.mean_pool) ? 1 : 0;
         P.time_position = d.time_position; P.time_emb = d.time_position ? buf(TGGCN_BUF_TIME_EMB) : nullptr;
         // no gradient pointers for time_position_mlp = it is off the gradient path of this call (strategy 'u' with every gate imposed)
         P.dtime = (d.time_position && !d.time_periodic && G(TGGCN_W_TIME_W) && G(TGGCN_W_TIME_B)) ? bb(BL.dtime) : nullptr;

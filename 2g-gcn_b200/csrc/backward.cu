@@ -321,7 +321,8 @@ __global__ void __launch_bounds__(256) frame_bwd_kernel(const FrameBwdParams P) 
             float dot = 0.0f;
             for (int sd = 0; sd < Es; ++sd) dot = fmaf(al[r * FB_MAXE + sd], dd[r * FB_MAXE + sd], dot);
             for (int sd = 0; sd < Es; ++sd)            // mean pooling: the weights do not depend on the states
-                dd[r * FB_MAXE + sd] = P.mean_pool ? 0.0f : al[r * FB_MAXE + sd] * (dd[r * FB_MAXE + sd] - dot) * scale;
+                dd[r * FB_MAXE + sd] = (P.mean_pool || P.dist_kind[recv_h ? (second ? 1 : 0) : (second ? 3 : 2)])
+                                           ? 0.0f : al[r * FB_MAXE + sd] * (dd[r * FB_MAXE + sd] - dot) * scale;
         }
     }
     __syncthreads();

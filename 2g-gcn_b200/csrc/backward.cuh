@@ -46,6 +46,7 @@ struct SegBwdParams {
     int B, T, H, O, D, hh, nk_h;
     int mean_pool;                                 // uniform sender weights: no gradient through attention logits
     int att_noscale;                               // attention_style 'v2': plain dot-product logits
+    int dist_kind[4];                              // message kind (hh, oh, ho, oo) used distance-based weights: no logit gradient either
     const float* hx_h; const float* hx_o;          // forward states (B,T,E,2D)
     const float* sgates_h; const float* sgates_o;  // (B,T,E,2,4D) r, z, n, hn
     const float* u_h; const float* u_o;            // hard gates (B,T,E)
@@ -78,6 +79,7 @@ struct FrameBwdParams {
     int mean_pool;                                 // uniform sender weights: no gradient through attention logits
     int att_noscale;                               // attention_style 'v2': plain dot-product logits
     int update_strategy;                           // 0 'ind', 1 'sah', 2 'coh' (tggcn_dims.update_strategy)
+    int dist_kind[4];                              // message kind (hh, oh, ho, oo) used distance-based weights: no logit gradient
     int tl;                                        // add_segment_length: one more block at the end of every xx row
     int gh;                                        // message_geometry_to_human: block m_gh after m_oh in the humans' rows
     const float* msg_gh;                           // (B,T,1,D) forward message, or null

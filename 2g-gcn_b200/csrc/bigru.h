@@ -44,6 +44,7 @@ struct SegParams {
     int hh;                       // humans->human messages on
     int mean_pool;                // message_aggregation 'mp': uniform weights over the valid senders instead of attention
     int att_noscale;              // attention_style 'v2': plain dot-product logits (no 1/sqrt(D))
+    const float* dist[3];         // distance-based attention: hh (B,T,H,H), ho (B,T,H,O), oo (B,T,O,O); each may be null
     // hoisted frame-part pre-activations (incl. b_ih) and gates
     const float* gs_h;            // (B,T,H,2,3D)
     const float* gs_o;            // (B,T,O,2,3D)

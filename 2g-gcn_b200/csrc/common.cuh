@@ -71,6 +71,26 @@ __device__ __forceinline__ float warp_max(float v) {
     return v;
 }
 
+// Distance-based attention (compute_distance_based_attention_weights, vhoi/models.py:1757-1775).  dist = {hh (B,T,H,H), ho (B,T,H,O),
+// oo (B,T,O,O)}, n = b*T + t, message kind 0 hh, 1 oh (receiver human, sender object), 2 ho (receiver object, sender human), 3 oo.
+// Returns false when the kind keeps its dot-product attention (no distances given); else `logit` = 1 / (d + 1e-7) and `valid` =
+// the distance is non-zero (zero distances are masked out like virtual senders).
+__device__ __forceinline__ const float* dist_of_kind(const float* const* dist, int kind) {
+    return kind == 0 ? dist[0] : (kind == 3 ? dist[2] : dist[1]);
+}
+__device__ __forceinline__ bool dist_logit(const float* const* dist, int kind, size_t n, int H, int O, int r, int s, float& logit,
+                                           bool& valid) {
+    const float* p = dist_of_kind(dist, kind);
+    if (p == nullptr) return false;
+    const float d = kind == 0 ? __ldg(p + (n * H + r) * H + s)
+                  : kind == 1 ? __ldg(p + (n * H + r) * O + s)
+                  : kind == 2 ? __ldg(p + (n * H + s) * O + r)
+                              : __ldg(p + (n * O + r) * O + s);
+    logit = 1.0f / (d + 1e-7f);
+    valid = d != 0.0f;
+    return true;
+}
+
 __device__ __forceinline__ float sigmoidf_acc(float x) { return 1.0f / (1.0f + expf(-x)); }
 
 // 16-byte async copy global -> shared, bypassing L1 (.cg): used for data other CTAs produced.

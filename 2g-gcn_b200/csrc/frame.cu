@@ -67,15 +67,25 @@ __global__ void __launch_bounds__(FM_THREADS) frame_messages_kernel(const FrameM
         float* out = recv_h ? (second ? a_oh : a_hh) : (second ? a_oo : a_ho);
         const bool same = (recv_h == send_h);
         if (!(recv_h && !second && !P.hh)) {
+            const int kind = recv_h ? (second ? 1 : 0) : (second ? 3 : 2);
             float m = -INFINITY;
             for (int sdr = 0; sdr < Es; ++sdr) {
                 bool ok = !(same && sdr == r);
                 if (!send_h) ok = ok && (om[sdr] != 0.0f);
+                float lg; bool dv;
+                if (!P.mean_pool && dist_logit(P.dist, kind, (size_t)n, H, O, r, sdr, lg, dv)) {   // models.py:1757-1775
+                    gram[e * NE + (send_h ? sdr : H + sdr)] = lg;      // entry (receiver e, this sender) is read by this thread only
+                    ok = ok && dv;
+                    if (!dv) out[r * FM_MAXE + sdr] = -1.0f;           // remembered for the second pass
+                    else out[r * FM_MAXE + sdr] = 0.0f;
+                } else {
+                    out[r * FM_MAXE + sdr] = 0.0f;
+                }
                 if (ok) m = fmaxf(m, gram[e * NE + (send_h ? sdr : H + sdr)]);
             }
             float sum = 0.0f;
             for (int sdr = 0; sdr < Es; ++sdr) {
-                bool ok = !(same && sdr == r);
+                bool ok = !(same && sdr == r) && out[r * FM_MAXE + sdr] == 0.0f;
                 if (!send_h) ok = ok && (om[sdr] != 0.0f);
                 // mean pooling (models.py:1033-1036): every valid sender weighs 1 / #valid
                 const float ex = ok ? (P.mean_pool ? 1.0f : expf(gram[e * NE + (send_h ? sdr : H + sdr)] - m)) : 0.0f;

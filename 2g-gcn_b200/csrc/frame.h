@@ -9,6 +9,7 @@ struct FrameMsgParams {
     int mean_pool;          // message_aggregation 'mp': uniform weights over the valid senders instead of attention
     int att_noscale;        // attention_style 'v2': plain dot-product logits
     int update_strategy;    // 0 'ind', 1 'sah' (object gates = the single human's), 2 'coh' (hard object gate x the human's)
+    const float* dist[3];   // distance-based attention: hh (B,T,H,H), ho (B,T,H,O), oo (B,T,O,O); each may be null
     int tl;                 // add_segment_length: one more block at the end of every xx row (written by launch_segment_length)
     int gh;                 // message_geometry_to_human: block m_gh after m_oh in the humans' xx rows and gate inputs
     const float* msg_gh;    // (B,T,1,D) ReLU(W_gh s_g + b), or null

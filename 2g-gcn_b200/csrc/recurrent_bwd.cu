@@ -289,7 +289,7 @@ __device__ __forceinline__ void seg_bwd_msg_item(const SegBwdParams& P, int item
         float dot = 0.0f;
         for (int q = 0; q < Es; ++q) dot = fmaf(sh.al[tid * Es + q], sh.da[tid * Es + q], dot);
         for (int q = 0; q < Es; ++q)                   // mean pooling: the weights do not depend on the states
-            sh.dl[tid * Es + q] = P.mean_pool ? 0.0f : sh.al[tid * Es + q] * (sh.da[tid * Es + q] - dot) * scale;
+            sh.dl[tid * Es + q] = (P.mean_pool || P.dist_kind[kind]) ? 0.0f : sh.al[tid * Es + q] * (sh.da[tid * Es + q] - dot) * scale;
     }
     __syncthreads();
     {   // gradient of the pre-activation of every sender's message MLP; attention-logit terms of the senders

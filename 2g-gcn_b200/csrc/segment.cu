@@ -174,7 +174,16 @@ __device__ __forceinline__ bool seg_message_tile(const SegParams& P, int tile, i
         }
         // logit of (receiver j, sender row) when both belong to the same video of the block
         const int li = sh.lidx[tid];
-        if (li >= 0) sh.logit[li] = acc[MSG_NG][0] * (P.att_noscale ? 1.0f : 1.0f / sqrtf((float)D));
+        if (li >= 0) {
+            float lg = acc[MSG_NG][0] * (P.att_noscale ? 1.0f : 1.0f / sqrtf((float)D));
+            if (!P.mean_pool && dist_of_kind(P.dist, kind) != nullptr) {     // distance-based weights (models.py:1757-1775)
+                const int sdr = li % Es, br = li / Es, bl = br / Er, r = br - bl * Er;
+                bool dv;
+                dist_logit(P.dist, kind, (size_t)(b0 + bl) * T + t, H, O, r, sdr, lg, dv);
+                if (!dv) lg = -INFINITY;                                     // a zero distance masks the sender
+            }
+            sh.logit[li] = lg;
+        }
     }
     __syncthreads();
     // masked softmax over the senders of each receiver (vhoi/models.py:1750-1753), one thread per (receiver, sender) pair:
@@ -186,13 +195,13 @@ __device__ __forceinline__ bool seg_message_tile(const SegParams& P, int tile, i
         float m = -INFINITY;
         for (int q = 0; q < Es; ++q)
             if ((mask >> q) & 1u) m = fmaxf(m, lrow[q]);
-        const float ex = (info >> 16) ? (P.mean_pool ? 1.0f : expf(lrow[sdr] - m)) : 0.0f;      // 'mp': weight 1 / #valid senders
+        const float ex = ((info >> 16) && (P.mean_pool || lrow[sdr] > -INFINITY)) ? (P.mean_pool ? 1.0f : expf(lrow[sdr] - m)) : 0.0f;   // 'mp': weight 1 / #valid senders
         sh.alpha[tid] = ex;
         float* attp = sh.rcv_att[br];
         float* salp = sh.rcv_sal[br];
         if (attp != nullptr || salp != nullptr) {            // the sum over this receiver's senders in sender order
             float sum = 0.0f;
-            for (int q = 0; q < Es; ++q) sum += ((mask >> q) & 1u) ? (P.mean_pool ? 1.0f : expf(lrow[q] - m)) : 0.0f;
+            for (int q = 0; q < Es; ++q) sum += (((mask >> q) & 1u) && (P.mean_pool || lrow[q] > -INFINITY)) ? (P.mean_pool ? 1.0f : expf(lrow[q] - m)) : 0.0f;
             const float a = ex * (sum > 0.0f ? 1.0f / sum : 0.0f);
             if (attp != nullptr) attp[sdr] = a;
             if (salp != nullptr) salp[sdr] = a;

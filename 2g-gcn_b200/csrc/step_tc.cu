@@ -539,6 +539,7 @@ constexpr int AT_THREADS = 256;
 struct AttendParams {
     int B, T, H, O, D, hh, nk_h, mean_pool, att_noscale, first, s, dir_base;
     const float* hx_h; const float* hx_o; const float* om;
+    const float* dist[3];                                  // distance-based attention (hh, ho, oo), each may be null
     const float* msg[2][4]; long long msg_bstride[4];      // per direction and kind: sender row (b, e) at msg + b*bstride + e*D
     void* mg16_h; void* mg16_o;                            // planes [dir][hi, lo] of [rows][nk*D]
     float* mg32_h; float* mg32_o; int mg_T;                // (2,B,mg_T,E,nk*D) fp32 copies for the backward, or null
@@ -594,6 +595,11 @@ template <int PREC> __global__ void __launch_bounds__(AT_THREADS) seg_attend_ker
             float m = -INFINITY;
             for (int sd = 0; sd < Es; ++sd) {
                 ok[sd] = !(same && sd == r) && (send_h || __ldg(P.om + b * O + sd) != 0.0f);
+                float lg; bool dv;
+                if (!P.mean_pool && dist_logit(P.dist, k, (size_t)b * T + t, H, O, r, sd, lg, dv)) {   // models.py:1757-1775
+                    alpha[k][r][sd] = lg;
+                    ok[sd] = ok[sd] && dv;
+                }
                 if (ok[sd]) m = fmaxf(m, alpha[k][r][sd]);
             }
             float ex[AT_MAXE], sum = 0.0f;
@@ -1028,6 +1034,7 @@ int launch_segment_big(SegParams& P, void* big_ws, int precision, int T_save, cu
             if (int rc = launch_step(LA, precision, shape, st)) return rc;
             // ---- phase A2: attention over the previous states + aggregation -> operand rows of the cell GEMM --------------------
             A.B = B; A.T = T; A.H = H; A.O = O; A.D = D; A.hh = P.hh; A.nk_h = nkh; A.mean_pool = P.mean_pool; A.att_noscale = P.att_noscale; A.first = s == 0; A.s = s;
+            for (int i = 0; i < 3; ++i) A.dist[i] = P.dist[i];
             A.dir_base = dir_lo;
             A.hx_h = P.hx_h; A.hx_o = P.hx_o; A.om = P.om;
             A.mg16_h = ws + BL.mg_h; A.mg16_o = ws + BL.mg_o;

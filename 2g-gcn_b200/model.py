@@ -382,8 +382,6 @@ class TGGCN(nn.Module):
 
     def _run(self, x_human, x_objects, objects_mask, human_segmentation, objects_segmentation, hh_d, ho_d, oo_d,
              inspect_model, stage_ms, steps_per_example=None):
-        if hh_d is not None or ho_d is not None or oo_d is not None:
-            raise NotImplementedError('distance-based attention (misc.make_attention_distance_based) is not supported')
         if not x_human.is_cuda:
             raise abi.TggcnError('2G-GCN B200 path runs on a CUDA device only (no CPU fallback); got a CPU tensor')
         self._poll_status()                 # status words of earlier calls that have landed by now
@@ -419,6 +417,15 @@ class TGGCN(nn.Module):
                         att_noscale=int(self.attention_style in _V2))
         dims.straight_through = int(self.discrete_optimization_strategy in _ST)
         dims.geo_to_human = int(self.message_geometry_to_human)
+        # misc.make_attention_distance_based (data_loading.py:1264-1276): meaningful under attention aggregation only (models.py:1033-1046)
+        dists = [None, None, None]
+        if self.message_aggregation in _ATT:
+            want = ((B, T, H, H), (B, T, H, O), (B, T, O, O))
+            for i, (t_, shp) in enumerate(zip((hh_d, ho_d, oo_d), want)):
+                if t_ is not None:
+                    if tuple(t_.shape) != shp:
+                        raise ValueError(f'distance tensor {i} must have shape {shp}, got {tuple(t_.shape)}')
+                    dists[i] = t_.to(device=dev, dtype=torch.float32).contiguous()
         steps = freq = None
         if self.add_time_position or self.add_segment_length:
             dims.time_position = (1 if self.time_position_strategy == 's' else 2) if self.add_time_position else 0
@@ -466,6 +473,7 @@ class TGGCN(nn.Module):
             io.object_seg = oseg.data_ptr() if oseg is not None else None
             io.noise = noise.data_ptr() if noise is not None else None
             io.steps_per_example = steps.data_ptr() if steps is not None else None
+            io.dist_hh, io.dist_ho, io.dist_oo = (t_.data_ptr() if t_ is not None else None for t_ in dists)
             io.time_freq = freq.data_ptr() if freq is not None else None
             io.y_hs, io.y_hss, io.y_os, io.y_oss = y_hs.data_ptr(), y_hss.data_ptr(), y_os.data_ptr(), y_oss.data_ptr()
             for i in range(4):
@@ -492,7 +500,7 @@ class TGGCN(nn.Module):
             pending[0].record(torch.cuda.current_stream(dev))
             self._pending_status.append(pending)
             # keep inputs alive until the queued work ran
-            keep = (x_human, x_objects, objects_mask, hseg, oseg, noise, steps, freq)
+            keep = (x_human, x_objects, objects_mask, hseg, oseg, noise, steps, freq, dists)
             self._last = (dims, ws, keep)
             if n_aff is None:
                 output = [y_hs, y_hss] + out_h

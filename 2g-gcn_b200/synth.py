@@ -55,6 +55,7 @@ def model_kwargs(shape: Shape, hidden_size: int = 512, stage: int = 1, **overrid
         message_geometry_to_human=False, message_segment=True, message_type='v2', message_granularity='v1',
         message_aggregation='att', object_segment_update_strategy='ind', share_level_mlps=0,
         update_segment_threshold=0.1 if stage == 2 else 0.5)
+    overrides = {k: v for k, v in overrides.items() if not k.startswith('_')}      # '_…' keys are test-case options, not kwargs
     kw.update(overrides)          # e.g. cat_level_states=1, share_level_mlps=1 (yaml: conf/models/2G-GCN_stage1.yaml:12,28)
     return kw
 
@@ -86,6 +87,20 @@ def make_batch(shape: Shape, B: int, T: int, seed: int = 1234, min_len_frac: flo
     xh = torch.cat([vis, geo], dim=-1).contiguous()
     return dict(x_human=xh, x_objects=xo.contiguous(), objects_mask=om,
                 steps_per_example=lengths.to(torch.float32), lengths=lengths)
+
+
+def make_distances(shape: Shape, B: int, T: int, seed: int = 77):
+    """Synthetic entity distances for misc.make_attention_distance_based (vhoi/data_loading.py:1264-1276): (hh, ho, oo) with
+    shapes (B,T,H,H) [None for CAD-120, whose loader has none], (B,T,H,O), (B,T,O,O); a tenth of the entries are exactly 0
+    ('no distance available': masked by compute_distance_based_attention_weights, vhoi/models.py:1769-1772)."""
+    g = torch.Generator().manual_seed(seed)
+    H, O = shape.H, shape.O
+
+    def one(*size):
+        d = 0.05 + torch.rand(*size, generator=g)
+        return torch.where(torch.rand(*size, generator=g) < 0.1, torch.zeros_like(d), d)
+    hh = one(B, T, H, H) if shape.dataset != 'cad120' else None
+    return hh, one(B, T, H, O), one(B, T, O, O)
 
 
 def make_targets(shape: Shape, lengths: torch.Tensor, T: int, seed: int = 4321) -> Dict[str, torch.Tensor]:

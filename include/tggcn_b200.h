@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define TGGCN_ABI_VERSION 12
+#define TGGCN_ABI_VERSION 13
 
 #if defined(__GNUC__)
 #define TGGCN_API __attribute__((visibility("default")))
@@ -229,6 +229,13 @@ typedef struct tggcn_io {
     float* bn_running_mean;      /* (4V) updated in place when bn_train                                  */
     float* bn_running_var;       /* (4V) updated in place when bn_train                                  */
     int64_t* bn_num_batches;     /* scalar, incremented when bn_train                                    */
+    /* misc.make_attention_distance_based (vhoi/data_loading.py:1264-1276): entity distances; where a pointer is given the attention
+     * weights of the message kinds it covers — frame level AND segment level — are softmax(1 / (d + 1e-7)) over the real senders
+     * at a non-zero distance (compute_distance_based_attention_weights, models.py:1757-1775) instead of the dot-product attention;
+     * no gradient flows through them.  Ignored under mean pooling.  Each may be NULL. */
+    const float* dist_hh;        /* (B,T,H,H) humans -> human                                            */
+    const float* dist_ho;        /* (B,T,H,O) objects -> human and human -> objects                      */
+    const float* dist_oo;        /* (B,T,O,O) objects -> object                                          */
     const float* steps_per_example; /* (B) number of real frames per video, or NULL; required when dims.time_position != 0   */
     const float* time_freq;      /* (D/2) periods w_i of the periodic encoding (dims.time_periodic), else NULL               */
     uint32_t* status_host;       /* PINNED HOST memory, 8 words, or NULL.  When set, tggcn_forward / tggcn_backward end with an

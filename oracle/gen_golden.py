@@ -41,6 +41,10 @@ sys.path.insert(0, os.path.join(ROOT, 'oracle'))
 import tggcn_oracle as orc                                            # noqa: E402
 
 
+def dists64(dists):
+    return None if dists is None else tuple(None if d is None else d.double() for d in dists)
+
+
 class Cfg(dict):
     def get(self, k, default_value=None):
         return dict.get(self, k, default_value)
@@ -83,6 +87,9 @@ CASES = [
     ('mphoi_s2_len_e', 'mphoi', 32, 2, 12, 2, False, 2.0, False, {'add_segment_length': 1}),
     ('cad120_nf_len_p', 'cad120', 32, 2, 11, 2, False, 2.0, False, {'add_segment_length': 1, 'positional_encoding_style': 'p', 'filter_discrete_updates': 0, 'update_segment_threshold': 0.5}),
     ('cad120_s2_time_len', 'cad120', 32, 2, 11, 2, False, 2.0, False, {'add_segment_length': 1, 'add_time_position': 1}),
+    # misc.make_attention_distance_based (data_loading.py:1264-1276; compute_distance_based_attention_weights, models.py:1757-1775)
+    ('mphoi_s2_dist', 'mphoi', 32, 2, 12, 2, False, 2.0, False, {'_distances': True}),
+    ('cad120_s2_dist', 'cad120', 32, 2, 11, 2, False, 2.0, False, {'_distances': True}),
     # the benchmarked configuration itself (BASELINE.json configs[1]: MPHOI, B=8, T=128, hidden 512, stage-2 settings)
     ('mphoi_s2_d512_full', 'mphoi', 512, 8, 128, 2, False, 1.0, False),
 ]
@@ -101,13 +108,16 @@ def run_case(name, shape_name, D, B, T, stage, train_mode, gain, inspect, extra=
     sd = {k: v.detach().clone() for k, v in model.state_dict().items()}   # snapshot (train mode mutates BN)
     model.train(train_mode)
     misc = dict(impose_segmentation_pattern=1 if stage == 1 else 0,
-                segmentation_loss=dict(add=(stage == 2), sigma=4.0 if stage == 2 else 0.0, weight=1.0))
+                segmentation_loss=dict(add=(stage == 2), sigma=4.0 if stage == 2 else 0.0, weight=1.0),
+                make_attention_distance_based=bool(extra.get('_distances')))
     feed = select_model_data_feeder('2G-GCN', 'multiple', dataset_name=shape.dataset, inspect_model=inspect, **misc)
     criterion, _ = select_loss('2G-GCN', 'multiple', shape.dataset, cfg=Cfg(misc=misc))
     thr = kw['update_segment_threshold']
     for attempt in range(50):
         data_seed, noise_seed = 100 + attempt, 500 + attempt
         batch = pkg.make_batch(shape, B, T, seed=data_seed)
+        dists = pkg.make_distances(shape, B, T, seed=data_seed + 5000) if extra.get('_distances') else None
+        dist_data = [None, None, None] if dists is None else [None if shape.dataset == 'cad120' else dists[0], dists[1], dists[2]]
         n_calls = orc.num_noise_draws(T, shape.H, shape.O, stage == 1, stage == 1 and shape.dataset == 'cad120',
                                       kw['object_segment_update_strategy'],
                                       kw['discrete_optimization_strategy'] in ('st', 'straight-through'))
@@ -118,7 +128,7 @@ def run_case(name, shape_name, D, B, T, stage, train_mode, gain, inspect, extra=
                 _, s_h, _, s_o = orc.forward({k: v.double() for k, v in sd.items()},
                                              orc.config_from_kwargs(kw),
                                              batch['x_human'].double(), batch['x_objects'].double(), batch['objects_mask'].double(),
-                                             None, None, noise.double(), gates_only=True, steps_per_example=batch['steps_per_example'])
+                                             None, None, noise.double(), gates_only=True, steps_per_example=batch['steps_per_example'], distances=dists64(dists))
             pre = 1.0
             for sft in (s_h, s_o):
                 pre = min(pre, float((sft - thr).abs().min()), float((sft[:, 1:] - sft[:, :-1]).abs().min()))
@@ -135,8 +145,7 @@ def run_case(name, shape_name, D, B, T, stage, train_mode, gain, inspect, extra=
         captured = {}
         hk = model.geometry_embedding_gcn.register_forward_hook(lambda m, i, o: captured.__setitem__('gcn_out', o.detach().clone()))
         # data tuple layout of gcn_fetcher (data_loading.py:1282-1315)
-        data = [batch['x_human'], batch['x_objects'], batch['objects_mask'], None, None, None, None,
-                batch['steps_per_example']]
+        data = [batch['x_human'], batch['x_objects'], batch['objects_mask'], None] + dist_data + [batch['steps_per_example']]
         with torch.no_grad():
             res = feed(model, data)
         hk.remove()
@@ -165,7 +174,7 @@ def run_case(name, shape_name, D, B, T, stage, train_mode, gain, inspect, extra=
     o64 = orc.forward(p64, ocfg, batch['x_human'].double(), batch['x_objects'].double(),
                       batch['objects_mask'].double(), None if hseg is None else hseg.double(),
                       None if oseg is None else oseg.double(), noise.double(), training=train_mode, taps=taps,
-                      steps_per_example=batch['steps_per_example'])
+                      steps_per_example=batch['steps_per_example'], distances=dists64(dists))
     o_margin = float((taps['y_oss'] - thr).abs().min()) if oseg is None else 1.0
     if o_margin <= CASE_MARGIN.get(name, 1e-4):
         raise RuntimeError(f'{name}: object gate margin too small ({o_margin}); change seeds')
@@ -226,6 +235,8 @@ GRAD_CASES = [
     ('grad_mphoi_s2_len_e', 'mphoi', 32, 2, 9, 2, 2.0, {'add_segment_length': 1}),
     ('grad_cad120_nf_len_p', 'cad120', 32, 2, 8, 2, 2.0, {'add_segment_length': 1, 'positional_encoding_style': 'p', 'filter_discrete_updates': 0, 'update_segment_threshold': 0.5}),
     ('grad_cad120_s2_time_len', 'cad120', 32, 2, 8, 2, 2.0, {'add_segment_length': 1, 'add_time_position': 1}),
+    ('grad_mphoi_s2_dist', 'mphoi', 32, 2, 9, 2, 2.0, {'_distances': True}),
+    ('grad_cad120_s2_dist', 'cad120', 32, 2, 8, 2, 2.0, {'_distances': True}),
     # no gradient case for discrete_optimization_strategy 'st': the reference's StraightThroughEstimator.backward returns one gradient
     # for two forward inputs and autograd rejects it (distributions.py:39-53) — the reference cannot train with it
     # hidden 512 (the benchmarked width), T = 32: the D=512 BPTT and split-K weight-gradient paths against the reference itself
@@ -238,10 +249,10 @@ GRAD_CASES = [
 # with attention such a sender usually carries a negligible weight.  Found on grad_cad120_s2_mp, seed 300: one
 # objects_to_object_message_mlp pre-activation of 5.3e-7 flipped under the GPU's 3xTF32 product and moved the bias gradient by
 # 0.7 %.  For these cases the seed search therefore also demands a margin on EVERY ReLU pre-activation of the oracle forward.
-RELU_STABLE_CASES = {'grad_mphoi_s2_mp', 'grad_cad120_s2_mp'}
+RELU_STABLE_CASES = {'grad_mphoi_s2_mp', 'grad_cad120_s2_mp', 'grad_mphoi_s2_dist', 'grad_cad120_s2_dist'}
 
 
-def _relu_margin(p64, ocfg, batch, hseg, oseg, noise, n_calls):
+def _relu_margin(p64, ocfg, batch, hseg, oseg, noise, n_calls, dists=None):
     worst = [float('inf')]
     orig = orc._relu_lin
 
@@ -253,7 +264,7 @@ def _relu_margin(p64, ocfg, batch, hseg, oseg, noise, n_calls):
     try:
         orc.forward(p64, ocfg, batch['x_human'].double(), batch['x_objects'].double(), batch['objects_mask'].double(),
                     None if hseg is None else hseg.double(), None if oseg is None else oseg.double(),
-                    noise.double() if n_calls else None, training=True, steps_per_example=batch['steps_per_example'])
+                    noise.double() if n_calls else None, training=True, steps_per_example=batch['steps_per_example'], distances=dists64(dists))
     finally:
         orc._relu_lin = orig
     return worst[0]
@@ -277,13 +288,16 @@ def run_grad_case(name, shape_name, D, B, T, stage, gain, extra=None):
     sd = {k: v.detach().clone() for k, v in model.state_dict().items()}
     model.train(True)
     misc = dict(impose_segmentation_pattern=1 if stage == 1 else 0,
-                segmentation_loss=dict(add=(stage == 2), sigma=4.0 if stage == 2 else 0.0, weight=1.0))
+                segmentation_loss=dict(add=(stage == 2), sigma=4.0 if stage == 2 else 0.0, weight=1.0),
+                make_attention_distance_based=bool(extra.get('_distances')))
     feed = select_model_data_feeder('2G-GCN', 'multiple', dataset_name=shape.dataset, **misc)
     criterion, _ = select_loss('2G-GCN', 'multiple', shape.dataset, cfg=Cfg(misc=misc))
     thr = kw['update_segment_threshold']
     for attempt in range(50):
         data_seed, noise_seed = 300 + attempt, 700 + attempt
         batch = pkg.make_batch(shape, B, T, seed=data_seed)
+        dists = pkg.make_distances(shape, B, T, seed=data_seed + 5000) if extra.get('_distances') else None
+        dist_data = [None, None, None] if dists is None else [None if shape.dataset == 'cad120' else dists[0], dists[1], dists[2]]
         n_calls = orc.num_noise_draws(T, shape.H, shape.O, stage == 1, stage == 1 and shape.dataset == 'cad120',
                                       kw['object_segment_update_strategy'],
                                       kw['discrete_optimization_strategy'] in ('st', 'straight-through'))
@@ -297,7 +311,7 @@ def run_grad_case(name, shape_name, D, B, T, stage, gain, extra=None):
         o64 = orc.forward(p64, ocfg, batch['x_human'].double(), batch['x_objects'].double(), batch['objects_mask'].double(),
                           None if hseg is None else hseg.double(), None if oseg is None else oseg.double(),
                           noise.double() if n_calls else None, training=True, taps=taps,
-                          steps_per_example=batch['steps_per_example'])
+                          steps_per_example=batch['steps_per_example'], distances=dists64(dists))
         softs = ([o64[1]] if shape.num_classes[1] is None else [o64[2], o64[3]]) if stage == 2 else []
         if oseg is None:
             softs.append(taps['y_oss'])
@@ -306,7 +320,7 @@ def run_grad_case(name, shape_name, D, B, T, stage, gain, extra=None):
             margin = min(margin, float((sft - thr).abs().min()))
             if kw['filter_discrete_updates']:
                 margin = min(margin, float((sft[:, 1:] - sft[:, :-1]).abs().min()))
-        if margin > CASE_MARGIN.get(name, 1e-4) and (name not in RELU_STABLE_CASES or _relu_margin(p64, ocfg, batch, hseg, oseg, noise, n_calls) > 2e-5):
+        if margin > CASE_MARGIN.get(name, 1e-4) and (name not in RELU_STABLE_CASES or _relu_margin(p64, ocfg, batch, hseg, oseg, noise, n_calls, dists) > 2e-5):
             break
     else:
         raise RuntimeError(f'no safe seed for {name}')
@@ -319,7 +333,7 @@ def run_grad_case(name, shape_name, D, B, T, stage, gain, extra=None):
     ref_dist.sample_from_gumbel_sigmoid = injected
     model.load_state_dict(sd)
     model.zero_grad()
-    data = [batch['x_human'], batch['x_objects'], batch['objects_mask'], None, None, None, None, batch['steps_per_example']]
+    data = [batch['x_human'], batch['x_objects'], batch['objects_mask'], None] + dist_data + [batch['steps_per_example']]
     out = feed(model, data)
     tg = pkg.make_targets(shape, batch['lengths'], T, seed=900 + attempt)
     targets = pkg.target_list(shape, tg)

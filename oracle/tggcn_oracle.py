@@ -152,7 +152,8 @@ def frame_level_rnn(p, x: Tensor, rnn: str, mlp: str) -> Tuple[Tensor, Tensor]:
     return _relu_lin(p, mlp + '.0', h_fr), h_fr
 
 
-def attend(query: Tensor, keys: Tensor, values: Tensor, mask: Tensor, mean_pool: bool = False, scaled: bool = True) -> Tuple[Tensor, Tensor]:
+def attend(query: Tensor, keys: Tensor, values: Tensor, mask: Tensor, mean_pool: bool = False, scaled: bool = True,
+           dist: Optional[Tensor] = None) -> Tuple[Tensor, Tensor]:
     """Scaled dot-product attention of compute_attention_weights (vhoi/models.py:1721-1754, style 'v3')
     followed by the weighted sum at e.g. :1047-1048.
     query (B,F), keys (B,S,F), values (B,S,D), mask (B,S) in {0,1}.  Fully masked rows give zeros
@@ -160,9 +161,13 @@ def attend(query: Tensor, keys: Tensor, values: Tensor, mask: Tensor, mean_pool:
     if mean_pool:       # 'mp': sum of the (masked) messages over clamp(#valid senders, min=1), e.g. models.py:1033-1036
         w = mask / torch.clamp(mask.sum(dim=1, keepdim=True), min=1.0)
         return (w[..., None] * values).sum(1), w
-    logits = (query[:, None, :] * keys).sum(-1)
-    if scaled:          # 'v3'; 'v2' is the plain dot product (models.py:1742-1745)
-        logits = logits / math.sqrt(keys.size(-1))
+    if dist is not None:        # compute_distance_based_attention_weights, models.py:1757-1775: softmax of 1 / (d + 1e-7) over the
+        logits = 1 / (dist + 1e-7)                                      # real senders at a non-zero distance
+        mask = mask * dist.bool().to(mask.dtype)
+    else:
+        logits = (query[:, None, :] * keys).sum(-1)
+        if scaled:      # 'v3'; 'v2' is the plain dot product (models.py:1742-1745)
+            logits = logits / math.sqrt(keys.size(-1))
     logits = torch.where(mask.bool(), logits, torch.full_like(logits, float('-inf')))
     w = torch.softmax(logits, dim=1)
     w = torch.where(torch.isnan(w), torch.zeros_like(w), w)
@@ -268,7 +273,8 @@ def segment_lengths(u: Tensor, steps_per_example: Tensor, periodic: bool) -> Ten
 def forward(p: Dict[str, Tensor], cfg: OracleConfig, x_human: Tensor, x_objects: Tensor, objects_mask: Tensor,
             human_segmentation: Optional[Tensor] = None, objects_segmentation: Optional[Tensor] = None,
             noise: Optional[Tensor] = None, training: bool = False, inspect_model: bool = False,
-            taps: Optional[dict] = None, gates_only: bool = False, steps_per_example: Optional[Tensor] = None):
+            taps: Optional[dict] = None, gates_only: bool = False, steps_per_example: Optional[Tensor] = None,
+            distances: Optional[Tuple[Optional[Tensor], Optional[Tensor], Optional[Tensor]]] = None):
     """TGGCN.forward, vhoi/models.py:584-933, for the shipped configuration family
     (message_type v2, granularity v1, attention aggregation style v3, update strategy 'ind',
     gumbel-sigmoid gates, message_segment on, geometry->objects on, geometry->human off).
@@ -285,6 +291,11 @@ def forward(p: Dict[str, Tensor], cfg: OracleConfig, x_human: Tensor, x_objects:
     O = x_objects.size(2)
     tap = (lambda k, v: taps.__setitem__(k, v)) if taps is not None else (lambda k, v: None)
     noise_it = iter(noise) if noise is not None else None
+    d_hh, d_ho, d_oo = distances if distances is not None else (None, None, None)      # (B,T,H,H), (B,T,H,O), (B,T,O,O) or None
+    dist_hh = lambda t, h: None if d_hh is None else _others(d_hh[:, t, h], h)          # models.py:1044-1045
+    dist_oh = lambda t, h: None if d_ho is None else d_ho[:, t, h]                      # receiver human h, senders objects (:683)
+    dist_ho = lambda t, k: None if d_ho is None else d_ho[:, t, :, k]                   # receiver object k, senders humans (:715)
+    dist_oo = lambda t, k: None if d_oo is None else _others(d_oo[:, t, k], k)          # :1327-1328
 
     # -- split, geometry GCN, scrambled view (models.py:631-645) -------------------------------
     vis = x_human[..., :2048]
@@ -324,10 +335,10 @@ def forward(p: Dict[str, Tensor], cfg: OracleConfig, x_human: Tensor, x_objects:
             gate_in = [x_h[:, t, h], h_h[:, t, h]]
             if hh_on:                                                   # :1004-1049
                 snd = _others(s_h, h)
-                m_hh, _ = attend(s_h[:, h], snd, _relu_lin(p, 'humans_to_human_message_mlp.0', snd), ones_h, cfg.mean_pool, cfg.att_scaled)
+                m_hh, _ = attend(s_h[:, h], snd, _relu_lin(p, 'humans_to_human_message_mlp.0', snd), ones_h, cfg.mean_pool, cfg.att_scaled, dist_hh(t, h))
                 parts.append(m_hh), gate_in.append(m_hh)
             val = _relu_lin(p, 'objects_to_human_message_mlp.0', s_o) * objects_mask[..., None]   # :1191-1237
-            m_oh, w_oh = attend(s_h[:, h], s_o, val, objects_mask, cfg.mean_pool, cfg.att_scaled)
+            m_oh, w_oh = attend(s_h[:, h], s_o, val, objects_mask, cfg.mean_pool, cfg.att_scaled, dist_oh(t, h))
             att_oh[h][t] = w_oh
             parts.append(m_oh), gate_in.append(m_oh)
             if cfg.geo_to_human:                                        # :690-695, :1432-1475: single sender, weight 1, no mask
@@ -348,12 +359,12 @@ def forward(p: Dict[str, Tensor], cfg: OracleConfig, x_human: Tensor, x_objects:
             xx_h[h][t] = torch.cat(parts, dim=-1)                       # :705  [h, m_hh, m_oh]
         for k in range(O):
             mk = objects_mask[:, k:k + 1]
-            m_ho, _ = attend(s_o[:, k], s_h, _relu_lin(p, 'human_to_object_message_mlp.0', s_h), ones_H, cfg.mean_pool, cfg.att_scaled)
+            m_ho, _ = attend(s_o[:, k], s_h, _relu_lin(p, 'human_to_object_message_mlp.0', s_h), ones_H, cfg.mean_pool, cfg.att_scaled, dist_ho(t, k))
             m_ho = m_ho * mk                                            # :1099-1143, :720
             m_go = _relu_lin(p, 'geometry_to_object_message_mlp.0', s_g[:, 0]) * mk   # :1384-1428, :729
             snd, snd_mask = _others(s_o, k), _others(objects_mask, k)   # :1286-1332
             val = _relu_lin(p, 'objects_to_object_message_mlp.0', snd) * snd_mask[..., None]
-            m_oo, _ = attend(s_o[:, k], snd, val, snd_mask, cfg.mean_pool, cfg.att_scaled)
+            m_oo, _ = attend(s_o[:, k], snd, val, snd_mask, cfg.mean_pool, cfg.att_scaled, dist_oo(t, k))
             if taps is not None:                                        # per-(t, receiver) tensors for gradient debugging
                 taps.setdefault('val_oo', {})[(t, k)] = val
                 taps.setdefault('m_oo', {})[(t, k)] = m_oo
@@ -405,18 +416,18 @@ def forward(p: Dict[str, Tensor], cfg: OracleConfig, x_human: Tensor, x_objects:
                 x = [xx_h[h][t]]
                 if hh_on:                                               # :1051-1097
                     snd = _others(sh, h)
-                    mg, _ = attend(SH[h], snd, _relu_lin(p, 'humans_to_human_segment_message_mlp.0', snd), ones_h, cfg.mean_pool, cfg.att_scaled)
+                    mg, _ = attend(SH[h], snd, _relu_lin(p, 'humans_to_human_segment_message_mlp.0', snd), ones_h, cfg.mean_pool, cfg.att_scaled, dist_hh(t, h))
                     x.append(mg)
                 val = _relu_lin(p, 'objects_to_human_segment_message_mlp.0', so) * objects_mask[..., None]
-                mg, w = attend(SH[h], so, val, objects_mask, cfg.mean_pool, cfg.att_scaled)            # :1239-1284
+                mg, w = attend(SH[h], so, val, objects_mask, cfg.mean_pool, cfg.att_scaled, dist_oh(t, h))            # :1239-1284
                 att[h][t] = w
                 x.append(mg)
                 newH.append(_seg_cell(p, hcell, torch.cat(x, dim=-1), y_hs[:, t, h:h + 1], SH[h]))
             for k in range(O):
-                mg_ho, _ = attend(SO[k], sh, _relu_lin(p, 'human_to_object_segment_message_mlp.0', sh), ones_H, cfg.mean_pool, cfg.att_scaled)
+                mg_ho, _ = attend(SO[k], sh, _relu_lin(p, 'human_to_object_segment_message_mlp.0', sh), ones_H, cfg.mean_pool, cfg.att_scaled, dist_ho(t, k))
                 snd, snd_mask = _others(so, k), _others(objects_mask, k)        # :1334-1381
                 val = _relu_lin(p, 'objects_to_object_segment_message_mlp.0', snd) * snd_mask[..., None]
-                mg_oo, _ = attend(SO[k], snd, val, snd_mask, cfg.mean_pool, cfg.att_scaled)
+                mg_oo, _ = attend(SO[k], snd, val, snd_mask, cfg.mean_pool, cfg.att_scaled, dist_oo(t, k))
                 x = torch.cat([xx_o[k][t], mg_ho, mg_oo], dim=-1)
                 newO.append(_seg_cell(p, ocell, x, y_os[:, t, k:k + 1], SO[k]))
             SH, SO = newH, newO                                         # commit, :875-880

@@ -38,6 +38,8 @@ CASES = {
     'mphoi_s2_len_e': ('mphoi', 32, 2, 12, 2, False, False, {'add_segment_length': 1}),
     'cad120_nf_len_p': ('cad120', 32, 2, 11, 2, False, False, {'add_segment_length': 1, 'positional_encoding_style': 'p', 'filter_discrete_updates': 0, 'update_segment_threshold': 0.5}),
     'cad120_s2_time_len': ('cad120', 32, 2, 11, 2, False, False, {'add_segment_length': 1, 'add_time_position': 1}),
+    'mphoi_s2_dist': ('mphoi', 32, 2, 12, 2, False, False, {'_distances': True}),
+    'cad120_s2_dist': ('cad120', 32, 2, 11, 2, False, False, {'_distances': True}),
 }
 
 # BASELINE.json configs[1] itself — what bench.py times (reference outputs; gate margin 2.5e-5).  Kept apart from CASES: the
@@ -71,6 +73,8 @@ GRAD_CASES = {
     'grad_mphoi_s2_len_e': ('mphoi', 32, 2, 9, 2, {'add_segment_length': 1}),
     'grad_cad120_nf_len_p': ('cad120', 32, 2, 8, 2, {'add_segment_length': 1, 'positional_encoding_style': 'p', 'filter_discrete_updates': 0, 'update_segment_threshold': 0.5}),
     'grad_cad120_s2_time_len': ('cad120', 32, 2, 8, 2, {'add_segment_length': 1, 'add_time_position': 1}),
+    'grad_mphoi_s2_dist': ('mphoi', 32, 2, 9, 2, {'_distances': True}),
+    'grad_cad120_s2_dist': ('cad120', 32, 2, 8, 2, {'_distances': True}),
 }
 
 # hidden 512 (the benchmarked width), T = 32.  Kept apart from GRAD_CASES: the reference's own fp32 autograd carries summation
@@ -79,6 +83,19 @@ GRAD_CASES = {
 FULL_GRAD_CASES = {
     'grad_mphoi_s2_d512': ('mphoi', 512, 8, 32, 2),
 }
+
+
+def dist_kwargs(dists, to=None):
+    """The three distance kwargs of TGGCN.forward (vhoi/models.py:585) from a (hh, ho, oo) tuple, optionally mapped through `to`."""
+    if dists is None:
+        return {}
+    f = to or (lambda t: t)
+    names = ('human_human_distances', 'human_object_distances', 'object_object_distances')
+    return {k: (None if d is None else f(d)) for k, d in zip(names, dists)}
+
+
+def dists64(dists):
+    return None if dists is None else tuple(None if d is None else d.double() for d in dists)
 
 
 def alias_shared_heads(params, extra):
@@ -106,6 +123,8 @@ class GoldenCase:
         self.kwargs = synth.model_kwargs(self.shape, hidden_size=D, stage=stage, **self.extra)
         self.thr = self.kwargs['update_segment_threshold']
         self.batch = synth.make_batch(self.shape, B, T, seed=data_seed)
+        # misc.make_attention_distance_based cases: (hh, ho, oo) distances, regenerated from the data seed like the generator did
+        self.dists = synth.make_distances(self.shape, B, T, seed=data_seed + 5000) if self.extra.get('_distances') else None
         H, O = self.shape.H, self.shape.O
         self.human_given = stage == 1
         self.objects_given = stage == 1 and self.shape.dataset == 'cad120'

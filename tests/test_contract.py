@@ -100,7 +100,7 @@ def test_library_loads_and_exports_every_declared_symbol(pkg):
     assert lib.tggcn_abi_version() == pkg.abi.ABI_VERSION == int(re.search(r'#define TGGCN_ABI_VERSION\s+(\d+)', header).group(1))
     # struct mirrors: 17 int32 + 1 float + 8 int32; io = 6 + 4 + 8 + 3 + 3 + 1 pointers
     assert ctypes.sizeof(pkg.abi.Dims) == 31 * 4
-    assert ctypes.sizeof(pkg.abi.IO) == 27 * 8
+    assert ctypes.sizeof(pkg.abi.IO) == 30 * 8
     # the status decoder is host-only: healthy words, a barrier time-out, an fp16-split range violation
     words = (ctypes.c_uint32 * 8)()
     assert lib.tggcn_status_decode(words) == 0

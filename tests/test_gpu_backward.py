@@ -10,7 +10,7 @@ import torch
 
 pytestmark = pytest.mark.gpu
 
-from golden_util import GRAD_CASES, alias_shared_heads      # noqa: E402
+from golden_util import GRAD_CASES, alias_shared_heads, dist_kwargs, dists64      # noqa: E402
 
 
 def _summarize(g):
@@ -42,7 +42,8 @@ def _setup(name, orc, synth, pkg):
     oseg = torch.ones(B, T, shape.O) if objects_given else None
     targets = synth.target_list(shape, synth.make_targets(shape, batch['lengths'], T, seed=target_seed))
     ocfg = orc.config_from_kwargs(kw)
-    return dict(blob=blob, shape=shape, stage=stage, model=model, batch=batch, noise=noise if n_calls else None, hseg=hseg,
+    dists = synth.make_distances(shape, B, T, seed=data_seed + 5000) if extra.get('_distances') else None
+    return dict(dists=dists, blob=blob, shape=shape, stage=stage, model=model, batch=batch, noise=noise if n_calls else None, hseg=hseg,
                 oseg=oseg, targets=targets, ocfg=ocfg, extra=extra)
 
 
@@ -53,7 +54,7 @@ def _oracle_grads(c, orc):
     b = c['batch']
     dd = lambda t: None if t is None else t.double()
     out = orc.forward(p, c['ocfg'], b['x_human'].double(), b['x_objects'].double(), b['objects_mask'].double(), dd(c['hseg']),
-                      dd(c['oseg']), dd(c['noise']), training=True, steps_per_example=b['steps_per_example'])
+                      dd(c['oseg']), dd(c['noise']), training=True, steps_per_example=b['steps_per_example'], distances=dists64(c.get('dists')))
     targets = [t.double() if t.is_floating_point() else t for t in c['targets']]
     losses = orc.multi_task_loss(out, targets, c['shape'].dataset, c['stage'])
     sum(losses).backward()
@@ -75,6 +76,7 @@ def test_backward_matches_reference_and_oracle(name, persistent, orc, synth, pkg
                   human_segmentation=cu(c['hseg']), steps_per_example=b['steps_per_example'].cuda())
     if c['oseg'] is not None:
         kwargs['objects_segmentation'] = cu(c['oseg'])
+    kwargs.update(dist_kwargs(c.get('dists'), cu))
     out = model(**kwargs)
     model.check_persistent_kernels()
     targets = [t.cuda() for t in c['targets']]
@@ -150,26 +152,29 @@ WIDE_CASES = {
 
 def _wide_setup(name, orc, synth, pkg):
     """Random case whose sampled gates keep a safe margin from every discrete decision (seed search like gen_golden.py)."""
-    shape_name, D, B, T, stage = WIDE_CASES[name]
+    shape_name, D, B, T, stage = WIDE_CASES[name][:5]
+    extra = WIDE_CASES[name][5] if len(WIDE_CASES[name]) > 5 else {}
     shape = synth.SHAPES[shape_name]
-    kw = synth.model_kwargs(shape, hidden_size=D, stage=stage)
+    kw = synth.model_kwargs(shape, hidden_size=D, stage=stage, **extra)
     thr = kw['update_segment_threshold']
     model = pkg.TGGCN(**kw)
     synth.deterministic_fill(model.state_dict(), seed=11, gain=2.0)
     human_given, objects_given = stage == 1, stage == 1 and shape.dataset == 'cad120'
-    n_calls = orc.num_noise_draws(T, shape.H, shape.O, human_given, objects_given)
+    n_calls = orc.num_noise_draws(T, shape.H, shape.O, human_given, objects_given, kw['object_segment_update_strategy'])
     hseg = torch.ones(B, T, shape.H) if human_given else None
     oseg = torch.ones(B, T, shape.O) if objects_given else None
-    ocfg = orc.OracleConfig(D, shape.V, shape.num_classes, shape.hh, stage == 2, thr)
+    ocfg = orc.config_from_kwargs(kw)
     p64 = {k: v.detach().double() for k, v in model.state_dict().items()}
     dd = lambda t: None if t is None else t.double()
     for attempt in range(40):
         batch = synth.make_batch(shape, B, T, seed=500 + attempt)
+        dists = synth.make_distances(shape, B, T, seed=5500 + attempt) if extra.get('_distances') else None
         noise = orc.draw_noise(max(n_calls, 1), B, torch.Generator().manual_seed(800 + attempt))[:n_calls] if n_calls else None
         taps = {}
         with torch.no_grad():
             o64 = orc.forward(p64, ocfg, batch['x_human'].double(), batch['x_objects'].double(), batch['objects_mask'].double(),
-                              dd(hseg), dd(oseg), dd(noise), training=True, taps=taps)
+                              dd(hseg), dd(oseg), dd(noise), training=True, taps=taps, steps_per_example=batch['steps_per_example'],
+                              distances=dists64(dists))
         softs = []
         if not human_given:
             softs.append(o64[1] if shape.num_classes[1] is None else o64[2])
@@ -185,13 +190,26 @@ def _wide_setup(name, orc, synth, pkg):
     else:
         pytest.skip('no seed with a safe gate margin')
     targets = synth.target_list(shape, synth.make_targets(shape, batch['lengths'], T, seed=900 + attempt))
-    return dict(shape=shape, stage=stage, model=model, batch=batch, noise=noise, hseg=hseg, oseg=oseg, targets=targets, ocfg=ocfg)
+    return dict(shape=shape, stage=stage, model=model, batch=batch, noise=noise, hseg=hseg, oseg=oseg, targets=targets, ocfg=ocfg,
+                dists=dists, extra=extra)
 
 
 # large-batch recurrent path (recurrent_mode 2): its forward must leave exactly what the BPTT kernels read (gates, aggregated
 # messages, per-sender messages, attention weights)
 BIG_PATH_CASES = ['mphoi_d128_s2_rows', 'cad120_d128_s2_big', 'bimanual_d128_s2_big']
 WIDE_CASES.update({'cad120_d128_s2_big': ('cad120', 128, 5, 14, 2), 'bimanual_d128_s2_big': ('bimanual', 128, 4, 8, 2)})
+# model variants at a width where the TMA projection kernel and — in mode 2 — the large-batch step kernels run, several
+# of them combined: wider segment-level input rows (time + length + geometry->human blocks), distance-based attention weights at both
+# levels, the human's gates driving the objects, the periodic time block in the gate inputs
+VARIANT_BIG_CASES = ['mphoi_d128_s2_blocks', 'cad120_d128_s2_dist', 'cad120_d128_s2_sah_u']
+WIDE_CASES.update({
+    'mphoi_d128_s2_blocks': ('mphoi', 128, 5, 10, 2, {'add_time_position': 1, 'add_segment_length': 1, 'message_geometry_to_human': True,
+                                                      '_distances': True}),
+    'cad120_d128_s2_dist': ('cad120', 128, 5, 12, 2, {'_distances': True}),
+    'cad120_d128_s2_sah_u': ('cad120', 128, 4, 11, 2, {'object_segment_update_strategy': 'sah', 'add_time_position': 1,
+                                                       'time_position_strategy': 'u', 'positional_encoding_style': 'p'}),
+})
+BIG_PATH_CASES += VARIANT_BIG_CASES
 
 
 @pytest.mark.parametrize('name,mode', [(n, 0) for n in sorted(WIDE_CASES)] + [(n, 2) for n in BIG_PATH_CASES])
@@ -204,9 +222,10 @@ def test_backward_wide_shapes_match_oracle(name, mode, orc, synth, pkg):
     b = c['batch']
     cu = lambda t: None if t is None else t.cuda()
     kwargs = dict(x_human=b['x_human'].cuda(), x_objects=b['x_objects'].cuda(), objects_mask=b['objects_mask'].cuda(),
-                  human_segmentation=cu(c['hseg']))
+                  human_segmentation=cu(c['hseg']), steps_per_example=b['steps_per_example'].cuda())
     if c['oseg'] is not None:
         kwargs['objects_segmentation'] = cu(c['oseg'])
+    kwargs.update(dist_kwargs(c.get('dists'), cu))
     out = model(**kwargs)
     model.check_persistent_kernels()
     losses = orc.multi_task_loss(out, [t.cuda() for t in c['targets']], c['shape'].dataset, c['stage'])

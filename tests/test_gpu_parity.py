@@ -10,7 +10,7 @@ import numpy as np
 import pytest
 import torch
 
-from golden_util import CASES, GoldenCase
+from golden_util import CASES, GoldenCase, dist_kwargs, dists64
 
 pytestmark = pytest.mark.gpu
 
@@ -34,7 +34,8 @@ def _run(model, case, inspect=False):
         res = model(x_human=b['x_human'].to(dev), x_objects=b['x_objects'].to(dev), objects_mask=b['objects_mask'].to(dev),
                     human_segmentation=None if case.hseg is None else case.hseg.to(dev),
                     objects_segmentation=None if case.oseg is None else case.oseg.to(dev),
-                    steps_per_example=b['steps_per_example'].to(dev), inspect_model=inspect)
+                    steps_per_example=b['steps_per_example'].to(dev), inspect_model=inspect,
+                    **dist_kwargs(case.dists, lambda t: t.to(dev)))
     torch.cuda.synchronize()
     model.check_persistent_kernels()
     return res
@@ -97,7 +98,7 @@ def test_intermediates_match_oracle(name, orc):
     b = case.batch
     dd = lambda t: None if t is None else t.double()
     orc.forward(p64, case.ocfg, dd(b['x_human']), dd(b['x_objects']), dd(b['objects_mask']), dd(case.hseg), dd(case.oseg),
-                dd(case.noise), training=case.train_mode, taps=taps, steps_per_example=b['steps_per_example'])
+                dd(case.noise), training=case.train_mode, taps=taps, steps_per_example=b['steps_per_example'], distances=dists64(case.dists))
     B, T, H, O, D, V = case.B, case.T, case.shape.H, case.shape.O, case.D, case.shape.V
     nkh = 2 if case.shape.hh else 1
     ws = model.workspace_tensor

@@ -24,7 +24,7 @@ def test_oracle_matches_reference(name, dtype, orc):
     b = case.batch
     res = orc.forward(p, case.ocfg, cast(b['x_human']), cast(b['x_objects']), cast(b['objects_mask']), cast(case.hseg),
                       cast(case.oseg), cast(case.noise), training=case.train_mode, inspect_model=case.inspect,
-                      steps_per_example=b['steps_per_example'])
+                      steps_per_example=b['steps_per_example'], distances=None if case.dists is None else tuple(None if d is None else cast(d) for d in case.dists))
     out, att = (res if case.inspect else (res, None))
     assert len(out) == len(case.outputs)
     n_gate = 2 if case.shape.num_classes[1] is None else 4
@@ -81,7 +81,7 @@ def test_reorder_and_filter_edge_cases(orc):
     assert f.ne(0).tolist() == [[False, True, False, False, False, True]]
 
 
-from golden_util import GRAD_CASES, FULL_GRAD_CASES, alias_shared_heads      # noqa: E402
+from golden_util import GRAD_CASES, FULL_GRAD_CASES, alias_shared_heads, dists64      # noqa: E402
 
 
 def _summarize(g):
@@ -120,7 +120,8 @@ def test_oracle_gradients_match_reference(name, orc, synth, pkg):
     oseg = torch.ones(B, T, shape.O).double() if objects_given else None
     ocfg = orc.config_from_kwargs(kw)
     out = orc.forward(p, ocfg, batch['x_human'].double(), batch['x_objects'].double(), batch['objects_mask'].double(),
-                      hseg, oseg, noise.double() if n_calls else None, training=True, steps_per_example=batch['steps_per_example'])
+                      hseg, oseg, noise.double() if n_calls else None, training=True, steps_per_example=batch['steps_per_example'],
+                      distances=dists64(synth.make_distances(shape, B, T, seed=data_seed + 5000) if extra.get('_distances') else None))
     targets = synth.target_list(shape, synth.make_targets(shape, batch['lengths'], T, seed=target_seed))
     targets = [t.double() if t.is_floating_point() else t for t in targets]
     losses = orc.multi_task_loss(out, targets, shape.dataset, stage)

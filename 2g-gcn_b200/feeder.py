@@ -11,7 +11,9 @@ right before the forward (``gcn_fetcher``, :1282-1315).  At GPU speed that copy 
     padded length changes results through the un-permuted geometry view (vhoi/models.py:644-645), so nothing is trimmed.
 
 ``DeviceBatchPipeline``  for data that does not fit (or arrives per step): ``depth`` device-side slots, batch i+1 is copied from
-    pinned host memory on a side stream while batch i computes; events order the two streams in both directions.
+    pinned host memory on a side stream while batch i computes; events order the two streams in both directions.  Call
+    ``submit`` for batch i+1 AFTER queueing the forward of batch i: the forward's own small host->device copy (the Gumbel draws)
+    shares the copy engine and would wait behind the 51 MB batch (measured: 4.60 -> 5.23 ms per step the other way round).
 """
 from __future__ import annotations
 

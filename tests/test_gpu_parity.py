@@ -132,6 +132,25 @@ def test_default_noise_reproduces_manual_seed(pkg):
     assert not torch.equal(a[1], c[1])
 
 
+def test_default_noise_equals_the_batched_cpu_draw(pkg):
+    """The default path draws in place in pinned buffers (no stream sync of a pageable copy): same bits as draw_gumbel_noise, call
+    after call (the ring has three buffers: run more calls than that)."""
+    case = GoldenCase('mphoi_s2_eval')
+    model = _build(case)
+    n_calls = case.T * (case.shape.H + case.shape.O)
+    torch.manual_seed(7)
+    want = []
+    for _ in range(5):
+        model.set_gumbel_noise(pkg.TGGCN.draw_gumbel_noise(n_calls, case.B))
+        want.append([o.clone() for o in _run(model, case)])
+    model.set_gumbel_noise(None)
+    torch.manual_seed(7)
+    for w in want:
+        got = _run(model, case)
+        for x, y in zip(got, w):
+            assert torch.equal(x, y)
+
+
 def test_unmasked_objects_do_not_leak(pkg):
     """Features of masked (virtual) objects must not influence the humans' outputs."""
     case = GoldenCase('mphoi_s2_eval')

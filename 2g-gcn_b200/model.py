@@ -238,6 +238,9 @@ class TGGCN(nn.Module):
                 self.object_frame_prediction_mlp = _mlp([2 * D, n_aff], ['logsoftmax'])
         # ---- runtime state (not part of state_dict) ------------------------------------------------------
         self._ptr_cache = None
+        self._dir = None                    # cached (owner module, attribute, is_parameter, name, tensor) of every state_dict entry
+        self._dir_version = 0
+        self._trainable_cache = {}
         self._ws = {}
         self._time_freq = None
         self._noise_ring = {}               # (n_calls, B) -> pinned buffers of the default Gumbel draws
@@ -315,9 +318,28 @@ class TGGCN(nn.Module):
         self._ws = {}
         return super()._apply(fn, *args, **kwargs)
 
+    def _tensor_directory(self):
+        """[(state_dict name, tensor, is_parameter)] in named_parameters() + named_buffers() order, cached: walking the module tree
+        costs ~0.7 ms per call and a training step used to do it four times.  The cache is validated by identity — every entry's
+        owner module must still hold that very tensor object under that attribute (~130 dict look-ups) — so replacing a parameter,
+        or the copies _apply() makes, rebuild it."""
+        d = self._dir
+        if d is not None and all((m._parameters if isp else m._buffers).get(a) is t for m, a, isp, _, t in d):
+            return d
+        d = []
+        for isp, items in ((True, self.named_parameters()), (False, self.named_buffers())):
+            for name, t in items:
+                owner, _, attr = name.rpartition('.')
+                d.append((self.get_submodule(owner) if owner else self, attr, isp, name, t))
+        self._dir = d
+        self._dir_version += 1
+        self._trainable_cache = {}
+        self._ptr_cache = None
+        return d
+
     def _weight_pointers(self, device):
-        sd_items = list(self.named_parameters()) + list(self.named_buffers())
-        probe = (sd_items[0][1].data_ptr(), sd_items[-1][1].data_ptr(), len(sd_items))
+        sd_items = [(name, t) for _, _, _, name, t in self._tensor_directory()]
+        probe = (sd_items[0][1].data_ptr(), sd_items[-1][1].data_ptr(), len(sd_items), self._dir_version)
         if self._ptr_cache is not None and self._ptr_cache[0] == probe:
             return self._ptr_cache[1]
         arr = (C.c_void_p * abi.N_WEIGHTS)()
@@ -423,7 +445,7 @@ class TGGCN(nn.Module):
         O = x_objects.size(2)
         n_sub, n_aff = self.num_classes
         f32 = dict(dtype=torch.float32, device=dev)
-        with_grad = torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters())
+        with_grad = torch.is_grad_enabled() and any(t.requires_grad for _, _, isp, _, t in self._tensor_directory() if isp)
         if inspect_model and self.message_aggregation in _MP:
             raise NotImplementedError('inspect_model has no attention weights to return under mean-pooling aggregation')
         if with_grad and self.discrete_optimization_strategy in _ST and (human_segmentation is None or objects_segmentation is None):
@@ -571,8 +593,15 @@ class TGGCN(nn.Module):
     def _trainable_table(self, dims):
         """Parameters of the weight table that are on the gradient path of this call (the others keep grad=None,
         like the 22-24 dead tensors of the reference)."""
+        directory = self._tensor_directory()
+        key = (dims.human_seg_given, dims.object_seg_given, dims.time_position)
+        hit = self._trainable_cache.get(key)
+        if hit is not None:
+            return hit
         names, params = [], []
-        for name, prm in self.named_parameters():
+        for _, _, isp, name, prm in directory:
+            if not isp:
+                continue
             if name not in abi.WEIGHT_INDEX:
                 continue                       # *_att_mlp, geometry_to_object_segment_message_mlp: never used
             if name.startswith('update_human_segment_mlp') and dims.human_seg_given:
@@ -583,6 +612,7 @@ class TGGCN(nn.Module):
                 continue                       # strategy 'u' feeds the gate MLPs only
             names.append(name)
             params.append(prm)
+        self._trainable_cache[key] = (names, params)
         return names, params
 
     def _backward(self, state, gouts):

@@ -17,6 +17,9 @@ B, T, D = 8, 128, 512
 torch.manual_seed(0)
 model = pkg.TGGCN(**pkg.synth.model_kwargs(shape, hidden_size=D, stage=2)).cuda()
 model.train(a.train)
+# fixed device-resident noise: the default path's pinned ring makes the host wait for the forward three calls back (back-pressure,
+# not enqueue cost)
+model.set_gumbel_noise(pkg.TGGCN.draw_gumbel_noise(T * (shape.H + shape.O), B).cuda())
 batch = pkg.synth.make_batch(shape, B, T, seed=1234)
 x = {k: batch[k].cuda() for k in ('x_human', 'x_objects', 'objects_mask')}
 targets = [t.cuda() for t in pkg.synth.target_list(shape, pkg.synth.make_targets(shape, batch['lengths'], T, seed=5))]

@@ -13,6 +13,7 @@ struct BiGruGroup {
     int E;                  // entities of this group
     int rows;               // B*E
     int cfg, jeff, n_rb, n_ub, tile_begin;   // tiling (filled by the launcher); cfg: see rec_cfg_for_rows
+    int skip_dirs;          // resident kernel only: bit d set = direction d of this group is computed elsewhere (hybrid launch)
 };
 
 struct BiGruParams {

@@ -273,6 +273,24 @@ __global__ void __launch_bounds__(REC_THREADS, 1) bigru_cluster_kernel(const BiG
 
 }  // namespace
 
+struct SideStream { cudaStream_t side; cudaEvent_t fork, join; };
+static int get_side_stream(SideStream& out) {
+    struct Entry { bool made; SideStream s; };
+    static Entry cache[64];
+    int dev = 0;
+    TG_CUDA_OK(cudaGetDevice(&dev));
+    TG_REQUIRE(dev >= 0 && dev < 64, "device ordinal %d out of range", dev);
+    Entry& e = cache[dev];
+    if (!e.made) {
+        TG_CUDA_OK(cudaStreamCreateWithFlags(&e.s.side, cudaStreamNonBlocking));
+        TG_CUDA_OK(cudaEventCreateWithFlags(&e.s.fork, cudaEventDisableTiming));
+        TG_CUDA_OK(cudaEventCreateWithFlags(&e.s.join, cudaEventDisableTiming));
+        e.made = true;
+    }
+    out = e.s;
+    return 0;
+}
+
 // Returns 0 when the cluster kernel was launched, -1 when this shape does not qualify (caller falls back), > 0 on error.
 int launch_bigru_cluster(BiGruParams& P, cudaStream_t stream) {
     static int enabled = -1;
@@ -346,6 +364,51 @@ int launch_bigru_cluster(BiGruParams& P, cudaStream_t stream) {
     if (force < 0) {
         const char* e = getenv("TGGCN_CL_PLAN");
         force = e != nullptr ? atoi(e) : 0;
+    }
+    // Hybrid (MPHOI B=8: 8 recurrences, 7 clusters fit): when exactly the LAST (group, direction) of the 16-row plan does not fit
+    // into the first wave, it runs on the SMEM-resident grid-barrier kernel (22 CTAs) on a side stream, on the SMs the clusters
+    // leave free, instead of a second wave of clusters.
+    static int hybrid = -1;
+    if (hybrid < 0) {
+        const char* e = getenv("TGGCN_BIGRU_HYBRID");
+        hybrid = e != nullptr ? atoi(e) : 1;        // measured at MPHOI B=8: BiGRU stage 0.973 -> 0.795 ms (6.2 us per step: the 22-CTA
+                                                    // resident kernel is the longer of the two; the seven clusters take 4.2 us)
+    }
+    if (hybrid && force == 0 && ok16 && plan16.count > max_clusters && plan16.count <= CL_MAX_CLUSTERS) {
+        const int lg = plan16.group[plan16.count - 1], ld = plan16.dir[plan16.count - 1];
+        int n_last = 0, first_last = plan16.count;
+        for (int i = 0; i < plan16.count; ++i)
+            if (plan16.group[i] == lg && plan16.dir[i] == ld) { ++n_last; if (i < first_last) first_last = i; }
+        if (plan16.count - n_last <= max_clusters && first_last == plan16.count - n_last && P.g[lg].rows <= 32) {
+            SideStream ss;
+            if (int rc = get_side_stream(ss)) return rc;
+            ClusterPlan head = plan16;
+            head.count = plan16.count - n_last;
+            TG_CUDA_OK(cudaEventRecord(ss.fork, stream));
+            TG_CUDA_OK(cudaStreamWaitEvent(ss.side, ss.fork, 0));
+            cfg.gridDim = dim3(head.count * CL);
+            TG_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, P, head));          // clusters first: they need whole GPCs' worth of free SMs
+            TG_LAUNCH_OK();
+            BiGruParams Q = P;
+            for (int g = 0; g < Q.ngroups; ++g) Q.g[g].skip_dirs = g == lg ? (ld == 0 ? 2 : 1) : 3;
+            const int rr = launch_bigru_resident(Q, ss.side);
+            if (rr != 0) {                                                // does not qualify after all: the last recurrence as a second wave
+                ClusterPlan tail;
+                memset(&tail, 0, sizeof(tail));
+                for (int i = head.count; i < plan16.count; ++i) {
+                    tail.group[tail.count] = plan16.group[i]; tail.dir[tail.count] = plan16.dir[i];
+                    tail.row0[tail.count] = plan16.row0[i]; tail.nrows[tail.count] = plan16.nrows[i];
+                    ++tail.count;
+                }
+                if (rr > 0) return rr;
+                cfg.gridDim = dim3(tail.count * CL);
+                TG_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, P, tail));
+                TG_LAUNCH_OK();
+            }
+            TG_CUDA_OK(cudaEventRecord(ss.join, ss.side));
+            TG_CUDA_OK(cudaStreamWaitEvent(stream, ss.join, 0));
+            return 0;
+        }
     }
     if (force == 16 && ok16) plan = plan16;
     else if (force == 32 && ok32) plan = plan32;

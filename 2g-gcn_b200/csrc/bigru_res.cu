@@ -47,8 +47,9 @@ __global__ void __launch_bounds__(REC_THREADS, 1) bigru_res_kernel(const BiGruPa
     const BiGruGroup& G = P.g[group];
     const int RG = G.n_rb;
     const int local = blockIdx.x - G.tile_begin;
-    const int dir = local / (RG * ctas_per_gd);
-    const int rg = (local - dir * RG * ctas_per_gd) / ctas_per_gd, c = local % ctas_per_gd;
+    const int dslot = local / (RG * ctas_per_gd);                     // slot among the directions this launch owns (skip_dirs)
+    const int dir = G.skip_dirs == 1 ? 1 : (G.skip_dirs == 2 ? 0 : dslot);
+    const int rg = (local - dslot * RG * ctas_per_gd) / ctas_per_gd, c = local % ctas_per_gd;
     const int rbase = rg * BR_ROWS;
     const int nblk = D / BR_UB;
     const int j0 = c * BR_NBLK;
@@ -284,11 +285,12 @@ int launch_bigru_resident(BiGruParams& P, cudaStream_t stream) {
     const int ctas_per_gd = cdiv(D / BR_UB, BR_NBLK);
     // row-block groups per (group, direction): as many as the row blocks while the grid fits on the GPU
     int rgs[3] = {1, 1, 1};
-    auto total = [&]() { int t = 0; for (int i = 0; i < P.ngroups; ++i) t += 2 * rgs[i] * ctas_per_gd; return t; };
+    auto ndirs = [&](int i) { return 2 - (P.g[i].skip_dirs & 1) - ((P.g[i].skip_dirs >> 1) & 1); };
+    auto total = [&]() { int t = 0; for (int i = 0; i < P.ngroups; ++i) t += ndirs(i) * rgs[i] * ctas_per_gd; return t; };
     for (bool grown = true; grown;) {
         grown = false;
         for (int i = 0; i < P.ngroups; ++i) {
-            if (rgs[i] < cdiv(P.g[i].rows, BR_ROWS)) {
+            if (ndirs(i) > 0 && rgs[i] < cdiv(P.g[i].rows, BR_ROWS)) {
                 ++rgs[i];
                 if (total() <= num_sms()) grown = true; else --rgs[i];
             }
@@ -298,7 +300,7 @@ int launch_bigru_resident(BiGruParams& P, cudaStream_t stream) {
     for (int i = 0; i < P.ngroups; ++i) {
         P.g[i].n_rb = rgs[i];
         P.g[i].tile_begin = grid;
-        grid += 2 * rgs[i] * ctas_per_gd;
+        grid += ndirs(i) * rgs[i] * ctas_per_gd;
     }
     auto kern = bigru_res_kernel;
     if (int rc = ensure_smem((const void*)kern, smem)) return rc;

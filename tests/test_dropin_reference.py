@@ -28,10 +28,18 @@ def ref():
     models.TGGCN = original
 
 
+VARIANTS = [{}, {'add_time_position': 1, 'add_segment_length': 1, 'message_geometry_to_human': True, '_distances': True},
+            {'object_segment_update_strategy': 'sah', 'add_time_position': 1, 'time_position_strategy': 'u',
+             'positional_encoding_style': 'p', 'discrete_optimization_strategy': 'st', '_distances': True}]
+
+
+@pytest.mark.parametrize('extra', VARIANTS, ids=['yaml', 'blocks+dist', 'sah+u+p+st+dist'])
 @pytest.mark.parametrize('shape_name,stage', [('mphoi', 1), ('mphoi', 2), ('cad120', 2), ('bimanual', 1)])
-def test_install_dropin_and_reference_plumbing(shape_name, stage, ref, pkg, synth):
+def test_install_dropin_and_reference_plumbing(shape_name, stage, extra, ref, pkg, synth):
     shape = synth.SHAPES[shape_name]
-    kwargs = synth.model_kwargs(shape, hidden_size=32, stage=stage)
+    if extra.get('object_segment_update_strategy') == 'sah' and shape.H != 1:
+        pytest.skip("'sah' needs exactly one human (the reference has no object gate MLP to fall back on)")
+    kwargs = synth.model_kwargs(shape, hidden_size=32, stage=stage, **extra)
     ref.models.TGGCN = ref.original
     ref_model = ref.models.select_model('2G-GCN')(**kwargs)
     pkg.install_dropin()
@@ -46,8 +54,11 @@ def test_install_dropin_and_reference_plumbing(shape_name, stage, ref, pkg, synt
     batch = synth.make_batch(shape, 2, 6, seed=1)
     tg = synth.target_list(shape, synth.make_targets(shape, batch['lengths'], 6, seed=2))
     zeros = torch.zeros(2, 1)
-    dataset = [batch['x_human'], batch['x_objects'], batch['objects_mask'], zeros, zeros, zeros, zeros, batch['steps_per_example']] + tg
-    misc = dict(impose_segmentation_pattern=1 if stage == 1 else 0, dataset_name=shape.dataset)
+    hh, ho, oo = synth.make_distances(shape, 2, 6, seed=3) if extra.get('_distances') else (zeros, zeros, zeros)
+    dataset = [batch['x_human'], batch['x_objects'], batch['objects_mask'], zeros, zeros if hh is None else hh, ho, oo,
+               batch['steps_per_example']] + tg
+    misc = dict(impose_segmentation_pattern=1 if stage == 1 else 0, dataset_name=shape.dataset,
+                make_attention_distance_based=bool(extra.get('_distances')))
     fetch = ref.data_loading.select_model_data_fetcher('2G-GCN', 'multiple', **misc)
     feed = ref.data_loading.select_model_data_feeder('2G-GCN', 'multiple', **misc)
     data, target = fetch(dataset, device='cpu')

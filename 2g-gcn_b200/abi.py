@@ -23,7 +23,7 @@ class Dims(C.Structure):
                                                                        ('cat_level_states', C.c_int32), ('mean_pool', C.c_int32),
                                                                        ('recurrent_mode', C.c_int32), ('no_fp16_split', C.c_int32),
                                                                        ('precision', C.c_int32), ('att_noscale', C.c_int32),
-                                                                       ('update_strategy', C.c_int32), ('time_position', C.c_int32), ('time_periodic', C.c_int32), ('straight_through', C.c_int32), ('geo_to_human', C.c_int32), ('segment_length', C.c_int32)]
+                                                                       ('update_strategy', C.c_int32), ('time_position', C.c_int32), ('time_periodic', C.c_int32), ('straight_through', C.c_int32), ('geo_to_human', C.c_int32), ('segment_length', C.c_int32), ('gate_layers', C.c_int32)]
 
 
 class GradOutputs(C.Structure):

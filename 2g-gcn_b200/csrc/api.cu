@@ -92,6 +92,10 @@ void make_layout(const tggcn_dims& d, Layout& L) {
     sz[TGGCN_BUF_TIME_EMB] = d.time_position ? N * D * f : 0;
     sz[TGGCN_BUF_MSG_GH] = d.geo_to_human ? N * D * f : 0;
     sz[TGGCN_BUF_SEG_LEN] = d.segment_length ? N * (H + O) * f : 0;
+    sz[TGGCN_BUF_GATE_IN_H] = gate2_of(d) ? N * H * (size_t)ginh_of(d) * f : 0;
+    sz[TGGCN_BUF_GATE_IN_O] = gate2_of(d) ? N * O * (size_t)gino_of(d) * f : 0;
+    sz[TGGCN_BUF_GATE_HID_H] = gate2_of(d) ? N * H * D * f : 0;
+    sz[TGGCN_BUF_GATE_HID_O] = gate2_of(d) ? N * O * D * f : 0;
     sz[TGGCN_BUF_GS_H] = N * H * 6 * D * f;
     sz[TGGCN_BUF_GS_O] = N * O * 6 * D * f;
     sz[TGGCN_BUF_HX_H] = N * H * 2 * D * f;
@@ -125,12 +129,13 @@ void make_layout(const tggcn_dims& d, Layout& L) {
     sz[TGGCN_BUF_SALPHA_OO] = sv * 2 * N * O * O * f;
     {   // operand planes of the largest projection stage (4 bytes per operand element: fp16 hi + lo, or bf16 + slack)
         const size_t kh = kh_of(d), ko = ko_of(d), KV = 128 * V;
-        const size_t st[6] = {N * (H + O) * 2048 + N * KV + 2 * D * 2048 + 2048 * KV,
+        const size_t st[7] = {N * (H + O) * 2048 + N * KV + 2 * D * 2048 + 2048 * KV,
                               N * 2048 + D * 2048,
                               N * (H + O + 1) * D + 6 * 3 * D * D,
                               N * (H + O + 1) * 2 * D + 3 * D * 2 * D,
                               N * (H + O + 2) * 2 * D + 6 * D * 2 * D,
-                              N * H * kh + N * O * ko + 2 * 3 * D * kh + 2 * 3 * D * ko};
+                              N * H * kh + N * O * ko + 2 * 3 * D * kh + 2 * 3 * D * ko,
+                              gate2_of(d) ? N * H * (size_t)ginh_of(d) + N * O * (size_t)gino_of(d) + D * (size_t)(ginh_of(d) + gino_of(d)) : 0};
         size_t m = 0;
         for (size_t v : st) m = v > m ? v : m;
         sz[TGGCN_BUF_PACK] = m * 4 + 32 * 256;
@@ -150,6 +155,7 @@ int check_dims(const tggcn_dims& d) {
     TG_REQUIRE(d.V >= 1 && d.V <= 32, "dims: gcn_node=%d unsupported", d.V);
     TG_REQUIRE(d.Fh == 2048 + 4 * d.V, "dims: human feature size %d != 2048 + 4*gcn_node", d.Fh);
     TG_REQUIRE(d.C_sub >= 1 && d.C_sub <= 32 && d.C_aff >= 0 && d.C_aff <= 32, "dims: class counts out of range");
+    TG_REQUIRE(d.gate_layers >= 0 && d.gate_layers <= 2, "dims: gate_layers=%d (discrete_networks_num_layers) must be 1 or 2", d.gate_layers);
     TG_REQUIRE(d.time_position >= 0 && d.time_position <= 2 && (d.time_periodic == 0 || d.time_periodic == 1),
                "dims: time_position / time_periodic out of range");
     TG_REQUIRE((size_t)d.B * d.T * (size_t)(d.H > d.O ? d.H : d.O) * 6 * d.D < (1ull << 31),
@@ -430,7 +436,29 @@ static int forward_impl(const tggcn_dims* dims, const void* const* weights, int 
         P.att_frame = d.inspect ? io->att_frame : nullptr;
         P.alpha_save = d.save_for_backward ? buf(TGGCN_BUF_ALPHA_F) : nullptr;
         P.pgate_save = d.save_for_backward ? buf(TGGCN_BUF_PGATE) : nullptr;
-        if (int rc = launch_frame_messages(P, stream)) return rc;
+        const bool sample_h = !d.human_seg_given, sample_o = !d.object_seg_given && d.update_strategy != 1;
+        if (gate2_of(d) && (sample_h || sample_o)) {
+            // discrete_networks_num_layers == 2 (models.py:532-547): gate inputs -> projection (Linear(in, D) + ReLU) -> layer 2 + sampling
+            P.gate_in_h = buf(TGGCN_BUF_GATE_IN_H); P.gin_h = ginh_of(d);
+            P.gate_in_o = buf(TGGCN_BUF_GATE_IN_O); P.gin_o = gino_of(d);
+            if (int rc = launch_frame_messages(P, stream)) return rc;
+            g.count = 0;
+            if (sample_h) {
+                TG_REQUIRE(W(TGGCN_W_UPD_H_W2) && W(TGGCN_W_UPD_H_B2) && W(TGGCN_W_UPD_H_B), "forward: two-layer human gate MLP weights missing");
+                gemm_add(g, P.gate_in_h, P.gin_h, W(TGGCN_W_UPD_H_W), P.gin_h, W(TGGCN_W_UPD_H_B), buf(TGGCN_BUF_GATE_HID_H), D, N * H, D, P.gin_h, 1);
+            }
+            if (sample_o) {
+                TG_REQUIRE(W(TGGCN_W_UPD_O_W2) && W(TGGCN_W_UPD_O_B2) && W(TGGCN_W_UPD_O_B), "forward: two-layer object gate MLP weights missing");
+                gemm_add(g, P.gate_in_o, P.gin_o, W(TGGCN_W_UPD_O_W), P.gin_o, W(TGGCN_W_UPD_O_B), buf(TGGCN_BUF_GATE_HID_O), D, N * O, D, P.gin_o, 1);
+            }
+            if (int rc = project(g)) return rc;
+            P.gate_hid_h = buf(TGGCN_BUF_GATE_HID_H); P.gate_hid_o = buf(TGGCN_BUF_GATE_HID_O);
+            P.w_uh = W(TGGCN_W_UPD_H_W2); P.b_uh = W(TGGCN_W_UPD_H_B2);
+            P.w_uo = W(TGGCN_W_UPD_O_W2); P.b_uo = W(TGGCN_W_UPD_O_B2);
+            if (int rc = launch_gate_sample(P, stream)) return rc;
+        } else {
+            if (int rc = launch_frame_messages(P, stream)) return rc;
+        }
     }
     STAGE_END();
     // 9. optional local-maximum filter + reorder gather index

@@ -25,7 +25,7 @@ struct BwdLayout {
         return o;
     }
     size_t dhfr[3], dhx[2], dgs[2], dghs[2], du[2], direct[2], dmg[2], dpre[2], lgr[4], lgs[4], dpre_all[4], gru_direct[3];
-    size_t dtime, dxx[2], ds[3], dmsg[6], dgi[3], dgh[3], bigru_scratch, dgeo_hid, dgcn_out, dxn, wt_seg, wt, tn, tn_floats;
+    size_t dghid[2], dgin[2], dtime, dxx[2], ds[3], dmsg[6], dgi[3], dgh[3], bigru_scratch, dgeo_hid, dgcn_out, dxn, wt_seg, wt, tn, tn_floats;
     size_t zero_begin, zero_end;     // region that must be zero before the kernels run (atomically accumulated)
 };
 
@@ -59,6 +59,10 @@ void make_bwd_layout(const tggcn_dims& d, BwdLayout& L) {
     L.dxx[0] = L.take(N * H * (size_t)kh_of(d));
     L.dxx[1] = L.take(N * O * (size_t)ko_of(d));
     L.dtime = L.take(d.time_position && !d.time_periodic ? N * D : 0);
+    L.dghid[0] = L.take(gate2_of(d) ? N * H * D : 0);
+    L.dghid[1] = L.take(gate2_of(d) ? N * O * D : 0);
+    L.dgin[0] = L.take(gate2_of(d) ? N * H * (size_t)ginh_of(d) : 0);
+    L.dgin[1] = L.take(gate2_of(d) ? N * O * (size_t)gino_of(d) : 0);
     for (int g = 0; g < 3; ++g) L.ds[g] = L.take(N * E[g] * 2 * D);
     L.dmsg[0] = L.take(N * H * D);
     L.dmsg[1] = L.take(N * H * D);
@@ -96,7 +100,8 @@ void make_bwd_layout(const tggcn_dims& d, BwdLayout& L) {
     // humans + objects (both directions), the embeddings + geometry MLP
     const size_t kh_ = kh_of(d);
     const size_t grp_cands[] = {rp * ((H ? 1 : 0) * (7 * D + kh_ + nkh * D) + 9 * D + ko_), 2 * rp * 15 * D,
-                                2 * rp * (D + 2048) + np * (D + 2048) + np * (2048 + 128 * V), 3 * rp * 4 * D + np * 6 * D};
+                                2 * rp * (D + 2048) + np * (D + 2048) + np * (2048 + 128 * V), 3 * rp * 4 * D + np * 6 * D,
+                                gate2_of(d) ? 2 * rp * (D + (size_t)(ginh_of(d) > gino_of(d) ? ginh_of(d) : gino_of(d))) : 0};
     for (size_t c : grp_cands)
         if (c > tmax) tmax = c;
     tmax += 4096;
@@ -145,7 +150,7 @@ size_t tggcn_backward_workspace_bytes(const tggcn_dims* dims) {
 
 int tggcn_backward_bucket(int id) {
     if (id < 0 || id >= TGGCN_W_COUNT) return -1;
-    if (id >= TGGCN_W_TIME_W && id <= TGGCN_W_LEN_B) return 1;            // time / length MLPs, geometry -> human message MLP            // formed with the frame-level graph
+    if (id >= TGGCN_W_TIME_W && id <= TGGCN_W_UPD_O_B2) return 1;         // time / length MLPs, geometry -> human message MLP, gate MLP layer 2            // formed with the frame-level graph
     if (id <= TGGCN_W_GCN_S2_B) return 3;                                   // GCN_* (first 13 entries of the table)
     if (id <= TGGCN_W_OBJ_EMB_B) return 2;                                  // geometry MLP, ROI embeddings
     if (id >= TGGCN_W_HSEG_F_WIH || (id >= TGGCN_W_SMSG_HH_W && id <= TGGCN_W_SMSG_OO_B)) return 0;   // cells, heads, segment MLPs
@@ -488,13 +493,53 @@ int tggcn_backward_ex(const tggcn_dims* dims, const void* const* weights, void* 
         P.dmsg_hh = bb(BL.dmsg[0]); P.dmsg_ho = bb(BL.dmsg[1]); P.dmsg_oh = bb(BL.dmsg[2]); P.dmsg_oo = bb(BL.dmsg[3]);
         P.dmsg_go = bb(BL.dmsg[4]);
         P.dw_uh = G(TGGCN_W_UPD_H_W); P.db_uh = G(TGGCN_W_UPD_H_B); P.dw_uo = G(TGGCN_W_UPD_O_W); P.db_uo = G(TGGCN_W_UPD_O_B);
-        if (!d.human_seg_given) {
-            TG_CUDA_OK(cudaMemsetAsync(P.dw_uh, 0, sizeof(float) * (size_t)(2 + nkh + gh_of(d) + tu_of(d)) * D, stream));
-            TG_CUDA_OK(cudaMemsetAsync(P.db_uh, 0, sizeof(float), stream));
-        }
-        if (!d.object_seg_given && d.update_strategy != 1) {
-            TG_CUDA_OK(cudaMemsetAsync(P.dw_uo, 0, sizeof(float) * (size_t)(5 + tu_of(d)) * D, stream));
-            TG_CUDA_OK(cudaMemsetAsync(P.db_uo, 0, sizeof(float), stream));
+        const bool sample_h = !d.human_seg_given, sample_o = !d.object_seg_given && d.update_strategy != 1;
+        if (gate2_of(d)) {
+            // two-layer gate MLPs: dlogit -> d hidden (+ layer-2 weight gradients), then d gate_in = d hidden . W1 and dW1 = d hidden^T gate_in
+            P.gate_layers = 2;
+            P.gin_h = ginh_of(d); P.gin_o = gino_of(d);
+            P.hid_h = buf(TGGCN_BUF_GATE_HID_H); P.hid_o = buf(TGGCN_BUF_GATE_HID_O);
+            P.w2_h = W(TGGCN_W_UPD_H_W2); P.w2_o = W(TGGCN_W_UPD_O_W2);
+            if (sample_h) {
+                TG_REQUIRE(P.w2_h && G(TGGCN_W_UPD_H_W2) && G(TGGCN_W_UPD_H_B2), "backward: layer-2 human gate pointers missing");
+                P.dhid_h = bb(BL.dghid[0]); P.dw2_h = G(TGGCN_W_UPD_H_W2); P.db2_h = G(TGGCN_W_UPD_H_B2);
+                TG_CUDA_OK(cudaMemsetAsync(P.dw2_h, 0, sizeof(float) * (size_t)D, stream));
+                TG_CUDA_OK(cudaMemsetAsync(P.db2_h, 0, sizeof(float), stream));
+            }
+            if (sample_o) {
+                TG_REQUIRE(P.w2_o && G(TGGCN_W_UPD_O_W2) && G(TGGCN_W_UPD_O_B2), "backward: layer-2 object gate pointers missing");
+                P.dhid_o = bb(BL.dghid[1]); P.dw2_o = G(TGGCN_W_UPD_O_W2); P.db2_o = G(TGGCN_W_UPD_O_B2);
+                TG_CUDA_OK(cudaMemsetAsync(P.dw2_o, 0, sizeof(float) * (size_t)D, stream));
+                TG_CUDA_OK(cudaMemsetAsync(P.db2_o, 0, sizeof(float), stream));
+            }
+            if (sample_h || sample_o) {
+                if (int rc = launch_gate_bwd(P, stream)) return rc;
+                float* wt = bb(BL.wt);
+                if (sample_h) {
+                    const WSrc w1[1] = {{W(TGGCN_W_UPD_H_W), P.gin_h, D}};
+                    if (int rc = dx_gemm(P.dhid_h, D, nullptr, 0, w1, 1, P.gin_h, bb(BL.dgin[0]), P.gin_h, N * H, 0, wt)) return rc;
+                    if (int rc = tn(P.dhid_h, D, nullptr, 0, buf(TGGCN_BUF_GATE_IN_H), P.gin_h, G(TGGCN_W_UPD_H_W), P.gin_h, N * H, D, P.gin_h,
+                                    0, 0, 0, stream, G(TGGCN_W_UPD_H_B))) return rc;
+                    P.dgin_h = bb(BL.dgin[0]);
+                }
+                if (sample_o) {
+                    const WSrc w1[1] = {{W(TGGCN_W_UPD_O_W), P.gin_o, D}};
+                    if (int rc = dx_gemm(P.dhid_o, D, nullptr, 0, w1, 1, P.gin_o, bb(BL.dgin[1]), P.gin_o, N * O, 0, wt)) return rc;
+                    if (int rc = tn(P.dhid_o, D, nullptr, 0, buf(TGGCN_BUF_GATE_IN_O), P.gin_o, G(TGGCN_W_UPD_O_W), P.gin_o, N * O, D, P.gin_o,
+                                    0, 0, 0, stream, G(TGGCN_W_UPD_O_B))) return rc;
+                    P.dgin_o = bb(BL.dgin[1]);
+                }
+                if (int rc = tn_flush(stream)) return rc;
+            }
+        } else {
+            if (sample_h) {
+                TG_CUDA_OK(cudaMemsetAsync(P.dw_uh, 0, sizeof(float) * (size_t)(2 + nkh + gh_of(d) + tu_of(d)) * D, stream));
+                TG_CUDA_OK(cudaMemsetAsync(P.db_uh, 0, sizeof(float), stream));
+            }
+            if (sample_o) {
+                TG_CUDA_OK(cudaMemsetAsync(P.dw_uo, 0, sizeof(float) * (size_t)(5 + tu_of(d)) * D, stream));
+                TG_CUDA_OK(cudaMemsetAsync(P.db_uo, 0, sizeof(float), stream));
+            }
         }
         if (int rc = launch_frame_bwd(P, stream)) return rc;
         if (P.dtime != nullptr) {      // time_position_mlp: Linear(1, D) + ReLU of (t+1) / steps

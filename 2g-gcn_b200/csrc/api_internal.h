@@ -20,6 +20,10 @@ inline int kh_of(const tggcn_dims& d) { return (1 + nkh_of(d) + gh_of(d) + ts_of
 inline int ldwh_of(const tggcn_dims& d) { return kh_of(d) + nkh_of(d) * d.D; }
 inline int ko_of(const tggcn_dims& d) { return (4 + ts_of(d) + tl_of(d)) * d.D; }               // xx_o row
 inline int ldwo_of(const tggcn_dims& d) { return ko_of(d) + 2 * d.D; }
+// gate MLP input widths: [x, h, m_hh?, m_oh, m_gh?, time_u?] / [x, h, m_ho, m_oo, m_go, time_u?]
+inline int ginh_of(const tggcn_dims& d) { return (2 + nkh_of(d) + gh_of(d) + tu_of(d)) * d.D; }
+inline int gino_of(const tggcn_dims& d) { return (5 + tu_of(d)) * d.D; }
+inline bool gate2_of(const tggcn_dims& d) { return d.gate_layers == 2; }
 void make_layout(const tggcn_dims& d, Layout& L);
 int check_dims(const tggcn_dims& d);
 

@@ -119,6 +119,103 @@ int launch_heads_bwd(const HeadsBwdParams& P, cudaStream_t stream) {
 // =============================================================================================================
 constexpr int FB_MAXE = 16;
 
+// Gradient of the gate logit of entity `lane` of frame n = (b, t); all 32 lanes of a warp call (lanes >= H + O return 0).
+// Straight-through / filter rule of the hard gates, Gumbel-sigmoid and sigmoid backward, and the
+// object_segment_update_strategy rules (one human, models.py:1523-1532): 'sah' — the object gates ARE the human's, so everything
+// that reaches them is handed to the human's soft gate; 'coh' — hard_o = st(y_o) * st(y_h): each factor receives the other's
+// decision as its weight.
+__device__ __forceinline__ float gate_dlogit(const FrameBwdParams& P, int n, int b, int t, int lane) {
+    const int H = P.H, O = P.O, T = P.T, NE = H + O;
+    const int strat = P.update_strategy;
+    const bool act = lane < NE, is_h = lane < H;
+    const int r = is_h ? lane : lane - H, E = is_h ? H : O;
+    const float* given = is_h ? P.human_seg : P.object_seg;
+    const bool sampled = act && given == nullptr;
+    float dy = 0.0f, hand_over = 0.0f, y = 0.0f;
+    if (sampled) {
+        const float* soft = is_h ? P.y_hss : P.y_oss;
+        const size_t oi = (size_t)(b * T + t) * E + r;
+        y = soft[oi];
+        float dhard = (is_h ? P.du_h : P.du_o)[oi];
+        const float* dyh = is_h ? P.dy_hs : P.dy_os;
+        if (dyh != nullptr) dhard += dyh[oi];
+        float pass;
+        if (P.filter) {
+            const float yp = t > 0 ? soft[oi - E] : 0.0f, yn = t + 1 < T ? soft[oi + E] : 0.0f;
+            const bool keep = (y > yp) && (y > yn) && (y >= P.thr);
+            pass = (keep || y < P.thr) ? 1.0f : 0.0f;       // models.py:1660-1662 (clamp(max=0) passes at u == 0)
+        } else {
+            pass = t == T - 1 ? 0.0f : 1.0f;                // last step overwritten by 1 (models.py:701-702)
+        }
+        dy = dhard * pass;
+        if (strat == 2 && !is_h) {
+            const float yh = P.y_hss[(size_t)(b * T + t) * H];
+            hand_over = dy * (y > P.thr ? 1.0f : 0.0f);
+            dy *= yh > P.thr ? 1.0f : 0.0f;
+        }
+        const float* dys = is_h ? P.dy_hss : P.dy_oss;
+        if (dys != nullptr) dy += dys[oi];
+        if (strat == 1 && !is_h) { hand_over = dy; dy = 0.0f; }
+    }
+    if (strat != 0) {
+        const float total = warp_sum(hand_over);
+        if (lane == 0) dy += total;
+    }
+    float dl_ = 0.0f;
+    if (sampled && !(strat == 1 && !is_h)) {
+        const float p = P.pgate[(size_t)n * NE + lane];
+        // y = sigmoid(log(p+eps) - log(1-p+eps) + g0 - g1), p = sigmoid(logit)
+        dl_ = P.straight_through ? dy * p * (1.0f - p)          // y = p
+                                 : dy * y * (1.0f - y) * (1.0f / (p + 1e-20f) + 1.0f / ((1.0f - p) + 1e-20f)) * p * (1.0f - p);
+    }
+    return dl_;
+}
+
+// Two-layer gate MLPs (discrete_networks_num_layers == 2), first half of their backward: one CTA per frame.  d hidden =
+// dlogit * w2 (.) [hidden > 0] for every sampled entity, dw2 += dlogit * hidden, db2 += dlogit (atomics).
+__global__ void __launch_bounds__(128) gate_bwd_kernel(const FrameBwdParams P) {
+    __shared__ float dlogit[32];
+    const int H = P.H, O = P.O, NE = H + O, D = P.D, T = P.T;
+    const int n = blockIdx.x, b = n / T, t = n - b * T, tid = threadIdx.x;
+    if (tid < 32) {
+        const float dl_ = gate_dlogit(P, n, b, t, tid);
+        if (tid < NE) dlogit[tid] = dl_;
+    }
+    __syncthreads();
+    for (int c = tid; c < D; c += 128) {
+        float aw_h = 0.0f, aw_o = 0.0f;
+        if (P.dhid_h != nullptr) {
+            const float w2 = __ldg(P.w2_h + c);
+            for (int h = 0; h < H; ++h) {
+                const float hv = P.hid_h[((size_t)n * H + h) * D + c];
+                P.dhid_h[((size_t)n * H + h) * D + c] = hv > 0.0f ? dlogit[h] * w2 : 0.0f;
+                aw_h = fmaf(dlogit[h], hv, aw_h);
+            }
+            atomicAdd(P.dw2_h + c, aw_h);
+        }
+        if (P.dhid_o != nullptr) {
+            const float w2 = __ldg(P.w2_o + c);
+            for (int k = 0; k < O; ++k) {
+                const float hv = P.hid_o[((size_t)n * O + k) * D + c];
+                P.dhid_o[((size_t)n * O + k) * D + c] = hv > 0.0f ? dlogit[H + k] * w2 : 0.0f;
+                aw_o = fmaf(dlogit[H + k], hv, aw_o);
+            }
+            atomicAdd(P.dw2_o + c, aw_o);
+        }
+    }
+    if (tid == 0) {
+        if (P.dhid_h != nullptr) { float v = 0.0f; for (int h = 0; h < H; ++h) v += dlogit[h]; atomicAdd(P.db2_h, v); }
+        if (P.dhid_o != nullptr) { float v = 0.0f; for (int k = 0; k < O; ++k) v += dlogit[H + k]; atomicAdd(P.db2_o, v); }
+    }
+}
+
+int launch_gate_bwd(const FrameBwdParams& P, cudaStream_t stream) {
+    TG_REQUIRE(P.H + P.O <= 32, "gate_bwd: at most 32 entities per frame");
+    gate_bwd_kernel<<<P.B * P.T, 128, 0, stream>>>(P);
+    TG_LAUNCH_OK();
+    return 0;
+}
+
 __global__ void __launch_bounds__(256) frame_bwd_kernel(const FrameBwdParams P) {
     extern __shared__ __align__(16) float sm[];
     const int D = P.D, H = P.H, O = P.O, T = P.T;
@@ -151,84 +248,41 @@ __global__ void __launch_bounds__(256) frame_bwd_kernel(const FrameBwdParams P) 
         for (int i = tid; i < O * O; i += 256) a_oo[(i / O) * FB_MAXE + i % O] = al[H * H + 2 * H * O + i];
     }
     // ---- gates: straight-through / filter rule, Gumbel-sigmoid, sigmoid -----------------------------------------
-    // update_strategy (one human, models.py:1523-1532): 'sah' — the object gates ARE the human's, so everything that reaches them is
-    // handed to the human's soft gate; 'coh' — hard_o = st(y_o) * st(y_h): each factor receives the other's decision as its weight.
+    // (two-layer gate MLPs: gate_bwd_kernel did this already and the gradient of the gate INPUTS arrives in dgin_h / dgin_o)
     if (tid < 32) {                             // NE <= 32: warp 0, one lane per entity
-        const int strat = P.update_strategy;
-        const bool act = tid < NE, is_h = tid < H;
-        const int r = is_h ? tid : tid - H, E = is_h ? H : O;
-        const float* given = is_h ? P.human_seg : P.object_seg;
-        const bool sampled = act && given == nullptr;
-        float dy = 0.0f, hand_over = 0.0f, y = 0.0f;
-        if (sampled) {
-            const float* soft = is_h ? P.y_hss : P.y_oss;
-            const size_t oi = (size_t)(b * T + t) * E + r;
-            y = soft[oi];
-            float dhard = (is_h ? P.du_h : P.du_o)[oi];
-            const float* dyh = is_h ? P.dy_hs : P.dy_os;
-            if (dyh != nullptr) dhard += dyh[oi];
-            float pass;
-            if (P.filter) {
-                const float yp = t > 0 ? soft[oi - E] : 0.0f, yn = t + 1 < T ? soft[oi + E] : 0.0f;
-                const bool keep = (y > yp) && (y > yn) && (y >= P.thr);
-                pass = (keep || y < P.thr) ? 1.0f : 0.0f;       // models.py:1660-1662 (clamp(max=0) passes at u == 0)
-            } else {
-                pass = t == T - 1 ? 0.0f : 1.0f;                // last step overwritten by 1 (models.py:701-702)
-            }
-            dy = dhard * pass;
-            if (strat == 2 && !is_h) {
-                const float yh = P.y_hss[(size_t)(b * T + t) * H];
-                hand_over = dy * (y > P.thr ? 1.0f : 0.0f);
-                dy *= yh > P.thr ? 1.0f : 0.0f;
-            }
-            const float* dys = is_h ? P.dy_hss : P.dy_oss;
-            if (dys != nullptr) dy += dys[oi];
-            if (strat == 1 && !is_h) { hand_over = dy; dy = 0.0f; }
-        }
-        if (strat != 0) {
-            const float total = warp_sum(hand_over);
-            if (tid == 0) dy += total;
-        }
-        float dl_ = 0.0f;
-        if (sampled && !(strat == 1 && !is_h)) {
-            const float p = P.pgate[(size_t)n * NE + tid];
-            // y = sigmoid(log(p+eps) - log(1-p+eps) + g0 - g1), p = sigmoid(logit)
-            dl_ = P.straight_through ? dy * p * (1.0f - p)          // y = p
-                                     : dy * y * (1.0f - y) * (1.0f / (p + 1e-20f) + 1.0f / ((1.0f - p) + 1e-20f)) * p * (1.0f - p);
-        }
-        if (act) dlogit[tid] = dl_;
+        const float dl_ = P.gate_layers == 2 ? 0.0f : gate_dlogit(P, n, b, t, tid);
+        if (tid < NE) dlogit[tid] = dl_;
     }
     __syncthreads();
+    // gradient that entity e's gate hands to column `col` of its gate input: one layer = dlogit x weight, two layers = a row of dgin
+    auto gin_h = [&](int h, int col) -> float {
+        if (P.gate_layers == 2) return P.dgin_h != nullptr ? P.dgin_h[((size_t)n * H + h) * P.gin_h + col] : 0.0f;
+        return dlogit[h] * __ldg(P.w_uh + col);
+    };
+    auto gin_o = [&](int k, int col) -> float {
+        if (P.gate_layers == 2) return P.dgin_o != nullptr ? P.dgin_o[((size_t)n * O + k) * P.gin_o + col] : 0.0f;
+        return P.w_uo != nullptr ? dlogit[H + k] * __ldg(P.w_uo + col) : 0.0f;
+    };
     // ---- gradient of the aggregated messages and the direct parts of d[x|h] ----------------------------------------
     for (int i = tid; i < H * D; i += 256) {
         const int h = i / D, c = i - h * D;
         const float* dx = P.dxx_h + ((size_t)n * H + h) * wh;
-        const float g = dlogit[h];
-        ds[h * D2 + c] = g * __ldg(P.w_uh + c);
-        ds[h * D2 + D + c] = g * __ldg(P.w_uh + D + c) + dx[c];
-        if (P.hh) dmh[h * nkh * D + c] = dx[D + c] + g * __ldg(P.w_uh + D2 + c);
-        dmh[h * nkh * D + (nkh - 1) * D + c] = dx[nkh * D + c] + g * __ldg(P.w_uh + D2 + (nkh - 1) * D + c);
+        ds[h * D2 + c] = gin_h(h, c);
+        ds[h * D2 + D + c] = gin_h(h, D + c) + dx[c];
+        if (P.hh) dmh[h * nkh * D + c] = dx[D + c] + gin_h(h, D2 + c);
+        dmh[h * nkh * D + (nkh - 1) * D + c] = dx[nkh * D + c] + gin_h(h, D2 + (nkh - 1) * D + c);
     }
     for (int i = tid; i < O * D; i += 256) {
         const int k = i / D, c = i - k * D;
         const float* dx = P.dxx_o + ((size_t)n * O + k) * wo;
-        const float g = dlogit[H + k];
-        if (P.w_uo == nullptr) {                                                        // 'sah': no object gate MLP
-            ds[(H + k) * D2 + c] = 0.0f;
-            ds[(H + k) * D2 + D + c] = dx[c];
-            dmo[k * 3 * D + c] = dx[D + c];
-            dmo[k * 3 * D + D + c] = dx[2 * D + c];
-            dmo[k * 3 * D + 2 * D + c] = dx[3 * D + c];
-            continue;
-        }
-        ds[(H + k) * D2 + c] = g * __ldg(P.w_uo + c);
-        ds[(H + k) * D2 + D + c] = g * __ldg(P.w_uo + D + c) + dx[c];
-        dmo[k * 3 * D + c] = dx[D + c] + g * __ldg(P.w_uo + D2 + c);                    // m_ho   (gate order x,h,m_ho,m_oo,m_go)
-        dmo[k * 3 * D + D + c] = dx[2 * D + c] + g * __ldg(P.w_uo + D2 + 2 * D + c);    // m_go
-        dmo[k * 3 * D + 2 * D + c] = dx[3 * D + c] + g * __ldg(P.w_uo + D2 + D + c);    // m_oo
+        ds[(H + k) * D2 + c] = gin_o(k, c);                                             // ('sah': no object gate MLP -> 0)
+        ds[(H + k) * D2 + D + c] = gin_o(k, D + c) + dx[c];
+        dmo[k * 3 * D + c] = dx[D + c] + gin_o(k, D2 + c);                              // m_ho   (gate order x,h,m_ho,m_oo,m_go)
+        dmo[k * 3 * D + D + c] = dx[2 * D + c] + gin_o(k, D2 + 2 * D + c);              // m_go
+        dmo[k * 3 * D + 2 * D + c] = dx[3 * D + c] + gin_o(k, D2 + D + c);              // m_oo
     }
     // time-position features (add_time_position): gradient of this frame's feature vector — strategy 's': the time blocks of all xx
-    // rows; strategy 'u': through the last block of the gate inputs, whose weight gradient is formed here too
+    // rows; strategy 'u': through the last block of the gate inputs, whose weight gradient (one-layer gates) is formed here too
     if (P.time_position != 0 && (tu || P.dtime != nullptr)) {
         const float* te = P.time_emb + (size_t)n * D;
         for (int c = tid; c < D; c += 256) {
@@ -237,11 +291,15 @@ __global__ void __launch_bounds__(256) frame_bwd_kernel(const FrameBwdParams P) 
                 for (int h = 0; h < H; ++h) v += P.dxx_h[((size_t)n * H + h) * wh + (1 + nkh + gh) * D + c];
                 for (int k = 0; k < O; ++k) v += P.dxx_o[((size_t)n * O + k) * wo + 4 * D + c];
             } else {
-                float gsum_h = 0.0f, go = 0.0f;
-                for (int h = 0; h < H; ++h) gsum_h += dlogit[h];
-                for (int k = 0; k < O; ++k) go += dlogit[H + k];
-                if (P.human_seg == nullptr) { v = fmaf(gsum_h, __ldg(P.w_uh + D2 + (nkh + gh) * D + c), v); atomicAdd(P.dw_uh + D2 + (nkh + gh) * D + c, gsum_h * __ldg(te + c)); }
-                if (P.object_seg == nullptr && P.dw_uo != nullptr) { v = fmaf(go, __ldg(P.w_uo + 5 * D + c), v); atomicAdd(P.dw_uo + 5 * D + c, go * __ldg(te + c)); }
+                if (P.human_seg == nullptr) for (int h = 0; h < H; ++h) v += gin_h(h, D2 + (nkh + gh) * D + c);
+                if (P.object_seg == nullptr) for (int k = 0; k < O; ++k) v += gin_o(k, 5 * D + c);
+                if (P.gate_layers != 2) {
+                    float gsum_h = 0.0f, go = 0.0f;
+                    for (int h = 0; h < H; ++h) gsum_h += dlogit[h];
+                    for (int k = 0; k < O; ++k) go += dlogit[H + k];
+                    if (P.human_seg == nullptr) atomicAdd(P.dw_uh + D2 + (nkh + gh) * D + c, gsum_h * __ldg(te + c));
+                    if (P.object_seg == nullptr && P.dw_uo != nullptr) atomicAdd(P.dw_uo + 5 * D + c, go * __ldg(te + c));
+                }
             }
             if (P.dtime != nullptr) P.dtime[(size_t)n * D + c] = v;
         }
@@ -252,13 +310,13 @@ __global__ void __launch_bounds__(256) frame_bwd_kernel(const FrameBwdParams P) 
             float v = 0.0f;
             for (int h = 0; h < H; ++h) {
                 v += P.dxx_h[((size_t)n * H + h) * wh + (1 + nkh) * D + c];
-                if (P.human_seg == nullptr) v = fmaf(dlogit[h], __ldg(P.w_uh + D2 + nkh * D + c), v);
+                if (P.human_seg == nullptr) v += gin_h(h, D2 + nkh * D + c);
             }
             P.dmsg_gh[(size_t)n * D + c] = v;
         }
     }
-    // gate weight gradients: d w[k] += sum_e dlogit[e] * input_e[k]
-    if (P.human_seg == nullptr) {
+    // gate weight gradients (one-layer gates): d w[k] += sum_e dlogit[e] * input_e[k]
+    if (P.human_seg == nullptr && P.gate_layers != 2) {
         for (int k = tid; k < D2 + (nkh + gh) * D; k += 256) {      // xx_h row = [h, m_hh, m_oh, m_gh ..]: the gate's message blocks in order
             float v = 0.0f;
             for (int h = 0; h < H; ++h) {
@@ -269,7 +327,7 @@ __global__ void __launch_bounds__(256) frame_bwd_kernel(const FrameBwdParams P) 
         }
         if (tid == 0) { float v = 0.0f; for (int h = 0; h < H; ++h) v += dlogit[h]; atomicAdd(P.db_uh, v); }
     }
-    if (P.object_seg == nullptr && P.dw_uo != nullptr) {
+    if (P.object_seg == nullptr && P.dw_uo != nullptr && P.gate_layers != 2) {
         for (int k = tid; k < 5 * D; k += 256) {
             float v = 0.0f;
             for (int o = 0; o < O; ++o) {

@@ -81,6 +81,15 @@ struct FrameBwdParams {
     int update_strategy;                           // 0 'ind', 1 'sah', 2 'coh' (tggcn_dims.update_strategy)
     int dist_kind[4];                              // message kind (hh, oh, ho, oo) used distance-based weights: no logit gradient
     int tl;                                        // add_segment_length: one more block at the end of every xx row
+    // discrete_networks_num_layers == 2: launch_gate_bwd turns the gate gradients into d hidden (and the layer-2 weight gradients),
+    // two GEMMs turn d hidden into the gradient of the gate INPUTS, which launch_frame_bwd then adds instead of dlogit x weight
+    int gate_layers;
+    const float* hid_h; const float* hid_o;        // (B,T,E,D) forward hidden layers (post-ReLU)
+    const float* w2_h; const float* w2_o;          // (D) layer-2 weights
+    float* dhid_h; float* dhid_o;                  // (B,T,E,D) out of launch_gate_bwd (null: that entity type is not sampled)
+    float* dw2_h; float* db2_h; float* dw2_o; float* db2_o;     // accumulated with atomics: zero before the launch
+    const float* dgin_h; int gin_h;                // (B,T,H,gin_h) gradient of the gate inputs, read by launch_frame_bwd, or null
+    const float* dgin_o; int gin_o;
     int gh;                                        // message_geometry_to_human: block m_gh after m_oh in the humans' rows
     const float* msg_gh;                           // (B,T,1,D) forward message, or null
     float* dmsg_gh;                                // (B,T,1,D) out: its gradient
@@ -106,6 +115,7 @@ struct FrameBwdParams {
     float* dw_uh; float* db_uh; float* dw_uo; float* db_uo;   // accumulated with atomics: zero before the launch
 };
 int launch_frame_bwd(const FrameBwdParams& P, cudaStream_t stream);
+int launch_gate_bwd(const FrameBwdParams& P, cudaStream_t stream);
 // add_segment_length backward (models.py:763-779, :954-979): from the gradient of the length blocks of the xx rows — the gradient
 // of the hard gates (added into du_h / du_o, reverse scan over the frames) and, for the embedding encoding, of segment_length_mlp
 struct SegLenBwdParams {

@@ -17,6 +17,62 @@ namespace tg {
 constexpr int FM_THREADS = 256;
 constexpr int FM_MAXE = 16;
 
+// Decision of one gate from its logit (discrete_estimator, models.py:1620-1627): 'gs' = Gumbel-sigmoid sample + threshold
+// (distributions.py:4-36), 'st' = the probability itself + threshold.  pos = index of the entity among the sampled ones.
+__device__ __forceinline__ void gate_decide(const FrameMsgParams& P, float logit, int b, int t, int n_sampled, int pos, float& y,
+                                            float& z, float& p) {
+    p = 1.0f / (1.0f + expf(-logit));
+    if (P.straight_through) {
+        y = p;
+        z = p > P.thr ? 1.0f : 0.0f;
+        return;
+    }
+    const float* g = P.noise + ((size_t)(t * n_sampled + pos) * P.B + b) * 2;
+    const float la = logf(p + 1e-20f) + __ldg(g);
+    const float lb = logf((1.0f - p) + 1e-20f) + __ldg(g + 1);
+    const float mx = fmaxf(la, lb);
+    const float ea = expf(la - mx), eb = expf(lb - mx);
+    y = ea / (ea + eb);
+    z = y > P.thr ? 1.0f : 0.0f;
+}
+
+// One warp publishes the gates of entity e of frame n = (b, t): imposed segmentation, or the sampled decision with the
+// object_segment_update_strategy rules (models.py:1523-1532).  logit_of(entity) is evaluated by all lanes of the warp.
+template <typename LogitFn>
+__device__ __forceinline__ void gate_publish(const FrameMsgParams& P, int n, int b, int t, int e, int lane, LogitFn logit_of) {
+    const int H = P.H, O = P.O, T = P.T, NE = H + O;
+    const int strat = P.update_strategy;
+    const int n_sampled = (P.human_seg ? 0 : H) + ((P.object_seg || strat == 1) ? 0 : O);
+    const bool is_h = e < H;
+    const int r = is_h ? e : e - H;
+    const float* given = is_h ? P.human_seg : P.object_seg;
+    float* y_hard = is_h ? P.y_hs : P.y_os;
+    float* y_soft = is_h ? P.y_hss : P.y_oss;
+    const int E = is_h ? H : O;
+    const size_t oi = (size_t)(b * T + t) * E + r;
+    if (given != nullptr) {
+        if (lane == 0) { const float v = __ldg(given + oi); y_hard[oi] = v; y_soft[oi] = v; }
+        return;
+    }
+    auto pos_of = [&](int ent) { return ent < H ? ent : (P.human_seg ? 0 : H) + (ent - H); };
+    const int src = (!is_h && strat == 1) ? 0 : e;     // 'sah': the object publishes the HUMAN's gate (no object MLP, no noise of its own)
+    float y, z, p;
+    gate_decide(P, logit_of(src), b, t, n_sampled, pos_of(src), y, z, p);
+    float human_hard = 1.0f;
+    if (!is_h && strat == 2) {                         // 'coh': hard decision x the human's
+        float yh, zh, ph;
+        gate_decide(P, logit_of(0), b, t, n_sampled, 0, yh, zh, ph);
+        human_hard = P.straight_through ? zh : (zh - yh) + yh;
+    }
+    if (lane == 0) {
+        if (P.pgate_save != nullptr) P.pgate_save[(size_t)n * NE + e] = p;
+        float hard = (P.straight_through ? z : (z - y) + y) * human_hard;  // straight-through value, distributions.py:35
+        if (t == T - 1) hard = 1.0f;                   // models.py:701-702, :744-745
+        y_soft[oi] = y;
+        y_hard[oi] = hard;
+    }
+}
+
 __global__ void __launch_bounds__(FM_THREADS) frame_messages_kernel(const FrameMsgParams P) {
     extern __shared__ __align__(16) float smem[];
     const int D = P.D, H = P.H, O = P.O, T = P.T;
@@ -165,12 +221,40 @@ __global__ void __launch_bounds__(FM_THREADS) frame_messages_kernel(const FrameM
     }
     __syncthreads();
     // -- segmentation gates, one warp per entity -----------------------------------------------------------
+    if (P.gate_in_h != nullptr) {
+        // discrete_networks_num_layers == 2: materialise the gate MLP inputs in the MLPs' own column order (models.py:1494, :1527);
+        // the hidden layer is a projection GEMM and gate_sample_kernel finishes.  Imposed segmentations are copied here as before.
+        for (int e = warp; e < NE; e += FM_THREADS / 32) {
+            const bool is_h = e < H;
+            const int r = is_h ? e : e - H, E = is_h ? H : O;
+            const float* given = is_h ? P.human_seg : P.object_seg;
+            const size_t oi = (size_t)(b * T + t) * E + r;
+            if (given != nullptr) {
+                if (lane == 0) { const float v = __ldg(given + oi); (is_h ? P.y_hs : P.y_os)[oi] = v; (is_h ? P.y_hss : P.y_oss)[oi] = v; }
+                continue;
+            }
+            float* row = is_h ? P.gate_in_h + ((size_t)n * H + r) * P.gin_h : P.gate_in_o + ((size_t)n * O + r) * P.gin_o;
+            const float* s = sv + e * D2;
+            for (int k = lane; k < D2; k += 32) row[k] = s[k];
+            int col = D2;
+            if (is_h) {
+                const float* m = mh + r * nkh * D;
+                for (int k = lane; k < nkh * D; k += 32) row[col + k] = m[k];
+                col += nkh * D;
+                if (P.gh) { for (int k = lane; k < D; k += 32) row[col + k] = __ldg(P.msg_gh + (size_t)n * D + k); col += D; }
+            } else {
+                const float* m = mo + r * 3 * D;          // smem order m_ho, m_go, m_oo -> gate order m_ho, m_oo, m_go
+                for (int k = lane; k < D; k += 32) { row[col + k] = m[k]; row[col + D + k] = m[2 * D + k]; row[col + 2 * D + k] = m[D + k]; }
+                col += 3 * D;
+            }
+            if (P.time_position == 2) for (int k = lane; k < D; k += 32) row[col + k] = __ldg(P.time_emb + (size_t)n * D + k);
+        }
+        return;
+    }
     // update_strategy (models.py:1523-1532, one human only): 'sah' — the object warps evaluate the HUMAN's gate and publish it as
     // their own (no object MLP, no noise of their own); 'coh' — they evaluate both and multiply the hard decisions.
-    const int strat = P.update_strategy;
-    const int n_sampled = (P.human_seg ? 0 : H) + ((P.object_seg || strat == 1) ? 0 : O);
-    // sampled gate of entity e: soft value y, hard decision z in {0, 1}, sigmoid probability p (all lanes call; lane 0 holds the result)
-    auto sample_gate = [&](int e, float& y, float& z, float& p) {
+    // logit of entity e's one-layer gate MLP (all lanes call; every lane holds the result)
+    auto gate_logit = [&](int e) -> float {
         const bool is_h = e < H;
         const int r = is_h ? e : e - H;
         const float* w = is_h ? P.w_uh : P.w_uo;
@@ -197,51 +281,10 @@ __global__ void __launch_bounds__(FM_THREADS) frame_messages_kernel(const FrameM
             const float* te = P.time_emb + (size_t)n * D;
             for (int k = lane; k < D; k += 32) acc = fmaf(__ldg(wt + k), __ldg(te + k), acc);
         }
-        acc = warp_sum(acc);
-        const float logit = acc + __ldg(is_h ? P.b_uh : P.b_uo);
-        p = 1.0f / (1.0f + expf(-logit));
-        if (P.straight_through) {                     // discrete_estimator 'st', models.py:1621-1622
-            y = p;
-            z = p > P.thr ? 1.0f : 0.0f;
-            return;
-        }
-        const int pos = is_h ? r : (P.human_seg ? 0 : H) + r;
-        const float* g = P.noise + ((size_t)(t * n_sampled + pos) * P.B + b) * 2;
-        const float la = logf(p + 1e-20f) + __ldg(g);
-        const float lb = logf((1.0f - p) + 1e-20f) + __ldg(g + 1);
-        const float mx = fmaxf(la, lb);
-        const float ea = expf(la - mx), eb = expf(lb - mx);
-        y = ea / (ea + eb);
-        z = y > P.thr ? 1.0f : 0.0f;
+        return warp_sum(acc) + __ldg(is_h ? P.b_uh : P.b_uo);
     };
-    for (int e = warp; e < NE; e += FM_THREADS / 32) {
-        const bool is_h = e < H;
-        const int r = is_h ? e : e - H;
-        const float* given = is_h ? P.human_seg : P.object_seg;
-        float* y_hard = is_h ? P.y_hs : P.y_os;
-        float* y_soft = is_h ? P.y_hss : P.y_oss;
-        const int E = is_h ? H : O;
-        const size_t oi = (size_t)(b * T + t) * E + r;
-        if (given != nullptr) {
-            if (lane == 0) { const float v = __ldg(given + oi); y_hard[oi] = v; y_soft[oi] = v; }
-            continue;
-        }
-        float y, z, p;
-        sample_gate((!is_h && strat == 1) ? 0 : e, y, z, p);
-        float human_hard = 1.0f;
-        if (!is_h && strat == 2) {
-            float yh, zh, ph;
-            sample_gate(0, yh, zh, ph);
-            human_hard = P.straight_through ? zh : (zh - yh) + yh;
-        }
-        if (lane == 0) {
-            if (P.pgate_save != nullptr) P.pgate_save[(size_t)n * NE + e] = p;
-            float hard = (P.straight_through ? z : (z - y) + y) * human_hard;  // straight-through value, distributions.py:35 (x the human's under 'coh')
-            if (t == T - 1) hard = 1.0f;              // models.py:701-702, :744-745
-            y_soft[oi] = y;
-            y_hard[oi] = hard;
-        }
-    }
+    for (int e = warp; e < NE; e += FM_THREADS / 32)
+        gate_publish(P, n, b, t, e, lane, gate_logit);
 }
 
 size_t frame_messages_smem(int H, int O, int D, int hh) {
@@ -257,6 +300,32 @@ int launch_frame_messages(const FrameMsgParams& P, cudaStream_t stream) {
     TG_REQUIRE(smem <= 200 * 1024, "frame_messages: shape needs %zu bytes of shared memory", smem);
     if (int rc = ensure_smem((const void*)frame_messages_kernel, smem)) return rc;
     frame_messages_kernel<<<P.B * P.T, FM_THREADS, smem, stream>>>(P);
+    TG_LAUNCH_OK();
+    return 0;
+}
+
+// Two-layer gate MLPs: logit = w2 . hidden + b2 from the hidden rows the projection wrote; one warp per (frame, entity).
+__global__ void __launch_bounds__(128) gate_sample_kernel(const FrameMsgParams P) {
+    const int H = P.H, O = P.O, NE = H + O, D = P.D, T = P.T;
+    const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (w >= P.B * T * NE) return;
+    const int n = w / NE, e = w - n * NE, b = n / T, t = n - b * T;
+    auto logit_of = [&](int ent) -> float {
+        const bool is_h = ent < H;
+        const float* hid = is_h ? P.gate_hid_h + ((size_t)n * H + ent) * D : P.gate_hid_o + ((size_t)n * O + (ent - H)) * D;
+        const float* w2 = is_h ? P.w_uh : P.w_uo;
+        float acc = 0.0f;
+        for (int k = lane; k < D; k += 32) acc = fmaf(__ldg(w2 + k), __ldg(hid + k), acc);
+        return warp_sum(acc) + __ldg(is_h ? P.b_uh : P.b_uo);
+    };
+    const float* given = e < H ? P.human_seg : P.object_seg;
+    if (given != nullptr) return;                      // the frame kernel copied the imposed segmentation
+    gate_publish(P, n, b, t, e, lane, logit_of);
+}
+
+int launch_gate_sample(const FrameMsgParams& P, cudaStream_t stream) {
+    const int warps = P.B * P.T * (P.H + P.O);
+    gate_sample_kernel<<<cdiv(warps * 32, 128), 128, 0, stream>>>(P);
     TG_LAUNCH_OK();
     return 0;
 }

@@ -10,6 +10,12 @@ struct FrameMsgParams {
     int att_noscale;        // attention_style 'v2': plain dot-product logits
     int update_strategy;    // 0 'ind', 1 'sah' (object gates = the single human's), 2 'coh' (hard object gate x the human's)
     const float* dist[3];   // distance-based attention: hh (B,T,H,H), ho (B,T,H,O), oo (B,T,O,O); each may be null
+    // discrete_networks_num_layers == 2: the frame kernel writes the gate MLP inputs instead of sampling; the hidden layer is a
+    // projection, launch_gate_sample finishes (Linear(D, 1) + sigmoid + sampling)
+    float* gate_in_h; int gin_h;    // (B,T,H,gin_h) [x, h, m_hh?, m_oh, m_gh?, time?] or null
+    float* gate_in_o; int gin_o;    // (B,T,O,gin_o) [x, h, m_ho, m_oo, m_go, time?]
+    const float* gate_hid_h;        // (B,T,H,D) ReLU(W1 gate_in + b1): read by launch_gate_sample only
+    const float* gate_hid_o;
     int tl;                 // add_segment_length: one more block at the end of every xx row (written by launch_segment_length)
     int gh;                 // message_geometry_to_human: block m_gh after m_oh in the humans' xx rows and gate inputs
     const float* msg_gh;    // (B,T,1,D) ReLU(W_gh s_g + b), or null
@@ -58,6 +64,8 @@ int launch_time_embed(const float* steps, const float* w, const float* bias, con
 int launch_segment_length(const float* y_hs, const float* y_os, const float* steps, const float* w, const float* bias,
                           const float* freq, float* len, float* xx_h, int ldh, float* xx_o, int ldo, int B, int T, int H, int O,
                           int D, int periodic, cudaStream_t stream);
+// Second layer of the two-layer gate MLPs + sampling: same FrameMsgParams (w_uh / w_uo = the (1, D) weights of layer 2)
+int launch_gate_sample(const FrameMsgParams& P, cudaStream_t stream);
 int launch_gate_post(float* y_hs, const float* y_hss, float* y_os, const float* y_oss, int* reidx, int B, int T, int H,
                      int O, int filter, float thr, cudaStream_t stream);
 int launch_heads(const HeadsParams& P, cudaStream_t stream);

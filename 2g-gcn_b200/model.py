@@ -124,7 +124,7 @@ class TGGCN(nn.Module):
                  share_level_mlps: bool = False, bias: bool = True):
         super().__init__()
         unsupported = []
-        if discrete_networks_num_layers != 1: unsupported.append('discrete_networks_num_layers != 1')
+        if discrete_networks_num_layers not in (1, 2): unsupported.append('discrete_networks_num_layers not in {1, 2}')
         if discrete_optimization_strategy not in _GS | _ST: unsupported.append('unknown discrete_optimization_strategy')
         if not (message_human_to_objects and message_objects_to_human and message_objects_to_object
                 and message_geometry_to_objects): unsupported.append('a human/object/geometry message switched off')
@@ -215,9 +215,12 @@ class TGGCN(nn.Module):
         if message_aggregation in _ATT:
             self.geometry_to_object_message_att_mlp = _mlp([4 * D, 1], ['relu'])
             self.geometry_to_object_segment_message_att_mlp = _mlp([2 * D, 1], ['relu'])
-        self.update_human_segment_mlp = _mlp([D * (2 + (1 if hh else 0) + 1 + gh + tu), 1], ['sigmoid'])
+        self.discrete_networks_num_layers = int(discrete_networks_num_layers)
+        gate_hidden = [D] * (self.discrete_networks_num_layers - 1)          # models.py:532-535
+        gate_act = ['relu'] * len(gate_hidden) + ['sigmoid']
+        self.update_human_segment_mlp = _mlp([D * (2 + (1 if hh else 0) + 1 + gh + tu)] + gate_hidden + [1], gate_act)
         if object_segment_update_strategy not in _SAH:            # models.py:537: no object gate MLP under 'sah'
-            self.update_object_segment_mlp = _mlp([(5 + tu) * D, 1], ['sigmoid'])
+            self.update_object_segment_mlp = _mlp([(5 + tu) * D] + gate_hidden + [1], gate_act)
         label_in = (4 if self.cat_level_states else 2) * D        # models.py:553-555
         self.human_recognition_mlp = _mlp([label_in, n_sub], ['logsoftmax'])
         self.human_prediction_mlp = _mlp([label_in, n_sub], ['logsoftmax'])
@@ -472,6 +475,7 @@ class TGGCN(nn.Module):
                         att_noscale=int(self.attention_style in _V2))
         dims.straight_through = int(self.discrete_optimization_strategy in _ST)
         dims.geo_to_human = int(self.message_geometry_to_human)
+        dims.gate_layers = self.discrete_networks_num_layers
         # misc.make_attention_distance_based (data_loading.py:1264-1276): meaningful under attention aggregation only (models.py:1033-1046)
         dists = [None, None, None]
         if self.message_aggregation in _ATT:

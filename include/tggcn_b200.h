@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define TGGCN_ABI_VERSION 13
+#define TGGCN_ABI_VERSION 14
 
 #if defined(__GNUC__)
 #define TGGCN_API __attribute__((visibility("default")))
@@ -84,6 +84,9 @@ typedef struct tggcn_dims {
                                     (time_periodic selects segment_length_mlp or the periodic encoding) of its entity's segment length: at
                                     a frame with a non-zero hard gate the (normalised) time since the previous such frame, else 0; the
                                     hard gates receive a gradient through it.  Needs tggcn_io.steps_per_example                  */
+    int32_t gate_layers;         /* discrete_networks_num_layers (models.py:532-547): 0 / 1 = Linear(in, 1) + sigmoid; 2 = Linear(in, D) +
+                                    ReLU + Linear(D, 1) + sigmoid: update_*_segment_mlp.0 is then (D, in) and .2 is (1, D); the gate
+                                    inputs are materialised (TGGCN_BUF_GATE_IN_*) and the hidden layer is a projection GEMM        */
 } tggcn_dims;
 
 /* Parameter table.  One device pointer per reference state_dict() entry, in this order
@@ -199,7 +202,11 @@ typedef struct tggcn_dims {
     X(MSG_GH_W,     "geometry_to_human_message_mlp.0.weight")                                          \
     X(MSG_GH_B,     "geometry_to_human_message_mlp.0.bias")                                            \
     X(LEN_W,        "segment_length_mlp.0.weight")                                                     \
-    X(LEN_B,        "segment_length_mlp.0.bias")
+    X(LEN_B,        "segment_length_mlp.0.bias")                                                       \
+    X(UPD_H_W2,     "update_human_segment_mlp.2.weight")                                               \
+    X(UPD_H_B2,     "update_human_segment_mlp.2.bias")                                                 \
+    X(UPD_O_W2,     "update_object_segment_mlp.2.weight")                                              \
+    X(UPD_O_B2,     "update_object_segment_mlp.2.bias")
 
 enum tggcn_weight_id {
 #define TGGCN_X_ENUM(id, key) TGGCN_W_##id,
@@ -294,6 +301,10 @@ enum tggcn_buf_id {
     TGGCN_BUF_TIME_EMB,      /* (B*T, D)             time-position features (empty unless dims.time_position)             */
     TGGCN_BUF_MSG_GH,        /* (B,T,1,D)            geometry -> human frame message (empty unless dims.geo_to_human)     */
     TGGCN_BUF_SEG_LEN,       /* (B,T,H+O)            segment lengths (empty unless dims.segment_length)                   */
+    TGGCN_BUF_GATE_IN_H,     /* (B,T,H,in_h)         gate MLP inputs [x, h, m_hh, m_oh, (m_gh), (time)] (dims.gate_layers == 2 only) */
+    TGGCN_BUF_GATE_IN_O,     /* (B,T,O,in_o)         [x, h, m_ho, m_oo, m_go, (time)]                                    */
+    TGGCN_BUF_GATE_HID_H,    /* (B,T,H,D)            hidden layer of the gate MLPs (post-ReLU)                            */
+    TGGCN_BUF_GATE_HID_O,    /* (B,T,O,D)                                                                                 */
     TGGCN_BUF_COUNT
 };
 

@@ -48,6 +48,8 @@ class OracleConfig:
     positional_encoding: str = 'e'          # 'e' = time_position_mlp (Linear(1, D) + ReLU) of (t+1)/steps, 'p' = periodic of (t+1)
     segment_length: bool = False            # add_segment_length (models.py:763-779, :954-979): per entity, the (normalised) length of
                                             # the segment closed at a frame, embedded like the time position, appended to the xx rows
+    gate_layers: int = 1                    # discrete_networks_num_layers (models.py:532-547): hidden Linear(in, D) + ReLU layers before
+                                            # the Linear(., 1) + sigmoid of the gate MLPs
     geo_to_human: bool = False              # message_geometry_to_human (models.py:690-695, :1432-1475): one more message block
                                             # ReLU(geometry_to_human_message_mlp([x_g | h_g])) in the humans' segment inputs and gate inputs
     straight_through: bool = False          # discrete_optimization_strategy 'st' (models.py:1621-1622): soft gate = the sigmoid
@@ -68,6 +70,7 @@ def config_from_kwargs(kw: dict) -> OracleConfig:
                         (kw.get('time_position_strategy', 's') if kw.get('add_time_position') else ''),
                         'e' if kw.get('positional_encoding_style', 'e') in ('e', 'embedding') else 'p',
                         bool(kw.get('add_segment_length', 0)),
+                        int(kw.get('discrete_networks_num_layers', 1)),
                         bool(kw.get('message_geometry_to_human', False)),
                         kw.get('discrete_optimization_strategy', 'gs') in ('st', 'straight-through'),
                         _UPD[kw.get('object_segment_update_strategy', 'ind')])
@@ -244,6 +247,14 @@ def time_embedding(p: Dict[str, Tensor], cfg: OracleConfig, steps_per_example: T
     return torch.cat([torch.sin(x / w), torch.cos(x / w)], dim=-1)
 
 
+def _gate_prob(p: Dict[str, Tensor], cfg: OracleConfig, mlp: str, x: Tensor) -> Tensor:
+    """update_*_segment_mlp (build_mlp, vhoi/models.py:532-547): gate_layers - 1 hidden Linear + ReLU layers, then Linear(., 1) + sigmoid;
+    nn.Sequential indices 0, 2, 4, ..."""
+    for i in range(cfg.gate_layers - 1):
+        x = _relu_lin(p, f'{mlp}.{2 * i}', x)
+    return torch.sigmoid(_lin(p, f'{mlp}.{2 * (cfg.gate_layers - 1)}', x))
+
+
 def _embed_positions(p: Dict[str, Tensor], cfg: OracleConfig, x: Tensor, mlp: str) -> Tensor:
     """(…, 1) position values -> (…, D): Linear(1, D) + ReLU ('e') or make_periodic_embedding ('p', models.py:1777-1794)."""
     if cfg.positional_encoding == 'e':
@@ -349,7 +360,7 @@ def forward(p: Dict[str, Tensor], cfg: OracleConfig, x_human: Tensor, x_objects:
             else:                                                       # :1477-1498, :700-702
                 if cfg.time_position == 'u':
                     gate_in.append(tt[t])
-                prob = torch.sigmoid(_lin(p, 'update_human_segment_mlp.0', torch.cat(gate_in, dim=-1)))
+                prob = _gate_prob(p, cfg, 'update_human_segment_mlp', torch.cat(gate_in, dim=-1))
                 z, ysoft = sample_gate(prob, next(noise_it) if (noise_it is not None and not cfg.straight_through) else None, thr, cfg.straight_through)
                 if t == T - 1:
                     z = torch.ones_like(z)
@@ -374,7 +385,7 @@ def forward(p: Dict[str, Tensor], cfg: OracleConfig, x_human: Tensor, x_objects:
                 hard_o[k][t], soft_o[k][t] = hard_h[0][t], soft_h[0][t]
             else:                                                       # :1500-1533 ('ind' / 'coh'); input order :1527
                 gate_in = torch.cat([x_o[:, t, k], h_o[:, t, k], m_ho, m_oo, m_go] + ([tt[t]] if cfg.time_position == 'u' else []), dim=-1)
-                prob = torch.sigmoid(_lin(p, 'update_object_segment_mlp.0', gate_in))
+                prob = _gate_prob(p, cfg, 'update_object_segment_mlp', gate_in)
                 z, ysoft = sample_gate(prob, next(noise_it) if (noise_it is not None and not cfg.straight_through) else None, thr, cfg.straight_through)
                 if cfg.update_strategy == 'coh' and H == 1:             # :1531-1532: object updates only where the human does
                     z = z * hard_h[0][t]

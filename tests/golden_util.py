@@ -40,6 +40,8 @@ CASES = {
     'cad120_s2_time_len': ('cad120', 32, 2, 11, 2, False, False, {'add_segment_length': 1, 'add_time_position': 1}),
     'mphoi_s2_dist': ('mphoi', 32, 2, 12, 2, False, False, {'_distances': True}),
     'cad120_s2_dist': ('cad120', 32, 2, 11, 2, False, False, {'_distances': True}),
+    'mphoi_s2_gate2': ('mphoi', 32, 2, 12, 2, False, False, {'discrete_networks_num_layers': 2}),
+    'cad120_nf_gate2_mix': ('cad120', 32, 2, 11, 2, False, False, {'discrete_networks_num_layers': 2, 'add_time_position': 1, 'time_position_strategy': 'u', 'message_geometry_to_human': True, 'filter_discrete_updates': 0, 'update_segment_threshold': 0.5, 'object_segment_update_strategy': 'coh'}),
 }
 
 # BASELINE.json configs[1] itself — what bench.py times (reference outputs; gate margin 2.5e-5).  Kept apart from CASES: the
@@ -75,6 +77,8 @@ GRAD_CASES = {
     'grad_cad120_s2_time_len': ('cad120', 32, 2, 8, 2, {'add_segment_length': 1, 'add_time_position': 1}),
     'grad_mphoi_s2_dist': ('mphoi', 32, 2, 9, 2, {'_distances': True}),
     'grad_cad120_s2_dist': ('cad120', 32, 2, 8, 2, {'_distances': True}),
+    'grad_mphoi_s2_gate2': ('mphoi', 32, 2, 9, 2, {'discrete_networks_num_layers': 2}),
+    'grad_cad120_nf_gate2_mix': ('cad120', 32, 2, 8, 2, {'discrete_networks_num_layers': 2, 'add_time_position': 1, 'time_position_strategy': 'u', 'message_geometry_to_human': True, 'filter_discrete_updates': 0, 'update_segment_threshold': 0.5, 'object_segment_update_strategy': 'coh'}),
 }
 
 # hidden 512 (the benchmarked width), T = 32.  Kept apart from GRAD_CASES: the reference's own fp32 autograd carries summation

@@ -201,11 +201,12 @@ WIDE_CASES.update({'cad120_d128_s2_big': ('cad120', 128, 5, 14, 2), 'bimanual_d1
 # model variants at a width where the TMA projection kernel and — in mode 2 — the large-batch step kernels run, several
 # of them combined: wider segment-level input rows (time + length + geometry->human blocks), distance-based attention weights at both
 # levels, the human's gates driving the objects, the periodic time block in the gate inputs
-VARIANT_BIG_CASES = ['mphoi_d128_s2_blocks', 'cad120_d128_s2_dist', 'cad120_d128_s2_sah_u']
+VARIANT_BIG_CASES = ['mphoi_d128_s2_blocks', 'cad120_d128_s2_dist', 'cad120_d128_s2_sah_u', 'mphoi_d128_s2_gate2']
 WIDE_CASES.update({
     'mphoi_d128_s2_blocks': ('mphoi', 128, 5, 10, 2, {'add_time_position': 1, 'add_segment_length': 1, 'message_geometry_to_human': True,
                                                       '_distances': True}),
     'cad120_d128_s2_dist': ('cad120', 128, 5, 12, 2, {'_distances': True}),
+    'mphoi_d128_s2_gate2': ('mphoi', 128, 5, 10, 2, {'discrete_networks_num_layers': 2, 'add_time_position': 1, 'time_position_strategy': 'u'}),
     'cad120_d128_s2_sah_u': ('cad120', 128, 4, 11, 2, {'object_segment_update_strategy': 'sah', 'add_time_position': 1,
                                                        'time_position_strategy': 'u', 'positional_encoding_style': 'p'}),
 })

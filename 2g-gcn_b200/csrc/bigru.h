@@ -29,7 +29,7 @@ struct BiGruParams {
 
 int launch_bigru(BiGruParams& P, int persistent, cudaStream_t stream);
 // SMEM-resident W_hh variant (bigru_res.cu): 0 = launched, -1 = shape does not qualify (use launch_bigru's streaming kernel), > 0 = error
-int launch_bigru_resident(BiGruParams& P, cudaStream_t stream);
+int launch_bigru_resident(BiGruParams& P, cudaStream_t stream, int nblk = 3);     // nblk: blocks of 8 hidden units per CTA (3 or 2)
 // cluster / distributed-shared-memory variant (bigru_cl.cu, hidden_size 512, small batches): same return convention
 int launch_bigru_cluster(BiGruParams& P, cudaStream_t stream);
 int launch_transpose(const float* in, int ldi, float* out, int ldo, int R, int C, cudaStream_t stream);

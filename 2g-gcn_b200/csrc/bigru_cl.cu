@@ -371,8 +371,9 @@ int launch_bigru_cluster(BiGruParams& P, cudaStream_t stream) {
     static int hybrid = -1;
     if (hybrid < 0) {
         const char* e = getenv("TGGCN_BIGRU_HYBRID");
-        hybrid = e != nullptr ? atoi(e) : 1;        // measured at MPHOI B=8: BiGRU stage 0.973 -> 0.795 ms (6.2 us per step: the 22-CTA
-                                                    // resident kernel is the longer of the two; the seven clusters take 4.2 us)
+        hybrid = e != nullptr ? atoi(e) : 1;        // measured at MPHOI B=8: BiGRU stage 0.973 -> 0.795 ms with the lone recurrence on 22
+                                                    // CTAs of 24 units (6.2 us per step), -> 0.652 ms on 32 CTAs of 16 units (5.1 us);
+                                                    // the seven clusters take 4.5 us per step
     }
     if (hybrid && force == 0 && ok16 && plan16.count > max_clusters && plan16.count <= CL_MAX_CLUSTERS) {
         const int lg = plan16.group[plan16.count - 1], ld = plan16.dir[plan16.count - 1];
@@ -391,7 +392,13 @@ int launch_bigru_cluster(BiGruParams& P, cudaStream_t stream) {
             TG_LAUNCH_OK();
             BiGruParams Q = P;
             for (int g = 0; g < Q.ngroups; ++g) Q.g[g].skip_dirs = g == lg ? (ld == 0 ? 2 : 1) : 3;
-            const int rr = launch_bigru_resident(Q, ss.side);
+            static int lone_nblk = -1;                                    // TGGCN_BIGRU_LONE_NBLK=3: the 22-CTA form (A/B aid)
+            if (lone_nblk < 0) {
+                const char* e = getenv("TGGCN_BIGRU_LONE_NBLK");
+                lone_nblk = (e != nullptr && atoi(e) == 3) ? 3 : 2;
+            }
+            // the lone recurrence on 32 CTAs of 16 units (the clusters leave 36 SMs free) rather than 22 of 24
+            const int rr = launch_bigru_resident(Q, ss.side, (num_sms() - head.count * CL) >= 32 ? lone_nblk : 3);
             if (rr != 0) {                                                // does not qualify after all: the last recurrence as a second wave
                 ClusterPlan tail;
                 memset(&tail, 0, sizeof(tail));

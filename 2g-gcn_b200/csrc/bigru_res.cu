@@ -22,14 +22,16 @@ namespace tg {
 namespace {
 
 constexpr int BR_UB = 8;          // hidden units per block (one n8 MMA tile per gate)
-constexpr int BR_NBLK = 3;        // unit blocks per CTA
-constexpr int BR_NT = 3 * BR_NBLK;   // n8 tiles per CTA: [gate][block]
+// unit blocks per CTA = template parameter NBLK: 3 (22 CTAs per (group, direction): the whole stage on 132 CTAs) or 2 (32 CTAs: the
+// lone recurrence of the hybrid launch, on the SMs the clusters leave free)
 constexpr int BR_ROWS = 32;       // state rows per pass (two m16 tiles)
-constexpr int BR_ACC = 2 * BR_NT * 4;   // accumulator floats per lane
 
 __device__ __forceinline__ int br_ld(int D) { return D + 8; }    // padded row stride (words): 64-bit fragment loads of a half-warp hit 16 distinct 8-byte slots
 
+template <int BR_NBLK>
 __global__ void __launch_bounds__(REC_THREADS, 1) bigru_res_kernel(const BiGruParams P, int ctas_per_gd) {
+    constexpr int BR_NT = 3 * BR_NBLK;       // n8 tiles per CTA: [gate][block]
+    constexpr int BR_ACC = 2 * BR_NT * 4;    // accumulator floats per lane
     extern __shared__ __align__(16) float smem[];
     __shared__ int s_fail;
     __shared__ long long rowoff[BR_ROWS];                // element offset of (video, entity) of each state row at t = 0 (first row block)
@@ -79,11 +81,11 @@ __global__ void __launch_bounds__(REC_THREADS, 1) bigru_res_kernel(const BiGruPa
         if (!(wmax * RES_WSCALE < RES_F16_MAX)) atomicOr(P.sync.error, 2u);
     }
     // epilogue constants: this thread's outputs o = tid + 256*q  ->  (m tile, block, accumulator register, lane)
-    float bh[3][3];
-    int o_row[3], o_unit[3], o_base[3];
-    bool o_ok[3];
+    float bh[BR_NBLK][3];
+    int o_row[BR_NBLK], o_unit[BR_NBLK], o_base[BR_NBLK];
+    bool o_ok[BR_NBLK];
 #pragma unroll
-    for (int q = 0; q < 3; ++q) {
+    for (int q = 0; q < BR_NBLK; ++q) {
         const int o = tid + REC_THREADS * q;
         const int ol = o & 31, reg = (o >> 5) & 3, blk = (o >> 7) % BR_NBLK, m = o / (128 * BR_NBLK);
         o_row[q] = m * 16 + (ol >> 2) + ((reg & 2) ? 8 : 0);
@@ -93,9 +95,9 @@ __global__ void __launch_bounds__(REC_THREADS, 1) bigru_res_kernel(const BiGruPa
 #pragma unroll
         for (int gt = 0; gt < 3; ++gt) bh[q][gt] = o_ok[q] ? __ldg(G.bhh[dir] + gt * D + o_unit[q]) : 0.0f;
     }
-    long long o_fe0[3];                                  // (video, entity) part of the frame-entity index at t = 0 (first row block)
+    long long o_fe0[BR_NBLK];                                  // (video, entity) part of the frame-entity index at t = 0 (first row block)
 #pragma unroll
-    for (int q = 0; q < 3; ++q) {
+    for (int q = 0; q < BR_NBLK; ++q) {
         const int r = rbase + o_row[q] < G.rows ? rbase + o_row[q] : 0, b = r / G.E, e = r - b * G.E;
         o_fe0[q] = (long long)b * T * G.E + e;
     }
@@ -104,15 +106,15 @@ __global__ void __launch_bounds__(REC_THREADS, 1) bigru_res_kernel(const BiGruPa
     unsigned int epoch = 0;
     bool ok = true;
     // epilogue operands of one (step, row block): input pre-activations, previous state, output offsets
-    float xg[3][3], hprev[3];
-    size_t orow[3];
-    float* gsave[3];
-    bool valid[3];
+    float xg[BR_NBLK][3], hprev[BR_NBLK];
+    size_t orow[BR_NBLK];
+    float* gsave[BR_NBLK];
+    bool valid[BR_NBLK];
     auto fetch = [&](int s, int rb0, int nrows) {
         const int t = dir == 0 ? s : T - 1 - s;
         const int tprev = dir == 0 ? t - 1 : t + 1;
 #pragma unroll
-        for (int q = 0; q < 3; ++q) {
+        for (int q = 0; q < BR_NBLK; ++q) {
             valid[q] = o_ok[q] && o_row[q] < nrows;
             xg[q][0] = xg[q][1] = xg[q][2] = 0.0f;
             if (!single_rb || s == 0) hprev[q] = 0.0f;           // single row block: hprev is carried in the register (own last output)
@@ -168,9 +170,9 @@ __global__ void __launch_bounds__(REC_THREADS, 1) bigru_res_kernel(const BiGruPa
             if (!single_rb) fetch(s, rb0, nrows);
             cp_async_wait<0>();
             __syncwarp();
-            float sum[3][3];
+            float sum[BR_NBLK][3];
 #pragma unroll
-            for (int q = 0; q < 3; ++q) sum[q][0] = sum[q][1] = sum[q][2] = 0.0f;
+            for (int q = 0; q < BR_NBLK; ++q) sum[q][0] = sum[q][1] = sum[q][2] = 0.0f;
             if (s > 0) {
                 // ---- 2. W_hh h on the tensor cores, operands from shared memory only --------------------------------
                 float acc[2][BR_NT][4];
@@ -238,7 +240,7 @@ __global__ void __launch_bounds__(REC_THREADS, 1) bigru_res_kernel(const BiGruPa
                         for (int r = 0; r < 4; ++r) red[(warp * BR_ACC + (m * BR_NT + nt) * 4 + r) * 32 + lane] = acc[m][nt][r];
                 __syncthreads();
 #pragma unroll
-                for (int q = 0; q < 3; ++q) {
+                for (int q = 0; q < BR_NBLK; ++q) {
                     if (!o_ok[q]) continue;
 #pragma unroll
                     for (int gt = 0; gt < 3; ++gt) {
@@ -250,7 +252,7 @@ __global__ void __launch_bounds__(REC_THREADS, 1) bigru_res_kernel(const BiGruPa
                 }
             }
 #pragma unroll
-            for (int q = 0; q < 3; ++q)
+            for (int q = 0; q < BR_NBLK; ++q)
                 if (valid[q]) {
                     const float hnew = gru_update(xg[q][0], xg[q][1], xg[q][2], sum[q][0] + bh[q][0], sum[q][1] + bh[q][1],
                                                   sum[q][2] + bh[q][2], hprev[q], gsave[q], D);
@@ -270,7 +272,9 @@ __global__ void __launch_bounds__(REC_THREADS, 1) bigru_res_kernel(const BiGruPa
 }  // namespace
 
 // Returns 0 when the resident kernel was launched, -1 when this shape does not qualify (caller falls back), > 0 on error.
-int launch_bigru_resident(BiGruParams& P, cudaStream_t stream) {
+int launch_bigru_resident(BiGruParams& P, cudaStream_t stream, int nblk) {
+    TG_REQUIRE(nblk == 2 || nblk == 3, "bigru (resident): %d unit blocks per CTA not built", nblk);
+    const int BR_NBLK = nblk, BR_NT = 3 * nblk, BR_ACC = 2 * BR_NT * 4;
     static int enabled = -1;
     if (enabled < 0) {
         const char* e = getenv("TGGCN_BIGRU_RES");
@@ -302,7 +306,7 @@ int launch_bigru_resident(BiGruParams& P, cudaStream_t stream) {
         P.g[i].tile_begin = grid;
         grid += ndirs(i) * rgs[i] * ctas_per_gd;
     }
-    auto kern = bigru_res_kernel;
+    auto kern = nblk == 2 ? bigru_res_kernel<2> : bigru_res_kernel<3>;
     if (int rc = ensure_smem((const void*)kern, smem)) return rc;
     int per_sm = 0;
     TG_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, REC_THREADS, smem));

@@ -15,7 +15,7 @@ Public surface (mirrors the reference's ``vhoi.models`` for this path):
     evaluate                                 -- device-side predict.py post-processing: up-sampling + argmax, F1@k (pyrutils/metrics.py)
     build                                    -- in-tree nvcc build of lib2ggcn_b200.so
 """
-from . import abi, dp, evaluate, feeder, losses, synth, trainer        # noqa: F401
+from . import abi, dp, evaluate, feeder, losses, optim, synth, trainer        # noqa: F401
 from .model import TGGCN, select_model, install_dropin   # noqa: F401
 
-__all__ = ['TGGCN', 'select_model', 'install_dropin', 'abi', 'dp', 'evaluate', 'feeder', 'losses', 'synth', 'trainer']
+__all__ = ['TGGCN', 'select_model', 'install_dropin', 'abi', 'dp', 'evaluate', 'feeder', 'losses', 'optim', 'synth', 'trainer']

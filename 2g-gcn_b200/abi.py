@@ -143,6 +143,9 @@ def lib():
     L.tggcn_upsample_argmax.argtypes = [C.c_void_p, C.c_void_p] + [C.c_int] * 6 + [C.c_void_p]
     L.tggcn_f1_at_k_scratch_bytes.restype = C.c_size_t
     L.tggcn_f1_at_k_scratch_bytes.argtypes = [C.c_int] * 3
+    L.tggcn_adam_step.restype = C.c_int
+    L.tggcn_adam_step.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_float, C.c_float, C.c_float,
+                                  C.c_float, C.c_float, C.c_int, C.c_void_p]
     L.tggcn_f1_at_k.restype = C.c_int
     L.tggcn_f1_at_k.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int64,
                                 C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]

@@ -16,7 +16,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, 'csrc')
 LIB = os.path.join(HERE, 'lib2ggcn_b200.so')
 STAMP = LIB + '.srchash'
-SOURCES = ['api.cu', 'api_bwd.cu', 'backward.cu', 'recurrent_bwd.cu', 'geo_gcn_bwd.cu', 'geo_gcn.cu', 'gemm_simt.cu', 'gemm_tc.cu', 'gemm16.cu', 'gemm_bwd.cu', 'bigru.cu', 'bigru_res.cu', 'bigru_cl.cu', 'bigru_bwd.cu', 'segment.cu', 'step_tc.cu', 'frame.cu', 'loss.cu', 'evaluate.cu']
+SOURCES = ['api.cu', 'api_bwd.cu', 'backward.cu', 'recurrent_bwd.cu', 'geo_gcn_bwd.cu', 'geo_gcn.cu', 'gemm_simt.cu', 'gemm_tc.cu', 'gemm16.cu', 'gemm_bwd.cu', 'bigru.cu', 'bigru_res.cu', 'bigru_cl.cu', 'bigru_bwd.cu', 'segment.cu', 'step_tc.cu', 'frame.cu', 'loss.cu', 'evaluate.cu', 'optim.cu']
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17',
               '-Xcompiler', '-fPIC', '-Xcompiler', '-fvisibility=hidden', '--expt-relaxed-constexpr',
               '-Xptxas', '-v'] + os.environ.get('TGGCN_NVCC_DEFS', '').split()       # e.g. "-DSEG_NO_SHADOW" for A/B experiments

@@ -710,6 +710,7 @@ class TGGCN(nn.Module):
         self._pending_status.append(pending)
         self._last_bwd = (keep, bws)
         self.flat_grad, self._flat_views = flat, (params, grads)
+        self._flat_layout = (params, tuple(offs), tuple(sizes), total)      # optim.FlatAdam lays its buffers out the same way
         self.grad_buckets = [(s, e, ev) for (s, e), ev in zip(bucket_ranges, events) if e > s]
         # gradients land in .grad here (autograd's accumulation semantics: a parameter that already holds a gradient adds to it)
         for prm, g in zip(params, grads):

@@ -317,7 +317,10 @@ def train_step_throughput(args, pkg, shape, kwargs, dev, rank, world, flush, bar
     model = pkg.TGGCN(**kwargs).to(dev).train()
     model.gemm_path = args.gemm_path
     model.set_precision(precision)
-    opt = torch.optim.Adam(model.parameters(), lr=1e-4, fused=True)      # torch's own Adam (train.py's optimiser), fused variant
+    # Adam with train.py:40's hyper-parameters: the training driver's one-launch form over the flat parameter / gradient buffers
+    # (2g-gcn_b200/optim.py, same update and state_dict as torch.optim.Adam: tests/test_gpu_optim.py); --torch-adam = torch's own
+    opt = (torch.optim.Adam(model.parameters(), lr=1e-4, fused=True) if getattr(args, 'torch_adam', False)
+           else pkg.optim.FlatAdam(model, lr=1e-4))
     reducer = pkg.dp.GradientAllReduce(model).attach()
     reducer.sync_parameters()
     B, T = args.B, args.T
@@ -432,7 +435,7 @@ def train_step_throughput(args, pkg, shape, kwargs, dev, rank, world, flush, bar
             'dtype': 'bf16' if precision == 'bf16' else 'f32',
             'what': 'forward(train-mode BN, saves) + fused criterion (BCE + 2x NLL) + tggcn_backward_ex + '
                     + ('bucketed NCCL all-reduce of the flat gradient overlapped with the backward + ' if world > 1 else '')
-                    + 'torch.optim.Adam(fused=True) step; '
+                    + ('torch.optim.Adam(fused=True) step; ' if getattr(args, 'torch_adam', False) else 'Adam step (one launch over the flat buffers, optim.FlatAdam); ')
                     + ('bf16 operands / fp32 accumulation in every projection and weight-gradient GEMM, fp32 gates, recurrences and optimiser'
                        if precision == 'bf16' else 'fp32-accurate products (3xTF32 / 3xFP16 split)'),
             'global_batch_videos': world * B}
@@ -499,7 +502,7 @@ def other_configs(args, pkg, dev, flush):
     for D in (64, 512):
         torch.manual_seed(0)
         m = pkg.TGGCN(**pkg.synth.model_kwargs(bim, hidden_size=D, stage=2)).to(dev).train()
-        opt = torch.optim.Adam(m.parameters(), lr=1e-4, fused=True)
+        opt = pkg.optim.FlatAdam(m, lr=1e-4)
         m.set_gumbel_noise(pkg.TGGCN.draw_gumbel_noise(Tb * (bim.H + bim.O), Bb).to(dev))
 
         def step():
@@ -611,6 +614,7 @@ def main():
     ap.add_argument('--gemm-path', type=int, default=2)
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-train', action='store_true', help='skip the training-step measurement')
+    ap.add_argument('--torch-adam', action='store_true', help='training step with torch.optim.Adam(fused=True) instead of optim.FlatAdam')
     ap.add_argument('--max-sweep-batch', type=int, default=256, help='largest batch of the CAD-120 sweep in other_configs (46 GB at 256)')
     ap.add_argument('--no-extras', action='store_true', help='skip the CAD-120 sweep and the Bimanual training configs (other_configs)')
     args = ap.parse_args()

@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define TGGCN_ABI_VERSION 14
+#define TGGCN_ABI_VERSION 15
 
 #if defined(__GNUC__)
 #define TGGCN_API __attribute__((visibility("default")))
@@ -465,6 +465,12 @@ TGGCN_API size_t tggcn_f1_at_k_scratch_bytes(int B, int Tt, int E);
 TGGCN_API int tggcn_f1_at_k(const int64_t* target, const int64_t* pred, int B, int Tt, int E, int num_classes,
                             const double* overlaps, int n_overlaps, int64_t ignore_value, void* scratch, double* f1_rows,
                             int32_t* valid_rows, void* stream);
+
+/* One step of torch.optim.Adam (the optimiser train.py:40 builds; amsgrad off, weight_decay added to the gradient) over flat,
+ * 16-byte aligned device buffers of n floats: parameters p, gradients g, first / second moments m, v (zero before step 1).
+ * `step` is the 1-based update count (bias corrections 1 - beta^step).  One launch; used by 2g-gcn_b200/optim.py (FlatAdam). */
+TGGCN_API int tggcn_adam_step(float* p, const float* g, float* m, float* v, size_t n, float lr, float beta1, float beta2, float eps,
+                              float weight_decay, int step, void* stream);
 
 #ifdef __cplusplus
 }

@@ -30,7 +30,7 @@ def main():
     dev = torch.device('cuda', 0)
     torch.manual_seed(0)
     model = pkg.TGGCN(**kwargs).to(dev).train()
-    opt = torch.optim.Adam(model.parameters(), lr=1e-4)
+    opt = pkg.optim.FlatAdam(model, lr=1e-4) if os.environ.get('TGGCN_TORCH_ADAM') != '1' else torch.optim.Adam(model.parameters(), lr=1e-4)
     B, T = args.B, args.T
     batch = pkg.synth.make_batch(shape, B, T, seed=1234)
     x = {k: batch[k].to(dev) for k in ('x_human', 'x_objects', 'objects_mask')}

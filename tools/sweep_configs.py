@@ -82,7 +82,7 @@ def train_case(shape, B, T, D, iters, max_gb):
     if gb > max_gb:
         print(f'{tag} skipped: inputs + workspaces = {gb:.1f} GB > {max_gb} GB', flush=True)
         return
-    opt = torch.optim.Adam(model.parameters(), lr=1e-4)
+    opt = pkg.optim.FlatAdam(model, lr=1e-4)
     batch = pkg.synth.make_batch(shape, B, T, seed=1234)
     x = {k: batch[k].cuda() for k in ('x_human', 'x_objects', 'objects_mask')}
     targets = [t.cuda() for t in pkg.synth.target_list(shape, pkg.synth.make_targets(shape, batch['lengths'], T, seed=5))]

@@ -273,6 +273,17 @@ __global__ void __launch_bounds__(REC_THREADS, 1) bigru_cluster_kernel(const BiG
 
 }  // namespace
 
+__global__ void side_delay_kernel(int ns) {
+    if (threadIdx.x == 0) {
+        unsigned long long t0, t1;
+        asm volatile("mov.u64 %0, %%globaltimer;\n" : "=l"(t0));
+        do {
+            __nanosleep(200);
+            asm volatile("mov.u64 %0, %%globaltimer;\n" : "=l"(t1));
+        } while (t1 - t0 < (unsigned long long)ns);
+    }
+}
+
 struct SideStream { cudaStream_t side; cudaEvent_t fork, join; };
 static int get_side_stream(SideStream& out) {
     struct Entry { bool made; SideStream s; };
@@ -398,6 +409,19 @@ int launch_bigru_cluster(BiGruParams& P, cudaStream_t stream) {
                 lone_nblk = (e != nullptr && atoi(e) == 3) ? 3 : 2;
             }
             // the lone recurrence on 32 CTAs of 16 units (the clusters leave 36 SMs free) rather than 22 of 24
+            // Both kernels become runnable at the same instant (the fork event) when the host runs ahead of the GPU; if the block
+            // scheduler places the 32 lone CTAs first, spread over the GPCs, fewer than seven GPCs keep 16 free SMs and the clusters
+            // fall into two waves (measured: the stage 0.65 -> 1.1 ms in some launch contexts).  A ~10 us spin on the side stream
+            // lets the clusters claim their SMs first.
+            static int delay_ns = -1;
+            if (delay_ns < 0) {
+                const char* e = getenv("TGGCN_BIGRU_LONE_DELAY_NS");
+                delay_ns = e != nullptr ? atoi(e) : 10000;
+            }
+            if (delay_ns > 0) {
+                side_delay_kernel<<<1, 32, 0, ss.side>>>(delay_ns);
+                TG_LAUNCH_OK();
+            }
             const int rr = launch_bigru_resident(Q, ss.side, (num_sms() - head.count * CL) >= 32 ? lone_nblk : 3);
             if (rr != 0) {                                                // does not qualify after all: the last recurrence as a second wave
                 ClusterPlan tail;

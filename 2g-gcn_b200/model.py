@@ -640,7 +640,8 @@ class TGGCN(nn.Module):
             for i in order:
                 if bucket_of[i] == k:
                     offs[i] = total
-                    total += (params[i].numel() + 3) // 4 * 4        # keep every gradient 16-byte aligned
+                    total += (params[i].numel() + 63) // 64 * 64     # every gradient (and, under optim.FlatAdam, every parameter) on a
+                                                                     # 256-byte boundary: the kernels read the weights in place
             total = (total + 63) // 64 * 64                          # buckets start on 256-byte boundaries
             bucket_ranges.append((start, total))
         flat = torch.empty(total, dtype=torch.float32, device=dev)

@@ -110,6 +110,17 @@ def test_library_loads_and_exports_every_declared_symbol(pkg):
     assert lib.tggcn_status_decode(words) == 3 and b'timed out' in lib.tggcn_last_error()
 
 
+def test_integration_doc_mirrors_the_structs(pkg):
+    """INTEGRATION.md shows the ctypes binding a maintainer would write: its field lists must be the ones of include/tggcn_b200.h
+    (= abi.Dims / abi.IO), in order."""
+    doc = open(os.path.join(ROOT, 'INTEGRATION.md')).read()
+    block = doc[doc.index('class Dims(C.Structure)'):doc.index('KEYS = re.findall')]
+    dims_doc = re.findall(r"'(\w+)'", block[:block.index('class IO(C.Structure)')])
+    io_doc = re.findall(r"'(\w+)'", block[block.index('class IO(C.Structure)'):])
+    assert dims_doc == [n for n, _ in pkg.abi.Dims._fields_]
+    assert io_doc == [n for n, _ in pkg.abi.IO._fields_]
+
+
 def test_workspace_query_needs_no_gpu(pkg):
     d = pkg.abi.Dims(B=8, T=128, H=2, O=4, V=26, D=512, Fh=2152, C_sub=13, C_aff=0, hh=1, filter=1, bn_train=0,
                      human_seg_given=0, object_seg_given=0, inspect=0, persistent=1, gemm_path=0, thr=0.1)

@@ -38,6 +38,9 @@ def _fwd(model, batch, noise, sl=slice(None), hseg=None, oseg=None):
                                  ('cad120', 32, 9, 11, 1, 0), ('mphoi', 64, 11, 9, 1, 0),
                                  # hidden 512, recurrent_mode 1: resident-weight kernels walking several row / video blocks per CTA
                                  ('mphoi', 512, 20, 6, 2, 0, 1), ('cad120', 512, 24, 5, 2, 1, 1), ('bimanual', 512, 9, 5, 2, 2, 1),
+                                 # hidden 512, default path selection: 7 and 8 videos = eight BiGRU recurrences of <= 16 rows (hybrid launch: seven
+                                 # clusters + the lone recurrence on the resident kernel), ragged row blocks
+                                 ('mphoi', 512, 7, 6, 2, 1), ('mphoi', 512, 8, 7, 2, 3),
                                  # recurrent_mode 2: the large-batch path (tcgen05 + TMA step kernels), also where rows < 128 pad a tile
                                  ('mphoi', 512, 20, 6, 2, 0, 2), ('cad120', 512, 24, 5, 2, 1, 2), ('bimanual', 512, 9, 5, 2, 2, 2),
                                  ('mphoi', 128, 5, 7, 1, 3, 2), ('cad120', 192, 3, 9, 2, 2, 2)])

@@ -264,6 +264,11 @@ def run_ours(args, rank, world, local_rank):
     tr = os.path.join(ROOT, 'profiles', 'ncu_traffic.json')
     traffic = json.load(open(tr)) if os.path.exists(tr) else {}
     roof['traffic'] = traffic.get(top)
+    if top in ('segment', 'bigru'):
+        # why the fraction is what it is: a chain of T dependent steps, each two grid barriers + L2 round trips;
+        # ncu: tensor pipe 17 % active, 127 MB of DRAM traffic for the whole launch, all weights resident on chip
+        roof['limited_by'] = ('latency chain: T dependent recurrent steps (2 grid barriers + L2 round trips each, 3-product fp16-split '
+                              'mma.sync on 16-32 activation rows); the on-chip storage of all 148 SMs is full of weights (46 MB as 4-byte words)')
     # the same two ratios for every stage (algorithmic FLOPs and bytes of stage_work over the live stage time): tensor-bound
     # stages are quoted against the sustained bf16 peak although they compute fp32-accurate products (3 MMAs per product)
     per_stage = {}

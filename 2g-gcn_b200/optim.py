@@ -47,6 +47,7 @@ class FlatAdam(torch.optim.Optimizer):
                     flat_v[o:o + n].view(p.shape).copy_(st['exp_avg_sq'])
                     self._steps = max(self._steps, int(st['step']))
         self._p, self._m, self._v, self._layout = flat_p, flat_m, flat_v, layout
+        self.model._ptr_cache = None                            # the weight-pointer table of the C ABI must be rebuilt: storages moved
         self._step_t = torch.tensor(float(self._steps))          # one tensor shared by every parameter's state
         for p, o, n in zip(params, offs, sizes):
             self.state[p] = dict(step=self._step_t, exp_avg=flat_m[o:o + n].view(p.shape), exp_avg_sq=flat_v[o:o + n].view(p.shape))

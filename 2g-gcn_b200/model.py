@@ -342,7 +342,9 @@ class TGGCN(nn.Module):
 
     def _weight_pointers(self, device):
         sd_items = [(name, t) for _, _, _, name, t in self._tensor_directory()]
-        probe = (sd_items[0][1].data_ptr(), sd_items[-1][1].data_ptr(), len(sd_items), self._dir_version)
+        # every storage address takes part (~20 us): a parameter whose .data was re-pointed (optim.FlatAdam, user code) must not be
+        # read through a stale pointer
+        probe = (hash(tuple(t.data_ptr() for _, t in sd_items)), len(sd_items), self._dir_version)
         if self._ptr_cache is not None and self._ptr_cache[0] == probe:
             return self._ptr_cache[1]
         arr = (C.c_void_p * abi.N_WEIGHTS)()

@@ -105,6 +105,9 @@ class OutputList(list):
     it with a single device->host copy instead of one per tensor; ``None`` under autograd."""
     flat = None
 
+    def __reduce__(self):          # pickles (torch.save of a prediction list) as the plain list the reference returns
+        return (list, (list(self),))
+
 
 class TGGCN(nn.Module):
     """B200-native 2G-GCN.  See module docstring; argument meaning as in vhoi/models.py:191-233."""

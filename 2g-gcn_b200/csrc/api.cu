@@ -96,6 +96,8 @@ void make_layout(const tggcn_dims& d, Layout& L) {
     sz[TGGCN_BUF_GATE_IN_O] = gate2_of(d) ? N * O * (size_t)gino_of(d) * f : 0;
     sz[TGGCN_BUF_GATE_HID_H] = gate2_of(d) ? N * H * D * f : 0;
     sz[TGGCN_BUF_GATE_HID_O] = gate2_of(d) ? N * O * D * f : 0;
+    sz[TGGCN_BUF_GATE_HID2_H] = gate3_of(d) ? N * H * D * f : 0;
+    sz[TGGCN_BUF_GATE_HID2_O] = gate3_of(d) ? N * O * D * f : 0;
     sz[TGGCN_BUF_GS_H] = N * H * 6 * D * f;
     sz[TGGCN_BUF_GS_O] = N * O * 6 * D * f;
     sz[TGGCN_BUF_HX_H] = N * H * 2 * D * f;
@@ -155,7 +157,7 @@ int check_dims(const tggcn_dims& d) {
     TG_REQUIRE(d.V >= 1 && d.V <= 32, "dims: gcn_node=%d unsupported", d.V);
     TG_REQUIRE(d.Fh == 2048 + 4 * d.V, "dims: human feature size %d != 2048 + 4*gcn_node", d.Fh);
     TG_REQUIRE(d.C_sub >= 1 && d.C_sub <= 32 && d.C_aff >= 0 && d.C_aff <= 32, "dims: class counts out of range");
-    TG_REQUIRE(d.gate_layers >= 0 && d.gate_layers <= 2, "dims: gate_layers=%d (discrete_networks_num_layers) must be 1 or 2", d.gate_layers);
+    TG_REQUIRE(d.gate_layers >= 0 && d.gate_layers <= 3, "dims: gate_layers=%d (discrete_networks_num_layers) must be 1, 2 or 3", d.gate_layers);
     TG_REQUIRE(d.time_position >= 0 && d.time_position <= 2 && (d.time_periodic == 0 || d.time_periodic == 1),
                "dims: time_position / time_periodic out of range");
     TG_REQUIRE((size_t)d.B * d.T * (size_t)(d.H > d.O ? d.H : d.O) * 6 * d.D < (1ull << 31),
@@ -453,8 +455,19 @@ static int forward_impl(const tggcn_dims* dims, const void* const* weights, int 
             }
             if (int rc = project(g)) return rc;
             P.gate_hid_h = buf(TGGCN_BUF_GATE_HID_H); P.gate_hid_o = buf(TGGCN_BUF_GATE_HID_O);
-            P.w_uh = W(TGGCN_W_UPD_H_W2); P.b_uh = W(TGGCN_W_UPD_H_B2);
-            P.w_uo = W(TGGCN_W_UPD_O_W2); P.b_uo = W(TGGCN_W_UPD_O_B2);
+            int last_h = TGGCN_W_UPD_H_W2, last_o = TGGCN_W_UPD_O_W2;         // weight slot of the Linear(D, 1) layer (bias = slot + 1)
+            if (gate3_of(d)) {                                                // one more Linear(D, D) + ReLU
+                g.count = 0;
+                if (sample_h) gemm_add(g, P.gate_hid_h, D, W(TGGCN_W_UPD_H_W2), D, W(TGGCN_W_UPD_H_B2), buf(TGGCN_BUF_GATE_HID2_H), D, N * H, D, D, 1);
+                if (sample_o) gemm_add(g, P.gate_hid_o, D, W(TGGCN_W_UPD_O_W2), D, W(TGGCN_W_UPD_O_B2), buf(TGGCN_BUF_GATE_HID2_O), D, N * O, D, D, 1);
+                if (int rc = project(g)) return rc;
+                P.gate_hid_h = buf(TGGCN_BUF_GATE_HID2_H); P.gate_hid_o = buf(TGGCN_BUF_GATE_HID2_O);
+                last_h = TGGCN_W_UPD_H_W4; last_o = TGGCN_W_UPD_O_W4;
+                if (sample_h) TG_REQUIRE(W(last_h) && W(last_h + 1), "forward: three-layer human gate MLP weights missing");
+                if (sample_o) TG_REQUIRE(W(last_o) && W(last_o + 1), "forward: three-layer object gate MLP weights missing");
+            }
+            P.w_uh = W(last_h); P.b_uh = W(last_h + 1);
+            P.w_uo = W(last_o); P.b_uo = W(last_o + 1);
             if (int rc = launch_gate_sample(P, stream)) return rc;
         } else {
             if (int rc = launch_frame_messages(P, stream)) return rc;

@@ -25,7 +25,7 @@ struct BwdLayout {
         return o;
     }
     size_t dhfr[3], dhx[2], dgs[2], dghs[2], du[2], direct[2], dmg[2], dpre[2], lgr[4], lgs[4], dpre_all[4], gru_direct[3];
-    size_t dghid[2], dgin[2], dtime, dxx[2], ds[3], dmsg[6], dgi[3], dgh[3], bigru_scratch, dgeo_hid, dgcn_out, dxn, wt_seg, wt, tn, tn_floats;
+    size_t dghid[2], dghid1[2], dgin[2], dtime, dxx[2], ds[3], dmsg[6], dgi[3], dgh[3], bigru_scratch, dgeo_hid, dgcn_out, dxn, wt_seg, wt, tn, tn_floats;
     size_t zero_begin, zero_end;     // region that must be zero before the kernels run (atomically accumulated)
 };
 
@@ -61,6 +61,8 @@ void make_bwd_layout(const tggcn_dims& d, BwdLayout& L) {
     L.dtime = L.take(d.time_position && !d.time_periodic ? N * D : 0);
     L.dghid[0] = L.take(gate2_of(d) ? N * H * D : 0);
     L.dghid[1] = L.take(gate2_of(d) ? N * O * D : 0);
+    L.dghid1[0] = L.take(gate3_of(d) ? N * H * D : 0);
+    L.dghid1[1] = L.take(gate3_of(d) ? N * O * D : 0);
     L.dgin[0] = L.take(gate2_of(d) ? N * H * (size_t)ginh_of(d) : 0);
     L.dgin[1] = L.take(gate2_of(d) ? N * O * (size_t)gino_of(d) : 0);
     for (int g = 0; g < 3; ++g) L.ds[g] = L.take(N * E[g] * 2 * D);
@@ -101,7 +103,7 @@ void make_bwd_layout(const tggcn_dims& d, BwdLayout& L) {
     const size_t kh_ = kh_of(d);
     const size_t grp_cands[] = {rp * ((H ? 1 : 0) * (7 * D + kh_ + nkh * D) + 9 * D + ko_), 2 * rp * 15 * D,
                                 2 * rp * (D + 2048) + np * (D + 2048) + np * (2048 + 128 * V), 3 * rp * 4 * D + np * 6 * D,
-                                gate2_of(d) ? 2 * rp * (D + (size_t)(ginh_of(d) > gino_of(d) ? ginh_of(d) : gino_of(d))) : 0};
+                                gate2_of(d) ? 2 * rp * (3 * D + (size_t)(ginh_of(d) > gino_of(d) ? ginh_of(d) : gino_of(d))) : 0};
     for (size_t c : grp_cands)
         if (c > tmax) tmax = c;
     tmax += 4096;
@@ -150,7 +152,7 @@ size_t tggcn_backward_workspace_bytes(const tggcn_dims* dims) {
 
 int tggcn_backward_bucket(int id) {
     if (id < 0 || id >= TGGCN_W_COUNT) return -1;
-    if (id >= TGGCN_W_TIME_W && id <= TGGCN_W_UPD_O_B2) return 1;         // time / length MLPs, geometry -> human message MLP, gate MLP layer 2            // formed with the frame-level graph
+    if (id >= TGGCN_W_TIME_W && id <= TGGCN_W_UPD_O_B4) return 1;         // time / length MLPs, geometry -> human message MLP, gate MLP layer 2            // formed with the frame-level graph
     if (id <= TGGCN_W_GCN_S2_B) return 3;                                   // GCN_* (first 13 entries of the table)
     if (id <= TGGCN_W_OBJ_EMB_B) return 2;                                  // geometry MLP, ROI embeddings
     if (id >= TGGCN_W_HSEG_F_WIH || (id >= TGGCN_W_SMSG_HH_W && id <= TGGCN_W_SMSG_OO_B)) return 0;   // cells, heads, segment MLPs
@@ -495,39 +497,50 @@ int tggcn_backward_ex(const tggcn_dims* dims, const void* const* weights, void* 
         P.dw_uh = G(TGGCN_W_UPD_H_W); P.db_uh = G(TGGCN_W_UPD_H_B); P.dw_uo = G(TGGCN_W_UPD_O_W); P.db_uo = G(TGGCN_W_UPD_O_B);
         const bool sample_h = !d.human_seg_given, sample_o = !d.object_seg_given && d.update_strategy != 1;
         if (gate2_of(d)) {
-            // two-layer gate MLPs: dlogit -> d hidden (+ layer-2 weight gradients), then d gate_in = d hidden . W1 and dW1 = d hidden^T gate_in
+            // gate MLPs with hidden layers: dlogit -> d (last hidden) (+ the last layer's weight gradients), then per hidden layer
+            // d input = d hidden . W and dW = d hidden^T input, down to the gate inputs
             P.gate_layers = 2;
             P.gin_h = ginh_of(d); P.gin_o = gino_of(d);
-            P.hid_h = buf(TGGCN_BUF_GATE_HID_H); P.hid_o = buf(TGGCN_BUF_GATE_HID_O);
-            P.w2_h = W(TGGCN_W_UPD_H_W2); P.w2_o = W(TGGCN_W_UPD_O_W2);
-            if (sample_h) {
-                TG_REQUIRE(P.w2_h && G(TGGCN_W_UPD_H_W2) && G(TGGCN_W_UPD_H_B2), "backward: layer-2 human gate pointers missing");
-                P.dhid_h = bb(BL.dghid[0]); P.dw2_h = G(TGGCN_W_UPD_H_W2); P.db2_h = G(TGGCN_W_UPD_H_B2);
-                TG_CUDA_OK(cudaMemsetAsync(P.dw2_h, 0, sizeof(float) * (size_t)D, stream));
-                TG_CUDA_OK(cudaMemsetAsync(P.db2_h, 0, sizeof(float), stream));
-            }
-            if (sample_o) {
-                TG_REQUIRE(P.w2_o && G(TGGCN_W_UPD_O_W2) && G(TGGCN_W_UPD_O_B2), "backward: layer-2 object gate pointers missing");
-                P.dhid_o = bb(BL.dghid[1]); P.dw2_o = G(TGGCN_W_UPD_O_W2); P.db2_o = G(TGGCN_W_UPD_O_B2);
-                TG_CUDA_OK(cudaMemsetAsync(P.dw2_o, 0, sizeof(float) * (size_t)D, stream));
-                TG_CUDA_OK(cudaMemsetAsync(P.db2_o, 0, sizeof(float), stream));
+            const bool three = gate3_of(d);
+            const int last_id[2] = {three ? TGGCN_W_UPD_H_W4 : TGGCN_W_UPD_H_W2, three ? TGGCN_W_UPD_O_W4 : TGGCN_W_UPD_O_W2};
+            const int hid1_buf[2] = {TGGCN_BUF_GATE_HID_H, TGGCN_BUF_GATE_HID_O}, hid2_buf[2] = {TGGCN_BUF_GATE_HID2_H, TGGCN_BUF_GATE_HID2_O};
+            const int gin_buf[2] = {TGGCN_BUF_GATE_IN_H, TGGCN_BUF_GATE_IN_O};
+            const int w1_id[2] = {TGGCN_W_UPD_H_W, TGGCN_W_UPD_O_W}, w2_id[2] = {TGGCN_W_UPD_H_W2, TGGCN_W_UPD_O_W2};
+            const bool sample[2] = {sample_h, sample_o};
+            const int Ee[2] = {H, O}, gin[2] = {P.gin_h, P.gin_o};
+            P.hid_h = buf(three ? hid2_buf[0] : hid1_buf[0]); P.hid_o = buf(three ? hid2_buf[1] : hid1_buf[1]);
+            P.w2_h = W(last_id[0]); P.w2_o = W(last_id[1]);
+            for (int k = 0; k < 2; ++k) {
+                if (!sample[k]) continue;
+                TG_REQUIRE(W(last_id[k]) && G(last_id[k]) && G(last_id[k] + 1) && W(w1_id[k]) && G(w1_id[k]) && G(w1_id[k] + 1),
+                           "backward: gate MLP pointers of entity type %d missing", k);
+                if (three) TG_REQUIRE(W(w2_id[k]) && G(w2_id[k]) && G(w2_id[k] + 1), "backward: middle gate layer pointers of entity type %d missing", k);
+                float* dh = bb(BL.dghid[k]);
+                float* dwl = G(last_id[k]);
+                float* dbl = G(last_id[k] + 1);
+                if (k == 0) { P.dhid_h = dh; P.dw2_h = dwl; P.db2_h = dbl; } else { P.dhid_o = dh; P.dw2_o = dwl; P.db2_o = dbl; }
+                TG_CUDA_OK(cudaMemsetAsync(dwl, 0, sizeof(float) * (size_t)D, stream));
+                TG_CUDA_OK(cudaMemsetAsync(dbl, 0, sizeof(float), stream));
             }
             if (sample_h || sample_o) {
                 if (int rc = launch_gate_bwd(P, stream)) return rc;
                 float* wt = bb(BL.wt);
-                if (sample_h) {
-                    const WSrc w1[1] = {{W(TGGCN_W_UPD_H_W), P.gin_h, D}};
-                    if (int rc = dx_gemm(P.dhid_h, D, nullptr, 0, w1, 1, P.gin_h, bb(BL.dgin[0]), P.gin_h, N * H, 0, wt)) return rc;
-                    if (int rc = tn(P.dhid_h, D, nullptr, 0, buf(TGGCN_BUF_GATE_IN_H), P.gin_h, G(TGGCN_W_UPD_H_W), P.gin_h, N * H, D, P.gin_h,
-                                    0, 0, 0, stream, G(TGGCN_W_UPD_H_B))) return rc;
-                    P.dgin_h = bb(BL.dgin[0]);
-                }
-                if (sample_o) {
-                    const WSrc w1[1] = {{W(TGGCN_W_UPD_O_W), P.gin_o, D}};
-                    if (int rc = dx_gemm(P.dhid_o, D, nullptr, 0, w1, 1, P.gin_o, bb(BL.dgin[1]), P.gin_o, N * O, 0, wt)) return rc;
-                    if (int rc = tn(P.dhid_o, D, nullptr, 0, buf(TGGCN_BUF_GATE_IN_O), P.gin_o, G(TGGCN_W_UPD_O_W), P.gin_o, N * O, D, P.gin_o,
-                                    0, 0, 0, stream, G(TGGCN_W_UPD_O_B))) return rc;
-                    P.dgin_o = bb(BL.dgin[1]);
+                for (int k = 0; k < 2; ++k) {
+                    if (!sample[k]) continue;
+                    const int M = N * Ee[k];
+                    const float* dz = bb(BL.dghid[k]);           // gradient of the last hidden layer, ReLU mask applied by gate_bwd_kernel
+                    const float* zmask = nullptr;
+                    if (three) {                                 // middle layer: hid2 = ReLU(W2 hid1 + b2)
+                        const WSrc w2[1] = {{W(w2_id[k]), D, D}};
+                        if (int rc = dx_gemm(dz, D, nullptr, 0, w2, 1, D, bb(BL.dghid1[k]), D, M, 0, wt)) return rc;
+                        if (int rc = tn(dz, D, nullptr, 0, buf(hid1_buf[k]), D, G(w2_id[k]), D, M, D, D, 0, 0, 0, stream, G(w2_id[k] + 1))) return rc;
+                        dz = bb(BL.dghid1[k]);                   // gradient of hid1 BEFORE its ReLU mask: the mask rides on the operand packs
+                        zmask = buf(hid1_buf[k]);
+                    }
+                    const WSrc w1[1] = {{W(w1_id[k]), gin[k], D}};
+                    if (int rc = dx_gemm(dz, D, zmask, D, w1, 1, gin[k], bb(BL.dgin[k]), gin[k], M, 0, wt)) return rc;
+                    if (int rc = tn(dz, D, zmask, D, buf(gin_buf[k]), gin[k], G(w1_id[k]), gin[k], M, D, gin[k], 0, 0, 0, stream, G(w1_id[k] + 1))) return rc;
+                    if (k == 0) P.dgin_h = bb(BL.dgin[0]); else P.dgin_o = bb(BL.dgin[1]);
                 }
                 if (int rc = tn_flush(stream)) return rc;
             }

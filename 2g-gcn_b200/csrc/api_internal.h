@@ -23,7 +23,8 @@ inline int ldwo_of(const tggcn_dims& d) { return ko_of(d) + 2 * d.D; }
 // gate MLP input widths: [x, h, m_hh?, m_oh, m_gh?, time_u?] / [x, h, m_ho, m_oo, m_go, time_u?]
 inline int ginh_of(const tggcn_dims& d) { return (2 + nkh_of(d) + gh_of(d) + tu_of(d)) * d.D; }
 inline int gino_of(const tggcn_dims& d) { return (5 + tu_of(d)) * d.D; }
-inline bool gate2_of(const tggcn_dims& d) { return d.gate_layers == 2; }
+inline bool gate2_of(const tggcn_dims& d) { return d.gate_layers >= 2; }      // gate MLPs with hidden layers
+inline bool gate3_of(const tggcn_dims& d) { return d.gate_layers == 3; }
 void make_layout(const tggcn_dims& d, Layout& L);
 int check_dims(const tggcn_dims& d);
 

@@ -127,7 +127,7 @@ class TGGCN(nn.Module):
                  share_level_mlps: bool = False, bias: bool = True):
         super().__init__()
         unsupported = []
-        if discrete_networks_num_layers not in (1, 2): unsupported.append('discrete_networks_num_layers not in {1, 2}')
+        if discrete_networks_num_layers not in (1, 2, 3): unsupported.append('discrete_networks_num_layers not in {1, 2, 3}')
         if discrete_optimization_strategy not in _GS | _ST: unsupported.append('unknown discrete_optimization_strategy')
         if not (message_human_to_objects and message_objects_to_human and message_objects_to_object
                 and message_geometry_to_objects): unsupported.append('a human/object/geometry message switched off')

@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define TGGCN_ABI_VERSION 15
+#define TGGCN_ABI_VERSION 16
 
 #if defined(__GNUC__)
 #define TGGCN_API __attribute__((visibility("default")))
@@ -85,8 +85,9 @@ typedef struct tggcn_dims {
                                     a frame with a non-zero hard gate the (normalised) time since the previous such frame, else 0; the
                                     hard gates receive a gradient through it.  Needs tggcn_io.steps_per_example                  */
     int32_t gate_layers;         /* discrete_networks_num_layers (models.py:532-547): 0 / 1 = Linear(in, 1) + sigmoid; 2 = Linear(in, D) +
-                                    ReLU + Linear(D, 1) + sigmoid: update_*_segment_mlp.0 is then (D, in) and .2 is (1, D); the gate
-                                    inputs are materialised (TGGCN_BUF_GATE_IN_*) and the hidden layer is a projection GEMM        */
+                                    ReLU + Linear(D, 1) + sigmoid: update_*_segment_mlp.0 is then (D, in) and .2 is (1, D); 3 = one more
+                                    Linear(D, D) + ReLU in between (.2 is (D, D), .4 is (1, D)).  From 2 on the gate inputs are
+                                    materialised (TGGCN_BUF_GATE_IN_*) and the hidden layers are projection GEMMs                  */
 } tggcn_dims;
 
 /* Parameter table.  One device pointer per reference state_dict() entry, in this order
@@ -206,7 +207,11 @@ typedef struct tggcn_dims {
     X(UPD_H_W2,     "update_human_segment_mlp.2.weight")                                               \
     X(UPD_H_B2,     "update_human_segment_mlp.2.bias")                                                 \
     X(UPD_O_W2,     "update_object_segment_mlp.2.weight")                                              \
-    X(UPD_O_B2,     "update_object_segment_mlp.2.bias")
+    X(UPD_O_B2,     "update_object_segment_mlp.2.bias")                                                \
+    X(UPD_H_W4,     "update_human_segment_mlp.4.weight")                                               \
+    X(UPD_H_B4,     "update_human_segment_mlp.4.bias")                                                 \
+    X(UPD_O_W4,     "update_object_segment_mlp.4.weight")                                              \
+    X(UPD_O_B4,     "update_object_segment_mlp.4.bias")
 
 enum tggcn_weight_id {
 #define TGGCN_X_ENUM(id, key) TGGCN_W_##id,
@@ -305,6 +310,8 @@ enum tggcn_buf_id {
     TGGCN_BUF_GATE_IN_O,     /* (B,T,O,in_o)         [x, h, m_ho, m_oo, m_go, (time)]                                    */
     TGGCN_BUF_GATE_HID_H,    /* (B,T,H,D)            hidden layer of the gate MLPs (post-ReLU)                            */
     TGGCN_BUF_GATE_HID_O,    /* (B,T,O,D)                                                                                 */
+    TGGCN_BUF_GATE_HID2_H,   /* (B,T,H,D)            second hidden layer (dims.gate_layers == 3 only)                     */
+    TGGCN_BUF_GATE_HID2_O,   /* (B,T,O,D)                                                                                 */
     TGGCN_BUF_COUNT
 };
 

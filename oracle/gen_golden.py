@@ -93,6 +93,8 @@ CASES = [
     # discrete_networks_num_layers = 2 (models.py:532-547): hidden layer in the gate MLPs; alone and with every gate-input block + 'coh'
     ('mphoi_s2_gate2', 'mphoi', 32, 2, 12, 2, False, 2.0, False, {'discrete_networks_num_layers': 2}),
     ('cad120_nf_gate2_mix', 'cad120', 32, 2, 11, 2, False, 2.0, False, {'discrete_networks_num_layers': 2, 'add_time_position': 1, 'time_position_strategy': 'u', 'message_geometry_to_human': True, 'filter_discrete_updates': 0, 'update_segment_threshold': 0.5, 'object_segment_update_strategy': 'coh'}),
+    ('mphoi_s2_gate3', 'mphoi', 32, 2, 12, 2, False, 2.0, False, {'discrete_networks_num_layers': 3}),
+    ('cad120_s2_gate3_sah_u', 'cad120', 32, 2, 11, 2, False, 2.0, False, {'discrete_networks_num_layers': 3, 'add_time_position': 1, 'time_position_strategy': 'u', 'object_segment_update_strategy': 'sah'}),
     # the benchmarked configuration itself (BASELINE.json configs[1]: MPHOI, B=8, T=128, hidden 512, stage-2 settings)
     ('mphoi_s2_d512_full', 'mphoi', 512, 8, 128, 2, False, 1.0, False),
 ]
@@ -242,6 +244,8 @@ GRAD_CASES = [
     ('grad_cad120_s2_dist', 'cad120', 32, 2, 8, 2, 2.0, {'_distances': True}),
     ('grad_mphoi_s2_gate2', 'mphoi', 32, 2, 9, 2, 2.0, {'discrete_networks_num_layers': 2}),
     ('grad_cad120_nf_gate2_mix', 'cad120', 32, 2, 8, 2, 2.0, {'discrete_networks_num_layers': 2, 'add_time_position': 1, 'time_position_strategy': 'u', 'message_geometry_to_human': True, 'filter_discrete_updates': 0, 'update_segment_threshold': 0.5, 'object_segment_update_strategy': 'coh'}),
+    ('grad_mphoi_s2_gate3', 'mphoi', 32, 2, 9, 2, 2.0, {'discrete_networks_num_layers': 3}),
+    ('grad_cad120_s2_gate3_sah_u', 'cad120', 32, 2, 8, 2, 2.0, {'discrete_networks_num_layers': 3, 'add_time_position': 1, 'time_position_strategy': 'u', 'object_segment_update_strategy': 'sah'}),
     # no gradient case for discrete_optimization_strategy 'st': the reference's StraightThroughEstimator.backward returns one gradient
     # for two forward inputs and autograd rejects it (distributions.py:39-53) — the reference cannot train with it
     # hidden 512 (the benchmarked width), T = 32: the D=512 BPTT and split-K weight-gradient paths against the reference itself

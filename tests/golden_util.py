@@ -42,6 +42,8 @@ CASES = {
     'cad120_s2_dist': ('cad120', 32, 2, 11, 2, False, False, {'_distances': True}),
     'mphoi_s2_gate2': ('mphoi', 32, 2, 12, 2, False, False, {'discrete_networks_num_layers': 2}),
     'cad120_nf_gate2_mix': ('cad120', 32, 2, 11, 2, False, False, {'discrete_networks_num_layers': 2, 'add_time_position': 1, 'time_position_strategy': 'u', 'message_geometry_to_human': True, 'filter_discrete_updates': 0, 'update_segment_threshold': 0.5, 'object_segment_update_strategy': 'coh'}),
+    'mphoi_s2_gate3': ('mphoi', 32, 2, 12, 2, False, False, {'discrete_networks_num_layers': 3}),
+    'cad120_s2_gate3_sah_u': ('cad120', 32, 2, 11, 2, False, False, {'discrete_networks_num_layers': 3, 'add_time_position': 1, 'time_position_strategy': 'u', 'object_segment_update_strategy': 'sah'}),
 }
 
 # BASELINE.json configs[1] itself — what bench.py times (reference outputs; gate margin 2.5e-5).  Kept apart from CASES: the
@@ -79,6 +81,8 @@ GRAD_CASES = {
     'grad_cad120_s2_dist': ('cad120', 32, 2, 8, 2, {'_distances': True}),
     'grad_mphoi_s2_gate2': ('mphoi', 32, 2, 9, 2, {'discrete_networks_num_layers': 2}),
     'grad_cad120_nf_gate2_mix': ('cad120', 32, 2, 8, 2, {'discrete_networks_num_layers': 2, 'add_time_position': 1, 'time_position_strategy': 'u', 'message_geometry_to_human': True, 'filter_discrete_updates': 0, 'update_segment_threshold': 0.5, 'object_segment_update_strategy': 'coh'}),
+    'grad_mphoi_s2_gate3': ('mphoi', 32, 2, 9, 2, {'discrete_networks_num_layers': 3}),
+    'grad_cad120_s2_gate3_sah_u': ('cad120', 32, 2, 8, 2, {'discrete_networks_num_layers': 3, 'add_time_position': 1, 'time_position_strategy': 'u', 'object_segment_update_strategy': 'sah'}),
 }
 
 # hidden 512 (the benchmarked width), T = 32.  Kept apart from GRAD_CASES: the reference's own fp32 autograd carries summation

@@ -26,7 +26,7 @@ def test_constructor_accepts_yaml_values_and_rejects_the_rest(pkg, synth):
     assert m.filter_discrete_updates and m.update_segment_threshold == pytest.approx(0.1)
     for bad in (dict(message_type='v1'), dict(attention_style='v1'), dict(message_aggregation='max'),
                 dict(object_segment_update_strategy='xyz'), dict(add_time_position=1, time_position_strategy='x'), dict(share_level_mlps=1, bias=False),
-                dict(discrete_networks_num_layers=3), dict(message_human_to_objects=False), dict(hidden_size=20)):
+                dict(discrete_networks_num_layers=4), dict(message_human_to_objects=False), dict(hidden_size=20)):
         with pytest.raises(NotImplementedError):
             pkg.TGGCN(**{**kw, **bad})
     assert pkg.select_model('2G-GCN') is pkg.TGGCN
@@ -82,7 +82,7 @@ def test_weight_table_covers_the_state_dict(pkg, synth):
         model = pkg.TGGCN(**synth.model_kwargs(synth.SHAPES[name], hidden_size=32, stage=1))
         keys = set(model.state_dict().keys())
         table = set(pkg.abi.WEIGHT_KEYS)
-        assert table <= keys | {k for k in table if k.startswith('object_') or k.startswith('humans_to_human') or k.startswith('time_position_mlp') or k.startswith('geometry_to_human') or k.startswith('segment_length_mlp') or '_segment_mlp.2.' in k}
+        assert table <= keys | {k for k in table if k.startswith('object_') or k.startswith('humans_to_human') or k.startswith('time_position_mlp') or k.startswith('geometry_to_human') or k.startswith('segment_length_mlp') or '_segment_mlp.2.' in k or '_segment_mlp.4.' in k}
         used_somewhere = {k for k in keys if k in table}
         # everything not in the table is a parameter the shipped configuration never reads
         dead = keys - used_somewhere
